@@ -1,0 +1,278 @@
+"""oracle/api.py -- TEST INFRASTRUCTURE: ctypes front-end of the CPU oracle.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs import this module.  The product package (abeille_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+from . import deck as _deck
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+
+_PD = C.POINTER(C.c_double)
+_PU64 = C.POINTER(C.c_uint64)
+
+
+class _Bank(C.Structure):
+    _fields_ = [("n", C.c_uint64)] + [(k, _PD) for k in ("x", "y", "z", "ux", "uy", "uz", "E", "wgt", "wgt2")] + [
+        ("id_a", _PU64), ("id_b", _PU64), ("id_c", _PU64)]
+
+
+BANK_F64 = ("x", "y", "z", "ux", "uy", "uz", "E", "wgt", "wgt2")
+BANK_U64 = ("id_a", "id_b", "id_c")
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.orc_load.restype = C.c_void_p
+        L.orc_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_last_error.argtypes = [C.c_void_p]
+        L.orc_rng_exponential.restype = C.c_double
+        L.orc_rng_exponential.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_double]
+        L.orc_tally_size.restype = C.c_uint64
+        for name in ("orc_free", "orc_set_nparticles", "orc_set_converged", "orc_set_kcol", "orc_set_trace",
+                     "orc_reset_counters", "orc_get_counters", "orc_get_majorant", "orc_ngroups", "orc_nparticles",
+                     "orc_find_cells", "orc_sample_source", "orc_set_history_counter", "orc_transport",
+                     "orc_get_trace", "orc_ntallies", "orc_tally_size", "orc_tally_shape", "orc_tally_get",
+                     "orc_tallies_record", "orc_tallies_clear", "orc_tallies_calc_gen", "orc_cancel_and_normalize",
+                     "orc_run_power_iteration"):
+            getattr(L, name).argtypes = None
+        _lib = L
+    return _lib
+
+
+def new_bank(n: int) -> dict:
+    b = {k: np.zeros(n, dtype=np.float64) for k in BANK_F64}
+    b.update({k: np.zeros(n, dtype=np.uint64) for k in BANK_U64})
+    return b
+
+
+def _as_struct(b: dict, n: int | None = None, allow_null=()):
+    s = _Bank()
+    s.n = int(len(b["x"]) if n is None else n)
+    for k in BANK_F64:
+        a = b.get(k)
+        if a is None:
+            a = np.zeros(s.n)
+            b[k] = a
+        assert a.dtype == np.float64 and a.flags.c_contiguous
+        setattr(s, k, a.ctypes.data_as(_PD))
+    for k in BANK_U64:
+        a = b.get(k)
+        if a is None and k in allow_null:
+            setattr(s, k, None)
+            continue
+        assert a.dtype == np.uint64 and a.flags.c_contiguous
+        setattr(s, k, a.ctypes.data_as(_PU64))
+    return s
+
+
+def set_math(mode: str) -> None:
+    """'libm' = glibc log/sin/cos like the reference; 'det' = the shared deterministic kernels."""
+    lib().orc_set_math(C.c_int(0 if mode == "libm" else 1))
+
+
+def set_threads(n: int) -> None:
+    lib().orc_set_threads(C.c_int(int(n)))
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
+
+
+class Oracle:
+    """One loaded problem (deck) on the CPU oracle."""
+
+    def __init__(self, yaml_path: str, overrides: dict | None = None):
+        L = lib()
+        with tempfile.NamedTemporaryFile("w", suffix=".orcdeck", delete=False) as f:
+            f.write(_deck.deck_to_text(_deck.apply_overrides(_deck.load_yaml(yaml_path), overrides)))
+            path = f.name
+        err = C.create_string_buffer(512)
+        self.h = L.orc_load(path.encode(), err, 512)
+        os.unlink(path)
+        if not self.h:
+            raise RuntimeError("oracle: " + err.value.decode())
+        self.h = C.c_void_p(self.h)
+        self.G = int(L.orc_ngroups(self.h))
+
+    def close(self):
+        if self.h:
+            lib().orc_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self):
+        return lib().orc_last_error(self.h).decode()
+
+    # --- settings ---
+    def set_nparticles(self, n): lib().orc_set_nparticles(self.h, C.c_int(int(n)))
+    def set_converged(self, c): lib().orc_set_converged(self.h, C.c_int(int(bool(c))))
+    def set_kcol(self, k): lib().orc_set_kcol(self.h, C.c_double(float(k)))
+    def set_trace(self, t): lib().orc_set_trace(self.h, C.c_int(int(bool(t))))
+    def set_history_counter(self, c): lib().orc_set_history_counter(self.h, C.c_uint64(int(c)))
+    def nparticles(self): return int(lib().orc_nparticles(self.h))
+
+    def majorant(self):
+        maj = np.zeros(self.G)
+        smp = np.zeros(self.G)
+        lib().orc_get_majorant(self.h, maj.ctypes.data_as(_PD), smp.ctypes.data_as(_PD))
+        return maj, smp
+
+    def counters(self) -> dict:
+        out = np.zeros(8, dtype=np.uint64)
+        lib().orc_get_counters(self.h, out.ctypes.data_as(_PU64))
+        keys = ("flights", "real_collisions", "virtual_collisions", "tl_bins", "fission_sites",
+                "boundary_events", "lost_at_birth", "coll_scores")
+        return {k: int(v) for k, v in zip(keys, out)}
+
+    def reset_counters(self): lib().orc_reset_counters(self.h)
+
+    # --- geometry probe ---
+    def find_cells(self, r: np.ndarray, u: np.ndarray):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        n = r.shape[0]
+        cell = np.zeros(n, dtype=np.int32)
+        mat = np.zeros(n, dtype=np.int32)
+        lib().orc_find_cells(self.h, C.c_int(n), r.ctypes.data_as(_PD), u.ctypes.data_as(_PD),
+                             cell.ctypes.data_as(C.POINTER(C.c_int32)), mat.ctypes.data_as(C.POINTER(C.c_int32)))
+        return cell, mat
+
+    # --- source / transport ---
+    def sample_source(self, n: int) -> dict:
+        """Bank dict: id_a = history id, id_b = family id, id_c = rng state after source sampling."""
+        b = new_bank(n)
+        s = _as_struct(b)
+        if lib().orc_sample_source(self.h, C.byref(s)) != 0:
+            raise RuntimeError("oracle: " + self._err())
+        return b
+
+    def transport(self, bank: dict, noise: bool = False, capacity: int | None = None):
+        """Returns (fission_bank dict, scores[6], n_out). Input id_c=None => rng from seed/stride/history id."""
+        n = len(bank["x"])
+        cap = int(capacity if capacity is not None else max(4 * n, 1024))
+        out = new_bank(cap)
+        sin = _as_struct(bank, allow_null=("id_c",))
+        sout = _as_struct(out)
+        nout = C.c_uint64(0)
+        scores = np.zeros(6)
+        rc = lib().orc_transport(self.h, C.byref(sin), C.c_int(int(noise)), C.byref(sout), C.byref(nout),
+                                 scores.ctypes.data_as(_PD))
+        if rc != 0:
+            raise RuntimeError("oracle: " + self._err())
+        m = int(nout.value)
+        if m > cap:
+            raise RuntimeError(f"oracle: fission bank capacity {cap} < {m}")
+        return {k: v[:m].copy() for k, v in out.items()}, scores, m
+
+    def trace(self, n: int) -> dict:
+        t = {k: np.zeros(n, dtype=np.uint32) for k in ("flights", "real", "virtual", "fission")}
+        t["hash"] = np.zeros(n, dtype=np.uint64)
+        t["rng_state"] = np.zeros(n, dtype=np.uint64)
+        P32 = C.POINTER(C.c_uint32)
+        lib().orc_get_trace(self.h, t["flights"].ctypes.data_as(P32), t["real"].ctypes.data_as(P32),
+                            t["virtual"].ctypes.data_as(P32), t["fission"].ctypes.data_as(P32),
+                            t["hash"].ctypes.data_as(_PU64), t["rng_state"].ctypes.data_as(_PU64))
+        return t
+
+    # --- tallies ---
+    def ntallies(self): return int(lib().orc_ntallies(self.h))
+
+    def tally_shape(self, t):
+        sh = np.zeros(4, dtype=np.uint64)
+        lib().orc_tally_shape(self.h, C.c_int(t), sh.ctypes.data_as(_PU64))
+        return tuple(int(v) for v in sh)
+
+    def tally(self, t: int, which: str = "gen") -> np.ndarray:
+        n = int(lib().orc_tally_size(self.h, C.c_int(t)))
+        out = np.zeros(n)
+        lib().orc_tally_get(self.h, C.c_int(t), C.c_int({"gen": 0, "avg": 1, "var": 2, "std": 3}[which]),
+                            out.ctypes.data_as(_PD))
+        return out.reshape(self.tally_shape(t))
+
+    def tallies_record(self, mult=1.0): lib().orc_tallies_record(self.h, C.c_double(mult))
+    def tallies_clear(self): lib().orc_tallies_clear(self.h)
+
+    def calc_gen_values(self):
+        out = np.zeros(6)
+        lib().orc_tallies_calc_gen(self.h, out.ctypes.data_as(_PD))
+        return out
+
+    def cancel_and_normalize(self, bank: dict, do_cancel: bool):
+        s = _as_struct(bank)
+        stats = np.zeros(6)
+        lib().orc_cancel_and_normalize(self.h, C.byref(s), C.c_int(int(do_cancel)), stats.ctypes.data_as(_PD))
+        return stats
+
+    def run_power_iteration(self, ngen: int, nignored: int) -> dict:
+        arr = {k: np.zeros(ngen) for k in ("kcol", "ktrk", "leak", "mig", "entropy")}
+        nbank = np.zeros(ngen, dtype=np.uint64)
+        summ = np.zeros(8)
+        rc = lib().orc_run_power_iteration(self.h, C.c_int(ngen), C.c_int(nignored),
+                                           *[arr[k].ctypes.data_as(_PD) for k in ("kcol", "ktrk", "leak", "mig", "entropy")],
+                                           nbank.ctypes.data_as(_PU64), summ.ctypes.data_as(_PD))
+        if rc != 0:
+            raise RuntimeError("oracle: " + self._err())
+        arr["nbank"] = nbank
+        arr.update(kcol_avg=summ[0], kcol_err=summ[1], ktrk_avg=summ[2], ktrk_err=summ[3], leak_avg=summ[4],
+                   leak_err=summ[5], seconds=summ[6], active_particles=summ[7])
+        return arr
+
+
+# --- RNG / math known-answer helpers ---
+def rng_stream(seed, stride, hid, n):
+    out = np.zeros(n, dtype=np.uint32)
+    lib().orc_rng_stream(C.c_uint64(seed), C.c_uint64(stride), C.c_uint64(hid), C.c_int(n),
+                         out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return out
+
+
+def rng_rand(seed, stride, hid, n):
+    out = np.zeros(n)
+    lib().orc_rng_rand(C.c_uint64(seed), C.c_uint64(stride), C.c_uint64(hid), C.c_int(n), out.ctypes.data_as(_PD))
+    return out
+
+
+def rng_exponential(seed, stride, hid, lam):
+    return float(lib().orc_rng_exponential(C.c_uint64(seed), C.c_uint64(stride), C.c_uint64(hid), C.c_double(lam)))
+
+
+def rng_discrete(seed, stride, hid, weights, ndraws):
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    out = np.zeros(ndraws, dtype=np.int32)
+    nd = lib().orc_rng_discrete(C.c_uint64(seed), C.c_uint64(stride), C.c_uint64(hid), w.ctypes.data_as(_PD),
+                                C.c_int(len(w)), C.c_int(ndraws), out.ctypes.data_as(C.POINTER(C.c_int32)))
+    return out, int(nd)
+
+
+def math_eval(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    lg, sn, cs = np.zeros_like(x), np.zeros_like(x), np.zeros_like(x)
+    lib().orc_math_eval(C.c_int(len(x)), x.ctypes.data_as(_PD), lg.ctypes.data_as(_PD), sn.ctypes.data_as(_PD),
+                        cs.ctypes.data_as(_PD))
+    return lg, sn, cs
