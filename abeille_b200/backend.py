@@ -1,0 +1,397 @@
+"""ctypes bindings of the two native libraries (see include/abeille_b200.h and host/capi.cpp)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBDIR = os.path.join(_HERE, "lib")
+
+_PD = C.POINTER(C.c_double)
+_PU64 = C.POINTER(C.c_uint64)
+_PU32 = C.POINTER(C.c_uint32)
+_PI32 = C.POINTER(C.c_int32)
+
+BANK_F64 = ("x", "y", "z", "ux", "uy", "uz", "E", "wgt", "wgt2")
+BANK_U64 = ("id_a", "id_b", "id_c")
+COUNTER_KEYS = ("flights", "real_collisions", "virtual_collisions", "tl_bins", "fission_sites", "boundary_events",
+                "lost_at_birth", "coll_scores")
+
+# every symbol include/abeille_b200.h declares (tests/test_abi.py checks the library exports all of them)
+ABI_SYMBOLS = (
+    "abl_create", "abl_destroy", "abl_last_error", "abl_device_info", "abl_transport", "abl_get_trace",
+    "abl_transport_device", "abl_tally_count", "abl_tally_shape", "abl_tallies_record", "abl_tallies_clear",
+    "abl_tally_fetch", "abl_tally_device_ptr", "abl_sample_source_device", "abl_bank_weight_stats_device",
+    "abl_bank_scale_weights_device", "abl_bank_to_particles_device", "abl_entropy_bin_device",
+    "abl_score_source_device", "abl_cancel_device", "abl_bank_alloc_device", "abl_bank_free_device",
+    "abl_bank_upload", "abl_bank_download", "abl_device_alloc", "abl_device_free", "abl_device_zero",
+    "abl_device_read", "abl_find_cells", "abl_rng_probe", "abl_math_probe")
+
+
+class BackendError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"abeille_b200 backend error {code}: {msg}")
+        self.code = code
+
+
+class AblBank(C.Structure):
+    _fields_ = [("n", C.c_uint64)] + [(k, _PD) for k in BANK_F64] + [(k, _PU64) for k in BANK_U64]
+
+
+class AblGenParams(C.Structure):
+    _fields_ = [("k_col", C.c_double), ("keff", C.c_double), ("converged", C.c_int32), ("noise", C.c_int32),
+                ("trace", C.c_int32), ("pad_", C.c_int32)]
+
+
+class AblTrace(C.Structure):
+    _fields_ = [("flights", _PU32), ("real", _PU32), ("virt", _PU32), ("fission", _PU32), ("hash", _PU64),
+                ("rng_state", _PU64)]
+
+
+def lib_paths():
+    return os.path.join(_LIBDIR, "libabeille_b200.so"), os.path.join(_LIBDIR, "libabeille_host.so")
+
+
+_backend_lib = None
+_host_lib = None
+
+
+def load_backend_lib():
+    """libabeille_b200.so; raises if it has not been built (there is no fallback)."""
+    global _backend_lib
+    if _backend_lib is None:
+        path = lib_paths()[0]
+        if not os.path.exists(path):
+            raise BackendError(-2, f"{path} is missing: build it with __graft_entry__.build() (make -C abeille_b200/csrc)")
+        L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        L.abl_last_error.restype = C.c_char_p
+        L.abl_last_error.argtypes = [C.c_void_p]
+        _backend_lib = L
+    return _backend_lib
+
+
+def load_host_lib():
+    global _host_lib
+    if _host_lib is None:
+        load_backend_lib()
+        path = lib_paths()[1]
+        if not os.path.exists(path):
+            raise BackendError(-2, f"{path} is missing: build it with __graft_entry__.build() (make -C abeille_b200/host)")
+        L = C.CDLL(path)
+        L.ablh_open.restype = C.c_void_p
+        L.ablh_open.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+        L.ablh_close.argtypes = [C.c_void_p]
+        L.ablh_last_error.restype = C.c_char_p
+        L.ablh_last_error.argtypes = [C.c_void_p]
+        L.ablh_backend.restype = C.c_void_p
+        L.ablh_backend.argtypes = [C.c_void_p]
+        _host_lib = L
+    return _host_lib
+
+
+def new_bank(n: int, wgt2: bool = True) -> dict:
+    b = {k: np.zeros(n, dtype=np.float64) for k in BANK_F64 if wgt2 or k != "wgt2"}
+    b.update({k: np.zeros(n, dtype=np.uint64) for k in BANK_U64})
+    return b
+
+
+def _host_struct(b: dict, n=None) -> AblBank:
+    """abl_bank over numpy arrays (missing / None entries become NULL)."""
+    s = AblBank()
+    s.n = int(len(b["x"]) if n is None else n)
+    for k in BANK_F64:
+        a = b.get(k)
+        if a is None:
+            setattr(s, k, None)
+            continue
+        assert a.dtype == np.float64 and a.flags.c_contiguous, k
+        setattr(s, k, a.ctypes.data_as(_PD))
+    for k in BANK_U64:
+        a = b.get(k)
+        if a is None:
+            setattr(s, k, None)
+            continue
+        assert a.dtype == np.uint64 and a.flags.c_contiguous, k
+        setattr(s, k, a.ctypes.data_as(_PU64))
+    return s
+
+
+def _device_struct(b: dict, n: int) -> AblBank:
+    """abl_bank over torch CUDA tensors (float64 / int64 viewed as uint64)."""
+    s = AblBank()
+    s.n = int(n)
+    for k in BANK_F64:
+        t = b.get(k)
+        setattr(s, k, C.cast(C.c_void_p(t.data_ptr()), _PD) if t is not None else None)
+    for k in BANK_U64:
+        t = b.get(k)
+        setattr(s, k, C.cast(C.c_void_p(t.data_ptr()), _PU64) if t is not None else None)
+    return s
+
+
+def parse_only(yaml_path: str):
+    """Host-only: parse + flatten a deck (no device).  Returns (info dict, sampling xs per group)."""
+    L = load_host_lib()
+    info = (C.c_int64 * 12)()
+    maj = (C.c_double * 64)()
+    err = C.create_string_buffer(1024)
+    rc = L.ablh_parse_only(yaml_path.encode(), info, maj, 64, err, 1024)
+    if rc != 0:
+        raise BackendError(rc, err.value.decode())
+    keys = ("ngroups", "nparticles", "ngenerations", "nignored", "ntallies", "tracking", "mode", "nsurfaces", "ncells",
+            "nuniverses", "nmaterials", "max_stack_depth")
+    d = {k: int(v) for k, v in zip(keys, info)}
+    return d, np.array(maj[: d["ngroups"]])
+
+
+def dump_tables(yaml_path: str) -> dict:
+    L = load_host_lib()
+    cap = 1 << 24
+    out = C.create_string_buffer(cap)
+    err = C.create_string_buffer(1024)
+    rc = L.ablh_dump_tables(yaml_path.encode(), out, C.c_int64(cap), err, 1024)
+    if rc != 0:
+        raise BackendError(rc, err.value.decode())
+    tables = {}
+    for line in out.value.decode().splitlines():
+        name, *vals = line.split()
+        if name in ("rpn", "universe_cells", "lattice_tiles", "angle"):
+            tables[name] = np.array([int(v) for v in vals], dtype=np.int64)
+        else:
+            tables[name] = np.array([float(v) for v in vals], dtype=np.float64)
+    return tables
+
+
+def yaml_roundtrip(text: str) -> str:
+    L = load_host_lib()
+    cap = 1 << 22
+    out = C.create_string_buffer(cap)
+    rc = L.ablh_yaml_roundtrip(text.encode(), out, C.c_int64(cap))
+    if rc != 0:
+        raise BackendError(rc, out.value.decode())
+    return out.value.decode()
+
+
+class Backend:
+    """One deck loaded through the C++ host onto one CUDA device."""
+
+    def __init__(self, yaml_path: str, device: int = 0):
+        self.H = load_host_lib()
+        self.L = load_backend_lib()
+        err = C.create_string_buffer(2048)
+        ctx = self.H.ablh_open(str(yaml_path).encode(), int(device), err, 2048)
+        if not ctx:
+            raise BackendError(-1, err.value.decode())
+        self.ctx = C.c_void_p(ctx)
+        self.h = C.c_void_p(self.H.ablh_backend(self.ctx))
+        self.device = int(device)
+        info = (C.c_int64 * 12)()
+        self.H.ablh_info(self.ctx, info)
+        keys = ("ngroups", "nparticles", "ngenerations", "nignored", "ntallies", "tracking", "mode", "nsurfaces",
+                "ncells", "nuniverses", "nmaterials", "max_stack_depth")
+        self.info = {k: int(v) for k, v in zip(keys, info)}
+
+    # ---- lifetime ----
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.H.ablh_close(self.ctx)
+            self.ctx = None
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BackendError(rc, self.L.abl_last_error(self.h).decode())
+
+    def _hcheck(self, rc):
+        if rc != 0:
+            raise BackendError(rc, self.H.ablh_last_error(self.ctx).decode())
+
+    def device_info(self) -> dict:
+        sm, ma, mi, nl = C.c_int(), C.c_int(), C.c_int(), C.c_uint64()
+        self._check(self.L.abl_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(nl)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "kernel_launches": int(nl.value)}
+
+    # ---- Transporter::transport, host buffers (C ABI) ----
+    def transport(self, bank: dict, k_col: float = 1.0, converged: bool = False, trace: bool = False,
+                  capacity: int | None = None, out: dict | None = None):
+        """abl_transport.  Returns (fission bank dict, scores[6], counters dict)."""
+        n = len(bank["x"])
+        cap = int(capacity if capacity is not None else max(int(2.5 * n) + 4096, 4096))
+        if out is None:
+            out = new_bank(cap, wgt2=False)
+        sin = _host_struct(bank)
+        sout = _host_struct(out, cap)
+        gp = AblGenParams(float(k_col), 1.0, int(bool(converged)), 0, int(bool(trace)), 0)
+        nout = C.c_uint64(0)
+        scores = np.zeros(6)
+        cn = np.zeros(8, dtype=np.uint64)
+        rc = self.L.abl_transport(self.h, C.byref(sin), C.byref(gp), C.byref(sout), C.byref(nout),
+                                  scores.ctypes.data_as(_PD), cn.ctypes.data_as(_PU64))
+        self._check(rc)
+        m = int(nout.value)
+        fis = {k: v[:m] for k, v in out.items() if v is not None}
+        return fis, scores, {k: int(v) for k, v in zip(COUNTER_KEYS, cn)}
+
+    def trace(self, n: int) -> dict:
+        t = {k: np.zeros(n, dtype=np.uint32) for k in ("flights", "real", "virtual", "fission")}
+        t["hash"] = np.zeros(n, dtype=np.uint64)
+        t["rng_state"] = np.zeros(n, dtype=np.uint64)
+        s = AblTrace(t["flights"].ctypes.data_as(_PU32), t["real"].ctypes.data_as(_PU32),
+                     t["virtual"].ctypes.data_as(_PU32), t["fission"].ctypes.data_as(_PU32),
+                     t["hash"].ctypes.data_as(_PU64), t["rng_state"].ctypes.data_as(_PU64))
+        self._check(self.L.abl_get_trace(self.h, C.c_uint64(n), C.byref(s)))
+        return t
+
+    # ---- Transporter::transport through the C++ GPUTransporter adapter (vector<Particle>) ----
+    def transport_vectors(self, bank: dict, k_col: float = 1.0, converged: bool = False, capacity: int | None = None):
+        n = len(bank["x"])
+        cap = int(capacity if capacity is not None else max(int(2.5 * n) + 4096, 4096))
+        out = new_bank(cap)
+        sin = _host_struct(bank)
+        sout = _host_struct(out, cap)
+        nout = C.c_uint64(0)
+        scores = np.zeros(6)
+        rc = self.H.ablh_transport(self.ctx, C.byref(sin), C.c_int(int(bool(converged))), C.c_double(float(k_col)),
+                                   C.byref(sout), C.byref(nout), scores.ctypes.data_as(_PD))
+        self._hcheck(rc)
+        m = int(nout.value)
+        return {k: v[:m] for k, v in out.items()}, scores
+
+    def run_power_iteration(self, ngen: int, nignored: int, resident: bool = True) -> dict:
+        arr = {k: np.zeros(ngen) for k in ("kcol", "ktrk", "leak", "mig", "entropy")}
+        nbank = np.zeros(ngen, dtype=np.uint64)
+        summ = np.zeros(10)
+        rc = self.H.ablh_run_power_iteration(self.ctx, C.c_int(ngen), C.c_int(nignored), C.c_int(int(bool(resident))),
+                                             *[arr[k].ctypes.data_as(_PD) for k in ("kcol", "ktrk", "leak", "mig", "entropy")],
+                                             nbank.ctypes.data_as(_PU64), summ.ctypes.data_as(_PD))
+        self._hcheck(rc)
+        arr["nbank"] = nbank
+        arr.update(kcol_avg=summ[0], kcol_err=summ[1], ktrk_avg=summ[2], ktrk_err=summ[3], leak_avg=summ[4],
+                   leak_err=summ[5], seconds=summ[6], active_particles=summ[7], real_collisions=summ[8], flights=summ[9])
+        return arr
+
+    def write_results(self, directory: str):
+        os.makedirs(directory, exist_ok=True)
+        self._hcheck(self.H.ablh_write_results(self.ctx, str(directory).encode()))
+
+    # ---- tallies ----
+    def ntallies(self) -> int:
+        return int(self.L.abl_tally_count(self.h))
+
+    def tally_shape(self, t: int):
+        sh = (C.c_uint64 * 4)()
+        self._check(self.L.abl_tally_shape(self.h, C.c_int(t), sh))
+        return tuple(int(v) for v in sh)
+
+    def tally(self, t: int, which: str = "gen") -> np.ndarray:
+        shape = self.tally_shape(t)
+        out = np.zeros(int(np.prod(shape)))
+        self._check(self.L.abl_tally_fetch(self.h, C.c_int(t), C.c_int({"gen": 0, "avg": 1, "var": 2, "std": 3}[which]),
+                                           out.ctypes.data_as(_PD)))
+        return out.reshape(shape)
+
+    def tallies_record(self, multiplier: float = 1.0):
+        self._check(self.L.abl_tallies_record(self.h, C.c_double(multiplier)))
+
+    def tallies_clear(self):
+        self._check(self.L.abl_tallies_clear(self.h))
+
+    def tally_device_ptr(self, t: int, which: int = 0):
+        p = C.POINTER(C.c_double)()
+        n = C.c_uint64()
+        self._check(self.L.abl_tally_device_ptr(self.h, C.c_int(t), C.c_int(which), C.byref(p), C.byref(n)))
+        return C.cast(p, C.c_void_p).value, int(n.value)
+
+    # ---- probes ----
+    def find_cells(self, r: np.ndarray, u: np.ndarray):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        n = r.shape[0]
+        cell = np.zeros(n, dtype=np.int32)
+        mat = np.zeros(n, dtype=np.int32)
+        self._check(self.L.abl_find_cells(self.h, C.c_uint64(n), r.ctypes.data_as(_PD), u.ctypes.data_as(_PD),
+                                          cell.ctypes.data_as(_PI32), mat.ctypes.data_as(_PI32)))
+        return cell, mat
+
+    def rng_probe(self, history_id: int, n: int):
+        u32 = np.zeros(n, dtype=np.uint32)
+        rnd = np.zeros(n)
+        self._check(self.L.abl_rng_probe(self.h, C.c_uint64(history_id), C.c_int(n), u32.ctypes.data_as(_PU32),
+                                         rnd.ctypes.data_as(_PD)))
+        return u32, rnd
+
+    def math_probe(self, x: np.ndarray):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        lg, sn, cs = np.zeros_like(x), np.zeros_like(x), np.zeros_like(x)
+        self._check(self.L.abl_math_probe(self.h, C.c_int(len(x)), x.ctypes.data_as(_PD), lg.ctypes.data_as(_PD),
+                                          sn.ctypes.data_as(_PD), cs.ctypes.data_as(_PD)))
+        return lg, sn, cs
+
+    # ---- device-resident banks (torch tensors own the memory) ----
+    def new_device_bank(self, capacity: int) -> dict:
+        import torch
+        dev = torch.device("cuda", self.device)
+        b = {k: torch.zeros(capacity, dtype=torch.float64, device=dev) for k in BANK_F64}
+        b.update({k: torch.zeros(capacity, dtype=torch.int64, device=dev) for k in BANK_U64})
+        return b
+
+    @staticmethod
+    def _stream():
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def sample_source_device(self, bank: dict, n: int, first_history_id: int = 0):
+        s = _device_struct(bank, len(bank["x"]))
+        self._check(self.L.abl_sample_source_device(self.h, C.c_uint64(n), C.c_uint64(first_history_id), C.byref(s),
+                                                    self._stream()))
+
+    def transport_device(self, bank: dict, n: int, out: dict, k_col: float = 1.0, converged: bool = False,
+                         trace: bool = False, use_rng_state: bool = False):
+        """abl_transport_device on torch tensors.  Returns (n_fission, scores[6], counters dict)."""
+        sin = _device_struct(bank, n)
+        if not use_rng_state:
+            sin.id_c = None
+        sout = _device_struct(out, len(out["x"]))
+        gp = AblGenParams(float(k_col), 1.0, int(bool(converged)), 0, int(bool(trace)), 0)
+        nout = C.c_uint64(0)
+        scores = np.zeros(6)
+        cn = np.zeros(8, dtype=np.uint64)
+        rc = self.L.abl_transport_device(self.h, C.byref(sin), C.byref(gp), C.byref(sout), C.byref(nout),
+                                         scores.ctypes.data_as(_PD), cn.ctypes.data_as(_PU64), self._stream())
+        self._check(rc)
+        return int(nout.value), scores, {k: int(v) for k, v in zip(COUNTER_KEYS, cn)}
+
+    def weight_stats_device(self, bank: dict, n: int):
+        s = _device_struct(bank, n)
+        st = np.zeros(4)
+        self._check(self.L.abl_bank_weight_stats_device(self.h, C.byref(s), st.ctypes.data_as(_PD), self._stream()))
+        return st
+
+    def scale_weights_device(self, bank: dict, n: int, factor: float):
+        s = _device_struct(bank, n)
+        self._check(self.L.abl_bank_scale_weights_device(self.h, C.byref(s), C.c_double(factor), self._stream()))
+
+    def to_particles_device(self, bank: dict, n: int, first_history_id: int):
+        s = _device_struct(bank, n)
+        self._check(self.L.abl_bank_to_particles_device(self.h, C.byref(s), C.c_uint64(first_history_id), self._stream()))
+
+    def entropy_bin_device(self, bank: dict, n: int, bins, total):
+        s = _device_struct(bank, n)
+        self._check(self.L.abl_entropy_bin_device(self.h, C.byref(s), C.c_void_p(bins.data_ptr()),
+                                                  C.c_void_p(total.data_ptr()), self._stream()))
+
+    def score_source_device(self, bank: dict, n: int, noise_source: bool = False):
+        s = _device_struct(bank, n)
+        self._check(self.L.abl_score_source_device(self.h, C.byref(s), C.c_int(int(noise_source)), self._stream()))
+
+    def cancel_device(self, bank: dict, n: int):
+        s = _device_struct(bank, n)
+        self._check(self.L.abl_cancel_device(self.h, C.byref(s), self._stream()))

@@ -1,0 +1,959 @@
+/* api.cu -- the C ABI of libabeille_b200.so (declared in include/abeille_b200.h).
+ *
+ * Owns the device-side copy of the flattened problem, the scratch buffers of the transport
+ * kernel and the mesh-tally arrays.  No CPU fallback exists: without a CUDA device abl_create fails.
+ */
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bank_ops.cuh"
+
+using namespace abl;
+
+namespace {
+
+struct DevSmall {  // small per-call block, zeroed before every transport launch
+  unsigned long long ticket, n_sites;
+  double scores[6];
+  unsigned long long counters[8];
+  int error[4];
+  double stats[4];
+  uint32_t grand_total;
+  uint32_t pad_;
+};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct abl_context {
+  int device = 0;
+  int sm_count = 0, cc_major = 0, cc_minor = 0;
+  cudaStream_t stream = nullptr;
+  DevProblem P{};
+  std::vector<void*> allocs;  // immutable tables
+  std::vector<uint64_t> tally_g;
+  // scratch
+  Site* sites = nullptr;
+  uint64_t site_cap = 0;
+  uint32_t *nfis = nullptr, *offsets = nullptr, *tile_sums = nullptr;
+  uint32_t *tr_flights = nullptr, *tr_real = nullptr, *tr_virtual = nullptr;
+  uint64_t *tr_hash = nullptr, *tr_rng = nullptr;
+  uint64_t hist_cap = 0, trace_cap = 0, trace_n = 0;
+  DevSmall* small_dev = nullptr;
+  DevSmall* small_host = nullptr;  // pinned
+  double* secondaries = nullptr;
+  uint64_t sec_threads = 0;
+  CancelBins cancel{nullptr, nullptr, nullptr};
+  bool cancel_has_w2 = false;
+  // staging banks of the host-buffer API
+  BankView stage_in{}, stage_out{};
+  uint64_t stage_in_cap = 0, stage_out_cap = 0;
+  double* probe_buf = nullptr;
+  uint64_t probe_cap = 0;
+  int blocks_per_sm[3] = {0, 0, 0};
+  uint64_t launches = 0;
+  cudaStream_t last_stream = nullptr;
+  bool has_last_stream = false;
+  std::string error;
+};
+
+namespace {
+
+#define ABL_CUDA(h, call)                                                                         \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      (h)->error = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+      return ABL_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+// Calls on a handle share scratch buffers: when the caller switches streams, drain the previous one first.
+cudaStream_t use_stream(abl_handle h, cudaStream_t s) {
+  if (h->has_last_stream && h->last_stream != s) cudaStreamSynchronize(h->last_stream);
+  h->last_stream = s;
+  h->has_last_stream = true;
+  return s;
+}
+
+int fail(abl_handle h, int code, const std::string& msg) {
+  h->error = msg;
+  return code;
+}
+
+template <typename T>
+int upload(abl_handle h, const T* src, size_t n, const T** dst) {
+  *dst = nullptr;
+  if (n == 0) return ABL_OK;
+  if (!src) return fail(h, ABL_ERR_INVALID, "null table pointer");
+  void* d = nullptr;
+  ABL_CUDA(h, cudaMalloc(&d, n * sizeof(T)));
+  h->allocs.push_back(d);
+  ABL_CUDA(h, cudaMemcpy(d, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  *dst = static_cast<const T*>(d);
+  return ABL_OK;
+}
+
+// libstdc++ discrete_distribution partial sums (bits/random.tcc:2655-2713)
+std::vector<double> discrete_table(const std::vector<double>& w) {
+  std::vector<double> cp;
+  if (w.size() < 2) return cp;
+  double sum = 0.0;
+  for (double v : w) sum += v;
+  std::vector<double> p(w.size());
+  for (size_t i = 0; i < w.size(); i++) p[i] = w[i] / sum;
+  cp.resize(w.size());
+  double acc = p[0];
+  cp[0] = acc;
+  for (size_t i = 1; i < w.size(); i++) {
+    acc = acc + p[i];
+    cp[i] = acc;
+  }
+  cp.back() = 1.0;
+  return cp;
+}
+
+int validate(abl_handle h, const abl_problem* p) {
+  if (p->ngroups < 1 || !p->energy_bounds) return fail(h, ABL_ERR_INVALID, "ngroups / energy_bounds");
+  if (p->tracking < ABL_TRACK_SURFACE || p->tracking > ABL_TRACK_CARTER) return fail(h, ABL_ERR_INVALID, "tracking");
+  if (p->mode != ABL_MODE_K_EIGENVALUE) return fail(h, ABL_ERR_UNSUPPORTED, "only k-eigenvalue transport is implemented on the device");
+  if (p->ntallies > ABL_MAX_TALLIES) return fail(h, ABL_ERR_UNSUPPORTED, "more than ABL_MAX_TALLIES mesh tallies");
+  if (p->root_universe < 0 || p->root_universe >= p->nuniverses) return fail(h, ABL_ERR_INVALID, "root universe");
+  for (int c = 0; c < p->ncells; c++) {
+    const abl_cell& cl = p->cells[c];
+    if (cl.rpn_offset < 0 || cl.rpn_len < 0 || cl.rpn_offset + cl.rpn_len > p->nrpn) return fail(h, ABL_ERR_INVALID, "cell rpn slice");
+    if (cl.rpn_len > 64) return fail(h, ABL_ERR_UNSUPPORTED, "cell region longer than 64 tokens");
+    for (int k = 0; k < cl.rpn_len; k++) {
+      const int32_t t = p->rpn[cl.rpn_offset + k];
+      if (t >= ABL_OP_UNION) continue;
+      const int s = t < 0 ? -t : t;
+      if (s < 1 || s > p->nsurfaces) return fail(h, ABL_ERR_INVALID, "cell references an unknown surface");
+    }
+    if (cl.fill_universe >= p->nuniverses || (cl.fill_universe < 0 && (cl.material < 0 || cl.material >= p->nmaterials)))
+      return fail(h, ABL_ERR_INVALID, "cell fill");
+  }
+  for (int u = 0; u < p->nuniverses; u++) {
+    const abl_universe& U = p->universes[u];
+    if (U.type == ABL_UNI_CELLS) {
+      if (U.cell_offset < 0 || U.cell_offset + U.ncells > p->n_universe_cells) return fail(h, ABL_ERR_INVALID, "universe cell slice");
+      for (int k = 0; k < U.ncells; k++)
+        if (p->universe_cells[U.cell_offset + k] < 0 || p->universe_cells[U.cell_offset + k] >= p->ncells)
+          return fail(h, ABL_ERR_INVALID, "universe cell index");
+    } else if (U.type == ABL_UNI_RECT) {
+      const long long nt = (long long)U.N[0] * U.N[1] * U.N[2];
+      if (nt <= 0 || U.tile_offset < 0 || U.tile_offset + nt > p->n_lattice_tiles) return fail(h, ABL_ERR_INVALID, "lattice tile slice");
+      for (long long k = 0; k < nt; k++)
+        if (p->lattice_tiles[U.tile_offset + k] >= p->nuniverses) return fail(h, ABL_ERR_INVALID, "lattice tile universe");
+      if (U.outer >= p->nuniverses) return fail(h, ABL_ERR_INVALID, "lattice outer universe");
+    } else {
+      return fail(h, ABL_ERR_UNSUPPORTED, "universe type");
+    }
+  }
+  if (p->tracking != ABL_TRACK_SURFACE && !p->sampling_xs) return fail(h, ABL_ERR_INVALID, "sampling_xs missing");
+  return ABL_OK;
+}
+
+DevMesh3 make_mesh3(const abl_mesh3& m, const double* tally_eb_dev) {
+  DevMesh3 d{};
+  d.present = m.present;
+  d.Nx = m.N[0]; d.Ny = m.N[1]; d.Nz = m.N[2];
+  d.lowx = m.low[0]; d.lowy = m.low[1]; d.lowz = m.low[2];
+  d.hix = m.hi[0]; d.hiy = m.hi[1]; d.hiz = m.hi[2];
+  if (m.present) {
+    d.dx = (m.hi[0] - m.low[0]) / static_cast<double>(m.N[0]);
+    d.dy = (m.hi[1] - m.low[1]) / static_cast<double>(m.N[1]);
+    d.dz = (m.hi[2] - m.low[2]) / static_cast<double>(m.N[2]);
+  }
+  if (m.n_energy_edges >= 2) {
+    d.Ne = m.n_energy_edges - 1;
+    d.eedges = tally_eb_dev + m.eedges_offset;
+  } else {
+    d.Ne = 1;
+    d.eedges = nullptr;
+  }
+  return d;
+}
+
+int grid_for(abl_handle h, uint64_t n, int threads) {
+  uint64_t blocks = (n + threads - 1) / threads;
+  const uint64_t cap = (uint64_t)h->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+BankView view_of(const abl_bank* b) {
+  BankView v;
+  v.n = b->n;
+  v.x = b->x; v.y = b->y; v.z = b->z; v.ux = b->ux; v.uy = b->uy; v.uz = b->uz;
+  v.E = b->E; v.wgt = b->wgt; v.wgt2 = b->wgt2;
+  v.id_a = b->id_a; v.id_b = b->id_b; v.id_c = b->id_c;
+  return v;
+}
+
+int ensure_history_scratch(abl_handle h, uint64_t n, bool trace) {
+  if (n > h->hist_cap) {
+    const uint64_t cap = n + n / 4 + 1024;
+    if (h->nfis) cudaFree(h->nfis);
+    if (h->offsets) cudaFree(h->offsets);
+    if (h->tile_sums) cudaFree(h->tile_sums);
+    h->nfis = h->offsets = h->tile_sums = nullptr;
+    h->hist_cap = 0;
+    ABL_CUDA(h, cudaMalloc(&h->nfis, cap * sizeof(uint32_t)));
+    ABL_CUDA(h, cudaMalloc(&h->offsets, cap * sizeof(uint32_t)));
+    ABL_CUDA(h, cudaMalloc(&h->tile_sums, (cap / ABL_SCAN_TILE + 2) * sizeof(uint32_t)));
+    h->hist_cap = cap;
+  }
+  if (trace && n > h->trace_cap) {
+    const uint64_t cap = n + 1024;
+    for (void* p : {(void*)h->tr_flights, (void*)h->tr_real, (void*)h->tr_virtual, (void*)h->tr_hash, (void*)h->tr_rng})
+      if (p) cudaFree(p);
+    h->trace_cap = 0;
+    ABL_CUDA(h, cudaMalloc(&h->tr_flights, cap * 4));
+    ABL_CUDA(h, cudaMalloc(&h->tr_real, cap * 4));
+    ABL_CUDA(h, cudaMalloc(&h->tr_virtual, cap * 4));
+    ABL_CUDA(h, cudaMalloc(&h->tr_hash, cap * 8));
+    ABL_CUDA(h, cudaMalloc(&h->tr_rng, cap * 8));
+    h->trace_cap = cap;
+  }
+  return ABL_OK;
+}
+
+int ensure_sites(abl_handle h, uint64_t cap) {
+  if (cap > h->site_cap) {
+    if (h->sites) cudaFree(h->sites);
+    h->sites = nullptr;
+    h->site_cap = 0;
+    ABL_CUDA(h, cudaMalloc(&h->sites, cap * sizeof(Site)));
+    h->site_cap = cap;
+  }
+  return ABL_OK;
+}
+
+void free_bank(BankView& b) {
+  for (void* p : {(void*)b.x, (void*)b.y, (void*)b.z, (void*)b.ux, (void*)b.uy, (void*)b.uz, (void*)b.E, (void*)b.wgt,
+                  (void*)b.wgt2, (void*)b.id_a, (void*)b.id_b, (void*)b.id_c})
+    if (p) cudaFree(p);
+  b = BankView{};
+}
+
+int alloc_bank(abl_handle h, BankView& b, uint64_t cap) {
+  free_bank(b);
+  double** dp[9] = {&b.x, &b.y, &b.z, &b.ux, &b.uy, &b.uz, &b.E, &b.wgt, &b.wgt2};
+  for (auto p : dp) ABL_CUDA(h, cudaMalloc(p, cap * sizeof(double)));
+  uint64_t** up[3] = {&b.id_a, &b.id_b, &b.id_c};
+  for (auto p : up) ABL_CUDA(h, cudaMalloc(p, cap * sizeof(uint64_t)));
+  b.n = cap;
+  return ABL_OK;
+}
+
+template <int TRK>
+int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s) {
+  auto kern = transport_kernel<TRK, false>;
+  if (h->blocks_per_sm[TRK] == 0) {
+    int nb = 0;
+    ABL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 128, 0));
+    if (nb < 1) nb = 1;
+    h->blocks_per_sm[TRK] = nb;
+  }
+  uint64_t blocks = (uint64_t)h->sm_count * h->blocks_per_sm[TRK];
+  const uint64_t need = (n + 127) / 128;
+  if (blocks > need) blocks = need;
+  if (blocks < 1) blocks = 1;
+  RunArgs B = A;
+  if (TRK == ABL_TRACK_CARTER) {
+    const uint64_t nthreads = blocks * 128;
+    if (nthreads > h->sec_threads) {
+      if (h->secondaries) cudaFree(h->secondaries);
+      h->secondaries = nullptr;
+      h->sec_threads = 0;
+      const uint64_t cap = (uint64_t)h->sm_count * h->blocks_per_sm[TRK] * 128;
+      ABL_CUDA(h, cudaMalloc(&h->secondaries, cap * ABL_SEC_CAP * 9 * sizeof(double)));
+      h->sec_threads = cap;
+    }
+    B.secondaries = h->secondaries;
+  }
+  kern<<<(unsigned)blocks, 128, 0, s>>>(h->P, B);
+  h->launches++;
+  ABL_CUDA(h, cudaGetLastError());
+  return ABL_OK;
+}
+
+int status_from_device_error(abl_handle h, const DevSmall& sm) {
+  if (sm.error[0] == 0) return ABL_OK;
+  const uint64_t hid = (uint64_t)(uint32_t)sm.error[1] | ((uint64_t)(uint32_t)sm.error[2] << 32);
+  char buf[160];
+  const char* what = "device error";
+  switch (sm.error[0]) {
+    case ABL_ERR_LOST: what = "particle became lost after a reflection / crossing / resurrection"; break;
+    case ABL_ERR_MAJORANT: what = "total cross section exceeded the majorant"; break;
+    case ABL_ERR_GEOMETRY: what = "geometry nesting deeper than ABL_MAX_PADS / ABL_MAX_FRAMES"; break;
+    case ABL_ERR_BANK_OVERFLOW: what = "secondary stack overflow (ABL_SEC_CAP)"; break;
+    case ABL_ERR_INVALID: what = "source sampling failed (point source outside the geometry or fissile-only rejection limit)"; break;
+  }
+  snprintf(buf, sizeof buf, "%s (history %llu)", what, (unsigned long long)hid);
+  h->error = buf;
+  return sm.error[0];
+}
+
+int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* params, const BankView& out, uint64_t* n_fission,
+                   double scores[6], uint64_t counters[8], cudaStream_t s) {
+  const uint64_t N = in.n;
+  if (N >= (1ull << 32)) return fail(h, ABL_ERR_UNSUPPORTED, "bank larger than 2^32-1 histories per device");
+  if (params->noise) return fail(h, ABL_ERR_UNSUPPORTED, "noise transport is not implemented on the device");
+  int rc = ensure_history_scratch(h, N, params->trace != 0);
+  if (rc) return rc;
+  rc = ensure_sites(h, out.n);
+  if (rc) return rc;
+  ABL_CUDA(h, cudaMemsetAsync(h->small_dev, 0, sizeof(DevSmall), s));
+  RunArgs A{};
+  A.bank = in;
+  A.ticket = &h->small_dev->ticket;
+  A.sites = h->sites;
+  A.n_sites = &h->small_dev->n_sites;
+  A.site_capacity = out.n;
+  A.nfis = h->nfis;
+  if (params->trace) {
+    A.tr_flights = h->tr_flights; A.tr_real = h->tr_real; A.tr_virtual = h->tr_virtual;
+    A.tr_hash = h->tr_hash; A.tr_rng = h->tr_rng;
+    h->trace_n = N;
+  }
+  A.scores = h->small_dev->scores;
+  A.counters = h->small_dev->counters;
+  A.error = h->small_dev->error;
+  A.secondaries = nullptr;
+  A.k_col = params->k_col;
+  A.keff = params->keff;
+  A.converged = params->converged;
+  if (N > 0) {
+    switch (h->P.tracking) {
+      case ABL_TRACK_SURFACE: rc = launch_transport<ABL_TRACK_SURFACE>(h, A, N, s); break;
+      case ABL_TRACK_DELTA: rc = launch_transport<ABL_TRACK_DELTA>(h, A, N, s); break;
+      default: rc = launch_transport<ABL_TRACK_CARTER>(h, A, N, s); break;
+    }
+    if (rc) return rc;
+    // fission bank in the reference's order: offsets = exclusive scan of per-history counts
+    const uint32_t ntiles = (uint32_t)((N + ABL_SCAN_TILE - 1) / ABL_SCAN_TILE);
+    scan_tile_sums_kernel<<<ntiles, ABL_SCAN_THREADS, 0, s>>>(h->nfis, N, h->tile_sums);
+    scan_top_kernel<<<1, ABL_SCAN_THREADS, 0, s>>>(h->tile_sums, ntiles, &h->small_dev->grand_total);
+    scan_apply_kernel<<<ntiles, ABL_SCAN_THREADS, 0, s>>>(h->nfis, N, h->tile_sums, h->offsets);
+    h->launches += 3;
+  }
+  ABL_CUDA(h, cudaMemcpyAsync(h->small_host, h->small_dev, sizeof(DevSmall), cudaMemcpyDeviceToHost, s));
+  ABL_CUDA(h, cudaStreamSynchronize(s));
+  const DevSmall& sm = *h->small_host;
+  for (int i = 0; i < 6; i++) scores[i] = sm.scores[i];
+  if (counters)
+    for (int i = 0; i < 8; i++) counters[i] = sm.counters[i];
+  *n_fission = sm.n_sites;
+  rc = status_from_device_error(h, sm);
+  if (rc) return rc;
+  if (sm.n_sites > out.n) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "fission bank overflow: %llu sites, capacity %llu", sm.n_sites, (unsigned long long)out.n);
+    return fail(h, ABL_ERR_BANK_OVERFLOW, buf);
+  }
+  if (sm.n_sites > 0) {
+    place_sites_kernel<<<grid_for(h, sm.n_sites, 256), 256, 0, s>>>(h->sites, sm.n_sites, h->offsets, in, out);
+    h->launches++;
+    ABL_CUDA(h, cudaGetLastError());
+  }
+  return ABL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* abl_last_error(abl_handle h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+void abl_destroy(abl_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  for (int t = 0; t < h->P.ntallies; t++) {
+    cudaFree(h->P.tally[t].gen);
+    cudaFree(h->P.tally[t].avg);
+    cudaFree(h->P.tally[t].var);
+  }
+  for (void* p : {(void*)h->sites, (void*)h->nfis, (void*)h->offsets, (void*)h->tile_sums, (void*)h->tr_flights, (void*)h->tr_real,
+                  (void*)h->tr_virtual, (void*)h->tr_hash, (void*)h->tr_rng, (void*)h->small_dev, (void*)h->secondaries,
+                  (void*)h->cancel.sum_w, (void*)h->cancel.sum_w2, (void*)h->cancel.count, (void*)h->probe_buf})
+    if (p) cudaFree(p);
+  free_bank(h->stage_in);
+  free_bank(h->stage_out);
+  if (h->small_host) cudaFreeHost(h->small_host);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int abl_create(const abl_problem* p, int device, abl_handle* out) {
+  if (!p || !out) {
+    g_create_error = "null argument";
+    return ABL_ERR_INVALID;
+  }
+  *out = nullptr;
+  abl_handle h = new abl_context();
+  auto bail = [&](int rc) {
+    g_create_error = h->error;
+    abl_destroy(h);
+    return rc;
+  };
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    h->error = "no CUDA device: the B200 backend has no CPU fallback";
+    return bail(ABL_ERR_CUDA);
+  }
+  if (device < 0 || device >= ndev) {
+    h->error = "device index out of range";
+    return bail(ABL_ERR_INVALID);
+  }
+  h->device = device;
+  int rc = validate(h, p);
+  if (rc) return bail(rc);
+  auto CU = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess) {
+      h->error = std::string(what) + ": " + cudaGetErrorString(e);
+      return true;
+    }
+    return false;
+  };
+  if (CU(cudaSetDevice(device), "cudaSetDevice")) return bail(ABL_ERR_CUDA);
+  cudaDeviceProp prop;
+  if (CU(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return bail(ABL_ERR_CUDA);
+  h->sm_count = prop.multiProcessorCount;
+  h->cc_major = prop.major;
+  h->cc_minor = prop.minor;
+  if (CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail(ABL_ERR_CUDA);
+  if (CU(cudaMalloc(&h->small_dev, sizeof(DevSmall)), "cudaMalloc")) return bail(ABL_ERR_CUDA);
+  if (CU(cudaMallocHost(&h->small_host, sizeof(DevSmall)), "cudaMallocHost")) return bail(ABL_ERR_CUDA);
+
+  DevProblem& P = h->P;
+  const int G = p->ngroups, M = p->nmaterials;
+  P.mode = p->mode;
+  P.tracking = p->tracking;
+  P.G = G;
+  P.inner_generations = p->inner_generations;
+  P.wgt_cutoff = p->wgt_cutoff;
+  P.wgt_survival = p->wgt_survival;
+  P.wgt_split = p->wgt_split;
+  P.min_energy = p->min_energy;
+  P.seed_state = pcg_seed_state(p->rng_seed);
+  P.stride = p->rng_stride;
+  P.w_noise = p->w_noise;
+  P.eta = p->eta;
+  P.nsurfaces = p->nsurfaces;
+  P.ncells = p->ncells;
+  P.nuniverses = p->nuniverses;
+  P.root = p->root_universe;
+  P.M = M;
+#define UP(src, n, dst)                                  \
+  if ((rc = upload(h, src, (size_t)(n), &dst)) != 0) return bail(rc)
+  UP(p->energy_bounds, G + 1, P.ebounds);
+  {
+    JumpTable jt;  // LCG jump-ahead by 2^k steps
+    jt.mult[0] = ABL_PCG_MULT;
+    jt.plus[0] = ABL_PCG_INC;
+    for (int k = 1; k < 64; k++) {
+      jt.plus[k] = (jt.mult[k - 1] + 1) * jt.plus[k - 1];
+      jt.mult[k] = jt.mult[k - 1] * jt.mult[k - 1];
+    }
+    UP(&jt, 1, P.jump);
+  }
+  UP(p->surfaces, p->nsurfaces, P.surfaces);
+  UP(p->cells, p->ncells, P.cells);
+  UP(p->rpn, p->nrpn, P.rpn);
+  UP(p->universes, p->nuniverses, P.universes);
+  UP(p->universe_cells, p->n_universe_cells, P.ucells);
+  UP(p->lattice_tiles, p->n_lattice_tiles, P.tiles);
+  const size_t MG = (size_t)M * G, MGG = MG * G;
+  UP(p->xs_total, MG, P.Et);
+  UP(p->xs_absorption, MG, P.Ea);
+  UP(p->xs_fission, MG, P.Ef);
+  UP(p->xs_elastic, MG, P.Es);
+  UP(p->nu_total, MG, P.nu);
+  UP(p->nu_delayed, MG, P.nud);
+  UP(p->speeds, MG, P.speed);
+  UP(p->chi_cdf, MGG, P.chi_cp);
+  UP(p->scatter_cdf, MGG, P.ps_cp);
+  UP(p->angle, MGG, P.angle);
+  UP(p->angle_mu, p->n_angle_points, P.amu);
+  UP(p->angle_pdf, p->n_angle_points, P.apdf);
+  UP(p->angle_cdf, p->n_angle_points, P.acdf);
+  UP(p->delayed_offset, M + 1, P.dg_off);
+  {
+    const int nd = p->delayed_offset ? p->delayed_offset[M] : 0;
+    UP(p->delayed_cdf, nd, P.dg_cp);
+    UP(p->delayed_lambda, nd, P.dg_lambda);
+  }
+  UP(p->fissile, M, P.fissile);
+  if (p->sampling_xs) UP(p->sampling_xs, G, P.smp);
+  const double* teb = nullptr;
+  UP(p->tally_energy_bounds, p->n_tally_energy_bounds, teb);
+  P.ntallies = p->ntallies;
+  P.n_coll_tallies = P.n_tl_tallies = 0;
+  h->tally_g.assign((size_t)p->ntallies, 0);
+  for (int t = 0; t < p->ntallies; t++) {
+    const abl_mesh_tally& mt = p->tallies[t];
+    DevTally& d = P.tally[t];
+    d.estimator = mt.estimator;
+    d.quantity = mt.quantity;
+    d.noise_source = mt.noise_source;
+    d.Nx = mt.N[0]; d.Ny = mt.N[1]; d.Nz = mt.N[2];
+    d.Ne = mt.n_energy_bins;
+    d.ebounds = teb + mt.ebounds_offset;
+    d.lowx = mt.low[0]; d.lowy = mt.low[1]; d.lowz = mt.low[2];
+    d.hix = mt.hi[0]; d.hiy = mt.hi[1]; d.hiz = mt.hi[2];
+    d.dx = (mt.hi[0] - mt.low[0]) / static_cast<double>(mt.N[0]);  // mesh_tally.cpp:66-101
+    d.dy = (mt.hi[1] - mt.low[1]) / static_cast<double>(mt.N[1]);
+    d.dz = (mt.hi[2] - mt.low[2]) / static_cast<double>(mt.N[2]);
+    d.dx_inv = 1. / d.dx;
+    d.dy_inv = 1. / d.dy;
+    d.dz_inv = 1. / d.dz;
+    d.net_weight = mt.net_weight;
+    d.size = (uint64_t)d.Ne * d.Nx * d.Ny * d.Nz;
+    if (mt.estimator == ABL_EST_COLLISION) P.n_coll_tallies++;
+    if (mt.estimator == ABL_EST_TRACK_LENGTH) P.n_tl_tallies++;
+    for (double** arr : {&d.gen, &d.avg, &d.var}) {
+      if (CU(cudaMalloc(arr, d.size * sizeof(double)), "cudaMalloc(tally)")) return bail(ABL_ERR_CUDA);
+      if (CU(cudaMemset(*arr, 0, d.size * sizeof(double)), "cudaMemset(tally)")) return bail(ABL_ERR_CUDA);
+    }
+  }
+  P.nsources = p->nsources;
+  UP(p->sources, p->nsources, P.sources);
+  if (p->nsources >= 2) {
+    std::vector<double> w;
+    for (int s = 0; s < p->nsources; s++) w.push_back(p->sources[s].weight);
+    std::vector<double> cp = discrete_table(w);
+    UP(cp.data(), cp.size(), P.source_cp);
+  }
+  P.entropy = make_mesh3(p->entropy, teb);
+  P.cancel = make_mesh3(p->cancelator, teb);
+#undef UP
+  if (CU(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return bail(ABL_ERR_CUDA);
+  *out = h;
+  return ABL_OK;
+}
+
+int abl_device_info(abl_handle h, int* sm_count, int* cc_major, int* cc_minor, uint64_t* kernel_launches) {
+  if (!h) return ABL_ERR_INVALID;
+  if (sm_count) *sm_count = h->sm_count;
+  if (cc_major) *cc_major = h->cc_major;
+  if (cc_minor) *cc_minor = h->cc_minor;
+  if (kernel_launches) *kernel_launches = h->launches;
+  return ABL_OK;
+}
+
+int abl_transport_device(abl_handle h, const abl_bank* bank_dev, const abl_gen_params* params, abl_bank* fission_dev,
+                         uint64_t* n_fission, double scores[6], uint64_t counters[8], void* stream) {
+  if (!h || !bank_dev || !params || !fission_dev || !n_fission || !scores) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  return transport_impl(h, view_of(bank_dev), params, view_of(fission_dev), n_fission, scores, counters, s);
+}
+
+int abl_transport(abl_handle h, const abl_bank* bank, const abl_gen_params* params, abl_bank* fission_out, uint64_t* n_fission,
+                  double scores[6], uint64_t counters[8]) {
+  if (!h || !bank || !params || !fission_out || !n_fission || !scores) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, h->stream);
+  const uint64_t N = bank->n, cap = fission_out->n;
+  int rc;
+  if (N > h->stage_in_cap) {
+    if ((rc = alloc_bank(h, h->stage_in, N + N / 4 + 1024)) != 0) return rc;
+    h->stage_in_cap = h->stage_in.n;
+  }
+  if (cap > h->stage_out_cap) {
+    if ((rc = alloc_bank(h, h->stage_out, cap)) != 0) return rc;
+    h->stage_out_cap = h->stage_out.n;
+  }
+  BankView in = h->stage_in, out = h->stage_out;
+  in.n = N;
+  out.n = cap;
+  const double* hin[9] = {bank->x, bank->y, bank->z, bank->ux, bank->uy, bank->uz, bank->E, bank->wgt, bank->wgt2};
+  double* din[9] = {in.x, in.y, in.z, in.ux, in.uy, in.uz, in.E, in.wgt, in.wgt2};
+  for (int k = 0; k < 9; k++) {
+    if (!hin[k]) {
+      if (k == 8) { in.wgt2 = nullptr; continue; }
+      return fail(h, ABL_ERR_INVALID, "null bank array");
+    }
+    if (N) ABL_CUDA(h, cudaMemcpyAsync(din[k], hin[k], N * sizeof(double), cudaMemcpyHostToDevice, s));
+  }
+  if (!bank->id_a) return fail(h, ABL_ERR_INVALID, "null history id array");
+  if (N) ABL_CUDA(h, cudaMemcpyAsync(in.id_a, bank->id_a, N * 8, cudaMemcpyHostToDevice, s));
+  if (bank->id_b) { if (N) ABL_CUDA(h, cudaMemcpyAsync(in.id_b, bank->id_b, N * 8, cudaMemcpyHostToDevice, s)); }
+  else in.id_b = nullptr;
+  if (bank->id_c) { if (N) ABL_CUDA(h, cudaMemcpyAsync(in.id_c, bank->id_c, N * 8, cudaMemcpyHostToDevice, s)); }
+  else in.id_c = nullptr;
+  if (!fission_out->wgt2) out.wgt2 = nullptr;
+  rc = transport_impl(h, in, params, out, n_fission, scores, counters, s);
+  if (rc) return rc;
+  const uint64_t m = *n_fission;
+  if (m) {
+    double* hout[9] = {fission_out->x, fission_out->y, fission_out->z, fission_out->ux, fission_out->uy, fission_out->uz,
+                       fission_out->E, fission_out->wgt, fission_out->wgt2};
+    double* dout[9] = {out.x, out.y, out.z, out.ux, out.uy, out.uz, out.E, out.wgt, out.wgt2};
+    for (int k = 0; k < 9; k++)
+      if (hout[k] && dout[k]) ABL_CUDA(h, cudaMemcpyAsync(hout[k], dout[k], m * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (fission_out->id_a) ABL_CUDA(h, cudaMemcpyAsync(fission_out->id_a, out.id_a, m * 8, cudaMemcpyDeviceToHost, s));
+    if (fission_out->id_b) ABL_CUDA(h, cudaMemcpyAsync(fission_out->id_b, out.id_b, m * 8, cudaMemcpyDeviceToHost, s));
+    if (fission_out->id_c) ABL_CUDA(h, cudaMemcpyAsync(fission_out->id_c, out.id_c, m * 8, cudaMemcpyDeviceToHost, s));
+  }
+  ABL_CUDA(h, cudaStreamSynchronize(s));
+  return ABL_OK;
+}
+
+int abl_get_trace(abl_handle h, uint64_t n, abl_trace* out) {
+  if (!h || !out) return ABL_ERR_INVALID;
+  if (n > h->trace_n) return fail(h, ABL_ERR_INVALID, "no trace of that size: pass params.trace = 1 to the transport call");
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  if (out->flights) ABL_CUDA(h, cudaMemcpy(out->flights, h->tr_flights, n * 4, cudaMemcpyDeviceToHost));
+  if (out->real) ABL_CUDA(h, cudaMemcpy(out->real, h->tr_real, n * 4, cudaMemcpyDeviceToHost));
+  if (out->virt) ABL_CUDA(h, cudaMemcpy(out->virt, h->tr_virtual, n * 4, cudaMemcpyDeviceToHost));
+  if (out->fission) ABL_CUDA(h, cudaMemcpy(out->fission, h->nfis, n * 4, cudaMemcpyDeviceToHost));
+  if (out->hash) ABL_CUDA(h, cudaMemcpy(out->hash, h->tr_hash, n * 8, cudaMemcpyDeviceToHost));
+  if (out->rng_state) ABL_CUDA(h, cudaMemcpy(out->rng_state, h->tr_rng, n * 8, cudaMemcpyDeviceToHost));
+  return ABL_OK;
+}
+
+// ---- tallies -----------------------------------------------------------------------------------------------------------
+int abl_tally_count(abl_handle h) { return h ? h->P.ntallies : ABL_ERR_INVALID; }
+
+int abl_tally_shape(abl_handle h, int t, uint64_t shape4[4]) {
+  if (!h || t < 0 || t >= h->P.ntallies) return ABL_ERR_INVALID;
+  const DevTally& d = h->P.tally[t];
+  shape4[0] = (uint64_t)d.Ne; shape4[1] = (uint64_t)d.Nx; shape4[2] = (uint64_t)d.Ny; shape4[3] = (uint64_t)d.Nz;
+  return ABL_OK;
+}
+
+int abl_tallies_record(abl_handle h, double multiplier) {
+  if (!h) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  use_stream(h, h->stream);
+  for (int t = 0; t < h->P.ntallies; t++) {
+    DevTally& d = h->P.tally[t];
+    h->tally_g[(size_t)t]++;
+    tally_record_kernel<<<grid_for(h, d.size, 256), 256, 0, h->stream>>>(d.gen, d.avg, d.var, d.size, multiplier,
+                                                                          static_cast<double>(h->tally_g[(size_t)t]));
+    h->launches++;
+  }
+  ABL_CUDA(h, cudaGetLastError());
+  ABL_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ABL_OK;
+}
+
+int abl_tallies_clear(abl_handle h) {
+  if (!h) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  use_stream(h, h->stream);
+  for (int t = 0; t < h->P.ntallies; t++)
+    ABL_CUDA(h, cudaMemsetAsync(h->P.tally[t].gen, 0, h->P.tally[t].size * sizeof(double), h->stream));
+  ABL_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ABL_OK;
+}
+
+int abl_tally_device_ptr(abl_handle h, int t, int which, double** out_dev, uint64_t* n) {
+  if (!h || t < 0 || t >= h->P.ntallies || which < 0 || which > 2 || !out_dev) return ABL_ERR_INVALID;
+  DevTally& d = h->P.tally[t];
+  *out_dev = which == 0 ? d.gen : (which == 1 ? d.avg : d.var);
+  if (n) *n = d.size;
+  return ABL_OK;
+}
+
+int abl_tally_fetch(abl_handle h, int t, int which, double* out_host) {
+  if (!h || t < 0 || t >= h->P.ntallies || which < 0 || which > 3 || !out_host) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  use_stream(h, h->stream);
+  DevTally& d = h->P.tally[t];
+  if (which < 3) {
+    const double* src = which == 0 ? d.gen : (which == 1 ? d.avg : d.var);
+    ABL_CUDA(h, cudaMemcpy(out_host, src, d.size * sizeof(double), cudaMemcpyDeviceToHost));
+    return ABL_OK;
+  }
+  double* tmp = nullptr;  // std = sqrt(var / g)  (mesh_tally.cpp:195-197)
+  ABL_CUDA(h, cudaMalloc(&tmp, d.size * sizeof(double)));
+  tally_std_kernel<<<grid_for(h, d.size, 256), 256, 0, h->stream>>>(d.var, tmp, d.size, static_cast<double>(h->tally_g[(size_t)t]));
+  h->launches++;
+  cudaError_t e = cudaMemcpyAsync(out_host, tmp, d.size * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(tmp);
+  ABL_CUDA(h, e);
+  return ABL_OK;
+}
+
+// ---- inter-generation pipeline --------------------------------------------------------------------------------------------
+int abl_sample_source_device(abl_handle h, uint64_t n, uint64_t first_history_id, abl_bank* bank_dev, void* stream) {
+  if (!h || !bank_dev) return ABL_ERR_INVALID;
+  if (h->P.nsources < 1) return fail(h, ABL_ERR_INVALID, "problem has no sources");
+  if (bank_dev->n < n) return fail(h, ABL_ERR_INVALID, "bank capacity too small");
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  BankView b = view_of(bank_dev);
+  b.n = n;
+  ABL_CUDA(h, cudaMemsetAsync(h->small_dev, 0, sizeof(DevSmall), s));
+  sample_source_kernel<<<grid_for(h, n, 128), 128, 0, s>>>(h->P, b, first_history_id, h->small_dev->error);
+  h->launches++;
+  ABL_CUDA(h, cudaGetLastError());
+  ABL_CUDA(h, cudaMemcpyAsync(h->small_host, h->small_dev, sizeof(DevSmall), cudaMemcpyDeviceToHost, s));
+  ABL_CUDA(h, cudaStreamSynchronize(s));
+  return status_from_device_error(h, *h->small_host);
+}
+
+int abl_bank_weight_stats_device(abl_handle h, const abl_bank* bank_dev, double stats[4], void* stream) {
+  if (!h || !bank_dev || !stats) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  ABL_CUDA(h, cudaMemsetAsync(h->small_dev->stats, 0, sizeof(double) * 4, s));
+  if (bank_dev->n) {
+    weight_stats_kernel<<<grid_for(h, bank_dev->n, 256), 256, 0, s>>>(bank_dev->wgt, bank_dev->n, h->small_dev->stats);
+    h->launches++;
+  }
+  ABL_CUDA(h, cudaMemcpyAsync(h->small_host->stats, h->small_dev->stats, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
+  ABL_CUDA(h, cudaStreamSynchronize(s));
+  for (int i = 0; i < 4; i++) stats[i] = h->small_host->stats[i];
+  return ABL_OK;
+}
+
+int abl_bank_scale_weights_device(abl_handle h, abl_bank* bank_dev, double factor, void* stream) {
+  if (!h || !bank_dev) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  if (bank_dev->n) {
+    scale_weights_kernel<<<grid_for(h, bank_dev->n, 256), 256, 0, s>>>(bank_dev->wgt, bank_dev->n, factor);
+    h->launches++;
+  }
+  ABL_CUDA(h, cudaGetLastError());
+  return ABL_OK;
+}
+
+int abl_bank_to_particles_device(abl_handle h, abl_bank* bank_dev, uint64_t first_history_id, void* stream) {
+  if (!h || !bank_dev) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  if (bank_dev->n) {
+    to_particles_kernel<<<grid_for(h, bank_dev->n, 256), 256, 0, s>>>(view_of(bank_dev), first_history_id);
+    h->launches++;
+  }
+  ABL_CUDA(h, cudaGetLastError());
+  return ABL_OK;
+}
+
+int abl_entropy_bin_device(abl_handle h, const abl_bank* bank_dev, double* bins_dev, double* total_dev, void* stream) {
+  if (!h || !bank_dev || !bins_dev || !total_dev) return ABL_ERR_INVALID;
+  if (!h->P.entropy.present) return fail(h, ABL_ERR_INVALID, "problem has no entropy mesh");
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  if (bank_dev->n) {
+    entropy_bin_kernel<<<grid_for(h, bank_dev->n, 256), 256, 0, s>>>(h->P.entropy, view_of(bank_dev), bins_dev, total_dev);
+    h->launches++;
+  }
+  ABL_CUDA(h, cudaGetLastError());
+  return ABL_OK;
+}
+
+int abl_score_source_device(abl_handle h, const abl_bank* bank_dev, int noise_source, void* stream) {
+  if (!h || !bank_dev) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  for (int t = 0; t < h->P.ntallies; t++) {
+    const DevTally& d = h->P.tally[t];
+    if (d.estimator != ABL_EST_SOURCE || (d.noise_source != 0) != (noise_source != 0) || bank_dev->n == 0) continue;
+    score_source_kernel<<<grid_for(h, bank_dev->n, 256), 256, 0, s>>>(d, view_of(bank_dev));
+    h->launches++;
+  }
+  ABL_CUDA(h, cudaGetLastError());
+  return ABL_OK;
+}
+
+int abl_cancel_device(abl_handle h, abl_bank* bank_dev, void* stream) {
+  if (!h || !bank_dev) return ABL_ERR_INVALID;
+  const DevMesh3& m = h->P.cancel;
+  if (!m.present) return fail(h, ABL_ERR_INVALID, "problem has no approximate cancelator");
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  const uint64_t nbins = (uint64_t)m.Nx * m.Ny * m.Nz * m.Ne;
+  if (!h->cancel.count) {
+    ABL_CUDA(h, cudaMalloc(&h->cancel.count, nbins * sizeof(uint32_t)));
+    ABL_CUDA(h, cudaMalloc(&h->cancel.sum_w, nbins * sizeof(double)));
+    ABL_CUDA(h, cudaMalloc(&h->cancel.sum_w2, nbins * sizeof(double)));
+    ABL_CUDA(h, cudaMemset(h->cancel.count, 0, nbins * sizeof(uint32_t)));
+    ABL_CUDA(h, cudaMemset(h->cancel.sum_w, 0, nbins * sizeof(double)));
+    ABL_CUDA(h, cudaMemset(h->cancel.sum_w2, 0, nbins * sizeof(double)));
+  }
+  if (bank_dev->n == 0) return ABL_OK;
+  const BankView b = view_of(bank_dev);
+  const int grid = grid_for(h, b.n, 256);
+  cancel_accumulate_kernel<<<grid, 256, 0, s>>>(m, b, h->cancel);
+  cancel_apply_kernel<<<grid, 256, 0, s>>>(m, b, h->cancel);
+  cancel_reset_kernel<<<grid, 256, 0, s>>>(m, b, h->cancel);
+  h->launches += 3;
+  ABL_CUDA(h, cudaGetLastError());
+  return ABL_OK;
+}
+
+// ---- device memory helpers ---------------------------------------------------------------------------------------------------
+int abl_bank_alloc_device(abl_handle h, uint64_t capacity, abl_bank* out_dev) {
+  if (!h || !out_dev) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  BankView b{};
+  int rc = alloc_bank(h, b, capacity ? capacity : 1);
+  if (rc) {
+    free_bank(b);
+    return rc;
+  }
+  out_dev->n = capacity;
+  out_dev->x = b.x; out_dev->y = b.y; out_dev->z = b.z; out_dev->ux = b.ux; out_dev->uy = b.uy; out_dev->uz = b.uz;
+  out_dev->E = b.E; out_dev->wgt = b.wgt; out_dev->wgt2 = b.wgt2;
+  out_dev->id_a = b.id_a; out_dev->id_b = b.id_b; out_dev->id_c = b.id_c;
+  return ABL_OK;
+}
+
+int abl_bank_free_device(abl_handle h, abl_bank* bank_dev) {
+  if (!h || !bank_dev) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  ABL_CUDA(h, cudaDeviceSynchronize());
+  BankView b = view_of(bank_dev);
+  free_bank(b);
+  *bank_dev = abl_bank{};
+  return ABL_OK;
+}
+
+static int copy_bank(abl_handle h, const abl_bank* src, abl_bank* dst, uint64_t n, cudaMemcpyKind kind) {
+  const double* s9[9] = {src->x, src->y, src->z, src->ux, src->uy, src->uz, src->E, src->wgt, src->wgt2};
+  double* d9[9] = {dst->x, dst->y, dst->z, dst->ux, dst->uy, dst->uz, dst->E, dst->wgt, dst->wgt2};
+  const uint64_t* s3[3] = {src->id_a, src->id_b, src->id_c};
+  uint64_t* d3[3] = {dst->id_a, dst->id_b, dst->id_c};
+  if (n == 0) return ABL_OK;
+  for (int k = 0; k < 9; k++)
+    if (s9[k] && d9[k]) ABL_CUDA(h, cudaMemcpy(d9[k], s9[k], n * sizeof(double), kind));
+  for (int k = 0; k < 3; k++)
+    if (s3[k] && d3[k]) ABL_CUDA(h, cudaMemcpy(d3[k], s3[k], n * sizeof(uint64_t), kind));
+  return ABL_OK;
+}
+
+int abl_bank_upload(abl_handle h, const abl_bank* host, abl_bank* bank_dev) {
+  if (!h || !host || !bank_dev) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  ABL_CUDA(h, cudaDeviceSynchronize());
+  int rc = copy_bank(h, host, bank_dev, host->n, cudaMemcpyHostToDevice);
+  if (rc) return rc;
+  if (!host->wgt2 && bank_dev->wgt2 && host->n) ABL_CUDA(h, cudaMemset(bank_dev->wgt2, 0, host->n * sizeof(double)));
+  bank_dev->n = host->n;
+  return ABL_OK;
+}
+
+int abl_bank_download(abl_handle h, const abl_bank* bank_dev, uint64_t n, abl_bank* host) {
+  if (!h || !host || !bank_dev) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  ABL_CUDA(h, cudaDeviceSynchronize());
+  return copy_bank(h, bank_dev, host, n, cudaMemcpyDeviceToHost);
+}
+
+int abl_device_alloc(abl_handle h, uint64_t bytes, void** out_dev) {
+  if (!h || !out_dev) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  ABL_CUDA(h, cudaMalloc(out_dev, bytes ? bytes : 8));
+  ABL_CUDA(h, cudaMemset(*out_dev, 0, bytes ? bytes : 8));
+  return ABL_OK;
+}
+
+int abl_device_free(abl_handle h, void* dev) {
+  if (!h) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  ABL_CUDA(h, cudaDeviceSynchronize());
+  if (dev) ABL_CUDA(h, cudaFree(dev));
+  return ABL_OK;
+}
+
+int abl_device_zero(abl_handle h, void* dev, uint64_t bytes, void* stream) {
+  if (!h || !dev) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  ABL_CUDA(h, cudaMemsetAsync(dev, 0, bytes, use_stream(h, (cudaStream_t)stream)));
+  return ABL_OK;
+}
+
+int abl_device_read(abl_handle h, void* dst_host, const void* src_dev, uint64_t bytes, void* stream) {
+  if (!h || !dst_host || !src_dev) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  ABL_CUDA(h, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, s));
+  ABL_CUDA(h, cudaStreamSynchronize(s));
+  return ABL_OK;
+}
+
+// ---- probes ------------------------------------------------------------------------------------------------------------------
+static int ensure_probe(abl_handle h, uint64_t bytes) {
+  use_stream(h, h->stream);
+  if (bytes > h->probe_cap) {
+    if (h->probe_buf) cudaFree(h->probe_buf);
+    h->probe_buf = nullptr;
+    h->probe_cap = 0;
+    ABL_CUDA(h, cudaMalloc(&h->probe_buf, bytes));
+    h->probe_cap = bytes;
+  }
+  return ABL_OK;
+}
+
+int abl_find_cells(abl_handle h, uint64_t n, const double* r3, const double* u3, int32_t* cell, int32_t* material) {
+  if (!h || !r3 || !u3 || !cell || !material) return ABL_ERR_INVALID;
+  if (n == 0) return ABL_OK;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_probe(h, n * (6 * sizeof(double) + 2 * sizeof(int32_t)));
+  if (rc) return rc;
+  double* dr = h->probe_buf;
+  double* du = dr + 3 * n;
+  int32_t* dc = reinterpret_cast<int32_t*>(du + 3 * n);
+  int32_t* dm = dc + n;
+  ABL_CUDA(h, cudaMemcpy(dr, r3, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+  ABL_CUDA(h, cudaMemcpy(du, u3, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+  find_cells_kernel<<<grid_for(h, n, 128), 128, 0, h->stream>>>(h->P, n, dr, du, dc, dm);
+  h->launches++;
+  ABL_CUDA(h, cudaGetLastError());
+  ABL_CUDA(h, cudaStreamSynchronize(h->stream));
+  ABL_CUDA(h, cudaMemcpy(cell, dc, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  ABL_CUDA(h, cudaMemcpy(material, dm, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return ABL_OK;
+}
+
+int abl_rng_probe(abl_handle h, uint64_t history_id, int n, uint32_t* out_u32, double* out_rand) {
+  if (!h || n < 0 || !out_u32 || !out_rand) return ABL_ERR_INVALID;
+  if (n == 0) return ABL_OK;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_probe(h, (uint64_t)n * 16);
+  if (rc) return rc;
+  double* dr = h->probe_buf;
+  uint32_t* du = reinterpret_cast<uint32_t*>(dr + n);
+  rng_probe_kernel<<<1, 32, 0, h->stream>>>(h->P, history_id, n, du, dr);
+  h->launches++;
+  ABL_CUDA(h, cudaGetLastError());
+  ABL_CUDA(h, cudaStreamSynchronize(h->stream));
+  ABL_CUDA(h, cudaMemcpy(out_u32, du, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  ABL_CUDA(h, cudaMemcpy(out_rand, dr, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  return ABL_OK;
+}
+
+int abl_math_probe(abl_handle h, int n, const double* x, double* lg, double* sn, double* cs) {
+  if (!h || n < 0 || !x || !lg || !sn || !cs) return ABL_ERR_INVALID;
+  if (n == 0) return ABL_OK;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_probe(h, (uint64_t)n * 32);
+  if (rc) return rc;
+  double* dx = h->probe_buf;
+  ABL_CUDA(h, cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+  math_probe_kernel<<<grid_for(h, (uint64_t)n, 128), 128, 0, h->stream>>>(n, dx, dx + n, dx + 2 * n, dx + 3 * n);
+  h->launches++;
+  ABL_CUDA(h, cudaGetLastError());
+  ABL_CUDA(h, cudaStreamSynchronize(h->stream));
+  ABL_CUDA(h, cudaMemcpy(lg, dx + n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  ABL_CUDA(h, cudaMemcpy(sn, dx + 2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  ABL_CUDA(h, cudaMemcpy(cs, dx + 3 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  return ABL_OK;
+}
+
+}  // extern "C"

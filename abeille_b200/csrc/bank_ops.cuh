@@ -1,0 +1,357 @@
+/* bank_ops.cuh -- everything that happens to a bank between two transport() calls, on the device.
+ *
+ *   place_sites          deterministic fission-bank order without a sort (see transport.cuh)
+ *   weight stats/scale   PowerIterator::normalize_weights            src/power_iterator.cpp:538-586
+ *   to_particles         bank rebuild with fresh history ids         src/power_iterator.cpp:386-404
+ *   entropy binning      Entropy::add_point                          src/entropy.cpp:32-60
+ *   score_source         SourceMeshTally::score_source               src/source_mesh_tally.cpp:30-78
+ *   cancellation         ApproximateMeshCancelator                   src/approximate_mesh_cancelator.cpp:97-190
+ *   source sampling      Simulation::sample_sources, Source::generate_particle
+ *                                                                    src/simulation.cpp:55-77, src/source.cpp:44-90
+ *   record_generation    MeshTally::record_generation                src/mesh_tally.cpp:121-150
+ * All of these are streaming kernels bounded by HBM bandwidth; grids are sized in multiples of the SM count.
+ */
+#pragma once
+#include "transport.cuh"
+
+namespace abl {
+
+// ---- exclusive scan of per-history site counts (three passes over 4096-element tiles) --------------------
+#define ABL_SCAN_THREADS 1024
+#define ABL_SCAN_ITEMS 4
+#define ABL_SCAN_TILE (ABL_SCAN_THREADS * ABL_SCAN_ITEMS)
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = warp_sums[lane];
+    uint32_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += n;
+    }
+    warp_sums[lane] = winc - w;  // exclusive
+    if (lane == 31) *total = winc;
+  }
+  __syncthreads();
+  const uint32_t r = warp_sums[wid] + inc - v;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(ABL_SCAN_THREADS) scan_tile_sums_kernel(const uint32_t* __restrict__ in, uint64_t n,
+                                                                           uint32_t* __restrict__ tile_sums) {
+  __shared__ uint32_t total;
+  const uint64_t base = (uint64_t)blockIdx.x * ABL_SCAN_TILE + (uint64_t)threadIdx.x * ABL_SCAN_ITEMS;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < ABL_SCAN_ITEMS; k++)
+    if (base + k < n) s += in[base + k];
+  (void)block_exclusive_scan_1024(s, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(ABL_SCAN_THREADS) scan_top_kernel(uint32_t* tile_sums, uint32_t ntiles, uint32_t* grand_total) {
+  __shared__ uint32_t total;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < ntiles; base += ABL_SCAN_THREADS) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < ntiles ? tile_sums[i] : 0;
+    const uint32_t ex = block_exclusive_scan_1024(v, &total);
+    if (i < ntiles) tile_sums[i] = carry + ex;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(ABL_SCAN_THREADS) scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t n,
+                                                                       const uint32_t* __restrict__ tile_offsets,
+                                                                       uint32_t* __restrict__ out) {
+  __shared__ uint32_t total;
+  const uint64_t base = (uint64_t)blockIdx.x * ABL_SCAN_TILE + (uint64_t)threadIdx.x * ABL_SCAN_ITEMS;
+  uint32_t v[ABL_SCAN_ITEMS];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < ABL_SCAN_ITEMS; k++) {
+    v[k] = base + k < n ? in[base + k] : 0;
+    s += v[k];
+  }
+  uint32_t ex = block_exclusive_scan_1024(s, &total) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < ABL_SCAN_ITEMS; k++) {
+    if (base + k < n) out[base + k] = ex;
+    ex += v[k];
+  }
+}
+
+// ---- fission bank placement ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) place_sites_kernel(const Site* __restrict__ sites, uint64_t n_sites,
+                                                          const uint32_t* __restrict__ offsets, BankView in, BankView out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sites; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double2* src = reinterpret_cast<const double2*>(sites + i);
+    const double2 a = src[0], b = src[1], c = src[2], d = src[3], e = src[4];
+    const uint32_t parent = (uint32_t)(__double_as_longlong(e.y) & 0xffffffffLL);
+    const uint32_t daughter = (uint32_t)((unsigned long long)__double_as_longlong(e.y) >> 32);
+    const uint64_t pos = (uint64_t)offsets[parent] + daughter;
+    if (pos >= out.n) continue;  // capacity overflow is reported by the host from the total count
+    out.x[pos] = a.x; out.y[pos] = a.y; out.z[pos] = b.x;
+    out.ux[pos] = b.y; out.uy[pos] = c.x; out.uz[pos] = c.y;
+    out.E[pos] = d.x; out.wgt[pos] = d.y;
+    if (out.wgt2) out.wgt2[pos] = e.x;
+    out.id_a[pos] = in.id_a[parent];
+    out.id_b[pos] = daughter;
+    out.id_c[pos] = in.id_b ? in.id_b[parent] : in.id_a[parent];
+  }
+}
+
+// ---- weights ------------------------------------------------------------------------------------------------------
+// out[0..3] += Npos, Nneg, Wpos, Wneg   (Wneg accumulated as a positive number, as the reference does)
+__global__ void __launch_bounds__(256) weight_stats_kernel(const double* __restrict__ w, uint64_t n, double* out) {
+  double np = 0., nn = 0., wp = 0., wn = 0.;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double v = w[i];
+    if (v > 0.) { wp += v; np += 1.; } else { wn -= v; nn += 1.; }
+  }
+  double vals[4] = {np, nn, wp, wn};
+  __shared__ double sm[8][4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    double v = vals[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[wid][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0.;
+    for (int k = 0; k < 8; k++) v += sm[k][threadIdx.x];
+    atomicAdd(&out[threadIdx.x], v);
+  }
+}
+
+__global__ void __launch_bounds__(256) scale_weights_kernel(double* w, uint64_t n, double f) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) w[i] *= f;
+}
+
+__global__ void __launch_bounds__(256) to_particles_kernel(BankView b, uint64_t first_id) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    b.id_b[i] = b.id_c[i];  // family id
+    b.id_a[i] = first_id + i;
+  }
+}
+
+// ---- entropy --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) entropy_bin_kernel(DevMesh3 m, BankView b, double* bins, double* total) {
+  double tw = 0.;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const int nx = (int)floor((b.x[i] - m.lowx) / m.dx);
+    const int ny = (int)floor((b.y[i] - m.lowy) / m.dy);
+    const int nz = (int)floor((b.z[i] - m.lowz) / m.dz);
+    if (nx >= 0 && nx < m.Nx && ny >= 0 && ny < m.Ny && nz >= 0 && nz < m.Nz) {
+      const double w = b.wgt[i];
+      tw += w;
+      red_add(bins + ((size_t)(m.Ny * m.Nz) * nx + (size_t)m.Nz * ny + nz), w);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) tw += __shfl_down_sync(0xffffffffu, tw, o);
+  if ((threadIdx.x & 31) == 0 && tw != 0.) atomicAdd(total, tw);
+}
+
+// ---- source mesh tally ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) score_source_kernel(DevTally t, BankView b) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const int ii = (int)floor((b.x[i] - t.lowx) / t.dx);  // division, not *dx_inv (source_mesh_tally.cpp:38-40)
+    const int jj = (int)floor((b.y[i] - t.lowy) / t.dy);
+    const int kk = (int)floor((b.z[i] - t.lowz) / t.dz);
+    const int l = tally_energy_bin(t, b.E[i]);
+    if (l == -1) continue;
+    if (ii >= 0 && ii < t.Nx && jj >= 0 && jj < t.Ny && kk >= 0 && kk < t.Nz) {
+      double scr = 1. / t.net_weight;
+      if (t.quantity == ABL_Q_IMAG_SOURCE) scr *= (b.wgt2 ? b.wgt2[i] : 0.);
+      else scr *= b.wgt[i];
+      red_add(t.gen + tally_index(t, l, ii, jj, kk), scr);
+    }
+  }
+}
+
+// ---- approximate mesh cancellation ---------------------------------------------------------------------------------
+struct CancelBins {  // dense per-bin accumulators, zeroed before each use
+  double* sum_w;
+  double* sum_w2;
+  uint32_t* count;  // low 28 bits: members; bits 28..31: has +w, -w, +w2, -w2
+};
+__device__ __forceinline__ long long cancel_key(const DevMesh3& m, double x, double y, double z, double E) {
+  const int i = (int)floor((x - m.lowx) / m.dx);
+  const int j = (int)floor((y - m.lowy) / m.dy);
+  const int k = (int)floor((z - m.lowz) / m.dz);
+  int l = -1;
+  if (m.eedges) {
+    for (int e = 0; e < m.Ne; e++)
+      if (__ldg(&m.eedges[e]) <= E && E <= __ldg(&m.eedges[e + 1])) { l = e; break; }
+  } else {
+    l = 0;
+  }
+  if (i < 0 || j < 0 || k < 0 || l < 0) return -1;
+  if (i >= m.Nx || j >= m.Ny || k >= m.Nz || l >= m.Ne) return -1;
+  return (long long)l + (long long)m.Ne * ((long long)k + (long long)m.Nz * ((long long)j + (long long)m.Ny * (long long)i));
+}
+__global__ void __launch_bounds__(256) cancel_accumulate_kernel(DevMesh3 m, BankView b, CancelBins cb) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const long long key = cancel_key(m, b.x[i], b.y[i], b.z[i], b.E[i]);
+    if (key < 0) continue;
+    const double w = b.wgt[i], w2 = b.wgt2 ? b.wgt2[i] : 0.;
+    uint32_t inc = 1u;
+    if (w > 0.) inc |= 1u << 28; else if (w < 0.) inc |= 1u << 29;
+    if (w2 > 0.) inc |= 1u << 30; else if (w2 < 0.) inc |= 1u << 31;
+    // count in the low bits, flags OR-ed in the high bits: two atomics on the same word
+    atomicAdd(&cb.count[key], 1u);
+    atomicOr(&cb.count[key], inc & 0xf0000000u);
+    red_add(&cb.sum_w[key], w);
+    if (b.wgt2) red_add(&cb.sum_w2[key], w2);
+  }
+}
+__global__ void __launch_bounds__(256) cancel_apply_kernel(DevMesh3 m, BankView b, CancelBins cb) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const long long key = cancel_key(m, b.x[i], b.y[i], b.z[i], b.E[i]);
+    if (key < 0) continue;
+    const uint32_t c = cb.count[key];
+    const uint32_t members = c & 0x0fffffffu;
+    if (members > 1) {
+      const double N = (double)members;
+      if ((c & (1u << 28)) && (c & (1u << 29))) b.wgt[i] = cb.sum_w[key] / N;
+      if (b.wgt2 && (c & (1u << 30)) && (c & (1u << 31))) b.wgt2[i] = cb.sum_w2[key] / N;
+    }
+  }
+}
+// re-zero only the bins that were touched (the mesh is usually far larger than the bank)
+__global__ void __launch_bounds__(256) cancel_reset_kernel(DevMesh3 m, BankView b, CancelBins cb) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const long long key = cancel_key(m, b.x[i], b.y[i], b.z[i], b.E[i]);
+    if (key < 0) continue;
+    cb.count[key] = 0;
+    cb.sum_w[key] = 0.;
+    if (cb.sum_w2) cb.sum_w2[key] = 0.;
+  }
+}
+
+// ---- initial source ---------------------------------------------------------------------------------------------------
+// include/utils/direction.hpp:44-64
+__device__ __forceinline__ V3 make_direction_mu_phi(double mu, double phi) {
+  if (mu < -1.) mu = -1.; else if (mu > 1.) mu = 1.;
+  if (phi < 0.) phi = 0.; else if (phi > 2 * ABL_PI) phi = 2 * ABL_PI;
+  double sn, cs;
+  det_sincos(phi, &sn, &cs);
+  return make_direction(sqrt(1. - mu * mu) * cs, sqrt(1. - mu * mu) * sn, mu);
+}
+
+__global__ void __launch_bounds__(128) sample_source_kernel(const DevProblem P, BankView out, uint64_t first_id, int* error) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < out.n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t hid = first_id + i;
+    uint64_t rng = pcg_advance(P.seed_state, P.stride * hid, P.jump);
+    int si = 0;
+    if (P.nsources >= 2) si = rng_discrete(rng, P.source_cp, P.nsources);
+    const abl_source* S = P.sources + si;
+    const double mu = 2. * rng_rand(rng) - 1.;  // isotropic.cpp:28-36
+    const double phi = 2. * ABL_PI * rng_rand(rng);
+    const V3 u = make_direction_mu_phi(mu, phi);
+    const double E = __ldg(&S->energy);
+    const bool is_box = __ldg(&S->is_box) != 0;
+    const double lx = __ldg(&S->low[0]), ly = __ldg(&S->low[1]), lz = __ldg(&S->low[2]);
+    const double hx = __ldg(&S->hi[0]), hy = __ldg(&S->hi[1]), hz = __ldg(&S->hi[2]);
+    V3 r;
+    Cursor c;
+    c.err = 0;
+    bool bad = false;
+    auto sample_pos = [&]() {
+      if (is_box) {  // box.cpp:37-42
+        r.x = (hx - lx) * rng_rand(rng) + lx;
+        r.y = (hy - ly) * rng_rand(rng) + ly;
+        r.z = (hz - lz) * rng_rand(rng) + lz;
+      } else {
+        r = {lx, ly, lz};
+      }
+      c.token = 0;
+      cursor_restart(P, c, r, u);
+    };
+    sample_pos();
+    int guard = 0;
+    while (c.cell < 0) {  // rejection until inside the geometry (source.cpp:61-70)
+      if (!is_box && ++guard > 1) { bad = true; break; }
+      sample_pos();
+    }
+    if (!bad && __ldg(&S->fissile_only)) {  // source.cpp:72-86
+      int count = 0;
+      while (c.cell < 0 || !__ldg(&P.fissile[c.mat])) {
+        if (count == 201) { bad = true; break; }
+        sample_pos();
+        count++;
+      }
+    }
+    if (bad) atomicCAS(error, 0, ABL_ERR_INVALID);
+    out.x[i] = r.x; out.y[i] = r.y; out.z[i] = r.z;
+    out.ux[i] = u.x; out.uy[i] = u.y; out.uz[i] = u.z;
+    out.E[i] = E;
+    out.wgt[i] = 1.0;
+    if (out.wgt2) out.wgt2[i] = 0.;
+    out.id_a[i] = hid;
+    out.id_b[i] = hid;
+    out.id_c[i] = rng;
+  }
+}
+
+// ---- tally statistics --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tally_record_kernel(double* __restrict__ gen, double* __restrict__ avg,
+                                                           double* __restrict__ var, uint64_t n, double multiplier, double dg) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double old_avg = avg[i];
+    const double val = gen[i] * multiplier;
+    const double a = old_avg + (val - old_avg) / dg;
+    avg[i] = a;
+    double v = var[i];
+    v = v + (((val - old_avg) * (val - a) - (v)) / dg);
+    var[i] = v;
+  }
+}
+__global__ void __launch_bounds__(256) tally_std_kernel(const double* __restrict__ var, double* __restrict__ out, uint64_t n, double dg) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = sqrt(var[i] / dg);
+}
+
+// ---- probes --------------------------------------------------------------------------------------------------------------
+__global__ void find_cells_kernel(const DevProblem P, uint64_t n, const double* r3, const double* u3, int32_t* cell, int32_t* mat) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    Cursor c;
+    c.err = 0;
+    c.token = 0;
+    const V3 r{r3[3 * i], r3[3 * i + 1], r3[3 * i + 2]}, u{u3[3 * i], u3[3 * i + 1], u3[3 * i + 2]};
+    cursor_restart(P, c, r, u);
+    cell[i] = c.cell;
+    mat[i] = c.mat;
+  }
+}
+__global__ void rng_probe_kernel(const DevProblem P, uint64_t history_id, int n, uint32_t* out_u32, double* out_rand) {
+  if (threadIdx.x || blockIdx.x) return;
+  uint64_t s = pcg_advance(P.seed_state, P.stride * history_id, P.jump);
+  for (int i = 0; i < n; i++) out_u32[i] = pcg_next(s);
+  s = pcg_advance(P.seed_state, P.stride * history_id, P.jump);
+  for (int i = 0; i < n; i++) out_rand[i] = rng_rand(s);
+}
+__global__ void math_probe_kernel(int n, const double* x, double* lg, double* sn, double* cs) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    lg[i] = det_log(x[i]);
+    det_sincos(x[i], &sn[i], &cs[i]);
+  }
+}
+
+}  // namespace abl

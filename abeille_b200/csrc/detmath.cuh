@@ -1,0 +1,173 @@
+/* detmath.cuh -- double-precision log / sin / cos for the transport kernels.
+ *
+ * The reference calls glibc's log/sin/cos (include/utils/rng.hpp:74-79,
+ * include/utils/direction.hpp:130-151).  CUDA's libdevice differs from glibc in the last
+ * bit on a fraction of arguments, which would make every sampled distance differ from a
+ * CPU run in the last ulp.  These routines evaluate the classic fdlibm algorithms
+ * (e_log.c, k_sin.c, k_cos.c, e_rem_pio2.c medium path; error < 1 ulp, the same accuracy
+ * class as glibc) using only IEEE +,-,*,/ -- the translation unit is compiled with
+ * -fmad=false -- so a CPU evaluation of the same operation sequence is bit-identical.
+ */
+#pragma once
+#include <stdint.h>
+
+namespace abl {
+
+__device__ __forceinline__ int32_t dm_hi(double x) { return __double2hiint(x); }
+__device__ __forceinline__ uint32_t dm_lo(double x) { return (uint32_t)__double2loint(x); }
+__device__ __forceinline__ double dm_set_hi(double x, int32_t hi) { return __hiloint2double(hi, __double2loint(x)); }
+
+__device__ __noinline__ double det_log(double x) {
+  const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+               two54 = 1.80143985094819840000e+16, Lg1 = 6.666666666666735130e-01,
+               Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+               Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01,
+               Lg6 = 1.531383769920937332e-01, Lg7 = 1.479819860511658591e-01;
+  int32_t hx = dm_hi(x);
+  uint32_t lx = dm_lo(x);
+  int32_t k = 0;
+  if (hx < 0x00100000) {
+    if (((hx & 0x7fffffff) | lx) == 0) return -two54 / 0.0;
+    if (hx < 0) return (x - x) / 0.0;
+    k -= 54;
+    x *= two54;
+    hx = dm_hi(x);
+  }
+  if (hx >= 0x7ff00000) return x + x;
+  k += (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  int32_t i = (hx + 0x95f64) & 0x100000;
+  x = dm_set_hi(x, hx | (i ^ 0x3ff00000));
+  k += (i >> 20);
+  const double f = x - 1.0;
+  if ((0x000fffff & (2 + hx)) < 3) {
+    if (f == 0.0) {
+      if (k == 0) return 0.0;
+      const double dk = (double)k;
+      return dk * ln2_hi + dk * ln2_lo;
+    }
+    const double R = f * f * (0.5 - 0.33333333333333333 * f);
+    if (k == 0) return f - R;
+    const double dk = (double)k;
+    return dk * ln2_hi - ((R - dk * ln2_lo) - f);
+  }
+  const double s = f / (2.0 + f);
+  const double dk = (double)k;
+  const double z = s * s;
+  i = hx - 0x6147a;
+  const double w = z * z;
+  const int32_t j = 0x6b851 - hx;
+  const double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+  const double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+  i |= j;
+  const double R = t2 + t1;
+  if (i > 0) {
+    const double hfsq = 0.5 * f * f;
+    if (k == 0) return f - (hfsq - s * (hfsq + R));
+    return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+  }
+  if (k == 0) return f - s * (f - R);
+  return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
+}
+
+__device__ __forceinline__ double det_ksin(double x, double y, int iy) {
+  const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+               S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+               S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+  const int32_t ix = dm_hi(x) & 0x7fffffff;
+  if (ix < 0x3e400000) {
+    if ((int)x == 0) return x;
+  }
+  const double z = x * x;
+  const double v = z * x;
+  const double r = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+  if (iy == 0) return x + v * (S1 + z * r);
+  return x - ((z * (0.5 * y - v * r) - y) - v * S1);
+}
+
+__device__ __forceinline__ double det_kcos(double x, double y) {
+  const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+               C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+               C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+  const int32_t ix = dm_hi(x) & 0x7fffffff;
+  if (ix < 0x3e400000) {
+    if (((int)x) == 0) return 1.0;
+  }
+  const double z = x * x;
+  const double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+  if (ix < 0x3FD33333) return 1.0 - (0.5 * z - (z * r - x * y));
+  double qx;
+  if (ix > 0x3fe90000)
+    qx = 0.28125;
+  else
+    qx = __hiloint2double(ix - 0x00200000, 0);
+  const double hz = 0.5 * z - qx;
+  const double a = 1.0 - qx;
+  return a - (hz - (z * r - x * y));
+}
+
+/* |x| < 2^19*pi/2 -> y0+y1 in [-pi/4, pi/4], returns the quadrant */
+__device__ __forceinline__ int det_rem_pio2(double x, double* y0, double* y1) {
+  const double invpio2 = 6.36619772367581382433e-01, pio2_1 = 1.57079632673412561417e+00,
+               pio2_1t = 6.07710050650619224932e-11, pio2_2 = 6.07710050630396597660e-11,
+               pio2_2t = 2.02226624879595063154e-21, pio2_3 = 2.02226624871116645580e-21,
+               pio2_3t = 8.47842766036889956997e-32;
+  const int32_t hx = dm_hi(x);
+  const int32_t ix = hx & 0x7fffffff;
+  double t = fabs(x);
+  const int n = (int)(t * invpio2 + 0.5);
+  const double fn = (double)n;
+  double r = t - fn * pio2_1;
+  double w = fn * pio2_1t;
+  const int32_t j = ix >> 20;
+  double a0 = r - w;
+  int32_t i = j - ((dm_hi(a0) >> 20) & 0x7ff);
+  if (i > 16) {
+    t = r;
+    w = fn * pio2_2;
+    r = t - w;
+    w = fn * pio2_2t - ((t - r) - w);
+    a0 = r - w;
+    i = j - ((dm_hi(a0) >> 20) & 0x7ff);
+    if (i > 49) {
+      t = r;
+      w = fn * pio2_3;
+      r = t - w;
+      w = fn * pio2_3t - ((t - r) - w);
+      a0 = r - w;
+    }
+  }
+  const double a1 = (r - a0) - w;
+  if (hx < 0) {
+    *y0 = -a0;
+    *y1 = -a1;
+    return -n;
+  }
+  *y0 = a0;
+  *y1 = a1;
+  return n;
+}
+
+__device__ __noinline__ void det_sincos(double x, double* sn, double* cs) {
+  const int32_t ix = dm_hi(x) & 0x7fffffff;
+  if (ix <= 0x3fe921fb) {
+    *sn = det_ksin(x, 0.0, 0);
+    *cs = det_kcos(x, 0.0);
+    return;
+  }
+  if (ix >= 0x7ff00000) {
+    *sn = *cs = x - x;
+    return;
+  }
+  double y0, y1;
+  const int n = det_rem_pio2(x, &y0, &y1);
+  const double s = det_ksin(y0, y1, 1), c = det_kcos(y0, y1);
+  switch (n & 3) {
+    case 0: *sn = s; *cs = c; break;
+    case 1: *sn = c; *cs = -s; break;
+    case 2: *sn = -s; *cs = -c; break;
+    default: *sn = -c; *cs = s; break;
+  }
+}
+
+}  // namespace abl

@@ -1,0 +1,616 @@
+/* geom.cuh -- CSG geometry on flattened tables: surfaces, cells (RPN half-space logic), cell
+ * universes, rectilinear lattices, and the per-history geometry cursor.
+ *
+ * Behaviour follows the reference (paths relative to the reference tree):
+ *   surfaces   sign / distance / norm      src/xplane.cpp:32-56, src/plane.cpp:33-60, src/zcylinder.cpp:33-80,
+ *                                          src/cylinder.cpp:60-110, src/sphere.cpp:33-80
+ *   cells      is_inside, distances        src/cell.cpp:71-201
+ *   universes  get_cell / boundary search  src/cell_universe.cpp:43-154, src/lattice.cpp:77-108
+ *   lattices   tile math                   src/rect_lattice.cpp:33-52,132-310
+ *   cursor     Tracker                     include/simulation/tracker.hpp:41-372
+ * Design differences (results are bit-identical): no virtual dispatch, no id->index maps, no heap.
+ * The cursor keeps the reference's stack of "lily pads", but pads that live in the same local
+ * coordinate frame share one r_local (the reference stores and increments a copy per pad; copies in
+ * one frame are always bitwise equal because they start equal and receive identical increments).
+ * A frame changes only when a lattice tile is entered (r_local = r - tile_center).
+ */
+#pragma once
+#include "tables.h"
+
+namespace abl {
+
+#define ABL_SURFACE_COINCIDENT 1E-12
+#define ABL_BOUNDRY_TOL (500. * 1E-12)
+
+struct V3 {
+  double x, y, z;
+};
+__device__ __forceinline__ double dot3(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double norm3(const V3& a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+// Direction constructors renormalise every time (include/utils/direction.hpp:37-43)
+__device__ __forceinline__ V3 make_direction(double x, double y, double z) {
+  const double m = sqrt(x * x + y * y + z * z);
+  return {x / m, y / m, z / m};
+}
+
+// include/utils/direction.hpp:130-151
+__device__ __forceinline__ V3 rotate_direction(const V3& u, double mu, double phi) {
+  double sn, cs;
+  det_sincos(phi, &sn, &cs);
+  const double sqrt_mu = sqrt(1. - mu * mu);
+  const double sqrt_w = sqrt(1. - u.z * u.z);
+  double ux, uy, uz;
+  if (sqrt_w > 1.E-10) {
+    ux = mu * u.x + sqrt_mu * (u.x * u.z * cs - u.y * sn) / sqrt_w;
+    uy = mu * u.y + sqrt_mu * (u.y * u.z * cs + u.x * sn) / sqrt_w;
+    uz = mu * u.z - sqrt_mu * sqrt_w * cs;
+  } else {
+    const double sqrt_v = sqrt(1. - u.y * u.y);
+    ux = mu * u.x + sqrt_mu * (u.x * u.y * cs + u.z * sn) / sqrt_v;
+    uy = mu * u.y - sqrt_mu * sqrt_v * cs;
+    uz = mu * u.z + sqrt_mu * (u.y * u.z * cs - u.x * sn) / sqrt_v;
+  }
+  return make_direction(ux, uy, uz);
+}
+
+// ---- surfaces ---------------------------------------------------------------------------------
+struct Surf {  // register copy of one table row
+  int type, bc;
+  double p0, p1, p2, p3, p4, p5, p6;
+};
+__device__ __forceinline__ Surf load_surface(const DevProblem& P, int i) {
+  const abl_surface* s = P.surfaces + i;
+  Surf r;
+  r.type = __ldg(&s->type);
+  r.bc = __ldg(&s->bc);
+  r.p0 = __ldg(&s->p[0]);
+  r.p1 = __ldg(&s->p[1]);
+  r.p2 = __ldg(&s->p[2]);
+  r.p3 = __ldg(&s->p[3]);
+  r.p4 = r.p5 = r.p6 = 0.;
+  if (r.type == ABL_SURF_CYL) {
+    r.p4 = __ldg(&s->p[4]);
+    r.p5 = __ldg(&s->p[5]);
+    r.p6 = __ldg(&s->p[6]);
+  }
+  return r;
+}
+
+__device__ __forceinline__ double surf_eval(const Surf& s, const V3& r) {
+  switch (s.type) {
+    case ABL_SURF_XPLANE: return r.x - s.p0;
+    case ABL_SURF_YPLANE: return r.y - s.p0;
+    case ABL_SURF_ZPLANE: return r.z - s.p0;
+    case ABL_SURF_PLANE: return s.p0 * r.x + s.p1 * r.y + s.p2 * r.z - s.p3;
+    case ABL_SURF_XCYL: { const double y = r.y - s.p0, z = r.z - s.p1; return y * y + z * z - s.p2 * s.p2; }
+    case ABL_SURF_YCYL: { const double x = r.x - s.p0, z = r.z - s.p1; return x * x + z * z - s.p2 * s.p2; }
+    case ABL_SURF_ZCYL: { const double x = r.x - s.p0, y = r.y - s.p1; return y * y + x * x - s.p2 * s.p2; }
+    case ABL_SURF_CYL: {
+      const double x = r.x - s.p0, y = r.y - s.p1, z = r.z - s.p2;
+      return s.p3 * x * x + s.p4 * y * y + s.p5 * z * z - s.p6 * s.p6;
+    }
+    default: {
+      const double x = r.x - s.p0, y = r.y - s.p1, z = r.z - s.p2;
+      return (x * x) + (y * y) + (z * z) - s.p3 * s.p3;
+    }
+  }
+}
+
+__device__ __noinline__ V3 surf_norm(const Surf& s, const V3& r) {
+  switch (s.type) {
+    case ABL_SURF_XPLANE: return make_direction(1., 0., 0.);
+    case ABL_SURF_YPLANE: return make_direction(0., 1., 0.);
+    case ABL_SURF_ZPLANE: return make_direction(0., 0., 1.);
+    case ABL_SURF_PLANE: return make_direction(s.p0, s.p1, s.p2);
+    case ABL_SURF_XCYL: return make_direction(0., r.y - s.p0, r.z - s.p1);
+    case ABL_SURF_YCYL: return make_direction(r.x - s.p0, 0., r.z - s.p1);
+    case ABL_SURF_ZCYL: return make_direction(r.x - s.p0, r.y - s.p1, 0.);
+    case ABL_SURF_CYL: return make_direction(s.p3 * (r.x - s.p0), s.p4 * (r.y - s.p1), s.p5 * (r.z - s.p2));
+    default: return make_direction(r.x - s.p0, r.y - s.p1, r.z - s.p2);
+  }
+}
+
+// +1 / -1 : which side of the surface; on-surface ties broken by the flight direction
+__device__ __forceinline__ int surf_sign(const Surf& s, const V3& r, const V3& u) {
+  const double e = surf_eval(s, r);
+  if (e > ABL_SURFACE_COINCIDENT) return 1;
+  if (e < -ABL_SURFACE_COINCIDENT) return -1;
+  const V3 n = surf_norm(s, r);
+  if (dot3(u, n) > 0.) return 1;
+  return -1;
+}
+
+__device__ __forceinline__ double quadric_distance(double a, double k, double c, bool on_surf) {
+  const double quad = k * k - a * c;
+  if (quad < 0.) return ABL_INF;
+  if (on_surf || fabs(c) < ABL_SURFACE_COINCIDENT) {
+    if (k >= 0.) return ABL_INF;
+    return (-k + sqrt(quad)) / a;
+  } else if (c < 0.) {
+    return (-k + sqrt(quad)) / a;
+  } else {
+    const double d = (-k - sqrt(quad)) / a;
+    if (d < 0.) return ABL_INF;
+    return d;
+  }
+}
+
+__device__ __forceinline__ double surf_distance(const Surf& s, const V3& r, const V3& u, bool on_surf) {
+  switch (s.type) {
+    case ABL_SURF_XPLANE:
+    case ABL_SURF_YPLANE:
+    case ABL_SURF_ZPLANE: {
+      const double rc = s.type == ABL_SURF_XPLANE ? r.x : (s.type == ABL_SURF_YPLANE ? r.y : r.z);
+      const double uc = s.type == ABL_SURF_XPLANE ? u.x : (s.type == ABL_SURF_YPLANE ? u.y : u.z);
+      const double diff = s.p0 - rc;
+      if (on_surf || fabs(diff) < ABL_SURFACE_COINCIDENT || uc == 0.) return ABL_INF;
+      const double d = diff / uc;
+      if (d < 0.) return ABL_INF;
+      return d;
+    }
+    case ABL_SURF_PLANE: {
+      const double num = s.p3 - s.p0 * r.x - s.p1 * r.y - s.p2 * r.z;
+      const double denom = s.p0 * u.x + s.p1 * u.y + s.p2 * u.z;
+      const double d = num / denom;
+      if (on_surf || fabs(d) < ABL_SURFACE_COINCIDENT || denom == 0.) return ABL_INF;
+      if (d < 0.) return ABL_INF;
+      return d;
+    }
+    case ABL_SURF_XCYL: {
+      const double a = u.y * u.y + u.z * u.z;
+      if (a == 0.) return ABL_INF;
+      const double y = r.y - s.p0, z = r.z - s.p1;
+      const double k = y * u.y + z * u.z;
+      const double c = y * y + z * z - s.p2 * s.p2;
+      return quadric_distance(a, k, c, on_surf);
+    }
+    case ABL_SURF_YCYL: {
+      const double a = u.x * u.x + u.z * u.z;
+      if (a == 0.) return ABL_INF;
+      const double x = r.x - s.p0, z = r.z - s.p1;
+      const double k = x * u.x + z * u.z;
+      const double c = x * x + z * z - s.p2 * s.p2;
+      return quadric_distance(a, k, c, on_surf);
+    }
+    case ABL_SURF_ZCYL: {
+      const double a = u.y * u.y + u.x * u.x;
+      if (a == 0.) return ABL_INF;
+      const double x = r.x - s.p0, y = r.y - s.p1;
+      const double k = y * u.y + x * u.x;
+      const double c = y * y + x * x - s.p2 * s.p2;
+      return quadric_distance(a, k, c, on_surf);
+    }
+    case ABL_SURF_CYL: {
+      const double a = s.p3 * u.x * u.x + s.p4 * u.y * u.y + s.p5 * u.z * u.z;
+      if (a == 0.) return ABL_INF;
+      const double x = r.x - s.p0, y = r.y - s.p1, z = r.z - s.p2;
+      const double k = s.p3 * x * u.x + s.p4 * y * u.y + s.p5 * z * u.z;
+      const double c = s.p3 * x * x + s.p4 * y * y + s.p5 * z * z - s.p6 * s.p6;
+      return quadric_distance(a, k, c, on_surf);
+    }
+    default: {  // sphere: no division by a
+      const double x = r.x - s.p0, y = r.y - s.p1, z = r.z - s.p2;
+      const double k = x * u.x + y * u.y + z * u.z;
+      const double c = x * x + y * y + z * z - s.p3 * s.p3;
+      const double quad = k * k - c;
+      if (quad < 0.) return ABL_INF;
+      if (on_surf || fabs(c) < ABL_SURFACE_COINCIDENT) {
+        if (k >= 0.) return ABL_INF;
+        return -k + sqrt(quad);
+      } else if (c < 0.) {
+        return -k + sqrt(quad);
+      } else {
+        const double d = -k - sqrt(quad);
+        if (d < 0.) return ABL_INF;
+        return d;
+      }
+    }
+  }
+}
+
+// ---- cells -------------------------------------------------------------------------------------
+__device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
+
+__device__ inline bool cell_is_inside(const DevProblem& P, int ci, const V3& r, const V3& u, int on_surf) {
+  const abl_cell* c = P.cells + ci;
+  const int off = __ldg(&c->rpn_offset), len = __ldg(&c->rpn_len);
+  if (__ldg(&c->simple)) {
+    for (int k = 0; k < len; k++) {
+      const int token = __ldg(&P.rpn[off + k]);
+      if (token == on_surf) {
+      } else if (-token == on_surf) {
+        return false;
+      } else {
+        const Surf s = load_surface(P, iabs(token) - 1);
+        const int sg = surf_sign(s, r, u);
+        if ((sg > 0 && token < 0) || (sg < 0 && token > 0)) return false;
+      }
+    }
+    return true;
+  }
+  // RPN evaluation; the boolean stack is a bit mask (host guarantees len <= 64)
+  uint64_t stck = 0;
+  int i_stck = -1;
+  for (int k = 0; k < len; k++) {
+    const int token = __ldg(&P.rpn[off + k]);
+    if (token == ABL_OP_UNION) {
+      const bool v = ((stck >> (i_stck - 1)) & 1ULL) || ((stck >> i_stck) & 1ULL);
+      i_stck--;
+      stck = (stck & ~(1ULL << i_stck)) | ((uint64_t)v << i_stck);
+    } else if (token == ABL_OP_INTERSECTION) {
+      const bool v = ((stck >> (i_stck - 1)) & 1ULL) && ((stck >> i_stck) & 1ULL);
+      i_stck--;
+      stck = (stck & ~(1ULL << i_stck)) | ((uint64_t)v << i_stck);
+    } else if (token == ABL_OP_COMPLEMENT) {
+      stck ^= (1ULL << i_stck);
+    } else {
+      i_stck++;
+      bool v;
+      if (token == on_surf) {
+        v = true;
+      } else if (-token == on_surf) {
+        v = false;
+      } else {
+        const Surf s = load_surface(P, iabs(token) - 1);
+        const int sg = surf_sign(s, r, u);
+        v = ((sg > 0 && token > 0) || (sg < 0 && token < 0));
+      }
+      stck = (stck & ~(1ULL << i_stck)) | ((uint64_t)v << i_stck);
+    }
+  }
+  if (i_stck == 0) return (stck & 1ULL) != 0;
+  return true;
+}
+
+// nearest surface of the cell along u (cell.cpp:79-142); bc_only = distance_to_boundary_condition
+__device__ inline void cell_distance(const DevProblem& P, int ci, const V3& r, const V3& u, int on_surf, bool bc_only,
+                                     double& min_dist, int& i_surf) {
+  min_dist = ABL_INF;
+  i_surf = 0;
+  const abl_cell* c = P.cells + ci;
+  if (bc_only && !__ldg(&c->vac_or_refl)) return;
+  const int off = __ldg(&c->rpn_offset), len = __ldg(&c->rpn_len);
+  for (int k = 0; k < len; k++) {
+    const int token = __ldg(&P.rpn[off + k]);
+    if (token >= ABL_OP_UNION) continue;
+    const bool coincident = iabs(token) == iabs(on_surf);
+    const Surf s = load_surface(P, iabs(token) - 1);
+    if (bc_only && s.bc == ABL_BC_NORMAL) continue;
+    const double d = surf_distance(s, r, u, coincident);
+    if (d < min_dist) {
+      if (fabs(d - min_dist) / min_dist >= 1e-14) {
+        min_dist = d;
+        i_surf = -token;
+      }
+    }
+  }
+}
+
+// ---- rectilinear lattice -------------------------------------------------------------------------
+struct Lat {
+  int Nx, Ny, Nz, tile_offset, outer;
+  double Px, Py, Pz, Pxi, Pyi, Pzi, Xl, Yl, Zl;
+};
+__device__ __forceinline__ Lat load_lattice(const abl_universe* U) {
+  Lat L;
+  L.Nx = __ldg(&U->N[0]); L.Ny = __ldg(&U->N[1]); L.Nz = __ldg(&U->N[2]);
+  L.tile_offset = __ldg(&U->tile_offset);
+  L.outer = __ldg(&U->outer);
+  L.Px = __ldg(&U->P[0]); L.Py = __ldg(&U->P[1]); L.Pz = __ldg(&U->P[2]);
+  L.Pxi = __ldg(&U->Pinv[0]); L.Pyi = __ldg(&U->Pinv[1]); L.Pzi = __ldg(&U->Pinv[2]);
+  L.Xl = __ldg(&U->Xl[0]); L.Yl = __ldg(&U->Xl[1]); L.Zl = __ldg(&U->Xl[2]);
+  return L;
+}
+__device__ __forceinline__ V3 tile_center(const Lat& L, int nx, int ny, int nz) {  // rect_lattice.cpp:303-309
+  return {((double)nx + 0.5) * L.Px + L.Xl, ((double)ny + 0.5) * L.Py + L.Yl, ((double)nz + 0.5) * L.Pz + L.Zl};
+}
+__device__ __forceinline__ void get_tile(const Lat& L, const V3& r, const V3& u, int& nx, int& ny, int& nz) {
+  nx = (int)floor((r.x - L.Xl) * L.Pxi);  // rect_lattice.cpp:209-237
+  ny = (int)floor((r.y - L.Yl) * L.Pyi);
+  nz = (int)floor((r.z - L.Zl) * L.Pzi);
+  const V3 rt = tile_center(L, nx, ny, nz);
+  const double xl = rt.x - L.Px * 0.5;
+  if (fabs(xl - r.x) < ABL_SURFACE_COINCIDENT && u.x < 0.) nx--;
+  const double xh = rt.x + L.Px * 0.5;
+  if (fabs(xh - r.x) < ABL_SURFACE_COINCIDENT && u.x >= 0.) nx++;
+  const double yl = rt.y - L.Py * 0.5;
+  if (fabs(yl - r.y) < ABL_SURFACE_COINCIDENT && u.y < 0.) ny--;
+  const double yh = rt.y + L.Py * 0.5;
+  if (fabs(yh - r.y) < ABL_SURFACE_COINCIDENT && u.y >= 0.) ny++;
+  const double zl = rt.z - L.Pz * 0.5;
+  if (fabs(zl - r.z) < ABL_SURFACE_COINCIDENT && u.z < 0.) nz--;
+  const double zh = rt.z + L.Pz * 0.5;
+  if (fabs(zh - r.z) < ABL_SURFACE_COINCIDENT && u.z >= 0.) nz++;
+}
+__device__ __forceinline__ bool tile_in_range(const Lat& L, int nx, int ny, int nz) {
+  return !((nx < 0 || nx >= L.Nx) || (ny < 0 || ny >= L.Ny) || (nz < 0 || nz >= L.Nz));
+}
+__device__ inline double distance_to_tile_boundary(const Lat& L, const V3& r_local, const V3& u, int nx, int ny, int nz) {
+  const V3 center = tile_center(L, nx, ny, nz);  // rect_lattice.cpp:239-282
+  const double tx = r_local.x - center.x, ty = r_local.y - center.y, tz = r_local.z - center.z;
+  double dist = ABL_INF;
+  const double diff_xl = -L.Px * 0.5 - tx;
+  const double diff_xh = L.Px * 0.5 - tx;
+  const double diff_yl = -L.Py * 0.5 - ty;
+  const double diff_yh = L.Py * 0.5 - ty;
+  const double diff_zl = -L.Pz * 0.5 - tz;
+  const double diff_zh = L.Pz * 0.5 - tz;
+  const double ux_inv = 1. / u.x, uy_inv = 1. / u.y, uz_inv = 1. / u.z;
+  const double d_xl = diff_xl * ux_inv, d_xh = diff_xh * ux_inv;
+  const double d_yl = diff_yl * uy_inv, d_yh = diff_yh * uy_inv;
+  const double d_zl = diff_zl * uz_inv, d_zh = diff_zh * uz_inv;
+  const double guard = 100 * ABL_SURFACE_COINCIDENT;
+  if (d_xl > 0. && d_xl < dist && fabs(diff_xl) > guard) dist = d_xl;
+  if (d_xh > 0. && d_xh < dist && fabs(diff_xh) > guard) dist = d_xh;
+  if (d_yl > 0. && d_yl < dist && fabs(diff_yl) > guard) dist = d_yl;
+  if (d_yh > 0. && d_yh < dist && fabs(diff_yh) > guard) dist = d_yh;
+  if (d_zl > 0. && d_zl < dist && fabs(diff_zl) > guard) dist = d_zl;
+  if (d_zh > 0. && d_zh < dist && fabs(diff_zh) > guard) dist = d_zh;
+  return dist;
+}
+
+// ---- boundaries ------------------------------------------------------------------------------------
+struct Boundary {  // include/geometry/boundary.hpp:33-42
+  double distance;
+  int surface_index;
+  int btype;
+  int token;
+};
+
+// candidate (d, i_surf) from a cell against the running nearest boundary (tracker.hpp:104-131,
+// cell_universe.cpp:121-147): takes it when closer by more than BOUNDRY_TOL and a surface was found
+__device__ __forceinline__ void take_cell_candidate(const DevProblem& P, double d, int i_surf, const V3& r, const V3& u,
+                                                    Boundary& b) {
+  if (d < b.distance && fabs(d - b.distance) > ABL_BOUNDRY_TOL) {
+    const int tmp_token = iabs(i_surf);
+    if (tmp_token) {
+      b.token = tmp_token;
+      b.distance = d;
+      b.surface_index = tmp_token - 1;
+      const Surf s = load_surface(P, b.surface_index);
+      b.btype = s.bc;
+      if (surf_sign(s, r, u) < 0) b.token *= -1;
+    }
+  }
+}
+
+// Universe::get_boundary_condition (cell_universe.cpp:111-154, lattice.cpp:77-92)
+__device__ inline Boundary universe_boundary_condition(const DevProblem& P, int uni, const V3& r, const V3& u, int on_surf) {
+  Boundary b{ABL_INF, -1, ABL_BC_VACUUM, 0};
+  const abl_universe* U = P.universes + uni;
+  while (__ldg(&U->type) != ABL_UNI_CELLS) {  // lattices defer to their outer universe
+    if (!__ldg(&U->has_bc)) return b;
+    U = P.universes + __ldg(&U->outer);
+  }
+  if (__ldg(&U->has_bc)) {
+    const int off = __ldg(&U->cell_offset), n = __ldg(&U->ncells);
+    for (int k = 0; k < n; k++) {
+      const int ci = __ldg(&P.ucells[off + k]);
+      if (!__ldg(&P.cells[ci].vac_or_refl)) continue;
+      double d;
+      int is;
+      cell_distance(P, ci, r, u, on_surf, true, d, is);
+      take_cell_candidate(P, d, is, r, u, b);
+    }
+  }
+  return b;
+}
+
+// ---- the geometry cursor -----------------------------------------------------------------------------
+enum { PAD_UNIVERSE = 0, PAD_LATTICE = 1, PAD_CELL = 2 };
+
+struct Cursor {
+  int token;     // surface the particle sits on: +-(surface index+1), 0 = none (tracker.hpp:367-370)
+  int cell, mat; // current cell / material index, -1 = lost
+  int np, nf;    // pads, frames in use
+  int err;       // ABL_ERR_* raised by the cursor (stack overflow, malformed nesting)
+  int pinfo[ABL_MAX_PADS];     // type | outside_flag<<2 | frame<<3 | index<<8
+  int ptile[ABL_MAX_PADS][3];  // lattice pads: tile found at descent
+  double fx[ABL_MAX_FRAMES], fy[ABL_MAX_FRAMES], fz[ABL_MAX_FRAMES];  // r_local of each frame; frame 0 = global r
+};
+
+__device__ __forceinline__ int pad_type(int info) { return info & 3; }
+__device__ __forceinline__ int pad_flag(int info) { return (info >> 2) & 1; }
+__device__ __forceinline__ int pad_frame(int info) { return (info >> 3) & 31; }
+__device__ __forceinline__ int pad_index(int info) { return info >> 8; }
+__device__ __forceinline__ int make_pad(int type, int flag, int frame, int index) {
+  return type | (flag << 2) | (frame << 3) | (index << 8);
+}
+__device__ __forceinline__ V3 frame_r(const Cursor& c, int f) { return {c.fx[f], c.fy[f], c.fz[f]}; }
+
+__device__ __forceinline__ bool push_pad(Cursor& c, int info, int tx = 0, int ty = 0, int tz = 0) {
+  if (c.np >= ABL_MAX_PADS) {
+    c.err = ABL_ERR_GEOMETRY;
+    return false;
+  }
+  c.pinfo[c.np] = info;
+  c.ptile[c.np][0] = tx;
+  c.ptile[c.np][1] = ty;
+  c.ptile[c.np][2] = tz;
+  c.np++;
+  return true;
+}
+
+// Universe::get_cell(stack, r, u, on_surf) made iterative (cell_universe.cpp:72-109, rect_lattice.cpp:132-207).
+// Descends from universe `uni` whose coordinates are frame f; returns the material cell or -1 (lost).
+__device__ inline int descend(const DevProblem& P, Cursor& c, int uni, int f, const V3& u) {
+  for (;;) {
+    const abl_universe* U = P.universes + uni;
+    const V3 r = frame_r(c, f);
+    if (__ldg(&U->type) == ABL_UNI_CELLS) {
+      if (!push_pad(c, make_pad(PAD_UNIVERSE, 0, f, uni))) return -1;
+      const int off = __ldg(&U->cell_offset), n = __ldg(&U->ncells);
+      int found = -1;
+      for (int k = 0; k < n; k++) {
+        const int ci = __ldg(&P.ucells[off + k]);
+        if (cell_is_inside(P, ci, r, u, c.token)) {
+          found = ci;
+          break;
+        }
+      }
+      c.nf = f + 1;
+      if (found < 0) return -1;
+      if (!push_pad(c, make_pad(PAD_CELL, 0, f, found))) return -1;
+      const int fill = __ldg(&P.cells[found].fill_universe);
+      if (fill < 0) return found;
+      uni = fill;
+      continue;
+    }
+    const Lat L = load_lattice(U);
+    int nx, ny, nz;
+    get_tile(L, r, u, nx, ny, nz);
+    int sub = -1;
+    if (tile_in_range(L, nx, ny, nz)) sub = __ldg(&P.tiles[L.tile_offset + nz * (L.Nx * L.Ny) + nx * L.Ny + ny]);
+    c.nf = f + 1;
+    if (sub >= 0) {
+      if (!push_pad(c, make_pad(PAD_LATTICE, 0, f, uni), nx, ny, nz)) return -1;
+      if (f + 1 >= ABL_MAX_FRAMES) {
+        c.err = ABL_ERR_GEOMETRY;
+        return -1;
+      }
+      const V3 ctr = tile_center(L, nx, ny, nz);
+      c.fx[f + 1] = r.x - ctr.x;
+      c.fy[f + 1] = r.y - ctr.y;
+      c.fz[f + 1] = r.z - ctr.z;
+      f++;
+      uni = sub;
+      continue;
+    }
+    if (L.outer >= 0) {  // outside the lattice or an empty tile: the outer universe, un-shifted r
+      if (!push_pad(c, make_pad(PAD_LATTICE, 1, f, uni), nx, ny, nz)) return -1;
+      uni = L.outer;
+      continue;
+    }
+    push_pad(c, make_pad(PAD_LATTICE, 0, f, uni), nx, ny, nz);
+    return -1;
+  }
+}
+
+// Tracker::restart_get_current (tracker.hpp:63-74): full lookup from the root at global position r
+__device__ inline void cursor_restart(const DevProblem& P, Cursor& c, const V3& r, const V3& u) {
+  c.np = 0;
+  c.fx[0] = r.x;
+  c.fy[0] = r.y;
+  c.fz[0] = r.z;
+  c.nf = 1;
+  c.cell = descend(P, c, P.root, 0, u);
+  c.mat = c.cell >= 0 ? __ldg(&P.cells[c.cell].material) : -1;
+}
+
+// Tracker::move (tracker.hpp:76-85): every frame advances by d*u, the surface token is dropped
+__device__ __forceinline__ void cursor_move(Cursor& c, double d, const V3& u) {
+  const double dx = d * u.x, dy = d * u.y, dz = d * u.z;
+#pragma unroll 1
+  for (int f = 0; f < c.nf; f++) {
+    c.fx[f] = c.fx[f] + dx;
+    c.fy[f] = c.fy[f] + dy;
+    c.fz[f] = c.fz[f] + dz;
+  }
+  c.token = 0;
+}
+
+// Tracker::get_current (tracker.hpp:235-306): re-validate the pads top-down, re-descend from the
+// first one that no longer holds.  (check_tree() is always true here: the cursor's global position
+// IS frame 0; the callers that reposition the particle call cursor_restart directly.)
+__device__ inline void cursor_get_current(const DevProblem& P, Cursor& c, const V3& u) {
+  int first_bad = c.np;
+  for (int it = 0; it < c.np; it++) {
+    const int info = c.pinfo[it];
+    const int type = pad_type(info);
+    if (type == PAD_CELL) {
+      if (!cell_is_inside(P, pad_index(info), frame_r(c, pad_frame(info)), u, c.token)) {
+        first_bad = it;
+        break;
+      }
+    } else if (type == PAD_LATTICE) {
+      const Lat L = load_lattice(P.universes + pad_index(info));
+      int nx, ny, nz;
+      get_tile(L, frame_r(c, pad_frame(info)), u, nx, ny, nz);
+      if (c.ptile[it][0] != nx || c.ptile[it][1] != ny || c.ptile[it][2] != nz) {
+        first_bad = it;
+        break;
+      }
+    }
+  }
+  if (first_bad == c.np) return;
+  if (first_bad == 0) {
+    cursor_restart(P, c, frame_r(c, 0), u);
+    return;
+  }
+  const int back = c.pinfo[first_bad - 1];
+  if (pad_type(back) == PAD_CELL) {
+    // A lattice sitting directly inside a universe-filled cell.  The reference looks the CELL id up in
+    // its universe-id map here (tracker.hpp:287), which lands in an unrelated universe; no shipped deck
+    // has this nesting.  The geometrically correct answer is a fresh lookup from the root.
+    cursor_restart(P, c, frame_r(c, 0), u);
+    return;
+  }
+  c.np = first_bad - 1;  // pop the universe / lattice pad and descend from it again
+  c.cell = descend(P, c, pad_index(back), pad_frame(back), u);
+  if (c.cell < 0) cursor_restart(P, c, frame_r(c, 0), u);
+  if (c.cell >= 0) c.mat = __ldg(&P.cells[c.cell].material);
+}
+
+// Tracker::get_boundary_condition (tracker.hpp:94-161)
+__device__ inline Boundary cursor_boundary_condition(const DevProblem& P, const Cursor& c, const V3& u) {
+  if (c.cell < 0) return universe_boundary_condition(P, P.root, frame_r(c, 0), u, c.token);
+  Boundary b{ABL_INF, -1, ABL_BC_VACUUM, 0};
+  for (int it = 0; it < c.np; it++) {
+    const int info = c.pinfo[it];
+    const V3 r = frame_r(c, pad_frame(info));
+    if (pad_type(info) == PAD_CELL) {
+      const int ci = pad_index(info);
+      if (!__ldg(&P.cells[ci].vac_or_refl)) continue;
+      double d;
+      int is;
+      cell_distance(P, ci, r, u, c.token, true, d, is);
+      take_cell_candidate(P, d, is, r, u, b);
+    } else {
+      const int ui = pad_index(info);
+      if (__ldg(&P.universes[ui].has_bc)) {
+        const Boundary ub = universe_boundary_condition(P, ui, r, u, c.token);
+        if (ub.distance < b.distance && fabs(ub.distance - b.distance) > ABL_BOUNDRY_TOL) b = ub;
+      }
+    }
+  }
+  return b;
+}
+
+// Tracker::get_nearest_boundary (tracker.hpp:163-225); the cursor is never lost when this is called
+__device__ inline Boundary cursor_nearest_boundary(const DevProblem& P, const Cursor& c, const V3& u) {
+  Boundary b = cursor_boundary_condition(P, c, u);
+  for (int it = 0; it < c.np; it++) {
+    const int info = c.pinfo[it];
+    const int type = pad_type(info);
+    const V3 r = frame_r(c, pad_frame(info));
+    if (type == PAD_LATTICE) {
+      const Lat L = load_lattice(P.universes + pad_index(info));
+      const double d = distance_to_tile_boundary(L, r, u, c.ptile[it][0], c.ptile[it][1], c.ptile[it][2]);
+      if (d < b.distance && fabs(d - b.distance) > ABL_BOUNDRY_TOL) {
+        b.distance = d;
+        b.btype = ABL_BC_NORMAL;
+        b.surface_index = -1;
+        b.token = 0;
+      }
+    } else if (type == PAD_CELL) {
+      double d;
+      int is;
+      cell_distance(P, pad_index(info), r, u, c.token, false, d, is);
+      if (d < b.distance && fabs(d - b.distance) > ABL_BOUNDRY_TOL) {
+        b.distance = d;
+        b.token = iabs(is);
+        b.surface_index = b.token ? b.token - 1 : -1;
+        if (b.surface_index >= 0) {
+          const Surf s = load_surface(P, b.surface_index);
+          b.btype = s.bc;
+          if (surf_sign(s, r, u) < 0) b.token *= -1;
+        } else {
+          b.btype = ABL_BC_NORMAL;
+        }
+      }
+    }
+  }
+  return b;
+}
+
+}  // namespace abl

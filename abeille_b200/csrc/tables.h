@@ -1,0 +1,73 @@
+/* tables.h -- device-side view of the flattened problem (immutable during a run).
+ *
+ * Everything the kernels read that is not particle state: CSG tables, multigroup cross sections,
+ * sampling tables, tally mesh descriptors.  For the reference decks the whole set is ~12 KB
+ * (C5G7: 7 surfaces, 8 cells, 10 universes, 582 lattice tiles, 7x7 groups), so it lives in L1/L2
+ * and is read through the read-only path.  The struct is passed to kernels by value.
+ */
+#pragma once
+#include <stdint.h>
+
+#include "../../include/abeille_b200.h"
+#include "rng.cuh"
+
+namespace abl {
+
+#define ABL_MAX_TALLIES 8
+
+struct DevTally {
+  int32_t estimator, quantity, noise_source;
+  int32_t Nx, Ny, Nz, Ne;
+  const double* ebounds;  // Ne+1
+  double lowx, lowy, lowz, hix, hiy, hiz;
+  double dx, dy, dz, dx_inv, dy_inv, dz_inv;  // mesh_tally.cpp:66-101
+  double net_weight;
+  double* gen;  // [Ne,Nx,Ny,Nz]
+  double* avg;
+  double* var;
+  uint64_t size;
+};
+
+struct DevMesh3 {
+  int32_t present, Nx, Ny, Nz, Ne;
+  const double* eedges;  // Ne+1 or null
+  double lowx, lowy, lowz, hix, hiy, hiz, dx, dy, dz;
+};
+
+struct DevProblem {
+  int32_t mode, tracking, G, inner_generations;
+  const double* ebounds;  // G+1
+  double wgt_cutoff, wgt_survival, wgt_split, min_energy;
+  uint64_t seed_state;  // pcg_seed_state(rng_seed)
+  uint64_t stride;
+  double w_noise, eta;
+  const JumpTable* jump;
+  // geometry
+  int32_t nsurfaces, ncells, nuniverses, root;
+  const abl_surface* surfaces;
+  const abl_cell* cells;
+  const int32_t* rpn;
+  const abl_universe* universes;
+  const int32_t* ucells;
+  const int32_t* tiles;
+  // materials [M*G]
+  int32_t M;
+  const double *Et, *Ea, *Ef, *Es, *nu, *nud, *speed;
+  const double *chi_cp, *ps_cp;  // [M*G*G]
+  const abl_angle_table* angle;  // [M*G*G]
+  const double *amu, *apdf, *acdf;
+  const int32_t* dg_off;  // [M+1]
+  const double *dg_cp, *dg_lambda;
+  const int32_t* fissile;
+  const double* smp;  // [G] sampling xs (majorant or ratio*majorant)
+  // tallies
+  int32_t ntallies, n_coll_tallies, n_tl_tallies;
+  DevTally tally[ABL_MAX_TALLIES];
+  // sources
+  int32_t nsources;
+  const abl_source* sources;
+  const double* source_cp;  // discrete table over source weights (nsources >= 2)
+  DevMesh3 entropy, cancel;
+};
+
+}  // namespace abl

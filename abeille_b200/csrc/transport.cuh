@@ -1,0 +1,555 @@
+/* transport.cuh -- the history kernel: Transporter::transport on the device.
+ *
+ * One persistent grid (SM count x resident CTAs).  Every thread owns ONE neutron history at a time and
+ * keeps its whole state -- position, direction, group, weight, pcg32 state, geometry cursor -- in
+ * registers / L1-resident local memory; when the history dies the thread takes the next bank index from
+ * a global ticket counter (one aggregated atomic per warp), so lanes never idle while the bank has work.
+ * HBM sees: 96 B read per history, 80 B written per fission site, one fp64 RED per tally score.
+ *
+ * Reference behaviour reproduced (paths in the reference tree):
+ *   DeltaTracker::transport     src/delta_tracker.cpp:72-263
+ *   SurfaceTracker::transport   src/surface_tracker.cpp:40-219
+ *   CarterTracker::transport    src/carter_tracker.cpp:92-294
+ *   Transporter::collision, branching_collision, make_fission_neutrons, russian_roulette, do_scatter
+ *                               src/transporter.cpp:35-93,269-487
+ *   MGNuclide samplers          src/mg_nuclide.cpp:442-543, include/materials/mg_angle_distribution.hpp:45-101
+ *   MaterialHelper              include/materials/material_helper.hpp:47-224 (one nuclide, N = 1 in MG)
+ *   Tracker::do_reflection      include/simulation/tracker.hpp:314-360
+ * Random numbers are consumed in exactly the reference's order, including the
+ * draws whose value is discarded (nuclide choice with one nuclide, wgt2 roulette in k-eigenvalue mode).
+ *
+ * The fission bank: sites are appended to a scratch array in arrival order (warp-aggregated ticket),
+ * each tagged (parent bank index, daughter number); place_sites_kernel then writes them at
+ * offset[parent] + daughter, offset = exclusive scan of the per-history site counts -- the reference's
+ * order (bank order, then creation order; delta_tracker.cpp:246-253) without a sort.
+ */
+#pragma once
+#include <cooperative_groups.h>
+
+#include "tally.cuh"
+
+namespace abl {
+namespace cg = cooperative_groups;
+
+struct alignas(16) Site {  // scratch fission site, 80 B
+  double x, y, z, ux, uy, uz, E, w, w2;
+  uint32_t parent, daughter;
+};
+
+struct BankView {  // SoA device arrays (abl_bank with device pointers)
+  uint64_t n;
+  double *x, *y, *z, *ux, *uy, *uz, *E, *wgt, *wgt2;
+  uint64_t *id_a, *id_b, *id_c;
+};
+
+#define ABL_SEC_CAP 24  // secondaries a single history may hold at once (carter splitting)
+
+struct RunArgs {
+  BankView bank;
+  unsigned long long* ticket;      // next bank index
+  Site* sites;                     // scratch fission sites
+  unsigned long long* n_sites;     // sites appended (may exceed capacity: overflow is reported)
+  uint64_t site_capacity;
+  uint32_t* nfis;                  // per history: sites produced
+  // trace (nullable)
+  uint32_t *tr_flights, *tr_real, *tr_virtual;
+  uint64_t *tr_hash, *tr_rng;
+  double* scores;                  // [6] k_col, k_abs, k_trk, k_tot, leak, mig
+  unsigned long long* counters;    // [8]
+  int* error;                      // [0] code (min = most severe first seen), [1..2] history id lo/hi
+  double* secondaries;             // [ABL_SEC_CAP][9][nthreads] or null
+  double k_col, keff;
+  int converged;
+};
+
+struct Hist {
+  V3 r, u, rb;  // position, direction, birth position
+  double E, w, w2;
+  uint64_t rng, hash;
+  uint32_t idx, daughter;
+  uint32_t n_flights, n_real, n_virtual, n_fis;
+  int g, mat;  // energy group, material of the MaterialHelper
+  int nsec;
+  bool alive;
+};
+
+struct Acc {  // per-thread accumulators, reduced once at kernel exit
+  double k_col, k_abs, k_trk, leak, mig;
+  uint32_t flights, real, virt, tl_bins, sites, boundary, lost, coll_scores;
+};
+
+__device__ __forceinline__ void note(Hist& h, uint64_t v) { h.hash = (h.hash ^ v) * 1099511628211ULL; }
+
+__device__ __forceinline__ int group_of(const DevProblem& P, double E) {  // mg_nuclide.cpp:382-392
+  int i = 0;
+  for (i = 0; i < P.G; i++)
+    if (__ldg(&P.ebounds[i]) <= E && E < __ldg(&P.ebounds[i + 1])) break;
+  return i;
+}
+__device__ __forceinline__ double group_mid(const DevProblem& P, int g) {
+  return 0.5 * (__ldg(&P.ebounds[g]) + __ldg(&P.ebounds[g + 1]));
+}
+
+__device__ __forceinline__ void raise_error(const RunArgs& A, int code, uint64_t history_id) {
+  if (atomicCAS(&A.error[0], 0, code) == 0) {
+    A.error[1] = (int)(history_id & 0xffffffffu);
+    A.error[2] = (int)(history_id >> 32);
+  }
+}
+
+// MGAngleDistribution::sample_mu (mg_angle_distribution.hpp:45-60,92-101)
+__device__ __forceinline__ double sample_mu(const DevProblem& P, const abl_angle_table* at, uint64_t& rng) {
+  const double xi = rng_rand(rng);
+  const int off = __ldg(&at->offset), n = __ldg(&at->n);
+  const double* cdf = P.acdf + off;
+  int lo = 0, len = n;
+  while (len > 0) {  // std::lower_bound
+    const int half = len >> 1;
+    if (__ldg(&cdf[lo + half]) < xi) {
+      lo = lo + half + 1;
+      len = len - half - 1;
+    } else {
+      len = half;
+    }
+  }
+  int l = lo;
+  const double* mu = P.amu + off;
+  if (xi == __ldg(&cdf[l])) return __ldg(&mu[l]);
+  l--;
+  const double* pdf = P.apdf + off;
+  const double p0 = __ldg(&pdf[l]), p1 = __ldg(&pdf[l + 1]);
+  if (p0 == p1) return __ldg(&mu[l]) + ((xi - __ldg(&cdf[l])) / p0);
+  const double m = (p1 - p0) / (__ldg(&mu[l + 1]) - __ldg(&mu[l]));
+  return __ldg(&mu[l]) + (1. / m) * (sqrt(p0 * p0 + 2. * m * (xi - __ldg(&cdf[l]))) - p0);
+}
+
+// warp-aggregated append of one fission site
+__device__ __forceinline__ void append_site(const RunArgs& A, const Site& s) {
+  cg::coalesced_group grp = cg::coalesced_threads();
+  unsigned long long base = 0;
+  if (grp.thread_rank() == 0) base = atomicAdd(A.n_sites, (unsigned long long)grp.size());
+  base = grp.shfl(base, 0);
+  const unsigned long long slot = base + grp.thread_rank();
+  if (slot < A.site_capacity) {
+    // 80 B record written as five 16 B stores
+    const double2* src = reinterpret_cast<const double2*>(&s);
+    double2* dst = reinterpret_cast<double2*>(A.sites + slot);
+#pragma unroll
+    for (int q = 0; q < 5; q++) dst[q] = src[q];
+  }
+}
+
+template <bool NOISE>
+__device__ __forceinline__ void russian_roulette(const DevProblem& P, Hist& h) {  // transporter.cpp:35-58
+  if (fabs(h.w) < P.wgt_cutoff) {
+    const double P_kill = 1.0 - (fabs(h.w) / P.wgt_survival);
+    if (rng_rand(h.rng) < P_kill) h.w = 0.;
+    else h.w = copysign(P.wgt_survival, h.w);
+  }
+  if (fabs(h.w2) < P.wgt_cutoff) {  // w2 == 0 outside noise mode: the draw is still consumed
+    const double P_kill = 1.0 - (fabs(h.w2) / P.wgt_survival);
+    if (rng_rand(h.rng) < P_kill) h.w2 = 0.;
+    else h.w2 = copysign(P.wgt_survival, h.w2);
+  }
+  if (h.w == 0. && h.w2 == 0.) h.alive = false;
+}
+
+// Transporter::collision + branching_collision (transporter.cpp:60-93,269-312), k-eigenvalue branch
+template <bool NOISE>
+__device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A, Hist& h, Acc& acc) {
+  const int mg = h.mat * P.G + h.g;
+  const double Et = __ldg(&P.Et[mg]), Ea = __ldg(&P.Ea[mg]), Ef = __ldg(&P.Ef[mg]), nu = __ldg(&P.nu[mg]);
+  acc.real++;
+  h.n_real++;
+  if (A.converged && P.n_coll_tallies) {
+    const MatXS mx{Et, Ea, Ef, __ldg(&P.Es[mg])};
+    for (int t = 0; t < P.ntallies; t++)
+      if (P.tally[t].estimator == ABL_EST_COLLISION) acc.coll_scores += score_collision(P.tally[t], h.r, h.E, h.w, h.w2, mx);
+  }
+  {
+    const double k_col_scr = h.w * (nu * Ef) / Et;
+    const V3 dr{h.r.x - h.rb.x, h.r.y - h.rb.y, h.r.z - h.rb.z};
+    const double mig_dist = norm3(dr);
+    const double mig_area_scr = h.w * Ea / Et * mig_dist * mig_dist;
+    acc.k_col += k_col_scr;
+    acc.mig += mig_area_scr;
+  }
+  // MaterialHelper::sample_nuclide always draws, even with a single nuclide (material_helper.hpp:189)
+  (void)rng_rand(h.rng);
+  const double k_abs_scr = h.w * nu * Ef / Et;
+  acc.k_abs += k_abs_scr;
+  // make_fission_neutrons (transporter.cpp:358-487)
+  const int n_new = (int)floor(fabs(k_abs_scr) / A.k_col + rng_rand(h.rng));
+  if (n_new > 0) {
+    const double P_delayed = __ldg(&P.nud[mg]) / nu;
+    const int dg0 = __ldg(&P.dg_off[h.mat]), ndg = __ldg(&P.dg_off[h.mat + 1]) - dg0;
+    for (int i = 0; i < n_new; i++) {
+      // MGNuclide::sample_fission (mg_nuclide.cpp:504-543)
+      int ei = 0;
+      if (P.G >= 2) ei = rng_discrete(h.rng, P.chi_cp + (size_t)mg * P.G, P.G);
+      const double E_out = group_mid(P, ei);
+      const double mu = 2. * rng_rand(h.rng) - 1.;
+      const double phi = 2. * ABL_PI * rng_rand(h.rng);
+      const V3 dir = rotate_direction(h.u, mu, phi);
+      if (rng_rand(h.rng) < P_delayed) {
+        if (ndg >= 2) (void)rng_discrete(h.rng, P.dg_cp + dg0, ndg);  // delayed family: only matters in noise mode
+      }
+      Site s;
+      s.x = h.r.x; s.y = h.r.y; s.z = h.r.z;
+      s.ux = dir.x; s.uy = dir.y; s.uz = dir.z;
+      s.E = E_out;
+      s.w = h.w > 0. ? 1. : -1.;
+      s.w2 = 0.;
+      s.parent = h.idx;
+      s.daughter = h.daughter++;
+      append_site(A, s);
+      h.n_fis++;
+      acc.sites++;
+    }
+  }
+  note(h, 0x5000000000000000ULL | (uint64_t)(uint32_t)n_new);
+  // implicit capture (transporter.cpp:295-298)
+  const double surv = 1. - (Ea + 0.) / Et;
+  h.w = h.w * surv;
+  h.w2 = h.w2 * surv;
+  russian_roulette<NOISE>(P, h);
+  if (h.alive) {
+    // MGNuclide::sample_scatter (mg_nuclide.cpp:442-461); the yield matrix is never applied
+    int ei = 0;
+    if (P.G >= 2) ei = rng_discrete(h.rng, P.ps_cp + (size_t)mg * P.G, P.G);
+    const double E_out = group_mid(P, ei);
+    const double mu = sample_mu(P, P.angle + (size_t)mg * P.G + ei, h.rng);
+    const double phi = 2. * ABL_PI * rng_rand(h.rng);
+    h.u = rotate_direction(h.u, mu, phi);
+    h.E = E_out;
+    h.g = ei;
+    h.w = h.w * 1.;
+    h.w2 = h.w2 * 1.;
+    if (h.E < P.min_energy) h.alive = false;
+  }
+  note(h, 0x6000000000000000ULL | (h.alive ? (uint64_t)(h.g + 1) : 0ULL));
+}
+
+// Tracker::do_reflection (tracker.hpp:314-360).  The reference sets the surface token and then wipes it
+// again through set_r(): after a reflection the token is 0.
+__device__ __forceinline__ bool do_reflection(const DevProblem& P, Cursor& c, Hist& h, const Boundary& b) {
+  if (b.surface_index < 0) return false;
+  const Surf s = load_surface(P, b.surface_index);
+  const V3 r_on{h.r.x + b.distance * h.u.x, h.r.y + b.distance * h.u.y, h.r.z + b.distance * h.u.z};
+  const V3 n = surf_norm(s, r_on);
+  const double f = 2. * dot3(h.u, n);
+  h.u = make_direction(h.u.x - n.x * f, h.u.y - n.y * f, h.u.z - n.z * f);
+  h.r = r_on;
+  c.token = 0;
+  cursor_restart(P, c, h.r, h.u);
+  return true;
+}
+
+__device__ __forceinline__ void leak(Hist& h, Acc& acc, const Boundary& b) {
+  h.alive = false;
+  acc.leak += h.w;
+  const V3 d{h.r.x + b.distance * h.u.x - h.rb.x, h.r.y + b.distance * h.u.y - h.rb.y, h.r.z + b.distance * h.u.z - h.rb.z};
+  acc.mig += h.w * dot3(d, d);
+}
+
+__device__ __forceinline__ void score_flight_all(const DevProblem& P, const RunArgs& A, const Hist& h, double d, Acc& acc) {
+  if (!(A.converged && P.n_tl_tallies)) return;
+  const int mg = h.mat * P.G + h.g;
+  const MatXS mx{__ldg(&P.Et[mg]), __ldg(&P.Ea[mg]), __ldg(&P.Ef[mg]), __ldg(&P.Es[mg])};
+  for (int t = 0; t < P.ntallies; t++)
+    if (P.tally[t].estimator == ABL_EST_TRACK_LENGTH) acc.tl_bins += score_flight(P.tally[t], h.r, h.u, d, h.E, h.w, h.w2, mx);
+}
+
+// secondaries (Particle::make_secondary / split / resurect, particle.hpp:150-186): a LIFO per thread
+__device__ __forceinline__ double* sec_slot(const RunArgs& A, int e, int f, uint32_t tid, uint32_t nthreads) {
+  return A.secondaries + ((size_t)(e * 9 + f) * nthreads + tid);
+}
+__device__ inline bool push_secondary(const RunArgs& A, Hist& h, const V3& u, double E, double w, double w2, uint32_t tid,
+                                      uint32_t nthreads) {
+  if (h.nsec >= ABL_SEC_CAP || A.secondaries == nullptr) return false;
+  const int e = h.nsec++;
+  *sec_slot(A, e, 0, tid, nthreads) = h.r.x;
+  *sec_slot(A, e, 1, tid, nthreads) = h.r.y;
+  *sec_slot(A, e, 2, tid, nthreads) = h.r.z;
+  *sec_slot(A, e, 3, tid, nthreads) = u.x;
+  *sec_slot(A, e, 4, tid, nthreads) = u.y;
+  *sec_slot(A, e, 5, tid, nthreads) = u.z;
+  *sec_slot(A, e, 6, tid, nthreads) = E;
+  *sec_slot(A, e, 7, tid, nthreads) = w;
+  *sec_slot(A, e, 8, tid, nthreads) = w2;
+  return true;
+}
+__device__ inline void pop_secondary(const DevProblem& P, const RunArgs& A, Hist& h, uint32_t tid, uint32_t nthreads) {
+  const int e = --h.nsec;
+  h.r.x = *sec_slot(A, e, 0, tid, nthreads);
+  h.r.y = *sec_slot(A, e, 1, tid, nthreads);
+  h.r.z = *sec_slot(A, e, 2, tid, nthreads);
+  h.u.x = *sec_slot(A, e, 3, tid, nthreads);
+  h.u.y = *sec_slot(A, e, 4, tid, nthreads);
+  h.u.z = *sec_slot(A, e, 5, tid, nthreads);
+  h.E = *sec_slot(A, e, 6, tid, nthreads);
+  h.w = *sec_slot(A, e, 7, tid, nthreads);
+  h.w2 = *sec_slot(A, e, 8, tid, nthreads);
+  h.g = group_of(P, h.E);
+  h.alive = true;
+}
+
+// ---- one flight (+ collision) of the three trackers ---------------------------------------------------------
+template <int TRK, bool NOISE>
+__device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hist& h, Cursor& c, Acc& acc, uint32_t tid,
+                                       uint32_t nthreads) {
+#define hid (A.bank.id_a[h.idx])
+  bool had_collision = false;
+  if (TRK == ABL_TRACK_SURFACE) {
+    // SurfaceTracker::transport loop body (surface_tracker.cpp:72-146)
+    const int mg = h.mat * P.G + h.g;
+    const double d_coll = rng_exponential(h.rng, __ldg(&P.Et[mg]));
+    const Boundary bound = cursor_nearest_boundary(P, c, h.u);
+    acc.flights++;
+    h.n_flights++;
+    const double d_min = fmin(d_coll, bound.distance);
+    score_flight_all(P, A, h, d_min, acc);
+    acc.k_trk += h.w * d_min * (__ldg(&P.nu[mg]) * __ldg(&P.Ef[mg]));
+    if (bound.distance < d_coll || fabs(bound.distance - d_coll) < ABL_BOUNDRY_TOL) {
+      acc.boundary++;
+      if (bound.btype == ABL_BC_VACUUM) {
+        note(h, 0x3000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
+        leak(h, acc, bound);
+      } else if (bound.btype == ABL_BC_REFLECTIVE) {
+        if (!do_reflection(P, c, h, bound) || c.cell < 0) {
+          raise_error(A, ABL_ERR_LOST, hid);
+          h.alive = false;
+          return;
+        }
+        note(h, 0x4000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
+      } else {
+        // Tracker::cross_surface + get_current (tracker.hpp:227-231)
+        cursor_move(c, bound.distance, h.u);
+        c.token = -bound.token;
+        cursor_get_current(P, c, h.u);
+        h.r.x = h.r.x + bound.distance * h.u.x;
+        h.r.y = h.r.y + bound.distance * h.u.y;
+        h.r.z = h.r.z + bound.distance * h.u.z;
+        if (c.cell < 0) {
+          raise_error(A, ABL_ERR_LOST, hid);
+          h.alive = false;
+          return;
+        }
+        h.mat = c.mat;
+        note(h, 0x7000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
+      }
+    } else {
+      h.r.x = h.r.x + d_coll * h.u.x;
+      h.r.y = h.r.y + d_coll * h.u.y;
+      h.r.z = h.r.z + d_coll * h.u.z;
+      cursor_move(c, d_coll, h.u);
+      had_collision = true;
+      note(h, 0x2000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
+    }
+    if (h.alive && had_collision) collision<NOISE>(P, A, h, acc);
+  } else {
+    // DeltaTracker / CarterTracker loop body (delta_tracker.cpp:100-195, carter_tracker.cpp:120-230)
+    const double Esample = __ldg(&P.smp[h.g]);
+    const double d_coll = rng_exponential(h.rng, Esample);
+    Boundary bound{ABL_INF, -1, ABL_BC_NORMAL, 0};
+    bool crossed = false;
+    acc.flights++;
+    h.n_flights++;
+    cursor_move(c, d_coll, h.u);
+    cursor_get_current(P, c, h.u);
+    if (c.cell < 0) {  // left the geometry: rewind to the pre-flight position and look for the boundary
+      c.token = 0;
+      cursor_restart(P, c, h.r, h.u);
+      bound = cursor_boundary_condition(P, c, h.u);
+      crossed = true;
+    }
+    score_flight_all(P, A, h, fmin(d_coll, bound.distance), acc);
+    if (crossed) {
+      acc.boundary++;
+      if (bound.btype == ABL_BC_VACUUM) {
+        note(h, 0x3000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
+        leak(h, acc, bound);
+      } else if (bound.btype == ABL_BC_REFLECTIVE) {
+        if (!do_reflection(P, c, h, bound) || c.cell < 0) {
+          raise_error(A, ABL_ERR_LOST, hid);
+          h.alive = false;
+          return;
+        }
+        note(h, 0x4000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
+      } else {
+        raise_error(A, ABL_ERR_LOST, hid);
+        h.alive = false;
+        return;
+      }
+    } else {
+      h.r.x = h.r.x + d_coll * h.u.x;
+      h.r.y = h.r.y + d_coll * h.u.y;
+      h.r.z = h.r.z + d_coll * h.u.z;
+      h.mat = c.mat;
+      const double Et = __ldg(&P.Et[h.mat * P.G + h.g]);
+      if (TRK == ABL_TRACK_DELTA) {
+        if (Et - Esample > 1.E-10) {
+          raise_error(A, ABL_ERR_MAJORANT, hid);
+          h.alive = false;
+          return;
+        }
+        if (rng_rand(h.rng) < (Et / Esample)) had_collision = true;
+      } else {
+        if (Esample >= Et) {
+          if (rng_rand(h.rng) < (Et / Esample)) had_collision = true;
+        } else {  // under-estimated sampling xs: signed-weight branch (carter_tracker.cpp:192-207)
+          const double D = Et / (2. * Et - Esample);
+          const double F = Et / (D * Esample);
+          if ((D - rng_rand(h.rng)) > 0.) {
+            h.w = h.w * F;
+            had_collision = true;
+          } else {
+            h.w = -h.w * F;
+          }
+        }
+      }
+      note(h, (had_collision ? 0x2000000000000000ULL : 0x1000000000000000ULL) | (uint64_t)(uint32_t)(c.cell + 1));
+    }
+    if (h.alive && had_collision) {
+      collision<NOISE>(P, A, h, acc);
+    } else if (h.alive) {
+      if (!crossed) {
+        acc.virt++;
+        h.n_virtual++;
+      }
+    }
+    if (TRK == ABL_TRACK_CARTER) {
+      if (h.alive && fabs(h.w) >= P.wgt_split) {  // Particle::split (particle.hpp:165-173)
+        const int n_new = (int)ceil(fabs(h.w));
+        if (n_new > 1) {
+          h.w = h.w / (double)n_new;
+          h.w2 = h.w2 / (double)n_new;
+          for (int np = 0; np < n_new - 1; np++)
+            if (!push_secondary(A, h, h.u, h.E, h.w, h.w2, tid, nthreads)) {
+              raise_error(A, ABL_ERR_BANK_OVERFLOW, hid);
+              break;
+            }
+        }
+      }
+    }
+  }
+}
+
+#undef hid
+
+template <int TRK, bool NOISE>
+__global__ void __launch_bounds__(128) transport_kernel(const DevProblem P, const RunArgs A) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  Acc acc;
+  acc.k_col = acc.k_abs = acc.k_trk = acc.leak = acc.mig = 0.;
+  acc.flights = acc.real = acc.virt = acc.tl_bins = acc.sites = acc.boundary = acc.lost = acc.coll_scores = 0;
+  Hist h;
+  h.alive = false;
+  h.nsec = 0;
+  Cursor c;
+  c.err = 0;
+  c.np = 0;
+  c.nf = 1;
+  bool have = false;
+  const uint64_t N = A.bank.n;
+
+  for (;;) {
+    if (!have) {
+      // take the next history (one atomic per converged group of lanes)
+      unsigned long long idx;
+      {
+        cg::coalesced_group grp = cg::coalesced_threads();
+        unsigned long long base = 0;
+        if (grp.thread_rank() == 0) base = atomicAdd(A.ticket, (unsigned long long)grp.size());
+        idx = grp.shfl(base, 0) + grp.thread_rank();
+      }
+      if (idx >= N) break;
+      have = true;
+      h.idx = (uint32_t)idx;
+      h.r = {A.bank.x[idx], A.bank.y[idx], A.bank.z[idx]};
+      h.u = {A.bank.ux[idx], A.bank.uy[idx], A.bank.uz[idx]};
+      h.rb = h.r;
+      h.E = A.bank.E[idx];
+      h.w = A.bank.wgt[idx];
+      h.w2 = (NOISE && A.bank.wgt2) ? A.bank.wgt2[idx] : 0.;
+      h.g = group_of(P, h.E);
+      if (A.bank.id_c) h.rng = A.bank.id_c[idx];
+      else h.rng = pcg_advance(P.seed_state, P.stride * A.bank.id_a[idx], P.jump);  // particle.hpp:188-193
+      h.hash = 1469598103934665603ULL;
+      h.daughter = 0;
+      h.n_flights = h.n_real = h.n_virtual = h.n_fis = 0;
+      h.nsec = 0;
+      h.alive = true;
+      c.token = 0;
+      cursor_restart(P, c, h.r, h.u);
+      h.mat = c.mat;
+      if (c.cell < 0) {  // lost at birth: warning + kill in the reference (delta_tracker.cpp:92-98)
+        acc.lost++;
+        h.alive = false;
+      }
+    }
+    if (h.alive) flight<TRK, NOISE>(P, A, h, c, acc, tid, nthreads);
+    if (!h.alive) {
+      if (h.nsec > 0) {  // Particle::resurect + Tracker restart (delta_tracker.cpp:197-229)
+        pop_secondary(P, A, h, tid, nthreads);
+        c.token = 0;
+        cursor_restart(P, c, h.r, h.u);
+        if (c.cell < 0) {
+          raise_error(A, ABL_ERR_LOST, A.bank.id_a[h.idx]);
+          h.alive = false;
+          h.nsec = 0;
+        } else {
+          h.mat = c.mat;
+        }
+      }
+      if (!h.alive) {  // history finished
+        A.nfis[h.idx] = h.n_fis;
+        if (A.tr_hash) {
+          A.tr_flights[h.idx] = h.n_flights;
+          A.tr_real[h.idx] = h.n_real;
+          A.tr_virtual[h.idx] = h.n_virtual;
+          A.tr_hash[h.idx] = h.hash;
+          A.tr_rng[h.idx] = h.rng;
+        }
+        have = false;
+      }
+    }
+    if (c.err) {
+      raise_error(A, c.err, have ? A.bank.id_a[h.idx] : 0);
+      c.err = 0;
+    }
+  }
+
+  // ---- reduce the per-thread accumulators: warp shuffle, then one atomic per warp -----------------------
+  __syncwarp();
+  double dv[5] = {acc.k_col, acc.k_abs, acc.k_trk, acc.leak, acc.mig};
+  unsigned long long cv[8] = {acc.flights, acc.real, acc.virt, acc.tl_bins, acc.sites, acc.boundary, acc.lost, acc.coll_scores};
+  __shared__ double sd[4][5];
+  __shared__ unsigned long long sc[4][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 5; q++) {
+    double v = dv[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sd[wid][q] = v;
+  }
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    unsigned long long v = cv[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sc[wid][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    const int q = threadIdx.x;
+    const double v = sd[0][q] + sd[1][q] + sd[2][q] + sd[3][q];
+    const int slot = q < 3 ? q : q + 1;  // scores layout: k_col,k_abs,k_trk,k_tot(unused),leak,mig
+    atomicAdd(&A.scores[slot], v);
+  } else if (threadIdx.x >= 32 && threadIdx.x < 40) {
+    const int q = threadIdx.x - 32;
+    atomicAdd(&A.counters[q], sc[0][q] + sc[1][q] + sc[2][q] + sc[3][q]);
+  }
+}
+
+}  // namespace abl

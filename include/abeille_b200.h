@@ -1,0 +1,249 @@
+/* abeille_b200.h -- C ABI of the B200 transport backend (libabeille_b200.so).
+ *
+ * This is the drop-in boundary for Abeille's particle-transport hot path.  The one
+ * reference interface it replaces is
+ *
+ *   class Transporter {
+ *     virtual std::vector<BankedParticle> transport(std::vector<Particle>& bank, bool noise,
+ *         std::vector<BankedParticle>* noise_bank, const NoiseMaker* noise_maker) = 0; };
+ *                                   (reference include/simulation/transporter.hpp:39-47)
+ *
+ * together with the state that call reads implicitly from globals (settings::*, geometry::*,
+ * materials, tallies->kcol(); reference src/transporter.cpp:371,399, include/utils/settings.hpp:54-128)
+ * and the side effects it has on the Tallies object (src/tallies.cpp:100-140, src/mesh_tally.cpp:121-152).
+ *
+ * Plain C: pointers and sizes only.  Two flavours of every data-path entry point:
+ *   abl_xxx         HOST buffers (what a reference-side adapter binds; copies are inside the call)
+ *   abl_xxx_device  DEVICE buffers owned by the caller (e.g. torch tensors), asynchronous on `stream`
+ * All functions return ABL_OK (0) or a negative abl_status; abl_last_error() gives the text.
+ * A handle is bound to one CUDA device; calls on one handle must be serialised by the caller
+ * (the reference's transport() is not re-entrant either).
+ */
+#ifndef ABEILLE_B200_H
+#define ABEILLE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct abl_context* abl_handle;
+
+typedef enum abl_status {
+  ABL_OK = 0,
+  ABL_ERR_INVALID = -1,       /* bad argument / inconsistent tables                                   */
+  ABL_ERR_CUDA = -2,          /* CUDA runtime error (no device, out of memory, launch failure)        */
+  ABL_ERR_BANK_OVERFLOW = -3, /* more fission sites / secondaries than the provided capacity          */
+  ABL_ERR_LOST = -4,          /* fatal: particle lost after reflection / crossing / resurrection      */
+  ABL_ERR_MAJORANT = -5,      /* fatal: total xs exceeded the majorant (delta_tracker.cpp:174-180)    */
+  ABL_ERR_GEOMETRY = -6,      /* geometry nesting deeper than ABL_MAX_PADS / malformed tables         */
+  ABL_ERR_UNSUPPORTED = -7
+} abl_status;
+
+#define ABL_MAX_PADS 10   /* geometry stack depth (reference reserves 10: tracker.hpp:46) */
+#define ABL_MAX_FRAMES 6  /* nested local coordinate frames (root + lattice levels)       */
+
+/* ---- enums mirrored from the reference --------------------------------------------------------- */
+enum { ABL_MODE_K_EIGENVALUE = 0, ABL_MODE_NOISE = 1 };                         /* settings.hpp        */
+enum { ABL_TRACK_SURFACE = 0, ABL_TRACK_DELTA = 1, ABL_TRACK_CARTER = 2 };      /* parser.cpp:889-911  */
+enum { ABL_BC_VACUUM = 0, ABL_BC_REFLECTIVE = 1, ABL_BC_NORMAL = 2 };           /* surface.hpp:34      */
+enum {
+  ABL_SURF_XPLANE = 0, ABL_SURF_YPLANE, ABL_SURF_ZPLANE, ABL_SURF_PLANE,
+  ABL_SURF_XCYL, ABL_SURF_YCYL, ABL_SURF_ZCYL, ABL_SURF_CYL, ABL_SURF_SPHERE
+};
+enum { ABL_UNI_CELLS = 0, ABL_UNI_RECT = 1 };
+enum { ABL_EST_COLLISION = 0, ABL_EST_TRACK_LENGTH = 1, ABL_EST_SOURCE = 2 };
+enum {
+  ABL_Q_FLUX = 0, ABL_Q_TOTAL, ABL_Q_ELASTIC, ABL_Q_ABSORPTION, ABL_Q_FISSION, ABL_Q_MT,
+  ABL_Q_REAL_FLUX, ABL_Q_IMAG_FLUX, ABL_Q_SOURCE, ABL_Q_REAL_SOURCE, ABL_Q_IMAG_SOURCE
+};
+/* RPN operator tokens of cell regions (cell.hpp:43-49); surface tokens are +-(surface index + 1) */
+#define ABL_OP_UNION (INT32_MAX - 4)
+#define ABL_OP_INTERSECTION (INT32_MAX - 3)
+#define ABL_OP_COMPLEMENT (INT32_MAX - 2)
+
+/* ---- flattened immutable problem tables (uploaded once by abl_create) ----------------------------- */
+typedef struct abl_surface {
+  int32_t type;  /* ABL_SURF_*                                                                        */
+  int32_t bc;    /* ABL_BC_*                                                                          */
+  double p[8];   /* planes: x0|y0|z0 or A,B,C,D; axis cylinders: c0,c1,R; sphere x0,y0,z0,R;
+                    general cylinder: x0,y0,z0,1-u0^2,1-v0^2,1-w0^2,R (cylinder.cpp:28-58)            */
+} abl_surface;
+
+typedef struct abl_cell {
+  int32_t rpn_offset, rpn_len; /* slice of abl_problem.rpn                                            */
+  int32_t simple;              /* 1: pure intersection list (cell.cpp:144-158)                        */
+  int32_t vac_or_refl;         /* touches a vacuum/reflective surface (cell.cpp:203-246)              */
+  int32_t fill_universe;       /* universe index, or -1 when filled with a material                   */
+  int32_t material;            /* material index, or -1                                               */
+} abl_cell;
+
+typedef struct abl_universe {
+  int32_t type;                 /* ABL_UNI_*                                                          */
+  int32_t has_bc;               /* cell_universe.cpp:30-41, lattice.cpp:45-52                         */
+  int32_t cell_offset, ncells;  /* ABL_UNI_CELLS: slice of abl_problem.universe_cells (cell indices)  */
+  int32_t N[3];                 /* ABL_UNI_RECT: tiles along x,y,z                                    */
+  int32_t tile_offset;          /* slice of abl_problem.lattice_tiles: universe index or -1, linear
+                                   index nz*Nx*Ny + nx*Ny + ny (rect_lattice.cpp:293-301)             */
+  int32_t outer;                /* outer universe index or -1                                         */
+  int32_t pad_;
+  double P[3], Pinv[3], Xl[3];  /* pitch, 1/pitch, lower corner origin - N*P/2 (rect_lattice.cpp:33-52) */
+} abl_universe;
+
+typedef struct abl_angle_table { /* linearised mu distribution of one (g_in,g_out) pair               */
+  int32_t offset, n;             /* slice of angle_mu / angle_pdf / angle_cdf                          */
+} abl_angle_table;
+
+typedef struct abl_mesh_tally {
+  int32_t estimator, quantity;   /* ABL_EST_*, ABL_Q_*                                                 */
+  int32_t noise_source;          /* source tally scored from the noise-source bank                    */
+  int32_t N[3];
+  int32_t n_energy_bins;
+  int32_t ebounds_offset;        /* slice (n_energy_bins+1 values) of abl_problem.tally_energy_bounds  */
+  double low[3], hi[3];
+  double net_weight;             /* tallies->total_weight (parser.cpp:870-871)                         */
+} abl_mesh_tally;
+
+typedef struct abl_source {      /* box | point, isotropic, mono-energetic (source.cpp:44-90)          */
+  double weight;
+  int32_t fissile_only, is_box;
+  double low[3], hi[3];          /* point: low == position                                             */
+  double energy;
+} abl_source;
+
+typedef struct abl_mesh3 {       /* entropy mesh (entropy.cpp) / approximate cancelator mesh           */
+  int32_t present;
+  int32_t N[3];
+  double low[3], hi[3];
+  int32_t n_energy_edges;        /* cancelator only; 0 = no energy binning                             */
+  int32_t eedges_offset;         /* slice of abl_problem.tally_energy_bounds                           */
+} abl_mesh3;
+
+typedef struct abl_problem {
+  int32_t mode, tracking, ngroups, inner_generations;
+  const double* energy_bounds;  /* [ngroups+1] */
+  double wgt_cutoff, wgt_survival, wgt_split, min_energy;
+  uint64_t rng_seed, rng_stride;
+  double w_noise, eta, keff;
+  /* geometry */
+  int32_t nsurfaces, ncells, nrpn, nuniverses, n_universe_cells, n_lattice_tiles, root_universe, pad0_;
+  const abl_surface* surfaces;
+  const abl_cell* cells;
+  const int32_t* rpn;
+  const abl_universe* universes;
+  const int32_t* universe_cells;
+  const int32_t* lattice_tiles;
+  /* materials: one MGNuclide each, atoms_bcm = 1 (material.cpp:50-62); all arrays [nmaterials*ngroups] */
+  int32_t nmaterials, n_angle_points;
+  const double *xs_total, *xs_absorption, *xs_fission, *xs_elastic, *nu_total, *nu_delayed, *speeds;
+  const double* chi_cdf;      /* [M*G*G] libstdc++ discrete_distribution partial sums of chi rows       */
+  const double* scatter_cdf;  /* [M*G*G] same for the normalised scatter rows                          */
+  const abl_angle_table* angle; /* [M*G*G] */
+  const double *angle_mu, *angle_pdf, *angle_cdf; /* pools, n_angle_points each                       */
+  const int32_t* delayed_offset; /* [M+1] slices of delayed_cdf / delayed_lambda                       */
+  const double *delayed_cdf, *delayed_lambda;
+  const int32_t* fissile;       /* [M] */
+  const double* sampling_xs;    /* [G] majorant (delta) or ratio*majorant (carter); majorant.cpp:133-176 */
+  /* tallies */
+  int32_t ntallies, n_tally_energy_bounds;
+  const abl_mesh_tally* tallies;
+  const double* tally_energy_bounds;
+  /* sources, entropy mesh, approximate cancelator */
+  int32_t nsources, pad1_;
+  const abl_source* sources;
+  abl_mesh3 entropy;
+  abl_mesh3 cancelator;
+} abl_problem;
+
+/* ---- banks --------------------------------------------------------------------------------------
+ * Structure-of-arrays view of a particle bank (input) or a fission-site bank (output).
+ * Particle bank  (Particle, particle.hpp:68-243):        id_a = history id, id_b = family id,
+ *                                                         id_c = pcg32 state or NULL (=> seed, advance(stride*history id))
+ * Fission bank   (BankedParticle, particle.hpp:38-66):   id_a = parent_history_id, id_b = parent_daughter_id,
+ *                                                         id_c = family_id
+ * wgt2 may be NULL outside noise mode (treated as 0 on input, not written on output).               */
+typedef struct abl_bank {
+  uint64_t n; /* particles (input) or capacity (output) */
+  double *x, *y, *z, *ux, *uy, *uz, *E, *wgt, *wgt2;
+  uint64_t *id_a, *id_b, *id_c;
+} abl_bank;
+
+typedef struct abl_gen_params {
+  double k_col;       /* tallies->kcol() of the previous generation (transporter.cpp:370-371)          */
+  double keff;        /* noise mode (transporter.cpp:399)                                              */
+  int32_t converged;  /* settings::converged: mesh tallies score only when set (tallies.hpp:49-63)     */
+  int32_t noise;      /* transport(bank, noise=true)                                                   */
+  int32_t trace;      /* keep per-history integer outcomes for abl_get_trace                           */
+  int32_t pad_;
+} abl_gen_params;
+
+/* scores[6] = raw sums k_col, k_abs, k_trk, k_tot, leakage, mig_area (tallies.cpp:100-140)           */
+/* counters[8] = flights, real collisions, virtual collisions, track-length bins, fission sites,
+ *               boundary events, lost at birth, collision-tally scores                                */
+typedef struct abl_trace { /* per history of the last traced transport call, arrays of length n      */
+  uint32_t *flights, *real, *virt, *fission;
+  uint64_t *hash, *rng_state;
+} abl_trace;
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+int abl_create(const abl_problem* problem, int device, abl_handle* out);
+void abl_destroy(abl_handle h);
+const char* abl_last_error(abl_handle h); /* h may be NULL: error of the last failed abl_create        */
+int abl_device_info(abl_handle h, int* sm_count, int* cc_major, int* cc_minor, uint64_t* kernel_launches);
+
+/* ---- Transporter::transport, host buffers (the reference-facing entry point) ------------------------ */
+int abl_transport(abl_handle h, const abl_bank* bank, const abl_gen_params* params, abl_bank* fission_out,
+                  uint64_t* n_fission, double scores[6], uint64_t counters[8]);
+int abl_get_trace(abl_handle h, uint64_t n, abl_trace* out);
+
+/* ---- Transporter::transport, device buffers (bank stays resident in HBM) ---------------------------- */
+int abl_transport_device(abl_handle h, const abl_bank* bank_dev, const abl_gen_params* params,
+                         abl_bank* fission_dev, uint64_t* n_fission, double scores[6], uint64_t counters[8],
+                         void* stream);
+
+/* ---- mesh tallies: MeshTally::record_generation / clear_generation / write (mesh_tally.cpp:121-206) - */
+int abl_tally_count(abl_handle h);
+int abl_tally_shape(abl_handle h, int tally, uint64_t shape4[4]); /* Ne, Nx, Ny, Nz */
+int abl_tallies_record(abl_handle h, double multiplier);
+int abl_tallies_clear(abl_handle h);
+/* which: 0 = tally_gen, 1 = tally_avg, 2 = tally_var, 3 = std = sqrt(var/g) */
+int abl_tally_fetch(abl_handle h, int tally, int which, double* out_host);
+int abl_tally_device_ptr(abl_handle h, int tally, int which, double** out_dev, uint64_t* n);
+
+/* ---- inter-generation bank pipeline on the device (power_iterator.cpp:341-404,538-586) ---------------- */
+/* Source sampling (simulation.cpp:55-77): n particles with history ids first_id.., written to bank_dev */
+int abl_sample_source_device(abl_handle h, uint64_t n, uint64_t first_history_id, abl_bank* bank_dev, void* stream);
+/* stats[6] = Npos, Nneg, Wpos, Wneg (unnormalised), and after scaling Wpos', Wneg'                      */
+int abl_bank_weight_stats_device(abl_handle h, const abl_bank* bank_dev, double stats[4], void* stream);
+int abl_bank_scale_weights_device(abl_handle h, abl_bank* bank_dev, double factor, void* stream);
+/* fission bank -> next particle bank: history ids first_id + i, family kept, rng from seed/stride       */
+int abl_bank_to_particles_device(abl_handle h, abl_bank* bank_dev, uint64_t first_history_id, void* stream);
+/* Shannon-entropy binning (entropy.cpp:32-60): bins_dev[Nx*Ny*Nz] += w, total_dev[0] += w               */
+int abl_entropy_bin_device(abl_handle h, const abl_bank* bank_dev, double* bins_dev, double* total_dev, void* stream);
+/* SourceMeshTally::score_source for every source tally (source_mesh_tally.cpp:30-78)                    */
+int abl_score_source_device(abl_handle h, const abl_bank* bank_dev, int noise_source, void* stream);
+/* ApproximateMeshCancelator (approximate_mesh_cancelator.cpp:97-190), weights replaced in place        */
+int abl_cancel_device(abl_handle h, abl_bank* bank_dev, void* stream);
+
+/* ---- device memory helpers for callers that do not link a CUDA runtime themselves ------------------------ */
+int abl_bank_alloc_device(abl_handle h, uint64_t capacity, abl_bank* out_dev); /* all 12 arrays, out_dev->n = capacity */
+int abl_bank_free_device(abl_handle h, abl_bank* bank_dev);
+int abl_bank_upload(abl_handle h, const abl_bank* host, abl_bank* bank_dev);   /* copies host->n entries, sets bank_dev->n */
+int abl_bank_download(abl_handle h, const abl_bank* bank_dev, uint64_t n, abl_bank* host);
+int abl_device_alloc(abl_handle h, uint64_t bytes, void** out_dev);            /* zero-initialised */
+int abl_device_free(abl_handle h, void* dev);
+int abl_device_zero(abl_handle h, void* dev, uint64_t bytes, void* stream);
+int abl_device_read(abl_handle h, void* dst_host, const void* src_dev, uint64_t bytes, void* stream); /* synchronises */
+
+/* ---- probes used by the parity tests ------------------------------------------------------------------ */
+/* cell / material index (or -1) of n points, fresh lookup from the root universe (geometry.cpp:43-55)   */
+int abl_find_cells(abl_handle h, uint64_t n, const double* r3, const double* u3, int32_t* cell, int32_t* material);
+/* first n pcg32 outputs / RNG::rand values of a history stream (particle.hpp:188-193, rng.hpp:41)        */
+int abl_rng_probe(abl_handle h, uint64_t history_id, int n, uint32_t* out_u32, double* out_rand);
+/* device log / sin / cos used by the kernels                                                             */
+int abl_math_probe(abl_handle h, int n, const double* x, double* lg, double* sn, double* cs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABEILLE_B200_H */
