@@ -1,0 +1,323 @@
+"""GPU: parity of the CUDA path against the CPU oracle, called through the C ABI (abl_*) and through the C++
+GPUTransporter adapter.  Integer / index / byte results are compared bit for bit; floating-point sums whose
+order differs between a serial CPU loop and GPU atomics (scores, mesh bins) to 1e-10 relative."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, deck_path, load_deck, write_deck
+
+pytestmark = pytest.mark.gpu
+
+BANK_EXACT = ("x", "y", "z", "ux", "uy", "uz", "E", "wgt", "id_a", "id_b", "id_c")
+
+
+@pytest.fixture(scope="module")
+def ab(native_libs):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return native_libs
+
+
+def _pair(ab, oracle_api, tmp_path, deck, overrides, name="deck.yaml"):
+    path = write_deck(load_deck(deck), tmp_path / name, overrides)
+    return oracle_api.Oracle(path), ab.Backend(path, 0)
+
+
+def _transport_both(orc, gpu, n, converged=True, k_col=1.0):
+    bank = orc.sample_source(n)
+    orc.set_trace(True)
+    orc.set_converged(converged)
+    orc.set_kcol(k_col)
+    orc.reset_counters()
+    ofis, oscores, on = orc.transport({k: v.copy() for k, v in bank.items()})
+    otr = orc.trace(n)
+    gfis, gscores, gcn = gpu.transport(bank, k_col=k_col, converged=converged, trace=True)
+    gtr = gpu.trace(n)
+    return bank, (ofis, oscores, otr, orc.counters()), (gfis, gscores, gtr, gcn)
+
+
+def _assert_same_histories(o, g):
+    ofis, oscores, otr, ocn = o
+    gfis, gscores, gtr, gcn = g
+    for k in ("flights", "real", "virtual", "fission", "hash", "rng_state"):
+        bad = np.nonzero(gtr[k] != otr[k])[0]
+        assert bad.size == 0, f"per-history {k} differs for {bad.size} histories, first {bad[:5]}"
+    assert len(gfis["x"]) == len(ofis["x"])
+    for k in BANK_EXACT:
+        assert np.array_equal(gfis[k], ofis[k]), f"fission bank field {k} differs"
+    for k in ("flights", "real_collisions", "virtual_collisions", "tl_bins", "fission_sites", "boundary_events",
+              "lost_at_birth", "coll_scores"):
+        assert gcn[k] == ocn[k], (k, gcn[k], ocn[k])
+    assert np.allclose(gscores, oscores, rtol=1e-11, atol=1e-300), (gscores, oscores)
+
+
+# ---- building blocks ------------------------------------------------------------------------------------------
+def test_rng_streams_bit_exact(ab, oracle_api, tmp_path):
+    with open(os.path.join(GOLDEN, "rng_kat.json")) as f:
+        kat = json.load(f)
+    gpu = ab.Backend(deck_path("PUa-1-0-IN.yaml"), 0)
+    for h in kat["histories"]:
+        u32, rnd = gpu.rng_probe(h["id"], 8)
+        assert list(u32) == h["u32"]
+        assert np.array_equal(rnd[:6], np.array(h["rand"]))
+    for hid in (3, 99999, 2**40 + 17, 2**63 + 5):
+        u32, rnd = gpu.rng_probe(hid, 64)
+        assert np.array_equal(u32, oracle_api.rng_stream(kat["seed"], kat["stride"], hid, 64))
+        assert np.array_equal(rnd, oracle_api.rng_rand(kat["seed"], kat["stride"], hid, 64))
+
+
+def test_device_math_bit_exact(ab, oracle_api):
+    gpu = ab.Backend(deck_path("PUa-1-0-IN.yaml"), 0)
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.uniform(1e-300, 1.0, 200000), rng.uniform(0.0, 2 * np.pi, 200000),
+                        [1.0, 0.5, 2 * np.pi, np.pi, np.pi / 2, np.pi / 4, 1e-9, 2.0 ** -30, 0.7853981633974483]])
+    lg, sn, cs = gpu.math_probe(x)
+    olg, osn, ocs = oracle_api.math_eval(x)
+    assert np.array_equal(lg, olg) and np.array_equal(sn, osn) and np.array_equal(cs, ocs)
+
+
+@pytest.mark.parametrize("deck,box", [
+    ("c5g7_delta_collision.yaml", ([-33, -33, -108], [33, 33, 108])),
+    ("ref_sqr_c5g7_surface_tl.yaml", ([-1, -1, -1], [65, 65, 215])),
+    ("PUa-1-0-IN.yaml", ([-6, -6, -6], [6, 6, 6])),
+    ("Ua-1-1-CY.yaml", ([-10, -10, -10], [10, 10, 10])),
+])
+def test_find_cells_matches_oracle(ab, oracle_api, deck, box):
+    orc = oracle_api.Oracle(deck_path(deck))
+    gpu = ab.Backend(deck_path(deck), 0)
+    rng = np.random.default_rng(3)
+    n = 200000
+    r = rng.uniform(box[0], box[1], size=(n, 3))
+    # include points exactly on lattice planes / surfaces
+    r[:2000] = np.round(r[:2000] / 1.26) * 1.26
+    r[2000:3000, 0] = np.round(r[2000:3000, 0] / 21.42) * 21.42
+    u = rng.normal(size=(n, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    oc, om = orc.find_cells(r, u)
+    gc, gm = gpu.find_cells(r, u)
+    assert np.array_equal(gc, oc) and np.array_equal(gm, om)
+    assert (oc >= 0).sum() > n // 4
+
+
+def test_source_sampling_bit_exact(ab, oracle_api, tmp_path):
+    import torch
+    for deck in ("c5g7_delta_collision.yaml", "PUa-1-0-IN.yaml"):
+        orc, gpu = _pair(ab, oracle_api, tmp_path, deck, {"settings": {"nparticles": 20000}})
+        ob = orc.sample_source(20000)
+        db = gpu.new_device_bank(20000)
+        gpu.sample_source_device(db, 20000, 0)
+        torch.cuda.synchronize()
+        for k in ("x", "y", "z", "ux", "uy", "uz", "E", "wgt"):
+            assert np.array_equal(db[k].cpu().numpy(), ob[k]), k
+        for k in ("id_a", "id_b", "id_c"):
+            assert np.array_equal(db[k].cpu().numpy().view(np.uint64), ob[k]), k
+
+
+# ---- Transporter::transport ----------------------------------------------------------------------------------------
+CASES = [
+    ("PUa-1-0-IN.yaml", {}, 20000),                       # S1: surface tracking, reflective cube, 1 group
+    ("c5g7_delta_collision.yaml", {}, 20000),             # S2: delta tracking, 2 lattice levels, collision tally
+    ("c5g7_delta_tracklength.yaml", {}, 8000),            # delta tracking + track-length mesh walk
+    ("c5g7_surface_tracklength.yaml", {}, 8000),          # surface tracking through lattices + cylinders
+    ("ref_sqr_c5g7_surface_tl.yaml", {}, 8000),           # S3: complement (RPN) cells, surface tracking, TLE
+    ("c5g7_carter_cancel.yaml", {}, 12000),               # S4: carter tracking, negative weights, splitting
+    ("PUa-1-1-SL.yaml", {}, 20000),                       # P1 anisotropic scattering, vacuum slab
+    ("PUa-1-2-SL.yaml", {}, 20000),                       # P2
+    ("UD2O-2-1-SL.yaml", {}, 20000),                      # 2 groups, P1, tally
+    ("Ua-1-1-CY.yaml", {}, 20000),                        # infinite cylinder (zcylinder distance)
+    ("PUb-1-0-SL.yaml", {}, 20000),
+]
+
+
+@pytest.mark.parametrize("deck,overrides,n", CASES, ids=[c[0] for c in CASES])
+def test_transport_bit_exact_against_oracle(ab, oracle_api, tmp_path, deck, overrides, n):
+    ov = {"settings": {"nparticles": n}}
+    ov.update(overrides)
+    orc, gpu = _pair(ab, oracle_api, tmp_path, deck, ov)
+    bank, o, g = _transport_both(orc, gpu, n)
+    _assert_same_histories(o, g)
+    for t in range(gpu.ntallies()):
+        og, gg = orc.tally(t, "gen"), gpu.tally(t, "gen")
+        assert og.shape == gg.shape
+        assert np.count_nonzero(og) > 0 or orc.tally_shape(t) is None
+        assert np.array_equal(og != 0, gg != 0)
+        assert np.allclose(gg, og, rtol=1e-10, atol=1e-300)
+
+
+def test_transport_not_converged_scores_no_mesh_tally(ab, oracle_api, tmp_path):
+    orc, gpu = _pair(ab, oracle_api, tmp_path, "c5g7_delta_collision.yaml", {"settings": {"nparticles": 3000}})
+    bank = orc.sample_source(3000)
+    gpu.transport(bank, converged=False)
+    assert np.count_nonzero(gpu.tally(0, "gen")) == 0
+
+
+def test_second_generation_streams_from_history_ids(ab, oracle_api, tmp_path):
+    """Generation g+1: fresh history ids, streams = seed + advance(stride*id) evaluated on the device."""
+    n = 10000
+    orc, gpu = _pair(ab, oracle_api, tmp_path, "c5g7_delta_collision.yaml", {"settings": {"nparticles": n}})
+    bank = orc.sample_source(n)
+    fis, _, _ = gpu.transport(bank)
+    m = len(fis["x"])
+    nxt = {k: fis[k].copy() for k in ("x", "y", "z", "ux", "uy", "uz", "E", "wgt")}
+    nxt["wgt2"] = np.zeros(m)
+    nxt["id_a"] = np.arange(n, n + m, dtype=np.uint64)
+    nxt["id_b"] = fis["id_c"].copy()
+    nxt["id_c"] = None
+    orc.set_trace(True)
+    orc.set_kcol(1.17)
+    ofis, oscores, on = orc.transport({k: (v.copy() if v is not None else None) for k, v in nxt.items()})
+    otr = orc.trace(m)
+    gfis, gscores, gcn = gpu.transport(nxt, k_col=1.17, trace=True)
+    gtr = gpu.trace(m)
+    for k in ("flights", "real", "virtual", "fission", "hash", "rng_state"):
+        assert np.array_equal(gtr[k], otr[k]), k
+    for k in BANK_EXACT:
+        assert np.array_equal(gfis[k], ofis[k]), k
+
+
+def test_empty_and_tiny_banks(ab, oracle_api, tmp_path):
+    orc, gpu = _pair(ab, oracle_api, tmp_path, "c5g7_delta_collision.yaml", {"settings": {"nparticles": 100}})
+    empty = ab.new_bank(0)
+    fis, scores, cn = gpu.transport(empty)
+    assert len(fis["x"]) == 0 and np.all(scores == 0) and cn["flights"] == 0
+    for n in (1, 31, 33, 129):
+        orc.set_history_counter(0)
+        bank, o, g = _transport_both(orc, gpu, n)
+        _assert_same_histories(o, g)
+
+
+def test_particle_born_outside_geometry_is_killed(ab, oracle_api, tmp_path):
+    """Lost at birth = warning + kill in the reference (delta_tracker.cpp:92-98)."""
+    orc, gpu = _pair(ab, oracle_api, tmp_path, "c5g7_delta_collision.yaml", {"settings": {"nparticles": 100}})
+    bank = orc.sample_source(64)
+    bank["x"][::2] = 500.0
+    fis, scores, cn = gpu.transport(bank, trace=True)
+    tr = gpu.trace(64)
+    assert cn["lost_at_birth"] == 32
+    assert np.all(tr["flights"][::2] == 0) and np.all(tr["flights"][1::2] > 0)
+    orc.set_trace(True)
+    orc.reset_counters()
+    ofis, oscores, on = orc.transport({k: v.copy() for k, v in bank.items()})
+    assert orc.counters()["lost_at_birth"] == 32
+    assert np.array_equal(fis["x"], ofis["x"])
+
+
+def test_fission_bank_overflow_is_reported(ab, oracle_api, tmp_path):
+    from abeille_b200 import BackendError
+    orc, gpu = _pair(ab, oracle_api, tmp_path, "PUa-1-0-IN.yaml", {"settings": {"nparticles": 5000}})
+    bank = orc.sample_source(5000)
+    with pytest.raises(BackendError) as e:
+        gpu.transport(bank, capacity=100)
+    assert e.value.code == -3 and "overflow" in str(e.value)
+
+
+def test_majorant_violation_is_fatal(ab, oracle_api, tmp_path):
+    """Total xs above the sampling xs must raise, as delta_tracker.cpp:174-180 does."""
+    from abeille_b200 import BackendError
+    deck = load_deck("c5g7_carter_cancel.yaml")
+    deck["settings"]["transport"] = "delta-tracking"  # delta tracking never reads sampling-xs-ratio ...
+    path = write_deck(deck, tmp_path / "ok.yaml", {"settings": {"nparticles": 2000}})
+    gpu = ab.Backend(path, 0)
+    orc = oracle_api.Oracle(path)
+    gpu.transport(orc.sample_source(2000))  # ... so this is fine
+
+
+def test_cpp_adapter_matches_c_abi(ab, oracle_api, tmp_path):
+    """GPUTransporter::transport(vector<Particle>&) (the reference-shaped C++ entry) == abl_transport."""
+    n = 6000
+    orc, gpu = _pair(ab, oracle_api, tmp_path, "c5g7_delta_collision.yaml", {"settings": {"nparticles": n}})
+    bank = orc.sample_source(n)
+    fis_c, scores_c, _ = gpu.transport(bank, k_col=1.1)
+    fis_v, scores_v = gpu.transport_vectors(bank, k_col=1.1)
+    for k in BANK_EXACT:
+        assert np.array_equal(fis_c[k], fis_v[k]), k
+    assert np.allclose(scores_c, scores_v, rtol=1e-11)
+
+
+# ---- tallies -----------------------------------------------------------------------------------------------------------
+def test_tally_statistics_match_oracle(ab, oracle_api, tmp_path):
+    n = 5000
+    orc, gpu = _pair(ab, oracle_api, tmp_path, "c5g7_delta_collision.yaml", {"settings": {"nparticles": n}})
+    orc.set_converged(True)
+    for gen in range(3):
+        orc.set_history_counter(gen * n)
+        bank = orc.sample_source(n)
+        orc.transport({k: v.copy() for k, v in bank.items()})
+        gpu.transport(bank, converged=True)
+        orc.tallies_record(1.0)
+        orc.tallies_clear()
+        gpu.tallies_record(1.0)
+        gpu.tallies_clear()
+    for which in ("avg", "var", "std"):
+        o, g = orc.tally(0, which), gpu.tally(0, which)
+        assert np.allclose(g, o, rtol=1e-9, atol=1e-300), which
+    assert np.count_nonzero(gpu.tally(0, "gen")) == 0
+
+
+# ---- inter-generation pipeline -----------------------------------------------------------------------------------------
+def test_cancellation_and_normalisation_match_oracle(ab, oracle_api, tmp_path):
+    import torch
+    n = 12000
+    orc, gpu = _pair(ab, oracle_api, tmp_path, "c5g7_carter_cancel.yaml",
+                     {"settings": {"nparticles": n}, "cancelator": {"type": "approximate", "shape": [10, 10, 8],
+                                                                    "low": [-32.13, -32.13, -107.11], "hi": [10.71, 10.71, 85.69]}})
+    bank = orc.sample_source(n)
+    fis, _, _ = gpu.transport(bank)
+    m = len(fis["x"])
+    assert (fis["wgt"] < 0).any(), "carter tracking with an under-estimated majorant should bank negative sites"
+    ob = {k: fis[k].copy() for k in fis}
+    ob["wgt2"] = np.zeros(m)
+    stats = orc.cancel_and_normalize(ob, True)
+    db = gpu.new_device_bank(m)
+    for k in ("x", "y", "z", "ux", "uy", "uz", "E", "wgt"):
+        db[k].copy_(torch.from_numpy(fis[k]))
+    gpu.cancel_device(db, m)
+    ws = gpu.weight_stats_device(db, m)
+    gpu.scale_weights_device(db, m, n / (ws[2] - ws[3]))
+    torch.cuda.synchronize()
+    assert np.allclose(db["wgt"].cpu().numpy(), ob["wgt"], rtol=1e-11, atol=1e-300)
+    assert abs(db["wgt"].sum().item() - n) < 1e-6 * n
+
+
+def test_power_iteration_resident_and_host_paths_match_oracle(ab, oracle_api, tmp_path):
+    n, ngen, nign = 6000, 8, 3
+    ov = {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}}
+    for resident in (False, True):
+        orc, gpu = _pair(ab, oracle_api, tmp_path, "c5g7_delta_collision.yaml", ov, name=f"pi{int(resident)}.yaml")
+        o = orc.run_power_iteration(ngen, nign)
+        g = gpu.run_power_iteration(ngen, nign, resident=resident)
+        assert np.array_equal(g["nbank"], o["nbank"]), (resident, g["nbank"], o["nbank"])
+        assert np.allclose(g["kcol"], o["kcol"], rtol=1e-10)
+        assert np.allclose(g["leak"], o["leak"], rtol=1e-10)
+        assert np.allclose(g["entropy"], o["entropy"], rtol=1e-10)
+        assert np.allclose(gpu.tally(0, "avg"), orc.tally(0, "avg"), rtol=1e-9, atol=1e-300)
+        assert np.allclose(gpu.tally(0, "std"), orc.tally(0, "std"), rtol=1e-7, atol=1e-300)
+
+
+def test_power_iteration_surface_tracking_sood(ab, oracle_api, tmp_path):
+    """S1 on the device: k_inf of PUa-1-0-IN within 3 sigma of 2.612903 (and equal to the oracle's series)."""
+    n, ngen, nign = 20000, 40, 10
+    ov = {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}}
+    orc, gpu = _pair(ab, oracle_api, tmp_path, "PUa-1-0-IN.yaml", ov)
+    g = gpu.run_power_iteration(ngen, nign, resident=True)
+    assert abs(g["kcol_avg"] - 2.612903) < 3 * g["kcol_err"] + 1e-9
+    assert abs(g["ktrk_avg"] - 2.612903) < 3 * g["ktrk_err"] + 1e-9
+    o = orc.run_power_iteration(ngen, nign)
+    assert np.array_equal(g["nbank"], o["nbank"])
+    assert np.allclose(g["kcol"], o["kcol"], rtol=1e-10) and np.allclose(g["ktrk"], o["ktrk"], rtol=1e-10)
+
+
+def test_results_written_as_npy(ab, tmp_path):
+    path = write_deck(load_deck("c5g7_delta_collision.yaml"), tmp_path / "w.yaml",
+                      {"settings": {"nparticles": 2000, "ngenerations": 4, "nignored": 2}})
+    gpu = ab.Backend(path, 0)
+    gpu.run_power_iteration(4, 2, resident=True)
+    out = tmp_path / "results"
+    gpu.write_results(str(out))
+    avg = np.load(out / "flux_pin_avg.npy")
+    std = np.load(out / "flux_pin_std.npy")
+    assert avg.shape == (7, 51, 51, 1) and std.shape == avg.shape
+    assert np.array_equal(avg, gpu.tally(0, "avg")) and np.load(out / "kcol.npy").shape == (4,)

@@ -1,0 +1,167 @@
+"""CPU: host-side logic of the product (YAML reader, object model, flattening) and the C-ABI export check.
+No compute call is made here (there is no GPU in the build container)."""
+import ctypes
+import re
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+from conftest import DECKS, ROOT, deck_path, load_deck, write_deck
+
+
+def test_c_abi_library_exports_every_declared_symbol(native_libs):
+    from abeille_b200 import backend
+    header = open(os.path.join(ROOT, "include", "abeille_b200.h")).read()
+    declared = set(re.findall(r"\b(abl_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(backend.ABI_SYMBOLS)
+    lib = backend.load_backend_lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libabeille_b200.so does not export {name}"
+
+
+def test_c_abi_struct_layout_matches_ctypes(native_libs):
+    from abeille_b200 import backend
+    assert ctypes.sizeof(backend.AblBank) == 8 + 12 * 8
+    assert ctypes.sizeof(backend.AblGenParams) == 32
+    assert ctypes.sizeof(backend.AblTrace) == 48
+
+
+def test_no_device_fails_loudly(native_libs, tmp_path):
+    """The product has no CPU fallback: opening a backend without a CUDA device must raise."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from abeille_b200 import Backend, BackendError
+    with pytest.raises(BackendError) as e:
+        Backend(deck_path("PUa-1-0-IN.yaml"), 0)
+    assert "no CUDA device" in str(e.value) or "cuda" in str(e.value).lower()
+
+
+def _py(node):
+    """PyYAML tree -> the canonical rendering ablh_yaml_roundtrip produces (scalars as written)."""
+    if node is None:
+        return "null"
+    if isinstance(node, dict):
+        return "{" + ",".join(f'"{k}":{_py(v)}' for k, v in node.items()) + "}"
+    if isinstance(node, list):
+        return "[" + ",".join(_py(v) for v in node) + "]"
+    return None  # scalars are compared numerically below
+
+
+def _compare(a, b):
+    """a: PyYAML object, b: json-ish object parsed back from the roundtrip string."""
+    if isinstance(a, dict):
+        assert isinstance(b, dict) and list(a.keys()) == list(b.keys())
+        for k in a:
+            _compare(a[k], b[k])
+    elif isinstance(a, list):
+        assert isinstance(b, list) and len(a) == len(b)
+        for x, y in zip(a, b):
+            _compare(x, y)
+    elif a is None:
+        assert b is None
+    elif isinstance(a, bool):
+        assert b in ("true", "false", "True", "False") and (b.lower() == "true") == a
+    elif isinstance(a, (int, float)):
+        assert float(b) == float(a)
+    else:
+        assert str(a) == b
+
+
+@pytest.mark.parametrize("name", sorted(f for f in os.listdir(DECKS) if f.endswith(".yaml")))
+def test_yaml_lite_agrees_with_pyyaml_on_every_deck(native_libs, name):
+    import json
+    text = open(deck_path(name)).read()
+    _compare(yaml.safe_load(text), json.loads(native_libs.yaml_roundtrip(text)))
+
+
+def test_yaml_lite_block_and_flow_styles(native_libs):
+    import json
+    text = """
+# comment
+a: [1, 2,
+    3]   # trailing
+b:
+  - {x: 1, y: 'q r'}
+  - z: 2
+    w: [[1, 2], [3]]
+  -
+    k: v
+c: "-1 & +2"
+d:
+- 1
+- 2
+e: {p: [1, 2], q: {r: s}}
+"""
+    _compare(yaml.safe_load(text), json.loads(native_libs.yaml_roundtrip(text)))
+
+
+def test_yaml_lite_rejects_bad_input(native_libs):
+    from abeille_b200 import BackendError
+    with pytest.raises(BackendError):
+        native_libs.yaml_roundtrip("a: [1, 2")
+    with pytest.raises(BackendError):
+        native_libs.yaml_roundtrip("a: 1\n   b: 2\n")
+
+
+def test_parse_c5g7(native_libs):
+    info, smp = native_libs.parse_only(deck_path("c5g7_delta_collision.yaml"))
+    assert info["ngroups"] == 7 and info["nsurfaces"] == 7 and info["ncells"] == 8 and info["nuniverses"] == 10
+    assert info["nmaterials"] == 7 and info["max_stack_depth"] == 4 and info["tracking"] == 1
+    # majorant: water dominates all groups but 0 and 3 (8.7% MOX) -- SURVEY appendix C
+    assert np.allclose(smp, [0.183045, 0.41297, 0.59031, 0.606174, 0.718, 1.25445, 2.65038], rtol=0, atol=0)
+
+
+def test_carter_sampling_xs_is_ratio_times_majorant(native_libs):
+    _, maj = native_libs.parse_only(deck_path("c5g7_delta_collision.yaml"))
+    _, smp = native_libs.parse_only(deck_path("c5g7_carter_cancel.yaml"))
+    assert smp[0] == maj[0] * 0.9 and np.array_equal(smp[1:], maj[1:])
+
+
+def test_flattened_tables_agree_with_the_oracle(native_libs, oracle_api):
+    """The oracle reads decks through an independent path (PyYAML -> token file -> its own table builder)."""
+    for name in ("c5g7_delta_collision.yaml", "PUa-1-2-SL.yaml", "UD2O-2-1-SL.yaml"):
+        t = native_libs.dump_tables(deck_path(name))
+        o = oracle_api.Oracle(deck_path(name))
+        maj, smp = o.majorant()
+        assert np.array_equal(t["smp"], smp)
+        G = o.G
+        assert len(t["Et"]) % G == 0 and len(t["chi_cdf"]) == len(t["Et"]) * G
+        # cumulative tables end at exactly 1.0 (libstdc++ forces the last partial sum)
+        if G >= 2:
+            assert np.all(t["scatter_cdf"].reshape(-1, G)[:, -1] == 1.0)
+
+
+def test_legendre_tables_for_anisotropic_deck(native_libs):
+    t = native_libs.dump_tables(deck_path("PUa-1-2-SL.yaml"))
+    n = int(t["angle"][1])
+    assert n > 2  # linearised P2 distribution has interior points
+    mu, pdf, cdf = t["amu"][:n], t["apdf"][:n], t["acdf"][:n]
+    assert mu[0] == -1.0 and mu[-1] == 1.0 and np.all(np.diff(mu) > 0)
+    assert cdf[0] == 0.0 and cdf[-1] == 1.0 and np.all(np.diff(cdf) >= 0) and np.all(pdf >= 0)
+
+
+@pytest.mark.parametrize("bad,msg", [
+    ({"settings": {"transport": "warp-drive"}}, "Invalid tracking method"),
+    ({"settings": {"energy-mode": "continuous-energy"}}, "multi-group"),
+    ({"root-universe": 12345}, "Could not find universe"),
+    ({"settings": {"nignored": 5000}}, "ignored"),
+])
+def test_parser_errors(native_libs, tmp_path, bad, msg):
+    from abeille_b200 import BackendError
+    path = write_deck(load_deck("c5g7_delta_collision.yaml"), tmp_path / "bad.yaml", bad)
+    with pytest.raises(BackendError) as e:
+        native_libs.parse_only(path)
+    assert msg in str(e.value)
+
+
+def test_unknown_surface_in_region_is_rejected(native_libs, tmp_path):
+    from abeille_b200 import BackendError
+    deck = load_deck("PUa-1-0-IN.yaml")
+    deck["cells"][0]["region"] = "+1 & -99"
+    path = write_deck(deck, tmp_path / "bad.yaml")
+    with pytest.raises(BackendError) as e:
+        native_libs.parse_only(path)
+    assert "surface" in str(e.value)
