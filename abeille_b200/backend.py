@@ -21,7 +21,7 @@ COUNTER_KEYS = ("flights", "real_collisions", "virtual_collisions", "tl_bins", "
 
 # every symbol include/abeille_b200.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = (
-    "abl_create", "abl_destroy", "abl_last_error", "abl_device_info", "abl_transport", "abl_get_trace",
+    "abl_create", "abl_destroy", "abl_last_error", "abl_device_info", "abl_last_transport_kernel", "abl_transport", "abl_get_trace",
     "abl_transport_device", "abl_tally_count", "abl_tally_shape", "abl_tallies_record", "abl_tallies_clear",
     "abl_tally_fetch", "abl_tally_device_ptr", "abl_sample_source_device", "abl_bank_weight_stats_device",
     "abl_bank_scale_weights_device", "abl_bank_to_particles_device", "abl_entropy_bin_device",
@@ -218,6 +218,11 @@ class Backend:
         sm, ma, mi, nl = C.c_int(), C.c_int(), C.c_int(), C.c_uint64()
         self._check(self.L.abl_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(nl)))
         return {"sm_count": sm.value, "cc": (ma.value, mi.value), "kernel_launches": int(nl.value)}
+
+    def last_transport_kernel(self) -> dict:
+        ms, g, b = C.c_float(), C.c_int(), C.c_int()
+        self._check(self.L.abl_last_transport_kernel(self.h, C.byref(ms), C.byref(g), C.byref(b)))
+        return {"ms": float(ms.value), "grid": g.value, "block": b.value}
 
     # ---- Transporter::transport, host buffers (C ABI) ----
     def transport(self, bank: dict, k_col: float = 1.0, converged: bool = False, trace: bool = False,

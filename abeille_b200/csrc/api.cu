@@ -58,6 +58,9 @@ struct abl_context {
   uint64_t probe_cap = 0;
   int blocks_per_sm[3] = {0, 0, 0};
   uint64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_kernel_ms = 0.f;
+  int last_grid = 0;
   cudaStream_t last_stream = nullptr;
   bool has_last_stream = false;
   std::string error;
@@ -279,7 +282,10 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
     }
     B.secondaries = h->secondaries;
   }
+  cudaEventRecord(h->ev0, s);
   kern<<<(unsigned)blocks, 128, 0, s>>>(h->P, B);
+  cudaEventRecord(h->ev1, s);
+  h->last_grid = (int)blocks;
   h->launches++;
   ABL_CUDA(h, cudaGetLastError());
   return ABL_OK;
@@ -347,6 +353,7 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
   }
   ABL_CUDA(h, cudaMemcpyAsync(h->small_host, h->small_dev, sizeof(DevSmall), cudaMemcpyDeviceToHost, s));
   ABL_CUDA(h, cudaStreamSynchronize(s));
+  if (N > 0) cudaEventElapsedTime(&h->last_kernel_ms, h->ev0, h->ev1);
   const DevSmall& sm = *h->small_host;
   for (int i = 0; i < 6; i++) scores[i] = sm.scores[i];
   if (counters)
@@ -389,6 +396,8 @@ void abl_destroy(abl_handle h) {
   free_bank(h->stage_in);
   free_bank(h->stage_out);
   if (h->small_host) cudaFreeHost(h->small_host);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -431,6 +440,7 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
   h->cc_major = prop.major;
   h->cc_minor = prop.minor;
   if (CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail(ABL_ERR_CUDA);
+  if (CU(cudaEventCreate(&h->ev0), "cudaEventCreate") || CU(cudaEventCreate(&h->ev1), "cudaEventCreate")) return bail(ABL_ERR_CUDA);
   if (CU(cudaMalloc(&h->small_dev, sizeof(DevSmall)), "cudaMalloc")) return bail(ABL_ERR_CUDA);
   if (CU(cudaMallocHost(&h->small_host, sizeof(DevSmall)), "cudaMallocHost")) return bail(ABL_ERR_CUDA);
 
@@ -547,6 +557,14 @@ int abl_device_info(abl_handle h, int* sm_count, int* cc_major, int* cc_minor, u
   if (cc_major) *cc_major = h->cc_major;
   if (cc_minor) *cc_minor = h->cc_minor;
   if (kernel_launches) *kernel_launches = h->launches;
+  return ABL_OK;
+}
+
+int abl_last_transport_kernel(abl_handle h, float* milliseconds, int* grid_blocks, int* block_threads) {
+  if (!h) return ABL_ERR_INVALID;
+  if (milliseconds) *milliseconds = h->last_kernel_ms;
+  if (grid_blocks) *grid_blocks = h->last_grid;
+  if (block_threads) *block_threads = 128;
   return ABL_OK;
 }
 

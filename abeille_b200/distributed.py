@@ -1,0 +1,169 @@
+"""Multi-GPU k-eigenvalue generation loop: one process per GPU, histories sharded by global history id.
+
+The reference shards the same way across MPI ranks (src/power_iterator.cpp:135-166,386-404) but funnels the
+fission bank through rank 0 every generation (Gatherv / Scatterv, src/simulation.cpp:113-135) and reduces every
+mesh tally to rank 0 (src/mesh_tally.cpp:129).  Here each GPU keeps its slice of the bank resident in HBM and
+the only exchange steps are (NCCL over NVLink, via torch.distributed):
+
+  1. one all_gather of a 20-double vector per generation: 6 scores, 8 event counters, site count, W+/W-/N+/N-
+     (replaces the 6 Allreduce of src/tallies.cpp:162-167 and the size Bcasts of the bank funnel);
+  2. global history ids from an exclusive scan of the gathered site counts, so the RNG streams -- and therefore
+     every integer outcome -- are independent of the number of GPUs, as in the reference;
+  3. an order-preserving all_to_all_single that moves partition boundaries back to an even split when the
+     slices drift apart (replaces gather-to-root + scatter);
+  4. on active generations an all_reduce of every tally_gen array before the Welford update, and a small
+     all_reduce of the entropy bins.
+
+With world_size == 1 (or no process group) every collective degenerates to a no-op and the loop is exactly the
+single-GPU device-resident loop of the C++ PowerIterator.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .backend import BANK_F64, BANK_U64, Backend
+
+
+def even_split(total: int, world: int):
+    """Partition boundaries of `total` items over `world` ranks, remainder to the first ranks
+    (src/power_iterator.cpp:138-157 distributes the same way)."""
+    base, rem = divmod(int(total), int(world))
+    counts = [base + (1 if r < rem else 0) for r in range(world)]
+    bounds = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return counts, bounds
+
+
+def rebalance_plan(counts, rank: int):
+    """Order-preserving re-partition: rank r holds global range [B_r, B_r+1) and must end with [B'_r, B'_r+1).
+    Returns (send_splits, recv_splits) for all_to_all_single; pieces arrive in source-rank order == global order."""
+    world = len(counts)
+    old = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    _, new = even_split(int(old[-1]), world)
+    send = [int(max(0, min(old[rank + 1], new[q + 1]) - max(old[rank], new[q]))) for q in range(world)]
+    recv = [int(max(0, min(old[q + 1], new[rank + 1]) - max(old[q], new[rank]))) for q in range(world)]
+    return send, recv
+
+
+class _DevPtr:
+    """Wraps a raw device pointer for torch.as_tensor through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+class DistributedPowerIterator:
+    def __init__(self, deck_path: str, device: int, nparticles_per_rank: int, group=None):
+        self.gpu = Backend(deck_path, device)
+        self.device = torch.device("cuda", device)
+        self.n_local = int(nparticles_per_rank)
+        self.use_dist = dist.is_available() and dist.is_initialized()
+        self.group = group
+        self.rank = dist.get_rank(group) if self.use_dist else 0
+        self.world = dist.get_world_size(group) if self.use_dist else 1
+        self.n_total = self.n_local * self.world  # tallies->total_weight; the deck's nparticles must equal this
+        if self.gpu.info["nparticles"] != self.n_total:
+            raise ValueError(f"deck nparticles {self.gpu.info['nparticles']} != world*n_local {self.n_total}")
+        self.cap = int(2.5 * self.n_local) + 4096
+        self.cur = self.gpu.new_device_bank(self.cap)
+        self.nxt = self.gpu.new_device_bank(self.cap)
+        self.n_cur = 0
+        self.use_state = True
+        self.k_col = 1.0
+        self.global_counter = 0
+        self.converged = False
+        self.gen = 0
+        self.kcol_series, self.nbank_series = [], []
+        self.counters = np.zeros(8)
+        self.active_particles = 0.0
+        self._tally_views = None
+
+    # ---- helpers ----
+    def _gather(self, vec: np.ndarray) -> np.ndarray:
+        """all_gather of a small fp64 vector -> [world, len] on the host."""
+        if self.world == 1:
+            return vec[None, :].copy()
+        t = torch.from_numpy(vec).to(self.device)
+        out = torch.empty(self.world * len(vec), dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        return out.cpu().numpy().reshape(self.world, len(vec))
+
+    def tally_tensors(self):
+        if self._tally_views is None:
+            self._tally_views = []
+            for t in range(self.gpu.ntallies()):
+                ptr, n = self.gpu.tally_device_ptr(t, 0)
+                self._tally_views.append(torch.as_tensor(_DevPtr(ptr, n), device=self.device))
+        return self._tally_views
+
+    # ---- Simulation::sample_sources: rank r samples the ids [r*n, (r+1)*n) ----
+    def initialize(self):
+        first = self.rank * self.n_local
+        self.gpu.sample_source_device(self.cur, self.n_local, first)
+        self.n_cur = self.n_local
+        self.use_state = True
+        self.global_counter = self.n_total
+
+    def _rebalance(self, counts):
+        """Moves partition boundaries back to an even split, preserving global order."""
+        send, recv = rebalance_plan(counts, self.rank)
+        m_new = int(sum(recv))
+        keys = [k for k in BANK_F64 if k != "wgt2"] + ["id_a", "id_b", "id_c"]
+        spare = self.cur  # the consumed particle bank is free to receive
+        for k in keys:
+            src = self.nxt[k][: int(sum(send))]
+            dst = spare[k][:m_new]
+            dist.all_to_all_single(dst, src, recv, send, group=self.group)
+        self.cur, self.nxt = self.nxt, self.cur  # keep the invariant: the fission bank lives in self.nxt
+        return m_new
+
+    def generation(self, converged: bool | None = None) -> dict:
+        """One power-iteration generation (src/power_iterator.cpp:325-428) on this rank's slice."""
+        if converged is not None:
+            self.converged = converged
+        gpu = self.gpu
+        n_in = self.n_cur
+        m, scores, cn = gpu.transport_device(self.cur, n_in, self.nxt, k_col=self.k_col, converged=self.converged,
+                                             use_rng_state=self.use_state)
+        local = np.concatenate([scores, np.array([cn[k] for k in cn], dtype=np.float64), [float(m), float(n_in)]])
+        allv = self._gather(local)
+        tot = allv.sum(axis=0)
+        counts = [int(v) for v in allv[:, 14]]
+        n_in_total = int(tot[15])
+        self.k_col = tot[0] / self.n_total  # Tallies::calc_gen_values: score / total_weight
+        self.counters += tot[6:14]
+        if self.converged:
+            self.active_particles += n_in_total
+        self.kcol_series.append(self.k_col)
+        self.nbank_series.append(n_in_total)
+        m_total = int(sum(counts))
+        if m_total == 0:
+            raise RuntimeError("No fission neutrons were produced.")
+        # weight normalisation over the global bank (src/power_iterator.cpp:538-586)
+        ws = gpu.weight_stats_device(self.nxt, m)
+        wall = self._gather(ws).sum(axis=0)
+        gpu.scale_weights_device(self.nxt, m, self.n_total / (wall[2] - wall[3]))
+        if self.converged:
+            if self.world > 1:
+                for t in self.tally_tensors():
+                    dist.all_reduce(t, group=self.group)
+            gpu.tallies_record(1.0)
+        gpu.tallies_clear()
+        # even out the slices when they drift (order-preserving), then assign global ids
+        if self.world > 1:
+            target, _ = even_split(m_total, self.world)
+            if max(abs(c - t) for c, t in zip(counts, target)) > max(0.01 * m_total / self.world, 64):
+                m = self._rebalance(counts)
+                counts = target
+        first = self.global_counter + int(sum(counts[: self.rank]))
+        gpu.to_particles_device(self.nxt, m, first)
+        self.global_counter += m_total
+        self.cur, self.nxt = self.nxt, self.cur
+        self.n_cur = m
+        self.use_state = False
+        self.gen += 1
+        return {"k_col": self.k_col, "n_in": n_in, "n_in_total": n_in_total, "m": m, "m_total": m_total,
+                "real_collisions": tot[7], "flights": tot[6], "coll_scores": tot[13], "tl_bins": tot[9],
+                "local_real_collisions": cn["real_collisions"], "local_coll_scores": cn["coll_scores"],
+                "local_tl_bins": cn["tl_bins"]}

@@ -190,6 +190,8 @@ int abl_create(const abl_problem* problem, int device, abl_handle* out);
 void abl_destroy(abl_handle h);
 const char* abl_last_error(abl_handle h); /* h may be NULL: error of the last failed abl_create        */
 int abl_device_info(abl_handle h, int* sm_count, int* cc_major, int* cc_minor, uint64_t* kernel_launches);
+/* device time (CUDA events on the launching stream) of the history kernel of the last transport call, and its grid */
+int abl_last_transport_kernel(abl_handle h, float* milliseconds, int* grid_blocks, int* block_threads);
 
 /* ---- Transporter::transport, host buffers (the reference-facing entry point) ------------------------ */
 int abl_transport(abl_handle h, const abl_bank* bank, const abl_gen_params* params, abl_bank* fission_out,
