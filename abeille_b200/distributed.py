@@ -138,6 +138,7 @@ class DistributedPowerIterator:
         self.kcol_series.append(self.k_col)
         self.nbank_series.append(n_in_total)
         m_total = int(sum(counts))
+        m_pre = m
         if m_total == 0:
             raise RuntimeError("No fission neutrons were produced.")
         # weight normalisation over the global bank (src/power_iterator.cpp:538-586)
@@ -163,7 +164,94 @@ class DistributedPowerIterator:
         self.n_cur = m
         self.use_state = False
         self.gen += 1
-        return {"k_col": self.k_col, "n_in": n_in, "n_in_total": n_in_total, "m": m, "m_total": m_total,
+        return {"k_col": self.k_col, "n_in": n_in, "n_in_total": n_in_total, "m": m, "m_pre": m_pre, "m_total": m_total,
                 "real_collisions": tot[7], "flights": tot[6], "coll_scores": tot[13], "tl_bins": tot[9],
                 "local_real_collisions": cn["real_collisions"], "local_coll_scores": cn["coll_scores"],
                 "local_tl_bins": cn["tl_bins"]}
+
+
+class HostBufferLoop:
+    """The reference's own data flow (src/power_iterator.cpp:325-428): every generation the bank crosses the
+    Transporter::transport() boundary as HOST arrays -- abl_transport copies it to the device, runs the kernels and
+    copies the fission bank and the scores back.  The caller-side steps (k_col, weight normalisation, fresh history
+    ids) are done on the host, as PowerIterator does.  Host arrays are pinned.  bench.py's `e2e` leg."""
+
+    F64_OUT = ("x", "y", "z", "ux", "uy", "uz", "E", "wgt")
+
+    def __init__(self, deck_path: str, device: int, nparticles_per_rank: int, group=None):
+        self.gpu = Backend(deck_path, device)
+        self.device = torch.device("cuda", device)
+        self.n_local = int(nparticles_per_rank)
+        self.use_dist = dist.is_available() and dist.is_initialized()
+        self.group = group
+        self.rank = dist.get_rank(group) if self.use_dist else 0
+        self.world = dist.get_world_size(group) if self.use_dist else 1
+        self.n_total = self.n_local * self.world
+        self.cap = int(2.5 * self.n_local) + 4096
+        self.bufs = [self._pinned_bank(self.cap), self._pinned_bank(self.cap)]
+        self.bank = None
+        self.k_col = 1.0
+        self.global_counter = 0
+        self.h2d_bytes = self.d2h_bytes = 0
+        self.gens = 0
+        self._tally_views = None
+
+    @staticmethod
+    def _pinned_bank(cap):
+        b = {k: torch.zeros(cap, dtype=torch.float64).pin_memory().numpy() for k in HostBufferLoop.F64_OUT}
+        b.update({k: torch.zeros(cap, dtype=torch.int64).pin_memory().numpy().view(np.uint64) for k in BANK_U64})
+        return b
+
+    _gather = DistributedPowerIterator._gather
+    tally_tensors = DistributedPowerIterator.tally_tensors
+
+    def initialize(self):
+        db = self.gpu.new_device_bank(self.n_local)
+        self.gpu.sample_source_device(db, self.n_local, self.rank * self.n_local)
+        torch.cuda.synchronize()
+        b = self.bufs[0]
+        n = self.n_local
+        for k in self.F64_OUT:
+            b[k][:n] = db[k].cpu().numpy()
+        for k in BANK_U64:
+            b[k][:n] = db[k].cpu().numpy().view(np.uint64)
+        self.bank = {k: b[k][:n] for k in self.F64_OUT + BANK_U64}
+        self.bank["wgt2"] = None
+        self.cur = 0
+        self.global_counter = self.n_total
+
+    def generation(self, converged: bool = True) -> dict:
+        gpu = self.gpu
+        n_in = len(self.bank["x"])
+        out = self.bufs[1 - self.cur]
+        out_full = dict(out)
+        out_full["wgt2"] = None
+        fis, scores, cn = gpu.transport(self.bank, k_col=self.k_col, converged=converged, capacity=self.cap, out=out_full)
+        m = len(fis["x"])
+        self.h2d_bytes += n_in * 8 * (8 + sum(1 for k in BANK_U64 if self.bank.get(k) is not None))
+        self.d2h_bytes += m * 8 * 11 + 6 * 8 + 8 * 8
+        wpos = float(fis["wgt"][fis["wgt"] > 0].sum()) if m else 0.0
+        wneg = float(-fis["wgt"][fis["wgt"] < 0].sum()) if m else 0.0
+        local = np.concatenate([scores, [cn["real_collisions"], float(m), float(n_in), wpos, wneg]])
+        allv = self._gather(local)
+        tot = allv.sum(axis=0)
+        counts = [int(v) for v in allv[:, 7]]
+        self.k_col = tot[0] / self.n_total
+        if sum(counts) == 0:
+            raise RuntimeError("No fission neutrons were produced.")
+        fis["wgt"] *= self.n_total / (tot[9] - tot[10])  # normalize_weights, power_iterator.cpp:561-569
+        if converged:
+            if self.world > 1:
+                for t in self.tally_tensors():
+                    dist.all_reduce(t, group=self.group)
+            gpu.tallies_record(1.0)
+        gpu.tallies_clear()
+        first = self.global_counter + int(sum(counts[: self.rank]))
+        family = fis["id_c"]
+        fis["id_a"][:] = np.arange(first, first + m, dtype=np.uint64)  # fresh history ids (power_iterator.cpp:397-399)
+        self.bank = {k: fis[k] for k in self.F64_OUT}
+        self.bank.update({"wgt2": None, "id_a": fis["id_a"], "id_b": family, "id_c": None})
+        self.global_counter += int(sum(counts))
+        self.cur = 1 - self.cur
+        self.gens += 1
+        return {"k_col": self.k_col, "n_in": n_in, "n_in_total": int(tot[8]), "m": m, "real_collisions": tot[6]}

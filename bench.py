@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the transport hot path on the BASELINE.json workload.
+
+Workload (configs[1]): C5G7, 7 groups, delta tracking, collision-estimator flux mesh tally on the deck's own
+1224 x 1224 x 10 x 7 mesh (tests/decks/c5g7_delta_collision_fullmesh.yaml), 10^7 particles per generation per
+GPU.  A "step" is one ACTIVE power-iteration generation: Transporter::transport over the whole bank, then the
+per-generation bookkeeping the reference does between transport calls (k_col, weight normalisation, tally
+record/clear, history-id / RNG re-seeding).  Histories shard across GPUs by global history id (weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+* value        active particles/s, bank resident in HBM, CUDA events around the K steps, max over ranks.
+* e2e          the same metric through the host-buffer C ABI (abl_transport): every step copies the bank
+               host->device from pinned memory and the fission bank + scores device->host.
+* roofline     the history kernel: algorithmic bytes / measured kernel time.
+* cpu_baseline the CPU oracle (a restatement of the reference's OpenMP path; oracle/) on this box's cores.
+* --impl reference: that CPU path as its own arm (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DECK = os.path.join(ROOT, "tests", "decks", "c5g7_delta_collision_fullmesh.yaml")
+METRIC = "active particles/sec (+ collisions/sec), C5G7 delta-tracking"
+WORKLOAD = "c5g7 7-group delta-tracking k-eigenvalue, collision-estimator flux mesh tally 1224x1224x10x7"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _write_deck(nparticles_total, path):
+    import yaml
+    with open(DECK) as f:
+        deck = yaml.safe_load(f)
+    deck["settings"]["nparticles"] = int(nparticles_total)
+    with open(path, "w") as f:
+        yaml.safe_dump(deck, f, default_flow_style=None, sort_keys=False, width=200)
+    return path
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, smax, reasons, pw = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_leg(nparticles, inactive, active, threads=None):
+    """The CPU oracle (restatement of the reference's OpenMP trackers) on a bounded sample of the workload."""
+    from oracle import api
+    api.build()
+    api.set_math("libm")  # glibc log/sin/cos, as the reference
+    nthreads = threads or (os.cpu_count() or 1)
+    api.set_threads(nthreads)
+    with tempfile.TemporaryDirectory() as td:
+        orc = api.Oracle(_write_deck(nparticles, os.path.join(td, "deck.yaml")))
+    orc.pi_init(inactive)
+    if inactive:
+        orc.pi_run(inactive)
+    r = orc.pi_run(active)
+    orc.close()
+    return {"particles_per_s": r["particles"] / r["seconds"], "collisions_per_s": r["real_collisions"] / r["seconds"],
+            "seconds": r["seconds"], "particles": r["particles"], "cores": nthreads,
+            "sample": f"{active} active generations of {nparticles} particles after {inactive} inactive, same deck and mesh, "
+                      f"OpenMP schedule(dynamic) over histories, {nthreads} threads, g++ -O2"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself cannot be built offline,
+    see DESIGN.md) on all host threads.  A step is one active generation of a bounded particle count."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.ref_particles
+    t0 = time.time()
+    r = cpu_leg(n, max(args.warmup, 1), args.steps)
+    out = {"impl": "reference", "metric": METRIC, "value": r["particles_per_s"], "unit": "particles/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "collisions_per_s": r["collisions_per_s"],
+           "config": {"workload": WORKLOAD, "particles_per_step": n, "host_threads": r["cores"]},
+           "cpu_baseline": {"value": r["particles_per_s"], "unit": "particles/s", "cores": r["cores"], "kind": "port",
+                            "sample": r["sample"]},
+           "e2e": {"value": r["particles_per_s"], "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": time.time() - t0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 backend has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build_if_missing()
+    if world > 1:
+        dist.barrier()
+    import abeille_b200 as ab
+    from abeille_b200.distributed import DistributedPowerIterator, HostBufferLoop
+
+    n_local = args.particles
+    n_total = n_local * world
+    td = tempfile.mkdtemp()
+    deck = _write_deck(n_total, os.path.join(td, f"bench_{rank}.yaml"))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident leg: `value` -------------------------------------------------------------------------------
+    sim = DistributedPowerIterator(deck, local, n_local)
+    sim.initialize()
+    for _ in range(args.warmup):
+        sim.generation(converged=True)
+    launches0 = sim.gpu.device_info()["kernel_launches"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    particles = collisions = sites = coll_scores = 0.0
+    local_particles = local_coll = local_sites = local_scores = 0.0
+    kernel_ms = []
+    for _ in range(args.steps):
+        g = sim.generation(converged=True)
+        particles += g["n_in_total"]; collisions += g["real_collisions"]; sites += g["m_total"]; coll_scores += g["coll_scores"]
+        local_particles += g["n_in"]; local_coll += g["local_real_collisions"]; local_sites += g["m_pre"]
+        local_scores += g["local_coll_scores"]
+        kernel_ms.append(sim.gpu.last_transport_kernel()["ms"])
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sim.gpu.device_info()["kernel_launches"] - launches0
+    kinfo = sim.gpu.last_transport_kernel()
+    k_col = sim.k_col
+    # roofline of the history kernel on this rank: SURVEY.md 8(d) algorithmic bytes per launch
+    alg_bytes = (96.0 * local_particles + 72.0 * local_sites + 16.0 * local_scores) / args.steps
+    k_ms = float(np.mean(kernel_ms))
+    peak, peak_src = _peaks()
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    tally_bins = sum(int(np.prod(sim.gpu.tally_shape(t))) for t in range(sim.gpu.ntallies()))
+    del sim
+    torch.cuda.empty_cache()
+
+    # ---- e2e leg: host buffers through abl_transport -----------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        loop = HostBufferLoop(deck, local, n_local)
+        loop.initialize()
+        for _ in range(min(args.warmup, 3)):
+            loop.generation(converged=True)
+        barrier()
+        t0 = time.perf_counter()
+        ep = 0.0
+        for _ in range(args.e2e_steps):
+            ep += loop.generation(converged=True)["n_in_total"]
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": ep / dt, "unit": "particles/s", "h2d_bytes_per_step": loop.h2d_bytes / loop.gens,
+               "d2h_bytes_per_step": loop.d2h_bytes / loop.gens, "steps": args.e2e_steps,
+               "api": "abl_transport (host buffers, pinned) + host-side normalisation as in PowerIterator::run"}
+        del loop
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_leg(args.cpu_particles, 2, args.cpu_steps)
+        cpu = {"value": r["particles_per_s"], "unit": "particles/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "collisions_per_s": r["collisions_per_s"]}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": particles / (ms * 1e-3), "unit": "particles/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "collisions_per_s": collisions / (ms * 1e-3),
+               "config": {"workload": WORKLOAD, "particles_per_generation_per_gpu": n_local, "particles_per_generation": n_total,
+                          "tally_bins": tally_bins, "source": "deck box source, then the fission source after the warm-up generations",
+                          "l2": "inputs larger than L2 (bank 96 B x 1e7 = 0.96 GB, tally mesh 0.84 GB)", "k_col": k_col,
+                          "collisions_per_particle": collisions / max(particles, 1)},
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": args.traffic, "kernel": "transport_kernel<delta>", "kernel_ms": k_ms,
+                            "grid": [kinfo["grid"], kinfo["block"]], "algorithmic_bytes_per_launch": alg_bytes,
+                            "peak_source": peak_src, "kernel_share_of_step": k_ms * args.steps / ms},
+               "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--particles", type=int, default=10_000_000, help="particles per generation per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-particles", type=int, default=100_000)
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--ref-particles", type=int, default=100_000, help="--impl reference: particles per step")
+    ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the history kernel (profiles/)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

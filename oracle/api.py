@@ -54,7 +54,7 @@ def lib():
                      "orc_find_cells", "orc_sample_source", "orc_set_history_counter", "orc_transport",
                      "orc_get_trace", "orc_ntallies", "orc_tally_size", "orc_tally_shape", "orc_tally_get",
                      "orc_tallies_record", "orc_tallies_clear", "orc_tallies_calc_gen", "orc_cancel_and_normalize",
-                     "orc_run_power_iteration"):
+                     "orc_run_power_iteration", "orc_pi_init", "orc_pi_run"):
             getattr(L, name).argtypes = None
         _lib = L
     return _lib
@@ -242,6 +242,18 @@ class Oracle:
         arr.update(kcol_avg=summ[0], kcol_err=summ[1], ktrk_avg=summ[2], ktrk_err=summ[3], leak_avg=summ[4],
                    leak_err=summ[5], seconds=summ[6], active_particles=summ[7])
         return arr
+
+
+    # stateful generation loop (bench.py CPU legs)
+    def pi_init(self, nignored: int):
+        if lib().orc_pi_init(self.h, C.c_int(int(nignored))) != 0:
+            raise RuntimeError("oracle: " + self._err())
+
+    def pi_run(self, ngen: int) -> dict:
+        out = np.zeros(4)
+        if lib().orc_pi_run(self.h, C.c_int(int(ngen)), out.ctypes.data_as(_PD)) != 0:
+            raise RuntimeError("oracle: " + self._err())
+        return {"seconds": out[0], "particles": out[1], "real_collisions": out[2], "k_col": out[3]}
 
 
 # --- RNG / math known-answer helpers ---

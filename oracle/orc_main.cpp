@@ -1016,7 +1016,6 @@ void* orc_load(const char* path, char* errbuf, int errlen) {
     return nullptr;
   }
 }
-void orc_free(void* h) { delete static_cast<Problem*>(h); }
 
 void orc_set_nparticles(void* h, int n) {
   Problem& P = *static_cast<Problem*>(h);
@@ -1184,55 +1183,112 @@ int orc_cancel_and_normalize(void* h, orc_bank* b, int do_cancel, double* stats6
 
 // Whole PowerIterator::run (k-eigenvalue). results: per generation kcol, ktrk, leak, mig, entropy, bank size
 // summary[0..7] = kcol_avg, kcol_err, ktrk_avg, ktrk_err, leak_avg, leak_err, wall seconds, active particles
+// ---- k-eigenvalue generation loop (PowerIterator::initialize / run, src/power_iterator.cpp:46-133,305-431) ----
+// Stateful so that a caller (bench.py's CPU baseline legs) can time generation by generation.
+struct PIState {
+  std::vector<Particle> bank;
+  int gen = 0, nignored = 0;
+  double active_particles = 0;
+};
+static std::map<Problem*, PIState> g_pi;
+
+static void pi_init(Problem& P, int nignored) {
+  PIState& S = g_pi[&P];
+  P.histories_counter = 0;
+  P.global_histories_counter = 0;
+  S.bank = sample_sources(P, (size_t)P.st.nparticles);  // PowerIterator::initialize
+  P.global_histories_counter += (uint64_t)P.st.nparticles;
+  for (auto& p : S.bank) p.family_id = p.history_id;
+  P.converged = (nignored == 0);
+  if (P.entropy.present) P.entropy.zero();
+  S.gen = 0;
+  S.nignored = nignored;
+  S.active_particles = 0;
+}
+
+// one generation; out5 = k_col, k_trk, leak, mig, entropy
+static void pi_generation(Problem& P, double* out5, uint64_t* nbank_in) {
+  PIState& S = g_pi[&P];
+  Tallies& T = P.tallies;
+  std::vector<Particle>& bank = S.bank;
+  const int g = ++S.gen;
+  if (P.converged) S.active_particles += (double)bank.size();
+  *nbank_in = bank.size();
+  auto next_gen = transport(P, bank, false, nullptr, false);
+  if (next_gen.empty()) throw std::runtime_error("No fission neutrons were produced.");
+  if (P.entropy.present) for (auto& p : next_gen) P.entropy.add_point(p.r, p.wgt);
+  T.calc_gen_values();
+  if (P.st.regional_cancellation && P.cancel.present) perform_regional_cancellation(P, next_gen);
+  normalize_weights(P, next_gen);
+  if (P.converged) {
+    for (const auto& p : next_gen)
+      for (auto& t : T.mesh) if (t.estimator == EST_SOURCE && !t.noise_source) t.score_source(p);
+    T.record_generation();
+  }
+  T.clear_generation();
+  out5[4] = P.entropy.present ? P.entropy.calculate_entropy() : 0.;
+  bank.clear();
+  P.histories_counter = P.global_histories_counter;
+  bank.reserve(next_gen.size());
+  for (auto& p : next_gen) {  // power_iterator.cpp:396-401
+    Particle np(p.r, p.u, p.E, p.wgt, P.histories_counter++);
+    np.initialize_rng(P.st.rng_seed, P.st.rng_stride);
+    np.family_id = p.family_id;
+    bank.push_back(std::move(np));
+  }
+  P.global_histories_counter += (uint64_t)next_gen.size();  // accumulate(node_nparticles); distribute_particles set it to bank.size() (simulation.cpp:128-135)
+  out5[0] = T.k_col; out5[1] = T.k_trk; out5[2] = T.leak; out5[3] = T.mig;
+  if (P.entropy.present) P.entropy.zero();
+  if (g == S.nignored) P.converged = true;
+}
+
+void orc_free(void* h) {
+  g_pi.erase(static_cast<Problem*>(h));
+  delete static_cast<Problem*>(h);
+}
+
+int orc_pi_init(void* h, int nignored) {
+  Problem& P = *static_cast<Problem*>(h);
+  try { pi_init(P, nignored); return 0; } catch (const std::exception& e) { P.error = e.what(); return 1; }
+}
+
+// runs ngen generations; out4 = seconds, particles entering transport, real collisions, last k_col
+int orc_pi_run(void* h, int ngen, double* out4) {
+  Problem& P = *static_cast<Problem*>(h);
+  try {
+    const uint64_t c0 = P.counters.real_collisions;
+    double o5[5] = {0, 0, 0, 0, 0}, particles = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    for (int g = 0; g < ngen; g++) {
+      uint64_t nb = 0;
+      pi_generation(P, o5, &nb);
+      particles += (double)nb;
+    }
+    out4[0] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    out4[1] = particles;
+    out4[2] = (double)(P.counters.real_collisions - c0);
+    out4[3] = o5[0];
+    return 0;
+  } catch (const std::exception& e) { P.error = e.what(); return 1; }
+}
+
 int orc_run_power_iteration(void* h, int ngen, int nignored, double* kcol, double* ktrk, double* leak, double* mig,
                             double* entropy, uint64_t* nbank, double* summary) {
   Problem& P = *static_cast<Problem*>(h);
   try {
     Tallies& T = P.tallies;
-    P.histories_counter = 0;
-    P.global_histories_counter = 0;
-    std::vector<Particle> bank = sample_sources(P, (size_t)P.st.nparticles);  // PowerIterator::initialize
-    P.global_histories_counter += (uint64_t)P.st.nparticles;
-    for (auto& p : bank) p.family_id = p.history_id;
-    P.converged = (nignored == 0);
-    if (P.entropy.present) P.entropy.zero();
+    pi_init(P, nignored);
     auto t0 = std::chrono::steady_clock::now();
-    double active_particles = 0;
     for (int g = 1; g <= ngen; g++) {
-      if (P.converged) active_particles += (double)bank.size();
-      nbank[g - 1] = bank.size();
-      auto next_gen = transport(P, bank, false, nullptr, false);
-      if (next_gen.empty()) throw std::runtime_error("No fission neutrons were produced.");
-      if (P.entropy.present) for (auto& p : next_gen) P.entropy.add_point(p.r, p.wgt);
-      T.calc_gen_values();
-      if (P.st.regional_cancellation && P.cancel.present) perform_regional_cancellation(P, next_gen);
-      normalize_weights(P, next_gen);
-      if (P.converged) {
-        for (const auto& p : next_gen)
-          for (auto& t : T.mesh) if (t.estimator == EST_SOURCE && !t.noise_source) t.score_source(p);
-        T.record_generation();
-      }
-      T.clear_generation();
-      entropy[g - 1] = P.entropy.present ? P.entropy.calculate_entropy() : 0.;
-      bank.clear();
-      P.histories_counter = P.global_histories_counter;
-      bank.reserve(next_gen.size());
-      for (auto& p : next_gen) {  // power_iterator.cpp:396-401
-        Particle np(p.r, p.u, p.E, p.wgt, P.histories_counter++);
-        np.initialize_rng(P.st.rng_seed, P.st.rng_stride);
-        np.family_id = p.family_id;
-        bank.push_back(std::move(np));
-      }
-      P.global_histories_counter += (uint64_t)next_gen.size();  // accumulate(node_nparticles); distribute_particles set it to bank.size() (simulation.cpp:128-135)
-      kcol[g - 1] = T.k_col; ktrk[g - 1] = T.k_trk; leak[g - 1] = T.leak; mig[g - 1] = T.mig;
-      if (P.entropy.present) P.entropy.zero();
-      if (g == nignored) P.converged = true;
+      double o5[5];
+      pi_generation(P, o5, &nbank[g - 1]);
+      kcol[g - 1] = o5[0]; ktrk[g - 1] = o5[1]; leak[g - 1] = o5[2]; mig[g - 1] = o5[3]; entropy[g - 1] = o5[4];
     }
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     summary[0] = T.k_col_avg; summary[1] = T.gen > 0 ? T.err(T.k_col_var) : 0.;
     summary[2] = T.k_trk_avg; summary[3] = T.gen > 0 ? T.err(T.k_trk_var) : 0.;
     summary[4] = T.leak_avg; summary[5] = T.gen > 0 ? T.err(T.leak_var) : 0.;
-    summary[6] = secs; summary[7] = active_particles;
+    summary[6] = secs; summary[7] = g_pi[&P].active_particles;
     return 0;
   } catch (const std::exception& e) { P.error = e.what(); return 1; }
 }
