@@ -46,6 +46,31 @@ def rebalance_plan(counts, rank: int):
     return send, recv
 
 
+def rebalance_bank(src: dict, dst: dict, keys, counts, rank: int, group=None) -> int:
+    """Order-preserving all_to_all of every bank array: src[k][:counts[rank]] -> dst[k][:new count].  Works on any
+    backend (NCCL on the GPUs, gloo in the CPU tests); returns this rank's new count."""
+    send, recv = rebalance_plan(counts, rank)
+    m_new = int(sum(recv))
+    for k in keys:
+        dist.all_to_all_single(dst[k][:m_new], src[k][: int(sum(send))], recv, send, group=group)
+    return m_new
+
+
+def gather_vector(vec: np.ndarray, world: int, device, group=None) -> np.ndarray:
+    """all_gather of a small fp64 vector -> [world, len] on the host."""
+    if world == 1:
+        return vec[None, :].copy()
+    t = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64)).to(device)
+    out = torch.empty(world * len(vec), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out.cpu().numpy().reshape(world, len(vec))
+
+
+def global_first_ids(counts, rank: int, global_counter: int) -> int:
+    """First history id of this rank's slice: exclusive scan of the gathered counts (power_iterator.cpp:389-394)."""
+    return int(global_counter) + int(sum(counts[:rank]))
+
+
 class _DevPtr:
     """Wraps a raw device pointer for torch.as_tensor through __cuda_array_interface__."""
 
@@ -81,13 +106,7 @@ class DistributedPowerIterator:
 
     # ---- helpers ----
     def _gather(self, vec: np.ndarray) -> np.ndarray:
-        """all_gather of a small fp64 vector -> [world, len] on the host."""
-        if self.world == 1:
-            return vec[None, :].copy()
-        t = torch.from_numpy(vec).to(self.device)
-        out = torch.empty(self.world * len(vec), dtype=torch.float64, device=self.device)
-        dist.all_gather_into_tensor(out, t, group=self.group)
-        return out.cpu().numpy().reshape(self.world, len(vec))
+        return gather_vector(vec, self.world, self.device, self.group)
 
     def tally_tensors(self):
         if self._tally_views is None:
@@ -107,14 +126,8 @@ class DistributedPowerIterator:
 
     def _rebalance(self, counts):
         """Moves partition boundaries back to an even split, preserving global order."""
-        send, recv = rebalance_plan(counts, self.rank)
-        m_new = int(sum(recv))
         keys = [k for k in BANK_F64 if k != "wgt2"] + ["id_a", "id_b", "id_c"]
-        spare = self.cur  # the consumed particle bank is free to receive
-        for k in keys:
-            src = self.nxt[k][: int(sum(send))]
-            dst = spare[k][:m_new]
-            dist.all_to_all_single(dst, src, recv, send, group=self.group)
+        m_new = rebalance_bank(self.nxt, self.cur, keys, counts, self.rank, self.group)  # the consumed bank receives
         self.cur, self.nxt = self.nxt, self.cur  # keep the invariant: the fission bank lives in self.nxt
         return m_new
 
@@ -157,7 +170,7 @@ class DistributedPowerIterator:
             if max(abs(c - t) for c, t in zip(counts, target)) > max(0.01 * m_total / self.world, 64):
                 m = self._rebalance(counts)
                 counts = target
-        first = self.global_counter + int(sum(counts[: self.rank]))
+        first = global_first_ids(counts, self.rank, self.global_counter)
         gpu.to_particles_device(self.nxt, m, first)
         self.global_counter += m_total
         self.cur, self.nxt = self.nxt, self.cur

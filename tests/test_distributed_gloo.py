@@ -1,0 +1,78 @@
+"""CPU: the multi-rank host logic of abeille_b200.distributed on a world_size-2 gloo group -- partition plans,
+the order-preserving bank rebalance (all_to_all), the scalar gather and the global history-id scan.  The GPU
+kernels are not involved (no device here); the same functions run over NCCL on the B200s."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from abeille_b200.distributed import even_split, gather_vector, global_first_ids, rebalance_bank, rebalance_plan
+
+
+def test_even_split_and_plan_cover_everything():
+    for world in (1, 2, 3, 8):
+        for counts in ([5] * world, list(range(1, world + 1)), [0] * (world - 1) + [1000], [17, 0, 3, 99, 1, 0, 0, 5][:world]):
+            total = sum(counts)
+            target, bounds = even_split(total, world)
+            assert sum(target) == total and max(target) - min(target) <= 1 and bounds[-1] == total
+            sends = [rebalance_plan(counts, r)[0] for r in range(world)]
+            recvs = [rebalance_plan(counts, r)[1] for r in range(world)]
+            for r in range(world):
+                assert sum(sends[r]) == counts[r] and sum(recvs[r]) == target[r]
+                for q in range(world):
+                    assert sends[r][q] == recvs[q][r]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, counts, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        old = np.concatenate([[0], np.cumsum(counts)])
+        n = counts[rank]
+        cap = sum(counts)
+        # global order = the value itself
+        src = {"x": torch.zeros(cap, dtype=torch.float64), "id_a": torch.zeros(cap, dtype=torch.int64)}
+        src["x"][:n] = torch.arange(old[rank], old[rank + 1], dtype=torch.float64)
+        src["id_a"][:n] = torch.arange(old[rank], old[rank + 1], dtype=torch.int64) * 7
+        dst = {k: torch.full((cap,), -1, dtype=v.dtype) for k, v in src.items()}
+        m = rebalance_bank(src, dst, ["x", "id_a"], counts, rank)
+        allv = gather_vector(np.array([float(m), float(rank), 2.5]), world, torch.device("cpu"))
+        new_counts = [int(v) for v in allv[:, 0]]
+        first = global_first_ids(new_counts, rank, 1000)
+        q.put((rank, m, dst["x"][:m].numpy().copy(), dst["id_a"][:m].numpy().copy(), allv, first))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("counts", [[10, 30], [0, 41], [25, 25], [1000, 3]])
+def test_rebalance_preserves_global_order_on_two_ranks(counts):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, counts, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = sum(counts)
+    target, bounds = even_split(total, world)
+    assert [r[1] for r in res] == target
+    xs = np.concatenate([r[2] for r in res])
+    assert np.array_equal(xs, np.arange(total, dtype=np.float64))          # global order preserved
+    assert np.array_equal(np.concatenate([r[3] for r in res]), np.arange(total) * 7)
+    for r in res:
+        assert np.array_equal(r[4][:, 1], [0.0, 1.0]) and np.all(r[4][:, 2] == 2.5)
+        assert r[5] == 1000 + int(bounds[r[0]])                             # contiguous global history ids
