@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "bank_ops.cuh"
+#include "history.cuh"
 
 using namespace abl;
 
@@ -56,7 +57,9 @@ struct abl_context {
   uint64_t stage_in_cap = 0, stage_out_cap = 0;
   double* probe_buf = nullptr;
   uint64_t probe_cap = 0;
-  int blocks_per_sm[3] = {0, 0, 0};
+  int blocks_per_sm[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+  uint64_t* rng_scratch = nullptr;  // pcg32 states seeded on the device when the caller passes id_c = NULL
+  uint64_t rng_cap = 0;
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_kernel_ms = 0.f;
@@ -256,16 +259,20 @@ int alloc_bank(abl_handle h, BankView& b, uint64_t cap) {
   return ABL_OK;
 }
 
-template <int TRK>
+template <int TRK, bool TRACE>
 int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s) {
-  auto kern = transport_kernel<TRK, false>;
-  if (h->blocks_per_sm[TRK] == 0) {
+  // surface tracking: per-lane history loop (transport.cuh); delta / carter: staged warp-synchronous loop (history.cuh)
+  void (*kern)(const DevProblem, const RunArgs) = nullptr;
+  if (TRK == ABL_TRACK_SURFACE) kern = transport_kernel<ABL_TRACK_SURFACE, false>;
+  else kern = history_kernel<(TRK == ABL_TRACK_SURFACE ? ABL_TRACK_DELTA : TRK), TRACE>;
+  int& bps = h->blocks_per_sm[TRK][TRACE ? 1 : 0];
+  if (bps == 0) {
     int nb = 0;
     ABL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 128, 0));
     if (nb < 1) nb = 1;
-    h->blocks_per_sm[TRK] = nb;
+    bps = nb;
   }
-  uint64_t blocks = (uint64_t)h->sm_count * h->blocks_per_sm[TRK];
+  uint64_t blocks = (uint64_t)h->sm_count * bps;
   const uint64_t need = (n + 127) / 128;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
@@ -276,11 +283,23 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
       if (h->secondaries) cudaFree(h->secondaries);
       h->secondaries = nullptr;
       h->sec_threads = 0;
-      const uint64_t cap = (uint64_t)h->sm_count * h->blocks_per_sm[TRK] * 128;
+      const uint64_t cap = (uint64_t)h->sm_count * bps * 128;
       ABL_CUDA(h, cudaMalloc(&h->secondaries, cap * ABL_SEC_CAP * 9 * sizeof(double)));
       h->sec_threads = cap;
     }
     B.secondaries = h->secondaries;
+  }
+  if (TRK != ABL_TRACK_SURFACE && B.bank.id_c == nullptr) {  // seed(seed); advance(stride * history id) for the whole bank
+    if (n > h->rng_cap) {
+      if (h->rng_scratch) cudaFree(h->rng_scratch);
+      h->rng_scratch = nullptr;
+      h->rng_cap = 0;
+      ABL_CUDA(h, cudaMalloc(&h->rng_scratch, (n + n / 4 + 1024) * sizeof(uint64_t)));
+      h->rng_cap = n + n / 4 + 1024;
+    }
+    seed_streams_kernel<<<grid_for(h, n, 256), 256, 0, s>>>(h->P, B.bank.id_a, n, h->rng_scratch);
+    h->launches++;
+    B.bank.id_c = h->rng_scratch;
   }
   cudaEventRecord(h->ev0, s);
   kern<<<(unsigned)blocks, 128, 0, s>>>(h->P, B);
@@ -289,6 +308,11 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
   h->launches++;
   ABL_CUDA(h, cudaGetLastError());
   return ABL_OK;
+}
+
+template <int TRK>
+int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s, bool trace) {
+  return trace ? launch_transport<TRK, true>(h, A, n, s) : launch_transport<TRK, false>(h, A, n, s);
 }
 
 int status_from_device_error(abl_handle h, const DevSmall& sm) {
@@ -339,9 +363,9 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
   A.converged = params->converged;
   if (N > 0) {
     switch (h->P.tracking) {
-      case ABL_TRACK_SURFACE: rc = launch_transport<ABL_TRACK_SURFACE>(h, A, N, s); break;
-      case ABL_TRACK_DELTA: rc = launch_transport<ABL_TRACK_DELTA>(h, A, N, s); break;
-      default: rc = launch_transport<ABL_TRACK_CARTER>(h, A, N, s); break;
+      case ABL_TRACK_SURFACE: rc = launch_transport<ABL_TRACK_SURFACE, false>(h, A, N, s); break;
+      case ABL_TRACK_DELTA: rc = launch_transport<ABL_TRACK_DELTA>(h, A, N, s, params->trace != 0); break;
+      default: rc = launch_transport<ABL_TRACK_CARTER>(h, A, N, s, params->trace != 0); break;
     }
     if (rc) return rc;
     // fission bank in the reference's order: offsets = exclusive scan of per-history counts
@@ -391,7 +415,7 @@ void abl_destroy(abl_handle h) {
   }
   for (void* p : {(void*)h->sites, (void*)h->nfis, (void*)h->offsets, (void*)h->tile_sums, (void*)h->tr_flights, (void*)h->tr_real,
                   (void*)h->tr_virtual, (void*)h->tr_hash, (void*)h->tr_rng, (void*)h->small_dev, (void*)h->secondaries,
-                  (void*)h->cancel.sum_w, (void*)h->cancel.sum_w2, (void*)h->cancel.count, (void*)h->probe_buf})
+                  (void*)h->cancel.sum_w, (void*)h->cancel.sum_w2, (void*)h->cancel.count, (void*)h->probe_buf, (void*)h->rng_scratch})
     if (p) cudaFree(p);
   free_bank(h->stage_in);
   free_bank(h->stage_out);
@@ -535,6 +559,7 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
       if (CU(cudaMemset(*arr, 0, d.size * sizeof(double)), "cudaMemset(tally)")) return bail(ABL_ERR_CUDA);
     }
   }
+  if (p->ntallies > 0) UP(P.tally, p->ntallies, P.tally_dev);
   P.nsources = p->nsources;
   UP(p->sources, p->nsources, P.sources);
   if (p->nsources >= 2) {

@@ -58,7 +58,8 @@ struct Surf {  // register copy of one table row
   int type, bc;
   double p0, p1, p2, p3, p4, p5, p6;
 };
-__device__ __forceinline__ Surf load_surface(const DevProblem& P, int i) {
+template <class PT>
+__device__ __forceinline__ Surf load_surface(const PT& P, int i) {
   const abl_surface* s = P.surfaces + i;
   Surf r;
   r.type = __ldg(&s->type);
@@ -263,7 +264,8 @@ __device__ inline bool cell_is_inside(const DevProblem& P, int ci, const V3& r, 
 }
 
 // nearest surface of the cell along u (cell.cpp:79-142); bc_only = distance_to_boundary_condition
-__device__ inline void cell_distance(const DevProblem& P, int ci, const V3& r, const V3& u, int on_surf, bool bc_only,
+template <class PT>
+__device__ inline void cell_distance(const PT& P, int ci, const V3& r, const V3& u, int on_surf, bool bc_only,
                                      double& min_dist, int& i_surf) {
   min_dist = ABL_INF;
   i_surf = 0;
@@ -349,6 +351,21 @@ __device__ inline double distance_to_tile_boundary(const Lat& L, const V3& r_loc
   return dist;
 }
 
+// the geometry tables alone (what a non-inlined helper needs; passing DevProblem by reference to a real
+// function call would force a local-memory copy of the whole kernel parameter block)
+struct GeoTables {
+  const abl_surface* surfaces;
+  const abl_cell* cells;
+  const int32_t* rpn;
+  const abl_universe* universes;
+  const int32_t* ucells;
+  const int32_t* tiles;
+  int32_t root;
+};
+__device__ __forceinline__ GeoTables geo_tables(const DevProblem& P) {
+  return GeoTables{P.surfaces, P.cells, P.rpn, P.universes, P.ucells, P.tiles, P.root};
+}
+
 // ---- boundaries ------------------------------------------------------------------------------------
 struct Boundary {  // include/geometry/boundary.hpp:33-42
   double distance;
@@ -359,7 +376,8 @@ struct Boundary {  // include/geometry/boundary.hpp:33-42
 
 // candidate (d, i_surf) from a cell against the running nearest boundary (tracker.hpp:104-131,
 // cell_universe.cpp:121-147): takes it when closer by more than BOUNDRY_TOL and a surface was found
-__device__ __forceinline__ void take_cell_candidate(const DevProblem& P, double d, int i_surf, const V3& r, const V3& u,
+template <class PT>
+__device__ __forceinline__ void take_cell_candidate(const PT& P, double d, int i_surf, const V3& r, const V3& u,
                                                     Boundary& b) {
   if (d < b.distance && fabs(d - b.distance) > ABL_BOUNDRY_TOL) {
     const int tmp_token = iabs(i_surf);
@@ -375,7 +393,8 @@ __device__ __forceinline__ void take_cell_candidate(const DevProblem& P, double 
 }
 
 // Universe::get_boundary_condition (cell_universe.cpp:111-154, lattice.cpp:77-92)
-__device__ inline Boundary universe_boundary_condition(const DevProblem& P, int uni, const V3& r, const V3& u, int on_surf) {
+template <class PT>
+__device__ inline Boundary universe_boundary_condition(const PT& P, int uni, const V3& r, const V3& u, int on_surf) {
   Boundary b{ABL_INF, -1, ABL_BC_VACUUM, 0};
   const abl_universe* U = P.universes + uni;
   while (__ldg(&U->type) != ABL_UNI_CELLS) {  // lattices defer to their outer universe
@@ -552,7 +571,8 @@ __device__ inline void cursor_get_current(const DevProblem& P, Cursor& c, const 
 }
 
 // Tracker::get_boundary_condition (tracker.hpp:94-161)
-__device__ inline Boundary cursor_boundary_condition(const DevProblem& P, const Cursor& c, const V3& u) {
+template <class PT>
+__device__ inline Boundary cursor_boundary_condition(const PT& P, const Cursor& c, const V3& u) {
   if (c.cell < 0) return universe_boundary_condition(P, P.root, frame_r(c, 0), u, c.token);
   Boundary b{ABL_INF, -1, ABL_BC_VACUUM, 0};
   for (int it = 0; it < c.np; it++) {

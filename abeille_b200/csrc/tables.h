@@ -63,6 +63,7 @@ struct DevProblem {
   // tallies
   int32_t ntallies, n_coll_tallies, n_tl_tallies;
   DevTally tally[ABL_MAX_TALLIES];
+  const DevTally* tally_dev;  // the same descriptors in global memory (for non-inlined scorers)
   // sources
   int32_t nsources;
   const abl_source* sources;
