@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -163,6 +164,51 @@ int validate(abl_handle h, const abl_problem* p) {
   }
   if (p->tracking != ABL_TRACK_SURFACE && !p->sampling_xs) return fail(h, ABL_ERR_INVALID, "sampling_xs missing");
   return ABL_OK;
+}
+
+// Cell regions that are a pure intersection of axis-aligned half-spaces (a box) or a single z-cylinder sense
+// get a compiled descriptor (tables.h: CellFast); everything else stays CF_GENERIC.
+std::vector<CellFast> compile_cells(const abl_problem* p) {
+  std::vector<CellFast> out((size_t)p->ncells);
+  const double inf = std::numeric_limits<double>::infinity();
+  for (int c = 0; c < p->ncells; c++) {
+    CellFast& f = out[(size_t)c];
+    std::memset(&f, 0, sizeof f);
+    f.kind = CF_GENERIC;
+    const abl_cell& cl = p->cells[c];
+    if (!cl.simple || cl.rpn_len < 1) continue;
+    bool all_planes = true;
+    for (int k = 0; k < cl.rpn_len; k++) {
+      const int32_t t = p->rpn[cl.rpn_offset + k];
+      if (t >= ABL_OP_UNION) { all_planes = false; break; }
+      const abl_surface& s = p->surfaces[(t < 0 ? -t : t) - 1];
+      if (s.type != ABL_SURF_XPLANE && s.type != ABL_SURF_YPLANE && s.type != ABL_SURF_ZPLANE) all_planes = false;
+    }
+    if (all_planes) {
+      f.kind = CF_BOX;
+      for (int a = 0; a < 3; a++) { f.a[2 * a] = -inf; f.a[2 * a + 1] = inf; }
+      for (int k = 0; k < cl.rpn_len; k++) {
+        const int32_t t = p->rpn[cl.rpn_offset + k];
+        const abl_surface& s = p->surfaces[(t < 0 ? -t : t) - 1];
+        const int a = s.type - ABL_SURF_XPLANE;
+        if (t > 0) { if (s.p[0] > f.a[2 * a]) f.a[2 * a] = s.p[0]; }          // r - p0 > 0
+        else { if (s.p[0] < f.a[2 * a + 1]) f.a[2 * a + 1] = s.p[0]; }        // r - p0 < 0
+      }
+      continue;
+    }
+    if (cl.rpn_len == 1) {
+      const int32_t t = p->rpn[cl.rpn_offset];
+      const abl_surface& s = p->surfaces[(t < 0 ? -t : t) - 1];
+      if (s.type == ABL_SURF_ZCYL) {
+        f.kind = CF_ZCYL;
+        f.sense = t < 0 ? -1 : 1;
+        f.a[0] = s.p[0];
+        f.a[1] = s.p[1];
+        f.a[2] = s.p[2] * s.p[2];  // the same IEEE product the generic evaluator forms (zcylinder.cpp:33-47)
+      }
+    }
+  }
+  return out;
 }
 
 DevMesh3 make_mesh3(const abl_mesh3& m, const double* tally_eb_dev) {
@@ -506,6 +552,10 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
   UP(p->universes, p->nuniverses, P.universes);
   UP(p->universe_cells, p->n_universe_cells, P.ucells);
   UP(p->lattice_tiles, p->n_lattice_tiles, P.tiles);
+  {
+    std::vector<CellFast> cf = compile_cells(p);
+    UP(cf.data(), cf.size(), P.cellfast);
+  }
   const size_t MG = (size_t)M * G, MGG = MG * G;
   UP(p->xs_total, MG, P.Et);
   UP(p->xs_absorption, MG, P.Ea);
@@ -516,7 +566,16 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
   UP(p->speeds, MG, P.speed);
   UP(p->chi_cdf, MGG, P.chi_cp);
   UP(p->scatter_cdf, MGG, P.ps_cp);
-  UP(p->angle, MGG, P.angle);
+  {
+    // default isotropic tables {mu:[-1,1], pdf:[.5,.5], cdf:[0,1]} are marked n = -2: sample_mu has a closed form
+    std::vector<abl_angle_table> at(p->angle, p->angle + MGG);
+    for (auto& a : at) {
+      if (a.n != 2 || a.offset < 0 || a.offset + 2 > p->n_angle_points) continue;
+      const double *mu = p->angle_mu + a.offset, *pdf = p->angle_pdf + a.offset, *cdf = p->angle_cdf + a.offset;
+      if (mu[0] == -1. && mu[1] == 1. && pdf[0] == 0.5 && pdf[1] == 0.5 && cdf[0] == 0. && cdf[1] == 1.) a.n = -2;
+    }
+    UP(at.data(), MGG, P.angle);
+  }
   UP(p->angle_mu, p->n_angle_points, P.amu);
   UP(p->angle_pdf, p->n_angle_points, P.apdf);
   UP(p->angle_cdf, p->n_angle_points, P.acdf);
@@ -560,6 +619,23 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
     }
   }
   if (p->ntallies > 0) UP(P.tally, p->ntallies, P.tally_dev);
+  {
+    std::vector<double> mid((size_t)G);
+    for (int g = 0; g < G; g++) mid[(size_t)g] = 0.5 * (p->energy_bounds[g] + p->energy_bounds[g + 1]);
+    UP(mid.data(), mid.size(), P.gmid);
+    std::vector<int32_t> gb((size_t)(p->ntallies > 0 ? p->ntallies : 1) * G, -1);
+    for (int t = 0; t < p->ntallies; t++) {
+      const abl_mesh_tally& mt = p->tallies[t];
+      const double* eb = p->tally_energy_bounds + mt.ebounds_offset;
+      for (int g = 0; g < G; g++)
+        for (int e = 0; e < mt.n_energy_bins; e++)  // "<= E <=", first match (collision_mesh_tally.cpp:50-56)
+          if (eb[e] <= mid[(size_t)g] && mid[(size_t)g] <= eb[e + 1]) {
+            gb[(size_t)t * G + g] = e;
+            break;
+          }
+    }
+    UP(gb.data(), gb.size(), P.tally_gbin);
+  }
   P.nsources = p->nsources;
   UP(p->sources, p->nsources, P.sources);
   if (p->nsources >= 2) {

@@ -209,10 +209,26 @@ __device__ __forceinline__ double surf_distance(const Surf& s, const V3& r, cons
   }
 }
 
+// the geometry tables alone (what a non-inlined helper needs; passing DevProblem by reference to a real
+// function call would force a local-memory copy of the whole kernel parameter block)
+struct GeoTables {
+  const abl_surface* surfaces;
+  const abl_cell* cells;
+  const int32_t* rpn;
+  const abl_universe* universes;
+  const int32_t* ucells;
+  const int32_t* tiles;
+  int32_t root;
+};
+__device__ __forceinline__ GeoTables geo_tables(const DevProblem& P) {
+  return GeoTables{P.surfaces, P.cells, P.rpn, P.universes, P.ucells, P.tiles, P.root};
+}
+
 // ---- cells -------------------------------------------------------------------------------------
 __device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
 
-__device__ inline bool cell_is_inside(const DevProblem& P, int ci, const V3& r, const V3& u, int on_surf) {
+template <class PT>
+__device__ inline bool cell_is_inside(const PT& P, int ci, const V3& r, const V3& u, int on_surf) {
   const abl_cell* c = P.cells + ci;
   const int off = __ldg(&c->rpn_offset), len = __ldg(&c->rpn_len);
   if (__ldg(&c->simple)) {
@@ -261,6 +277,34 @@ __device__ inline bool cell_is_inside(const DevProblem& P, int ci, const V3& r, 
   }
   if (i_stck == 0) return (stck & 1ULL) != 0;
   return true;
+}
+
+// the generic evaluator as a real function call: keeps the cold path out of the hot loop's instruction footprint
+__device__ __noinline__ bool cell_is_inside_nl(const GeoTables G, int ci, const V3 r, const V3 u, int on_surf) {
+  return cell_is_inside(G, ci, r, u, on_surf);
+}
+
+// Cell::is_inside through the compiled descriptor (tables.h: CellFast).  Falls back to the generic evaluator
+// when the particle sits on a surface or is within SURFACE_COINCIDENT of one (direction-dependent ties).
+__device__ __forceinline__ bool cell_is_inside_fast(const DevProblem& P, int ci, const V3& r, const V3& u, int on_surf) {
+  const CellFast* cf = P.cellfast + ci;
+  const int kind = __ldg(&cf->kind);
+  if (on_surf == 0 && kind == CF_BOX) {
+    const double2 bx = __ldg(reinterpret_cast<const double2*>(&cf->a[0]));
+    const double2 by = __ldg(reinterpret_cast<const double2*>(&cf->a[2]));
+    const double2 bz = __ldg(reinterpret_cast<const double2*>(&cf->a[4]));
+    const double e0 = r.x - bx.x, e1 = r.x - bx.y, e2 = r.y - by.x, e3 = r.y - by.y, e4 = r.z - bz.x, e5 = r.z - bz.y;
+    const double T = ABL_SURFACE_COINCIDENT;
+    const bool tie = (fabs(e0) <= T) | (fabs(e1) <= T) | (fabs(e2) <= T) | (fabs(e3) <= T) | (fabs(e4) <= T) | (fabs(e5) <= T);
+    if (!tie) return (e0 > T) & (e1 < -T) & (e2 > T) & (e3 < -T) & (e4 > T) & (e5 < -T);
+  } else if (on_surf == 0 && kind == CF_ZCYL) {
+    const double2 xy = __ldg(reinterpret_cast<const double2*>(&cf->a[0]));
+    const double r2 = __ldg(&cf->a[2]);
+    const double x = r.x - xy.x, y = r.y - xy.y;
+    const double e = y * y + x * x - r2;
+    if (fabs(e) > ABL_SURFACE_COINCIDENT) return (__ldg(&cf->sense) < 0) ? (e < 0.) : (e > 0.);
+  }
+  return cell_is_inside_nl(geo_tables(P), ci, r, u, on_surf);
 }
 
 // nearest surface of the cell along u (cell.cpp:79-142); bc_only = distance_to_boundary_condition
@@ -351,21 +395,6 @@ __device__ inline double distance_to_tile_boundary(const Lat& L, const V3& r_loc
   return dist;
 }
 
-// the geometry tables alone (what a non-inlined helper needs; passing DevProblem by reference to a real
-// function call would force a local-memory copy of the whole kernel parameter block)
-struct GeoTables {
-  const abl_surface* surfaces;
-  const abl_cell* cells;
-  const int32_t* rpn;
-  const abl_universe* universes;
-  const int32_t* ucells;
-  const int32_t* tiles;
-  int32_t root;
-};
-__device__ __forceinline__ GeoTables geo_tables(const DevProblem& P) {
-  return GeoTables{P.surfaces, P.cells, P.rpn, P.universes, P.ucells, P.tiles, P.root};
-}
-
 // ---- boundaries ------------------------------------------------------------------------------------
 struct Boundary {  // include/geometry/boundary.hpp:33-42
   double distance;
@@ -452,6 +481,7 @@ __device__ __forceinline__ bool push_pad(Cursor& c, int info, int tx = 0, int ty
 
 // Universe::get_cell(stack, r, u, on_surf) made iterative (cell_universe.cpp:72-109, rect_lattice.cpp:132-207).
 // Descends from universe `uni` whose coordinates are frame f; returns the material cell or -1 (lost).
+template <bool FAST = false>
 __device__ inline int descend(const DevProblem& P, Cursor& c, int uni, int f, const V3& u) {
   for (;;) {
     const abl_universe* U = P.universes + uni;
@@ -462,7 +492,7 @@ __device__ inline int descend(const DevProblem& P, Cursor& c, int uni, int f, co
       int found = -1;
       for (int k = 0; k < n; k++) {
         const int ci = __ldg(&P.ucells[off + k]);
-        if (cell_is_inside(P, ci, r, u, c.token)) {
+        if (FAST ? cell_is_inside_fast(P, ci, r, u, c.token) : cell_is_inside(P, ci, r, u, c.token)) {
           found = ci;
           break;
         }

@@ -39,7 +39,7 @@ __device__ __forceinline__ int cursor_validate(const DevProblem& P, const Cursor
     const int info = c.pinfo[it];
     const int type = pad_type(info);
     if (type == PAD_CELL) {
-      if (!cell_is_inside(P, pad_index(info), frame_r(c, pad_frame(info)), u, c.token)) {
+      if (!cell_is_inside_fast(P, pad_index(info), frame_r(c, pad_frame(info)), u, c.token)) {
         first_bad = it;
         break;
       }
@@ -75,7 +75,7 @@ __device__ __forceinline__ void cursor_relocate(const DevProblem& P, Cursor& c, 
     c.nf = 1;
   }
   for (;;) {
-    c.cell = descend(P, c, uni, f, u);
+    c.cell = descend<true>(P, c, uni, f, u);
     if (c.cell >= 0 || full) break;
     full = true;  // partial re-descent failed: full restart from the root
     c.np = 0;
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(128, 4) history_kernel(const DevProblem P, con
         h.w = A.bank.wgt[idx];
         h.w2 = 0.;
         h.g = group_of(P, h.E);
+        h.emid = h.g < P.G && h.E == group_mid(P, h.g);
         h.rng = A.bank.id_c[idx];  // pcg32 state: seeded by seed_streams_kernel / source sampling
         h.hash = 1469598103934665603ULL;
         h.daughter = 0;

@@ -28,6 +28,18 @@ struct DevTally {
   uint64_t size;
 };
 
+// Compiled form of a cell region for the common shapes (built once by abl_create).  The boolean it yields is
+// the one Cell::is_inside (src/cell.cpp:144-201) yields; whenever a point is within SURFACE_COINCIDENT of one
+// of the cell's surfaces -- where the reference breaks the tie with the flight direction -- or the particle
+// sits on a surface (token != 0), the generic evaluator is used instead.
+enum { CF_GENERIC = 0, CF_BOX = 1, CF_ZCYL = 2 };
+struct alignas(16) CellFast {
+  double a[6];     // CF_BOX: lo/hi per axis (x0 < x < x1 ...), +-inf when unbounded; CF_ZCYL: x0, y0, R*R
+  int32_t kind;
+  int32_t sense;   // CF_ZCYL: -1 inside the cylinder, +1 outside
+  int32_t pad_[2];
+};
+
 struct DevMesh3 {
   int32_t present, Nx, Ny, Nz, Ne;
   const double* eedges;  // Ne+1 or null
@@ -50,6 +62,7 @@ struct DevProblem {
   const abl_universe* universes;
   const int32_t* ucells;
   const int32_t* tiles;
+  const CellFast* cellfast;  // [ncells]
   // materials [M*G]
   int32_t M;
   const double *Et, *Ea, *Ef, *Es, *nu, *nud, *speed;
@@ -63,7 +76,9 @@ struct DevProblem {
   // tallies
   int32_t ntallies, n_coll_tallies, n_tl_tallies;
   DevTally tally[ABL_MAX_TALLIES];
-  const DevTally* tally_dev;  // the same descriptors in global memory (for non-inlined scorers)
+  const DevTally* tally_dev;
+  const int32_t* tally_gbin;  // [ntallies*G] energy bin of each tally for E = mid-point of group g (-1: none)
+  const double* gmid;         // [G] group mid-points 0.5*(b[g]+b[g+1])  // the same descriptors in global memory (for non-inlined scorers)
   // sources
   int32_t nsources;
   const abl_source* sources;

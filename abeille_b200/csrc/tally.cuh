@@ -47,12 +47,12 @@ __device__ __forceinline__ double quantity_factor(int quantity, double w, double
 }
 
 // returns 1 when a bin was scored
-__device__ inline int score_collision(const DevTally& t, const V3& r, double E, double w, double w2, const MatXS& m) {
+// l = energy bin of the particle (tally_energy_bin, or the per-group table for mid-point energies)
+__device__ inline int score_collision(const DevTally& t, const V3& r, int l, double w, double w2, const MatXS& m) {
   double scr = 1. / (m.Et * t.net_weight);
   const int i = (int)floor((r.x - t.lowx) * t.dx_inv);
   const int j = (int)floor((r.y - t.lowy) * t.dy_inv);
   const int k = (int)floor((r.z - t.lowz) * t.dz_inv);
-  const int l = tally_energy_bin(t, E);
   if (l == -1) return 0;
   if (i >= 0 && i < t.Nx && j >= 0 && j < t.Ny && k >= 0 && k < t.Nz) {
     if (t.quantity <= ABL_Q_IMAG_FLUX) scr *= quantity_factor(t.quantity, w, w2, m);

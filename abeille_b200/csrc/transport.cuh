@@ -71,6 +71,7 @@ struct Hist {
   int g, mat;  // energy group, material of the MaterialHelper
   int nsec;
   bool alive;
+  bool emid;  // E is exactly the mid-point of group g (true after any scatter / for fission sites): tally bins by table
 };
 
 struct Acc {  // per-thread accumulators, reduced once at kernel exit
@@ -86,9 +87,7 @@ __device__ __forceinline__ int group_of(const DevProblem& P, double E) {  // mg_
     if (__ldg(&P.ebounds[i]) <= E && E < __ldg(&P.ebounds[i + 1])) break;
   return i;
 }
-__device__ __forceinline__ double group_mid(const DevProblem& P, int g) {
-  return 0.5 * (__ldg(&P.ebounds[g]) + __ldg(&P.ebounds[g + 1]));
-}
+__device__ __forceinline__ double group_mid(const DevProblem& P, int g) { return __ldg(&P.gmid[g]); }  // 0.5*(b[g]+b[g+1])
 
 __device__ __forceinline__ void raise_error(const RunArgs& A, int code, uint64_t history_id) {
   if (atomicCAS(&A.error[0], 0, code) == 0) {
@@ -97,11 +96,10 @@ __device__ __forceinline__ void raise_error(const RunArgs& A, int code, uint64_t
   }
 }
 
-// MGAngleDistribution::sample_mu (mg_angle_distribution.hpp:45-60,92-101)
-__device__ __forceinline__ double sample_mu(const DevProblem& P, const abl_angle_table* at, uint64_t& rng) {
-  const double xi = rng_rand(rng);
-  const int off = __ldg(&at->offset), n = __ldg(&at->n);
-  const double* cdf = P.acdf + off;
+// inverse CDF on a linearly interpolable pdf (mg_angle_distribution.hpp:45-60)
+__device__ __noinline__ double sample_mu_table(const double* __restrict__ acdf, const double* __restrict__ amu,
+                                               const double* __restrict__ apdf, int off, int n, double xi) {
+  const double* cdf = acdf + off;
   int lo = 0, len = n;
   while (len > 0) {  // std::lower_bound
     const int half = len >> 1;
@@ -113,14 +111,24 @@ __device__ __forceinline__ double sample_mu(const DevProblem& P, const abl_angle
     }
   }
   int l = lo;
-  const double* mu = P.amu + off;
+  const double* mu = amu + off;
   if (xi == __ldg(&cdf[l])) return __ldg(&mu[l]);
   l--;
-  const double* pdf = P.apdf + off;
+  const double* pdf = apdf + off;
   const double p0 = __ldg(&pdf[l]), p1 = __ldg(&pdf[l + 1]);
   if (p0 == p1) return __ldg(&mu[l]) + ((xi - __ldg(&cdf[l])) / p0);
   const double m = (p1 - p0) / (__ldg(&mu[l + 1]) - __ldg(&mu[l]));
   return __ldg(&mu[l]) + (1. / m) * (sqrt(p0 * p0 + 2. * m * (xi - __ldg(&cdf[l]))) - p0);
+}
+
+// MGAngleDistribution::sample_mu (mg_angle_distribution.hpp:45-60,92-101)
+__device__ __forceinline__ double sample_mu(const DevProblem& P, const abl_angle_table* at, uint64_t& rng) {
+  const double xi = rng_rand(rng);
+  const int off = __ldg(&at->offset), n = __ldg(&at->n);
+  // n < 0 marks the default isotropic table {mu:[-1,1], pdf:[.5,.5], cdf:[0,1]} (mg_angle_distribution.cpp:32-33):
+  // the general formula below reduces to this expression, evaluated identically
+  if (n < 0) return -1. + ((xi - 0.) / 0.5);
+  return sample_mu_table(P.acdf, P.amu, P.apdf, off, n, xi);
 }
 
 // warp-aggregated append of one fission site
@@ -136,6 +144,51 @@ __device__ __forceinline__ void append_site(const RunArgs& A, const Site& s) {
     double2* dst = reinterpret_cast<double2*>(A.sites + slot);
 #pragma unroll
     for (int q = 0; q < 5; q++) dst[q] = src[q];
+  }
+}
+
+// n_new x MGNuclide::sample_fission (mg_nuclide.cpp:504-543) + Particle::add_fission_particle, as a real function
+// call: about 2 % of the collisions bank sites, so this stays out of the hot loop's instruction footprint.
+struct FissionTables {
+  const double* chi_cp;
+  const double* dg_cp;
+  const int32_t* dg_off;
+  const double* gmid;
+  int G;
+};
+__device__ __noinline__ void bank_fission_sites(const FissionTables T, Site* sites, unsigned long long* n_sites, uint64_t capacity,
+                                                uint64_t& rng, const V3 r, const V3 u, double w, uint32_t parent, uint32_t daughter0,
+                                                int n_new, int mat, int mg, double P_delayed) {
+  const int dg0 = __ldg(&T.dg_off[mat]), ndg = __ldg(&T.dg_off[mat + 1]) - dg0;
+  for (int i = 0; i < n_new; i++) {
+    int ei = 0;
+    if (T.G >= 2) ei = rng_discrete(rng, T.chi_cp + (size_t)mg * T.G, T.G);
+    const double E_out = __ldg(&T.gmid[ei]);
+    const double mu = 2. * rng_rand(rng) - 1.;
+    const double phi = 2. * ABL_PI * rng_rand(rng);
+    const V3 dir = rotate_direction(u, mu, phi);
+    if (rng_rand(rng) < P_delayed) {
+      if (ndg >= 2) (void)rng_discrete(rng, T.dg_cp + dg0, ndg);  // delayed family: only matters in noise mode
+    }
+    Site s;
+    s.x = r.x; s.y = r.y; s.z = r.z;
+    s.ux = dir.x; s.uy = dir.y; s.uz = dir.z;
+    s.E = E_out;
+    s.w = w > 0. ? 1. : -1.;
+    s.w2 = 0.;
+    s.parent = parent;
+    s.daughter = daughter0 + (uint32_t)i;
+    cg::coalesced_group grp = cg::coalesced_threads();
+    unsigned long long base = 0;
+    if (grp.thread_rank() == 0) base = atomicAdd(n_sites, (unsigned long long)grp.size());
+    base = grp.shfl(base, 0);
+    const unsigned long long slot = base + grp.thread_rank();
+    if (slot < capacity) {  // 80 B record written as five 16 B stores
+      const double2* src = reinterpret_cast<const double2*>(&s);
+      double2* dst = reinterpret_cast<double2*>(sites + slot);
+#pragma unroll
+      for (int q = 0; q < 5; q++) dst[q] = src[q];
+    }
   }
 }
 
@@ -164,7 +217,10 @@ __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A,
   if (A.converged && P.n_coll_tallies) {
     const MatXS mx{Et, Ea, Ef, __ldg(&P.Es[mg])};
     for (int t = 0; t < P.ntallies; t++)
-      if (P.tally[t].estimator == ABL_EST_COLLISION) acc.coll_scores += score_collision(P.tally[t], h.r, h.E, h.w, h.w2, mx);
+      if (P.tally[t].estimator == ABL_EST_COLLISION) {
+        const int l = h.emid ? __ldg(&P.tally_gbin[t * P.G + h.g]) : tally_energy_bin(P.tally[t], h.E);
+        acc.coll_scores += score_collision(P.tally[t], h.r, l, h.w, h.w2, mx);
+      }
   }
   {
     const double k_col_scr = h.w * (nu * Ef) / Et;
@@ -181,31 +237,12 @@ __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A,
   // make_fission_neutrons (transporter.cpp:358-487)
   const int n_new = (int)floor(fabs(k_abs_scr) / A.k_col + rng_rand(h.rng));
   if (n_new > 0) {
-    const double P_delayed = __ldg(&P.nud[mg]) / nu;
-    const int dg0 = __ldg(&P.dg_off[h.mat]), ndg = __ldg(&P.dg_off[h.mat + 1]) - dg0;
-    for (int i = 0; i < n_new; i++) {
-      // MGNuclide::sample_fission (mg_nuclide.cpp:504-543)
-      int ei = 0;
-      if (P.G >= 2) ei = rng_discrete(h.rng, P.chi_cp + (size_t)mg * P.G, P.G);
-      const double E_out = group_mid(P, ei);
-      const double mu = 2. * rng_rand(h.rng) - 1.;
-      const double phi = 2. * ABL_PI * rng_rand(h.rng);
-      const V3 dir = rotate_direction(h.u, mu, phi);
-      if (rng_rand(h.rng) < P_delayed) {
-        if (ndg >= 2) (void)rng_discrete(h.rng, P.dg_cp + dg0, ndg);  // delayed family: only matters in noise mode
-      }
-      Site s;
-      s.x = h.r.x; s.y = h.r.y; s.z = h.r.z;
-      s.ux = dir.x; s.uy = dir.y; s.uz = dir.z;
-      s.E = E_out;
-      s.w = h.w > 0. ? 1. : -1.;
-      s.w2 = 0.;
-      s.parent = h.idx;
-      s.daughter = h.daughter++;
-      append_site(A, s);
-      h.n_fis++;
-      acc.sites++;
-    }
+    const FissionTables ft{P.chi_cp, P.dg_cp, P.dg_off, P.gmid, P.G};
+    bank_fission_sites(ft, A.sites, A.n_sites, A.site_capacity, h.rng, h.r, h.u, h.w, h.idx, h.daughter, n_new, h.mat, mg,
+                       __ldg(&P.nud[mg]) / nu);
+    h.daughter += (uint32_t)n_new;
+    h.n_fis += (uint32_t)n_new;
+    acc.sites += (uint32_t)n_new;
   }
   note(h, 0x5000000000000000ULL | (uint64_t)(uint32_t)n_new);
   // implicit capture (transporter.cpp:295-298)
@@ -223,6 +260,7 @@ __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A,
     h.u = rotate_direction(h.u, mu, phi);
     h.E = E_out;
     h.g = ei;
+    h.emid = true;
     h.w = h.w * 1.;
     h.w2 = h.w2 * 1.;
     if (h.E < P.min_energy) h.alive = false;
@@ -291,6 +329,7 @@ __device__ inline void pop_secondary(const DevProblem& P, const RunArgs& A, Hist
   h.w = *sec_slot(A, e, 7, tid, nthreads);
   h.w2 = *sec_slot(A, e, 8, tid, nthreads);
   h.g = group_of(P, h.E);
+  h.emid = h.g < P.G && h.E == group_mid(P, h.g);
   h.alive = true;
 }
 
@@ -474,6 +513,7 @@ __global__ void __launch_bounds__(128) transport_kernel(const DevProblem P, cons
       h.w = A.bank.wgt[idx];
       h.w2 = (NOISE && A.bank.wgt2) ? A.bank.wgt2[idx] : 0.;
       h.g = group_of(P, h.E);
+      h.emid = h.g < P.G && h.E == group_mid(P, h.g);
       if (A.bank.id_c) h.rng = A.bank.id_c[idx];
       else h.rng = pcg_advance(P.seed_state, P.stride * A.bank.id_a[idx], P.jump);  // particle.hpp:188-193
       h.hash = 1469598103934665603ULL;

@@ -7,7 +7,7 @@ with tempfile.TemporaryDirectory() as td:
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=td, stdout=subprocess.DEVNULL)
     cub = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
     txt = subprocess.run(["nvdisasm", "--print-line-info", cub], cwd=td, capture_output=True, text=True).stdout
-cnt = collections.Counter(); sub = collections.Counter()
+cnt = collections.Counter(); sub = collections.Counter(); only = sys.argv[4] if len(sys.argv) > 4 else None
 insec = False; cur = None; cursub = "main"
 for line in txt.splitlines():
     m = re.match(r"\s*\.section\s+\.text\.(\S+),", line)
@@ -22,7 +22,8 @@ for line in txt.splitlines():
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2))); continue
     if re.match(r"\s+/\*[0-9a-f]+\*/\s+\S", line):
-        cnt[cur] += 1; sub[cursub] += 1
+        sub[cursub] += 1
+        if only is None or only in cursub: cnt[cur] += 1
 byfile = collections.Counter()
 for k, c in cnt.items(): byfile[k[0] if k else None] += c
 print("total", sum(cnt.values())); print("by subroutine", sub.most_common()); print("by file", byfile.most_common())
