@@ -64,7 +64,7 @@ struct abl_context {
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_kernel_ms = 0.f;
-  int last_grid = 0;
+  int last_grid = 0, last_block = 128;
   cudaStream_t last_stream = nullptr;
   bool has_last_stream = false;
   std::string error;
@@ -311,25 +311,26 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
   void (*kern)(const DevProblem, const RunArgs) = nullptr;
   if (TRK == ABL_TRACK_SURFACE) kern = transport_kernel<ABL_TRACK_SURFACE, false>;
   else kern = history_kernel<(TRK == ABL_TRACK_SURFACE ? ABL_TRACK_DELTA : TRK), TRACE>;
+  const int threads = TRK == ABL_TRACK_SURFACE ? 128 : HK_THREADS;
   int& bps = h->blocks_per_sm[TRK][TRACE ? 1 : 0];
   if (bps == 0) {
     int nb = 0;
-    ABL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 128, 0));
+    ABL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, 0));
     if (nb < 1) nb = 1;
     bps = nb;
   }
   uint64_t blocks = (uint64_t)h->sm_count * bps;
-  const uint64_t need = (n + 127) / 128;
+  const uint64_t need = (n + threads - 1) / threads;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   RunArgs B = A;
   if (TRK == ABL_TRACK_CARTER) {
-    const uint64_t nthreads = blocks * 128;
+    const uint64_t nthreads = blocks * threads;
     if (nthreads > h->sec_threads) {
       if (h->secondaries) cudaFree(h->secondaries);
       h->secondaries = nullptr;
       h->sec_threads = 0;
-      const uint64_t cap = (uint64_t)h->sm_count * bps * 128;
+      const uint64_t cap = (uint64_t)h->sm_count * bps * threads;
       ABL_CUDA(h, cudaMalloc(&h->secondaries, cap * ABL_SEC_CAP * 9 * sizeof(double)));
       h->sec_threads = cap;
     }
@@ -348,7 +349,8 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
     B.bank.id_c = h->rng_scratch;
   }
   cudaEventRecord(h->ev0, s);
-  kern<<<(unsigned)blocks, 128, 0, s>>>(h->P, B);
+  kern<<<(unsigned)blocks, threads, 0, s>>>(h->P, B);
+  h->last_block = threads;
   cudaEventRecord(h->ev1, s);
   h->last_grid = (int)blocks;
   h->launches++;
@@ -665,7 +667,7 @@ int abl_last_transport_kernel(abl_handle h, float* milliseconds, int* grid_block
   if (!h) return ABL_ERR_INVALID;
   if (milliseconds) *milliseconds = h->last_kernel_ms;
   if (grid_blocks) *grid_blocks = h->last_grid;
-  if (block_threads) *block_threads = 128;
+  if (block_threads) *block_threads = h->last_block;
   return ABL_OK;
 }
 

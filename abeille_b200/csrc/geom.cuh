@@ -26,32 +26,41 @@ struct V3 {
   double x, y, z;
 };
 __device__ __forceinline__ double dot3(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ double norm3(const V3& a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+template <class M = InlineMath>
+__device__ __forceinline__ double norm3(const V3& a) { return M::sqrt_(a.x * a.x + a.y * a.y + a.z * a.z); }
 // Direction constructors renormalise every time (include/utils/direction.hpp:37-43)
+template <class M = InlineMath>
 __device__ __forceinline__ V3 make_direction(double x, double y, double z) {
-  const double m = sqrt(x * x + y * y + z * z);
-  return {x / m, y / m, z / m};
+  const double m = M::sqrt_(x * x + y * y + z * z);
+  return {M::div(x, m), M::div(y, m), M::div(z, m)};
 }
 
 // include/utils/direction.hpp:130-151
+template <class M = InlineMath>
 __device__ __forceinline__ V3 rotate_direction(const V3& u, double mu, double phi) {
   double sn, cs;
   det_sincos(phi, &sn, &cs);
-  const double sqrt_mu = sqrt(1. - mu * mu);
-  const double sqrt_w = sqrt(1. - u.z * u.z);
+  const double sqrt_mu = M::sqrt_(1. - mu * mu);
+  const double sqrt_w = M::sqrt_(1. - u.z * u.z);
   double ux, uy, uz;
   if (sqrt_w > 1.E-10) {
-    ux = mu * u.x + sqrt_mu * (u.x * u.z * cs - u.y * sn) / sqrt_w;
-    uy = mu * u.y + sqrt_mu * (u.y * u.z * cs + u.x * sn) / sqrt_w;
+    ux = mu * u.x + M::div(sqrt_mu * (u.x * u.z * cs - u.y * sn), sqrt_w);
+    uy = mu * u.y + M::div(sqrt_mu * (u.y * u.z * cs + u.x * sn), sqrt_w);
     uz = mu * u.z - sqrt_mu * sqrt_w * cs;
   } else {
-    const double sqrt_v = sqrt(1. - u.y * u.y);
-    ux = mu * u.x + sqrt_mu * (u.x * u.y * cs + u.z * sn) / sqrt_v;
+    const double sqrt_v = M::sqrt_(1. - u.y * u.y);
+    ux = mu * u.x + M::div(sqrt_mu * (u.x * u.y * cs + u.z * sn), sqrt_v);
     uy = mu * u.y - sqrt_mu * sqrt_v * cs;
-    uz = mu * u.z + sqrt_mu * (u.y * u.z * cs - u.x * sn) / sqrt_v;
+    uz = mu * u.z + M::div(sqrt_mu * (u.y * u.z * cs - u.x * sn), sqrt_v);
   }
-  return make_direction(ux, uy, uz);
+  return make_direction<M>(ux, uy, uz);
 }
+// one shared copy for kernels that use CallMath (scatter in the hot loop, fission banking in the cold path)
+__device__ __noinline__ V3 rotate_direction_call(const V3 u, double mu, double phi) { return rotate_direction<CallMath>(u, mu, phi); }
+template <class M>
+__device__ __forceinline__ V3 rotate_dir(const V3& u, double mu, double phi) { return rotate_direction<M>(u, mu, phi); }
+template <>
+__device__ __forceinline__ V3 rotate_dir<CallMath>(const V3& u, double mu, double phi) { return rotate_direction_call(u, mu, phi); }
 
 // ---- surfaces ---------------------------------------------------------------------------------
 struct Surf {  // register copy of one table row

@@ -102,8 +102,24 @@ __device__ __noinline__ int score_flight_all_nl(const DevTally* __restrict__ tal
   return nb;
 }
 
+// One CTA per SM.  All its warps execute the loop in lock step (block-wide vote at the top, barriers between the
+// stages): the SM instruction cache is much smaller than the loop body, and ncu showed the free-running version
+// bound by instruction-cache misses (sm__icc hit rate 57 %, 60 % of stall samples "no instruction").  In lock step
+// a line fetched for one warp is a hit (or a hit under miss) for the other fifteen.
+#ifndef HK_THREADS
+#define HK_THREADS 512
+#endif
+#ifndef HK_STAGE_SYNC
+#define HK_STAGE_SYNC 1
+#endif
+#if HK_STAGE_SYNC
+#define HK_SYNC() __syncthreads()
+#else
+#define HK_SYNC() __syncwarp()
+#endif
+
 template <int TRK, bool TRACE>
-__global__ void __launch_bounds__(128, 4) history_kernel(const DevProblem P, const RunArgs A) {
+__global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem P, const RunArgs A) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
   const unsigned FULL = 0xffffffffu;
@@ -163,18 +179,18 @@ __global__ void __launch_bounds__(128, 4) history_kernel(const DevProblem P, con
         phase = PH_BIRTH;
       }
     }
-    if (__all_sync(FULL, phase == PH_DEAD)) break;
+    if (__syncthreads_and(phase == PH_DEAD)) break;
 
     // ---- M: sample the flight, move the cursor, re-validate its pads ----------------------------------------------------------
     if (phase == PH_FLIGHT) {
-      d_coll = rng_exponential(h.rng, __ldg(&P.smp[h.g]));
+      d_coll = rng_exponential<CallMath>(h.rng, __ldg(&P.smp[h.g]));
       acc.flights++;
       if (TRACE) h.n_flights++;
       cursor_move(c, d_coll, h.u);
       const int first_bad = cursor_validate(P, c, h.u);
       if (first_bad < c.np) need = first_bad;
     }
-    __syncwarp();
+    HK_SYNC();
 
     // ---- L: (re-)descent through the universe tree -----------------------------------------------------------------------------------
     if (need >= 0) {
@@ -185,7 +201,7 @@ __global__ void __launch_bounds__(128, 4) history_kernel(const DevProblem P, con
         c.err = 0;
       }
     }
-    __syncwarp();
+    HK_SYNC();
 
     // ---- B1: what did the move do? -------------------------------------------------------------------------------------------------------
     double tle_d = -1.;
@@ -227,7 +243,7 @@ __global__ void __launch_bounds__(128, 4) history_kernel(const DevProblem P, con
         const V3 r_on{h.r.x + bound.distance * h.u.x, h.r.y + bound.distance * h.u.y, h.r.z + bound.distance * h.u.z};
         const V3 n = surf_norm(s, r_on);
         const double f = 2. * dot3(h.u, n);
-        h.u = make_direction(h.u.x - n.x * f, h.u.y - n.y * f, h.u.z - n.z * f);
+        h.u = make_direction<CallMath>(h.u.x - n.x * f, h.u.y - n.y * f, h.u.z - n.z * f);
         h.r = r_on;
         c.token = 0;
         c.fx[0] = h.r.x;
@@ -269,7 +285,7 @@ __global__ void __launch_bounds__(128, 4) history_kernel(const DevProblem P, con
       }
       phase = PH_FLIGHT;
     }
-    __syncwarp();
+    HK_SYNC();
 
     // ---- C: arrive, real or virtual collision (delta_tracker.cpp:167-195, carter_tracker.cpp:189-207) ----------------------------------------
     if (test_collision) {
@@ -286,16 +302,16 @@ __global__ void __launch_bounds__(128, 4) history_kernel(const DevProblem P, con
           raise_error(A, ABL_ERR_MAJORANT, A.bank.id_a[h.idx]);
           h.alive = false;
           h.nsec = 0;
-        } else if (rng_rand(h.rng) < (Et / Esample)) {
+        } else if (CallMath::rand(h.rng) < CallMath::div(Et, Esample)) {
           had_collision = true;
         }
       } else {
         if (Esample >= Et) {
-          if (rng_rand(h.rng) < (Et / Esample)) had_collision = true;
+          if (CallMath::rand(h.rng) < CallMath::div(Et, Esample)) had_collision = true;
         } else {  // under-estimated sampling xs: signed-weight branch (carter_tracker.cpp:192-207)
-          const double D = Et / (2. * Et - Esample);
-          const double F = Et / (D * Esample);
-          if ((D - rng_rand(h.rng)) > 0.) {
+          const double D = CallMath::div(Et, 2. * Et - Esample);
+          const double F = CallMath::div(Et, D * Esample);
+          if ((D - CallMath::rand(h.rng)) > 0.) {
             h.w = h.w * F;
             had_collision = true;
           } else {
@@ -306,7 +322,7 @@ __global__ void __launch_bounds__(128, 4) history_kernel(const DevProblem P, con
       if (h.alive) {
         if (TRACE) note(h, (had_collision ? 0x2000000000000000ULL : 0x1000000000000000ULL) | (uint64_t)(uint32_t)(c.cell + 1));
         if (had_collision) {
-          collision<false>(P, A, h, acc);
+          collision<false, CallMath>(P, A, h, acc);
         } else {
           acc.virt++;
           if (TRACE) h.n_virtual++;
@@ -327,7 +343,7 @@ __global__ void __launch_bounds__(128, 4) history_kernel(const DevProblem P, con
         }
       }
     }
-    __syncwarp();
+    HK_SYNC();
 
     // ---- E: secondaries, end of history -----------------------------------------------------------------------------------------------------------
     if (phase == PH_FLIGHT && !h.alive) {
@@ -356,8 +372,9 @@ __global__ void __launch_bounds__(128, 4) history_kernel(const DevProblem P, con
   // ---- reduce the per-thread accumulators: warp shuffle, then one atomic per block ------------------------------------
   double dv[5] = {acc.k_col, acc.k_abs, acc.k_trk, acc.leak, acc.mig};
   unsigned long long cv[8] = {acc.flights, acc.real, acc.virt, acc.tl_bins, acc.sites, acc.boundary, acc.lost, acc.coll_scores};
-  __shared__ double sd[4][5];
-  __shared__ unsigned long long sc[4][8];
+  constexpr int NW = HK_THREADS / 32;
+  __shared__ double sd[NW][5];
+  __shared__ unsigned long long sc[NW][8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int q = 0; q < 5; q++) {
@@ -374,12 +391,15 @@ __global__ void __launch_bounds__(128, 4) history_kernel(const DevProblem P, con
   __syncthreads();
   if (threadIdx.x < 5) {
     const int q = threadIdx.x;
-    const double v = sd[0][q] + sd[1][q] + sd[2][q] + sd[3][q];
+    double v = 0.;
+    for (int w = 0; w < NW; w++) v += sd[w][q];
     const int slot = q < 3 ? q : q + 1;  // scores layout: k_col,k_abs,k_trk,k_tot(unused),leak,mig
     atomicAdd(&A.scores[slot], v);
   } else if (threadIdx.x >= 32 && threadIdx.x < 40) {
     const int q = threadIdx.x - 32;
-    atomicAdd(&A.counters[q], sc[0][q] + sc[1][q] + sc[2][q] + sc[3][q]);
+    unsigned long long v = 0;
+    for (int w = 0; w < NW; w++) v += sc[w][q];
+    atomicAdd(&A.counters[q], v);
   }
 }
 

@@ -59,14 +59,57 @@ __device__ __forceinline__ double rng_rand(uint64_t& state) {
   return ret;
 }
 
+// ---- math policies ------------------------------------------------------------------------------------------
+// The same IEEE operations either expanded inline (InlineMath) or issued as calls to ONE shared copy per
+// kernel (CallMath).  fp64 division, sqrt and the pcg32 -> double conversion expand to 15-40 instructions each;
+// the delta-tracking loop uses dozens of them, and ncu showed the kernel bound by SM instruction-cache misses
+// (sm__icc hit rate 57 %), so the hot loop trades a call for the footprint.  Results are bit-identical.
+struct RandOut {
+  double v;
+  uint64_t state;
+};
+__device__ __noinline__ RandOut rng_rand_call(uint64_t state) {
+  RandOut o;
+  o.v = rng_rand(state);
+  o.state = state;
+  return o;
+}
+__device__ __noinline__ double ddiv_call(double a, double b) { return a / b; }
+__device__ __noinline__ double dsqrt_call(double a) { return sqrt(a); }
+
+struct InlineMath {
+  static __device__ __forceinline__ double rand(uint64_t& s) { return rng_rand(s); }
+  static __device__ __forceinline__ double div(double a, double b) { return a / b; }
+  static __device__ __forceinline__ double sqrt_(double a) { return sqrt(a); }
+};
+struct CallMath {
+  static __device__ __forceinline__ double rand(uint64_t& s) {
+    const RandOut o = rng_rand_call(s);
+    s = o.state;
+    return o.v;
+  }
+  static __device__ __forceinline__ double div(double a, double b) { return ddiv_call(a, b); }
+  static __device__ __forceinline__ double sqrt_(double a) { return dsqrt_call(a); }
+};
+
+template <class M = InlineMath>
 __device__ __forceinline__ double rng_exponential(uint64_t& state, double lambda) {
   if (lambda == 0.) return ABL_INF;
-  return -det_log(1.0 - rng_rand(state)) / lambda;
+  return M::div(-det_log(1.0 - M::rand(state)), lambda);
 }
 
-// lower_bound over a cumulative table of n >= 2 entries (the caller handles n < 2: no draw)
+// lower_bound over a cumulative table of n >= 2 entries (the caller handles n < 2: no draw).  The table is
+// non-decreasing, so the lower bound is the number of entries below p: up to 8 entries are counted without a
+// branch (multigroup decks have a handful of groups), longer tables use the binary search.
+template <class M = InlineMath>
 __device__ __forceinline__ int rng_discrete(uint64_t& state, const double* __restrict__ cp, int n) {
-  const double p = rng_rand(state);
+  const double p = M::rand(state);
+  if (n <= 8) {
+    int lo = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) lo += (i < n && __ldg(&cp[i < n ? i : 0]) < p) ? 1 : 0;
+    return lo;
+  }
   int lo = 0, len = n;
   while (len > 0) {
     const int half = len >> 1;
@@ -79,5 +122,10 @@ __device__ __forceinline__ int rng_discrete(uint64_t& state, const double* __res
   }
   return lo;
 }
+
+// a / b for a finite b > 0.  A zero numerator (nu*Sigma_f in a non-fissile material, wgt2 outside noise mode)
+// would send CUDA's division through its slow-path subroutine; 0 / b is 0 with the sign of a, exactly.
+template <class M = InlineMath>
+__device__ __forceinline__ double ddiv_pos(double a, double b) { return (a == 0.) ? a : M::div(a, b); }
 
 }  // namespace abl

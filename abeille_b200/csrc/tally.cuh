@@ -48,8 +48,9 @@ __device__ __forceinline__ double quantity_factor(int quantity, double w, double
 
 // returns 1 when a bin was scored
 // l = energy bin of the particle (tally_energy_bin, or the per-group table for mid-point energies)
+template <class M = InlineMath>
 __device__ inline int score_collision(const DevTally& t, const V3& r, int l, double w, double w2, const MatXS& m) {
-  double scr = 1. / (m.Et * t.net_weight);
+  double scr = M::div(1., m.Et * t.net_weight);
   const int i = (int)floor((r.x - t.lowx) * t.dx_inv);
   const int j = (int)floor((r.y - t.lowy) * t.dy_inv);
   const int k = (int)floor((r.z - t.lowz) * t.dz_inv);

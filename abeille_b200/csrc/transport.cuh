@@ -122,8 +122,9 @@ __device__ __noinline__ double sample_mu_table(const double* __restrict__ acdf, 
 }
 
 // MGAngleDistribution::sample_mu (mg_angle_distribution.hpp:45-60,92-101)
+template <class M = InlineMath>
 __device__ __forceinline__ double sample_mu(const DevProblem& P, const abl_angle_table* at, uint64_t& rng) {
-  const double xi = rng_rand(rng);
+  const double xi = M::rand(rng);
   const int off = __ldg(&at->offset), n = __ldg(&at->n);
   // n < 0 marks the default isotropic table {mu:[-1,1], pdf:[.5,.5], cdf:[0,1]} (mg_angle_distribution.cpp:32-33):
   // the general formula below reduces to this expression, evaluated identically
@@ -156,19 +157,20 @@ struct FissionTables {
   const double* gmid;
   int G;
 };
+template <class M>
 __device__ __noinline__ void bank_fission_sites(const FissionTables T, Site* sites, unsigned long long* n_sites, uint64_t capacity,
                                                 uint64_t& rng, const V3 r, const V3 u, double w, uint32_t parent, uint32_t daughter0,
                                                 int n_new, int mat, int mg, double P_delayed) {
   const int dg0 = __ldg(&T.dg_off[mat]), ndg = __ldg(&T.dg_off[mat + 1]) - dg0;
   for (int i = 0; i < n_new; i++) {
     int ei = 0;
-    if (T.G >= 2) ei = rng_discrete(rng, T.chi_cp + (size_t)mg * T.G, T.G);
+    if (T.G >= 2) ei = rng_discrete<M>(rng, T.chi_cp + (size_t)mg * T.G, T.G);
     const double E_out = __ldg(&T.gmid[ei]);
-    const double mu = 2. * rng_rand(rng) - 1.;
-    const double phi = 2. * ABL_PI * rng_rand(rng);
-    const V3 dir = rotate_direction(u, mu, phi);
-    if (rng_rand(rng) < P_delayed) {
-      if (ndg >= 2) (void)rng_discrete(rng, T.dg_cp + dg0, ndg);  // delayed family: only matters in noise mode
+    const double mu = 2. * M::rand(rng) - 1.;
+    const double phi = 2. * ABL_PI * M::rand(rng);
+    const V3 dir = rotate_dir<M>(u, mu, phi);
+    if (M::rand(rng) < P_delayed) {
+      if (ndg >= 2) (void)rng_discrete<M>(rng, T.dg_cp + dg0, ndg);  // delayed family: only matters in noise mode
     }
     Site s;
     s.x = r.x; s.y = r.y; s.z = r.z;
@@ -192,23 +194,23 @@ __device__ __noinline__ void bank_fission_sites(const FissionTables T, Site* sit
   }
 }
 
-template <bool NOISE>
+template <bool NOISE, class M = InlineMath>
 __device__ __forceinline__ void russian_roulette(const DevProblem& P, Hist& h) {  // transporter.cpp:35-58
   if (fabs(h.w) < P.wgt_cutoff) {
-    const double P_kill = 1.0 - (fabs(h.w) / P.wgt_survival);
-    if (rng_rand(h.rng) < P_kill) h.w = 0.;
+    const double P_kill = 1.0 - M::div(fabs(h.w), P.wgt_survival);
+    if (M::rand(h.rng) < P_kill) h.w = 0.;
     else h.w = copysign(P.wgt_survival, h.w);
   }
   if (fabs(h.w2) < P.wgt_cutoff) {  // w2 == 0 outside noise mode: the draw is still consumed
-    const double P_kill = 1.0 - (fabs(h.w2) / P.wgt_survival);
-    if (rng_rand(h.rng) < P_kill) h.w2 = 0.;
+    const double P_kill = 1.0 - ddiv_pos<M>(fabs(h.w2), P.wgt_survival);
+    if (M::rand(h.rng) < P_kill) h.w2 = 0.;
     else h.w2 = copysign(P.wgt_survival, h.w2);
   }
   if (h.w == 0. && h.w2 == 0.) h.alive = false;
 }
 
 // Transporter::collision + branching_collision (transporter.cpp:60-93,269-312), k-eigenvalue branch
-template <bool NOISE>
+template <bool NOISE, class M = InlineMath>
 __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A, Hist& h, Acc& acc) {
   const int mg = h.mat * P.G + h.g;
   const double Et = __ldg(&P.Et[mg]), Ea = __ldg(&P.Ea[mg]), Ef = __ldg(&P.Ef[mg]), nu = __ldg(&P.nu[mg]);
@@ -219,45 +221,45 @@ __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A,
     for (int t = 0; t < P.ntallies; t++)
       if (P.tally[t].estimator == ABL_EST_COLLISION) {
         const int l = h.emid ? __ldg(&P.tally_gbin[t * P.G + h.g]) : tally_energy_bin(P.tally[t], h.E);
-        acc.coll_scores += score_collision(P.tally[t], h.r, l, h.w, h.w2, mx);
+        acc.coll_scores += score_collision<M>(P.tally[t], h.r, l, h.w, h.w2, mx);
       }
   }
   {
-    const double k_col_scr = h.w * (nu * Ef) / Et;
+    const double k_col_scr = ddiv_pos<M>(h.w * (nu * Ef), Et);
     const V3 dr{h.r.x - h.rb.x, h.r.y - h.rb.y, h.r.z - h.rb.z};
-    const double mig_dist = norm3(dr);
-    const double mig_area_scr = h.w * Ea / Et * mig_dist * mig_dist;
+    const double mig_dist = norm3<M>(dr);
+    const double mig_area_scr = ddiv_pos<M>(h.w * Ea, Et) * mig_dist * mig_dist;
     acc.k_col += k_col_scr;
     acc.mig += mig_area_scr;
   }
   // MaterialHelper::sample_nuclide always draws, even with a single nuclide (material_helper.hpp:189)
-  (void)rng_rand(h.rng);
-  const double k_abs_scr = h.w * nu * Ef / Et;
+  (void)M::rand(h.rng);
+  const double k_abs_scr = ddiv_pos<M>(h.w * nu * Ef, Et);
   acc.k_abs += k_abs_scr;
   // make_fission_neutrons (transporter.cpp:358-487)
-  const int n_new = (int)floor(fabs(k_abs_scr) / A.k_col + rng_rand(h.rng));
+  const int n_new = (int)floor(ddiv_pos<M>(fabs(k_abs_scr), A.k_col) + M::rand(h.rng));
   if (n_new > 0) {
     const FissionTables ft{P.chi_cp, P.dg_cp, P.dg_off, P.gmid, P.G};
-    bank_fission_sites(ft, A.sites, A.n_sites, A.site_capacity, h.rng, h.r, h.u, h.w, h.idx, h.daughter, n_new, h.mat, mg,
-                       __ldg(&P.nud[mg]) / nu);
+    bank_fission_sites<M>(ft, A.sites, A.n_sites, A.site_capacity, h.rng, h.r, h.u, h.w, h.idx, h.daughter, n_new, h.mat, mg,
+                          __ldg(&P.nud[mg]) / nu);
     h.daughter += (uint32_t)n_new;
     h.n_fis += (uint32_t)n_new;
     acc.sites += (uint32_t)n_new;
   }
   note(h, 0x5000000000000000ULL | (uint64_t)(uint32_t)n_new);
   // implicit capture (transporter.cpp:295-298)
-  const double surv = 1. - (Ea + 0.) / Et;
+  const double surv = 1. - ddiv_pos<M>(Ea + 0., Et);
   h.w = h.w * surv;
   h.w2 = h.w2 * surv;
-  russian_roulette<NOISE>(P, h);
+  russian_roulette<NOISE, M>(P, h);
   if (h.alive) {
     // MGNuclide::sample_scatter (mg_nuclide.cpp:442-461); the yield matrix is never applied
     int ei = 0;
-    if (P.G >= 2) ei = rng_discrete(h.rng, P.ps_cp + (size_t)mg * P.G, P.G);
+    if (P.G >= 2) ei = rng_discrete<M>(h.rng, P.ps_cp + (size_t)mg * P.G, P.G);
     const double E_out = group_mid(P, ei);
-    const double mu = sample_mu(P, P.angle + (size_t)mg * P.G + ei, h.rng);
-    const double phi = 2. * ABL_PI * rng_rand(h.rng);
-    h.u = rotate_direction(h.u, mu, phi);
+    const double mu = sample_mu<M>(P, P.angle + (size_t)mg * P.G + ei, h.rng);
+    const double phi = 2. * ABL_PI * M::rand(h.rng);
+    h.u = rotate_dir<M>(h.u, mu, phi);
     h.E = E_out;
     h.g = ei;
     h.emid = true;
