@@ -51,7 +51,10 @@ class AblTrace(C.Structure):
 
 
 def lib_paths():
-    return os.path.join(_LIBDIR, "libabeille_b200.so"), os.path.join(_LIBDIR, "libabeille_host.so")
+    """(CUDA library, host library).  ABEILLE_B200_LIB selects another build of the CUDA library (kernel tuning
+    experiments: same ABI, different compile-time constants)."""
+    cuda = os.environ.get("ABEILLE_B200_LIB") or os.path.join(_LIBDIR, "libabeille_b200.so")
+    return cuda, os.path.join(_LIBDIR, "libabeille_host.so")
 
 
 _backend_lib = None

@@ -293,26 +293,35 @@ __device__ __noinline__ bool cell_is_inside_nl(const GeoTables G, int ci, const 
   return cell_is_inside(G, ci, r, u, on_surf);
 }
 
-// Cell::is_inside through the compiled descriptor (tables.h: CellFast).  Falls back to the generic evaluator
-// when the particle sits on a surface or is within SURFACE_COINCIDENT of one (direction-dependent ties).
-__device__ __forceinline__ bool cell_is_inside_fast(const DevProblem& P, int ci, const V3& r, const V3& u, int on_surf) {
-  const CellFast* cf = P.cellfast + ci;
+// Cell::is_inside through the compiled descriptor (tables.h: CellFast): 1 inside, 0 outside, -1 undecided --
+// the particle sits on a surface or is within SURFACE_COINCIDENT of one (direction-dependent tie), or the
+// region has no compiled form; the caller then runs the generic evaluator.  One shared copy per kernel.
+__device__ __noinline__ int cell_fast_nl(const CellFast* __restrict__ cf, const V3 r, int on_surf) {
   const int kind = __ldg(&cf->kind);
-  if (on_surf == 0 && kind == CF_BOX) {
+  if (on_surf != 0) return -1;
+  if (kind == CF_BOX) {
     const double2 bx = __ldg(reinterpret_cast<const double2*>(&cf->a[0]));
     const double2 by = __ldg(reinterpret_cast<const double2*>(&cf->a[2]));
     const double2 bz = __ldg(reinterpret_cast<const double2*>(&cf->a[4]));
     const double e0 = r.x - bx.x, e1 = r.x - bx.y, e2 = r.y - by.x, e3 = r.y - by.y, e4 = r.z - bz.x, e5 = r.z - bz.y;
     const double T = ABL_SURFACE_COINCIDENT;
     const bool tie = (fabs(e0) <= T) | (fabs(e1) <= T) | (fabs(e2) <= T) | (fabs(e3) <= T) | (fabs(e4) <= T) | (fabs(e5) <= T);
-    if (!tie) return (e0 > T) & (e1 < -T) & (e2 > T) & (e3 < -T) & (e4 > T) & (e5 < -T);
-  } else if (on_surf == 0 && kind == CF_ZCYL) {
+    const bool in = (e0 > T) & (e1 < -T) & (e2 > T) & (e3 < -T) & (e4 > T) & (e5 < -T);
+    return tie ? -1 : (in ? 1 : 0);
+  }
+  if (kind == CF_ZCYL) {
     const double2 xy = __ldg(reinterpret_cast<const double2*>(&cf->a[0]));
     const double r2 = __ldg(&cf->a[2]);
     const double x = r.x - xy.x, y = r.y - xy.y;
     const double e = y * y + x * x - r2;
-    if (fabs(e) > ABL_SURFACE_COINCIDENT) return (__ldg(&cf->sense) < 0) ? (e < 0.) : (e > 0.);
+    const bool in = (__ldg(&cf->sense) < 0) ? (e < 0.) : (e > 0.);
+    return fabs(e) > ABL_SURFACE_COINCIDENT ? (in ? 1 : 0) : -1;
   }
+  return -1;
+}
+__device__ __forceinline__ bool cell_is_inside_fast(const DevProblem& P, int ci, const V3& r, const V3& u, int on_surf) {
+  const int q = cell_fast_nl(P.cellfast + ci, r, on_surf);
+  if (q >= 0) return q != 0;
   return cell_is_inside_nl(geo_tables(P), ci, r, u, on_surf);
 }
 
@@ -376,6 +385,16 @@ __device__ __forceinline__ void get_tile(const Lat& L, const V3& r, const V3& u,
   if (fabs(zl - r.z) < ABL_SURFACE_COINCIDENT && u.z < 0.) nz--;
   const double zh = rt.z + L.Pz * 0.5;
   if (fabs(zh - r.z) < ABL_SURFACE_COINCIDENT && u.z >= 0.) nz++;
+}
+// Lattice::get_tile as one shared copy per kernel (used by the pad validation and by the descent)
+struct Tile3 {
+  int nx, ny, nz;
+};
+__device__ __noinline__ Tile3 lattice_tile_nl(const abl_universe* __restrict__ U, const V3 r, const V3 u) {
+  const Lat L = load_lattice(U);
+  Tile3 t;
+  get_tile(L, r, u, t.nx, t.ny, t.nz);
+  return t;
 }
 __device__ __forceinline__ bool tile_in_range(const Lat& L, int nx, int ny, int nz) {
   return !((nx < 0 || nx >= L.Nx) || (ny < 0 || ny >= L.Ny) || (nz < 0 || nz >= L.Nz));
@@ -514,9 +533,20 @@ __device__ inline int descend(const DevProblem& P, Cursor& c, int uni, int f, co
       uni = fill;
       continue;
     }
-    const Lat L = load_lattice(U);
     int nx, ny, nz;
-    get_tile(L, r, u, nx, ny, nz);
+    Lat L;
+    if (FAST) {
+      const Tile3 t3 = lattice_tile_nl(U, r, u);
+      nx = t3.nx; ny = t3.ny; nz = t3.nz;
+      L.Nx = __ldg(&U->N[0]); L.Ny = __ldg(&U->N[1]); L.Nz = __ldg(&U->N[2]);
+      L.tile_offset = __ldg(&U->tile_offset);
+      L.outer = __ldg(&U->outer);
+      L.Px = __ldg(&U->P[0]); L.Py = __ldg(&U->P[1]); L.Pz = __ldg(&U->P[2]);
+      L.Xl = __ldg(&U->Xl[0]); L.Yl = __ldg(&U->Xl[1]); L.Zl = __ldg(&U->Xl[2]);
+    } else {
+      L = load_lattice(U);
+      get_tile(L, r, u, nx, ny, nz);
+    }
     int sub = -1;
     if (tile_in_range(L, nx, ny, nz)) sub = __ldg(&P.tiles[L.tile_offset + nz * (L.Nx * L.Ny) + nx * L.Ny + ny]);
     c.nf = f + 1;

@@ -44,10 +44,8 @@ __device__ __forceinline__ int cursor_validate(const DevProblem& P, const Cursor
         break;
       }
     } else if (type == PAD_LATTICE) {
-      const Lat L = load_lattice(P.universes + pad_index(info));
-      int nx, ny, nz;
-      get_tile(L, frame_r(c, pad_frame(info)), u, nx, ny, nz);
-      if (c.ptile[it][0] != nx || c.ptile[it][1] != ny || c.ptile[it][2] != nz) {
+      const Tile3 t3 = lattice_tile_nl(P.universes + pad_index(info), frame_r(c, pad_frame(info)), u);
+      if (c.ptile[it][0] != t3.nx || c.ptile[it][1] != t3.ny || c.ptile[it][2] != t3.nz) {
         first_bad = it;
         break;
       }
@@ -90,6 +88,22 @@ __device__ __noinline__ Boundary cursor_boundary_condition_nl(const GeoTables G,
   return cursor_boundary_condition(G, c, u);
 }
 
+// Tracker::do_reflection (tracker.hpp:314-360), the arithmetic part: point on the surface and reflected direction
+struct Reflected {
+  V3 r, u;
+};
+__device__ __noinline__ Reflected reflect_nl(const abl_surface* __restrict__ surfaces, int surface_index, const V3 r, const V3 u, double distance) {
+  GeoTables G{};
+  G.surfaces = surfaces;
+  const Surf s = load_surface(G, surface_index);
+  Reflected o;
+  o.r = V3{r.x + distance * u.x, r.y + distance * u.y, r.z + distance * u.z};
+  const V3 n = surf_norm(s, o.r);
+  const double f = 2. * dot3(u, n);
+  o.u = make_direction(u.x - n.x * f, u.y - n.y * f, u.z - n.z * f);
+  return o;
+}
+
 // every track-length tally (tallies.hpp:57-63); returns the number of bins scored
 __device__ __noinline__ int score_flight_all_nl(const DevTally* __restrict__ tallies, int ntallies, const V3 r, const V3 u, double d,
                                                 double E, double w, double w2, const MatXS mx) {
@@ -107,10 +121,16 @@ __device__ __noinline__ int score_flight_all_nl(const DevTally* __restrict__ tal
 // bound by instruction-cache misses (sm__icc hit rate 57 %, 60 % of stall samples "no instruction").  In lock step
 // a line fetched for one warp is a hit (or a hit under miss) for the other fifteen.
 #ifndef HK_THREADS
-#define HK_THREADS 512
+#define HK_THREADS 768
 #endif
 #ifndef HK_STAGE_SYNC
 #define HK_STAGE_SYNC 1
+#endif
+#ifndef HK_MATH
+#define HK_MATH CallMath
+#endif
+#ifndef HK_VOTE_EVERY
+#define HK_VOTE_EVERY 1  // block-wide vote (and re-alignment of the warps) every this many iterations (power of two)
 #endif
 #if HK_STAGE_SYNC
 #define HK_SYNC() __syncthreads()
@@ -142,6 +162,7 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
   bool exhausted = false;
   const uint64_t N = A.bank.n;
   const bool tle = A.converged && P.n_tl_tallies;
+  uint32_t iter = 0;
 
   for (;;) {
     // ---- R: refill ---------------------------------------------------------------------------------------------
@@ -179,11 +200,13 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
         phase = PH_BIRTH;
       }
     }
-    if (__syncthreads_and(phase == PH_DEAD)) break;
+    if ((iter++ & (HK_VOTE_EVERY - 1)) == 0) {
+      if (__syncthreads_and(phase == PH_DEAD)) break;
+    }
 
     // ---- M: sample the flight, move the cursor, re-validate its pads ----------------------------------------------------------
     if (phase == PH_FLIGHT) {
-      d_coll = rng_exponential<CallMath>(h.rng, __ldg(&P.smp[h.g]));
+      d_coll = rng_exponential<HK_MATH>(h.rng, __ldg(&P.smp[h.g]));
       acc.flights++;
       if (TRACE) h.n_flights++;
       cursor_move(c, d_coll, h.u);
@@ -239,12 +262,9 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
         phase = PH_FLIGHT;
       } else if (bound.btype == ABL_BC_REFLECTIVE && bound.surface_index >= 0) {
         // Tracker::do_reflection (tracker.hpp:314-360); the full lookup happens in the next L stage
-        const Surf s = load_surface(P, bound.surface_index);
-        const V3 r_on{h.r.x + bound.distance * h.u.x, h.r.y + bound.distance * h.u.y, h.r.z + bound.distance * h.u.z};
-        const V3 n = surf_norm(s, r_on);
-        const double f = 2. * dot3(h.u, n);
-        h.u = make_direction<CallMath>(h.u.x - n.x * f, h.u.y - n.y * f, h.u.z - n.z * f);
-        h.r = r_on;
+        const Reflected rf = reflect_nl(P.surfaces, bound.surface_index, h.r, h.u, bound.distance);
+        h.u = rf.u;
+        h.r = rf.r;
         c.token = 0;
         c.fx[0] = h.r.x;
         c.fy[0] = h.r.y;
@@ -302,16 +322,16 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
           raise_error(A, ABL_ERR_MAJORANT, A.bank.id_a[h.idx]);
           h.alive = false;
           h.nsec = 0;
-        } else if (CallMath::rand(h.rng) < CallMath::div(Et, Esample)) {
+        } else if (HK_MATH::rand(h.rng) < HK_MATH::div(Et, Esample)) {
           had_collision = true;
         }
       } else {
         if (Esample >= Et) {
-          if (CallMath::rand(h.rng) < CallMath::div(Et, Esample)) had_collision = true;
+          if (HK_MATH::rand(h.rng) < HK_MATH::div(Et, Esample)) had_collision = true;
         } else {  // under-estimated sampling xs: signed-weight branch (carter_tracker.cpp:192-207)
-          const double D = CallMath::div(Et, 2. * Et - Esample);
-          const double F = CallMath::div(Et, D * Esample);
-          if ((D - CallMath::rand(h.rng)) > 0.) {
+          const double D = HK_MATH::div(Et, 2. * Et - Esample);
+          const double F = HK_MATH::div(Et, D * Esample);
+          if ((D - HK_MATH::rand(h.rng)) > 0.) {
             h.w = h.w * F;
             had_collision = true;
           } else {
@@ -322,7 +342,7 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
       if (h.alive) {
         if (TRACE) note(h, (had_collision ? 0x2000000000000000ULL : 0x1000000000000000ULL) | (uint64_t)(uint32_t)(c.cell + 1));
         if (had_collision) {
-          collision<false, CallMath>(P, A, h, acc);
+          collision<false, HK_MATH>(P, A, h, acc);
         } else {
           acc.virt++;
           if (TRACE) h.n_virtual++;

@@ -256,7 +256,7 @@ def run_b200(args):
                           "l2": "inputs larger than L2 (bank 96 B x 1e7 = 0.96 GB, tally mesh 0.84 GB)", "k_col": k_col,
                           "collisions_per_particle": collisions / max(particles, 1)},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": args.traffic, "kernel": "transport_kernel<delta>", "kernel_ms": k_ms,
+                            "traffic": args.traffic, "kernel": "history_kernel<delta>", "kernel_ms": k_ms,
                             "grid": [kinfo["grid"], kinfo["block"]], "algorithmic_bytes_per_launch": alg_bytes,
                             "peak_source": peak_src, "kernel_share_of_step": k_ms * args.steps / ms},
                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
