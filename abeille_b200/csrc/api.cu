@@ -307,20 +307,25 @@ int alloc_bank(abl_handle h, BankView& b, uint64_t cap) {
 
 template <int TRK, bool TRACE>
 int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s) {
-  // surface tracking: per-lane history loop (transport.cuh); delta / carter: staged warp-synchronous loop (history.cuh)
+  // surface tracking: per-lane history loop (transport.cuh); delta / carter: staged lock-step loop with the cursors in
+  // shared memory and service warps for the rare events (history.cuh)
   void (*kern)(const DevProblem, const RunArgs) = nullptr;
   if (TRK == ABL_TRACK_SURFACE) kern = transport_kernel<ABL_TRACK_SURFACE, false>;
   else kern = history_kernel<(TRK == ABL_TRACK_SURFACE ? ABL_TRACK_DELTA : TRK), TRACE>;
-  const int threads = TRK == ABL_TRACK_SURFACE ? 128 : HK_THREADS;
+  const bool staged = TRK != ABL_TRACK_SURFACE;
+  const int threads = staged ? HK_THREADS : 128;
+  const int worker_threads = staged ? HK_HIST : 128;  // threads of a block that own histories
+  const size_t smem = staged ? sizeof(HKShared) : 0;
   int& bps = h->blocks_per_sm[TRK][TRACE ? 1 : 0];
   if (bps == 0) {
+    if (smem) ABL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
-    ABL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, 0));
+    ABL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem));
     if (nb < 1) nb = 1;
     bps = nb;
   }
   uint64_t blocks = (uint64_t)h->sm_count * bps;
-  const uint64_t need = (n + threads - 1) / threads;
+  const uint64_t need = (n + worker_threads - 1) / worker_threads;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   RunArgs B = A;
@@ -349,7 +354,7 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
     B.bank.id_c = h->rng_scratch;
   }
   cudaEventRecord(h->ev0, s);
-  kern<<<(unsigned)blocks, threads, 0, s>>>(h->P, B);
+  kern<<<(unsigned)blocks, threads, smem, s>>>(h->P, B);
   h->last_block = threads;
   cudaEventRecord(h->ev1, s);
   h->last_grid = (int)blocks;
@@ -637,6 +642,20 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
           }
     }
     UP(gb.data(), gb.size(), P.tally_gbin);
+  }
+  {
+    std::vector<double> rf(MG, 0.), sf(MG, 0.), is((size_t)(p->ntallies > 0 ? p->ntallies : 1) * MG, 0.);
+    for (int m = 0; m < M; m++)
+      for (int g = 0; g < G; g++) {
+        const size_t mg = (size_t)m * G + g;
+        const double Et = p->xs_total[mg], Ea = p->xs_absorption[mg] + 0.;
+        if (p->sampling_xs) rf[mg] = Et / p->sampling_xs[g];
+        sf[mg] = 1. - (Ea == 0. ? Ea : Ea / Et);  // ddiv_pos
+        for (int t = 0; t < p->ntallies; t++) is[(size_t)t * MG + mg] = 1. / (Et * p->tallies[t].net_weight);
+      }
+    UP(rf.data(), rf.size(), P.real_frac);
+    UP(sf.data(), sf.size(), P.surv_frac);
+    UP(is.data(), is.size(), P.inv_score);
   }
   P.nsources = p->nsources;
   UP(p->sources, p->nsources, P.sources);

@@ -148,26 +148,58 @@ __device__ __forceinline__ int det_rem_pio2(double x, double* y0, double* y1) {
   return n;
 }
 
+// sin and cos of x together.  Same operation sequence per value as the fdlibm routines above (__sin / __cos:
+// |x| <= pi/4 -> kernel polynomials on x itself, otherwise argument reduction + the kernels with the tail y1), but
+// written without data-dependent branches: the lanes of a warp hold angles from every octant, and with branches
+// ncu showed this routine running with 10 of the 23 lanes that enter it.  Both kernel polynomials are evaluated
+// once per lane and the octant-specific pieces are selected.
 __device__ __noinline__ void det_sincos(double x, double* sn, double* cs) {
   const int32_t ix = dm_hi(x) & 0x7fffffff;
-  if (ix <= 0x3fe921fb) {
-    *sn = det_ksin(x, 0.0, 0);
-    *cs = det_kcos(x, 0.0);
-    return;
-  }
   if (ix >= 0x7ff00000) {
     *sn = *cs = x - x;
     return;
   }
-  double y0, y1;
-  const int n = det_rem_pio2(x, &y0, &y1);
-  const double s = det_ksin(y0, y1, 1), c = det_kcos(y0, y1);
-  switch (n & 3) {
-    case 0: *sn = s; *cs = c; break;
-    case 1: *sn = c; *cs = -s; break;
-    case 2: *sn = -s; *cs = -c; break;
-    default: *sn = -c; *cs = s; break;
+  const bool direct = ix <= 0x3fe921fb;  // |x| <= pi/4: no reduction, iy = 0
+  double r0, r1;
+  const int nr = det_rem_pio2(x, &r0, &r1);
+  const double y0 = direct ? x : r0, y1 = direct ? 0.0 : r1;
+  const int n = direct ? 0 : nr;
+  const int32_t iy0 = dm_hi(y0) & 0x7fffffff;
+  const bool tiny = iy0 < 0x3e400000;  // |y0| < 2^-27: (int)y0 == 0 always holds here
+  const double z = y0 * y0;
+  // __kernel_sin(y0, y1, iy)
+  double s;
+  {
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double v = z * y0;
+    const double r = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+    const double s_direct = y0 + v * (S1 + z * r);
+    const double s_tail = y0 - ((z * (0.5 * y1 - v * r) - y1) - v * S1);
+    s = direct ? s_direct : s_tail;
+    s = tiny ? y0 : s;
   }
+  // __kernel_cos(y0, y1)
+  double c;
+  {
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+    const double t = z * r - y0 * y1;
+    const double c_small = 1.0 - (0.5 * z - t);
+    const double qx = iy0 > 0x3fe90000 ? 0.28125 : __hiloint2double(iy0 - 0x00200000, 0);
+    const double hz = 0.5 * z - qx;
+    const double a = 1.0 - qx;
+    const double c_big = a - (hz - t);
+    c = iy0 < 0x3FD33333 ? c_small : c_big;
+    c = tiny ? 1.0 : c;
+  }
+  const int q = n & 3;
+  const double so = (q & 1) ? c : s, co = (q & 1) ? s : c;
+  *sn = (q == 2 || q == 3) ? -so : so;
+  *cs = (q == 1 || q == 2) ? -co : co;
 }
 
 }  // namespace abl

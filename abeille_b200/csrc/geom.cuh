@@ -492,25 +492,45 @@ __device__ __forceinline__ int pad_index(int info) { return info >> 8; }
 __device__ __forceinline__ int make_pad(int type, int flag, int frame, int index) {
   return type | (flag << 2) | (frame << 3) | (index << 8);
 }
+// Storage accessors.  The algorithms below (descent, move, validation) are written against these, so the same
+// code drives the local-memory Cursor and the shared-memory cursor of the history kernel (history.cuh: SCursor).
 __device__ __forceinline__ V3 frame_r(const Cursor& c, int f) { return {c.fx[f], c.fy[f], c.fz[f]}; }
+__device__ __forceinline__ void set_frame(Cursor& c, int f, double x, double y, double z) {
+  c.fx[f] = x;
+  c.fy[f] = y;
+  c.fz[f] = z;
+}
+__device__ __forceinline__ void shift_frame(Cursor& c, int f, double dx, double dy, double dz) {
+  c.fx[f] = c.fx[f] + dx;
+  c.fy[f] = c.fy[f] + dy;
+  c.fz[f] = c.fz[f] + dz;
+}
+__device__ __forceinline__ int pad_info(const Cursor& c, int i) { return c.pinfo[i]; }
+__device__ __forceinline__ void store_pad(Cursor& c, int i, int info, int tx, int ty, int tz) {
+  c.pinfo[i] = info;
+  c.ptile[i][0] = tx;
+  c.ptile[i][1] = ty;
+  c.ptile[i][2] = tz;
+}
+__device__ __forceinline__ bool pad_tile_is(const Cursor& c, int i, int nx, int ny, int nz) {
+  return c.ptile[i][0] == nx && c.ptile[i][1] == ny && c.ptile[i][2] == nz;
+}
 
-__device__ __forceinline__ bool push_pad(Cursor& c, int info, int tx = 0, int ty = 0, int tz = 0) {
+template <class CUR>
+__device__ __forceinline__ bool push_pad(CUR& c, int info, int tx = 0, int ty = 0, int tz = 0) {
   if (c.np >= ABL_MAX_PADS) {
     c.err = ABL_ERR_GEOMETRY;
     return false;
   }
-  c.pinfo[c.np] = info;
-  c.ptile[c.np][0] = tx;
-  c.ptile[c.np][1] = ty;
-  c.ptile[c.np][2] = tz;
+  store_pad(c, c.np, info, tx, ty, tz);
   c.np++;
   return true;
 }
 
 // Universe::get_cell(stack, r, u, on_surf) made iterative (cell_universe.cpp:72-109, rect_lattice.cpp:132-207).
 // Descends from universe `uni` whose coordinates are frame f; returns the material cell or -1 (lost).
-template <bool FAST = false>
-__device__ inline int descend(const DevProblem& P, Cursor& c, int uni, int f, const V3& u) {
+template <bool FAST = false, class CUR = Cursor>
+__device__ inline int descend(const DevProblem& P, CUR& c, int uni, int f, const V3& u) {
   for (;;) {
     const abl_universe* U = P.universes + uni;
     const V3 r = frame_r(c, f);
@@ -557,9 +577,7 @@ __device__ inline int descend(const DevProblem& P, Cursor& c, int uni, int f, co
         return -1;
       }
       const V3 ctr = tile_center(L, nx, ny, nz);
-      c.fx[f + 1] = r.x - ctr.x;
-      c.fy[f + 1] = r.y - ctr.y;
-      c.fz[f + 1] = r.z - ctr.z;
+      set_frame(c, f + 1, r.x - ctr.x, r.y - ctr.y, r.z - ctr.z);
       f++;
       uni = sub;
       continue;
@@ -586,14 +604,11 @@ __device__ inline void cursor_restart(const DevProblem& P, Cursor& c, const V3& 
 }
 
 // Tracker::move (tracker.hpp:76-85): every frame advances by d*u, the surface token is dropped
-__device__ __forceinline__ void cursor_move(Cursor& c, double d, const V3& u) {
+template <class CUR>
+__device__ __forceinline__ void cursor_move(CUR& c, double d, const V3& u) {
   const double dx = d * u.x, dy = d * u.y, dz = d * u.z;
 #pragma unroll 1
-  for (int f = 0; f < c.nf; f++) {
-    c.fx[f] = c.fx[f] + dx;
-    c.fy[f] = c.fy[f] + dy;
-    c.fz[f] = c.fz[f] + dz;
-  }
+  for (int f = 0; f < c.nf; f++) shift_frame(c, f, dx, dy, dz);
   c.token = 0;
 }
 

@@ -73,6 +73,11 @@ struct DevProblem {
   const double *dg_cp, *dg_lambda;
   const int32_t* fissile;
   const double* smp;  // [G] sampling xs (majorant or ratio*majorant)
+  // quotients of table entries, evaluated once on the host with the same IEEE division the kernels would use
+  // (bit-identical): they take three fp64 divisions out of every flight / collision of the history kernel
+  const double* real_frac;  // [M*G] Et / smp[g]: probability that a tentative collision is real (delta_tracker.cpp:182)
+  const double* surv_frac;  // [M*G] 1 - Ea / Et: implicit-capture weight factor (transporter.cpp:295-298)
+  const double* inv_score;  // [ntallies*M*G] 1 / (Et * net_weight): the collision-estimator score (collision_mesh_tally.cpp:35-40)
   // tallies
   int32_t ntallies, n_coll_tallies, n_tl_tallies;
   DevTally tally[ABL_MAX_TALLIES];

@@ -48,9 +48,14 @@ __device__ __forceinline__ double quantity_factor(int quantity, double w, double
 
 // returns 1 when a bin was scored
 // l = energy bin of the particle (tally_energy_bin, or the per-group table for mid-point energies)
+// scr0 = 1 / (Et * net_weight) (collision_mesh_tally.cpp:35-40), evaluated by the caller or read from DevProblem::inv_score
+__device__ inline int score_collision_pre(const DevTally& t, const V3& r, int l, double w, double w2, const MatXS& m, double scr0);
 template <class M = InlineMath>
 __device__ inline int score_collision(const DevTally& t, const V3& r, int l, double w, double w2, const MatXS& m) {
-  double scr = M::div(1., m.Et * t.net_weight);
+  return score_collision_pre(t, r, l, w, w2, m, M::div(1., m.Et * t.net_weight));
+}
+__device__ inline int score_collision_pre(const DevTally& t, const V3& r, int l, double w, double w2, const MatXS& m, double scr0) {
+  double scr = scr0;
   const int i = (int)floor((r.x - t.lowx) * t.dx_inv);
   const int j = (int)floor((r.y - t.lowy) * t.dy_inv);
   const int k = (int)floor((r.z - t.lowz) * t.dz_inv);

@@ -41,7 +41,7 @@ typedef enum abl_status {
 } abl_status;
 
 #define ABL_MAX_PADS 10   /* geometry stack depth (reference reserves 10: tracker.hpp:46) */
-#define ABL_MAX_FRAMES 6  /* nested local coordinate frames (root + lattice levels)       */
+#define ABL_MAX_FRAMES 5  /* nested local coordinate frames (root + lattice levels)       */
 
 /* ---- enums mirrored from the reference --------------------------------------------------------- */
 enum { ABL_MODE_K_EIGENVALUE = 0, ABL_MODE_NOISE = 1 };                         /* settings.hpp        */
