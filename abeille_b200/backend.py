@@ -51,10 +51,12 @@ class AblTrace(C.Structure):
 
 
 def lib_paths():
-    """(CUDA library, host library).  ABEILLE_B200_LIB selects another build of the CUDA library (kernel tuning
-    experiments: same ABI, different compile-time constants)."""
-    cuda = os.environ.get("ABEILLE_B200_LIB") or os.path.join(_LIBDIR, "libabeille_b200.so")
-    return cuda, os.path.join(_LIBDIR, "libabeille_host.so")
+    """(CUDA library, host library).  ABEILLE_B200_LIBDIR selects another build of the pair (kernel tuning experiments:
+    same ABI, different compile-time constants).  It must be a whole directory: the host library names
+    libabeille_b200.so as a dependency (rpath $ORIGIN), and two builds of the CUDA library in one process would
+    register their kernels under the same host symbols."""
+    d = os.environ.get("ABEILLE_B200_LIBDIR") or _LIBDIR
+    return os.path.join(d, "libabeille_b200.so"), os.path.join(d, "libabeille_host.so")
 
 
 _backend_lib = None

@@ -56,7 +56,7 @@ __device__ __forceinline__ V3 rotate_direction(const V3& u, double mu, double ph
   return make_direction<M>(ux, uy, uz);
 }
 // one shared copy for kernels that use CallMath (scatter in the hot loop, fission banking in the cold path)
-__device__ __noinline__ V3 rotate_direction_call(const V3 u, double mu, double phi) { return rotate_direction<CallMath>(u, mu, phi); }
+__device__ ABL_HOT_CALL V3 rotate_direction_call(const V3 u, double mu, double phi) { return rotate_direction<CallMath>(u, mu, phi); }
 template <class M>
 __device__ __forceinline__ V3 rotate_dir(const V3& u, double mu, double phi) { return rotate_direction<M>(u, mu, phi); }
 template <>
@@ -296,7 +296,7 @@ __device__ __noinline__ bool cell_is_inside_nl(const GeoTables G, int ci, const 
 // Cell::is_inside through the compiled descriptor (tables.h: CellFast): 1 inside, 0 outside, -1 undecided --
 // the particle sits on a surface or is within SURFACE_COINCIDENT of one (direction-dependent tie), or the
 // region has no compiled form; the caller then runs the generic evaluator.  One shared copy per kernel.
-__device__ __noinline__ int cell_fast_nl(const CellFast* __restrict__ cf, const V3 r, int on_surf) {
+__device__ ABL_HOT_CALL int cell_fast_nl(const CellFast* __restrict__ cf, const V3 r, int on_surf) {
   const int kind = __ldg(&cf->kind);
   if (on_surf != 0) return -1;
   if (kind == CF_BOX) {
@@ -390,7 +390,7 @@ __device__ __forceinline__ void get_tile(const Lat& L, const V3& r, const V3& u,
 struct Tile3 {
   int nx, ny, nz;
 };
-__device__ __noinline__ Tile3 lattice_tile_nl(const abl_universe* __restrict__ U, const V3 r, const V3 u) {
+__device__ ABL_HOT_CALL Tile3 lattice_tile_nl(const abl_universe* __restrict__ U, const V3 r, const V3 u) {
   const Lat L = load_lattice(U);
   Tile3 t;
   get_tile(L, r, u, t.nx, t.ny, t.nz);

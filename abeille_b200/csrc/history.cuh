@@ -86,6 +86,135 @@ __device__ __forceinline__ void cursor_relocate(const DevProblem& P, CUR& c, int
   c.mat = c.cell >= 0 ? __ldg(&P.cells[c.cell].material) : -1;
 }
 
+// One step of Universe::get_cell through a lattice (rect_lattice.cpp:132-207): 0 = descend further (uni / f updated),
+// -1 = no universe here (lost)
+template <class CUR>
+__device__ __forceinline__ int descend_lattice_step(const DevProblem& P, CUR& c, int& uni, int& f, const V3& u) {
+  const abl_universe* U = P.universes + uni;
+  const V3 r = frame_r(c, f);
+  const Tile3 t3 = lattice_tile_nl(U, r, u);
+  Lat L;
+  L.Nx = __ldg(&U->N[0]); L.Ny = __ldg(&U->N[1]); L.Nz = __ldg(&U->N[2]);
+  L.tile_offset = __ldg(&U->tile_offset);
+  L.outer = __ldg(&U->outer);
+  int sub = -1;
+  if (tile_in_range(L, t3.nx, t3.ny, t3.nz)) sub = __ldg(&P.tiles[L.tile_offset + t3.nz * (L.Nx * L.Ny) + t3.nx * L.Ny + t3.ny]);
+  c.nf = f + 1;
+  if (sub >= 0) {
+    if (!push_pad(c, make_pad(PAD_LATTICE, 0, f, uni), t3.nx, t3.ny, t3.nz)) return -1;
+    if (f + 1 >= ABL_MAX_FRAMES) {
+      c.err = ABL_ERR_GEOMETRY;
+      return -1;
+    }
+    L.Px = __ldg(&U->P[0]); L.Py = __ldg(&U->P[1]); L.Pz = __ldg(&U->P[2]);
+    L.Xl = __ldg(&U->Xl[0]); L.Yl = __ldg(&U->Xl[1]); L.Zl = __ldg(&U->Xl[2]);
+    const V3 ctr = tile_center(L, t3.nx, t3.ny, t3.nz);
+    set_frame(c, f + 1, r.x - ctr.x, r.y - ctr.y, r.z - ctr.z);
+    f++;
+    uni = sub;
+    return 0;
+  }
+  if (L.outer >= 0) {  // outside the lattice or an empty tile: the outer universe, un-shifted r
+    if (!push_pad(c, make_pad(PAD_LATTICE, 1, f, uni), t3.nx, t3.ny, t3.nz)) return -1;
+    uni = L.outer;
+    return 0;
+  }
+  push_pad(c, make_pad(PAD_LATTICE, 0, f, uni), t3.nx, t3.ny, t3.nz);
+  return -1;
+}
+
+// One step through a cell universe (cell_universe.cpp:72-109): 0 = descend into the fill universe, 1 = material cell
+// found (cell), -1 = no cell here (lost)
+template <class CUR>
+__device__ __forceinline__ int descend_cells_step(const DevProblem& P, CUR& c, int& uni, int f, const V3& u, int& cell) {
+  const abl_universe* U = P.universes + uni;
+  const V3 r = frame_r(c, f);
+  if (!push_pad(c, make_pad(PAD_UNIVERSE, 0, f, uni))) return -1;
+  const int off = __ldg(&U->cell_offset), n = __ldg(&U->ncells);
+  int found = -1;
+  for (int k = 0; k < n; k++) {
+    const int ci = __ldg(&P.ucells[off + k]);
+    if (cell_is_inside_fast(P, ci, r, u, c.token)) {
+      found = ci;
+      break;
+    }
+  }
+  c.nf = f + 1;
+  if (found < 0) return -1;
+  if (!push_pad(c, make_pad(PAD_CELL, 0, f, found))) return -1;
+  const int fill = __ldg(&P.cells[found].fill_universe);
+  if (fill < 0) {
+    cell = found;
+    return 1;
+  }
+  uni = fill;
+  return 0;
+}
+
+// cursor_relocate for the lanes `mask` of a warp together (every lane of mask must call it).  The same per-lane
+// operation sequence, but the lanes advance in step by universe TYPE: lattice steps while any lane stands at a lattice,
+// then one cell-universe step for everybody.  Lanes re-descend from different depths (a changed pin cell: the cell
+// universe only; a changed tile: the lattices above it first), and a plain per-lane loop made the warp run the
+// cell-universe code once per distinct depth with a handful of lanes each (ncu: 5 of 32).
+template <class CUR>
+__device__ __forceinline__ void cursor_relocate_sync(const DevProblem& P, CUR& c, int from, const V3& u, unsigned mask) {
+  int uni = P.root, f = 0;
+  bool full = true;
+  if (from > 0) {
+    const int back = pad_info(c, from - 1);
+    if (pad_type(back) != PAD_CELL) {
+      c.np = from - 1;
+      uni = pad_index(back);
+      f = pad_frame(back);
+      full = false;
+    }
+  }
+  if (full) {
+    c.np = 0;
+    c.nf = 1;
+  }
+  bool active = true;
+  int cell = -1;
+  for (;;) {
+    for (;;) {
+      const bool at_lattice = active && __ldg(&P.universes[uni].type) != ABL_UNI_CELLS;
+      if (!__any_sync(mask, at_lattice)) break;
+      int st = 0;
+      if (at_lattice) st = descend_lattice_step(P, c, uni, f, u);
+      if (st < 0) {
+        if (full) {
+          active = false;
+        } else {  // partial re-descent failed: full restart from the root
+          full = true;
+          c.np = 0;
+          c.nf = 1;
+          uni = P.root;
+          f = 0;
+        }
+      }
+    }
+    if (!__any_sync(mask, active)) break;
+    if (active) {
+      const int st = descend_cells_step(P, c, uni, f, u, cell);
+      if (st > 0) {
+        active = false;
+      } else if (st < 0) {
+        if (full) {
+          active = false;
+        } else {
+          full = true;
+          c.np = 0;
+          c.nf = 1;
+          uni = P.root;
+          f = 0;
+        }
+      }
+    }
+  }
+  c.cell = cell;
+  c.mat = cell >= 0 ? __ldg(&P.cells[cell].material) : -1;
+}
+
 __device__ __noinline__ Boundary cursor_boundary_condition_nl(const GeoTables G, const Cursor& c, const V3 u) {
   return cursor_boundary_condition(G, c, u);
 }
@@ -137,17 +266,17 @@ __device__ __noinline__ int score_flight_all_nl(const DevTally* __restrict__ tal
 //   draws the sites consume (a table jump) and goes on.  A job queue is single-consumer (history warp w posts to
 //   service warp w % HK_SERVICE_WARPS) and lives in shared memory.
 #ifndef HK_THREADS
-#define HK_THREADS 768
+#define HK_THREADS 512
 #endif
 #ifndef HK_SERVICE_WARPS
-#define HK_SERVICE_WARPS 2
+#define HK_SERVICE_WARPS 1
 #endif
 #define HK_HIST (HK_THREADS - 32 * HK_SERVICE_WARPS)
 #ifndef HK_STAGE_SYNC
-#define HK_STAGE_SYNC 1
+#define HK_STAGE_SYNC 0
 #endif
 #ifndef HK_MATH
-#define HK_MATH CallMath
+#define HK_MATH InlineMath
 #endif
 #ifndef HK_FQ
 #define HK_FQ 64  // fission-job ring entries per service warp (a full ring makes the owner bank its sites inline)
@@ -538,8 +667,13 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
       HK_SYNC();
 
       // ---- L: (re-)descent through the universe tree -----------------------------------------------------------------------------------
+      const unsigned relocating = __ballot_sync(FULL, need >= 0);
       if (need >= 0) {
+#ifdef HK_PER_LANE_RELOCATE
         cursor_relocate(P, c, need, h.u);
+#else
+        cursor_relocate_sync(P, c, need, h.u, relocating);
+#endif
         need = -1;
         if (c.err) {
           raise_error(A, c.err, A.bank.id_a[h.idx]);
