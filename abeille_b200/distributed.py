@@ -243,8 +243,10 @@ class HostBufferLoop:
         m = len(fis["x"])
         self.h2d_bytes += n_in * 8 * (8 + sum(1 for k in BANK_U64 if self.bank.get(k) is not None))
         self.d2h_bytes += m * 8 * 11 + 6 * 8 + 8 * 8
-        wpos = float(fis["wgt"][fis["wgt"] > 0].sum()) if m else 0.0
-        wneg = float(-fis["wgt"][fis["wgt"] < 0].sum()) if m else 0.0
+        # host-side caller steps on the (pinned) numpy arrays, through torch's multi-threaded CPU kernels
+        wt = torch.from_numpy(fis["wgt"])
+        wpos = float(torch.clamp(wt, min=0.).sum()) if m else 0.0
+        wneg = float(-torch.clamp(wt, max=0.).sum()) if m else 0.0
         local = np.concatenate([scores, [cn["real_collisions"], float(m), float(n_in), wpos, wneg]])
         allv = self._gather(local)
         tot = allv.sum(axis=0)
@@ -252,7 +254,7 @@ class HostBufferLoop:
         self.k_col = tot[0] / self.n_total
         if sum(counts) == 0:
             raise RuntimeError("No fission neutrons were produced.")
-        fis["wgt"] *= self.n_total / (tot[9] - tot[10])  # normalize_weights, power_iterator.cpp:561-569
+        wt.mul_(self.n_total / (tot[9] - tot[10]))  # normalize_weights, power_iterator.cpp:561-569
         if converged:
             if self.world > 1:
                 for t in self.tally_tensors():
@@ -261,7 +263,8 @@ class HostBufferLoop:
         gpu.tallies_clear()
         first = self.global_counter + int(sum(counts[: self.rank]))
         family = fis["id_c"]
-        fis["id_a"][:] = np.arange(first, first + m, dtype=np.uint64)  # fresh history ids (power_iterator.cpp:397-399)
+        if m:  # fresh history ids (power_iterator.cpp:397-399)
+            torch.arange(first, first + m, dtype=torch.int64, out=torch.from_numpy(fis["id_a"].view(np.int64)))
         self.bank = {k: fis[k] for k in self.F64_OUT}
         self.bank.update({"wgt2": None, "id_a": fis["id_a"], "id_b": family, "id_c": None})
         self.global_counter += int(sum(counts))
