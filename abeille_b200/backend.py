@@ -22,7 +22,8 @@ COUNTER_KEYS = ("flights", "real_collisions", "virtual_collisions", "tl_bins", "
 # every symbol include/abeille_b200.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = (
     "abl_create", "abl_destroy", "abl_last_error", "abl_device_info", "abl_last_transport_kernel", "abl_transport", "abl_get_trace",
-    "abl_transport_device", "abl_tally_count", "abl_tally_shape", "abl_tallies_record", "abl_tallies_clear",
+    "abl_transport_device", "abl_transport_noise_device", "abl_bank_weight_magnitude_device", "abl_bank_divide_weights_device",
+    "abl_tally_count", "abl_tally_shape", "abl_tallies_record", "abl_tallies_clear",
     "abl_tally_fetch", "abl_tally_device_ptr", "abl_sample_source_device", "abl_bank_weight_stats_device",
     "abl_bank_scale_weights_device", "abl_bank_to_particles_device", "abl_entropy_bin_device",
     "abl_score_source_device", "abl_cancel_device", "abl_bank_alloc_device", "abl_bank_free_device",
@@ -42,7 +43,7 @@ class AblBank(C.Structure):
 
 class AblGenParams(C.Structure):
     _fields_ = [("k_col", C.c_double), ("keff", C.c_double), ("converged", C.c_int32), ("noise", C.c_int32),
-                ("trace", C.c_int32), ("pad_", C.c_int32)]
+                ("trace", C.c_int32), ("sample_noise_source", C.c_int32)]
 
 
 class AblTrace(C.Structure):
@@ -378,6 +379,37 @@ class Backend:
                                          scores.ctypes.data_as(_PD), cn.ctypes.data_as(_PU64), self._stream())
         self._check(rc)
         return int(nout.value), scores, {k: int(v) for k, v in zip(COUNTER_KEYS, cn)}
+
+    def transport_noise_device(self, bank: dict, n: int, out: dict, noise_out: dict | None = None, k_col: float = 1.0,
+                               keff: float = 1.0, converged: bool = False, noise: bool = False, sample_noise: bool = False,
+                               trace: bool = False, use_rng_state: bool = False):
+        """abl_transport_noise_device (simulation: noise).  noise=True transports noise particles (complex weights);
+        sample_noise=True is a power-iteration generation that fills noise_out with the sampled noise source.
+        Returns (n_fission, n_noise, scores[6], counters dict)."""
+        sin = _device_struct(bank, n)
+        if not use_rng_state:
+            sin.id_c = None
+        sout = _device_struct(out, len(out["x"]))
+        snoise = _device_struct(noise_out, len(noise_out["x"])) if noise_out is not None else None
+        gp = AblGenParams(float(k_col), float(keff), int(bool(converged)), int(bool(noise)), int(bool(trace)), int(bool(sample_noise)))
+        nout, nnoise = C.c_uint64(0), C.c_uint64(0)
+        scores = np.zeros(6)
+        cn = np.zeros(8, dtype=np.uint64)
+        rc = self.L.abl_transport_noise_device(self.h, C.byref(sin), C.byref(gp), C.byref(sout), C.byref(nout),
+                                               C.byref(snoise) if snoise is not None else None, C.byref(nnoise),
+                                               scores.ctypes.data_as(_PD), cn.ctypes.data_as(_PU64), self._stream())
+        self._check(rc)
+        return int(nout.value), int(nnoise.value), scores, {k: int(v) for k, v in zip(COUNTER_KEYS, cn)}
+
+    def weight_magnitude_device(self, bank: dict, n: int) -> float:
+        s = _device_struct(bank, n)
+        out = C.c_double(0.)
+        self._check(self.L.abl_bank_weight_magnitude_device(self.h, C.byref(s), C.byref(out), self._stream()))
+        return float(out.value)
+
+    def divide_weights_device(self, bank: dict, n: int, divisor: float):
+        s = _device_struct(bank, n)
+        self._check(self.L.abl_bank_divide_weights_device(self.h, C.byref(s), C.c_double(divisor), self._stream()))
 
     def weight_stats_device(self, bank: dict, n: int):
         s = _device_struct(bank, n)

@@ -26,7 +26,8 @@ struct DevSmall {  // small per-call block, zeroed before every transport launch
   int error[4];
   double stats[4];
   uint32_t grand_total;
-  uint32_t pad_;
+  uint32_t grand_total_noise;
+  unsigned long long n_nsites;
 };
 
 thread_local std::string g_create_error;
@@ -51,6 +52,11 @@ struct abl_context {
   DevSmall* small_host = nullptr;  // pinned
   double* secondaries = nullptr;
   uint64_t sec_threads = 0;
+  // noise mode: scratch noise particles, per-history counts / offsets, daughter ids of the scratch sites
+  Site* nsites = nullptr;
+  uint64_t nsite_cap = 0, did_cap = 0, ndid_cap = 0, nnoise_cap = 0;
+  uint32_t *nnoise = nullptr, *noffsets = nullptr, *ntile_sums = nullptr, *site_did = nullptr, *nsite_did = nullptr;
+  int nm_blocks_per_sm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   CancelBins cancel{nullptr, nullptr, nullptr};
   bool cancel_has_w2 = false;
   // staging banks of the host-buffer API
@@ -310,7 +316,7 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
   // surface tracking: per-lane history loop (transport.cuh); delta / carter: staged lock-step loop with the cursors in
   // shared memory and service warps for the rare events (history.cuh)
   void (*kern)(const DevProblem, const RunArgs) = nullptr;
-  if (TRK == ABL_TRACK_SURFACE) kern = transport_kernel<ABL_TRACK_SURFACE, false>;
+  if (TRK == ABL_TRACK_SURFACE) kern = transport_kernel<ABL_TRACK_SURFACE, 0>;
   else kern = history_kernel<(TRK == ABL_TRACK_SURFACE ? ABL_TRACK_DELTA : TRK), TRACE>;
   const bool staged = TRK != ABL_TRACK_SURFACE;
   const int threads = staged ? HK_THREADS : 128;
@@ -363,6 +369,52 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
   return ABL_OK;
 }
 
+// noise-mode runs (simulation: noise) use the per-lane history loop for every tracker: MODE 1 = power-iteration
+// generation (may sample the noise source), MODE 2 = noise particles (noise.cuh)
+template <int TRK, int MODE>
+int launch_transport_nm(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s) {
+  void (*kern)(const DevProblem, const RunArgs) = transport_kernel<TRK, MODE>;
+  const int threads = 128;
+  int& bps = h->nm_blocks_per_sm[TRK][MODE];
+  if (bps == 0) {
+    int nb = 0;
+    ABL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, 0));
+    bps = nb < 1 ? 1 : nb;
+  }
+  uint64_t blocks = (uint64_t)h->sm_count * bps;
+  const uint64_t need = (n + threads - 1) / threads;
+  if (blocks > need) blocks = need;
+  if (blocks < 1) blocks = 1;
+  RunArgs B = A;
+  if (MODE == 2 || TRK == ABL_TRACK_CARTER) {  // secondaries: noise copies, carter splitting, noise fission without inner generations
+    const uint64_t cap = (uint64_t)h->sm_count * bps * threads;
+    if (cap > h->sec_threads) {
+      if (h->secondaries) cudaFree(h->secondaries);
+      h->secondaries = nullptr;
+      h->sec_threads = 0;
+      ABL_CUDA(h, cudaMalloc(&h->secondaries, cap * ABL_SEC_CAP * 9 * sizeof(double)));
+      h->sec_threads = cap;
+    }
+    B.secondaries = h->secondaries;
+  }
+  cudaEventRecord(h->ev0, s);
+  kern<<<(unsigned)blocks, threads, 0, s>>>(h->P, B);
+  cudaEventRecord(h->ev1, s);
+  h->last_block = threads;
+  h->last_grid = (int)blocks;
+  h->launches++;
+  ABL_CUDA(h, cudaGetLastError());
+  return ABL_OK;
+}
+template <int MODE>
+int launch_transport_nm(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s) {
+  switch (h->P.tracking) {
+    case ABL_TRACK_SURFACE: return launch_transport_nm<ABL_TRACK_SURFACE, MODE>(h, A, n, s);
+    case ABL_TRACK_DELTA: return launch_transport_nm<ABL_TRACK_DELTA, MODE>(h, A, n, s);
+    default: return launch_transport_nm<ABL_TRACK_CARTER, MODE>(h, A, n, s);
+  }
+}
+
 template <int TRK>
 int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s, bool trace) {
   return trace ? launch_transport<TRK, true>(h, A, n, s) : launch_transport<TRK, false>(h, A, n, s);
@@ -385,15 +437,59 @@ int status_from_device_error(abl_handle h, const DevSmall& sm) {
   return sm.error[0];
 }
 
+int grow_u32(abl_handle h, uint32_t*& p, uint64_t& cap, uint64_t need) {
+  if (need > cap) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    ABL_CUDA(h, cudaMalloc(&p, need * sizeof(uint32_t)));
+    cap = need;
+  }
+  return ABL_OK;
+}
+
 int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* params, const BankView& out, uint64_t* n_fission,
-                   double scores[6], uint64_t counters[8], cudaStream_t s) {
+                   double scores[6], uint64_t counters[8], cudaStream_t s, const BankView* noise_out = nullptr,
+                   uint64_t* n_noise = nullptr) {
   const uint64_t N = in.n;
   if (N >= (1ull << 32)) return fail(h, ABL_ERR_UNSUPPORTED, "bank larger than 2^32-1 histories per device");
-  if (params->noise) return fail(h, ABL_ERR_UNSUPPORTED, "noise transport is not implemented on the device");
+  const bool noise_mode = h->P.mode == ABL_MODE_NOISE;
+  const bool sample_noise = params->sample_noise_source != 0;
+  if ((params->noise || sample_noise) && !noise_mode)
+    return fail(h, ABL_ERR_INVALID, "noise transport / noise-source sampling needs a problem with simulation: noise");
+  if (params->noise && sample_noise) return fail(h, ABL_ERR_INVALID, "the noise source is sampled in power-iteration generations only");
+  if (sample_noise && (!noise_out || !n_noise)) return fail(h, ABL_ERR_INVALID, "noise-source sampling needs a noise bank");
+  if (params->noise && !in.wgt2) return fail(h, ABL_ERR_INVALID, "noise transport needs the second weight (wgt2)");
+  if (n_noise) *n_noise = 0;
   int rc = ensure_history_scratch(h, N, params->trace != 0);
   if (rc) return rc;
   rc = ensure_sites(h, out.n);
   if (rc) return rc;
+  if (noise_mode) {
+    if ((rc = grow_u32(h, h->site_did, h->did_cap, out.n)) != 0) return rc;
+    if (sample_noise) {
+      if (noise_out->n > h->nsite_cap) {
+        if (h->nsites) cudaFree(h->nsites);
+        h->nsites = nullptr;
+        h->nsite_cap = 0;
+        ABL_CUDA(h, cudaMalloc(&h->nsites, noise_out->n * sizeof(Site)));
+        h->nsite_cap = noise_out->n;
+      }
+      if ((rc = grow_u32(h, h->nsite_did, h->ndid_cap, noise_out->n)) != 0) return rc;
+      if (N > h->nnoise_cap) {
+        const uint64_t cap = N + N / 4 + 1024;
+        for (uint32_t** p : {&h->nnoise, &h->noffsets, &h->ntile_sums}) {
+          if (*p) cudaFree(*p);
+          *p = nullptr;
+        }
+        h->nnoise_cap = 0;
+        ABL_CUDA(h, cudaMalloc(&h->nnoise, cap * sizeof(uint32_t)));
+        ABL_CUDA(h, cudaMalloc(&h->noffsets, cap * sizeof(uint32_t)));
+        ABL_CUDA(h, cudaMalloc(&h->ntile_sums, (cap / ABL_SCAN_TILE + 2) * sizeof(uint32_t)));
+        h->nnoise_cap = cap;
+      }
+    }
+  }
   ABL_CUDA(h, cudaMemsetAsync(h->small_dev, 0, sizeof(DevSmall), s));
   RunArgs A{};
   A.bank = in;
@@ -414,11 +510,26 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
   A.k_col = params->k_col;
   A.keff = params->keff;
   A.converged = params->converged;
+  A.sample_noise = sample_noise ? 1 : 0;
+  A.site_did = h->site_did;
+  if (sample_noise) {
+    A.nsites = h->nsites;
+    A.n_nsites = &h->small_dev->n_nsites;
+    A.nsite_capacity = noise_out->n;
+    A.nnoise = h->nnoise;
+    A.nsite_did = h->nsite_did;
+  }
   if (N > 0) {
-    switch (h->P.tracking) {
-      case ABL_TRACK_SURFACE: rc = launch_transport<ABL_TRACK_SURFACE, false>(h, A, N, s); break;
-      case ABL_TRACK_DELTA: rc = launch_transport<ABL_TRACK_DELTA>(h, A, N, s, params->trace != 0); break;
-      default: rc = launch_transport<ABL_TRACK_CARTER>(h, A, N, s, params->trace != 0); break;
+    if (noise_mode) {
+      if (in.id_c == nullptr) {  // seed(seed); advance(stride * history id) happens in the kernel (transport.cuh)
+      }
+      rc = params->noise ? launch_transport_nm<2>(h, A, N, s) : launch_transport_nm<1>(h, A, N, s);
+    } else {
+      switch (h->P.tracking) {
+        case ABL_TRACK_SURFACE: rc = launch_transport<ABL_TRACK_SURFACE, false>(h, A, N, s); break;
+        case ABL_TRACK_DELTA: rc = launch_transport<ABL_TRACK_DELTA>(h, A, N, s, params->trace != 0); break;
+        default: rc = launch_transport<ABL_TRACK_CARTER>(h, A, N, s, params->trace != 0); break;
+      }
     }
     if (rc) return rc;
     // fission bank in the reference's order: offsets = exclusive scan of per-history counts
@@ -427,6 +538,12 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
     scan_top_kernel<<<1, ABL_SCAN_THREADS, 0, s>>>(h->tile_sums, ntiles, &h->small_dev->grand_total);
     scan_apply_kernel<<<ntiles, ABL_SCAN_THREADS, 0, s>>>(h->nfis, N, h->tile_sums, h->offsets);
     h->launches += 3;
+    if (sample_noise) {  // the same for the noise bank
+      scan_tile_sums_kernel<<<ntiles, ABL_SCAN_THREADS, 0, s>>>(h->nnoise, N, h->ntile_sums);
+      scan_top_kernel<<<1, ABL_SCAN_THREADS, 0, s>>>(h->ntile_sums, ntiles, &h->small_dev->grand_total_noise);
+      scan_apply_kernel<<<ntiles, ABL_SCAN_THREADS, 0, s>>>(h->nnoise, N, h->ntile_sums, h->noffsets);
+      h->launches += 3;
+    }
   }
   ABL_CUDA(h, cudaMemcpyAsync(h->small_host, h->small_dev, sizeof(DevSmall), cudaMemcpyDeviceToHost, s));
   ABL_CUDA(h, cudaStreamSynchronize(s));
@@ -444,9 +561,23 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
     return fail(h, ABL_ERR_BANK_OVERFLOW, buf);
   }
   if (sm.n_sites > 0) {
-    place_sites_kernel<<<grid_for(h, sm.n_sites, 256), 256, 0, s>>>(h->sites, sm.n_sites, h->offsets, in, out);
+    place_sites_kernel<<<grid_for(h, sm.n_sites, 256), 256, 0, s>>>(h->sites, sm.n_sites, h->offsets, in, out,
+                                                                     noise_mode ? h->site_did : nullptr);
     h->launches++;
     ABL_CUDA(h, cudaGetLastError());
+  }
+  if (sample_noise) {
+    *n_noise = sm.n_nsites;
+    if (sm.n_nsites > noise_out->n) {
+      char buf[128];
+      snprintf(buf, sizeof buf, "noise bank overflow: %llu particles, capacity %llu", sm.n_nsites, (unsigned long long)noise_out->n);
+      return fail(h, ABL_ERR_BANK_OVERFLOW, buf);
+    }
+    if (sm.n_nsites > 0) {
+      place_sites_kernel<<<grid_for(h, sm.n_nsites, 256), 256, 0, s>>>(h->nsites, sm.n_nsites, h->noffsets, in, *noise_out, h->nsite_did);
+      h->launches++;
+      ABL_CUDA(h, cudaGetLastError());
+    }
   }
   return ABL_OK;
 }
@@ -468,7 +599,8 @@ void abl_destroy(abl_handle h) {
   }
   for (void* p : {(void*)h->sites, (void*)h->nfis, (void*)h->offsets, (void*)h->tile_sums, (void*)h->tr_flights, (void*)h->tr_real,
                   (void*)h->tr_virtual, (void*)h->tr_hash, (void*)h->tr_rng, (void*)h->small_dev, (void*)h->secondaries,
-                  (void*)h->cancel.sum_w, (void*)h->cancel.sum_w2, (void*)h->cancel.count, (void*)h->probe_buf, (void*)h->rng_scratch})
+                  (void*)h->cancel.sum_w, (void*)h->cancel.sum_w2, (void*)h->cancel.count, (void*)h->probe_buf, (void*)h->rng_scratch,
+                  (void*)h->nsites, (void*)h->nnoise, (void*)h->noffsets, (void*)h->ntile_sums, (void*)h->site_did, (void*)h->nsite_did})
     if (p) cudaFree(p);
   free_bank(h->stage_in);
   free_bank(h->stage_out);
@@ -665,6 +797,25 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
     std::vector<double> cp = discrete_table(w);
     UP(cp.data(), cp.size(), P.source_cp);
   }
+  {  // square-oscillation noise sources; the frequency gate of every factor (square_oscillation_noise_source.cpp:85-170)
+    std::vector<DevNoiseSrc> ns((size_t)(p->n_noise_sources > 0 ? p->n_noise_sources : 0));
+    for (size_t i = 0; i < ns.size(); i++) {
+      const abl_noise_source& f = p->noise_sources[i];
+      for (int k = 0; k < 3; k++) {
+        ns[i].low[k] = f.low[k];
+        ns[i].hi[k] = f.hi[k];
+      }
+      const double w = p->w_noise, w0 = f.angular_frequency;
+      const int32_t n = static_cast<int32_t>(std::round(w / w0));
+      const double err = (n * w0 - w) / w;
+      ns[i].on = ((n == 1 || n == -1) && std::abs(err) < 0.01) ? 1 : 0;
+      ns[i].eps_t = f.eps_total;
+      ns[i].eps_f_pi = f.eps_fission * ABL_PI;
+      ns[i].eps_s_pi = f.eps_scatter * ABL_PI;
+    }
+    P.n_noise_src = (int32_t)ns.size();
+    UP(ns.data(), ns.size(), P.noise_src);
+  }
   P.entropy = make_mesh3(p->entropy, teb);
   P.cancel = make_mesh3(p->cancelator, teb);
 #undef UP
@@ -696,6 +847,44 @@ int abl_transport_device(abl_handle h, const abl_bank* bank_dev, const abl_gen_p
   ABL_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = use_stream(h, (cudaStream_t)stream);
   return transport_impl(h, view_of(bank_dev), params, view_of(fission_dev), n_fission, scores, counters, s);
+}
+
+int abl_transport_noise_device(abl_handle h, const abl_bank* bank_dev, const abl_gen_params* params, abl_bank* fission_dev,
+                               uint64_t* n_fission, abl_bank* noise_dev, uint64_t* n_noise, double scores[6], uint64_t counters[8],
+                               void* stream) {
+  if (!h || !bank_dev || !params || !fission_dev || !n_fission || !scores) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  BankView nv{};
+  if (noise_dev) nv = view_of(noise_dev);
+  return transport_impl(h, view_of(bank_dev), params, view_of(fission_dev), n_fission, scores, counters, s, noise_dev ? &nv : nullptr,
+                        n_noise);
+}
+
+int abl_bank_weight_magnitude_device(abl_handle h, const abl_bank* bank_dev, double* sum, void* stream) {
+  if (!h || !bank_dev || !sum || !bank_dev->wgt || !bank_dev->wgt2) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  ABL_CUDA(h, cudaMemsetAsync(h->small_dev->stats, 0, sizeof(double) * 4, s));
+  if (bank_dev->n) {
+    weight_magnitude_kernel<<<grid_for(h, bank_dev->n, 256), 256, 0, s>>>(bank_dev->wgt, bank_dev->wgt2, bank_dev->n, h->small_dev->stats);
+    h->launches++;
+  }
+  ABL_CUDA(h, cudaMemcpyAsync(sum, h->small_dev->stats, sizeof(double), cudaMemcpyDeviceToHost, s));
+  ABL_CUDA(h, cudaStreamSynchronize(s));
+  return ABL_OK;
+}
+
+int abl_bank_divide_weights_device(abl_handle h, abl_bank* bank_dev, double divisor, void* stream) {
+  if (!h || !bank_dev || !bank_dev->wgt || !bank_dev->wgt2) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  if (bank_dev->n) {
+    divide_weights_kernel<<<grid_for(h, bank_dev->n, 256), 256, 0, s>>>(bank_dev->wgt, bank_dev->wgt2, bank_dev->n, divisor);
+    h->launches++;
+    ABL_CUDA(h, cudaGetLastError());
+  }
+  return ABL_OK;
 }
 
 int abl_transport(abl_handle h, const abl_bank* bank, const abl_gen_params* params, abl_bank* fission_out, uint64_t* n_fission,

@@ -96,8 +96,10 @@ __global__ void __launch_bounds__(ABL_SCAN_THREADS) scan_apply_kernel(const uint
 }
 
 // ---- fission bank placement ---------------------------------------------------------------------------------
+// did: daughter ids of the scratch sites when they differ from the rank carried by the site (noise mode), else null
 __global__ void __launch_bounds__(256) place_sites_kernel(const Site* __restrict__ sites, uint64_t n_sites,
-                                                          const uint32_t* __restrict__ offsets, BankView in, BankView out) {
+                                                          const uint32_t* __restrict__ offsets, BankView in, BankView out,
+                                                          const uint32_t* __restrict__ did) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sites; i += (uint64_t)gridDim.x * blockDim.x) {
     const double2* src = reinterpret_cast<const double2*>(sites + i);
     const double2 a = src[0], b = src[1], c = src[2], d = src[3], e = src[4];
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(256) place_sites_kernel(const Site* __restrict
     out.E[pos] = d.x; out.wgt[pos] = d.y;
     if (out.wgt2) out.wgt2[pos] = e.x;
     out.id_a[pos] = in.id_a[parent];
-    out.id_b[pos] = daughter;
+    out.id_b[pos] = did ? did[i] : daughter;
     out.id_c[pos] = in.id_b ? in.id_b[parent] : in.id_a[parent];
   }
 }
@@ -137,6 +139,28 @@ __global__ void __launch_bounds__(256) weight_stats_kernel(const double* __restr
     double v = 0.;
     for (int k = 0; k < 8; k++) v += sm[k][threadIdx.x];
     atomicAdd(&out[threadIdx.x], v);
+  }
+}
+
+// noise.cpp:438-456: sum of |w| over complex weights; w /= d
+__global__ void __launch_bounds__(256) weight_magnitude_kernel(const double* __restrict__ w, const double* __restrict__ w2, uint64_t n, double* out) {
+  double v = 0.;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    v += sqrt(w[i] * w[i] + w2[i] * w2[i]);
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __shared__ double sv[8];
+  if ((threadIdx.x & 31) == 0) sv[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.;
+    for (int k = 0; k < 8; k++) t += sv[k];
+    atomicAdd(out, t);
+  }
+}
+__global__ void __launch_bounds__(256) divide_weights_kernel(double* w, double* w2, uint64_t n, double d) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    w[i] = w[i] / d;
+    w2[i] = w2[i] / d;
   }
 }
 

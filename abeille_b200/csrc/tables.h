@@ -40,6 +40,13 @@ struct alignas(16) CellFast {
   int32_t pad_[2];
 };
 
+struct DevNoiseSrc {  // SquareOscillationNoiseSource (square_oscillation_noise_source.cpp): box, gated amplitude factors
+  double low[3], hi[3];
+  double eps_t;               // dEt = eps_t * Sigma_t * pi
+  double eps_f_pi, eps_s_pi;  // dEf/Ef = eps_f * pi, dEs/Es = eps_s * pi
+  int32_t on, pad_;           // the run's noise frequency is the source's fundamental (|n| == 1 within 1 %)
+};
+
 struct DevMesh3 {
   int32_t present, Nx, Ny, Nz, Ne;
   const double* eedges;  // Ne+1 or null
@@ -89,6 +96,9 @@ struct DevProblem {
   const abl_source* sources;
   const double* source_cp;  // discrete table over source weights (nsources >= 2)
   DevMesh3 entropy, cancel;
+  // noise sources
+  int32_t n_noise_src;
+  const DevNoiseSrc* noise_src;
 };
 
 }  // namespace abl

@@ -60,6 +60,13 @@ struct RunArgs {
   double* secondaries;             // [ABL_SEC_CAP][9][nthreads] or null
   double k_col, keff;
   int converged;
+  // noise mode (noise.cuh)
+  int sample_noise;                // this power-iteration generation samples the noise source
+  Site* nsites;                    // scratch noise particles
+  unsigned long long* n_nsites;
+  uint64_t nsite_capacity;
+  uint32_t* nnoise;                // per history: noise particles produced
+  uint32_t *site_did, *nsite_did;  // daughter ids of the scratch sites (the Site itself carries the rank)
 };
 
 struct Hist {
@@ -67,7 +74,7 @@ struct Hist {
   double E, w, w2;
   uint64_t rng, hash;
   uint32_t idx, daughter;
-  uint32_t n_flights, n_real, n_virtual, n_fis;
+  uint32_t n_flights, n_real, n_virtual, n_fis, n_noise;
   int g, mat;  // energy group, material of the MaterialHelper
   int nsec;
   bool alive;
@@ -335,8 +342,24 @@ __device__ inline void pop_secondary(const DevProblem& P, const RunArgs& A, Hist
   h.alive = true;
 }
 
+}  // namespace abl
+#include "noise.cuh"
+namespace abl {
+
 // ---- one flight (+ collision) of the three trackers ---------------------------------------------------------
-template <int TRK, bool NOISE>
+// MODE 0: k-eigenvalue run; 1: power-iteration generation of a noise run; 2: noise particles (see noise.cuh)
+template <int MODE>
+__device__ __forceinline__ void collide(const DevProblem& P, const RunArgs& A, Hist& h, Acc& acc, uint32_t tid, uint32_t nthreads) {
+  if (MODE == 0) collision<false>(P, A, h, acc);
+  else collision_nm<MODE>(P, A, h, acc, tid, nthreads);
+}
+// the copy "cross section" eta * omega / v of noise transport (material_helper.hpp:65-84)
+template <int MODE>
+__device__ __forceinline__ double noise_xs(const DevProblem& P, int mat, int g) {
+  return MODE == 2 ? P.eta * P.w_noise / __ldg(&P.speed[mat * P.G + g]) : 0.;
+}
+
+template <int TRK, int MODE>
 __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hist& h, Cursor& c, Acc& acc, uint32_t tid,
                                        uint32_t nthreads) {
 #define hid (A.bank.id_a[h.idx])
@@ -344,7 +367,7 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
   if (TRK == ABL_TRACK_SURFACE) {
     // SurfaceTracker::transport loop body (surface_tracker.cpp:72-146)
     const int mg = h.mat * P.G + h.g;
-    const double d_coll = rng_exponential(h.rng, __ldg(&P.Et[mg]));
+    const double d_coll = rng_exponential(h.rng, MODE == 2 ? __ldg(&P.Et[mg]) + noise_xs<MODE>(P, h.mat, h.g) : __ldg(&P.Et[mg]));
     const Boundary bound = cursor_nearest_boundary(P, c, h.u);
     acc.flights++;
     h.n_flights++;
@@ -387,10 +410,10 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
       had_collision = true;
       note(h, 0x2000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
     }
-    if (h.alive && had_collision) collision<NOISE>(P, A, h, acc);
+    if (h.alive && had_collision) collide<MODE>(P, A, h, acc, tid, nthreads);
   } else {
     // DeltaTracker / CarterTracker loop body (delta_tracker.cpp:100-195, carter_tracker.cpp:120-230)
-    const double Esample = __ldg(&P.smp[h.g]);
+    const double Esample = MODE == 2 ? __ldg(&P.smp[h.g]) + noise_xs<MODE>(P, h.mat, h.g) : __ldg(&P.smp[h.g]);
     const double d_coll = rng_exponential(h.rng, Esample);
     Boundary bound{ABL_INF, -1, ABL_BC_NORMAL, 0};
     bool crossed = false;
@@ -427,7 +450,7 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
       h.r.y = h.r.y + d_coll * h.u.y;
       h.r.z = h.r.z + d_coll * h.u.z;
       h.mat = c.mat;
-      const double Et = __ldg(&P.Et[h.mat * P.G + h.g]);
+      const double Et = MODE == 2 ? __ldg(&P.Et[h.mat * P.G + h.g]) + noise_xs<MODE>(P, h.mat, h.g) : __ldg(&P.Et[h.mat * P.G + h.g]);
       if (TRK == ABL_TRACK_DELTA) {
         if (Et - Esample > 1.E-10) {
           raise_error(A, ABL_ERR_MAJORANT, hid);
@@ -452,7 +475,7 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
       note(h, (had_collision ? 0x2000000000000000ULL : 0x1000000000000000ULL) | (uint64_t)(uint32_t)(c.cell + 1));
     }
     if (h.alive && had_collision) {
-      collision<NOISE>(P, A, h, acc);
+      collide<MODE>(P, A, h, acc, tid, nthreads);
     } else if (h.alive) {
       if (!crossed) {
         acc.virt++;
@@ -478,7 +501,7 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
 
 #undef hid
 
-template <int TRK, bool NOISE>
+template <int TRK, int MODE>
 __global__ void __launch_bounds__(128) transport_kernel(const DevProblem P, const RunArgs A) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
@@ -513,14 +536,14 @@ __global__ void __launch_bounds__(128) transport_kernel(const DevProblem P, cons
       h.rb = h.r;
       h.E = A.bank.E[idx];
       h.w = A.bank.wgt[idx];
-      h.w2 = (NOISE && A.bank.wgt2) ? A.bank.wgt2[idx] : 0.;
+      h.w2 = (MODE == 2 && A.bank.wgt2) ? A.bank.wgt2[idx] : 0.;
       h.g = group_of(P, h.E);
       h.emid = h.g < P.G && h.E == group_mid(P, h.g);
       if (A.bank.id_c) h.rng = A.bank.id_c[idx];
       else h.rng = pcg_advance(P.seed_state, P.stride * A.bank.id_a[idx], P.jump);  // particle.hpp:188-193
       h.hash = 1469598103934665603ULL;
       h.daughter = 0;
-      h.n_flights = h.n_real = h.n_virtual = h.n_fis = 0;
+      h.n_flights = h.n_real = h.n_virtual = h.n_fis = h.n_noise = 0;
       h.nsec = 0;
       h.alive = true;
       c.token = 0;
@@ -531,7 +554,7 @@ __global__ void __launch_bounds__(128) transport_kernel(const DevProblem P, cons
         h.alive = false;
       }
     }
-    if (h.alive) flight<TRK, NOISE>(P, A, h, c, acc, tid, nthreads);
+    if (h.alive) flight<TRK, MODE>(P, A, h, c, acc, tid, nthreads);
     if (!h.alive) {
       if (h.nsec > 0) {  // Particle::resurect + Tracker restart (delta_tracker.cpp:197-229)
         pop_secondary(P, A, h, tid, nthreads);
@@ -547,6 +570,7 @@ __global__ void __launch_bounds__(128) transport_kernel(const DevProblem P, cons
       }
       if (!h.alive) {  // history finished
         A.nfis[h.idx] = h.n_fis;
+        if (MODE == 1 && A.nnoise) A.nnoise[h.idx] = h.n_noise;
         if (A.tr_hash) {
           A.tr_flights[h.idx] = h.n_flights;
           A.tr_real[h.idx] = h.n_real;

@@ -631,6 +631,35 @@ Problem Problem::from_yaml(const Node& input) {
   else
     fatal_error("No source specified for problem.");
   if (input["entropy"] && input["entropy"].IsMap()) P.entropy = make_mesh_spec(input["entropy"], "entropy mesh");
+  // noise sources (src/noise_maker.cpp:39-58, src/square_oscillation_noise_source.cpp:38-83,177-250)
+  if (input["noise-sources"] && input["noise-sources"].IsSequence())
+    for (size_t n = 0; n < input["noise-sources"].size(); n++) {
+      const Node& ns = input["noise-sources"][n];
+      const std::string type = ns["type"] ? ns["type"].as_string() : std::string("");
+      if (type != "square-oscillation")
+        fatal_error("Noise source type \"" + type + "\" is not provided by the B200 backend (square-oscillation only).");
+      abl_noise_source f{};
+      const auto vec3 = [&](const char* key, double out[3]) {
+        if (!ns[key] || !ns[key].IsSequence() || ns[key].size() != 3) fatal_error(std::string("No valid ") + key + " entry for oscillation noise source.");
+        const std::vector<double> v = ns[key].as_doubles();
+        for (int k = 0; k < 3; k++) out[k] = v[static_cast<size_t>(k)];
+      };
+      vec3("low", f.low);
+      vec3("hi", f.hi);
+      const auto scalar = [&](const char* key) {
+        if (!ns[key]) fatal_error(std::string("No valid ") + key + " entry for oscillation noise source.");
+        return ns[key].as_double();
+      };
+      f.angular_frequency = scalar("angular-frequency");
+      f.eps_total = scalar("epsilon-total");
+      f.eps_fission = scalar("epsilon-fission");
+      f.eps_scatter = scalar("epsilon-scatter");
+      if (f.low[0] >= f.hi[0] || f.low[1] >= f.hi[1] || f.low[2] >= f.hi[2]) fatal_error("Low is greater than or equal to hi in OscillationNoiseSource.");
+      if (f.angular_frequency <= 0.) fatal_error("Negative or zero frequency provided to OscillationNoiseSource.");
+      if (f.eps_total <= 0. || f.eps_fission <= 0. || f.eps_scatter <= 0.) fatal_error("Negative or zero epsilon provided to OscillationNoiseSource.");
+      P.noise_sources.push_back(f);
+    }
+  if (P.settings.mode == ABL_MODE_NOISE && P.noise_sources.empty()) fatal_error("No noise source specified for noise problem.");
   // majorant: per group max over materials (src/majorant.cpp:133-176)
   const size_t G = static_cast<size_t>(P.settings.ngroups);
   P.majorant.assign(G, 0.);
@@ -850,6 +879,9 @@ void Problem::flatten(FlatProblem& F) const {
   for (const auto& s : sources) F.sources.push_back(s.flat);
   p.nsources = static_cast<int32_t>(F.sources.size());
   p.sources = F.sources.data();
+  F.noise_sources = noise_sources;
+  p.n_noise_sources = static_cast<int32_t>(F.noise_sources.size());
+  p.noise_sources = F.noise_sources.data();
 }
 
 }  // namespace abeille

@@ -104,6 +104,7 @@ struct FlatProblem {
   std::vector<abl_angle_table> angle;
   std::vector<abl_mesh_tally> tallies;
   std::vector<abl_source> sources;
+  std::vector<abl_noise_source> noise_sources;
 };
 
 class Problem {
@@ -114,6 +115,7 @@ class Problem {
   std::vector<Universe> universes;
   std::vector<MGNuclide> materials;
   std::vector<Source> sources;
+  std::vector<abl_noise_source> noise_sources;  // square-oscillation only (src/noise_maker.cpp:39-58)
   std::vector<MeshTallySpec> tallies;
   MeshSpec entropy, cancelator;
   int root_universe = -1;

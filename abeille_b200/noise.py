@@ -1,0 +1,133 @@
+"""Frequency-domain neutron-noise simulation on the B200 backend: the reference's `Noise` driver
+(src/noise.cpp:211-559) over the device entry points of the C ABI.  Banks never leave HBM.
+
+    Noise::run               noise.cpp:211-303   nignored power-iteration generations, then ngenerations noise batches
+                                                 of (nskip - 1) plain generations + one that samples the noise source
+    Noise::power_iteration   noise.cpp:305-372   transport -> k values -> (regional cancellation) -> normalise -> new bank
+    Noise::noise_simulation  noise.cpp:425-559   normalise the noise source by its mean |w|, score it, transport the noise
+                                                 particles generation by generation (inner generations) until none is
+                                                 left, record the tallies scaled back by the mean |w|
+Settings that only this driver reads (nskip, keff, noise-cancellation ...) come straight from the deck with the
+reference's defaults (src/settings.cpp:37-82); everything the kernels need went through the C++ host already.
+"""
+import numpy as np
+import yaml
+
+from .backend import Backend
+
+_INT_MAX = 2147483647
+
+
+class NoiseSimulation:
+    def __init__(self, deck_path: str, device: int = 0):
+        with open(deck_path) as f:
+            st = yaml.safe_load(f).get("settings", {})
+        if st.get("simulation") != "noise":
+            raise ValueError("NoiseSimulation needs a deck with `simulation: noise`")
+        self.gpu = Backend(deck_path, device)
+        self.nparticles = int(st.get("nparticles", 100000))
+        self.nbatches = int(st.get("ngenerations", 120))
+        self.nignored = int(st.get("nignored", 20))
+        self.nskip = int(st.get("nskip", 10))
+        self.keff = float(st.get("keff", 1.0))
+        self.cancel_pi = bool(st.get("cancellation", False))
+        self.cancel_noise = bool(st.get("noise-cancellation", False))
+        self.n_cancel_noise_gens = int(st.get("cancel-noise-gens", _INT_MAX))
+        self.normalize_noise_source = bool(st.get("normalize-noise-source", True))
+        n = self.nparticles
+        self.cap = int(3.0 * n) + 4096
+        self.noise_cap = int(6.0 * n) + 4096
+        g = self.gpu
+        self.bank, self.next = g.new_device_bank(self.cap), g.new_device_bank(self.cap)
+        self.noise_bank = g.new_device_bank(self.noise_cap)
+        self.nb_a, self.nb_b = g.new_device_bank(self.noise_cap), g.new_device_bank(self.noise_cap)
+        self.n_bank = 0
+        self.k_col = 1.0
+        self.history_counter = 0
+        self.pi_gen = 0
+        self.converged = False
+        self.k_history, self.noise_generations, self.noise_particles = [], [], []
+
+    # ---- PowerIterator-like initial source (noise.cpp:75-133 does what power_iterator.cpp:46-133 does) ----
+    def initialize(self):
+        self.gpu.sample_source_device(self.bank, self.nparticles, 0)
+        self.n_bank = self.nparticles
+        self.history_counter = self.nparticles
+        self._use_state = True  # the first generation continues the source-sampling streams (simulation.cpp:70-73)
+
+    def power_iteration(self, sample_noise: bool) -> int:
+        """One generation (noise.cpp:305-372).  Returns the number of noise particles sampled."""
+        g = self.gpu
+        m, n_noise, scores, _ = g.transport_noise_device(
+            self.bank, self.n_bank, self.next, self.noise_bank if sample_noise else None, k_col=self.k_col, keff=self.keff,
+            converged=self.converged, noise=False, sample_noise=sample_noise, use_rng_state=self._use_state)
+        self._use_state = False
+        if m == 0:
+            raise RuntimeError("No fission neutrons were produced.")
+        self.k_col = scores[0] / self.nparticles  # tallies->calc_gen_values(): score / total_weight
+        g.tallies_clear()                         # tallies->clear_generation()
+        if self.cancel_pi:
+            g.cancel_device(self.next, m)
+        ws = g.weight_stats_device(self.next, m)  # Noise::normalize_weights (noise.cpp:631-674)
+        g.scale_weights_device(self.next, m, self.nparticles / (ws[2] - ws[3]))
+        g.to_particles_device(self.next, m, self.history_counter)
+        self.history_counter += m
+        self.bank, self.next = self.next, self.bank
+        self.n_bank = m
+        self.k_history.append(self.k_col)
+        return n_noise
+
+    def noise_simulation(self, n_noise: int):
+        """Noise::noise_simulation (noise.cpp:425-559) on the noise bank sampled by the last generation."""
+        g = self.gpu
+        original_kcol = self.k_col
+        avg_wgt_mag = 1.0
+        if self.normalize_noise_source and n_noise:
+            avg_wgt_mag = g.weight_magnitude_device(self.noise_bank, n_noise) / float(n_noise)
+            g.divide_weights_device(self.noise_bank, n_noise, avg_wgt_mag)
+        if self.converged and n_noise:
+            g.score_source_device(self.noise_bank, n_noise, noise_source=True)
+        cur, nxt = self.noise_bank, self.nb_a
+        g.to_particles_device(cur, n_noise, self.history_counter)
+        self.history_counter += n_noise
+        n, gen, total = n_noise, 0, 0
+        while n != 0:
+            gen += 1
+            total += n
+            m, _, _, _ = g.transport_noise_device(cur, n, nxt, None, k_col=self.k_col, keff=self.keff,
+                                                  converged=self.converged, noise=True, sample_noise=False)
+            if self.cancel_noise and gen <= self.n_cancel_noise_gens and m:
+                g.cancel_device(nxt, m)
+            g.to_particles_device(nxt, m, self.history_counter)
+            self.history_counter += m
+            cur, nxt = nxt, (self.nb_b if nxt is self.nb_a else self.nb_a)
+            n = m
+        g.tallies_record(avg_wgt_mag)  # tallies->record_generation(avg_wgt_mag); calc_gen_values' k is discarded
+        g.tallies_clear()
+        self.k_col = original_kcol     # tallies->set_kcol(original_kcol)
+        self.noise_generations.append(gen)
+        self.noise_particles.append(total)
+
+    def run(self):
+        """Noise::run (noise.cpp:211-303)."""
+        self.initialize()
+        self.converged = False
+        for _ in range(self.nignored):
+            self.pi_gen += 1
+            self.power_iteration(False)
+        self.converged = True
+        for _ in range(self.nbatches):
+            for _ in range(self.nskip - 1):
+                self.pi_gen += 1
+                self.power_iteration(False)
+            self.pi_gen += 1
+            n_noise = self.power_iteration(True)
+            self.noise_simulation(n_noise)
+        return {"k_col": np.array(self.k_history), "noise_generations": self.noise_generations,
+                "noise_particles": self.noise_particles}
+
+    def tally(self, t: int, which: str = "avg") -> np.ndarray:
+        return self.gpu.tally(t, which)
+
+    def close(self):
+        self.gpu.close()

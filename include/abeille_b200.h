@@ -119,6 +119,11 @@ typedef struct abl_mesh3 {       /* entropy mesh (entropy.cpp) / approximate can
   int32_t eedges_offset;         /* slice of abl_problem.tally_energy_bounds                           */
 } abl_mesh3;
 
+typedef struct abl_noise_source { /* square-oscillation noise source (square_oscillation_noise_source.cpp:38-83)   */
+  double low[3], hi[3];
+  double angular_frequency, eps_total, eps_fission, eps_scatter;
+} abl_noise_source;
+
 typedef struct abl_problem {
   int32_t mode, tracking, ngroups, inner_generations;
   const double* energy_bounds;  /* [ngroups+1] */
@@ -153,6 +158,9 @@ typedef struct abl_problem {
   const abl_source* sources;
   abl_mesh3 entropy;
   abl_mesh3 cancelator;
+  /* noise sources (noise mode; noise_maker.cpp:39-58) */
+  int32_t n_noise_sources, pad2_;
+  const abl_noise_source* noise_sources;
 } abl_problem;
 
 /* ---- banks --------------------------------------------------------------------------------------
@@ -174,7 +182,8 @@ typedef struct abl_gen_params {
   int32_t converged;  /* settings::converged: mesh tallies score only when set (tallies.hpp:49-63)     */
   int32_t noise;      /* transport(bank, noise=true)                                                   */
   int32_t trace;      /* keep per-history integer outcomes for abl_get_trace                           */
-  int32_t pad_;
+  int32_t sample_noise_source; /* transport(bank, false, &noise_bank, &noise_maker) (noise.cpp:312-314): noise
+                                  mode only; the noise particles go to the bank given to abl_transport_noise_device */
 } abl_gen_params;
 
 /* scores[6] = raw sums k_col, k_abs, k_trk, k_tot, leakage, mig_area (tallies.cpp:100-140)           */
@@ -202,6 +211,17 @@ int abl_get_trace(abl_handle h, uint64_t n, abl_trace* out);
 int abl_transport_device(abl_handle h, const abl_bank* bank_dev, const abl_gen_params* params,
                          abl_bank* fission_dev, uint64_t* n_fission, double scores[6], uint64_t counters[8],
                          void* stream);
+
+/* Transporter::transport with the noise-source bank (noise.cpp:305-318): as abl_transport_device; when
+ * params->sample_noise_source is set, every real collision inside a noise source also samples NoiseMaker::sample_noise_source
+ * (noise_maker.cpp:277-445) and the noise particles are written to noise_dev in bank order (noise_dev->n = capacity on
+ * entry, *n_noise = count).  noise_dev may be NULL when nothing is sampled. */
+int abl_transport_noise_device(abl_handle h, const abl_bank* bank_dev, const abl_gen_params* params, abl_bank* fission_dev,
+                               uint64_t* n_fission, abl_bank* noise_dev, uint64_t* n_noise, double scores[6],
+                               uint64_t counters[8], void* stream);
+/* sum over the bank of sqrt(wgt^2 + wgt2^2), and wgt /= d, wgt2 /= d (Noise::noise_simulation, noise.cpp:438-456) */
+int abl_bank_weight_magnitude_device(abl_handle h, const abl_bank* bank_dev, double* sum, void* stream);
+int abl_bank_divide_weights_device(abl_handle h, abl_bank* bank_dev, double divisor, void* stream);
 
 /* ---- mesh tallies: MeshTally::record_generation / clear_generation / write (mesh_tally.cpp:121-206) - */
 int abl_tally_count(abl_handle h);

@@ -190,6 +190,31 @@ class Oracle:
             raise RuntimeError(f"oracle: fission bank capacity {cap} < {m}")
         return {k: v[:m].copy() for k, v in out.items()}, scores, m
 
+    def transport_noise(self, bank: dict, noise: bool, sample_noise: bool, capacity: int | None = None):
+        """Transporter::transport(bank, noise, &noise_bank, &noise_maker).  Returns (fission bank, noise-source bank,
+        scores[6]); the noise-source bank is empty unless sample_noise."""
+        n = len(bank["x"])
+        cap = int(capacity if capacity is not None else max(6 * n, 1024))
+        out, nout_bank = new_bank(cap), new_bank(cap)
+        sin = _as_struct(bank, allow_null=("id_c",))
+        sout, snoise = _as_struct(out), _as_struct(nout_bank)
+        nout, nnoise = C.c_uint64(0), C.c_uint64(0)
+        scores = np.zeros(6)
+        rc = lib().orc_transport_noise(self.h, C.byref(sin), C.c_int(int(noise)), C.c_int(int(sample_noise)), C.byref(sout),
+                                       C.byref(nout), C.byref(snoise), C.byref(nnoise), scores.ctypes.data_as(_PD))
+        if rc != 0:
+            raise RuntimeError("oracle: " + self._err())
+        m, mn = int(nout.value), int(nnoise.value)
+        if m > cap or mn > cap:
+            raise RuntimeError(f"oracle: bank capacity {cap} < {max(m, mn)}")
+        return {k: v[:m].copy() for k, v in out.items()}, {k: v[:mn].copy() for k, v in nout_bank.items()}, scores
+
+    def set_keff(self, k): lib().orc_set_keff(self.h, C.c_double(float(k)))
+
+    def score_source(self, bank: dict, noise_source: bool = False):
+        s = _as_struct(bank, allow_null=("id_c",))
+        lib().orc_score_source(self.h, C.byref(s), C.c_int(int(noise_source)))
+
     def trace(self, n: int) -> dict:
         t = {k: np.zeros(n, dtype=np.uint32) for k in ("flights", "real", "virtual", "fission")}
         t["hash"] = np.zeros(n, dtype=np.uint64)
@@ -228,6 +253,89 @@ class Oracle:
         stats = np.zeros(6)
         lib().orc_cancel_and_normalize(self.h, C.byref(s), C.c_int(int(do_cancel)), stats.ctypes.data_as(_PD))
         return stats
+
+    def cancel(self, bank: dict):
+        s = _as_struct(bank)
+        lib().orc_cancel(self.h, C.byref(s))
+
+    def run_noise(self, settings: dict) -> dict:
+        """The reference's Noise driver (src/noise.cpp:211-559) over the oracle's transport: nignored power-iteration
+        generations, then `ngenerations` noise batches of (nskip - 1) plain generations, one generation that samples
+        the noise source, and the noise simulation of that source (inner generations until no particle is left)."""
+        st = settings
+        N = int(st.get("nparticles", 100000))
+        nbatches, nignored, nskip = int(st.get("ngenerations", 120)), int(st.get("nignored", 20)), int(st.get("nskip", 10))
+        keff = float(st.get("keff", 1.0))
+        cancel_pi, cancel_noise = bool(st.get("cancellation", False)), bool(st.get("noise-cancellation", False))
+        n_cancel_gens = int(st.get("cancel-noise-gens", 2147483647))
+        normalize_src = bool(st.get("normalize-noise-source", True))
+        self.set_keff(keff)
+        bank = self.sample_source(N)
+        counter = N
+        k_col = 1.0
+        out = {"k_col": [], "noise_generations": [], "noise_particles": []}
+
+        def to_particles(fis, first):  # Particle(p.r, p.u, p.E, p.wgt[, p.wgt2], histories_counter++) + initialize_rng
+            b = {k: fis[k] for k in BANK_F64}
+            m = len(fis["x"])
+            b["id_a"] = np.arange(first, first + m, dtype=np.uint64)
+            b["id_b"] = fis["id_c"].copy()
+            b["id_c"] = None
+            return b
+
+        def power_iteration(sample_noise):  # noise.cpp:305-372
+            nonlocal bank, counter, k_col
+            self.set_kcol(k_col)
+            fis, nb, scores = self.transport_noise(bank, False, sample_noise)
+            if len(fis["x"]) == 0:
+                raise RuntimeError("No fission neutrons were produced.")
+            k_col = scores[0] / N
+            self.tallies_clear()
+            self.cancel_and_normalize(fis, cancel_pi)
+            bank = to_particles(fis, counter)
+            counter += len(fis["x"])
+            out["k_col"].append(k_col)
+            return nb
+
+        def noise_simulation(nb):  # noise.cpp:425-559
+            nonlocal counter
+            n = len(nb["x"])
+            avg = 1.0
+            if normalize_src and n:
+                avg = float(np.sqrt(nb["wgt"] * nb["wgt"] + nb["wgt2"] * nb["wgt2"]).sum()) / float(n)
+                nb["wgt"] = nb["wgt"] / avg
+                nb["wgt2"] = nb["wgt2"] / avg
+            if n:
+                self.score_source(nb, noise_source=True)
+            cur = to_particles(nb, counter)
+            counter += n
+            gen = total = 0
+            while n != 0:
+                gen += 1
+                total += n
+                fis, _, _ = self.transport_noise(cur, True, False)
+                m = len(fis["x"])
+                if cancel_noise and gen <= n_cancel_gens and m:
+                    self.cancel(fis)
+                cur = to_particles(fis, counter)
+                counter += m
+                n = m
+            self.tallies_record(avg)
+            self.tallies_clear()
+            out["noise_generations"].append(gen)
+            out["noise_particles"].append(total)
+
+        self.set_converged(False)
+        for _ in range(nignored):
+            power_iteration(False)
+        self.set_converged(True)
+        for _ in range(nbatches):
+            for _ in range(nskip - 1):
+                power_iteration(False)
+            nb = power_iteration(True)
+            noise_simulation(nb)
+        out["k_col"] = np.array(out["k_col"])
+        return out
 
     def run_power_iteration(self, ngen: int, nignored: int) -> dict:
         arr = {k: np.zeros(ngen) for k in ("kcol", "ktrk", "leak", "mig", "entropy")}

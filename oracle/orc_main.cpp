@@ -861,11 +861,86 @@ static std::vector<BankedParticle> transport(Problem& P, std::vector<Particle>& 
 }
 
 // ---- noise source (config 5) -------------------------------------------------------------------
-// src/noise_maker.cpp:277-445 with a single square-oscillation source list
+// Frequency gate shared by every SquareOscillationNoiseSource factor (square_oscillation_noise_source.cpp:85-170):
+// the factor is eps * pi (times Sigma_t for dEt) when w is the source's fundamental +-w0 within 1 %, else 0.
+static bool sqosc_on(const NoiseSource& ns, double w) {
+  int32_t n = static_cast<int32_t>(std::round(w / ns.w0));
+  double err = (n * ns.w0 - w) / w;
+  return (n == 1 || n == -1) && std::abs(err) < 0.01;
+}
+
+// NoiseMaker::sample_noise_source (src/noise_maker.cpp:277-445) with square-oscillation sources only (the vibration list
+// is empty, so sample_vibration_noise_source returns at once): the noise copy (:155-181), then the oscillation
+// fission (:383-445) and scatter (:325-381) sources.  Noise particles go to the history's noise bank.
 static void sample_noise_source(Ctx& cx, Particle& p, const Mat& mat, double keff, double w) {
-  (void)cx; (void)p; (void)mat; (void)keff; (void)w;
-  // Row S5 (noise) is not restated yet; noise-mode parity is NOT claimed.
-  throw std::runtime_error("oracle: noise-source sampling not implemented yet");
+  Problem& P = *cx.P;
+  bool inside = false;  // NoiseMaker::is_inside :93-104
+  for (const auto& ns : P.noise_sources) if (ns.is_inside(p.r())) inside = true;
+  if (!inside) return;
+
+  {  // sample_noise_copy :155-181; NoiseMaker::dEt :60-78 sums SquareOscillationNoiseSource::dEt (:85-113), which
+     // looks the material up again with a fresh Tracker at r with direction (1,0,0)
+    std::complex<double> dEt{0., 0.};
+    for (const auto& ns : P.noise_sources) {
+      if (!ns.is_inside(p.r())) continue;
+      Tracker trkr(&P.geo, p.r(), Vec{1., 0., 0.});
+      if (trkr.current_mat < 0) throw std::runtime_error("No material found at the position of a noise-source sample.");
+      Mat fm(&P, trkr.current_mat);
+      double xs = fm.Et(p.E());
+      if (sqosc_on(ns, w)) dEt += std::complex<double>{ns.eps_t * xs * PI, 0.};
+      else dEt += std::complex<double>{0., 0.};
+    }
+    const std::complex<double> dEt_Et = dEt / mat.Et(p.E());
+    std::complex<double> weight_copy{p.wgt(), p.wgt2()};
+    weight_copy *= -dEt_Et;
+    BankedParticle np{p.r(), p.u(), p.E(), weight_copy.real(), weight_copy.imag(), p.history_id, p.daughter_counter(), p.family_id};
+    p.history_noise_bank.push_back(np);
+  }
+
+  // sample_oscillation_noise_source :293-323 (we are inside at least one oscillation source)
+  MicroXS microxs = mat.sample_nuclide(p.E(), p.rng, false);
+  const Material& nuc = mat.mat();
+  if (nuc.fissile) {  // sample_oscillation_noise_fission :383-445
+    const double k_abs = microxs.nu_total * microxs.fission / microxs.total;
+    const int n_new = static_cast<int>(std::floor(k_abs / keff + rng_rand(p.rng)));
+    const double P_delayed = microxs.nu_delayed / microxs.nu_total;
+    std::complex<double> dEf_Ef{0., 0.};
+    for (const auto& ns : P.noise_sources)
+      if (ns.is_inside(p.r())) dEf_Ef += sqosc_on(ns, w) ? std::complex<double>{ns.eps_f * PI, 0.} : std::complex<double>{0., 0.};
+    for (int i = 0; i < n_new; i++) {
+      auto finfo = sample_fission(P, nuc, p.u(), microxs.energy_index, P_delayed, p.rng);
+      BankedParticle bnp{p.r(), finfo.direction, finfo.energy, p.wgt(), p.wgt2(), p.history_id, p.daughter_counter(), p.family_id};
+      if (finfo.delayed) {
+        std::complex<double> wgt_cmpx{bnp.wgt, bnp.wgt2};
+        double lambda = finfo.lambda;
+        double denom = (lambda * lambda) + (w * w);
+        std::complex<double> mult{lambda * lambda / denom, -lambda * w / denom};
+        wgt_cmpx *= mult;
+        bnp.wgt = wgt_cmpx.real();
+        bnp.wgt2 = wgt_cmpx.imag();
+      }
+      std::complex<double> fnp_weight{bnp.wgt, bnp.wgt2};
+      fnp_weight *= dEf_Ef;
+      bnp.wgt = fnp_weight.real();
+      bnp.wgt2 = fnp_weight.imag();
+      p.history_noise_bank.push_back(bnp);
+    }
+  }
+  const double P_scatter = 1. - (microxs.absorption / microxs.total);
+  {  // sample_oscillation_noise_scatter :325-381 (MG: mt == 2, yield == 1)
+    ScatterInfo sinfo = sample_scatter(P, nuc, p.u(), microxs.energy_index, p.rng);
+    BankedParticle p_noise{p.r(), sinfo.direction, sinfo.energy, 0., 0., p.history_id, p.daughter_counter(), p.family_id};
+    std::complex<double> wgt{p.wgt(), p.wgt2()};
+    wgt *= 1.;
+    wgt *= P_scatter;
+    std::complex<double> dE_E{0., 0.};
+    for (const auto& ns : P.noise_sources)
+      if (ns.is_inside(p.r())) dE_E += sqosc_on(ns, w) ? std::complex<double>{ns.eps_s * PI, 0.} : std::complex<double>{0., 0.};
+    wgt *= dE_E;
+    p_noise.wgt = wgt.real();
+    p_noise.wgt2 = wgt.imag();
+    p.history_noise_bank.push_back(p_noise);
+  }
 }
 
 // ---- inter-generation steps --------------------------------------------------------------------
@@ -1132,6 +1207,37 @@ int orc_transport(void* h, const orc_bank* in, int noise, orc_bank* out, uint64_
   } catch (const std::exception& e) { P.error = e.what(); return 1; }
 }
 
+// Transporter::transport(bank, noise, &noise_bank, &noise_maker): as orc_transport, plus the noise-source bank when
+// sample_noise != 0 (noise_out->n is its capacity on entry, *n_noise the true count)
+int orc_transport_noise(void* h, const orc_bank* in, int noise, int sample_noise, orc_bank* out, uint64_t* n_out,
+                        orc_bank* noise_out, uint64_t* n_noise, double* scores6) {
+  Problem& P = *static_cast<Problem*>(h);
+  try {
+    auto bank = bank_from(P, in);
+    Tallies& T = P.tallies;
+    double b[6] = {T.k_col_score, T.k_abs_score, T.k_trk_score, T.k_tot_score, T.leak_score, T.mig_area_score};
+    std::vector<BankedParticle> nb;
+    auto fis = transport(P, bank, noise != 0, sample_noise ? &nb : nullptr, sample_noise != 0);
+    scores6[0] = T.k_col_score - b[0]; scores6[1] = T.k_abs_score - b[1]; scores6[2] = T.k_trk_score - b[2];
+    scores6[3] = T.k_tot_score - b[3]; scores6[4] = T.leak_score - b[4]; scores6[5] = T.mig_area_score - b[5];
+    *n_out = fis.size();
+    bank_to(fis, out);
+    *n_noise = nb.size();
+    if (noise_out) bank_to(nb, noise_out);
+    return 0;
+  } catch (const std::exception& e) { P.error = e.what(); return 1; }
+}
+void orc_set_keff(void* h, double keff) { static_cast<Problem*>(h)->tallies.keff_ = keff; }
+// Tallies::score_noise_source / score_source over a bank (tallies.hpp:65-92)
+void orc_score_source(void* h, const orc_bank* b, int noise_source) {
+  Problem& P = *static_cast<Problem*>(h);
+  for (uint64_t i = 0; i < b->n; i++) {
+    BankedParticle p{Vec{b->x[i], b->y[i], b->z[i]}, Vec{b->ux[i], b->uy[i], b->uz[i]}, b->E[i], b->wgt[i], b->wgt2 ? b->wgt2[i] : 0., 0, 0, 0};
+    for (auto& t : P.tallies.mesh)
+      if (t.estimator == EST_SOURCE && (t.noise_source != 0) == (noise_source != 0)) t.score_source(p);
+  }
+}
+
 // per-history trace of the last transport call (needs orc_set_trace(1))
 void orc_get_trace(void* h, uint32_t* flights, uint32_t* real, uint32_t* virt, uint32_t* fis, uint64_t* hash, uint64_t* rng_state) {
   Problem& P = *static_cast<Problem*>(h);
@@ -1177,6 +1283,20 @@ int orc_cancel_and_normalize(void* h, orc_bank* b, int do_cancel, double* stats6
   if (do_cancel && P.cancel.present) perform_regional_cancellation(P, v);
   GenStats s = normalize_weights(P, v);
   stats6[0] = s.Npos; stats6[1] = s.Nneg; stats6[2] = s.Ntot; stats6[3] = s.Nnet; stats6[4] = s.Wpos; stats6[5] = s.Wneg;
+  bank_to(v, b);
+  return 0;
+}
+
+// approximate cancellation alone (Noise::perform_regional_cancellation on a noise fission bank, noise.cpp:508-515)
+int orc_cancel(void* h, orc_bank* b) {
+  Problem& P = *static_cast<Problem*>(h);
+  std::vector<BankedParticle> v(b->n);
+  for (size_t i = 0; i < v.size(); i++) {
+    v[i].r = {b->x[i], b->y[i], b->z[i]}; v[i].u = {b->ux[i], b->uy[i], b->uz[i]};
+    v[i].E = b->E[i]; v[i].wgt = b->wgt[i]; v[i].wgt2 = b->wgt2[i];
+    v[i].parent_history_id = b->id_a[i]; v[i].parent_daughter_id = b->id_b[i]; v[i].family_id = b->id_c[i];
+  }
+  if (P.cancel.present) perform_regional_cancellation(P, v);
   bank_to(v, b);
   return 0;
 }

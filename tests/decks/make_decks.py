@@ -99,3 +99,14 @@ dump(s4, "c5g7_carter_cancel.yaml",
 s5 = copy.deepcopy(s2t)
 s5["settings"].update({"transport": "surface-tracking"})
 dump(s5, "c5g7_surface_tracklength.yaml", "c5g7 geometry with transport: surface-tracking and a track-length flux tally.")
+
+# S5: noise_oscillation.yaml verbatim (frequency-domain noise, square-oscillation source, approximate cancellation of the
+# noise fission banks) with run sizes small enough for a parity test; plus a delta-tracking variant of the same problem
+ns = load("noise_oscillation.yaml")
+ns["settings"].update({"nparticles": 4000, "ngenerations": 2, "nignored": 2, "nskip": 2})
+dump(ns, "noise_oscillation.yaml",
+     "S5: reference input_files/noise_oscillation.yaml (BASELINE config 5), run sizes reduced for the parity tests\n"
+     "(nparticles 100000 -> 4000, 2000 noise batches -> 2, nignored 10 -> 2, nskip 3 -> 2).")
+nsd = copy.deepcopy(ns)
+nsd["settings"]["transport"] = "delta-tracking"
+dump(nsd, "noise_oscillation_delta.yaml", "S5 variant: noise_oscillation.yaml with transport: delta-tracking.")
