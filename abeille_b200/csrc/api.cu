@@ -135,7 +135,12 @@ std::vector<double> discrete_table(const std::vector<double>& w) {
 int validate(abl_handle h, const abl_problem* p) {
   if (p->ngroups < 1 || !p->energy_bounds) return fail(h, ABL_ERR_INVALID, "ngroups / energy_bounds");
   if (p->tracking < ABL_TRACK_SURFACE || p->tracking > ABL_TRACK_CARTER) return fail(h, ABL_ERR_INVALID, "tracking");
-  if (p->mode != ABL_MODE_K_EIGENVALUE) return fail(h, ABL_ERR_UNSUPPORTED, "only k-eigenvalue transport is implemented on the device");
+  if (p->mode != ABL_MODE_K_EIGENVALUE && p->mode != ABL_MODE_NOISE)
+    return fail(h, ABL_ERR_UNSUPPORTED, "simulation modes on the device: k-eigenvalue, noise");
+  if (p->mode == ABL_MODE_NOISE) {
+    if (p->n_noise_sources < 1 || !p->noise_sources) return fail(h, ABL_ERR_INVALID, "noise mode without a noise source");
+    if (!(p->w_noise > 0.)) return fail(h, ABL_ERR_INVALID, "noise mode needs a positive noise-angular-frequency");
+  }
   if (p->ntallies > ABL_MAX_TALLIES) return fail(h, ABL_ERR_UNSUPPORTED, "more than ABL_MAX_TALLIES mesh tallies");
   if (p->root_universe < 0 || p->root_universe >= p->nuniverses) return fail(h, ABL_ERR_INVALID, "root universe");
   for (int c = 0; c < p->ncells; c++) {

@@ -127,5 +127,6 @@ def test_noise_oracle_source_and_driver(oracle_api):
     assert len(keys) == len(nb["x"]) + len(fis["x"])
     r1 = oracle_api.Oracle(path, {"settings": {"nparticles": 1500}}).run_noise(st)
     r2 = oracle_api.Oracle(path, {"settings": {"nparticles": 1500}}).run_noise(st)
-    assert np.array_equal(r1["k_col"], r2["k_col"]) and r1["noise_particles"] == r2["noise_particles"]
+    # (scores are summed per OpenMP thread: k differs in rounding order between runs, integer outcomes do not)
+    assert np.allclose(r1["k_col"], r2["k_col"], rtol=1e-12) and r1["noise_particles"] == r2["noise_particles"]
     assert r1["noise_generations"][0] > 1
