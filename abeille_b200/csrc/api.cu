@@ -324,8 +324,8 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
   if (TRK == ABL_TRACK_SURFACE) kern = transport_kernel<ABL_TRACK_SURFACE, 0>;
   else kern = history_kernel<(TRK == ABL_TRACK_SURFACE ? ABL_TRACK_DELTA : TRK), TRACE>;
   const bool staged = TRK != ABL_TRACK_SURFACE;
-  const int threads = staged ? HK_THREADS : 128;
-  const int worker_threads = staged ? HK_HIST : 128;  // threads of a block that own histories
+  const int threads = staged ? HK_THREADS : TK_THREADS;
+  const int worker_threads = staged ? HK_HIST : TK_THREADS;  // threads of a block that own histories
   const size_t smem = staged ? sizeof(HKShared) : 0;
   int& bps = h->blocks_per_sm[TRK][TRACE ? 1 : 0];
   if (bps == 0) {
@@ -379,7 +379,7 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
 template <int TRK, int MODE>
 int launch_transport_nm(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s) {
   void (*kern)(const DevProblem, const RunArgs) = transport_kernel<TRK, MODE>;
-  const int threads = 128;
+  const int threads = TK_THREADS;
   int& bps = h->nm_blocks_per_sm[TRK][MODE];
   if (bps == 0) {
     int nb = 0;

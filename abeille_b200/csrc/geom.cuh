@@ -327,8 +327,8 @@ __device__ __forceinline__ bool cell_is_inside_fast(const DevProblem& P, int ci,
 
 // nearest surface of the cell along u (cell.cpp:79-142); bc_only = distance_to_boundary_condition
 template <class PT>
-__device__ inline void cell_distance(const PT& P, int ci, const V3& r, const V3& u, int on_surf, bool bc_only,
-                                     double& min_dist, int& i_surf) {
+__device__ inline void cell_distance_impl(const PT& P, int ci, const V3& r, const V3& u, int on_surf, bool bc_only,
+                                          double& min_dist, int& i_surf) {
   min_dist = ABL_INF;
   i_surf = 0;
   const abl_cell* c = P.cells + ci;
@@ -348,6 +348,27 @@ __device__ inline void cell_distance(const PT& P, int ci, const V3& r, const V3&
       }
     }
   }
+}
+
+// one shared copy for the callers that work on the bare geometry tables (the per-lane kernel and the service warp reach
+// this from three places; the surface-distance switch inside is several hundred instructions)
+__device__ __noinline__ void cell_distance_nl(const GeoTables G, int ci, const V3 r, const V3 u, int on_surf, bool bc_only,
+                                              double* min_dist, int* i_surf) {
+  double d;
+  int is;
+  cell_distance_impl(G, ci, r, u, on_surf, bc_only, d, is);
+  *min_dist = d;
+  *i_surf = is;
+}
+template <class PT>
+__device__ __forceinline__ void cell_distance(const PT& P, int ci, const V3& r, const V3& u, int on_surf, bool bc_only,
+                                              double& min_dist, int& i_surf) {
+  cell_distance_impl(P, ci, r, u, on_surf, bc_only, min_dist, i_surf);
+}
+template <>
+__device__ __forceinline__ void cell_distance<GeoTables>(const GeoTables& P, int ci, const V3& r, const V3& u, int on_surf, bool bc_only,
+                                                         double& min_dist, int& i_surf) {
+  cell_distance_nl(P, ci, r, u, on_surf, bc_only, &min_dist, &i_surf);
 }
 
 // ---- rectilinear lattice -------------------------------------------------------------------------
@@ -529,8 +550,8 @@ __device__ __forceinline__ bool push_pad(CUR& c, int info, int tx = 0, int ty = 
 
 // Universe::get_cell(stack, r, u, on_surf) made iterative (cell_universe.cpp:72-109, rect_lattice.cpp:132-207).
 // Descends from universe `uni` whose coordinates are frame f; returns the material cell or -1 (lost).
-template <bool FAST = false, class CUR = Cursor>
-__device__ inline int descend(const DevProblem& P, CUR& c, int uni, int f, const V3& u) {
+template <bool FAST = false, class CUR = Cursor, class PT = DevProblem>
+__device__ inline int descend(const PT& P, CUR& c, int uni, int f, const V3& u) {
   for (;;) {
     const abl_universe* U = P.universes + uni;
     const V3 r = frame_r(c, f);
@@ -540,7 +561,10 @@ __device__ inline int descend(const DevProblem& P, CUR& c, int uni, int f, const
       int found = -1;
       for (int k = 0; k < n; k++) {
         const int ci = __ldg(&P.ucells[off + k]);
-        if (FAST ? cell_is_inside_fast(P, ci, r, u, c.token) : cell_is_inside(P, ci, r, u, c.token)) {
+        bool in;
+        if constexpr (FAST) in = cell_is_inside_fast(P, ci, r, u, c.token);
+        else in = cell_is_inside(P, ci, r, u, c.token);
+        if (in) {
           found = ci;
           break;
         }
@@ -593,13 +617,14 @@ __device__ inline int descend(const DevProblem& P, CUR& c, int uni, int f, const
 }
 
 // Tracker::restart_get_current (tracker.hpp:63-74): full lookup from the root at global position r
-__device__ inline void cursor_restart(const DevProblem& P, Cursor& c, const V3& r, const V3& u) {
+template <class PT>
+__device__ inline void cursor_restart(const PT& P, Cursor& c, const V3& r, const V3& u) {
   c.np = 0;
   c.fx[0] = r.x;
   c.fy[0] = r.y;
   c.fz[0] = r.z;
   c.nf = 1;
-  c.cell = descend(P, c, P.root, 0, u);
+  c.cell = descend<false, Cursor, PT>(P, c, P.root, 0, u);
   c.mat = c.cell >= 0 ? __ldg(&P.cells[c.cell].material) : -1;
 }
 
@@ -615,7 +640,8 @@ __device__ __forceinline__ void cursor_move(CUR& c, double d, const V3& u) {
 // Tracker::get_current (tracker.hpp:235-306): re-validate the pads top-down, re-descend from the
 // first one that no longer holds.  (check_tree() is always true here: the cursor's global position
 // IS frame 0; the callers that reposition the particle call cursor_restart directly.)
-__device__ inline void cursor_get_current(const DevProblem& P, Cursor& c, const V3& u) {
+template <class PT>
+__device__ inline void cursor_get_current(const PT& P, Cursor& c, const V3& u) {
   int first_bad = c.np;
   for (int it = 0; it < c.np; it++) {
     const int info = c.pinfo[it];
@@ -636,22 +662,35 @@ __device__ inline void cursor_get_current(const DevProblem& P, Cursor& c, const 
     }
   }
   if (first_bad == c.np) return;
-  if (first_bad == 0) {
-    cursor_restart(P, c, frame_r(c, 0), u);
-    return;
+  // re-descend from the pad above the first bad one; a full lookup from the root when there is none, when that pad is a
+  // cell (a lattice sitting directly inside a universe-filled cell: the reference looks the CELL id up in its
+  // universe-id map here (tracker.hpp:287), which lands in an unrelated universe; no shipped deck has this nesting, and
+  // the geometrically correct answer is a fresh lookup), or when the partial descent finds nothing
+  int uni = P.root, f = 0;
+  bool full = true;
+  if (first_bad > 0) {
+    const int back = c.pinfo[first_bad - 1];
+    if (pad_type(back) != PAD_CELL) {
+      c.np = first_bad - 1;
+      uni = pad_index(back);
+      f = pad_frame(back);
+      full = false;
+    }
   }
-  const int back = c.pinfo[first_bad - 1];
-  if (pad_type(back) == PAD_CELL) {
-    // A lattice sitting directly inside a universe-filled cell.  The reference looks the CELL id up in
-    // its universe-id map here (tracker.hpp:287), which lands in an unrelated universe; no shipped deck
-    // has this nesting.  The geometrically correct answer is a fresh lookup from the root.
-    cursor_restart(P, c, frame_r(c, 0), u);
-    return;
+  if (full) {
+    c.np = 0;
+    c.nf = 1;
   }
-  c.np = first_bad - 1;  // pop the universe / lattice pad and descend from it again
-  c.cell = descend(P, c, pad_index(back), pad_frame(back), u);
-  if (c.cell < 0) cursor_restart(P, c, frame_r(c, 0), u);
-  if (c.cell >= 0) c.mat = __ldg(&P.cells[c.cell].material);
+  for (;;) {
+    c.cell = descend<false, Cursor, PT>(P, c, uni, f, u);
+    if (c.cell >= 0 || full) break;
+    full = true;
+    c.np = 0;
+    c.nf = 1;
+    uni = P.root;
+    f = 0;
+  }
+  c.mat = c.cell >= 0 ? __ldg(&P.cells[c.cell].material) : -1;
 }
 
 // Tracker::get_boundary_condition (tracker.hpp:94-161)
@@ -681,7 +720,8 @@ __device__ inline Boundary cursor_boundary_condition(const PT& P, const Cursor& 
 }
 
 // Tracker::get_nearest_boundary (tracker.hpp:163-225); the cursor is never lost when this is called
-__device__ inline Boundary cursor_nearest_boundary(const DevProblem& P, const Cursor& c, const V3& u) {
+template <class PT>
+__device__ inline Boundary cursor_nearest_boundary(const PT& P, const Cursor& c, const V3& u) {
   Boundary b = cursor_boundary_condition(P, c, u);
   for (int it = 0; it < c.np; it++) {
     const int info = c.pinfo[it];
@@ -715,6 +755,18 @@ __device__ inline Boundary cursor_nearest_boundary(const DevProblem& P, const Cu
     }
   }
   return b;
+}
+
+// The cursor operations as real function calls on the geometry tables alone: the per-lane kernel (transport.cuh) calls
+// each of them from several places, and inlined copies made it 230 KB of SASS -- ncu showed it waiting for instructions
+// (21 stall cycles per issue "no instruction", instruction-cache hit rate 53 %).
+__device__ __noinline__ void cursor_restart_nl(const GeoTables G, Cursor& c, const V3 r, const V3 u) { cursor_restart(G, c, r, u); }
+__device__ __noinline__ void cursor_get_current_nl(const GeoTables G, Cursor& c, const V3 u) { cursor_get_current(G, c, u); }
+__device__ __noinline__ Boundary cursor_nearest_boundary_nl(const GeoTables G, const Cursor& c, const V3 u) {
+  return cursor_nearest_boundary(G, c, u);
+}
+__device__ __noinline__ Boundary cursor_boundary_condition_nl(const GeoTables G, const Cursor& c, const V3 u) {
+  return cursor_boundary_condition(G, c, u);
 }
 
 }  // namespace abl

@@ -215,9 +215,6 @@ __device__ __forceinline__ void cursor_relocate_sync(const DevProblem& P, CUR& c
   c.mat = cell >= 0 ? __ldg(&P.cells[cell].material) : -1;
 }
 
-__device__ __noinline__ Boundary cursor_boundary_condition_nl(const GeoTables G, const Cursor& c, const V3 u) {
-  return cursor_boundary_condition(G, c, u);
-}
 
 // Tracker::do_reflection (tracker.hpp:314-360), the arithmetic part: point on the surface and reflected direction
 struct Reflected {

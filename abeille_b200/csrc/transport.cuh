@@ -288,7 +288,7 @@ __device__ __forceinline__ bool do_reflection(const DevProblem& P, Cursor& c, Hi
   h.u = make_direction(h.u.x - n.x * f, h.u.y - n.y * f, h.u.z - n.z * f);
   h.r = r_on;
   c.token = 0;
-  cursor_restart(P, c, h.r, h.u);
+  cursor_restart_nl(geo_tables(P), c, h.r, h.u);
   return true;
 }
 
@@ -368,7 +368,7 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
     // SurfaceTracker::transport loop body (surface_tracker.cpp:72-146)
     const int mg = h.mat * P.G + h.g;
     const double d_coll = rng_exponential(h.rng, MODE == 2 ? __ldg(&P.Et[mg]) + noise_xs<MODE>(P, h.mat, h.g) : __ldg(&P.Et[mg]));
-    const Boundary bound = cursor_nearest_boundary(P, c, h.u);
+    const Boundary bound = cursor_nearest_boundary_nl(geo_tables(P), c, h.u);
     acc.flights++;
     h.n_flights++;
     const double d_min = fmin(d_coll, bound.distance);
@@ -390,7 +390,7 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
         // Tracker::cross_surface + get_current (tracker.hpp:227-231)
         cursor_move(c, bound.distance, h.u);
         c.token = -bound.token;
-        cursor_get_current(P, c, h.u);
+        cursor_get_current_nl(geo_tables(P), c, h.u);
         h.r.x = h.r.x + bound.distance * h.u.x;
         h.r.y = h.r.y + bound.distance * h.u.y;
         h.r.z = h.r.z + bound.distance * h.u.z;
@@ -420,11 +420,11 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
     acc.flights++;
     h.n_flights++;
     cursor_move(c, d_coll, h.u);
-    cursor_get_current(P, c, h.u);
+    cursor_get_current_nl(geo_tables(P), c, h.u);
     if (c.cell < 0) {  // left the geometry: rewind to the pre-flight position and look for the boundary
       c.token = 0;
-      cursor_restart(P, c, h.r, h.u);
-      bound = cursor_boundary_condition(P, c, h.u);
+      cursor_restart_nl(geo_tables(P), c, h.r, h.u);
+      bound = cursor_boundary_condition_nl(geo_tables(P), c, h.u);
       crossed = true;
     }
     score_flight_all(P, A, h, fmin(d_coll, bound.distance), acc);
@@ -501,8 +501,14 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
 
 #undef hid
 
+// One CTA of TK_THREADS per SM whose warps meet at a block-wide vote once per flight: like the staged kernel
+// (history.cuh), the loop body is far larger than the SM's instruction cache, and warps that stay within one iteration of
+// each other share the lines they fetch.
+#ifndef TK_THREADS
+#define TK_THREADS 512
+#endif
 template <int TRK, int MODE>
-__global__ void __launch_bounds__(128) transport_kernel(const DevProblem P, const RunArgs A) {
+__global__ void __launch_bounds__(TK_THREADS, 1) transport_kernel(const DevProblem P, const RunArgs A) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
   Acc acc;
@@ -515,11 +521,11 @@ __global__ void __launch_bounds__(128) transport_kernel(const DevProblem P, cons
   c.err = 0;
   c.np = 0;
   c.nf = 1;
-  bool have = false;
+  bool have = false, exhausted = false;
   const uint64_t N = A.bank.n;
 
   for (;;) {
-    if (!have) {
+    if (!have && !exhausted) {
       // take the next history (one atomic per converged group of lanes)
       unsigned long long idx;
       {
@@ -528,7 +534,8 @@ __global__ void __launch_bounds__(128) transport_kernel(const DevProblem P, cons
         if (grp.thread_rank() == 0) base = atomicAdd(A.ticket, (unsigned long long)grp.size());
         idx = grp.shfl(base, 0) + grp.thread_rank();
       }
-      if (idx >= N) break;
+      exhausted = idx >= N;
+      if (!exhausted) {
       have = true;
       h.idx = (uint32_t)idx;
       h.r = {A.bank.x[idx], A.bank.y[idx], A.bank.z[idx]};
@@ -547,19 +554,21 @@ __global__ void __launch_bounds__(128) transport_kernel(const DevProblem P, cons
       h.nsec = 0;
       h.alive = true;
       c.token = 0;
-      cursor_restart(P, c, h.r, h.u);
+      cursor_restart_nl(geo_tables(P), c, h.r, h.u);
       h.mat = c.mat;
       if (c.cell < 0) {  // lost at birth: warning + kill in the reference (delta_tracker.cpp:92-98)
         acc.lost++;
         h.alive = false;
       }
+      }
     }
-    if (h.alive) flight<TRK, MODE>(P, A, h, c, acc, tid, nthreads);
-    if (!h.alive) {
+    if (__syncthreads_and(!have)) break;  // nobody holds a history and the bank is empty
+    if (have && h.alive) flight<TRK, MODE>(P, A, h, c, acc, tid, nthreads);
+    if (have && !h.alive) {
       if (h.nsec > 0) {  // Particle::resurect + Tracker restart (delta_tracker.cpp:197-229)
         pop_secondary(P, A, h, tid, nthreads);
         c.token = 0;
-        cursor_restart(P, c, h.r, h.u);
+        cursor_restart_nl(geo_tables(P), c, h.r, h.u);
         if (c.cell < 0) {
           raise_error(A, ABL_ERR_LOST, A.bank.id_a[h.idx]);
           h.alive = false;
@@ -591,8 +600,9 @@ __global__ void __launch_bounds__(128) transport_kernel(const DevProblem P, cons
   __syncwarp();
   double dv[5] = {acc.k_col, acc.k_abs, acc.k_trk, acc.leak, acc.mig};
   unsigned long long cv[8] = {acc.flights, acc.real, acc.virt, acc.tl_bins, acc.sites, acc.boundary, acc.lost, acc.coll_scores};
-  __shared__ double sd[4][5];
-  __shared__ unsigned long long sc[4][8];
+  constexpr int NW = TK_THREADS / 32;
+  __shared__ double sd[NW][5];
+  __shared__ unsigned long long sc[NW][8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int q = 0; q < 5; q++) {
@@ -609,12 +619,15 @@ __global__ void __launch_bounds__(128) transport_kernel(const DevProblem P, cons
   __syncthreads();
   if (threadIdx.x < 5) {
     const int q = threadIdx.x;
-    const double v = sd[0][q] + sd[1][q] + sd[2][q] + sd[3][q];
+    double v = 0.;
+    for (int w = 0; w < NW; w++) v += sd[w][q];
     const int slot = q < 3 ? q : q + 1;  // scores layout: k_col,k_abs,k_trk,k_tot(unused),leak,mig
     atomicAdd(&A.scores[slot], v);
   } else if (threadIdx.x >= 32 && threadIdx.x < 40) {
     const int q = threadIdx.x - 32;
-    atomicAdd(&A.counters[q], sc[0][q] + sc[1][q] + sc[2][q] + sc[3][q]);
+    unsigned long long v = 0;
+    for (int w = 0; w < NW; w++) v += sc[w][q];
+    atomicAdd(&A.counters[q], v);
   }
 }
 

@@ -276,7 +276,10 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=100_000)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--ref-particles", type=int, default=100_000, help="--impl reference: particles per step")
-    ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the history kernel (profiles/)")
+    ap.add_argument("--traffic", type=float, default=3.194e10,
+                    help="ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of the history kernel at 1e7 histories "
+                         "(profiles/r1n_history_kernel_v2_summary.txt); 23.7 GB of it is the 32 B-sector read-modify-write of "
+                         "the random 8 B mesh-tally updates")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

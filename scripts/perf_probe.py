@@ -12,7 +12,7 @@ def run(deck, n, gens=4, converged=True):
         yaml.safe_dump(d, f, default_flow_style=None, sort_keys=False, width=200)
         path = f.name
     gpu = ab.Backend(path, 0)
-    cap = int(2.5 * n) + 4096
+    cap = int(4 * n) + 4096
     a, b = gpu.new_device_bank(cap), gpu.new_device_bank(cap)
     gpu.sample_source_device(a, n, 0)
     cur_n, use_state, k, first = n, True, 1.0, n
@@ -37,9 +37,10 @@ def run(deck, n, gens=4, converged=True):
     gpu.close()
 
 if __name__ == "__main__":
-    run("c5g7_delta_collision.yaml", 1_000_000, 4, True)
-    run("c5g7_delta_collision.yaml", 10_000_000, 3, False)
-    run("c5g7_delta_collision_fullmesh.yaml", 10_000_000, 3, True)
+    if "--others" not in sys.argv:
+        run("c5g7_delta_collision.yaml", 1_000_000, 4, True)
+        run("c5g7_delta_collision.yaml", 10_000_000, 3, False)
+        run("c5g7_delta_collision_fullmesh.yaml", 10_000_000, 3, True)
     run("PUa-1-0-IN.yaml", 400_000, 3, True)
     run("c5g7_surface_tracklength.yaml", 1_000_000, 2, True)
     run("c5g7_carter_cancel.yaml", 1_000_000, 3, True)
