@@ -106,18 +106,23 @@ __device__ __forceinline__ double surf_eval(const Surf& s, const V3& r) {
   }
 }
 
+// Surface::norm: the gradient direction, normalised by the Direction constructor (direction.hpp:37-43).  One
+// normalisation after the switch instead of one per case; for the axis planes the constructor yields (1,0,0) etc.
+// exactly (sqrt(1) = 1, x / 1 = x), so they return at once.
 __device__ __noinline__ V3 surf_norm(const Surf& s, const V3& r) {
+  double nx, ny, nz;
   switch (s.type) {
-    case ABL_SURF_XPLANE: return make_direction(1., 0., 0.);
-    case ABL_SURF_YPLANE: return make_direction(0., 1., 0.);
-    case ABL_SURF_ZPLANE: return make_direction(0., 0., 1.);
-    case ABL_SURF_PLANE: return make_direction(s.p0, s.p1, s.p2);
-    case ABL_SURF_XCYL: return make_direction(0., r.y - s.p0, r.z - s.p1);
-    case ABL_SURF_YCYL: return make_direction(r.x - s.p0, 0., r.z - s.p1);
-    case ABL_SURF_ZCYL: return make_direction(r.x - s.p0, r.y - s.p1, 0.);
-    case ABL_SURF_CYL: return make_direction(s.p3 * (r.x - s.p0), s.p4 * (r.y - s.p1), s.p5 * (r.z - s.p2));
-    default: return make_direction(r.x - s.p0, r.y - s.p1, r.z - s.p2);
+    case ABL_SURF_XPLANE: return V3{1., 0., 0.};
+    case ABL_SURF_YPLANE: return V3{0., 1., 0.};
+    case ABL_SURF_ZPLANE: return V3{0., 0., 1.};
+    case ABL_SURF_PLANE: nx = s.p0; ny = s.p1; nz = s.p2; break;
+    case ABL_SURF_XCYL: nx = 0.; ny = r.y - s.p0; nz = r.z - s.p1; break;
+    case ABL_SURF_YCYL: nx = r.x - s.p0; ny = 0.; nz = r.z - s.p1; break;
+    case ABL_SURF_ZCYL: nx = r.x - s.p0; ny = r.y - s.p1; nz = 0.; break;
+    case ABL_SURF_CYL: nx = s.p3 * (r.x - s.p0); ny = s.p4 * (r.y - s.p1); nz = s.p5 * (r.z - s.p2); break;
+    default: nx = r.x - s.p0; ny = r.y - s.p1; nz = r.z - s.p2; break;
   }
+  return make_direction(nx, ny, nz);
 }
 
 // +1 / -1 : which side of the surface; on-surface ties broken by the flight direction
@@ -342,7 +347,8 @@ __device__ inline void cell_distance_impl(const PT& P, int ci, const V3& r, cons
     if (bc_only && s.bc == ABL_BC_NORMAL) continue;
     const double d = surf_distance(s, r, u, coincident);
     if (d < min_dist) {
-      if (fabs(d - min_dist) / min_dist >= 1e-14) {
+      // (against the initial min_dist = DBL_MAX the quotient is 1 - d/DBL_MAX >= 1e-14 for every d < DBL_MAX: no division)
+      if (min_dist == ABL_INF || fabs(d - min_dist) / min_dist >= 1e-14) {
         min_dist = d;
         i_surf = -token;
       }
