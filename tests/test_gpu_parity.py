@@ -335,3 +335,33 @@ def test_results_written_as_npy(ab, tmp_path):
     std = np.load(out / "flux_pin_std.npy")
     assert avg.shape == (7, 51, 51, 1) and std.shape == avg.shape
     assert np.array_equal(avg, gpu.tally(0, "avg")) and np.load(out / "kcol.npy").shape == (4,)
+
+
+def test_full_size_generation_properties(ab, tmp_path):
+    """BASELINE size (10^7 histories, the deck's own 1224x1224x10x7 mesh): properties that do not need the oracle.
+    Every flight ends in exactly one of a real collision, a virtual collision or a boundary event; the collision
+    estimator scores once per real collision; k_col == k_abs (one nuclide per material); the fission bank comes out in
+    the reference's order (parent bank index, then daughter number 0..n-1) and is bit-identical between two runs."""
+    import torch
+    n = 10_000_000
+    path = write_deck(load_deck("c5g7_delta_collision_fullmesh.yaml"), tmp_path / "full.yaml", {"settings": {"nparticles": n}})
+    gpu = ab.Backend(path, 0)
+    cap = int(2.0 * n)
+    src, out1, out2 = gpu.new_device_bank(n), gpu.new_device_bank(cap), gpu.new_device_bank(cap)
+    gpu.sample_source_device(src, n, 0)
+    m1, s1, c1 = gpu.transport_device(src, n, out1, k_col=1.0, converged=True, use_rng_state=True)
+    tally_sum = float(torch.as_tensor(gpu.tally(0, "gen")).sum())
+    gpu.tallies_clear()
+    m2, s2, c2 = gpu.transport_device(src, n, out2, k_col=1.0, converged=True, use_rng_state=True)
+    assert m1 == m2 == c1["fission_sites"] and c1 == c2
+    assert c1["flights"] == c1["real_collisions"] + c1["virtual_collisions"] + c1["boundary_events"]
+    assert c1["coll_scores"] == c1["real_collisions"]
+    assert abs(s1[0] - s1[1]) <= 1e-12 * abs(s1[0])  # k_col == k_abs
+    assert np.allclose(s1, s2, rtol=1e-11)
+    for k in BANK_EXACT:
+        assert torch.equal(out1[k][:m1], out2[k][:m1]), f"two runs differ in {k}"
+    ida, idb = out1["id_a"][:m1], out1["id_b"][:m1]
+    assert bool((ida[1:] >= ida[:-1]).all()), "fission bank not in bank order"
+    same = ida[1:] == ida[:-1]
+    assert bool((idb[1:][same] == idb[:-1][same] + 1).all()) and bool((idb[1:][~same] == 0).all()) and int(idb[0]) == 0
+    assert tally_sum > 0.
