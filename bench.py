@@ -154,6 +154,9 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (the B200 backend has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # torchrun exports OMP_NUM_THREADS=1; the e2e leg's caller-side steps (PowerIterator::normalize_weights on the host
+    # bank) are CPU work that the reference spreads over the host's cores: give every rank its share
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
