@@ -320,10 +320,8 @@ template <int TRK, bool TRACE>
 int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s) {
   // surface tracking: per-lane history loop (transport.cuh); delta / carter: staged lock-step loop with the cursors in
   // shared memory and service warps for the rare events (history.cuh)
-  void (*kern)(const DevProblem, const RunArgs) = nullptr;
-  if (TRK == ABL_TRACK_SURFACE) kern = transport_kernel<ABL_TRACK_SURFACE, 0>;
-  else kern = history_kernel<(TRK == ABL_TRACK_SURFACE ? ABL_TRACK_DELTA : TRK), TRACE>;
-  const bool staged = TRK != ABL_TRACK_SURFACE;
+  void (*kern)(const DevProblem, const RunArgs) = history_kernel<TRK, TRACE>;
+  const bool staged = true;
   const int threads = staged ? HK_THREADS : TK_THREADS;
   const int worker_threads = staged ? HK_HIST : TK_THREADS;  // threads of a block that own histories
   const size_t smem = staged ? sizeof(HKShared) : 0;
@@ -352,7 +350,7 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
     }
     B.secondaries = h->secondaries;
   }
-  if (TRK != ABL_TRACK_SURFACE && B.bank.id_c == nullptr) {  // seed(seed); advance(stride * history id) for the whole bank
+  if (B.bank.id_c == nullptr) {  // seed(seed); advance(stride * history id) for the whole bank
     if (n > h->rng_cap) {
       if (h->rng_scratch) cudaFree(h->rng_scratch);
       h->rng_scratch = nullptr;
@@ -531,7 +529,7 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
       rc = params->noise ? launch_transport_nm<2>(h, A, N, s) : launch_transport_nm<1>(h, A, N, s);
     } else {
       switch (h->P.tracking) {
-        case ABL_TRACK_SURFACE: rc = launch_transport<ABL_TRACK_SURFACE, false>(h, A, N, s); break;
+        case ABL_TRACK_SURFACE: rc = launch_transport<ABL_TRACK_SURFACE>(h, A, N, s, params->trace != 0); break;
         case ABL_TRACK_DELTA: rc = launch_transport<ABL_TRACK_DELTA>(h, A, N, s, params->trace != 0); break;
         default: rc = launch_transport<ABL_TRACK_CARTER>(h, A, N, s, params->trace != 0); break;
       }

@@ -539,6 +539,7 @@ __device__ __forceinline__ void store_pad(Cursor& c, int i, int info, int tx, in
   c.ptile[i][1] = ty;
   c.ptile[i][2] = tz;
 }
+__device__ __forceinline__ Tile3 pad_tile3(const Cursor& c, int i) { return Tile3{c.ptile[i][0], c.ptile[i][1], c.ptile[i][2]}; }
 __device__ __forceinline__ bool pad_tile_is(const Cursor& c, int i, int nx, int ny, int nz) {
   return c.ptile[i][0] == nx && c.ptile[i][1] == ny && c.ptile[i][2] == nz;
 }
@@ -700,12 +701,12 @@ __device__ inline void cursor_get_current(const PT& P, Cursor& c, const V3& u) {
 }
 
 // Tracker::get_boundary_condition (tracker.hpp:94-161)
-template <class PT>
-__device__ inline Boundary cursor_boundary_condition(const PT& P, const Cursor& c, const V3& u) {
+template <class PT, class CUR>
+__device__ inline Boundary cursor_boundary_condition(const PT& P, const CUR& c, const V3& u) {
   if (c.cell < 0) return universe_boundary_condition(P, P.root, frame_r(c, 0), u, c.token);
   Boundary b{ABL_INF, -1, ABL_BC_VACUUM, 0};
   for (int it = 0; it < c.np; it++) {
-    const int info = c.pinfo[it];
+    const int info = pad_info(c, it);
     const V3 r = frame_r(c, pad_frame(info));
     if (pad_type(info) == PAD_CELL) {
       const int ci = pad_index(info);
@@ -726,16 +727,17 @@ __device__ inline Boundary cursor_boundary_condition(const PT& P, const Cursor& 
 }
 
 // Tracker::get_nearest_boundary (tracker.hpp:163-225); the cursor is never lost when this is called
-template <class PT>
-__device__ inline Boundary cursor_nearest_boundary(const PT& P, const Cursor& c, const V3& u) {
+template <class PT, class CUR>
+__device__ inline Boundary cursor_nearest_boundary(const PT& P, const CUR& c, const V3& u) {
   Boundary b = cursor_boundary_condition(P, c, u);
   for (int it = 0; it < c.np; it++) {
-    const int info = c.pinfo[it];
+    const int info = pad_info(c, it);
     const int type = pad_type(info);
     const V3 r = frame_r(c, pad_frame(info));
     if (type == PAD_LATTICE) {
       const Lat L = load_lattice(P.universes + pad_index(info));
-      const double d = distance_to_tile_boundary(L, r, u, c.ptile[it][0], c.ptile[it][1], c.ptile[it][2]);
+      const Tile3 t3 = pad_tile3(c, it);
+      const double d = distance_to_tile_boundary(L, r, u, t3.nx, t3.ny, t3.nz);
       if (d < b.distance && fabs(d - b.distance) > ABL_BOUNDRY_TOL) {
         b.distance = d;
         b.btype = ABL_BC_NORMAL;

@@ -30,7 +30,7 @@
 
 namespace abl {
 
-enum { PH_DEAD = 0, PH_FLIGHT, PH_BIRTH, PH_LOST, PH_REFLECTED, PH_RESURRECT };
+enum { PH_DEAD = 0, PH_FLIGHT, PH_BIRTH, PH_LOST, PH_REFLECTED, PH_RESURRECT, PH_CROSSED };
 
 // Tracker::get_current, first half (tracker.hpp:235-270): index of the first pad that no longer holds, or np
 template <class CUR>
@@ -294,7 +294,9 @@ struct alignas(16) FisJob {  // 80 B
 // (sites banked, boundary events, lost-at-birth, leakage) add to CTA-wide shared-memory accumulators instead.
 struct HAcc {
   double k_col, k_abs, mig;
+  double k_trk;       // surface tracking only (surface_tracker.cpp:81-83)
   uint32_t flights, real, virt, tl_bins, coll_scores;
+  uint32_t boundary;  // surface tracking only: a boundary event every few flights (delta / carter: rare, counted in shared memory)
 };
 enum { RC_SITES = 0, RC_BOUNDARY, RC_LOST, RC_N };
 
@@ -346,6 +348,19 @@ __device__ __forceinline__ void store_pad(SCursor& c, int i, int info, int tx, i
 }
 __device__ __forceinline__ bool pad_tile_is(const SCursor& c, int i, int nx, int ny, int nz) {
   return HKS.ptile[i][c.t] == pack_tile(nx, ny, nz);
+}
+
+__device__ __forceinline__ int unpack_tile_field(unsigned long long v) {
+  const int x = (int)(v & 0x1fffffu);
+  return (x ^ 0x100000) - 0x100000;  // sign-extend 21 bits
+}
+__device__ __forceinline__ Tile3 pad_tile3(const SCursor& c, int i) {
+  const unsigned long long p = HKS.ptile[i][c.t];
+  return Tile3{unpack_tile_field(p), unpack_tile_field(p >> 21), unpack_tile_field(p >> 42)};
+}
+// Tracker::get_nearest_boundary (tracker.hpp:163-225) on the shared-memory cursor, one copy per kernel
+__device__ __noinline__ Boundary cursor_nearest_boundary_s(const GeoTables G, const SCursor c, const V3 u) {
+  return cursor_nearest_boundary(G, c, u);
 }
 
 // barrier 1: the history threads only (the service warps never join it)
@@ -587,8 +602,8 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
   __syncthreads();
 
   HAcc acc;
-  acc.k_col = acc.k_abs = acc.mig = 0.;
-  acc.flights = acc.real = acc.virt = acc.tl_bins = acc.coll_scores = 0;
+  acc.k_col = acc.k_abs = acc.mig = acc.k_trk = 0.;
+  acc.flights = acc.real = acc.virt = acc.tl_bins = acc.coll_scores = acc.boundary = 0;
 
   if (wid >= HK_HIST / 32) {
     service_loop<HK_MATH>(P, A, wid - HK_HIST / 32);
@@ -653,7 +668,64 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
       if (hist_all(phase == PH_DEAD)) break;
 
       // ---- M: sample the flight, move the cursor, re-validate its pads ----------------------------------------------------------
-      if (phase == PH_FLIGHT) {
+      bool collide_now = false;  // surface tracking: the flight ended in a collision inside the current cell
+      if (TRK == ABL_TRACK_SURFACE) {
+        // SurfaceTracker::transport loop body (surface_tracker.cpp:72-146): distance to collision against the nearest
+        // boundary over all pads; the track-length estimators score the segment from the pre-move position
+        if (phase == PH_FLIGHT) {
+          const int mg = h.mat * P.G + h.g;
+          d_coll = rng_exponential<HK_MATH>(h.rng, __ldg(&P.Et[mg]));
+          const Boundary sb = cursor_nearest_boundary_s(geo_tables(P), c, h.u);
+          acc.flights++;
+          if (TRACE) h.n_flights++;
+          const double d_min = fmin(d_coll, sb.distance);
+          if (tle) {
+            const MatXS mx{__ldg(&P.Et[mg]), __ldg(&P.Ea[mg]), __ldg(&P.Ef[mg]), __ldg(&P.Es[mg])};
+            acc.tl_bins += score_flight_all_nl(P.tally_dev, P.ntallies, h.r, h.u, d_min, h.E, h.w, h.w2, mx);
+          }
+          acc.k_trk += h.w * d_min * (__ldg(&P.nu[mg]) * __ldg(&P.Ef[mg]));
+          if (sb.distance < d_coll || fabs(sb.distance - d_coll) < ABL_BOUNDRY_TOL) {
+            acc.boundary++;
+            if (sb.btype == ABL_BC_VACUUM) {
+              if (TRACE) note(h, 0x3000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
+              h.alive = false;  // leak (surface_tracker.cpp:95-99)
+              const V3 d{h.r.x + sb.distance * h.u.x - S.rb[0][c.t], h.r.y + sb.distance * h.u.y - S.rb[1][c.t],
+                         h.r.z + sb.distance * h.u.z - S.rb[2][c.t]};
+              atomicAdd(&S.leak, h.w);
+              atomicAdd(&S.leak_mig, h.w * dot3(d, d));
+            } else if (sb.btype == ABL_BC_REFLECTIVE) {
+              if (sb.surface_index < 0) {
+                raise_error(A, ABL_ERR_LOST, A.bank.id_a[h.idx]);
+                h.alive = false;
+                h.nsec = 0;
+              } else {  // Tracker::do_reflection (tracker.hpp:314-360); the full lookup happens in the L stage
+                const Reflected rf = reflect_nl(P.surfaces, sb.surface_index, h.r, h.u, sb.distance);
+                h.u = rf.u;
+                h.r = rf.r;
+                c.token = 0;
+                set_frame(c, 0, h.r.x, h.r.y, h.r.z);
+                need = 0;
+                phase = PH_REFLECTED;
+              }
+            } else {  // Tracker::cross_surface + get_current (tracker.hpp:227-231)
+              cursor_move(c, sb.distance, h.u);
+              c.token = -sb.token;
+              const int first_bad = cursor_validate(P, c, h.u);
+              if (first_bad < c.np) need = first_bad;
+              h.r.x = h.r.x + sb.distance * h.u.x;
+              h.r.y = h.r.y + sb.distance * h.u.y;
+              h.r.z = h.r.z + sb.distance * h.u.z;
+              phase = PH_CROSSED;
+            }
+          } else {
+            h.r.x = h.r.x + d_coll * h.u.x;
+            h.r.y = h.r.y + d_coll * h.u.y;
+            h.r.z = h.r.z + d_coll * h.u.z;
+            cursor_move(c, d_coll, h.u);
+            collide_now = true;
+          }
+        }
+      } else if (phase == PH_FLIGHT) {
         d_coll = rng_exponential<HK_MATH>(h.rng, __ldg(&P.smp[h.g]));
         acc.flights++;
         if (TRACE) h.n_flights++;
@@ -684,7 +756,9 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
       bool test_collision = false, flight_done = false, answered = false;
       Boundary bound{ABL_INF, -1, ABL_BC_NORMAL, 0};
       int cell_before = -1;
-      if (phase == PH_FLIGHT) {
+      if (TRK == ABL_TRACK_SURFACE) {
+        // (the boundary was found before the move: nothing to ask the service warp)
+      } else if (phase == PH_FLIGHT) {
         if (c.cell < 0) {  // left the geometry: a service warp looks for the boundary from the pre-flight position
           post_boundary_request(c, h.r, h.u, sw);
           phase = PH_WAIT;
@@ -708,7 +782,7 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
         }
       }
       // ---- T: track-length mesh tallies, scored from the pre-move position -----------------------------------------------------------------
-      if (tle && tle_d >= 0.) {
+      if (TRK != ABL_TRACK_SURFACE && tle && tle_d >= 0.) {
         const int mg = h.mat * P.G + h.g;
         const MatXS mx{__ldg(&P.Et[mg]), __ldg(&P.Ea[mg]), __ldg(&P.Ef[mg]), __ldg(&P.Es[mg])};
         acc.tl_bins += score_flight_all_nl(P.tally_dev, P.ntallies, h.r, h.u, tle_d, h.E, h.w, h.w2, mx);
@@ -751,6 +825,16 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
         }
         flight_done = true;
         phase = PH_FLIGHT;
+      } else if (TRK == ABL_TRACK_SURFACE && phase == PH_CROSSED && need < 0) {
+        if (c.cell < 0) {
+          raise_error(A, ABL_ERR_LOST, A.bank.id_a[h.idx]);
+          h.alive = false;
+          h.nsec = 0;
+        } else {
+          h.mat = c.mat;
+          if (TRACE) note(h, 0x7000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
+        }
+        phase = PH_FLIGHT;
       } else if (phase == PH_BIRTH) {
         if (c.cell < 0) {  // lost at birth: warning + kill in the reference (delta_tracker.cpp:92-98)
           atomicAdd(&S.rare[RC_LOST], 1u);
@@ -772,7 +856,12 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
       HK_SYNC();
 
       // ---- C: arrive, real or virtual collision (delta_tracker.cpp:167-195, carter_tracker.cpp:189-207) ----------------------------------------
-      if (test_collision) {
+      if (TRK == ABL_TRACK_SURFACE) {
+        if (collide_now && h.alive) {
+          if (TRACE) note(h, 0x2000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
+          collision_hk<HK_MATH, TRACE>(P, A, h, acc, sw, c.t);
+        }
+      } else if (test_collision) {
         bool had_collision = false;
         flight_done = true;
         h.r.x = h.r.x + d_coll * h.u.x;
@@ -857,8 +946,8 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
   }
 
   // ---- reduce the per-thread accumulators: warp shuffle, then one atomic per block ------------------------------------
-  double dv[5] = {acc.k_col, acc.k_abs, 0., 0., acc.mig};
-  unsigned long long cv[8] = {acc.flights, acc.real, acc.virt, acc.tl_bins, 0, 0, 0, acc.coll_scores};
+  double dv[5] = {acc.k_col, acc.k_abs, acc.k_trk, 0., acc.mig};
+  unsigned long long cv[8] = {acc.flights, acc.real, acc.virt, acc.tl_bins, 0, acc.boundary, 0, acc.coll_scores};
   constexpr int NW = HK_THREADS / 32;
 #pragma unroll
   for (int q = 0; q < 5; q++) {
