@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "bank_ops.cuh"
-#include "history.cuh"
+#include "kernel_entry.h"
 
 using namespace abl;
 
@@ -320,7 +320,8 @@ template <int TRK, bool TRACE>
 int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s) {
   // surface tracking: per-lane history loop (transport.cuh); delta / carter: staged lock-step loop with the cursors in
   // shared memory and service warps for the rare events (history.cuh)
-  void (*kern)(const DevProblem, const RunArgs) = history_kernel<TRK, TRACE>;
+  TransportKernel kern = TRK == ABL_TRACK_SURFACE ? history_kernel_surface(TRACE)
+                                                   : (TRK == ABL_TRACK_DELTA ? history_kernel_delta(TRACE) : history_kernel_carter(TRACE));
   const bool staged = true;
   const int threads = staged ? HK_THREADS : TK_THREADS;
   const int worker_threads = staged ? HK_HIST : TK_THREADS;  // threads of a block that own histories
@@ -376,7 +377,7 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
 // generation (may sample the noise source), MODE 2 = noise particles (noise.cuh)
 template <int TRK, int MODE>
 int launch_transport_nm(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s) {
-  void (*kern)(const DevProblem, const RunArgs) = transport_kernel<TRK, MODE>;
+  TransportKernel kern = lane_kernel(TRK, MODE);
   const int threads = TK_THREADS;
   int& bps = h->nm_blocks_per_sm[TRK][MODE];
   if (bps == 0) {

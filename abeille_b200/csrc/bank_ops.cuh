@@ -378,4 +378,11 @@ __global__ void math_probe_kernel(int n, const double* x, double* lg, double* sn
   }
 }
 
+// pcg32 state of every history of a bank: seed(seed); advance(stride * history_id) (particle.hpp:188-193)
+__global__ void __launch_bounds__(256) seed_streams_kernel(const DevProblem P, const uint64_t* __restrict__ history_id, uint64_t n,
+                                                           uint64_t* __restrict__ state) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    state[i] = pcg_advance(P.seed_state, P.stride * history_id[i], P.jump);
+}
+
 }  // namespace abl

@@ -24,7 +24,7 @@ __device__ __forceinline__ int32_t dm_hi(double x) { return __double2hiint(x); }
 __device__ __forceinline__ uint32_t dm_lo(double x) { return (uint32_t)__double2loint(x); }
 __device__ __forceinline__ double dm_set_hi(double x, int32_t hi) { return __hiloint2double(hi, __double2loint(x)); }
 
-__device__ ABL_HOT_CALL double det_log(double x) {
+static __device__ ABL_HOT_CALL double det_log(double x) {
   const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
                two54 = 1.80143985094819840000e+16, Lg1 = 6.666666666666735130e-01,
                Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
@@ -160,7 +160,7 @@ __device__ __forceinline__ int det_rem_pio2(double x, double* y0, double* y1) {
 // written without data-dependent branches: the lanes of a warp hold angles from every octant, and with branches
 // ncu showed this routine running with 10 of the 23 lanes that enter it.  Both kernel polynomials are evaluated
 // once per lane and the octant-specific pieces are selected.
-__device__ ABL_HOT_CALL void det_sincos(double x, double* sn, double* cs) {
+static __device__ ABL_HOT_CALL void det_sincos(double x, double* sn, double* cs) {
   const int32_t ix = dm_hi(x) & 0x7fffffff;
   if (ix >= 0x7ff00000) {
     *sn = *cs = x - x;

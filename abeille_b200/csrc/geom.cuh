@@ -56,7 +56,7 @@ __device__ __forceinline__ V3 rotate_direction(const V3& u, double mu, double ph
   return make_direction<M>(ux, uy, uz);
 }
 // one shared copy for kernels that use CallMath (scatter in the hot loop, fission banking in the cold path)
-__device__ ABL_HOT_CALL V3 rotate_direction_call(const V3 u, double mu, double phi) { return rotate_direction<CallMath>(u, mu, phi); }
+static __device__ ABL_HOT_CALL V3 rotate_direction_call(const V3 u, double mu, double phi) { return rotate_direction<CallMath>(u, mu, phi); }
 template <class M>
 __device__ __forceinline__ V3 rotate_dir(const V3& u, double mu, double phi) { return rotate_direction<M>(u, mu, phi); }
 template <>
@@ -109,7 +109,7 @@ __device__ __forceinline__ double surf_eval(const Surf& s, const V3& r) {
 // Surface::norm: the gradient direction, normalised by the Direction constructor (direction.hpp:37-43).  One
 // normalisation after the switch instead of one per case; for the axis planes the constructor yields (1,0,0) etc.
 // exactly (sqrt(1) = 1, x / 1 = x), so they return at once.
-__device__ __noinline__ V3 surf_norm(const Surf& s, const V3& r) {
+static __device__ __noinline__ V3 surf_norm(const Surf& s, const V3& r) {
   double nx, ny, nz;
   switch (s.type) {
     case ABL_SURF_XPLANE: return V3{1., 0., 0.};
@@ -294,14 +294,14 @@ __device__ inline bool cell_is_inside(const PT& P, int ci, const V3& r, const V3
 }
 
 // the generic evaluator as a real function call: keeps the cold path out of the hot loop's instruction footprint
-__device__ __noinline__ bool cell_is_inside_nl(const GeoTables G, int ci, const V3 r, const V3 u, int on_surf) {
+static __device__ __noinline__ bool cell_is_inside_nl(const GeoTables G, int ci, const V3 r, const V3 u, int on_surf) {
   return cell_is_inside(G, ci, r, u, on_surf);
 }
 
 // Cell::is_inside through the compiled descriptor (tables.h: CellFast): 1 inside, 0 outside, -1 undecided --
 // the particle sits on a surface or is within SURFACE_COINCIDENT of one (direction-dependent tie), or the
 // region has no compiled form; the caller then runs the generic evaluator.  One shared copy per kernel.
-__device__ ABL_HOT_CALL int cell_fast_nl(const CellFast* __restrict__ cf, const V3 r, int on_surf) {
+static __device__ ABL_HOT_CALL int cell_fast_nl(const CellFast* __restrict__ cf, const V3 r, int on_surf) {
   const int kind = __ldg(&cf->kind);
   if (on_surf != 0) return -1;
   if (kind == CF_BOX) {
@@ -358,7 +358,7 @@ __device__ inline void cell_distance_impl(const PT& P, int ci, const V3& r, cons
 
 // one shared copy for the callers that work on the bare geometry tables (the per-lane kernel and the service warp reach
 // this from three places; the surface-distance switch inside is several hundred instructions)
-__device__ __noinline__ void cell_distance_nl(const GeoTables G, int ci, const V3 r, const V3 u, int on_surf, bool bc_only,
+static __device__ __noinline__ void cell_distance_nl(const GeoTables G, int ci, const V3 r, const V3 u, int on_surf, bool bc_only,
                                               double* min_dist, int* i_surf) {
   double d;
   int is;
@@ -417,7 +417,7 @@ __device__ __forceinline__ void get_tile(const Lat& L, const V3& r, const V3& u,
 struct Tile3 {
   int nx, ny, nz;
 };
-__device__ ABL_HOT_CALL Tile3 lattice_tile_nl(const abl_universe* __restrict__ U, const V3 r, const V3 u) {
+static __device__ ABL_HOT_CALL Tile3 lattice_tile_nl(const abl_universe* __restrict__ U, const V3 r, const V3 u) {
   const Lat L = load_lattice(U);
   Tile3 t;
   get_tile(L, r, u, t.nx, t.ny, t.nz);
@@ -768,12 +768,12 @@ __device__ inline Boundary cursor_nearest_boundary(const PT& P, const CUR& c, co
 // The cursor operations as real function calls on the geometry tables alone: the per-lane kernel (transport.cuh) calls
 // each of them from several places, and inlined copies made it 230 KB of SASS -- ncu showed it waiting for instructions
 // (21 stall cycles per issue "no instruction", instruction-cache hit rate 53 %).
-__device__ __noinline__ void cursor_restart_nl(const GeoTables G, Cursor& c, const V3 r, const V3 u) { cursor_restart(G, c, r, u); }
-__device__ __noinline__ void cursor_get_current_nl(const GeoTables G, Cursor& c, const V3 u) { cursor_get_current(G, c, u); }
-__device__ __noinline__ Boundary cursor_nearest_boundary_nl(const GeoTables G, const Cursor& c, const V3 u) {
+static __device__ __noinline__ void cursor_restart_nl(const GeoTables G, Cursor& c, const V3 r, const V3 u) { cursor_restart(G, c, r, u); }
+static __device__ __noinline__ void cursor_get_current_nl(const GeoTables G, Cursor& c, const V3 u) { cursor_get_current(G, c, u); }
+static __device__ __noinline__ Boundary cursor_nearest_boundary_nl(const GeoTables G, const Cursor& c, const V3 u) {
   return cursor_nearest_boundary(G, c, u);
 }
-__device__ __noinline__ Boundary cursor_boundary_condition_nl(const GeoTables G, const Cursor& c, const V3 u) {
+static __device__ __noinline__ Boundary cursor_boundary_condition_nl(const GeoTables G, const Cursor& c, const V3 u) {
   return cursor_boundary_condition(G, c, u);
 }
 

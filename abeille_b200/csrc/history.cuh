@@ -220,7 +220,7 @@ __device__ __forceinline__ void cursor_relocate_sync(const DevProblem& P, CUR& c
 struct Reflected {
   V3 r, u;
 };
-__device__ __noinline__ Reflected reflect_nl(const abl_surface* __restrict__ surfaces, int surface_index, const V3 r, const V3 u, double distance) {
+static __device__ __noinline__ Reflected reflect_nl(const abl_surface* __restrict__ surfaces, int surface_index, const V3 r, const V3 u, double distance) {
   GeoTables G{};
   G.surfaces = surfaces;
   const Surf s = load_surface(G, surface_index);
@@ -233,7 +233,7 @@ __device__ __noinline__ Reflected reflect_nl(const abl_surface* __restrict__ sur
 }
 
 // every track-length tally (tallies.hpp:57-63); returns the number of bins scored
-__device__ __noinline__ int score_flight_all_nl(const DevTally* __restrict__ tallies, int ntallies, const V3 r, const V3 u, double d,
+static __device__ __noinline__ int score_flight_all_nl(const DevTally* __restrict__ tallies, int ntallies, const V3 r, const V3 u, double d,
                                                 double E, double w, double w2, const MatXS mx) {
   int nb = 0;
   for (int t = 0; t < ntallies; t++) {
@@ -359,7 +359,7 @@ __device__ __forceinline__ Tile3 pad_tile3(const SCursor& c, int i) {
   return Tile3{unpack_tile_field(p), unpack_tile_field(p >> 21), unpack_tile_field(p >> 42)};
 }
 // Tracker::get_nearest_boundary (tracker.hpp:163-225) on the shared-memory cursor, one copy per kernel
-__device__ __noinline__ Boundary cursor_nearest_boundary_s(const GeoTables G, const SCursor c, const V3 u) {
+static __device__ __noinline__ Boundary cursor_nearest_boundary_s(const GeoTables G, const SCursor c, const V3 u) {
   return cursor_nearest_boundary(G, c, u);
 }
 
@@ -946,8 +946,8 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
   }
 
   // ---- reduce the per-thread accumulators: warp shuffle, then one atomic per block ------------------------------------
-  double dv[5] = {acc.k_col, acc.k_abs, acc.k_trk, 0., acc.mig};
-  unsigned long long cv[8] = {acc.flights, acc.real, acc.virt, acc.tl_bins, 0, acc.boundary, 0, acc.coll_scores};
+  double dv[5] = {acc.k_col, acc.k_abs, TRK == ABL_TRACK_SURFACE ? acc.k_trk : 0., 0., acc.mig};
+  unsigned long long cv[8] = {acc.flights, acc.real, acc.virt, acc.tl_bins, 0, TRK == ABL_TRACK_SURFACE ? acc.boundary : 0u, 0, acc.coll_scores};
   constexpr int NW = HK_THREADS / 32;
 #pragma unroll
   for (int q = 0; q < 5; q++) {
@@ -974,13 +974,6 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
     for (int w = 0; w < NW; w++) v += S.sc[w][q];
     atomicAdd(&A.counters[q], v);
   }
-}
-
-// pcg32 state of every history of a bank: seed(seed); advance(stride * history_id) (particle.hpp:188-193)
-__global__ void __launch_bounds__(256) seed_streams_kernel(const DevProblem P, const uint64_t* __restrict__ history_id, uint64_t n,
-                                                           uint64_t* __restrict__ state) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    state[i] = pcg_advance(P.seed_state, P.stride * history_id[i], P.jump);
 }
 
 }  // namespace abl

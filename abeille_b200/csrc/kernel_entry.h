@@ -1,0 +1,19 @@
+/* kernel_entry.h -- the history kernels, one translation unit per tracker.
+ *
+ * nvcc compiles each .cu as a whole program: the non-inlined device helpers (boundary search, track-length scorer,
+ * fission banking ...) get ONE register allocation per translation unit, negotiated over all the kernels that call them.
+ * With every instantiation in one file, adding the surface-tracking kernel changed the register allocation of the
+ * delta-tracking kernel (96 -> 132 bytes of spills, 3 % slower on the bench workload) although not a line of its code had
+ * changed.  So each tracker's kernels live in their own file and the host code gets them as function pointers.
+ */
+#pragma once
+#include "history.cuh"
+
+namespace abl {
+typedef void (*TransportKernel)(const DevProblem, const RunArgs);
+TransportKernel history_kernel_delta(bool trace);    // kernels_delta.cu
+TransportKernel history_kernel_carter(bool trace);   // kernels_carter.cu
+TransportKernel history_kernel_surface(bool trace);  // kernels_surface.cu
+TransportKernel history_kernel_traced(int tracking); // kernels_trace.cu
+TransportKernel lane_kernel(int tracking, int mode); // kernels_lane.cu: per-lane kernel of the noise modes (mode 1 | 2)
+}  // namespace abl

@@ -58,7 +58,7 @@ struct FisSample {
   bool delayed;
 };
 // MGNuclide::sample_fission (mg_nuclide.cpp:504-543)
-__device__ __noinline__ FisSample sample_fission_nm(const FissionTables T, const double* __restrict__ dg_lambda, uint64_t* rng_io,
+static __device__ __noinline__ FisSample sample_fission_nm(const FissionTables T, const double* __restrict__ dg_lambda, uint64_t* rng_io,
                                                     const V3 u, int mat, int mg, double P_delayed) {
   uint64_t rng = *rng_io;
   int ei = 0;

@@ -68,14 +68,14 @@ struct RandOut {
   double v;
   uint64_t state;
 };
-__device__ __noinline__ RandOut rng_rand_call(uint64_t state) {
+static __device__ __noinline__ RandOut rng_rand_call(uint64_t state) {
   RandOut o;
   o.v = rng_rand(state);
   o.state = state;
   return o;
 }
-__device__ __noinline__ double ddiv_call(double a, double b) { return a / b; }
-__device__ __noinline__ double dsqrt_call(double a) { return sqrt(a); }
+static __device__ __noinline__ double ddiv_call(double a, double b) { return a / b; }
+static __device__ __noinline__ double dsqrt_call(double a) { return sqrt(a); }
 
 struct InlineMath {
   static __device__ __forceinline__ double rand(uint64_t& s) { return rng_rand(s); }

@@ -104,7 +104,7 @@ __device__ __forceinline__ void raise_error(const RunArgs& A, int code, uint64_t
 }
 
 // inverse CDF on a linearly interpolable pdf (mg_angle_distribution.hpp:45-60)
-__device__ __noinline__ double sample_mu_table(const double* __restrict__ acdf, const double* __restrict__ amu,
+static __device__ __noinline__ double sample_mu_table(const double* __restrict__ acdf, const double* __restrict__ amu,
                                                const double* __restrict__ apdf, int off, int n, double xi) {
   const double* cdf = acdf + off;
   int lo = 0, len = n;
@@ -165,7 +165,7 @@ struct FissionTables {
   int G;
 };
 template <class M>
-__device__ __noinline__ void bank_fission_sites(const FissionTables T, Site* sites, unsigned long long* n_sites, uint64_t capacity,
+static __device__ __noinline__ void bank_fission_sites(const FissionTables T, Site* sites, unsigned long long* n_sites, uint64_t capacity,
                                                 uint64_t& rng, const V3 r, const V3 u, double w, uint32_t parent, uint32_t daughter0,
                                                 int n_new, int mat, int mg, double P_delayed) {
   const int dg0 = __ldg(&T.dg_off[mat]), ndg = __ldg(&T.dg_off[mat + 1]) - dg0;
