@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <limits>
@@ -28,6 +29,7 @@ struct DevSmall {  // small per-call block, zeroed before every transport launch
   uint32_t grand_total;
   uint32_t grand_total_noise;
   unsigned long long n_nsites;
+  unsigned long long avail;  // rows of a streamed input bank that have arrived (abl_transport)
 };
 
 thread_local std::string g_create_error;
@@ -57,6 +59,11 @@ struct abl_context {
   uint64_t nsite_cap = 0, did_cap = 0, ndid_cap = 0, nnoise_cap = 0;
   uint32_t *nnoise = nullptr, *noffsets = nullptr, *ntile_sums = nullptr, *site_did = nullptr, *nsite_did = nullptr;
   int nm_blocks_per_sm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  // host-buffer entry point: the bank is copied in row chunks on its own stream while the history kernel runs
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_ids = nullptr, ev_zeroed = nullptr;
+  unsigned long long* chunk_ends = nullptr;  // pinned
+  bool streamed_input = false;
   CancelBins cancel{nullptr, nullptr, nullptr};
   bool cancel_has_w2 = false;
   // staging banks of the host-buffer API
@@ -494,7 +501,8 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
       }
     }
   }
-  ABL_CUDA(h, cudaMemsetAsync(h->small_dev, 0, sizeof(DevSmall), s));
+  // (a streamed input bank keeps its arrival counter, the last member, across this reset)
+  ABL_CUDA(h, cudaMemsetAsync(h->small_dev, 0, h->streamed_input ? offsetof(DevSmall, avail) : sizeof(DevSmall), s));
   RunArgs A{};
   A.bank = in;
   A.ticket = &h->small_dev->ticket;
@@ -514,6 +522,7 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
   A.k_col = params->k_col;
   A.keff = params->keff;
   A.converged = params->converged;
+  A.avail = h->streamed_input ? &h->small_dev->avail : nullptr;
   A.sample_noise = sample_noise ? 1 : 0;
   A.site_did = h->site_did;
   if (sample_noise) {
@@ -611,6 +620,10 @@ void abl_destroy(abl_handle h) {
   if (h->small_host) cudaFreeHost(h->small_host);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->ev_ids) cudaEventDestroy(h->ev_ids);
+  if (h->ev_zeroed) cudaEventDestroy(h->ev_zeroed);
+  if (h->chunk_ends) cudaFreeHost(h->chunk_ends);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -911,22 +924,57 @@ int abl_transport(abl_handle h, const abl_bank* bank, const abl_gen_params* para
   out.n = cap;
   const double* hin[9] = {bank->x, bank->y, bank->z, bank->ux, bank->uy, bank->uz, bank->E, bank->wgt, bank->wgt2};
   double* din[9] = {in.x, in.y, in.z, in.ux, in.uy, in.uz, in.E, in.wgt, in.wgt2};
-  for (int k = 0; k < 9; k++) {
-    if (!hin[k]) {
-      if (k == 8) { in.wgt2 = nullptr; continue; }
-      return fail(h, ABL_ERR_INVALID, "null bank array");
-    }
-    if (N) ABL_CUDA(h, cudaMemcpyAsync(din[k], hin[k], N * sizeof(double), cudaMemcpyHostToDevice, s));
-  }
+  for (int k = 0; k < 8; k++)
+    if (!hin[k]) return fail(h, ABL_ERR_INVALID, "null bank array");
   if (!bank->id_a) return fail(h, ABL_ERR_INVALID, "null history id array");
-  if (N) ABL_CUDA(h, cudaMemcpyAsync(in.id_a, bank->id_a, N * 8, cudaMemcpyHostToDevice, s));
-  if (bank->id_b) { if (N) ABL_CUDA(h, cudaMemcpyAsync(in.id_b, bank->id_b, N * 8, cudaMemcpyHostToDevice, s)); }
-  else in.id_b = nullptr;
-  if (bank->id_c) { if (N) ABL_CUDA(h, cudaMemcpyAsync(in.id_c, bank->id_c, N * 8, cudaMemcpyHostToDevice, s)); }
-  else in.id_c = nullptr;
+  if (!hin[8]) in.wgt2 = nullptr;
+  if (!bank->id_b) in.id_b = nullptr;
+  if (!bank->id_c) in.id_c = nullptr;
+  // Large k-eigenvalue banks are STREAMED: the ids go first (the RNG streams are seeded from them), then the other
+  // arrays in row chunks on a second stream, each chunk followed by an update of the arrival counter that the history
+  // kernel polls before it loads a row -- the PCIe copy (17 ms for 1e7 particles) hides behind the kernel.
+  constexpr int NCHUNK = 16;
+  const bool streamed = h->P.mode != ABL_MODE_NOISE && !params->noise && N >= (1u << 18);
+  if (streamed) {
+    if (!h->copy_stream) {
+      ABL_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+      ABL_CUDA(h, cudaEventCreateWithFlags(&h->ev_ids, cudaEventDisableTiming));
+      ABL_CUDA(h, cudaEventCreateWithFlags(&h->ev_zeroed, cudaEventDisableTiming));
+      ABL_CUDA(h, cudaMallocHost(&h->chunk_ends, NCHUNK * sizeof(unsigned long long)));
+    }
+    cudaStream_t cs = h->copy_stream;
+    ABL_CUDA(h, cudaMemsetAsync(&h->small_dev->avail, 0, sizeof(unsigned long long), s));
+    ABL_CUDA(h, cudaEventRecord(h->ev_zeroed, s));
+    ABL_CUDA(h, cudaStreamWaitEvent(cs, h->ev_zeroed, 0));
+    ABL_CUDA(h, cudaMemcpyAsync(in.id_a, bank->id_a, N * 8, cudaMemcpyHostToDevice, cs));
+    if (bank->id_b) ABL_CUDA(h, cudaMemcpyAsync(in.id_b, bank->id_b, N * 8, cudaMemcpyHostToDevice, cs));
+    ABL_CUDA(h, cudaEventRecord(h->ev_ids, cs));
+    ABL_CUDA(h, cudaStreamWaitEvent(s, h->ev_ids, 0));
+    for (int c = 0; c < NCHUNK; c++) {
+      const uint64_t r0 = N * c / NCHUNK, r1 = N * (c + 1) / NCHUNK;
+      if (r1 > r0) {
+        for (int k = 0; k < 9; k++)
+          if (hin[k]) ABL_CUDA(h, cudaMemcpyAsync(din[k] + r0, hin[k] + r0, (r1 - r0) * sizeof(double), cudaMemcpyHostToDevice, cs));
+        if (bank->id_c) ABL_CUDA(h, cudaMemcpyAsync(in.id_c + r0, bank->id_c + r0, (r1 - r0) * 8, cudaMemcpyHostToDevice, cs));
+      }
+      h->chunk_ends[c] = r1;
+      ABL_CUDA(h, cudaMemcpyAsync(&h->small_dev->avail, &h->chunk_ends[c], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
+    }
+  } else {
+    for (int k = 0; k < 9; k++)
+      if (hin[k] && N) ABL_CUDA(h, cudaMemcpyAsync(din[k], hin[k], N * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (N) ABL_CUDA(h, cudaMemcpyAsync(in.id_a, bank->id_a, N * 8, cudaMemcpyHostToDevice, s));
+    if (bank->id_b && N) ABL_CUDA(h, cudaMemcpyAsync(in.id_b, bank->id_b, N * 8, cudaMemcpyHostToDevice, s));
+    if (bank->id_c && N) ABL_CUDA(h, cudaMemcpyAsync(in.id_c, bank->id_c, N * 8, cudaMemcpyHostToDevice, s));
+  }
+  h->streamed_input = streamed;
   if (!fission_out->wgt2) out.wgt2 = nullptr;
   rc = transport_impl(h, in, params, out, n_fission, scores, counters, s);
-  if (rc) return rc;
+  h->streamed_input = false;
+  if (rc) {
+    if (streamed) cudaStreamSynchronize(h->copy_stream);
+    return rc;
+  }
   const uint64_t m = *n_fission;
   if (m) {
     double* hout[9] = {fission_out->x, fission_out->y, fission_out->z, fission_out->ux, fission_out->uy, fission_out->uz,

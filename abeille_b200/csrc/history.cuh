@@ -625,35 +625,44 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
     int phase = PH_DEAD;
     int need = -1;        // pending (re-)descent: first bad pad, 0 = full lookup from the root, -1 = none
     double d_coll = 0.;   // sampled flight distance (kept across the iterations of a boundary event)
-    bool exhausted = false;
+    bool exhausted = false, have_ticket = false;
     const uint64_t N = A.bank.n;
     const bool tle = A.converged && P.n_tl_tallies;
 
     for (;;) {
       // ---- R: refill ---------------------------------------------------------------------------------------------
+      // (with a streamed bank -- A.avail -- a lane that holds a ticket waits here until its row has been copied)
       if (phase == PH_DEAD && !exhausted) {
-        unsigned long long idx;
-        {
-          cg::coalesced_group grp = cg::coalesced_threads();
-          unsigned long long base = 0;
-          if (grp.thread_rank() == 0) base = atomicAdd(A.ticket, (unsigned long long)grp.size());
-          idx = grp.shfl(base, 0) + grp.thread_rank();
+        if (!have_ticket) {
+          unsigned long long idx;
+          {
+            cg::coalesced_group grp = cg::coalesced_threads();
+            unsigned long long base = 0;
+            if (grp.thread_rank() == 0) base = atomicAdd(A.ticket, (unsigned long long)grp.size());
+            idx = grp.shfl(base, 0) + grp.thread_rank();
+          }
+          if (idx >= N) {
+            exhausted = true;
+          } else {
+            have_ticket = true;
+            h.idx = (uint32_t)idx;
+          }
         }
-        if (idx >= N) {
-          exhausted = true;
-        } else {
-          h.idx = (uint32_t)idx;
-          h.r = {A.bank.x[idx], A.bank.y[idx], A.bank.z[idx]};
-          h.u = {A.bank.ux[idx], A.bank.uy[idx], A.bank.uz[idx]};
+        if (have_ticket && (A.avail == nullptr || (unsigned long long)h.idx < *(const volatile unsigned long long*)A.avail)) {
+          const uint32_t idx = h.idx;
+          have_ticket = false;
+          // (L2 loads: with a streamed bank a cached L1 line could hold neighbouring rows from before they arrived)
+          h.r = {__ldcg(&A.bank.x[idx]), __ldcg(&A.bank.y[idx]), __ldcg(&A.bank.z[idx])};
+          h.u = {__ldcg(&A.bank.ux[idx]), __ldcg(&A.bank.uy[idx]), __ldcg(&A.bank.uz[idx])};
           S.rb[0][c.t] = h.r.x;
           S.rb[1][c.t] = h.r.y;
           S.rb[2][c.t] = h.r.z;
-          h.E = A.bank.E[idx];
-          h.w = A.bank.wgt[idx];
+          h.E = __ldcg(&A.bank.E[idx]);
+          h.w = __ldcg(&A.bank.wgt[idx]);
           h.w2 = 0.;
           h.g = group_of(P, h.E);
           h.emid = h.g < P.G && h.E == group_mid(P, h.g);
-          h.rng = A.bank.id_c[idx];  // pcg32 state: seeded by seed_streams_kernel / source sampling
+          h.rng = __ldcg(&A.bank.id_c[idx]);  // pcg32 state: seeded by seed_streams_kernel / source sampling
           h.hash = 1469598103934665603ULL;
           h.daughter = 0;
           h.n_flights = h.n_real = h.n_virtual = 0;
@@ -665,7 +674,7 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
           phase = PH_BIRTH;
         }
       }
-      if (hist_all(phase == PH_DEAD)) break;
+      if (hist_all(phase == PH_DEAD && !have_ticket)) break;
 
       // ---- M: sample the flight, move the cursor, re-validate its pads ----------------------------------------------------------
       bool collide_now = false;  // surface tracking: the flight ended in a collision inside the current cell

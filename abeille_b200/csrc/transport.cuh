@@ -60,6 +60,8 @@ struct RunArgs {
   double* secondaries;             // [ABL_SEC_CAP][9][nthreads] or null
   double k_col, keff;
   int converged;
+  // rows of the bank that have arrived in HBM (host-buffer entry point: the copy overlaps the kernel), or null
+  const unsigned long long* avail;
   // noise mode (noise.cuh)
   int sample_noise;                // this power-iteration generation samples the noise source
   Site* nsites;                    // scratch noise particles
