@@ -183,6 +183,19 @@ class DistributedPowerIterator:
                 "local_tl_bins": cn["tl_bins"]}
 
 
+def _positive_negative_sums(w: "torch.Tensor"):
+    """(sum of the positive weights, minus the sum of the negative ones) of a host bank (power_iterator.cpp:538-560),
+    without bank-sized temporaries: all-positive banks (every tracker but carter) need one min and one sum, mixed banks
+    are reduced in cache-sized chunks."""
+    if float(w.min()) >= 0.:
+        return float(w.sum()), 0.0
+    pos = neg = 0.0
+    for c in w.split(1 << 18):
+        pos += float(torch.clamp(c, min=0.).sum())
+        neg -= float(torch.clamp(c, max=0.).sum())
+    return pos, neg
+
+
 class HostBufferLoop:
     """The reference's own data flow (src/power_iterator.cpp:325-428): every generation the bank crosses the
     Transporter::transport() boundary as HOST arrays -- abl_transport copies it to the device, runs the kernels and
@@ -245,8 +258,7 @@ class HostBufferLoop:
         self.d2h_bytes += m * 8 * 11 + 6 * 8 + 8 * 8
         # host-side caller steps on the (pinned) numpy arrays, through torch's multi-threaded CPU kernels
         wt = torch.from_numpy(fis["wgt"])
-        wpos = float(torch.clamp(wt, min=0.).sum()) if m else 0.0
-        wneg = float(-torch.clamp(wt, max=0.).sum()) if m else 0.0
+        wpos, wneg = _positive_negative_sums(wt) if m else (0.0, 0.0)
         local = np.concatenate([scores, [cn["real_collisions"], float(m), float(n_in), wpos, wneg]])
         allv = self._gather(local)
         tot = allv.sum(axis=0)
