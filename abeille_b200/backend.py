@@ -26,7 +26,8 @@ ABI_SYMBOLS = (
     "abl_tally_count", "abl_tally_shape", "abl_tallies_record", "abl_tallies_clear",
     "abl_tally_fetch", "abl_tally_device_ptr", "abl_sample_source_device", "abl_bank_weight_stats_device",
     "abl_bank_scale_weights_device", "abl_bank_to_particles_device", "abl_entropy_bin_device",
-    "abl_score_source_device", "abl_cancel_device", "abl_bank_alloc_device", "abl_bank_free_device",
+    "abl_score_source_device", "abl_cancel_device", "abl_cancel_accumulate_device", "abl_cancel_apply_device",
+    "abl_cancel_bins_device", "abl_bank_alloc_device", "abl_bank_free_device",
     "abl_bank_upload", "abl_bank_download", "abl_device_alloc", "abl_device_free", "abl_device_zero",
     "abl_device_read", "abl_find_cells", "abl_rng_probe", "abl_math_probe")
 
@@ -437,3 +438,19 @@ class Backend:
     def cancel_device(self, bank: dict, n: int):
         s = _device_struct(bank, n)
         self._check(self.L.abl_cancel_device(self.h, C.byref(s), self._stream()))
+
+    def cancel_accumulate_device(self, bank: dict, n: int):
+        s = _device_struct(bank, n)
+        self._check(self.L.abl_cancel_accumulate_device(self.h, C.byref(s), self._stream()))
+
+    def cancel_apply_device(self, bank: dict, n: int):
+        s = _device_struct(bank, n)
+        self._check(self.L.abl_cancel_apply_device(self.h, C.byref(s), self._stream()))
+
+    def cancel_bins_device(self):
+        """Device pointers of the dense cancellation bins: ([4 fp64 sum arrays], u32 member counts, number of bins)."""
+        sums = (C.c_void_p * 4)()
+        count = C.c_void_p()
+        nb = C.c_uint64(0)
+        self._check(self.L.abl_cancel_bins_device(self.h, sums, C.byref(count), C.byref(nb)))
+        return [int(p) for p in sums], int(count.value), int(nb.value)

@@ -64,8 +64,7 @@ struct abl_context {
   cudaEvent_t ev_ids = nullptr, ev_zeroed = nullptr;
   unsigned long long* chunk_ends = nullptr;  // pinned
   bool streamed_input = false;
-  CancelBins cancel{nullptr, nullptr, nullptr};
-  bool cancel_has_w2 = false;
+  CancelBins cancel{nullptr, nullptr, nullptr, nullptr, nullptr};
   // staging banks of the host-buffer API
   BankView stage_in{}, stage_out{};
   uint64_t stage_in_cap = 0, stage_out_cap = 0;
@@ -612,7 +611,8 @@ void abl_destroy(abl_handle h) {
   }
   for (void* p : {(void*)h->sites, (void*)h->nfis, (void*)h->offsets, (void*)h->tile_sums, (void*)h->tr_flights, (void*)h->tr_real,
                   (void*)h->tr_virtual, (void*)h->tr_hash, (void*)h->tr_rng, (void*)h->small_dev, (void*)h->secondaries,
-                  (void*)h->cancel.sum_w, (void*)h->cancel.sum_w2, (void*)h->cancel.count, (void*)h->probe_buf, (void*)h->rng_scratch,
+                  (void*)h->cancel.sum_pos, (void*)h->cancel.sum_neg, (void*)h->cancel.sum_pos2, (void*)h->cancel.sum_neg2,
+                  (void*)h->cancel.count, (void*)h->probe_buf, (void*)h->rng_scratch,
                   (void*)h->nsites, (void*)h->nnoise, (void*)h->noffsets, (void*)h->ntile_sums, (void*)h->site_did, (void*)h->nsite_did})
     if (p) cudaFree(p);
   free_bank(h->stage_in);
@@ -1152,30 +1152,69 @@ int abl_score_source_device(abl_handle h, const abl_bank* bank_dev, int noise_so
   return ABL_OK;
 }
 
-int abl_cancel_device(abl_handle h, abl_bank* bank_dev, void* stream) {
-  if (!h || !bank_dev) return ABL_ERR_INVALID;
+namespace {
+int ensure_cancel_bins(abl_handle h, uint64_t* nbins_out) {
   const DevMesh3& m = h->P.cancel;
   if (!m.present) return fail(h, ABL_ERR_INVALID, "problem has no approximate cancelator");
-  ABL_CUDA(h, cudaSetDevice(h->device));
-  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
   const uint64_t nbins = (uint64_t)m.Nx * m.Ny * m.Nz * m.Ne;
   if (!h->cancel.count) {
     ABL_CUDA(h, cudaMalloc(&h->cancel.count, nbins * sizeof(uint32_t)));
-    ABL_CUDA(h, cudaMalloc(&h->cancel.sum_w, nbins * sizeof(double)));
-    ABL_CUDA(h, cudaMalloc(&h->cancel.sum_w2, nbins * sizeof(double)));
     ABL_CUDA(h, cudaMemset(h->cancel.count, 0, nbins * sizeof(uint32_t)));
-    ABL_CUDA(h, cudaMemset(h->cancel.sum_w, 0, nbins * sizeof(double)));
-    ABL_CUDA(h, cudaMemset(h->cancel.sum_w2, 0, nbins * sizeof(double)));
+    for (double** p : {&h->cancel.sum_pos, &h->cancel.sum_neg, &h->cancel.sum_pos2, &h->cancel.sum_neg2}) {
+      ABL_CUDA(h, cudaMalloc(p, nbins * sizeof(double)));
+      ABL_CUDA(h, cudaMemset(*p, 0, nbins * sizeof(double)));
+    }
   }
+  if (nbins_out) *nbins_out = nbins;
+  return ABL_OK;
+}
+}  // namespace
+
+// accumulate -> [all-reduce of the bins across GPUs: abl_cancel_bins_device] -> apply (which also re-zeroes the bins)
+int abl_cancel_accumulate_device(abl_handle h, const abl_bank* bank_dev, void* stream) {
+  if (!h || !bank_dev) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_cancel_bins(h, nullptr);
+  if (rc) return rc;
   if (bank_dev->n == 0) return ABL_OK;
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
   const BankView b = view_of(bank_dev);
-  const int grid = grid_for(h, b.n, 256);
-  cancel_accumulate_kernel<<<grid, 256, 0, s>>>(m, b, h->cancel);
-  cancel_apply_kernel<<<grid, 256, 0, s>>>(m, b, h->cancel);
-  cancel_reset_kernel<<<grid, 256, 0, s>>>(m, b, h->cancel);
-  h->launches += 3;
+  cancel_accumulate_kernel<<<grid_for(h, b.n, 256), 256, 0, s>>>(h->P.cancel, b, h->cancel);
+  h->launches++;
   ABL_CUDA(h, cudaGetLastError());
   return ABL_OK;
+}
+
+int abl_cancel_apply_device(abl_handle h, abl_bank* bank_dev, void* stream) {
+  if (!h || !bank_dev) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_cancel_bins(h, nullptr);
+  if (rc) return rc;
+  if (bank_dev->n == 0) return ABL_OK;
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  const BankView b = view_of(bank_dev);
+  const int grid = grid_for(h, b.n, 256);
+  cancel_apply_kernel<<<grid, 256, 0, s>>>(h->P.cancel, b, h->cancel);
+  cancel_reset_kernel<<<grid, 256, 0, s>>>(h->P.cancel, b, h->cancel);
+  h->launches += 2;
+  ABL_CUDA(h, cudaGetLastError());
+  return ABL_OK;
+}
+
+int abl_cancel_bins_device(abl_handle h, double* sums_dev[4], uint32_t** count_dev, uint64_t* nbins) {
+  if (!h || !sums_dev || !count_dev || !nbins) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_cancel_bins(h, nbins);
+  if (rc) return rc;
+  sums_dev[0] = h->cancel.sum_pos; sums_dev[1] = h->cancel.sum_neg; sums_dev[2] = h->cancel.sum_pos2; sums_dev[3] = h->cancel.sum_neg2;
+  *count_dev = h->cancel.count;
+  return ABL_OK;
+}
+
+int abl_cancel_device(abl_handle h, abl_bank* bank_dev, void* stream) {
+  int rc = abl_cancel_accumulate_device(h, bank_dev, stream);
+  if (rc) return rc;
+  return abl_cancel_apply_device(h, bank_dev, stream);
 }
 
 // ---- device memory helpers ---------------------------------------------------------------------------------------------------

@@ -210,10 +210,13 @@ __global__ void __launch_bounds__(256) score_source_kernel(DevTally t, BankView 
 }
 
 // ---- approximate mesh cancellation ---------------------------------------------------------------------------------
-struct CancelBins {  // dense per-bin accumulators, zeroed before each use
-  double* sum_w;
-  double* sum_w2;
-  uint32_t* count;  // low 28 bits: members; bits 28..31: has +w, -w, +w2, -w2
+// Dense per-bin accumulators, zeroed before each use.  Everything is a SUM, so the bins of several GPUs combine with one
+// all-reduce: the weights of each sign are accumulated separately ("a particle with positive weight is in the bin" <=>
+// its positive sum is > 0), members are counted.
+struct CancelBins {
+  double *sum_pos, *sum_neg;    // wgt:  sum of the positive / of the negative weights
+  double *sum_pos2, *sum_neg2;  // wgt2
+  uint32_t* count;              // members
 };
 __device__ __forceinline__ long long cancel_key(const DevMesh3& m, double x, double y, double z, double E) {
   const int i = (int)floor((x - m.lowx) / m.dx);
@@ -235,26 +238,28 @@ __global__ void __launch_bounds__(256) cancel_accumulate_kernel(DevMesh3 m, Bank
     const long long key = cancel_key(m, b.x[i], b.y[i], b.z[i], b.E[i]);
     if (key < 0) continue;
     const double w = b.wgt[i], w2 = b.wgt2 ? b.wgt2[i] : 0.;
-    uint32_t inc = 1u;
-    if (w > 0.) inc |= 1u << 28; else if (w < 0.) inc |= 1u << 29;
-    if (w2 > 0.) inc |= 1u << 30; else if (w2 < 0.) inc |= 1u << 31;
-    // count in the low bits, flags OR-ed in the high bits: two atomics on the same word
     atomicAdd(&cb.count[key], 1u);
-    atomicOr(&cb.count[key], inc & 0xf0000000u);
-    red_add(&cb.sum_w[key], w);
-    if (b.wgt2) red_add(&cb.sum_w2[key], w2);
+    if (w > 0.) red_add(&cb.sum_pos[key], w);
+    else if (w < 0.) red_add(&cb.sum_neg[key], w);
+    if (w2 > 0.) red_add(&cb.sum_pos2[key], w2);
+    else if (w2 < 0.) red_add(&cb.sum_neg2[key], w2);
   }
 }
+// approximate_mesh_cancelator.cpp:147-190: a bin with more than one member and both signs present gives every member
+// the bin's mean weight (per weight component)
 __global__ void __launch_bounds__(256) cancel_apply_kernel(DevMesh3 m, BankView b, CancelBins cb) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += (uint64_t)gridDim.x * blockDim.x) {
     const long long key = cancel_key(m, b.x[i], b.y[i], b.z[i], b.E[i]);
     if (key < 0) continue;
-    const uint32_t c = cb.count[key];
-    const uint32_t members = c & 0x0fffffffu;
+    const uint32_t members = cb.count[key];
     if (members > 1) {
       const double N = (double)members;
-      if ((c & (1u << 28)) && (c & (1u << 29))) b.wgt[i] = cb.sum_w[key] / N;
-      if (b.wgt2 && (c & (1u << 30)) && (c & (1u << 31))) b.wgt2[i] = cb.sum_w2[key] / N;
+      const double sp = cb.sum_pos[key], sn = cb.sum_neg[key];
+      if (sp > 0. && sn < 0.) b.wgt[i] = (sp + sn) / N;
+      if (b.wgt2) {
+        const double sp2 = cb.sum_pos2[key], sn2 = cb.sum_neg2[key];
+        if (sp2 > 0. && sn2 < 0.) b.wgt2[i] = (sp2 + sn2) / N;
+      }
     }
   }
 }
@@ -264,8 +269,10 @@ __global__ void __launch_bounds__(256) cancel_reset_kernel(DevMesh3 m, BankView 
     const long long key = cancel_key(m, b.x[i], b.y[i], b.z[i], b.E[i]);
     if (key < 0) continue;
     cb.count[key] = 0;
-    cb.sum_w[key] = 0.;
-    if (cb.sum_w2) cb.sum_w2[key] = 0.;
+    cb.sum_pos[key] = 0.;
+    cb.sum_neg[key] = 0.;
+    cb.sum_pos2[key] = 0.;
+    cb.sum_neg2[key] = 0.;
   }
 }
 

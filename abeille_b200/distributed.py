@@ -74,8 +74,8 @@ def global_first_ids(counts, rank: int, global_counter: int) -> int:
 class _DevPtr:
     """Wraps a raw device pointer for torch.as_tensor through __cuda_array_interface__."""
 
-    def __init__(self, ptr: int, n: int):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    def __init__(self, ptr: int, n: int, typestr: str = "<f8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 class DistributedPowerIterator:
@@ -103,6 +103,12 @@ class DistributedPowerIterator:
         self.counters = np.zeros(8)
         self.active_particles = 0.0
         self._tally_views = None
+        self._cancel_views = None
+        # regional cancellation (settings: cancellation + an approximate cancelator; power_iterator.cpp:355-364)
+        import yaml
+        with open(deck_path) as f:
+            deck = yaml.safe_load(f)
+        self.cancellation = bool(deck.get("settings", {}).get("cancellation", False)) and "cancelator" in deck
 
     # ---- helpers ----
     def _gather(self, vec: np.ndarray) -> np.ndarray:
@@ -115,6 +121,27 @@ class DistributedPowerIterator:
                 ptr, n = self.gpu.tally_device_ptr(t, 0)
                 self._tally_views.append(torch.as_tensor(_DevPtr(ptr, n), device=self.device))
         return self._tally_views
+
+    def _cancel(self, m: int):
+        """PowerIterator::perform_regional_cancellation (power_iterator.cpp:751-777) over the GLOBAL fission bank: every rank
+        accumulates its slice into its dense bins, one all-reduce (sum) per bin array replaces the reference's gather of the
+        whole bank on the master, then every rank applies the bin means to its own particles."""
+        gpu = self.gpu
+        if self.world == 1:
+            gpu.cancel_device(self.nxt, m)
+            return
+        gpu.cancel_accumulate_device(self.nxt, m)
+        if self._cancel_views is None:
+            sums, count, nb = gpu.cancel_bins_device()
+            self._cancel_views = [torch.as_tensor(_DevPtr(p, nb), device=self.device) for p in sums]
+            self._cancel_views.append(torch.as_tensor(_DevPtr(count, nb, "<i4"), device=self.device))  # counts stay < 2^31
+        torch.cuda.current_stream().synchronize()
+        for t in self._cancel_views:
+            dist.all_reduce(t, group=self.group)
+        gpu.cancel_apply_device(self.nxt, m)
+        # the bins this rank touched are zero again; bins only other ranks touched still hold the global sums
+        for t in self._cancel_views:
+            t.zero_()
 
     # ---- Simulation::sample_sources: rank r samples the ids [r*n, (r+1)*n) ----
     def initialize(self):
@@ -154,6 +181,8 @@ class DistributedPowerIterator:
         m_pre = m
         if m_total == 0:
             raise RuntimeError("No fission neutrons were produced.")
+        if self.cancellation:
+            self._cancel(m)
         # weight normalisation over the global bank (src/power_iterator.cpp:538-586)
         ws = gpu.weight_stats_device(self.nxt, m)
         wall = self._gather(ws).sum(axis=0)

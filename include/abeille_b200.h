@@ -246,6 +246,12 @@ int abl_entropy_bin_device(abl_handle h, const abl_bank* bank_dev, double* bins_
 int abl_score_source_device(abl_handle h, const abl_bank* bank_dev, int noise_source, void* stream);
 /* ApproximateMeshCancelator (approximate_mesh_cancelator.cpp:97-190), weights replaced in place        */
 int abl_cancel_device(abl_handle h, abl_bank* bank_dev, void* stream);
+/* The same in two steps, for several GPUs: accumulate this GPU's bank into the dense bins, all-reduce (sum) the five bin
+ * arrays across the GPUs (the reference gathers the whole bank on the master instead, power_iterator.cpp:751-777), apply
+ * (which also re-zeroes the touched bins).  sums_dev = positive / negative sums of wgt, then of wgt2. */
+int abl_cancel_accumulate_device(abl_handle h, const abl_bank* bank_dev, void* stream);
+int abl_cancel_apply_device(abl_handle h, abl_bank* bank_dev, void* stream);
+int abl_cancel_bins_device(abl_handle h, double* sums_dev[4], uint32_t** count_dev, uint64_t* nbins);
 
 /* ---- device memory helpers for callers that do not link a CUDA runtime themselves ------------------------ */
 int abl_bank_alloc_device(abl_handle h, uint64_t capacity, abl_bank* out_dev); /* all 12 arrays, out_dev->n = capacity */

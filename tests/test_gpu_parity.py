@@ -390,3 +390,20 @@ def test_streamed_host_bank_matches_resident_bank(ab, oracle_api, tmp_path):
             ref = dout[k][:m].cpu().numpy()
             got = fis[k] if fis[k].dtype == ref.dtype else fis[k].view(ref.dtype)
             assert np.array_equal(got, ref), f"streamed call {rep}: {k} differs"
+
+
+def test_distributed_iterator_with_cancellation_matches_oracle(ab, oracle_api, tmp_path):
+    """Config 4 (carter tracking, under-estimated majorant, approximate regional cancellation) through the multi-GPU
+    driver on one rank: k and bank sizes of every generation against the oracle's PowerIterator."""
+    from abeille_b200.distributed import DistributedPowerIterator
+    n, ngen = 20000, 4
+    path = write_deck(load_deck("c5g7_carter_cancel.yaml"), tmp_path / "carter.yaml",
+                      {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": 1}})
+    ref = oracle_api.Oracle(path).run_power_iteration(ngen, 1)
+    sim = DistributedPowerIterator(path, 0, n)
+    assert sim.cancellation
+    sim.initialize()
+    for g in range(ngen):
+        sim.generation(converged=g >= 1)
+    assert [int(v) for v in sim.nbank_series] == [int(v) for v in ref["nbank"]]
+    assert np.allclose(sim.kcol_series, ref["kcol"], rtol=1e-10)
