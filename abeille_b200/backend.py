@@ -21,7 +21,8 @@ COUNTER_KEYS = ("flights", "real_collisions", "virtual_collisions", "tl_bins", "
 
 # every symbol include/abeille_b200.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = (
-    "abl_create", "abl_destroy", "abl_last_error", "abl_device_info", "abl_last_transport_kernel", "abl_transport", "abl_get_trace",
+    "abl_create", "abl_destroy", "abl_last_error", "abl_device_info", "abl_last_transport_kernel", "abl_transport",
+    "abl_transport_noise", "abl_get_trace",
     "abl_transport_device", "abl_transport_noise_device", "abl_bank_weight_magnitude_device", "abl_bank_divide_weights_device",
     "abl_tally_count", "abl_tally_shape", "abl_tallies_record", "abl_tallies_clear",
     "abl_tally_fetch", "abl_tally_device_ptr", "abl_sample_source_device", "abl_bank_weight_stats_device",
@@ -276,6 +277,22 @@ class Backend:
         self._hcheck(rc)
         m = int(nout.value)
         return {k: v[:m] for k, v in out.items()}, scores
+
+    def transport_vectors_noise(self, bank: dict, k_col: float = 1.0, keff: float = 1.0, converged: bool = False,
+                                noise: bool = False, sample_noise: bool = False, capacity: int | None = None):
+        """GPUTransporter::transport(bank, noise, &noise_bank, &noise_maker) through the C++ adapter (host vectors)."""
+        n = len(bank["x"])
+        cap = int(capacity if capacity is not None else max(6 * n + 4096, 4096))
+        out, nout_bank = new_bank(cap), new_bank(cap)
+        sin = _host_struct(bank)
+        sout, snoise = _host_struct(out, cap), _host_struct(nout_bank, cap)
+        nout, nnoise = C.c_uint64(0), C.c_uint64(0)
+        rc = self.H.ablh_transport_noise(self.ctx, C.byref(sin), C.c_int(int(bool(converged))), C.c_double(float(k_col)),
+                                         C.c_double(float(keff)), C.c_int(int(bool(noise))), C.c_int(int(bool(sample_noise))),
+                                         C.byref(sout), C.byref(nout), C.byref(snoise), C.byref(nnoise))
+        self._hcheck(rc)
+        m, mn = int(nout.value), int(nnoise.value)
+        return {k: v[:m] for k, v in out.items()}, {k: v[:mn] for k, v in nout_bank.items()}
 
     def run_power_iteration(self, ngen: int, nignored: int, resident: bool = True) -> dict:
         arr = {k: np.zeros(ngen) for k in ("kcol", "ktrk", "leak", "mig", "entropy")}

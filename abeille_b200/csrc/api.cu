@@ -990,6 +990,38 @@ int abl_transport(abl_handle h, const abl_bank* bank, const abl_gen_params* para
   return ABL_OK;
 }
 
+int abl_transport_noise(abl_handle h, const abl_bank* bank, const abl_gen_params* params, abl_bank* fission_out, uint64_t* n_fission,
+                        abl_bank* noise_out, uint64_t* n_noise, double scores[6], uint64_t counters[8]) {
+  if (!h || !bank || !params || !fission_out || !n_fission || !noise_out || !n_noise || !scores) return ABL_ERR_INVALID;
+  for (const abl_bank* b : {(const abl_bank*)fission_out, (const abl_bank*)noise_out})
+    if (!b->x || !b->y || !b->z || !b->ux || !b->uy || !b->uz || !b->E || !b->wgt || !b->wgt2 || !b->id_a || !b->id_b || !b->id_c)
+      return fail(h, ABL_ERR_INVALID, "abl_transport_noise: output banks need all twelve arrays");
+  if (!bank->x || !bank->y || !bank->z || !bank->ux || !bank->uy || !bank->uz || !bank->E || !bank->wgt || !bank->id_a)
+    return fail(h, ABL_ERR_INVALID, "null bank array");
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  // noise runs are small (the shipped deck: 1e5 particles per generation): plain staged copies through device banks
+  abl_bank din{}, dfis{}, dnoise{};
+  int rc = abl_bank_alloc_device(h, bank->n ? bank->n : 1, &din);
+  if (!rc) rc = abl_bank_alloc_device(h, fission_out->n ? fission_out->n : 1, &dfis);
+  if (!rc) rc = abl_bank_alloc_device(h, noise_out->n ? noise_out->n : 1, &dnoise);
+  if (!rc) rc = abl_bank_upload(h, bank, &din);  // (null wgt2 -> zeros; null id_b / id_c are skipped)
+  if (!rc) {
+    abl_bank dview = din;
+    dview.n = bank->n;
+    if (!bank->id_b) dview.id_b = nullptr;
+    if (!bank->id_c) dview.id_c = nullptr;  // the device seeds the streams from seed / stride / history id
+    rc = abl_transport_noise_device(h, &dview, params, &dfis, n_fission, &dnoise, n_noise, scores, counters, nullptr);
+  }
+  if (!rc && *n_fission) rc = abl_bank_download(h, &dfis, *n_fission, fission_out);
+  if (!rc && *n_noise) rc = abl_bank_download(h, &dnoise, *n_noise, noise_out);
+  const std::string keep = h->error;
+  if (din.x) abl_bank_free_device(h, &din);
+  if (dfis.x) abl_bank_free_device(h, &dfis);
+  if (dnoise.x) abl_bank_free_device(h, &dnoise);
+  if (rc) h->error = keep;
+  return rc;
+}
+
 int abl_get_trace(abl_handle h, uint64_t n, abl_trace* out) {
   if (!h || !out) return ABL_ERR_INVALID;
   if (n > h->trace_n) return fail(h, ABL_ERR_INVALID, "no trace of that size: pass params.trace = 1 to the transport call");

@@ -171,6 +171,56 @@ int ablh_transport(void* c, const abl_bank* in, int converged, double k_col, abl
   }
 }
 
+/* Transporter::transport(bank, noise, &noise_bank, &noise_maker) through the C++ adapter (noise mode, src/noise.cpp:312-314,492):
+ * noise != 0 transports noise particles (in->wgt2 is their second weight); sample_noise != 0 is a power-iteration generation
+ * that also fills noise_out with the sampled noise source.  Output banks need all twelve arrays. */
+int ablh_transport_noise(void* c, const abl_bank* in, int converged, double k_col, double keff, int noise, int sample_noise,
+                         abl_bank* out, uint64_t* n_out, abl_bank* noise_out, uint64_t* n_noise) {
+  HostContext* ctx = static_cast<HostContext*>(c);
+  try {
+    std::vector<Particle> bank;
+    bank.reserve(in->n);
+    for (uint64_t i = 0; i < in->n; i++) {
+      Particle p(Position{in->x[i], in->y[i], in->z[i]}, Direction{in->ux[i], in->uy[i], in->uz[i]}, in->E[i], in->wgt[i], in->id_a[i]);
+      if (in->wgt2) p.set_weight2(in->wgt2[i]);
+      if (in->id_b) p.set_family_id(in->id_b[i]);
+      if (in->id_c) {
+        p.has_rng_state = true;
+        p.rng_state = in->id_c[i];
+      }
+      bank.push_back(p);
+    }
+    Tallies& T = *ctx->sim->tallies;
+    T.set_kcol(k_col);
+    T.set_keff(keff);
+    ctx->sim->transporter->converged = converged != 0;
+    std::vector<BankedParticle> nb;
+    const int maker = 1;  // stands for the NoiseMaker: the sources live in the flattened problem tables
+    std::vector<BankedParticle> fis = ctx->sim->transporter->transport(bank, noise != 0, sample_noise ? &nb : nullptr, sample_noise ? &maker : nullptr);
+    abl_handle keep = T.backend;  // zero the scalar scores without clearing the mesh arrays
+    T.backend = nullptr;
+    T.clear_generation();
+    T.backend = keep;
+    const auto put = [](const std::vector<BankedParticle>& v, abl_bank* o) {
+      if (v.size() > o->n) throw std::runtime_error("ablh_transport_noise: output capacity too small");
+      for (size_t i = 0; i < v.size(); i++) {
+        o->x[i] = v[i].r.x; o->y[i] = v[i].r.y; o->z[i] = v[i].r.z;
+        o->ux[i] = v[i].u.x; o->uy[i] = v[i].u.y; o->uz[i] = v[i].u.z;
+        o->E[i] = v[i].E; o->wgt[i] = v[i].wgt; o->wgt2[i] = v[i].wgt2;
+        o->id_a[i] = v[i].parent_history_id; o->id_b[i] = v[i].parent_daughter_id; o->id_c[i] = v[i].family_id;
+      }
+    };
+    *n_out = fis.size();
+    put(fis, out);
+    *n_noise = nb.size();
+    if (noise_out) put(nb, noise_out);
+    return bank.empty() ? 0 : 2;
+  } catch (const std::exception& e) {
+    ctx->error = e.what();
+    return 1;
+  }
+}
+
 /* PowerIterator::run.  Per generation: kcol, ktrk, leak, mig, entropy, bank size.
  * summary[0..9] = kcol_avg, kcol_err, ktrk_avg, ktrk_err, leak_avg, leak_err, seconds, active particles,
  *                 real collisions, flights */

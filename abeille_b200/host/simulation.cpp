@@ -71,8 +71,9 @@ GPUTransporter::~GPUTransporter() {
 
 std::vector<BankedParticle> GPUTransporter::transport(std::vector<Particle>& bank, bool noise, std::vector<BankedParticle>* noise_bank,
                                                       const void* noise_maker) {
-  (void)noise_bank;
-  (void)noise_maker;
+  // noise_maker != nullptr: this power-iteration generation also samples the noise source into *noise_bank
+  // (Noise::power_iteration, src/noise.cpp:305-318); the sources themselves were flattened into the problem tables
+  const bool sample_noise = noise_bank != nullptr && noise_maker != nullptr;
   const size_t N = bank.size();
   for (auto& b : buf_) b.resize(N);
   ida_.resize(N);
@@ -102,6 +103,8 @@ std::vector<BankedParticle> GPUTransporter::transport(std::vector<Particle>& ban
   gp.keff = tallies->keff();
   gp.converged = converged ? 1 : 0;
   gp.noise = noise ? 1 : 0;
+  gp.sample_noise_source = sample_noise ? 1 : 0;
+  const bool complex_out = noise || sample_noise;
   uint64_t cap = static_cast<uint64_t>(2.5 * static_cast<double>(N)) + 4096;
   for (int attempt = 0;; attempt++) {
     for (auto& b : obuf_) b.resize(cap);
@@ -110,11 +113,27 @@ std::vector<BankedParticle> GPUTransporter::transport(std::vector<Particle>& ban
     out.n = cap;
     out.x = obuf_[0].data(); out.y = obuf_[1].data(); out.z = obuf_[2].data();
     out.ux = obuf_[3].data(); out.uy = obuf_[4].data(); out.uz = obuf_[5].data();
-    out.E = obuf_[6].data(); out.wgt = obuf_[7].data(); out.wgt2 = noise ? obuf_[8].data() : nullptr;
+    out.E = obuf_[6].data(); out.wgt = obuf_[7].data(); out.wgt2 = complex_out ? obuf_[8].data() : nullptr;
     out.id_a = oa_.data(); out.id_b = ob_.data(); out.id_c = oc_.data();
-    uint64_t n_fis = 0, cn[8];
+    uint64_t n_fis = 0, n_noise = 0, cn[8];
     double scores[6];
-    const int rc = abl_transport(h_, &in, &gp, &out, &n_fis, scores, cn);
+    int rc;
+    std::vector<double> nbuf[9];
+    std::vector<uint64_t> nids[3];
+    if (sample_noise) {
+      const uint64_t ncap = 6 * static_cast<uint64_t>(N) + 4096;
+      for (auto& b : nbuf) b.resize(ncap);
+      for (auto& b : nids) b.resize(ncap);
+      abl_bank nout{};
+      nout.n = ncap;
+      nout.x = nbuf[0].data(); nout.y = nbuf[1].data(); nout.z = nbuf[2].data();
+      nout.ux = nbuf[3].data(); nout.uy = nbuf[4].data(); nout.uz = nbuf[5].data();
+      nout.E = nbuf[6].data(); nout.wgt = nbuf[7].data(); nout.wgt2 = nbuf[8].data();
+      nout.id_a = nids[0].data(); nout.id_b = nids[1].data(); nout.id_c = nids[2].data();
+      rc = abl_transport_noise(h_, &in, &gp, &out, &n_fis, &nout, &n_noise, scores, cn);
+    } else {
+      rc = abl_transport(h_, &in, &gp, &out, &n_fis, scores, cn);
+    }
     if (rc == ABL_ERR_BANK_OVERFLOW && attempt == 0 && n_fis > cap) {
       // A retry would score the generation's tallies twice; the reference has no such limit, so size
       // generously instead (2.5x the bank) and treat a second overflow as fatal.
@@ -141,6 +160,18 @@ std::vector<BankedParticle> GPUTransporter::transport(std::vector<Particle>& ban
       f.parent_history_id = oa_[i];
       f.parent_daughter_id = ob_[i];
       f.family_id = oc_[i];
+    }
+    for (uint64_t i = 0; i < n_noise; i++) {  // Particle::empty_noise_bank order: bank order, then creation order
+      BankedParticle f;
+      f.r = {nbuf[0][i], nbuf[1][i], nbuf[2][i]};
+      f.u = {nbuf[3][i], nbuf[4][i], nbuf[5][i]};
+      f.E = nbuf[6][i];
+      f.wgt = nbuf[7][i];
+      f.wgt2 = nbuf[8][i];
+      f.parent_history_id = nids[0][i];
+      f.parent_daughter_id = nids[1][i];
+      f.family_id = nids[2][i];
+      noise_bank->push_back(f);
     }
     bank.clear();  // delta_tracker.cpp:262
     return fission;

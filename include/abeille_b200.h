@@ -205,6 +205,10 @@ int abl_last_transport_kernel(abl_handle h, float* milliseconds, int* grid_block
 /* ---- Transporter::transport, host buffers (the reference-facing entry point) ------------------------ */
 int abl_transport(abl_handle h, const abl_bank* bank, const abl_gen_params* params, abl_bank* fission_out,
                   uint64_t* n_fission, double scores[6], uint64_t counters[8]);
+/* The same with the noise-source bank (transport(bank, false, &noise_bank, &noise_maker), noise.cpp:312-314): host
+ * buffers in, fission bank and noise bank out (noise_out->n = capacity, *n_noise = count; wgt2 is written). */
+int abl_transport_noise(abl_handle h, const abl_bank* bank, const abl_gen_params* params, abl_bank* fission_out,
+                        uint64_t* n_fission, abl_bank* noise_out, uint64_t* n_noise, double scores[6], uint64_t counters[8]);
 int abl_get_trace(abl_handle h, uint64_t n, abl_trace* out);
 
 /* ---- Transporter::transport, device buffers (bank stays resident in HBM) ---------------------------- */

@@ -119,3 +119,24 @@ def test_noise_run_matches_oracle(ab, oracle_api, tmp_path):
         scale = np.abs(b).max()
         assert np.allclose(a, b, rtol=1e-7, atol=1e-9 * scale), f"tally {t}: max diff {np.abs(a - b).max()} of {scale}"
     sim.close()
+
+
+def test_cpp_adapter_noise_bank_matches_device_entry_point(ab, oracle_api, tmp_path):
+    """GPUTransporter::transport(bank, false, &noise_bank, &noise_maker) and transport(bank, true) through the C++ adapter
+    (host vectors, abl_transport_noise / abl_transport) against the oracle."""
+    deck = "noise_oscillation.yaml"
+    n = 3000
+    path = write_deck(load_deck(deck), tmp_path / deck, {"settings": {"nparticles": n}})
+    keff = float(load_deck(deck)["settings"]["keff"])
+    orc, gpu = oracle_api.Oracle(path), ab.Backend(path, 0)
+    orc.set_keff(keff)
+    orc.set_kcol(1.0)
+    bank = orc.sample_source(n)
+    ofis, onoise, _ = orc.transport_noise({k: v.copy() for k, v in bank.items()}, False, True)
+    gfis, gnoise = gpu.transport_vectors_noise(bank, k_col=1.0, keff=keff, sample_noise=True)
+    _assert_banks_equal(gfis, ofis, "adapter fission bank")
+    _assert_banks_equal(gnoise, onoise, "adapter noise bank")
+    cur = _particles(onoise, n)
+    ofis2, _, _ = orc.transport_noise({k: (v.copy() if v is not None else None) for k, v in cur.items()}, True, False)
+    gfis2, _ = gpu.transport_vectors_noise(cur, k_col=1.0, keff=keff, noise=True)
+    _assert_banks_equal(gfis2, ofis2, "adapter noise fission bank")
