@@ -829,6 +829,24 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
       ns[i].eps_t = f.eps_total;
       ns[i].eps_f_pi = f.eps_fission * ABL_PI;
       ns[i].eps_s_pi = f.eps_scatter * ABL_PI;
+      ns[i].vibration = f.type == ABL_NOISE_FLAT_VIBRATION ? 1 : 0;
+      if (ns[i].vibration) {  // flat_vibration_noise_source.cpp:66-82,222-244
+        if (f.material_pos < 0 || f.material_pos >= M || f.material_neg < 0 || f.material_neg >= M) {
+          h->error = "flat-vibration noise source: material index out of range";
+          return bail(ABL_ERR_INVALID);
+        }
+        ns[i].basis = f.basis;
+        ns[i].mat_pos = f.material_pos;
+        ns[i].mat_neg = f.material_neg;
+        ns[i].x0 = 0.5 * (f.low[f.basis] + f.hi[f.basis]);
+        ns[i].eps = (f.hi[f.basis] - f.low[f.basis]) / 2.;
+        const double verr = ((n * w0) - w) / w;
+        ns[i].harmonic = std::abs(verr) > 0.01 ? 0 : n;
+        if (ns[i].harmonic < 0 || ns[i].harmonic > 2) {  // C_R / C_L for n = 0 need asin, for n >= 3 sin / acos / exp
+          h->error = "flat-vibration noise source: only the first and second harmonic of the source frequency are implemented";
+          return bail(ABL_ERR_UNSUPPORTED);
+        }
+      }
     }
     P.n_noise_src = (int32_t)ns.size();
     UP(ns.data(), ns.size(), P.noise_src);

@@ -87,23 +87,69 @@ __device__ __forceinline__ Cplx delayed_factor(double wr, double wi, double lamb
   return cmul(wr, wi, lambda * lambda / denom, -lambda * w_noise / denom);
 }
 
-// NoiseMaker::sample_noise_source (noise_maker.cpp:277-445), oscillation sources only
+// FlatVibrationNoiseSource::C_R / C_L (flat_vibration_noise_source.cpp:155-192) for the harmonics 1 and 2 (abl_create
+// rejects the others); C_L == C_R for n != 0
+__device__ __forceinline__ Cplx vib_C(const DevNoiseSrc& ns, double x) {
+  double rel_diff = (x - ns.x0) / ns.eps;
+  if (rel_diff > 1.) rel_diff = 1.;
+  else if (rel_diff < -1.) rel_diff = -1.;
+  const double root = sqrt(1. - (rel_diff * rel_diff));
+  if (ns.harmonic == 1) return Cplx{0., -2. * root};
+  return Cplx{-2. * rel_diff * root, 0.};
+}
+__device__ __forceinline__ double vib_get_x(const DevNoiseSrc& ns, const V3& r) { return ns.basis == 0 ? r.x : (ns.basis == 1 ? r.y : r.z); }
+
+// MGNuclide::sample_scatter of material pm (mg_nuclide.cpp:442-461): outgoing group mid-point energy and direction
+struct ScatSample {
+  V3 dir;
+  double E;
+};
+__device__ __forceinline__ ScatSample sample_scatter_nm(const DevProblem& P, uint64_t& rng, const V3& u, int pmg) {
+  int ei = 0;
+  if (P.G >= 2) ei = rng_discrete(rng, P.ps_cp + (size_t)pmg * P.G, P.G);
+  ScatSample sc;
+  sc.E = group_mid(P, ei);
+  const double mu = sample_mu(P, P.angle + (size_t)pmg * P.G + ei, rng);
+  const double phi = 2. * ABL_PI * rng_rand(rng);
+  sc.dir = rotate_direction(u, mu, phi);
+  return sc;
+}
+
+// NoiseMaker::sample_noise_source (noise_maker.cpp:277-501): the noise copy, the vibration sources (with the homogenised
+// "fake" material of :106-153), the oscillation sources.  In MG a material is one nuclide with atoms_bcm = 1 and the
+// nuclide id is the material index.
 __device__ __forceinline__ void sample_noise_source_dev(const DevProblem& P, const RunArgs& A, Hist& h, Acc& acc) {
-  bool inside = false;
+  bool inside_vib = false, inside_osc = false;
   for (int s = 0; s < P.n_noise_src; s++)
-    if (noise_src_contains(P.noise_src[s], h.r)) inside = true;
-  if (!inside) return;
+    if (noise_src_contains(P.noise_src[s], h.r)) {
+      if (P.noise_src[s].vibration) inside_vib = true;
+      else inside_osc = true;
+    }
+  if (!inside_vib && !inside_osc) return;
   const int mg = h.mat * P.G + h.g;
   const double Et = __ldg(&P.Et[mg]), Ea = __ldg(&P.Ea[mg]), Ef = __ldg(&P.Ef[mg]), nu = __ldg(&P.nu[mg]);
-  {  // sample_noise_copy (:155-181): dEt sums eps_t * Sigma_t(material found again at r with direction (1,0,0)) * pi
+  {  // sample_noise_copy (:155-181); NoiseMaker::dEt (:60-78): vibration sources first, then oscillation sources
     double dEt_re = 0., dEt_im = 0.;
-    for (int s = 0; s < P.n_noise_src; s++) {
+    for (int s = 0; s < P.n_noise_src; s++) {  // FlatVibrationNoiseSource::dEt (:222-244): (Et_neg - Et_pos) * C
       const DevNoiseSrc& ns = P.noise_src[s];
-      if (!noise_src_contains(ns, h.r)) continue;
+      if (!ns.vibration || !noise_src_contains(ns, h.r)) continue;
+      if (ns.harmonic == 0) {
+        dEt_re += 0.;
+        dEt_im += 0.;
+        continue;
+      }
+      const double D_Et = __ldg(&P.Et[ns.mat_neg * P.G + h.g]) - __ldg(&P.Et[ns.mat_pos * P.G + h.g]);
+      const Cplx C = vib_C(ns, vib_get_x(ns, h.r));
+      dEt_re += C.re * D_Et;
+      dEt_im += C.im * D_Et;
+    }
+    for (int s = 0; s < P.n_noise_src; s++) {  // SquareOscillationNoiseSource::dEt (:85-113): eps_t * Sigma_t(material
+      const DevNoiseSrc& ns = P.noise_src[s];    // found again at r with direction (1,0,0)) * pi
+      if (ns.vibration || !noise_src_contains(ns, h.r)) continue;
       Cursor lc;
       lc.err = 0;
       lc.token = 0;
-      cursor_restart(P, lc, h.r, V3{1., 0., 0.});
+      cursor_restart_nl(geo_tables(P), lc, h.r, V3{1., 0., 0.});
       if (lc.mat < 0) {
         raise_error(A, ABL_ERR_LOST, A.bank.id_a[h.idx]);
         return;
@@ -116,15 +162,128 @@ __device__ __forceinline__ void sample_noise_source_dev(const DevProblem& P, con
     const Cplx wc = cmul(h.w, h.w2, -qre, -qim);
     append_site_nm(A.nsites, A.n_nsites, A.nsite_capacity, A.nsite_did, h.r, h.u, h.E, wc.re, wc.im, h.idx, h.n_noise++, h.daughter++);
   }
-  // sample_oscillation_noise_source (:293-323)
-  (void)rng_rand(h.rng);  // mat.sample_nuclide
+
+  if (inside_vib) {  // sample_vibration_noise_source (:446-501)
+    // make_fake_material (:106-153): sorted union of the nuclides of the sources we are in; with a single nuclide list per
+    // source {neg, pos} the concentration is 1 for every member (the mean of equal entries).  At most ABL_VIB_NUC nuclides.
+    constexpr int ABL_VIB_NUC = 8;
+    int nuc[ABL_VIB_NUC];
+    int nn = 0;
+    bool bad = false;
+    for (int s = 0; s < P.n_noise_src; s++) {
+      const DevNoiseSrc& ns = P.noise_src[s];
+      if (!ns.vibration || !noise_src_contains(ns, h.r)) continue;
+      for (int q = 0; q < 2; q++) {
+        const int m = q == 0 ? ns.mat_neg : ns.mat_pos;
+        bool have = false;
+        for (int k = 0; k < nn; k++) have = have || nuc[k] == m;
+        if (!have) {
+          if (nn < ABL_VIB_NUC) nuc[nn++] = m;
+          else bad = true;
+        }
+      }
+    }
+    for (int i = 1; i < nn; i++)  // insertion sort (ids ascending)
+      for (int k = i; k > 0 && nuc[k - 1] > nuc[k]; k--) {
+        const int t = nuc[k];
+        nuc[k] = nuc[k - 1];
+        nuc[k - 1] = t;
+      }
+    // every source we are in must hold every nuclide of the union (the reference's map::at would throw otherwise)
+    for (int s = 0; s < P.n_noise_src; s++) {
+      const DevNoiseSrc& ns = P.noise_src[s];
+      if (!ns.vibration || !noise_src_contains(ns, h.r)) continue;
+      for (int k = 0; k < nn; k++)
+        if (nuc[k] != ns.mat_neg && nuc[k] != ns.mat_pos) bad = true;
+    }
+    if (bad) {
+      raise_error(A, ABL_ERR_UNSUPPORTED, A.bank.id_a[h.idx]);
+      return;
+    }
+    double conc[ABL_VIB_NUC];
+    {
+      double num_sources = 0.;
+      for (int s = 0; s < P.n_noise_src; s++)
+        if (P.noise_src[s].vibration && noise_src_contains(P.noise_src[s], h.r)) num_sources += 1.;
+      for (int k = 0; k < nn; k++) {
+        double conc_sum = 0.;
+        for (int s = 0; s < P.n_noise_src; s++) {
+          const DevNoiseSrc& ns = P.noise_src[s];
+          if (!ns.vibration || !noise_src_contains(ns, h.r)) continue;
+          conc_sum += ns.mat_neg == ns.mat_pos ? (1. + 1.) / 2. : 1.;
+        }
+        conc[k] = conc_sum / num_sources;
+      }
+    }
+    double Et_fake = 0.;
+    for (int k = 0; k < nn; k++) Et_fake += conc[k] * __ldg(&P.Et[nuc[k] * P.G + h.g]);
+    // fake_mat.sample_nuclide (material_helper.hpp:178-224)
+    const double invs_Et = 1. / Et_fake;
+    const double xi = rng_rand(h.rng);
+    int pick = nn - 1;
+    double prob_sum = 0.;
+    for (int k = 0; k < nn; k++) {
+      const double nuc_prob = invs_Et * conc[k] * __ldg(&P.Et[nuc[k] * P.G + h.g]);
+      prob_sum += nuc_prob;
+      if (xi <= prob_sum) {
+        pick = k;
+        break;
+      }
+    }
+    const int pm = nuc[pick], pmg = pm * P.G + h.g;
+    const double N = conc[pick];
+    const double pEt = __ldg(&P.Et[pmg]), pEa = __ldg(&P.Ea[pmg]), pEf = __ldg(&P.Ef[pmg]), pnu = __ldg(&P.nu[pmg]);
+    double dN_re = 0., dN_im = 0.;  // NoiseMaker::dN (:80-91), FlatVibrationNoiseSource::dN (:277-312)
+    for (int s = 0; s < P.n_noise_src; s++) {
+      const DevNoiseSrc& ns = P.noise_src[s];
+      if (!ns.vibration || !noise_src_contains(ns, h.r)) continue;
+      if ((pm != ns.mat_neg && pm != ns.mat_pos) || ns.harmonic == 0) {
+        dN_re += 0.;
+        dN_im += 0.;
+        continue;
+      }
+      const double D_N = (ns.mat_neg == pm ? 1. : 0.) - (ns.mat_pos == pm ? 1. : 0.);
+      const Cplx C = vib_C(ns, vib_get_x(ns, h.r));
+      dN_re += C.re * D_N;
+      dN_im += C.im * D_N;
+    }
+    const double dNN_re = dN_re / N, dNN_im = dN_im / N;
+    const double Etfake_Et = Et_fake / Et;
+    if (__ldg(&P.fissile[pm])) {  // sample_vibration_noise_fission (:183-237)
+      const double k_abs = pnu * pEf / pEt;
+      const int n_new = (int)floor(k_abs / A.keff + rng_rand(h.rng));
+      const double P_delayed = __ldg(&P.nud[pmg]) / pnu;
+      const FissionTables ft{P.chi_cp, P.dg_cp, P.dg_off, P.gmid, P.G};
+      for (int i = 0; i < n_new; i++) {
+        const FisSample f = sample_fission_nm(ft, P.dg_lambda, &h.rng, h.u, pm, pmg, P_delayed);
+        Cplx wgt{h.w, h.w2};
+        if (f.delayed) wgt = delayed_factor(wgt.re, wgt.im, f.lambda, P.w_noise);
+        wgt = cmul(wgt.re, wgt.im, dNN_re, dNN_im);
+        wgt.re = wgt.re * Etfake_Et;
+        wgt.im = wgt.im * Etfake_Et;
+        append_site_nm(A.nsites, A.n_nsites, A.nsite_capacity, A.nsite_did, h.r, f.dir, f.E, wgt.re, wgt.im, h.idx, h.n_noise++, h.daughter++);
+      }
+    }
+    const double P_scatter = 1. - (pEa / pEt);
+    {  // sample_vibration_noise_scatter (:239-275)
+      const ScatSample sc = sample_scatter_nm(P, h.rng, h.u, pmg);
+      Cplx wgt{h.w * 1., h.w2 * 1.};
+      wgt.re = wgt.re * P_scatter;
+      wgt.im = wgt.im * P_scatter;
+      wgt = cmul(wgt.re, wgt.im, dNN_re * Etfake_Et, dNN_im * Etfake_Et);
+      append_site_nm(A.nsites, A.n_nsites, A.nsite_capacity, A.nsite_did, h.r, sc.dir, sc.E, wgt.re, wgt.im, h.idx, h.n_noise++, h.daughter++);
+    }
+  }
+
+  if (!inside_osc) return;  // sample_oscillation_noise_source (:293-323)
+  (void)rng_rand(h.rng);    // mat.sample_nuclide
   if (__ldg(&P.fissile[h.mat])) {  // sample_oscillation_noise_fission (:383-445)
     const double k_abs = nu * Ef / Et;
     const int n_new = (int)floor(k_abs / A.keff + rng_rand(h.rng));
     const double P_delayed = __ldg(&P.nud[mg]) / nu;
     double dEf_re = 0., dEf_im = 0.;
     for (int s = 0; s < P.n_noise_src; s++)
-      if (noise_src_contains(P.noise_src[s], h.r)) {
+      if (!P.noise_src[s].vibration && noise_src_contains(P.noise_src[s], h.r)) {
         dEf_re += P.noise_src[s].on ? P.noise_src[s].eps_f_pi : 0.;
         dEf_im += 0.;
       }
@@ -139,23 +298,18 @@ __device__ __forceinline__ void sample_noise_source_dev(const DevProblem& P, con
   }
   const double P_scatter = 1. - (Ea / Et);
   {  // sample_oscillation_noise_scatter (:325-381); MG: mt == 2, yield == 1
-    int ei = 0;
-    if (P.G >= 2) ei = rng_discrete(h.rng, P.ps_cp + (size_t)mg * P.G, P.G);
-    const double E_out = group_mid(P, ei);
-    const double mu = sample_mu(P, P.angle + (size_t)mg * P.G + ei, h.rng);
-    const double phi = 2. * ABL_PI * rng_rand(h.rng);
-    const V3 dir = rotate_direction(h.u, mu, phi);
+    const ScatSample sc = sample_scatter_nm(P, h.rng, h.u, mg);
     Cplx wgt{h.w * 1., h.w2 * 1.};
     wgt.re = wgt.re * P_scatter;
     wgt.im = wgt.im * P_scatter;
     double dE_re = 0., dE_im = 0.;
     for (int s = 0; s < P.n_noise_src; s++)
-      if (noise_src_contains(P.noise_src[s], h.r)) {
+      if (!P.noise_src[s].vibration && noise_src_contains(P.noise_src[s], h.r)) {
         dE_re += P.noise_src[s].on ? P.noise_src[s].eps_s_pi : 0.;
         dE_im += 0.;
       }
     wgt = cmul(wgt.re, wgt.im, dE_re, dE_im);
-    append_site_nm(A.nsites, A.n_nsites, A.nsite_capacity, A.nsite_did, h.r, dir, E_out, wgt.re, wgt.im, h.idx, h.n_noise++, h.daughter++);
+    append_site_nm(A.nsites, A.n_nsites, A.nsite_capacity, A.nsite_did, h.r, sc.dir, sc.E, wgt.re, wgt.im, h.idx, h.n_noise++, h.daughter++);
   }
   (void)acc;
 }

@@ -40,11 +40,16 @@ struct alignas(16) CellFast {
   int32_t pad_[2];
 };
 
-struct DevNoiseSrc {  // SquareOscillationNoiseSource (square_oscillation_noise_source.cpp): box, gated amplitude factors
+struct DevNoiseSrc {  // a noise source region (box) with the run's frequency already matched against its own
   double low[3], hi[3];
+  // square oscillation (square_oscillation_noise_source.cpp): gated amplitude factors
   double eps_t;               // dEt = eps_t * Sigma_t * pi
   double eps_f_pi, eps_s_pi;  // dEf/Ef = eps_f * pi, dEs/Es = eps_s * pi
-  int32_t on, pad_;           // the run's noise frequency is the source's fundamental (|n| == 1 within 1 %)
+  int32_t on;                 // the run's noise frequency is the source's fundamental (|n| == 1 within 1 %)
+  // flat vibration (flat_vibration_noise_source.cpp): interface at x0 along `basis`, half width eps, materials on the
+  // two sides, harmonic n = round(w / w0) of the run's frequency (0: no component, gate |n w0 - w| / w <= 0.01)
+  int32_t vibration, basis, mat_pos, mat_neg, harmonic;
+  double x0, eps;
 };
 
 struct DevMesh3 {

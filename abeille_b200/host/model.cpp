@@ -636,9 +636,10 @@ Problem Problem::from_yaml(const Node& input) {
     for (size_t n = 0; n < input["noise-sources"].size(); n++) {
       const Node& ns = input["noise-sources"][n];
       const std::string type = ns["type"] ? ns["type"].as_string() : std::string("");
-      if (type != "square-oscillation")
-        fatal_error("Noise source type \"" + type + "\" is not provided by the B200 backend (square-oscillation only).");
+      if (type != "square-oscillation" && type != "flat-vibration") fatal_error("Invalid noise source type " + type + ".");
       abl_noise_source f{};
+      f.type = type == "flat-vibration" ? ABL_NOISE_FLAT_VIBRATION : ABL_NOISE_SQUARE_OSCILLATION;
+      f.material_pos = f.material_neg = -1;
       const auto vec3 = [&](const char* key, double out[3]) {
         if (!ns[key] || !ns[key].IsSequence() || ns[key].size() != 3) fatal_error(std::string("No valid ") + key + " entry for oscillation noise source.");
         const std::vector<double> v = ns[key].as_doubles();
@@ -651,12 +652,29 @@ Problem Problem::from_yaml(const Node& input) {
         return ns[key].as_double();
       };
       f.angular_frequency = scalar("angular-frequency");
-      f.eps_total = scalar("epsilon-total");
-      f.eps_fission = scalar("epsilon-fission");
-      f.eps_scatter = scalar("epsilon-scatter");
-      if (f.low[0] >= f.hi[0] || f.low[1] >= f.hi[1] || f.low[2] >= f.hi[2]) fatal_error("Low is greater than or equal to hi in OscillationNoiseSource.");
-      if (f.angular_frequency <= 0.) fatal_error("Negative or zero frequency provided to OscillationNoiseSource.");
-      if (f.eps_total <= 0. || f.eps_fission <= 0. || f.eps_scatter <= 0.) fatal_error("Negative or zero epsilon provided to OscillationNoiseSource.");
+      if (f.low[0] >= f.hi[0] || f.low[1] >= f.hi[1] || f.low[2] >= f.hi[2]) fatal_error("Low is greater than or equal to hi in noise source.");
+      if (f.angular_frequency <= 0.) fatal_error("Negative or zero frequency provided to noise source.");
+      if (f.type == ABL_NOISE_SQUARE_OSCILLATION) {
+        f.eps_total = scalar("epsilon-total");
+        f.eps_fission = scalar("epsilon-fission");
+        f.eps_scatter = scalar("epsilon-scatter");
+        if (f.eps_total <= 0. || f.eps_fission <= 0. || f.eps_scatter <= 0.) fatal_error("Negative or zero epsilon provided to OscillationNoiseSource.");
+      } else {  // src/flat_vibration_noise_source.cpp:314-407
+        if (!ns["direction"]) fatal_error("No valid \"direction\" entry for flat vibration noise source.");
+        const std::string dir = ns["direction"].as_string();
+        if (dir == "x" || dir == "X") f.basis = 0;
+        else if (dir == "y" || dir == "Y") f.basis = 1;
+        else if (dir == "z" || dir == "Z") f.basis = 2;
+        else fatal_error("Invalid direction for flat vibration noise source.");
+        const auto material = [&](const char* key) {
+          if (!ns[key]) fatal_error(std::string("No valid ") + key + " entry given for flat vibration noise source.");
+          const auto it = P.material_id_to_indx.find(static_cast<uint32_t>(ns[key].as_int()));
+          if (it == P.material_id_to_indx.end()) fatal_error(std::string(key) + " not found for flat vibration noise source.");
+          return it->second;
+        };
+        f.material_pos = material("positive-material");
+        f.material_neg = material("negative-material");
+      }
       P.noise_sources.push_back(f);
     }
   if (P.settings.mode == ABL_MODE_NOISE && P.noise_sources.empty()) fatal_error("No noise source specified for noise problem.");

@@ -119,9 +119,14 @@ typedef struct abl_mesh3 {       /* entropy mesh (entropy.cpp) / approximate can
   int32_t eedges_offset;         /* slice of abl_problem.tally_energy_bounds                           */
 } abl_mesh3;
 
-typedef struct abl_noise_source { /* square-oscillation noise source (square_oscillation_noise_source.cpp:38-83)   */
+enum { ABL_NOISE_SQUARE_OSCILLATION = 0, ABL_NOISE_FLAT_VIBRATION = 1 };
+typedef struct abl_noise_source { /* square_oscillation_noise_source.cpp:38-83, flat_vibration_noise_source.cpp:34-118 */
   double low[3], hi[3];
-  double angular_frequency, eps_total, eps_fission, eps_scatter;
+  double angular_frequency;
+  double eps_total, eps_fission, eps_scatter; /* square oscillation                                           */
+  int32_t type;                               /* ABL_NOISE_*                                                  */
+  int32_t basis;                              /* flat vibration: 0 x, 1 y, 2 z (the direction of the motion)  */
+  int32_t material_pos, material_neg;         /* flat vibration: material indices on the two sides            */
 } abl_noise_source;
 
 typedef struct abl_problem {

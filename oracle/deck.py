@@ -197,11 +197,17 @@ def deck_to_text(deck: dict) -> str:
         out.append("entropy 0")
     ns = deck.get("noise-sources", []) or []
     out.append(f"nnoise {len(ns)}")
+    mat_ids = [int(m["id"]) for m in deck["materials"]]
     for n in ns:
-        if n["type"] != "square-oscillation":
-            raise ValueError("oracle: square-oscillation noise sources only")
-        out.append(f"sqosc {_fl(n['low'])} {_fl(n['hi'])} {_f(n['angular-frequency'])} {_f(n['epsilon-total'])} "
-                   f"{_f(n['epsilon-fission'])} {_f(n['epsilon-scatter'])}")
+        if n["type"] == "square-oscillation":
+            out.append(f"sqosc {_fl(n['low'])} {_fl(n['hi'])} {_f(n['angular-frequency'])} {_f(n['epsilon-total'])} "
+                       f"{_f(n['epsilon-fission'])} {_f(n['epsilon-scatter'])}")
+        elif n["type"] == "flat-vibration":
+            basis = {"x": 0, "y": 1, "z": 2}[str(n["direction"]).lower()]
+            out.append(f"flatvib {_fl(n['low'])} {_fl(n['hi'])} {_f(n['angular-frequency'])} {basis} "
+                       f"{mat_ids.index(int(n['positive-material']))} {mat_ids.index(int(n['negative-material']))}")
+        else:
+            raise ValueError("oracle: square-oscillation and flat-vibration noise sources only")
     return "\n".join(out) + "\n"
 
 

@@ -100,9 +100,12 @@ struct EntropyMesh {  // src/entropy.cpp + include/simulation/entropy.hpp
   }
 };
 
-struct NoiseSource {  // src/square_oscillation_noise_source.cpp
+struct NoiseSource {  // src/square_oscillation_noise_source.cpp, src/flat_vibration_noise_source.cpp
+  bool vibration = false;
   Vec low{0, 0, 0}, hi{0, 0, 0};
-  double w0 = 0, eps_t = 0, eps_f = 0, eps_s = 0;
+  double w0 = 0, eps_t = 0, eps_f = 0, eps_s = 0;  // oscillation
+  int basis = 0, mat_pos = -1, mat_neg = -1;       // vibration: axis, material indices (== nuclide ids in MG)
+  double x0 = 0, eps = 0;                          // vibration: interface position and half width (:66-82)
   bool is_inside(const Vec& r) const {
     return r.x > low.x && r.y > low.y && r.z > low.z && r.x < hi.x && r.y < hi.y && r.z < hi.z;
   }
@@ -424,10 +427,22 @@ static Problem* load_problem(const char* path) {
   size_t NN = (size_t)tk.ll();
   for (size_t n = 0; n < NN; n++) {
     NoiseSource ns;
-    tk.expect("sqosc");
+    const std::string kind = tk.next();
     ns.low = {tk.d(), tk.d(), tk.d()};
     ns.hi = {tk.d(), tk.d(), tk.d()};
-    ns.w0 = tk.d(); ns.eps_t = tk.d(); ns.eps_f = tk.d(); ns.eps_s = tk.d();
+    ns.w0 = tk.d();
+    if (kind == "sqosc") {
+      ns.eps_t = tk.d(); ns.eps_f = tk.d(); ns.eps_s = tk.d();
+    } else if (kind == "flatvib") {
+      ns.vibration = true;
+      ns.basis = (int)tk.ll(); ns.mat_pos = (int)tk.ll(); ns.mat_neg = (int)tk.ll();
+      const double lo = ns.basis == 0 ? ns.low.x : (ns.basis == 1 ? ns.low.y : ns.low.z);
+      const double hi = ns.basis == 0 ? ns.hi.x : (ns.basis == 1 ? ns.hi.y : ns.hi.z);
+      ns.x0 = 0.5 * (lo + hi);
+      ns.eps = (hi - lo) / 2.;
+    } else {
+      throw std::runtime_error("unknown noise source kind " + kind);
+    }
     P->noise_sources.push_back(ns);
   }
   P->build_majorant();
@@ -869,21 +884,54 @@ static bool sqosc_on(const NoiseSource& ns, double w) {
   return (n == 1 || n == -1) && std::abs(err) < 0.01;
 }
 
-// NoiseMaker::sample_noise_source (src/noise_maker.cpp:277-445) with square-oscillation sources only (the vibration list
-// is empty, so sample_vibration_noise_source returns at once): the noise copy (:155-181), then the oscillation
-// fission (:383-445) and scatter (:325-381) sources.  Noise particles go to the history's noise bank.
+// FlatVibrationNoiseSource::C_R / C_L (src/flat_vibration_noise_source.cpp:155-192) for the harmonics this restatement
+// covers (n = 1, 2; n = 0 needs asin, n >= 3 sin/acos/exp -- the shipped deck runs at the fundamental).  C_L differs from
+// C_R for n = 0 only.
+static std::complex<double> vib_C(const NoiseSource& ns, uint32_t n, double x) {
+  double rel_diff = (x - ns.x0) / ns.eps;
+  if (rel_diff > 1.) rel_diff = 1.;
+  else if (rel_diff < -1.) rel_diff = -1.;
+  if (n == 1) return {0., -2. * std::sqrt(1. - (rel_diff * rel_diff))};
+  if (n == 2) return {-2. * rel_diff * std::sqrt(1. - (rel_diff * rel_diff)), 0.};
+  throw std::runtime_error("oracle: flat-vibration harmonics other than 1 and 2 are not restated");
+}
+// the frequency gate and harmonic of dEt / dN (:222-244,277-312): 0 = no component at this frequency
+static int vib_harmonic(const NoiseSource& ns, double w) {
+  int32_t n = static_cast<int32_t>(std::round(w / ns.w0));
+  double err = ((n * ns.w0) - w) / w;
+  if (std::abs(err) > 0.01) return 0;
+  return n;
+}
+static double vib_get_x(const NoiseSource& ns, const Vec& r) { return ns.basis == 0 ? r.x : (ns.basis == 1 ? r.y : r.z); }
+
+// NoiseMaker::sample_noise_source (src/noise_maker.cpp:277-501): the noise copy (:155-181), the vibration sources
+// (:446-501 with the homogenised "fake" material of :106-153) and the oscillation sources (:293-445).  Noise particles go
+// to the history's noise bank.  In MG every material is one nuclide with atoms_bcm = 1 and nuclide id == material index.
 static void sample_noise_source(Ctx& cx, Particle& p, const Mat& mat, double keff, double w) {
   Problem& P = *cx.P;
-  bool inside = false;  // NoiseMaker::is_inside :93-104
-  for (const auto& ns : P.noise_sources) if (ns.is_inside(p.r())) inside = true;
+  bool inside = false, inside_vib = false, inside_osc = false;  // NoiseMaker::is_inside :93-104
+  for (const auto& ns : P.noise_sources)
+    if (ns.is_inside(p.r())) {
+      inside = true;
+      (ns.vibration ? inside_vib : inside_osc) = true;
+    }
   if (!inside) return;
+  const size_t g = P.st.group(p.E());
 
-  {  // sample_noise_copy :155-181; NoiseMaker::dEt :60-78 sums SquareOscillationNoiseSource::dEt (:85-113), which
-     // looks the material up again with a fresh Tracker at r with direction (1,0,0)
+  {  // sample_noise_copy :155-181; NoiseMaker::dEt :60-78: vibration sources first, then oscillation sources
     std::complex<double> dEt{0., 0.};
     for (const auto& ns : P.noise_sources) {
-      if (!ns.is_inside(p.r())) continue;
-      Tracker trkr(&P.geo, p.r(), Vec{1., 0., 0.});
+      if (!ns.vibration || !ns.is_inside(p.r())) continue;  // FlatVibrationNoiseSource::dEt :222-244
+      const double x = vib_get_x(ns, p.r());
+      const double D_Et = Mat(&P, ns.mat_neg).Et(p.E()) - Mat(&P, ns.mat_pos).Et(p.E());
+      const int n = vib_harmonic(ns, w);
+      if (n == 0) { dEt += std::complex<double>{0., 0.}; continue; }
+      if (n < 0) throw std::runtime_error("oracle: negative noise frequency");
+      dEt += D_Et * vib_C(ns, (uint32_t)n, x);
+    }
+    for (const auto& ns : P.noise_sources) {
+      if (ns.vibration || !ns.is_inside(p.r())) continue;  // SquareOscillationNoiseSource::dEt :85-113: looks the
+      Tracker trkr(&P.geo, p.r(), Vec{1., 0., 0.});         // material up again with a fresh Tracker, direction (1,0,0)
       if (trkr.current_mat < 0) throw std::runtime_error("No material found at the position of a noise-source sample.");
       Mat fm(&P, trkr.current_mat);
       double xs = fm.Et(p.E());
@@ -897,7 +945,97 @@ static void sample_noise_source(Ctx& cx, Particle& p, const Mat& mat, double kef
     p.history_noise_bank.push_back(np);
   }
 
-  // sample_oscillation_noise_source :293-323 (we are inside at least one oscillation source)
+  if (inside_vib) {  // sample_vibration_noise_source :446-501
+    // make_fake_material :106-153: union of the nuclides of the sources we are in (sorted ids), each with the mean over
+    // those sources of the source's own concentration (the mean of the two materials' where both hold the nuclide)
+    std::vector<int> nuclides;
+    std::vector<const NoiseSource*> sources;
+    for (const auto& ns : P.noise_sources)
+      if (ns.vibration && ns.is_inside(p.r())) {
+        sources.push_back(&ns);
+        for (int m : {ns.mat_neg, ns.mat_pos})
+          if (std::find(nuclides.begin(), nuclides.end(), m) == nuclides.end()) nuclides.push_back(m);
+      }
+    std::sort(nuclides.begin(), nuclides.end());
+    std::vector<double> conc(nuclides.size(), 0.);
+    const double num_sources = static_cast<double>(sources.size());
+    for (size_t i = 0; i < nuclides.size(); i++) {
+      double conc_sum = 0.;
+      for (const NoiseSource* ns : sources) {
+        if (nuclides[i] != ns->mat_neg && nuclides[i] != ns->mat_pos)
+          throw std::runtime_error("overlapping vibration noise sources with different nuclides");  // map::at throws
+        double c = 1.;                                       // nuclide_info_: atoms_bcm of the one material that holds it,
+        if (ns->mat_neg == ns->mat_pos) c = (1. + 1.) / 2.;  // or the mean of the two (:91-104)
+        conc_sum += c;
+      }
+      conc[i] = conc_sum / num_sources;
+    }
+    double Et_fake = 0.;  // MaterialHelper::Et of the fake material
+    for (size_t i = 0; i < nuclides.size(); i++) Et_fake += conc[i] * P.materials[(size_t)nuclides[i]].micro(g).total;
+    // fake_mat.sample_nuclide(E, rng) :178-224
+    const double invs_Et = 1. / Et_fake;
+    const double xi = rng_rand(p.rng);
+    size_t pick = nuclides.size() - 1;
+    double prob_sum = 0.;
+    for (size_t i = 0; i < nuclides.size(); i++) {
+      const double nuc_prob = invs_Et * conc[i] * P.materials[(size_t)nuclides[i]].micro(g).total;
+      prob_sum += nuc_prob;
+      if (xi <= prob_sum) { pick = i; break; }
+    }
+    const int nuclide_id = nuclides[pick];
+    const Material& nuc = P.materials[(size_t)nuclide_id];
+    const MicroXS microxs = nuc.micro(g);
+    const double N = conc[pick];
+    std::complex<double> dN{0., 0.};  // NoiseMaker::dN :80-91, FlatVibrationNoiseSource::dN :277-312
+    for (const NoiseSource* ns : sources) {
+      if (nuclide_id != ns->mat_neg && nuclide_id != ns->mat_pos) { dN += std::complex<double>{0., 0.}; continue; }
+      const double N_neg = ns->mat_neg == nuclide_id ? 1. : 0., N_pos = ns->mat_pos == nuclide_id ? 1. : 0.;
+      const double D_N = N_neg - N_pos;
+      const int n = vib_harmonic(*ns, w);
+      if (n == 0) { dN += std::complex<double>{0., 0.}; continue; }
+      dN += D_N * vib_C(*ns, (uint32_t)n, vib_get_x(*ns, p.r()));
+    }
+    const std::complex<double> dN_N = dN / N;
+    const double Etfake_Et = Et_fake / mat.Et(p.E());
+    if (nuc.fissile) {  // sample_vibration_noise_fission :183-237
+      const double k_abs = microxs.nu_total * microxs.fission / microxs.total;
+      const int n_new = static_cast<int>(std::floor(k_abs / keff + rng_rand(p.rng)));
+      const double P_delayed = microxs.nu_delayed / microxs.nu_total;
+      for (int i = 0; i < n_new; i++) {
+        auto finfo = sample_fission(P, nuc, p.u(), microxs.energy_index, P_delayed, p.rng);
+        BankedParticle bnp{p.r(), finfo.direction, finfo.energy, p.wgt(), p.wgt2(), p.history_id, p.daughter_counter(), p.family_id};
+        if (finfo.delayed) {
+          std::complex<double> wgt_cmpx{bnp.wgt, bnp.wgt2};
+          double lambda = finfo.lambda;
+          double denom = (lambda * lambda) + (w * w);
+          std::complex<double> mult{lambda * lambda / denom, -lambda * w / denom};
+          wgt_cmpx *= mult;
+          bnp.wgt = wgt_cmpx.real();
+          bnp.wgt2 = wgt_cmpx.imag();
+        }
+        std::complex<double> bnp_wgt{bnp.wgt, bnp.wgt2};
+        bnp_wgt *= dN_N;
+        bnp_wgt *= Etfake_Et;
+        bnp.wgt = bnp_wgt.real();
+        bnp.wgt2 = bnp_wgt.imag();
+        p.history_noise_bank.push_back(bnp);
+      }
+    }
+    const double P_scatter = 1. - (microxs.absorption / microxs.total);
+    {  // sample_vibration_noise_scatter :239-275
+      ScatterInfo sinfo = sample_scatter(P, nuc, p.u(), microxs.energy_index, p.rng);
+      BankedParticle p_noise{p.r(), sinfo.direction, sinfo.energy, 0., 0., p.history_id, p.daughter_counter(), p.family_id};
+      std::complex<double> wgt{p.wgt(), p.wgt2()};
+      wgt *= 1.;
+      wgt *= P_scatter;
+      wgt *= dN_N * Etfake_Et;
+      p_noise.wgt = wgt.real();
+      p_noise.wgt2 = wgt.imag();
+      p.history_noise_bank.push_back(p_noise);
+    }
+  }
+
+  if (!inside_osc) return;  // sample_oscillation_noise_source :293-323
   MicroXS microxs = mat.sample_nuclide(p.E(), p.rng, false);
   const Material& nuc = mat.mat();
   if (nuc.fissile) {  // sample_oscillation_noise_fission :383-445
@@ -906,7 +1044,7 @@ static void sample_noise_source(Ctx& cx, Particle& p, const Mat& mat, double kef
     const double P_delayed = microxs.nu_delayed / microxs.nu_total;
     std::complex<double> dEf_Ef{0., 0.};
     for (const auto& ns : P.noise_sources)
-      if (ns.is_inside(p.r())) dEf_Ef += sqosc_on(ns, w) ? std::complex<double>{ns.eps_f * PI, 0.} : std::complex<double>{0., 0.};
+      if (!ns.vibration && ns.is_inside(p.r())) dEf_Ef += sqosc_on(ns, w) ? std::complex<double>{ns.eps_f * PI, 0.} : std::complex<double>{0., 0.};
     for (int i = 0; i < n_new; i++) {
       auto finfo = sample_fission(P, nuc, p.u(), microxs.energy_index, P_delayed, p.rng);
       BankedParticle bnp{p.r(), finfo.direction, finfo.energy, p.wgt(), p.wgt2(), p.history_id, p.daughter_counter(), p.family_id};
@@ -935,7 +1073,7 @@ static void sample_noise_source(Ctx& cx, Particle& p, const Mat& mat, double kef
     wgt *= P_scatter;
     std::complex<double> dE_E{0., 0.};
     for (const auto& ns : P.noise_sources)
-      if (ns.is_inside(p.r())) dE_E += sqosc_on(ns, w) ? std::complex<double>{ns.eps_s * PI, 0.} : std::complex<double>{0., 0.};
+      if (!ns.vibration && ns.is_inside(p.r())) dE_E += sqosc_on(ns, w) ? std::complex<double>{ns.eps_s * PI, 0.} : std::complex<double>{0., 0.};
     wgt *= dE_E;
     p_noise.wgt = wgt.real();
     p_noise.wgt2 = wgt.imag();

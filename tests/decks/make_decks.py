@@ -110,3 +110,10 @@ dump(ns, "noise_oscillation.yaml",
 nsd = copy.deepcopy(ns)
 nsd["settings"]["transport"] = "delta-tracking"
 dump(nsd, "noise_oscillation_delta.yaml", "S5 variant: noise_oscillation.yaml with transport: delta-tracking.")
+
+# noise_vibration.yaml verbatim (flat-vibration noise sources: a fuel pin moving in y), run sizes reduced
+nv = load("noise_vibration.yaml")
+nv["settings"].update({"nparticles": 4000, "ngenerations": 2, "nignored": 2, "nskip": 2})
+dump(nv, "noise_vibration.yaml",
+     "reference input_files/noise_vibration.yaml (flat-vibration noise sources), run sizes reduced for the parity tests\n"
+     "(nparticles 100000 -> 4000, 2100 noise batches -> 2, nignored 10 -> 2, nskip 3 -> 2).")

@@ -58,7 +58,7 @@ def _particles(fis, first):
     return b
 
 
-@pytest.mark.parametrize("deck", ["noise_oscillation.yaml", "noise_oscillation_delta.yaml"])
+@pytest.mark.parametrize("deck", ["noise_oscillation.yaml", "noise_oscillation_delta.yaml", "noise_vibration.yaml"])
 def test_noise_source_and_noise_transport_bit_exact(ab, oracle_api, tmp_path, deck):
     path = write_deck(load_deck(deck), tmp_path / deck, {"settings": {"nparticles": 6000}})
     keff = float(load_deck(deck)["settings"]["keff"])
@@ -103,9 +103,10 @@ def test_noise_source_and_noise_transport_bit_exact(ab, oracle_api, tmp_path, de
         assert np.allclose(gpu.tally(t, "gen"), orc.tally(t, "gen"), rtol=1e-9, atol=1e-300), f"tally {t}"
 
 
-def test_noise_run_matches_oracle(ab, oracle_api, tmp_path):
+@pytest.mark.parametrize("deck", ["noise_oscillation.yaml", "noise_vibration.yaml"])
+def test_noise_run_matches_oracle(ab, oracle_api, tmp_path, deck):
     from abeille_b200.noise import NoiseSimulation
-    path = deck_path("noise_oscillation.yaml")
+    path = deck_path(deck)
     st = yaml.safe_load(open(path))["settings"]
     orc = oracle_api.Oracle(path)
     ref = orc.run_noise(st)

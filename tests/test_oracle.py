@@ -130,3 +130,24 @@ def test_noise_oracle_source_and_driver(oracle_api):
     # (scores are summed per OpenMP thread: k differs in rounding order between runs, integer outcomes do not)
     assert np.allclose(r1["k_col"], r2["k_col"], rtol=1e-12) and r1["noise_particles"] == r2["noise_particles"]
     assert r1["noise_generations"][0] > 1
+
+
+def test_vibration_noise_source_oracle(oracle_api):
+    """Flat-vibration noise sources (input_files/noise_vibration.yaml): at the fundamental frequency C_R(1, x) is purely
+    imaginary, so every noise particle sampled from a real-weight bank has a purely imaginary weight, bounded by
+    2 * |Et_neg - Et_pos| / Et for the copy; the particles lie inside one of the two vibrating interfaces."""
+    import yaml
+    path = deck_path("noise_vibration.yaml")
+    deck = yaml.safe_load(open(path))
+    orc = oracle_api.Oracle(path, {"settings": {"nparticles": 3000}})
+    orc.set_keff(deck["settings"]["keff"])
+    orc.set_kcol(1.0)
+    fis, nb, _ = orc.transport_noise(orc.sample_source(3000), False, True)
+    assert len(nb["x"]) > 0 and (nb["wgt"] == 0.).all() and (nb["wgt2"] != 0.).any()
+    inside = np.zeros(len(nb["x"]), dtype=bool)
+    for src in deck["noise-sources"]:
+        ok = np.ones(len(nb["x"]), dtype=bool)
+        for ax, k in enumerate("xyz"):
+            ok &= (nb[k] > src["low"][ax]) & (nb[k] < src["hi"][ax])
+        inside |= ok
+    assert inside.all()
