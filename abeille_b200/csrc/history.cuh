@@ -1,29 +1,30 @@
-/* history.cuh -- the delta- / carter-tracking history kernel (v1): warp-synchronous staged state machine.
+/* history.cuh -- the staged history kernel (delta, carter and surface tracking; k-eigenvalue mode).
  *
- * Same arithmetic, same RNG consumption and same per-history outcomes as transport_kernel (transport.cuh), which
- * follows DeltaTracker::transport (src/delta_tracker.cpp:72-263) and CarterTracker::transport
- * (src/carter_tracker.cpp:92-294) of the reference.  What changes is how the 32 lanes of a warp walk through it.
+ * Same arithmetic, same RNG consumption and same per-history outcomes as the per-lane kernel (transport.cuh), which
+ * follows DeltaTracker::transport (src/delta_tracker.cpp:72-263), CarterTracker::transport
+ * (src/carter_tracker.cpp:92-294) and SurfaceTracker::transport (src/surface_tracker.cpp:40-219) of the reference.
+ * What changes is how the lanes of a warp walk through it.
  *
- * v0 let every lane run the reference's control flow on its own; ncu showed 7.6 of 32 lanes active per issued
- * instruction and an instruction-cache bound kernel (228 KB of SASS), because the rare, long paths (history
- * start-up, geometry re-descent, boundary search, reflection, fission banking) were inlined at every call site
- * and executed by one or two lanes while the rest of the warp waited.
+ * Left to itself (every lane running the reference's control flow) the loop executed with 7.6 of 32 lanes active and
+ * was bound by instruction-cache misses (228 KB of SASS): the rare, long paths -- history start-up, geometry
+ * re-descent, boundary search, reflection, fission banking -- were inlined at every call site and executed by one or
+ * two lanes while the rest of the warp waited.
  *
- * v1 gives every lane a small phase variable and runs ONE loop body per warp whose stages appear exactly once
- * in the code:
+ * Here every lane carries a small phase variable and a warp runs ONE loop body whose stages appear exactly once:
  *
- *     R  refill    dead lanes take the next bank index (one aggregated atomic per warp)
+ *     R  refill    dead lanes take the next bank index (one aggregated atomic per warp); with a streamed input bank
+ *                  (abl_transport) a lane waits here until its row has arrived
  *     M  move      lanes in flight sample the distance, advance the geometry cursor, re-validate its pads
- *     L  locate    every lane that needs a (re-)descent through the universe tree does it here -- births,
- *                  tile / cell changes, the rewind of a lost particle, reflections, resurrected secondaries
- *     B  boundary  lost particles: boundary-condition search, leak or reflect
- *     T  track-length tally (one call site)
- *     C  collide   real / virtual decision, Transporter::collision
+ *                  (surface tracking: nearest-boundary search, track-length score, crossing / reflection / collision)
+ *     L  locate    every lane that needs a (re-)descent through the universe tree does it here, all lanes of the warp
+ *                  in step by universe type -- births, tile / cell changes, crossings, reflections, secondaries
+ *     B  boundary  delta / carter: a lane that left the geometry posts a request to the service warp and parks
+ *     T  track-length tally (delta / carter; one call site)
+ *     C  collide   real / virtual decision, Transporter::collision (fission sites go to the service warp as jobs)
  *     E  end       secondaries, history epilogue
  *
- * A lane whose particle needs a rare path simply sits out the stages it cannot take part in for one or two
- * iterations (e.g. lost -> [L at the old position] -> B -> [L at the reflected position]); the common path
- * M -> L -> C runs with most lanes active.  __all_sync at the top of the loop is the reconvergence point.
+ * The geometry cursors live in shared memory, the rare long events run on a service warp; see "CTA layout" below.
+ * DESIGN.md section 3.1 has the measurements behind each of these choices.
  */
 #pragma once
 #include "transport.cuh"

@@ -1,6 +1,10 @@
-/* transport.cuh -- the history kernel: Transporter::transport on the device.
+/* transport.cuh -- particle state, collision physics and the PER-LANE history kernel (transport_kernel).
  *
- * One persistent grid (SM count x resident CTAs).  Every thread owns ONE neutron history at a time and
+ * The per-lane kernel is the direct form of Transporter::transport: every thread runs the reference's control flow for
+ * its history, one whole flight per loop iteration.  It serves the noise modes (noise.cuh); k-eigenvalue runs use the
+ * staged kernel (history.cuh), which shares everything in this file but the loop.
+ *
+ * One persistent grid, one lock-step CTA per SM.  Every thread owns ONE neutron history at a time and
  * keeps its whole state -- position, direction, group, weight, pcg32 state, geometry cursor -- in
  * registers / L1-resident local memory; when the history dies the thread takes the next bank index from
  * a global ticket counter (one aggregated atomic per warp), so lanes never idle while the bank has work.
