@@ -689,6 +689,8 @@ Problem Problem::from_yaml(const Node& input) {
   if (P.settings.tracking == ABL_TRACK_CARTER && P.settings.sample_xs_ratio.size() != G)
     fatal_error("The length of sampling-xs-ratio must be equal to ngroups.");
   if (P.max_stack_depth() > ABL_MAX_PADS) fatal_error("Geometry nesting is deeper than the backend's stack (ABL_MAX_PADS).");
+  if (P.max_frame_depth() > ABL_MAX_FRAMES)
+    fatal_error("Lattices are nested deeper than the backend's coordinate frames (ABL_MAX_FRAMES).");
   return P;
 }
 
@@ -710,6 +712,27 @@ int Problem::max_stack_depth() const {
     return std::max(best, 1);
   };
   return depth(root_universe, 0);
+}
+
+// local coordinate frames a particle can hold at once: the global one plus one per nested lattice tile entered
+int Problem::max_frame_depth() const {
+  std::function<int(int, int)> depth = [&](int uni, int guard) -> int {
+    if (guard > 64) fatal_error("Universe nesting is recursive.");
+    const Universe& U = universes[static_cast<size_t>(uni)];
+    int best = 0;
+    if (U.type == ABL_UNI_CELLS) {
+      for (int ci : U.cell_indices) {
+        const Cell& c = cells[static_cast<size_t>(ci)];
+        if (c.fill_is_universe) best = std::max(best, depth(c.universe_index, guard + 1));
+      }
+      return best;
+    }
+    for (int t : U.tiles)
+      if (t >= 0) best = std::max(best, 1 + depth(t, guard + 1));
+    if (U.outer >= 0) best = std::max(best, depth(U.outer, guard + 1));
+    return best;
+  };
+  return 1 + depth(root_universe, 0);
 }
 
 void Problem::flatten(FlatProblem& F) const {

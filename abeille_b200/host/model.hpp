@@ -126,6 +126,7 @@ class Problem {
   static Problem from_yaml(const yaml_lite::Node& input);  // parse_input_file (src/parser.cpp:77-137)
   void flatten(FlatProblem& out) const;
   int max_stack_depth() const;
+  int max_frame_depth() const;
 };
 
 // libstdc++ std::discrete_distribution partial sums (what RNG::discrete builds on every call, rng.hpp:88-96)

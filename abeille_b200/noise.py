@@ -21,7 +21,9 @@ _INT_MAX = 2147483647
 class NoiseSimulation:
     def __init__(self, deck_path: str, device: int = 0):
         with open(deck_path) as f:
-            st = yaml.safe_load(f).get("settings", {})
+            deck = yaml.safe_load(f)
+        st = deck.get("settings", {})
+        self.tally_names = [str(t.get("name", f"tally{i}")) for i, t in enumerate(deck.get("tallies", []) or [])]
         if st.get("simulation") != "noise":
             raise ValueError("NoiseSimulation needs a deck with `simulation: noise`")
         self.gpu = Backend(deck_path, device)
@@ -128,6 +130,17 @@ class NoiseSimulation:
 
     def tally(self, t: int, which: str = "avg") -> np.ndarray:
         return self.gpu.tally(t, which)
+
+    def write_results(self, directory: str):
+        """Tallies as .npy, [Ne,Nx,Ny,Nz] mean and standard deviation over the noise batches (MeshTally::write_tally,
+        src/mesh_tally.cpp:154-206: std = sqrt(var / g)), named <tally>_avg.npy / <tally>_std.npy like the k-eigenvalue
+        writer (host/simulation.cpp), plus the k_col series of the power-iteration generations."""
+        import os
+        os.makedirs(directory, exist_ok=True)
+        np.save(os.path.join(directory, "kcol.npy"), np.array(self.k_history))
+        for t, name in enumerate(self.tally_names):
+            np.save(os.path.join(directory, f"{name}_avg.npy"), self.gpu.tally(t, "avg"))
+            np.save(os.path.join(directory, f"{name}_std.npy"), self.gpu.tally(t, "std"))
 
     def close(self):
         self.gpu.close()

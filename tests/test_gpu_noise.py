@@ -119,6 +119,10 @@ def test_noise_run_matches_oracle(ab, oracle_api, tmp_path, deck):
         a, b = sim.tally(t, "avg"), orc.tally(t, "avg")
         scale = np.abs(b).max()
         assert np.allclose(a, b, rtol=1e-7, atol=1e-9 * scale), f"tally {t}: max diff {np.abs(a - b).max()} of {scale}"
+    sim.write_results(str(tmp_path / "out"))
+    for t, name in enumerate(sim.tally_names):
+        assert np.array_equal(np.load(tmp_path / "out" / f"{name}_avg.npy"), sim.tally(t, "avg"))
+        assert np.load(tmp_path / "out" / f"{name}_std.npy").shape == orc.tally_shape(t)
     sim.close()
 
 
