@@ -465,6 +465,9 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
   if (N >= (1ull << 32)) return fail(h, ABL_ERR_UNSUPPORTED, "bank larger than 2^32-1 histories per device");
   const bool noise_mode = h->P.mode == ABL_MODE_NOISE;
   const bool sample_noise = params->sample_noise_source != 0;
+  // a power-iteration generation of a noise run that does not sample the noise source is a plain k-eigenvalue generation:
+  // it goes through the staged kernel; noise particles and sampling generations use the per-lane kernel (noise.cuh)
+  const bool lane_kernel_call = noise_mode && (params->noise != 0 || sample_noise);
   if ((params->noise || sample_noise) && !noise_mode)
     return fail(h, ABL_ERR_INVALID, "noise transport / noise-source sampling needs a problem with simulation: noise");
   if (params->noise && sample_noise) return fail(h, ABL_ERR_INVALID, "the noise source is sampled in power-iteration generations only");
@@ -532,9 +535,7 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
     A.nsite_did = h->nsite_did;
   }
   if (N > 0) {
-    if (noise_mode) {
-      if (in.id_c == nullptr) {  // seed(seed); advance(stride * history id) happens in the kernel (transport.cuh)
-      }
+    if (lane_kernel_call) {  // (the per-lane kernel seeds the streams itself when id_c is NULL)
       rc = params->noise ? launch_transport_nm<2>(h, A, N, s) : launch_transport_nm<1>(h, A, N, s);
     } else {
       switch (h->P.tracking) {
@@ -574,7 +575,7 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
   }
   if (sm.n_sites > 0) {
     place_sites_kernel<<<grid_for(h, sm.n_sites, 256), 256, 0, s>>>(h->sites, sm.n_sites, h->offsets, in, out,
-                                                                     noise_mode ? h->site_did : nullptr);
+                                                                     lane_kernel_call ? h->site_did : nullptr);
     h->launches++;
     ABL_CUDA(h, cudaGetLastError());
   }
