@@ -426,7 +426,9 @@ static __device__ ABL_HOT_CALL Tile3 lattice_tile_nl(const abl_universe* __restr
 __device__ __forceinline__ bool tile_in_range(const Lat& L, int nx, int ny, int nz) {
   return !((nx < 0 || nx >= L.Nx) || (ny < 0 || ny >= L.Ny) || (nz < 0 || nz >= L.Nz));
 }
-__device__ inline double distance_to_tile_boundary(const Lat& L, const V3& r_local, const V3& u, int nx, int ny, int nz) {
+// u_inv = (1/u.x, 1/u.y, 1/u.z): the reference evaluates the three reciprocals in every call; they depend on the
+// direction only, so the caller computes them once per boundary search
+__device__ inline double distance_to_tile_boundary(const Lat& L, const V3& r_local, const V3& u_inv, int nx, int ny, int nz) {
   const V3 center = tile_center(L, nx, ny, nz);  // rect_lattice.cpp:239-282
   const double tx = r_local.x - center.x, ty = r_local.y - center.y, tz = r_local.z - center.z;
   double dist = ABL_INF;
@@ -436,7 +438,7 @@ __device__ inline double distance_to_tile_boundary(const Lat& L, const V3& r_loc
   const double diff_yh = L.Py * 0.5 - ty;
   const double diff_zl = -L.Pz * 0.5 - tz;
   const double diff_zh = L.Pz * 0.5 - tz;
-  const double ux_inv = 1. / u.x, uy_inv = 1. / u.y, uz_inv = 1. / u.z;
+  const double ux_inv = u_inv.x, uy_inv = u_inv.y, uz_inv = u_inv.z;
   const double d_xl = diff_xl * ux_inv, d_xh = diff_xh * ux_inv;
   const double d_yl = diff_yl * uy_inv, d_yh = diff_yh * uy_inv;
   const double d_zl = diff_zl * uz_inv, d_zh = diff_zh * uz_inv;
@@ -730,6 +732,8 @@ __device__ inline Boundary cursor_boundary_condition(const PT& P, const CUR& c, 
 template <class PT, class CUR>
 __device__ inline Boundary cursor_nearest_boundary(const PT& P, const CUR& c, const V3& u) {
   Boundary b = cursor_boundary_condition(P, c, u);
+  V3 u_inv{0., 0., 0.};
+  bool have_u_inv = false;
   for (int it = 0; it < c.np; it++) {
     const int info = pad_info(c, it);
     const int type = pad_type(info);
@@ -737,7 +741,11 @@ __device__ inline Boundary cursor_nearest_boundary(const PT& P, const CUR& c, co
     if (type == PAD_LATTICE) {
       const Lat L = load_lattice(P.universes + pad_index(info));
       const Tile3 t3 = pad_tile3(c, it);
-      const double d = distance_to_tile_boundary(L, r, u, t3.nx, t3.ny, t3.nz);
+      if (!have_u_inv) {
+        u_inv = V3{1. / u.x, 1. / u.y, 1. / u.z};
+        have_u_inv = true;
+      }
+      const double d = distance_to_tile_boundary(L, r, u_inv, t3.nx, t3.ny, t3.nz);
       if (d < b.distance && fabs(d - b.distance) > ABL_BOUNDRY_TOL) {
         b.distance = d;
         b.btype = ABL_BC_NORMAL;
