@@ -1257,6 +1257,60 @@ void orc_rng_stream(uint64_t seed, uint64_t stride, uint64_t history_id, int n, 
   Pcg32 g; g.seed(seed); g.advance(stride * history_id);
   for (int i = 0; i < n; i++) out_u32[i] = g.next();
 }
+// ---- probes of the pieces that tests/test_reference_pins.py compares with the reference's own code (oracle/ref_probe.cpp)
+int orc_surface_probe(int type, const double* params, int n, const double* r3, const double* u3, const int* on_surf, int* sign,
+                      double* dist, double* norm3) {
+  Surface s;
+  s.type = type;
+  for (int k = 0; k < 7; k++) s.p[k] = params[k];
+  if (type == S_CYL) {  // Cylinder(x0,y0,z0,u0,v0,w0,R): axis normalised into alpha, beta, gamma (cylinder.cpp:28-58)
+    s.p[6] = params[6];
+    s.finish_general_cylinder(params[3], params[4], params[5]);
+  }
+  for (int i = 0; i < n; i++) {
+    const Vec r{r3[3 * i], r3[3 * i + 1], r3[3 * i + 2]};
+    const Vec u = make_direction(u3[3 * i], u3[3 * i + 1], u3[3 * i + 2]);
+    sign[i] = s.sign(r, u);
+    dist[i] = s.distance(r, u, on_surf[i] != 0);
+    const Vec nn = s.norm(r);
+    norm3[3 * i] = nn.x; norm3[3 * i + 1] = nn.y; norm3[3 * i + 2] = nn.z;
+  }
+  return 0;
+}
+void orc_direction_probe(int n, const double* xyz, double* out) {
+  for (int i = 0; i < n; i++) {
+    const Vec d = make_direction(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
+  }
+}
+void orc_rotate_direction_probe(int n, const double* u3, const double* mu, const double* phi, double* out) {
+  for (int i = 0; i < n; i++) {
+    const Vec u = make_direction(u3[3 * i], u3[3 * i + 1], u3[3 * i + 2]);
+    const Vec d = rotate_direction(u, mu[i], phi[i]);
+    out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
+  }
+}
+void orc_sample_mu_probe(const double* mu, const double* pdf, const double* cdf, int npts, uint64_t seed, uint64_t stride,
+                         uint64_t id, int n, double* out) {
+  AngleDist d;
+  d.mu.assign(mu, mu + npts); d.pdf.assign(pdf, pdf + npts); d.cdf.assign(cdf, cdf + npts);
+  Pcg32 rng;
+  rng.seed(seed);
+  rng.advance(stride * id);
+  for (int i = 0; i < n; i++) out[i] = d.sample_mu(rng);
+}
+int orc_legendre_linearize_probe(const double* a, int na, int cap, double* mu, double* pdf, double* cdf) {
+  Legendre L;  // LegendreDistribution(a): a[l-1] is the l-th moment, the 0th (= 1) is implied (legendre_distribution.cpp:41-60)
+  for (int l = 1; l <= na; l++) L.set_moment((size_t)l, a[l - 1]);
+  const AngleDist d = L.linearize();
+  const int n = (int)d.mu.size();
+  if (n > cap) return -n;
+  std::memcpy(mu, d.mu.data(), n * sizeof(double));
+  std::memcpy(pdf, d.pdf.data(), n * sizeof(double));
+  std::memcpy(cdf, d.cdf.data(), n * sizeof(double));
+  return n;
+}
+
 void orc_rng_rand(uint64_t seed, uint64_t stride, uint64_t history_id, int n, double* out) {
   Pcg32 g; g.seed(seed); g.advance(stride * history_id);
   for (int i = 0; i < n; i++) out[i] = rng_rand(g);
@@ -1270,6 +1324,13 @@ int orc_rng_discrete(uint64_t seed, uint64_t stride, uint64_t history_id, const 
   auto cp = discrete_table(w, (size_t)nw);
   for (int i = 0; i < ndraws; i++) out[i] = rng_discrete(g, cp);
   return (int)g.ndraw;
+}
+// ndraws x RNG::discrete, then one RNG::rand: the value shows how many engine steps the draws consumed
+double orc_rng_discrete_probe(uint64_t seed, uint64_t stride, uint64_t history_id, const double* w, int nw, int ndraws, int* out) {
+  Pcg32 g; g.seed(seed); g.advance(stride * history_id);
+  auto cp = discrete_table(w, (size_t)nw);
+  for (int i = 0; i < ndraws; i++) out[i] = rng_discrete(g, cp);
+  return rng_rand(g);
 }
 void orc_math_eval(int n, const double* x, double* lg, double* sn, double* cs) {
   for (int i = 0; i < n; i++) { lg[i] = g_math.log(x[i]); sn[i] = g_math.sin(x[i]); cs[i] = g_math.cos(x[i]); }

@@ -1,0 +1,210 @@
+"""oracle/ref_pins.py -- TEST INFRASTRUCTURE: pins the oracle against the reference's own compiled code.
+
+oracle/_ref/libabeille_ref.so (oracle/Makefile target `ref`, driver oracle/ref_probe.cpp) is built from the reference's
+own translation units where they lie under /root/reference: the nine surface classes, Direction / rotate_direction, the
+RNG helpers over pcg32, MGAngleDistribution::sample_mu and LegendreDistribution::linearize.  `evaluate("reference")`
+runs the seeded cases below through it, `evaluate("oracle")` through the oracle's restatement (orc_*_probe entry points
+of oracle/orc_main.cpp).  Both return {name: ndarray}; tests/test_reference_pins.py demands bit-equality, and
+scripts/make_ref_pins.py stores the reference's outputs as tests/golden/ref_pins.npz so that the comparison also runs on
+machines without /root/reference (the GPU box).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import api
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_LIB = os.path.join(_HERE, "_ref", "libabeille_ref.so")
+REFERENCE_ROOT = "/root/reference"
+
+_PD = C.POINTER(C.c_double)
+_PI = C.POINTER(C.c_int)
+_ref = None
+
+SEED, STRIDE = 19073486328125, 152917  # settings.hpp defaults (rng_seed, rng_stride)
+
+
+def reference_available() -> bool:
+    return os.path.exists(REF_LIB) or os.path.isdir(os.path.join(REFERENCE_ROOT, "src"))
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_LIB):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        _ref = C.CDLL(REF_LIB)
+        _ref.ref_rng_exponential.restype = C.c_double
+        _ref.ref_rng_discrete.restype = C.c_double
+    return _ref
+
+
+def _d(a):
+    return a.ctypes.data_as(_PD)
+
+
+# ---------------------------------------------------------------------------------------------------------- cases
+SURFACE_NAMES = ("xplane", "yplane", "zplane", "plane", "xcyl", "ycyl", "zcyl", "cyl", "sphere")
+
+
+def surface_cases(n=1500):
+    """Per surface type: 7 parameters in the order of the constructors (xplane.hpp ... sphere.hpp), n positions,
+    directions and on_surf flags.  A third of the positions are projected onto (or within an ulp-scale distance of) the
+    surface, so the SURFACE_COINCIDENT / on_surf branches of distance() and sign() are exercised."""
+    rng = np.random.default_rng(20261017)
+    out = []
+    for t, name in enumerate(SURFACE_NAMES):
+        p = np.zeros(7)
+        if t <= 2:
+            p[0] = rng.uniform(-2, 2)
+        elif t == 3:
+            p[:3] = rng.normal(size=3)
+            p[:3] /= np.linalg.norm(p[:3])
+            p[3] = rng.uniform(-1, 1)
+        elif t <= 6:
+            p[:2] = rng.uniform(-1, 1, 2)
+            p[2] = rng.uniform(0.3, 2.5)
+        elif t == 7:
+            p[:3] = rng.uniform(-1, 1, 3)
+            p[3:6] = rng.normal(size=3)
+            p[6] = rng.uniform(0.3, 2.5)
+        else:
+            p[:3] = rng.uniform(-1, 1, 3)
+            p[3] = rng.uniform(0.3, 2.5)
+        r = rng.uniform(-4, 4, (n, 3))
+        u = rng.normal(size=(n, 3))
+        # axis-aligned and grazing directions
+        u[::17] = np.eye(3)[rng.integers(0, 3, len(u[::17]))] * rng.choice([-1., 1.], (len(u[::17]), 1))
+        near = slice(0, n // 3)
+        r[near] = _project(t, p, r[near])
+        r[near.start:near.stop:2] += rng.normal(scale=1e-10, size=(len(r[near.start:near.stop:2]), 3))
+        on = (rng.random(n) < 0.25).astype(np.int32)
+        out.append((t, name, p, np.ascontiguousarray(r), np.ascontiguousarray(u), on))
+    return out
+
+
+def _project(t, p, r):
+    r = r.copy()
+    if t <= 2:
+        r[:, t] = p[0]
+    elif t == 3:
+        nrm = p[:3]
+        r -= np.outer(r @ nrm - p[3], nrm)
+    elif t <= 6:
+        ax = t - 4
+        oth = [k for k in range(3) if k != ax]
+        c = np.zeros(3)
+        c[oth] = p[:2]
+        d = r - c
+        d[:, ax] = 0
+        d *= (p[2] / np.linalg.norm(d, axis=1))[:, None]
+        r[:, oth] = (c + d)[:, oth]
+    elif t == 7:
+        a = p[3:6] / np.linalg.norm(p[3:6])
+        d = r - p[:3]
+        par = np.outer(d @ a, a)
+        perp = d - par
+        perp *= (p[6] / np.linalg.norm(perp, axis=1))[:, None]
+        r = p[:3] + par + perp
+    else:
+        d = r - p[:3]
+        d *= (p[3] / np.linalg.norm(d, axis=1))[:, None]
+        r = p[:3] + d
+    return r
+
+
+def direction_cases(n=4000):
+    rng = np.random.default_rng(7)
+    xyz = rng.normal(size=(n, 3)) * rng.choice([1e-3, 1., 1e3], (n, 1))
+    u = rng.normal(size=(n, 3))
+    u[:50] = np.array([0., 0., 1.]) * rng.choice([-1., 1.], (50, 1))  # the |w| == 1 pole of rotate_direction
+    u[50:100, :2] *= 1e-9
+    mu = rng.uniform(-1, 1, n)
+    mu[:10] = [-1., 1., 0., -1., 1., 0., 0.5, -0.5, 1., -1.]
+    phi = rng.uniform(0, 2 * np.pi, n)
+    return np.ascontiguousarray(xyz), np.ascontiguousarray(u), mu, phi
+
+
+LEGENDRE_CASES = ([0.3], [0.3, 0.1], [-0.2, 0.05, 0.01], [0.1, 0.2, 0.05, 0.02, 0.01], [0.9, 0.7, 0.5, 0.3, 0.2, 0.1])
+DISCRETE_WEIGHTS = ([1.0], [0.2, 0.8], [0.0, 0.3, 0.0, 0.7], [1e-3, 0.5, 0.25, 0.249],
+                    [0.1, 0.2, 0.3, 0.05, 0.15, 0.1, 0.1])
+HISTORY_IDS = (0, 1, 2, 1000, 123456789, 10 ** 12 + 7)
+
+
+# ------------------------------------------------------------------------------------------------------ evaluation
+def evaluate(impl: str) -> dict:
+    """Run every case through `impl` ("reference": oracle/_ref, "oracle": the restatement)."""
+    ref = impl == "reference"
+    L = ref_lib() if ref else api.lib()
+    out = {}
+    # surfaces
+    fn = L.ref_surface if ref else L.orc_surface_probe
+    for t, name, p, r, u, on in surface_cases():
+        n = len(r)
+        sign = np.zeros(n, dtype=np.int32)
+        dist, norm = np.zeros(n), np.zeros((n, 3))
+        rc = fn(C.c_int(t), _d(p), C.c_int(n), _d(r), _d(u), on.ctypes.data_as(_PI), sign.ctypes.data_as(_PI), _d(dist),
+                _d(norm))
+        assert rc == 0
+        out[f"surf_{name}_sign"], out[f"surf_{name}_dist"], out[f"surf_{name}_norm"] = sign, dist, norm
+    # directions
+    xyz, u, mu, phi = direction_cases()
+    n = len(xyz)
+    d = np.zeros((n, 3))
+    (L.ref_direction if ref else L.orc_direction_probe)(C.c_int(n), _d(xyz), _d(d))
+    out["direction"] = d
+    d2 = np.zeros((n, 3))
+    (L.ref_rotate_direction if ref else L.orc_rotate_direction_probe)(C.c_int(n), _d(u), _d(mu), _d(phi), _d(d2))
+    out["rotate_direction"] = d2
+    # RNG
+    for hid in HISTORY_IDS:
+        v = np.zeros(64)
+        (L.ref_rng_rand if ref else L.orc_rng_rand)(C.c_uint64(SEED), C.c_uint64(STRIDE), C.c_uint64(hid), C.c_int(64), _d(v))
+        out[f"rand_{hid}"] = v
+        f = L.ref_rng_exponential if ref else L.orc_rng_exponential
+        f.restype = C.c_double
+        out[f"exp_{hid}"] = np.array([f(C.c_uint64(SEED), C.c_uint64(STRIDE), C.c_uint64(hid), C.c_double(lam))
+                                      for lam in (0.1, 1.0, 2.5, 37.0)])
+        for k, w in enumerate(DISCRETE_WEIGHTS):
+            w = np.asarray(w, dtype=np.float64)
+            draws = np.zeros(200, dtype=np.int32)
+            f = L.ref_rng_discrete if ref else L.orc_rng_discrete_probe
+            f.restype = C.c_double
+            nxt = f(C.c_uint64(SEED), C.c_uint64(STRIDE), C.c_uint64(hid), _d(w), C.c_int(len(w)), C.c_int(200),
+                    draws.ctypes.data_as(_PI))
+            out[f"discrete_{hid}_{k}"] = draws
+            out[f"discrete_next_{hid}_{k}"] = np.array([nxt])
+    # Legendre linearisation, then sample_mu from the table the REFERENCE produced (so a table mismatch does not hide
+    # behind a sampling mismatch: the golden table is the input of both)
+    lin = L.ref_legendre_linearize if ref else L.orc_legendre_linearize_probe
+    smp = L.ref_sample_mu if ref else L.orc_sample_mu_probe
+    cap = 1 << 16
+    for k, a in enumerate(LEGENDRE_CASES):
+        a = np.asarray(a, dtype=np.float64)
+        mu_t, pdf_t, cdf_t = np.zeros(cap), np.zeros(cap), np.zeros(cap)
+        npts = lin(_d(a), C.c_int(len(a)), C.c_int(cap), _d(mu_t), _d(pdf_t), _d(cdf_t))
+        assert npts > 1, f"linearize failed for {a}: {npts}"
+        out[f"legendre_{k}_mu"], out[f"legendre_{k}_pdf"], out[f"legendre_{k}_cdf"] = mu_t[:npts].copy(), pdf_t[:npts].copy(), \
+            cdf_t[:npts].copy()
+    return out
+
+
+def sample_mu(impl: str, tables: dict) -> dict:
+    """sample_mu over the given (golden) tables: 500 draws of three histories per Legendre case."""
+    ref = impl == "reference"
+    L = ref_lib() if ref else api.lib()
+    smp = L.ref_sample_mu if ref else L.orc_sample_mu_probe
+    out = {}
+    for k in range(len(LEGENDRE_CASES)):
+        mu_t, pdf_t, cdf_t = (np.ascontiguousarray(tables[f"legendre_{k}_{q}"]) for q in ("mu", "pdf", "cdf"))
+        for hid in HISTORY_IDS[:3]:
+            v = np.zeros(500)
+            smp(_d(mu_t), _d(pdf_t), _d(cdf_t), C.c_int(len(mu_t)), C.c_uint64(SEED), C.c_uint64(STRIDE), C.c_uint64(hid),
+                C.c_int(500), _d(v))
+            out[f"sample_mu_{k}_{hid}"] = v
+    return out
