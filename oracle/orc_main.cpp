@@ -1325,6 +1325,58 @@ int orc_rng_discrete(uint64_t seed, uint64_t stride, uint64_t history_id, const 
   for (int i = 0; i < ndraws; i++) out[i] = rng_discrete(g, cp);
   return (int)g.ndraw;
 }
+// the counterpart of ref_mg_nuclide (oracle/ref_probe.cpp): same arrays in, same draws out
+int orc_mg_nuclide_probe(int G, const double* ebounds, const double* Et, const double* Ea, const double* Ef, const double* nu_p,
+                         const double* nu_d, const double* chi, const double* Es, int nleg, const double* leg, int ndg,
+                         const double* Pd, const double* lam, uint64_t seed, uint64_t stride, int nhist, int ndraw,
+                         double* micro, double* scat, double* fis) {
+  const size_t g = (size_t)G;
+  Problem P;
+  P.st.ngroups = (uint32_t)G;
+  P.st.energy_bounds.assign(ebounds, ebounds + G + 1);
+  Material m;
+  m.G = g;
+  m.Et.assign(Et, Et + g); m.Ea.assign(Ea, Ea + g); m.Ef.assign(Ef, Ef + g); m.nu_p.assign(nu_p, nu_p + g);
+  m.has_nu_d = nu_d != nullptr;
+  if (nu_d) m.nu_d.assign(nu_d, nu_d + g);
+  m.speeds.assign(g, 1.);
+  m.chi.resize(g); m.Ps.resize(g);
+  for (size_t i = 0; i < g; i++) { m.chi[i].assign(chi + i * g, chi + (i + 1) * g); m.Ps[i].assign(Es + i * g, Es + (i + 1) * g); }
+  std::vector<std::vector<Legendre>> legendre(g, std::vector<Legendre>(g));
+  for (int l = 1; l <= nleg; l++)
+    for (size_t i = 0; i < g; i++)
+      for (size_t o = 0; o < g; o++) legendre[i][o].set_moment((size_t)l, leg[((size_t)(l - 1) * g + i) * g + o]);
+  m.angle.assign(g, std::vector<AngleDist>(g));
+  for (size_t i = 0; i < g; i++)
+    for (size_t o = 0; o < g; o++) m.angle[i][o] = legendre[i][o].linearize();
+  m.P_delayed_group.assign(Pd, Pd + ndg);
+  m.decay_constants.assign(lam, lam + ndg);
+  m.finish();
+  for (size_t i = 0; i < g; i++) {
+    if (P.st.group(0.5 * (ebounds[i] + ebounds[i + 1])) != i) return 2;
+    const MicroXS xs = m.micro(i);
+    double* q = micro + 6 * i;
+    q[0] = xs.total; q[1] = xs.fission; q[2] = xs.absorption; q[3] = xs.elastic; q[4] = xs.nu_total; q[5] = xs.nu_delayed;
+  }
+  for (int h = 0; h < nhist; h++) {
+    Pcg32 rng; rng.seed(seed); rng.advance(stride * (uint64_t)h);
+    Vec u = make_direction(0., 0., 1.);
+    for (int d = 0; d < ndraw; d++) {
+      const size_t gi = (size_t)(h + d) % g;
+      const MicroXS xs = m.micro(gi);
+      const ScatterInfo si = sample_scatter(P, m, u, gi, rng);
+      double* s = scat + 4 * ((size_t)h * ndraw + d);
+      s[0] = si.energy; s[1] = si.direction.x; s[2] = si.direction.y; s[3] = si.direction.z;
+      u = si.direction;
+      const double Pdelayed = xs.nu_total > 0. ? xs.nu_delayed / xs.nu_total : 0.;
+      const FissionInfo fi = sample_fission(P, m, u, gi, Pdelayed, rng);
+      double* f = fis + 6 * ((size_t)h * ndraw + d);
+      f[0] = fi.energy; f[1] = fi.direction.x; f[2] = fi.direction.y; f[3] = fi.direction.z;
+      f[4] = fi.delayed ? 1. : 0.; f[5] = fi.lambda;
+    }
+  }
+  return 0;
+}
 // ndraws x RNG::discrete, then one RNG::rand: the value shows how many engine steps the draws consumed
 double orc_rng_discrete_probe(uint64_t seed, uint64_t stride, uint64_t history_id, const double* w, int nw, int ndraws, int* out) {
   Pcg32 g; g.seed(seed); g.advance(stride * history_id);

@@ -136,6 +136,59 @@ DISCRETE_WEIGHTS = ([1.0], [0.2, 0.8], [0.0, 0.3, 0.0, 0.7], [1e-3, 0.5, 0.25, 0
 HISTORY_IDS = (0, 1, 2, 1000, 123456789, 10 ** 12 + 7)
 
 
+def mg_material_cases():
+    """Materials of the shipped multigroup decks (tests/decks) plus one synthetic 3-group material with P1..P3 moments and
+    delayed groups, as the flat arrays ref_mg_nuclide / orc_mg_nuclide_probe take.  A single chi row is replicated for
+    every incoming group (src/mg_nuclide.cpp:836-852); non-fissile materials get a flat chi so that both sides normalise
+    finite numbers (their fission branch is never reached in transport)."""
+    from . import deck as _deck
+    decks = os.path.join(os.path.dirname(_HERE), "tests", "decks")
+    cases = []
+    for fname in ("c5g7_delta_collision.yaml", "UD2O-2-1-SL.yaml", "PUa-1-2-SL.yaml", "Ua-1-1-CY.yaml", "noise_oscillation.yaml"):
+        d = _deck.load_yaml(os.path.join(decks, fname))
+        G = int(d["settings"]["ngroups"])
+        eb = np.asarray(d["settings"]["energy-bounds"], dtype=np.float64)
+        for m in d["materials"]:
+            cases.append((f"{fname.split('.')[0]}_m{m['id']}", _material_arrays(m, G, eb)))
+    G = 3
+    rng = np.random.default_rng(3)
+    Es = rng.uniform(0.05, 0.6, (G, G))
+    Es[2, 0] = 0.0  # a zero-probability transfer
+    m = {"total": (Es.sum(1) + 0.3).tolist(), "absorption": [0.3] * G, "fission": [0.1, 0.12, 0.2],
+         "nu_prompt": [2.4, 2.45, 2.5], "nu_delayed": [0.02, 0.018, 0.016],
+         "chi": [[0.7, 0.3, 0.0], [0.6, 0.3, 0.1], [0.5, 0.25, 0.25]], "scatter": Es.tolist(),
+         "P1": (0.3 * rng.random((G, G))).tolist(), "P2": (0.1 * rng.random((G, G))).tolist(),
+         "P3": (0.03 * rng.random((G, G))).tolist(),
+         "delayed_groups": {"probabilities": [0.1, 0.2, 0.3, 0.4], "constants": [0.012, 0.03, 0.11, 0.3]}}
+    cases.append(("synthetic_3g", _material_arrays(m, G, np.array([0., 1., 2., 3.]))))
+    return cases
+
+
+def _material_arrays(m, G, eb):
+    f = lambda k, dflt: np.asarray(m.get(k, dflt), dtype=np.float64)  # noqa: E731
+    if "nu" in m:
+        nup, nud = f("nu", None), np.zeros(G)  # nu is nu_prompt, nu_delayed = 0 (mg_nuclide.cpp:742-752)
+    elif "nu_prompt" in m:
+        nup, nud = f("nu_prompt", None), f("nu_delayed", None)
+    else:
+        nup, nud = np.zeros(G), np.zeros(G)
+    chi = np.asarray(m.get("chi", [[1.0] * G]), dtype=np.float64)
+    if chi.shape[0] == 1:
+        chi = np.repeat(chi, G, axis=0)
+    if not chi.any():
+        chi = np.ones((G, G))
+    legs = [np.asarray(m[f"P{l}"], dtype=np.float64) for l in range(1, 6) if f"P{l}" in m]
+    assert all(f"P{l}" in m for l in range(1, len(legs) + 1)), "moments must be contiguous for the probe"
+    dg = m.get("delayed_groups") or {"probabilities": [], "constants": []}
+    return dict(G=G, eb=eb, Et=f("total", None), Ea=f("absorption", None), Ef=f("fission", [0.0] * G), nup=nup, nud=nud,
+                chi=np.ascontiguousarray(chi), Es=np.ascontiguousarray(f("scatter", None)),
+                leg=np.ascontiguousarray(np.stack(legs)) if legs else np.zeros(1), nleg=len(legs),
+                Pd=np.asarray(dg["probabilities"], dtype=np.float64), lam=np.asarray(dg["constants"], dtype=np.float64))
+
+
+NHIST_MG, NDRAW_MG = 8, 250
+
+
 # ------------------------------------------------------------------------------------------------------ evaluation
 def evaluate(impl: str) -> dict:
     """Run every case through `impl` ("reference": oracle/_ref, "oracle": the restatement)."""
@@ -191,6 +244,19 @@ def evaluate(impl: str) -> dict:
         assert npts > 1, f"linearize failed for {a}: {npts}"
         out[f"legendre_{k}_mu"], out[f"legendre_{k}_pdf"], out[f"legendre_{k}_cdf"] = mu_t[:npts].copy(), pdf_t[:npts].copy(), \
             cdf_t[:npts].copy()
+    # MGNuclide: micro XS, sample_scatter, sample_fission
+    fn = L.ref_mg_nuclide if ref else L.orc_mg_nuclide_probe
+    for name, a in mg_material_cases():
+        G = a["G"]
+        micro = np.zeros((G, 6))
+        scat, fis = np.zeros((NHIST_MG, NDRAW_MG, 4)), np.zeros((NHIST_MG, NDRAW_MG, 6))
+        Pd, lam = (a["Pd"], a["lam"]) if len(a["Pd"]) else (np.zeros(1), np.zeros(1))
+        rc = fn(C.c_int(G), _d(a["eb"]), _d(a["Et"]), _d(a["Ea"]), _d(a["Ef"]), _d(a["nup"]),
+                _d(a["nud"]) if a["nud"] is not None else None, _d(a["chi"]), _d(a["Es"]), C.c_int(a["nleg"]), _d(a["leg"]),
+                C.c_int(len(a["Pd"])), _d(Pd), _d(lam), C.c_uint64(SEED), C.c_uint64(STRIDE), C.c_int(NHIST_MG),
+                C.c_int(NDRAW_MG), _d(micro), _d(scat), _d(fis))
+        assert rc == 0, f"mg nuclide probe failed for {name}: {rc}"
+        out[f"mg_{name}_micro"], out[f"mg_{name}_scatter"], out[f"mg_{name}_fission"] = micro, scat, fis
     return out
 
 

@@ -21,9 +21,11 @@
 #include <geometry/surfaces/zplane.hpp>
 #include <materials/legendre_distribution.hpp>
 #include <materials/mg_angle_distribution.hpp>
+#include <materials/mg_nuclide.hpp>
 #include <utils/direction.hpp>
 #include <utils/error.hpp>
 #include <utils/rng.hpp>
+#include <utils/settings.hpp>
 
 #include <cstdio>
 #include <cstring>
@@ -36,6 +38,21 @@ void fatal_error(std::string mssg, std::source_location loc) {
   throw std::runtime_error(mssg + " (" + loc.file_name() + ":" + std::to_string(loc.line()) + ")");
 }
 void warning(std::string mssg, std::source_location) { std::fprintf(stderr, "reference warning: %s\n", mssg.c_str()); }
+
+// src/settings.cpp needs HighFive (utils/output.hpp); the driver defines the few settings the multigroup sources read,
+// with the declarations of include/utils/settings.hpp
+namespace settings {
+uint32_t ngroups = 0;
+SimulationMode mode = SimulationMode::K_EIGENVALUE;
+pcg32 rng;
+std::vector<double> energy_bounds;
+bool chi_matrix = false;
+bool use_virtual_collisions = true;
+}  // namespace settings
+// src/nuclide.cpp is one line of data definitions behind the same heavy includes
+std::map<uint32_t, std::shared_ptr<Nuclide>> nuclides;
+std::unordered_set<uint32_t> zaids_with_urr;
+uint32_t Nuclide::id_counter = 0;
 
 namespace {
 // surface type codes of include/abeille_b200.h / oracle/orc_geom.h
@@ -139,6 +156,69 @@ int ref_legendre_linearize(const double* a, int na, int cap, double* mu, double*
   } catch (const std::exception& e) {
     std::fprintf(stderr, "ref_legendre_linearize: %s\n", e.what());
     return 0;
+  }
+}
+
+// MGNuclide built through its vector constructor (src/mg_nuclide.cpp:36-70) from the arrays make_mg_nuclide would have
+// read from the YAML material (:579-922; the Legendre moments go through LegendreDistribution::set_moment and linearize()
+// as at :555-575 and :700-710).  micro: per group total, fission, absorption, elastic, nu_total, nu_delayed of
+// get_micro_xs.  Per history h < nhist (stream seed / stride / h) and draw d < ndraw, from group (h + d) % G and the
+// direction of the previous draw: sample_scatter -> scat[4] = E, u; sample_fission(Pdelayed = nu_delayed / nu_total)
+// -> fis[6] = E, u, delayed, lambda.
+int ref_mg_nuclide(int G, const double* ebounds, const double* Et, const double* Ea, const double* Ef, const double* nu_p,
+                   const double* nu_d, const double* chi, const double* Es, int nleg, const double* leg, int ndg,
+                   const double* Pd, const double* lam, uint64_t seed, uint64_t stride, int nhist, int ndraw, double* micro,
+                   double* scat, double* fis) {
+  try {
+    const std::size_t g = (std::size_t)G;
+    settings::ngroups = (uint32_t)G;
+    settings::energy_bounds.assign(ebounds, ebounds + G + 1);
+    auto vec = [g](const double* p) { return p ? std::vector<double>(p, p + g) : std::vector<double>(); };
+    auto mat = [g](const double* p) {
+      std::vector<std::vector<double>> m(g);
+      for (std::size_t i = 0; i < g; i++) m[i].assign(p + i * g, p + (i + 1) * g);
+      return m;
+    };
+    std::vector<std::vector<LegendreDistribution>> legendre(g, std::vector<LegendreDistribution>(g));
+    for (int l = 1; l <= nleg; l++)
+      for (std::size_t i = 0; i < g; i++)
+        for (std::size_t o = 0; o < g; o++) legendre[i][o].set_moment((std::size_t)l, leg[((std::size_t)(l - 1) * g + i) * g + o]);
+    std::vector<std::vector<MGAngleDistribution>> angles(g, std::vector<MGAngleDistribution>(g));
+    for (std::size_t i = 0; i < g; i++)
+      for (std::size_t o = 0; o < g; o++) angles[i][o] = legendre[i][o].linearize();
+    const std::vector<std::vector<double>> yields(g, std::vector<double>(g, 1.));
+    const MGNuclide nuc(std::vector<double>(g, 1.), vec(Et), vec(Ea), vec(Ef), vec(nu_p), vec(nu_d), mat(chi), mat(Es), yields,
+                        angles, std::vector<double>(Pd, Pd + ndg), std::vector<double>(lam, lam + ndg));
+    for (std::size_t i = 0; i < g; i++) {
+      const MicroXSs xs = nuc.get_micro_xs(0.5 * (ebounds[i] + ebounds[i + 1]));
+      if (xs.energy_index != i) return 2;
+      double* m = micro + 6 * i;
+      m[0] = xs.total; m[1] = xs.fission; m[2] = xs.absorption; m[3] = xs.elastic; m[4] = xs.nu_total; m[5] = xs.nu_delayed;
+    }
+    for (int h = 0; h < nhist; h++) {
+      pcg32 rng;
+      rng.seed(seed);
+      rng.advance(stride * (uint64_t)h);
+      Direction u(0., 0., 1.);
+      for (int d = 0; d < ndraw; d++) {
+        const std::size_t gi = (std::size_t)(h + d) % g;
+        const double E = 0.5 * (ebounds[gi] + ebounds[gi + 1]);
+        const MicroXSs xs = nuc.get_micro_xs(E);
+        const ScatterInfo si = nuc.sample_scatter(E, u, xs, rng);
+        double* s = scat + 4 * ((std::size_t)h * ndraw + d);
+        s[0] = si.energy; s[1] = si.direction.x(); s[2] = si.direction.y(); s[3] = si.direction.z();
+        u = si.direction;
+        const double Pdelayed = xs.nu_total > 0. ? xs.nu_delayed / xs.nu_total : 0.;
+        const FissionInfo fi = nuc.sample_fission(E, u, xs.energy_index, Pdelayed, rng);
+        double* f = fis + 6 * ((std::size_t)h * ndraw + d);
+        f[0] = fi.energy; f[1] = fi.direction.x(); f[2] = fi.direction.y(); f[3] = fi.direction.z();
+        f[4] = fi.delayed ? 1. : 0.; f[5] = fi.precursor_decay_constant;
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "ref_mg_nuclide: %s\n", e.what());
+    return 1;
   }
 }
 
