@@ -1398,6 +1398,79 @@ void orc_find_cells(void* h, int n, const double* r3, const double* u3, int32_t*
   }
 }
 
+// counterparts of ref_geometry_walk_surface / ref_geometry_walk_delta (oracle/ref_probe.cpp): same rays in, same rows out
+static void walk_put(double* o, const Geometry& geo, const Tracker& t) {
+  o[0] = t.is_lost() ? -1. : static_cast<double>(geo.cells[(size_t)t.current_cell].id);
+  o[1] = t.is_lost() ? -1. : static_cast<double>(t.current_mat);
+  o[2] = 0.;
+}
+int orc_geometry_walk_surface(void* h, int n, const double* r3, const double* u3, int nsteps, double* out) {
+  Problem& P = *static_cast<Problem*>(h);
+  try {
+    for (int i = 0; i < n; i++) {
+      double* o = out + static_cast<size_t>(i) * (nsteps + 1) * 8;
+      Particle p(Vec{r3[3 * i], r3[3 * i + 1], r3[3 * i + 2]}, make_direction(u3[3 * i], u3[3 * i + 1], u3[3 * i + 2]), 1., 1.);
+      Tracker trkr(&P.geo, p.r(), p.u());
+      walk_put(o, P.geo, trkr); o[7] = 1.;
+      for (int s = 1; s <= nsteps && !trkr.is_lost(); s++) {
+        o += 8;
+        const Boundary b = trkr.get_nearest_boundary();
+        o[3] = b.distance; o[4] = b.surface_index; o[5] = b.boundary_type; o[6] = b.token; o[7] = 1.;
+        if (b.boundary_type == BC_VACUUM) { o[0] = o[1] = -2.; break; }
+        if (b.boundary_type == BC_REFLECTIVE) {
+          do_reflection(trkr, p, b);
+        } else {
+          trkr.cross_surface(b);
+          trkr.get_current();
+          p.move(b.distance);
+        }
+        walk_put(o, P.geo, trkr);
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) { P.error = e.what(); return 1; }
+}
+int orc_geometry_walk_delta(void* h, int n, const double* r3, const double* u3, int nsteps, const double* d, const double* unew3,
+                            double* out) {
+  Problem& P = *static_cast<Problem*>(h);
+  try {
+    for (int i = 0; i < n; i++) {
+      double* o = out + static_cast<size_t>(i) * (nsteps + 1) * 8;
+      Particle p(Vec{r3[3 * i], r3[3 * i + 1], r3[3 * i + 2]}, make_direction(u3[3 * i], u3[3 * i + 1], u3[3 * i + 2]), 1., 1.);
+      Tracker trkr(&P.geo, p.r(), p.u());
+      walk_put(o, P.geo, trkr); o[7] = 1.;
+      for (int s = 1; s <= nsteps && !trkr.is_lost(); s++) {
+        o += 8;
+        const size_t k = static_cast<size_t>(i) * nsteps + (s - 1);
+        Boundary b(INF, -1, BC_NORMAL);
+        bool crossed_boundary = false;
+        trkr.move(d[k]);
+        trkr.get_current();
+        if (trkr.is_lost()) {
+          trkr.set_r(p.r());
+          trkr.get_current();
+          b = trkr.get_boundary_condition();
+          crossed_boundary = true;
+        }
+        o[3] = b.distance; o[4] = b.surface_index; o[5] = b.boundary_type; o[6] = b.token; o[7] = 1.;
+        if (crossed_boundary) {
+          if (b.boundary_type == BC_VACUUM) { o[0] = o[1] = -2.; break; }
+          if (b.boundary_type != BC_REFLECTIVE) throw std::runtime_error("Help me, how did I get here ?");
+          do_reflection(trkr, p, b);
+        } else {
+          p.move(d[k]);
+          if (s % 2 == 0) {
+            p.state.direction = make_direction(unew3[3 * k], unew3[3 * k + 1], unew3[3 * k + 2]);
+            trkr.set_u(p.u());
+          }
+        }
+        walk_put(o, P.geo, trkr);
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) { P.error = e.what(); return 1; }
+}
+
 // Source sampling: n particles with history ids continuing P.histories_counter
 int orc_sample_source(void* h, orc_bank* out) {
   Problem& P = *static_cast<Problem*>(h);

@@ -188,6 +188,43 @@ def _material_arrays(m, G, eb):
 
 NHIST_MG, NDRAW_MG = 8, 250
 
+# geometry walks: deck, bounding box of the ray origins, number of rays, steps per ray, mean flight of the delta walk
+GEOMETRY_CASES = (
+    ("c5g7_delta_collision.yaml", (-32.13, -32.13, -0.5), (32.13, 32.13, 0.5), 600, 60, 1.2),       # nested RectLattices
+    ("ref_sqr_c5g7_surface_tl.yaml", None, None, 600, 60, 1.2),                                       # reflective quarter core
+    ("Ua-1-1-CY.yaml", None, None, 300, 12, 2.0),                                                     # z-cylinder, vacuum
+    ("PUa-1-0-SL.yaml", None, None, 300, 12, 1.0),                                                    # slab
+    ("UD2O-2-1-SL.yaml", None, None, 300, 12, 3.0),
+    ("noise_oscillation.yaml", None, None, 300, 20, 2.0),
+)
+
+
+def geometry_text(deck: dict):
+    """The surfaces / cells / universes / root lines of the oracle's flat deck (oracle/deck.py), and the material ids."""
+    from . import deck as _deck
+    lines = _deck.deck_to_text(deck).splitlines()
+    a = next(i for i, l in enumerate(lines) if l.startswith("nsurf "))
+    b = next(i for i, l in enumerate(lines) if l.startswith("root "))
+    return "\n".join(lines[a:b + 1]) + "\n", np.asarray([int(m["id"]) for m in deck["materials"]], dtype=np.int32)
+
+
+def geometry_rays(deck: dict, low, hi, n, nsteps, mean_flight, seed):
+    """Seeded ray origins inside the source box of the deck (or the given box), isotropic directions with axis-aligned and
+    lattice-diagonal ones mixed in, exponential flight lengths and post-collision directions for the delta walk."""
+    rng = np.random.default_rng(seed)
+    if low is None:
+        sp = deck["sources"][0]["spatial"]
+        low, hi = (sp["low"], sp["hi"]) if sp["type"] == "box" else (np.asarray(sp["position"]) - 0.3, np.asarray(sp["position"]) + 0.3)
+    r = rng.uniform(low, hi, (n, 3))
+    u = rng.normal(size=(n, 3))
+    u[::11] = np.eye(3)[rng.integers(0, 2, len(u[::11]))] * rng.choice([-1., 1.], (len(u[::11]), 1))
+    u[5::13, 2] = 0.0                                   # in-plane flights of a 2D core
+    u[7::29] = np.array([1., 1., 0.]) * rng.choice([-1., 1.], (len(u[7::29]), 1))  # through lattice corners
+    r[3::31, 0] = np.round(r[3::31, 0] / 1.26) * 1.26  # born on a pin-cell (tile) boundary
+    d = rng.exponential(mean_flight, (n, nsteps))
+    unew = rng.normal(size=(n, nsteps, 3))
+    return np.ascontiguousarray(r), np.ascontiguousarray(u), np.ascontiguousarray(d), np.ascontiguousarray(unew)
+
 
 # ------------------------------------------------------------------------------------------------------ evaluation
 def evaluate(impl: str) -> dict:
@@ -257,6 +294,25 @@ def evaluate(impl: str) -> dict:
                 C.c_int(NDRAW_MG), _d(micro), _d(scat), _d(fis))
         assert rc == 0, f"mg nuclide probe failed for {name}: {rc}"
         out[f"mg_{name}_micro"], out[f"mg_{name}_scatter"], out[f"mg_{name}_fission"] = micro, scat, fis
+    # geometry: the Tracker walking the decks' CSG trees (surface-tracking and delta-tracking call sequences)
+    from . import deck as _deck
+    decks = os.path.join(os.path.dirname(_HERE), "tests", "decks")
+    for ci, (fname, low, hi, n, nsteps, flight) in enumerate(GEOMETRY_CASES):
+        deck = _deck.load_yaml(os.path.join(decks, fname))
+        r, u, d, unew = geometry_rays(deck, low, hi, n, nsteps, flight, 100 + ci)
+        ws, wd = np.zeros((n, nsteps + 1, 8)), np.zeros((n, nsteps + 1, 8))
+        if ref:
+            text, mids = geometry_text(deck)
+            assert L.ref_geometry_load(text.encode(), C.c_int(len(mids)), mids.ctypes.data_as(_PI)) == 0
+            assert L.ref_geometry_walk_surface(C.c_int(n), _d(r), _d(u), C.c_int(nsteps), _d(ws)) == 0
+            assert L.ref_geometry_walk_delta(C.c_int(n), _d(r), _d(u), C.c_int(nsteps), _d(d), _d(unew), _d(wd)) == 0
+        else:
+            o = api.Oracle(os.path.join(decks, fname))
+            assert L.orc_geometry_walk_surface(o.h, C.c_int(n), _d(r), _d(u), C.c_int(nsteps), _d(ws)) == 0, o._err()
+            assert L.orc_geometry_walk_delta(o.h, C.c_int(n), _d(r), _d(u), C.c_int(nsteps), _d(d), _d(unew), _d(wd)) == 0, o._err()
+            o.close()
+        name = fname.split(".")[0]
+        out[f"geo_{name}_surface_walk"], out[f"geo_{name}_delta_walk"] = ws, wd
     return out
 
 

@@ -4,11 +4,18 @@
  * its CMake), but a part of the hot path compiles from its own sources as they lie under /root/reference:
  *   surfaces     src/{x,y,z}plane.cpp, plane.cpp, {x,y,z}cylinder.cpp, cylinder.cpp, sphere.cpp, surface.cpp
  *   directions   include/utils/direction.hpp (Direction constructors, rotate_direction)
- *   RNG          include/utils/rng.hpp over the pcg32 engine (pcg header vendored by pyarrow, see ref_shim/pcg_random.hpp)
+ *   RNG          include/utils/rng.hpp, src/rng.cpp over the pcg32 engine (pcg header vendored by pyarrow, ref_shim/pcg_random.hpp)
  *   angles       src/mg_angle_distribution.cpp, src/legendre_distribution.cpp (sample_mu, linearize)
- * oracle/Makefile compiles those files in place (nothing is copied) together with this driver into
- * oracle/_ref/libabeille_ref.so.  tests/test_reference_pins.py compares the oracle's restatement with it bit for bit on
- * seeded inputs and keeps golden vectors generated from it (tests/golden/ref_pins.json) for machines without the reference.
+ *   nuclide      src/mg_nuclide.cpp (vector constructor, get_micro_xs, sample_scatter, sample_fission)
+ *   geometry     src/cell.cpp, universe.cpp, cell_universe.cpp, lattice.cpp, rect_lattice.cpp, hex_lattice.cpp, geometry.cpp,
+ *                particle.cpp and the header-only Tracker (include/simulation/tracker.hpp)
+ * oracle/Makefile (target `ref`) compiles those files in place (nothing is copied) together with this driver into
+ * oracle/_ref/libabeille_ref.so.  Stand-in headers under oracle/ref_shim/ replace what the reference's CMake downloads
+ * (yaml-cpp, PapillonNDL) and two reference headers that would drag the whole simulation layer in (utils/parser.hpp,
+ * plotting/slice_plot.hpp); each says what it stands in for.  Not built: the trackers' transport loops, Transporter::collision,
+ * tallies, power iteration (they need boost, HighFive, NDArray and PapillonNDL's majorant classes).
+ * oracle/ref_pins.py runs seeded cases through this library and through the oracle; tests/test_reference_pins.py compares
+ * them bit for bit and keeps the reference's outputs as tests/golden/ref_pins.npz for machines without the reference.
  */
 #include <geometry/surfaces/cylinder.hpp>
 #include <geometry/surfaces/plane.hpp>
@@ -19,9 +26,14 @@
 #include <geometry/surfaces/yplane.hpp>
 #include <geometry/surfaces/zcylinder.hpp>
 #include <geometry/surfaces/zplane.hpp>
+#include <geometry/cell_universe.hpp>
+#include <geometry/geometry.hpp>
+#include <geometry/rect_lattice.hpp>
 #include <materials/legendre_distribution.hpp>
 #include <materials/mg_angle_distribution.hpp>
 #include <materials/mg_nuclide.hpp>
+#include <plotting/plotter.hpp>
+#include <simulation/tracker.hpp>
 #include <utils/direction.hpp>
 #include <utils/error.hpp>
 #include <utils/rng.hpp>
@@ -29,7 +41,9 @@
 
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <vector>
 
@@ -49,6 +63,16 @@ std::vector<double> energy_bounds;
 bool chi_matrix = false;
 bool use_virtual_collisions = true;
 }  // namespace settings
+// src/parser.cpp and src/plotter.cpp (the whole simulation layer) are not built: the id -> index maps they own are defined
+// here, and the geometry is assembled by ref_geometry_load below
+std::map<uint32_t, size_t> surface_id_to_indx;
+std::map<uint32_t, size_t> cell_id_to_indx;
+std::map<uint32_t, size_t> universe_id_to_indx;
+void find_universe(const YAML::Node&, uint32_t) { throw std::runtime_error("YAML factory called in oracle/_ref"); }
+namespace plotter {
+std::map<uint32_t, Pixel> cell_id_to_color;
+std::map<uint32_t, Pixel> material_id_to_color;
+}  // namespace plotter
 // src/nuclide.cpp is one line of data definitions behind the same heavy includes
 std::map<uint32_t, std::shared_ptr<Nuclide>> nuclides;
 std::unordered_set<uint32_t> zaids_with_urr;
@@ -218,6 +242,267 @@ int ref_mg_nuclide(int G, const double* ebounds, const double* Et, const double*
     return 0;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "ref_mg_nuclide: %s\n", e.what());
+    return 1;
+  }
+}
+
+}  // extern "C"
+
+// ---- geometry: the reference's Surface / Cell / CellUniverse / RectLattice objects and its Tracker -----------------------
+namespace {
+struct CellDef { uint32_t id; bool fill_universe; uint32_t fill; std::string region; };
+struct UniDef {
+  uint32_t id; bool lattice; std::vector<uint32_t> cells;
+  uint32_t shape[3]; double pitch[3], origin[3]; int32_t outer; std::vector<int32_t> tiles;
+};
+struct GeoDeck {
+  std::vector<CellDef> cells;
+  std::vector<UniDef> unis;
+  std::map<uint32_t, std::shared_ptr<Material>> materials;  // empty Material objects: the cursor only hands the pointer back
+  std::map<const Material*, int> material_index;
+} deck;
+
+// what make_universe / find_universe / make_cell_universe / make_rect_lattice do with a YAML node (src/parser.cpp:295-339,
+// src/cell_universe.cpp:292-341, src/rect_lattice.cpp:312-424), from the parsed records: same recursion, same order of
+// geometry::universes
+void need_universe(uint32_t id);
+void build_universe(const UniDef& d) {
+  if (universe_id_to_indx.count(d.id)) return;
+  if (!d.lattice) {
+    std::vector<uint32_t> cells;
+    for (uint32_t cid : d.cells) {
+      if (!cell_id_to_indx.count(cid)) throw std::runtime_error("Referenced cell id could not be found.");
+      cells.push_back(static_cast<uint32_t>(cell_id_to_indx[cid]));
+    }
+    universe_id_to_indx[d.id] = geometry::universes.size();
+    geometry::universes.push_back(std::make_shared<CellUniverse>(cells, d.id, ""));
+    return;
+  }
+  std::vector<int32_t> uni_indicies;
+  for (int32_t u_id : d.tiles) {
+    if (u_id == -1) { uni_indicies.push_back(u_id); continue; }
+    need_universe(static_cast<uint32_t>(u_id));
+    uni_indicies.push_back(static_cast<int32_t>(universe_id_to_indx[static_cast<uint32_t>(u_id)]));
+  }
+  std::shared_ptr<Lattice> lat = std::make_shared<RectLattice>(d.shape[0], d.shape[1], d.shape[2], d.pitch[0], d.pitch[1],
+                                                               d.pitch[2], d.origin[0], d.origin[1], d.origin[2], d.id, "");
+  lat->set_elements(uni_indicies);
+  if (d.outer != -1) {
+    need_universe(static_cast<uint32_t>(d.outer));
+    lat->set_outisde_universe(static_cast<int32_t>(universe_id_to_indx[static_cast<uint32_t>(d.outer)]));
+  }
+  universe_id_to_indx[d.id] = geometry::universes.size();
+  geometry::universes.push_back(lat);
+}
+void need_universe(uint32_t id) {
+  if (universe_id_to_indx.count(id)) return;
+  for (const auto& d : deck.unis)
+    if (d.id == id) { build_universe(d); return; }
+  throw std::runtime_error("Could not find universe.");
+}
+
+// the tokeniser of make_cell (src/cell.cpp:311-357), then the reference's own infix_to_rpn and Cell constructors
+void build_cell(const CellDef& c) {
+  std::vector<int32_t> region;
+  std::string temp;
+  auto flush = [&]() {
+    if (temp.empty()) return;
+    const int32_t signed_id = std::stoi(temp);
+    int32_t indx = static_cast<int32_t>(surface_id_to_indx.at(static_cast<uint32_t>(std::abs(signed_id)))) + 1;
+    if (signed_id < 0) indx *= -1;
+    region.push_back(indx);
+    temp.clear();
+  };
+  for (char ch : c.region) {
+    if (ch == '&' || ch == '(' || ch == ')' || ch == 'U' || ch == '~') {
+      flush();
+      region.push_back(ch == '&' ? OP::INTR : ch == '(' ? OP::L_PAR : ch == ')' ? OP::R_PAR : ch == 'U' ? OP::UNIN : OP::COMP);
+    } else if (ch == '+' || ch == '-' || (ch >= '0' && ch <= '9')) {
+      temp += ch;
+    } else if (ch != ' ') {
+      throw std::runtime_error("Invalid character in cell region definition.");
+    }
+  }
+  flush();
+  region = infix_to_rpn(region);
+  std::shared_ptr<Cell> cell;
+  if (!c.fill_universe) {
+    cell = std::make_shared<Cell>(region, deck.materials.at(c.fill), c.id, "");
+  } else {
+    need_universe(c.fill);
+    cell = std::make_shared<Cell>(region, geometry::universes[universe_id_to_indx[c.fill]], c.id, "");
+  }
+  cell_id_to_indx[c.id] = geometry::cells.size();
+  geometry::cells.push_back(cell);
+}
+
+std::unique_ptr<Surface> make_bc(int type, const double* p, BoundaryType b, uint32_t id) {
+  switch (type) {
+    case 0: return std::make_unique<XPlane>(p[0], b, id, "");
+    case 1: return std::make_unique<YPlane>(p[0], b, id, "");
+    case 2: return std::make_unique<ZPlane>(p[0], b, id, "");
+    case 3: return std::make_unique<Plane>(p[0], p[1], p[2], p[3], b, id, "");
+    case 4: return std::make_unique<XCylinder>(p[0], p[1], p[2], b, id, "");
+    case 5: return std::make_unique<YCylinder>(p[0], p[1], p[2], b, id, "");
+    case 6: return std::make_unique<ZCylinder>(p[0], p[1], p[2], b, id, "");
+    case 7: return std::make_unique<Cylinder>(p[0], p[1], p[2], p[3], p[4], p[5], p[6], b, id, "");
+    default: return std::make_unique<Sphere>(p[0], p[1], p[2], p[3], b, id, "");
+  }
+}
+
+inline void put(double* o, Tracker& t) {
+  o[0] = t.is_lost() ? -1. : static_cast<double>(t.cell()->id());
+  o[1] = t.is_lost() || !t.material() ? -1. : static_cast<double>(deck.material_index.at(t.material()));
+  o[2] = 0.;  // (cell instances are not on the multigroup hot path; the oracle does not restate them)
+}
+}  // namespace
+
+extern "C" {
+
+// The geometry section of the oracle's flat deck text (oracle/deck.py: "nmat"-independent lines nsurf ... root), i.e. the
+// surfaces, cells, universes and root-universe entries of the YAML deck, assembled in the order make_geometry
+// (src/parser.cpp:178-246) assembles them.  material ids are listed so that cells can be handed (empty) Material objects.
+int ref_geometry_load(const char* text, int nmat, const int* material_ids) {
+  try {
+    geometry::surfaces.clear(); geometry::cells.clear(); geometry::universes.clear(); geometry::root_universe = nullptr;
+    surface_id_to_indx.clear(); cell_id_to_indx.clear(); universe_id_to_indx.clear();
+    deck = GeoDeck();
+    for (int m = 0; m < nmat; m++) {
+      auto mat = std::make_shared<Material>();
+      deck.materials[static_cast<uint32_t>(material_ids[m])] = mat;
+      deck.material_index[mat.get()] = m;
+    }
+    static const std::map<std::string, int> types = {{"xplane", 0}, {"yplane", 1}, {"zplane", 2}, {"plane", 3}, {"xcylinder", 4},
+                                                     {"ycylinder", 5}, {"zcylinder", 6}, {"cylinder", 7}, {"sphere", 8}};
+    std::istringstream in(text);
+    std::string key;
+    uint32_t root = 0;
+    while (in >> key) {
+      if (key == "nsurf" || key == "ncell" || key == "nuni") { int n; in >> n; continue; }
+      if (key == "surf") {
+        uint32_t id; std::string type, bc; int np; double p[7] = {0, 0, 0, 0, 0, 0, 0};
+        in >> id >> type >> bc >> np;
+        for (int k = 0; k < np; k++) in >> p[k];
+        const BoundaryType b = bc == "vacuum" ? BoundaryType::Vacuum : bc == "reflective" ? BoundaryType::Reflective : BoundaryType::Normal;
+        surface_id_to_indx[id] = geometry::surfaces.size();
+        geometry::surfaces.push_back(make_bc(types.at(type), p, b, id));
+      } else if (key == "cell") {
+        CellDef c; std::string kind;
+        in >> c.id >> kind >> c.fill >> c.region;
+        c.fill_universe = kind == "u";
+        deck.cells.push_back(c);
+      } else if (key == "uni") {
+        UniDef u; std::string kind;
+        in >> u.id >> kind;
+        u.lattice = kind == "rect";
+        if (!u.lattice) {
+          size_t n; in >> n; u.cells.resize(n);
+          for (auto& c : u.cells) in >> c;
+        } else {
+          size_t n;
+          in >> u.shape[0] >> u.shape[1] >> u.shape[2] >> u.pitch[0] >> u.pitch[1] >> u.pitch[2] >> u.origin[0] >> u.origin[1] >>
+              u.origin[2] >> u.outer >> n;
+          u.tiles.resize(n);
+          for (auto& t : u.tiles) in >> t;
+        }
+        deck.unis.push_back(u);
+      } else if (key == "root") {
+        in >> root;
+      } else {
+        throw std::runtime_error("unknown key " + key);
+      }
+    }
+    for (const auto& c : deck.cells) build_cell(c);
+    for (const auto& u : deck.unis) build_universe(u);
+    for (auto& uni : geometry::universes) uni->make_offset_map();
+    geometry::root_universe = geometry::universes[universe_id_to_indx.at(root)];
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "ref_geometry_load: %s\n", e.what());
+    return 1;
+  }
+}
+
+// Surface-tracking walk of n rays through the loaded geometry, the geometry calls of SurfaceTracker::transport
+// (src/surface_tracker.cpp:60-140) without physics: Tracker(r, u); then up to nsteps times get_nearest_boundary() and
+// Vacuum -> stop / Reflective -> Tracker::do_reflection / Normal -> cross_surface + get_current.
+// out[ray][step][8] = cell id, material index, 0 (after the step; step 0 = at birth), boundary distance,
+// surface index, boundary type, token, 1 (row written).  A lost ray ends its walk.
+int ref_geometry_walk_surface(int n, const double* r3, const double* u3, int nsteps, double* out) {
+  try {
+    for (int i = 0; i < n; i++) {
+      double* o = out + static_cast<size_t>(i) * (nsteps + 1) * 8;
+      Particle p(Position(r3[3 * i], r3[3 * i + 1], r3[3 * i + 2]), Direction(u3[3 * i], u3[3 * i + 1], u3[3 * i + 2]), 1., 1.);
+      Tracker trkr(p.r(), p.u());
+      put(o, trkr); o[7] = 1.;
+      for (int s = 1; s <= nsteps && !trkr.is_lost(); s++) {
+        o += 8;
+        const Boundary b = trkr.get_nearest_boundary();
+        o[3] = b.distance; o[4] = b.surface_index; o[5] = static_cast<double>(static_cast<int>(b.boundary_type)); o[6] = b.token;
+        o[7] = 1.;
+        if (b.boundary_type == BoundaryType::Vacuum) { o[0] = o[1] = -2.; break; }
+        if (b.boundary_type == BoundaryType::Reflective) {
+          trkr.do_reflection(p, b);
+        } else {
+          trkr.cross_surface(b);
+          trkr.get_current();
+          p.move(b.distance);
+        }
+        put(o, trkr);
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "ref_geometry_walk_surface: %s\n", e.what());
+    return 1;
+  }
+}
+
+// Delta-tracking walk, the geometry calls of DeltaTracker::transport (src/delta_tracker.cpp:113-160) without physics:
+// Tracker(r, u); per step move(d[ray][step]) + get_current(); when that loses the particle, set_r(back) + get_current() +
+// get_boundary_condition(), then Vacuum -> stop / Reflective -> Tracker::do_reflection.  Every second completed flight is
+// followed by a direction change to unew[ray][step] (set_u), as after a collision.  Row layout as in the surface walk; the
+// boundary columns are INF, -1, Normal, 0 for a flight that stayed inside.
+int ref_geometry_walk_delta(int n, const double* r3, const double* u3, int nsteps, const double* d, const double* unew3,
+                            double* out) {
+  try {
+    for (int i = 0; i < n; i++) {
+      double* o = out + static_cast<size_t>(i) * (nsteps + 1) * 8;
+      Particle p(Position(r3[3 * i], r3[3 * i + 1], r3[3 * i + 2]), Direction(u3[3 * i], u3[3 * i + 1], u3[3 * i + 2]), 1., 1.);
+      Tracker trkr(p.r(), p.u());
+      put(o, trkr); o[7] = 1.;
+      for (int s = 1; s <= nsteps && !trkr.is_lost(); s++) {
+        o += 8;
+        const size_t k = static_cast<size_t>(i) * nsteps + (s - 1);
+        Boundary b(INF, -1, BoundaryType::Normal);
+        bool crossed_boundary = false;
+        trkr.move(d[k]);
+        trkr.get_current();
+        if (trkr.is_lost()) {
+          trkr.set_r(p.r());
+          trkr.get_current();
+          b = trkr.get_boundary_condition();
+          crossed_boundary = true;
+        }
+        o[3] = b.distance; o[4] = b.surface_index; o[5] = static_cast<double>(static_cast<int>(b.boundary_type)); o[6] = b.token;
+        o[7] = 1.;
+        if (crossed_boundary) {
+          if (b.boundary_type == BoundaryType::Vacuum) { o[0] = o[1] = -2.; break; }
+          if (b.boundary_type != BoundaryType::Reflective) throw std::runtime_error("Help me, how did I get here ?");
+          trkr.do_reflection(p, b);
+        } else {
+          p.move(d[k]);
+          if (s % 2 == 0) {
+            p.set_direction(Direction(unew3[3 * k], unew3[3 * k + 1], unew3[3 * k + 2]));
+            trkr.set_u(p.u());
+          }
+        }
+        put(o, trkr);
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "ref_geometry_walk_delta: %s\n", e.what());
     return 1;
   }
 }
