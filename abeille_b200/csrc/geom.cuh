@@ -26,6 +26,11 @@ struct V3 {
   double x, y, z;
 };
 __device__ __forceinline__ double dot3(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// Migration-area score of a leak, `p.wgt() * (r_leak - r_birth) * (r_leak - r_birth)` (src/delta_tracker.cpp:236-238,
+// surface_tracker.cpp:91-92): C++ groups it as (w * d) . d -- the weight scales the vector first -- not w * (d . d).
+__device__ __forceinline__ double leak_mig_score(double w, const V3& d) {
+  return (d.x * w) * d.x + (d.y * w) * d.y + (d.z * w) * d.z;
+}
 template <class M = InlineMath>
 __device__ __forceinline__ double norm3(const V3& a) { return M::sqrt_(a.x * a.x + a.y * a.y + a.z * a.z); }
 // Direction constructors renormalise every time (include/utils/direction.hpp:37-43)

@@ -702,7 +702,7 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
               const V3 d{h.r.x + sb.distance * h.u.x - S.rb[0][c.t], h.r.y + sb.distance * h.u.y - S.rb[1][c.t],
                          h.r.z + sb.distance * h.u.z - S.rb[2][c.t]};
               atomicAdd(&S.leak, h.w);
-              atomicAdd(&S.leak_mig, h.w * dot3(d, d));
+              atomicAdd(&S.leak_mig, leak_mig_score(h.w, d));
             } else if (sb.btype == ABL_BC_REFLECTIVE) {
               if (sb.surface_index < 0) {
                 raise_error(A, ABL_ERR_LOST, A.bank.id_a[h.idx]);
@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(HK_THREADS, 1) history_kernel(const DevProblem
             const V3 d{h.r.x + bound.distance * h.u.x - S.rb[0][c.t], h.r.y + bound.distance * h.u.y - S.rb[1][c.t],
                        h.r.z + bound.distance * h.u.z - S.rb[2][c.t]};
             atomicAdd(&S.leak, h.w);
-            atomicAdd(&S.leak_mig, h.w * dot3(d, d));
+            atomicAdd(&S.leak_mig, leak_mig_score(h.w, d));
           }
           phase = PH_FLIGHT;
         } else if (bound.btype == ABL_BC_REFLECTIVE && bound.surface_index >= 0) {

@@ -302,7 +302,7 @@ __device__ __forceinline__ void leak(Hist& h, Acc& acc, const Boundary& b) {
   h.alive = false;
   acc.leak += h.w;
   const V3 d{h.r.x + b.distance * h.u.x - h.rb.x, h.r.y + b.distance * h.u.y - h.rb.y, h.r.z + b.distance * h.u.z - h.rb.z};
-  acc.mig += h.w * dot3(d, d);
+  acc.mig += leak_mig_score(h.w, d);
 }
 
 __device__ __forceinline__ void score_flight_all(const DevProblem& P, const RunArgs& A, const Hist& h, double d, Acc& acc) {

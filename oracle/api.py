@@ -91,6 +91,10 @@ def set_math(mode: str) -> None:
     lib().orc_set_math(C.c_int(0 if mode == "libm" else 1))
 
 
+def get_math() -> str:
+    return "libm" if int(lib().orc_get_math()) == 0 else "det"
+
+
 def set_threads(n: int) -> None:
     lib().orc_set_threads(C.c_int(int(n)))
 

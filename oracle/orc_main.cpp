@@ -672,7 +672,11 @@ static void leak(Ctx& cx, Particle& p, const Boundary& bound) {
   p.kill();
   cx.ts.leakage += p.wgt();
   Vec r_leak = p.r() + bound.distance * p.u();
-  cx.ts.mig += p.wgt() * ((r_leak - p.r_birth).dot(r_leak - p.r_birth));
+  // `p.wgt() * (r_leak - r_birth) * (r_leak - r_birth)` groups as (w * d) . d (position.hpp:80-96), not w * (d . d):
+  // found by running the reference's own transport() next to this one (tests/test_reference_pins.py)
+  const Vec d = r_leak - p.r_birth;
+  const Vec wd{d.x * p.wgt(), d.y * p.wgt(), d.z * p.wgt()};
+  cx.ts.mig += wd.dot(d);
 }
 
 static void try_resurrect(Ctx& cx, Particle& p, Tracker& trkr, Mat& mat) {
@@ -1214,7 +1218,10 @@ struct orc_bank {  // SoA view of a particle / fission bank, all arrays length n
 
 const char* orc_last_error(void* h) { return static_cast<Problem*>(h)->error.c_str(); }
 
+static int g_math_mode = 0;
+int orc_get_math() { return g_math_mode; }
 void orc_set_math(int mode) {
+  g_math_mode = mode == 0 ? 0 : 1;
   if (mode == 0) g_math = {libm_log, libm_sin, libm_cos};
   else g_math = {orc_log, orc_sin, orc_cos};
 }

@@ -10,6 +10,7 @@ machines without /root/reference (the GPU box).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 import subprocess
@@ -46,6 +47,24 @@ def ref_lib():
 
 def _d(a):
     return a.ctypes.data_as(_PD)
+
+
+@contextlib.contextmanager
+def _reference_math(impl):
+    """The reference calls glibc's log / sin / cos; the oracle is compared with it in its "libm" math mode and on one thread
+    (score sums in bank order).  Its "det" mode (the operation sequence shared with the CUDA kernels) differs from glibc by
+    an ulp on a fraction of the arguments, which tests/test_oracle.py quantifies."""
+    if impl == "reference":
+        yield
+        return
+    mode = api.get_math()
+    api.set_math("libm")
+    api.set_threads(1)
+    try:
+        yield
+    finally:
+        api.set_math(mode)
+        api.set_threads(api.max_threads())
 
 
 # ---------------------------------------------------------------------------------------------------------- cases
@@ -226,9 +245,45 @@ def geometry_rays(deck: dict, low, hi, n, nsteps, mean_flight, seed):
     return np.ascontiguousarray(r), np.ascontiguousarray(u), np.ascontiguousarray(d), np.ascontiguousarray(unew)
 
 
+# whole transport() calls: deck, particles, k_col of the previous generation
+TRANSPORT_CASES = (
+    ("PUa-1-0-IN.yaml", 1000, 1.0), ("PUa-1-0-SL.yaml", 1000, 0.97), ("PUa-1-1-SL.yaml", 1000, 1.0), ("PUa-1-2-SL.yaml", 1000, 1.02),
+    ("PUb-1-0-IN.yaml", 1000, 1.0), ("PUb-1-0-SL.yaml", 1000, 1.0), ("UD2O-2-1-SL.yaml", 1000, 1.01), ("Ua-1-1-CY.yaml", 1000, 0.99),
+    ("Ua-1-1-IN.yaml", 1000, 1.0),
+    ("c5g7_delta_collision.yaml", 2500, 1.17), ("c5g7_carter_cancel.yaml", 2500, 1.17), ("c5g7_surface_tracklength.yaml", 1500, 1.17),
+    ("c5g7_delta_tracklength.yaml", 1500, 1.17), ("ref_sqr_c5g7_surface_tl.yaml", 1500, 1.1),
+)
+
+
+def transport_bank(deck: dict, n: int, seed: int, negative: bool):
+    """A seeded bank inside the deck's source region: unit directions, the source energy, weights in [0.3, 1.7] (a tenth of
+    them negative for the carter deck, as after an under-estimated majorant), history ids with gaps."""
+    rng = np.random.default_rng(seed)
+    src = deck["sources"][0]
+    sp = src["spatial"]
+    low, hi = (sp["low"], sp["hi"]) if sp["type"] == "box" else (np.asarray(sp["position"]) - 0.25, np.asarray(sp["position"]) + 0.25)
+    r = rng.uniform(low, hi, (n, 3))
+    u = rng.normal(size=(n, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    G = int(deck["settings"]["ngroups"])
+    eb = np.asarray(deck["settings"]["energy-bounds"], dtype=np.float64)
+    g = rng.integers(0, G, n)
+    E = 0.5 * (eb[g] + eb[g + 1])  # particles of every group, at the group mid-point as the samplers leave them
+    w = rng.uniform(0.3, 1.7, n)
+    if negative:
+        w[::10] *= -1.0
+    hid = (np.arange(n, dtype=np.uint64) * np.uint64(3) + np.uint64(11))
+    return np.ascontiguousarray(r), np.ascontiguousarray(u), E, w, hid
+
+
 # ------------------------------------------------------------------------------------------------------ evaluation
 def evaluate(impl: str) -> dict:
     """Run every case through `impl` ("reference": oracle/_ref, "oracle": the restatement)."""
+    with _reference_math(impl):
+        return _evaluate(impl)
+
+
+def _evaluate(impl: str) -> dict:
     ref = impl == "reference"
     L = ref_lib() if ref else api.lib()
     out = {}
@@ -318,6 +373,11 @@ def evaluate(impl: str) -> dict:
 
 def sample_mu(impl: str, tables: dict) -> dict:
     """sample_mu over the given (golden) tables: 500 draws of three histories per Legendre case."""
+    with _reference_math(impl):
+        return _sample_mu(impl, tables)
+
+
+def _sample_mu(impl: str, tables: dict) -> dict:
     ref = impl == "reference"
     L = ref_lib() if ref else api.lib()
     smp = L.ref_sample_mu if ref else L.orc_sample_mu_probe
@@ -329,4 +389,45 @@ def sample_mu(impl: str, tables: dict) -> dict:
             smp(_d(mu_t), _d(pdf_t), _d(cdf_t), C.c_int(len(mu_t)), C.c_uint64(SEED), C.c_uint64(STRIDE), C.c_uint64(hid),
                 C.c_int(500), _d(v))
             out[f"sample_mu_{k}_{hid}"] = v
+    return out
+
+
+def evaluate_transport(impl: str) -> dict:
+    """One Transporter::transport(bank) per case through the reference's own SurfaceTracker / DeltaTracker / CarterTracker
+    (oracle/_ref, one OpenMP thread) or the oracle (glibc math, one thread): the fission bank in the order it is returned
+    (9 doubles and parent history id, daughter id, family id per site) and the six generation values of
+    Tallies::calc_gen_values (k_col, k_abs, k_trk, k_tot, leakage, migration area)."""
+    from . import deck as _deck
+    ref = impl == "reference"
+    L = ref_lib() if ref else api.lib()
+    decks = os.path.join(os.path.dirname(_HERE), "tests", "decks")
+    PU = C.POINTER(C.c_uint64)
+    out = {}
+    with _reference_math(impl):
+        for ci, (fname, n, k_col) in enumerate(TRANSPORT_CASES):
+            path = os.path.join(decks, fname)
+            ov = {"settings": {"nparticles": n}}
+            deck = _deck.apply_overrides(_deck.load_yaml(path), ov)
+            r, u, E, w, hid = transport_bank(deck, n, 500 + ci, "carter" in fname)
+            name = fname.split(".")[0]
+            if ref:
+                assert L.ref_problem_load(_deck.deck_to_text(deck).encode()) == 0
+                cap = 16 * n
+                f9, ids, nout, k6 = np.zeros((cap, 9)), np.zeros((cap, 3), dtype=np.uint64), C.c_uint64(0), np.zeros(6)
+                rc = L.ref_transport(C.c_uint64(n), _d(r), _d(u), _d(E), _d(w), hid.ctypes.data_as(PU), hid.ctypes.data_as(PU),
+                                     C.c_double(k_col), C.c_uint64(cap), _d(f9), ids.ctypes.data_as(PU), C.byref(nout), _d(k6))
+                assert rc == 0 and nout.value <= cap
+                f9, ids = f9[:nout.value].copy(), ids[:nout.value].copy()
+            else:
+                o = api.Oracle(path, ov)
+                bank = {k: np.ascontiguousarray(v) for k, v in zip(("x", "y", "z"), r.T)}
+                bank.update({k: np.ascontiguousarray(v) for k, v in zip(("ux", "uy", "uz"), u.T)})
+                bank.update(E=E, wgt=w, wgt2=np.zeros(n), id_a=hid, id_b=hid.copy(), id_c=None)
+                o.set_kcol(k_col)
+                fb, scores, m = o.transport(bank, False, capacity=16 * n)
+                f9 = np.ascontiguousarray(np.stack([fb[k] for k in api.BANK_F64], 1))
+                ids = np.ascontiguousarray(np.stack([fb["id_a"], fb["id_b"], fb["id_c"]], 1))
+                k6 = scores / float(n)
+                o.close()
+            out[f"transport_{name}_sites"], out[f"transport_{name}_ids"], out[f"transport_{name}_k"] = f9, ids, k6
     return out

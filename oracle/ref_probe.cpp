@@ -9,11 +9,17 @@
  *   nuclide      src/mg_nuclide.cpp (vector constructor, get_micro_xs, sample_scatter, sample_fission)
  *   geometry     src/cell.cpp, universe.cpp, cell_universe.cpp, lattice.cpp, rect_lattice.cpp, hex_lattice.cpp, geometry.cpp,
  *                particle.cpp and the header-only Tracker (include/simulation/tracker.hpp)
+ *   transport    src/surface_tracker.cpp, delta_tracker.cpp, carter_tracker.cpp, transporter.cpp, material_helper.cpp,
+ *                tallies.cpp, mesh_tally.cpp, collision_mesh_tally.cpp, track_length_mesh_tally.cpp, source_mesh_tally.cpp,
+ *                noise_maker.cpp and the two noise sources, mpi.cpp (no-MPI build), output.cpp, header.cpp, logo.cpp:
+ *                ref_transport runs the reference's own Transporter::transport on a bank
  * oracle/Makefile (target `ref`) compiles those files in place (nothing is copied) together with this driver into
  * oracle/_ref/libabeille_ref.so.  Stand-in headers under oracle/ref_shim/ replace what the reference's CMake downloads
- * (yaml-cpp, PapillonNDL) and two reference headers that would drag the whole simulation layer in (utils/parser.hpp,
- * plotting/slice_plot.hpp); each says what it stands in for.  Not built: the trackers' transport loops, Transporter::collision,
- * tallies, power iteration (they need boost, HighFive, NDArray and PapillonNDL's majorant classes).
+ * (yaml-cpp, PapillonNDL, Boost.Unordered, HighFive, NDArray) and two reference headers that would drag the plotter and the
+ * YAML parser in (utils/parser.hpp, plotting/slice_plot.hpp); each says what it stands in for and why it cannot change a
+ * result.  Restated in this file because their translation units cannot be compiled: the multigroup branch of
+ * make_majorant_xs (src/majorant.cpp:131-176), the settings globals (src/settings.cpp) and the assembly of materials and
+ * geometry from a deck (the YAML factory functions).  Not covered: PowerIterator / Noise drivers, cancelators, entropy.
  * oracle/ref_pins.py runs seeded cases through this library and through the oracle; tests/test_reference_pins.py compares
  * them bit for bit and keeps the reference's outputs as tests/golden/ref_pins.npz for machines without the reference.
  */
@@ -33,11 +39,19 @@
 #include <materials/mg_angle_distribution.hpp>
 #include <materials/mg_nuclide.hpp>
 #include <plotting/plotter.hpp>
+#include <simulation/carter_tracker.hpp>
+#include <simulation/delta_tracker.hpp>
+#include <simulation/surface_tracker.hpp>
 #include <simulation/tracker.hpp>
 #include <utils/direction.hpp>
 #include <utils/error.hpp>
+#include <utils/majorant.hpp>
+#include <utils/mpi.hpp>
+#include <utils/output.hpp>
 #include <utils/rng.hpp>
 #include <utils/settings.hpp>
+
+#include <omp.h>
 
 #include <cstdio>
 #include <cstring>
@@ -56,10 +70,39 @@ void warning(std::string mssg, std::source_location) { std::fprintf(stderr, "ref
 // src/settings.cpp needs HighFive (utils/output.hpp); the driver defines the few settings the multigroup sources read,
 // with the declarations of include/utils/settings.hpp
 namespace settings {
+int nparticles = 100000;
+int ngenerations = 120;
+int nignored = 20;
+int nskip = 10;
 uint32_t ngroups = 0;
+int n_cancel_noise_gens = INT32_MAX;
+bool plotting_mode = false;
+double min_energy = 0.;
+double max_energy = 100000.;
 SimulationMode mode = SimulationMode::K_EIGENVALUE;
+TrackingMode tracking = TrackingMode::SURFACE_TRACKING;
+EnergyMode energy_mode = EnergyMode::MG;
+uint64_t rng_seed = 19073486328125;
+uint64_t rng_stride = 152917;
 pcg32 rng;
+double wgt_cutoff = 0.25;
+double wgt_survival = 1.0;
+double wgt_split = 2.0;
+double w_noise = -1.;
+double eta = 1.;
+double keff = 1.;
+bool use_urr_ptables = false;  // src/parser.cpp switches the tables off in multigroup mode
+bool converged = false;
+bool regional_cancellation = false;
+bool regional_cancellation_noise = false;
+bool inner_generations = true;
+bool normalize_noise_source = true;
+bool rng_stride_warnings = false;
+bool branchless_splitting = false;
+bool branchless_combing = false;
+bool branchless_material = true;
 std::vector<double> energy_bounds;
+std::vector<double> sample_xs_ratio;
 bool chi_matrix = false;
 bool use_virtual_collisions = true;
 }  // namespace settings
@@ -73,6 +116,36 @@ namespace plotter {
 std::map<uint32_t, Pixel> cell_id_to_color;
 std::map<uint32_t, Pixel> material_id_to_color;
 }  // namespace plotter
+// src/material.cpp needs the plotter and HighFive; the material table it owns is defined here
+std::map<uint32_t, std::shared_ptr<Material>> materials;
+
+// src/majorant.cpp cannot be compiled (its continuous-energy branch needs PapillonNDL's thermal-scattering classes).
+// This is a restatement of its MULTIGROUP branch (src/majorant.cpp:131-176), statement for statement.
+std::pair<std::vector<double>, std::vector<double>> make_majorant_xs() {
+  std::vector<double> egrid;
+  egrid.push_back(settings::energy_bounds[0]);
+  if (egrid.front() == 0.) egrid.front() = 1.E-11;
+  for (size_t i = 1; i < settings::energy_bounds.size() - 1; i++) {
+    egrid.push_back(settings::energy_bounds[i]);
+    egrid.push_back(settings::energy_bounds[i]);
+  }
+  egrid.push_back(settings::energy_bounds.back());
+  std::vector<double> maj_xs(egrid.size(), 0.);
+  for (const auto& material : materials) {
+    MaterialHelper mat(material.second.get(), 1.);
+    for (uint32_t g = 0; g < settings::ngroups; g++) {
+      size_t i = g * 2;
+      double Eg = 0.5 * (egrid[i] + egrid[i + 1]);
+      double xs = mat.Et(Eg);
+      if (xs > maj_xs[i]) {
+        maj_xs[i] = xs;
+        maj_xs[i + 1] = xs;
+      }
+    }
+  }
+  return {egrid, maj_xs};
+}
+
 // src/nuclide.cpp is one line of data definitions behind the same heavy includes
 std::map<uint32_t, std::shared_ptr<Nuclide>> nuclides;
 std::unordered_set<uint32_t> zaids_with_urr;
@@ -372,6 +445,10 @@ int ref_geometry_load(const char* text, int nmat, const int* material_ids) {
       deck.materials[static_cast<uint32_t>(material_ids[m])] = mat;
       deck.material_index[mat.get()] = m;
     }
+    if (nmat < 0) {  // called by ref_problem_load: the cells get the real materials
+      int m = 0;
+      for (const auto& kv : materials) { deck.materials[kv.first] = kv.second; deck.material_index[kv.second.get()] = m++; }
+    }
     static const std::map<std::string, int> types = {{"xplane", 0}, {"yplane", 1}, {"zplane", 2}, {"plane", 3}, {"xcylinder", 4},
                                                      {"ycylinder", 5}, {"zcylinder", 6}, {"cylinder", 7}, {"sphere", 8}};
     std::istringstream in(text);
@@ -503,6 +580,188 @@ int ref_geometry_walk_delta(int n, const double* r3, const double* u3, int nstep
     return 0;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "ref_geometry_walk_delta: %s\n", e.what());
+    return 1;
+  }
+}
+
+}  // extern "C"
+
+// ---- the whole hot path: the reference's SurfaceTracker / DeltaTracker / CarterTracker::transport ------------------------
+namespace {
+struct Tok {
+  std::istringstream in;
+  explicit Tok(const char* t) : in(t) {}
+  std::string next() { std::string s; if (!(in >> s)) throw std::runtime_error("deck: unexpected end"); return s; }
+  void expect(const char* k) { const std::string s = next(); if (s != k) throw std::runtime_error("deck: expected " + std::string(k) + ", got " + s); }
+  double d() { return std::stod(next()); }
+  long long ll() { return std::stoll(next()); }
+  std::vector<double> dv(size_t n) { std::vector<double> v(n); for (auto& x : v) x = d(); return v; }
+};
+// A bank direction bit for bit: in the reference a particle's direction is a copy of the Direction object the source or the
+// fission sampler made (src/power_iterator.cpp: Particle(p.r, p.u, ...)), never normalised a second time, and Direction has
+// no constructor that skips the normalisation.
+static_assert(sizeof(Direction) == 3 * sizeof(double), "Direction is three doubles");
+Direction raw_direction(const double* u) {
+  Direction d;
+  std::memcpy(static_cast<void*>(&d), u, sizeof(Direction));
+  return d;
+}
+std::shared_ptr<Tallies> g_tallies;
+std::shared_ptr<Transporter> g_transporter;
+}  // namespace
+
+extern "C" {
+
+// Loads the oracle's flat deck text (oracle/deck.py) up to the root universe: settings, materials (MGNuclide through its
+// vector constructor, with the fissile gate and the chi-row replication of make_mg_nuclide, src/mg_nuclide.cpp:716-852;
+// Material() + add_component({1., nuclide}) as Material(nuc, id) does, src/material.cpp:51-63), geometry (as
+// ref_geometry_load), then Tallies(nparticles) and the tracker the deck names.
+int ref_problem_load(const char* text) {
+  try {
+    Output::set_output_filename("/nonexistent-dir/oracle_ref.h5");  // never opened: HighFive is a stand-in
+    Tok tk(text);
+    tk.expect("ORCDECK"); tk.ll();
+    tk.expect("mode");
+    settings::mode = tk.next() == "noise" ? settings::SimulationMode::NOISE : settings::SimulationMode::K_EIGENVALUE;
+    tk.expect("tracking");
+    const std::string trk = tk.next();
+    settings::tracking = trk == "delta" ? settings::TrackingMode::DELTA_TRACKING
+                         : trk == "carter" ? settings::TrackingMode::CARTER_TRACKING : settings::TrackingMode::SURFACE_TRACKING;
+    tk.expect("ngroups");
+    const size_t G = (size_t)tk.ll();
+    settings::ngroups = (uint32_t)G;
+    tk.expect("ebounds");
+    settings::energy_bounds = tk.dv(G + 1);
+    tk.expect("nparticles"); settings::nparticles = (int)tk.ll();
+    tk.expect("ngenerations"); settings::ngenerations = (int)tk.ll();
+    tk.expect("nignored"); settings::nignored = (int)tk.ll();
+    tk.expect("nskip"); settings::nskip = (int)tk.ll();
+    tk.expect("wgt"); settings::wgt_cutoff = tk.d(); settings::wgt_survival = tk.d(); settings::wgt_split = tk.d();
+    tk.expect("seed"); settings::rng_seed = (uint64_t)std::stoull(tk.next());
+    tk.expect("stride"); settings::rng_stride = (uint64_t)std::stoull(tk.next());
+    tk.expect("ratios");
+    settings::sample_xs_ratio = tk.dv((size_t)tk.ll());
+    tk.expect("cancel"); tk.ll(); tk.ll(); tk.ll();
+    tk.expect("noise");
+    settings::w_noise = tk.d(); settings::keff = tk.d();
+    settings::inner_generations = tk.ll() != 0; settings::normalize_noise_source = tk.ll() != 0;
+    settings::min_energy = 0.; settings::max_energy = 100000.;
+    settings::converged = false;
+    settings::chi_matrix = false; settings::use_virtual_collisions = true;
+
+    materials.clear();
+    std::vector<int> material_ids;
+    tk.expect("nmat");
+    const size_t M = (size_t)tk.ll();
+    for (size_t m = 0; m < M; m++) {
+      tk.expect("mat");
+      const uint32_t id = (uint32_t)tk.ll();
+      tk.expect("total"); auto Et = tk.dv(G);
+      tk.expect("absorption"); auto Ea = tk.dv(G);
+      tk.expect("fission"); auto Ef = tk.dv(G);
+      tk.expect("nu_p"); auto nu_p = tk.dv(G);
+      tk.expect("nu_d"); auto nu_d = tk.dv(G);
+      tk.expect("speeds"); auto speeds = tk.dv(G);
+      tk.expect("chi");
+      const size_t nrows = (size_t)tk.ll();
+      std::vector<std::vector<double>> chi(G, std::vector<double>(G, 0.)), rows(nrows);
+      for (auto& r : rows) r = tk.dv(G);
+      tk.expect("scatter");
+      std::vector<std::vector<double>> Es(G);
+      for (auto& r : Es) r = tk.dv(G);
+      tk.expect("nleg");
+      const size_t L = (size_t)tk.ll();
+      std::vector<std::vector<LegendreDistribution>> legendre(G, std::vector<LegendreDistribution>(G));
+      for (size_t l = 1; l <= L; l++) {
+        tk.expect("P");
+        const size_t order = (size_t)tk.ll();
+        for (size_t i = 0; i < G; i++)
+          for (size_t o = 0; o < G; o++) legendre[i][o].set_moment(order, tk.d());
+      }
+      std::vector<std::vector<MGAngleDistribution>> angles(G, std::vector<MGAngleDistribution>(G));
+      for (size_t i = 0; i < G; i++)
+        for (size_t o = 0; o < G; o++) angles[i][o] = legendre[i][o].linearize();
+      tk.expect("ndg");
+      const size_t ND = (size_t)tk.ll();
+      auto Pd = tk.dv(ND);
+      auto lam = tk.dv(ND);
+      bool fissile = false;
+      for (double v : Ef) if (v > 0.) fissile = true;
+      if (!fissile) {
+        nu_p.assign(G, 0.); nu_d.assign(G, 0.);
+      } else if (nrows == G) {
+        chi = rows;
+        settings::chi_matrix = true;
+      } else {
+        for (size_t i = 0; i < G; i++) chi[i] = rows[0];
+      }
+      const std::vector<std::vector<double>> yields(G, std::vector<double>(G, 1.));
+      auto nuc = std::make_shared<MGNuclide>(speeds, Et, Ea, Ef, nu_p, nu_d, chi, Es, yields, angles, Pd, lam);
+      auto mat = std::make_shared<Material>();
+      mat->add_component({1., nuc});
+      materials[id] = mat;
+      material_ids.push_back((int)id);
+    }
+    for (const auto& mat : materials) {  // src/parser.cpp:157-168
+      const double emax = mat.second->max_energy(), emin = mat.second->min_energy();
+      if (emin > settings::min_energy) settings::min_energy = emin;
+      if (emax < settings::max_energy) settings::max_energy = emax;
+    }
+    // geometry: the rest of the text up to and including "root"
+    std::string rest, line;
+    std::getline(tk.in, line);
+    while (std::getline(tk.in, line)) {
+      rest += line + "\n";
+      if (line.rfind("root ", 0) == 0) break;
+    }
+    if (ref_geometry_load(rest.c_str(), -1, nullptr) != 0) return 1;
+
+    g_tallies = std::make_shared<Tallies>(static_cast<double>(settings::nparticles));
+    switch (settings::tracking) {
+      case settings::TrackingMode::DELTA_TRACKING: g_transporter = std::make_shared<DeltaTracker>(g_tallies); break;
+      case settings::TrackingMode::CARTER_TRACKING: g_transporter = std::make_shared<CarterTracker>(g_tallies); break;
+      default: g_transporter = std::make_shared<SurfaceTracker>(g_tallies); break;
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "ref_problem_load: %s\n", e.what());
+    return 1;
+  }
+}
+
+// One Transporter::transport(bank) call of the reference, as PowerIterator::run makes it (src/power_iterator.cpp:371):
+// particles Particle(r, u, E, wgt, history id) with set_family_id and initialize_rng(seed, stride) (:196-200), k_col of the previous
+// generation in the tallies.  Out: the fission bank in the order transport() returns it (9 doubles + parent history id,
+// parent daughter id, family id per site) and the generation values Tallies::calc_gen_values makes of the scores (k_col,
+// k_abs, k_trk, k_tot, leakage, migration area).  One OpenMP thread, so that the score sums are accumulated in bank order.
+int ref_transport(uint64_t n, const double* r3, const double* u3, const double* E, const double* wgt, const uint64_t* hid,
+                  const uint64_t* family, double k_col, uint64_t cap, double* out9, uint64_t* out_ids3, uint64_t* n_out, double* scores6) {
+  try {
+    omp_set_num_threads(1);
+    std::vector<Particle> bank;
+    bank.reserve(n);
+    for (uint64_t i = 0; i < n; i++) {
+      bank.emplace_back(Position(r3[3 * i], r3[3 * i + 1], r3[3 * i + 2]), raw_direction(u3 + 3 * i), E[i], wgt[i], hid[i]);
+      bank.back().set_family_id(family[i]);
+      bank.back().initialize_rng(settings::rng_seed, settings::rng_stride);
+    }
+    g_tallies->clear_generation();
+    g_tallies->set_kcol(k_col);
+    const std::vector<BankedParticle> fis = g_transporter->transport(bank, false, nullptr, nullptr);
+    g_tallies->calc_gen_values();  // score sums / total weight (src/tallies.cpp:159-181)
+    scores6[0] = g_tallies->kcol(); scores6[1] = g_tallies->kabs(); scores6[2] = g_tallies->ktrk();
+    scores6[3] = g_tallies->ktot(); scores6[4] = g_tallies->leakage(); scores6[5] = g_tallies->mig_area();
+    *n_out = fis.size();
+    for (uint64_t i = 0; i < fis.size() && i < cap; i++) {
+      double* o = out9 + 9 * i;
+      o[0] = fis[i].r.x(); o[1] = fis[i].r.y(); o[2] = fis[i].r.z();
+      o[3] = fis[i].u.x(); o[4] = fis[i].u.y(); o[5] = fis[i].u.z();
+      o[6] = fis[i].E; o[7] = fis[i].wgt; o[8] = fis[i].wgt2;
+      out_ids3[3 * i] = fis[i].parent_history_id; out_ids3[3 * i + 1] = fis[i].parent_daughter_id; out_ids3[3 * i + 2] = fis[i].family_id;
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "ref_transport: %s\n", e.what());
     return 1;
   }
 }
