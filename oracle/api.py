@@ -232,6 +232,8 @@ class Oracle:
     # --- tallies ---
     def ntallies(self): return int(lib().orc_ntallies(self.h))
 
+    def tally_estimator(self, t): return int(lib().orc_tally_estimator(self.h, C.c_int(t)))  # 0 collision, 1 track-length, 2 source
+
     def tally_shape(self, t):
         sh = np.zeros(4, dtype=np.uint64)
         lib().orc_tally_shape(self.h, C.c_int(t), sh.ctypes.data_as(_PU64))

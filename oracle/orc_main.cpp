@@ -1579,6 +1579,7 @@ void orc_get_trace(void* h, uint32_t* flights, uint32_t* real, uint32_t* virt, u
 }
 
 // mesh tallies
+int orc_tally_estimator(void* h, int t) { return (int)static_cast<Problem*>(h)->tallies.mesh[(size_t)t].estimator; }
 int orc_ntallies(void* h) { return (int)static_cast<Problem*>(h)->tallies.mesh.size(); }
 uint64_t orc_tally_size(void* h, int t) { return static_cast<Problem*>(h)->tallies.mesh[(size_t)t].tally_gen.size(); }
 void orc_tally_shape(void* h, int t, uint64_t* shape4) {

@@ -395,8 +395,9 @@ def _sample_mu(impl: str, tables: dict) -> dict:
 def evaluate_transport(impl: str) -> dict:
     """One Transporter::transport(bank) per case through the reference's own SurfaceTracker / DeltaTracker / CarterTracker
     (oracle/_ref, one OpenMP thread) or the oracle (glibc math, one thread): the fission bank in the order it is returned
-    (9 doubles and parent history id, daughter id, family id per site) and the six generation values of
-    Tallies::calc_gen_values (k_col, k_abs, k_trk, k_tot, leakage, migration area)."""
+    (9 doubles and parent history id, daughter id, family id per site), the six generation values of
+    Tallies::calc_gen_values (k_col, k_abs, k_trk, k_tot, leakage, migration area) and, with settings::converged set, the
+    generation scores of every collision / track-length mesh tally of the deck."""
     from . import deck as _deck
     ref = impl == "reference"
     L = ref_lib() if ref else api.lib()
@@ -415,19 +416,31 @@ def evaluate_transport(impl: str) -> dict:
                 cap = 16 * n
                 f9, ids, nout, k6 = np.zeros((cap, 9)), np.zeros((cap, 3), dtype=np.uint64), C.c_uint64(0), np.zeros(6)
                 rc = L.ref_transport(C.c_uint64(n), _d(r), _d(u), _d(E), _d(w), hid.ctypes.data_as(PU), hid.ctypes.data_as(PU),
-                                     C.c_double(k_col), C.c_uint64(cap), _d(f9), ids.ctypes.data_as(PU), C.byref(nout), _d(k6))
+                                     C.c_double(k_col), C.c_int(1), C.c_uint64(cap), _d(f9), ids.ctypes.data_as(PU), C.byref(nout), _d(k6))
                 assert rc == 0 and nout.value <= cap
                 f9, ids = f9[:nout.value].copy(), ids[:nout.value].copy()
+                L.ref_tally_size.restype = C.c_uint64
+                tallies = []
+                for t in range(L.ref_ntallies()):
+                    a = np.zeros(int(L.ref_tally_size(C.c_int(t))))
+                    if a.size:
+                        L.ref_tally_get(C.c_int(t), _d(a))
+                    tallies.append(a)
             else:
                 o = api.Oracle(path, ov)
                 bank = {k: np.ascontiguousarray(v) for k, v in zip(("x", "y", "z"), r.T)}
                 bank.update({k: np.ascontiguousarray(v) for k, v in zip(("ux", "uy", "uz"), u.T)})
                 bank.update(E=E, wgt=w, wgt2=np.zeros(n), id_a=hid, id_b=hid.copy(), id_c=None)
                 o.set_kcol(k_col)
+                o.set_converged(True)
+                o.tallies_clear()
                 fb, scores, m = o.transport(bank, False, capacity=16 * n)
+                tallies = [np.ravel(o.tally(t, "gen")) if o.tally_estimator(t) != 2 else np.zeros(0) for t in range(o.ntallies())]
                 f9 = np.ascontiguousarray(np.stack([fb[k] for k in api.BANK_F64], 1))
                 ids = np.ascontiguousarray(np.stack([fb["id_a"], fb["id_b"], fb["id_c"]], 1))
                 k6 = scores / float(n)
                 o.close()
             out[f"transport_{name}_sites"], out[f"transport_{name}_ids"], out[f"transport_{name}_k"] = f9, ids, k6
+            for t, a in enumerate(tallies):
+                out[f"transport_{name}_tally{t}"] = a
     return out

@@ -608,6 +608,18 @@ Direction raw_direction(const double* u) {
 }
 std::shared_ptr<Tallies> g_tallies;
 std::shared_ptr<Transporter> g_transporter;
+// the generation array of a mesh tally is a protected member (include/simulation/mesh_tally.hpp:79); the probe's tallies are
+// created as these derived types so that it can be read back.  Nothing is overridden.
+struct CollisionTallyProbe : CollisionMeshTally {
+  using CollisionMeshTally::CollisionMeshTally;
+  const NDArray<double>& gen() const { return tally_gen; }
+  static void forget_names() { used_tally_names.clear(); }
+};
+struct TrackLengthTallyProbe : TrackLengthMeshTally {
+  using TrackLengthMeshTally::TrackLengthMeshTally;
+  const NDArray<double>& gen() const { return tally_gen; }
+};
+std::vector<const NDArray<double>*> g_tally_gen;
 }  // namespace
 
 extern "C" {
@@ -717,6 +729,35 @@ int ref_problem_load(const char* text) {
     if (ref_geometry_load(rest.c_str(), -1, nullptr) != 0) return 1;
 
     g_tallies = std::make_shared<Tallies>(static_cast<double>(settings::nparticles));
+    // mesh tallies: "tally name estimator quantity noise_like nx ny nz low[3] hi[3] nE ebounds[nE]" lines of the deck text,
+    // through the plain constructors (collision_mesh_tally.hpp:34-37, track_length_mesh_tally.hpp:34-37); the quantity code
+    // is the position in MeshTally::Quantity.  Source-estimator tallies are not scored inside transport() and are skipped.
+    g_tally_gen.clear();
+    CollisionTallyProbe::forget_names();
+    while (std::getline(tk.in, line)) {
+      if (line.rfind("tally ", 0) != 0) continue;
+      std::istringstream ls(line);
+      std::string key, name;
+      int est, qty, noise_like;
+      uint64_t nx, ny, nz;
+      double lo[3], hi[3];
+      size_t ne;
+      ls >> key >> name >> est >> qty >> noise_like >> nx >> ny >> nz >> lo[0] >> lo[1] >> lo[2] >> hi[0] >> hi[1] >> hi[2] >> ne;
+      std::vector<double> eb(ne);
+      for (auto& e : eb) ls >> e;
+      const auto q = static_cast<MeshTally::Quantity>(qty);
+      if (est == 0) {
+        auto t = std::make_shared<CollisionTallyProbe>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), nx, ny, nz, eb, q, name);
+        g_tallies->add_collision_mesh_tally(t);
+        g_tally_gen.push_back(&t->gen());
+      } else if (est == 1) {
+        auto t = std::make_shared<TrackLengthTallyProbe>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), nx, ny, nz, eb, q, name);
+        g_tallies->add_track_length_mesh_tally(t);
+        g_tally_gen.push_back(&t->gen());
+      } else {
+        g_tally_gen.push_back(nullptr);
+      }
+    }
     switch (settings::tracking) {
       case settings::TrackingMode::DELTA_TRACKING: g_transporter = std::make_shared<DeltaTracker>(g_tallies); break;
       case settings::TrackingMode::CARTER_TRACKING: g_transporter = std::make_shared<CarterTracker>(g_tallies); break;
@@ -735,7 +776,7 @@ int ref_problem_load(const char* text) {
 // parent daughter id, family id per site) and the generation values Tallies::calc_gen_values makes of the scores (k_col,
 // k_abs, k_trk, k_tot, leakage, migration area).  One OpenMP thread, so that the score sums are accumulated in bank order.
 int ref_transport(uint64_t n, const double* r3, const double* u3, const double* E, const double* wgt, const uint64_t* hid,
-                  const uint64_t* family, double k_col, uint64_t cap, double* out9, uint64_t* out_ids3, uint64_t* n_out, double* scores6) {
+                  const uint64_t* family, double k_col, int converged, uint64_t cap, double* out9, uint64_t* out_ids3, uint64_t* n_out, double* scores6) {
   try {
     omp_set_num_threads(1);
     std::vector<Particle> bank;
@@ -747,6 +788,7 @@ int ref_transport(uint64_t n, const double* r3, const double* u3, const double* 
     }
     g_tallies->clear_generation();
     g_tallies->set_kcol(k_col);
+    settings::converged = converged != 0;  // mesh tallies score only then (tallies.hpp:49-63)
     const std::vector<BankedParticle> fis = g_transporter->transport(bank, false, nullptr, nullptr);
     g_tallies->calc_gen_values();  // score sums / total weight (src/tallies.cpp:159-181)
     scores6[0] = g_tallies->kcol(); scores6[1] = g_tallies->kabs(); scores6[2] = g_tallies->ktrk();
@@ -764,6 +806,14 @@ int ref_transport(uint64_t n, const double* r3, const double* u3, const double* 
     std::fprintf(stderr, "ref_transport: %s\n", e.what());
     return 1;
   }
+}
+
+// generation scores of mesh tally t after the last ref_transport (C order [E][x][y][z]); size 0 for a source tally
+uint64_t ref_tally_size(int t) { return g_tally_gen[(size_t)t] ? g_tally_gen[(size_t)t]->size() : 0; }
+int ref_ntallies() { return (int)g_tally_gen.size(); }
+void ref_tally_get(int t, double* out) {
+  const NDArray<double>& a = *g_tally_gen[(size_t)t];
+  for (size_t i = 0; i < a.size(); i++) out[i] = a[i];
 }
 
 }  // extern "C"
