@@ -13,7 +13,8 @@ record/clear, history-id / RNG re-seeding).  Histories shard across GPUs by glob
 * e2e          the same metric through the host-buffer C ABI (abl_transport): every step copies the bank
                host->device from pinned memory and the fission bank + scores device->host.
 * roofline     the history kernel: algorithmic bytes / measured kernel time.
-* cpu_baseline the CPU oracle (a restatement of the reference's OpenMP path; oracle/) on this box's cores.
+* cpu_baseline the reference's own DeltaTracker::transport (oracle/_ref, compiled from the reference's sources; kind
+               "reference") on this box's cores; the CPU oracle port (oracle/) when that library was not built.
 * --impl reference: that CPU path as its own arm (rank 0 only).
 """
 import argparse
@@ -120,21 +121,79 @@ def cpu_leg(nparticles, inactive, active, threads=None):
                       f"OpenMP schedule(dynamic) over histories, {nthreads} threads, g++ -O2"}
 
 
+def ref_leg(nparticles, warm, active, threads=None):
+    """The REFERENCE'S OWN DeltaTracker::transport (oracle/_ref/libabeille_ref.so: the reference's multigroup sources compiled
+    in place by oracle/Makefile, see oracle/ref_probe.cpp) on a bounded sample of the workload, all host threads, its own
+    CollisionMeshTally on the deck's full mesh scoring.  A step is one active generation: the timed region is the
+    transport() call; between calls the bank of the next generation is made from the fission bank as PowerIterator::run
+    does (weights normalised to the particle count, new history ids).  Returns None when the library is not there."""
+    import ctypes as C
+    import numpy as np
+    from oracle import ref_pins, deck as _deck
+    if not os.path.exists(ref_pins.REF_LIB):
+        return None
+    L = C.CDLL(ref_pins.REF_LIB)
+    L.ref_last_transport_seconds.restype = C.c_double
+    nthreads = threads or (os.cpu_count() or 1)
+    deck = _deck.apply_overrides(_deck.load_yaml(DECK), {"settings": {"nparticles": int(nparticles)}})
+    if L.ref_problem_load(_deck.deck_to_text(deck).encode()) != 0:
+        raise RuntimeError("oracle/_ref: ref_problem_load failed")
+    L.ref_set_threads(C.c_int(nthreads))
+    PD, PU = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
+    rng = np.random.default_rng(1)
+    sp = deck["sources"][0]["spatial"]
+    n = int(nparticles)
+    r = np.ascontiguousarray(rng.uniform(sp["low"], sp["hi"], (n, 3)))
+    u = rng.normal(size=(n, 3))
+    u = np.ascontiguousarray(u / np.linalg.norm(u, axis=1)[:, None])
+    eb = deck["settings"]["energy-bounds"]
+    E = np.full(n, 0.5 * (eb[0] + eb[1]))
+    w = np.ones(n)
+    k_col, next_id, seconds, particles = 1.0, 0, 0.0, 0
+    cap = 4 * n
+    f9, ids, k6 = np.zeros((cap, 9)), np.zeros((cap, 3), dtype=np.uint64), np.zeros(6)
+    for g in range(warm + active):
+        m = len(w)
+        hid = np.arange(next_id, next_id + m, dtype=np.uint64)
+        next_id += m
+        nout = C.c_uint64(0)
+        rc = L.ref_transport(C.c_uint64(m), r.ctypes.data_as(PD), u.ctypes.data_as(PD), E.ctypes.data_as(PD), w.ctypes.data_as(PD),
+                             hid.ctypes.data_as(PU), hid.ctypes.data_as(PU), C.c_double(k_col), C.c_int(int(g >= warm)),
+                             C.c_uint64(cap), f9.ctypes.data_as(PD), ids.ctypes.data_as(PU), C.byref(nout), k6.ctypes.data_as(PD))
+        if rc != 0 or nout.value > cap or nout.value == 0:
+            raise RuntimeError(f"oracle/_ref: ref_transport failed (rc {rc}, {nout.value} sites)")
+        if g >= warm:
+            seconds += float(L.ref_last_transport_seconds())
+            particles += m
+        k_col = float(k6[0])
+        k = int(nout.value)
+        r, u = np.ascontiguousarray(f9[:k, 0:3]), np.ascontiguousarray(f9[:k, 3:6])
+        E = np.ascontiguousarray(f9[:k, 6])
+        w = np.ascontiguousarray(f9[:k, 7] * (n / f9[:k, 7].sum()))  # PowerIterator::normalize_weights
+    return {"particles_per_s": particles / seconds, "collisions_per_s": None, "seconds": seconds, "particles": particles,
+            "cores": nthreads, "k_col": k_col,
+            "sample": f"{active} active generations of ~{n} particles after {warm} inactive, same deck and 1224x1224x10x7 mesh, "
+                      f"the reference's own DeltaTracker::transport + CollisionMeshTally compiled from /root/reference "
+                      f"(oracle/_ref), OpenMP schedule(dynamic), {nthreads} threads, g++ -O3; transport() calls timed"}
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself cannot be built offline,
-    see DESIGN.md) on all host threads.  A step is one active generation of a bounded particle count."""
+    """--impl reference: the reference's own CPU transport (oracle/_ref; the oracle port if that library is absent) on all
+    host threads.  A step is one active generation of a bounded particle count."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n = args.ref_particles
     t0 = time.time()
-    r = cpu_leg(n, max(args.warmup, 1), args.steps)
+    r, kind = ref_leg(n, max(args.warmup, 1), args.steps), "reference"
+    if r is None:  # oracle/_ref was not built (no /root/reference at build time): the oracle port
+        r, kind = cpu_leg(n, max(args.warmup, 1), args.steps), "port"
     out = {"impl": "reference", "metric": METRIC, "value": r["particles_per_s"], "unit": "particles/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "collisions_per_s": r["collisions_per_s"],
            "config": {"workload": WORKLOAD, "particles_per_step": n, "host_threads": r["cores"]},
-           "cpu_baseline": {"value": r["particles_per_s"], "unit": "particles/s", "cores": r["cores"], "kind": "port",
+           "cpu_baseline": {"value": r["particles_per_s"], "unit": "particles/s", "cores": r["cores"], "kind": kind,
                             "sample": r["sample"]},
            "e2e": {"value": r["particles_per_s"], "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": time.time() - t0}
@@ -245,9 +304,14 @@ def run_b200(args):
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = cpu_leg(args.cpu_particles, 2, args.cpu_steps)
-        cpu = {"value": r["particles_per_s"], "unit": "particles/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+        r, kind = ref_leg(args.cpu_particles, 2, args.cpu_steps), "reference"
+        if r is None:
+            r, kind = cpu_leg(args.cpu_particles, 2, args.cpu_steps), "port"
+        cpu = {"value": r["particles_per_s"], "unit": "particles/s", "cores": r["cores"], "kind": kind, "sample": r["sample"],
                "collisions_per_s": r["collisions_per_s"]}
+        if kind == "reference":  # the oracle port beside it, for the record
+            rp = cpu_leg(args.cpu_particles, 2, args.cpu_steps)
+            cpu["port_value"] = rp["particles_per_s"]
 
     if rank == 0:
         out = {"metric": METRIC, "value": particles / (ms * 1e-3), "unit": "particles/s", "n_gpus": world, "steps": args.steps,

@@ -620,6 +620,8 @@ struct TrackLengthTallyProbe : TrackLengthMeshTally {
   const NDArray<double>& gen() const { return tally_gen; }
 };
 std::vector<const NDArray<double>*> g_tally_gen;
+int g_threads = 1;
+double g_last_transport_seconds = 0.;
 }  // namespace
 
 extern "C" {
@@ -774,11 +776,11 @@ int ref_problem_load(const char* text) {
 // particles Particle(r, u, E, wgt, history id) with set_family_id and initialize_rng(seed, stride) (:196-200), k_col of the previous
 // generation in the tallies.  Out: the fission bank in the order transport() returns it (9 doubles + parent history id,
 // parent daughter id, family id per site) and the generation values Tallies::calc_gen_values makes of the scores (k_col,
-// k_abs, k_trk, k_tot, leakage, migration area).  One OpenMP thread, so that the score sums are accumulated in bank order.
+// k_abs, k_trk, k_tot, leakage, migration area).  ref_set_threads(1) (the default) accumulates the score sums in bank order.
 int ref_transport(uint64_t n, const double* r3, const double* u3, const double* E, const double* wgt, const uint64_t* hid,
                   const uint64_t* family, double k_col, int converged, uint64_t cap, double* out9, uint64_t* out_ids3, uint64_t* n_out, double* scores6) {
   try {
-    omp_set_num_threads(1);
+    omp_set_num_threads(g_threads);
     std::vector<Particle> bank;
     bank.reserve(n);
     for (uint64_t i = 0; i < n; i++) {
@@ -789,7 +791,9 @@ int ref_transport(uint64_t n, const double* r3, const double* u3, const double* 
     g_tallies->clear_generation();
     g_tallies->set_kcol(k_col);
     settings::converged = converged != 0;  // mesh tallies score only then (tallies.hpp:49-63)
+    const double t0 = omp_get_wtime();
     const std::vector<BankedParticle> fis = g_transporter->transport(bank, false, nullptr, nullptr);
+    g_last_transport_seconds = omp_get_wtime() - t0;
     g_tallies->calc_gen_values();  // score sums / total weight (src/tallies.cpp:159-181)
     scores6[0] = g_tallies->kcol(); scores6[1] = g_tallies->kabs(); scores6[2] = g_tallies->ktrk();
     scores6[3] = g_tallies->ktot(); scores6[4] = g_tallies->leakage(); scores6[5] = g_tallies->mig_area();
@@ -808,6 +812,10 @@ int ref_transport(uint64_t n, const double* r3, const double* u3, const double* 
   }
 }
 
+// OpenMP threads of the next ref_transport calls (1 for the bit-exact pins: score sums in bank order; all cores for timing)
+void ref_set_threads(int n) { g_threads = n > 0 ? n : 1; }
+// wall time of the transport() call alone inside the last ref_transport (bank construction and copies excluded)
+double ref_last_transport_seconds() { return g_last_transport_seconds; }
 // generation scores of mesh tally t after the last ref_transport (C order [E][x][y][z]); size 0 for a source tally
 uint64_t ref_tally_size(int t) { return g_tally_gen[(size_t)t] ? g_tally_gen[(size_t)t]->size() : 0; }
 int ref_ntallies() { return (int)g_tally_gen.size(); }
