@@ -4,15 +4,18 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs.  The product (abeille_b200/) never links or calls it.
  *
- * PARITY PIN STATUS: the reference ships no tests or golden vectors
- *  and cannot be compiled here (yaml-cpp, PapillonNDL,
- * pcg-cpp, HighFive, NDArray, Boost are fetched from the network by its
- * CMakeLists.txt:37-131).  The pins that exist are (i) RNG known-answer
- * vectors from pcg32 + libstdc++ themselves (tests/golden/rng_kat.json),
- * (ii) the Sood analytic k values quoted in the reference's decks
- * (input_files/PUa-1-0-IN.yaml:2 ...), (iii) the MG identity k_col == k_abs.
- * Everything else is "parity unpinned" against reference OUTPUT and rests on
- * line-by-line restatement with citations.
+ * PARITY PIN STATUS: PINNED against the reference's own compiled code for the k-eigenvalue hot path.  The reference
+ * ships no tests or golden vectors and its CMake build needs the network, but its multigroup
+ * translation units compile where they lie under /root/reference with stand-in headers for the downloaded libraries
+ * (oracle/Makefile target `ref`, oracle/ref_probe.cpp, oracle/ref_shim/): oracle/_ref/libabeille_ref.so runs the
+ * reference's own SurfaceTracker / DeltaTracker / CarterTracker::transport, and this oracle reproduces its fission bank,
+ * generation values and mesh-tally scores bit for bit on 14 decks, as well as surfaces, directions, RNG helpers, angle
+ * tables, MGNuclide sampling and the geometry cursor piece by piece (tests/test_reference_pins.py, golden vectors in
+ * tests/golden/ref_pins.npz made by scripts/make_ref_pins.py).  Further pins: RNG known-answer vectors from pcg32 +
+ * libstdc++ (tests/golden/rng_kat.json), the Sood analytic k values quoted in the reference's decks, k_col == k_abs.
+ * NOT pinned against reference output (restatement with citations only): noise mode (transport with complex weights,
+ * noise-source sampling), the PowerIterator / Noise drivers between transport calls, cancellation, entropy, source
+ * sampling.
  *
  * Follows: src/delta_tracker.cpp:72-263, src/surface_tracker.cpp:40-219,
  * src/carter_tracker.cpp:53-294, src/transporter.cpp:35-93,269-487,
