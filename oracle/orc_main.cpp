@@ -13,9 +13,9 @@
  * tables, MGNuclide sampling and the geometry cursor piece by piece (tests/test_reference_pins.py, golden vectors in
  * tests/golden/ref_pins.npz made by scripts/make_ref_pins.py).  Further pins: RNG known-answer vectors from pcg32 +
  * libstdc++ (tests/golden/rng_kat.json), the Sood analytic k values quoted in the reference's decks, k_col == k_abs.
- * NOT pinned against reference output (restatement with citations only): noise mode (transport with complex weights,
- * noise-source sampling), the PowerIterator / Noise drivers between transport calls, cancellation, entropy, source
- * sampling.
+ * Noise mode is pinned the same way (transport with complex weights; NoiseMaker::sample_noise_source with the square-
+ * oscillation and flat-vibration sources).  NOT pinned against reference output (restatement with citations only): the
+ * PowerIterator / Noise drivers between transport calls, cancellation, entropy, source sampling.
  *
  * Follows: src/delta_tracker.cpp:72-263, src/surface_tracker.cpp:40-219,
  * src/carter_tracker.cpp:53-294, src/transporter.cpp:35-93,269-487,

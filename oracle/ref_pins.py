@@ -444,3 +444,66 @@ def evaluate_transport(impl: str) -> dict:
             for t, a in enumerate(tallies):
                 out[f"transport_{name}_tally{t}"] = a
     return out
+
+
+# noise mode: deck, particles
+NOISE_CASES = (("noise_oscillation.yaml", 4000), ("noise_oscillation_delta.yaml", 4000), ("noise_vibration.yaml", 4000))
+
+
+def evaluate_noise(impl: str) -> dict:
+    """Noise mode through the reference's own code (oracle/_ref) or the oracle.  Per deck two transport calls:
+    (A) a power-iteration generation that samples the noise source at its collisions -- transport(bank, noise = false,
+        &noise_bank, &noise_maker), NoiseMaker::sample_noise_source with the deck's square-oscillation / flat-vibration
+        sources -> fission bank, noise-source bank, generation values;
+    (B) a noise generation -- transport(bank, noise = true) over a seeded bank with complex weights -> fission bank
+        (complex weights, delayed-neutron factor), generation values."""
+    from . import deck as _deck
+    ref = impl == "reference"
+    L = ref_lib() if ref else api.lib()
+    decks = os.path.join(os.path.dirname(_HERE), "tests", "decks")
+    PU = C.POINTER(C.c_uint64)
+    out = {}
+    with _reference_math(impl):
+        for ci, (fname, n) in enumerate(NOISE_CASES):
+            path = os.path.join(decks, fname)
+            ov = {"settings": {"nparticles": n}}
+            deck = _deck.apply_overrides(_deck.load_yaml(path), ov)
+            keff = float(deck["settings"].get("keff", 1.0))
+            r, u, E, w, hid = transport_bank(deck, n, 900 + ci, False)
+            rng = np.random.default_rng(950 + ci)
+            w2 = rng.uniform(-0.8, 0.8, n)
+            name = fname.split(".")[0]
+            if ref:
+                assert L.ref_problem_load(_deck.deck_to_text(deck).encode()) == 0
+            else:
+                o = api.Oracle(path, ov)
+            for phase, noise, sample, wa, wb in (("A", 0, 1, w, np.zeros(n)), ("B", 1, 0, w, w2)):
+                cap = 24 * n
+                if ref:
+                    f9, fi, b9, bi = np.zeros((cap, 9)), np.zeros((cap, 3), dtype=np.uint64), np.zeros((cap, 9)), np.zeros((cap, 3), dtype=np.uint64)
+                    nf, nb, k6 = C.c_uint64(0), C.c_uint64(0), np.zeros(6)
+                    rc = L.ref_transport_noise(C.c_uint64(n), _d(r), _d(u), _d(E), _d(wa), _d(wb), hid.ctypes.data_as(PU),
+                                               hid.ctypes.data_as(PU), C.c_double(1.0), C.c_double(keff), C.c_int(noise), C.c_int(sample),
+                                               C.c_uint64(cap), _d(f9), fi.ctypes.data_as(PU), C.byref(nf), _d(b9), bi.ctypes.data_as(PU),
+                                               C.byref(nb), _d(k6))
+                    assert rc == 0 and nf.value <= cap and nb.value <= cap
+                    f9, fi, b9, bi = f9[:nf.value].copy(), fi[:nf.value].copy(), b9[:nb.value].copy(), bi[:nb.value].copy()
+                else:
+                    bank = {k: np.ascontiguousarray(v) for k, v in zip(("x", "y", "z"), r.T)}
+                    bank.update({k: np.ascontiguousarray(v) for k, v in zip(("ux", "uy", "uz"), u.T)})
+                    bank.update(E=E, wgt=np.ascontiguousarray(wa), wgt2=np.ascontiguousarray(wb), id_a=hid, id_b=hid.copy(), id_c=None)
+                    o.set_kcol(1.0)
+                    o.set_keff(keff)
+                    o.set_converged(False)
+                    o.tallies_clear()
+                    fb, nbk, scores = o.transport_noise(bank, bool(noise), bool(sample), capacity=cap)
+                    st = lambda b: (np.ascontiguousarray(np.stack([b[k] for k in api.BANK_F64], 1)).reshape(-1, 9),  # noqa: E731
+                                    np.ascontiguousarray(np.stack([b["id_a"], b["id_b"], b["id_c"]], 1)).reshape(-1, 3))
+                    (f9, fi), (b9, bi) = st(fb), st(nbk)
+                    k6 = scores / float(n)
+                out[f"noise_{name}_{phase}_sites"], out[f"noise_{name}_{phase}_ids"] = f9, fi
+                out[f"noise_{name}_{phase}_source"], out[f"noise_{name}_{phase}_source_ids"] = b9, bi
+                out[f"noise_{name}_{phase}_k"] = k6
+            if not ref:
+                o.close()
+    return out

@@ -12,7 +12,7 @@
  *   transport    src/surface_tracker.cpp, delta_tracker.cpp, carter_tracker.cpp, transporter.cpp, material_helper.cpp,
  *                tallies.cpp, mesh_tally.cpp, collision_mesh_tally.cpp, track_length_mesh_tally.cpp, source_mesh_tally.cpp,
  *                noise_maker.cpp and the two noise sources, mpi.cpp (no-MPI build), output.cpp, header.cpp, logo.cpp:
- *                ref_transport runs the reference's own Transporter::transport on a bank
+ *                ref_transport / ref_transport_noise run the reference's own Transporter::transport on a bank
  * oracle/Makefile (target `ref`) compiles those files in place (nothing is copied) together with this driver into
  * oracle/_ref/libabeille_ref.so.  Stand-in headers under oracle/ref_shim/ replace what the reference's CMake downloads
  * (yaml-cpp, PapillonNDL, Boost.Unordered, HighFive, NDArray) and two reference headers that would drag the plotter and the
@@ -41,6 +41,9 @@
 #include <plotting/plotter.hpp>
 #include <simulation/carter_tracker.hpp>
 #include <simulation/delta_tracker.hpp>
+#include <simulation/flat_vibration_noise_source.hpp>
+#include <simulation/noise_maker.hpp>
+#include <simulation/square_oscillation_noise_source.hpp>
 #include <simulation/surface_tracker.hpp>
 #include <simulation/tracker.hpp>
 #include <utils/direction.hpp>
@@ -620,6 +623,7 @@ struct TrackLengthTallyProbe : TrackLengthMeshTally {
   const NDArray<double>& gen() const { return tally_gen; }
 };
 std::vector<const NDArray<double>*> g_tally_gen;
+std::unique_ptr<NoiseMaker> g_noise_maker;
 int g_threads = 1;
 double g_last_transport_seconds = 0.;
 }  // namespace
@@ -664,6 +668,7 @@ int ref_problem_load(const char* text) {
     settings::chi_matrix = false; settings::use_virtual_collisions = true;
 
     materials.clear();
+    nuclides.clear();
     std::vector<int> material_ids;
     tk.expect("nmat");
     const size_t M = (size_t)tk.ll();
@@ -711,6 +716,7 @@ int ref_problem_load(const char* text) {
       }
       const std::vector<std::vector<double>> yields(G, std::vector<double>(G, 1.));
       auto nuc = std::make_shared<MGNuclide>(speeds, Et, Ea, Ef, nu_p, nu_d, chi, Es, yields, angles, Pd, lam);
+      nuclides[nuc->id()] = nuc;  // as make_mg_nuclide does (src/mg_nuclide.cpp:919); the vibration sources look nuclides up
       auto mat = std::make_shared<Material>();
       mat->add_component({1., nuc});
       materials[id] = mat;
@@ -736,7 +742,29 @@ int ref_problem_load(const char* text) {
     // is the position in MeshTally::Quantity.  Source-estimator tallies are not scored inside transport() and are skipped.
     g_tally_gen.clear();
     CollisionTallyProbe::forget_names();
+    g_noise_maker = std::make_unique<NoiseMaker>();
     while (std::getline(tk.in, line)) {
+      if (line.rfind("sqosc ", 0) == 0 || line.rfind("flatvib ", 0) == 0) {
+        // noise sources through their plain constructors (square_oscillation_noise_source.hpp:35-37,
+        // flat_vibration_noise_source.hpp:40-43); materials of a vibration are given as positions in the deck's material list
+        std::istringstream ns(line);
+        std::string kind;
+        double lo[3], hi[3], w0;
+        ns >> kind >> lo[0] >> lo[1] >> lo[2] >> hi[0] >> hi[1] >> hi[2] >> w0;
+        if (kind == "sqosc") {
+          double et, ef, es;
+          ns >> et >> ef >> es;
+          g_noise_maker->add_noise_source(std::shared_ptr<OscillationNoiseSource>(std::make_shared<SquareOscillationNoiseSource>(
+              Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), et, ef, es, w0)));
+        } else {
+          int basis, ip, in;
+          ns >> basis >> ip >> in;
+          g_noise_maker->add_noise_source(std::shared_ptr<VibrationNoiseSource>(std::make_shared<FlatVibrationNoiseSource>(
+              Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), static_cast<FlatVibrationNoiseSource::Basis>(basis),
+              materials.at((uint32_t)material_ids[(size_t)ip]), materials.at((uint32_t)material_ids[(size_t)in]), w0)));
+        }
+        continue;
+      }
       if (line.rfind("tally ", 0) != 0) continue;
       std::istringstream ls(line);
       std::string key, name;
@@ -808,6 +836,53 @@ int ref_transport(uint64_t n, const double* r3, const double* u3, const double* 
     return 0;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "ref_transport: %s\n", e.what());
+    return 1;
+  }
+}
+
+// Transporter::transport(bank, noise, &noise_bank, &noise_maker) as PowerIterator::run (noise == 0, the noise source is
+// sampled at the collisions: src/power_iterator.cpp:371, src/transporter.cpp:74-78) and Noise::run (noise != 0: complex
+// weights wgt + i wgt2, src/noise.cpp:312-314) make it.  keff is what Tallies::keff() returns to the samplers.  Out: fission
+// bank and noise-source bank, 9 doubles + 3 ids per particle each.
+int ref_transport_noise(uint64_t n, const double* r3, const double* u3, const double* E, const double* wgt, const double* wgt2,
+                        const uint64_t* hid, const uint64_t* family, double k_col, double keff, int noise, int sample_noise,
+                        uint64_t cap, double* out9, uint64_t* out_ids3, uint64_t* n_out, double* noise9, uint64_t* noise_ids3,
+                        uint64_t* n_noise, double* scores6) {
+  try {
+    omp_set_num_threads(g_threads);
+    std::vector<Particle> bank;
+    bank.reserve(n);
+    for (uint64_t i = 0; i < n; i++) {
+      bank.emplace_back(Position(r3[3 * i], r3[3 * i + 1], r3[3 * i + 2]), raw_direction(u3 + 3 * i), E[i], wgt[i], wgt2[i], hid[i]);
+      bank.back().set_family_id(family[i]);
+      bank.back().initialize_rng(settings::rng_seed, settings::rng_stride);
+    }
+    g_tallies->clear_generation();
+    g_tallies->set_kcol(k_col);
+    g_tallies->set_keff(keff);
+    settings::converged = false;
+    std::vector<BankedParticle> nb;
+    const std::vector<BankedParticle> fis =
+        g_transporter->transport(bank, noise != 0, sample_noise ? &nb : nullptr, sample_noise ? g_noise_maker.get() : nullptr);
+    g_tallies->calc_gen_values();
+    scores6[0] = g_tallies->kcol(); scores6[1] = g_tallies->kabs(); scores6[2] = g_tallies->ktrk();
+    scores6[3] = g_tallies->ktot(); scores6[4] = g_tallies->leakage(); scores6[5] = g_tallies->mig_area();
+    auto put_bank = [cap](const std::vector<BankedParticle>& v, double* o9, uint64_t* oi) {
+      for (uint64_t i = 0; i < v.size() && i < cap; i++) {
+        double* o = o9 + 9 * i;
+        o[0] = v[i].r.x(); o[1] = v[i].r.y(); o[2] = v[i].r.z();
+        o[3] = v[i].u.x(); o[4] = v[i].u.y(); o[5] = v[i].u.z();
+        o[6] = v[i].E; o[7] = v[i].wgt; o[8] = v[i].wgt2;
+        oi[3 * i] = v[i].parent_history_id; oi[3 * i + 1] = v[i].parent_daughter_id; oi[3 * i + 2] = v[i].family_id;
+      }
+    };
+    *n_out = fis.size();
+    put_bank(fis, out9, out_ids3);
+    *n_noise = nb.size();
+    put_bank(nb, noise9, noise_ids3);
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "ref_transport_noise: %s\n", e.what());
     return 1;
   }
 }

@@ -17,6 +17,7 @@ from oracle import ref_pins  # noqa: E402
 out = ref_pins.evaluate("reference")
 out.update(ref_pins.sample_mu("reference", out))
 out.update(ref_pins.evaluate_transport("reference"))
+out.update(ref_pins.evaluate_noise("reference"))
 path = os.path.join(ROOT, "tests", "golden", "ref_pins.npz")
 np.savez_compressed(path, **out)
 print(f"{path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")

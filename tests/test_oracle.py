@@ -102,8 +102,8 @@ def test_math_mode_does_not_change_integer_outcomes(oracle_api, tmp_path):
 def test_noise_oracle_source_and_driver(oracle_api):
     """Noise mode (config 5): the sampled noise source lies inside the oscillating region, carries purely real weights
     (the square-oscillation factors are real), its fission part appears only in the fuel, and the driver is
-    deterministic.  (The reference ships no golden output for this deck and noise mode is not among the pieces pinned against the
-    reference's own code)"""
+    deterministic.  (The transport calls of noise mode are pinned against the reference's own code by tests/test_reference_pins.py; the
+    Noise driver between them is restatement only)"""
     import yaml
     path = deck_path("noise_oscillation.yaml")
     deck = yaml.safe_load(open(path))
