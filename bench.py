@@ -121,7 +121,27 @@ def cpu_leg(nparticles, inactive, active, threads=None):
                       f"OpenMP schedule(dynamic) over histories, {nthreads} threads, g++ -O2"}
 
 
+class _StdoutToStderr:
+    """The reference's Output singleton writes its progress lines to stdout; bench.py's stdout is the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        import ctypes
+        ctypes.CDLL(None).fflush(None)
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def ref_leg(nparticles, warm, active, threads=None):
+    with _StdoutToStderr():
+        return _ref_leg(nparticles, warm, active, threads)
+
+
+def _ref_leg(nparticles, warm, active, threads=None):
     """The REFERENCE'S OWN DeltaTracker::transport (oracle/_ref/libabeille_ref.so: the reference's multigroup sources compiled
     in place by oracle/Makefile, see oracle/ref_probe.cpp) on a bounded sample of the workload, all host threads, its own
     CollisionMeshTally on the deck's full mesh scoring.  A step is one active generation: the timed region is the

@@ -7,6 +7,7 @@
 namespace HighFive {
 struct DataSpace {
   DataSpace() = default;
+  std::vector<std::size_t> getDimensions() const { return {}; }
   template <class... A>
   DataSpace(A&&...) {}
   static DataSpace From(...) { return DataSpace(); }
@@ -19,6 +20,14 @@ struct Attribute {
 };
 struct DataSet {
   template <class T>
+  void read(T&) const {}
+  template <class T>
+  void read(T*) const {}
+  template <class T>
+  void read_raw(T*) const {}
+  DataSpace getSpace() const { return DataSpace(); }
+  std::vector<std::size_t> getDimensions() const { return {}; }
+  template <class T>
   void write_raw(const T*) {}
   template <class T>
   void write(const T&) {}
@@ -30,6 +39,7 @@ struct DataSet {
 struct Group {
   Group createGroup(const std::string&) { return Group(); }
   Group getGroup(const std::string&) const { return Group(); }
+  DataSet getDataSet(const std::string&) const { return DataSet(); }
   bool exist(const std::string&) const { return false; }
   template <class T>
   DataSet createDataSet(const std::string&, const DataSpace&) { return DataSet(); }

@@ -4,6 +4,7 @@
 // (oracle/ref_probe.cpp constructs the surfaces through their ordinary constructors), and every accessor throws.
 #pragma once
 #include <cstddef>
+#include <array>
 #include <map>
 #include <set>
 #include <memory>
