@@ -14,8 +14,9 @@
  * tests/golden/ref_pins.npz made by scripts/make_ref_pins.py).  Further pins: RNG known-answer vectors from pcg32 +
  * libstdc++ (tests/golden/rng_kat.json), the Sood analytic k values quoted in the reference's decks, k_col == k_abs.
  * Noise mode is pinned the same way (transport with complex weights; NoiseMaker::sample_noise_source with the square-
- * oscillation and flat-vibration sources).  NOT pinned against reference output (restatement with citations only): the
- * PowerIterator / Noise drivers between transport calls, cancellation, entropy, source sampling.
+ * oscillation and flat-vibration sources), and so are whole k-eigenvalue simulations: the reference's PowerIterator::run with
+ * source sampling, entropy, approximate mesh cancellation, normalisation and tally statistics.  NOT pinned against reference
+ * output (restatement with citations only): the Noise driver between the noise transport calls.
  *
  * Follows: src/delta_tracker.cpp:72-263, src/surface_tracker.cpp:40-219,
  * src/carter_tracker.cpp:53-294, src/transporter.cpp:35-93,269-487,

@@ -507,3 +507,75 @@ def evaluate_noise(impl: str) -> dict:
             if not ref:
                 o.close()
     return out
+
+
+# whole k-eigenvalue simulations: deck, particles, generations, ignored generations
+POWER_ITERATION_CASES = (
+    ("PUa-1-0-SL.yaml", 2000, 12, 4), ("PUa-1-0-IN.yaml", 2000, 10, 3), ("Ua-1-1-CY.yaml", 2000, 10, 3), ("UD2O-2-1-SL.yaml", 2000, 10, 3),
+    ("c5g7_delta_collision.yaml", 3000, 8, 3), ("c5g7_carter_cancel.yaml", 3000, 8, 3), ("ref_sqr_c5g7_surface_tl.yaml", 2000, 6, 2),
+)
+
+
+def evaluate_power_iteration(impl: str, only: int | None = None) -> dict:
+    """The reference's own PowerIterator::initialize() + run() (oracle/_ref: source sampling through Source / Box / Point /
+    Isotropic / MonoEnergetic, transport, Entropy, ApproximateMeshCancelator, weight normalisation, history-id hand-out,
+    Tallies statistics, MeshTally::record_generation) against the oracle's driver: per generation k_col, k_trk, leakage,
+    migration area and entropy; the final averages and errors; the average and the error of the mean of the deck's
+    collision / track-length mesh tallies as MeshTally::write_tally leaves them."""
+    from . import deck as _deck
+    ref = impl == "reference"
+    L = ref_lib() if ref else api.lib()
+    decks = os.path.join(os.path.dirname(_HERE), "tests", "decks")
+    keys = ("kcol", "ktrk", "leak", "mig", "entropy")
+    out = {}
+    if ref and only is None:
+        # The reference is a one-simulation-per-process program (settings, MPI bookkeeping and id counters are process
+        # globals that PowerIterator::run leaves changed): every case gets a fresh process, as the reference itself would.
+        import subprocess
+        import sys
+        import tempfile
+        for i in range(len(POWER_ITERATION_CASES)):
+            with tempfile.TemporaryDirectory() as td:
+                path = os.path.join(td, "pi.npz")
+                code = (f"import sys; sys.path.insert(0, {os.path.dirname(_HERE)!r}); import numpy as np; "
+                        f"from oracle import ref_pins; np.savez({path!r}, **ref_pins.evaluate_power_iteration('reference', only={i}))")
+                subprocess.run([sys.executable, "-c", code], check=True, stdout=subprocess.DEVNULL)
+                out.update(dict(np.load(path)))
+        return out
+    with _reference_math(impl):
+        for fname, n, ngen, nign in (POWER_ITERATION_CASES if only is None else POWER_ITERATION_CASES[only:only + 1]):
+            path = os.path.join(decks, fname)
+            ov = {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}}
+            name = fname.split(".")[0]
+            tal = {}
+            if ref:
+                deck = _deck.apply_overrides(_deck.load_yaml(path), ov)
+                a = {k: np.zeros(ngen) for k in keys}
+                summ = np.zeros(6)
+                L.ref_set_threads(C.c_int(1))
+                rc = L.ref_power_iteration(_deck.deck_to_text(deck).encode(), C.c_int(ngen), C.c_int(nign), *[_d(a[k]) for k in keys],
+                                           _d(summ))
+                assert rc == 0
+                L.ref_tally_size.restype = C.c_uint64
+                for t in range(L.ref_ntallies()):
+                    size = int(L.ref_tally_size(C.c_int(t)))
+                    if size:
+                        for which, wname in ((1, "avg"), (2, "std")):  # write_tally has turned var into the error of the mean
+                            v = np.zeros(size)
+                            L.ref_tally_get_stat(C.c_int(t), C.c_int(which), _d(v))
+                            tal[f"tally{t}_{wname}"] = v
+            else:
+                o = api.Oracle(path, ov)
+                r = o.run_power_iteration(ngen, nign)
+                a = {k: r[k] for k in keys}
+                summ = np.array([r[k] for k in ("kcol_avg", "kcol_err", "ktrk_avg", "ktrk_err", "leak_avg", "leak_err")])
+                for t in range(o.ntallies()):
+                    if o.tally_estimator(t) != 2:
+                        tal[f"tally{t}_avg"], tal[f"tally{t}_std"] = np.ravel(o.tally(t, "avg")), np.ravel(o.tally(t, "std"))
+                o.close()
+            for k in keys:
+                out[f"pi_{name}_{k}"] = np.ascontiguousarray(a[k])
+            out[f"pi_{name}_summary"] = summ
+            for k, v in tal.items():
+                out[f"pi_{name}_{k}"] = np.ascontiguousarray(v)
+    return out

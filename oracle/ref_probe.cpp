@@ -19,7 +19,9 @@
  * YAML parser in (utils/parser.hpp, plotting/slice_plot.hpp); each says what it stands in for and why it cannot change a
  * result.  Restated in this file because their translation units cannot be compiled: the multigroup branch of
  * make_majorant_xs (src/majorant.cpp:131-176), the settings globals (src/settings.cpp) and the assembly of materials and
- * geometry from a deck (the YAML factory functions).  Not covered: PowerIterator / Noise drivers, cancelators, entropy.
+ * geometry from a deck (the YAML factory functions).  ref_power_iteration runs the reference's PowerIterator (power_iterator.cpp,
+ * simulation.cpp, entropy.cpp, source.cpp + distributions, cancelator.cpp, approximate_mesh_cancelator.cpp).  Not covered: the
+ * Noise driver, exact cancelators.
  * oracle/ref_pins.py runs seeded cases through this library and through the oracle; tests/test_reference_pins.py compares
  * them bit for bit and keeps the reference's outputs as tests/golden/ref_pins.npz for machines without the reference.
  */
@@ -42,7 +44,15 @@
 #include <simulation/carter_tracker.hpp>
 #include <simulation/delta_tracker.hpp>
 #include <simulation/flat_vibration_noise_source.hpp>
+#include <simulation/approximate_mesh_cancelator.hpp>
+#include <simulation/box.hpp>
+#include <simulation/entropy.hpp>
+#include <simulation/isotropic.hpp>
+#include <simulation/mono_energetic.hpp>
 #include <simulation/noise_maker.hpp>
+#include <simulation/point.hpp>
+#include <simulation/power_iterator.hpp>
+#include <simulation/source.hpp>
 #include <simulation/square_oscillation_noise_source.hpp>
 #include <simulation/surface_tracker.hpp>
 #include <simulation/tracker.hpp>
@@ -108,6 +118,16 @@ std::vector<double> energy_bounds;
 std::vector<double> sample_xs_ratio;
 bool chi_matrix = false;
 bool use_virtual_collisions = true;
+Timer alpha_omega_timer;
+double max_time = INF;
+bool pair_distance_sqrd = false;
+bool families = false;
+bool empty_entropy_bins = false;
+bool load_source_file = false;
+void initialize_global_rng() {  // src/settings.cpp
+  rng.seed(rng_seed);
+  rng.set_stream(2);
+}
 }  // namespace settings
 // src/parser.cpp and src/plotter.cpp (the whole simulation layer) are not built: the id -> index maps they own are defined
 // here, and the geometry is assembled by ref_geometry_load below
@@ -623,6 +643,7 @@ struct TrackLengthTallyProbe : TrackLengthMeshTally {
   const NDArray<double>& gen() const { return tally_gen; }
 };
 std::vector<const NDArray<double>*> g_tally_gen;
+std::vector<const MeshTally*> g_mesh_tallies;
 std::unique_ptr<NoiseMaker> g_noise_maker;
 int g_threads = 1;
 double g_last_transport_seconds = 0.;
@@ -657,6 +678,7 @@ int ref_problem_load(const char* text) {
     tk.expect("wgt"); settings::wgt_cutoff = tk.d(); settings::wgt_survival = tk.d(); settings::wgt_split = tk.d();
     tk.expect("seed"); settings::rng_seed = (uint64_t)std::stoull(tk.next());
     tk.expect("stride"); settings::rng_stride = (uint64_t)std::stoull(tk.next());
+    settings::initialize_global_rng();  // the stream cancellation draws from (called once the seed is known)
     tk.expect("ratios");
     settings::sample_xs_ratio = tk.dv((size_t)tk.ll());
     tk.expect("cancel"); tk.ll(); tk.ll(); tk.ll();
@@ -741,6 +763,7 @@ int ref_problem_load(const char* text) {
     // through the plain constructors (collision_mesh_tally.hpp:34-37, track_length_mesh_tally.hpp:34-37); the quantity code
     // is the position in MeshTally::Quantity.  Source-estimator tallies are not scored inside transport() and are skipped.
     g_tally_gen.clear();
+    g_mesh_tallies.clear();
     CollisionTallyProbe::forget_names();
     g_noise_maker = std::make_unique<NoiseMaker>();
     while (std::getline(tk.in, line)) {
@@ -780,12 +803,15 @@ int ref_problem_load(const char* text) {
         auto t = std::make_shared<CollisionTallyProbe>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), nx, ny, nz, eb, q, name);
         g_tallies->add_collision_mesh_tally(t);
         g_tally_gen.push_back(&t->gen());
+        g_mesh_tallies.push_back(t.get());
       } else if (est == 1) {
         auto t = std::make_shared<TrackLengthTallyProbe>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), nx, ny, nz, eb, q, name);
         g_tallies->add_track_length_mesh_tally(t);
         g_tally_gen.push_back(&t->gen());
+        g_mesh_tallies.push_back(t.get());
       } else {
         g_tally_gen.push_back(nullptr);
+        g_mesh_tallies.push_back(nullptr);
       }
     }
     switch (settings::tracking) {
@@ -887,6 +913,12 @@ int ref_transport_noise(uint64_t n, const double* r3, const double* u3, const do
   }
 }
 
+// average (which = 1) / error of the mean (which = 2: write_tally has converted the variance accumulator in place) of mesh
+// tally t after ref_power_iteration (src/mesh_tally.cpp:121-150,195-197; private members, see ref_power_iteration)
+void ref_tally_get_stat(int t, int which, double* out) {
+  const NDArray<double>& a = which == 1 ? g_mesh_tallies[(size_t)t]->tally_avg : g_mesh_tallies[(size_t)t]->tally_var;
+  for (size_t i = 0; i < a.size(); i++) out[i] = a[i];
+}
 // OpenMP threads of the next ref_transport calls (1 for the bit-exact pins: score sums in bank order; all cores for timing)
 void ref_set_threads(int n) { g_threads = n > 0 ? n : 1; }
 // wall time of the transport() call alone inside the last ref_transport (bank construction and copies excluded)
@@ -897,6 +929,105 @@ int ref_ntallies() { return (int)g_tally_gen.size(); }
 void ref_tally_get(int t, double* out) {
   const NDArray<double>& a = *g_tally_gen[(size_t)t];
   for (size_t i = 0; i < a.size(); i++) out[i] = a[i];
+}
+
+// The reference's own PowerIterator::initialize() + run() (src/power_iterator.cpp:170-473) on the deck text: sources,
+// entropy mesh and cancelator are built through their plain constructors from the "src", "entropy" and "cancelator" lines
+// (src/source.cpp:92-140, src/parser.cpp:1008-1054, src/cancelator.cpp:32-78).  Out, per generation g < ngen: k_col, k_trk,
+// leakage, migration area (Tallies' generation vectors), the total pre-cancellation entropy; summary = k_col avg / err,
+// k_trk avg / err, leakage avg / err.  (This file is compiled with -fno-access-control to read the private per-generation
+// vectors; access control does not enter the object layout.)
+int ref_power_iteration(const char* text, int ngen, int nignored, double* kcol, double* ktrk, double* leak, double* mig,
+                        double* entropy, double* summary) {
+  try {
+    if (ref_problem_load(text) != 0) return 1;
+    omp_set_num_threads(g_threads);
+    settings::ngenerations = ngen;
+    settings::nignored = nignored;
+    std::vector<std::shared_ptr<Source>> sources;
+    std::shared_ptr<Cancelator> cancelator;
+    std::shared_ptr<PowerIterator> pi;
+    std::istringstream in(text);
+    std::string line;
+    std::vector<std::string> entropy_line;
+    while (std::getline(in, line)) {
+      std::istringstream ls(line);
+      std::string key;
+      ls >> key;
+      if (key == "src") {
+        double w, lo[3], hi[3], E;
+        int fissile_only;
+        std::string kind, ekey;
+        ls >> w >> fissile_only >> kind;
+        std::shared_ptr<SpatialDistribution> sp;
+        if (kind == "box") {
+          ls >> lo[0] >> lo[1] >> lo[2] >> hi[0] >> hi[1] >> hi[2];
+          sp = std::make_shared<Box>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]));
+        } else {
+          ls >> lo[0] >> lo[1] >> lo[2];
+          sp = std::make_shared<Point>(Position(lo[0], lo[1], lo[2]));
+        }
+        ls >> ekey >> E;
+        sources.push_back(std::make_shared<Source>(sp, std::make_shared<Isotropic>(), std::make_shared<MonoEnergetic>(E),
+                                                   fissile_only != 0, w));
+      } else if (key == "cancel") {
+        int a, b;
+        ls >> a >> b;
+        settings::regional_cancellation = a != 0;
+        settings::regional_cancellation_noise = b != 0;
+      } else if (key == "cancelator") {
+        int on;
+        ls >> on;
+        if (on) {
+          uint32_t nx, ny, nz;
+          double lo[3], hi[3];
+          size_t ne;
+          ls >> nx >> ny >> nz >> lo[0] >> lo[1] >> lo[2] >> hi[0] >> hi[1] >> hi[2] >> ne;
+          std::vector<double> eb(ne);
+          for (auto& e : eb) ls >> e;
+          if (ne)
+            cancelator = std::make_shared<ApproximateMeshCancelator>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), nx, ny, nz, eb);
+          else
+            cancelator = std::make_shared<ApproximateMeshCancelator>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), nx, ny, nz);
+        }
+      } else if (key == "entropy") {
+        entropy_line.push_back(line);
+      }
+    }
+    pi = cancelator ? std::make_shared<PowerIterator>(g_tallies, g_transporter, sources, cancelator)
+                    : std::make_shared<PowerIterator>(g_tallies, g_transporter, sources);
+    for (const auto& el : entropy_line) {
+      std::istringstream ls(el);
+      std::string key;
+      int on;
+      ls >> key >> on;
+      if (!on) continue;
+      double lo[3], hi[3];
+      uint32_t sh[3];
+      ls >> lo[0] >> lo[1] >> lo[2] >> hi[0] >> hi[1] >> hi[2] >> sh[0] >> sh[1] >> sh[2];
+      const Position low_r(lo[0], lo[1], lo[2]), hi_r(hi[0], hi[1], hi[2]);
+      const std::array<uint32_t, 3> shp{sh[0], sh[1], sh[2]};
+      pi->set_p_pre_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Positive));
+      pi->set_n_pre_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Negative));
+      pi->set_t_pre_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Total));
+      pi->set_p_post_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Positive));
+      pi->set_n_post_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Negative));
+      pi->set_t_post_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Total));
+    }
+    pi->initialize();
+    pi->run();
+    const Tallies& T = *g_tallies;
+    for (int g = 0; g < ngen; g++) {
+      kcol[g] = T.k_col_vec[(size_t)g]; ktrk[g] = T.k_trk_vec[(size_t)g]; leak[g] = T.leak_vec[(size_t)g]; mig[g] = T.mig_vec[(size_t)g];
+      entropy[g] = (size_t)g < pi->t_pre_entropy_vec.size() ? pi->t_pre_entropy_vec[(size_t)g] : 0.;
+    }
+    summary[0] = T.kcol_avg(); summary[1] = T.kcol_err(); summary[2] = T.ktrk_avg(); summary[3] = T.ktrk_err();
+    summary[4] = T.leakage_avg(); summary[5] = T.leakage_err();
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "ref_power_iteration: %s\n", e.what());
+    return 1;
+  }
 }
 
 }  // extern "C"
