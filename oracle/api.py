@@ -308,7 +308,12 @@ class Oracle:
             n = len(nb["x"])
             avg = 1.0
             if normalize_src and n:
-                avg = float(np.sqrt(nb["wgt"] * nb["wgt"] + nb["wgt2"] * nb["wgt2"]).sum()) / float(n)
+                # summed in bank order as the reference does (src/noise.cpp:443-447); numpy's pairwise sum differs in the
+                # last bits, and the normalised weights feed every later comparison
+                total_mag = 0.0
+                for mag in np.sqrt(nb["wgt"] * nb["wgt"] + nb["wgt2"] * nb["wgt2"]).tolist():
+                    total_mag += mag
+                avg = total_mag / float(n)
                 nb["wgt"] = nb["wgt"] / avg
                 nb["wgt2"] = nb["wgt2"] / avg
             if n:
@@ -341,6 +346,7 @@ class Oracle:
             nb = power_iteration(True)
             noise_simulation(nb)
         out["k_col"] = np.array(out["k_col"])
+        out["final_bank"] = (len(bank["x"]), int(bank["id_a"][0]) if len(bank["x"]) else 0, int(counter))
         return out
 
     def run_power_iteration(self, ngen: int, nignored: int) -> dict:

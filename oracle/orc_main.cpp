@@ -15,8 +15,8 @@
  * libstdc++ (tests/golden/rng_kat.json), the Sood analytic k values quoted in the reference's decks, k_col == k_abs.
  * Noise mode is pinned the same way (transport with complex weights; NoiseMaker::sample_noise_source with the square-
  * oscillation and flat-vibration sources), and so are whole k-eigenvalue simulations: the reference's PowerIterator::run with
- * source sampling, entropy, approximate mesh cancellation, normalisation and tally statistics.  NOT pinned against reference
- * output (restatement with citations only): the Noise driver between the noise transport calls.
+ * source sampling, entropy, approximate mesh cancellation, normalisation and tally statistics.  The Noise driver (oracle/api.py run_noise) is
+ * pinned against the reference's Noise::run the same way.
  *
  * Follows: src/delta_tracker.cpp:72-263, src/surface_tracker.cpp:40-219,
  * src/carter_tracker.cpp:53-294, src/transporter.cpp:35-93,269-487,

@@ -579,3 +579,66 @@ def evaluate_power_iteration(impl: str, only: int | None = None) -> dict:
             for k, v in tal.items():
                 out[f"pi_{name}_{k}"] = np.ascontiguousarray(v)
     return out
+
+
+# whole noise simulations: deck, particles, noise batches, ignored generations, nskip
+NOISE_DRIVER_CASES = (("noise_oscillation.yaml", 600, 2, 1, 2), ("noise_oscillation_delta.yaml", 500, 2, 2, 1),
+                      ("noise_vibration.yaml", 500, 2, 1, 2))
+
+
+def evaluate_noise_driver(impl: str, only: int | None = None) -> dict:
+    """The reference's own Noise::initialize() + run() (src/noise.cpp: power-iteration generations, noise-source sampling
+    and normalisation, inner noise generations with regional cancellation of the noise fission banks, tally statistics)
+    against the oracle's driver (oracle/api.py run_noise): k_col of every power-iteration generation, the final bank size /
+    first history id / history counter, and average and error of the mean of every mesh tally (noise-source tallies,
+    real / imaginary flux)."""
+    from . import deck as _deck
+    ref = impl == "reference"
+    out = {}
+    if ref and only is None:  # one simulation per process, as for the power iteration
+        import subprocess
+        import sys
+        import tempfile
+        for i in range(len(NOISE_DRIVER_CASES)):
+            with tempfile.TemporaryDirectory() as td:
+                path = os.path.join(td, "nd.npz")
+                code = (f"import sys; sys.path.insert(0, {os.path.dirname(_HERE)!r}); import numpy as np; "
+                        f"from oracle import ref_pins; np.savez({path!r}, **ref_pins.evaluate_noise_driver('reference', only={i}))")
+                subprocess.run([sys.executable, "-c", code], check=True, stdout=subprocess.DEVNULL)
+                out.update(dict(np.load(path)))
+        return out
+    L = ref_lib() if ref else api.lib()
+    decks = os.path.join(os.path.dirname(_HERE), "tests", "decks")
+    with _reference_math(impl):
+        for fname, n, nb, nign, nskip in (NOISE_DRIVER_CASES if only is None else NOISE_DRIVER_CASES[only:only + 1]):
+            path = os.path.join(decks, fname)
+            ov = {"settings": {"nparticles": n, "ngenerations": nb, "nignored": nign, "nskip": nskip}}
+            deck = _deck.apply_overrides(_deck.load_yaml(path), ov)
+            name = fname.split(".")[0]
+            if ref:
+                kc, nk, fb3 = np.zeros(4096), C.c_int(0), np.zeros(3, dtype=np.uint64)
+                L.ref_set_threads(C.c_int(1))
+                rc = L.ref_noise_run(_deck.deck_to_text(deck).encode(), C.c_int(nb), C.c_int(nign), C.c_int(nskip), _d(kc), C.byref(nk),
+                                     fb3.ctypes.data_as(C.POINTER(C.c_uint64)))
+                assert rc == 0
+                kcol = kc[:nk.value]
+                kcol = kcol[kcol != 0.0]  # Tallies::calc_gen_values after a noise batch appends a 0 (no k score in noise mode)
+                o = api.Oracle(path, ov)  # only for the tally shapes
+                tal = []
+                for t in range(o.ntallies()):
+                    size = int(np.prod(o.tally_shape(t)))
+                    a, e = np.zeros(size), np.zeros(size)
+                    L.ref_tally_get_stat(C.c_int(t), C.c_int(1), _d(a))
+                    L.ref_tally_get_stat(C.c_int(t), C.c_int(2), _d(e))
+                    tal.append((a, e))
+                o.close()
+            else:
+                o = api.Oracle(path, ov)
+                r = o.run_noise(deck["settings"])
+                kcol, fb3 = np.asarray(r["k_col"]), np.asarray(r["final_bank"], dtype=np.uint64)
+                tal = [(np.ravel(o.tally(t, "avg")), np.ravel(o.tally(t, "std"))) for t in range(o.ntallies())]
+                o.close()
+            out[f"nd_{name}_kcol"], out[f"nd_{name}_final_bank"] = np.ascontiguousarray(kcol), fb3
+            for t, (a, e) in enumerate(tal):
+                out[f"nd_{name}_tally{t}_avg"], out[f"nd_{name}_tally{t}_std"] = a, e
+    return out

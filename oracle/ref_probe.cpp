@@ -20,8 +20,8 @@
  * result.  Restated in this file because their translation units cannot be compiled: the multigroup branch of
  * make_majorant_xs (src/majorant.cpp:131-176), the settings globals (src/settings.cpp) and the assembly of materials and
  * geometry from a deck (the YAML factory functions).  ref_power_iteration runs the reference's PowerIterator (power_iterator.cpp,
- * simulation.cpp, entropy.cpp, source.cpp + distributions, cancelator.cpp, approximate_mesh_cancelator.cpp).  Not covered: the
- * Noise driver, exact cancelators.
+ * simulation.cpp, entropy.cpp, source.cpp + distributions, cancelator.cpp, approximate_mesh_cancelator.cpp).  ref_noise_run runs the reference's
+ * Noise driver (noise.cpp).  Not covered: exact cancelators, fixed-source / branchless drivers (out of scope).
  * oracle/ref_pins.py runs seeded cases through this library and through the oracle; tests/test_reference_pins.py compares
  * them bit for bit and keeps the reference's outputs as tests/golden/ref_pins.npz for machines without the reference.
  */
@@ -49,6 +49,7 @@
 #include <simulation/entropy.hpp>
 #include <simulation/isotropic.hpp>
 #include <simulation/mono_energetic.hpp>
+#include <simulation/noise.hpp>
 #include <simulation/noise_maker.hpp>
 #include <simulation/point.hpp>
 #include <simulation/power_iterator.hpp>
@@ -759,6 +760,7 @@ int ref_problem_load(const char* text) {
     if (ref_geometry_load(rest.c_str(), -1, nullptr) != 0) return 1;
 
     g_tallies = std::make_shared<Tallies>(static_cast<double>(settings::nparticles));
+    g_tallies->set_keff(settings::keff);  // src/parser.cpp:885
     // mesh tallies: "tally name estimator quantity noise_like nx ny nz low[3] hi[3] nE ebounds[nE]" lines of the deck text,
     // through the plain constructors (collision_mesh_tally.hpp:34-37, track_length_mesh_tally.hpp:34-37); the quantity code
     // is the position in MeshTally::Quantity.  Source-estimator tallies are not scored inside transport() and are skipped.
@@ -809,9 +811,13 @@ int ref_problem_load(const char* text) {
         g_tallies->add_track_length_mesh_tally(t);
         g_tally_gen.push_back(&t->gen());
         g_mesh_tallies.push_back(t.get());
-      } else {
+      } else {  // source estimator (source_mesh_tally.hpp:36-40): scored by the drivers, not inside transport()
+        auto t = std::make_shared<SourceMeshTally>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), nx, ny, nz, eb,
+                                                   static_cast<SourceMeshTally::Quantity>(qty - 8), name);
+        if (t->noise_like_score()) g_tallies->add_noise_source_mesh_tally(t);
+        else g_tallies->add_source_mesh_tally(t);
         g_tally_gen.push_back(nullptr);
-        g_mesh_tallies.push_back(nullptr);
+        g_mesh_tallies.push_back(t.get());
       }
     }
     switch (settings::tracking) {
@@ -931,6 +937,90 @@ void ref_tally_get(int t, double* out) {
   for (size_t i = 0; i < a.size(); i++) out[i] = a[i];
 }
 
+}  // extern "C"
+
+namespace {
+struct DriverParts {
+  std::vector<std::shared_ptr<Source>> sources;
+  std::shared_ptr<Cancelator> cancelator;
+  std::vector<std::string> entropy_lines;
+};
+// sources, cancelator and entropy lines of the deck text through the reference's plain constructors
+DriverParts driver_parts(const char* text) {
+  DriverParts d;
+  std::istringstream in(text);
+  std::string line;
+  while (std::getline(in, line)) {
+    std::istringstream ls(line);
+    std::string key;
+    ls >> key;
+    if (key == "src") {
+      double w, lo[3], hi[3], E;
+      int fissile_only;
+      std::string kind, ekey;
+      ls >> w >> fissile_only >> kind;
+      std::shared_ptr<SpatialDistribution> sp;
+      if (kind == "box") {
+        ls >> lo[0] >> lo[1] >> lo[2] >> hi[0] >> hi[1] >> hi[2];
+        sp = std::make_shared<Box>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]));
+      } else {
+        ls >> lo[0] >> lo[1] >> lo[2];
+        sp = std::make_shared<Point>(Position(lo[0], lo[1], lo[2]));
+      }
+      ls >> ekey >> E;
+      d.sources.push_back(std::make_shared<Source>(sp, std::make_shared<Isotropic>(), std::make_shared<MonoEnergetic>(E),
+                                                   fissile_only != 0, w));
+    } else if (key == "cancel") {
+      int a, b, c;
+      ls >> a >> b >> c;
+      settings::regional_cancellation = a != 0;
+      settings::regional_cancellation_noise = b != 0;
+      settings::n_cancel_noise_gens = c;
+    } else if (key == "cancelator") {
+      int on;
+      ls >> on;
+      if (on) {
+        uint32_t nx, ny, nz;
+        double lo[3], hi[3];
+        size_t ne;
+        ls >> nx >> ny >> nz >> lo[0] >> lo[1] >> lo[2] >> hi[0] >> hi[1] >> hi[2] >> ne;
+        std::vector<double> eb(ne);
+        for (auto& e : eb) ls >> e;
+        if (ne)
+          d.cancelator = std::make_shared<ApproximateMeshCancelator>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), nx, ny, nz, eb);
+        else
+          d.cancelator = std::make_shared<ApproximateMeshCancelator>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), nx, ny, nz);
+      }
+    } else if (key == "entropy") {
+      d.entropy_lines.push_back(line);
+    }
+  }
+  return d;
+}
+void set_entropy(Simulation& sim, const std::vector<std::string>& lines) {
+  for (const auto& el : lines) {
+    std::istringstream ls(el);
+    std::string key;
+    int on;
+    ls >> key >> on;
+    if (!on) continue;
+    double lo[3], hi[3];
+    uint32_t sh[3];
+    ls >> lo[0] >> lo[1] >> lo[2] >> hi[0] >> hi[1] >> hi[2] >> sh[0] >> sh[1] >> sh[2];
+    const Position low_r(lo[0], lo[1], lo[2]), hi_r(hi[0], hi[1], hi[2]);
+    const std::array<uint32_t, 3> shp{sh[0], sh[1], sh[2]};
+    sim.set_p_pre_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Positive));
+    sim.set_n_pre_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Negative));
+    sim.set_t_pre_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Total));
+    sim.set_p_post_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Positive));
+    sim.set_n_post_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Negative));
+    sim.set_t_post_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Total));
+  }
+}
+}  // namespace
+
+extern "C" {
+
 // The reference's own PowerIterator::initialize() + run() (src/power_iterator.cpp:170-473) on the deck text: sources,
 // entropy mesh and cancelator are built through their plain constructors from the "src", "entropy" and "cancelator" lines
 // (src/source.cpp:92-140, src/parser.cpp:1008-1054, src/cancelator.cpp:32-78).  Out, per generation g < ngen: k_col, k_trk,
@@ -944,76 +1034,11 @@ int ref_power_iteration(const char* text, int ngen, int nignored, double* kcol, 
     omp_set_num_threads(g_threads);
     settings::ngenerations = ngen;
     settings::nignored = nignored;
-    std::vector<std::shared_ptr<Source>> sources;
-    std::shared_ptr<Cancelator> cancelator;
+    DriverParts d = driver_parts(text);
     std::shared_ptr<PowerIterator> pi;
-    std::istringstream in(text);
-    std::string line;
-    std::vector<std::string> entropy_line;
-    while (std::getline(in, line)) {
-      std::istringstream ls(line);
-      std::string key;
-      ls >> key;
-      if (key == "src") {
-        double w, lo[3], hi[3], E;
-        int fissile_only;
-        std::string kind, ekey;
-        ls >> w >> fissile_only >> kind;
-        std::shared_ptr<SpatialDistribution> sp;
-        if (kind == "box") {
-          ls >> lo[0] >> lo[1] >> lo[2] >> hi[0] >> hi[1] >> hi[2];
-          sp = std::make_shared<Box>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]));
-        } else {
-          ls >> lo[0] >> lo[1] >> lo[2];
-          sp = std::make_shared<Point>(Position(lo[0], lo[1], lo[2]));
-        }
-        ls >> ekey >> E;
-        sources.push_back(std::make_shared<Source>(sp, std::make_shared<Isotropic>(), std::make_shared<MonoEnergetic>(E),
-                                                   fissile_only != 0, w));
-      } else if (key == "cancel") {
-        int a, b;
-        ls >> a >> b;
-        settings::regional_cancellation = a != 0;
-        settings::regional_cancellation_noise = b != 0;
-      } else if (key == "cancelator") {
-        int on;
-        ls >> on;
-        if (on) {
-          uint32_t nx, ny, nz;
-          double lo[3], hi[3];
-          size_t ne;
-          ls >> nx >> ny >> nz >> lo[0] >> lo[1] >> lo[2] >> hi[0] >> hi[1] >> hi[2] >> ne;
-          std::vector<double> eb(ne);
-          for (auto& e : eb) ls >> e;
-          if (ne)
-            cancelator = std::make_shared<ApproximateMeshCancelator>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), nx, ny, nz, eb);
-          else
-            cancelator = std::make_shared<ApproximateMeshCancelator>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), nx, ny, nz);
-        }
-      } else if (key == "entropy") {
-        entropy_line.push_back(line);
-      }
-    }
-    pi = cancelator ? std::make_shared<PowerIterator>(g_tallies, g_transporter, sources, cancelator)
-                    : std::make_shared<PowerIterator>(g_tallies, g_transporter, sources);
-    for (const auto& el : entropy_line) {
-      std::istringstream ls(el);
-      std::string key;
-      int on;
-      ls >> key >> on;
-      if (!on) continue;
-      double lo[3], hi[3];
-      uint32_t sh[3];
-      ls >> lo[0] >> lo[1] >> lo[2] >> hi[0] >> hi[1] >> hi[2] >> sh[0] >> sh[1] >> sh[2];
-      const Position low_r(lo[0], lo[1], lo[2]), hi_r(hi[0], hi[1], hi[2]);
-      const std::array<uint32_t, 3> shp{sh[0], sh[1], sh[2]};
-      pi->set_p_pre_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Positive));
-      pi->set_n_pre_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Negative));
-      pi->set_t_pre_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Total));
-      pi->set_p_post_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Positive));
-      pi->set_n_post_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Negative));
-      pi->set_t_post_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Total));
-    }
+    pi = d.cancelator ? std::make_shared<PowerIterator>(g_tallies, g_transporter, d.sources, d.cancelator)
+                      : std::make_shared<PowerIterator>(g_tallies, g_transporter, d.sources);
+    set_entropy(*pi, d.entropy_lines);
     pi->initialize();
     pi->run();
     const Tallies& T = *g_tallies;
@@ -1026,6 +1051,36 @@ int ref_power_iteration(const char* text, int ngen, int nignored, double* kcol, 
     return 0;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "ref_power_iteration: %s\n", e.what());
+    return 1;
+  }
+}
+
+// The reference's own Noise::initialize() + run() (src/noise.cpp:211-559): nignored power-iteration generations, then
+// nbatches noise batches of nskip - 1 plain generations, one generation that samples the noise source, and the noise
+// simulation of that source (inner generations, regional cancellation of the noise fission banks).  Out: k_col of every
+// power-iteration generation and 0 per noise batch (Tallies' generation vector); final_bank3 = size of the last bank, its
+// first history id, the global history counter; the mesh tallies are read with ref_tally_get_stat.
+int ref_noise_run(const char* text, int nbatches, int nignored, int nskip, double* kcol, int* n_kcol, uint64_t* final_bank3) {
+  try {
+    if (ref_problem_load(text) != 0) return 1;
+    omp_set_num_threads(g_threads);
+    settings::ngenerations = nbatches;
+    settings::nignored = nignored;
+    settings::nskip = nskip;
+    DriverParts d = driver_parts(text);
+    std::shared_ptr<Noise> sim = d.cancelator ? std::make_shared<Noise>(g_tallies, g_transporter, d.sources, d.cancelator, *g_noise_maker)
+                                              : std::make_shared<Noise>(g_tallies, g_transporter, d.sources, *g_noise_maker);
+    set_entropy(*sim, d.entropy_lines);
+    sim->initialize();
+    sim->run();
+    const Tallies& T = *g_tallies;
+    final_bank3[0] = sim->bank.size(); final_bank3[1] = sim->bank.empty() ? 0 : sim->bank.front().history_id();
+    final_bank3[2] = sim->global_histories_counter;
+    *n_kcol = (int)T.k_col_vec.size();
+    for (size_t g = 0; g < T.k_col_vec.size(); g++) kcol[g] = T.k_col_vec[g];
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "ref_noise_run: %s\n", e.what());
     return 1;
   }
 }

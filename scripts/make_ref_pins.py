@@ -19,6 +19,7 @@ out.update(ref_pins.sample_mu("reference", out))
 out.update(ref_pins.evaluate_transport("reference"))
 out.update(ref_pins.evaluate_noise("reference"))
 out.update(ref_pins.evaluate_power_iteration("reference"))
+out.update(ref_pins.evaluate_noise_driver("reference"))
 # mesh-tally arrays of more than 20 000 elements are kept as the SHA-256 of their bytes plus shape: the comparison in
 # tests/test_reference_pins.py is bit for bit either way, and the fixture stays small
 import hashlib  # noqa: E402
