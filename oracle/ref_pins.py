@@ -209,8 +209,8 @@ NHIST_MG, NDRAW_MG = 8, 250
 
 # geometry walks: deck, bounding box of the ray origins, number of rays, steps per ray, mean flight of the delta walk
 GEOMETRY_CASES = (
-    ("c5g7_delta_collision.yaml", (-32.13, -32.13, -0.5), (32.13, 32.13, 0.5), 600, 60, 1.2),       # nested RectLattices
-    ("ref_sqr_c5g7_surface_tl.yaml", None, None, 600, 60, 1.2),                                       # reflective quarter core
+    ("c5g7_delta_collision.yaml", (-32.13, -32.13, -0.5), (32.13, 32.13, 0.5), 300, 50, 1.2),       # nested RectLattices
+    ("ref_sqr_c5g7_surface_tl.yaml", None, None, 300, 50, 1.2),                                       # reflective quarter core
     ("Ua-1-1-CY.yaml", None, None, 300, 12, 2.0),                                                     # z-cylinder, vacuum
     ("PUa-1-0-SL.yaml", None, None, 300, 12, 1.0),                                                    # slab
     ("UD2O-2-1-SL.yaml", None, None, 300, 12, 3.0),

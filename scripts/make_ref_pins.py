@@ -20,13 +20,13 @@ out.update(ref_pins.evaluate_transport("reference"))
 out.update(ref_pins.evaluate_noise("reference"))
 out.update(ref_pins.evaluate_power_iteration("reference"))
 out.update(ref_pins.evaluate_noise_driver("reference"))
-# mesh-tally arrays of more than 20 000 elements are kept as the SHA-256 of their bytes plus shape: the comparison in
+# mesh-tally arrays of more than 100 000 elements are kept as the SHA-256 of their bytes plus shape: the comparison in
 # tests/test_reference_pins.py is bit for bit either way, and the fixture stays small
 import hashlib  # noqa: E402
 
 small = {}
 for k, v in out.items():
-    if v.size > 20000 and "tally" in k:
+    if v.size > 100000 and "tally" in k:
         small[k + "__sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(v).tobytes()).digest(), dtype=np.uint8)
         small[k + "__shape"] = np.asarray(v.shape, dtype=np.int64)
     else:
