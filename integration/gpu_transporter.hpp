@@ -1,0 +1,104 @@
+/* integration/gpu_transporter.hpp -- the adapter of INTEGRATION.md section 1, written against the REFERENCE'S OWN types.
+ *
+ * `GPUTransporter : Transporter` (include/simulation/transporter.hpp:39-47 of the reference) forwards
+ * Transporter::transport(bank) to abl_transport() of libabeille_b200.so (include/abeille_b200.h) and hands the reference
+ * back what its own trackers would: the fission bank as std::vector<BankedParticle> in the reference's order and the k /
+ * leakage / migration-area scores through Tallies' public score_*() methods.  It is the file a maintainer of the reference
+ * would add; here it is compiled into oracle/_ref/libabeille_ref.so next to the reference's sources (oracle/ref_probe.cpp,
+ * ref_power_iteration_gpu), so that the reference's own PowerIterator::run() drives the B200 backend in
+ * tests/test_gpu_reference_golden.py.  The C ABI is resolved with dlsym, so the library loads on machines without CUDA.
+ *
+ * Not done here (INTEGRATION.md section 1, table of edits): flatten_problem() from the reference's geometry / material
+ * objects -- the handle comes from this repo's host library, which flattens the same YAML deck (ablh_open, ablh_backend);
+ * mesh tallies stay on the device and are not forwarded to the reference's MeshTally objects.  k-eigenvalue mode only.
+ */
+#pragma once
+#include <dlfcn.h>
+
+#include <simulation/transporter.hpp>
+#include <utils/error.hpp>
+#include <utils/settings.hpp>
+
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../include/abeille_b200.h"
+
+class GPUTransporter : public Transporter {
+ public:
+  GPUTransporter(std::shared_ptr<Tallies> tallies, const std::string& host_library, const std::string& yaml_deck, int device)
+      : Transporter(tallies) {
+    lib_ = dlopen(host_library.c_str(), RTLD_NOW | RTLD_GLOBAL);
+    if (!lib_) fatal_error(std::string("GPUTransporter: ") + dlerror());
+    open_ = reinterpret_cast<open_fn>(dlsym(lib_, "ablh_open"));
+    close_ = reinterpret_cast<close_fn>(dlsym(lib_, "ablh_close"));
+    backend_ = reinterpret_cast<backend_fn>(dlsym(lib_, "ablh_backend"));
+    transport_ = reinterpret_cast<transport_fn>(dlsym(lib_, "abl_transport"));
+    last_error_ = reinterpret_cast<error_fn>(dlsym(lib_, "abl_last_error"));
+    if (!open_ || !close_ || !backend_ || !transport_ || !last_error_) fatal_error("GPUTransporter: C ABI symbols missing");
+    char err[512] = {0};
+    ctx_ = open_(yaml_deck.c_str(), device, err, 512);
+    if (!ctx_) fatal_error(std::string("GPUTransporter: ") + err);
+    h_ = backend_(ctx_);
+  }
+  ~GPUTransporter() {
+    if (ctx_) close_(ctx_);
+  }
+
+  std::vector<BankedParticle> transport(std::vector<Particle>& bank, bool noise = false,
+                                        std::vector<BankedParticle>* noise_bank = nullptr,
+                                        const NoiseMaker* noise_maker = nullptr) override {
+    if (noise || noise_bank || noise_maker) fatal_error("GPUTransporter (integration demo): k-eigenvalue mode only");
+    const std::size_t N = bank.size();
+    for (auto* v : {&x_, &y_, &z_, &ux_, &uy_, &uz_, &E_, &w_}) v->resize(N);
+    id_.resize(N); fam_.resize(N); rng_.resize(N);
+    for (std::size_t i = 0; i < N; i++) {  // AoS -> SoA (particle.hpp:68-243)
+      const Particle& p = bank[i];
+      x_[i] = p.r().x(); y_[i] = p.r().y(); z_[i] = p.r().z();
+      ux_[i] = p.u().x(); uy_[i] = p.u().y(); uz_[i] = p.u().z();
+      E_[i] = p.E(); w_[i] = p.wgt();
+      id_[i] = p.history_id(); fam_[i] = p.family_id();
+      rng_[i] = p.rng.state_;  // source particles continue the stream they were sampled with (src/simulation.cpp:70-73)
+    }
+    const std::size_t cap = 3 * N + 4096;
+    for (auto* v : {&ox_, &oy_, &oz_, &oux_, &ouy_, &ouz_, &oE_, &ow_}) v->resize(cap);
+    oa_.resize(cap); ob_.resize(cap); oc_.resize(cap);
+    abl_bank in{N, x_.data(), y_.data(), z_.data(), ux_.data(), uy_.data(), uz_.data(), E_.data(), w_.data(), nullptr,
+                id_.data(), fam_.data(), rng_.data()};
+    abl_bank out{cap, ox_.data(), oy_.data(), oz_.data(), oux_.data(), ouy_.data(), ouz_.data(), oE_.data(), ow_.data(), nullptr,
+                 oa_.data(), ob_.data(), oc_.data()};
+    abl_gen_params gp{tallies->kcol(), tallies->keff(), settings::converged ? 1 : 0, 0, 0, 0};
+    uint64_t m = 0, counters[8];
+    double s[6];
+    if (transport_(h_, &in, &gp, &out, &m, s, counters) != 0) fatal_error(std::string("GPUTransporter: ") + last_error_(h_));
+    tallies->score_k_col(s[0]); tallies->score_k_abs(s[1]); tallies->score_k_trk(s[2]); tallies->score_k_tot(s[3]);
+    tallies->score_leak(s[4]); tallies->score_mig_area(s[5]);  // tallies.hpp:97-102
+    std::vector<BankedParticle> fis(m);  // already in the reference's order (bank order, then creation order)
+    for (std::size_t i = 0; i < m; i++) {
+      BankedParticle& f = fis[i];
+      f.r = Position(ox_[i], oy_[i], oz_[i]);
+      const double u3[3] = {oux_[i], ouy_[i], ouz_[i]};
+      std::memcpy(static_cast<void*>(&f.u), u3, sizeof(Direction));  // bit for bit: Direction(x, y, z) would renormalise
+      f.E = oE_[i]; f.wgt = ow_[i]; f.wgt2 = 0.;
+      f.parent_history_id = oa_[i]; f.parent_daughter_id = ob_[i]; f.family_id = oc_[i];
+    }
+    return fis;
+  }
+
+ private:
+  using open_fn = void* (*)(const char*, int, char*, int);
+  using close_fn = void (*)(void*);
+  using backend_fn = abl_handle (*)(void*);
+  using transport_fn = int (*)(abl_handle, const abl_bank*, const abl_gen_params*, abl_bank*, uint64_t*, double*, uint64_t*);
+  using error_fn = const char* (*)(abl_handle);
+  void* lib_ = nullptr;
+  void* ctx_ = nullptr;
+  abl_handle h_ = nullptr;
+  open_fn open_ = nullptr; close_fn close_ = nullptr; backend_fn backend_ = nullptr; transport_fn transport_ = nullptr;
+  error_fn last_error_ = nullptr;
+  std::vector<double> x_, y_, z_, ux_, uy_, uz_, E_, w_, ox_, oy_, oz_, oux_, ouy_, ouz_, oE_, ow_;
+  std::vector<uint64_t> id_, fam_, rng_, oa_, ob_, oc_;
+};

@@ -642,3 +642,23 @@ def evaluate_noise_driver(impl: str, only: int | None = None) -> dict:
             for t, (a, e) in enumerate(tal):
                 out[f"nd_{name}_tally{t}_avg"], out[f"nd_{name}_tally{t}_std"] = a, e
     return out
+
+
+def power_iteration_through_gpu_transporter(only: int, host_library: str, yaml_deck: str, device: int = 0) -> dict:
+    """The reference's own PowerIterator::run() with its transporter replaced by GPUTransporter
+    (integration/gpu_transporter.hpp): the drop-in of INTEGRATION.md, live.  Needs a GPU; one case per process."""
+    from . import deck as _deck
+    fname, n, ngen, nign = POWER_ITERATION_CASES[only]
+    deck = _deck.load_yaml(yaml_deck)
+    L = ref_lib()
+    keys = ("kcol", "ktrk", "leak", "mig", "entropy")
+    a = {k: np.zeros(ngen) for k in keys}
+    summ = np.zeros(6)
+    L.ref_set_threads(C.c_int(1))
+    rc = L.ref_power_iteration_gpu(_deck.deck_to_text(deck).encode(), host_library.encode(), yaml_deck.encode(), C.c_int(device),
+                                   C.c_int(ngen), C.c_int(nign), *[_d(a[k]) for k in keys], _d(summ))
+    assert rc == 0
+    name = fname.split(".")[0]
+    out = {f"pi_{name}_{k}": a[k] for k in keys}
+    out[f"pi_{name}_summary"] = summ
+    return out

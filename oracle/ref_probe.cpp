@@ -67,6 +67,8 @@
 
 #include <omp.h>
 
+#include "../integration/gpu_transporter.hpp"
+
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -1027,10 +1029,27 @@ extern "C" {
 // leakage, migration area (Tallies' generation vectors), the total pre-cancellation entropy; summary = k_col avg / err,
 // k_trk avg / err, leakage avg / err.  (This file is compiled with -fno-access-control to read the private per-generation
 // vectors; access control does not enter the object layout.)
+int ref_power_iteration_gpu(const char* text, const char* host_library, const char* yaml_deck, int device, int ngen, int nignored,
+                            double* kcol, double* ktrk, double* leak, double* mig, double* entropy, double* summary);
 int ref_power_iteration(const char* text, int ngen, int nignored, double* kcol, double* ktrk, double* leak, double* mig,
                         double* entropy, double* summary) {
+  return ref_power_iteration_gpu(text, nullptr, nullptr, 0, ngen, nignored, kcol, ktrk, leak, mig, entropy, summary);
+}
+// The same, with the transporter replaced by GPUTransporter (integration/gpu_transporter.hpp) when host_library is given:
+// the reference's PowerIterator::run() -- its own source sampling, entropy, cancellation, normalisation and statistics --
+// drives the B200 backend through the C ABI.  yaml_deck is the YAML file of the same deck (the backend's host library
+// flattens it); mesh tallies are then scored on the device only and the reference's Tallies object holds none.
+int ref_power_iteration_gpu(const char* text, const char* host_library, const char* yaml_deck, int device, int ngen, int nignored,
+                            double* kcol, double* ktrk, double* leak, double* mig, double* entropy, double* summary) {
   try {
     if (ref_problem_load(text) != 0) return 1;
+    if (host_library) {
+      g_tallies = std::make_shared<Tallies>(static_cast<double>(settings::nparticles));
+      g_tallies->set_keff(settings::keff);
+      g_tally_gen.clear();
+      g_mesh_tallies.clear();
+      g_transporter = std::make_shared<GPUTransporter>(g_tallies, host_library, yaml_deck, device);
+    }
     omp_set_num_threads(g_threads);
     settings::ngenerations = ngen;
     settings::nignored = nignored;

@@ -160,3 +160,31 @@ def test_noise_simulation_reproduces_the_references_noise_driver(ab, golden, tmp
             assert np.array_equal(a != 0, ref != 0) or abs(a.sum() - ref.sum()) <= 0.5 * np.abs(ref).sum(), tname
     assert len(sim.tally_names) == 4
     sim.close()
+
+
+@pytest.mark.parametrize("ci", range(len(ref_pins.POWER_ITERATION_CASES)),
+                         ids=[c[0].split(".")[0] for c in ref_pins.POWER_ITERATION_CASES])
+def test_references_power_iterator_drives_the_gpu_transporter(ab, golden, tmp_path, ci):
+    """The drop-in, live: the reference's OWN PowerIterator::run() (compiled from its sources into oracle/_ref) with its
+    transporter replaced by integration/gpu_transporter.hpp -- `GPUTransporter : Transporter` written against the
+    reference's types, forwarding transport() to abl_transport() of libabeille_b200.so.  The reference's source sampling,
+    entropy, cancellation, normalisation and statistics run unchanged; every generation's k_col, k_trk, leakage, migration
+    area and entropy must equal what the reference obtained with its own CPU trackers (golden vectors) to 1e-9."""
+    import subprocess
+    import sys
+    if not os.path.exists(ref_pins.REF_LIB):
+        pytest.skip("oracle/_ref/libabeille_ref.so was not built (needs /root/reference at build time)")
+    from abeille_b200 import backend
+    _, host_lib = backend.lib_paths()
+    fname, n, ngen, nign = ref_pins.POWER_ITERATION_CASES[ci]
+    name = fname.split(".")[0]
+    path = write_deck(load_deck(fname), tmp_path / fname, {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}})
+    out = str(tmp_path / "pi_gpu.npz")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (f"import sys; sys.path.insert(0, {root!r}); import numpy as np; from oracle import ref_pins; "
+            f"np.savez({out!r}, **ref_pins.power_iteration_through_gpu_transporter({ci}, {host_lib!r}, {str(path)!r}))")
+    subprocess.run([sys.executable, "-c", code], check=True, stdout=subprocess.DEVNULL)  # one simulation per process
+    got = dict(np.load(out))
+    for k in ("kcol", "ktrk", "leak", "mig", "entropy"):
+        assert np.allclose(got[f"pi_{name}_{k}"], golden[f"pi_{name}_{k}"], rtol=1e-9, atol=1e-12), (k, got[f"pi_{name}_{k}"])
+    assert np.allclose(got[f"pi_{name}_summary"], golden[f"pi_{name}_summary"], rtol=1e-7, atol=1e-12)
