@@ -650,6 +650,7 @@ std::vector<const MeshTally*> g_mesh_tallies;
 std::unique_ptr<NoiseMaker> g_noise_maker;
 int g_threads = 1;
 double g_last_transport_seconds = 0.;
+double g_last_simulation_seconds = 0.;
 }  // namespace
 
 extern "C" {
@@ -927,6 +928,8 @@ void ref_tally_get_stat(int t, int which, double* out) {
   const NDArray<double>& a = which == 1 ? g_mesh_tallies[(size_t)t]->tally_avg : g_mesh_tallies[(size_t)t]->tally_var;
   for (size_t i = 0; i < a.size(); i++) out[i] = a[i];
 }
+// the reference's own simulation_timer of the last ref_power_iteration[_gpu]: the generation loop without initialisation
+double ref_last_simulation_seconds() { return g_last_simulation_seconds; }
 // OpenMP threads of the next ref_transport calls (1 for the bit-exact pins: score sums in bank order; all cores for timing)
 void ref_set_threads(int n) { g_threads = n > 0 ? n : 1; }
 // wall time of the transport() call alone inside the last ref_transport (bank construction and copies excluded)
@@ -1060,6 +1063,7 @@ int ref_power_iteration_gpu(const char* text, const char* host_library, const ch
     set_entropy(*pi, d.entropy_lines);
     pi->initialize();
     pi->run();
+    g_last_simulation_seconds = pi->simulation_timer.elapsed_time();  // the generation loop (src/power_iterator.cpp:316-318,432)
     const Tallies& T = *g_tallies;
     for (int g = 0; g < ngen; g++) {
       kcol[g] = T.k_col_vec[(size_t)g]; ktrk[g] = T.k_trk_vec[(size_t)g]; leak[g] = T.leak_vec[(size_t)g]; mig[g] = T.mig_vec[(size_t)g];
