@@ -10,7 +10,8 @@
  *
  * Not done here (INTEGRATION.md section 1, table of edits): flatten_problem() from the reference's geometry / material
  * objects -- the handle comes from this repo's host library, which flattens the same YAML deck (ablh_open, ablh_backend);
- * mesh tallies stay on the device and are not forwarded to the reference's MeshTally objects.  k-eigenvalue mode only.
+ * the reference's MeshTally objects are not edited: the device tallies are recorded / cleared by the adapter itself (see
+ * close_generation) and read back with tally().  k-eigenvalue mode only.
  */
 #pragma once
 #include <dlfcn.h>
@@ -38,7 +39,13 @@ class GPUTransporter : public Transporter {
     backend_ = reinterpret_cast<backend_fn>(dlsym(lib_, "ablh_backend"));
     transport_ = reinterpret_cast<transport_fn>(dlsym(lib_, "abl_transport"));
     last_error_ = reinterpret_cast<error_fn>(dlsym(lib_, "abl_last_error"));
-    if (!open_ || !close_ || !backend_ || !transport_ || !last_error_) fatal_error("GPUTransporter: C ABI symbols missing");
+    record_ = reinterpret_cast<record_fn>(dlsym(lib_, "abl_tallies_record"));
+    clear_ = reinterpret_cast<clear_fn>(dlsym(lib_, "abl_tallies_clear"));
+    fetch_ = reinterpret_cast<fetch_fn>(dlsym(lib_, "abl_tally_fetch"));
+    shape_ = reinterpret_cast<shape_fn>(dlsym(lib_, "abl_tally_shape"));
+    count_ = reinterpret_cast<count_fn>(dlsym(lib_, "abl_tally_count"));
+    if (!open_ || !close_ || !backend_ || !transport_ || !last_error_ || !record_ || !clear_ || !fetch_ || !shape_ || !count_)
+      fatal_error("GPUTransporter: C ABI symbols missing");
     char err[512] = {0};
     ctx_ = open_(yaml_deck.c_str(), device, err, 512);
     if (!ctx_) fatal_error(std::string("GPUTransporter: ") + err);
@@ -48,10 +55,33 @@ class GPUTransporter : public Transporter {
     if (ctx_) close_(ctx_);
   }
 
+  // Mesh tallies live in HBM and are scored inside the kernels.  Between two transport() calls the reference does
+  // tallies->record_generation() (if converged) and tallies->clear_generation() on its own MeshTally objects
+  // (src/power_iterator.cpp:378-382); the edit of INTEGRATION.md forwards those to abl_tallies_record / _clear.  Without
+  // touching the reference's MeshTally, the adapter does the same for the device arrays at the next transport() call --
+  // nothing reads them in between -- and once more from finish() after the last generation.
+  void close_generation() {
+    if (scored_ && record_(h_, 1.0) != 0) fatal_error(std::string("GPUTransporter: ") + last_error_(h_));
+    if (clear_(h_) != 0) fatal_error(std::string("GPUTransporter: ") + last_error_(h_));
+    scored_ = false;
+  }
+  void finish() { close_generation(); }
+  int ntallies() const { return count_(h_); }
+  // average (which = 1) or error of the mean (which = 3) of mesh tally t, as MeshTally::write_tally would store them
+  std::vector<double> tally(int t, int which) const {
+    uint64_t sh[4];
+    if (shape_(h_, t, sh) != 0) fatal_error("GPUTransporter: bad tally index");
+    std::vector<double> out(sh[0] * sh[1] * sh[2] * sh[3]);
+    if (fetch_(h_, t, which, out.data()) != 0) fatal_error(std::string("GPUTransporter: ") + last_error_(h_));
+    return out;
+  }
+
   std::vector<BankedParticle> transport(std::vector<Particle>& bank, bool noise = false,
                                         std::vector<BankedParticle>* noise_bank = nullptr,
                                         const NoiseMaker* noise_maker = nullptr) override {
     if (noise || noise_bank || noise_maker) fatal_error("GPUTransporter (integration demo): k-eigenvalue mode only");
+    close_generation();
+    scored_ = settings::converged;
     const std::size_t N = bank.size();
     for (auto* v : {&x_, &y_, &z_, &ux_, &uy_, &uz_, &E_, &w_}) v->resize(N);
     id_.resize(N); fam_.resize(N); rng_.resize(N);
@@ -94,6 +124,13 @@ class GPUTransporter : public Transporter {
   using backend_fn = abl_handle (*)(void*);
   using transport_fn = int (*)(abl_handle, const abl_bank*, const abl_gen_params*, abl_bank*, uint64_t*, double*, uint64_t*);
   using error_fn = const char* (*)(abl_handle);
+  using record_fn = int (*)(abl_handle, double);
+  using clear_fn = int (*)(abl_handle);
+  using fetch_fn = int (*)(abl_handle, int, int, double*);
+  using shape_fn = int (*)(abl_handle, int, uint64_t*);
+  using count_fn = int (*)(abl_handle);
+  record_fn record_ = nullptr; clear_fn clear_ = nullptr; fetch_fn fetch_ = nullptr; shape_fn shape_ = nullptr; count_fn count_ = nullptr;
+  bool scored_ = false;
   void* lib_ = nullptr;
   void* ctx_ = nullptr;
   abl_handle h_ = nullptr;

@@ -661,4 +661,12 @@ def power_iteration_through_gpu_transporter(only: int, host_library: str, yaml_d
     name = fname.split(".")[0]
     out = {f"pi_{name}_{k}": a[k] for k in keys}
     out[f"pi_{name}_summary"] = summ
+    L.ref_gpu_tally_get.restype = C.c_uint64
+    for t in range(L.ref_gpu_ntallies()):  # the device's mesh tallies, recorded / cleared by the adapter between generations
+        size = int(L.ref_gpu_tally_get(C.c_int(t), C.c_int(1), None, C.c_uint64(0)))
+        for which, wname in ((1, "avg"), (3, "std")):
+            v = np.zeros(size)
+            L.ref_gpu_tally_get(C.c_int(t), C.c_int(which), _d(v), C.c_uint64(size))
+            out[f"pi_{name}_tally{t}_{wname}"] = v
+    L.ref_gpu_release()
     return out

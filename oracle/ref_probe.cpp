@@ -634,6 +634,7 @@ Direction raw_direction(const double* u) {
 }
 std::shared_ptr<Tallies> g_tallies;
 std::shared_ptr<Transporter> g_transporter;
+std::shared_ptr<GPUTransporter> g_gpu_transporter;
 // the generation array of a mesh tally is a protected member (include/simulation/mesh_tally.hpp:79); the probe's tallies are
 // created as these derived types so that it can be read back.  Nothing is overridden.
 struct CollisionTallyProbe : CollisionMeshTally {
@@ -928,6 +929,14 @@ void ref_tally_get_stat(int t, int which, double* out) {
   const NDArray<double>& a = which == 1 ? g_mesh_tallies[(size_t)t]->tally_avg : g_mesh_tallies[(size_t)t]->tally_var;
   for (size_t i = 0; i < a.size(); i++) out[i] = a[i];
 }
+// mesh tallies of the device after ref_power_iteration_gpu: number, size, and average (which = 1) / error of the mean (3)
+int ref_gpu_ntallies() { return g_gpu_transporter ? g_gpu_transporter->ntallies() : 0; }
+uint64_t ref_gpu_tally_get(int t, int which, double* out, uint64_t cap) {
+  const std::vector<double> v = g_gpu_transporter->tally(t, which);
+  for (uint64_t i = 0; i < v.size() && i < cap; i++) out[i] = v[i];
+  return v.size();
+}
+void ref_gpu_release() { g_gpu_transporter.reset(); g_transporter.reset(); }
 // the reference's own simulation_timer of the last ref_power_iteration[_gpu]: the generation loop without initialisation
 double ref_last_simulation_seconds() { return g_last_simulation_seconds; }
 // OpenMP threads of the next ref_transport calls (1 for the bit-exact pins: score sums in bank order; all cores for timing)
@@ -1051,7 +1060,8 @@ int ref_power_iteration_gpu(const char* text, const char* host_library, const ch
       g_tallies->set_keff(settings::keff);
       g_tally_gen.clear();
       g_mesh_tallies.clear();
-      g_transporter = std::make_shared<GPUTransporter>(g_tallies, host_library, yaml_deck, device);
+      g_gpu_transporter = std::make_shared<GPUTransporter>(g_tallies, host_library, yaml_deck, device);
+      g_transporter = g_gpu_transporter;
     }
     omp_set_num_threads(g_threads);
     settings::ngenerations = ngen;
@@ -1064,6 +1074,7 @@ int ref_power_iteration_gpu(const char* text, const char* host_library, const ch
     pi->initialize();
     pi->run();
     g_last_simulation_seconds = pi->simulation_timer.elapsed_time();  // the generation loop (src/power_iterator.cpp:316-318,432)
+    if (host_library) g_gpu_transporter->finish();
     const Tallies& T = *g_tallies;
     for (int g = 0; g < ngen; g++) {
       kcol[g] = T.k_col_vec[(size_t)g]; ktrk[g] = T.k_trk_vec[(size_t)g]; leak[g] = T.leak_vec[(size_t)g]; mig[g] = T.mig_vec[(size_t)g];

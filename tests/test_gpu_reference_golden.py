@@ -188,3 +188,9 @@ def test_references_power_iterator_drives_the_gpu_transporter(ab, golden, tmp_pa
     for k in ("kcol", "ktrk", "leak", "mig", "entropy"):
         assert np.allclose(got[f"pi_{name}_{k}"], golden[f"pi_{name}_{k}"], rtol=1e-9, atol=1e-12), (k, got[f"pi_{name}_{k}"])
     assert np.allclose(got[f"pi_{name}_summary"], golden[f"pi_{name}_summary"], rtol=1e-7, atol=1e-12)
+    # the device's mesh tallies (recorded / cleared by the adapter where the reference records / clears its own) against the
+    # average and error of the mean the reference's MeshTally objects ended with
+    for key in [k for k in got if "_tally" in k and k in golden]:
+        scale = np.abs(golden[key]).max()
+        assert got[key].shape == golden[key].shape
+        assert np.abs(got[key] - golden[key]).max() <= 1e-9 * scale, (key, np.abs(got[key] - golden[key]).max(), scale)
