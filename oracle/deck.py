@@ -62,7 +62,8 @@ def deck_to_text(deck: dict) -> str:
     sim = st["simulation"]
     if sim not in ("k-eigenvalue", "noise"):
         raise ValueError(f"unsupported simulation {sim}")
-    tr = {"surface-tracking": "surface", "delta-tracking": "delta", "carter-tracking": "carter"}[
+    tr = {"surface-tracking": "surface", "delta-tracking": "delta", "carter-tracking": "carter",
+          "implicit-leakage-delta-tracking": "implicit"}[
         st.get("transport", "surface-tracking")]
     out.append(f"mode {'noise' if sim == 'noise' else 'k'} tracking {tr}")
     out.append(f"ngroups {G}")

@@ -85,6 +85,51 @@ static inline double orc_log(double x) {
   return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
 }
 
+// fdlibm e_exp.c (same operation sequence as det_exp in abeille_b200/csrc/detmath.cuh)
+static inline double orc_exp(double x) {
+  const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10,
+               invln2 = 1.44269504088896338700e+00, P1 = 1.66666666666666019037e-01,
+               P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
+               P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08,
+               o_threshold = 7.09782712893383973096e+02, u_threshold = -7.45133219101941108420e+02,
+               twom1000 = 9.33263618503218878990e-302;
+  int32_t hx = orc_hi(x);
+  const int xsb = (hx >> 31) & 1;
+  hx &= 0x7fffffff;
+  double hi = 0., lo = 0.;
+  int32_t k = 0;
+  if (hx >= 0x40862E42) {  // |x| >= 709.78...
+    if (hx >= 0x7ff00000) {
+      if (((hx & 0xfffff) | orc_lo(x)) != 0) return x + x;  // NaN
+      return xsb == 0 ? x : 0.0;                        // exp(+-inf)
+    }
+    if (x > o_threshold) return 1.0e+300 * 1.0e+300;
+    if (x < u_threshold) return twom1000 * twom1000;
+  }
+  if (hx > 0x3fd62e42) {     // |x| > 0.5 ln2
+    if (hx < 0x3FF0A2B2) {   // |x| < 1.5 ln2
+      hi = xsb ? x + ln2HI : x - ln2HI;
+      lo = xsb ? -ln2LO : ln2LO;
+      k = 1 - xsb - xsb;
+    } else {
+      k = (int32_t)(invln2 * x + (xsb ? -0.5 : 0.5));
+      const double t = (double)k;
+      hi = x - t * ln2HI;
+      lo = t * ln2LO;
+    }
+    x = hi - lo;
+  } else if (hx < 0x3e300000) {  // |x| < 2^-28
+    return 1.0 + x;
+  }
+  const double t = x * x;
+  const double c = x - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+  if (k == 0) return 1.0 - ((x * c) / (c - 2.0) - x);
+  double y = 1.0 - ((lo - (x * c) / (2.0 - c)) - hi);
+  if (k >= -1021) return orc_set_hi(y, orc_hi(y) + k * 1048576);
+  y = orc_set_hi(y, orc_hi(y) + (k + 1000) * 1048576);
+  return y * twom1000;
+}
+
 static inline double orc_ksin(double x, double y, int iy) {
   const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
                S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,

@@ -49,7 +49,8 @@ namespace orc {
 static double libm_log(double x) { return std::log(x); }
 static double libm_sin(double x) { return std::sin(x); }
 static double libm_cos(double x) { return std::cos(x); }
-MathFns g_math = {libm_log, libm_sin, libm_cos};
+static double libm_exp(double x) { return std::exp(x); }
+MathFns g_math = {libm_log, libm_sin, libm_cos, libm_exp};
 
 // ------------------------------------------------------------------------------------
 struct Source {  // src/source.cpp, box.cpp, point.cpp, isotropic.cpp, mono_energetic.cpp
@@ -200,7 +201,9 @@ static Problem* load_problem(const char* path) {
   tk.expect("tracking");
   {
     std::string t = tk.next();
-    st.tracking = t == "delta" ? Settings::DELTA : (t == "carter" ? Settings::CARTER : Settings::SURFACE);
+    st.tracking = t == "delta" ? Settings::DELTA
+                  : t == "carter" ? Settings::CARTER
+                  : t == "implicit" ? Settings::IMPLICIT_LEAKAGE : Settings::SURFACE;
   }
   tk.expect("ngroups");
   st.ngroups = (uint32_t)tk.ll();
@@ -776,6 +779,87 @@ static void history_delta_or_carter(Ctx& cx, Particle& p, bool carter) {
   }
 }
 
+// ImplicitLeakageDeltaTracker::transport (src/implicit_leakage_delta_tracker.cpp:73-263): delta tracking that asks for the
+// boundary condition before every flight; towards a vacuum boundary the weight that would fly out is scored as leakage
+// and the flight distance is sampled from the exponential truncated at the boundary.
+static void history_implicit_leakage(Ctx& cx, Particle& p) {
+  Problem& P = *cx.P;
+  const Settings& st = P.st;
+  const bool noise = cx.noise;
+  Tracker trkr(&P.geo, p.r(), p.u());
+  if (trkr.is_lost()) {
+    cx.cn.lost_at_birth++;
+    p.kill();
+  }
+  Mat mat(&P, trkr.current_mat);
+  while (p.alive) {
+    bool had_collision = false, crossed_boundary = false;
+    const size_t g = st.group(p.E());
+    const double Emajorant = P.majorant[g] + mat.Ew(p.E(), noise);
+    Boundary bound = trkr.get_boundary_condition();
+    cx.cn.flights++;
+    p.n_flights++;
+    double d_coll = 0.;
+    if (bound.boundary_type == BC_VACUUM) {  // :117-153
+      const double P_leak = g_math.exp(-Emajorant * bound.distance);
+      const double P_no_leak = 1. - P_leak;
+      const double wgt_leak = p.wgt() * P_leak, wgt2_leak = p.wgt2() * P_leak;
+      const double wgt_collides = p.wgt() * P_no_leak, wgt2_collides = p.wgt2() * P_no_leak;
+      cx.ts.leakage += wgt_leak;
+      {
+        Vec r_leak = p.r() + bound.distance * p.u();
+        const Vec d = r_leak - p.r_birth;
+        const Vec wd{d.x * wgt_leak, d.y * wgt_leak, d.z * wgt_leak};  // (w * d) . d, as in leak()
+        cx.ts.mig += wd.dot(d);
+      }
+      d_coll = -g_math.log(1. - P_no_leak * rng_rand(p.rng)) / Emajorant;
+      p.state.weight = wgt_leak;
+      p.state.weight2 = wgt2_leak;
+      score_flight(cx, p, bound.distance, mat);
+      p.state.weight = wgt_collides;
+      p.state.weight2 = wgt2_collides;
+      score_flight(cx, p, d_coll, mat);
+    } else {
+      d_coll = rng_exponential(p.rng, Emajorant);
+      score_flight(cx, p, std::min(d_coll, bound.distance), mat);
+    }
+    if (bound.distance < d_coll || std::abs(bound.distance - d_coll) < BOUNDRY_TOL) {  // :165-194
+      crossed_boundary = true;
+      cx.cn.boundary_events++;
+      p.n_boundary++;
+      if (bound.boundary_type == BC_VACUUM) {
+        p.note(0x3000000000000000ULL | (uint64_t)(uint32_t)(trkr.current_cell + 1));
+        leak(cx, p, bound);
+      } else if (bound.boundary_type == BC_REFLECTIVE) {
+        do_reflection(trkr, p, bound);
+        if (trkr.is_lost()) throw std::runtime_error("Particle has become lost after reflection.");
+        p.note(0x4000000000000000ULL | (uint64_t)(uint32_t)(trkr.current_cell + 1));
+      } else {
+        throw std::runtime_error("Help me, how did I get here ?");
+      }
+    } else {  // :195-231
+      p.move(d_coll);
+      trkr.move(d_coll);
+      trkr.get_current();
+      if (trkr.is_lost()) throw std::runtime_error("Particle has become lost after a flight.");
+      mat.m = trkr.current_mat;
+      double Et = mat.Et(p.E(), noise);
+      if (Et - Emajorant > 1.E-10) throw std::runtime_error("Total cross section excedeed majorant");
+      if (rng_rand(p.rng) < (Et / Emajorant)) had_collision = true;
+      p.note((had_collision ? 0x2000000000000000ULL : 0x1000000000000000ULL) | (uint64_t)(uint32_t)(trkr.current_cell + 1));
+    }
+    if (p.alive && had_collision) {
+      collision(cx, p, mat, noise);
+      trkr.set_u(p.u());
+      p.previous_collision_virtual = false;
+    } else if (p.alive) {
+      if (!crossed_boundary) { cx.cn.virtual_collisions++; p.n_virtual++; }
+      p.previous_collision_virtual = true;
+    }
+    if (!p.alive) try_resurrect(cx, p, trkr, mat);
+  }
+}
+
 static void history_surface(Ctx& cx, Particle& p) {
   Problem& P = *cx.P;
   const bool noise = cx.noise;
@@ -841,6 +925,7 @@ static std::vector<BankedParticle> transport(Problem& P, std::vector<Particle>& 
       try {
         Particle& p = bank[n];
         if (P.st.tracking == Settings::SURFACE) history_surface(cx, p);
+        else if (P.st.tracking == Settings::IMPLICIT_LEAKAGE) history_implicit_leakage(cx, p);
         else history_delta_or_carter(cx, p, P.st.tracking == Settings::CARTER);
       } catch (const std::exception& e) {
 #pragma omp critical
@@ -1226,8 +1311,8 @@ static int g_math_mode = 0;
 int orc_get_math() { return g_math_mode; }
 void orc_set_math(int mode) {
   g_math_mode = mode == 0 ? 0 : 1;
-  if (mode == 0) g_math = {libm_log, libm_sin, libm_cos};
-  else g_math = {orc_log, orc_sin, orc_cos};
+  if (mode == 0) g_math = {libm_log, libm_sin, libm_cos, libm_exp};
+  else g_math = {orc_log, orc_sin, orc_cos, orc_exp};
 }
 void orc_set_threads(int n) { omp_set_num_threads(n); }
 int orc_max_threads() { return omp_get_max_threads(); }

@@ -159,7 +159,7 @@ struct Material {
 
 struct Settings {
   enum Mode { K_EIGENVALUE, NOISE } mode = K_EIGENVALUE;
-  enum Tracking { SURFACE, DELTA, CARTER } tracking = SURFACE;
+  enum Tracking { SURFACE, DELTA, CARTER, IMPLICIT_LEAKAGE } tracking = SURFACE;
   uint32_t ngroups = 1;
   std::vector<double> energy_bounds;
   int nparticles = 100000, ngenerations = 120, nignored = 20, nskip = 10;

@@ -33,6 +33,7 @@ struct MathFns {
   double (*log)(double);
   double (*sin)(double);
   double (*cos)(double);
+  double (*exp)(double);
 };
 extern MathFns g_math;  // selected by orc_set_math()
 

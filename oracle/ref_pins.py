@@ -392,7 +392,15 @@ def _sample_mu(impl: str, tables: dict) -> dict:
     return out
 
 
-def evaluate_transport(impl: str) -> dict:
+# ImplicitLeakageDeltaTracker::transport (src/implicit_leakage_delta_tracker.cpp:73-263): vacuum slabs (every flight splits
+# its weight into a leaking and a colliding part) and c5g7 (reflective sides, vacuum top / right) with both estimators
+IMPLICIT_CASES = (
+    ("PUa-1-0-SL_implicit.yaml", 1000, 0.97), ("UD2O-2-1-SL_implicit.yaml", 1000, 1.01),
+    ("c5g7_implicit_collision.yaml", 2500, 1.17), ("c5g7_implicit_tracklength.yaml", 1500, 1.17),
+)
+
+
+def evaluate_transport(impl: str, cases=None, seed0: int = 500) -> dict:
     """One Transporter::transport(bank) per case through the reference's own SurfaceTracker / DeltaTracker / CarterTracker
     (oracle/_ref, one OpenMP thread) or the oracle (glibc math, one thread): the fission bank in the order it is returned
     (9 doubles and parent history id, daughter id, family id per site), the six generation values of
@@ -405,11 +413,11 @@ def evaluate_transport(impl: str) -> dict:
     PU = C.POINTER(C.c_uint64)
     out = {}
     with _reference_math(impl):
-        for ci, (fname, n, k_col) in enumerate(TRANSPORT_CASES):
+        for ci, (fname, n, k_col) in enumerate(TRANSPORT_CASES if cases is None else cases):
             path = os.path.join(decks, fname)
             ov = {"settings": {"nparticles": n}}
             deck = _deck.apply_overrides(_deck.load_yaml(path), ov)
-            r, u, E, w, hid = transport_bank(deck, n, 500 + ci, "carter" in fname)
+            r, u, E, w, hid = transport_bank(deck, n, seed0 + ci, "carter" in fname)
             name = fname.split(".")[0]
             if ref:
                 assert L.ref_problem_load(_deck.deck_to_text(deck).encode()) == 0

@@ -43,6 +43,7 @@
 #include <plotting/plotter.hpp>
 #include <simulation/carter_tracker.hpp>
 #include <simulation/delta_tracker.hpp>
+#include <simulation/implicit_leakage_delta_tracker.hpp>
 #include <simulation/flat_vibration_noise_source.hpp>
 #include <simulation/approximate_mesh_cancelator.hpp>
 #include <simulation/box.hpp>
@@ -670,7 +671,9 @@ int ref_problem_load(const char* text) {
     tk.expect("tracking");
     const std::string trk = tk.next();
     settings::tracking = trk == "delta" ? settings::TrackingMode::DELTA_TRACKING
-                         : trk == "carter" ? settings::TrackingMode::CARTER_TRACKING : settings::TrackingMode::SURFACE_TRACKING;
+                         : trk == "carter" ? settings::TrackingMode::CARTER_TRACKING
+                         : trk == "implicit" ? settings::TrackingMode::IMPLICIT_LEAKAGE_DELTA_TRACKING
+                                             : settings::TrackingMode::SURFACE_TRACKING;
     tk.expect("ngroups");
     const size_t G = (size_t)tk.ll();
     settings::ngroups = (uint32_t)G;
@@ -827,6 +830,9 @@ int ref_problem_load(const char* text) {
     switch (settings::tracking) {
       case settings::TrackingMode::DELTA_TRACKING: g_transporter = std::make_shared<DeltaTracker>(g_tallies); break;
       case settings::TrackingMode::CARTER_TRACKING: g_transporter = std::make_shared<CarterTracker>(g_tallies); break;
+      case settings::TrackingMode::IMPLICIT_LEAKAGE_DELTA_TRACKING:
+        g_transporter = std::make_shared<ImplicitLeakageDeltaTracker>(g_tallies);
+        break;
       default: g_transporter = std::make_shared<SurfaceTracker>(g_tallies); break;
     }
     return 0;
