@@ -59,6 +59,7 @@ struct abl_context {
   uint64_t nsite_cap = 0, did_cap = 0, ndid_cap = 0, nnoise_cap = 0;
   uint32_t *nnoise = nullptr, *noffsets = nullptr, *ntile_sums = nullptr, *site_did = nullptr, *nsite_did = nullptr;
   int nm_blocks_per_sm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  int implicit_blocks_per_sm[3] = {0, 0, 0};  // implicit-leakage delta tracking: per-lane kernel in modes 0 | 1 | 2
   // host-buffer entry point: the bank is copied in row chunks on its own stream while the history kernel runs
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_ids = nullptr, ev_zeroed = nullptr;
@@ -140,7 +141,7 @@ std::vector<double> discrete_table(const std::vector<double>& w) {
 
 int validate(abl_handle h, const abl_problem* p) {
   if (p->ngroups < 1 || !p->energy_bounds) return fail(h, ABL_ERR_INVALID, "ngroups / energy_bounds");
-  if (p->tracking < ABL_TRACK_SURFACE || p->tracking > ABL_TRACK_CARTER) return fail(h, ABL_ERR_INVALID, "tracking");
+  if (p->tracking < ABL_TRACK_SURFACE || p->tracking > ABL_TRACK_IMPLICIT_LEAKAGE) return fail(h, ABL_ERR_INVALID, "tracking");
   if (p->mode != ABL_MODE_K_EIGENVALUE && p->mode != ABL_MODE_NOISE)
     return fail(h, ABL_ERR_UNSUPPORTED, "simulation modes on the device: k-eigenvalue, noise");
   if (p->mode == ABL_MODE_NOISE) {
@@ -383,9 +384,10 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
 // generation (may sample the noise source), MODE 2 = noise particles (noise.cuh)
 template <int TRK, int MODE>
 int launch_transport_nm(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s) {
-  TransportKernel kern = lane_kernel(TRK, MODE);
+  const bool implicit = TRK == ABL_TRACK_IMPLICIT_LEAKAGE;
+  TransportKernel kern = implicit ? implicit_kernel(MODE) : lane_kernel(TRK, MODE);
   const int threads = TK_THREADS;
-  int& bps = h->nm_blocks_per_sm[TRK][MODE];
+  int& bps = implicit ? h->implicit_blocks_per_sm[MODE] : h->nm_blocks_per_sm[implicit ? 0 : TRK][MODE];
   if (bps == 0) {
     int nb = 0;
     ABL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, 0));
@@ -421,6 +423,7 @@ int launch_transport_nm(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t
   switch (h->P.tracking) {
     case ABL_TRACK_SURFACE: return launch_transport_nm<ABL_TRACK_SURFACE, MODE>(h, A, n, s);
     case ABL_TRACK_DELTA: return launch_transport_nm<ABL_TRACK_DELTA, MODE>(h, A, n, s);
+    case ABL_TRACK_IMPLICIT_LEAKAGE: return launch_transport_nm<ABL_TRACK_IMPLICIT_LEAKAGE, MODE>(h, A, n, s);
     default: return launch_transport_nm<ABL_TRACK_CARTER, MODE>(h, A, n, s);
   }
 }
@@ -537,6 +540,8 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
   if (N > 0) {
     if (lane_kernel_call) {  // (the per-lane kernel seeds the streams itself when id_c is NULL)
       rc = params->noise ? launch_transport_nm<2>(h, A, N, s) : launch_transport_nm<1>(h, A, N, s);
+    } else if (h->P.tracking == ABL_TRACK_IMPLICIT_LEAKAGE) {  // k-eigenvalue generation through the per-lane kernel
+      rc = launch_transport_nm<ABL_TRACK_IMPLICIT_LEAKAGE, 0>(h, A, N, s);
     } else {
       switch (h->P.tracking) {
         case ABL_TRACK_SURFACE: rc = launch_transport<ABL_TRACK_SURFACE>(h, A, N, s, params->trace != 0); break;
@@ -953,7 +958,8 @@ int abl_transport(abl_handle h, const abl_bank* bank, const abl_gen_params* para
   // arrays in row chunks on a second stream, each chunk followed by an update of the arrival counter that the history
   // kernel polls before it loads a row -- the PCIe copy (17 ms for 1e7 particles) hides behind the kernel.
   constexpr int NCHUNK = 16;
-  const bool streamed = h->P.mode != ABL_MODE_NOISE && !params->noise && N >= (1u << 18);
+  // (only the staged kernel polls the arrival counter of a streamed bank)
+  const bool streamed = h->P.mode != ABL_MODE_NOISE && !params->noise && N >= (1u << 18) && h->P.tracking != ABL_TRACK_IMPLICIT_LEAKAGE;
   if (streamed) {
     if (!h->copy_stream) {
       ABL_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));

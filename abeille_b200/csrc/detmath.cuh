@@ -228,7 +228,7 @@ static __device__ __noinline__ double det_exp(double x) {
       return xsb == 0 ? x : 0.0;                        // exp(+-inf)
     }
     if (x > o_threshold) return 1.0e+300 * 1.0e+300;
-    if (x < u_threshold) return twom1000 * twom1000;
+    if (x < u_threshold) return 0.0;
   }
   if (hx > 0x3fd62e42) {     // |x| > 0.5 ln2
     if (hx < 0x3FF0A2B2) {   // |x| < 1.5 ln2

@@ -16,4 +16,5 @@ TransportKernel history_kernel_carter(bool trace);   // kernels_carter.cu
 TransportKernel history_kernel_surface(bool trace);  // kernels_surface.cu
 TransportKernel history_kernel_traced(int tracking); // kernels_trace.cu
 TransportKernel lane_kernel(int tracking, int mode); // kernels_lane.cu: per-lane kernel of the noise modes (mode 1 | 2)
+TransportKernel implicit_kernel(int mode);            // kernels_implicit.cu: implicit-leakage delta tracking, per-lane kernel (mode 0 | 1 | 2)
 }  // namespace abl

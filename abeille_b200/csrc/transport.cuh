@@ -417,6 +417,81 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
       note(h, 0x2000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
     }
     if (h.alive && had_collision) collide<MODE>(P, A, h, acc, tid, nthreads);
+  } else if (TRK == ABL_TRACK_IMPLICIT_LEAKAGE) {
+    // ImplicitLeakageDeltaTracker::transport loop body (implicit_leakage_delta_tracker.cpp:105-246): the boundary condition
+    // is looked up before every flight; towards a vacuum boundary the leaking share of the weight is scored at once and the
+    // flight distance is drawn from the exponential truncated at the boundary
+    const double Emaj = MODE == 2 ? __ldg(&P.smp[h.g]) + noise_xs<MODE>(P, h.mat, h.g) : __ldg(&P.smp[h.g]);
+    const Boundary bound = cursor_boundary_condition_nl(geo_tables(P), c, h.u);
+    acc.flights++;
+    h.n_flights++;
+    double d_coll;
+    if (bound.btype == ABL_BC_VACUUM) {
+      const double P_leak = det_exp(-Emaj * bound.distance);
+      const double P_no_leak = 1. - P_leak;
+      const double w_leak = h.w * P_leak, w2_leak = h.w2 * P_leak;
+      const double w_coll = h.w * P_no_leak, w2_coll = h.w2 * P_no_leak;
+      acc.leak += w_leak;
+      const V3 d{h.r.x + bound.distance * h.u.x - h.rb.x, h.r.y + bound.distance * h.u.y - h.rb.y,
+                 h.r.z + bound.distance * h.u.z - h.rb.z};
+      acc.mig += leak_mig_score(w_leak, d);
+      d_coll = -det_log(1. - P_no_leak * rng_rand(h.rng)) / Emaj;
+      h.w = w_leak;
+      h.w2 = w2_leak;
+      score_flight_all(P, A, h, bound.distance, acc);
+      h.w = w_coll;
+      h.w2 = w2_coll;
+      score_flight_all(P, A, h, d_coll, acc);
+    } else {
+      d_coll = rng_exponential(h.rng, Emaj);
+      score_flight_all(P, A, h, fmin(d_coll, bound.distance), acc);
+    }
+    bool crossed = false;
+    if (bound.distance < d_coll || fabs(bound.distance - d_coll) < ABL_BOUNDRY_TOL) {
+      crossed = true;
+      acc.boundary++;
+      if (bound.btype == ABL_BC_VACUUM) {
+        note(h, 0x3000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
+        leak(h, acc, bound);
+      } else if (bound.btype == ABL_BC_REFLECTIVE) {
+        if (!do_reflection(P, c, h, bound) || c.cell < 0) {
+          raise_error(A, ABL_ERR_LOST, hid);
+          h.alive = false;
+          return;
+        }
+        note(h, 0x4000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
+      } else {
+        raise_error(A, ABL_ERR_LOST, hid);
+        h.alive = false;
+        return;
+      }
+    } else {
+      h.r.x = h.r.x + d_coll * h.u.x;
+      h.r.y = h.r.y + d_coll * h.u.y;
+      h.r.z = h.r.z + d_coll * h.u.z;
+      cursor_move(c, d_coll, h.u);
+      cursor_get_current_nl(geo_tables(P), c, h.u);
+      if (c.cell < 0) {
+        raise_error(A, ABL_ERR_LOST, hid);
+        h.alive = false;
+        return;
+      }
+      h.mat = c.mat;
+      const double Et = MODE == 2 ? __ldg(&P.Et[h.mat * P.G + h.g]) + noise_xs<MODE>(P, h.mat, h.g) : __ldg(&P.Et[h.mat * P.G + h.g]);
+      if (Et - Emaj > 1.E-10) {
+        raise_error(A, ABL_ERR_MAJORANT, hid);
+        h.alive = false;
+        return;
+      }
+      if (rng_rand(h.rng) < (Et / Emaj)) had_collision = true;
+      note(h, (had_collision ? 0x2000000000000000ULL : 0x1000000000000000ULL) | (uint64_t)(uint32_t)(c.cell + 1));
+    }
+    if (h.alive && had_collision) {
+      collide<MODE>(P, A, h, acc, tid, nthreads);
+    } else if (h.alive && !crossed) {
+      acc.virt++;
+      h.n_virtual++;
+    }
   } else {
     // DeltaTracker / CarterTracker loop body (delta_tracker.cpp:100-195, carter_tracker.cpp:120-230)
     const double Esample = MODE == 2 ? __ldg(&P.smp[h.g]) + noise_xs<MODE>(P, h.mat, h.g) : __ldg(&P.smp[h.g]);

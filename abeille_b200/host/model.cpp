@@ -36,6 +36,7 @@ void make_settings(const Node& input, Settings& st) {
     const std::string t = s["transport"].as_string();
     if (t == "delta-tracking") st.tracking = ABL_TRACK_DELTA;
     else if (t == "surface-tracking") st.tracking = ABL_TRACK_SURFACE;
+    else if (t == "implicit-leakage-delta-tracking") st.tracking = ABL_TRACK_IMPLICIT_LEAKAGE;  // parser.cpp:415-418
     else if (t == "carter-tracking") {
       st.tracking = ABL_TRACK_CARTER;
       if (!input["sampling-xs-ratio"] || !input["sampling-xs-ratio"].IsSequence())

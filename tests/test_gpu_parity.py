@@ -145,6 +145,10 @@ CASES = [
     ("UD2O-2-1-SL.yaml", {}, 20000),                      # 2 groups, P1, tally
     ("Ua-1-1-CY.yaml", {}, 20000),                        # infinite cylinder (zcylinder distance)
     ("PUb-1-0-SL.yaml", {}, 20000),
+    ("PUa-1-0-SL_implicit.yaml", {}, 20000),              # implicit-leakage delta tracking, vacuum slab: every flight splits
+    ("UD2O-2-1-SL_implicit.yaml", {}, 20000),             # ... two groups, P1, tally
+    ("c5g7_implicit_collision.yaml", {}, 20000),          # ... lattices, reflective + vacuum sides, collision tally
+    ("c5g7_implicit_tracklength.yaml", {}, 8000),         # ... track-length tally of the leaking and the colliding share
 ]
 
 
@@ -309,6 +313,22 @@ def test_power_iteration_resident_and_host_paths_match_oracle(ab, oracle_api, tm
         assert np.allclose(g["entropy"], o["entropy"], rtol=1e-10)
         assert np.allclose(gpu.tally(0, "avg"), orc.tally(0, "avg"), rtol=1e-9, atol=1e-300)
         assert np.allclose(gpu.tally(0, "std"), orc.tally(0, "std"), rtol=1e-7, atol=1e-300)
+
+
+def test_power_iteration_implicit_leakage_matches_oracle(ab, oracle_api, tmp_path):
+    """Whole k-eigenvalue runs with transport: implicit-leakage-delta-tracking (per-lane kernel in mode 0), resident and
+    host-buffer paths, against the oracle's driver: bank sizes exactly, k / leakage / entropy series and tallies to 1e-10."""
+    n, ngen, nign = 6000, 8, 3
+    ov = {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}}
+    for resident in (False, True):
+        orc, gpu = _pair(ab, oracle_api, tmp_path, "c5g7_implicit_collision.yaml", ov, name=f"pil{int(resident)}.yaml")
+        o = orc.run_power_iteration(ngen, nign)
+        g = gpu.run_power_iteration(ngen, nign, resident=resident)
+        assert np.array_equal(g["nbank"], o["nbank"]), (resident, g["nbank"], o["nbank"])
+        assert np.allclose(g["kcol"], o["kcol"], rtol=1e-10)
+        assert np.allclose(g["leak"], o["leak"], rtol=1e-10) and o["leak"].min() > 0.0
+        assert np.allclose(g["entropy"], o["entropy"], rtol=1e-10)
+        assert np.allclose(gpu.tally(0, "avg"), orc.tally(0, "avg"), rtol=1e-9, atol=1e-300)
 
 
 def test_power_iteration_surface_tracking_sood(ab, oracle_api, tmp_path):

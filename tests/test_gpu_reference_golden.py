@@ -36,11 +36,27 @@ def ab(native_libs):
 @pytest.mark.parametrize("ci", range(len(ref_pins.TRANSPORT_CASES)), ids=[c[0].split(".")[0] for c in ref_pins.TRANSPORT_CASES])
 def test_kernels_reproduce_the_references_transport(ab, golden, tmp_path, ci):
     fname, n, k_col = ref_pins.TRANSPORT_CASES[ci]
+    _transport_case(ab, golden, tmp_path, fname, n, k_col, 500 + ci)
+
+
+GOLDEN_IMPLICIT = os.path.join(os.path.dirname(__file__), "golden", "ref_pins_implicit.npz")
+
+
+@pytest.mark.parametrize("ci", range(len(ref_pins.IMPLICIT_CASES)), ids=[c[0].split(".")[0] for c in ref_pins.IMPLICIT_CASES])
+def test_kernels_reproduce_the_references_implicit_leakage_transport(ab, tmp_path, ci):
+    """ImplicitLeakageDeltaTracker::transport of the reference (scripts/make_ref_pins_implicit.py) against the per-lane
+    kernel: here the reference's weights carry glibc's exp, the device's the shared fdlibm sequence, so the implicit
+    leakage / migration scores and the tallies agree to 1e-9 and the integer outcomes exactly."""
+    fname, n, k_col = ref_pins.IMPLICIT_CASES[ci]
+    _transport_case(ab, dict(np.load(GOLDEN_IMPLICIT)), tmp_path, fname, n, k_col, 700 + ci)
+
+
+def _transport_case(ab, golden, tmp_path, fname, n, k_col, seed):
     name = fname.split(".")[0]
     deck = load_deck(fname)
     path = write_deck(deck, tmp_path / fname, {"settings": {"nparticles": n}})
     deck["settings"]["nparticles"] = n
-    r, u, E, w, hid = ref_pins.transport_bank(deck, n, 500 + ci, "carter" in fname)
+    r, u, E, w, hid = ref_pins.transport_bank(deck, n, seed, "carter" in fname)
     bank = {k: np.ascontiguousarray(v) for k, v in zip(("x", "y", "z"), r.T)}
     bank.update({k: np.ascontiguousarray(v) for k, v in zip(("ux", "uy", "uz"), u.T)})
     bank.update(E=np.ascontiguousarray(E), wgt=np.ascontiguousarray(w), wgt2=np.zeros(n), id_a=hid, id_b=hid.copy(), id_c=None)
