@@ -46,7 +46,8 @@ typedef enum abl_status {
 /* ---- enums mirrored from the reference --------------------------------------------------------- */
 enum { ABL_MODE_K_EIGENVALUE = 0, ABL_MODE_NOISE = 1 };                         /* settings.hpp        */
 enum { ABL_TRACK_SURFACE = 0, ABL_TRACK_DELTA = 1, ABL_TRACK_CARTER = 2,
-       ABL_TRACK_IMPLICIT_LEAKAGE = 3 };                                          /* parser.cpp:889-911  */
+       ABL_TRACK_IMPLICIT_LEAKAGE = 3 };  /* parser.cpp:408-420,889-911; 3 replaces ImplicitLeakageDeltaTracker::transport
+                                             (src/implicit_leakage_delta_tracker.cpp:73-263) */
 enum { ABL_BC_VACUUM = 0, ABL_BC_REFLECTIVE = 1, ABL_BC_NORMAL = 2 };           /* surface.hpp:34      */
 enum {
   ABL_SURF_XPLANE = 0, ABL_SURF_YPLANE, ABL_SURF_ZPLANE, ABL_SURF_PLANE,

@@ -458,7 +458,10 @@ def evaluate_transport(impl: str, cases=None, seed0: int = 500) -> dict:
 NOISE_CASES = (("noise_oscillation.yaml", 4000), ("noise_oscillation_delta.yaml", 4000), ("noise_vibration.yaml", 4000))
 
 
-def evaluate_noise(impl: str) -> dict:
+IMPLICIT_NOISE_CASES = (("noise_oscillation_implicit.yaml", 4000),)
+
+
+def evaluate_noise(impl: str, cases=None, seed0: int = 900) -> dict:
     """Noise mode through the reference's own code (oracle/_ref) or the oracle.  Per deck two transport calls:
     (A) a power-iteration generation that samples the noise source at its collisions -- transport(bank, noise = false,
         &noise_bank, &noise_maker), NoiseMaker::sample_noise_source with the deck's square-oscillation / flat-vibration
@@ -472,13 +475,13 @@ def evaluate_noise(impl: str) -> dict:
     PU = C.POINTER(C.c_uint64)
     out = {}
     with _reference_math(impl):
-        for ci, (fname, n) in enumerate(NOISE_CASES):
+        for ci, (fname, n) in enumerate(NOISE_CASES if cases is None else cases):
             path = os.path.join(decks, fname)
             ov = {"settings": {"nparticles": n}}
             deck = _deck.apply_overrides(_deck.load_yaml(path), ov)
             keff = float(deck["settings"].get("keff", 1.0))
-            r, u, E, w, hid = transport_bank(deck, n, 900 + ci, False)
-            rng = np.random.default_rng(950 + ci)
+            r, u, E, w, hid = transport_bank(deck, n, seed0 + ci, False)
+            rng = np.random.default_rng(seed0 + 50 + ci)
             w2 = rng.uniform(-0.8, 0.8, n)
             name = fname.split(".")[0]
             if ref:

@@ -16,6 +16,7 @@ sys.path.insert(0, ROOT)
 from oracle import ref_pins  # noqa: E402
 
 out = ref_pins.evaluate_transport("reference", ref_pins.IMPLICIT_CASES, seed0=700)
+out.update(ref_pins.evaluate_noise("reference", ref_pins.IMPLICIT_NOISE_CASES, seed0=1100))  # noise mode, complex weights
 path = os.path.join(ROOT, "tests", "golden", "ref_pins_implicit.npz")
 np.savez_compressed(path, **out)
 print(f"{path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")

@@ -37,6 +37,11 @@ def run(deck, n, gens=4, converged=True):
     gpu.close()
 
 if __name__ == "__main__":
+    if "--implicit" in sys.argv:  # implicit-leakage delta tracking (per-lane kernel) next to plain delta tracking (staged kernel)
+        run("c5g7_implicit_collision.yaml", 1_000_000, 3, True)
+        run("c5g7_delta_collision.yaml", 1_000_000, 3, True)
+        run("PUa-1-0-SL_implicit.yaml", 1_000_000, 3, True)
+        sys.exit(0)
     if "--others" not in sys.argv:
         run("c5g7_delta_collision.yaml", 1_000_000, 4, True)
         run("c5g7_delta_collision.yaml", 10_000_000, 3, False)

@@ -58,7 +58,8 @@ def _particles(fis, first):
     return b
 
 
-@pytest.mark.parametrize("deck", ["noise_oscillation.yaml", "noise_oscillation_delta.yaml", "noise_vibration.yaml"])
+@pytest.mark.parametrize("deck", ["noise_oscillation.yaml", "noise_oscillation_delta.yaml", "noise_vibration.yaml",
+                                  "noise_oscillation_implicit.yaml"])
 def test_noise_source_and_noise_transport_bit_exact(ab, oracle_api, tmp_path, deck):
     path = write_deck(load_deck(deck), tmp_path / deck, {"settings": {"nparticles": 6000}})
     keff = float(load_deck(deck)["settings"]["keff"])
