@@ -527,6 +527,12 @@ POWER_ITERATION_CASES = (
 )
 
 
+# whole simulations with the fourth tracker (golden vectors in tests/golden/ref_pins_implicit.npz): addressed by `only` = an
+# index into ALL_PI_CASES; `only` = None keeps meaning the cases of tests/golden/ref_pins.npz
+IMPLICIT_POWER_ITERATION_CASES = (("c5g7_implicit_collision.yaml", 3000, 8, 3), ("PUa-1-0-SL_implicit.yaml", 2000, 12, 4))
+ALL_PI_CASES = POWER_ITERATION_CASES + IMPLICIT_POWER_ITERATION_CASES
+
+
 def evaluate_power_iteration(impl: str, only: int | None = None) -> dict:
     """The reference's own PowerIterator::initialize() + run() (oracle/_ref: source sampling through Source / Box / Point /
     Isotropic / MonoEnergetic, transport, Entropy, ApproximateMeshCancelator, weight normalisation, history-id hand-out,
@@ -554,7 +560,7 @@ def evaluate_power_iteration(impl: str, only: int | None = None) -> dict:
                 out.update(dict(np.load(path)))
         return out
     with _reference_math(impl):
-        for fname, n, ngen, nign in (POWER_ITERATION_CASES if only is None else POWER_ITERATION_CASES[only:only + 1]):
+        for fname, n, ngen, nign in (POWER_ITERATION_CASES if only is None else ALL_PI_CASES[only:only + 1]):
             path = os.path.join(decks, fname)
             ov = {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}}
             name = fname.split(".")[0]
@@ -659,7 +665,7 @@ def power_iteration_through_gpu_transporter(only: int, host_library: str, yaml_d
     """The reference's own PowerIterator::run() with its transporter replaced by GPUTransporter
     (integration/gpu_transporter.hpp): the drop-in of INTEGRATION.md, live.  Needs a GPU; one case per process."""
     from . import deck as _deck
-    fname, n, ngen, nign = POWER_ITERATION_CASES[only]
+    fname, n, ngen, nign = ALL_PI_CASES[only]
     deck = _deck.load_yaml(yaml_deck)
     L = ref_lib()
     keys = ("kcol", "ktrk", "leak", "mig", "entropy")

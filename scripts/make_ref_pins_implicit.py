@@ -17,6 +17,17 @@ from oracle import ref_pins  # noqa: E402
 
 out = ref_pins.evaluate_transport("reference", ref_pins.IMPLICIT_CASES, seed0=700)
 out.update(ref_pins.evaluate_noise("reference", ref_pins.IMPLICIT_NOISE_CASES, seed0=1100))  # noise mode, complex weights
+# whole simulations through the reference's own PowerIterator::run() over its ImplicitLeakageDeltaTracker: one per process
+import subprocess  # noqa: E402
+import tempfile  # noqa: E402
+
+for i in range(len(ref_pins.POWER_ITERATION_CASES), len(ref_pins.ALL_PI_CASES)):
+    with tempfile.TemporaryDirectory() as td:
+        tmp = os.path.join(td, "pi.npz")
+        code = (f"import sys; sys.path.insert(0, {ROOT!r}); import numpy as np; from oracle import ref_pins; "
+                f"np.savez({tmp!r}, **ref_pins.evaluate_power_iteration('reference', only={i}))")
+        subprocess.run([sys.executable, "-c", code], check=True, stdout=subprocess.DEVNULL)
+        out.update(dict(np.load(tmp)))
 path = os.path.join(ROOT, "tests", "golden", "ref_pins_implicit.npz")
 np.savez_compressed(path, **out)
 print(f"{path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")

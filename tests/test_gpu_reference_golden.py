@@ -120,14 +120,15 @@ def test_kernels_reproduce_the_references_noise_mode(ab, golden, tmp_path, ci):
 
 
 @pytest.mark.parametrize("resident", [True, False], ids=["resident", "host-buffers"])
-@pytest.mark.parametrize("ci", range(len(ref_pins.POWER_ITERATION_CASES)),
-                         ids=[c[0].split(".")[0] for c in ref_pins.POWER_ITERATION_CASES])
+@pytest.mark.parametrize("ci", range(len(ref_pins.ALL_PI_CASES)), ids=[c[0].split(".")[0] for c in ref_pins.ALL_PI_CASES])
 def test_power_iteration_reproduces_the_references_power_iterator(ab, golden, tmp_path, ci, resident):
     """Whole k-eigenvalue simulations -- the C++ host's PowerIterator over the GPU transporter, bank resident in HBM or
     through host buffers -- against the reference's own PowerIterator::run(): every generation's k_col, k_trk, leakage,
     migration area and entropy, and the final averages and errors, to 1e-9 relative (floating-point sums are taken in a
     different order on the device; the histories themselves are the same)."""
-    fname, n, ngen, nign = ref_pins.POWER_ITERATION_CASES[ci]
+    fname, n, ngen, nign = ref_pins.ALL_PI_CASES[ci]
+    if ci >= len(ref_pins.POWER_ITERATION_CASES):  # the implicit-leakage tracker's simulations
+        golden = dict(np.load(GOLDEN_IMPLICIT))
     name = fname.split(".")[0]
     path = write_deck(load_deck(fname), tmp_path / fname, {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}})
     gpu = ab.Backend(path, 0)
@@ -178,8 +179,7 @@ def test_noise_simulation_reproduces_the_references_noise_driver(ab, golden, tmp
     sim.close()
 
 
-@pytest.mark.parametrize("ci", range(len(ref_pins.POWER_ITERATION_CASES)),
-                         ids=[c[0].split(".")[0] for c in ref_pins.POWER_ITERATION_CASES])
+@pytest.mark.parametrize("ci", range(len(ref_pins.ALL_PI_CASES)), ids=[c[0].split(".")[0] for c in ref_pins.ALL_PI_CASES])
 def test_references_power_iterator_drives_the_gpu_transporter(ab, golden, tmp_path, ci):
     """The drop-in, live: the reference's OWN PowerIterator::run() (compiled from its sources into oracle/_ref) with its
     transporter replaced by integration/gpu_transporter.hpp -- `GPUTransporter : Transporter` written against the
@@ -192,7 +192,9 @@ def test_references_power_iterator_drives_the_gpu_transporter(ab, golden, tmp_pa
         pytest.skip("oracle/_ref/libabeille_ref.so was not built (needs /root/reference at build time)")
     from abeille_b200 import backend
     _, host_lib = backend.lib_paths()
-    fname, n, ngen, nign = ref_pins.POWER_ITERATION_CASES[ci]
+    fname, n, ngen, nign = ref_pins.ALL_PI_CASES[ci]
+    if ci >= len(ref_pins.POWER_ITERATION_CASES):
+        golden = dict(np.load(GOLDEN_IMPLICIT))
     name = fname.split(".")[0]
     path = write_deck(load_deck(fname), tmp_path / fname, {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}})
     out = str(tmp_path / "pi_gpu.npz")
