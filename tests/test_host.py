@@ -114,6 +114,16 @@ def test_parse_c5g7(native_libs):
     assert np.allclose(smp, [0.183045, 0.41297, 0.59031, 0.606174, 0.718, 1.25445, 2.65038], rtol=0, atol=0)
 
 
+def test_implicit_leakage_tracking_is_parsed(native_libs):
+    """settings: transport: implicit-leakage-delta-tracking (src/parser.cpp:415-418) -> ABL_TRACK_IMPLICIT_LEAKAGE, sampling
+    cross section = the majorant, as for delta tracking (src/implicit_leakage_delta_tracker.cpp:52-57)"""
+    _, maj = native_libs.parse_only(deck_path("c5g7_delta_collision.yaml"))
+    info, smp = native_libs.parse_only(deck_path("c5g7_implicit_collision.yaml"))
+    assert info["tracking"] == 3 and np.array_equal(smp, maj)
+    info, _ = native_libs.parse_only(deck_path("noise_oscillation_implicit.yaml"))
+    assert info["tracking"] == 3 and info["mode"] == 1
+
+
 def test_carter_sampling_xs_is_ratio_times_majorant(native_libs):
     _, maj = native_libs.parse_only(deck_path("c5g7_delta_collision.yaml"))
     _, smp = native_libs.parse_only(deck_path("c5g7_carter_cancel.yaml"))
