@@ -240,6 +240,11 @@ def run_b200(args):
     # torchrun exports OMP_NUM_THREADS=1; the e2e leg's caller-side steps (PowerIterator::normalize_weights on the host
     # bank) are CPU work that the reference spreads over the host's cores: give every rank its share
     torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
+    # NCCL prints its version banner on stdout when the first communicator is made (N > 1): the file descriptor is pointed at
+    # stderr for the whole run and restored for the one JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -351,8 +356,15 @@ def run_b200(args):
                             "grid": [kinfo["grid"], kinfo["block"]], "algorithmic_bytes_per_launch": alg_bytes,
                             "peak_source": peak_src, "kernel_share_of_step": k_ms * args.steps / ms},
                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    import ctypes
+    sys.stdout.flush()
+    ctypes.CDLL(None).fflush(None)
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
+    if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
