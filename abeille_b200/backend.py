@@ -30,7 +30,7 @@ ABI_SYMBOLS = (
     "abl_score_source_device", "abl_cancel_device", "abl_cancel_accumulate_device", "abl_cancel_apply_device",
     "abl_cancel_bins_device", "abl_bank_alloc_device", "abl_bank_free_device",
     "abl_bank_upload", "abl_bank_download", "abl_device_alloc", "abl_device_free", "abl_device_zero",
-    "abl_device_read", "abl_find_cells", "abl_rng_probe", "abl_math_probe")
+    "abl_device_read", "abl_find_cells", "abl_rng_probe", "abl_math_probe", "abl_surface_probe", "abl_set_sampling_xs", "abl_fission_capacity_hint")
 
 
 class BackendError(RuntimeError):
@@ -76,6 +76,8 @@ def load_backend_lib():
         L = C.CDLL(path, mode=C.RTLD_GLOBAL)
         L.abl_last_error.restype = C.c_char_p
         L.abl_last_error.argtypes = [C.c_void_p]
+        L.abl_fission_capacity_hint.restype = C.c_uint64
+        L.abl_fission_capacity_hint.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_double]
         _backend_lib = L
     return _backend_lib
 
@@ -237,7 +239,7 @@ class Backend:
                   capacity: int | None = None, out: dict | None = None):
         """abl_transport.  Returns (fission bank dict, scores[6], counters dict)."""
         n = len(bank["x"])
-        cap = int(capacity if capacity is not None else max(int(2.5 * n) + 4096, 4096))
+        cap = int(capacity if capacity is not None else self.fission_capacity(n, float(np.abs(bank["wgt"]).sum()), k_col))
         if out is None:
             out = new_bank(cap, wgt2=False)
         sin = _host_struct(bank)
@@ -266,7 +268,7 @@ class Backend:
     # ---- Transporter::transport through the C++ GPUTransporter adapter (vector<Particle>) ----
     def transport_vectors(self, bank: dict, k_col: float = 1.0, converged: bool = False, capacity: int | None = None):
         n = len(bank["x"])
-        cap = int(capacity if capacity is not None else max(int(2.5 * n) + 4096, 4096))
+        cap = int(capacity if capacity is not None else self.fission_capacity(n, float(np.abs(bank["wgt"]).sum()), k_col))
         out = new_bank(cap)
         sin = _host_struct(bank)
         sout = _host_struct(out, cap)
@@ -349,6 +351,28 @@ class Backend:
         self._check(self.L.abl_find_cells(self.h, C.c_uint64(n), r.ctypes.data_as(_PD), u.ctypes.data_as(_PD),
                                           cell.ctypes.data_as(_PI32), mat.ctypes.data_as(_PI32)))
         return cell, mat
+
+    def surface_probe(self, surface_index: int, r: np.ndarray, u: np.ndarray, on_surf: np.ndarray):
+        """Surface::sign / distance / norm of one surface of the problem at n points (include/abeille_b200.h)."""
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        on = np.ascontiguousarray(on_surf, dtype=np.int32)
+        n = r.shape[0]
+        sign = np.zeros(n, dtype=np.int32)
+        dist, norm = np.zeros(n), np.zeros((n, 3))
+        self._check(self.L.abl_surface_probe(self.h, C.c_int(surface_index), C.c_uint64(n), r.ctypes.data_as(_PD),
+                                             u.ctypes.data_as(_PD), on.ctypes.data_as(_PI32), sign.ctypes.data_as(_PI32),
+                                             dist.ctypes.data_as(_PD), norm.ctypes.data_as(_PD)))
+        return sign, dist, norm
+
+    def fission_capacity(self, n: int, sum_abs_weight: float | None = None, k_col: float = 1.0) -> int:
+        """Output-bank capacity for n histories (abl_fission_capacity_hint: sized from the problem's most reactive material)."""
+        w = float(n if sum_abs_weight is None else sum_abs_weight)
+        return int(self.L.abl_fission_capacity_hint(self.h, C.c_uint64(int(n)), C.c_double(w), C.c_double(float(k_col))))
+
+    def set_sampling_xs(self, xs):
+        xs = np.ascontiguousarray(xs, dtype=np.float64)
+        self._check(self.L.abl_set_sampling_xs(self.h, xs.ctypes.data_as(_PD), C.c_int(len(xs))))
 
     def rng_probe(self, history_id: int, n: int):
         u32 = np.zeros(n, dtype=np.uint32)

@@ -5,12 +5,15 @@
  */
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "bank_ops.cuh"
@@ -43,6 +46,8 @@ struct abl_context {
   DevProblem P{};
   std::vector<void*> allocs;  // immutable tables
   std::vector<uint64_t> tally_g;
+  double k_site_max = 1.;       // max over (material, group) of nu Sigma_f / Sigma_a: sites per unit weight, bound
+  std::vector<double> host_Et;  // [M*G] total cross sections (abl_set_sampling_xs rebuilds the quotient table from them)
   // scratch
   Site* sites = nullptr;
   uint64_t site_cap = 0;
@@ -71,7 +76,10 @@ struct abl_context {
   uint64_t stage_in_cap = 0, stage_out_cap = 0;
   double* probe_buf = nullptr;
   uint64_t probe_cap = 0;
-  int blocks_per_sm[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+  int blocks_per_sm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // by tracker and kernel build (plain, track-length, traced)
+  int hk_slots[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // histories per CTA of the staged kernel (by tracker, trace)
+  int geo_frames = 1, geo_pads = 2;  // nesting depth of the geometry: coordinate frames / stack pads a history can hold
+  int smem_optin = 0, smem_total_sm = 0;  // shared memory a CTA may opt in to / an SM has
   uint64_t* rng_scratch = nullptr;  // pcg32 states seeded on the device when the caller passes id_c = NULL
   uint64_t rng_cap = 0;
   uint64_t launches = 0;
@@ -229,6 +237,48 @@ std::vector<CellFast> compile_cells(const abl_problem* p) {
   return out;
 }
 
+// Nesting depth of the geometry: the most pads (universe / lattice / cell entries of the Tracker's stack,
+// tracker.hpp:41-50) and coordinate frames (the global one plus one per lattice tile entered) a history can hold.
+// They size the per-history columns of the staged kernel's shared memory (history.cuh).
+void geometry_depth(const abl_problem* p, int& frames, int& pads) {
+  std::vector<int> pd((size_t)p->nuniverses, -1), fd((size_t)p->nuniverses, -1);
+  std::function<void(int, int)> visit = [&](int u, int guard) {
+    if (u < 0 || u >= p->nuniverses || pd[(size_t)u] >= 0 || guard > 64) return;
+    const abl_universe& U = p->universes[u];
+    int bp = 1, bf = 0;
+    pd[(size_t)u] = 0;  // (marks the visit; recursion is rejected by validate())
+    if (U.type == ABL_UNI_CELLS) {
+      bp = 2;
+      for (int k = 0; k < U.ncells; k++) {
+        const int fill = p->cells[p->universe_cells[U.cell_offset + k]].fill_universe;
+        if (fill < 0) continue;
+        visit(fill, guard + 1);
+        bp = std::max(bp, 2 + pd[(size_t)fill]);
+        bf = std::max(bf, fd[(size_t)fill]);
+      }
+    } else {
+      const int nt = U.N[0] * U.N[1] * U.N[2];
+      for (int k = 0; k < nt; k++) {
+        const int t = p->lattice_tiles[U.tile_offset + k];
+        if (t < 0) continue;
+        visit(t, guard + 1);
+        bp = std::max(bp, 1 + pd[(size_t)t]);
+        bf = std::max(bf, 1 + fd[(size_t)t]);
+      }
+      if (U.outer >= 0) {
+        visit(U.outer, guard + 1);
+        bp = std::max(bp, 1 + pd[(size_t)U.outer]);
+        bf = std::max(bf, fd[(size_t)U.outer]);
+      }
+    }
+    pd[(size_t)u] = bp;
+    fd[(size_t)u] = bf;
+  };
+  visit(p->root_universe, 0);
+  pads = std::min(std::max(pd[(size_t)p->root_universe], 2), ABL_MAX_PADS);
+  frames = std::min(1 + std::max(fd[(size_t)p->root_universe], 0), ABL_MAX_FRAMES);
+}
+
 DevMesh3 make_mesh3(const abl_mesh3& m, const double* tally_eb_dev) {
   DevMesh3 d{};
   d.present = m.present;
@@ -325,27 +375,61 @@ int alloc_bank(abl_handle h, BankView& b, uint64_t cap) {
 
 template <int TRK, bool TRACE>
 int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s) {
-  // surface tracking: per-lane history loop (transport.cuh); delta / carter: staged lock-step loop with the cursors in
-  // shared memory and service warps for the rare events (history.cuh)
-  TransportKernel kern = TRK == ABL_TRACK_SURFACE ? history_kernel_surface(TRACE)
-                                                   : (TRK == ABL_TRACK_DELTA ? history_kernel_delta(TRACE) : history_kernel_carter(TRACE));
-  const bool staged = true;
-  const int threads = staged ? HK_THREADS : TK_THREADS;
-  const int worker_threads = staged ? HK_HIST : TK_THREADS;  // threads of a block that own histories
-  const size_t smem = staged ? sizeof(HKShared) : 0;
-  int& bps = h->blocks_per_sm[TRK][TRACE ? 1 : 0];
+  // the staged lock-step loop with the histories in shared-memory columns and service warps for the rare events
+  // (history.cuh); one translation unit per tracker, each with its own launch shape
+  const bool tle = A.converged && h->P.n_tl_tallies;
+  const HistoryKernel hk = TRK == ABL_TRACK_SURFACE ? history_kernel_surface(TRACE, tle)
+                                                     : (TRK == ABL_TRACK_DELTA ? history_kernel_delta(TRACE, tle) : history_kernel_carter(TRACE, tle));
+  TransportKernel kern = hk.fn;
+  const int threads = hk.threads;
+  int& bps = h->blocks_per_sm[TRK][TRACE ? 2 : (tle ? 1 : 0)];
+  int& slots = h->hk_slots[TRK][TRACE ? 2 : (tle ? 1 : 0)];
+  const int nf = h->geo_frames < HK_MIN_FRAMES ? HK_MIN_FRAMES : h->geo_frames, np = h->geo_pads;
+  const unsigned slot_bytes = hk_slot_bytes(nf, np, TRACE);
   if (bps == 0) {
-    if (smem) ABL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // as many histories per CTA as the shared memory holds (a multiple of 32, at most one per history thread); two CTAs
+    // per SM when the kernel was built for that
+    cudaFuncAttributes fa;
+    ABL_CUDA(h, cudaFuncGetAttributes(&fa, kern));
+    int want_blocks = 1;
+    {
+      int regs_limit = 65536 / (fa.numRegs * threads > 0 ? fa.numRegs * threads : 1);
+      if (regs_limit >= 2 && 2 * threads <= 2048) want_blocks = 2;
+    }
+    const int budget = (want_blocks == 2 ? (h->smem_total_sm / 2 - 1024) : h->smem_optin) - (int)hk.fixed_bytes - (int)fa.sharedSizeBytes;
+    int sl = budget / (int)slot_bytes;
+    sl -= sl % 32;
+    if (sl > hk.hist_threads) sl = hk.hist_threads;
+    if (sl < 32) {
+      h->error = "geometry nesting too deep for the staged history kernel's shared memory";
+      return ABL_ERR_GEOMETRY;
+    }
+    slots = sl;
+    const size_t smem = hk.fixed_bytes + (size_t)slot_bytes * (size_t)sl;
+    ABL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
     ABL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem));
     if (nb < 1) nb = 1;
     bps = nb;
   }
+  const size_t smem = hk.fixed_bytes + (size_t)slot_bytes * (size_t)slots;
+  const int worker_threads = slots;  // threads of a block that own histories
   uint64_t blocks = (uint64_t)h->sm_count * bps;
   const uint64_t need = (n + worker_threads - 1) / worker_threads;
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   RunArgs B = A;
+  B.hk_slots = slots;
+  B.hk_nf = nf;
+  B.hk_np = np;
+  {
+    static const double timeout_s = [] {
+      const char* e = getenv("ABEILLE_B200_KERNEL_TIMEOUT_S");
+      const double v = e ? atof(e) : 0.;
+      return v > 0. ? v : 120.;
+    }();
+    B.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  }
   if (TRK == ABL_TRACK_CARTER) {
     const uint64_t nthreads = blocks * threads;
     if (nthreads > h->sec_threads) {
@@ -443,6 +527,7 @@ int status_from_device_error(abl_handle h, const DevSmall& sm) {
     case ABL_ERR_MAJORANT: what = "total cross section exceeded the majorant"; break;
     case ABL_ERR_GEOMETRY: what = "geometry nesting deeper than ABL_MAX_PADS / ABL_MAX_FRAMES"; break;
     case ABL_ERR_BANK_OVERFLOW: what = "secondary stack overflow (ABL_SEC_CAP)"; break;
+    case ABL_ERR_TIMEOUT: what = "history kernel ran past its deadline and was wound down (ABEILLE_B200_KERNEL_TIMEOUT_S)"; break;
     case ABL_ERR_INVALID: what = "source sampling failed (point source outside the geometry or fissile-only rejection limit)"; break;
   }
   snprintf(buf, sizeof buf, "%s (history %llu)", what, (unsigned long long)hid);
@@ -671,6 +756,9 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
   h->sm_count = prop.multiProcessorCount;
   h->cc_major = prop.major;
   h->cc_minor = prop.minor;
+  h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  h->smem_total_sm = (int)prop.sharedMemPerMultiprocessor;
+  geometry_depth(p, h->geo_frames, h->geo_pads);
   if (CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail(ABL_ERR_CUDA);
   if (CU(cudaEventCreate(&h->ev0), "cudaEventCreate") || CU(cudaEventCreate(&h->ev1), "cudaEventCreate")) return bail(ABL_ERR_CUDA);
   if (CU(cudaMalloc(&h->small_dev, sizeof(DevSmall)), "cudaMalloc")) return bail(ABL_ERR_CUDA);
@@ -809,6 +897,12 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
         for (int t = 0; t < p->ntallies; t++) is[(size_t)t * MG + mg] = 1. / (Et * p->tallies[t].net_weight);
       }
     UP(rf.data(), rf.size(), P.real_frac);
+    h->host_Et.assign(p->xs_total, p->xs_total + MG);
+    h->k_site_max = 0.;
+    for (size_t mg = 0; mg < MG; mg++) {
+      const double Ea = p->xs_absorption[mg], nf = p->nu_total[mg] * p->xs_fission[mg];
+      if (nf > 0.) h->k_site_max = std::max(h->k_site_max, Ea > 0. ? nf / Ea : 1e6);
+    }
     UP(sf.data(), sf.size(), P.surv_frac);
     UP(is.data(), is.size(), P.inv_score);
   }
@@ -1395,6 +1489,56 @@ int abl_find_cells(abl_handle h, uint64_t n, const double* r3, const double* u3,
   ABL_CUDA(h, cudaStreamSynchronize(h->stream));
   ABL_CUDA(h, cudaMemcpy(cell, dc, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
   ABL_CUDA(h, cudaMemcpy(material, dm, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return ABL_OK;
+}
+
+int abl_surface_probe(abl_handle h, int surface_index, uint64_t n, const double* r3, const double* u3, const int32_t* on_surf,
+                      int32_t* sign, double* distance, double* norm3) {
+  if (!h || !r3 || !u3 || !on_surf || !sign || !distance || !norm3) return ABL_ERR_INVALID;
+  if (surface_index < 0 || surface_index >= h->P.nsurfaces) return ABL_ERR_INVALID;
+  if (n == 0) return ABL_OK;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_probe(h, n * (10 * sizeof(double) + 2 * sizeof(int32_t)));
+  if (rc) return rc;
+  double* dr = h->probe_buf;
+  double* du = dr + 3 * n;
+  double* dd = du + 3 * n;
+  double* dn = dd + n;
+  int32_t* don = reinterpret_cast<int32_t*>(dn + 3 * n);
+  int32_t* ds = don + n;
+  ABL_CUDA(h, cudaMemcpy(dr, r3, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+  ABL_CUDA(h, cudaMemcpy(du, u3, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+  ABL_CUDA(h, cudaMemcpy(don, on_surf, n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  surface_probe_kernel<<<grid_for(h, n, 128), 128, 0, h->stream>>>(h->P, surface_index, n, dr, du, don, ds, dd, dn);
+  h->launches++;
+  ABL_CUDA(h, cudaGetLastError());
+  ABL_CUDA(h, cudaStreamSynchronize(h->stream));
+  ABL_CUDA(h, cudaMemcpy(sign, ds, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  ABL_CUDA(h, cudaMemcpy(distance, dd, n * sizeof(double), cudaMemcpyDeviceToHost));
+  ABL_CUDA(h, cudaMemcpy(norm3, dn, 3 * n * sizeof(double), cudaMemcpyDeviceToHost));
+  return ABL_OK;
+}
+
+uint64_t abl_fission_capacity_hint(abl_handle h, uint64_t n_particles, double sum_abs_weight, double k_col) {
+  if (!h) return 0;
+  const double W = std::max(sum_abs_weight, static_cast<double>(n_particles));
+  const double k = (k_col > 1e-3) ? k_col : 1e-3;
+  const double mean = W * std::max(h->k_site_max, 0.05) / k;
+  const double cap = 1.25 * mean + 8. * std::sqrt(mean) + 8192.;
+  return cap < 1.8e19 ? static_cast<uint64_t>(cap) : ~0ULL;
+}
+
+int abl_set_sampling_xs(abl_handle h, const double* sampling_xs, int ngroups) {
+  if (!h || !sampling_xs || ngroups != h->P.G || !h->P.smp) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  use_stream(h, h->stream);
+  ABL_CUDA(h, cudaStreamSynchronize(h->stream));
+  const int G = h->P.G, M = h->P.M;
+  std::vector<double> rf((size_t)M * G);
+  for (int m = 0; m < M; m++)
+    for (int g = 0; g < G; g++) rf[(size_t)m * G + g] = h->host_Et[(size_t)m * G + g] / sampling_xs[g];  // delta_tracker.cpp:182
+  ABL_CUDA(h, cudaMemcpy(const_cast<double*>(h->P.smp), sampling_xs, (size_t)G * sizeof(double), cudaMemcpyHostToDevice));
+  ABL_CUDA(h, cudaMemcpy(const_cast<double*>(h->P.real_frac), rf.data(), rf.size() * sizeof(double), cudaMemcpyHostToDevice));
   return ABL_OK;
 }
 

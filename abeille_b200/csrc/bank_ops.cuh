@@ -371,6 +371,19 @@ __global__ void find_cells_kernel(const DevProblem P, uint64_t n, const double* 
     mat[i] = c.mat;
   }
 }
+__global__ void surface_probe_kernel(const DevProblem P, int si, uint64_t n, const double* r3, const double* u3, const int32_t* on,
+                                     int32_t* sign, double* dist, double* norm3) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const Surf s = load_surface(P, si);
+    const V3 r{r3[3 * i], r3[3 * i + 1], r3[3 * i + 2]}, u{u3[3 * i], u3[3 * i + 1], u3[3 * i + 2]};
+    sign[i] = surf_sign(s, r, u);
+    dist[i] = surf_distance(s, r, u, on[i] != 0);
+    const V3 nn = surf_norm(s, r);
+    norm3[3 * i] = nn.x;
+    norm3[3 * i + 1] = nn.y;
+    norm3[3 * i + 2] = nn.z;
+  }
+}
 __global__ void rng_probe_kernel(const DevProblem P, uint64_t history_id, int n, uint32_t* out_u32, double* out_rand) {
   if (threadIdx.x || blockIdx.x) return;
   uint64_t s = pcg_advance(P.seed_state, P.stride * history_id, P.jump);

@@ -11,10 +11,19 @@
 
 namespace abl {
 typedef void (*TransportKernel)(const DevProblem, const RunArgs);
-TransportKernel history_kernel_delta(bool trace);    // kernels_delta.cu
-TransportKernel history_kernel_carter(bool trace);   // kernels_carter.cu
-TransportKernel history_kernel_surface(bool trace);  // kernels_surface.cu
-TransportKernel history_kernel_traced(int tracking); // kernels_trace.cu
+// a staged history kernel with the launch shape its translation unit was compiled for (HK_THREADS may differ per unit)
+struct HistoryKernel {
+  TransportKernel fn;
+  int threads;           // threads per CTA (history threads + service warps)
+  int hist_threads;      // threads that own a history
+  unsigned fixed_bytes;  // shared memory before the per-history columns (HK_COLS_OFFSET)
+};
+#define HK_THIS_UNIT(fn) HistoryKernel{fn, HK_THREADS, HK_HIST, HK_COLS_OFFSET}
+// tle = the run scores track-length tallies this generation (a build without the scorer serves the others)
+HistoryKernel history_kernel_delta(bool trace, bool tle);    // kernels_delta.cu
+HistoryKernel history_kernel_carter(bool trace, bool tle);   // kernels_carter.cu
+HistoryKernel history_kernel_surface(bool trace, bool tle);  // kernels_surface.cu
+HistoryKernel history_kernel_traced(int tracking); // kernels_trace.cu
 TransportKernel lane_kernel(int tracking, int mode); // kernels_lane.cu: per-lane kernel of the noise modes (mode 1 | 2)
 TransportKernel implicit_kernel(int mode);            // kernels_implicit.cu: implicit-leakage delta tracking, per-lane kernel (mode 0 | 1 | 2)
 }  // namespace abl

@@ -2,7 +2,9 @@
 // is its own translation unit).
 #include "kernel_entry.h"
 namespace abl {
-TransportKernel history_kernel_carter(bool trace) {
-  return trace ? history_kernel_traced(ABL_TRACK_CARTER) : history_kernel<ABL_TRACK_CARTER, false>;
+HistoryKernel history_kernel_carter(bool trace, bool tle) {
+  if (trace) return history_kernel_traced(ABL_TRACK_CARTER);
+  if (tle) return HK_THIS_UNIT((history_kernel<ABL_TRACK_CARTER, false, true>));
+  return HK_THIS_UNIT((history_kernel<ABL_TRACK_CARTER, false, false>));
 }
 }  // namespace abl

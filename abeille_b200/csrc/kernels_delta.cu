@@ -2,7 +2,9 @@
 // is its own translation unit).
 #include "kernel_entry.h"
 namespace abl {
-TransportKernel history_kernel_delta(bool trace) {
-  return trace ? history_kernel_traced(ABL_TRACK_DELTA) : history_kernel<ABL_TRACK_DELTA, false>;
+HistoryKernel history_kernel_delta(bool trace, bool tle) {
+  if (trace) return history_kernel_traced(ABL_TRACK_DELTA);
+  if (tle) return HK_THIS_UNIT((history_kernel<ABL_TRACK_DELTA, false, true>));
+  return HK_THIS_UNIT((history_kernel<ABL_TRACK_DELTA, false, false>));
 }
 }  // namespace abl

@@ -2,7 +2,9 @@
 // is its own translation unit).
 #include "kernel_entry.h"
 namespace abl {
-TransportKernel history_kernel_surface(bool trace) {
-  return trace ? history_kernel_traced(ABL_TRACK_SURFACE) : history_kernel<ABL_TRACK_SURFACE, false>;
+HistoryKernel history_kernel_surface(bool trace, bool tle) {
+  if (trace) return history_kernel_traced(ABL_TRACK_SURFACE);
+  if (tle) return HK_THIS_UNIT((history_kernel<ABL_TRACK_SURFACE, false, true>));
+  return HK_THIS_UNIT((history_kernel<ABL_TRACK_SURFACE, false, false>));
 }
 }  // namespace abl

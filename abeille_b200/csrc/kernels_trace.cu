@@ -2,11 +2,11 @@
 // parity tests compare with the oracle), all trackers (see kernel_entry.h for why this is its own translation unit).
 #include "kernel_entry.h"
 namespace abl {
-TransportKernel history_kernel_traced(int tracking) {
+HistoryKernel history_kernel_traced(int tracking) {
   switch (tracking) {
-    case ABL_TRACK_SURFACE: return history_kernel<ABL_TRACK_SURFACE, true>;
-    case ABL_TRACK_DELTA: return history_kernel<ABL_TRACK_DELTA, true>;
-    default: return history_kernel<ABL_TRACK_CARTER, true>;
+    case ABL_TRACK_SURFACE: return HK_THIS_UNIT((history_kernel<ABL_TRACK_SURFACE, true, true>));
+    case ABL_TRACK_DELTA: return HK_THIS_UNIT((history_kernel<ABL_TRACK_DELTA, true, true>));
+    default: return HK_THIS_UNIT((history_kernel<ABL_TRACK_CARTER, true, true>));
   }
 }
 }  // namespace abl

@@ -73,6 +73,10 @@ struct RunArgs {
   uint64_t nsite_capacity;
   uint32_t* nnoise;                // per history: noise particles produced
   uint32_t *site_did, *nsite_did;  // daughter ids of the scratch sites (the Site itself carries the rank)
+  // staged history kernel (history.cuh): histories per CTA and the geometry's nesting depth (frames, pads), which size
+  // the per-history columns in shared memory
+  int hk_slots, hk_nf, hk_np;
+  unsigned long long timeout_ns;  // the staged kernel's watchdog: a CTA that runs longer winds down with ABL_ERR_TIMEOUT
 };
 
 struct Hist {

@@ -11,8 +11,8 @@ the only exchange steps are (NCCL over NVLink, via torch.distributed):
      every integer outcome -- are independent of the number of GPUs, as in the reference;
   3. an order-preserving all_to_all_single that moves partition boundaries back to an even split when the
      slices drift apart (replaces gather-to-root + scatter);
-  4. on active generations an all_reduce of every tally_gen array before the Welford update, and a small
-     all_reduce of the entropy bins.
+  4. on active generations an all_reduce of every tally_gen array before the Welford update (after the source-estimator
+     tallies were scored from the normalised fission bank), and a small all_reduce of the entropy bins + total weight.
 
 With world_size == 1 (or no process group) every collective degenerates to a no-op and the loop is exactly the
 single-GPU device-resident loop of the C++ PowerIterator.
@@ -90,7 +90,8 @@ class DistributedPowerIterator:
         self.n_total = self.n_local * self.world  # tallies->total_weight; the deck's nparticles must equal this
         if self.gpu.info["nparticles"] != self.n_total:
             raise ValueError(f"deck nparticles {self.gpu.info['nparticles']} != world*n_local {self.n_total}")
-        self.cap = int(2.5 * self.n_local) + 4096
+        # output bank sized from the problem (the first generation runs with k_col = 1 and banks ~ k_inf sites per particle)
+        self.cap = self.gpu.fission_capacity(self.n_local, k_col=1.0)
         self.cur = self.gpu.new_device_bank(self.cap)
         self.nxt = self.gpu.new_device_bank(self.cap)
         self.n_cur = 0
@@ -109,6 +110,12 @@ class DistributedPowerIterator:
         with open(deck_path) as f:
             deck = yaml.safe_load(f)
         self.cancellation = bool(deck.get("settings", {}).get("cancellation", False)) and "cancelator" in deck
+        # Shannon entropy of the fission source (src/entropy.cpp:32-93): bins + total weight, summed over the ranks
+        self.entropy_series = []
+        self._ebins = None
+        if "entropy" in deck:
+            nb = int(np.prod([int(v) for v in deck["entropy"]["shape"]]))
+            self._ebins = torch.zeros(nb + 1, dtype=torch.float64, device=self.device)
 
     # ---- helpers ----
     def _gather(self, vec: np.ndarray) -> np.ndarray:
@@ -143,6 +150,33 @@ class DistributedPowerIterator:
         for t in self._cancel_views:
             t.zero_()
 
+    def _grow(self, need: int):
+        """Reallocates both ping-pong banks when the (global) population outgrows them; contents of self.nxt[:keep] survive."""
+        if need <= self.cap:
+            return
+        new_cap = int(need + need // 4 + 4096)
+        for name in ("cur", "nxt"):
+            old = getattr(self, name)
+            new = self.gpu.new_device_bank(new_cap)
+            for k in old:
+                new[k][: self.cap].copy_(old[k][: self.cap])
+            setattr(self, name, new)
+        self.cap = new_cap
+
+    def _entropy(self, m: int) -> float:
+        if self._ebins is None:
+            return 0.0
+        self._ebins.zero_()
+        self.gpu.entropy_bin_device(self.nxt, m, self._ebins[:-1], self._ebins[-1:])
+        if self.world > 1:
+            torch.cuda.current_stream().synchronize()
+            dist.all_reduce(self._ebins, group=self.group)
+        b = self._ebins.cpu().numpy()
+        total = b[-1]
+        p = np.abs(b[:-1]) / total
+        p = p[(p != 0.) & (p <= 1.0)]
+        return float(-(p * np.log2(p)).sum())
+
     # ---- Simulation::sample_sources: rank r samples the ids [r*n, (r+1)*n) ----
     def initialize(self):
         first = self.rank * self.n_local
@@ -164,8 +198,21 @@ class DistributedPowerIterator:
             self.converged = converged
         gpu = self.gpu
         n_in = self.n_cur
-        m, scores, cn = gpu.transport_device(self.cur, n_in, self.nxt, k_col=self.k_col, converged=self.converged,
-                                             use_rng_state=self.use_state)
+        from .backend import BackendError
+        for attempt in range(3):
+            try:
+                m, scores, cn = gpu.transport_device(self.cur, n_in, self.nxt, k_col=self.k_col, converged=self.converged,
+                                                     use_rng_state=self.use_state)
+                break
+            except BackendError as e:
+                # more sites than the output bank holds: the message carries the count; grow and repeat the generation
+                # (scores come back per call; tally_gen holds only this generation's scores and is cleared first)
+                if e.code != -3 or "fission bank overflow" not in str(e) or attempt == 2:
+                    raise
+                need = int(str(e).split("overflow: ")[1].split(" sites")[0])
+                self._grow(need)
+                if self.converged:
+                    gpu.tallies_clear()
         local = np.concatenate([scores, np.array([cn[k] for k in cn], dtype=np.float64), [float(m), float(n_in)]])
         allv = self._gather(local)
         tot = allv.sum(axis=0)
@@ -181,6 +228,7 @@ class DistributedPowerIterator:
         m_pre = m
         if m_total == 0:
             raise RuntimeError("No fission neutrons were produced.")
+        self.entropy_series.append(self._entropy(m))  # Entropy::add_point over the un-normalised fission bank (power_iterator.cpp:341-353)
         if self.cancellation:
             self._cancel(m)
         # weight normalisation over the global bank (src/power_iterator.cpp:538-586)
@@ -188,7 +236,9 @@ class DistributedPowerIterator:
         wall = self._gather(ws).sum(axis=0)
         gpu.scale_weights_device(self.nxt, m, self.n_total / (wall[2] - wall[3]))
         if self.converged:
+            gpu.score_source_device(self.nxt, m)  # SourceMeshTally::score_source on the normalised bank (power_iterator.cpp:366-372)
             if self.world > 1:
+                torch.cuda.current_stream().synchronize()
                 for t in self.tally_tensors():
                     dist.all_reduce(t, group=self.group)
             gpu.tallies_record(1.0)
@@ -197,8 +247,11 @@ class DistributedPowerIterator:
         if self.world > 1:
             target, _ = even_split(m_total, self.world)
             if max(abs(c - t) for c, t in zip(counts, target)) > max(0.01 * m_total / self.world, 64):
+                self._grow(max(target))
                 m = self._rebalance(counts)
                 counts = target
+        # next generation's output must hold what this population can bank at the new k_col
+        self._grow(gpu.fission_capacity(m, float(self.n_total) / self.world, self.k_col))
         first = global_first_ids(counts, self.rank, self.global_counter)
         gpu.to_particles_device(self.nxt, m, first)
         self.global_counter += m_total
@@ -242,7 +295,7 @@ class HostBufferLoop:
         self.rank = dist.get_rank(group) if self.use_dist else 0
         self.world = dist.get_world_size(group) if self.use_dist else 1
         self.n_total = self.n_local * self.world
-        self.cap = int(2.5 * self.n_local) + 4096
+        self.cap = self.gpu.fission_capacity(self.n_local, k_col=1.0)
         self.bufs = [self._pinned_bank(self.cap), self._pinned_bank(self.cap)]
         self.bank = None
         self.k_col = 1.0

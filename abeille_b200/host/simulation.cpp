@@ -1,6 +1,7 @@
 /* simulation.cpp -- Tallies, GPUTransporter, PowerIterator.  See simulation.hpp. */
 #include "simulation.hpp"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -105,7 +106,13 @@ std::vector<BankedParticle> GPUTransporter::transport(std::vector<Particle>& ban
   gp.noise = noise ? 1 : 0;
   gp.sample_noise_source = sample_noise ? 1 : 0;
   const bool complex_out = noise || sample_noise;
-  uint64_t cap = static_cast<uint64_t>(2.5 * static_cast<double>(N)) + 4096;
+  // the output bank is sized from the problem (most reactive material, bank weight, k_col); should a generation still bank
+  // more, the call is repeated with the capacity it reported -- its scores come back per call and, in a k-eigenvalue run,
+  // tally_gen holds nothing but this call's scores, so it is cleared first (the reference's vectors simply grow)
+  double sum_abs_w = 0.;
+  for (size_t i = 0; i < N; i++) sum_abs_w += std::fabs(buf_[7][i]);
+  uint64_t cap = abl_fission_capacity_hint(h_, N, sum_abs_w, gp.k_col);
+  if (complex_out) cap = std::max<uint64_t>(cap, 3 * static_cast<uint64_t>(N) + 4096);
   for (int attempt = 0;; attempt++) {
     for (auto& b : obuf_) b.resize(cap);
     oa_.resize(cap); ob_.resize(cap); oc_.resize(cap);
@@ -134,10 +141,10 @@ std::vector<BankedParticle> GPUTransporter::transport(std::vector<Particle>& ban
     } else {
       rc = abl_transport(h_, &in, &gp, &out, &n_fis, scores, cn);
     }
-    if (rc == ABL_ERR_BANK_OVERFLOW && attempt == 0 && n_fis > cap) {
-      // A retry would score the generation's tallies twice; the reference has no such limit, so size
-      // generously instead (2.5x the bank) and treat a second overflow as fatal.
-      fatal_error(std::string("GPUTransporter: ") + abl_last_error(h_));
+    if (rc == ABL_ERR_BANK_OVERFLOW && n_fis > cap && attempt < 2 && !complex_out) {
+      cap = n_fis + n_fis / 8 + 4096;
+      if (converged) check(h_, abl_tallies_clear(h_), "abl_tallies_clear");
+      continue;
     }
     check(h_, rc, "abl_transport");
     tallies->score_k_col(scores[0]);
@@ -352,7 +359,8 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
   abl_handle h = transporter->handle();
   transporter->converged = (nignored == 0);
   const uint64_t N0 = bank_.size();
-  uint64_t cap = static_cast<uint64_t>(2.5 * static_cast<double>(std::max<uint64_t>(N0, static_cast<uint64_t>(st.nparticles)))) + 4096;
+  // (the first generation runs with k_col = 1, so it banks about k_inf sites per particle: tallies.cpp:48)
+  uint64_t cap = abl_fission_capacity_hint(h, std::max<uint64_t>(N0, static_cast<uint64_t>(st.nparticles)), 0., std::min(1., tallies->kcol()));
   // cur / nxt are views (n and id_c change per generation); *_alloc keep the full allocations
   DeviceBank cur, nxt;
   alloc_device_bank(cur, cap);
@@ -399,7 +407,23 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
     out.n = nxt.cap;
     uint64_t n_fis = 0, cn[8];
     double scores[6];
-    check(h, abl_transport_device(h, &cur.b, &gp, &out, &n_fis, scores, cn, nullptr), "abl_transport_device");
+    for (int attempt = 0;; attempt++) {
+      const int rc = abl_transport_device(h, &cur.b, &gp, &out, &n_fis, scores, cn, nullptr);
+      if (rc == ABL_ERR_BANK_OVERFLOW && n_fis > nxt.cap && attempt < 2) {
+        // more sites than the output bank holds: grow it to what the call reported and repeat the generation (its scores
+        // come back per call; tally_gen holds only this generation's scores and is cleared first)
+        free_device_bank(nxt_alloc);
+        alloc_device_bank(nxt_alloc, n_fis + n_fis / 8 + 4096);
+        nxt.b = nxt_alloc.b;
+        nxt.cap = nxt_alloc.cap;
+        out = nxt.b;
+        out.n = nxt.cap;
+        if (transporter->converged) check(h, abl_tallies_clear(h), "abl_tallies_clear");
+        continue;
+      }
+      check(h, rc, "abl_transport_device");
+      break;
+    }
     if (n_fis == 0) fatal_error("No fission neutrons were produced.");
     tallies->score_k_col(scores[0]); tallies->score_k_abs(scores[1]); tallies->score_k_trk(scores[2]);
     tallies->score_k_tot(scores[3]); tallies->score_leak(scores[4]); tallies->score_mig_area(scores[5]);
@@ -438,9 +462,10 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
     cur.b.id_c = nullptr;
     nxt.b = nxt_alloc.b;
     nxt.cap = nxt_alloc.cap;
-    if (static_cast<double>(n_fis) * 2.0 > static_cast<double>(nxt.cap)) {  // the population drifted upwards: regrow the output bank
+    const uint64_t want = abl_fission_capacity_hint(h, n_fis, static_cast<double>(st.nparticles), tallies->kcol());
+    if (want > nxt.cap) {  // the population drifted upwards: regrow the output bank
       free_device_bank(nxt_alloc);
-      alloc_device_bank(nxt_alloc, static_cast<uint64_t>(2.5 * static_cast<double>(n_fis)) + 4096);
+      alloc_device_bank(nxt_alloc, want + want / 8);
       nxt.b = nxt_alloc.b;
       nxt.cap = nxt_alloc.cap;
     }

@@ -37,7 +37,8 @@ typedef enum abl_status {
   ABL_ERR_LOST = -4,          /* fatal: particle lost after reflection / crossing / resurrection      */
   ABL_ERR_MAJORANT = -5,      /* fatal: total xs exceeded the majorant (delta_tracker.cpp:174-180)    */
   ABL_ERR_GEOMETRY = -6,      /* geometry nesting deeper than ABL_MAX_PADS / malformed tables         */
-  ABL_ERR_UNSUPPORTED = -7
+  ABL_ERR_UNSUPPORTED = -7,
+  ABL_ERR_TIMEOUT = -8        /* a history kernel ran past its deadline (ABEILLE_B200_KERNEL_TIMEOUT_S, default 120 s) and was wound down */
 } abl_status;
 
 #define ABL_MAX_PADS 10   /* geometry stack depth (reference reserves 10: tracker.hpp:46) */
@@ -274,6 +275,13 @@ int abl_device_free(abl_handle h, void* dev);
 int abl_device_zero(abl_handle h, void* dev, uint64_t bytes, void* stream);
 int abl_device_read(abl_handle h, void* dst_host, const void* src_dev, uint64_t bytes, void* stream); /* synchronises */
 
+/* Fission-bank capacity that holds the sites `n_particles` histories of total |weight| `sum_abs_weight` can bank at
+ * fission normalisation k_col (src/transporter.cpp:370-371): a history of weight w banks at most
+ * w * max_{material,group}(nu Sigma_f / Sigma_a) / k_col sites on average (implicit capture: the collision weights form
+ * a geometric series), so 1.25 x that bound plus a fixed slack covers the fluctuation.  The reference's vectors grow
+ * without limit; callers size their output banks with this instead of a fixed multiple of the bank.   */
+uint64_t abl_fission_capacity_hint(abl_handle h, uint64_t n_particles, double sum_abs_weight, double k_col);
+
 /* ---- probes used by the parity tests ------------------------------------------------------------------ */
 /* cell / material index (or -1) of n points, fresh lookup from the root universe (geometry.cpp:43-55)   */
 int abl_find_cells(abl_handle h, uint64_t n, const double* r3, const double* u3, int32_t* cell, int32_t* material);
@@ -281,6 +289,16 @@ int abl_find_cells(abl_handle h, uint64_t n, const double* r3, const double* u3,
 int abl_rng_probe(abl_handle h, uint64_t history_id, int n, uint32_t* out_u32, double* out_rand);
 /* device log / sin / cos used by the kernels                                                             */
 int abl_math_probe(abl_handle h, int n, const double* x, double* lg, double* sn, double* cs);
+/* Surface::sign / distance / norm of surface `surface_index` of the problem at n points (e.g. src/plane.cpp:33-60,
+ * src/sphere.cpp:33-80, src/cylinder.cpp:60-110): u3 are unit directions, on_surf[i] != 0 = "the particle sits on this
+ * surface" (the argument of Surface::distance)                                                            */
+int abl_surface_probe(abl_handle h, int surface_index, uint64_t n, const double* r3, const double* u3, const int32_t* on_surf,
+                      int32_t* sign, double* distance, double* norm3);
+/* Replaces the per-group sampling cross section (the majorant of delta tracking, ratio * majorant of carter tracking:
+ * src/majorant.cpp:158-173, src/carter_tracker.cpp:60-75) and the quotients derived from it.  A caller that changes
+ * materials between runs uses it; the parity tests use it to provoke the reference's "total xs above the majorant" fatal
+ * error (src/delta_tracker.cpp:174-180).                                                                 */
+int abl_set_sampling_xs(abl_handle h, const double* sampling_xs, int ngroups);
 
 #ifdef __cplusplus
 }

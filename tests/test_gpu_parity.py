@@ -233,14 +233,87 @@ def test_fission_bank_overflow_is_reported(ab, oracle_api, tmp_path):
 
 
 def test_majorant_violation_is_fatal(ab, oracle_api, tmp_path):
-    """Total xs above the sampling xs must raise, as delta_tracker.cpp:174-180 does."""
+    """A total cross section above the majorant must abort the run with the offending history's id, as
+    delta_tracker.cpp:174-180 does (`if (Et - Emaj > 1e-10) fatal_error(...)`): ABL_ERR_MAJORANT through every entry point."""
     from abeille_b200 import BackendError
-    deck = load_deck("c5g7_carter_cancel.yaml")
-    deck["settings"]["transport"] = "delta-tracking"  # delta tracking never reads sampling-xs-ratio ...
-    path = write_deck(deck, tmp_path / "ok.yaml", {"settings": {"nparticles": 2000}})
+    n = 3000
+    path = write_deck(load_deck("c5g7_delta_collision.yaml"), tmp_path / "maj.yaml", {"settings": {"nparticles": n}})
     gpu = ab.Backend(path, 0)
     orc = oracle_api.Oracle(path)
-    gpu.transport(orc.sample_source(2000))  # ... so this is fine
+    bank = orc.sample_source(n)
+    gpu.transport(bank)  # the deck's own majorant: fine
+    from abeille_b200 import backend
+    smp = np.array(backend.dump_tables(path)["smp"])
+    low = smp.copy()
+    low[6] *= 0.5  # thermal group: water's total xs (2.65) is now above the "majorant" (1.33)
+    gpu.set_sampling_xs(low)
+    for trace in (False, True):
+        with pytest.raises(BackendError) as e:
+            gpu.transport(bank, trace=trace)
+        assert e.value.code == -5 and "majorant" in str(e.value)
+        hid = int(str(e.value).split("history ")[1].rstrip(")"))
+        assert 0 <= hid < n  # one of this bank's histories (which one is first is a race, as under OpenMP)
+    gpu.set_sampling_xs(smp)  # restored: the same handle runs again, bit-exact
+    fis, _, _ = gpu.transport(bank)
+    ofis, _, _ = orc.transport({k: v.copy() for k, v in bank.items()})
+    for k in BANK_EXACT:
+        assert np.array_equal(fis[k], ofis[k]), k
+
+
+def _holed_deck(transport):
+    """A fuel sphere inside a reflective box whose cells do not fill the box: the shell 2 < |r| < 3 belongs to no cell."""
+    d = load_deck("PUa-1-0-IN.yaml")
+    d["surfaces"] = d["surfaces"] + [{"type": "sphere", "x0": 0.0, "y0": 0.0, "z0": 0.0, "r": 2.0, "id": 7},
+                                     {"type": "sphere", "x0": 0.0, "y0": 0.0, "z0": 0.0, "r": 3.0, "id": 8}]
+    d["cells"] = [{"region": "-7", "material": 1, "name": "ball", "id": 1},
+                  {"region": "+8 & +1 & -2 & +3 & -4 & +5 & -6", "material": 1, "name": "rest", "id": 2}]
+    d["universes"] = [{"cells": [1, 2], "id": 1}]
+    d["settings"]["transport"] = transport
+    return d
+
+
+def test_lost_particle_is_fatal(ab, oracle_api, tmp_path):
+    """A particle that crosses a surface into a point no cell covers is lost: fatal in the reference
+    (surface_tracker.cpp:126-133 "Particle became lost" after cross_surface) -> ABL_ERR_LOST with its history id."""
+    from abeille_b200 import BackendError
+    n = 2000
+    path = write_deck(_holed_deck("surface-tracking"), tmp_path / "hole.yaml", {"settings": {"nparticles": n}})
+    gpu = ab.Backend(path, 0)
+    bank = oracle_api.Oracle(path).sample_source(n)
+    for trace in (False, True):
+        with pytest.raises(BackendError) as e:
+            gpu.transport(bank, trace=trace)
+        assert e.value.code == -4 and "lost" in str(e.value)
+        assert 0 <= int(str(e.value).split("history ")[1].rstrip(")")) < n
+
+
+def test_lost_at_birth_is_a_warning_not_an_error(ab, oracle_api, tmp_path):
+    """Source particles born where no cell is are killed with a warning (delta_tracker.cpp:92-98) and counted."""
+    n = 2000
+    path = write_deck(_holed_deck("delta-tracking"), tmp_path / "hole.yaml", {"settings": {"nparticles": n}})
+    orc, gpu = oracle_api.Oracle(path), ab.Backend(path, 0)
+    bank = orc.sample_source(n)
+    rng = np.random.default_rng(5)
+    dirs = rng.normal(size=(n, 3))
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    bank["x"][:], bank["y"][:], bank["z"][:] = (2.5 * dirs).T  # inside the hole
+    fis, scores, cn = gpu.transport(bank)
+    assert cn["lost_at_birth"] == n and len(fis["x"]) == 0 and cn["flights"] == 0
+
+
+def test_secondary_stack_overflow_is_reported(ab, oracle_api, tmp_path):
+    """Carter tracking splits a particle of weight w into ceil(|w|) copies (particle.hpp:165-173); the device keeps at most
+    ABL_SEC_CAP of them per history and reports an overflow instead of dropping copies."""
+    from abeille_b200 import BackendError
+    n = 500
+    path = write_deck(load_deck("c5g7_carter_cancel.yaml"), tmp_path / "carter.yaml", {"settings": {"nparticles": n}})
+    gpu = ab.Backend(path, 0)
+    bank = oracle_api.Oracle(path).sample_source(n)
+    bank["wgt"][:] = 40.0
+    with pytest.raises(BackendError) as e:
+        gpu.transport(bank)
+    assert e.value.code == -3 and "secondary" in str(e.value)
+    assert 0 <= int(str(e.value).split("history ")[1].rstrip(")")) < n
 
 
 def test_cpp_adapter_matches_c_abi(ab, oracle_api, tmp_path):
@@ -427,3 +500,49 @@ def test_distributed_iterator_with_cancellation_matches_oracle(ab, oracle_api, t
         sim.generation(converged=g >= 1)
     assert [int(v) for v in sim.nbank_series] == [int(v) for v in ref["nbank"]]
     assert np.allclose(sim.kcol_series, ref["kcol"], rtol=1e-10)
+
+
+def test_sood_k_inf_deck_at_large_n_does_not_overflow(ab, oracle_api, tmp_path):
+    """PUa-1-0-IN (k_inf = 2.61) banks 2.61 sites per particle in the first generation (k_col starts at 1,
+    tallies.cpp:48): the output banks are sized from the problem (abl_fission_capacity_hint), not as a fixed multiple
+    of the bank -- with N = 2*10^5 a 2.5 N bank would overflow (522 000 sites vs 504 096)."""
+    n, ngen, nign = 200000, 3, 1
+    ov = {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}}
+    for resident in (True, False):
+        path = write_deck(load_deck("PUa-1-0-IN.yaml"), tmp_path / f"big{int(resident)}.yaml", ov)
+        gpu = ab.Backend(path, 0)
+        g = gpu.run_power_iteration(ngen, nign, resident=resident)
+        assert g["nbank"][1] > 2.55 * n and abs(g["kcol"][0] - 2.612903) < 0.02
+    assert gpu.fission_capacity(n) > 2.7 * n
+    gpu1 = ab.Backend(write_deck(load_deck("c5g7_delta_collision.yaml"), tmp_path / "c.yaml"), 0)
+    assert 1.3 * n < gpu1.fission_capacity(n) < 3.5 * n
+
+
+def test_distributed_iterator_regrows_its_banks(ab, oracle_api, tmp_path):
+    """An output bank that turns out too small is grown and the generation repeated (scores come back per call, tally_gen
+    is cleared before the retry): same bank sizes, k and tallies as a run whose banks were large enough from the start,
+    entropy and source-estimator tallies included."""
+    from abeille_b200.distributed import DistributedPowerIterator
+    n, ngen = 8000, 4
+    deck = load_deck("c5g7_delta_collision.yaml")
+    deck["tallies"] = deck["tallies"] + [{"name": "src", "low": [-32.13, -32.13, -107.1], "hi": [32.13, 32.13, 107.1], "shape": [17, 17, 1],
+                                          "energy-bounds": [0, 7], "quantity": "source", "estimator": "source"}]
+    path = write_deck(deck, tmp_path / "d.yaml", {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": 1}})
+    ref = oracle_api.Oracle(path).run_power_iteration(ngen, 1)
+    runs = []
+    for small in (False, True):
+        sim = DistributedPowerIterator(path, 0, n)
+        if small:  # banks that hold the source but not the fission sites of the first generation
+            sim.cap = n + 64
+            sim.cur, sim.nxt = sim.gpu.new_device_bank(sim.cap), sim.gpu.new_device_bank(sim.cap)
+        sim.initialize()
+        for g in range(ngen):
+            sim.generation(converged=g >= 1)
+        runs.append(sim)
+        assert [int(v) for v in sim.nbank_series] == [int(v) for v in ref["nbank"]]
+        assert np.allclose(sim.kcol_series, ref["kcol"], rtol=1e-10)
+        assert np.allclose(sim.entropy_series, ref["entropy"], rtol=1e-10)
+    assert runs[1].cap > n + 64
+    for t in range(runs[0].gpu.ntallies()):
+        a, b = runs[0].gpu.tally(t, "avg"), runs[1].gpu.tally(t, "avg")
+        assert np.allclose(a, b, rtol=1e-12, atol=0) and a.sum() > 0
