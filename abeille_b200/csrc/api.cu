@@ -3,6 +3,7 @@
  * Owns the device-side copy of the flattened problem, the scratch buffers of the transport
  * kernel and the mesh-tally arrays.  No CPU fallback exists: without a CUDA device abl_create fails.
  */
+#define ABL_TABLES_GLOBAL 1  // this unit's kernels read the tables from global memory (detmath.cuh: ldt)
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -13,6 +14,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <type_traits>
 #include <functional>
 #include <vector>
 
@@ -77,9 +79,15 @@ struct abl_context {
   double* probe_buf = nullptr;
   uint64_t probe_cap = 0;
   int blocks_per_sm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // by tracker and kernel build (plain, track-length, traced)
-  int hk_slots[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // histories per CTA of the staged kernel (by tracker, trace)
+  int hk_slots[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  int hk_tables[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // bytes of tables staged in shared memory (0: read from global memory)  // histories per CTA of the staged kernel (by tracker, trace)
   int geo_frames = 1, geo_pads = 2;  // nesting depth of the geometry: coordinate frames / stack pads a history can hold
   int smem_optin = 0, smem_total_sm = 0;  // shared memory a CTA may opt in to / an SM has
+  // the small immutable tables live in one arena, so the staged history kernel can copy them into shared memory in one
+  // sweep and run with its table pointers redirected there (stage_tables)
+  unsigned char* arena = nullptr;
+  size_t arena_used = 0, arena_cap = 0;
+  unsigned long long smem_generic_base = 0;  // generic address of byte 0 of a kernel's dynamic shared memory
   uint64_t* rng_scratch = nullptr;  // pcg32 states seeded on the device when the caller passes id_c = NULL
   uint64_t rng_cap = 0;
   uint64_t launches = 0;
@@ -115,15 +123,23 @@ int fail(abl_handle h, int code, const std::string& msg) {
   return code;
 }
 
+constexpr size_t ARENA_CAP = 48 * 1024, ARENA_MAX_TABLE = 16 * 1024;
+
 template <typename T>
 int upload(abl_handle h, const T* src, size_t n, const T** dst) {
   *dst = nullptr;
   if (n == 0) return ABL_OK;
   if (!src) return fail(h, ABL_ERR_INVALID, "null table pointer");
   void* d = nullptr;
-  ABL_CUDA(h, cudaMalloc(&d, n * sizeof(T)));
-  h->allocs.push_back(d);
-  ABL_CUDA(h, cudaMemcpy(d, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  const size_t bytes = n * sizeof(T), at = (h->arena_used + 15) & ~size_t(15);
+  if (h->arena && bytes <= ARENA_MAX_TABLE && at + bytes <= h->arena_cap) {
+    d = h->arena + at;
+    h->arena_used = at + bytes;
+  } else {
+    ABL_CUDA(h, cudaMalloc(&d, bytes));
+    h->allocs.push_back(d);
+  }
+  ABL_CUDA(h, cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
   *dst = static_cast<const T*>(d);
   return ABL_OK;
 }
@@ -373,6 +389,25 @@ int alloc_bank(abl_handle h, BankView& b, uint64_t cap) {
   return ABL_OK;
 }
 
+// The staged history kernel copies the table arena into its shared memory (at HK_COLS_OFFSET) and runs on a DevProblem
+// whose table pointers point at that copy: generic addresses of the shared window, the same for every CTA.  Pointers
+// outside the arena (tables too large for it, tally arrays) are left alone.
+DevProblem stage_tables(abl_handle h, unsigned smem_offset) {
+  DevProblem Q = h->P;
+  const unsigned char *lo = h->arena, *hi = h->arena + h->arena_used;
+  const long long delta = (long long)(h->smem_generic_base + smem_offset) - (long long)reinterpret_cast<uintptr_t>(lo);
+  auto mv = [&](auto& ptr) {
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(ptr);
+    if (b >= lo && b < hi) ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(reinterpret_cast<uintptr_t>(b) + delta);
+  };
+  mv(Q.ebounds); mv(Q.jump); mv(Q.surfaces); mv(Q.cells); mv(Q.rpn); mv(Q.universes); mv(Q.ucells); mv(Q.tiles); mv(Q.cellfast);
+  mv(Q.Et); mv(Q.Ea); mv(Q.Ef); mv(Q.Es); mv(Q.nu); mv(Q.nud); mv(Q.speed); mv(Q.chi_cp); mv(Q.ps_cp); mv(Q.angle);
+  mv(Q.amu); mv(Q.apdf); mv(Q.acdf); mv(Q.dg_off); mv(Q.dg_cp); mv(Q.dg_lambda); mv(Q.fissile); mv(Q.smp);
+  mv(Q.real_frac); mv(Q.surv_frac); mv(Q.inv_score); mv(Q.tally_gbin); mv(Q.gmid); mv(Q.tally_dev);
+  for (int t = 0; t < Q.ntallies; t++) mv(Q.tally[t].ebounds);
+  return Q;
+}
+
 template <int TRK, bool TRACE>
 int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s) {
   // the staged lock-step loop with the histories in shared-memory columns and service warps for the rare events
@@ -396,23 +431,32 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
       int regs_limit = 65536 / (fa.numRegs * threads > 0 ? fa.numRegs * threads : 1);
       if (regs_limit >= 2 && 2 * threads <= 2048) want_blocks = 2;
     }
-    const int budget = (want_blocks == 2 ? (h->smem_total_sm / 2 - 1024) : h->smem_optin) - (int)hk.fixed_bytes - (int)fa.sharedSizeBytes;
-    int sl = budget / (int)slot_bytes;
+    const int room = (want_blocks == 2 ? (h->smem_total_sm / 2 - 1024) : h->smem_optin) - (int)hk.fixed_bytes - (int)fa.sharedSizeBytes;
+    // the tables are staged in shared memory when that costs at most a quarter of the histories the CTA could hold
+    const int tables = (int)((h->arena_used + 15) & ~size_t(15));
+    int sl_plain = room / (int)slot_bytes, sl = (room - tables) / (int)slot_bytes;
+    sl_plain -= sl_plain % 32;
     sl -= sl % 32;
+    if (sl_plain > hk.hist_threads) sl_plain = hk.hist_threads;
     if (sl > hk.hist_threads) sl = hk.hist_threads;
+    bool stage = h->smem_generic_base != 0 && fa.sharedSizeBytes == 0 && sl >= 32 && 4 * sl >= 3 * sl_plain;
+    if (getenv("ABEILLE_B200_NO_SMEM_TABLES")) stage = false;
+    if (!stage) sl = sl_plain;
+    h->hk_tables[TRK][TRACE ? 2 : (tle ? 1 : 0)] = stage ? tables : 0;
     if (sl < 32) {
       h->error = "geometry nesting too deep for the staged history kernel's shared memory";
       return ABL_ERR_GEOMETRY;
     }
     slots = sl;
-    const size_t smem = hk.fixed_bytes + (size_t)slot_bytes * (size_t)sl;
+    const size_t smem = hk.fixed_bytes + (size_t)(stage ? tables : 0) + (size_t)slot_bytes * (size_t)sl;
     ABL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
     ABL_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem));
     if (nb < 1) nb = 1;
     bps = nb;
   }
-  const size_t smem = hk.fixed_bytes + (size_t)slot_bytes * (size_t)slots;
+  const int tables = h->hk_tables[TRK][TRACE ? 2 : (tle ? 1 : 0)];
+  const size_t smem = hk.fixed_bytes + (size_t)tables + (size_t)slot_bytes * (size_t)slots;
   const int worker_threads = slots;  // threads of a block that own histories
   uint64_t blocks = (uint64_t)h->sm_count * bps;
   const uint64_t need = (n + worker_threads - 1) / worker_threads;
@@ -422,6 +466,9 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
   B.hk_slots = slots;
   B.hk_nf = nf;
   B.hk_np = np;
+  B.hk_tables = tables;
+  B.arena = h->arena;
+  B.smem_generic_base = h->smem_generic_base;
   {
     static const double timeout_s = [] {
       const char* e = getenv("ABEILLE_B200_KERNEL_TIMEOUT_S");
@@ -455,7 +502,7 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
     B.bank.id_c = h->rng_scratch;
   }
   cudaEventRecord(h->ev0, s);
-  kern<<<(unsigned)blocks, threads, smem, s>>>(h->P, B);
+  kern<<<(unsigned)blocks, threads, smem, s>>>(tables ? stage_tables(h, hk.fixed_bytes) : h->P, B);
   h->last_block = threads;
   cudaEventRecord(h->ev1, s);
   h->last_grid = (int)blocks;
@@ -764,6 +811,18 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
   if (CU(cudaMalloc(&h->small_dev, sizeof(DevSmall)), "cudaMalloc")) return bail(ABL_ERR_CUDA);
   if (CU(cudaMallocHost(&h->small_host, sizeof(DevSmall)), "cudaMallocHost")) return bail(ABL_ERR_CUDA);
 
+  if (CU(cudaMalloc(&h->arena, ARENA_CAP), "cudaMalloc")) return bail(ABL_ERR_CUDA);
+  h->allocs.push_back(h->arena);
+  h->arena_cap = ARENA_CAP;
+  if (CU(cudaMemset(h->arena, 0, ARENA_CAP), "cudaMemset")) return bail(ABL_ERR_CUDA);
+  {
+    smem_base_probe_kernel<<<1, 32, 64, h->stream>>>(reinterpret_cast<unsigned long long*>(h->small_dev));
+    unsigned long long base = 0;
+    if (CU(cudaMemcpyAsync(&base, h->small_dev, sizeof base, cudaMemcpyDeviceToHost, h->stream), "cudaMemcpyAsync") ||
+        CU(cudaStreamSynchronize(h->stream), "smem_base_probe_kernel"))
+      return bail(ABL_ERR_CUDA);
+    h->smem_generic_base = base;
+  }
   DevProblem& P = h->P;
   const int G = p->ngroups, M = p->nmaterials;
   P.mode = p->mode;

@@ -225,7 +225,7 @@ __device__ __forceinline__ long long cancel_key(const DevMesh3& m, double x, dou
   int l = -1;
   if (m.eedges) {
     for (int e = 0; e < m.Ne; e++)
-      if (__ldg(&m.eedges[e]) <= E && E <= __ldg(&m.eedges[e + 1])) { l = e; break; }
+      if (ldt(&m.eedges[e]) <= E && E <= ldt(&m.eedges[e + 1])) { l = e; break; }
   } else {
     l = 0;
   }
@@ -296,10 +296,10 @@ __global__ void __launch_bounds__(128) sample_source_kernel(const DevProblem P, 
     const double mu = 2. * rng_rand(rng) - 1.;  // isotropic.cpp:28-36
     const double phi = 2. * ABL_PI * rng_rand(rng);
     const V3 u = make_direction_mu_phi(mu, phi);
-    const double E = __ldg(&S->energy);
-    const bool is_box = __ldg(&S->is_box) != 0;
-    const double lx = __ldg(&S->low[0]), ly = __ldg(&S->low[1]), lz = __ldg(&S->low[2]);
-    const double hx = __ldg(&S->hi[0]), hy = __ldg(&S->hi[1]), hz = __ldg(&S->hi[2]);
+    const double E = ldt(&S->energy);
+    const bool is_box = ldt(&S->is_box) != 0;
+    const double lx = ldt(&S->low[0]), ly = ldt(&S->low[1]), lz = ldt(&S->low[2]);
+    const double hx = ldt(&S->hi[0]), hy = ldt(&S->hi[1]), hz = ldt(&S->hi[2]);
     V3 r;
     Cursor c;
     c.err = 0;
@@ -321,9 +321,9 @@ __global__ void __launch_bounds__(128) sample_source_kernel(const DevProblem P, 
       if (!is_box && ++guard > 1) { bad = true; break; }
       sample_pos();
     }
-    if (!bad && __ldg(&S->fissile_only)) {  // source.cpp:72-86
+    if (!bad && ldt(&S->fissile_only)) {  // source.cpp:72-86
       int count = 0;
-      while (c.cell < 0 || !__ldg(&P.fissile[c.mat])) {
+      while (c.cell < 0 || !ldt(&P.fissile[c.mat])) {
         if (count == 201) { bad = true; break; }
         sample_pos();
         count++;
@@ -357,6 +357,11 @@ __global__ void __launch_bounds__(256) tally_record_kernel(double* __restrict__ 
 __global__ void __launch_bounds__(256) tally_std_kernel(const double* __restrict__ var, double* __restrict__ out, uint64_t n, double dg) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
     out[i] = sqrt(var[i] / dg);
+}
+
+__global__ void smem_base_probe_kernel(unsigned long long* out) {
+  extern __shared__ __align__(16) unsigned char probe_raw[];
+  if (threadIdx.x == 0) *out = (unsigned long long)(uintptr_t)(void*)probe_raw;  // generic address of the dynamic shared memory
 }
 
 // ---- probes --------------------------------------------------------------------------------------------------------------

@@ -20,6 +20,23 @@
 
 namespace abl {
 
+// Table load.  Every immutable problem table (geometry, cross sections, sampling tables) is read through this.  The
+// staged history kernel runs with the tables copied into shared memory and the table pointers of its DevProblem
+// redirected there by the host (api.cu: stage_tables), so in its translation units this is a GENERIC load: the pointer is
+// passed through an empty asm first, because nvcc assumes that pointers reaching a kernel through its parameters are
+// global and would emit ld.global, which faults on a shared-window address.  Translation units whose kernels always read
+// the tables from global memory (ABL_TABLES_GLOBAL) keep the read-only path (ld.global.nc).
+template <class T>
+__device__ __forceinline__ T ldt(const T* p) {
+#ifdef ABL_TABLES_GLOBAL
+  return __ldg(p);
+#else
+  asm("" : "+l"(p));
+  return *p;
+#endif
+}
+
+
 __device__ __forceinline__ int32_t dm_hi(double x) { return __double2hiint(x); }
 __device__ __forceinline__ uint32_t dm_lo(double x) { return (uint32_t)__double2loint(x); }
 __device__ __forceinline__ double dm_set_hi(double x, int32_t hi) { return __hiloint2double(hi, __double2loint(x)); }

@@ -76,17 +76,17 @@ template <class PT>
 __device__ __forceinline__ Surf load_surface(const PT& P, int i) {
   const abl_surface* s = P.surfaces + i;
   Surf r;
-  r.type = __ldg(&s->type);
-  r.bc = __ldg(&s->bc);
-  r.p0 = __ldg(&s->p[0]);
-  r.p1 = __ldg(&s->p[1]);
-  r.p2 = __ldg(&s->p[2]);
-  r.p3 = __ldg(&s->p[3]);
+  r.type = ldt(&s->type);
+  r.bc = ldt(&s->bc);
+  r.p0 = ldt(&s->p[0]);
+  r.p1 = ldt(&s->p[1]);
+  r.p2 = ldt(&s->p[2]);
+  r.p3 = ldt(&s->p[3]);
   r.p4 = r.p5 = r.p6 = 0.;
   if (r.type == ABL_SURF_CYL) {
-    r.p4 = __ldg(&s->p[4]);
-    r.p5 = __ldg(&s->p[5]);
-    r.p6 = __ldg(&s->p[6]);
+    r.p4 = ldt(&s->p[4]);
+    r.p5 = ldt(&s->p[5]);
+    r.p6 = ldt(&s->p[6]);
   }
   return r;
 }
@@ -249,10 +249,10 @@ __device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
 template <class PT>
 __device__ inline bool cell_is_inside(const PT& P, int ci, const V3& r, const V3& u, int on_surf) {
   const abl_cell* c = P.cells + ci;
-  const int off = __ldg(&c->rpn_offset), len = __ldg(&c->rpn_len);
-  if (__ldg(&c->simple)) {
+  const int off = ldt(&c->rpn_offset), len = ldt(&c->rpn_len);
+  if (ldt(&c->simple)) {
     for (int k = 0; k < len; k++) {
-      const int token = __ldg(&P.rpn[off + k]);
+      const int token = ldt(&P.rpn[off + k]);
       if (token == on_surf) {
       } else if (-token == on_surf) {
         return false;
@@ -268,7 +268,7 @@ __device__ inline bool cell_is_inside(const PT& P, int ci, const V3& r, const V3
   uint64_t stck = 0;
   int i_stck = -1;
   for (int k = 0; k < len; k++) {
-    const int token = __ldg(&P.rpn[off + k]);
+    const int token = ldt(&P.rpn[off + k]);
     if (token == ABL_OP_UNION) {
       const bool v = ((stck >> (i_stck - 1)) & 1ULL) || ((stck >> i_stck) & 1ULL);
       i_stck--;
@@ -307,12 +307,12 @@ static __device__ __noinline__ bool cell_is_inside_nl(const GeoTables G, int ci,
 // the particle sits on a surface or is within SURFACE_COINCIDENT of one (direction-dependent tie), or the
 // region has no compiled form; the caller then runs the generic evaluator.  One shared copy per kernel.
 static __device__ ABL_HOT_CALL int cell_fast_nl(const CellFast* __restrict__ cf, const V3 r, int on_surf) {
-  const int kind = __ldg(&cf->kind);
+  const int kind = ldt(&cf->kind);
   if (on_surf != 0) return -1;
   if (kind == CF_BOX) {
-    const double2 bx = __ldg(reinterpret_cast<const double2*>(&cf->a[0]));
-    const double2 by = __ldg(reinterpret_cast<const double2*>(&cf->a[2]));
-    const double2 bz = __ldg(reinterpret_cast<const double2*>(&cf->a[4]));
+    const double2 bx = ldt(reinterpret_cast<const double2*>(&cf->a[0]));
+    const double2 by = ldt(reinterpret_cast<const double2*>(&cf->a[2]));
+    const double2 bz = ldt(reinterpret_cast<const double2*>(&cf->a[4]));
     const double e0 = r.x - bx.x, e1 = r.x - bx.y, e2 = r.y - by.x, e3 = r.y - by.y, e4 = r.z - bz.x, e5 = r.z - bz.y;
     const double T = ABL_SURFACE_COINCIDENT;
     const bool tie = (fabs(e0) <= T) | (fabs(e1) <= T) | (fabs(e2) <= T) | (fabs(e3) <= T) | (fabs(e4) <= T) | (fabs(e5) <= T);
@@ -320,11 +320,11 @@ static __device__ ABL_HOT_CALL int cell_fast_nl(const CellFast* __restrict__ cf,
     return tie ? -1 : (in ? 1 : 0);
   }
   if (kind == CF_ZCYL) {
-    const double2 xy = __ldg(reinterpret_cast<const double2*>(&cf->a[0]));
-    const double r2 = __ldg(&cf->a[2]);
+    const double2 xy = ldt(reinterpret_cast<const double2*>(&cf->a[0]));
+    const double r2 = ldt(&cf->a[2]);
     const double x = r.x - xy.x, y = r.y - xy.y;
     const double e = y * y + x * x - r2;
-    const bool in = (__ldg(&cf->sense) < 0) ? (e < 0.) : (e > 0.);
+    const bool in = (ldt(&cf->sense) < 0) ? (e < 0.) : (e > 0.);
     return fabs(e) > ABL_SURFACE_COINCIDENT ? (in ? 1 : 0) : -1;
   }
   return -1;
@@ -342,10 +342,10 @@ __device__ inline void cell_distance_impl(const PT& P, int ci, const V3& r, cons
   min_dist = ABL_INF;
   i_surf = 0;
   const abl_cell* c = P.cells + ci;
-  if (bc_only && !__ldg(&c->vac_or_refl)) return;
-  const int off = __ldg(&c->rpn_offset), len = __ldg(&c->rpn_len);
+  if (bc_only && !ldt(&c->vac_or_refl)) return;
+  const int off = ldt(&c->rpn_offset), len = ldt(&c->rpn_len);
   for (int k = 0; k < len; k++) {
-    const int token = __ldg(&P.rpn[off + k]);
+    const int token = ldt(&P.rpn[off + k]);
     if (token >= ABL_OP_UNION) continue;
     const bool coincident = iabs(token) == iabs(on_surf);
     const Surf s = load_surface(P, iabs(token) - 1);
@@ -389,12 +389,12 @@ struct Lat {
 };
 __device__ __forceinline__ Lat load_lattice(const abl_universe* U) {
   Lat L;
-  L.Nx = __ldg(&U->N[0]); L.Ny = __ldg(&U->N[1]); L.Nz = __ldg(&U->N[2]);
-  L.tile_offset = __ldg(&U->tile_offset);
-  L.outer = __ldg(&U->outer);
-  L.Px = __ldg(&U->P[0]); L.Py = __ldg(&U->P[1]); L.Pz = __ldg(&U->P[2]);
-  L.Pxi = __ldg(&U->Pinv[0]); L.Pyi = __ldg(&U->Pinv[1]); L.Pzi = __ldg(&U->Pinv[2]);
-  L.Xl = __ldg(&U->Xl[0]); L.Yl = __ldg(&U->Xl[1]); L.Zl = __ldg(&U->Xl[2]);
+  L.Nx = ldt(&U->N[0]); L.Ny = ldt(&U->N[1]); L.Nz = ldt(&U->N[2]);
+  L.tile_offset = ldt(&U->tile_offset);
+  L.outer = ldt(&U->outer);
+  L.Px = ldt(&U->P[0]); L.Py = ldt(&U->P[1]); L.Pz = ldt(&U->P[2]);
+  L.Pxi = ldt(&U->Pinv[0]); L.Pyi = ldt(&U->Pinv[1]); L.Pzi = ldt(&U->Pinv[2]);
+  L.Xl = ldt(&U->Xl[0]); L.Yl = ldt(&U->Xl[1]); L.Zl = ldt(&U->Xl[2]);
   return L;
 }
 __device__ __forceinline__ V3 tile_center(const Lat& L, int nx, int ny, int nz) {  // rect_lattice.cpp:303-309
@@ -488,15 +488,15 @@ template <class PT>
 __device__ inline Boundary universe_boundary_condition(const PT& P, int uni, const V3& r, const V3& u, int on_surf) {
   Boundary b{ABL_INF, -1, ABL_BC_VACUUM, 0};
   const abl_universe* U = P.universes + uni;
-  while (__ldg(&U->type) != ABL_UNI_CELLS) {  // lattices defer to their outer universe
-    if (!__ldg(&U->has_bc)) return b;
-    U = P.universes + __ldg(&U->outer);
+  while (ldt(&U->type) != ABL_UNI_CELLS) {  // lattices defer to their outer universe
+    if (!ldt(&U->has_bc)) return b;
+    U = P.universes + ldt(&U->outer);
   }
-  if (__ldg(&U->has_bc)) {
-    const int off = __ldg(&U->cell_offset), n = __ldg(&U->ncells);
+  if (ldt(&U->has_bc)) {
+    const int off = ldt(&U->cell_offset), n = ldt(&U->ncells);
     for (int k = 0; k < n; k++) {
-      const int ci = __ldg(&P.ucells[off + k]);
-      if (!__ldg(&P.cells[ci].vac_or_refl)) continue;
+      const int ci = ldt(&P.ucells[off + k]);
+      if (!ldt(&P.cells[ci].vac_or_refl)) continue;
       double d;
       int is;
       cell_distance(P, ci, r, u, on_surf, true, d, is);
@@ -569,12 +569,12 @@ __device__ inline int descend(const PT& P, CUR& c, int uni, int f, const V3& u) 
   for (;;) {
     const abl_universe* U = P.universes + uni;
     const V3 r = frame_r(c, f);
-    if (__ldg(&U->type) == ABL_UNI_CELLS) {
+    if (ldt(&U->type) == ABL_UNI_CELLS) {
       if (!push_pad(c, make_pad(PAD_UNIVERSE, 0, f, uni))) return -1;
-      const int off = __ldg(&U->cell_offset), n = __ldg(&U->ncells);
+      const int off = ldt(&U->cell_offset), n = ldt(&U->ncells);
       int found = -1;
       for (int k = 0; k < n; k++) {
-        const int ci = __ldg(&P.ucells[off + k]);
+        const int ci = ldt(&P.ucells[off + k]);
         bool in;
         if constexpr (FAST) in = cell_is_inside_fast(P, ci, r, u, c.token);
         else in = cell_is_inside(P, ci, r, u, c.token);
@@ -586,7 +586,7 @@ __device__ inline int descend(const PT& P, CUR& c, int uni, int f, const V3& u) 
       c.nf = f + 1;
       if (found < 0) return -1;
       if (!push_pad(c, make_pad(PAD_CELL, 0, f, found))) return -1;
-      const int fill = __ldg(&P.cells[found].fill_universe);
+      const int fill = ldt(&P.cells[found].fill_universe);
       if (fill < 0) return found;
       uni = fill;
       continue;
@@ -596,17 +596,17 @@ __device__ inline int descend(const PT& P, CUR& c, int uni, int f, const V3& u) 
     if (FAST) {
       const Tile3 t3 = lattice_tile_nl(U, r, u);
       nx = t3.nx; ny = t3.ny; nz = t3.nz;
-      L.Nx = __ldg(&U->N[0]); L.Ny = __ldg(&U->N[1]); L.Nz = __ldg(&U->N[2]);
-      L.tile_offset = __ldg(&U->tile_offset);
-      L.outer = __ldg(&U->outer);
-      L.Px = __ldg(&U->P[0]); L.Py = __ldg(&U->P[1]); L.Pz = __ldg(&U->P[2]);
-      L.Xl = __ldg(&U->Xl[0]); L.Yl = __ldg(&U->Xl[1]); L.Zl = __ldg(&U->Xl[2]);
+      L.Nx = ldt(&U->N[0]); L.Ny = ldt(&U->N[1]); L.Nz = ldt(&U->N[2]);
+      L.tile_offset = ldt(&U->tile_offset);
+      L.outer = ldt(&U->outer);
+      L.Px = ldt(&U->P[0]); L.Py = ldt(&U->P[1]); L.Pz = ldt(&U->P[2]);
+      L.Xl = ldt(&U->Xl[0]); L.Yl = ldt(&U->Xl[1]); L.Zl = ldt(&U->Xl[2]);
     } else {
       L = load_lattice(U);
       get_tile(L, r, u, nx, ny, nz);
     }
     int sub = -1;
-    if (tile_in_range(L, nx, ny, nz)) sub = __ldg(&P.tiles[L.tile_offset + nz * (L.Nx * L.Ny) + nx * L.Ny + ny]);
+    if (tile_in_range(L, nx, ny, nz)) sub = ldt(&P.tiles[L.tile_offset + nz * (L.Nx * L.Ny) + nx * L.Ny + ny]);
     c.nf = f + 1;
     if (sub >= 0) {
       if (!push_pad(c, make_pad(PAD_LATTICE, 0, f, uni), nx, ny, nz)) return -1;
@@ -639,7 +639,7 @@ __device__ inline void cursor_restart(const PT& P, Cursor& c, const V3& r, const
   c.fz[0] = r.z;
   c.nf = 1;
   c.cell = descend<false, Cursor, PT>(P, c, P.root, 0, u);
-  c.mat = c.cell >= 0 ? __ldg(&P.cells[c.cell].material) : -1;
+  c.mat = c.cell >= 0 ? ldt(&P.cells[c.cell].material) : -1;
 }
 
 // Tracker::move (tracker.hpp:76-85): every frame advances by d*u, the surface token is dropped
@@ -704,7 +704,7 @@ __device__ inline void cursor_get_current(const PT& P, Cursor& c, const V3& u) {
     uni = P.root;
     f = 0;
   }
-  c.mat = c.cell >= 0 ? __ldg(&P.cells[c.cell].material) : -1;
+  c.mat = c.cell >= 0 ? ldt(&P.cells[c.cell].material) : -1;
 }
 
 // Tracker::get_boundary_condition (tracker.hpp:94-161)
@@ -717,14 +717,14 @@ __device__ inline Boundary cursor_boundary_condition(const PT& P, const CUR& c, 
     const V3 r = frame_r(c, pad_frame(info));
     if (pad_type(info) == PAD_CELL) {
       const int ci = pad_index(info);
-      if (!__ldg(&P.cells[ci].vac_or_refl)) continue;
+      if (!ldt(&P.cells[ci].vac_or_refl)) continue;
       double d;
       int is;
       cell_distance(P, ci, r, u, c.token, true, d, is);
       take_cell_candidate(P, d, is, r, u, b);
     } else {
       const int ui = pad_index(info);
-      if (__ldg(&P.universes[ui].has_bc)) {
+      if (ldt(&P.universes[ui].has_bc)) {
         const Boundary ub = universe_boundary_condition(P, ui, r, u, c.token);
         if (ub.distance < b.distance && fabs(ub.distance - b.distance) > ABL_BOUNDRY_TOL) b = ub;
       }

@@ -85,7 +85,7 @@ __device__ __forceinline__ void cursor_relocate(const DevProblem& P, CUR& c, int
     uni = P.root;
     f = 0;
   }
-  c.mat = c.cell >= 0 ? __ldg(&P.cells[c.cell].material) : -1;
+  c.mat = c.cell >= 0 ? ldt(&P.cells[c.cell].material) : -1;
 }
 
 // One step of Universe::get_cell through a lattice (rect_lattice.cpp:132-207): 0 = descend further (uni / f updated),
@@ -96,11 +96,11 @@ __device__ __forceinline__ int descend_lattice_step(const DevProblem& P, CUR& c,
   const V3 r = frame_r(c, f);
   const Tile3 t3 = lattice_tile_nl(U, r, u);
   Lat L;
-  L.Nx = __ldg(&U->N[0]); L.Ny = __ldg(&U->N[1]); L.Nz = __ldg(&U->N[2]);
-  L.tile_offset = __ldg(&U->tile_offset);
-  L.outer = __ldg(&U->outer);
+  L.Nx = ldt(&U->N[0]); L.Ny = ldt(&U->N[1]); L.Nz = ldt(&U->N[2]);
+  L.tile_offset = ldt(&U->tile_offset);
+  L.outer = ldt(&U->outer);
   int sub = -1;
-  if (tile_in_range(L, t3.nx, t3.ny, t3.nz)) sub = __ldg(&P.tiles[L.tile_offset + t3.nz * (L.Nx * L.Ny) + t3.nx * L.Ny + t3.ny]);
+  if (tile_in_range(L, t3.nx, t3.ny, t3.nz)) sub = ldt(&P.tiles[L.tile_offset + t3.nz * (L.Nx * L.Ny) + t3.nx * L.Ny + t3.ny]);
   c.nf = f + 1;
   if (sub >= 0) {
     if (!push_pad(c, make_pad(PAD_LATTICE, 0, f, uni), t3.nx, t3.ny, t3.nz)) return -1;
@@ -108,8 +108,8 @@ __device__ __forceinline__ int descend_lattice_step(const DevProblem& P, CUR& c,
       c.err = ABL_ERR_GEOMETRY;
       return -1;
     }
-    L.Px = __ldg(&U->P[0]); L.Py = __ldg(&U->P[1]); L.Pz = __ldg(&U->P[2]);
-    L.Xl = __ldg(&U->Xl[0]); L.Yl = __ldg(&U->Xl[1]); L.Zl = __ldg(&U->Xl[2]);
+    L.Px = ldt(&U->P[0]); L.Py = ldt(&U->P[1]); L.Pz = ldt(&U->P[2]);
+    L.Xl = ldt(&U->Xl[0]); L.Yl = ldt(&U->Xl[1]); L.Zl = ldt(&U->Xl[2]);
     const V3 ctr = tile_center(L, t3.nx, t3.ny, t3.nz);
     set_frame(c, f + 1, r.x - ctr.x, r.y - ctr.y, r.z - ctr.z);
     f++;
@@ -132,10 +132,10 @@ __device__ __forceinline__ int descend_cells_step(const DevProblem& P, CUR& c, i
   const abl_universe* U = P.universes + uni;
   const V3 r = frame_r(c, f);
   if (!push_pad(c, make_pad(PAD_UNIVERSE, 0, f, uni))) return -1;
-  const int off = __ldg(&U->cell_offset), n = __ldg(&U->ncells);
+  const int off = ldt(&U->cell_offset), n = ldt(&U->ncells);
   int found = -1;
   for (int k = 0; k < n; k++) {
-    const int ci = __ldg(&P.ucells[off + k]);
+    const int ci = ldt(&P.ucells[off + k]);
     if (cell_is_inside_fast(P, ci, r, u, c.token)) {
       found = ci;
       break;
@@ -144,7 +144,7 @@ __device__ __forceinline__ int descend_cells_step(const DevProblem& P, CUR& c, i
   c.nf = f + 1;
   if (found < 0) return -1;
   if (!push_pad(c, make_pad(PAD_CELL, 0, f, found))) return -1;
-  const int fill = __ldg(&P.cells[found].fill_universe);
+  const int fill = ldt(&P.cells[found].fill_universe);
   if (fill < 0) {
     cell = found;
     return 1;
@@ -179,7 +179,7 @@ __device__ __forceinline__ void cursor_relocate_sync(const DevProblem& P, CUR& c
   int cell = -1;
   for (;;) {
     for (;;) {
-      const bool at_lattice = active && __ldg(&P.universes[uni].type) != ABL_UNI_CELLS;
+      const bool at_lattice = active && ldt(&P.universes[uni].type) != ABL_UNI_CELLS;
       if (!__any_sync(mask, at_lattice)) break;
       int st = 0;
       if (at_lattice) st = descend_lattice_step(P, c, uni, f, u);
@@ -214,7 +214,7 @@ __device__ __forceinline__ void cursor_relocate_sync(const DevProblem& P, CUR& c
     }
   }
   c.cell = cell;
-  c.mat = cell >= 0 ? __ldg(&P.cells[cell].material) : -1;
+  c.mat = cell >= 0 ? ldt(&P.cells[cell].material) : -1;
 }
 
 
@@ -332,14 +332,14 @@ struct Cols {  // byte offsets from hk_shared_raw of one thread's entries
   unsigned j0;  // HI_IDX (the 4-byte fields HI_* follow at stride S4)
   unsigned S8, S4, F8;  // column strides: 8 S, 4 S, 8 S NF
 };
-__device__ __forceinline__ Cols make_cols(int t, int S, int NF, int NP, bool trace) {
+__device__ __forceinline__ Cols make_cols(int t, int S, int NF, int NP, bool trace, int tables) {
   Cols q;
   q.S8 = 8u * S;
   q.S4 = 4u * S;
   q.F8 = q.S8 * NF;
-  q.d0 = HK_COLS_OFFSET + 8u * t;
+  q.d0 = HK_COLS_OFFSET + (unsigned)tables + 8u * t;
   q.r0 = q.d0 + 3u * q.F8;
-  q.i0 = HK_COLS_OFFSET + hk_cols8(NF, NP, trace) * q.S8 + 4u * t;
+  q.i0 = HK_COLS_OFFSET + (unsigned)tables + hk_cols8(NF, NP, trace) * q.S8 + 4u * t;
   q.j0 = q.i0 + q.S4 * NP;
   return q;
 }
@@ -417,12 +417,12 @@ struct TleArgs {
   int ntallies;
 };
 static __device__ __noinline__ int score_flight_cols(const TleArgs T, const Cols q, int mg, double d) {
-  const MatXS mx{__ldg(&T.Et[mg]), __ldg(&T.Ea[mg]), __ldg(&T.Ef[mg]), __ldg(&T.Es[mg])};
+  const MatXS mx{ldt(&T.Et[mg]), ldt(&T.Ea[mg]), ldt(&T.Ef[mg]), ldt(&T.Es[mg])};
   const V3 r = hk_ld3(q, HD_R), u = hk_ld3(q, HD_U);
   const double E = HK_D(q, HD_E), w = HK_D(q, HD_W);
   int nb = 0;
   for (int t = 0; t < T.ntallies; t++) {
-    if (__ldg(&T.tallies[t].estimator) != ABL_EST_TRACK_LENGTH) continue;
+    if (ldt(&T.tallies[t].estimator) != ABL_EST_TRACK_LENGTH) continue;
     const DevTally Y = T.tallies[t];
     nb += score_flight(Y, r, u, d, E, w, 0., mx);
   }
@@ -468,7 +468,7 @@ struct ServiceArgs {
   Site* sites;
   unsigned long long* n_sites;
   uint64_t site_capacity;
-  int slots, nf, np, trace;
+  int slots, nf, np, trace, tables;
 };
 
 // boundary request of the history thread with columns q: Tracker::restart_get_current at the pre-flight position +
@@ -500,7 +500,7 @@ __device__ __forceinline__ void serve_fission(const ServiceArgs& X, const FisJob
   uint64_t rng = j.rng;
   const int mat = j.mg / X.ft.G;
   bank_fission_sites<M>(X.ft, X.sites, X.n_sites, X.site_capacity, rng, V3{j.x, j.y, j.z}, V3{j.ux, j.uy, j.uz}, j.w, j.parent, j.daughter0,
-                        j.n_new, mat, j.mg, __ldg(&X.nud[j.mg]) / __ldg(&X.nu[j.mg]));
+                        j.n_new, mat, j.mg, ldt(&X.nud[j.mg]) / ldt(&X.nu[j.mg]));
 }
 
 template <class M>
@@ -522,7 +522,7 @@ static __device__ __noinline__ void service_loop(const ServiceArgs X, int sw) {
           if (t != HK_BQ_EMPTY) {
             S.bq[sw][slot] = HK_BQ_EMPTY;
             __threadfence_block();
-            serve_boundary(X.G, make_cols((int)t, X.slots, X.nf, X.np, X.trace != 0));
+            serve_boundary(X.G, make_cols((int)t, X.slots, X.nf, X.np, X.trace != 0, X.tables));
           }
         }
         __syncwarp();
@@ -591,9 +591,9 @@ __device__ __forceinline__ void post_fission_job(const FisJob& j, int sw) {
 template <class M>
 __device__ __forceinline__ uint64_t skip_fission_draws(const DevProblem& P, uint64_t rng, int n_new, int mat, int mg) {
   const unsigned per_site = 2u * ((P.G >= 2 ? 1u : 0u) + 3u);
-  const int ndg = __ldg(&P.dg_off[mat + 1]) - __ldg(&P.dg_off[mat]);
+  const int ndg = ldt(&P.dg_off[mat + 1]) - ldt(&P.dg_off[mat]);
   if (ndg < 2) return pcg_advance(rng, (uint64_t)per_site * (unsigned)n_new, P.jump);
-  const double P_delayed = __ldg(&P.nud[mg]) / __ldg(&P.nu[mg]);
+  const double P_delayed = ldt(&P.nud[mg]) / ldt(&P.nu[mg]);
   for (int i = 0; i < n_new; i++) {
     rng = pcg_advance(rng, per_site - 2u, P.jump);
     if (M::rand(rng) < P_delayed) rng = pcg_advance(rng, 2u, P.jump);
@@ -619,16 +619,16 @@ __device__ __forceinline__ void collision_cols(const DevProblem& P, const RunArg
   const int gi = HK_I(q, HI_G);
   const int g = gi & 0xff;
   const int mg = hmat * P.G + g;
-  const double Et = __ldg(&P.Et[mg]), Ea = __ldg(&P.Ea[mg]), Ef = __ldg(&P.Ef[mg]), nu = __ldg(&P.nu[mg]);
+  const double Et = ldt(&P.Et[mg]), Ea = ldt(&P.Ea[mg]), Ef = ldt(&P.Ef[mg]), nu = ldt(&P.nu[mg]);
   double w = HK_D(q, HD_W);
   ic.real++;
   if (TRACE) HK_I(q, HI_NRE) = HK_I(q, HI_NRE) + 1;
   if (A.converged && P.n_coll_tallies) {
-    const MatXS mx{Et, Ea, Ef, __ldg(&P.Es[mg])};
+    const MatXS mx{Et, Ea, Ef, ldt(&P.Es[mg])};
     for (int t = 0; t < P.ntallies; t++)
       if (P.tally[t].estimator == ABL_EST_COLLISION) {
-        const int l = (gi >> 8) ? __ldg(&P.tally_gbin[t * P.G + g]) : tally_energy_bin(P.tally[t], HK_D(q, HD_E));
-        ic.coll_scores += score_collision_pre(P.tally[t], r, l, w, 0., mx, __ldg(&P.inv_score[t * (P.M * P.G) + mg]));
+        const int l = (gi >> 8) ? ldt(&P.tally_gbin[t * P.G + g]) : tally_energy_bin(P.tally[t], HK_D(q, HD_E));
+        ic.coll_scores += score_collision_pre(P.tally[t], r, l, w, 0., mx, ldt(&P.inv_score[t * (P.M * P.G) + mg]));
       }
   }
   {
@@ -664,7 +664,7 @@ __device__ __forceinline__ void collision_cols(const DevProblem& P, const RunArg
   }
   note_col<TRACE>(q, A.hk_np, 0x5000000000000000ULL | (uint64_t)(uint32_t)n_new);
   {
-    const double surv = __ldg(&P.surv_frac[mg]);  // 1 - Ea / Et: implicit capture (transporter.cpp:295-298)
+    const double surv = ldt(&P.surv_frac[mg]);  // 1 - Ea / Et: implicit capture (transporter.cpp:295-298)
     Hist hh;  // (wgt2 is zero throughout a k-eigenvalue run; its roulette still draws: transporter.cpp:47-54)
     hh.w = w * surv;
     hh.w2 = 0. * surv;
@@ -715,7 +715,17 @@ __global__ void __launch_bounds__(HK_THREADS, HK_MINBLOCKS) history_kernel(const
     S.leak = S.leak_mig = 0.;
     for (int q = 0; q < RC_N; q++) S.rare[q] = 0;
   }
-  const Cols q = make_cols(threadIdx.x, A.hk_slots, A.hk_nf, A.hk_np, TRACE);
+  // the table arena, staged behind the fixed part (the host already pointed P's tables at this copy)
+  if (A.hk_tables) {
+    const uint4* src = reinterpret_cast<const uint4*>(A.arena);
+    uint4* dst = reinterpret_cast<uint4*>(hk_shared_raw + HK_COLS_OFFSET);
+    for (int i = threadIdx.x; i < A.hk_tables / 16; i += HK_THREADS) dst[i] = src[i];
+    if (threadIdx.x == 0 && (unsigned long long)(uintptr_t)(void*)hk_shared_raw != A.smem_generic_base) {
+      raise_error(A, ABL_ERR_CUDA, 0);  // the shared window is not where the host assumed: the table pointers are wrong
+      S.abort = 1;
+    }
+  }
+  const Cols q = make_cols(threadIdx.x, A.hk_slots, A.hk_nf, A.hk_np, TRACE, A.hk_tables);
   if (threadIdx.x < A.hk_slots) *(volatile int*)&HK_I(q, HI_BDONE) = 0;
   __syncthreads();
 
@@ -732,6 +742,7 @@ __global__ void __launch_bounds__(HK_THREADS, HK_MINBLOCKS) history_kernel(const
     X.nf = A.hk_nf;
     X.np = A.hk_np;
     X.trace = TRACE ? 1 : 0;
+    X.tables = A.hk_tables;
     service_loop<HK_MATH>(X, wid - HK_HIST / 32);
   } else {
     const uint32_t tid = blockIdx.x * HK_HIST + threadIdx.x;  // index among the history threads of the grid
@@ -839,14 +850,14 @@ __global__ void __launch_bounds__(HK_THREADS, HK_MINBLOCKS) history_kernel(const
           V3 r = hk_ld3(q, HD_R);
           V3 u = hk_ld3(q, HD_U);
           const double w = HK_D(q, HD_W);
-          const double d_coll = rng_exponential<HK_MATH>(rng, __ldg(&P.Et[mg]));
+          const double d_coll = rng_exponential<HK_MATH>(rng, ldt(&P.Et[mg]));
           HK_U(q, HD_RNG) = rng;
           const Boundary sb = cursor_nearest_boundary_s(geo_tables(P), c, u);
           did_flight = true;
           if (TRACE) HK_I(q, HI_NFL) = HK_I(q, HI_NFL) + 1;
           const double d_min = fmin(d_coll, sb.distance);
           if (tle) ic.tl_bins += score_flight_cols(tle_args(P), q, mg, d_min);
-          acc.k_trk += w * d_min * (__ldg(&P.nu[mg]) * __ldg(&P.Ef[mg]));
+          acc.k_trk += w * d_min * (ldt(&P.nu[mg]) * ldt(&P.Ef[mg]));
           if (sb.distance < d_coll || fabs(sb.distance - d_coll) < ABL_BOUNDRY_TOL) {
             did_boundary = true;
             if (sb.btype == ABL_BC_VACUUM) {
@@ -903,7 +914,7 @@ __global__ void __launch_bounds__(HK_THREADS, HK_MINBLOCKS) history_kernel(const
         uint64_t rng = HK_U(q, HD_RNG);
         const int g = HK_I(q, HI_G) & 0xff;
         const V3 u = hk_ld3(q, HD_U);
-        const double d_coll = rng_exponential<HK_MATH>(rng, __ldg(&P.smp[g]));
+        const double d_coll = rng_exponential<HK_MATH>(rng, ldt(&P.smp[g]));
         HK_U(q, HD_RNG) = rng;
         HK_D(q, HD_DC) = d_coll;
         did_flight = true;
@@ -1052,9 +1063,9 @@ __global__ void __launch_bounds__(HK_THREADS, HK_MINBLOCKS) history_kernel(const
         const int hmat = HK_I(q, HI_MAT);
         HK_I(q, HI_HMAT) = hmat;
         bool had_collision = false;
-        const double Esample = __ldg(&P.smp[g]);
-        const double Et = __ldg(&P.Et[hmat * P.G + g]);
-        const double real_frac = __ldg(&P.real_frac[hmat * P.G + g]);  // Et / Esample
+        const double Esample = ldt(&P.smp[g]);
+        const double Et = ldt(&P.Et[hmat * P.G + g]);
+        const double real_frac = ldt(&P.real_frac[hmat * P.G + g]);  // Et / Esample
         uint64_t rng = HK_U(q, HD_RNG);
         if (TRK == ABL_TRACK_DELTA) {
           if (Et - Esample > 1.E-10) {

@@ -1,5 +1,6 @@
 // Per-lane history kernel of the noise modes: MODE 1 = power-iteration generation that may sample the noise source,
 // MODE 2 = noise particles (transport.cuh, noise.cuh; see kernel_entry.h for why this is its own translation unit).
+#define ABL_TABLES_GLOBAL 1  // this unit's kernels read the tables from global memory (detmath.cuh: ldt)
 #include "kernel_entry.h"
 namespace abl {
 template <int MODE>

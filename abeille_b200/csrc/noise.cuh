@@ -64,18 +64,18 @@ static __device__ __noinline__ FisSample sample_fission_nm(const FissionTables T
   int ei = 0;
   if (T.G >= 2) ei = rng_discrete(rng, T.chi_cp + (size_t)mg * T.G, T.G);
   FisSample f;
-  f.E = __ldg(&T.gmid[ei]);
+  f.E = ldt(&T.gmid[ei]);
   const double mu = 2. * rng_rand(rng) - 1.;
   const double phi = 2. * ABL_PI * rng_rand(rng);
   f.dir = rotate_direction(u, mu, phi);
   f.delayed = false;
   f.lambda = 0.;
   if (rng_rand(rng) < P_delayed) {
-    const int dg0 = __ldg(&T.dg_off[mat]), ndg = __ldg(&T.dg_off[mat + 1]) - dg0;
+    const int dg0 = ldt(&T.dg_off[mat]), ndg = ldt(&T.dg_off[mat + 1]) - dg0;
     int k = 0;
     if (ndg >= 2) k = rng_discrete(rng, T.dg_cp + dg0, ndg);
     f.delayed = true;
-    f.lambda = ndg > 0 ? __ldg(&dg_lambda[dg0 + k]) : 0.;
+    f.lambda = ndg > 0 ? ldt(&dg_lambda[dg0 + k]) : 0.;
   }
   *rng_io = rng;
   return f;
@@ -127,7 +127,7 @@ __device__ __forceinline__ void sample_noise_source_dev(const DevProblem& P, con
     }
   if (!inside_vib && !inside_osc) return;
   const int mg = h.mat * P.G + h.g;
-  const double Et = __ldg(&P.Et[mg]), Ea = __ldg(&P.Ea[mg]), Ef = __ldg(&P.Ef[mg]), nu = __ldg(&P.nu[mg]);
+  const double Et = ldt(&P.Et[mg]), Ea = ldt(&P.Ea[mg]), Ef = ldt(&P.Ef[mg]), nu = ldt(&P.nu[mg]);
   {  // sample_noise_copy (:155-181); NoiseMaker::dEt (:60-78): vibration sources first, then oscillation sources
     double dEt_re = 0., dEt_im = 0.;
     for (int s = 0; s < P.n_noise_src; s++) {  // FlatVibrationNoiseSource::dEt (:222-244): (Et_neg - Et_pos) * C
@@ -138,7 +138,7 @@ __device__ __forceinline__ void sample_noise_source_dev(const DevProblem& P, con
         dEt_im += 0.;
         continue;
       }
-      const double D_Et = __ldg(&P.Et[ns.mat_neg * P.G + h.g]) - __ldg(&P.Et[ns.mat_pos * P.G + h.g]);
+      const double D_Et = ldt(&P.Et[ns.mat_neg * P.G + h.g]) - ldt(&P.Et[ns.mat_pos * P.G + h.g]);
       const Cplx C = vib_C(ns, vib_get_x(ns, h.r));
       dEt_re += C.re * D_Et;
       dEt_im += C.im * D_Et;
@@ -154,7 +154,7 @@ __device__ __forceinline__ void sample_noise_source_dev(const DevProblem& P, con
         raise_error(A, ABL_ERR_LOST, A.bank.id_a[h.idx]);
         return;
       }
-      const double xs = __ldg(&P.Et[lc.mat * P.G + h.g]);
+      const double xs = ldt(&P.Et[lc.mat * P.G + h.g]);
       dEt_re += ns.on ? ns.eps_t * xs * ABL_PI : 0.;
       dEt_im += 0.;
     }
@@ -216,14 +216,14 @@ __device__ __forceinline__ void sample_noise_source_dev(const DevProblem& P, con
       }
     }
     double Et_fake = 0.;
-    for (int k = 0; k < nn; k++) Et_fake += conc[k] * __ldg(&P.Et[nuc[k] * P.G + h.g]);
+    for (int k = 0; k < nn; k++) Et_fake += conc[k] * ldt(&P.Et[nuc[k] * P.G + h.g]);
     // fake_mat.sample_nuclide (material_helper.hpp:178-224)
     const double invs_Et = 1. / Et_fake;
     const double xi = rng_rand(h.rng);
     int pick = nn - 1;
     double prob_sum = 0.;
     for (int k = 0; k < nn; k++) {
-      const double nuc_prob = invs_Et * conc[k] * __ldg(&P.Et[nuc[k] * P.G + h.g]);
+      const double nuc_prob = invs_Et * conc[k] * ldt(&P.Et[nuc[k] * P.G + h.g]);
       prob_sum += nuc_prob;
       if (xi <= prob_sum) {
         pick = k;
@@ -232,7 +232,7 @@ __device__ __forceinline__ void sample_noise_source_dev(const DevProblem& P, con
     }
     const int pm = nuc[pick], pmg = pm * P.G + h.g;
     const double N = conc[pick];
-    const double pEt = __ldg(&P.Et[pmg]), pEa = __ldg(&P.Ea[pmg]), pEf = __ldg(&P.Ef[pmg]), pnu = __ldg(&P.nu[pmg]);
+    const double pEt = ldt(&P.Et[pmg]), pEa = ldt(&P.Ea[pmg]), pEf = ldt(&P.Ef[pmg]), pnu = ldt(&P.nu[pmg]);
     double dN_re = 0., dN_im = 0.;  // NoiseMaker::dN (:80-91), FlatVibrationNoiseSource::dN (:277-312)
     for (int s = 0; s < P.n_noise_src; s++) {
       const DevNoiseSrc& ns = P.noise_src[s];
@@ -249,10 +249,10 @@ __device__ __forceinline__ void sample_noise_source_dev(const DevProblem& P, con
     }
     const double dNN_re = dN_re / N, dNN_im = dN_im / N;
     const double Etfake_Et = Et_fake / Et;
-    if (__ldg(&P.fissile[pm])) {  // sample_vibration_noise_fission (:183-237)
+    if (ldt(&P.fissile[pm])) {  // sample_vibration_noise_fission (:183-237)
       const double k_abs = pnu * pEf / pEt;
       const int n_new = (int)floor(k_abs / A.keff + rng_rand(h.rng));
-      const double P_delayed = __ldg(&P.nud[pmg]) / pnu;
+      const double P_delayed = ldt(&P.nud[pmg]) / pnu;
       const FissionTables ft{P.chi_cp, P.dg_cp, P.dg_off, P.gmid, P.G};
       for (int i = 0; i < n_new; i++) {
         const FisSample f = sample_fission_nm(ft, P.dg_lambda, &h.rng, h.u, pm, pmg, P_delayed);
@@ -277,10 +277,10 @@ __device__ __forceinline__ void sample_noise_source_dev(const DevProblem& P, con
 
   if (!inside_osc) return;  // sample_oscillation_noise_source (:293-323)
   (void)rng_rand(h.rng);    // mat.sample_nuclide
-  if (__ldg(&P.fissile[h.mat])) {  // sample_oscillation_noise_fission (:383-445)
+  if (ldt(&P.fissile[h.mat])) {  // sample_oscillation_noise_fission (:383-445)
     const double k_abs = nu * Ef / Et;
     const int n_new = (int)floor(k_abs / A.keff + rng_rand(h.rng));
-    const double P_delayed = __ldg(&P.nud[mg]) / nu;
+    const double P_delayed = ldt(&P.nud[mg]) / nu;
     double dEf_re = 0., dEf_im = 0.;
     for (int s = 0; s < P.n_noise_src; s++)
       if (!P.noise_src[s].vibration && noise_src_contains(P.noise_src[s], h.r)) {
@@ -320,14 +320,14 @@ template <int MODE>
 __device__ __forceinline__ void collision_nm(const DevProblem& P, const RunArgs& A, Hist& h, Acc& acc, uint32_t tid, uint32_t nthreads) {
   constexpr bool NOISE = MODE == 2;
   const int mg = h.mat * P.G + h.g;
-  const double Et0 = __ldg(&P.Et[mg]), Ea = __ldg(&P.Ea[mg]), Ef = __ldg(&P.Ef[mg]), nu = __ldg(&P.nu[mg]);
+  const double Et0 = ldt(&P.Et[mg]), Ea = ldt(&P.Ea[mg]), Ef = ldt(&P.Ef[mg]), nu = ldt(&P.nu[mg]);
   acc.real++;
   h.n_real++;
   if (A.converged && P.n_coll_tallies) {  // mat.Et(E) without the noise term (collision_mesh_tally.cpp:35)
-    const MatXS mx{Et0, Ea, Ef, __ldg(&P.Es[mg])};
+    const MatXS mx{Et0, Ea, Ef, ldt(&P.Es[mg])};
     for (int t = 0; t < P.ntallies; t++)
       if (P.tally[t].estimator == ABL_EST_COLLISION) {
-        const int l = h.emid ? __ldg(&P.tally_gbin[t * P.G + h.g]) : tally_energy_bin(P.tally[t], h.E);
+        const int l = h.emid ? ldt(&P.tally_gbin[t * P.G + h.g]) : tally_energy_bin(P.tally[t], h.E);
         acc.coll_scores += score_collision(P.tally[t], h.r, l, h.w, h.w2, mx);
       }
   }
@@ -344,7 +344,7 @@ __device__ __forceinline__ void collision_nm(const DevProblem& P, const RunArgs&
   // MaterialHelper::sample_nuclide (material_helper.hpp:178-224): one draw; in noise transport the nuclide's total
   // carries the copy cross section eta*omega/v
   (void)rng_rand(h.rng);
-  const double noise_copy = NOISE ? (P.eta * P.w_noise / __ldg(&P.speed[mg])) / (1. * 1.) : 0.;
+  const double noise_copy = NOISE ? (P.eta * P.w_noise / ldt(&P.speed[mg])) / (1. * 1.) : 0.;
   const double total = NOISE ? Et0 + noise_copy : Et0;
   const double k_abs_scr = ddiv_pos(h.w * nu * Ef, total);
   if (!NOISE) acc.k_abs += k_abs_scr;
@@ -353,7 +353,7 @@ __device__ __forceinline__ void collision_nm(const DevProblem& P, const RunArgs&
   if (!NOISE) n_new = (int)floor(ddiv_pos(fabs(k_abs_scr), A.k_col) + rng_rand(h.rng));
   else n_new = (int)floor((nu * Ef / (total * A.keff)) + rng_rand(h.rng));
   if (n_new > 0) {
-    const double P_delayed = __ldg(&P.nud[mg]) / nu;
+    const double P_delayed = ldt(&P.nud[mg]) / nu;
     const FissionTables ft{P.chi_cp, P.dg_cp, P.dg_off, P.gmid, P.G};
     for (int i = 0; i < n_new; i++) {
       const FisSample f = sample_fission_nm(ft, P.dg_lambda, &h.rng, h.u, h.mat, mg, P_delayed);

@@ -34,7 +34,7 @@ __host__ __device__ inline uint64_t pcg_seed_state(uint64_t seed) { return (seed
 __device__ __forceinline__ uint64_t pcg_advance(uint64_t state, uint64_t delta, const JumpTable* __restrict__ jt) {
   while (delta) {
     const int k = __ffsll((long long)delta) - 1;
-    state = __ldg(&jt->mult[k]) * state + __ldg(&jt->plus[k]);
+    state = ldt(&jt->mult[k]) * state + ldt(&jt->plus[k]);
     delta &= delta - 1;
   }
   return state;
@@ -107,13 +107,13 @@ __device__ __forceinline__ int rng_discrete(uint64_t& state, const double* __res
   if (n <= 8) {
     int lo = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) lo += (i < n && __ldg(&cp[i < n ? i : 0]) < p) ? 1 : 0;
+    for (int i = 0; i < 8; i++) lo += (i < n && ldt(&cp[i < n ? i : 0]) < p) ? 1 : 0;
     return lo;
   }
   int lo = 0, len = n;
   while (len > 0) {
     const int half = len >> 1;
-    if (__ldg(&cp[lo + half]) < p) {
+    if (ldt(&cp[lo + half]) < p) {
       lo = lo + half + 1;
       len = len - half - 1;
     } else {

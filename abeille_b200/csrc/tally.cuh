@@ -20,7 +20,7 @@ struct MatXS {
 
 __device__ __forceinline__ int tally_energy_bin(const DevTally& t, double E) {  // "<= E <=", first match
   for (int e = 0; e < t.Ne; e++)
-    if (__ldg(&t.ebounds[e]) <= E && E <= __ldg(&t.ebounds[e + 1])) return e;
+    if (ldt(&t.ebounds[e]) <= E && E <= ldt(&t.ebounds[e + 1])) return e;
   return -1;
 }
 

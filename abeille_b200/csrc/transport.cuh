@@ -76,6 +76,11 @@ struct RunArgs {
   // staged history kernel (history.cuh): histories per CTA and the geometry's nesting depth (frames, pads), which size
   // the per-history columns in shared memory
   int hk_slots, hk_nf, hk_np;
+  // tables staged in shared memory: bytes (0 = none), their global-memory source, and the generic address the host assumed
+  // for byte 0 of the dynamic shared memory when it redirected the table pointers (verified by the kernel)
+  int hk_tables;
+  const unsigned char* arena;
+  unsigned long long smem_generic_base;
   unsigned long long timeout_ns;  // the staged kernel's watchdog: a CTA that runs longer winds down with ABL_ERR_TIMEOUT
 };
 
@@ -101,10 +106,10 @@ __device__ __forceinline__ void note(Hist& h, uint64_t v) { h.hash = (h.hash ^ v
 __device__ __forceinline__ int group_of(const DevProblem& P, double E) {  // mg_nuclide.cpp:382-392
   int i = 0;
   for (i = 0; i < P.G; i++)
-    if (__ldg(&P.ebounds[i]) <= E && E < __ldg(&P.ebounds[i + 1])) break;
+    if (ldt(&P.ebounds[i]) <= E && E < ldt(&P.ebounds[i + 1])) break;
   return i;
 }
-__device__ __forceinline__ double group_mid(const DevProblem& P, int g) { return __ldg(&P.gmid[g]); }  // 0.5*(b[g]+b[g+1])
+__device__ __forceinline__ double group_mid(const DevProblem& P, int g) { return ldt(&P.gmid[g]); }  // 0.5*(b[g]+b[g+1])
 
 __device__ __forceinline__ void raise_error(const RunArgs& A, int code, uint64_t history_id) {
   if (atomicCAS(&A.error[0], 0, code) == 0) {
@@ -120,7 +125,7 @@ static __device__ __noinline__ double sample_mu_table(const double* __restrict__
   int lo = 0, len = n;
   while (len > 0) {  // std::lower_bound
     const int half = len >> 1;
-    if (__ldg(&cdf[lo + half]) < xi) {
+    if (ldt(&cdf[lo + half]) < xi) {
       lo = lo + half + 1;
       len = len - half - 1;
     } else {
@@ -129,20 +134,20 @@ static __device__ __noinline__ double sample_mu_table(const double* __restrict__
   }
   int l = lo;
   const double* mu = amu + off;
-  if (xi == __ldg(&cdf[l])) return __ldg(&mu[l]);
+  if (xi == ldt(&cdf[l])) return ldt(&mu[l]);
   l--;
   const double* pdf = apdf + off;
-  const double p0 = __ldg(&pdf[l]), p1 = __ldg(&pdf[l + 1]);
-  if (p0 == p1) return __ldg(&mu[l]) + ((xi - __ldg(&cdf[l])) / p0);
-  const double m = (p1 - p0) / (__ldg(&mu[l + 1]) - __ldg(&mu[l]));
-  return __ldg(&mu[l]) + (1. / m) * (sqrt(p0 * p0 + 2. * m * (xi - __ldg(&cdf[l]))) - p0);
+  const double p0 = ldt(&pdf[l]), p1 = ldt(&pdf[l + 1]);
+  if (p0 == p1) return ldt(&mu[l]) + ((xi - ldt(&cdf[l])) / p0);
+  const double m = (p1 - p0) / (ldt(&mu[l + 1]) - ldt(&mu[l]));
+  return ldt(&mu[l]) + (1. / m) * (sqrt(p0 * p0 + 2. * m * (xi - ldt(&cdf[l]))) - p0);
 }
 
 // MGAngleDistribution::sample_mu (mg_angle_distribution.hpp:45-60,92-101)
 template <class M = InlineMath>
 __device__ __forceinline__ double sample_mu(const DevProblem& P, const abl_angle_table* at, uint64_t& rng) {
   const double xi = M::rand(rng);
-  const int off = __ldg(&at->offset), n = __ldg(&at->n);
+  const int off = ldt(&at->offset), n = ldt(&at->n);
   // n < 0 marks the default isotropic table {mu:[-1,1], pdf:[.5,.5], cdf:[0,1]} (mg_angle_distribution.cpp:32-33):
   // the general formula below reduces to this expression, evaluated identically
   if (n < 0) return -1. + ((xi - 0.) / 0.5);
@@ -178,11 +183,11 @@ template <class M>
 static __device__ __noinline__ void bank_fission_sites(const FissionTables T, Site* sites, unsigned long long* n_sites, uint64_t capacity,
                                                 uint64_t& rng, const V3 r, const V3 u, double w, uint32_t parent, uint32_t daughter0,
                                                 int n_new, int mat, int mg, double P_delayed) {
-  const int dg0 = __ldg(&T.dg_off[mat]), ndg = __ldg(&T.dg_off[mat + 1]) - dg0;
+  const int dg0 = ldt(&T.dg_off[mat]), ndg = ldt(&T.dg_off[mat + 1]) - dg0;
   for (int i = 0; i < n_new; i++) {
     int ei = 0;
     if (T.G >= 2) ei = rng_discrete<M>(rng, T.chi_cp + (size_t)mg * T.G, T.G);
-    const double E_out = __ldg(&T.gmid[ei]);
+    const double E_out = ldt(&T.gmid[ei]);
     const double mu = 2. * M::rand(rng) - 1.;
     const double phi = 2. * ABL_PI * M::rand(rng);
     const V3 dir = rotate_dir<M>(u, mu, phi);
@@ -230,14 +235,14 @@ __device__ __forceinline__ void russian_roulette(const DevProblem& P, Hist& h) {
 template <bool NOISE, class M = InlineMath>
 __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A, Hist& h, Acc& acc) {
   const int mg = h.mat * P.G + h.g;
-  const double Et = __ldg(&P.Et[mg]), Ea = __ldg(&P.Ea[mg]), Ef = __ldg(&P.Ef[mg]), nu = __ldg(&P.nu[mg]);
+  const double Et = ldt(&P.Et[mg]), Ea = ldt(&P.Ea[mg]), Ef = ldt(&P.Ef[mg]), nu = ldt(&P.nu[mg]);
   acc.real++;
   h.n_real++;
   if (A.converged && P.n_coll_tallies) {
-    const MatXS mx{Et, Ea, Ef, __ldg(&P.Es[mg])};
+    const MatXS mx{Et, Ea, Ef, ldt(&P.Es[mg])};
     for (int t = 0; t < P.ntallies; t++)
       if (P.tally[t].estimator == ABL_EST_COLLISION) {
-        const int l = h.emid ? __ldg(&P.tally_gbin[t * P.G + h.g]) : tally_energy_bin(P.tally[t], h.E);
+        const int l = h.emid ? ldt(&P.tally_gbin[t * P.G + h.g]) : tally_energy_bin(P.tally[t], h.E);
         acc.coll_scores += score_collision<M>(P.tally[t], h.r, l, h.w, h.w2, mx);
       }
   }
@@ -258,7 +263,7 @@ __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A,
   if (n_new > 0) {
     const FissionTables ft{P.chi_cp, P.dg_cp, P.dg_off, P.gmid, P.G};
     bank_fission_sites<M>(ft, A.sites, A.n_sites, A.site_capacity, h.rng, h.r, h.u, h.w, h.idx, h.daughter, n_new, h.mat, mg,
-                          __ldg(&P.nud[mg]) / nu);
+                          ldt(&P.nud[mg]) / nu);
     h.daughter += (uint32_t)n_new;
     h.n_fis += (uint32_t)n_new;
     acc.sites += (uint32_t)n_new;
@@ -312,7 +317,7 @@ __device__ __forceinline__ void leak(Hist& h, Acc& acc, const Boundary& b) {
 __device__ __forceinline__ void score_flight_all(const DevProblem& P, const RunArgs& A, const Hist& h, double d, Acc& acc) {
   if (!(A.converged && P.n_tl_tallies)) return;
   const int mg = h.mat * P.G + h.g;
-  const MatXS mx{__ldg(&P.Et[mg]), __ldg(&P.Ea[mg]), __ldg(&P.Ef[mg]), __ldg(&P.Es[mg])};
+  const MatXS mx{ldt(&P.Et[mg]), ldt(&P.Ea[mg]), ldt(&P.Ef[mg]), ldt(&P.Es[mg])};
   for (int t = 0; t < P.ntallies; t++)
     if (P.tally[t].estimator == ABL_EST_TRACK_LENGTH) acc.tl_bins += score_flight(P.tally[t], h.r, h.u, d, h.E, h.w, h.w2, mx);
 }
@@ -366,7 +371,7 @@ __device__ __forceinline__ void collide(const DevProblem& P, const RunArgs& A, H
 // the copy "cross section" eta * omega / v of noise transport (material_helper.hpp:65-84)
 template <int MODE>
 __device__ __forceinline__ double noise_xs(const DevProblem& P, int mat, int g) {
-  return MODE == 2 ? P.eta * P.w_noise / __ldg(&P.speed[mat * P.G + g]) : 0.;
+  return MODE == 2 ? P.eta * P.w_noise / ldt(&P.speed[mat * P.G + g]) : 0.;
 }
 
 template <int TRK, int MODE>
@@ -377,13 +382,13 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
   if (TRK == ABL_TRACK_SURFACE) {
     // SurfaceTracker::transport loop body (surface_tracker.cpp:72-146)
     const int mg = h.mat * P.G + h.g;
-    const double d_coll = rng_exponential(h.rng, MODE == 2 ? __ldg(&P.Et[mg]) + noise_xs<MODE>(P, h.mat, h.g) : __ldg(&P.Et[mg]));
+    const double d_coll = rng_exponential(h.rng, MODE == 2 ? ldt(&P.Et[mg]) + noise_xs<MODE>(P, h.mat, h.g) : ldt(&P.Et[mg]));
     const Boundary bound = cursor_nearest_boundary_nl(geo_tables(P), c, h.u);
     acc.flights++;
     h.n_flights++;
     const double d_min = fmin(d_coll, bound.distance);
     score_flight_all(P, A, h, d_min, acc);
-    acc.k_trk += h.w * d_min * (__ldg(&P.nu[mg]) * __ldg(&P.Ef[mg]));
+    acc.k_trk += h.w * d_min * (ldt(&P.nu[mg]) * ldt(&P.Ef[mg]));
     if (bound.distance < d_coll || fabs(bound.distance - d_coll) < ABL_BOUNDRY_TOL) {
       acc.boundary++;
       if (bound.btype == ABL_BC_VACUUM) {
@@ -425,7 +430,7 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
     // ImplicitLeakageDeltaTracker::transport loop body (implicit_leakage_delta_tracker.cpp:105-246): the boundary condition
     // is looked up before every flight; towards a vacuum boundary the leaking share of the weight is scored at once and the
     // flight distance is drawn from the exponential truncated at the boundary
-    const double Emaj = MODE == 2 ? __ldg(&P.smp[h.g]) + noise_xs<MODE>(P, h.mat, h.g) : __ldg(&P.smp[h.g]);
+    const double Emaj = MODE == 2 ? ldt(&P.smp[h.g]) + noise_xs<MODE>(P, h.mat, h.g) : ldt(&P.smp[h.g]);
     const Boundary bound = cursor_boundary_condition_nl(geo_tables(P), c, h.u);
     acc.flights++;
     h.n_flights++;
@@ -481,7 +486,7 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
         return;
       }
       h.mat = c.mat;
-      const double Et = MODE == 2 ? __ldg(&P.Et[h.mat * P.G + h.g]) + noise_xs<MODE>(P, h.mat, h.g) : __ldg(&P.Et[h.mat * P.G + h.g]);
+      const double Et = MODE == 2 ? ldt(&P.Et[h.mat * P.G + h.g]) + noise_xs<MODE>(P, h.mat, h.g) : ldt(&P.Et[h.mat * P.G + h.g]);
       if (Et - Emaj > 1.E-10) {
         raise_error(A, ABL_ERR_MAJORANT, hid);
         h.alive = false;
@@ -498,7 +503,7 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
     }
   } else {
     // DeltaTracker / CarterTracker loop body (delta_tracker.cpp:100-195, carter_tracker.cpp:120-230)
-    const double Esample = MODE == 2 ? __ldg(&P.smp[h.g]) + noise_xs<MODE>(P, h.mat, h.g) : __ldg(&P.smp[h.g]);
+    const double Esample = MODE == 2 ? ldt(&P.smp[h.g]) + noise_xs<MODE>(P, h.mat, h.g) : ldt(&P.smp[h.g]);
     const double d_coll = rng_exponential(h.rng, Esample);
     Boundary bound{ABL_INF, -1, ABL_BC_NORMAL, 0};
     bool crossed = false;
@@ -535,7 +540,7 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
       h.r.y = h.r.y + d_coll * h.u.y;
       h.r.z = h.r.z + d_coll * h.u.z;
       h.mat = c.mat;
-      const double Et = MODE == 2 ? __ldg(&P.Et[h.mat * P.G + h.g]) + noise_xs<MODE>(P, h.mat, h.g) : __ldg(&P.Et[h.mat * P.G + h.g]);
+      const double Et = MODE == 2 ? ldt(&P.Et[h.mat * P.G + h.g]) + noise_xs<MODE>(P, h.mat, h.g) : ldt(&P.Et[h.mat * P.G + h.g]);
       if (TRK == ABL_TRACK_DELTA) {
         if (Et - Esample > 1.E-10) {
           raise_error(A, ABL_ERR_MAJORANT, hid);

@@ -79,11 +79,13 @@ class _DevPtr:
 
 
 class DistributedPowerIterator:
-    def __init__(self, deck_path: str, device: int, nparticles_per_rank: int, group=None):
+    def __init__(self, deck_path: str, device: int, nparticles_per_rank: int, group=None, single: bool = False):
         self.gpu = Backend(deck_path, device)
         self.device = torch.device("cuda", device)
         self.n_local = int(nparticles_per_rank)
-        self.use_dist = dist.is_available() and dist.is_initialized()
+        # single = True: this process runs the whole population alone even inside a process group (the 1-rank replay that
+        # bench.py compares a multi-rank run with)
+        self.use_dist = dist.is_available() and dist.is_initialized() and not single
         self.group = group
         self.rank = dist.get_rank(group) if self.use_dist else 0
         self.world = dist.get_world_size(group) if self.use_dist else 1
@@ -262,7 +264,7 @@ class DistributedPowerIterator:
         return {"k_col": self.k_col, "n_in": n_in, "n_in_total": n_in_total, "m": m, "m_pre": m_pre, "m_total": m_total,
                 "real_collisions": tot[7], "flights": tot[6], "coll_scores": tot[13], "tl_bins": tot[9],
                 "local_real_collisions": cn["real_collisions"], "local_coll_scores": cn["coll_scores"],
-                "local_tl_bins": cn["tl_bins"]}
+                "local_tl_bins": cn["tl_bins"], "local_flights": cn["flights"]}
 
 
 def _positive_negative_sums(w: "torch.Tensor"):

@@ -286,7 +286,7 @@ def run_b200(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    particles = collisions = sites = coll_scores = 0.0
+    particles = collisions = sites = coll_scores = flights = 0.0
     local_particles = local_coll = local_sites = local_scores = 0.0
     kernel_ms = []
     for _ in range(args.steps):
@@ -294,6 +294,7 @@ def run_b200(args):
         particles += g["n_in_total"]; collisions += g["real_collisions"]; sites += g["m_total"]; coll_scores += g["coll_scores"]
         local_particles += g["n_in"]; local_coll += g["local_real_collisions"]; local_sites += g["m_pre"]
         local_scores += g["local_coll_scores"]
+        flights += g["local_flights"]
         kernel_ms.append(sim.gpu.last_transport_kernel()["ms"])
     e1.record()
     barrier()
@@ -342,6 +343,16 @@ def run_b200(args):
             rp = cpu_leg(args.cpu_particles, 2, args.cpu_steps)
             cpu["port_value"] = rp["particles_per_s"]
 
+    # ---- one kernel launch under ncu (N = 1): DRAM traffic, lanes, issue utilisation -----------------------------------
+    prof = None
+    if rank == 0 and world == 1 and not args.no_ncu:
+        torch.cuda.synchronize()
+        prof = ncu_kernel_metrics(args)
+    # ---- N > 1: sharded run == 1-rank replay -------------------------------------------------------------------------------
+    rcheck = None
+    if world > 1 and not args.no_ranks_check:
+        rcheck = ranks_check(world, rank, local, dev)
+
     if rank == 0:
         out = {"metric": METRIC, "value": particles / (ms * 1e-3), "unit": "particles/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -352,10 +363,15 @@ def run_b200(args):
                           "l2": "inputs larger than L2 (bank 96 B x 1e7 = 0.96 GB, tally mesh 0.84 GB)", "k_col": k_col,
                           "collisions_per_particle": collisions / max(particles, 1)},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": args.traffic, "kernel": "history_kernel<delta>", "kernel_ms": k_ms,
+                            "traffic": prof["dram_bytes"] if prof else None, "kernel": "history_kernel<delta>", "kernel_ms": k_ms,
+                            "profile": prof, "flights_per_launch": flights / args.steps,
+                            "warp_instructions_per_flight": (prof["warp_instructions"] / (flights / args.steps))
+                            if prof and prof.get("warp_instructions") and flights else None,
                             "grid": [kinfo["grid"], kinfo["block"]], "algorithmic_bytes_per_launch": alg_bytes,
                             "peak_source": peak_src, "kernel_share_of_step": k_ms * args.steps / ms},
                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        if rcheck is not None:
+            out["ranks_check"] = rcheck
     import ctypes
     sys.stdout.flush()
     ctypes.CDLL(None).fflush(None)
@@ -366,6 +382,102 @@ def run_b200(args):
     if world > 1:
         os.dup2(2, 1)
         dist.destroy_process_group()
+
+
+def ncu_child(args):
+    """The resident leg alone, a few generations, no output: the process `ncu_kernel_metrics` profiles."""
+    import torch
+    import __graft_entry__ as ge
+    ge.build_if_missing()
+    from abeille_b200.distributed import DistributedPowerIterator
+    td = tempfile.mkdtemp()
+    sim = DistributedPowerIterator(_write_deck(args.particles, os.path.join(td, "ncu.yaml")), 0, args.particles)
+    sim.initialize()
+    for _ in range(4):
+        sim.generation(converged=True)
+    torch.cuda.synchronize()
+
+
+def ncu_kernel_metrics(args):
+    """DRAM bytes, lanes per instruction, issue utilisation and instruction count of ONE history-kernel launch of this very
+    workload, captured by running this script's resident leg under ncu (4th generation: the fission source, tallies on).
+    Returns None when ncu is not there or the capture fails -- the bench line then carries no traffic figure."""
+    import csv, io, shutil
+    ncu = shutil.which("ncu") or ("/usr/local/cuda/bin/ncu" if os.path.exists("/usr/local/cuda/bin/ncu") else None)
+    if ncu is None:
+        return None
+    metrics = ["dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed.sum",
+               "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+               "gpu__time_duration.sum"]
+    cmd = [ncu, "--metrics", ",".join(metrics), "--clock-control", "none", "-k", "regex:history_kernel", "-s", "3", "-c", "1", "--csv",
+           sys.executable, os.path.abspath(__file__), "--ncu-child", "--particles", str(args.particles)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        rows = [row for row in csv.reader(io.StringIO(r.stdout)) if len(row) > 5]
+        hdr = next(row for row in rows if "Metric Name" in row)
+        iname, ival, iunit = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+        vals = {}
+        for row in rows:
+            if row is hdr or len(row) <= ival:
+                continue
+            try:
+                v = float(row[ival].replace(",", ""))
+            except ValueError:
+                continue
+            unit = row[iunit].lower()
+            scale = {"kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12, "usecond": 1e-3, "msecond": 1.0, "second": 1e3,
+                     "nsecond": 1e-6}.get(unit, 1.0)
+            vals[row[iname]] = v * scale
+        if "dram__bytes_read.sum" not in vals:
+            return None
+        return {"dram_bytes": vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"],
+                "warp_instructions": vals.get("smsp__inst_executed.sum"),
+                "lanes_per_instruction": (vals["smsp__thread_inst_executed.sum"] / vals["smsp__inst_executed.sum"])
+                if vals.get("smsp__inst_executed.sum") else None,
+                "issue_active_pct": vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "warps_active_pct": vals.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                "kernel_ms_under_ncu": vals.get("gpu__time_duration.sum"),
+                "how": "ncu --metrics ... -k regex:history_kernel -s 3 -c 1 on `bench.py --ncu-child` (same deck and bank size, 4th "
+                       "generation), run by this bench after the timed legs"}
+    except Exception as e:  # noqa: BLE001 -- a failed capture must not cost the bench line
+        print(f"bench.py: ncu capture failed ({type(e).__name__}: {e})", file=sys.stderr)
+        return None
+
+
+def ranks_check(world, rank, local, dev, n_total=1_600_000, gens=3):
+    """N > 1: the sharded run against a 1-rank replay.  Histories shard by global history id and RNG streams are a function
+    of that id, so bank sizes must be IDENTICAL for any GPU count and k_col equal up to summation order.
+    Every rank runs `gens` generations of n_total particles sharded; rank 0 then replays the same generations alone."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from abeille_b200.distributed import DistributedPowerIterator
+    td = tempfile.mkdtemp()
+    n_total -= n_total % world
+    deck = _write_deck(n_total, os.path.join(td, f"check_{rank}.yaml"))
+    sim = DistributedPowerIterator(deck, local, n_total // world)
+    sim.initialize()
+    for g in range(gens):
+        sim.generation(converged=g >= 1)
+    torch.cuda.synchronize()
+    sharded = (list(sim.nbank_series), list(sim.kcol_series), float(sim.counters[1]))
+    del sim
+    out = None
+    if rank == 0:
+        one = DistributedPowerIterator(deck, local, n_total, single=True)
+        one.initialize()
+        for g in range(gens):
+            one.generation(converged=g >= 1)
+        torch.cuda.synchronize()
+        k1, kn = np.array(one.kcol_series), np.array(sharded[1])
+        out = {"particles": n_total, "generations": gens, "ranks": world,
+               "bank_sizes_equal": [int(v) for v in one.nbank_series] == [int(v) for v in sharded[0]],
+               "collisions_equal": float(one.counters[1]) == sharded[2],
+               "k_col_max_rel_diff": float(np.max(np.abs(k1 - kn) / np.abs(k1))),
+               "what": "sharded run vs a 1-rank replay of the same generations on rank 0 (deck source, then fission source)"}
+        del one
+    dist.barrier()
+    return out
 
 
 def main():
@@ -379,14 +491,15 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=100_000)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--ref-particles", type=int, default=100_000, help="--impl reference: particles per step")
-    ap.add_argument("--traffic", type=float, default=3.194e10,
-                    help="ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of the history kernel at 1e7 histories "
-                         "(profiles/r1n_history_kernel_v2_summary.txt); 23.7 GB of it is the 32 B-sector read-modify-write of "
-                         "the random 8 B mesh-tally updates")
+    ap.add_argument("--no-ncu", action="store_true", help="skip the ncu capture of one kernel launch (roofline.traffic = null)")
+    ap.add_argument("--no-ranks-check", action="store_true", help="N > 1: skip the sharded-vs-1-rank consistency run")
+    ap.add_argument("--ncu-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.ncu_child:
+        ncu_child(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
