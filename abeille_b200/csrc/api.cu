@@ -413,8 +413,13 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
   // the staged lock-step loop with the histories in shared-memory columns and service warps for the rare events
   // (history.cuh); one translation unit per tracker, each with its own launch shape
   const bool tle = A.converged && h->P.n_tl_tallies;
+  // delta and carter tracking run the event-queue kernel (events.cuh); ABEILLE_B200_STAGED=1 selects the staged kernel
+  // they ran before (kept for comparison); surface tracking has the staged kernel only
+  static const bool staged_only = getenv("ABEILLE_B200_STAGED") != nullptr;
+  const bool events = TRK != ABL_TRACK_SURFACE && !staged_only;
   const HistoryKernel hk = TRK == ABL_TRACK_SURFACE ? history_kernel_surface(TRACE, tle)
-                                                     : (TRK == ABL_TRACK_DELTA ? history_kernel_delta(TRACE, tle) : history_kernel_carter(TRACE, tle));
+                           : events ? (TRK == ABL_TRACK_DELTA ? event_kernel_delta(TRACE, tle) : event_kernel_carter(TRACE, tle))
+                                    : (TRK == ABL_TRACK_DELTA ? history_kernel_delta(TRACE, tle) : history_kernel_carter(TRACE, tle));
   TransportKernel kern = hk.fn;
   const int threads = hk.threads;
   int& bps = h->blocks_per_sm[TRK][TRACE ? 2 : (tle ? 1 : 0)];
@@ -427,7 +432,7 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
     cudaFuncAttributes fa;
     ABL_CUDA(h, cudaFuncGetAttributes(&fa, kern));
     int want_blocks = 1;
-    {
+    if (!hk.events) {
       int regs_limit = 65536 / (fa.numRegs * threads > 0 ? fa.numRegs * threads : 1);
       if (regs_limit >= 2 && 2 * threads <= 2048) want_blocks = 2;
     }
@@ -442,6 +447,11 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
     bool stage = h->smem_generic_base != 0 && fa.sharedSizeBytes == 0 && sl >= 32 && 4 * sl >= 3 * sl_plain;
     if (getenv("ABEILLE_B200_NO_SMEM_TABLES")) stage = false;
     if (!stage) sl = sl_plain;
+    if (hk.events) {  // (tuning aid: fewer slots per CTA than the shared memory holds)
+      const char* e = getenv("ABEILLE_B200_EQ_SLOTS");
+      const int v = e ? atoi(e) : 0;
+      if (v >= 32 && v < sl) sl = v - v % 32;
+    }
     h->hk_tables[TRK][TRACE ? 2 : (tle ? 1 : 0)] = stage ? tables : 0;
     if (sl < 32) {
       h->error = "geometry nesting too deep for the staged history kernel's shared memory";
@@ -478,12 +488,14 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
     B.timeout_ns = (unsigned long long)(timeout_s * 1e9);
   }
   if (TRK == ABL_TRACK_CARTER) {
-    const uint64_t nthreads = blocks * threads;
+    // one LIFO per history in flight: per thread in the staged kernel, per slot in the event kernel
+    const int owners = hk.events ? slots : threads;
+    const uint64_t nthreads = blocks * owners;
     if (nthreads > h->sec_threads) {
       if (h->secondaries) cudaFree(h->secondaries);
       h->secondaries = nullptr;
       h->sec_threads = 0;
-      const uint64_t cap = (uint64_t)h->sm_count * bps * threads;
+      const uint64_t cap = (uint64_t)h->sm_count * bps * owners;
       ABL_CUDA(h, cudaMalloc(&h->secondaries, cap * ABL_SEC_CAP * 9 * sizeof(double)));
       h->sec_threads = cap;
     }

@@ -332,16 +332,20 @@ struct Cols {  // byte offsets from hk_shared_raw of one thread's entries
   unsigned j0;  // HI_IDX (the 4-byte fields HI_* follow at stride S4)
   unsigned S8, S4, F8;  // column strides: 8 S, 4 S, 8 S NF
 };
-__device__ __forceinline__ Cols make_cols(int t, int S, int NF, int NP, bool trace, int tables) {
+// base = byte offset of the columns from hk_shared_raw (fixed part + staged tables), t = the history's slot
+__device__ __forceinline__ Cols make_cols_at(unsigned base, int t, int S, int NF, int NP, bool trace) {
   Cols q;
   q.S8 = 8u * S;
   q.S4 = 4u * S;
   q.F8 = q.S8 * NF;
-  q.d0 = HK_COLS_OFFSET + (unsigned)tables + 8u * t;
+  q.d0 = base + 8u * t;
   q.r0 = q.d0 + 3u * q.F8;
-  q.i0 = HK_COLS_OFFSET + (unsigned)tables + hk_cols8(NF, NP, trace) * q.S8 + 4u * t;
+  q.i0 = base + hk_cols8(NF, NP, trace) * q.S8 + 4u * t;
   q.j0 = q.i0 + q.S4 * NP;
   return q;
+}
+__device__ __forceinline__ Cols make_cols(int t, int S, int NF, int NP, bool trace, int tables) {
+  return make_cols_at(HK_COLS_OFFSET + (unsigned)tables, t, S, NF, NP, trace);
 }
 #define HK_D(q, k) (*reinterpret_cast<double*>(hk_shared_raw + ((q).r0 + (unsigned)(k) * (q).S8)))
 #define HK_U(q, k) (*reinterpret_cast<unsigned long long*>(hk_shared_raw + ((q).r0 + (unsigned)(k) * (q).S8)))
@@ -613,7 +617,13 @@ __device__ __forceinline__ void note_col(const Cols& q, int NP, uint64_t v) {
 // sequence as collision<> in transport.cuh on the history's shared-memory columns -- every field is loaded where it is
 // first needed and stored when it is final, so the stage needs few registers -- with the fission sites handed to a service
 // warp.  r = the collision site (already in the R column), hmat = the material there.
-template <class M, bool TRACE>
+// POST: where the fission sites of a collision go -- post(P, A, job, sw) hands the job over (the staged kernel: to a service
+// warp; the event kernel: to its job ring), sites(n) counts them.
+struct ServicePost {
+  static __device__ __forceinline__ void post(const DevProblem&, const RunArgs&, const FisJob& j, int sw) { post_fission_job(j, sw); }
+  static __device__ __forceinline__ void sites(unsigned n) { atomicAdd(&HKS.rare[RC_SITES], n); }
+};
+template <class M, bool TRACE, class POST = ServicePost>
 __device__ __forceinline__ void collision_cols(const DevProblem& P, const RunArgs& A, const Cols& q, const V3 r, int hmat, HAcc& acc,
                                                ICount& ic, int sw, bool& alive) {
   const int gi = HK_I(q, HI_G);
@@ -657,10 +667,10 @@ __device__ __forceinline__ void collision_cols(const DevProblem& P, const RunArg
     j.daughter0 = daughter;
     j.n_new = n_new;
     j.mg = mg;
-    post_fission_job(j, sw);
+    POST::post(P, A, j, sw);
     rng = skip_fission_draws<M>(P, rng, n_new, hmat, mg);
     HK_I(q, HI_DAU) = (int)(daughter + (uint32_t)n_new);
-    atomicAdd(&HKS.rare[RC_SITES], (unsigned)n_new);
+    POST::sites((unsigned)n_new);
   }
   note_col<TRACE>(q, A.hk_np, 0x5000000000000000ULL | (uint64_t)(uint32_t)n_new);
   {

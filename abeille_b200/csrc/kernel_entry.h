@@ -7,7 +7,7 @@
  * changed.  So each tracker's kernels live in their own file and the host code gets them as function pointers.
  */
 #pragma once
-#include "history.cuh"
+#include "events.cuh"
 
 namespace abl {
 typedef void (*TransportKernel)(const DevProblem, const RunArgs);
@@ -17,13 +17,19 @@ struct HistoryKernel {
   int threads;           // threads per CTA (history threads + service warps)
   int hist_threads;      // threads that own a history
   unsigned fixed_bytes;  // shared memory before the per-history columns (HK_COLS_OFFSET)
+  bool events;           // the event-queue kernel (events.cuh): hist_threads = the most slots a CTA can hold
 };
-#define HK_THIS_UNIT(fn) HistoryKernel{fn, HK_THREADS, HK_HIST, HK_COLS_OFFSET}
+#define HK_THIS_UNIT(fn) HistoryKernel{fn, HK_THREADS, HK_HIST, HK_COLS_OFFSET, false}
+#define EQ_THIS_UNIT(fn) HistoryKernel{fn, EQ_THREADS, EQ_MAX_SLOTS, EQ_COLS_OFFSET, true}
 // tle = the run scores track-length tallies this generation (a build without the scorer serves the others)
 HistoryKernel history_kernel_delta(bool trace, bool tle);    // kernels_delta.cu
 HistoryKernel history_kernel_carter(bool trace, bool tle);   // kernels_carter.cu
 HistoryKernel history_kernel_surface(bool trace, bool tle);  // kernels_surface.cu
 HistoryKernel history_kernel_traced(int tracking); // kernels_trace.cu
+// the event-queue kernel (events.cuh), delta and carter tracking
+HistoryKernel event_kernel_delta(bool trace, bool tle);   // kernels_events.cu
+HistoryKernel event_kernel_carter(bool trace, bool tle);  // kernels_events_carter.cu
+HistoryKernel event_kernel_traced(int tracking);          // kernels_events_trace.cu
 TransportKernel lane_kernel(int tracking, int mode); // kernels_lane.cu: per-lane kernel of the noise modes (mode 1 | 2)
 TransportKernel implicit_kernel(int mode);            // kernels_implicit.cu: implicit-leakage delta tracking, per-lane kernel (mode 0 | 1 | 2)
 }  // namespace abl

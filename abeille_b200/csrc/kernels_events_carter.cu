@@ -1,0 +1,10 @@
+// Event-queue history kernel, carter tracking, production build without the per-history trace (see kernel_entry.h for why
+// this is its own translation unit).
+#include "kernel_entry.h"
+namespace abl {
+HistoryKernel event_kernel_carter(bool trace, bool tle) {
+  if (trace) return event_kernel_traced(ABL_TRACK_CARTER);
+  if (tle) return EQ_THIS_UNIT((event_kernel<ABL_TRACK_CARTER, false, true>));
+  return EQ_THIS_UNIT((event_kernel<ABL_TRACK_CARTER, false, false>));
+}
+}  // namespace abl
