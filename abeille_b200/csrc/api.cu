@@ -34,6 +34,7 @@ struct DevSmall {  // small per-call block, zeroed before every transport launch
   uint32_t grand_total;
   uint32_t grand_total_noise;
   unsigned long long n_nsites;
+  unsigned long long eq_stats[16];  // event kernel: tasks and lanes per event (ABEILLE_B200_EQ_STATS=1)
   unsigned long long avail;  // rows of a streamed input bank that have arrived (abl_transport)
 };
 
@@ -479,6 +480,8 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
   B.hk_tables = tables;
   B.arena = h->arena;
   B.smem_generic_base = h->smem_generic_base;
+  static const bool eq_stats = getenv("ABEILLE_B200_EQ_STATS") != nullptr;
+  B.eq_stats = hk.events && eq_stats ? h->small_dev->eq_stats : nullptr;
   {
     static const double timeout_s = [] {
       const char* e = getenv("ABEILLE_B200_KERNEL_TIMEOUT_S");
@@ -711,6 +714,13 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
   ABL_CUDA(h, cudaStreamSynchronize(s));
   if (N > 0) cudaEventElapsedTime(&h->last_kernel_ms, h->ev0, h->ev1);
   const DevSmall& sm = *h->small_host;
+  if (getenv("ABEILLE_B200_EQ_STATS") && sm.eq_stats[0] + sm.eq_stats[1]) {  // (development aid; order: events.cuh Q_*)
+    static const char* names[] = {"step", "loc_tree", "loc_cell", "boundary", "refill", "fission"};
+    fprintf(stderr, "event kernel:");
+    for (int q = 0; q < 6; q++)
+      fprintf(stderr, " %s %llu tasks x %.1f lanes;", names[q], sm.eq_stats[q], sm.eq_stats[q] ? (double)sm.eq_stats[6 + q] / sm.eq_stats[q] : 0.);
+    fprintf(stderr, " idle polls %llu\n", sm.eq_stats[12]);
+  }
   for (int i = 0; i < 6; i++) scores[i] = sm.scores[i];
   if (counters)
     for (int i = 0; i < 8; i++) counters[i] = sm.counters[i];

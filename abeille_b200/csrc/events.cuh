@@ -11,13 +11,15 @@
  * through per-event queues:
  *
  *     REFILL  a finished slot takes the next bank index, loads the particle             -> LOCATE (full lookup)
- *     MOVE    sample the flight distance, advance the cursor, re-validate its pads     -> LOCATE | arrive
+ *     STEP    the flight arrives: real or virtual collision; Transporter::collision (scores, tally, fission,
+ *             roulette, scatter); then the next flight: sample the distance, advance the cursor, re-validate
+ *             its pads                                                                  -> STEP | LOCATE | REFILL
  *     LOCATE  (re-)descent through the universe tree; two queues: histories that only change cell inside their
- *             universe, and histories that go through the lattices                      -> arrive | BOUNDARY
- *     arrive  (inline, end of MOVE / LOCATE) real or virtual collision                  -> COLLIDE | MOVE
- *     COLLIDE Transporter::collision: scores, tally, fission, roulette, scatter         -> MOVE | REFILL
+ *             universe, and histories that go through the lattices                      -> STEP | BOUNDARY
  *     BOUNDARY a particle left the geometry: boundary search, leak or reflection        -> LOCATE | REFILL
  *     FISSION jobs (not slots): n_new sites of a collision are sampled and appended to the scratch bank
+ *
+ * 55 % of the flights go STEP -> STEP (the pads still hold after the move), 45 % STEP -> LOCATE -> STEP.
  *
  * A warp repeatedly picks the event queue that fills most of its lanes, takes one slot per lane, runs that event for all of
  * them, and pushes every slot to the queue of its next event.  No thread is bound to a history, no warp to a stage, and
@@ -38,15 +40,23 @@ namespace abl {
 #ifndef EQ_FQ
 #define EQ_FQ 128  // fission-job ring entries (a full ring makes the collision bank its sites inline)
 #endif
+#ifndef EQ_STICKY
+#define EQ_STICKY 24  // lanes the CTA's current event must still fill for a warp to stay with it
+#endif
 #define EQ_RING 32  // ring entries per (queue, lane) = the most slots a lane can own
 #define EQ_MAX_SLOTS (32 * EQ_RING)
 #define EQ_EMPTY 0xffu
 
-// queues in the order the dispatcher breaks ties (the later stages of a flight first)
-enum { Q_COLLIDE = 0, Q_LOC_TREE, Q_LOC_CELL, Q_MOVE, Q_BOUNDARY, Q_REFILL, Q_N, Q_FISSION = Q_N };
+// queues in the order the dispatcher breaks ties
+enum { Q_STEP = 0, Q_LOC_TREE, Q_LOC_CELL, Q_BOUNDARY, Q_REFILL, Q_N, Q_FISSION = Q_N };
 // what a LOCATE event is part of (history.cuh: PH_*)
 enum { EP_FLIGHT = 0, EP_BIRTH, EP_REFLECTED, EP_RESURRECT };
-#define HI_EVT HI_BDONE  // the slot's pending event: need (first bad pad, 0 = full lookup) | EP_* << 8
+// the slot's pending event.  LOCATE: need (first bad pad, 0 = full lookup) | EP_* << 8; STEP: 0 = the flight arrives at its
+// tentative collision site, EV_MOVE_ONLY = a particle that starts a flight (birth, reflection, resurrection)
+#define HI_EVT HI_BDONE
+#define EV_MOVE_ONLY 0x10000
+enum { X_COLLIDE = 100, X_MOVE = 101 };  // inside a STEP: what the slot does next (not queues)
+enum { ST_TASKS = 0, ST_LANES = Q_N + 1, ST_IDLE = 2 * (Q_N + 1), ST_N };  // dispatcher statistics (RunArgs::eq_stats)
 
 struct EQFixed {  // the fixed part of the dynamic shared memory; staged tables and the slot columns follow it
   FisJob fq[EQ_FQ];
@@ -56,15 +66,26 @@ struct EQFixed {  // the fixed part of the dynamic shared memory; staged tables 
   int cnt[Q_N][32];                      // entries pushed and not yet claimed (may dip below 0 for a moment)
   unsigned head[Q_N][32], tail[Q_N][32];
   int live;  // slots that may still receive a history
+  volatile int cur;  // the event most warps are running (see the dispatcher)
   volatile int abort;
   unsigned long long deadline_ns;
   unsigned rare[RC_N];
   double leak, leak_mig;
   double sd[EQ_THREADS / 32][3];
   unsigned long long wcnt[EQ_THREADS / 32][WC_N];
+  unsigned long long stat[ST_N];
 };
 #define EQS (*reinterpret_cast<EQFixed*>(hk_shared_raw))
 #define EQ_COLS_OFFSET ((unsigned)((sizeof(EQFixed) + 15) & ~size_t(15)))
+
+// Orders a slot's column stores before the ring entry that publishes it (and the reader's column loads after the entry it
+// took).  EQ_FENCE_SOFT makes it a compiler barrier only (an experiment: shared-memory accesses of a warp are performed in
+// order by the hardware, but the PTX memory model does not promise it).
+#ifdef EQ_FENCE_SOFT
+#define EQ_FENCE() asm volatile("" ::: "memory")
+#else
+#define EQ_FENCE() __threadfence_block()
+#endif
 
 // ---- slot queues ---------------------------------------------------------------------------------------------------------
 // (every store to the slot's columns happens before the push: the fence orders them before the ring entry becomes visible)
@@ -72,7 +93,7 @@ __device__ __forceinline__ void eq_push(EQFixed& S, int qi, int lane, int k) {
   const unsigned pos = atomicAdd(&S.tail[qi][lane], 1u) & (EQ_RING - 1);
   volatile unsigned char* cell = &S.ring[qi][pos][lane];
   while (*cell != EQ_EMPTY && !S.abort) {}  // (a lane owns at most EQ_RING slots, so the cell is free unless a reader is mid-way)
-  __threadfence_block();
+  EQ_FENCE();
   *cell = (unsigned char)k;
   atomicAdd(&S.cnt[qi][lane], 1);
 }
@@ -236,11 +257,11 @@ __device__ __forceinline__ int eq_arrive(const DevProblem& P, const RunArgs& A, 
     return eq_particle_dead<TRK, TRACE>(P, A, q, gslot, nslots);
   }
   note_col<TRACE>(q, A.hk_np, (had_collision ? 0x2000000000000000ULL : 0x1000000000000000ULL) | (uint64_t)(uint32_t)(ccell + 1));
-  if (had_collision) return Q_COLLIDE;
+  if (had_collision) return X_COLLIDE;
   ec.virt++;
   if (TRACE) HK_I(q, HI_NVI) = HK_I(q, HI_NVI) + 1;
   if (TRK == ABL_TRACK_CARTER) eq_carter_split<TRACE>(P, A, q, gslot, nslots);
-  return Q_MOVE;
+  return X_MOVE;
 }
 
 template <int TRK, bool TRACE, bool TLE>
@@ -258,9 +279,11 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
   }
   for (int i = threadIdx.x; i < EQ_FQ; i += EQ_THREADS) S.fq_seq[i] = (unsigned)i;
   for (int i = threadIdx.x; i < (EQ_THREADS / 32) * WC_N; i += EQ_THREADS) (&S.wcnt[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < ST_N; i += EQ_THREADS) S.stat[i] = 0;
   if (threadIdx.x == 0) {
     S.fq_head = S.fq_tail = 0;
     S.live = nslots_cta;
+    S.cur = Q_REFILL;
     S.abort = 0;
     S.deadline_ns = hk_now_ns() + A.timeout_ns;
     S.leak = S.leak_mig = 0.;
@@ -288,27 +311,45 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
   const uint32_t nslots = gridDim.x * (uint32_t)nslots_cta;  // of the grid (the secondaries' stride)
   const uint64_t N = A.bank.n;
   const bool tle = TLE && A.converged && P.n_tl_tallies;
+  const bool stats = A.eq_stats != nullptr;
   HAcc acc;
   acc.k_col = acc.k_abs = acc.mig = acc.k_trk = 0.;
   unsigned iter = 0;
 
+  // (every decision that steers the loop is made warp-uniform -- shuffle from lane 0 or a vote --: the lanes of a warp do not
+  // read a shared variable at the same instant once they have diverged, and a warp that splits here would meet its own
+  // full-mask votes with lanes missing)
   for (;;) {
     // watchdog: a loop that runs past the deadline is wound down with ABL_ERR_TIMEOUT instead of spinning for ever
     if ((++iter & 63u) == 0 && lane == 0 && hk_now_ns() > S.deadline_ns && !S.abort) {
       S.abort = 1;
       raise_error(A, ABL_ERR_TIMEOUT, 0);
     }
-    if (S.abort) break;
-    // ---- pick the event that fills most lanes ------------------------------------------------------------------------------
+    if (__any_sync(FULL, S.abort != 0)) break;
+    // ---- pick the event: the one the other warps are running while it still fills most of a warp -- warps that run the same
+    // event at the same time share the instruction-cache lines they fetch (the loop body is several times the size of the
+    // SM's instruction cache; without this clustering ncu showed 5.3 stall cycles per issue waiting for instructions) --
+    // otherwise the event that fills most lanes, which becomes the CTA's current event
     int qi = -1, best = 0;
     const bool scavenge = (iter & 63u) == 32u;  // now and then the emptiest queue goes first, so that no slot waits for ever
-#pragma unroll
-    for (int c = 0; c < Q_N; c++) {
-      const int n = __popc(__ballot_sync(FULL, *(volatile int*)&S.cnt[c][lane] > 0));
-      if (scavenge ? (n > 0 && (qi < 0 || n < best)) : (n > best)) {
+    if (!scavenge) {
+      const int cur = __shfl_sync(FULL, S.cur, 0);
+      const int n = __popc(__ballot_sync(FULL, *(volatile int*)&S.cnt[cur][lane] > 0));
+      if (n >= EQ_STICKY) {
+        qi = cur;
         best = n;
-        qi = c;
       }
+    }
+    if (qi < 0) {
+#pragma unroll
+      for (int c = 0; c < Q_N; c++) {
+        const int n = __popc(__ballot_sync(FULL, *(volatile int*)&S.cnt[c][lane] > 0));
+        if (scavenge ? (n > 0 && (qi < 0 || n < best)) : (n > best)) {
+          best = n;
+          qi = c;
+        }
+      }
+      if (!scavenge && qi >= 0 && lane == 0) S.cur = qi;
     }
     {
       const unsigned nj = *(volatile unsigned*)&S.fq_head - *(volatile unsigned*)&S.fq_tail;
@@ -318,7 +359,8 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
     if (qi < 0) {
       const int fin = *(volatile int*)&S.live <= 0;
       if (__shfl_sync(FULL, fin, 0)) break;  // every slot is retired (so nothing can post a job any more)
-      __nanosleep(128);
+      if (stats && lane == 0) atomicAdd(&S.stat[ST_IDLE], 1ULL);
+      __nanosleep(200);
       continue;
     }
     if (qi == Q_FISSION) {
@@ -333,6 +375,10 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
       }
       t = __shfl_sync(FULL, t, 0);
       n = __shfl_sync(FULL, n, 0);
+      if (stats && lane == 0 && n) {
+        atomicAdd(&S.stat[ST_TASKS + Q_FISSION], 1ULL);
+        atomicAdd(&S.stat[ST_LANES + Q_FISSION], (unsigned long long)n);
+      }
       if ((unsigned)lane < n) {
         const unsigned pos = t + lane, cell = pos % EQ_FQ;
         while (S.fq_seq[cell] != pos + 1 && !S.abort) {}
@@ -355,14 +401,124 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
     const bool have = k >= 0;
     const unsigned act = __ballot_sync(FULL, have);
     if (act == 0) continue;
-    __threadfence_block();
+    EQ_FENCE();
+    if (stats && lane == 0) {
+      atomicAdd(&S.stat[ST_TASKS + qi], 1ULL);
+      atomicAdd(&S.stat[ST_LANES + qi], (unsigned long long)__popc(act));
+    }
     const int slot = (k << 5) | lane;
     const Cols q = make_cols_at(cols_base, have ? slot : lane, nslots_cta, A.hk_nf, A.hk_np, TRACE);
     const uint32_t gslot = blockIdx.x * (uint32_t)nslots_cta + (uint32_t)slot;
     int dest = -1;
-    EvCount ec{0u, 0u, 0u, 0u};
 
-    if (qi == Q_REFILL) {
+    if (qi == Q_STEP) {
+      // ---- STEP: arrive (real or virtual collision), collide, start the next flight ------------------------------------------------
+      EvCount ec{0u, 0u, 0u, 0u};
+      bool flew = false;
+      if (have) {
+        int next = X_MOVE;
+        if (!(HK_I(q, HI_EVT) & EV_MOVE_ONLY)) next = eq_arrive<TRK, TRACE>(P, A, q, HK_I(q, HI_CELL), tle, ec, gslot, nslots);
+        if (next == X_COLLIDE) {  // Transporter::collision (transporter.cpp:60-93,269-312)
+          bool alive = true;
+          ICount ic{0u, 0u, 0u, 0u};
+          collision_cols<HK_MATH, TRACE, EventPost>(P, A, q, hk_ld3(q, HD_R), HK_I(q, HI_HMAT), acc, ic, 0, alive);
+          ec.real += ic.real;
+          ec.coll_scores += ic.coll_scores;
+          if (alive) {
+            if (TRK == ABL_TRACK_CARTER) eq_carter_split<TRACE>(P, A, q, gslot, nslots);
+            next = X_MOVE;
+          } else {
+            next = eq_particle_dead<TRK, TRACE>(P, A, q, gslot, nslots);
+          }
+        }
+        if (next == X_MOVE) {
+          // sample the flight, move the cursor, re-validate its pads (delta_tracker.cpp:105-118)
+          flew = true;
+          uint64_t rng = HK_U(q, HD_RNG);
+          const int g = HK_I(q, HI_G) & 0xff;
+          const V3 u = hk_ld3(q, HD_U);
+          const double d_coll = rng_exponential<HK_MATH>(rng, ldt(&P.smp[g]));
+          HK_U(q, HD_RNG) = rng;
+          HK_D(q, HD_DC) = d_coll;
+          if (TRACE) HK_I(q, HI_NFL) = HK_I(q, HI_NFL) + 1;
+          SCursor c;
+          c.q = q;
+          c.err = 0;
+          const int pf = HK_I(q, HI_NPNF);
+          c.np = pf & 0xff;
+          c.nf = pf >> 8;
+          cursor_move(c, d_coll, u);
+          HK_I(q, HI_TOK) = 0;
+          const int first_bad = cursor_validate(P, c, u);
+          if (first_bad < c.np) {
+            HK_I(q, HI_EVT) = first_bad | (EP_FLIGHT << 8);
+            // a re-descent that starts at a cell universe stays inside it (the pin cell changed, the tile did not)
+            dest = (first_bad > 0 && pad_type(pad_info(c, first_bad - 1)) == PAD_UNIVERSE) ? Q_LOC_CELL : Q_LOC_TREE;
+          } else {
+            HK_I(q, HI_EVT) = 0;
+            dest = Q_STEP;
+          }
+        } else {
+          dest = next;
+        }
+      }
+      if (have && dest >= 0) eq_push(S, dest, lane, k);
+      __syncwarp();
+      const unsigned nf = __popc(__ballot_sync(FULL, flew));
+      const unsigned nr = __reduce_add_sync(FULL, ec.real);
+      const unsigned nv = __reduce_add_sync(FULL, ec.virt);
+      const unsigned ns = __reduce_add_sync(FULL, ec.coll_scores);
+      unsigned nt = 0;
+      if (tle) nt = __reduce_add_sync(FULL, ec.tl_bins);
+      if (lane == 0) {
+        S.wcnt[wid][WC_FLIGHTS] += nf;
+        S.wcnt[wid][WC_REAL] += nr;
+        S.wcnt[wid][WC_VIRT] += nv;
+        S.wcnt[wid][WC_COLLSCORES] += ns;
+        if (tle) S.wcnt[wid][WC_TLBINS] += nt;
+      }
+      continue;
+    }
+    unsigned tl_bins = 0;
+    if (qi == Q_LOC_TREE || qi == Q_LOC_CELL) {
+      // ---- LOCATE: (re-)descent through the universe tree, all lanes in step by universe type -------------------------------------
+      if (have) {
+        SCursor c;
+        cursor_load(c, q);
+        const V3 u = hk_ld3(q, HD_U);
+        const int ev = HK_I(q, HI_EVT);
+        const int need = ev & 0xff, part = ev >> 8;
+        cursor_relocate_sync(P, c, need, u, act);
+        cursor_store(c);
+        if (c.err) raise_error(A, c.err, A.bank.id_a[(uint32_t)HK_I(q, HI_IDX)]);
+        const int ccell = c.cell;
+        if (part == EP_FLIGHT) {
+          if (ccell < 0) {
+            dest = Q_BOUNDARY;  // left the geometry: the boundary is looked for from the pre-flight position
+          } else {
+            HK_I(q, HI_EVT) = 0;
+            dest = Q_STEP;
+          }
+        } else if (ccell < 0) {
+          if (part == EP_BIRTH) {  // lost at birth: warning + kill in the reference (delta_tracker.cpp:92-98)
+            atomicAdd(&S.rare[RC_LOST], 1u);
+          } else {
+            raise_error(A, ABL_ERR_LOST, A.bank.id_a[(uint32_t)HK_I(q, HI_IDX)]);
+            if (TRK == ABL_TRACK_CARTER) HK_I(q, HI_NSEC) = 0;
+          }
+          dest = eq_particle_dead<TRK, TRACE>(P, A, q, gslot, nslots);
+        } else {
+          if (part == EP_REFLECTED) {
+            note_col<TRACE>(q, A.hk_np, 0x4000000000000000ULL | (uint64_t)(uint32_t)(ccell + 1));
+            if (TRK == ABL_TRACK_CARTER) eq_carter_split<TRACE>(P, A, q, gslot, nslots);
+          } else {  // birth, resurrection: the MaterialHelper of the new particle
+            HK_I(q, HI_HMAT) = c.mat;
+          }
+          HK_I(q, HI_EVT) = EV_MOVE_ONLY;
+          dest = Q_STEP;
+        }
+      }
+    } else if (qi == Q_REFILL) {
       // ---- REFILL: the next bank index (one aggregated atomic per warp) ----------------------------------------------------------
       if (have) {
         unsigned long long idx;
@@ -411,93 +567,6 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
           dest = Q_LOC_TREE;
         }
       }
-    } else if (qi == Q_MOVE) {
-      // ---- MOVE: sample the flight, move the cursor, re-validate its pads (delta_tracker.cpp:105-118) ----------------------------
-      if (have) {
-        uint64_t rng = HK_U(q, HD_RNG);
-        const int g = HK_I(q, HI_G) & 0xff;
-        const V3 u = hk_ld3(q, HD_U);
-        const double d_coll = rng_exponential<HK_MATH>(rng, ldt(&P.smp[g]));
-        HK_U(q, HD_RNG) = rng;
-        HK_D(q, HD_DC) = d_coll;
-        if (TRACE) HK_I(q, HI_NFL) = HK_I(q, HI_NFL) + 1;
-        SCursor c;
-        c.q = q;
-        c.err = 0;
-        const int pf = HK_I(q, HI_NPNF);
-        c.np = pf & 0xff;
-        c.nf = pf >> 8;
-        cursor_move(c, d_coll, u);
-        HK_I(q, HI_TOK) = 0;
-        const int first_bad = cursor_validate(P, c, u);
-        if (first_bad < c.np) {
-          HK_I(q, HI_EVT) = first_bad | (EP_FLIGHT << 8);
-          // a re-descent that starts at a cell universe stays inside it (the pin cell changed, the tile did not)
-          dest = (first_bad > 0 && pad_type(pad_info(c, first_bad - 1)) == PAD_UNIVERSE) ? Q_LOC_CELL : Q_LOC_TREE;
-        } else {
-          dest = eq_arrive<TRK, TRACE>(P, A, q, HK_I(q, HI_CELL), tle, ec, gslot, nslots);
-        }
-      }
-      if (lane == 0) S.wcnt[wid][WC_FLIGHTS] += __popc(act);
-    } else if (qi == Q_LOC_TREE || qi == Q_LOC_CELL) {
-      // ---- LOCATE: (re-)descent through the universe tree, all lanes in step by universe type -------------------------------------
-      if (have) {
-        SCursor c;
-        cursor_load(c, q);
-        const V3 u = hk_ld3(q, HD_U);
-        const int ev = HK_I(q, HI_EVT);
-        const int need = ev & 0xff, part = ev >> 8;
-        cursor_relocate_sync(P, c, need, u, act);
-        cursor_store(c);
-        if (c.err) raise_error(A, c.err, A.bank.id_a[(uint32_t)HK_I(q, HI_IDX)]);
-        const int ccell = c.cell;
-        if (part == EP_FLIGHT) {
-          if (ccell < 0) dest = Q_BOUNDARY;  // left the geometry: the boundary is looked for from the pre-flight position
-          else dest = eq_arrive<TRK, TRACE>(P, A, q, ccell, tle, ec, gslot, nslots);
-        } else if (part == EP_BIRTH) {
-          if (ccell < 0) {  // lost at birth: warning + kill in the reference (delta_tracker.cpp:92-98)
-            atomicAdd(&S.rare[RC_LOST], 1u);
-            dest = eq_particle_dead<TRK, TRACE>(P, A, q, gslot, nslots);
-          } else {
-            HK_I(q, HI_HMAT) = c.mat;
-            dest = Q_MOVE;
-          }
-        } else if (part == EP_REFLECTED) {
-          if (ccell < 0) {
-            raise_error(A, ABL_ERR_LOST, A.bank.id_a[(uint32_t)HK_I(q, HI_IDX)]);
-            if (TRK == ABL_TRACK_CARTER) HK_I(q, HI_NSEC) = 0;
-            dest = eq_particle_dead<TRK, TRACE>(P, A, q, gslot, nslots);
-          } else {
-            note_col<TRACE>(q, A.hk_np, 0x4000000000000000ULL | (uint64_t)(uint32_t)(ccell + 1));
-            if (TRK == ABL_TRACK_CARTER) eq_carter_split<TRACE>(P, A, q, gslot, nslots);
-            dest = Q_MOVE;
-          }
-        } else {  // EP_RESURRECT
-          if (ccell < 0) {
-            raise_error(A, ABL_ERR_LOST, A.bank.id_a[(uint32_t)HK_I(q, HI_IDX)]);
-            if (TRK == ABL_TRACK_CARTER) HK_I(q, HI_NSEC) = 0;
-            dest = eq_particle_dead<TRK, TRACE>(P, A, q, gslot, nslots);
-          } else {
-            HK_I(q, HI_HMAT) = c.mat;
-            dest = Q_MOVE;
-          }
-        }
-      }
-    } else if (qi == Q_COLLIDE) {
-      // ---- COLLIDE: Transporter::collision (transporter.cpp:60-93,269-312) -----------------------------------------------------------
-      if (have) {
-        bool alive = true;
-        ICount ic{0u, 0u, 0u, 0u};
-        collision_cols<HK_MATH, TRACE, EventPost>(P, A, q, hk_ld3(q, HD_R), HK_I(q, HI_HMAT), acc, ic, 0, alive);
-        ec.real += ic.real;
-        ec.coll_scores += ic.coll_scores;
-        if (alive) {
-          if (TRK == ABL_TRACK_CARTER) eq_carter_split<TRACE>(P, A, q, gslot, nslots);
-          dest = Q_MOVE;
-        } else {
-          dest = eq_particle_dead<TRK, TRACE>(P, A, q, gslot, nslots);
-        }
-      }
     } else {
       // ---- BOUNDARY: Tracker::restart_get_current at the pre-flight position + get_boundary_condition
       // (delta_tracker.cpp:120-127), then leak (delta_tracker.cpp:233-238) or Tracker::do_reflection (tracker.hpp:314-360) --------
@@ -514,7 +583,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
         const double w = HK_D(q, HD_W);
         if (tle) {  // delta_tracker.cpp:133: scored from the pre-move position over min(d_coll, boundary distance)
           const int mg = HK_I(q, HI_HMAT) * P.G + (HK_I(q, HI_G) & 0xff);
-          ec.tl_bins += score_flight_cols(tle_args(P), q, mg, fmin(HK_D(q, HD_DC), b.distance));
+          tl_bins += score_flight_cols(tle_args(P), q, mg, fmin(HK_D(q, HD_DC), b.distance));
         }
         atomicAdd(&S.rare[RC_BOUNDARY], 1u);
         if (b.btype == ABL_BC_VACUUM) {
@@ -544,18 +613,9 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
     // ---- hand every slot to its next event -------------------------------------------------------------------------------------
     if (have && dest >= 0) eq_push(S, dest, lane, k);
     __syncwarp();
-    {
-      const unsigned nr = __reduce_add_sync(FULL, ec.real);
-      const unsigned nv = __reduce_add_sync(FULL, ec.virt);
-      const unsigned ns = __reduce_add_sync(FULL, ec.coll_scores);
-      unsigned nt = 0;
-      if (tle) nt = __reduce_add_sync(FULL, ec.tl_bins);
-      if (lane == 0 && (nr | nv | ns | nt)) {
-        S.wcnt[wid][WC_REAL] += nr;
-        S.wcnt[wid][WC_VIRT] += nv;
-        S.wcnt[wid][WC_COLLSCORES] += ns;
-        S.wcnt[wid][WC_TLBINS] += nt;
-      }
+    if (tle && qi == Q_BOUNDARY) {
+      const unsigned nt = __reduce_add_sync(FULL, tl_bins);
+      if (lane == 0) S.wcnt[wid][WC_TLBINS] += nt;
     }
   }
 
@@ -594,6 +654,8 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
     if (wc >= 0)
       for (int w = 0; w < NW; w++) v += S.wcnt[w][wc];
     atomicAdd(&A.counters[kk], v);
+  } else if (stats && threadIdx.x >= 64 && threadIdx.x < 64 + ST_N) {
+    atomicAdd(&A.eq_stats[threadIdx.x - 64], S.stat[threadIdx.x - 64]);
   }
 }
 

@@ -81,6 +81,7 @@ struct RunArgs {
   int hk_tables;
   const unsigned char* arena;
   unsigned long long smem_generic_base;
+  unsigned long long* eq_stats;   // event kernel: dispatcher statistics (tasks and lanes per event; events.cuh ST_*), or null
   unsigned long long timeout_ns;  // the staged kernel's watchdog: a CTA that runs longer winds down with ABL_ERR_TIMEOUT
 };
 

@@ -9,10 +9,12 @@ for name, path in libs:
     env = dict(os.environ)
     if path: env["ABEILLE_B200_LIBDIR"] = path
     try:
-        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd=root)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=100, cwd=root)
         lines = [l for l in out.stdout.splitlines() if "kernel" in l]
         print(f"== {name}: rc {out.returncode}")
         for l in lines[-2:]: print("   ", l[l.index("gen"):][:200])
+        for l in out.stderr.splitlines():
+            if "event kernel" in l: print("   ", l[:400])
         if out.returncode: print(out.stderr[-800:])
     except subprocess.TimeoutExpired:
         print(f"== {name}: TIMEOUT")
