@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
       }
       if (!scavenge && qi >= 0 && lane == 0) S.cur = qi;
     }
-    {
+    if (qi < 0 || (iter & 3u) == 0) {  // (the job ring holds EQ_FQ jobs and an event posts about one: every 4th look is enough)
       const unsigned nj = *(volatile unsigned*)&S.fq_head - *(volatile unsigned*)&S.fq_tail;
       const int njobs = __shfl_sync(FULL, (int)min(nj, 32u), 0);
       if (njobs > 0 && (njobs >= 32 || njobs > best || qi < 0)) qi = Q_FISSION;
@@ -415,8 +415,9 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
       // ---- STEP: arrive (real or virtual collision), collide, start the next flight ------------------------------------------------
       EvCount ec{0u, 0u, 0u, 0u};
       bool flew = false;
+      int next = -1;
       if (have) {
-        int next = X_MOVE;
+        next = X_MOVE;
         if (!(HK_I(q, HI_EVT) & EV_MOVE_ONLY)) next = eq_arrive<TRK, TRACE>(P, A, q, HK_I(q, HI_CELL), tle, ec, gslot, nslots);
         if (next == X_COLLIDE) {  // Transporter::collision (transporter.cpp:60-93,269-312)
           bool alive = true;
@@ -431,50 +432,51 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
             next = eq_particle_dead<TRK, TRACE>(P, A, q, gslot, nslots);
           }
         }
-        if (next == X_MOVE) {
-          // sample the flight, move the cursor, re-validate its pads (delta_tracker.cpp:105-118)
-          flew = true;
-          uint64_t rng = HK_U(q, HD_RNG);
-          const int g = HK_I(q, HI_G) & 0xff;
-          const V3 u = hk_ld3(q, HD_U);
-          const double d_coll = rng_exponential<HK_MATH>(rng, ldt(&P.smp[g]));
-          HK_U(q, HD_RNG) = rng;
-          HK_D(q, HD_DC) = d_coll;
-          if (TRACE) HK_I(q, HI_NFL) = HK_I(q, HI_NFL) + 1;
-          SCursor c;
-          c.q = q;
-          c.err = 0;
-          const int pf = HK_I(q, HI_NPNF);
-          c.np = pf & 0xff;
-          c.nf = pf >> 8;
-          cursor_move(c, d_coll, u);
-          HK_I(q, HI_TOK) = 0;
-          const int first_bad = cursor_validate(P, c, u);
-          if (first_bad < c.np) {
-            HK_I(q, HI_EVT) = first_bad | (EP_FLIGHT << 8);
-            // a re-descent that starts at a cell universe stays inside it (the pin cell changed, the tile did not)
-            dest = (first_bad > 0 && pad_type(pad_info(c, first_bad - 1)) == PAD_UNIVERSE) ? Q_LOC_CELL : Q_LOC_TREE;
-          } else {
-            HK_I(q, HI_EVT) = 0;
-            dest = Q_STEP;
-          }
+      }
+      const unsigned movers = __ballot_sync(FULL, next == X_MOVE);  // the lanes that start a flight (they vote in the validation)
+      flew = next == X_MOVE;
+      if (flew) {
+        // sample the flight, move the cursor, re-validate its pads (delta_tracker.cpp:105-118)
+        uint64_t rng = HK_U(q, HD_RNG);
+        const int g = HK_I(q, HI_G) & 0xff;
+        const V3 u = hk_ld3(q, HD_U);
+        const double d_coll = rng_exponential<HK_MATH>(rng, ldt(&P.smp[g]));
+        HK_U(q, HD_RNG) = rng;
+        HK_D(q, HD_DC) = d_coll;
+        if (TRACE) HK_I(q, HI_NFL) = HK_I(q, HI_NFL) + 1;
+        SCursor c;
+        c.q = q;
+        c.err = 0;
+        const int pf = HK_I(q, HI_NPNF);
+        c.np = pf & 0xff;
+        c.nf = pf >> 8;
+        cursor_move(c, d_coll, u);
+        HK_I(q, HI_TOK) = 0;
+        const int first_bad = cursor_validate(P, c, u);
+        if (first_bad < c.np) {
+          HK_I(q, HI_EVT) = first_bad | (EP_FLIGHT << 8);
+          // a re-descent that starts at a cell universe stays inside it (the pin cell changed, the tile did not)
+          dest = (first_bad > 0 && pad_type(pad_info(c, first_bad - 1)) == PAD_UNIVERSE) ? Q_LOC_CELL : Q_LOC_TREE;
         } else {
-          dest = next;
+          HK_I(q, HI_EVT) = 0;
+          dest = Q_STEP;
         }
+      } else if (have) {
+        dest = next;
       }
       if (have && dest >= 0) eq_push(S, dest, lane, k);
       __syncwarp();
+      // the event's counters: flights by ballot; real / virtual collisions and tally scores summed in one packed reduction
+      // (a lane adds at most 1, 1 and ABL_MAX_TALLIES: 10-bit fields cannot overflow over 32 lanes)
       const unsigned nf = __popc(__ballot_sync(FULL, flew));
-      const unsigned nr = __reduce_add_sync(FULL, ec.real);
-      const unsigned nv = __reduce_add_sync(FULL, ec.virt);
-      const unsigned ns = __reduce_add_sync(FULL, ec.coll_scores);
+      const unsigned packed = __reduce_add_sync(FULL, ec.real | (ec.virt << 10) | (ec.coll_scores << 20));
       unsigned nt = 0;
       if (tle) nt = __reduce_add_sync(FULL, ec.tl_bins);
       if (lane == 0) {
         S.wcnt[wid][WC_FLIGHTS] += nf;
-        S.wcnt[wid][WC_REAL] += nr;
-        S.wcnt[wid][WC_VIRT] += nv;
-        S.wcnt[wid][WC_COLLSCORES] += ns;
+        S.wcnt[wid][WC_REAL] += packed & 1023u;
+        S.wcnt[wid][WC_VIRT] += (packed >> 10) & 1023u;
+        S.wcnt[wid][WC_COLLSCORES] += packed >> 20;
         if (tle) S.wcnt[wid][WC_TLBINS] += nt;
       }
       continue;

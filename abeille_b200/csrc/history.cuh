@@ -57,6 +57,39 @@ __device__ __forceinline__ int cursor_validate(const DevProblem& P, const CUR& c
   return first_bad;
 }
 
+// The same result with the pads visited by TYPE -- every lattice pad of every lane first, then the cell pads above the first
+// lattice that failed -- so that the lanes of a warp run the tile test together and the cell test together whatever the
+// depth of their pad stacks (a history in the reflector holds [lattice, universe, cell], one in a pin [lattice, lattice,
+// universe, cell]: visited in index order the cell test of the one met the lattice test of the other).  The pads hold or
+// fail independently of each other, so the first bad pad in index order is the smaller of the first bad lattice and the first
+// bad cell below it.  mask = the lanes that call this together.
+template <class CUR>
+__device__ __forceinline__ int cursor_validate_by_type(const DevProblem& P, const CUR& c, const V3& u, unsigned mask) {
+  int lim = c.np;
+  for (int pass = 0; pass < 2; pass++) {
+    const int want = pass == 0 ? PAD_LATTICE : PAD_CELL;
+    int it = 0;
+    for (;;) {
+      while (it < lim && pad_type(pad_info(c, it)) != want) it++;
+      const bool go = it < lim;
+      if (!__any_sync(mask, go)) break;
+      if (go) {
+        const int info = pad_info(c, it);
+        bool ok;
+        if (pass == 0) {
+          const Tile3 t3 = lattice_tile_nl(P.universes + pad_index(info), frame_r(c, pad_frame(info)), u);
+          ok = pad_tile_is(c, it, t3.nx, t3.ny, t3.nz);
+        } else {
+          ok = cell_is_inside_fast(P, pad_index(info), frame_r(c, pad_frame(info)), u, c.token);
+        }
+        if (!ok) lim = it;  // nothing above a bad pad matters
+        it++;
+      }
+    }
+  }
+  return lim;
+}
+
 // Tracker::get_current, second half (tracker.hpp:272-306) and Tracker::restart_get_current (tracker.hpp:63-74):
 // re-descend from the pad above the first bad one; from == 0 is a full lookup from the root at frame 0.
 template <class CUR>

@@ -14,6 +14,8 @@ for name, path in libs:
         print(f"== {name}: rc {out.returncode}")
         for l in lines[-2:]: print("   ", l[l.index("gen"):][:200])
         for l in out.stderr.splitlines():
+            if "event kernel" in l: print("   ", l[:500])
+        for l in out.stderr.splitlines():
             if "event kernel" in l: print("   ", l[:400])
         if out.returncode: print(out.stderr[-800:])
     except subprocess.TimeoutExpired:
