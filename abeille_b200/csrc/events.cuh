@@ -43,6 +43,20 @@ namespace abl {
 #ifndef EQ_STICKY
 #define EQ_STICKY 24  // lanes the CTA's current event must still fill for a warp to stay with it
 #endif
+// a warp that finds fewer than EQ_MINFILL lanes of work naps EQ_NAP ns (at most EQ_PATIENCE times in a row) while the running
+// events push more, instead of running a thin batch
+#ifndef EQ_MINFILL
+#define EQ_MINFILL 0
+#endif
+#ifndef EQ_PATIENCE
+#define EQ_PATIENCE 2
+#endif
+#ifndef EQ_NAP
+#define EQ_NAP 300
+#endif
+#ifndef EQ_REFILL_AT
+#define EQ_REFILL_AT 33  // (33 = never: measured 132-166 ms at 16 / 8 / 4 against 115 ms -- thin REFILL and BOUNDARY batches cost more than the idle slots)
+#endif
 #define EQ_RING 32  // ring entries per (queue, lane) = the most slots a lane can own
 #define EQ_MAX_SLOTS (32 * EQ_RING)
 #define EQ_EMPTY 0xffu
@@ -315,6 +329,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
   HAcc acc;
   acc.k_col = acc.k_abs = acc.mig = acc.k_trk = 0.;
   unsigned iter = 0;
+  int patience = 0;
 
   // (every decision that steers the loop is made warp-uniform -- shuffle from lane 0 or a vote --: the lanes of a warp do not
   // read a shared variable at the same instant once they have diverged, and a warp that splits here would meet its own
@@ -332,7 +347,20 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
     // otherwise the event that fills most lanes, which becomes the CTA's current event
     int qi = -1, best = 0;
     const bool scavenge = (iter & 63u) == 32u;  // now and then the emptiest queue goes first, so that no slot waits for ever
-    if (!scavenge) {
+    // finished slots first once half a warp of them waits: a slot in the REFILL (or BOUNDARY) queue is a slot that carries no
+    // history, and the largest-queue rule below would leave them there (these queues grow at 1/45 of the rate of STEP)
+    if ((iter & 3u) == 1u) {
+      const int nr = __popc(__ballot_sync(FULL, *(volatile int*)&S.cnt[Q_REFILL][lane] > 0));
+      const int nb = __popc(__ballot_sync(FULL, *(volatile int*)&S.cnt[Q_BOUNDARY][lane] > 0));
+      if (nr >= EQ_REFILL_AT) {
+        qi = Q_REFILL;
+        best = nr;
+      } else if (nb >= EQ_REFILL_AT) {
+        qi = Q_BOUNDARY;
+        best = nb;
+      }
+    }
+    if (qi < 0 && !scavenge) {
       const int cur = __shfl_sync(FULL, S.cur, 0);
       const int n = __popc(__ballot_sync(FULL, *(volatile int*)&S.cnt[cur][lane] > 0));
       if (n >= EQ_STICKY) {
@@ -349,7 +377,7 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
           qi = c;
         }
       }
-      if (!scavenge && qi >= 0 && lane == 0) S.cur = qi;
+      if (!scavenge && qi >= 0 && qi < Q_BOUNDARY && lane == 0) S.cur = qi;
     }
     if (qi < 0 || (iter & 3u) == 0) {  // (the job ring holds EQ_FQ jobs and an event posts about one: every 4th look is enough)
       const unsigned nj = *(volatile unsigned*)&S.fq_head - *(volatile unsigned*)&S.fq_tail;
@@ -397,6 +425,12 @@ __global__ void __launch_bounds__(EQ_THREADS, 1) event_kernel(const DevProblem P
       continue;
     }
     // ---- take one slot per lane ------------------------------------------------------------------------------------------------
+    if (EQ_MINFILL > 0 && best < EQ_MINFILL && patience < EQ_PATIENCE && !scavenge) {
+      patience++;
+      __nanosleep(EQ_NAP);
+      continue;
+    }
+    patience = 0;
     const int k = eq_pop(S, qi, lane);
     const bool have = k >= 0;
     const unsigned act = __ballot_sync(FULL, have);
