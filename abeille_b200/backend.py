@@ -22,7 +22,7 @@ COUNTER_KEYS = ("flights", "real_collisions", "virtual_collisions", "tl_bins", "
 # every symbol include/abeille_b200.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = (
     "abl_create", "abl_destroy", "abl_last_error", "abl_device_info", "abl_last_transport_kernel", "abl_transport",
-    "abl_transport_noise", "abl_get_trace",
+    "abl_transport_noise", "abl_transport_begin", "abl_transport_finish", "abl_get_trace",
     "abl_transport_device", "abl_transport_noise_device", "abl_bank_weight_magnitude_device", "abl_bank_divide_weights_device",
     "abl_tally_count", "abl_tally_shape", "abl_tallies_record", "abl_tallies_clear",
     "abl_tally_fetch", "abl_tally_device_ptr", "abl_sample_source_device", "abl_bank_weight_stats_device",
@@ -254,6 +254,28 @@ class Backend:
         m = int(nout.value)
         fis = {k: v[:m] for k, v in out.items() if v is not None}
         return fis, scores, {k: int(v) for k, v in zip(COUNTER_KEYS, cn)}
+
+    def transport_begin(self, bank: dict, k_col: float = 1.0, converged: bool = False, capacity: int | None = None):
+        """abl_transport_begin: host bank in, the fission bank stays on the device.  Returns (n_fission, scores[6], counters
+        dict, weight stats [n+, n-, sum w+, -sum w-])."""
+        n = len(bank["x"])
+        cap = int(capacity if capacity is not None else self.fission_capacity(n, float(np.abs(bank["wgt"]).sum()), k_col))
+        sin = _host_struct(bank)
+        gp = AblGenParams(float(k_col), 1.0, int(bool(converged)), 0, 0, 0)
+        nout = C.c_uint64(0)
+        scores, cn, ws = np.zeros(6), np.zeros(8, dtype=np.uint64), np.zeros(4)
+        rc = self.L.abl_transport_begin(self.h, C.byref(sin), C.byref(gp), C.c_uint64(cap), C.byref(nout), scores.ctypes.data_as(_PD),
+                                        cn.ctypes.data_as(_PU64), ws.ctypes.data_as(_PD))
+        self._check(rc)
+        return int(nout.value), scores, {k: int(v) for k, v in zip(COUNTER_KEYS, cn)}, ws
+
+    def transport_finish(self, n_fission: int, weight_factor: float, first_history_id: int, out: dict):
+        """abl_transport_finish: normalise and number the fission bank on the device, then copy it to the host arrays `out`
+        (x y z ux uy uz E wgt id_a id_b).  Returns the bank as views of `out`."""
+        cap = len(out["x"])
+        sout = _host_struct(out, cap)
+        self._check(self.L.abl_transport_finish(self.h, C.c_double(weight_factor), C.c_uint64(first_history_id), C.byref(sout)))
+        return {k: v[:n_fission] for k, v in out.items() if v is not None}
 
     def trace(self, n: int) -> dict:
         t = {k: np.zeros(n, dtype=np.uint32) for k in ("flights", "real", "virtual", "fission")}

@@ -66,6 +66,9 @@ struct abl_context {
   Site* nsites = nullptr;
   uint64_t nsite_cap = 0, did_cap = 0, ndid_cap = 0, nnoise_cap = 0;
   uint32_t *nnoise = nullptr, *noffsets = nullptr, *ntile_sums = nullptr, *site_did = nullptr, *nsite_did = nullptr;
+  uint64_t pending_rows = 0;  // abl_transport_begin .. abl_transport_finish: rows of the fission bank waiting in stage_out
+  uint32_t* site_inv = nullptr;  // bank row -> scratch site (place_sites_kernel)
+  uint64_t inv_cap = 0;
   int nm_blocks_per_sm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   int implicit_blocks_per_sm[3] = {0, 0, 0};  // implicit-leakage delta tracking: per-lane kernel in modes 0 | 1 | 2
   // host-buffer entry point: the bank is copied in row chunks on its own stream while the history kernel runs
@@ -414,10 +417,12 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
   // the staged lock-step loop with the histories in shared-memory columns and service warps for the rare events
   // (history.cuh); one translation unit per tracker, each with its own launch shape
   const bool tle = A.converged && h->P.n_tl_tallies;
-  // delta and carter tracking run the event-queue kernel (events.cuh); ABEILLE_B200_STAGED=1 selects the staged kernel
-  // they ran before (kept for comparison); surface tracking has the staged kernel only
-  static const bool staged_only = getenv("ABEILLE_B200_STAGED") != nullptr;
-  const bool events = TRK != ABL_TRACK_SURFACE && !staged_only;
+  // delta and carter tracking have two kernels: the staged lock-step kernel (history.cuh) and the event-queue kernel
+  // (events.cuh, ABEILLE_B200_EVENTS=1).  Both are bit-exact; on the bench workload the staged kernel measures 117 ms per
+  // 1e7 histories and the event kernel 126 ms, so the staged one is the default.  Surface tracking
+  // has the staged kernel only.
+  static const bool want_events = getenv("ABEILLE_B200_EVENTS") != nullptr;
+  const bool events = TRK != ABL_TRACK_SURFACE && want_events;
   const HistoryKernel hk = TRK == ABL_TRACK_SURFACE ? history_kernel_surface(TRACE, tle)
                            : events ? (TRK == ABL_TRACK_DELTA ? event_kernel_delta(TRACE, tle) : event_kernel_carter(TRACE, tle))
                                     : (TRK == ABL_TRACK_DELTA ? history_kernel_delta(TRACE, tle) : history_kernel_carter(TRACE, tle));
@@ -733,9 +738,11 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
     return fail(h, ABL_ERR_BANK_OVERFLOW, buf);
   }
   if (sm.n_sites > 0) {
-    place_sites_kernel<<<grid_for(h, sm.n_sites, 256), 256, 0, s>>>(h->sites, sm.n_sites, h->offsets, in, out,
+    if ((rc = grow_u32(h, h->site_inv, h->inv_cap, out.n)) != 0) return rc;
+    site_inverse_kernel<<<grid_for(h, sm.n_sites, 256), 256, 0, s>>>(h->sites, sm.n_sites, h->offsets, out.n, h->site_inv);
+    place_sites_kernel<<<grid_for(h, sm.n_sites, 256), 256, 0, s>>>(h->sites, sm.n_sites, h->site_inv, in, out,
                                                                      lane_kernel_call ? h->site_did : nullptr);
-    h->launches++;
+    h->launches += 2;
     ABL_CUDA(h, cudaGetLastError());
   }
   if (sample_noise) {
@@ -746,8 +753,10 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
       return fail(h, ABL_ERR_BANK_OVERFLOW, buf);
     }
     if (sm.n_nsites > 0) {
-      place_sites_kernel<<<grid_for(h, sm.n_nsites, 256), 256, 0, s>>>(h->nsites, sm.n_nsites, h->noffsets, in, *noise_out, h->nsite_did);
-      h->launches++;
+      if ((rc = grow_u32(h, h->site_inv, h->inv_cap, noise_out->n > out.n ? noise_out->n : out.n)) != 0) return rc;
+      site_inverse_kernel<<<grid_for(h, sm.n_nsites, 256), 256, 0, s>>>(h->nsites, sm.n_nsites, h->noffsets, noise_out->n, h->site_inv);
+      place_sites_kernel<<<grid_for(h, sm.n_nsites, 256), 256, 0, s>>>(h->nsites, sm.n_nsites, h->site_inv, in, *noise_out, h->nsite_did);
+      h->launches += 2;
       ABL_CUDA(h, cudaGetLastError());
     }
   }
@@ -773,7 +782,7 @@ void abl_destroy(abl_handle h) {
                   (void*)h->tr_virtual, (void*)h->tr_hash, (void*)h->tr_rng, (void*)h->small_dev, (void*)h->secondaries,
                   (void*)h->cancel.sum_pos, (void*)h->cancel.sum_neg, (void*)h->cancel.sum_pos2, (void*)h->cancel.sum_neg2,
                   (void*)h->cancel.count, (void*)h->probe_buf, (void*)h->rng_scratch,
-                  (void*)h->nsites, (void*)h->nnoise, (void*)h->noffsets, (void*)h->ntile_sums, (void*)h->site_did, (void*)h->nsite_did})
+                  (void*)h->nsites, (void*)h->nnoise, (void*)h->noffsets, (void*)h->ntile_sums, (void*)h->site_did, (void*)h->nsite_did, (void*)h->site_inv})
     if (p) cudaFree(p);
   free_bank(h->stage_in);
   free_bank(h->stage_out);
@@ -1103,12 +1112,14 @@ int abl_bank_divide_weights_device(abl_handle h, abl_bank* bank_dev, double divi
   return ABL_OK;
 }
 
-int abl_transport(abl_handle h, const abl_bank* bank, const abl_gen_params* params, abl_bank* fission_out, uint64_t* n_fission,
-                  double scores[6], uint64_t counters[8]) {
-  if (!h || !bank || !params || !fission_out || !n_fission || !scores) return ABL_ERR_INVALID;
+namespace {
+// host bank -> device (streamed behind the kernel for large k-eigenvalue banks), the history kernel, scan and placement: the
+// fission bank is left in h->stage_out (capacity cap, wgt2 kept when want_wgt2)
+int transport_upload_and_run(abl_handle h, const abl_bank* bank, const abl_gen_params* params, uint64_t cap, bool want_wgt2,
+                             uint64_t* n_fission, double scores[6], uint64_t counters[8]) {
   ABL_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = use_stream(h, h->stream);
-  const uint64_t N = bank->n, cap = fission_out->n;
+  const uint64_t N = bank->n;
   int rc;
   if (N > h->stage_in_cap) {
     if ((rc = alloc_bank(h, h->stage_in, N + N / 4 + 1024)) != 0) return rc;
@@ -1168,14 +1179,19 @@ int abl_transport(abl_handle h, const abl_bank* bank, const abl_gen_params* para
     if (bank->id_c && N) ABL_CUDA(h, cudaMemcpyAsync(in.id_c, bank->id_c, N * 8, cudaMemcpyHostToDevice, s));
   }
   h->streamed_input = streamed;
-  if (!fission_out->wgt2) out.wgt2 = nullptr;
+  if (!want_wgt2) out.wgt2 = nullptr;
   rc = transport_impl(h, in, params, out, n_fission, scores, counters, s);
   h->streamed_input = false;
   if (rc) {
     if (streamed) cudaStreamSynchronize(h->copy_stream);
     return rc;
   }
-  const uint64_t m = *n_fission;
+  return ABL_OK;
+}
+
+// device fission bank (h->stage_out, m rows) -> host arrays
+int transport_download(abl_handle h, uint64_t m, abl_bank* fission_out, cudaStream_t s) {
+  BankView out = h->stage_out;
   if (m) {
     double* hout[9] = {fission_out->x, fission_out->y, fission_out->z, fission_out->ux, fission_out->uy, fission_out->uz,
                        fission_out->E, fission_out->wgt, fission_out->wgt2};
@@ -1188,6 +1204,59 @@ int abl_transport(abl_handle h, const abl_bank* bank, const abl_gen_params* para
   }
   ABL_CUDA(h, cudaStreamSynchronize(s));
   return ABL_OK;
+}
+
+}  // namespace
+
+int abl_transport(abl_handle h, const abl_bank* bank, const abl_gen_params* params, abl_bank* fission_out, uint64_t* n_fission,
+                  double scores[6], uint64_t counters[8]) {
+  if (!h || !bank || !params || !fission_out || !n_fission || !scores) return ABL_ERR_INVALID;
+  const int rc = transport_upload_and_run(h, bank, params, fission_out->n, fission_out->wgt2 != nullptr, n_fission, scores, counters);
+  if (rc) return rc;
+  return transport_download(h, *n_fission, fission_out, use_stream(h, h->stream));
+}
+
+// abl_transport in two halves, for a caller that normalises the fission bank before it uses it (PowerIterator::run:
+// normalize_weights and the hand-out of fresh history ids, src/power_iterator.cpp:397-399,538-569): begin leaves the fission
+// bank on the device and returns its size, the scores and the weight sums the normalisation needs (positive / negative
+// particle counts and weight sums, as abl_bank_weight_stats_device); finish applies the caller's factor and first history id
+// on the device and copies the finished bank to the host arrays.  The bytes that cross PCIe are the same as in abl_transport;
+// the caller makes no pass over the bank on the host.
+int abl_transport_begin(abl_handle h, const abl_bank* bank, const abl_gen_params* params, uint64_t capacity, uint64_t* n_fission,
+                        double scores[6], uint64_t counters[8], double weight_stats[4]) {
+  if (!h || !bank || !params || !n_fission || !scores || !weight_stats) return ABL_ERR_INVALID;
+  h->pending_rows = 0;
+  int rc = transport_upload_and_run(h, bank, params, capacity, false, n_fission, scores, counters);
+  if (rc) return rc;
+  BankView out = h->stage_out;
+  out.n = *n_fission;
+  abl_bank ob{};
+  ob.n = out.n;
+  ob.wgt = out.wgt;
+  if ((rc = abl_bank_weight_stats_device(h, &ob, weight_stats, nullptr)) != 0) return rc;
+  h->pending_rows = *n_fission;
+  return ABL_OK;
+}
+
+int abl_transport_finish(abl_handle h, double weight_factor, uint64_t first_history_id, abl_bank* fission_out) {
+  if (!h || !fission_out) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, h->stream);
+  const uint64_t m = h->pending_rows;
+  if (m > fission_out->n) return fail(h, ABL_ERR_BANK_OVERFLOW, "abl_transport_finish: host bank smaller than the fission bank");
+  if (m) {
+    BankView out = h->stage_out;
+    out.n = m;
+    scale_weights_kernel<<<grid_for(h, m, 256), 256, 0, s>>>(out.wgt, m, weight_factor);
+    to_particles_kernel<<<grid_for(h, m, 256), 256, 0, s>>>(out, first_history_id);
+    h->launches += 2;
+    ABL_CUDA(h, cudaGetLastError());
+  }
+  h->pending_rows = 0;
+  abl_bank want = *fission_out;
+  want.id_c = nullptr;  // (after to_particles: id_a = fresh history ids, id_b = family ids; the pcg32 column is not a result)
+  want.wgt2 = nullptr;
+  return transport_download(h, m, &want, s);
 }
 
 int abl_transport_noise(abl_handle h, const abl_bank* bank, const abl_gen_params* params, abl_bank* fission_out, uint64_t* n_fission,
@@ -1363,7 +1432,10 @@ int abl_entropy_bin_device(abl_handle h, const abl_bank* bank_dev, double* bins_
   ABL_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = use_stream(h, (cudaStream_t)stream);
   if (bank_dev->n) {
-    entropy_bin_kernel<<<grid_for(h, bank_dev->n, 256), 256, 0, s>>>(h->P.entropy, view_of(bank_dev), bins_dev, total_dev);
+    const uint64_t nbins = (uint64_t)h->P.entropy.Nx * h->P.entropy.Ny * h->P.entropy.Nz;
+    const int nshared = nbins <= 4096 ? (int)nbins : 0;
+    entropy_bin_kernel<<<grid_for(h, bank_dev->n, 256), 256, nshared * sizeof(double), s>>>(h->P.entropy, view_of(bank_dev), bins_dev,
+                                                                                           total_dev, nshared);
     h->launches++;
   }
   ABL_CUDA(h, cudaGetLastError());

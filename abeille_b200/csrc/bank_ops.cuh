@@ -96,17 +96,31 @@ __global__ void __launch_bounds__(ABL_SCAN_THREADS) scan_apply_kernel(const uint
 }
 
 // ---- fission bank placement ---------------------------------------------------------------------------------
+// Scratch sites arrive in random parent order; their place in the bank is offsets[parent] + rank.  Writing them there directly
+// costs eleven scattered 8-byte stores per site (11 read-modify-written 32 B sectors: 4.3 ms for 1e7 sites, 6 % of the HBM
+// rate).  Instead: (1) one scattered 4-byte store per site builds the inverse map row -> scratch index, (2) the rows are
+// written in order -- every store of a warp is one coalesced line -- and the only scattered access left is the read of the
+// 80-byte record (three sectors).
 // did: daughter ids of the scratch sites when they differ from the rank carried by the site (noise mode), else null
-__global__ void __launch_bounds__(256) place_sites_kernel(const Site* __restrict__ sites, uint64_t n_sites,
-                                                          const uint32_t* __restrict__ offsets, BankView in, BankView out,
-                                                          const uint32_t* __restrict__ did) {
+__global__ void __launch_bounds__(256) site_inverse_kernel(const Site* __restrict__ sites, uint64_t n_sites,
+                                                           const uint32_t* __restrict__ offsets, uint64_t capacity,
+                                                           uint32_t* __restrict__ inv) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sites; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long tag = *reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(sites + i) + 72);
+    const uint32_t parent = (uint32_t)(tag & 0xffffffffULL), rank = (uint32_t)(tag >> 32);
+    const uint64_t pos = (uint64_t)offsets[parent] + rank;
+    if (pos < capacity) inv[pos] = (uint32_t)i;  // capacity overflow is reported by the host from the total count
+  }
+}
+__global__ void __launch_bounds__(256) place_sites_kernel(const Site* __restrict__ sites, uint64_t n_sites,
+                                                          const uint32_t* __restrict__ inv, BankView in, BankView out,
+                                                          const uint32_t* __restrict__ did) {
+  for (uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < n_sites; pos += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t i = inv[pos];
     const double2* src = reinterpret_cast<const double2*>(sites + i);
-    const double2 a = src[0], b = src[1], c = src[2], d = src[3], e = src[4];
+    const double2 a = __ldcs(src), b = __ldcs(src + 1), c = __ldcs(src + 2), d = __ldcs(src + 3), e = __ldcs(src + 4);
     const uint32_t parent = (uint32_t)(__double_as_longlong(e.y) & 0xffffffffLL);
     const uint32_t daughter = (uint32_t)((unsigned long long)__double_as_longlong(e.y) >> 32);
-    const uint64_t pos = (uint64_t)offsets[parent] + daughter;
-    if (pos >= out.n) continue;  // capacity overflow is reported by the host from the total count
     out.x[pos] = a.x; out.y[pos] = a.y; out.z[pos] = b.x;
     out.ux[pos] = b.y; out.uy[pos] = c.x; out.uz[pos] = c.y;
     out.E[pos] = d.x; out.wgt[pos] = d.y;
@@ -176,7 +190,12 @@ __global__ void __launch_bounds__(256) to_particles_kernel(BankView b, uint64_t 
 }
 
 // ---- entropy --------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) entropy_bin_kernel(DevMesh3 m, BankView b, double* bins, double* total) {
+// nshared = bins held in the block's dynamic shared memory (the whole mesh, or 0: meshes too large for it add to global
+// memory directly).  The entropy mesh is a few hundred bins: 1e7 atomics on them in L2 took 2.5 ms, privatised 0.1 ms.
+__global__ void __launch_bounds__(256) entropy_bin_kernel(DevMesh3 m, BankView b, double* bins, double* total, int nshared) {
+  extern __shared__ double ent_bins[];
+  for (int i = threadIdx.x; i < nshared; i += blockDim.x) ent_bins[i] = 0.;
+  __syncthreads();
   double tw = 0.;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < b.n; i += (uint64_t)gridDim.x * blockDim.x) {
     const int nx = (int)floor((b.x[i] - m.lowx) / m.dx);
@@ -185,9 +204,14 @@ __global__ void __launch_bounds__(256) entropy_bin_kernel(DevMesh3 m, BankView b
     if (nx >= 0 && nx < m.Nx && ny >= 0 && ny < m.Ny && nz >= 0 && nz < m.Nz) {
       const double w = b.wgt[i];
       tw += w;
-      red_add(bins + ((size_t)(m.Ny * m.Nz) * nx + (size_t)m.Nz * ny + nz), w);
+      const size_t bin = (size_t)(m.Ny * m.Nz) * nx + (size_t)m.Nz * ny + nz;
+      if (nshared) atomicAdd(&ent_bins[bin], w);
+      else red_add(bins + bin, w);
     }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nshared; i += blockDim.x)
+    if (ent_bins[i] != 0.) red_add(bins + i, ent_bins[i]);
   for (int o = 16; o > 0; o >>= 1) tw += __shfl_down_sync(0xffffffffu, tw, o);
   if ((threadIdx.x & 31) == 0 && tw != 0.) atomicAdd(total, tw);
 }

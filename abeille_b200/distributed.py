@@ -336,33 +336,30 @@ class HostBufferLoop:
         out = self.bufs[1 - self.cur]
         out_full = dict(out)
         out_full["wgt2"] = None
-        fis, scores, cn = gpu.transport(self.bank, k_col=self.k_col, converged=converged, capacity=self.cap, out=out_full)
-        m = len(fis["x"])
+        # abl_transport_begin: H2D (streamed behind the kernel), kernels; the fission bank waits on the device while the ranks
+        # exchange what normalize_weights sums (power_iterator.cpp:538-569)
+        m, scores, cn, ws = gpu.transport_begin(self.bank, k_col=self.k_col, converged=converged, capacity=self.cap)
         self.h2d_bytes += n_in * 8 * (8 + sum(1 for k in BANK_U64 if self.bank.get(k) is not None))
-        self.d2h_bytes += m * 8 * 11 + 6 * 8 + 8 * 8
-        # host-side caller steps on the (pinned) numpy arrays, through torch's multi-threaded CPU kernels
-        wt = torch.from_numpy(fis["wgt"])
-        wpos, wneg = _positive_negative_sums(wt) if m else (0.0, 0.0)
-        local = np.concatenate([scores, [cn["real_collisions"], float(m), float(n_in), wpos, wneg]])
+        local = np.concatenate([scores, [cn["real_collisions"], float(m), float(n_in), ws[2], ws[3]]])
         allv = self._gather(local)
         tot = allv.sum(axis=0)
         counts = [int(v) for v in allv[:, 7]]
         self.k_col = tot[0] / self.n_total
         if sum(counts) == 0:
             raise RuntimeError("No fission neutrons were produced.")
-        wt.mul_(self.n_total / (tot[9] - tot[10]))  # normalize_weights, power_iterator.cpp:561-569
         if converged:
             if self.world > 1:
                 for t in self.tally_tensors():
                     dist.all_reduce(t, group=self.group)
             gpu.tallies_record(1.0)
         gpu.tallies_clear()
+        # abl_transport_finish: weights normalised and fresh history ids (power_iterator.cpp:397-399) on the device, D2H
         first = self.global_counter + int(sum(counts[: self.rank]))
-        family = fis["id_c"]
-        if m:  # fresh history ids (power_iterator.cpp:397-399)
-            torch.arange(first, first + m, dtype=torch.int64, out=torch.from_numpy(fis["id_a"].view(np.int64)))
+        out_full.update({"id_c": None})
+        fis = gpu.transport_finish(m, self.n_total / (tot[9] - tot[10]), first, out_full)
+        self.d2h_bytes += m * 8 * 10 + 6 * 8 + 8 * 8 + 4 * 8
         self.bank = {k: fis[k] for k in self.F64_OUT}
-        self.bank.update({"wgt2": None, "id_a": fis["id_a"], "id_b": family, "id_c": None})
+        self.bank.update({"wgt2": None, "id_a": fis["id_a"], "id_b": fis["id_b"], "id_c": None})
         self.global_counter += int(sum(counts))
         self.cur = 1 - self.cur
         self.gens += 1

@@ -328,7 +328,7 @@ def run_b200(args):
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": ep / dt, "unit": "particles/s", "h2d_bytes_per_step": loop.h2d_bytes / loop.gens,
                "d2h_bytes_per_step": loop.d2h_bytes / loop.gens, "steps": args.e2e_steps,
-               "api": "abl_transport (host buffers, pinned) + host-side normalisation as in PowerIterator::run"}
+               "api": "abl_transport_begin + abl_transport_finish (host buffers, pinned): the bank crosses PCIe both ways every generation; normalize_weights and the fresh history ids of PowerIterator::run are applied on the device between the two calls"}
         del loop
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------------------
@@ -409,7 +409,7 @@ def ncu_kernel_metrics(args):
     metrics = ["dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed.sum",
                "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
                "gpu__time_duration.sum"]
-    cmd = [ncu, "--metrics", ",".join(metrics), "--clock-control", "none", "-k", "regex:history_kernel", "-s", "3", "-c", "1", "--csv",
+    cmd = [ncu, "--metrics", ",".join(metrics), "--clock-control", "none", "-k", "regex:history_kernel|event_kernel", "-s", "3", "-c", "1", "--csv",
            sys.executable, os.path.abspath(__file__), "--ncu-child", "--particles", str(args.particles)]
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
@@ -426,7 +426,7 @@ def ncu_kernel_metrics(args):
                 continue
             unit = row[iunit].lower()
             scale = {"kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12, "usecond": 1e-3, "msecond": 1.0, "second": 1e3,
-                     "nsecond": 1e-6}.get(unit, 1.0)
+                     "nsecond": 1e-6, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1.0)
             vals[row[iname]] = v * scale
         if "dram__bytes_read.sum" not in vals:
             return None

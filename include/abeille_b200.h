@@ -217,6 +217,16 @@ int abl_transport(abl_handle h, const abl_bank* bank, const abl_gen_params* para
  * buffers in, fission bank and noise bank out (noise_out->n = capacity, *n_noise = count; wgt2 is written). */
 int abl_transport_noise(abl_handle h, const abl_bank* bank, const abl_gen_params* params, abl_bank* fission_out,
                         uint64_t* n_fission, abl_bank* noise_out, uint64_t* n_noise, double scores[6], uint64_t counters[8]);
+/* abl_transport in two halves, for a caller that normalises the fission bank before it uses it, as PowerIterator::run does
+ * (normalize_weights and the hand-out of fresh history ids, src/power_iterator.cpp:397-399,538-569).  begin: host bank in,
+ * kernels, the fission bank stays on the device; returns its size, the scores and weight_stats = {particles with positive
+ * weight, with negative weight, sum of the positive weights, minus the sum of the negative ones} (what normalize_weights
+ * sums; with MPI / several GPUs the caller adds these over the ranks).  finish: wgt *= weight_factor, id_a = first_history_id
+ * + row, id_b = family id, on the device; then the bank is copied to fission_out (host; x y z ux uy uz E wgt id_a id_b).
+ * Same bytes over PCIe as abl_transport, no pass over the bank on the host. */
+int abl_transport_begin(abl_handle h, const abl_bank* bank, const abl_gen_params* params, uint64_t capacity,
+                        uint64_t* n_fission, double scores[6], uint64_t counters[8], double weight_stats[4]);
+int abl_transport_finish(abl_handle h, double weight_factor, uint64_t first_history_id, abl_bank* fission_out);
 int abl_get_trace(abl_handle h, uint64_t n, abl_trace* out);
 
 /* ---- Transporter::transport, device buffers (bank stays resident in HBM) ---------------------------- */
