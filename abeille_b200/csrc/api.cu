@@ -84,6 +84,7 @@ struct abl_context {
   uint64_t probe_cap = 0;
   int blocks_per_sm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // by tracker and kernel build (plain, track-length, traced)
   int hk_slots[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  int hk_fixed[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   int hk_tables[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // bytes of tables staged in shared memory (0: read from global memory)  // histories per CTA of the staged kernel (by tracker, trace)
   int geo_frames = 1, geo_pads = 2;  // nesting depth of the geometry: coordinate frames / stack pads a history can hold
   int smem_optin = 0, smem_total_sm = 0;  // shared memory a CTA may opt in to / an SM has
@@ -423,14 +424,22 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
   // has the staged kernel only.
   static const bool want_events = getenv("ABEILLE_B200_EVENTS") != nullptr;
   const bool events = TRK != ABL_TRACK_SURFACE && want_events;
-  const HistoryKernel hk = TRK == ABL_TRACK_SURFACE ? history_kernel_surface(TRACE, tle)
-                           : events ? (TRK == ABL_TRACK_DELTA ? event_kernel_delta(TRACE, tle) : event_kernel_carter(TRACE, tle))
-                                    : (TRK == ABL_TRACK_DELTA ? history_kernel_delta(TRACE, tle) : history_kernel_carter(TRACE, tle));
+  const int nf = h->geo_frames < HK_MIN_FRAMES ? HK_MIN_FRAMES : h->geo_frames, np = h->geo_pads;
+  // the build with the column shape compiled in when the geometry has that nesting depth (and the shared memory holds a
+  // history per thread: checked below, remembered in hk_fixed)
+  int& slots = h->hk_slots[TRK][TRACE ? 2 : (tle ? 1 : 0)];
+  int& fixed_state = h->hk_fixed[TRK][TRACE ? 2 : (tle ? 1 : 0)];  // 0 untried, 1 in use, -1 does not fit
+  static const bool no_fixed = getenv("ABEILLE_B200_NO_FIXED_SHAPE") != nullptr;
+  const bool fixed = !TRACE && !events && !no_fixed && nf == HK_FIXED_NF && np == HK_FIXED_NP && fixed_state >= 0;
+  auto pick = [&](bool fx) {
+    return TRK == ABL_TRACK_SURFACE ? history_kernel_surface(TRACE, tle, fx)
+           : events ? (TRK == ABL_TRACK_DELTA ? event_kernel_delta(TRACE, tle) : event_kernel_carter(TRACE, tle))
+                    : (TRK == ABL_TRACK_DELTA ? history_kernel_delta(TRACE, tle, fx) : history_kernel_carter(TRACE, tle, fx));
+  };
+  HistoryKernel hk = pick(fixed);
   TransportKernel kern = hk.fn;
   const int threads = hk.threads;
   int& bps = h->blocks_per_sm[TRK][TRACE ? 2 : (tle ? 1 : 0)];
-  int& slots = h->hk_slots[TRK][TRACE ? 2 : (tle ? 1 : 0)];
-  const int nf = h->geo_frames < HK_MIN_FRAMES ? HK_MIN_FRAMES : h->geo_frames, np = h->geo_pads;
   const unsigned slot_bytes = hk_slot_bytes(nf, np, TRACE);
   if (bps == 0) {
     // as many histories per CTA as the shared memory holds (a multiple of 32, at most one per history thread); two CTAs
@@ -463,6 +472,11 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
       h->error = "geometry nesting too deep for the staged history kernel's shared memory";
       return ABL_ERR_GEOMETRY;
     }
+    if (fixed && sl != hk.fixed_slots) {  // the fixed-shape build needs exactly its slot count: use the general one
+      fixed_state = -1;
+      return launch_transport<TRK, TRACE>(h, A, n, s);
+    }
+    if (fixed) fixed_state = 1;
     slots = sl;
     const size_t smem = hk.fixed_bytes + (size_t)(stage ? tables : 0) + (size_t)slot_bytes * (size_t)sl;
     ABL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -2,8 +2,10 @@
 // is its own translation unit).
 #include "kernel_entry.h"
 namespace abl {
-HistoryKernel history_kernel_delta(bool trace, bool tle) {
+HistoryKernel history_kernel_delta(bool trace, bool tle, bool fixed) {
   if (trace) return history_kernel_traced(ABL_TRACK_DELTA);
+  if (fixed && !tle) return HK_THIS_UNIT_FIXED((history_kernel<ABL_TRACK_DELTA, false, false, HK_FIXED_NF, HK_FIXED_NP, HK_HIST>), HK_FIXED_NF, HK_FIXED_NP);
+  if (fixed) return HK_THIS_UNIT_FIXED((history_kernel<ABL_TRACK_DELTA, false, true, HK_FIXED_NF, HK_FIXED_NP, HK_HIST>), HK_FIXED_NF, HK_FIXED_NP);
   if (tle) return HK_THIS_UNIT((history_kernel<ABL_TRACK_DELTA, false, true>));
   return HK_THIS_UNIT((history_kernel<ABL_TRACK_DELTA, false, false>));
 }

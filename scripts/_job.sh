@@ -1,7 +1,7 @@
-set -x
 export ABEILLE_B200_KERNEL_TIMEOUT_S=30
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/t3b_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/t3b_pytest.log
-tail -12 gpurun_out/t3b_pytest.log
-( time timeout 900 python bench.py > gpurun_out/t3b_bench_n1.json 2> gpurun_out/t3b_bench.err ) 2>&1 | tail -3
-cat gpurun_out/t3b_bench_n1.json
-tail -3 gpurun_out/t3b_bench.err
+for mode in fixed general fixed general; do
+  if [ $mode = general ]; then export ABEILLE_B200_NO_FIXED_SHAPE=1; else unset ABEILLE_B200_NO_FIXED_SHAPE; fi
+  timeout 300 python bench.py --no-e2e --no-cpu --no-ncu 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$mode', 'value %.4g ms/step %.2f kernel_ms %.2f share %.3f'%(d['value'], d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['kernel_share_of_step']))"
+done
+unset ABEILLE_B200_NO_FIXED_SHAPE
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
