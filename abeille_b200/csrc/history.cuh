@@ -338,6 +338,7 @@ struct HKFixed {  // the fixed part of the dynamic shared memory; the per-histor
   unsigned bq_head[HK_SERVICE_WARPS], fq_head[HK_SERVICE_WARPS];
   volatile unsigned bq_tail[HK_SERVICE_WARPS], fq_tail[HK_SERVICE_WARPS];
   volatile int done;
+  int groups_done;
   unsigned long long deadline_ns;  // %globaltimer value at which the watchdog fires
   volatile int abort;  // the watchdog fired: every loop of the CTA winds down (a kernel must never spin forever)
   unsigned rare[RC_N];
@@ -352,7 +353,11 @@ extern __shared__ __align__(16) unsigned char hk_shared_raw[];
 // ---- the per-history columns -------------------------------------------------------------------------------------------------
 // 8-byte columns: frame[a][f] (3 NF), then r u rb (3 each), w, d_coll, E, rng, ptile[i] (NP), [trace: hash];
 // 4-byte columns: pinfo[i] (NP), then the HI_* fields below.  S = slots (histories) of the CTA.
+#ifdef HK_TEST_ALIAS_RB  // (occupancy experiment only: the birth position shares the position's columns -- wrong migration area)
+enum { HD_R = 0, HD_U = 3, HD_RB = 0, HD_W = 6, HD_DC = 7, HD_E = 8, HD_RNG = 9, HD_PT = 10 };
+#else
 enum { HD_R = 0, HD_U = 3, HD_RB = 6, HD_W = 9, HD_DC = 10, HD_E = 11, HD_RNG = 12, HD_PT = 13 };
+#endif
 enum { HI_IDX = 0, HI_DAU, HI_TOK, HI_CELL, HI_MAT, HI_HMAT, HI_G, HI_NPNF, HI_BDONE, HI_NSEC, HI_N, HI_NFL = HI_N, HI_NRE, HI_NVI, HI_N_TRACE };
 __host__ __device__ inline unsigned hk_cols8(int NF, int NP, bool trace) { return 3u * NF + HD_PT + NP + (trace ? 1u : 0u); }
 __host__ __device__ inline unsigned hk_cols4(int NP, bool trace) { return (unsigned)NP + (trace ? HI_N_TRACE : HI_N); }
@@ -480,6 +485,20 @@ __device__ __forceinline__ unsigned long long hk_now_ns() {
 
 // barrier 1: the history threads only (the service warps never join it)
 __device__ __forceinline__ void hist_sync() { asm volatile("bar.sync 1, %0;" ::"n"(HK_HIST) : "memory"); }
+// the vote of ONE group of history warps (HK_VOTE_GROUPS > 1: the history warps keep lock step within a group only -- fewer
+// warps wait for the slowest one; the groups drift apart and share fewer instruction-cache lines)
+#ifndef HK_VOTE_GROUPS
+#define HK_VOTE_GROUPS 1
+#endif
+__device__ __forceinline__ bool hist_all_group(bool pred, int barrier_id, int nthreads) {
+  int r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbar.red.and.pred q, %2, %3, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+      : "=r"(r)
+      : "r"((int)pred), "r"(barrier_id), "r"(nthreads)
+      : "memory");
+  return r != 0;
+}
 __device__ __forceinline__ bool hist_all(bool pred) {
   int r;
   asm volatile(
@@ -757,6 +776,7 @@ __global__ void __launch_bounds__(HK_THREADS, HK_MINBLOCKS) history_kernel(const
   }
   if (threadIdx.x == 0) {
     S.done = 0;
+    S.groups_done = 0;
     S.abort = 0;
     S.deadline_ns = hk_now_ns() + A.timeout_ns;
     S.leak = S.leak_mig = 0.;
@@ -797,7 +817,13 @@ __global__ void __launch_bounds__(HK_THREADS, HK_MINBLOCKS) history_kernel(const
     const int sw = wid % HK_SERVICE_WARPS;
     int phase = PH_DEAD;
     int need = -1;  // pending (re-)descent: first bad pad, 0 = full lookup from the root, -1 = none
-    bool exhausted = (int)threadIdx.x >= hk_slots;  // threads beyond the CTA's slots (deep geometries) own no history
+    bool exhausted = (int)threadIdx.x >= hk_slots;
+#if HK_VOTE_GROUPS > 1
+    constexpr int NHW = HK_HIST / 32;  // history warps, split into HK_VOTE_GROUPS runs of consecutive warps
+    const int vgrp = wid * HK_VOTE_GROUPS / NHW;
+    const int vgrp_first = (vgrp * NHW + HK_VOTE_GROUPS - 1) / HK_VOTE_GROUPS;
+    const int vgrp_threads = 32 * ((((vgrp + 1) * NHW + HK_VOTE_GROUPS - 1) / HK_VOTE_GROUPS) - vgrp_first);
+#endif  // threads beyond the CTA's slots (deep geometries) own no history
     bool have_ticket = false;
     const uint64_t N = A.bank.n;
     // (TLE = false: a build without the track-length scorer, for runs that have no track-length tally to score)
@@ -875,7 +901,11 @@ __global__ void __launch_bounds__(HK_THREADS, HK_MINBLOCKS) history_kernel(const
 #if HK_VOTE_EVERY > 1
       if ((iter % HK_VOTE_EVERY) == 0)
 #endif
+#if HK_VOTE_GROUPS > 1
+      if (hist_all_group(phase == PH_DEAD && !have_ticket, 1 + vgrp, vgrp_threads)) break;
+#else
       if (hist_all(phase == PH_DEAD && !have_ticket)) break;
+#endif
 
       HAcc acc;
       acc.k_col = acc.k_abs = acc.mig = acc.k_trk = 0.;
@@ -1238,8 +1268,12 @@ __global__ void __launch_bounds__(HK_THREADS, HK_MINBLOCKS) history_kernel(const
       }
     }
     // every history of this CTA is finished and nothing more will be posted: release the service warps
+#if HK_VOTE_GROUPS > 1
+    if ((int)threadIdx.x == 32 * vgrp_first && atomicAdd(&S.groups_done, 1) == HK_VOTE_GROUPS - 1) S.done = 1;
+#else
     hist_sync();
     if (threadIdx.x == 0) S.done = 1;
+#endif
   }
 
   // ---- the per-warp sums: one atomic per block --------------------------------------------------------------------------
