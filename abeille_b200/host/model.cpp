@@ -478,6 +478,9 @@ MeshTallySpec make_mesh_tally(const Node& t, const Settings& st) {
   const auto it = qmap.find(q);
   if (it == qmap.end()) fatal_error("Unknown tally quantity \"" + q + "\".");
   f.quantity = it->second;
+  m.quantity_str = q;
+  m.estimator_str = est;
+  if (f.quantity == ABL_Q_MT && t["mt"] && t["mt"].IsScalar()) m.mt = t["mt"].as_int();
   const bool source_q = f.quantity >= ABL_Q_SOURCE;
   if ((f.estimator == ABL_EST_SOURCE) != source_q) fatal_error("Quantity \"" + q + "\" is not valid for estimator \"" + est + "\".");
   if (f.estimator == ABL_EST_TRACK_LENGTH && f.quantity == ABL_Q_MT) fatal_error("Track-length tallies score flux-like quantities only.");

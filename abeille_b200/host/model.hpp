@@ -84,6 +84,9 @@ struct MeshTallySpec {
   std::string name;
   abl_mesh_tally flat{};
   std::vector<double> energy_bounds;
+  // what MeshTally::write_tally stores as attributes beside the arrays (src/mesh_tally.cpp:154-206)
+  std::string quantity_str, estimator_str;
+  long long mt = 0;
 };
 
 struct MeshSpec {

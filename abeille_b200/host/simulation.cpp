@@ -534,6 +534,36 @@ void PowerIterator::write_results(const std::string& dir) const {
     write_npy(dir + "/" + problem.tallies[static_cast<size_t>(t)].name + "_avg.npy", buf, shape);
     check(h, abl_tally_fetch(h, t, 3, buf.data()), "abl_tally_fetch");
     write_npy(dir + "/" + problem.tallies[static_cast<size_t>(t)].name + "_std.npy", buf, shape);
+    // the attributes MeshTally::write_tally stores with the arrays (src/mesh_tally.cpp:166-190): mesh coordinates, energy
+    // bounds, quantity, estimator (HDF5 attributes in the reference; here one .npy per array and a text file)
+    const MeshTallySpec& spec = problem.tallies[static_cast<size_t>(t)];
+    const char* axis[3] = {"x", "y", "z"};
+    for (int a = 0; a < 3; a++) {
+      const uint64_t n = static_cast<uint64_t>(spec.flat.N[a]);
+      const double d = (spec.flat.hi[a] - spec.flat.low[a]) / static_cast<double>(n);
+      std::vector<double> bounds(n + 1);
+      for (uint64_t i = 0; i <= n; i++) bounds[i] = (static_cast<double>(i) * d) + spec.flat.low[a];
+      write_npy(dir + "/" + spec.name + "_" + axis[a] + "-bounds.npy", bounds, {n + 1});
+    }
+    write_npy(dir + "/" + spec.name + "_energy-bounds.npy", spec.energy_bounds, {spec.energy_bounds.size()});
+    std::ofstream attrs(dir + "/" + spec.name + "_attributes.txt");
+    if (!attrs) fatal_error("cannot write the attributes of tally " + spec.name);
+    attrs << "quantity: " << spec.quantity_str << "\n";
+    if (spec.quantity_str == "mt") attrs << "mt: " << spec.mt << "\n";
+    attrs << "estimator: " << spec.estimator_str << "\n";
+  }
+  // the final source bank, one row per particle: x y z ux uy uz E wgt wgt2 (Simulation::write_source,
+  // src/simulation.cpp:137-175)
+  {
+    std::vector<double> src(bank_.size() * 9);
+    for (size_t i = 0; i < bank_.size(); i++) {
+      const Particle& p = bank_[i];
+      double* row = &src[i * 9];
+      row[0] = p.r().x; row[1] = p.r().y; row[2] = p.r().z;
+      row[3] = p.u().x; row[4] = p.u().y; row[5] = p.u().z;
+      row[6] = p.E(); row[7] = p.wgt(); row[8] = p.wgt2();
+    }
+    write_npy(dir + "/source.npy", src, {static_cast<uint64_t>(bank_.size()), 9});
   }
 }
 

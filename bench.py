@@ -34,6 +34,25 @@ DECK = os.path.join(ROOT, "tests", "decks", "c5g7_delta_collision_fullmesh.yaml"
 METRIC = "active particles/sec (+ collisions/sec), C5G7 delta-tracking"
 WORKLOAD = "c5g7 7-group delta-tracking k-eigenvalue, collision-estimator flux mesh tally 1224x1224x10x7"
 
+# The other configurations of BASELINE.json (`--config N`; the default, 2, is the contract's bench line).  Each prints one
+# JSON line of the same shape for its own deck (resident leg only) and runs its parity tests (tests/, the only place besides
+# the CPU legs that uses the oracle) as a subprocess in the same run.
+CONFIGS = {
+    1: {"deck": "PUa-1-0-IN.yaml", "particles": 1_000_000, "kernel": "history_kernel<surface>",
+        "metric": "active particles/sec (+ collisions/sec), Sood PUa-1-0-IN surface-tracking",
+        "workload": "Sood PUa-1-0-IN one-group infinite medium, surface tracking (k_inf = 2.612903)",
+        "tests": ["tests/test_gpu_parity.py", "-k", "PUa-1-0-IN or sood"]},
+    3: {"deck": "ref_sqr_c5g7_surface_tl.yaml", "particles": 2_000_000, "kernel": "history_kernel<surface, track-length>",
+        "metric": "active particles/sec (+ collisions/sec), C5G7 surface-tracking + track-length tally",
+        "workload": "ref_sqr c5g7 7-group surface-tracking k-eigenvalue, track-length flux mesh tally 102x102x5x7",
+        "tests": ["tests/test_gpu_parity.py", "tests/test_gpu_reference_golden.py", "-k", "surface or ref_sqr"]},
+    4: {"deck": "c5g7_carter_cancel.yaml", "particles": 12_500_000, "kernel": "history_kernel<carter>",
+        "metric": "active particles/sec (+ collisions/sec), C5G7 carter-tracking + approximate mesh cancellation",
+        "workload": "c5g7 7-group carter tracking with an under-estimated sampling cross section, approximate mesh weight "
+                    "cancellation (170x170x765 bins, dense-bin all-reduce across ranks), 1.25e7 particles per generation per GPU",
+        "tests": ["tests/test_gpu_parity.py", "-k", "carter or cancel"]},
+}
+
 
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -43,9 +62,9 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _write_deck(nparticles_total, path):
+def _write_deck(nparticles_total, path, deck_path=None):
     import yaml
-    with open(DECK) as f:
+    with open(deck_path or DECK) as f:
         deck = yaml.safe_load(f)
     deck["settings"]["nparticles"] = int(nparticles_total)
     with open(path, "w") as f:
@@ -256,10 +275,16 @@ def run_b200(args):
     import abeille_b200 as ab
     from abeille_b200.distributed import DistributedPowerIterator, HostBufferLoop
 
+    cfg = CONFIGS.get(args.config)
+    metric, workload, kernel_name = (cfg["metric"], cfg["workload"], cfg["kernel"]) if cfg else (METRIC, WORKLOAD, "history_kernel<delta>")
+    if cfg and args.particles == 10_000_000:
+        args.particles = cfg["particles"]
+    if cfg:  # the other configurations: the resident leg and their parity tests
+        args.no_e2e = args.no_cpu = args.no_ncu = args.no_ranks_check = True
     n_local = args.particles
     n_total = n_local * world
     td = tempfile.mkdtemp()
-    deck = _write_deck(n_total, os.path.join(td, f"bench_{rank}.yaml"))
+    deck = _write_deck(n_total, os.path.join(td, f"bench_{rank}.yaml"), os.path.join(ROOT, "tests", "decks", cfg["deck"]) if cfg else None)
 
     def barrier():
         torch.cuda.synchronize()
@@ -293,7 +318,7 @@ def run_b200(args):
         g = sim.generation(converged=True)
         particles += g["n_in_total"]; collisions += g["real_collisions"]; sites += g["m_total"]; coll_scores += g["coll_scores"]
         local_particles += g["n_in"]; local_coll += g["local_real_collisions"]; local_sites += g["m_pre"]
-        local_scores += g["local_coll_scores"]
+        local_scores += g["local_coll_scores"] + g["local_tl_bins"]
         flights += g["local_flights"]
         kernel_ms.append(sim.gpu.last_transport_kernel()["ms"])
     e1.record()
@@ -354,16 +379,16 @@ def run_b200(args):
         rcheck = ranks_check(world, rank, local, dev)
 
     if rank == 0:
-        out = {"metric": METRIC, "value": particles / (ms * 1e-3), "unit": "particles/s", "n_gpus": world, "steps": args.steps,
+        out = {"metric": metric, "value": particles / (ms * 1e-3), "unit": "particles/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "collisions_per_s": collisions / (ms * 1e-3),
-               "config": {"workload": WORKLOAD, "particles_per_generation_per_gpu": n_local, "particles_per_generation": n_total,
+               "config": {"workload": workload, "particles_per_generation_per_gpu": n_local, "particles_per_generation": n_total,
                           "tally_bins": tally_bins, "source": "deck box source, then the fission source after the warm-up generations",
-                          "l2": "inputs larger than L2 (bank 96 B x 1e7 = 0.96 GB, tally mesh 0.84 GB)", "k_col": k_col,
+                          "l2": "inputs larger than L2 (bank 96 B x %.3g = %.2f GB)" % (n_local, 96e-9 * n_local), "k_col": k_col,
                           "collisions_per_particle": collisions / max(particles, 1)},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": prof["dram_bytes"] if prof else None, "kernel": "history_kernel<delta>", "kernel_ms": k_ms,
+                            "traffic": prof["dram_bytes"] if prof else None, "kernel": kernel_name, "kernel_ms": k_ms,
                             "profile": prof, "flights_per_launch": flights / args.steps,
                             "warp_instructions_per_flight": (prof["warp_instructions"] / (flights / args.steps))
                             if prof and prof.get("warp_instructions") and flights else None,
@@ -372,6 +397,13 @@ def run_b200(args):
                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         if rcheck is not None:
             out["ranks_check"] = rcheck
+        if cfg and not args.no_parity:  # the configuration's parity tests, in the same run (rank 0's GPU)
+            t0 = time.time()
+            r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x"] + cfg["tests"], cwd=ROOT, capture_output=True,
+                               text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=str(local)))
+            tail = [l for l in r.stdout.strip().splitlines() if l.strip()][-1:] or [""]
+            out["parity"] = {"passed": r.returncode == 0, "summary": tail[0], "seconds": time.time() - t0,
+                             "what": "pytest -m gpu " + " ".join(cfg["tests"]) + " (bit-exact against the oracle / the reference's golden vectors)"}
     import ctypes
     sys.stdout.flush()
     ctypes.CDLL(None).fflush(None)
@@ -494,6 +526,9 @@ def main():
     ap.add_argument("--no-ncu", action="store_true", help="skip the ncu capture of one kernel launch (roofline.traffic = null)")
     ap.add_argument("--no-ranks-check", action="store_true", help="N > 1: skip the sharded-vs-1-rank consistency run")
     ap.add_argument("--ncu-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4],
+                    help="BASELINE.json configuration: 2 = the bench line (default); 1, 3, 4 = the other k-eigenvalue configurations")
+    ap.add_argument("--no-parity", action="store_true", help="--config 1|3|4: skip the configuration's parity tests")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -428,6 +428,20 @@ def test_results_written_as_npy(ab, tmp_path):
     std = np.load(out / "flux_pin_std.npy")
     assert avg.shape == (7, 51, 51, 1) and std.shape == avg.shape
     assert np.array_equal(avg, gpu.tally(0, "avg")) and np.load(out / "kcol.npy").shape == (4,)
+    # what MeshTally::write_tally stores beside the arrays (src/mesh_tally.cpp:166-190) and Simulation::write_source's
+    # [N, 9] source array (src/simulation.cpp:137-175)
+    xb = np.load(out / "flux_pin_x-bounds.npy")
+    deck = load_deck("c5g7_delta_collision.yaml")
+    t = [m for m in deck["tallies"] if m["name"] == "flux_pin"][0]
+    assert xb.shape == (52,) and xb[0] == t["low"][0] and abs(xb[-1] - t["hi"][0]) < 1e-12
+    assert np.load(out / "flux_pin_z-bounds.npy").shape == (2,)
+    assert np.array_equal(np.load(out / "flux_pin_energy-bounds.npy"), np.array(t["energy-bounds"], dtype=float))
+    attrs = dict(l.split(": ") for l in (out / "flux_pin_attributes.txt").read_text().splitlines())
+    assert attrs == {"quantity": t["quantity"], "estimator": t.get("estimator", "collision")}
+    src = np.load(out / "source.npy")
+    assert src.ndim == 2 and src.shape[1] == 9 and src.shape[0] > 1000
+    assert np.allclose(np.linalg.norm(src[:, 3:6], axis=1), 1.0, atol=1e-12) and np.all(src[:, 8] == 0.0)
+    assert abs(src[:, 7].sum() - 2000.0) < 1e-6  # the bank leaves the last generation normalised to nparticles
 
 
 def test_full_size_generation_properties(ab, tmp_path):
