@@ -60,6 +60,8 @@ def gather_vector(vec: np.ndarray, world: int, device, group=None) -> np.ndarray
     """all_gather of a small fp64 vector -> [world, len] on the host."""
     if world == 1:
         return vec[None, :].copy()
+    if dist.get_backend(group) == "gloo":  # (gloo gathers host tensors only: the CPU tests, and two ranks sharing one GPU)
+        device = torch.device("cpu")
     t = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64)).to(device)
     out = torch.empty(world * len(vec), dtype=torch.float64, device=device)
     dist.all_gather_into_tensor(out, t, group=group)

@@ -144,3 +144,151 @@ class NoiseSimulation:
 
     def close(self):
         self.gpu.close()
+
+
+class DistributedNoiseSimulation(NoiseSimulation):
+    """The noise simulation sharded over the ranks of a torch.distributed group, one process per GPU (the reference shards
+    it over MPI ranks the same way: src/noise.cpp:312-372,425-559 with `mpi::Allreduce_sum` / `sync_banks`,
+    src/simulation.cpp:84-111).  Every bank -- the power-iteration bank, the noise-source bank, the noise fission banks of
+    the inner generations -- is split into contiguous slices in rank order, and history ids are handed out by an exclusive
+    scan over the ranks' counts, so the global order and every history's RNG stream are those of a one-rank run: the integer
+    outcomes (bank sizes, noise generations per batch, particles per generation) do not depend on the number of GPUs; sums
+    (k, tallies, cancellation bins) differ in rounding order only.  Per generation the ranks exchange one small vector
+    (all_gather), with regional cancellation the dense cancellation bins (all_reduce), and once per noise batch the tally
+    arrays (all_reduce before MeshTally::record_generation)."""
+
+    def __init__(self, deck_path: str, device: int = 0, group=None):
+        import torch
+        import torch.distributed as dist
+        super().__init__(deck_path, device)
+        self._torch, self._dist = torch, dist
+        self.group = group
+        self.use_dist = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.use_dist else 0
+        self.world = dist.get_world_size(group) if self.use_dist else 1
+        self.tdev = torch.device("cuda", device)
+        self._cancel_views = None
+        self._tally_views = None
+        self._noise_counts = [0] * self.world
+
+    # ---- collectives ----
+    def _gather(self, values) -> np.ndarray:
+        from .distributed import gather_vector
+        return gather_vector(np.asarray(values, dtype=np.float64), self.world, self.tdev, self.group)
+
+    def _views(self):
+        from .distributed import _DevPtr
+        if self._tally_views is None:
+            self._tally_views = []
+            for t in range(self.gpu.ntallies()):
+                ptr, n = self.gpu.tally_device_ptr(t, 0)
+                self._tally_views.append(self._torch.as_tensor(_DevPtr(ptr, n), device=self.tdev))
+        return self._tally_views
+
+    def _cancel(self, bank, m: int):
+        """Regional cancellation over the GLOBAL bank (noise.cpp:387,449,649-653): dense bins, one all_reduce per bin array."""
+        from .distributed import _DevPtr
+        gpu, torch = self.gpu, self._torch
+        if self.world == 1:
+            if m:
+                gpu.cancel_device(bank, m)
+            return
+        if m:
+            gpu.cancel_accumulate_device(bank, m)
+        if self._cancel_views is None:
+            sums, count, nb = gpu.cancel_bins_device()
+            self._cancel_views = [torch.as_tensor(_DevPtr(p, nb), device=self.tdev) for p in sums]
+            self._cancel_views.append(torch.as_tensor(_DevPtr(count, nb, "<i4"), device=self.tdev))
+        torch.cuda.current_stream().synchronize()
+        for t in self._cancel_views:
+            self._dist.all_reduce(t, group=self.group)
+        if m:
+            gpu.cancel_apply_device(bank, m)
+        for t in self._cancel_views:  # bins only other ranks touched still hold the global sums
+            t.zero_()
+
+    def _reduce_tallies(self):
+        if self.world > 1:
+            self._torch.cuda.current_stream().synchronize()
+            for t in self._views():
+                self._dist.all_reduce(t, group=self.group)
+
+    # ---- the driver, rank-local slices ----
+    def initialize(self):
+        from .distributed import even_split
+        counts, bounds = even_split(self.nparticles, self.world)
+        self.gpu.sample_source_device(self.bank, counts[self.rank], int(bounds[self.rank]))
+        self.n_bank = counts[self.rank]
+        self.history_counter = self.nparticles
+        self._use_state = True
+
+    def power_iteration(self, sample_noise: bool) -> int:
+        g = self.gpu
+        m = n_noise = 0
+        scores = np.zeros(6)
+        if self.n_bank:
+            m, n_noise, scores, _ = g.transport_noise_device(
+                self.bank, self.n_bank, self.next, self.noise_bank if sample_noise else None, k_col=self.k_col, keff=self.keff,
+                converged=self.converged, noise=False, sample_noise=sample_noise, use_rng_state=self._use_state)
+        self._use_state = False
+        allv = self._gather([scores[0], float(m), float(n_noise)])
+        tot = allv.sum(axis=0)
+        counts = [int(v) for v in allv[:, 1]]
+        if sum(counts) == 0:
+            raise RuntimeError("No fission neutrons were produced.")
+        self.k_col = tot[0] / self.nparticles
+        g.tallies_clear()
+        if self.cancel_pi:
+            self._cancel(self.next, m)
+        ws = g.weight_stats_device(self.next, m) if m else np.zeros(4)
+        wall = self._gather([ws[2], ws[3]]).sum(axis=0)
+        if m:
+            g.scale_weights_device(self.next, m, self.nparticles / (wall[0] - wall[1]))
+            g.to_particles_device(self.next, m, self.history_counter + int(sum(counts[: self.rank])))
+        self.history_counter += int(sum(counts))
+        self.bank, self.next = self.next, self.bank
+        self.n_bank = m
+        self.k_history.append(self.k_col)
+        self._noise_counts = [int(v) for v in allv[:, 2]]
+        return n_noise
+
+    def noise_simulation(self, n_noise: int):
+        g = self.gpu
+        original_kcol = self.k_col
+        counts = self._noise_counts
+        n_total = int(sum(counts))
+        avg_wgt_mag = 1.0
+        if self.normalize_noise_source and n_total:
+            mag = g.weight_magnitude_device(self.noise_bank, n_noise) if n_noise else 0.0
+            avg_wgt_mag = float(self._gather([mag]).sum()) / float(n_total)
+            if n_noise:
+                g.divide_weights_device(self.noise_bank, n_noise, avg_wgt_mag)
+        if self.converged and n_noise:
+            g.score_source_device(self.noise_bank, n_noise, noise_source=True)
+        cur, nxt = self.noise_bank, self.nb_a
+        if n_noise:
+            g.to_particles_device(cur, n_noise, self.history_counter + int(sum(counts[: self.rank])))
+        self.history_counter += n_total
+        n, n_glob, gen, total = n_noise, n_total, 0, 0
+        while n_glob != 0:
+            gen += 1
+            total += n_glob
+            m = 0
+            if n:
+                m, _, _, _ = g.transport_noise_device(cur, n, nxt, None, k_col=self.k_col, keff=self.keff,
+                                                      converged=self.converged, noise=True, sample_noise=False)
+            mc = [int(v) for v in self._gather([float(m)])[:, 0]]
+            m_glob = int(sum(mc))
+            if self.cancel_noise and gen <= self.n_cancel_noise_gens and m_glob:
+                self._cancel(nxt, m)
+            if m:
+                g.to_particles_device(nxt, m, self.history_counter + int(sum(mc[: self.rank])))
+            self.history_counter += m_glob
+            cur, nxt = nxt, (self.nb_b if nxt is self.nb_a else self.nb_a)
+            n, n_glob = m, m_glob
+        self._reduce_tallies()          # mpi::Reduce_sum of the generation's scores before record_generation
+        g.tallies_record(avg_wgt_mag)
+        g.tallies_clear()
+        self.k_col = original_kcol
+        self.noise_generations.append(gen)
+        self.noise_particles.append(total)

@@ -72,6 +72,37 @@ def _write_deck(nparticles_total, path, deck_path=None):
     return path
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Run this process on the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host memory is allocated (first touch
+    puts the pages on that node): with 8 ranks on a two-socket host the bank copies (1.7 GB per rank and generation) otherwise
+    cross the socket interconnect for half the GPUs.  Returns a short description for the bench line, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # nvml pads the domain to 8 digits, sysfs uses 4
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"gpu": gpu_index, "numa_node": node, "cpus": len(allowed)}
+    except Exception:  # noqa: BLE001 -- placement is an optimisation, never a reason to fail the bench
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -254,11 +285,12 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 backend has no CPU fallback)")
+    numa = bind_to_gpu_numa_node(local) if not args.no_numa else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # torchrun exports OMP_NUM_THREADS=1; the e2e leg's caller-side steps (PowerIterator::normalize_weights on the host
     # bank) are CPU work that the reference spreads over the host's cores: give every rank its share
-    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
+    torch.set_num_threads(max(1, min(len(os.sched_getaffinity(0)), (os.cpu_count() or 1) // max(world, 1))))
     # NCCL prints its version banner on stdout when the first communicator is made (N > 1): the file descriptor is pointed at
     # stderr for the whole run and restored for the one JSON line
     sys.stdout.flush()
@@ -394,7 +426,7 @@ def run_b200(args):
                             if prof and prof.get("warp_instructions") and flights else None,
                             "grid": [kinfo["grid"], kinfo["block"]], "algorithmic_bytes_per_launch": alg_bytes,
                             "peak_source": peak_src, "kernel_share_of_step": k_ms * args.steps / ms},
-               "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+               "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "host_placement": numa}
         if rcheck is not None:
             out["ranks_check"] = rcheck
         if cfg and not args.no_parity:  # the configuration's parity tests, in the same run (rank 0's GPU)
@@ -529,6 +561,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4],
                     help="BASELINE.json configuration: 2 = the bench line (default); 1, 3, 4 = the other k-eigenvalue configurations")
     ap.add_argument("--no-parity", action="store_true", help="--config 1|3|4: skip the configuration's parity tests")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

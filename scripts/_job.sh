@@ -1,6 +1,3 @@
 export ABEILLE_B200_KERNEL_TIMEOUT_S=60
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for c in 1 3 4; do
-  timeout 600 python bench.py --config $c --steps 4 --warmup 3 > gpurun_out/t5a_bench_config$c.json 2> gpurun_out/t5a_bench_config$c.err
-  python -c "import json; d=json.load(open('gpurun_out/t5a_bench_config$c.json')); print('config $c', 'value %.4g ms/step %.2f kernel_ms %.2f coll/part %.1f k %.5f'%(d['value'], d['ms_per_step'], d['roofline']['kernel_ms'], d['config']['collisions_per_particle'], d['config']['k_col']), d.get('parity'))" || tail -5 gpurun_out/t5a_bench_config$c.err
-done
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 8 --warmup 4 > gpurun_out/t5b_bench_n8.json 2> gpurun_out/t5b_bench_n8.err
+cat gpurun_out/t5b_bench_n8.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('N=8 value %.4g ms/step %.2f e2e %.4g ranks_check %s'%(d['value'], d['ms_per_step'], d['e2e']['value'], d.get('ranks_check')))" || tail -20 gpurun_out/t5b_bench_n8.err

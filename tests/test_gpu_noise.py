@@ -146,3 +146,62 @@ def test_cpp_adapter_noise_bank_matches_device_entry_point(ab, oracle_api, tmp_p
     ofis2, _, _ = orc.transport_noise({k: (v.copy() if v is not None else None) for k, v in cur.items()}, True, False)
     gfis2, _ = gpu.transport_vectors_noise(cur, k_col=1.0, keff=keff, noise=True)
     _assert_banks_equal(gfis2, ofis2, "adapter noise fission bank")
+
+
+# ---- the noise simulation sharded over two ranks (BASELINE config 5: "sharded across 8 x B200") ---------------------------------
+# Two processes, one rank each, both on GPU 0 with the gloo backend (NCCL refuses two ranks on one device; on the multi-GPU
+# box the same class runs over NCCL): bank slices, history ids and the collectives are exactly those of a two-GPU run.
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _sharded_noise_worker(rank, world, port, path, q):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from abeille_b200.noise import DistributedNoiseSimulation
+        sim = DistributedNoiseSimulation(path, 0)
+        got = sim.run()
+        out = {"k_col": got["k_col"], "noise_generations": got["noise_generations"], "noise_particles": got["noise_particles"],
+               "history_counter": sim.history_counter, "tallies": [sim.tally(t, "avg") for t in range(sim.gpu.ntallies())]}
+        sim.close()
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("deck", ["noise_oscillation.yaml"])
+def test_noise_run_sharded_over_two_ranks_matches_one_rank(ab, tmp_path, deck):
+    import torch.multiprocessing as mp
+    from abeille_b200.noise import NoiseSimulation
+    path = deck_path(deck)
+    one = NoiseSimulation(path, 0)
+    ref = one.run()
+    ref_tallies = [one.tally(t, "avg") for t in range(one.gpu.ntallies())]
+    ref_counter = one.history_counter
+    one.close()
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_noise_worker, args=(r, world, port, path, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        got = res[r]
+        # integer outcomes do not depend on the number of ranks
+        assert got["noise_generations"] == ref["noise_generations"] and got["noise_particles"] == ref["noise_particles"]
+        assert got["history_counter"] == ref_counter
+        assert np.allclose(got["k_col"], ref["k_col"], rtol=1e-12)
+        for t, (a, b) in enumerate(zip(got["tallies"], ref_tallies)):
+            scale = np.abs(b).max()
+            assert np.allclose(a, b, rtol=1e-7, atol=1e-9 * scale), f"rank {r} tally {t}: max diff {np.abs(a - b).max()} of {scale}"
