@@ -51,8 +51,14 @@ def rebalance_bank(src: dict, dst: dict, keys, counts, rank: int, group=None) ->
     backend (NCCL on the GPUs, gloo in the CPU tests); returns this rank's new count."""
     send, recv = rebalance_plan(counts, rank)
     m_new = int(sum(recv))
+    via_host = dist.get_backend(group) == "gloo"  # (gloo exchanges host tensors only: two test ranks sharing one GPU)
     for k in keys:
-        dist.all_to_all_single(dst[k][:m_new], src[k][: int(sum(send))], recv, send, group=group)
+        if via_host and dst[k].is_cuda:
+            out = torch.empty(m_new, dtype=dst[k].dtype)
+            dist.all_to_all_single(out, src[k][: int(sum(send))].cpu(), recv, send, group=group)
+            dst[k][:m_new].copy_(out)
+        else:
+            dist.all_to_all_single(dst[k][:m_new], src[k][: int(sum(send))], recv, send, group=group)
     return m_new
 
 
