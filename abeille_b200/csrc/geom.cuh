@@ -778,6 +778,94 @@ __device__ inline Boundary cursor_nearest_boundary(const PT& P, const CUR& c, co
   return b;
 }
 
+// Tracker::get_nearest_boundary when the boundary conditions are known to lie further than bc_floor (a certified lower
+// bound of the distance to every vacuum / reflective surface, minus BOUNDRY_TOL: see DevProblem::bc_*).  The reference
+// evaluates the boundary-condition search first and then compares every pad's candidate against it; while the running
+// nearest boundary is still "some boundary condition beyond bc_floor", a candidate below bc_floor wins against it whatever
+// its exact distance is, and from then on the comparisons are the reference's.  When a candidate is not below bc_floor before
+// one was accepted (or there is none) the boundary-condition search is evaluated after all and the comparisons are replayed
+// against its real result; the candidates' distances are computed once either way.  The result is the reference's, bit for
+// bit; the six plane distances (six fp64 divisions) of the boundary-condition search -- up to three times per flight in the
+// reflector -- are evaluated only for flights that end near a boundary condition.
+template <class PT, class CUR>
+__device__ inline Boundary cursor_nearest_boundary_lazy(const PT& P, const CUR& c, const V3& u, double bc_floor) {
+  // every pad's candidate distance first (the expensive part, the same evaluations as the reference's)
+  double cd[ABL_MAX_PADS];
+  int cis[ABL_MAX_PADS];  // cell pads: the surface token the cell reported; lattice pads: 0
+  V3 u_inv{0., 0., 0.};
+  bool have_u_inv = false;
+  for (int it = 0; it < c.np; it++) {
+    const int info = pad_info(c, it);
+    const int type = pad_type(info);
+    cd[it] = ABL_INF;
+    cis[it] = 0;
+    if (type == PAD_LATTICE) {
+      const Lat L = load_lattice(P.universes + pad_index(info));
+      const Tile3 t3 = pad_tile3(c, it);
+      if (!have_u_inv) {
+        u_inv = V3{1. / u.x, 1. / u.y, 1. / u.z};
+        have_u_inv = true;
+      }
+      cd[it] = distance_to_tile_boundary(L, frame_r(c, pad_frame(info)), u_inv, t3.nx, t3.ny, t3.nz);
+    } else if (type == PAD_CELL) {
+      cell_distance(P, pad_index(info), frame_r(c, pad_frame(info)), u, c.token, false, cd[it], cis[it]);
+    }
+  }
+  // the reference's chain of comparisons with the boundary condition still symbolic ("beyond bc_floor")
+  int win = -1;
+  double best = ABL_INF;
+  bool need_bc = false;
+  for (int it = 0; it < c.np && !need_bc; it++) {
+    if (pad_type(pad_info(c, it)) == PAD_UNIVERSE) continue;
+    const double d = cd[it];
+    if (win < 0) {
+      if (d < bc_floor) {
+        win = it;
+        best = d;
+      } else {
+        need_bc = true;
+      }
+    } else if (d < best && fabs(d - best) > ABL_BOUNDRY_TOL) {
+      win = it;
+      best = d;
+    }
+  }
+  Boundary b{ABL_INF, -1, ABL_BC_VACUUM, 0};
+  if (need_bc || win < 0) {  // the boundary conditions can matter: evaluate them and replay the chain against the real value
+    b = cursor_boundary_condition(P, c, u);
+    win = -1;
+    best = b.distance;
+    for (int it = 0; it < c.np; it++) {
+      if (pad_type(pad_info(c, it)) == PAD_UNIVERSE) continue;
+      const double d = cd[it];
+      if (d < best && fabs(d - best) > ABL_BOUNDRY_TOL) {
+        win = it;
+        best = d;
+      }
+    }
+    if (win < 0) return b;
+  }
+  // the winner's description (what the reference fills in whenever a candidate is taken; only the last one survives)
+  const int info = pad_info(c, win);
+  b.distance = best;
+  if (pad_type(info) == PAD_LATTICE) {
+    b.btype = ABL_BC_NORMAL;
+    b.surface_index = -1;
+    b.token = 0;
+  } else {
+    b.token = iabs(cis[win]);
+    b.surface_index = b.token ? b.token - 1 : -1;
+    if (b.surface_index >= 0) {
+      const Surf s = load_surface(P, b.surface_index);
+      b.btype = s.bc;
+      if (surf_sign(s, frame_r(c, pad_frame(info)), u) < 0) b.token *= -1;
+    } else {
+      b.btype = ABL_BC_NORMAL;
+    }
+  }
+  return b;
+}
+
 // The cursor operations as real function calls on the geometry tables alone: the per-lane kernel (transport.cuh) calls
 // each of them from several places, and inlined copies made it 230 KB of SASS -- ncu showed it waiting for instructions
 // (21 stall cycles per issue "no instruction", instruction-cache hit rate 53 %).

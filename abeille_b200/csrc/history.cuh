@@ -476,6 +476,21 @@ __device__ __forceinline__ TleArgs tle_args(const DevProblem& P) { return TleArg
 static __device__ __noinline__ Boundary cursor_nearest_boundary_s(const GeoTables G, const SCursor c, const V3 u) {
   return cursor_nearest_boundary(G, c, u);
 }
+// ... with the boundary-condition search skipped when bc_floor allows it (geom.cuh: cursor_nearest_boundary_lazy)
+static __device__ __noinline__ Boundary cursor_nearest_boundary_floor(const GeoTables G, const SCursor c, const V3 u, double bc_floor) {
+  return cursor_nearest_boundary_lazy(G, c, u, bc_floor);
+}
+// a lower bound of the distance from the global position r to every boundary-condition surface, shrunk by the tolerances
+// the comparison needs (|u| is 1 to rounding; candidates within BOUNDRY_TOL of each other are ties); -1: no bound
+__device__ __forceinline__ double bc_floor_of(const DevProblem& P, const V3& r) {
+  if (P.n_bc_planes == 0) return -1.;
+  double lo = ABL_INF;
+  for (int k = 0; k < P.n_bc_planes; k++) {
+    const double rc = P.bc_axis[k] == 0 ? r.x : (P.bc_axis[k] == 1 ? r.y : r.z);
+    lo = fmin(lo, fabs(P.bc_p0[k] - rc));
+  }
+  return lo * (1. - 1e-9) - 2. * ABL_BOUNDRY_TOL;
+}
 
 __device__ __forceinline__ unsigned long long hk_now_ns() {
   unsigned long long t;
@@ -929,7 +944,9 @@ __global__ void __launch_bounds__(HK_THREADS, HK_MINBLOCKS) history_kernel(const
           const double w = HK_D(q, HD_W);
           const double d_coll = rng_exponential<HK_MATH>(rng, ldt(&P.Et[mg]));
           HK_U(q, HD_RNG) = rng;
-          const Boundary sb = cursor_nearest_boundary_s(geo_tables(P), c, u);
+          const double bc_floor = bc_floor_of(P, r);
+          const Boundary sb = P.n_bc_planes ? cursor_nearest_boundary_floor(geo_tables(P), c, u, bc_floor)
+                                            : cursor_nearest_boundary_s(geo_tables(P), c, u);
           did_flight = true;
           if (TRACE) HK_I(q, HI_NFL) = HK_I(q, HI_NFL) + 1;
           const double d_min = fmin(d_coll, sb.distance);

@@ -14,6 +14,7 @@
 namespace abl {
 
 #define ABL_MAX_TALLIES 8
+#define ABL_MAX_BC_PLANES 8
 
 struct DevTally {
   int32_t estimator, quantity, noise_source;
@@ -75,6 +76,13 @@ struct DevProblem {
   const int32_t* ucells;
   const int32_t* tiles;
   const CellFast* cellfast;  // [ncells]
+  // Boundary-condition surfaces when ALL of them are axis planes that are only ever evaluated in the global frame
+  // (api.cu: boundary_planes): |p0 - r[axis]| of the nearest one is a lower bound of the distance to any boundary condition
+  // in any direction, which lets the surface tracker skip the boundary-condition search of a flight that ends far inside
+  // (geom.cuh: cursor_nearest_boundary_lazy).  n_bc_planes = 0: no such bound.
+  int32_t n_bc_planes;
+  int32_t bc_axis[ABL_MAX_BC_PLANES];
+  double bc_p0[ABL_MAX_BC_PLANES];
   // materials [M*G]
   int32_t M;
   const double *Et, *Ea, *Ef, *Es, *nu, *nud, *speed;

@@ -1,7 +1,4 @@
 export ABEILLE_B200_KERNEL_TIMEOUT_S=60
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 8 --warmup 4 --no-ranks-check > gpurun_out/t5c_bench_n8.json 2> gpurun_out/t5c_bench_n8.err
-python -c "import json; d=json.load(open('gpurun_out/t5c_bench_n8.json')); print('N=8 value %.4g ms/step %.2f e2e %.4g placement %s'%(d['value'], d['ms_per_step'], d['e2e']['value'], d.get('host_placement')))" || tail -20 gpurun_out/t5c_bench_n8.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --config 4 --steps 4 --warmup 3 --no-parity > gpurun_out/t5c_bench_config4_n8.json 2> gpurun_out/t5c_bench_config4_n8.err
-python -c "import json; d=json.load(open('gpurun_out/t5c_bench_config4_n8.json')); print('config4 N=8 value %.4g ms/step %.2f kernel %.2f n/gen %d'%(d['value'], d['ms_per_step'], d['roofline']['kernel_ms'], d['config']['particles_per_generation']))" || tail -20 gpurun_out/t5c_bench_config4_n8.err
-lscpu | grep -E "NUMA|Socket|Model name|^CPU\(s\)" | head -8
-nvidia-smi topo -m | head -14
+timeout 900 python -m pytest tests -m gpu -x -q -k "surface or ref_sqr or sood or PUa or golden" 2>&1 | tail -3
+timeout 300 python bench.py --config 3 --steps 4 --warmup 3 --no-parity 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('config3 lazy', 'value %.4g ms/step %.2f'%(d['value'], d['ms_per_step']))"
+ABEILLE_B200_NO_BC_BOUND=1 timeout 300 python bench.py --config 3 --steps 4 --warmup 3 --no-parity 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('config3 full', 'value %.4g ms/step %.2f'%(d['value'], d['ms_per_step']))"
