@@ -199,7 +199,8 @@ int validate(abl_handle h, const abl_problem* p) {
       for (int k = 0; k < U.ncells; k++)
         if (p->universe_cells[U.cell_offset + k] < 0 || p->universe_cells[U.cell_offset + k] >= p->ncells)
           return fail(h, ABL_ERR_INVALID, "universe cell index");
-    } else if (U.type == ABL_UNI_RECT) {
+    } else if (U.type == ABL_UNI_RECT || U.type == ABL_UNI_HEX) {
+      if (U.type == ABL_UNI_HEX && (U.N[0] != U.N[1] || U.N[0] != 2 * ((U.pad_ & 0xffff) - 1) + 1)) return fail(h, ABL_ERR_INVALID, "hexagonal lattice shape");
       const long long nt = (long long)U.N[0] * U.N[1] * U.N[2];
       if (nt <= 0 || U.tile_offset < 0 || U.tile_offset + nt > p->n_lattice_tiles) return fail(h, ABL_ERR_INVALID, "lattice tile slice");
       for (long long k = 0; k < nt; k++)
@@ -472,7 +473,7 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
   int& slots = h->hk_slots[TRK][TRACE ? 2 : (tle ? 1 : 0)];
   int& fixed_state = h->hk_fixed[TRK][TRACE ? 2 : (tle ? 1 : 0)];  // 0 untried, 1 in use, -1 does not fit
   static const bool no_fixed = getenv("ABEILLE_B200_NO_FIXED_SHAPE") != nullptr;
-  const bool fixed = !TRACE && !events && !no_fixed && nf == HK_FIXED_NF && np == HK_FIXED_NP && fixed_state >= 0;
+  const bool fixed = !TRACE && !events && !no_fixed && nf == HK_FIXED_NF && np == HK_FIXED_NP && fixed_state >= 0 && !h->P.has_hex;
   auto pick = [&](bool fx) {
     return TRK == ABL_TRACK_SURFACE ? history_kernel_surface(TRACE, tle, fx)
            : events ? (TRK == ABL_TRACK_DELTA ? event_kernel_delta(TRACE, tle) : event_kernel_carter(TRACE, tle))
@@ -893,6 +894,8 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
   h->smem_optin = (int)prop.sharedMemPerBlockOptin;
   h->smem_total_sm = (int)prop.sharedMemPerMultiprocessor;
   geometry_depth(p, h->geo_frames, h->geo_pads);
+  for (int u = 0; u < p->nuniverses; u++)
+    if (p->universes[u].type == ABL_UNI_HEX) h->P.has_hex = 1;
   // (off by default: bit-exact, but a warp runs the boundary-condition search as soon as ONE lane needs it, and with the
   // reflector holding 40 % of the histories every warp does -- measured 226 ms against 190 ms per 2e6 histories on config 3)
   h->P.n_bc_planes = getenv("ABEILLE_B200_BC_BOUND") ? boundary_planes(p, h->P.bc_axis, h->P.bc_p0) : 0;

@@ -418,11 +418,155 @@ __device__ __forceinline__ void get_tile(const Lat& L, const V3& r, const V3& u,
   const double zh = rt.z + L.Pz * 0.5;
   if (fabs(zh - r.z) < ABL_SURFACE_COINCIDENT && u.z >= 0.) nz++;
 }
-// Lattice::get_tile as one shared copy per kernel (used by the pad validation and by the descent)
 struct Tile3 {
   int nx, ny, nz;
 };
+
+// ---- hexagonal lattice (src/hex_lattice.cpp; table layout: abl_universe in include/abeille_b200.h) --------------------------
+// The reference's quirks are kept: get_cell shifts the position by the lattice origin before it looks for the tile while the
+// Tracker's pad validation and distance_to_tile_boundary use the pad's un-shifted position, and the z bin subtracts Z_o twice
+// on the get_cell path (hex_lattice.cpp:89-96,283-288).  With the origin at zero none of that matters.
+struct HexLat {
+  int nrings, width, nz, top, tile_offset, outer;
+  double pitch, pitch_z, X_o, Y_o, Z_o, cos_pi_6, sin_pi_6, cos_pi_3, sin_pi_3;
+};
+__device__ __forceinline__ HexLat load_hex(const abl_universe* U) {
+  HexLat H;
+  const int packed = ldt(&U->pad_);
+  H.nrings = packed & 0xffff;
+  H.top = packed >> 16;
+  H.width = ldt(&U->N[0]);
+  H.nz = ldt(&U->N[2]);
+  H.tile_offset = ldt(&U->tile_offset);
+  H.outer = ldt(&U->outer);
+  H.pitch = ldt(&U->P[0]); H.sin_pi_3 = ldt(&U->P[1]); H.pitch_z = ldt(&U->P[2]);
+  H.cos_pi_6 = ldt(&U->Pinv[0]); H.sin_pi_6 = ldt(&U->Pinv[1]); H.cos_pi_3 = ldt(&U->Pinv[2]);
+  H.X_o = ldt(&U->Xl[0]); H.Y_o = ldt(&U->Xl[1]); H.Z_o = ldt(&U->Xl[2]);
+  return H;
+}
+__device__ inline Tile3 hex_get_tile(const HexLat& H, const V3& p) {  // get_nearest_hex + get_tile, hex_lattice.cpp:238-288
+  double q, r, det;
+  if (H.top == 1) {
+    det = -H.pitch * H.pitch * H.sin_pi_3;
+    q = (H.pitch / det) * (0. * p.x - 1. * p.y);
+    r = (H.pitch / det) * (-H.sin_pi_3 * p.x + H.cos_pi_3 * p.y);
+  } else {
+    det = -H.pitch * H.pitch * H.cos_pi_6;
+    q = (H.pitch / det) * (H.sin_pi_6 * p.x - H.cos_pi_6 * p.y);
+    r = (H.pitch / det) * (-1. * p.x - 0. * p.y);
+  }
+  const double x = q, z = r, y = -x - z;
+  double rx = round(x), ry = round(y), rz = round(z);
+  const double x_diff = fabs(rx - x), y_diff = fabs(ry - y), z_diff = fabs(rz - z);
+  if (x_diff > y_diff && x_diff > z_diff) {
+    rx = -ry - rz;
+  } else if (y_diff > x_diff && y_diff > z_diff) {
+    ry = -rx - rz;
+  } else {
+    rz = -rx - ry;
+  }
+  const double Z_low = H.Z_o - 0.5 * (double)H.nz * H.pitch_z;
+  Tile3 t;
+  t.nx = (int)rx;
+  t.ny = (int)rz;
+  t.nz = (int)floor((p.z - Z_low) / H.pitch_z);
+  return t;
+}
+__device__ inline V3 hex_tile_center(const HexLat& H, int q_, int r_, int nz) {  // hex_lattice.cpp:290-331
+  const double q = (double)q_, r = (double)r_;
+  double x, y;
+  if (H.top == 1) {
+    x = H.pitch * (H.cos_pi_3 * q + 1. * r);
+    y = H.pitch * (H.sin_pi_3 * q + 0. * r);
+  } else {
+    x = H.pitch * (0. * q + H.cos_pi_6 * r);
+    y = H.pitch * (1. * q + H.sin_pi_6 * r);
+  }
+  const double Z_low = H.Z_o - 0.5 * (double)H.nz * H.pitch_z;
+  return V3{x, y, ((double)nz + 0.5) * H.pitch_z + Z_low};
+}
+__device__ __forceinline__ int hex_ring(int x, int z) {  // hex_lattice.cpp:333-345
+  const int y = -x - z;
+  return max(max(iabs(x), iabs(y)), iabs(z));
+}
+__device__ __forceinline__ double hex_distance_to_line(const V3& r, const V3& u, double x1, double y1, double x2, double y2) {
+  const double A = y2 - y1, B = x1 - x2;  // hex_lattice.cpp:437-455
+  const double D = (x2 - x1) * y1 - (y2 - y1) * x1;
+  const double num = D - A * r.x - B * r.y;
+  const double denom = A * u.x + B * u.y;
+  const double d = num / denom;
+  if (d < 0.) return __longlong_as_double(0x7ff0000000000000LL);  // INFINITY
+  return d;
+}
+static __device__ __noinline__ double hex_distance_to_tile_boundary(const abl_universe* __restrict__ U, const V3 r_local, const V3 u,
+                                                                    const Tile3 tile) {  // hex_lattice.cpp:347-435
+  const HexLat H = load_hex(U);
+  const V3 center = hex_tile_center(H, tile.nx, tile.ny, tile.nz);
+  const V3 r_tile{r_local.x - center.x, r_local.y - center.y, r_local.z - center.z};
+  double d1, d2, d3, d4, d5, d6;
+  if (H.top == 0) {
+    const double x1 = 0., y1 = H.pitch / (2. * H.cos_pi_6), x2 = H.pitch / 2., y2 = H.pitch / (2. * H.sin_pi_6);
+    d1 = hex_distance_to_line(r_tile, u, x1, y1, x2, y1);
+    d2 = hex_distance_to_line(r_tile, u, x2, y2, x2, -y2);
+    d3 = hex_distance_to_line(r_tile, u, x2, -y2, x1, -y1);
+    d4 = hex_distance_to_line(r_tile, u, x1, -y1, -x2, -y2);
+    d5 = hex_distance_to_line(r_tile, u, -x2, -y2, -x2, y2);
+    d6 = hex_distance_to_line(r_tile, u, -x2, y2, x1, y1);
+  } else {
+    const double x1 = H.pitch / (2. * H.sin_pi_6), y1 = H.pitch / 2., x2 = H.pitch / (2. * H.cos_pi_6), y2 = 0.;
+    d1 = hex_distance_to_line(r_tile, u, x1, y1, x2, y1);
+    d2 = hex_distance_to_line(r_tile, u, x2, y2, x1, -y1);
+    d3 = hex_distance_to_line(r_tile, u, x1, -y1, -x1, -y1);
+    d4 = hex_distance_to_line(r_tile, u, -x1, -y1, -x2, -y2);
+    d5 = hex_distance_to_line(r_tile, u, -x2, -y2, -x1, y1);
+    d6 = hex_distance_to_line(r_tile, u, -x1, y1, x1, y1);
+  }
+  const double dzl = (-H.pitch_z * 0.5 - r_tile.z) / u.z;
+  const double dzu = (H.pitch_z * 0.5 - r_tile.z) / u.z;
+  double d = ABL_INF;
+  if (d1 > 0. && d1 < d) d = d1;
+  if (d2 > 0. && d2 < d) d = d2;
+  if (d3 > 0. && d3 < d) d = d3;
+  if (d4 > 0. && d4 < d) d = d4;
+  if (d5 > 0. && d5 < d) d = d5;
+  if (d6 > 0. && d6 < d) d = d6;
+  if (dzl > 0. && dzl < d) d = dzl;
+  if (dzu > 0. && dzu < d) d = dzu;
+  return d;
+}
+// One step of HexLattice::get_cell (hex_lattice.cpp:140-202): the tile of r, the universe inside it (-1: none: the outer
+// universe or nothing) and the position in the tile's frame
+struct HexStep {
+  Tile3 t;
+  int sub, outer;
+  V3 r_tile;
+};
+static __device__ __noinline__ HexStep hex_lattice_step(const abl_universe* __restrict__ U, const int32_t* __restrict__ tiles, const V3 r) {
+  const HexLat H = load_hex(U);
+  const V3 r_o{r.x - H.X_o, r.y - H.Y_o, r.z - H.Z_o};
+  HexStep s;
+  s.t = hex_get_tile(H, r_o);
+  s.outer = H.outer;
+  s.sub = -1;
+  s.r_tile = r;
+  if (hex_ring(s.t.nx, s.t.ny) < H.nrings && !(s.t.nz < 0 || s.t.nz >= H.nz)) {
+    const int mid = H.width / 2;
+    s.sub = ldt(&tiles[H.tile_offset + s.t.nz * (H.width * H.width) + (s.t.ny + mid) * H.width + (s.t.nx + mid)]);
+    if (s.sub >= 0) {
+      const V3 ctr = hex_tile_center(H, s.t.nx, s.t.ny, s.t.nz);
+      s.r_tile = V3{r_o.x - ctr.x, r_o.y - ctr.y, r_o.z - ctr.z};
+    }
+  }
+  return s;
+}
+static __device__ __noinline__ Tile3 hex_tile_nl(const abl_universe* __restrict__ U, const V3 p) { return hex_get_tile(load_hex(U), p); }
+
+// Lattice::get_tile as one shared copy per kernel (used by the pad validation and by the descent)
+// HEX = false: a build for problems without a hexagonal lattice (the host checks: DevProblem::has_hex); the hexagonal branch
+// costs the rectilinear hot path registers (107 -> 113 ms per 1e7 histories on the bench workload when it is compiled in)
+template <bool HEX = true>
 static __device__ ABL_HOT_CALL Tile3 lattice_tile_nl(const abl_universe* __restrict__ U, const V3 r, const V3 u) {
+  if (HEX && ldt(&U->type) == ABL_UNI_HEX) return hex_tile_nl(U, r);  // (the position as handed in: see the note on the reference's quirks)
   const Lat L = load_lattice(U);
   Tile3 t;
   get_tile(L, r, u, t.nx, t.ny, t.nz);
@@ -591,6 +735,28 @@ __device__ inline int descend(const PT& P, CUR& c, int uni, int f, const V3& u) 
       uni = fill;
       continue;
     }
+    if (ldt(&U->type) == ABL_UNI_HEX) {
+      const HexStep hs = hex_lattice_step(U, P.tiles, r);
+      c.nf = f + 1;
+      if (hs.sub >= 0) {
+        if (!push_pad(c, make_pad(PAD_LATTICE, 0, f, uni), hs.t.nx, hs.t.ny, hs.t.nz)) return -1;
+        if (f + 1 >= ABL_MAX_FRAMES) {
+          c.err = ABL_ERR_GEOMETRY;
+          return -1;
+        }
+        set_frame(c, f + 1, hs.r_tile.x, hs.r_tile.y, hs.r_tile.z);
+        f++;
+        uni = hs.sub;
+        continue;
+      }
+      if (hs.outer >= 0) {
+        if (!push_pad(c, make_pad(PAD_LATTICE, 1, f, uni), hs.t.nx, hs.t.ny, hs.t.nz)) return -1;
+        uni = hs.outer;
+        continue;
+      }
+      push_pad(c, make_pad(PAD_LATTICE, 0, f, uni), hs.t.nx, hs.t.ny, hs.t.nz);
+      return -1;
+    }
     int nx, ny, nz;
     Lat L;
     if (FAST) {
@@ -666,9 +832,8 @@ __device__ inline void cursor_get_current(const PT& P, Cursor& c, const V3& u) {
         break;
       }
     } else if (type == PAD_LATTICE) {
-      const Lat L = load_lattice(P.universes + pad_index(info));
-      int nx, ny, nz;
-      get_tile(L, frame_r(c, pad_frame(info)), u, nx, ny, nz);
+      const Tile3 tt = lattice_tile_nl(P.universes + pad_index(info), frame_r(c, pad_frame(info)), u);
+      const int nx = tt.nx, ny = tt.ny, nz = tt.nz;
       if (c.ptile[it][0] != nx || c.ptile[it][1] != ny || c.ptile[it][2] != nz) {
         first_bad = it;
         break;
@@ -744,13 +909,19 @@ __device__ inline Boundary cursor_nearest_boundary(const PT& P, const CUR& c, co
     const int type = pad_type(info);
     const V3 r = frame_r(c, pad_frame(info));
     if (type == PAD_LATTICE) {
-      const Lat L = load_lattice(P.universes + pad_index(info));
+      const abl_universe* LU = P.universes + pad_index(info);
       const Tile3 t3 = pad_tile3(c, it);
-      if (!have_u_inv) {
-        u_inv = V3{1. / u.x, 1. / u.y, 1. / u.z};
-        have_u_inv = true;
+      double d;
+      if (ldt(&LU->type) == ABL_UNI_HEX) {
+        d = hex_distance_to_tile_boundary(LU, r, u, t3);
+      } else {
+        const Lat L = load_lattice(LU);
+        if (!have_u_inv) {
+          u_inv = V3{1. / u.x, 1. / u.y, 1. / u.z};
+          have_u_inv = true;
+        }
+        d = distance_to_tile_boundary(L, r, u_inv, t3.nx, t3.ny, t3.nz);
       }
-      const double d = distance_to_tile_boundary(L, r, u_inv, t3.nx, t3.ny, t3.nz);
       if (d < b.distance && fabs(d - b.distance) > ABL_BOUNDRY_TOL) {
         b.distance = d;
         b.btype = ABL_BC_NORMAL;
@@ -800,13 +971,18 @@ __device__ inline Boundary cursor_nearest_boundary_lazy(const PT& P, const CUR& 
     cd[it] = ABL_INF;
     cis[it] = 0;
     if (type == PAD_LATTICE) {
-      const Lat L = load_lattice(P.universes + pad_index(info));
+      const abl_universe* LU = P.universes + pad_index(info);
       const Tile3 t3 = pad_tile3(c, it);
-      if (!have_u_inv) {
-        u_inv = V3{1. / u.x, 1. / u.y, 1. / u.z};
-        have_u_inv = true;
+      if (ldt(&LU->type) == ABL_UNI_HEX) {
+        cd[it] = hex_distance_to_tile_boundary(LU, frame_r(c, pad_frame(info)), u, t3);
+      } else {
+        const Lat L = load_lattice(LU);
+        if (!have_u_inv) {
+          u_inv = V3{1. / u.x, 1. / u.y, 1. / u.z};
+          have_u_inv = true;
+        }
+        cd[it] = distance_to_tile_boundary(L, frame_r(c, pad_frame(info)), u_inv, t3.nx, t3.ny, t3.nz);
       }
-      cd[it] = distance_to_tile_boundary(L, frame_r(c, pad_frame(info)), u_inv, t3.nx, t3.ny, t3.nz);
     } else if (type == PAD_CELL) {
       cell_distance(P, pad_index(info), frame_r(c, pad_frame(info)), u, c.token, false, cd[it], cis[it]);
     }

@@ -35,7 +35,7 @@ namespace abl {
 enum { PH_DEAD = 0, PH_FLIGHT, PH_BIRTH, PH_LOST, PH_REFLECTED, PH_RESURRECT, PH_CROSSED };
 
 // Tracker::get_current, first half (tracker.hpp:235-270): index of the first pad that no longer holds, or np
-template <class CUR>
+template <class CUR, bool HEX = true>
 __device__ __forceinline__ int cursor_validate(const DevProblem& P, const CUR& c, const V3& u) {
   int first_bad = c.np;
   for (int it = 0; it < c.np; it++) {
@@ -47,7 +47,7 @@ __device__ __forceinline__ int cursor_validate(const DevProblem& P, const CUR& c
         break;
       }
     } else if (type == PAD_LATTICE) {
-      const Tile3 t3 = lattice_tile_nl(P.universes + pad_index(info), frame_r(c, pad_frame(info)), u);
+      const Tile3 t3 = lattice_tile_nl<HEX>(P.universes + pad_index(info), frame_r(c, pad_frame(info)), u);
       if (!pad_tile_is(c, it, t3.nx, t3.ny, t3.nz)) {
         first_bad = it;
         break;
@@ -123,11 +123,33 @@ __device__ __forceinline__ void cursor_relocate(const DevProblem& P, CUR& c, int
 
 // One step of Universe::get_cell through a lattice (rect_lattice.cpp:132-207): 0 = descend further (uni / f updated),
 // -1 = no universe here (lost)
-template <class CUR>
+template <class CUR, bool HEX = true>
 __device__ __forceinline__ int descend_lattice_step(const DevProblem& P, CUR& c, int& uni, int& f, const V3& u) {
   const abl_universe* U = P.universes + uni;
   const V3 r = frame_r(c, f);
-  const Tile3 t3 = lattice_tile_nl(U, r, u);
+  if (HEX && ldt(&U->type) == ABL_UNI_HEX) {  // HexLattice::get_cell, hex_lattice.cpp:140-202
+    const HexStep hs = hex_lattice_step(U, P.tiles, r);
+    c.nf = f + 1;
+    if (hs.sub >= 0) {
+      if (!push_pad(c, make_pad(PAD_LATTICE, 0, f, uni), hs.t.nx, hs.t.ny, hs.t.nz)) return -1;
+      if (f + 1 >= ABL_MAX_FRAMES) {
+        c.err = ABL_ERR_GEOMETRY;
+        return -1;
+      }
+      set_frame(c, f + 1, hs.r_tile.x, hs.r_tile.y, hs.r_tile.z);
+      f++;
+      uni = hs.sub;
+      return 0;
+    }
+    if (hs.outer >= 0) {
+      if (!push_pad(c, make_pad(PAD_LATTICE, 1, f, uni), hs.t.nx, hs.t.ny, hs.t.nz)) return -1;
+      uni = hs.outer;
+      return 0;
+    }
+    push_pad(c, make_pad(PAD_LATTICE, 0, f, uni), hs.t.nx, hs.t.ny, hs.t.nz);
+    return -1;
+  }
+  const Tile3 t3 = lattice_tile_nl<HEX>(U, r, u);
   Lat L;
   L.Nx = ldt(&U->N[0]); L.Ny = ldt(&U->N[1]); L.Nz = ldt(&U->N[2]);
   L.tile_offset = ldt(&U->tile_offset);
@@ -191,7 +213,7 @@ __device__ __forceinline__ int descend_cells_step(const DevProblem& P, CUR& c, i
 // then one cell-universe step for everybody.  Lanes re-descend from different depths (a changed pin cell: the cell
 // universe only; a changed tile: the lattices above it first), and a plain per-lane loop made the warp run the
 // cell-universe code once per distinct depth with a handful of lanes each (ncu: 5 of 32).
-template <class CUR>
+template <class CUR, bool HEX = true>
 __device__ __forceinline__ void cursor_relocate_sync(const DevProblem& P, CUR& c, int from, const V3& u, unsigned mask) {
   int uni = P.root, f = 0;
   bool full = true;
@@ -215,7 +237,7 @@ __device__ __forceinline__ void cursor_relocate_sync(const DevProblem& P, CUR& c
       const bool at_lattice = active && ldt(&P.universes[uni].type) != ABL_UNI_CELLS;
       if (!__any_sync(mask, at_lattice)) break;
       int st = 0;
-      if (at_lattice) st = descend_lattice_step(P, c, uni, f, u);
+      if (at_lattice) st = descend_lattice_step<CUR, HEX>(P, c, uni, f, u);
       if (st < 0) {
         if (full) {
           active = false;
@@ -778,6 +800,7 @@ template <int TRK, bool TRACE, bool TLE, int NFC = 0, int NPC = 0, int SC = 0>
 __global__ void __launch_bounds__(HK_THREADS, HK_MINBLOCKS) history_kernel(const DevProblem P, const RunArgs A) {
   HKFixed& S = HKS;
   const int hk_slots = SC ? SC : A.hk_slots, hk_nf = NFC ? NFC : A.hk_nf, hk_np = NPC ? NPC : A.hk_np;
+  constexpr bool HEX = NFC == 0;  // the fixed-shape builds are also the builds without the hexagonal-lattice branches
   const unsigned FULL = 0xffffffffu;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // ---- set-up: queues empty, then everyone meets once ---------------------------------------------------------------------
@@ -1021,7 +1044,7 @@ __global__ void __launch_bounds__(HK_THREADS, HK_MINBLOCKS) history_kernel(const
         c.nf = pf >> 8;
         cursor_move(c, d_coll, u);
         HK_I(q, HI_TOK) = 0;
-        const int first_bad = cursor_validate(P, c, u);
+        const int first_bad = cursor_validate<SCursor, HEX>(P, c, u);
         if (first_bad < c.np) need = first_bad;
       }
       HK_SYNC();
@@ -1035,7 +1058,7 @@ __global__ void __launch_bounds__(HK_THREADS, HK_MINBLOCKS) history_kernel(const
 #ifdef HK_PER_LANE_RELOCATE
         cursor_relocate(P, c, need, u);
 #else
-        cursor_relocate_sync(P, c, need, u, relocating);
+        cursor_relocate_sync<SCursor, HEX>(P, c, need, u, relocating);
 #endif
         need = -1;
         cursor_store(c);

@@ -417,7 +417,46 @@ Universe make_universe(const Node& u, const Problem& P) {
     }
   } else if (u["pitch"]) {
     const std::string type = u["type"] ? u["type"].as_string() : std::string("");
-    if (type != "rectlinear") fatal_error("Lattice type \"" + type + "\" is not provided by the B200 backend (rectlinear only).");
+    if (type == "hexagonal") {  // make_hex_lattice + HexLattice::HexLattice + set_elements (src/hex_lattice.cpp:30-56,204-222,457-577)
+      uni.type = ABL_UNI_HEX;
+      if (!u["shape"] || u["shape"].size() != 2) fatal_error("Lattice must have a valid shape.");
+      const long long nrings = u["shape"][0].as_int(), nz = u["shape"][1].as_int();
+      if (nrings < 1 || nz < 1 || nrings > 1000) fatal_error("Lattice must have a valid shape.");
+      const std::vector<double> pitch = doubles(u["pitch"], 2, "lattice pitch");
+      if (!u["origin"]) fatal_error("Lattice must have a valid origin.");
+      const std::vector<double> origin = doubles(u["origin"], 3, "lattice origin");
+      int top = 0;
+      if (u["top"]) {
+        const std::string t = u["top"].as_string();
+        if (t == "pointy") top = 0;
+        else if (t == "flat") top = 1;
+        else fatal_error(" Uknown top for hexagonal lattice " + t + ".");
+      }
+      const int width = 2 * (static_cast<int>(nrings) - 1) + 1, mid = width / 2;
+      uni.N = {width, width, static_cast<int>(nz)};
+      uni.hex_rings = static_cast<int>(nrings);
+      uni.hex_top = top;
+      uni.P = {pitch[0], std::sin(3.14159265358979323846264338327950288 / 3.0), pitch[1]};
+      uni.Pinv = {std::cos(3.14159265358979323846264338327950288 / 6.0), std::sin(3.14159265358979323846264338327950288 / 6.0),
+                  std::cos(3.14159265358979323846264338327950288 / 3.0)};
+      uni.Xl = {origin[0], origin[1], origin[2]};
+      if (u["outer"]) uni.outer_id = u["outer"].as_int();
+      const Node& ids = u["universes"];
+      size_t nhex = 0;
+      for (long long r = 0; r < nrings; r++) nhex += r == 0 ? 1 : static_cast<size_t>(6 * r);
+      if (!ids || !ids.IsSequence() || ids.size() != nhex * static_cast<size_t>(nz)) fatal_error("Improper number of universes for HexLattice.");
+      uni.tile_ids.assign(static_cast<size_t>(width) * static_cast<size_t>(width) * static_cast<size_t>(nz), -1);
+      size_t indx = 0;
+      for (int az = 0; az < nz; az++)
+        for (int ar = 0; ar < width; ar++)
+          for (int aq = 0; aq < width; aq++) {
+            const int q = aq - mid, r = ar - mid, y = -q - r;
+            const int ring = std::max(std::max(std::abs(q), std::abs(y)), std::abs(r));
+            if (ring < nrings) uni.tile_ids[static_cast<size_t>(az) * static_cast<size_t>(width * width) + static_cast<size_t>(ar * width + aq)] = ids[indx++].as_int();
+          }
+      return uni;
+    }
+    if (type != "rectlinear") fatal_error("Lattice type \"" + type + "\" is not provided by the B200 backend (rectlinear and hexagonal).");
     uni.type = ABL_UNI_RECT;
     if (!u["shape"] || u["shape"].size() != 3) fatal_error("Lattice must have a valid shape.");
     for (int k = 0; k < 3; k++) uni.N[static_cast<size_t>(k)] = static_cast<int>(u["shape"][k].as_int());
@@ -596,7 +635,7 @@ Problem Problem::from_yaml(const Node& input) {
     return it->second;
   };
   for (auto& U : P.universes) {
-    if (U.type != ABL_UNI_RECT) continue;
+    if (U.type == ABL_UNI_CELLS) continue;
     for (long long id : U.tile_ids) U.tiles.push_back(id < 0 ? -1 : uni_index(id, "lattice " + std::to_string(U.id)));
     U.outer = U.outer_id < 0 ? -1 : uni_index(U.outer_id, "lattice " + std::to_string(U.id) + " outer");
   }
@@ -793,6 +832,7 @@ void Problem::flatten(FlatProblem& F) const {
         fu.Pinv[k] = U.Pinv[k];
         fu.Xl[k] = U.Xl[k];
       }
+      if (U.type == ABL_UNI_HEX) fu.pad_ = U.hex_rings | (U.hex_top << 16);
       fu.tile_offset = static_cast<int32_t>(F.lattice_tiles.size());
       F.lattice_tiles.insert(F.lattice_tiles.end(), U.tiles.begin(), U.tiles.end());
       fu.outer = U.outer;

@@ -48,7 +48,7 @@ struct Cell {  // include/geometry/cell.hpp
   int material_index = -1, universe_index = -1;
 };
 
-struct Universe {  // CellUniverse | RectLattice
+struct Universe {  // CellUniverse | RectLattice | HexLattice
   uint32_t id = 0;
   std::string name;
   int type = ABL_UNI_CELLS;
@@ -60,6 +60,7 @@ struct Universe {  // CellUniverse | RectLattice
   std::vector<int> tiles;           // universe indices
   long long outer_id = -1;
   int outer = -1;
+  int hex_rings = 0, hex_top = 0;  // HexLattice: N = {width, width, nz}; tile_ids laid out by HexLattice::linear_index, -1 outside
 };
 
 struct AngleTable {  // MGAngleDistribution

@@ -54,7 +54,7 @@ enum {
   ABL_SURF_XPLANE = 0, ABL_SURF_YPLANE, ABL_SURF_ZPLANE, ABL_SURF_PLANE,
   ABL_SURF_XCYL, ABL_SURF_YCYL, ABL_SURF_ZCYL, ABL_SURF_CYL, ABL_SURF_SPHERE
 };
-enum { ABL_UNI_CELLS = 0, ABL_UNI_RECT = 1 };
+enum { ABL_UNI_CELLS = 0, ABL_UNI_RECT = 1, ABL_UNI_HEX = 2 };  /* CellUniverse, RectLattice, HexLattice */
 enum { ABL_EST_COLLISION = 0, ABL_EST_TRACK_LENGTH = 1, ABL_EST_SOURCE = 2 };
 enum {
   ABL_Q_FLUX = 0, ABL_Q_TOTAL, ABL_Q_ELASTIC, ABL_Q_ABSORPTION, ABL_Q_FISSION, ABL_Q_MT,
@@ -89,8 +89,13 @@ typedef struct abl_universe {
   int32_t tile_offset;          /* slice of abl_problem.lattice_tiles: universe index or -1, linear
                                    index nz*Nx*Ny + nx*Ny + ny (rect_lattice.cpp:293-301)             */
   int32_t outer;                /* outer universe index or -1                                         */
-  int32_t pad_;
+  int32_t pad_;                 /* ABL_UNI_HEX: nrings | top << 16 (top: 0 pointy, 1 flat)            */
   double P[3], Pinv[3], Xl[3];  /* pitch, 1/pitch, lower corner origin - N*P/2 (rect_lattice.cpp:33-52) */
+  /* ABL_UNI_HEX (src/hex_lattice.cpp:30-56): N = {width, width, nz} with width = 2 (nrings - 1) + 1, tiles in the
+   * reference's linear_index order nz*width*width + (r + width/2)*width + (q + width/2), -1 outside the hexagon;
+   * P[0] = pitch, P[2] = pitch_z, Xl = origin of the centre hexagon (X_o, Y_o, Z_o), and the four constants the reference
+   * evaluates with std::cos / std::sin at construction (hex_lattice.hpp:60-63): Pinv[0] = cos(pi/6), Pinv[1] = sin(pi/6),
+   * Pinv[2] = cos(pi/3), P[1] = sin(pi/3) */
 } abl_universe;
 
 typedef struct abl_angle_table { /* linearised mu distribution of one (g_in,g_out) pair               */

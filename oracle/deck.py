@@ -144,9 +144,15 @@ def deck_to_text(deck: dict) -> str:
     for u in unis:
         if "cells" in u:
             out.append(f"uni {int(u['id'])} cells {len(u['cells'])} " + " ".join(str(int(c)) for c in u["cells"]))
+        elif "pitch" in u and u.get("type") == "hexagonal":  # make_hex_lattice, src/hex_lattice.cpp:457-577
+            sh, pt, org = u["shape"], u["pitch"], u["origin"]
+            top = {"pointy": 0, "flat": 1}[u.get("top", "pointy")]
+            ids = u["universes"]
+            out.append(f"uni {int(u['id'])} hex {int(sh[0])} {int(sh[1])} {_fl(pt)} {_fl(org)} {top} "
+                       f"{int(u.get('outer', -1))} {len(ids)} " + " ".join(str(int(i)) for i in ids))
         elif "pitch" in u:
             if u.get("type", "rectlinear") != "rectlinear":
-                raise ValueError("oracle: only rectlinear lattices")
+                raise ValueError("oracle: only rectlinear and hexagonal lattices")
             sh, pt = u["shape"], u["pitch"]
             org = u.get("origin", [0.0, 0.0, 0.0])
             ids = u["universes"]

@@ -237,7 +237,7 @@ struct Cell {
   uint32_t id = 0;
 };
 
-enum UniType { U_CELLS, U_RECT };
+enum UniType { U_CELLS, U_RECT, U_HEX };
 
 struct Universe {
   int type = U_CELLS;
@@ -249,6 +249,11 @@ struct Universe {
   double Px = 0, Py = 0, Pz = 0, Px_inv = 0, Py_inv = 0, Pz_inv = 0, Xl = 0, Yl = 0, Zl = 0;
   std::vector<int32_t> lattice_universes;  // universe index or -1
   int32_t outer_universe_index = -1;
+  // U_HEX (src/hex_lattice.cpp:30-56; include/geometry/hex_lattice.hpp:58-66): Nz and lattice_universes as above
+  uint32_t Nrings = 0, width = 0, mid_qr = 0;
+  int top = 0;  // 0 pointy, 1 flat
+  double pitch = 0, pitch_z = 0, X_o = 0, Y_o = 0, Z_o = 0;
+  double cos_pi_6 = 0, sin_pi_6 = 0, cos_pi_3 = 0, sin_pi_3 = 0;  // std::cos(PI / 6.0) ... as the reference evaluates them
 };
 
 // include/geometry/geo_lily_pad.hpp:33-49
@@ -340,6 +345,113 @@ struct Geometry {
     return {min_dist, i_surf};
   }
 
+  // ---- HexLattice (src/hex_lattice.cpp) -------------------------------------
+  static std::array<int32_t, 2> hex_nearest(const Universe& L, const Vec& p) {  // get_nearest_hex :238-281
+    double q, r, det;
+    if (L.top == 1) {
+      det = -L.pitch * L.pitch * L.sin_pi_3;
+      q = (L.pitch / det) * (0. * p.x - 1. * p.y);
+      r = (L.pitch / det) * (-L.sin_pi_3 * p.x + L.cos_pi_3 * p.y);
+    } else {
+      det = -L.pitch * L.pitch * L.cos_pi_6;
+      q = (L.pitch / det) * (L.sin_pi_6 * p.x - L.cos_pi_6 * p.y);
+      r = (L.pitch / det) * (-1. * p.x - 0. * p.y);
+    }
+    double x = q, z = r, y = -x - z;
+    double rx = std::round(x), ry = std::round(y), rz = std::round(z);
+    double x_diff = std::abs(rx - x), y_diff = std::abs(ry - y), z_diff = std::abs(rz - z);
+    if (x_diff > y_diff && x_diff > z_diff) {
+      rx = -ry - rz;
+    } else if (y_diff > x_diff && y_diff > z_diff) {
+      ry = -rx - rz;
+    } else {
+      rz = -rx - ry;
+    }
+    return {static_cast<int32_t>(rx), static_cast<int32_t>(rz)};
+  }
+  static std::array<int32_t, 3> hex_get_tile(const Universe& L, const Vec& p) {  // get_tile :283-288
+    auto qr = hex_nearest(L, p);
+    double Z_low = L.Z_o - 0.5 * static_cast<double>(L.Nz) * L.pitch_z;
+    int32_t nz = static_cast<int32_t>(std::floor((p.z - Z_low) / L.pitch_z));
+    return {qr[0], qr[1], nz};
+  }
+  static Vec hex_tile_center(const Universe& L, int q_, int r_, int nz) {  // get_hex_center + tile_center :290-331
+    double x, y;
+    double q = static_cast<double>(q_), r = static_cast<double>(r_);
+    if (L.top == 1) {
+      x = L.pitch * (L.cos_pi_3 * q + 1. * r);
+      y = L.pitch * (L.sin_pi_3 * q + 0. * r);
+    } else {
+      x = L.pitch * (0. * q + L.cos_pi_6 * r);
+      y = L.pitch * (1. * q + L.sin_pi_6 * r);
+    }
+    double Z_low = L.Z_o - 0.5 * static_cast<double>(L.Nz) * L.pitch_z;
+    double z = (static_cast<double>(nz) + 0.5) * L.pitch_z + Z_low;
+    return {x, y, z};
+  }
+  static uint32_t hex_ring(int32_t x, int32_t z) {  // get_ring :333-345
+    int32_t y = -x - z;
+    uint32_t ax = static_cast<uint32_t>(std::abs(x)), ay = static_cast<uint32_t>(std::abs(y)), az = static_cast<uint32_t>(std::abs(z));
+    return std::max(std::max(ax, ay), az);
+  }
+  static size_t hex_linear_index(const Universe& L, int32_t q_, int32_t r_, int32_t z) {  // :224-236
+    uint32_t q = static_cast<uint32_t>(q_) + L.mid_qr, r = static_cast<uint32_t>(r_) + L.mid_qr;
+    return static_cast<size_t>(static_cast<uint32_t>(z) * (L.width * L.width) + r * L.width + q);
+  }
+  static double hex_distance_to_line(const Vec& r, const Vec& u, double x1, double y1, double x2, double y2) {  // :437-455
+    double A = y2 - y1, B = x1 - x2;
+    double D = (x2 - x1) * y1 - (y2 - y1) * x1;
+    double num = D - A * r.x - B * r.y;
+    double denom = A * u.x + B * u.y;
+    double d = num / denom;
+    if (d < 0.) return INFINITY;
+    return d;
+  }
+  static double hex_distance_to_tile_boundary(const Universe& L, const Vec& r_local, const Vec& u,
+                                              const std::array<int32_t, 3>& tile) {  // :347-435
+    Vec center = hex_tile_center(L, tile[0], tile[1], tile[2]);
+    Vec r_tile = r_local - center;
+    double d1, d2, d3, d4, d5, d6;
+    if (L.top == 0) {
+      double x1 = 0., y1 = L.pitch / (2. * L.cos_pi_6), x2 = L.pitch / 2., y2 = L.pitch / (2. * L.sin_pi_6);
+      d1 = hex_distance_to_line(r_tile, u, x1, y1, x2, y1);
+      d2 = hex_distance_to_line(r_tile, u, x2, y2, x2, -y2);
+      d3 = hex_distance_to_line(r_tile, u, x2, -y2, x1, -y1);
+      d4 = hex_distance_to_line(r_tile, u, x1, -y1, -x2, -y2);
+      d5 = hex_distance_to_line(r_tile, u, -x2, -y2, -x2, y2);
+      d6 = hex_distance_to_line(r_tile, u, -x2, y2, x1, y1);
+    } else {
+      double x1 = L.pitch / (2. * L.sin_pi_6), y1 = L.pitch / 2., x2 = L.pitch / (2. * L.cos_pi_6), y2 = 0.;
+      d1 = hex_distance_to_line(r_tile, u, x1, y1, x2, y1);
+      d2 = hex_distance_to_line(r_tile, u, x2, y2, x1, -y1);
+      d3 = hex_distance_to_line(r_tile, u, x1, -y1, -x1, -y1);
+      d4 = hex_distance_to_line(r_tile, u, -x1, -y1, -x2, -y2);
+      d5 = hex_distance_to_line(r_tile, u, -x2, -y2, -x1, y1);
+      d6 = hex_distance_to_line(r_tile, u, -x1, y1, x1, y1);
+    }
+    double dzl = (-L.pitch_z * 0.5 - r_tile.z) / u.z;
+    double dzu = (L.pitch_z * 0.5 - r_tile.z) / u.z;
+    double d = INF;
+    if (d1 > 0. && d1 < d) d = d1;
+    if (d2 > 0. && d2 < d) d = d2;
+    if (d3 > 0. && d3 < d) d = d3;
+    if (d4 > 0. && d4 < d) d = d4;
+    if (d5 > 0. && d5 < d) d = d5;
+    if (d6 > 0. && d6 < d) d = d6;
+    if (dzl > 0. && dzl < d) d = dzl;
+    if (dzu > 0. && dzu < d) d = dzu;
+    return d;
+  }
+  static bool hex_is_inside(const Universe& L, const Vec& r) {  // :58-81
+    Vec r_o{r.x - L.X_o, r.y - L.Y_o, r.z - L.Z_o};
+    auto qr = hex_nearest(L, r_o);
+    if (hex_ring(qr[0], qr[1]) >= L.Nrings) return false;
+    double Z_low = L.Z_o - 0.5 * static_cast<double>(L.Nz) * L.pitch_z;
+    int32_t nz = static_cast<int32_t>(std::floor((r.z - Z_low) / L.pitch_z));
+    if (nz < 0 || nz >= static_cast<int32_t>(L.Nz)) return false;
+    return true;
+  }
+
   // ---- RectLattice (src/rect_lattice.cpp) ----------------------------------
   static Vec tile_center(const Universe& L, int nx, int ny, int nz) {  // :303-309
     double x = (static_cast<double>(nx) + 0.5) * L.Px + L.Xl;
@@ -348,6 +460,7 @@ struct Geometry {
     return {x, y, z};
   }
   static std::array<int32_t, 3> get_tile(const Universe& L, const Vec& r, const Vec& u) {  // :209-237
+    if (L.type == U_HEX) return hex_get_tile(L, r);  // (the position as handed in: Tracker passes the pad's un-shifted r_local)
     if (L.type != U_RECT) return {0, 0, 0};  // universe.cpp:31-34
     int32_t nx = static_cast<int32_t>(std::floor((r.x - L.Xl) * L.Px_inv));
     int32_t ny = static_cast<int32_t>(std::floor((r.y - L.Yl) * L.Py_inv));
@@ -369,6 +482,7 @@ struct Geometry {
   }
   static double distance_to_tile_boundary(const Universe& L, const Vec& r_local, const Vec& u,
                                           const std::array<int32_t, 3>& tile) {  // :239-282
+    if (L.type == U_HEX) return hex_distance_to_tile_boundary(L, r_local, u, tile);
     if (L.type != U_RECT) return INF;  // universe.cpp:36-40
     Vec center = tile_center(L, tile[0], tile[1], tile[2]);
     Vec r_tile = r_local - center;
@@ -413,6 +527,27 @@ struct Geometry {
         }
       }
       return -1;
+    }
+    if (U.type == U_HEX) {  // HexLattice::get_cell(stack, ...) hex_lattice.cpp:140-202
+      Vec r_o{r.x - U.X_o, r.y - U.Y_o, r.z - U.Z_o};
+      auto qrz = hex_get_tile(U, r_o);
+      bool in = hex_ring(qrz[0], qrz[1]) < U.Nrings && !(qrz[2] < 0 || qrz[2] >= static_cast<int32_t>(U.Nz));
+      size_t indx = 0;
+      if (in) {
+        indx = hex_linear_index(U, qrz[0], qrz[1], qrz[2]);
+        in = U.lattice_universes[indx] != -1;
+      }
+      if (!in) {
+        if (U.outer_universe_index == -1) {
+          stack.push_back({GeoLilyPad::PLattice, uni, r, qrz, false});
+          return -1;
+        }
+        stack.push_back({GeoLilyPad::PLattice, uni, r, qrz, true});
+        return get_cell(U.outer_universe_index, stack, r, u, on_surf);
+      }
+      Vec r_tile = r_o - hex_tile_center(U, qrz[0], qrz[1], qrz[2]);
+      stack.push_back({GeoLilyPad::PLattice, uni, r, qrz, false});
+      return get_cell(U.lattice_universes[indx], stack, r_tile, u, on_surf);
     }
     auto tile = get_tile(U, r, u);
     int nx = tile[0], ny = tile[1], nz = tile[2];
@@ -482,6 +617,12 @@ struct Geometry {
   // lost_get_boundary : cell_universe.cpp:172-230 (cells), lattice.cpp:94-108
   Boundary universe_lost_get_boundary(int uni, const Vec& r, const Vec& u, int32_t on_surf) const {
     const Universe& U = universes[static_cast<size_t>(uni)];
+    if (U.type == U_HEX) {  // Lattice::lost_get_boundary with HexLattice::is_inside (lattice.cpp:94-108, hex_lattice.cpp:58-81)
+      if (U.outer_universe_index >= 0 && !hex_is_inside(U, r)) return universe_lost_get_boundary(U.outer_universe_index, r, u, on_surf);
+      Boundary b(hex_distance_to_tile_boundary(U, r, u, hex_get_tile(U, r)), -1, BC_NORMAL);
+      b.token = 0;
+      return b;
+    }
     if (U.type != U_CELLS) {
       auto tile = get_tile(U, r, u);
       bool inside = !((tile[0] < 0 || tile[0] >= (int)U.Nx) || (tile[1] < 0 || tile[1] >= (int)U.Ny) ||

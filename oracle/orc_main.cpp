@@ -349,6 +349,20 @@ static Problem* load_problem(const char* path) {
       outer_ids[u] = tk.ll();
       size_t n = (size_t)tk.ll();
       for (size_t i = 0; i < n; i++) lat_ids[u].push_back(tk.ll());
+    } else if (kind == "hex") {  // make_hex_lattice, src/hex_lattice.cpp:457-577: nrings nz pitch pitch_z origin top outer n ids
+      uni.type = U_HEX;
+      uni.Nrings = (uint32_t)tk.ll(); uni.Nz = (uint32_t)tk.ll();
+      uni.pitch = tk.d(); uni.pitch_z = tk.d();
+      uni.X_o = tk.d(); uni.Y_o = tk.d(); uni.Z_o = tk.d();
+      uni.top = (int)tk.ll();
+      uni.width = 2 * (uni.Nrings - 1) + 1;  // hex_lattice.cpp:53-55
+      uni.mid_qr = uni.width / 2;
+      const double PI_ = 3.14159265358979323846264338327950288;  // utils/constants.hpp; hex_lattice.hpp:60-63
+      uni.cos_pi_6 = std::cos(PI_ / 6.0); uni.sin_pi_6 = std::sin(PI_ / 6.0);
+      uni.cos_pi_3 = std::cos(PI_ / 3.0); uni.sin_pi_3 = std::sin(PI_ / 3.0);
+      outer_ids[u] = tk.ll();
+      size_t n = (size_t)tk.ll();
+      for (size_t i = 0; i < n; i++) lat_ids[u].push_back(tk.ll());
     } else {
       throw std::runtime_error("deck: unsupported universe kind " + kind);
     }
@@ -359,6 +373,22 @@ static Problem* load_problem(const char* path) {
     Universe& uni = geo.universes[u];
     if (uni.type == U_RECT) {
       for (long long id : lat_ids[u]) uni.lattice_universes.push_back(id < 0 ? -1 : geo.universe_id_to_indx.at((uint32_t)id));
+      uni.outer_universe_index = outer_ids[u] < 0 ? -1 : geo.universe_id_to_indx.at((uint32_t)outer_ids[u]);
+    } else if (uni.type == U_HEX) {  // HexLattice::set_elements, hex_lattice.cpp:204-222: the ids fill the hexagon row by row
+      uint32_t nhex = 0;
+      for (uint32_t r = 0; r < uni.Nrings; r++) nhex += r == 0 ? 1 : 6 * r;
+      if (lat_ids[u].size() != (size_t)nhex * uni.Nz) throw std::runtime_error("deck: Improper number of universes for HexLattice.");
+      uni.lattice_universes.assign((size_t)uni.width * uni.width * uni.Nz, -1);
+      size_t indx = 0;
+      for (uint32_t az = 0; az < uni.Nz; az++)
+        for (uint32_t ar = 0; ar < uni.width; ar++)
+          for (uint32_t aq = 0; aq < uni.width; aq++) {
+            const int32_t q = static_cast<int32_t>(aq - uni.mid_qr), r = static_cast<int32_t>(ar - uni.mid_qr);
+            if (Geometry::hex_ring(q, r) < uni.Nrings) {
+              const long long id = lat_ids[u][indx++];
+              uni.lattice_universes[Geometry::hex_linear_index(uni, q, r, (int32_t)az)] = id < 0 ? -1 : geo.universe_id_to_indx.at((uint32_t)id);
+            }
+          }
       uni.outer_universe_index = outer_ids[u] < 0 ? -1 : geo.universe_id_to_indx.at((uint32_t)outer_ids[u]);
     }
   }

@@ -255,6 +255,11 @@ TRANSPORT_CASES = (
 )
 
 
+# HexLattice (src/hex_lattice.cpp) through DeltaTracker::transport: pointy top with the origin at zero, flat top with the origin
+# off zero.  (The reference's SurfaceTracker does not terminate on a hexagonal lattice: tests/decks/make_hex_decks.py.)
+HEX_CASES = (("hex_delta_collision.yaml", 2000, 1.1), ("hex_delta_flat_offset.yaml", 2000, 0.95))
+
+
 def transport_bank(deck: dict, n: int, seed: int, negative: bool):
     """A seeded bank inside the deck's source region: unit directions, the source energy, weights in [0.3, 1.7] (a tenth of
     them negative for the carter deck, as after an under-estimated majorant), history ids with gaps."""

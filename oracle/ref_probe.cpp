@@ -36,6 +36,7 @@
 #include <geometry/surfaces/zplane.hpp>
 #include <geometry/cell_universe.hpp>
 #include <geometry/geometry.hpp>
+#include <geometry/hex_lattice.hpp>
 #include <geometry/rect_lattice.hpp>
 #include <materials/legendre_distribution.hpp>
 #include <materials/mg_angle_distribution.hpp>
@@ -354,6 +355,7 @@ struct CellDef { uint32_t id; bool fill_universe; uint32_t fill; std::string reg
 struct UniDef {
   uint32_t id; bool lattice; std::vector<uint32_t> cells;
   uint32_t shape[3]; double pitch[3], origin[3]; int32_t outer; std::vector<int32_t> tiles;
+  bool hex = false; int top = 0;  // hexagonal lattice: shape = {nrings, nz}, pitch = {pitch, pitch_z}
 };
 struct GeoDeck {
   std::vector<CellDef> cells;
@@ -384,8 +386,13 @@ void build_universe(const UniDef& d) {
     need_universe(static_cast<uint32_t>(u_id));
     uni_indicies.push_back(static_cast<int32_t>(universe_id_to_indx[static_cast<uint32_t>(u_id)]));
   }
-  std::shared_ptr<Lattice> lat = std::make_shared<RectLattice>(d.shape[0], d.shape[1], d.shape[2], d.pitch[0], d.pitch[1],
-                                                               d.pitch[2], d.origin[0], d.origin[1], d.origin[2], d.id, "");
+  std::shared_ptr<Lattice> lat;
+  if (d.hex)  // make_hex_lattice, src/hex_lattice.cpp:546-552
+    lat = std::make_shared<HexLattice>(d.shape[0], d.shape[1], d.pitch[0], d.pitch[1], d.origin[0], d.origin[1], d.origin[2],
+                                       d.top ? HexLattice::Top::Flat : HexLattice::Top::Pointy, d.id, "");
+  else
+    lat = std::make_shared<RectLattice>(d.shape[0], d.shape[1], d.shape[2], d.pitch[0], d.pitch[1], d.pitch[2], d.origin[0],
+                                        d.origin[1], d.origin[2], d.id, "");
   lat->set_elements(uni_indicies);
   if (d.outer != -1) {
     need_universe(static_cast<uint32_t>(d.outer));
@@ -498,10 +505,16 @@ int ref_geometry_load(const char* text, int nmat, const int* material_ids) {
       } else if (key == "uni") {
         UniDef u; std::string kind;
         in >> u.id >> kind;
-        u.lattice = kind == "rect";
+        u.lattice = kind == "rect" || kind == "hex";
+        u.hex = kind == "hex";
         if (!u.lattice) {
           size_t n; in >> n; u.cells.resize(n);
           for (auto& c : u.cells) in >> c;
+        } else if (u.hex) {
+          size_t n;
+          in >> u.shape[0] >> u.shape[1] >> u.pitch[0] >> u.pitch[1] >> u.origin[0] >> u.origin[1] >> u.origin[2] >> u.top >> u.outer >> n;
+          u.tiles.resize(n);
+          for (auto& t : u.tiles) in >> t;
         } else {
           size_t n;
           in >> u.shape[0] >> u.shape[1] >> u.shape[2] >> u.pitch[0] >> u.pitch[1] >> u.pitch[2] >> u.origin[0] >> u.origin[1] >>

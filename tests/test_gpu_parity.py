@@ -149,6 +149,8 @@ CASES = [
     ("UD2O-2-1-SL_implicit.yaml", {}, 20000),             # ... two groups, P1, tally
     ("c5g7_implicit_collision.yaml", {}, 20000),          # ... lattices, reflective + vacuum sides, collision tally
     ("c5g7_implicit_tracklength.yaml", {}, 8000),         # ... track-length tally of the leaking and the colliding share
+    ("hex_delta_collision.yaml", {}, 20000),              # HexLattice (pointy top) under delta tracking, an empty position, outer universe
+    ("hex_delta_flat_offset.yaml", {}, 20000),            # ... flat top, origin off zero (the reference's un-shifted tile check)
 ]
 
 
