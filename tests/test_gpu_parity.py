@@ -624,3 +624,21 @@ def test_power_iteration_sharded_over_two_ranks_matches_one_rank(ab, tmp_path, d
         for t, (a, b) in enumerate(zip(got["tallies"], ref["tallies"])):
             scale = np.abs(b).max()
             assert np.allclose(a, b, rtol=1e-7, atol=1e-9 * scale), f"tally {t}"
+
+
+def test_million_histories_full_mesh_generation_against_oracle(ab, oracle_api, tmp_path):
+    """The bench workload at 1e6 histories against the oracle: the deck's 1224 x 1224 x 10 x 7 mesh (105 M bins), a fission
+    source, the host-buffer entry point -- so the streamed input bank, the ticket refill over many waves per thread and the
+    32-bit site offsets run at scale -- with every history's integer outcome and the whole fission bank compared bit for bit
+    and the mesh tally bin by bin."""
+    n = 1_000_000
+    orc, gpu = _pair(ab, oracle_api, tmp_path, "c5g7_delta_collision_fullmesh.yaml", {"settings": {"nparticles": n}})
+    oracle_api.set_threads(os.cpu_count() or 1)
+    bank, o, g = _transport_both(orc, gpu, n, converged=True, k_col=1.17, second_generation=True)
+    assert len(bank["x"]) > n  # the fission source of the first generation (k_col = 1 there banks ~1.6 sites per history)
+    _assert_same_histories(o, g)
+    og, gg = orc.tally(0, "gen"), gpu.tally(0, "gen")
+    assert og.shape == gg.shape == (7, 1224, 1224, 10)
+    assert np.array_equal(og != 0, gg != 0)
+    assert np.allclose(gg, og, rtol=1e-10, atol=1e-300)
+    assert abs(gg.sum() - og.sum()) <= 1e-9 * abs(og.sum())
