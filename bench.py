@@ -51,6 +51,11 @@ CONFIGS = {
         "workload": "c5g7 7-group carter tracking with an under-estimated sampling cross section, approximate mesh weight "
                     "cancellation (170x170x765 bins, dense-bin all-reduce across ranks), 1.25e7 particles per generation per GPU",
         "tests": ["tests/test_gpu_parity.py", "-k", "carter or cancel"]},
+    5: {"deck": "noise_oscillation.yaml", "particles": 100_000, "kernel": "transport_kernel<surface, noise>",
+        "metric": "noise batch: particles/sec (power-iteration + noise particles), frequency-domain neutron noise",
+        "workload": "noise_oscillation.yaml: nskip power-iteration generations (the last one samples the noise source), then the "
+                    "inner noise generations (complex weights, regional cancellation) until the noise bank is empty",
+        "tests": ["tests/test_gpu_noise.py", "-k", "noise"]},
 }
 
 
@@ -308,6 +313,8 @@ def run_b200(args):
     from abeille_b200.distributed import DistributedPowerIterator, HostBufferLoop
 
     cfg = CONFIGS.get(args.config)
+    if args.config == 5:
+        return run_noise_config(args, rank, world, local, dev, saved_stdout)
     metric, workload, kernel_name = (cfg["metric"], cfg["workload"], cfg["kernel"]) if cfg else (METRIC, WORKLOAD, "history_kernel<delta>")
     if cfg and args.particles == 10_000_000:
         args.particles = cfg["particles"]
@@ -448,6 +455,90 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_noise_config(args, rank, world, local, dev, saved_stdout):
+    """--config 5: noise batches of the shipped noise_oscillation deck through DistributedNoiseSimulation (one process per GPU,
+    every bank sharded in rank order).  A step is one noise batch: nskip power-iteration generations and the inner noise
+    generations that follow; value = (power-iteration particles + noise particles) of the timed batches / device time."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import yaml
+    from abeille_b200.noise import DistributedNoiseSimulation
+    cfg = CONFIGS[5]
+    n_total = (cfg["particles"] if args.particles == 10_000_000 else args.particles) * world
+    td = tempfile.mkdtemp()
+    with open(os.path.join(ROOT, "tests", "decks", cfg["deck"])) as f:
+        deck = yaml.safe_load(f)
+    deck["settings"].update({"nparticles": int(n_total), "nignored": 2, "nskip": 2, "ngenerations": args.steps})
+    path = os.path.join(td, f"noise_{rank}.yaml")
+    with open(path, "w") as f:
+        yaml.safe_dump(deck, f, default_flow_style=None, sort_keys=False, width=200)
+    sim = DistributedNoiseSimulation(path, local)
+    sim.initialize()
+    sim.converged = False
+    for _ in range(sim.nignored):
+        sim.power_iteration(False)
+    sim.converged = True
+
+    def batch():
+        pi = 0
+        for _ in range(sim.nskip - 1):
+            sim.power_iteration(False)
+            pi += sim.nparticles
+        n_noise = sim.power_iteration(True)
+        pi += sim.nparticles
+        sim.noise_simulation(n_noise)
+        return pi + sim.noise_particles[-1]
+
+    for _ in range(min(args.warmup, 1)):
+        batch()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = sim.gpu.device_info()["kernel_launches"]
+    e0.record()
+    particles = 0
+    first = len(sim.noise_generations)
+    for _ in range(args.steps):
+        particles += batch()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    out = None
+    if rank == 0:
+        out = {"metric": cfg["metric"], "value": particles / (ms * 1e-3), "unit": "particles/s", "n_gpus": world, "steps": args.steps,
+               "warmup": min(args.warmup, 1), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": cfg["workload"], "particles_per_generation": int(n_total), "nskip": sim.nskip,
+                          "noise_generations_per_batch": sim.noise_generations[first:],
+                          "noise_particles_per_batch": sim.noise_particles[first:], "k_col": float(sim.k_col)},
+               "gpu_launches": int(sim.gpu.device_info()["kernel_launches"] - launches0)}
+        if not args.no_parity:
+            t0 = time.time()
+            r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x"] + cfg["tests"], cwd=ROOT, capture_output=True,
+                               text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=str(local)))
+            tail = [l for l in r.stdout.strip().splitlines() if l.strip()][-1:] or [""]
+            out["parity"] = {"passed": r.returncode == 0, "summary": tail[0], "seconds": time.time() - t0,
+                             "what": "pytest -m gpu " + " ".join(cfg["tests"])}
+    import ctypes
+    sys.stdout.flush()
+    ctypes.CDLL(None).fflush(None)
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        os.dup2(2, 1)
+        dist.destroy_process_group()
+
+
 def ncu_child(args):
     """The resident leg alone, a few generations, no output: the process `ncu_kernel_metrics` profiles."""
     import torch
@@ -558,8 +649,8 @@ def main():
     ap.add_argument("--no-ncu", action="store_true", help="skip the ncu capture of one kernel launch (roofline.traffic = null)")
     ap.add_argument("--no-ranks-check", action="store_true", help="N > 1: skip the sharded-vs-1-rank consistency run")
     ap.add_argument("--ncu-child", action="store_true", help=argparse.SUPPRESS)
-    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4],
-                    help="BASELINE.json configuration: 2 = the bench line (default); 1, 3, 4 = the other k-eigenvalue configurations")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json configuration: 2 = the bench line (default); 1, 3, 4 = the other k-eigenvalue configurations; 5 = noise batches")
     ap.add_argument("--no-parity", action="store_true", help="--config 1|3|4: skip the configuration's parity tests")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-e2e", action="store_true")
