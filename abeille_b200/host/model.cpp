@@ -28,7 +28,10 @@ void make_settings(const Node& input, Settings& st) {
     const std::string sim = s["simulation"].as_string();
     if (sim == "k-eigenvalue") st.mode = ABL_MODE_K_EIGENVALUE;
     else if (sim == "noise") st.mode = ABL_MODE_NOISE;
-    else fatal_error("Simulation mode \"" + sim + "\" is not provided by the B200 backend (k-eigenvalue, noise).");
+    // modified-fixed-source (src/modified_fixed_source.cpp) transports with the k-eigenvalue kernels: its make_fission_neutrons
+    // drops the division by k_col (transporter.cpp:381-386), which the driver (abeille_b200/fixed_source.py) gets with k_col = 1
+    else if (sim == "modified-fixed-source") { st.mode = ABL_MODE_K_EIGENVALUE; st.fixed_source = true; }
+    else fatal_error("Simulation mode \"" + sim + "\" is not provided by the B200 backend (k-eigenvalue, noise, modified-fixed-source).");
   } else {
     fatal_error("No simulation type provided.");
   }
@@ -62,9 +65,9 @@ void make_settings(const Node& input, Settings& st) {
   if (!s["ngenerations"]) fatal_error("Number of generations not specified in settings.");
   st.ngenerations = static_cast<int>(s["ngenerations"].as_int());
   if (s["nignored"]) st.nignored = static_cast<int>(s["nignored"].as_int());
-  else if (st.mode == ABL_MODE_K_EIGENVALUE) fatal_error("Number of ignored generations not specified in settings.");
+  else if (st.mode == ABL_MODE_K_EIGENVALUE && !st.fixed_source) fatal_error("Number of ignored generations not specified in settings.");
   else st.nignored = 0;
-  if (st.mode == ABL_MODE_K_EIGENVALUE && st.nignored >= st.ngenerations)
+  if (st.mode == ABL_MODE_K_EIGENVALUE && !st.fixed_source && st.nignored >= st.ngenerations)
     fatal_error("Number of ignored generations is greater than or equal to the number of total generations.");
   if (s["nskip"]) st.nskip = static_cast<int>(s["nskip"].as_int());
   if (s["wgt-cutoff"]) {

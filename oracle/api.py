@@ -349,6 +349,42 @@ class Oracle:
         out["final_bank"] = (len(bank["x"]), int(bank["id_a"][0]) if len(bank["x"]) else 0, int(counter))
         return out
 
+    def run_modified_fixed_source(self, nbatches: int) -> dict:
+        """ModifiedFixedSource::run (src/modified_fixed_source.cpp:59-141): every batch samples the source and follows the whole
+        fission chain -- the fission bank of a transport call becomes the next call's bank with its weights kept and fresh
+        history ids (Particle(p.r, p.u, p.E, p.wgt, p.wgt2, histories_counter++) + initialize_rng) until it is empty; then
+        Tallies::calc_gen_values / record_generation.  make_fission_neutrons does not divide by k_col in this mode
+        (transporter.cpp:381-386), which is k_col = 1 here (x / 1 is x exactly)."""
+        n = self.nparticles()
+        self.set_converged(True)
+        counter = 0
+        kcol, leak, mig = [], [], []
+        transported = 0
+        for _ in range(nbatches):
+            self.set_history_counter(counter)
+            bank = self.sample_source(n)
+            counter += n
+            totals = np.zeros(6)
+            while len(bank["x"]):
+                self.set_kcol(1.0)
+                m_in = len(bank["x"])
+                fis, scores, _ = self.transport(bank)
+                transported += m_in
+                totals += scores
+                m = len(fis["x"])
+                bank = {k: fis[k].copy() for k in ("x", "y", "z", "ux", "uy", "uz", "E", "wgt")}
+                bank["wgt2"] = fis["wgt2"].copy() if fis.get("wgt2") is not None else np.zeros(m)
+                bank["id_a"] = np.arange(counter, counter + m, dtype=np.uint64)
+                bank["id_b"] = np.zeros(m, dtype=np.uint64)
+                bank["id_c"] = None
+                counter += m
+            kcol.append(totals[0] / n)
+            leak.append(totals[4] / n)
+            mig.append(totals[5] / n)
+            self.tallies_record(1.0)
+            self.tallies_clear()
+        return {"kcol": np.array(kcol), "leak": np.array(leak), "mig": np.array(mig), "transported": transported}
+
     def run_power_iteration(self, ngen: int, nignored: int) -> dict:
         arr = {k: np.zeros(ngen) for k in ("kcol", "ktrk", "leak", "mig", "entropy")}
         nbank = np.zeros(ngen, dtype=np.uint64)

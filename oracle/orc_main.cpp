@@ -197,6 +197,8 @@ static Problem* load_problem(const char* path) {
   tk.expect("ORCDECK");
   tk.ll();
   tk.expect("mode");
+  // ("mfs": modified-fixed-source.  Its transport is the k-eigenvalue one with n_new = floor(|k_abs_scr| + xi) -- no division by
+  // k_col (transporter.cpp:381-386) --, which the driver obtains by setting k_col to 1: x / 1 is x exactly.)
   st.mode = tk.next() == "noise" ? Settings::NOISE : Settings::K_EIGENVALUE;
   tk.expect("tracking");
   {

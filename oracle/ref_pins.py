@@ -608,6 +608,52 @@ NOISE_DRIVER_CASES = (("noise_oscillation.yaml", 600, 2, 1, 2), ("noise_oscillat
                       ("noise_vibration.yaml", 500, 2, 1, 2))
 
 
+# modified-fixed-source: deck, particles per batch, batches
+MFS_CASES = (("PUa-1-0-SL_subcritical_mfs.yaml", 3000, 6),)
+
+
+def evaluate_modified_fixed_source(impl: str) -> dict:
+    """The reference's own ModifiedFixedSource::run() (oracle/_ref) against the oracle's driver: k_col, leakage and migration
+    area of every batch, the histories transported (source + every fission generation of every chain), and the mesh tallies'
+    average and error of the mean.  One case: the reference keeps its state in process globals."""
+    from . import deck as _deck
+    ref = impl == "reference"
+    decks = os.path.join(os.path.dirname(_HERE), "tests", "decks")
+    out = {}
+    with _reference_math(impl):
+        for fname, n, nb in MFS_CASES:
+            path = os.path.join(decks, fname)
+            ov = {"settings": {"nparticles": n, "ngenerations": nb}}
+            name = fname.split(".")[0]
+            if ref:
+                L = ref_lib()
+                deck = _deck.apply_overrides(_deck.load_yaml(path), ov)
+                a = {k: np.zeros(nb) for k in ("kcol", "leak", "mig")}
+                tr = C.c_uint64(0)
+                L.ref_set_threads(C.c_int(1))
+                rc = L.ref_modified_fixed_source(_deck.deck_to_text(deck).encode(), C.c_int(nb), _d(a["kcol"]), _d(a["leak"]), _d(a["mig"]),
+                                                 C.byref(tr))
+                assert rc == 0
+                # (tr is 0 in the reference: it adds bank.size() after transport() has cleared the bank; not compared)
+                L.ref_tally_size.restype = C.c_uint64
+                for t in range(L.ref_ntallies()):
+                    size = int(L.ref_tally_size(C.c_int(t)))
+                    for which, wname in ((1, "avg"), (2, "std")):
+                        v = np.zeros(size)
+                        L.ref_tally_get_stat(C.c_int(t), C.c_int(which), _d(v))
+                        a[f"tally{t}_{wname}"] = v
+            else:
+                o = api.Oracle(path, ov)
+                r = o.run_modified_fixed_source(nb)
+                a = {k: r[k] for k in ("kcol", "leak", "mig")}
+                for t in range(o.ntallies()):
+                    a[f"tally{t}_avg"], a[f"tally{t}_std"] = np.ravel(o.tally(t, "avg")), np.ravel(o.tally(t, "std"))
+                o.close()
+            for k, v in a.items():
+                out[f"mfs_{name}_{k}"] = np.ascontiguousarray(v)
+    return out
+
+
 def evaluate_noise_driver(impl: str, only: int | None = None) -> dict:
     """The reference's own Noise::initialize() + run() (src/noise.cpp: power-iteration generations, noise-source sampling
     and normalisation, inner noise generations with regional cancellation of the noise fission banks, tally statistics)

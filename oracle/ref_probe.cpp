@@ -37,6 +37,7 @@
 #include <geometry/cell_universe.hpp>
 #include <geometry/geometry.hpp>
 #include <geometry/hex_lattice.hpp>
+#include <simulation/modified_fixed_source.hpp>
 #include <geometry/rect_lattice.hpp>
 #include <materials/legendre_distribution.hpp>
 #include <materials/mg_angle_distribution.hpp>
@@ -680,7 +681,12 @@ int ref_problem_load(const char* text) {
     Tok tk(text);
     tk.expect("ORCDECK"); tk.ll();
     tk.expect("mode");
-    settings::mode = tk.next() == "noise" ? settings::SimulationMode::NOISE : settings::SimulationMode::K_EIGENVALUE;
+    {
+      const std::string mode = tk.next();
+      settings::mode = mode == "noise" ? settings::SimulationMode::NOISE
+                       : mode == "mfs" ? settings::SimulationMode::MODIFIED_FIXED_SOURCE
+                                       : settings::SimulationMode::K_EIGENVALUE;
+    }
     tk.expect("tracking");
     const std::string trk = tk.next();
     settings::tracking = trk == "delta" ? settings::TrackingMode::DELTA_TRACKING
@@ -1113,6 +1119,31 @@ int ref_power_iteration_gpu(const char* text, const char* host_library, const ch
 // simulation of that source (inner generations, regional cancellation of the noise fission banks).  Out: k_col of every
 // power-iteration generation and 0 per noise batch (Tallies' generation vector); final_bank3 = size of the last bank, its
 // first history id, the global history counter; the mesh tallies are read with ref_tally_get_stat.
+// The reference's ModifiedFixedSource::run() (src/modified_fixed_source.cpp:59-141): per batch the source is sampled and
+// transported, the fission bank becomes the next bank (weights kept, fresh history ids) until it is empty, then the
+// generation values and mesh tallies are recorded.  Out: k_col, leakage and migration area of every batch, the number of
+// histories transported; the mesh tallies are read with ref_tally_get_stat.
+int ref_modified_fixed_source(const char* text, int nbatches, double* kcol, double* leak, double* mig, uint64_t* transported) {
+  try {
+    if (ref_problem_load(text) != 0) return 1;
+    omp_set_num_threads(g_threads);
+    settings::ngenerations = nbatches;
+    DriverParts d = driver_parts(text);
+    auto sim = std::make_shared<ModifiedFixedSource>(g_tallies, g_transporter, d.sources);
+    sim->initialize();
+    sim->run();
+    const Tallies& T = *g_tallies;
+    for (int g = 0; g < nbatches; g++) {
+      kcol[g] = T.k_col_vec[(size_t)g]; leak[g] = T.leak_vec[(size_t)g]; mig[g] = T.mig_vec[(size_t)g];
+    }
+    *transported = sim->transported_histories;
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "ref_modified_fixed_source: %s\n", e.what());
+    return 1;
+  }
+}
+
 int ref_noise_run(const char* text, int nbatches, int nignored, int nskip, double* kcol, int* n_kcol, uint64_t* final_bank3) {
   try {
     if (ref_problem_load(text) != 0) return 1;

@@ -642,3 +642,30 @@ def test_million_histories_full_mesh_generation_against_oracle(ab, oracle_api, t
     assert np.array_equal(og != 0, gg != 0)
     assert np.allclose(gg, og, rtol=1e-10, atol=1e-300)
     assert abs(gg.sum() - og.sum()) <= 1e-9 * abs(og.sum())
+
+
+def test_modified_fixed_source_driver_matches_oracle_and_reference(ab, oracle_api, tmp_path):
+    """abeille_b200.fixed_source.ModifiedFixedSource (the reference's ModifiedFixedSource::run over the device entry points)
+    on a subcritical slab: every batch's k_col, leakage and migration area and the mesh tally statistics against the oracle's
+    driver (det math: 1e-10) and against the reference's own run (tests/golden/ref_pins_mfs.npz: 1e-9)."""
+    from abeille_b200.fixed_source import ModifiedFixedSource
+    from oracle import ref_pins
+    fname, n, nb = ref_pins.MFS_CASES[0]
+    path = write_deck(load_deck(fname), tmp_path / fname, {"settings": {"nparticles": n, "ngenerations": nb}})
+    orc = oracle_api.Oracle(path)
+    ref = orc.run_modified_fixed_source(nb)
+    sim = ModifiedFixedSource(path, 0)
+    got = sim.run()
+    assert got["transported"] == ref["transported"] and min(got["chain_generations"]) > 3
+    for k in ("kcol", "leak", "mig"):
+        assert np.allclose(got[k], ref[k], rtol=1e-10), (k, got[k], ref[k])
+    for t in range(orc.ntallies()):
+        for which in ("avg", "std"):
+            a, b = sim.tally(t, which), orc.tally(t, which)
+            assert np.allclose(a, b, rtol=1e-8, atol=1e-12 * np.abs(b).max()), (t, which)
+    gold = dict(np.load(os.path.join(GOLDEN, "ref_pins_mfs.npz")))
+    name = fname.split(".")[0]
+    for k in ("kcol", "leak", "mig"):
+        assert np.allclose(got[k], gold[f"mfs_{name}_{k}"], rtol=1e-9), k
+    assert np.allclose(np.ravel(sim.tally(0, "avg")), gold[f"mfs_{name}_tally0_avg"], rtol=1e-7, atol=1e-12)
+    sim.close()
