@@ -398,6 +398,8 @@ int ensure_history_scratch(abl_handle h, uint64_t n, bool trace) {
     const uint64_t cap = n + 1024;
     for (void* p : {(void*)h->tr_flights, (void*)h->tr_real, (void*)h->tr_virtual, (void*)h->tr_hash, (void*)h->tr_rng})
       if (p) cudaFree(p);
+    h->tr_flights = h->tr_real = h->tr_virtual = nullptr;  // (so that a failed allocation below leaves no dangling pointer)
+    h->tr_hash = h->tr_rng = nullptr;
     h->trace_cap = 0;
     ABL_CUDA(h, cudaMalloc(&h->tr_flights, cap * 4));
     ABL_CUDA(h, cudaMalloc(&h->tr_real, cap * 4));
@@ -1183,11 +1185,15 @@ int transport_upload_and_run(abl_handle h, const abl_bank* bank, const abl_gen_p
   cudaStream_t s = use_stream(h, h->stream);
   const uint64_t N = bank->n;
   int rc;
+  // (the recorded capacity is dropped BEFORE the old arrays are freed: a failed allocation must not leave a capacity that
+  // lets a later, smaller call skip the reallocation and copy into freed pointers)
   if (N > h->stage_in_cap) {
+    h->stage_in_cap = 0;
     if ((rc = alloc_bank(h, h->stage_in, N + N / 4 + 1024)) != 0) return rc;
     h->stage_in_cap = h->stage_in.n;
   }
   if (cap > h->stage_out_cap) {
+    h->stage_out_cap = 0;
     if ((rc = alloc_bank(h, h->stage_out, cap)) != 0) return rc;
     h->stage_out_cap = h->stage_out.n;
   }
