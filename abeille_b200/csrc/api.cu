@@ -171,7 +171,7 @@ std::vector<double> discrete_table(const std::vector<double>& w) {
 int validate(abl_handle h, const abl_problem* p) {
   if (p->ngroups < 1 || !p->energy_bounds) return fail(h, ABL_ERR_INVALID, "ngroups / energy_bounds");
   if (p->tracking < ABL_TRACK_SURFACE || p->tracking > ABL_TRACK_IMPLICIT_LEAKAGE) return fail(h, ABL_ERR_INVALID, "tracking");
-  if (p->mode != ABL_MODE_K_EIGENVALUE && p->mode != ABL_MODE_NOISE)
+  if (p->mode != ABL_MODE_K_EIGENVALUE && p->mode != ABL_MODE_NOISE && p->mode != ABL_MODE_FIXED_SOURCE)
     return fail(h, ABL_ERR_UNSUPPORTED, "simulation modes on the device: k-eigenvalue, noise");
   if (p->mode == ABL_MODE_NOISE) {
     if (p->n_noise_sources < 1 || !p->noise_sources) return fail(h, ABL_ERR_INVALID, "noise mode without a noise source");
@@ -608,7 +608,7 @@ int launch_transport_nm(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   RunArgs B = A;
-  if (MODE == 2 || TRK == ABL_TRACK_CARTER) {  // secondaries: noise copies, carter splitting, noise fission without inner generations
+  if (MODE == 2 || TRK == ABL_TRACK_CARTER || h->P.mode == ABL_MODE_FIXED_SOURCE) {  // secondaries: noise copies, carter splitting, noise fission without inner generations, fixed-source fission
     const uint64_t cap = (uint64_t)h->sm_count * bps * threads;
     if (cap > h->sec_threads) {
       if (h->secondaries) cudaFree(h->secondaries);
@@ -681,7 +681,9 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
   const bool sample_noise = params->sample_noise_source != 0;
   // a power-iteration generation of a noise run that does not sample the noise source is a plain k-eigenvalue generation:
   // it goes through the staged kernel; noise particles and sampling generations use the per-lane kernel (noise.cuh)
-  const bool lane_kernel_call = noise_mode && (params->noise != 0 || sample_noise);
+  // fixed-source problems (fission neutrons as secondaries of their history) run the per-lane kernel in its k-eigenvalue mode
+  const bool fixed_source = h->P.mode == ABL_MODE_FIXED_SOURCE;
+  const bool lane_kernel_call = (noise_mode && (params->noise != 0 || sample_noise)) || fixed_source;
   if ((params->noise || sample_noise) && !noise_mode)
     return fail(h, ABL_ERR_INVALID, "noise transport / noise-source sampling needs a problem with simulation: noise");
   if (params->noise && sample_noise) return fail(h, ABL_ERR_INVALID, "the noise source is sampled in power-iteration generations only");
@@ -750,7 +752,7 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
   }
   if (N > 0) {
     if (lane_kernel_call) {  // (the per-lane kernel seeds the streams itself when id_c is NULL)
-      rc = params->noise ? launch_transport_nm<2>(h, A, N, s) : launch_transport_nm<1>(h, A, N, s);
+      rc = fixed_source ? launch_transport_nm<0>(h, A, N, s) : (params->noise ? launch_transport_nm<2>(h, A, N, s) : launch_transport_nm<1>(h, A, N, s));
     } else if (h->P.tracking == ABL_TRACK_IMPLICIT_LEAKAGE) {  // k-eigenvalue generation through the per-lane kernel
       rc = launch_transport_nm<ABL_TRACK_IMPLICIT_LEAKAGE, 0>(h, A, N, s);
     } else {

@@ -217,6 +217,30 @@ static __device__ __noinline__ void bank_fission_sites(const FissionTables T, Si
   }
 }
 
+__device__ inline bool push_secondary(const RunArgs& A, Hist& h, const V3& u, double E, double w, double w2, uint32_t tid,
+                                      uint32_t nthreads);  // (defined with the secondaries' LIFO below)
+
+// Fixed-source problems: the n_new fission neutrons of a collision become secondaries of the history (Particle::make_secondary,
+// transporter.cpp:460-463) instead of bank entries.  The same draws per neutron as bank_fission_sites.
+template <class M>
+static __device__ __noinline__ bool fission_to_secondaries(const FissionTables T, const RunArgs& A, Hist& h, int n_new, int mat, int mg,
+                                                           double P_delayed, uint32_t tid, uint32_t nthreads) {
+  const int dg0 = ldt(&T.dg_off[mat]), ndg = ldt(&T.dg_off[mat + 1]) - dg0;
+  for (int i = 0; i < n_new; i++) {
+    int ei = 0;
+    if (T.G >= 2) ei = rng_discrete<M>(h.rng, T.chi_cp + (size_t)mg * T.G, T.G);
+    const double E_out = ldt(&T.gmid[ei]);
+    const double mu = 2. * M::rand(h.rng) - 1.;
+    const double phi = 2. * ABL_PI * M::rand(h.rng);
+    const V3 dir = rotate_dir<M>(h.u, mu, phi);
+    if (M::rand(h.rng) < P_delayed) {
+      if (ndg >= 2) (void)rng_discrete<M>(h.rng, T.dg_cp + dg0, ndg);
+    }
+    if (!push_secondary(A, h, dir, E_out, h.w > 0. ? 1. : -1., 0., tid, nthreads)) return false;
+  }
+  return true;
+}
+
 template <bool NOISE, class M = InlineMath>
 __device__ __forceinline__ void russian_roulette(const DevProblem& P, Hist& h) {  // transporter.cpp:35-58
   if (fabs(h.w) < P.wgt_cutoff) {
@@ -234,7 +258,7 @@ __device__ __forceinline__ void russian_roulette(const DevProblem& P, Hist& h) {
 
 // Transporter::collision + branching_collision (transporter.cpp:60-93,269-312), k-eigenvalue branch
 template <bool NOISE, class M = InlineMath>
-__device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A, Hist& h, Acc& acc) {
+__device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A, Hist& h, Acc& acc, uint32_t tid = 0, uint32_t nthreads = 0) {
   const int mg = h.mat * P.G + h.g;
   const double Et = ldt(&P.Et[mg]), Ea = ldt(&P.Ea[mg]), Ef = ldt(&P.Ef[mg]), nu = ldt(&P.nu[mg]);
   acc.real++;
@@ -263,11 +287,18 @@ __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A,
   const int n_new = (int)floor(ddiv_pos<M>(fabs(k_abs_scr), A.k_col) + M::rand(h.rng));
   if (n_new > 0) {
     const FissionTables ft{P.chi_cp, P.dg_cp, P.dg_off, P.gmid, P.G};
-    bank_fission_sites<M>(ft, A.sites, A.n_sites, A.site_capacity, h.rng, h.r, h.u, h.w, h.idx, h.daughter, n_new, h.mat, mg,
-                          ldt(&P.nud[mg]) / nu);
-    h.daughter += (uint32_t)n_new;
-    h.n_fis += (uint32_t)n_new;
-    acc.sites += (uint32_t)n_new;
+    if (P.mode == ABL_MODE_FIXED_SOURCE) {  // the neutrons continue this history (src/fixed_source.cpp: the returned bank is empty)
+      if (!fission_to_secondaries<M>(ft, A, h, n_new, h.mat, mg, ldt(&P.nud[mg]) / nu, tid, nthreads))
+        raise_error(A, ABL_ERR_BANK_OVERFLOW, A.bank.id_a[h.idx]);
+      h.daughter += (uint32_t)n_new;  // (Particle::make_secondary does not number daughters; kept for the trace only)
+      acc.sites += (uint32_t)n_new;
+    } else {
+      bank_fission_sites<M>(ft, A.sites, A.n_sites, A.site_capacity, h.rng, h.r, h.u, h.w, h.idx, h.daughter, n_new, h.mat, mg,
+                            ldt(&P.nud[mg]) / nu);
+      h.daughter += (uint32_t)n_new;
+      h.n_fis += (uint32_t)n_new;
+      acc.sites += (uint32_t)n_new;
+    }
   }
   note(h, 0x5000000000000000ULL | (uint64_t)(uint32_t)n_new);
   // implicit capture (transporter.cpp:295-298)
@@ -366,7 +397,7 @@ namespace abl {
 // MODE 0: k-eigenvalue run; 1: power-iteration generation of a noise run; 2: noise particles (see noise.cuh)
 template <int MODE>
 __device__ __forceinline__ void collide(const DevProblem& P, const RunArgs& A, Hist& h, Acc& acc, uint32_t tid, uint32_t nthreads) {
-  if (MODE == 0) collision<false>(P, A, h, acc);
+  if (MODE == 0) collision<false>(P, A, h, acc, tid, nthreads);
   else collision_nm<MODE>(P, A, h, acc, tid, nthreads);
 }
 // the copy "cross section" eta * omega / v of noise transport (material_helper.hpp:65-84)

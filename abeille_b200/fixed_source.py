@@ -1,4 +1,12 @@
-"""Modified-fixed-source simulation on the B200 backend: the reference's `ModifiedFixedSource` driver
+"""Fixed-source and modified-fixed-source simulations on the B200 backend.
+
+`FixedSource` (src/fixed_source.cpp:81-175): every batch samples the source and transports it once; the fission neutrons of
+a collision continue the history that made them as secondaries (src/transporter.cpp:374-379,460-463: n_new = floor(|w nu Sf /
+St| + xi), Particle::make_secondary), so the transport call returns an empty bank.  The deck's `simulation: fixed-source`
+reaches the kernels as ABL_MODE_FIXED_SOURCE; the per-lane kernel runs it (its secondaries LIFO is the one carter splitting
+and noise copies use).
+
+`ModifiedFixedSource`: the reference's `ModifiedFixedSource` driver
 (src/modified_fixed_source.cpp:59-141) over the device entry points of the C ABI.  Banks never leave HBM.
 
 Every batch samples `nparticles` source particles (Simulation::sample_sources, src/simulation.cpp:55-77) and follows the whole
@@ -13,6 +21,46 @@ import numpy as np
 import yaml
 
 from .backend import Backend
+
+
+class FixedSource:
+    def __init__(self, deck_path: str, device: int = 0):
+        with open(deck_path) as f:
+            deck = yaml.safe_load(f)
+        st = deck.get("settings", {})
+        if st.get("simulation") != "fixed-source":
+            raise ValueError("FixedSource needs a deck with `simulation: fixed-source`")
+        self.gpu = Backend(deck_path, device)
+        self.nparticles = int(st.get("nparticles", 100000))
+        self.nbatches = int(st.get("ngenerations", 120))
+        self.tally_names = [str(t.get("name", f"tally{i}")) for i, t in enumerate(deck.get("tallies", []) or [])]
+        self.cur, self.nxt = self.gpu.new_device_bank(self.nparticles), self.gpu.new_device_bank(4096)
+        self.history_counter = 0
+        self.k_col, self.leakage, self.mig_area = [], [], []
+
+    def batch(self):
+        g, n = self.gpu, self.nparticles
+        g.sample_source_device(self.cur, n, self.history_counter)
+        self.history_counter += n  # (FixedSource::mpi_advance: the next batch starts nparticles further)
+        m, scores, _ = g.transport_device(self.cur, n, self.nxt, k_col=1.0, converged=True, use_rng_state=True)
+        if m:
+            raise RuntimeError("Returned bank not empty on fixed-source transport.")
+        self.k_col.append(scores[0] / n)
+        self.leakage.append(scores[4] / n)
+        self.mig_area.append(scores[5] / n)
+        g.tallies_record(1.0)
+        g.tallies_clear()
+
+    def run(self):
+        for _ in range(self.nbatches):
+            self.batch()
+        return {"kcol": np.array(self.k_col), "leak": np.array(self.leakage), "mig": np.array(self.mig_area)}
+
+    def tally(self, t: int, which: str = "avg") -> np.ndarray:
+        return self.gpu.tally(t, which)
+
+    def close(self):
+        self.gpu.close()
 
 
 class ModifiedFixedSource:

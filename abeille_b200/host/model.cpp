@@ -31,7 +31,9 @@ void make_settings(const Node& input, Settings& st) {
     // modified-fixed-source (src/modified_fixed_source.cpp) transports with the k-eigenvalue kernels: its make_fission_neutrons
     // drops the division by k_col (transporter.cpp:381-386), which the driver (abeille_b200/fixed_source.py) gets with k_col = 1
     else if (sim == "modified-fixed-source") { st.mode = ABL_MODE_K_EIGENVALUE; st.fixed_source = true; }
-    else fatal_error("Simulation mode \"" + sim + "\" is not provided by the B200 backend (k-eigenvalue, noise, modified-fixed-source).");
+    // fixed-source (src/fixed_source.cpp): fission neutrons are secondaries of their history; driver abeille_b200/fixed_source.py
+    else if (sim == "fixed-source") { st.mode = ABL_MODE_FIXED_SOURCE; st.fixed_source = true; }
+    else fatal_error("Simulation mode \"" + sim + "\" is not provided by the B200 backend (k-eigenvalue, noise, fixed-source, modified-fixed-source).");
   } else {
     fatal_error("No simulation type provided.");
   }

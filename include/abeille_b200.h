@@ -45,7 +45,9 @@ typedef enum abl_status {
 #define ABL_MAX_FRAMES 5  /* nested local coordinate frames (root + lattice levels)       */
 
 /* ---- enums mirrored from the reference --------------------------------------------------------- */
-enum { ABL_MODE_K_EIGENVALUE = 0, ABL_MODE_NOISE = 1 };                         /* settings.hpp        */
+enum { ABL_MODE_K_EIGENVALUE = 0, ABL_MODE_NOISE = 1,
+       ABL_MODE_FIXED_SOURCE = 2 };  /* settings.hpp; FIXED_SOURCE: fission neutrons continue their history as secondaries
+                                        and transport returns an empty bank (src/transporter.cpp:374-379,460-463) */
 enum { ABL_TRACK_SURFACE = 0, ABL_TRACK_DELTA = 1, ABL_TRACK_CARTER = 2,
        ABL_TRACK_IMPLICIT_LEAKAGE = 3 };  /* parser.cpp:408-420,889-911; 3 replaces ImplicitLeakageDeltaTracker::transport
                                              (src/implicit_leakage_delta_tracker.cpp:73-263) */

@@ -349,6 +349,28 @@ class Oracle:
         out["final_bank"] = (len(bank["x"]), int(bank["id_a"][0]) if len(bank["x"]) else 0, int(counter))
         return out
 
+    def run_fixed_source(self, nbatches: int) -> dict:
+        """FixedSource::run (src/fixed_source.cpp:81-175), one rank: every batch samples the source and transports it; the
+        fission neutrons are secondaries of their history (the deck's mode makes make_fission_neutrons do that), so the
+        returned bank must be empty; then Tallies::calc_gen_values / record_generation."""
+        n = self.nparticles()
+        self.set_converged(True)
+        counter = 0
+        kcol, leak, mig = [], [], []
+        for _ in range(nbatches):
+            self.set_history_counter(counter)
+            bank = self.sample_source(n)
+            counter += n
+            fis, scores, _ = self.transport(bank)
+            if len(fis["x"]):
+                raise RuntimeError("Returned bank not empty on fixed-source transport.")
+            kcol.append(scores[0] / n)
+            leak.append(scores[4] / n)
+            mig.append(scores[5] / n)
+            self.tallies_record(1.0)
+            self.tallies_clear()
+        return {"kcol": np.array(kcol), "leak": np.array(leak), "mig": np.array(mig)}
+
     def run_modified_fixed_source(self, nbatches: int) -> dict:
         """ModifiedFixedSource::run (src/modified_fixed_source.cpp:59-141): every batch samples the source and follows the whole
         fission chain -- the fission bank of a transport call becomes the next call's bank with its weights kept and fresh

@@ -60,12 +60,13 @@ def deck_to_text(deck: dict) -> str:
     G = int(st["ngroups"])
     out = ["ORCDECK 1"]
     sim = st["simulation"]
-    if sim not in ("k-eigenvalue", "noise", "modified-fixed-source"):
+    if sim not in ("k-eigenvalue", "noise", "modified-fixed-source", "fixed-source"):
         raise ValueError(f"unsupported simulation {sim}")
     tr = {"surface-tracking": "surface", "delta-tracking": "delta", "carter-tracking": "carter",
           "implicit-leakage-delta-tracking": "implicit"}[
         st.get("transport", "surface-tracking")]
-    out.append(f"mode {'noise' if sim == 'noise' else ('mfs' if sim == 'modified-fixed-source' else 'k')} tracking {tr}")
+    mode = {"noise": "noise", "modified-fixed-source": "mfs", "fixed-source": "fs"}.get(sim, "k")
+    out.append(f"mode {mode} tracking {tr}")
     out.append(f"ngroups {G}")
     eb = st["energy-bounds"]
     assert len(eb) == G + 1

@@ -199,7 +199,10 @@ static Problem* load_problem(const char* path) {
   tk.expect("mode");
   // ("mfs": modified-fixed-source.  Its transport is the k-eigenvalue one with n_new = floor(|k_abs_scr| + xi) -- no division by
   // k_col (transporter.cpp:381-386) --, which the driver obtains by setting k_col to 1: x / 1 is x exactly.)
-  st.mode = tk.next() == "noise" ? Settings::NOISE : Settings::K_EIGENVALUE;
+  {
+    const std::string mode = tk.next();
+    st.mode = mode == "noise" ? Settings::NOISE : (mode == "fs" ? Settings::FIXED_SOURCE : Settings::K_EIGENVALUE);
+  }
   tk.expect("tracking");
   {
     std::string t = tk.next();
@@ -585,6 +588,8 @@ static void make_fission_neutrons(Ctx& cx, Particle& p, const MicroXS& microxs, 
   int n_new = 0;
   if (st.mode == Settings::K_EIGENVALUE || (st.mode == Settings::NOISE && !noise)) {
     n_new = static_cast<int>(std::floor(std::abs(k_abs_scr) / cx.P->tallies.k_col + rng_rand(p.rng)));
+  } else if (st.mode == Settings::FIXED_SOURCE) {  // transporter.cpp:374-379: no normalisation by k
+    n_new = static_cast<int>(std::floor(std::abs(k_abs_scr) + rng_rand(p.rng)));
   } else {
     n_new = static_cast<int>(std::floor((microxs.nu_total * microxs.fission / (microxs.total * cx.P->tallies.keff_)) + rng_rand(p.rng)));
   }
@@ -607,7 +612,9 @@ static void make_fission_neutrons(Ctx& cx, Particle& p, const MicroXS& microxs, 
       }
     }
     BankedParticle fp{p.r(), finfo.direction, finfo.energy, wgt, wgt2, p.history_id, p.daughter_counter(), p.family_id};
-    if (st.mode == Settings::K_EIGENVALUE || !noise || st.inner_generations) {
+    if (st.mode == Settings::FIXED_SOURCE) {  // transporter.cpp:460-463: the fission neutron continues the history
+      p.make_secondary(fp.u, fp.E, fp.wgt, fp.wgt2);
+    } else if (st.mode == Settings::K_EIGENVALUE || !noise || st.inner_generations) {
       p.history_fission_bank.push_back(fp);
     } else {
       p.make_secondary(fp.u, fp.E, fp.wgt, fp.wgt2);

@@ -158,7 +158,7 @@ struct Material {
 };
 
 struct Settings {
-  enum Mode { K_EIGENVALUE, NOISE } mode = K_EIGENVALUE;
+  enum Mode { K_EIGENVALUE, NOISE, FIXED_SOURCE } mode = K_EIGENVALUE;  // FIXED_SOURCE: src/fixed_source.cpp (fission neutrons are secondaries)
   enum Tracking { SURFACE, DELTA, CARTER, IMPLICIT_LEAKAGE } tracking = SURFACE;
   uint32_t ngroups = 1;
   std::vector<double> energy_bounds;

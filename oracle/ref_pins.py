@@ -610,9 +610,17 @@ NOISE_DRIVER_CASES = (("noise_oscillation.yaml", 600, 2, 1, 2), ("noise_oscillat
 
 # modified-fixed-source: deck, particles per batch, batches
 MFS_CASES = (("PUa-1-0-SL_subcritical_mfs.yaml", 3000, 6),)
+# fixed-source (fission neutrons as secondaries): deck, particles per batch, batches
+FS_CASES = (("PUa-1-0-SL_subcritical_fs.yaml", 3000, 6),)
 
 
-def evaluate_modified_fixed_source(impl: str) -> dict:
+def evaluate_fixed_source(impl: str) -> dict:
+    """The reference's own FixedSource::run() (oracle/_ref) against the oracle's driver: k_col, leakage and migration area of
+    every batch and the mesh tallies' average and error of the mean."""
+    return evaluate_modified_fixed_source(impl, FS_CASES, "fs")
+
+
+def evaluate_modified_fixed_source(impl: str, cases=None, kind: str = "mfs") -> dict:
     """The reference's own ModifiedFixedSource::run() (oracle/_ref) against the oracle's driver: k_col, leakage and migration
     area of every batch, the histories transported (source + every fission generation of every chain), and the mesh tallies'
     average and error of the mean.  One case: the reference keeps its state in process globals."""
@@ -621,7 +629,7 @@ def evaluate_modified_fixed_source(impl: str) -> dict:
     decks = os.path.join(os.path.dirname(_HERE), "tests", "decks")
     out = {}
     with _reference_math(impl):
-        for fname, n, nb in MFS_CASES:
+        for fname, n, nb in (MFS_CASES if cases is None else cases):
             path = os.path.join(decks, fname)
             ov = {"settings": {"nparticles": n, "ngenerations": nb}}
             name = fname.split(".")[0]
@@ -631,8 +639,11 @@ def evaluate_modified_fixed_source(impl: str) -> dict:
                 a = {k: np.zeros(nb) for k in ("kcol", "leak", "mig")}
                 tr = C.c_uint64(0)
                 L.ref_set_threads(C.c_int(1))
-                rc = L.ref_modified_fixed_source(_deck.deck_to_text(deck).encode(), C.c_int(nb), _d(a["kcol"]), _d(a["leak"]), _d(a["mig"]),
-                                                 C.byref(tr))
+                if kind == "mfs":
+                    rc = L.ref_modified_fixed_source(_deck.deck_to_text(deck).encode(), C.c_int(nb), _d(a["kcol"]), _d(a["leak"]),
+                                                     _d(a["mig"]), C.byref(tr))
+                else:
+                    rc = L.ref_fixed_source(_deck.deck_to_text(deck).encode(), C.c_int(nb), _d(a["kcol"]), _d(a["leak"]), _d(a["mig"]))
                 assert rc == 0
                 # (tr is 0 in the reference: it adds bank.size() after transport() has cleared the bank; not compared)
                 L.ref_tally_size.restype = C.c_uint64
@@ -644,13 +655,13 @@ def evaluate_modified_fixed_source(impl: str) -> dict:
                         a[f"tally{t}_{wname}"] = v
             else:
                 o = api.Oracle(path, ov)
-                r = o.run_modified_fixed_source(nb)
+                r = o.run_modified_fixed_source(nb) if kind == "mfs" else o.run_fixed_source(nb)
                 a = {k: r[k] for k in ("kcol", "leak", "mig")}
                 for t in range(o.ntallies()):
                     a[f"tally{t}_avg"], a[f"tally{t}_std"] = np.ravel(o.tally(t, "avg")), np.ravel(o.tally(t, "std"))
                 o.close()
             for k, v in a.items():
-                out[f"mfs_{name}_{k}"] = np.ascontiguousarray(v)
+                out[f"{kind}_{name}_{k}"] = np.ascontiguousarray(v)
     return out
 
 

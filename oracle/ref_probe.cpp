@@ -37,6 +37,7 @@
 #include <geometry/cell_universe.hpp>
 #include <geometry/geometry.hpp>
 #include <geometry/hex_lattice.hpp>
+#include <simulation/fixed_source.hpp>
 #include <simulation/modified_fixed_source.hpp>
 #include <geometry/rect_lattice.hpp>
 #include <materials/legendre_distribution.hpp>
@@ -685,6 +686,7 @@ int ref_problem_load(const char* text) {
       const std::string mode = tk.next();
       settings::mode = mode == "noise" ? settings::SimulationMode::NOISE
                        : mode == "mfs" ? settings::SimulationMode::MODIFIED_FIXED_SOURCE
+                       : mode == "fs" ? settings::SimulationMode::FIXED_SOURCE
                                        : settings::SimulationMode::K_EIGENVALUE;
     }
     tk.expect("tracking");
@@ -1140,6 +1142,28 @@ int ref_modified_fixed_source(const char* text, int nbatches, double* kcol, doub
     return 0;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "ref_modified_fixed_source: %s\n", e.what());
+    return 1;
+  }
+}
+
+// The reference's FixedSource::run() (src/fixed_source.cpp:81-175): every batch samples the source and transports it; fission
+// neutrons are secondaries of the history that made them (transporter.cpp:460-463), so transport() returns an empty bank.
+int ref_fixed_source(const char* text, int nbatches, double* kcol, double* leak, double* mig) {
+  try {
+    if (ref_problem_load(text) != 0) return 1;
+    omp_set_num_threads(g_threads);
+    settings::ngenerations = nbatches;
+    DriverParts d = driver_parts(text);
+    auto sim = std::make_shared<FixedSource>(g_tallies, g_transporter, d.sources);
+    sim->initialize();
+    sim->run();
+    const Tallies& T = *g_tallies;
+    for (int g = 0; g < nbatches; g++) {
+      kcol[g] = T.k_col_vec[(size_t)g]; leak[g] = T.leak_vec[(size_t)g]; mig[g] = T.mig_vec[(size_t)g];
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "ref_fixed_source: %s\n", e.what());
     return 1;
   }
 }

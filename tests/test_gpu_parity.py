@@ -696,3 +696,29 @@ def test_two_phase_host_transport_matches_the_resident_loop(ab, tmp_path):
     assert np.allclose(got_k, ks, rtol=1e-12)
     assert np.allclose(loop.gpu.tally(0, "avg"), tally, rtol=1e-9, atol=1e-12 * np.abs(tally).max())
     assert loop.h2d_bytes > 0 and loop.d2h_bytes > 0
+
+
+def test_fixed_source_driver_matches_oracle_and_reference(ab, oracle_api, tmp_path):
+    """abeille_b200.fixed_source.FixedSource (the reference's FixedSource::run: fission neutrons continue their history as
+    secondaries, transport returns an empty bank) on a subcritical slab against the oracle's driver and the reference's own
+    run (tests/golden/ref_pins_mfs.npz)."""
+    from abeille_b200.fixed_source import FixedSource
+    from oracle import ref_pins
+    fname, n, nb = ref_pins.FS_CASES[0]
+    path = write_deck(load_deck(fname), tmp_path / fname, {"settings": {"nparticles": n, "ngenerations": nb}})
+    orc = oracle_api.Oracle(path)
+    ref = orc.run_fixed_source(nb)
+    sim = FixedSource(path, 0)
+    got = sim.run()
+    for k in ("kcol", "leak", "mig"):
+        assert np.allclose(got[k], ref[k], rtol=1e-10), (k, got[k], ref[k])
+    for t in range(orc.ntallies()):
+        for which in ("avg", "std"):
+            a, b = sim.tally(t, which), orc.tally(t, which)
+            assert np.allclose(a, b, rtol=1e-8, atol=1e-12 * np.abs(b).max()), (t, which)
+    gold = dict(np.load(os.path.join(GOLDEN, "ref_pins_mfs.npz")))
+    name = fname.split(".")[0]
+    for k in ("kcol", "leak", "mig"):
+        assert np.allclose(got[k], gold[f"fs_{name}_{k}"], rtol=1e-9), k
+    assert got["leak"].min() > 1.0  # every source neutron's chain leaks more than one neutron's weight: the slab multiplies
+    sim.close()
