@@ -264,6 +264,19 @@ class Oracle:
         s = _as_struct(bank)
         lib().orc_cancel(self.h, C.byref(s))
 
+    def comb(self, bank: dict, rng2):
+        """BranchlessPowerIterator::comb_particles on a (normalised) fission bank; rng2 = (state, increment) of the global
+        engine.  Returns (combed bank, (state, increment) afterwards)."""
+        n = len(bank["x"])
+        out = new_bank(2 * n + int(np.ceil(np.abs(bank["wgt"]).sum())) + 16)
+        r = np.array(rng2, dtype=np.uint64)
+        nout = C.c_uint64(0)
+        if lib().orc_comb(self.h, C.byref(_as_struct(bank)), C.byref(_as_struct(out)), C.byref(nout),
+                          r.ctypes.data_as(_PU64)) != 0:
+            raise RuntimeError("oracle: " + self._err())
+        m = int(nout.value)
+        return {k: v[:m].copy() for k, v in out.items()}, (int(r[0]), int(r[1]))
+
     def run_noise(self, settings: dict) -> dict:
         """The reference's Noise driver (src/noise.cpp:211-559) over the oracle's transport: nignored power-iteration
         generations, then `ngenerations` noise batches of (nskip - 1) plain generations, one generation that samples

@@ -60,12 +60,15 @@ def deck_to_text(deck: dict) -> str:
     G = int(st["ngroups"])
     out = ["ORCDECK 1"]
     sim = st["simulation"]
-    if sim not in ("k-eigenvalue", "noise", "modified-fixed-source", "fixed-source"):
+    if sim not in ("k-eigenvalue", "noise", "modified-fixed-source", "fixed-source", "branchless-k-eigenvalue"):
         raise ValueError(f"unsupported simulation {sim}")
     tr = {"surface-tracking": "surface", "delta-tracking": "delta", "carter-tracking": "carter",
           "implicit-leakage-delta-tracking": "implicit"}[
         st.get("transport", "surface-tracking")]
     mode = {"noise": "noise", "modified-fixed-source": "mfs", "fixed-source": "fs"}.get(sim, "k")
+    if sim == "branchless-k-eigenvalue":  # parser.cpp:367-409; defaults settings.cpp:87-89
+        mode = (f"branchless {int(bool(st.get('branchless-material', True)))} {int(bool(st.get('branchless-splitting', False)))} "
+                f"{int(bool(st.get('branchless-combing', True)))}")
     out.append(f"mode {mode} tracking {tr}")
     out.append(f"ngroups {G}")
     eb = st["energy-bounds"]

@@ -130,6 +130,7 @@ struct Problem {
   std::vector<double> sampling;  // carter: ratio*majorant (src/carter_tracker.cpp:60-75)
   bool converged = false;
   uint64_t histories_counter = 0, global_histories_counter = 0;
+  Pcg32Stream global_rng;  // settings::rng
   Counters counters;
   std::string error;
   // per-history trace of the LAST transport call (instrumentation)
@@ -201,7 +202,12 @@ static Problem* load_problem(const char* path) {
   // k_col (transporter.cpp:381-386) --, which the driver obtains by setting k_col to 1: x / 1 is x exactly.)
   {
     const std::string mode = tk.next();
-    st.mode = mode == "noise" ? Settings::NOISE : (mode == "fs" ? Settings::FIXED_SOURCE : Settings::K_EIGENVALUE);
+    st.mode = mode == "noise" ? Settings::NOISE : (mode == "fs" ? Settings::FIXED_SOURCE : (mode == "branchless" ? Settings::BRANCHLESS : Settings::K_EIGENVALUE));
+    if (st.mode == Settings::BRANCHLESS) {  // branchless-k-eigenvalue: material, splitting, combing (parser.cpp:367-409)
+      st.branchless_material = tk.ll() != 0;
+      st.branchless_splitting = tk.ll() != 0;
+      st.branchless_combing = tk.ll() != 0;
+    }
   }
   tk.expect("tracking");
   {
@@ -520,6 +526,16 @@ struct Mat {  // include/materials/material_helper.hpp
     return v;
   }
   double Eelastic(double E) const { double v = 0.; v += 1. * mat().micro(P->st.group(E)).elastic; return v; }
+  double Es(double E) const {  // :100-113
+    double v = 0.;
+    const MicroXS x = mat().micro(P->st.group(E));
+    v += 1. * std::max(x.total - x.absorption, 0.);
+    return v;
+  }
+  MicroXS sample_branchless_nuclide(double E, Pcg32& rng) const {  // :226-275: one nuclide, xi = rand * sum <= sum always picks it
+    (void)rng_rand(rng);
+    return mat().micro(P->st.group(E));
+  }
   MeshTally::MatXS tally_xs(double E) const { return {Et(E), Ea(E), Ef(E), Eelastic(E)}; }
   MicroXS sample_nuclide(double E, Pcg32& rng, bool noise) const {  // :178-224
     const double Ew_ = Ew(E, noise);
@@ -625,6 +641,60 @@ static void make_fission_neutrons(Ctx& cx, Particle& p, const MicroXS& microxs, 
   p.note(0x5000000000000000ULL | (uint64_t)(uint32_t)n_new);
 }
 
+// Transporter::branchless_collision_iso / _mat (transporter.cpp:104-267): every collision is either a scatter that carries the
+// multiplicity m in its weight or a fission that banks ONE site of weight w*m and ends the particle.
+static void branchless_collision(Ctx& cx, Particle& p, const Mat& mat) {
+  const Settings& st = cx.P->st;
+  const Material& nuc = mat.mat();
+  MicroXS microxs;
+  double Pscatter, m;
+  bool scatter = false;
+  if (st.branchless_material) {  // :183-267
+    const double Es = mat.Es(p.E());
+    const double vEf = mat.vEf(p.E());
+    const double Et = mat.Et(p.E());
+    Pscatter = Es / (vEf + Es);
+    m = (vEf + Es) / Et;
+    if (rng_rand(p.rng) < Pscatter) scatter = true;
+    microxs = mat.sample_branchless_nuclide(p.E(), p.rng);
+    const double m_i = (microxs.nu_total * microxs.fission + (microxs.total - microxs.absorption)) / microxs.total;
+    const double k_abs_scr = (m / m_i) * p.wgt() * microxs.nu_total * microxs.fission / microxs.total;
+    cx.ts.k_abs += k_abs_scr;
+    russian_roulette(st, p);
+    if (!p.alive) return;
+  } else {  // :104-181
+    microxs = mat.sample_nuclide(p.E(), p.rng, false);
+    const double k_abs_scr = p.wgt() * microxs.nu_total * microxs.fission / microxs.total;
+    cx.ts.k_abs += k_abs_scr;
+    Pscatter = (microxs.total - microxs.absorption) / (microxs.nu_total * microxs.fission + (microxs.total - microxs.absorption));
+    m = (microxs.nu_total * microxs.fission + (microxs.total - microxs.absorption)) / microxs.total;
+    russian_roulette(st, p);
+    if (!p.alive) return;
+    if (rng_rand(p.rng) < Pscatter) scatter = true;
+  }
+  if (scatter) {
+    ScatterInfo s = sample_scatter(*cx.P, nuc, p.u(), microxs.energy_index, p.rng);  // (yield == 1 in multi-group)
+    p.state.energy = s.energy;
+    p.state.direction = s.direction;
+    p.state.weight = p.wgt() * m * 1.;
+    p.state.weight2 = p.wgt2() * m * 1.;
+    if (p.E() < st.min_energy) p.kill();
+    if (st.branchless_splitting && p.alive && std::abs(p.wgt()) >= st.wgt_split) {
+      // the material flavour rounds up, the isotope flavour down (:239-241 against :151-155)
+      const int n_new = static_cast<int>(st.branchless_material ? std::ceil(std::abs(p.wgt())) : std::floor(std::abs(p.wgt())));
+      p.split(n_new);
+    }
+  } else {
+    const double P_delayed = microxs.nu_delayed / microxs.nu_total;
+    auto finfo = sample_fission(*cx.P, nuc, p.u(), microxs.energy_index, P_delayed, p.rng);
+    BankedParticle fp{p.r(), finfo.direction, finfo.energy, p.wgt() * m, p.wgt2() * m, p.history_id, p.daughter_counter(), p.family_id};
+    p.history_fission_bank.push_back(fp);
+    p.n_fission++;
+    cx.cn.fission_sites++;
+    p.kill();
+  }
+}
+
 // noise source sampling (src/noise_maker.cpp:277-445, square_oscillation_noise_source.cpp:76-170)
 static void sample_noise_source(Ctx& cx, Particle& p, const Mat& mat, double keff, double w);
 
@@ -646,6 +716,12 @@ static void collision(Ctx& cx, Particle& p, const Mat& mat, bool noise) {  // :6
     cx.ts.mig += mig_area_scr;
   }
   if (cx.sample_noise_source) sample_noise_source(cx, p, mat, P.tallies.keff_, st.w_noise);
+  if (st.mode == Settings::BRANCHLESS) {  // :81-88
+    if (noise) throw std::runtime_error("Cannot perform noise simulations with branchless collisions.");
+    branchless_collision(cx, p, mat);
+    p.note(0x6000000000000000ULL | (p.alive ? (uint64_t)(st.group(p.E()) + 1) : 0ULL));
+    return;
+  }
 
   // branching_collision :269-312
   MicroXS microxs = mat.sample_nuclide(p.E(), p.rng, noise);
@@ -1274,6 +1350,49 @@ static GenStats normalize_weights(Problem& P, std::vector<BankedParticle>& next_
   return s;
 }
 
+// BranchlessPowerIterator::comb_particles (src/branchless_power_iterator.cpp:592-651), as written: the negative comb divides by
+// Npos and copies POSITIVE particles (it only runs when negative weights exist).  std::shuffle is libstdc++'s, on the global engine.
+static void comb_particles(Problem& P, std::vector<BankedParticle>& next_gen) {
+  std::vector<BankedParticle> positive_particles, negative_particles;
+  positive_particles.reserve(next_gen.size());
+  negative_particles.reserve(next_gen.size() / 3);
+  double Wpos = 0., Wneg = 0.;
+  for (size_t i = 0; i < next_gen.size(); i++) {
+    if (next_gen[i].wgt > 0.) { Wpos += next_gen[i].wgt; positive_particles.push_back(next_gen[i]); }
+    else { Wneg += next_gen[i].wgt; negative_particles.push_back(next_gen[i]); }
+  }
+  next_gen.clear();
+  size_t Npos = static_cast<size_t>(std::ceil(Wpos));
+  size_t Nneg = static_cast<size_t>(std::ceil(std::abs(Wneg)));
+  next_gen.reserve(Npos + Nneg);
+  std::shuffle(positive_particles.begin(), positive_particles.end(), P.global_rng);
+  double avg_pos_wgt = Wpos / static_cast<double>(Npos);
+  double comb_pos = rng_rand(P.global_rng) * avg_pos_wgt;
+  double current_particle = 0.;
+  for (size_t i = 0; i < positive_particles.size(); i++) {
+    current_particle += positive_particles[i].wgt;
+    while (comb_pos < current_particle) {
+      next_gen.push_back(positive_particles[i]);
+      next_gen.back().wgt = avg_pos_wgt;
+      comb_pos += avg_pos_wgt;
+    }
+  }
+  std::shuffle(negative_particles.begin(), negative_particles.end(), P.global_rng);
+  double avg_neg_wgt = std::abs(Wneg) / static_cast<double>(Npos);
+  comb_pos = rng_rand(P.global_rng) * avg_neg_wgt;
+  current_particle = 0.;
+  for (size_t i = 0; i < negative_particles.size(); i++) {
+    current_particle -= negative_particles[i].wgt;
+    while (comb_pos < current_particle) {
+      if (i >= positive_particles.size()) throw std::runtime_error("comb_particles: the reference reads past its positive buffer here");
+      next_gen.push_back(positive_particles[i]);
+      next_gen.back().wgt = -avg_neg_wgt;
+      comb_pos += avg_neg_wgt;
+    }
+  }
+  std::shuffle(next_gen.begin(), next_gen.end(), P.global_rng);
+}
+
 // Simulation::sample_sources + Source::generate_particle
 static std::vector<Particle> sample_sources(Problem& P, size_t N) {
   std::vector<double> wgts;
@@ -1747,6 +1866,25 @@ int orc_cancel_and_normalize(void* h, orc_bank* b, int do_cancel, double* stats6
   return 0;
 }
 
+// BranchlessPowerIterator::comb_particles alone.  rng2 = {state, increment} of settings::rng, updated; out->n = capacity on entry.
+int orc_comb(void* h, const orc_bank* in, orc_bank* out, uint64_t* n_out, uint64_t* rng2) {
+  Problem& P = *static_cast<Problem*>(h);
+  try {
+    std::vector<BankedParticle> v(in->n);
+    for (size_t i = 0; i < v.size(); i++) {
+      v[i].r = {in->x[i], in->y[i], in->z[i]}; v[i].u = {in->ux[i], in->uy[i], in->uz[i]};
+      v[i].E = in->E[i]; v[i].wgt = in->wgt[i]; v[i].wgt2 = in->wgt2[i];
+      v[i].parent_history_id = in->id_a[i]; v[i].parent_daughter_id = in->id_b[i]; v[i].family_id = in->id_c[i];
+    }
+    P.global_rng.state = rng2[0]; P.global_rng.inc = rng2[1];
+    comb_particles(P, v);
+    rng2[0] = P.global_rng.state; rng2[1] = P.global_rng.inc;
+    *n_out = v.size();
+    bank_to(v, out);
+    return 0;
+  } catch (const std::exception& e) { P.error = e.what(); return 1; }
+}
+
 // approximate cancellation alone (Noise::perform_regional_cancellation on a noise fission bank, noise.cpp:508-515)
 int orc_cancel(void* h, orc_bank* b) {
   Problem& P = *static_cast<Problem*>(h);
@@ -1776,6 +1914,7 @@ static void pi_init(Problem& P, int nignored) {
   PIState& S = g_pi[&P];
   P.histories_counter = 0;
   P.global_histories_counter = 0;
+  P.global_rng.seed_global(P.st.rng_seed);  // (no parser here: the colour draws of make_material / make_cell are not taken)
   S.bank = sample_sources(P, (size_t)P.st.nparticles);  // PowerIterator::initialize
   P.global_histories_counter += (uint64_t)P.st.nparticles;
   for (auto& p : S.bank) p.family_id = p.history_id;
@@ -1800,6 +1939,7 @@ static void pi_generation(Problem& P, double* out5, uint64_t* nbank_in) {
   T.calc_gen_values();
   if (P.st.regional_cancellation && P.cancel.present) perform_regional_cancellation(P, next_gen);
   normalize_weights(P, next_gen);
+  if (P.st.mode == Settings::BRANCHLESS && P.st.branchless_combing) comb_particles(P, next_gen);  // branchless_power_iterator.cpp:361-363
   if (P.converged) {
     for (const auto& p : next_gen)
       for (auto& t : T.mesh) if (t.estimator == EST_SOURCE && !t.noise_source) t.score_source(p);

@@ -158,7 +158,8 @@ struct Material {
 };
 
 struct Settings {
-  enum Mode { K_EIGENVALUE, NOISE, FIXED_SOURCE } mode = K_EIGENVALUE;  // FIXED_SOURCE: src/fixed_source.cpp (fission neutrons are secondaries)
+  enum Mode { K_EIGENVALUE, NOISE, FIXED_SOURCE, BRANCHLESS } mode = K_EIGENVALUE;  // FIXED_SOURCE: src/fixed_source.cpp (fission neutrons are secondaries)
+  bool branchless_material = true, branchless_splitting = false, branchless_combing = true;  // settings.cpp:87-89
   enum Tracking { SURFACE, DELTA, CARTER, IMPLICIT_LEAKAGE } tracking = SURFACE;
   uint32_t ngroups = 1;
   std::vector<double> energy_bounds;

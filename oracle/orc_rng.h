@@ -70,8 +70,31 @@ struct Pcg32 {
   }
 };
 
+// settings::rng (settings.cpp:59,116-119): the one global engine, seeded with rng_seed on the default stream and then switched to
+// stream 2 (pcg-cpp set_stream: inc = (2 << 1) | 1, the state is kept).  Regional cancellation and the branchless comb draw from
+// it; it also is the UniformRandomBitGenerator handed to std::shuffle (branchless_power_iterator.cpp:619-650), hence the typedefs.
+struct Pcg32Stream {
+  using result_type = uint32_t;
+  static constexpr result_type min() { return 0u; }
+  static constexpr result_type max() { return 0xffffffffu; }
+  uint64_t state = 0, inc = Pcg32::INC;
+  void seed_global(uint64_t s) {  // initialize_global_rng()
+    state = (s + Pcg32::INC) * Pcg32::MULT + Pcg32::INC;
+    inc = (2ULL << 1) | 1ULL;
+  }
+  uint32_t next() {
+    const uint64_t old = state;
+    state = old * Pcg32::MULT + inc;
+    const uint32_t xorshifted = static_cast<uint32_t>(((old >> 18u) ^ old) >> 27u);
+    const uint32_t rot = static_cast<uint32_t>(old >> 59u);
+    return (xorshifted >> rot) | (xorshifted << ((32u - rot) & 31u));
+  }
+  result_type operator()() { return next(); }
+};
+
 // RNG::rand  (rng.hpp:41) == libstdc++ generate_canonical<double,53>(pcg32)
-inline double rng_rand(Pcg32& g) {
+template <class Engine>
+inline double rng_rand(Engine& g) {
   double sum = 0.0, tmp = 1.0;
   sum += static_cast<double>(g.next()) * tmp;
   tmp *= 4294967296.0;

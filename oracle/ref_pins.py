@@ -535,7 +535,11 @@ POWER_ITERATION_CASES = (
 # whole simulations with the fourth tracker (golden vectors in tests/golden/ref_pins_implicit.npz): addressed by `only` = an
 # index into ALL_PI_CASES; `only` = None keeps meaning the cases of tests/golden/ref_pins.npz
 IMPLICIT_POWER_ITERATION_CASES = (("c5g7_implicit_collision.yaml", 3000, 8, 3), ("PUa-1-0-SL_implicit.yaml", 2000, 12, 4))
-ALL_PI_CASES = POWER_ITERATION_CASES + IMPLICIT_POWER_ITERATION_CASES
+# branchless-k-eigenvalue (src/branchless_power_iterator.cpp + Transporter::branchless_collision_{mat,iso}): material flavour with the
+# comb, isotope flavour with splitting and no comb, material flavour with splitting and the comb (tests/golden/ref_pins_branchless.npz)
+BRANCHLESS_PI_CASES = (("c5g7_delta_branchless.yaml", 3000, 8, 3), ("PUa-1-0-SL_branchless_iso_split.yaml", 2000, 10, 3),
+                       ("UD2O-2-1-SL_branchless_split_comb.yaml", 2000, 10, 3))
+ALL_PI_CASES = POWER_ITERATION_CASES + IMPLICIT_POWER_ITERATION_CASES + BRANCHLESS_PI_CASES
 
 
 def evaluate_power_iteration(impl: str, only: int | None = None) -> dict:

@@ -57,6 +57,7 @@
 #include <simulation/noise_maker.hpp>
 #include <simulation/point.hpp>
 #include <simulation/power_iterator.hpp>
+#include <simulation/branchless_power_iterator.hpp>
 #include <simulation/source.hpp>
 #include <simulation/square_oscillation_noise_source.hpp>
 #include <simulation/surface_tracker.hpp>
@@ -200,6 +201,7 @@ std::unique_ptr<Surface> make(int type, const double* p) {
 }  // namespace
 
 extern "C" {
+
 
 // n evaluations of one surface: sign, distance (on_surf as given) and norm
 int ref_surface(int type, const double* params, int n, const double* r3, const double* u3, const int* on_surf, int* sign,
@@ -687,7 +689,13 @@ int ref_problem_load(const char* text) {
       settings::mode = mode == "noise" ? settings::SimulationMode::NOISE
                        : mode == "mfs" ? settings::SimulationMode::MODIFIED_FIXED_SOURCE
                        : mode == "fs" ? settings::SimulationMode::FIXED_SOURCE
+                       : mode == "branchless" ? settings::SimulationMode::BRANCHLESS_K_EIGENVALUE
                                        : settings::SimulationMode::K_EIGENVALUE;
+      if (settings::mode == settings::SimulationMode::BRANCHLESS_K_EIGENVALUE) {  // parser.cpp:367-409
+        settings::branchless_material = tk.ll() != 0;
+        settings::branchless_splitting = tk.ll() != 0;
+        settings::branchless_combing = tk.ll() != 0;
+      }
     }
     tk.expect("tracking");
     const std::string trk = tk.next();
@@ -1038,6 +1046,7 @@ DriverParts driver_parts(const char* text) {
   }
   return d;
 }
+uint64_t g_last_bank_size = 0;
 void set_entropy(Simulation& sim, const std::vector<std::string>& lines) {
   for (const auto& el : lines) {
     std::istringstream ls(el);
@@ -1058,9 +1067,27 @@ void set_entropy(Simulation& sim, const std::vector<std::string>& lines) {
     sim.set_t_post_entropy(std::make_shared<Entropy>(low_r, hi_r, shp, Entropy::Sign::Total));
   }
 }
+template <class Iterator>
+void run_iterator(DriverParts& d, int ngen, double* kcol, double* ktrk, double* leak, double* mig, double* entropy) {
+  std::shared_ptr<Iterator> pi;
+  pi = d.cancelator ? std::make_shared<Iterator>(g_tallies, g_transporter, d.sources, d.cancelator)
+                    : std::make_shared<Iterator>(g_tallies, g_transporter, d.sources);
+  set_entropy(*pi, d.entropy_lines);
+  pi->initialize();
+  pi->run();
+  g_last_simulation_seconds = pi->simulation_timer.elapsed_time();  // the generation loop (src/power_iterator.cpp:316-318,432)
+  g_last_bank_size = pi->bank.size();
+  const Tallies& T = *g_tallies;
+  for (int g = 0; g < ngen; g++) {
+    kcol[g] = T.k_col_vec[(size_t)g]; ktrk[g] = T.k_trk_vec[(size_t)g]; leak[g] = T.leak_vec[(size_t)g]; mig[g] = T.mig_vec[(size_t)g];
+    entropy[g] = (size_t)g < pi->t_pre_entropy_vec.size() ? pi->t_pre_entropy_vec[(size_t)g] : 0.;
+  }
+}
 }  // namespace
 
 extern "C" {
+// size of the source bank the last ref_power_iteration ended with (after combing, for a branchless deck)
+uint64_t ref_last_bank_size() { return g_last_bank_size; }
 
 // The reference's own PowerIterator::initialize() + run() (src/power_iterator.cpp:170-473) on the deck text: sources,
 // entropy mesh and cancelator are built through their plain constructors from the "src", "entropy" and "cancelator" lines
@@ -1094,19 +1121,14 @@ int ref_power_iteration_gpu(const char* text, const char* host_library, const ch
     settings::ngenerations = ngen;
     settings::nignored = nignored;
     DriverParts d = driver_parts(text);
-    std::shared_ptr<PowerIterator> pi;
-    pi = d.cancelator ? std::make_shared<PowerIterator>(g_tallies, g_transporter, d.sources, d.cancelator)
-                      : std::make_shared<PowerIterator>(g_tallies, g_transporter, d.sources);
-    set_entropy(*pi, d.entropy_lines);
-    pi->initialize();
-    pi->run();
-    g_last_simulation_seconds = pi->simulation_timer.elapsed_time();  // the generation loop (src/power_iterator.cpp:316-318,432)
+    // branchless-k-eigenvalue decks run the reference's BranchlessPowerIterator (src/branchless_power_iterator.cpp: the same loop
+    // plus comb_particles), which draws from settings::rng as ref_problem_load left it (seeded, stream 2, no colour draws)
+    if (settings::mode == settings::SimulationMode::BRANCHLESS_K_EIGENVALUE)
+      run_iterator<BranchlessPowerIterator>(d, ngen, kcol, ktrk, leak, mig, entropy);
+    else
+      run_iterator<PowerIterator>(d, ngen, kcol, ktrk, leak, mig, entropy);
     if (host_library) g_gpu_transporter->finish();
     const Tallies& T = *g_tallies;
-    for (int g = 0; g < ngen; g++) {
-      kcol[g] = T.k_col_vec[(size_t)g]; ktrk[g] = T.k_trk_vec[(size_t)g]; leak[g] = T.leak_vec[(size_t)g]; mig[g] = T.mig_vec[(size_t)g];
-      entropy[g] = (size_t)g < pi->t_pre_entropy_vec.size() ? pi->t_pre_entropy_vec[(size_t)g] : 0.;
-    }
     summary[0] = T.kcol_avg(); summary[1] = T.kcol_err(); summary[2] = T.ktrk_avg(); summary[3] = T.ktrk_err();
     summary[4] = T.leakage_avg(); summary[5] = T.leakage_err();
     return 0;
