@@ -174,6 +174,29 @@ def dump_tables(yaml_path: str) -> dict:
     return tables
 
 
+def global_rng_state(seed: int = 19073486328125):
+    """(state, increment) of the reference's settings::rng when a simulation starts (settings.cpp:116-119, simulation.cpp:52)."""
+    mask = (1 << 64) - 1
+    inc = 1442695040888963407
+    return ((seed + inc) * 6364136223846793005 + inc) & mask, 5
+
+
+def comb_particles(bank: dict, rng2):
+    """BranchlessPowerIterator::comb_particles (src/branchless_power_iterator.cpp:592-651) on a host bank: the C++ host's
+    serial restatement (std::shuffle on the global engine).  Returns (combed bank, (state, increment) afterwards)."""
+    L = load_host_lib()
+    n = len(bank["x"])
+    out = new_bank(2 * n + int(np.ceil(np.abs(bank["wgt"]).sum())) + 16)
+    r = (C.c_uint64 * 2)(int(rng2[0]), int(rng2[1]))
+    nout = C.c_uint64(0)
+    L.ablh_comb_particles.argtypes = [C.POINTER(AblBank), C.POINTER(AblBank), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    rc = L.ablh_comb_particles(C.byref(_host_struct(bank)), C.byref(_host_struct(out)), C.byref(nout), r)
+    if rc != 0:
+        raise BackendError(rc, L.ablh_last_error(None).decode())
+    m = int(nout.value)
+    return {k: v[:m].copy() for k, v in out.items()}, (int(r[0]), int(r[1]))
+
+
 def yaml_roundtrip(text: str) -> str:
     L = load_host_lib()
     cap = 1 << 22

@@ -171,7 +171,7 @@ std::vector<double> discrete_table(const std::vector<double>& w) {
 int validate(abl_handle h, const abl_problem* p) {
   if (p->ngroups < 1 || !p->energy_bounds) return fail(h, ABL_ERR_INVALID, "ngroups / energy_bounds");
   if (p->tracking < ABL_TRACK_SURFACE || p->tracking > ABL_TRACK_IMPLICIT_LEAKAGE) return fail(h, ABL_ERR_INVALID, "tracking");
-  if (p->mode != ABL_MODE_K_EIGENVALUE && p->mode != ABL_MODE_NOISE && p->mode != ABL_MODE_FIXED_SOURCE)
+  if (p->mode != ABL_MODE_K_EIGENVALUE && p->mode != ABL_MODE_NOISE && p->mode != ABL_MODE_FIXED_SOURCE && p->mode != ABL_MODE_BRANCHLESS)
     return fail(h, ABL_ERR_UNSUPPORTED, "simulation modes on the device: k-eigenvalue, noise");
   if (p->mode == ABL_MODE_NOISE) {
     if (p->n_noise_sources < 1 || !p->noise_sources) return fail(h, ABL_ERR_INVALID, "noise mode without a noise source");
@@ -563,7 +563,7 @@ int launch_transport(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t s)
       h->secondaries = nullptr;
       h->sec_threads = 0;
       const uint64_t cap = (uint64_t)h->sm_count * bps * owners;
-      ABL_CUDA(h, cudaMalloc(&h->secondaries, cap * ABL_SEC_CAP * 9 * sizeof(double)));
+      ABL_CUDA(h, cudaMalloc(&h->secondaries, cap * ABL_SEC_CAP * ABL_SEC_FIELDS * sizeof(double)));
       h->sec_threads = cap;
     }
     B.secondaries = h->secondaries;
@@ -608,13 +608,13 @@ int launch_transport_nm(abl_handle h, const RunArgs& A, uint64_t n, cudaStream_t
   if (blocks > need) blocks = need;
   if (blocks < 1) blocks = 1;
   RunArgs B = A;
-  if (MODE == 2 || TRK == ABL_TRACK_CARTER || h->P.mode == ABL_MODE_FIXED_SOURCE) {  // secondaries: noise copies, carter splitting, noise fission without inner generations, fixed-source fission
+  if (MODE == 2 || TRK == ABL_TRACK_CARTER || h->P.mode == ABL_MODE_FIXED_SOURCE || h->P.mode == ABL_MODE_BRANCHLESS) {  // secondaries: noise copies, carter / branchless splitting, noise fission without inner generations, fixed-source fission
     const uint64_t cap = (uint64_t)h->sm_count * bps * threads;
     if (cap > h->sec_threads) {
       if (h->secondaries) cudaFree(h->secondaries);
       h->secondaries = nullptr;
       h->sec_threads = 0;
-      ABL_CUDA(h, cudaMalloc(&h->secondaries, cap * ABL_SEC_CAP * 9 * sizeof(double)));
+      ABL_CUDA(h, cudaMalloc(&h->secondaries, cap * ABL_SEC_CAP * ABL_SEC_FIELDS * sizeof(double)));
       h->sec_threads = cap;
     }
     B.secondaries = h->secondaries;
@@ -682,7 +682,8 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
   // a power-iteration generation of a noise run that does not sample the noise source is a plain k-eigenvalue generation:
   // it goes through the staged kernel; noise particles and sampling generations use the per-lane kernel (noise.cuh)
   // fixed-source problems (fission neutrons as secondaries of their history) run the per-lane kernel in its k-eigenvalue mode
-  const bool fixed_source = h->P.mode == ABL_MODE_FIXED_SOURCE;
+  // and so do branchless collisions (their splitting needs the secondaries LIFO as well)
+  const bool fixed_source = h->P.mode == ABL_MODE_FIXED_SOURCE || h->P.mode == ABL_MODE_BRANCHLESS;
   const bool lane_kernel_call = (noise_mode && (params->noise != 0 || sample_noise)) || fixed_source;
   if ((params->noise || sample_noise) && !noise_mode)
     return fail(h, ABL_ERR_INVALID, "noise transport / noise-source sampling needs a problem with simulation: noise");
@@ -923,6 +924,7 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
   DevProblem& P = h->P;
   const int G = p->ngroups, M = p->nmaterials;
   P.mode = p->mode;
+  P.branchless = p->mode == ABL_MODE_BRANCHLESS ? p->branchless_flags : 0;
   P.tracking = p->tracking;
   P.G = G;
   P.inner_generations = p->inner_generations;

@@ -80,6 +80,7 @@ struct DevProblem {
   // (api.cu: boundary_planes): |p0 - r[axis]| of the nearest one is a lower bound of the distance to any boundary condition
   // in any direction, which lets the surface tracker skip the boundary-condition search of a flight that ends far inside
   // (geom.cuh: cursor_nearest_boundary_lazy).  n_bc_planes = 0: no such bound.
+  int32_t branchless;  // ABL_BRANCHLESS_* bits (mode == ABL_MODE_BRANCHLESS)
   int32_t has_hex;  // the geometry holds a hexagonal lattice (the fixed-shape kernel builds leave those branches out)
   int32_t n_bc_planes;
   int32_t bc_axis[ABL_MAX_BC_PLANES];

@@ -46,7 +46,8 @@ struct BankView {  // SoA device arrays (abl_bank with device pointers)
   uint64_t *id_a, *id_b, *id_c;
 };
 
-#define ABL_SEC_CAP 24  // secondaries a single history may hold at once (carter splitting)
+#define ABL_SEC_CAP 24     // LIFO entries a single history may hold at once (an entry is one secondary or `count` identical copies)
+#define ABL_SEC_FIELDS 10  // r, u, E, wgt, wgt2, count
 
 struct RunArgs {
   BankView bank;
@@ -218,7 +219,7 @@ static __device__ __noinline__ void bank_fission_sites(const FissionTables T, Si
 }
 
 __device__ inline bool push_secondary(const RunArgs& A, Hist& h, const V3& u, double E, double w, double w2, uint32_t tid,
-                                      uint32_t nthreads);  // (defined with the secondaries' LIFO below)
+                                      uint32_t nthreads, int count = 1);  // (defined with the secondaries' LIFO below)
 
 // Fixed-source problems: the n_new fission neutrons of a collision become secondaries of the history (Particle::make_secondary,
 // transporter.cpp:460-463) instead of bank entries.  The same draws per neutron as bank_fission_sites.
@@ -256,6 +257,99 @@ __device__ __forceinline__ void russian_roulette(const DevProblem& P, Hist& h) {
   if (h.w == 0. && h.w2 == 0.) h.alive = false;
 }
 
+// Transporter::branchless_collision_mat / _iso (transporter.cpp:104-267): the collision is EITHER a scatter that carries the
+// multiplicity m = (nu Sigma_f + Sigma_s) / Sigma_t in its weight, OR a fission that banks one site of weight w*m and ends the
+// particle.  One nuclide per material (atoms_bcm = 1), so sample_nuclide / sample_branchless_nuclide reduce to their single draw.
+// A function call: only branchless-k-eigenvalue problems come here.
+template <class M>
+static __device__ __noinline__ void branchless_collision(const DevProblem& P, const RunArgs& A, Hist& h, Acc& acc, uint32_t tid,
+                                                         uint32_t nthreads) {
+  const int mg = h.mat * P.G + h.g;
+  const double Et = ldt(&P.Et[mg]), Ea = ldt(&P.Ea[mg]), Ef = ldt(&P.Ef[mg]), nu = ldt(&P.nu[mg]);
+  const double vEf_i = nu * Ef, Es_i = Et - Ea;
+  bool scatter = false;
+  double m;
+  if (P.branchless & ABL_BRANCHLESS_MATERIAL) {
+    // MaterialHelper::Es / vEf / Et: sums over the components starting from 0. (material_helper.hpp:47-63,100-113)
+    const double Es = 0. + 1. * fmax(Es_i, 0.);
+    const double vEf = 0. + 1. * nu * Ef;
+    const double Pscatter = ddiv_pos<M>(Es, vEf + Es);
+    m = ddiv_pos<M>(vEf + Es, Et);
+    if (M::rand(h.rng) < Pscatter) scatter = true;
+    (void)M::rand(h.rng);  // sample_branchless_nuclide: xi = rand * sum (material_helper.hpp:249)
+    const double m_i = ddiv_pos<M>(vEf_i + Es_i, Et);
+    acc.k_abs += (m / m_i) * h.w * nu * Ef / Et;
+    russian_roulette<false, M>(P, h);
+    if (!h.alive) return;
+  } else {
+    (void)M::rand(h.rng);  // sample_nuclide (material_helper.hpp:189)
+    acc.k_abs += h.w * nu * Ef / Et;
+    const double Pscatter = Es_i / (vEf_i + Es_i);
+    m = (vEf_i + Es_i) / Et;
+    russian_roulette<false, M>(P, h);
+    if (!h.alive) return;
+    if (M::rand(h.rng) < Pscatter) scatter = true;
+  }
+  if (scatter) {
+    int ei = 0;
+    if (P.G >= 2) ei = rng_discrete<M>(h.rng, P.ps_cp + (size_t)mg * P.G, P.G);
+    const double E_out = group_mid(P, ei);
+    const double mu = sample_mu<M>(P, P.angle + (size_t)mg * P.G + ei, h.rng);
+    const double phi = 2. * ABL_PI * M::rand(h.rng);
+    h.u = rotate_dir<M>(h.u, mu, phi);
+    h.E = E_out;
+    h.g = ei;
+    h.emid = true;
+    h.w = h.w * m * 1.;
+    h.w2 = h.w2 * m * 1.;
+    if (h.E < P.min_energy) h.alive = false;
+    if ((P.branchless & ABL_BRANCHLESS_SPLITTING) && h.alive && fabs(h.w) >= P.wgt_split) {
+      // the material flavour rounds up, the isotope flavour down (transporter.cpp:239-241 against :151-155)
+      const int n_new = (int)((P.branchless & ABL_BRANCHLESS_MATERIAL) ? ceil(fabs(h.w)) : floor(fabs(h.w)));
+      if (n_new > 1) {  // Particle::split (particle.hpp:165-173)
+        h.w = h.w / (double)n_new;
+        h.w2 = h.w2 / (double)n_new;
+        if (!push_secondary(A, h, h.u, h.E, h.w, h.w2, tid, nthreads, n_new - 1)) raise_error(A, ABL_ERR_BANK_OVERFLOW, A.bank.id_a[h.idx]);
+      }
+    }
+  } else {
+    // MGNuclide::sample_fission (mg_nuclide.cpp:504-543), one neutron
+    const int dg0 = ldt(&P.dg_off[h.mat]), ndg = ldt(&P.dg_off[h.mat + 1]) - dg0;
+    int ei = 0;
+    if (P.G >= 2) ei = rng_discrete<M>(h.rng, P.chi_cp + (size_t)mg * P.G, P.G);
+    const double E_out = ldt(&P.gmid[ei]);
+    const double mu = 2. * M::rand(h.rng) - 1.;
+    const double phi = 2. * ABL_PI * M::rand(h.rng);
+    const V3 dir = rotate_dir<M>(h.u, mu, phi);
+    if (M::rand(h.rng) < ldt(&P.nud[mg]) / nu) {
+      if (ndg >= 2) (void)rng_discrete<M>(h.rng, P.dg_cp + dg0, ndg);
+    }
+    Site s;
+    s.x = h.r.x; s.y = h.r.y; s.z = h.r.z;
+    s.ux = dir.x; s.uy = dir.y; s.uz = dir.z;
+    s.E = E_out;
+    s.w = h.w * m;
+    s.w2 = h.w2 * m;
+    s.parent = h.idx;
+    s.daughter = h.daughter;
+    cg::coalesced_group grp = cg::coalesced_threads();
+    unsigned long long base = 0;
+    if (grp.thread_rank() == 0) base = atomicAdd(A.n_sites, (unsigned long long)grp.size());
+    base = grp.shfl(base, 0);
+    const unsigned long long slot = base + grp.thread_rank();
+    if (slot < A.site_capacity) {
+      const double2* src = reinterpret_cast<const double2*>(&s);
+      double2* dst = reinterpret_cast<double2*>(A.sites + slot);
+#pragma unroll
+      for (int q = 0; q < 5; q++) dst[q] = src[q];
+    }
+    h.daughter += 1u;
+    h.n_fis += 1u;
+    acc.sites += 1u;
+    h.alive = false;
+  }
+}
+
 // Transporter::collision + branching_collision (transporter.cpp:60-93,269-312), k-eigenvalue branch
 template <bool NOISE, class M = InlineMath>
 __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A, Hist& h, Acc& acc, uint32_t tid = 0, uint32_t nthreads = 0) {
@@ -278,6 +372,11 @@ __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A,
     const double mig_area_scr = ddiv_pos<M>(h.w * Ea, Et) * mig_dist * mig_dist;
     acc.k_col += k_col_scr;
     acc.mig += mig_area_scr;
+  }
+  if (!NOISE && P.mode == ABL_MODE_BRANCHLESS) {  // transporter.cpp:80-88
+    branchless_collision<M>(P, A, h, acc, tid, nthreads);
+    note(h, 0x6000000000000000ULL | (h.alive ? (uint64_t)(h.g + 1) : 0ULL));
+    return;
   }
   // MaterialHelper::sample_nuclide always draws, even with a single nuclide (material_helper.hpp:189)
   (void)M::rand(h.rng);
@@ -356,10 +455,13 @@ __device__ __forceinline__ void score_flight_all(const DevProblem& P, const RunA
 
 // secondaries (Particle::make_secondary / split / resurect, particle.hpp:150-186): a LIFO per thread
 __device__ __forceinline__ double* sec_slot(const RunArgs& A, int e, int f, uint32_t tid, uint32_t nthreads) {
-  return A.secondaries + ((size_t)(e * 9 + f) * nthreads + tid);
+  return A.secondaries + ((size_t)(e * ABL_SEC_FIELDS + f) * nthreads + tid);
 }
+// `count` identical copies (Particle::split pushes n_new - 1 of them) take one entry: they pop one at a time, and whatever a
+// copy pushes while it runs sits above the entry -- the order of the reference's vector of individual copies.
 __device__ inline bool push_secondary(const RunArgs& A, Hist& h, const V3& u, double E, double w, double w2, uint32_t tid,
-                                      uint32_t nthreads) {
+                                      uint32_t nthreads, int count) {
+  if (count < 1) return true;
   if (h.nsec >= ABL_SEC_CAP || A.secondaries == nullptr) return false;
   const int e = h.nsec++;
   *sec_slot(A, e, 0, tid, nthreads) = h.r.x;
@@ -371,10 +473,14 @@ __device__ inline bool push_secondary(const RunArgs& A, Hist& h, const V3& u, do
   *sec_slot(A, e, 6, tid, nthreads) = E;
   *sec_slot(A, e, 7, tid, nthreads) = w;
   *sec_slot(A, e, 8, tid, nthreads) = w2;
+  *sec_slot(A, e, 9, tid, nthreads) = (double)count;
   return true;
 }
 __device__ inline void pop_secondary(const DevProblem& P, const RunArgs& A, Hist& h, uint32_t tid, uint32_t nthreads) {
-  const int e = --h.nsec;
+  const int e = h.nsec - 1;
+  const double left = *sec_slot(A, e, 9, tid, nthreads) - 1.;
+  if (left >= 1.) *sec_slot(A, e, 9, tid, nthreads) = left;
+  else h.nsec = e;
   h.r.x = *sec_slot(A, e, 0, tid, nthreads);
   h.r.y = *sec_slot(A, e, 1, tid, nthreads);
   h.r.z = *sec_slot(A, e, 2, tid, nthreads);
@@ -610,11 +716,7 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
         if (n_new > 1) {
           h.w = h.w / (double)n_new;
           h.w2 = h.w2 / (double)n_new;
-          for (int np = 0; np < n_new - 1; np++)
-            if (!push_secondary(A, h, h.u, h.E, h.w, h.w2, tid, nthreads)) {
-              raise_error(A, ABL_ERR_BANK_OVERFLOW, hid);
-              break;
-            }
+          if (!push_secondary(A, h, h.u, h.E, h.w, h.w2, tid, nthreads, n_new - 1)) raise_error(A, ABL_ERR_BANK_OVERFLOW, hid);
         }
       }
     }

@@ -100,6 +100,14 @@ class DistributedPowerIterator:
         self.n_total = self.n_local * self.world  # tallies->total_weight; the deck's nparticles must equal this
         if self.gpu.info["nparticles"] != self.n_total:
             raise ValueError(f"deck nparticles {self.gpu.info['nparticles']} != world*n_local {self.n_total}")
+        if self.gpu.info["mode"] == 3:  # ABL_MODE_BRANCHLESS
+            import yaml
+            with open(deck_path) as f:
+                if yaml.safe_load(f)["settings"].get("branchless-combing", True):
+                    # comb_particles shuffles the gathered bank with the one global engine on rank 0 (branchless_power_iterator.cpp:
+                    # 592-651): a serial host step, provided by the one-GPU driver (Backend.run_power_iteration)
+                    raise NotImplementedError("branchless-combing is a serial step on the gathered bank: run it through "
+                                              "Backend.run_power_iteration, or set branchless-combing: false for the sharded driver")
         # output bank sized from the problem (the first generation runs with k_col = 1 and banks ~ k_inf sites per particle)
         self.cap = self.gpu.fission_capacity(self.n_local, k_col=1.0)
         self.cur = self.gpu.new_device_bank(self.cap)
@@ -194,6 +202,56 @@ class DistributedPowerIterator:
         self.n_cur = self.n_local
         self.use_state = True
         self.global_counter = self.n_total
+
+    # ---- PowerIterator::load_source_from_file (src/power_iterator.cpp:60-133): restart from a saved source ----
+    @classmethod
+    def from_source(cls, deck_path: str, source, device: int, group=None):
+        """The reference's `settings: insource`: `source` is the [N, 9] array Simulation::write_source saves (x y z ux uy uz E
+        wgt wgt2; here the `source.npy` of write_results, or an array).  nparticles and the tallies' total weight become
+        round(sum of wgt), every rank takes its contiguous share of the rows (the remainder goes to the first ranks), history ids
+        are the row numbers, family id = history id, and the RNG streams are seeded from the ids."""
+        import tempfile
+        import yaml
+        src = np.load(source) if isinstance(source, (str, bytes)) or hasattr(source, "__fspath__") else np.asarray(source, dtype=np.float64)
+        if src.ndim != 2 or src.shape[1] != 9:
+            raise ValueError("Invalid source from file dimensions.")
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        counts, bounds = even_split(len(src), world)
+        n_total = int(round(float(src[:, 7].sum())))
+        with open(deck_path) as f:
+            deck = yaml.safe_load(f)
+        deck["settings"]["nparticles"] = n_total
+        deck["settings"].pop("insource", None)
+        tmp = tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False)
+        yaml.safe_dump(deck, tmp, default_flow_style=None, sort_keys=False, width=200)
+        tmp.close()
+        sim = cls.__new__(cls)
+        # (the constructor sizes everything from n_local * world == nparticles; a restart's row count is not its weight)
+        if n_total % world != 0:
+            raise ValueError("restart: round(total weight) must be divisible by the number of ranks")
+        cls.__init__(sim, tmp.name, device, n_total // world, group)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        m = hi - lo
+        sim._grow(m)
+        part = torch.from_numpy(np.ascontiguousarray(src[lo:hi].T)).to(sim.device)
+        for k, key in enumerate(("x", "y", "z", "ux", "uy", "uz", "E", "wgt", "wgt2")):
+            sim.cur[key][:m] = part[k]
+        ids = torch.arange(lo, hi, dtype=torch.int64, device=sim.device)
+        sim.cur["id_a"][:m] = ids
+        sim.cur["id_b"][:m] = ids  # PowerIterator::initialize: family id = history id
+        sim.n_cur = m
+        sim.use_state = False  # initialize_rng(seed, stride) from the history id
+        sim.global_counter = len(src)
+        return sim
+
+    def source_array(self) -> np.ndarray:
+        """This rank's bank as Simulation::write_source lays it out ([n, 9]: x y z ux uy uz E wgt wgt2)."""
+        m = self.n_cur
+        out = np.zeros((m, 9))
+        for k, key in enumerate(("x", "y", "z", "ux", "uy", "uz", "E", "wgt", "wgt2")):
+            out[:, k] = self.cur[key][:m].cpu().numpy()
+        return out
 
     def _rebalance(self, counts):
         """Moves partition boundaries back to an even split, preserving global order."""

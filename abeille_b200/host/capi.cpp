@@ -259,6 +259,38 @@ int ablh_write_results(void* c, const char* dir) {
   }
 }
 
+/* BranchlessPowerIterator::comb_particles on host columns (no device involved): in->n particles in, at most out->n (capacity)
+ * written, *n_out = the combed population; rng2 = {state, increment} of settings::rng, updated. */
+int ablh_comb_particles(const abl_bank* in, abl_bank* out, uint64_t* n_out, uint64_t rng2[2]) {
+  try {
+    std::vector<abeille::BankedParticle> v(in->n);
+    for (uint64_t i = 0; i < in->n; i++) {
+      v[i].r = abeille::Position{in->x[i], in->y[i], in->z[i]};
+      v[i].u = abeille::Direction{in->ux[i], in->uy[i], in->uz[i]};
+      v[i].E = in->E[i]; v[i].wgt = in->wgt[i]; v[i].wgt2 = in->wgt2 ? in->wgt2[i] : 0.;
+      v[i].parent_history_id = in->id_a[i]; v[i].parent_daughter_id = in->id_b[i]; v[i].family_id = in->id_c[i];
+    }
+    abeille::GlobalRng rng;
+    rng.state = rng2[0];
+    rng.inc = rng2[1];
+    abeille::comb_particles(v, rng);
+    rng2[0] = rng.state;
+    rng2[1] = rng.inc;
+    *n_out = v.size();
+    for (uint64_t i = 0; i < v.size() && i < out->n; i++) {
+      out->x[i] = v[i].r.x; out->y[i] = v[i].r.y; out->z[i] = v[i].r.z;
+      out->ux[i] = v[i].u.x; out->uy[i] = v[i].u.y; out->uz[i] = v[i].u.z;
+      out->E[i] = v[i].E; out->wgt[i] = v[i].wgt;
+      if (out->wgt2) out->wgt2[i] = v[i].wgt2;
+      out->id_a[i] = v[i].parent_history_id; out->id_b[i] = v[i].parent_daughter_id; out->id_c[i] = v[i].family_id;
+    }
+    return v.size() > out->n ? 2 : 0;
+  } catch (const std::exception& e) {
+    g_open_error = e.what();
+    return 1;
+  }
+}
+
 /* yaml_lite self-test hook: parses text, returns a canonical one-line rendering */
 int ablh_yaml_roundtrip(const char* text, char* out, int64_t out_cap) {
   try {

@@ -33,7 +33,13 @@ void make_settings(const Node& input, Settings& st) {
     else if (sim == "modified-fixed-source") { st.mode = ABL_MODE_K_EIGENVALUE; st.fixed_source = true; }
     // fixed-source (src/fixed_source.cpp): fission neutrons are secondaries of their history; driver abeille_b200/fixed_source.py
     else if (sim == "fixed-source") { st.mode = ABL_MODE_FIXED_SOURCE; st.fixed_source = true; }
-    else fatal_error("Simulation mode \"" + sim + "\" is not provided by the B200 backend (k-eigenvalue, noise, fixed-source, modified-fixed-source).");
+    else if (sim == "branchless-k-eigenvalue") {  // parser.cpp:355-409
+      st.mode = ABL_MODE_BRANCHLESS;
+      if (s["branchless-splitting"]) st.branchless_splitting = s["branchless-splitting"].as_bool();
+      if (s["branchless-combing"]) st.branchless_combing = s["branchless-combing"].as_bool();
+      if (s["branchless-material"]) st.branchless_material = s["branchless-material"].as_bool();
+    }
+    else fatal_error("Simulation mode \"" + sim + "\" is not provided by the B200 backend (k-eigenvalue, branchless-k-eigenvalue, noise, fixed-source, modified-fixed-source).");
   } else {
     fatal_error("No simulation type provided.");
   }
@@ -67,9 +73,9 @@ void make_settings(const Node& input, Settings& st) {
   if (!s["ngenerations"]) fatal_error("Number of generations not specified in settings.");
   st.ngenerations = static_cast<int>(s["ngenerations"].as_int());
   if (s["nignored"]) st.nignored = static_cast<int>(s["nignored"].as_int());
-  else if (st.mode == ABL_MODE_K_EIGENVALUE && !st.fixed_source) fatal_error("Number of ignored generations not specified in settings.");
+  else if ((st.mode == ABL_MODE_K_EIGENVALUE || st.mode == ABL_MODE_BRANCHLESS) && !st.fixed_source) fatal_error("Number of ignored generations not specified in settings.");
   else st.nignored = 0;
-  if (st.mode == ABL_MODE_K_EIGENVALUE && !st.fixed_source && st.nignored >= st.ngenerations)
+  if ((st.mode == ABL_MODE_K_EIGENVALUE || st.mode == ABL_MODE_BRANCHLESS) && !st.fixed_source && st.nignored >= st.ngenerations)
     fatal_error("Number of ignored generations is greater than or equal to the number of total generations.");
   if (s["nskip"]) st.nskip = static_cast<int>(s["nskip"].as_int());
   if (s["wgt-cutoff"]) {
@@ -789,6 +795,7 @@ void Problem::flatten(FlatProblem& F) const {
   abl_problem& p = F.p;
   p = abl_problem{};
   p.mode = st.mode;
+  p.branchless_flags = (st.branchless_material ? ABL_BRANCHLESS_MATERIAL : 0) | (st.branchless_splitting ? ABL_BRANCHLESS_SPLITTING : 0);
   p.tracking = st.tracking;
   p.ngroups = st.ngroups;
   p.inner_generations = st.inner_generations ? 1 : 0;

@@ -20,6 +20,7 @@ namespace abeille {
 struct Settings {  // include/utils/settings.hpp:54-128, defaults src/settings.cpp:34-114
   int mode = ABL_MODE_K_EIGENVALUE;
   bool fixed_source = false;  // simulation: modified-fixed-source (transport is the k-eigenvalue one; no ignored generations)
+  bool branchless_splitting = false, branchless_combing = true, branchless_material = true;  // settings.cpp:87-89
   int tracking = ABL_TRACK_SURFACE;
   int ngroups = 0;
   std::vector<double> energy_bounds;

@@ -191,6 +191,99 @@ struct PowerIterator::DeviceBank {
   uint64_t cap = 0;
 };
 
+namespace {
+// a fission bank as the columns the C ABI takes
+struct HostColumns {
+  std::vector<double> f[9];
+  std::vector<uint64_t> ia, ib, ic;
+  void resize(uint64_t n) {
+    for (auto& v : f) v.resize(n);
+    ia.resize(n); ib.resize(n); ic.resize(n);
+  }
+  void from(const std::vector<BankedParticle>& bank) {
+    resize(bank.size());
+    for (uint64_t i = 0; i < bank.size(); i++) {
+      const BankedParticle& p = bank[i];
+      f[0][i] = p.r.x; f[1][i] = p.r.y; f[2][i] = p.r.z; f[3][i] = p.u.x; f[4][i] = p.u.y; f[5][i] = p.u.z;
+      f[6][i] = p.E; f[7][i] = p.wgt; f[8][i] = p.wgt2;
+      ia[i] = p.parent_history_id; ib[i] = p.parent_daughter_id; ic[i] = p.family_id;
+    }
+  }
+  void to(std::vector<BankedParticle>& bank) const {
+    bank.resize(ia.size());
+    for (uint64_t i = 0; i < bank.size(); i++) {
+      BankedParticle& p = bank[i];
+      p.r = Position{f[0][i], f[1][i], f[2][i]}; p.u = Direction{f[3][i], f[4][i], f[5][i]};
+      p.E = f[6][i]; p.wgt = f[7][i]; p.wgt2 = f[8][i];
+      p.parent_history_id = ia[i]; p.parent_daughter_id = ib[i]; p.family_id = ic[i];
+    }
+  }
+  abl_bank view() {
+    abl_bank b{};
+    b.n = ia.size();
+    b.x = f[0].data(); b.y = f[1].data(); b.z = f[2].data(); b.ux = f[3].data(); b.uy = f[4].data(); b.uz = f[5].data();
+    b.E = f[6].data(); b.wgt = f[7].data(); b.wgt2 = f[8].data();
+    b.id_a = ia.data(); b.id_b = ib.data(); b.id_c = ic.data();
+    return b;
+  }
+};
+}  // namespace
+
+double GlobalRng::rand() {
+  double sum = 0.0, tmp = 1.0;
+  sum += static_cast<double>((*this)()) * tmp;
+  tmp *= 4294967296.0;
+  sum += static_cast<double>((*this)()) * tmp;
+  tmp *= 4294967296.0;
+  double ret = sum / tmp;
+  if (ret >= 1.0) ret = std::nextafter(1.0, 0.0);
+  return ret;
+}
+
+void comb_particles(std::vector<BankedParticle>& next_gen, GlobalRng& rng) {
+  std::vector<BankedParticle> positive_particles, negative_particles;
+  positive_particles.reserve(next_gen.size());
+  negative_particles.reserve(next_gen.size() / 3);
+  double Wpos = 0., Wneg = 0.;
+  for (const auto& p : next_gen) {
+    if (p.wgt > 0.) { Wpos += p.wgt; positive_particles.push_back(p); }
+    else { Wneg += p.wgt; negative_particles.push_back(p); }
+  }
+  next_gen.clear();
+  const size_t Npos = static_cast<size_t>(std::ceil(Wpos));
+  const size_t Nneg = static_cast<size_t>(std::ceil(std::abs(Wneg)));
+  next_gen.reserve(Npos + Nneg);
+  // teeth every avg_pos_wgt along the shuffled positive weight, the first one at a random offset
+  std::shuffle(positive_particles.begin(), positive_particles.end(), rng);
+  const double avg_pos_wgt = Wpos / static_cast<double>(Npos);
+  double comb_pos = rng.rand() * avg_pos_wgt;
+  double current_particle = 0.;
+  for (size_t i = 0; i < positive_particles.size(); i++) {
+    current_particle += positive_particles[i].wgt;
+    while (comb_pos < current_particle) {
+      next_gen.push_back(positive_particles[i]);
+      next_gen.back().wgt = avg_pos_wgt;
+      comb_pos += avg_pos_wgt;
+    }
+  }
+  // the negative comb as the reference has it: its tooth spacing divides by Npos and it copies the i-th POSITIVE particle
+  // (branchless_power_iterator.cpp:637-646); with no negative weights only its one draw is taken
+  std::shuffle(negative_particles.begin(), negative_particles.end(), rng);
+  const double avg_neg_wgt = std::abs(Wneg) / static_cast<double>(Npos);
+  comb_pos = rng.rand() * avg_neg_wgt;
+  current_particle = 0.;
+  for (size_t i = 0; i < negative_particles.size(); i++) {
+    current_particle -= negative_particles[i].wgt;
+    while (comb_pos < current_particle) {
+      if (i >= positive_particles.size()) fatal_error("comb_particles: more negative than positive particles (the reference reads past its buffer here).");
+      next_gen.push_back(positive_particles[i]);
+      next_gen.back().wgt = -avg_neg_wgt;
+      comb_pos += avg_neg_wgt;
+    }
+  }
+  std::shuffle(next_gen.begin(), next_gen.end(), rng);
+}
+
 PowerIterator::PowerIterator(const Problem& p, int device) : problem(p), device_(device) {
   tallies = std::make_shared<Tallies>(static_cast<double>(p.settings.nparticles));
   transporter = std::make_shared<GPUTransporter>(tallies, p, device);
@@ -236,6 +329,7 @@ void PowerIterator::initialize() {
   }
   histories_counter_ += N;
   global_histories_counter_ = histories_counter_;
+  global_rng_.initialize(problem.settings.rng_seed);  // Simulation::Simulation (simulation.cpp:52)
   initialized_ = true;
 }
 
@@ -273,6 +367,8 @@ void PowerIterator::run_host(int ngenerations, int nignored) {
   for (const auto& t : problem.tallies)
     if (t.flat.estimator == ABL_EST_SOURCE && !t.flat.noise_source) have_source_tally = true;
   const bool cancel = st.regional_cancellation && problem.cancelator.present;
+  // branchless-k-eigenvalue: the normalised bank is combed before the source tally sees it (branchless_power_iterator.cpp:358-384)
+  const bool comb = st.mode == ABL_MODE_BRANCHLESS && st.branchless_combing;
   const auto t0 = std::chrono::steady_clock::now();
   for (int g = 1; g <= ngenerations; g++) {
     if (transporter->converged) active_particles += static_cast<double>(bank_.size());
@@ -293,7 +389,10 @@ void PowerIterator::run_host(int ngenerations, int nignored) {
       }
     }
     tallies->calc_gen_values();
-    if (cancel || (have_source_tally && transporter->converged)) {
+    // (with the comb the weights are normalised on the host in the reference's serial order: ceil(sum of weights) decides the
+    // combed population, and that sum sits within rounding of an integer)
+    const bool device_block = cancel || (have_source_tally && transporter->converged && !comb);
+    if (device_block) {
       // cancellation and the source mesh tally run on the device (bank_ops.cuh) on an uploaded copy
       const uint64_t M = next_gen.size();
       std::vector<double> f[9];
@@ -314,18 +413,21 @@ void PowerIterator::run_host(int ngenerations, int nignored) {
       alloc_device_bank(d, M);
       check(h, abl_bank_upload(h, &host, &d.b), "abl_bank_upload");
       if (cancel) check(h, abl_cancel_device(h, &d.b, nullptr), "abl_cancel_device");
-      double ws[4];
-      check(h, abl_bank_weight_stats_device(h, &d.b, ws, nullptr), "abl_bank_weight_stats_device");
-      const double w_per_part = static_cast<double>(st.nparticles) / (ws[2] - ws[3]);
-      check(h, abl_bank_scale_weights_device(h, &d.b, w_per_part, nullptr), "abl_bank_scale_weights_device");
-      if (transporter->converged) check(h, abl_score_source_device(h, &d.b, 0, nullptr), "abl_score_source_device");
+      if (!comb) {
+        double ws[4];
+        check(h, abl_bank_weight_stats_device(h, &d.b, ws, nullptr), "abl_bank_weight_stats_device");
+        const double w_per_part = static_cast<double>(st.nparticles) / (ws[2] - ws[3]);
+        check(h, abl_bank_scale_weights_device(h, &d.b, w_per_part, nullptr), "abl_bank_scale_weights_device");
+        if (transporter->converged) check(h, abl_score_source_device(h, &d.b, 0, nullptr), "abl_score_source_device");
+      }
       abl_bank wonly{};
       wonly.n = M;
       wonly.wgt = f[7].data();
       check(h, abl_bank_download(h, &d.b, M, &wonly), "abl_bank_download");
       free_device_bank(d);
       for (uint64_t i = 0; i < M; i++) next_gen[i].wgt = f[7][i];
-    } else {
+    }
+    if (!device_block || comb) {
       // normalize_weights (power_iterator.cpp:538-586)
       double W_neg = 0., W_pos = 0.;
       for (const auto& p : next_gen) {
@@ -334,6 +436,19 @@ void PowerIterator::run_host(int ngenerations, int nignored) {
       }
       const double w_per_part = static_cast<double>(st.nparticles) / (W_pos - W_neg);
       for (auto& p : next_gen) p.wgt *= w_per_part;
+    }
+    if (comb) {
+      comb_particles(next_gen, global_rng_);
+      if (have_source_tally && transporter->converged) {
+        HostColumns cols;
+        cols.from(next_gen);
+        abl_bank host = cols.view();
+        DeviceBank d;
+        alloc_device_bank(d, host.n);
+        check(h, abl_bank_upload(h, &host, &d.b), "abl_bank_upload");
+        check(h, abl_score_source_device(h, &d.b, 0, nullptr), "abl_score_source_device");
+        free_device_bank(d);
+      }
     }
     if (transporter->converged) tallies->record_generation();
     tallies->clear_generation();
@@ -394,6 +509,7 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
   std::vector<double> ebins(nebins + 1, 0.);
   if (have_entropy) check(h, abl_device_alloc(h, (nebins + 1) * sizeof(double), reinterpret_cast<void**>(&ebins_dev)), "abl_device_alloc");
   const bool cancel = st.regional_cancellation && problem.cancelator.present;
+  const bool comb = st.mode == ABL_MODE_BRANCHLESS && st.branchless_combing;
   const auto t0 = std::chrono::steady_clock::now();
   for (int g = 1; g <= ngenerations; g++) {
     const uint64_t N = cur.b.n;
@@ -441,10 +557,42 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
     }
     tallies->calc_gen_values();
     if (cancel) check(h, abl_cancel_device(h, &out, nullptr), "abl_cancel_device");
-    double ws[4];
-    check(h, abl_bank_weight_stats_device(h, &out, ws, nullptr), "abl_bank_weight_stats_device");
-    const double w_per_part = static_cast<double>(st.nparticles) / (ws[2] - ws[3]);
-    check(h, abl_bank_scale_weights_device(h, &out, w_per_part, nullptr), "abl_bank_scale_weights_device");
+    if (!comb) {
+      double ws[4];
+      check(h, abl_bank_weight_stats_device(h, &out, ws, nullptr), "abl_bank_weight_stats_device");
+      const double w_per_part = static_cast<double>(st.nparticles) / (ws[2] - ws[3]);
+      check(h, abl_bank_scale_weights_device(h, &out, w_per_part, nullptr), "abl_bank_scale_weights_device");
+    } else {
+      // the comb is the reference's serial host step on the gathered bank (std::shuffle on the one global engine): the bank makes
+      // one round trip through host memory per generation.  The weights are normalised there too, in the reference's serial
+      // order -- ceil(sum of weights) decides the combed population and that sum sits within rounding of an integer.
+      HostColumns cols;
+      cols.resize(n_fis);
+      abl_bank host = cols.view();
+      check(h, abl_bank_download(h, &out, n_fis, &host), "abl_bank_download");
+      std::vector<BankedParticle> next_gen;
+      cols.to(next_gen);
+      double W_neg = 0., W_pos = 0.;
+      for (const auto& p : next_gen) {
+        if (p.wgt > 0.) W_pos += p.wgt;
+        else W_neg -= p.wgt;
+      }
+      const double w_per_part = static_cast<double>(st.nparticles) / (W_pos - W_neg);
+      for (auto& p : next_gen) p.wgt *= w_per_part;
+      comb_particles(next_gen, global_rng_);
+      cols.from(next_gen);
+      host = cols.view();
+      if (host.n > nxt.cap) {
+        free_device_bank(nxt_alloc);
+        alloc_device_bank(nxt_alloc, host.n + host.n / 8 + 4096);
+        nxt.b = nxt_alloc.b;
+        nxt.cap = nxt_alloc.cap;
+      }
+      out = nxt.b;
+      check(h, abl_bank_upload(h, &host, &out), "abl_bank_upload");
+      n_fis = host.n;
+      out.n = n_fis;
+    }
     if (transporter->converged) {
       check(h, abl_score_source_device(h, &out, 0, nullptr), "abl_score_source_device");
       tallies->record_generation();

@@ -138,7 +138,33 @@ class GPUTransporter : public Transporter {
   std::vector<uint64_t> ida_, idb_, idc_, oa_, ob_, oc_;
 };
 
-class PowerIterator {  // src/power_iterator.cpp
+// settings::rng (src/settings.cpp:59,116-119): pcg32 seeded with rng_seed on the default stream, then switched to stream 2 (the
+// increment becomes (2 << 1) | 1, the state is kept).  The Simulation constructor re-initialises it (simulation.cpp:52), so a run
+// starts from exactly this state.  It is the UniformRandomBitGenerator of the comb's std::shuffle calls.
+struct GlobalRng {
+  using result_type = uint32_t;
+  static constexpr result_type min() { return 0u; }
+  static constexpr result_type max() { return 0xffffffffu; }
+  uint64_t state = 0, inc = 1442695040888963407ULL;
+  void initialize(uint64_t seed) {
+    state = (seed + 1442695040888963407ULL) * 6364136223846793005ULL + 1442695040888963407ULL;
+    inc = (2ULL << 1) | 1ULL;
+  }
+  result_type operator()() {
+    const uint64_t old = state;
+    state = old * 6364136223846793005ULL + inc;
+    const uint32_t xorshifted = static_cast<uint32_t>(((old >> 18u) ^ old) >> 27u);
+    const uint32_t rot = static_cast<uint32_t>(old >> 59u);
+    return (xorshifted >> rot) | (xorshifted << ((32u - rot) & 31u));
+  }
+  double rand();  // RNG::rand (rng.hpp:41): libstdc++ generate_canonical<double, 53>
+};
+
+// BranchlessPowerIterator::comb_particles (src/branchless_power_iterator.cpp:592-651): a serial host step on the gathered bank in
+// the reference too; std::shuffle of this libstdc++ on the global engine, so the combed bank is the reference's particle for particle.
+void comb_particles(std::vector<BankedParticle>& next_gen, GlobalRng& rng);
+
+class PowerIterator {  // src/power_iterator.cpp (and src/branchless_power_iterator.cpp: the same loop plus the comb)
  public:
   PowerIterator(const Problem& problem, int device);
   ~PowerIterator();
@@ -164,6 +190,7 @@ class PowerIterator {  // src/power_iterator.cpp
   void run_resident(int ngenerations, int nignored);
   double entropy_from_bins(const std::vector<double>& bins, double total) const;  // entropy.cpp:62-93
   std::vector<Particle> bank_;
+  GlobalRng global_rng_;
   uint64_t histories_counter_ = 0, global_histories_counter_ = 0;
   bool initialized_ = false;
   int device_ = 0;

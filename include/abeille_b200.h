@@ -46,8 +46,12 @@ typedef enum abl_status {
 
 /* ---- enums mirrored from the reference --------------------------------------------------------- */
 enum { ABL_MODE_K_EIGENVALUE = 0, ABL_MODE_NOISE = 1,
-       ABL_MODE_FIXED_SOURCE = 2 };  /* settings.hpp; FIXED_SOURCE: fission neutrons continue their history as secondaries
+       ABL_MODE_FIXED_SOURCE = 2,    /* settings.hpp; FIXED_SOURCE: fission neutrons continue their history as secondaries
                                         and transport returns an empty bank (src/transporter.cpp:374-379,460-463) */
+       ABL_MODE_BRANCHLESS = 3 };    /* BRANCHLESS_K_EIGENVALUE: Transporter::branchless_collision_mat / _iso
+                                        (src/transporter.cpp:95-267); the flavour is abl_problem::branchless_flags */
+enum { ABL_BRANCHLESS_MATERIAL = 1,    /* settings::branchless_material (collision on the material, else on the isotope) */
+       ABL_BRANCHLESS_SPLITTING = 2 }; /* settings::branchless_splitting (split when |wgt| >= wgt_split)                 */
 enum { ABL_TRACK_SURFACE = 0, ABL_TRACK_DELTA = 1, ABL_TRACK_CARTER = 2,
        ABL_TRACK_IMPLICIT_LEAKAGE = 3 };  /* parser.cpp:408-420,889-911; 3 replaces ImplicitLeakageDeltaTracker::transport
                                              (src/implicit_leakage_delta_tracker.cpp:73-263) */
@@ -146,7 +150,8 @@ typedef struct abl_problem {
   uint64_t rng_seed, rng_stride;
   double w_noise, eta, keff;
   /* geometry */
-  int32_t nsurfaces, ncells, nrpn, nuniverses, n_universe_cells, n_lattice_tiles, root_universe, pad0_;
+  int32_t nsurfaces, ncells, nrpn, nuniverses, n_universe_cells, n_lattice_tiles, root_universe,
+      branchless_flags;  /* ABL_BRANCHLESS_* bits; read when mode == ABL_MODE_BRANCHLESS */
   const abl_surface* surfaces;
   const abl_cell* cells;
   const int32_t* rpn;

@@ -540,6 +540,13 @@ IMPLICIT_POWER_ITERATION_CASES = (("c5g7_implicit_collision.yaml", 3000, 8, 3), 
 BRANCHLESS_PI_CASES = (("c5g7_delta_branchless.yaml", 3000, 8, 3), ("PUa-1-0-SL_branchless_iso_split.yaml", 2000, 10, 3),
                        ("UD2O-2-1-SL_branchless_split_comb.yaml", 2000, 10, 3))
 ALL_PI_CASES = POWER_ITERATION_CASES + IMPLICIT_POWER_ITERATION_CASES + BRANCHLESS_PI_CASES
+IMPLICIT_PI_RANGE = range(len(POWER_ITERATION_CASES), len(POWER_ITERATION_CASES) + len(IMPLICIT_POWER_ITERATION_CASES))
+BRANCHLESS_PI_RANGE = range(IMPLICIT_PI_RANGE.stop, len(ALL_PI_CASES))
+
+
+def pi_golden_file(ci: int) -> str:
+    """The file under tests/golden/ that holds the reference's output for ALL_PI_CASES[ci]."""
+    return "ref_pins_branchless.npz" if ci in BRANCHLESS_PI_RANGE else ("ref_pins_implicit.npz" if ci in IMPLICIT_PI_RANGE else "ref_pins.npz")
 
 
 def evaluate_power_iteration(impl: str, only: int | None = None) -> dict:

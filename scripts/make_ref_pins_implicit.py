@@ -21,7 +21,7 @@ out.update(ref_pins.evaluate_noise("reference", ref_pins.IMPLICIT_NOISE_CASES, s
 import subprocess  # noqa: E402
 import tempfile  # noqa: E402
 
-for i in range(len(ref_pins.POWER_ITERATION_CASES), len(ref_pins.ALL_PI_CASES)):
+for i in ref_pins.IMPLICIT_PI_RANGE:
     with tempfile.TemporaryDirectory() as td:
         tmp = os.path.join(td, "pi.npz")
         code = (f"import sys; sys.path.insert(0, {ROOT!r}); import numpy as np; from oracle import ref_pins; "

@@ -151,6 +151,9 @@ CASES = [
     ("c5g7_implicit_tracklength.yaml", {}, 8000),         # ... track-length tally of the leaking and the colliding share
     ("hex_delta_collision.yaml", {}, 20000),              # HexLattice (pointy top) under delta tracking, an empty position, outer universe
     ("hex_delta_flat_offset.yaml", {}, 20000),            # ... flat top, origin off zero (the reference's un-shifted tile check)
+    ("c5g7_delta_branchless.yaml", {"second_generation": True}, 8000),            # branchless collisions on the material (weights carry m)
+    ("PUa-1-0-SL_branchless_iso_split.yaml", {"second_generation": True}, 8000),  # ... on the isotope, with splitting (floor)
+    ("UD2O-2-1-SL_branchless_split_comb.yaml", {"second_generation": True}, 8000),  # ... on the material, with splitting (ceil), 2 groups
 ]
 
 
@@ -722,3 +725,63 @@ def test_fixed_source_driver_matches_oracle_and_reference(ab, oracle_api, tmp_pa
         assert np.allclose(got[k], gold[f"fs_{name}_{k}"], rtol=1e-9), k
     assert got["leak"].min() > 1.0  # every source neutron's chain leaks more than one neutron's weight: the slab multiplies
     sim.close()
+
+
+def test_restart_from_a_saved_source_matches_oracle(ab, oracle_api, tmp_path):
+    """settings: insource (PowerIterator::load_source_from_file, power_iterator.cpp:60-133): the saved [N, 9] source
+    becomes the bank, history ids are the row numbers, the streams are seeded from them and nparticles is the rounded
+    total weight.  The first generation after the restart against the oracle transporting the same rows."""
+    from abeille_b200.distributed import DistributedPowerIterator
+    n = 6000
+    path = write_deck(load_deck("c5g7_delta_collision.yaml"), tmp_path / "d.yaml",
+                      {"settings": {"nparticles": n, "ngenerations": 4, "nignored": 1}})
+    a = DistributedPowerIterator(path, 0, n)
+    a.initialize()
+    for g in range(2):
+        a.generation(converged=False)
+    src = a.source_array()
+    assert src.shape == (a.n_cur, 9) and src.shape[0] != n and int(round(src[:, 7].sum())) == n
+    np.save(tmp_path / "source.npy", src)
+
+    b = DistributedPowerIterator.from_source(path, str(tmp_path / "source.npy"), 0)
+    assert b.n_total == n and b.n_cur == len(src) and b.global_counter == len(src)
+    r = b.generation(converged=False)
+
+    orc = oracle_api.Oracle(path)
+    bank = {k: np.ascontiguousarray(src[:, i]) for i, k in enumerate(("x", "y", "z", "ux", "uy", "uz", "E", "wgt", "wgt2"))}
+    bank["id_a"] = np.arange(len(src), dtype=np.uint64)
+    bank["id_b"] = bank["id_a"].copy()
+    bank["id_c"] = None
+    orc.set_converged(False)
+    orc.set_kcol(1.0)
+    ofis, oscores, om = orc.transport(bank)
+    assert r["m_total"] == om
+    assert np.isclose(b.k_col, oscores[0] / n, rtol=1e-11)
+    got = b.source_array()
+    for i, k in enumerate(("x", "y", "z", "ux", "uy", "uz", "E")):
+        assert np.array_equal(got[:, i], ofis[k]), k
+    assert np.allclose(got[:, 7], ofis["wgt"] * n / ofis["wgt"].sum(), rtol=1e-12)
+    with pytest.raises(ValueError):
+        DistributedPowerIterator.from_source(path, src[:, :8], 0)
+
+
+@pytest.mark.parametrize("deck", ["c5g7_delta_branchless.yaml", "PUa-1-0-SL_branchless_iso_split.yaml", "UD2O-2-1-SL_branchless_split_comb.yaml"])
+def test_branchless_power_iteration_matches_oracle(ab, oracle_api, tmp_path, deck):
+    """simulation: branchless-k-eigenvalue (src/branchless_power_iterator.cpp) -- branchless collisions on the device, the comb as
+    the serial host step it is in the reference -- with the bank resident in HBM and through host buffers, against the oracle's
+    driver (itself bit-for-bit the reference's, tests/test_reference_pins.py): bank sizes exactly, the series to 1e-10."""
+    n, ngen, nign = 5000, 7, 2
+    ov = {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}}
+    for resident in (False, True):
+        orc, gpu = _pair(ab, oracle_api, tmp_path, deck, ov, name=f"bl{int(resident)}.yaml")
+        o = orc.run_power_iteration(ngen, nign)
+        g = gpu.run_power_iteration(ngen, nign, resident=resident)
+        assert np.array_equal(g["nbank"], o["nbank"]), (resident, g["nbank"], o["nbank"])
+        assert np.allclose(g["kcol"], o["kcol"], rtol=1e-10)
+        assert np.allclose(g["leak"], o["leak"], rtol=1e-10, atol=1e-300)
+        assert np.allclose(g["mig"], o["mig"], rtol=1e-10)
+        assert np.allclose(g["entropy"], o["entropy"], rtol=1e-10)
+        for t in range(gpu.ntallies()):
+            assert np.allclose(gpu.tally(t, "avg"), orc.tally(t, "avg"), rtol=1e-9, atol=1e-300)
+        if "comb" in deck or deck.startswith("c5g7"):  # a combed bank holds nparticles (or one more) particles of equal weight
+            assert all(abs(int(v) - n) <= 1 for v in g["nbank"][1:])

@@ -139,8 +139,8 @@ def test_power_iteration_reproduces_the_references_power_iterator(ab, golden, tm
     migration area and entropy, and the final averages and errors, to 1e-9 relative (floating-point sums are taken in a
     different order on the device; the histories themselves are the same)."""
     fname, n, ngen, nign = ref_pins.ALL_PI_CASES[ci]
-    if ci >= len(ref_pins.POWER_ITERATION_CASES):  # the implicit-leakage tracker's simulations
-        golden = dict(np.load(GOLDEN_IMPLICIT))
+    if ci >= len(ref_pins.POWER_ITERATION_CASES):  # the implicit-leakage tracker's and the branchless iterator's simulations
+        golden = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", ref_pins.pi_golden_file(ci))))
     name = fname.split(".")[0]
     path = write_deck(load_deck(fname), tmp_path / fname, {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}})
     gpu = ab.Backend(path, 0)
@@ -206,7 +206,7 @@ def test_references_power_iterator_drives_the_gpu_transporter(ab, golden, tmp_pa
     _, host_lib = backend.lib_paths()
     fname, n, ngen, nign = ref_pins.ALL_PI_CASES[ci]
     if ci >= len(ref_pins.POWER_ITERATION_CASES):
-        golden = dict(np.load(GOLDEN_IMPLICIT))
+        golden = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", ref_pins.pi_golden_file(ci))))
     name = fname.split(".")[0]
     path = write_deck(load_deck(fname), tmp_path / fname, {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}})
     out = str(tmp_path / "pi_gpu.npz")
