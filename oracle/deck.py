@@ -198,6 +198,11 @@ def deck_to_text(deck: dict) -> str:
         ceb = c.get("energy-bounds", [])
         sh = c["shape"]
         out.append(f"cancelator 1 {int(sh[0])} {int(sh[1])} {int(sh[2])} {_fl(c['low'])} {_fl(c['hi'])} {len(ceb)} {_fl(ceb)}")
+    elif c and c.get("type") == "basic-exact":  # src/basic_exact_mg_cancelator.cpp:610-705 (sobol defaults to true, n-samples to 10)
+        sh = c["shape"]
+        beta = {"zero": 0, "minimum": 1, "average-f": 2, "average-g": 3}[c["beta"]]
+        out.append(f"cancelator 2 {int(sh[0])} {int(sh[1])} {int(sh[2])} {_fl(c['low'])} {_fl(c['hi'])} {beta} "
+                   f"{int(bool(c.get('sobol', True)))} {int(c.get('n-samples', 10))}")
     else:
         out.append("cancelator 0")
     e = deck.get("entropy")

@@ -61,8 +61,11 @@ struct Source {  // src/source.cpp, box.cpp, point.cpp, isotropic.cpp, mono_ener
   double energy = 1.;
 };
 
-struct Cancelator {  // approximate only
+struct Cancelator {  // kind 1: ApproximateMeshCancelator, kind 2: BasicExactMGCancelator (beta 0 zero, 1 minimum, 2 average-f, 3 average-g)
   bool present = false;
+  int kind = 1, beta = 0;
+  bool sobol = true;
+  uint32_t nsamples = 10;
   Vec low{0, 0, 0}, hi{0, 0, 0};
   uint32_t shape[4] = {1, 1, 1, 1};
   std::vector<double> energy_edges;
@@ -116,6 +119,20 @@ struct NoiseSource {  // src/square_oscillation_noise_source.cpp, src/flat_vibra
   }
 };
 
+// BasicExactMGCancelator's bins (include/simulation/basic_exact_mg_cancelator.hpp:48-90).  The reference keys the outer map with
+// {i, j, k} hashed as std::hash<int>(k + Nz (j + Ny i)) and the inner one with the Material pointer; here the outer key is that
+// integer (same hash values, same insertion sequence, same libstdc++: same iteration order) and the inner key the material index
+// (identical for bins that hold one material; with several the reference's order follows heap addresses).
+struct ExactCancelBin {
+  struct Averages { double f = 0., f_inv = 0.; };
+  double uniform_wgt = 0., uniform_wgt2 = 0., W = 0., W2 = 0., sum_c = 0., sum_c_wgt = 0., sum_c_wgt2 = 0.;
+  uint64_t rng_seed_advance = 0;
+  bool can_cancel = true;
+  std::vector<BankedParticle*> particles;
+  std::vector<Averages> averages;
+};
+using ExactBins = std::unordered_map<int, std::unordered_map<int, ExactCancelBin>>;
+
 struct Problem {
   Settings st;
   Geometry geo;
@@ -131,6 +148,7 @@ struct Problem {
   bool converged = false;
   uint64_t histories_counter = 0, global_histories_counter = 0;
   Pcg32Stream global_rng;  // settings::rng
+  ExactBins exact_bins;    // BasicExactMGCancelator::bins (kept across generations: clear() keeps the bucket array)
   Counters counters;
   std::string error;
   // per-history trace of the LAST transport call (instrumentation)
@@ -449,15 +467,20 @@ static Problem* load_problem(const char* path) {
   }
   P->tallies.keff_ = st.keff;
   tk.expect("cancelator");
-  if (tk.ll() != 0) {
+  if (const long long ckind = tk.ll(); ckind != 0) {
     Cancelator& c = P->cancel;
     c.present = true;
+    c.kind = (int)ckind;
     c.shape[0] = (uint32_t)tk.ll(); c.shape[1] = (uint32_t)tk.ll(); c.shape[2] = (uint32_t)tk.ll();
     c.low = {tk.d(), tk.d(), tk.d()};
     c.hi = {tk.d(), tk.d(), tk.d()};
-    size_t ne = (size_t)tk.ll();
-    c.energy_edges = tk.dv(ne);
-    c.shape[3] = ne >= 2 ? (uint32_t)(ne - 1) : 1;
+    if (c.kind == 2) {
+      c.beta = (int)tk.ll(); c.sobol = tk.ll() != 0; c.nsamples = (uint32_t)tk.ll();
+    } else {
+      size_t ne = (size_t)tk.ll();
+      c.energy_edges = tk.dv(ne);
+      c.shape[3] = ne >= 2 ? (uint32_t)(ne - 1) : 1;
+    }
     c.dx = (c.hi.x - c.low.x) / static_cast<double>(c.shape[0]);
     c.dy = (c.hi.y - c.low.y) / static_cast<double>(c.shape[1]);
     c.dz = (c.hi.z - c.low.z) / static_cast<double>(c.shape[2]);
@@ -569,7 +592,8 @@ static ScatterInfo sample_scatter(const Problem& P, const Material& nuc, const V
   return {E_out, rotate_direction(u, mu, phi)};
 }
 struct FissionInfo { double energy; Vec direction; bool delayed; double lambda; };
-static FissionInfo sample_fission(const Problem& P, const Material& nuc, const Vec& u, size_t g, double Pdelayed, Pcg32& rng) {
+template <class Engine>
+static FissionInfo sample_fission(const Problem& P, const Material& nuc, const Vec& u, size_t g, double Pdelayed, Engine& rng) {
   size_t ei = static_cast<size_t>(rng_discrete(rng, nuc.chi_cp[g]));
   double E_out = 0.5 * (P.st.energy_bounds[ei] + P.st.energy_bounds[ei + 1]);
   double mu = 2. * rng_rand(rng) - 1.;
@@ -628,6 +652,8 @@ static void make_fission_neutrons(Ctx& cx, Particle& p, const MicroXS& microxs, 
       }
     }
     BankedParticle fp{p.r(), finfo.direction, finfo.energy, wgt, wgt2, p.history_id, p.daughter_counter(), p.family_id};
+    fp.parents_previous_position = p.previous_position;
+    fp.Esmp_parent = p.Esmp_;
     if (st.mode == Settings::FIXED_SOURCE) {  // transporter.cpp:460-463: the fission neutron continues the history
       p.make_secondary(fp.u, fp.E, fp.wgt, fp.wgt2);
     } else if (st.mode == Settings::K_EIGENVALUE || !noise || st.inner_generations) {
@@ -688,6 +714,8 @@ static void branchless_collision(Ctx& cx, Particle& p, const Mat& mat) {
     const double P_delayed = microxs.nu_delayed / microxs.nu_total;
     auto finfo = sample_fission(*cx.P, nuc, p.u(), microxs.energy_index, P_delayed, p.rng);
     BankedParticle fp{p.r(), finfo.direction, finfo.energy, p.wgt() * m, p.wgt2() * m, p.history_id, p.daughter_counter(), p.family_id};
+    fp.parents_previous_position = p.previous_position;
+    fp.Esmp_parent = p.Esmp_;
     p.history_fission_bank.push_back(fp);
     p.n_fission++;
     cx.cn.fission_sites++;
@@ -828,6 +856,7 @@ static void history_delta_or_carter(Ctx& cx, Particle& p, bool carter) {
     bool had_collision = false, crossed_boundary = false;
     const size_t g = st.group(p.E());
     double Esample = (carter ? P.sampling[g] : P.majorant[g]) + mat.Ew(p.E(), noise);
+    p.Esmp_ = Esample;  // "Sampling XS saved for cancellation"
     double d_coll = rng_exponential(p.rng, Esample);
     Boundary bound(INF, -1, BC_NORMAL);
     cx.cn.flights++;
@@ -1290,8 +1319,10 @@ static void sample_noise_source(Ctx& cx, Particle& p, const Mat& mat, double kef
 }
 
 // ---- inter-generation steps --------------------------------------------------------------------
+static void perform_exact_cancellation(Problem& P, std::vector<BankedParticle>& next_gen);
 static void perform_regional_cancellation(Problem& P, std::vector<BankedParticle>& next_gen) {  // power_iterator.cpp:751-777
   const Cancelator& c = P.cancel;
+  if (c.kind == 2) return perform_exact_cancellation(P, next_gen);
   std::unordered_map<int, std::vector<BankedParticle*>> bins;
   for (auto& p : next_gen) {  // approximate_mesh_cancelator.cpp:97-145
     int i = static_cast<int>(std::floor((p.r.x - c.low.x) / c.dx));
@@ -1328,6 +1359,266 @@ static void perform_regional_cancellation(Problem& P, std::vector<BankedParticle
       }
     }
   }
+}
+
+// ---- BasicExactMGCancelator (src/basic_exact_mg_cancelator.cpp) --------------------------------------------------------------
+// Sobol points (vendor/sobol: Gruenschloss' 52-bit matrices of the Joe-Kuo direction numbers new-joe-kuo-6.21201).  The first three
+// dimensions, generated from the published recurrence instead of the table: dimension 0 is the van der Corput sequence (m_i = 1),
+// dimension 1 has the polynomial x + 1 with m_1 = 1, dimension 2 has x^2 + x + 1 with m = {1, 3}.  Checked against the
+// reference's vendored table by tests/test_reference_pins.py.
+struct SobolMatrices {
+  unsigned long long m[3][52];
+  SobolMatrices() {
+    unsigned long long d1[53], d2[53];
+    d1[1] = 1;
+    for (int i = 2; i <= 52; i++) d1[i] = (2 * d1[i - 1]) ^ d1[i - 1];                       // s = 1, a = 0
+    d2[1] = 1; d2[2] = 3;
+    for (int i = 3; i <= 52; i++) d2[i] = (2 * d2[i - 1]) ^ (4 * d2[i - 2]) ^ d2[i - 2];     // s = 2, a_1 = 1
+    for (int i = 1; i <= 52; i++) {
+      m[0][i - 1] = 1ULL << (52 - i);
+      m[1][i - 1] = d1[i] << (52 - i);
+      m[2][i - 1] = d2[i] << (52 - i);
+    }
+  }
+};
+static double sobol_sample(unsigned long long index, unsigned dimension) {  // vendor/sobol/include/sobol/sobol.hpp:36-51, scramble = 0
+  static const SobolMatrices M;
+  unsigned long long result = 0;
+  for (unsigned i = 0; index; index >>= 1, ++i)
+    if (index & 1) result ^= M.m[dimension][i];
+  return static_cast<double>(result) * (1.0 / (1ULL << 52));
+}
+
+struct ExactCancel {
+  Problem& P;
+  const Cancelator& c;
+  static constexpr uint32_t N_MAX_POS = 100;
+  explicit ExactCancel(Problem& p) : P(p), c(p.cancel) {}
+  int get_material(const Vec& r) const {  // :178-196: geometry::get_cell(r, {1, 0, 0}); -1 where there is no cell
+    Tracker t(&P.geo, r, Vec{1., 0., 0.});
+    return t.is_lost() ? -1 : t.current_mat;
+  }
+  void ijk(int key, int& i, int& j, int& k) const {
+    k = key % (int)c.shape[2];
+    j = (key / (int)c.shape[2]) % (int)c.shape[1];
+    i = key / ((int)c.shape[2] * (int)c.shape[1]);
+  }
+  bool add_particle(BankedParticle& p) {  // :68-108
+    int i = static_cast<int>(std::floor((p.r.x - c.low.x) / c.dx));
+    int j = static_cast<int>(std::floor((p.r.y - c.low.y) / c.dy));
+    int k = static_cast<int>(std::floor((p.r.z - c.low.z) / c.dz));
+    if (i < 0 || j < 0 || k < 0) return false;
+    if (i >= (int)c.shape[0] || j >= (int)c.shape[1] || k >= (int)c.shape[2]) return false;
+    const int key = k + (int)c.shape[2] * (j + (int)c.shape[1] * i);
+    const int mat = get_material(p.r);
+    if (P.exact_bins.find(key) == P.exact_bins.end()) P.exact_bins[key] = std::unordered_map<int, ExactCancelBin>();
+    if (P.exact_bins[key].find(mat) == P.exact_bins[key].end()) P.exact_bins[key][mat] = ExactCancelBin();
+    ExactCancelBin& b = P.exact_bins[key][mat];
+    b.particles.push_back(&p);
+    b.W += p.wgt;
+    b.W2 += p.wgt2;
+    return true;
+  }
+  template <class Engine>
+  bool sample_position(int key, int mat, Engine& rng, Vec& out) const {  // :110-142
+    int i, j, k;
+    ijk(key, i, j, k);
+    double Xl = c.low.x + i * c.dx, Yl = c.low.y + j * c.dy, Zl = c.low.z + k * c.dz;
+    uint32_t N_TRIES = 0;
+    bool position_sampled = false;
+    while (N_TRIES < N_MAX_POS && !position_sampled) {
+      double x = Xl + rng_rand(rng) * c.dx;
+      double y = Yl + rng_rand(rng) * c.dy;
+      double z = Zl + rng_rand(rng) * c.dz;
+      out = Vec{x, y, z};
+      if (get_material(out) == mat) position_sampled = true;
+      N_TRIES++;
+    }
+    return position_sampled;
+  }
+  bool sample_position_sobol(int key, int mat, unsigned long long& idx, Vec& out) const {  // :144-176
+    int i, j, k;
+    ijk(key, i, j, k);
+    double Xl = c.low.x + i * c.dx, Yl = c.low.y + j * c.dy, Zl = c.low.z + k * c.dz;
+    uint32_t N_TRIES = 0;
+    bool position_sampled = false;
+    while (N_TRIES < N_MAX_POS && !position_sampled) {
+      double x = Xl + sobol_sample(idx, 0) * c.dx;
+      double y = Yl + sobol_sample(idx, 1) * c.dy;
+      double z = Zl + sobol_sample(idx, 2) * c.dz;
+      out = Vec{x, y, z};
+      if (get_material(out) == mat) position_sampled = true;
+      N_TRIES++;
+      idx++;
+    }
+    return position_sampled;
+  }
+  static double get_f(const Vec& r, const Vec& r_parent, double Esmp) {  // :198-224 (std::pow(x, 2.) is x * x exactly)
+    double d = std::sqrt((r.x - r_parent.x) * (r.x - r_parent.x) + (r.y - r_parent.y) * (r.y - r_parent.y) +
+                         (r.z - r_parent.z) * (r.z - r_parent.z));
+    return (1. / (d * d)) * g_math.exp(-Esmp * d);
+  }
+  double get_min_f(int key, const Vec& r_parent, double Esmp) const {  // :226-262
+    int i, j, k;
+    ijk(key, i, j, k);
+    double Xl = c.low.x + i * c.dx, Xh = Xl + c.dx, Yl = c.low.y + j * c.dy, Yh = Yl + c.dy, Zl = c.low.z + k * c.dz, Zh = Zl + c.dz;
+    double f1 = get_f({Xh, Yh, Zh}, r_parent, Esmp), f2 = get_f({Xh, Yh, Zl}, r_parent, Esmp), f3 = get_f({Xh, Yl, Zh}, r_parent, Esmp),
+           f4 = get_f({Xh, Yl, Zl}, r_parent, Esmp), f5 = get_f({Xl, Yh, Zh}, r_parent, Esmp), f6 = get_f({Xl, Yh, Zl}, r_parent, Esmp),
+           f7 = get_f({Xl, Yl, Zh}, r_parent, Esmp), f8 = get_f({Xl, Yl, Zl}, r_parent, Esmp);
+    return std::min(std::min(std::min(f1, f2), std::min(f3, f4)), std::min(std::min(f5, f6), std::min(f7, f8)));
+  }
+  template <class Engine>
+  void get_averages(int key, int mat, ExactCancelBin& bin, Engine* rng) const {  // :264-312 (rng) and :314-364 (sobol: rng == nullptr)
+    bin.averages.resize(bin.particles.size());
+    std::vector<Vec> r_smps;
+    r_smps.reserve(c.nsamples);
+    unsigned long long sobol_index = 0;
+    for (size_t j = 0; j < c.nsamples; j++) {
+      Vec r;
+      const bool ok = rng ? sample_position(key, mat, *rng, r) : sample_position_sobol(key, mat, sobol_index, r);
+      if (!ok) { bin.can_cancel = false; return; }
+      r_smps.push_back(r);
+    }
+    for (size_t i = 0; i < bin.particles.size(); i++) {
+      const Vec r_parent = bin.particles[i]->parents_previous_position;
+      const double Esmp = bin.particles[i]->Esmp_parent;
+      double sum_f = 0., sum_f_inv = 0.;
+      for (const auto& r_smp : r_smps) {
+        double f = get_f(r_smp, r_parent, Esmp);
+        sum_f += f;
+        sum_f_inv += 1. / f;
+      }
+      bin.averages[i].f = sum_f / static_cast<double>(c.nsamples);
+      bin.averages[i].f_inv = sum_f_inv / static_cast<double>(c.nsamples);
+    }
+    if (c.beta == 3) {
+      auto C = [](double f, double f_inv) { return 1. / (2. * f * f_inv - 1.); };
+      double sum_c = 0.;
+      for (size_t i = 0; i < bin.particles.size(); i++) sum_c += C(bin.averages[i].f, bin.averages[i].f_inv);
+      double sum_c_wgt = 0., sum_c_wgt2 = 0.;
+      for (size_t i = 0; i < bin.particles.size(); i++) {
+        sum_c_wgt += C(bin.averages[i].f, bin.averages[i].f_inv) * bin.particles[i]->wgt;
+        sum_c_wgt2 += C(bin.averages[i].f, bin.averages[i].f_inv) * bin.particles[i]->wgt2;
+      }
+      bin.sum_c = sum_c; bin.sum_c_wgt = sum_c_wgt; bin.sum_c_wgt2 = sum_c_wgt2;
+    }
+  }
+  double get_beta(int key, const ExactCancelBin& bin, size_t i, const Vec& r_parent, double Esmp, double wgt, bool first_wgt) const {  // :366-406
+    if (!bin.can_cancel) return 0.;
+    switch (c.beta) {
+      case 0: return 0.;
+      case 1: return get_min_f(key, r_parent, Esmp);
+      case 2: {
+        double f = bin.averages[i].f;
+        double N = static_cast<double>(bin.particles.size());
+        double W = first_wgt ? bin.W : bin.W2;
+        return f * (1. - ((W) / ((N + 1.) * wgt)));
+      }
+      default: {
+        double sum_c_wgt = first_wgt ? bin.sum_c_wgt : bin.sum_c_wgt2;
+        double S = sum_c_wgt / (1. + bin.sum_c);
+        double f = bin.averages[i].f, f_inv = bin.averages[i].f_inv;
+        return f * (1. / (2. * f * f_inv - 1.)) * (1. - (S / wgt));
+      }
+    }
+  }
+  void cancel_bin(int key, ExactCancelBin& bin, bool first_wgt) const {  // :408-455
+    for (size_t i = 0; i < bin.particles.size(); i++) {
+      const Vec r_parent = bin.particles[i]->parents_previous_position;
+      const double Esmp = bin.particles[i]->Esmp_parent;
+      double wgt = first_wgt ? bin.particles[i]->wgt : bin.particles[i]->wgt2;
+      if (wgt == 0.) return;
+      const double B = get_beta(key, bin, i, r_parent, Esmp, wgt, first_wgt);
+      const double f = get_f(bin.particles[i]->r, r_parent, Esmp);
+      const double P_p = (f - B) / f;
+      const double P_u = B / f;
+      if (std::isinf(P_u) || std::isinf(P_p) || std::isnan(P_u) || std::isnan(P_p)) return;
+      if (first_wgt) {
+        bin.uniform_wgt += bin.particles[i]->wgt * P_u;
+        bin.particles[i]->wgt *= P_p;
+      } else {
+        bin.uniform_wgt2 += bin.particles[i]->wgt2 * P_u;
+        bin.particles[i]->wgt2 *= P_p;
+      }
+    }
+  }
+  void perform_cancellation(Pcg32Stream& rng) {  // :457-555
+    ExactBins& bins = P.exact_bins;
+    if (c.beta == 0) return;
+    if (bins.size() == 0) return;
+    std::vector<std::pair<int, int>> keys;
+    keys.reserve(bins.size());
+    for (const auto& kb : bins)
+      for (const auto& mb : kb.second) keys.push_back({kb.first, mb.first});
+    uint64_t seed_advance = 0;
+    if (c.beta != 1) {
+      uint64_t max_rn_per_part = (uint64_t)c.nsamples * N_MAX_POS * (c.beta == 3 ? 2 : 1);
+      bins[keys[0].first][keys[0].second].rng_seed_advance = 0;
+      seed_advance = bins[keys[0].first][keys[0].second].particles.size() * max_rn_per_part;
+      for (size_t i = 1; i < keys.size(); i++) {
+        bins[keys[i].first][keys[i].second].rng_seed_advance = seed_advance;
+        seed_advance += bins[keys[i].first][keys[i].second].particles.size() * max_rn_per_part;
+      }
+    }
+    for (size_t i = 0; i < keys.size(); i++) {
+      const int key = keys[i].first, mat = keys[i].second;
+      ExactCancelBin& bin = bins[key][mat];
+      Pcg32Stream rng_local = rng;
+      rng_local.advance(bin.rng_seed_advance);
+      if (bin.particles.size() > 1) {
+        bool has_pos_w1 = false, has_neg_w1 = false, has_pos_w2 = false, has_neg_w2 = false;
+        for (const auto& p : bin.particles) {
+          if (p->wgt > 0.) has_pos_w1 = true; else if (p->wgt < 0.) has_neg_w1 = true;
+          if (p->wgt2 > 0.) has_pos_w2 = true; else if (p->wgt2 < 0.) has_neg_w2 = true;
+          if (has_pos_w1 && has_neg_w1 && has_pos_w2 && has_neg_w2) break;
+        }
+        if (((has_pos_w1 && has_neg_w1) || (has_pos_w2 && has_neg_w2)) && (c.beta == 2 || c.beta == 3))
+          get_averages(key, mat, bin, c.sobol ? static_cast<Pcg32Stream*>(nullptr) : &rng_local);
+        if (has_pos_w1 && has_neg_w1) cancel_bin(key, bin, true);
+        if (has_pos_w2 && has_neg_w2) cancel_bin(key, bin, false);
+        bin.particles.clear();
+        bin.averages.clear();
+        bin.sum_c = 0.; bin.sum_c_wgt = 0.; bin.sum_c_wgt2 = 0.;
+      }
+    }
+    if (c.beta != 1) rng.advance(seed_advance);
+  }
+  std::vector<BankedParticle> get_new_particles(Pcg32Stream& rng) {  // :557-617
+    if (c.beta == 0) return {};
+    std::vector<BankedParticle> uniform_particles;
+    for (auto& kb : P.exact_bins) {
+      const int key = kb.first;
+      for (auto& mb : kb.second) {
+        const int mat = mb.first;
+        ExactCancelBin& bin = mb.second;
+        uint32_t N = static_cast<uint32_t>(std::ceil(std::max(std::abs(bin.uniform_wgt), std::abs(bin.uniform_wgt2))));
+        if (N > 0) {
+          double w = bin.uniform_wgt / N, w2 = bin.uniform_wgt2 / N;
+          for (size_t i = 0; i < N; i++) {
+            Vec r;
+            if (!sample_position(key, mat, rng, r)) throw std::runtime_error("Couldn't sample position for uniform particle.");
+            FissionInfo finfo = sample_fission(P, P.materials[(size_t)mat], Vec{0., 0., 1.}, 0, 0., rng);
+            BankedParticle up{r, finfo.direction, finfo.energy, w, w2, 0, 0, 0};
+            uniform_particles.push_back(up);
+          }
+        }
+        bin.uniform_wgt = 0.;
+        bin.uniform_wgt2 = 0.;
+      }
+    }
+    return uniform_particles;
+  }
+};
+
+// PowerIterator::perform_regional_cancellation with an exact cancelator (power_iterator.cpp:751-777): the uniform particles are
+// appended to the bank
+static void perform_exact_cancellation(Problem& P, std::vector<BankedParticle>& next_gen) {
+  ExactCancel ec(P);
+  for (auto& p : next_gen) (void)ec.add_particle(p);
+  ec.perform_cancellation(P.global_rng);
+  auto tmp = ec.get_new_particles(P.global_rng);
+  next_gen.insert(next_gen.end(), tmp.begin(), tmp.end());
+  P.exact_bins.clear();
 }
 
 struct GenStats { int Npos = 0, Nneg = 0, Ntot = 0, Nnet = 0; double Wpos = 0, Wneg = 0; };
@@ -1864,6 +2155,11 @@ int orc_cancel_and_normalize(void* h, orc_bank* b, int do_cancel, double* stats6
   stats6[0] = s.Npos; stats6[1] = s.Nneg; stats6[2] = s.Ntot; stats6[3] = s.Nnet; stats6[4] = s.Wpos; stats6[5] = s.Wneg;
   bank_to(v, b);
   return 0;
+}
+
+void orc_sobol_points(int n, double* out3n) {
+  for (int i = 0; i < n; i++)
+    for (unsigned d = 0; d < 3; d++) out3n[3 * i + d] = sobol_sample(static_cast<unsigned long long>(i), d);
 }
 
 // BranchlessPowerIterator::comb_particles alone.  rng2 = {state, increment} of settings::rng, updated; out->n = capacity on entry.

@@ -187,6 +187,10 @@ struct BankedParticle {
   Vec r, u;
   double E, wgt, wgt2;
   uint64_t parent_history_id, parent_daughter_id, family_id;
+  // what the exact cancelators read (particle.hpp:52-57): where the parent was before the flight that ended in this fission,
+  // and the sampling cross section of that flight
+  Vec parents_previous_position{0, 0, 0};
+  double Esmp_parent = 0.;
 };
 
 struct ParticleState { Vec position, direction; double energy, weight, weight2; };
@@ -198,6 +202,7 @@ struct Particle {  // particle.hpp:68-243
   std::vector<BankedParticle> history_fission_bank, history_noise_bank;
   bool alive = true, reflected = false, previous_collision_virtual = false;
   Vec previous_position{0, 0, 0}, r_birth{0, 0, 0};
+  double Esmp_ = 0.;  // sampling cross section of the current flight (delta_tracker.cpp:111, carter_tracker.cpp:130)
   Pcg32 rng;
   // instrumentation (not in the reference): per-history integer outcomes
   uint32_t n_flights = 0, n_real = 0, n_virtual = 0, n_fission = 0, n_boundary = 0;

@@ -90,6 +90,19 @@ struct Pcg32Stream {
     return (xorshifted >> rot) | (xorshifted << ((32u - rot) & 31u));
   }
   result_type operator()() { return next(); }
+  void advance(uint64_t delta) {
+    uint64_t acc_mult = 1, acc_plus = 0, cur_mult = Pcg32::MULT, cur_plus = inc;
+    while (delta > 0) {
+      if (delta & 1) {
+        acc_mult *= cur_mult;
+        acc_plus = acc_plus * cur_mult + cur_plus;
+      }
+      cur_plus = (cur_mult + 1) * cur_plus;
+      cur_mult *= cur_mult;
+      delta >>= 1;
+    }
+    state = acc_mult * state + acc_plus;
+  }
 };
 
 // RNG::rand  (rng.hpp:41) == libstdc++ generate_canonical<double,53>(pcg32)
@@ -132,7 +145,8 @@ inline std::vector<double> discrete_table(const double* w, size_t n) {
 }
 
 // RNG::discrete (rng.hpp:88-96) with the table above
-inline int rng_discrete(Pcg32& g, const std::vector<double>& cp) {
+template <class Engine>
+inline int rng_discrete(Engine& g, const std::vector<double>& cp) {
   if (cp.empty()) return 0;
   const double p = rng_rand(g);
   size_t lo = 0, len = cp.size();  // std::lower_bound

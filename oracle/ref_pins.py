@@ -539,13 +539,21 @@ IMPLICIT_POWER_ITERATION_CASES = (("c5g7_implicit_collision.yaml", 3000, 8, 3), 
 # comb, isotope flavour with splitting and no comb, material flavour with splitting and the comb (tests/golden/ref_pins_branchless.npz)
 BRANCHLESS_PI_CASES = (("c5g7_delta_branchless.yaml", 3000, 8, 3), ("PUa-1-0-SL_branchless_iso_split.yaml", 2000, 10, 3),
                        ("UD2O-2-1-SL_branchless_split_comb.yaml", 2000, 10, 3))
-ALL_PI_CASES = POWER_ITERATION_CASES + IMPLICIT_POWER_ITERATION_CASES + BRANCHLESS_PI_CASES
+# carter tracking with negative weights and the basic-exact regional cancelator (src/basic_exact_mg_cancelator.cpp): beta minimum
+# in a reflective cube, average-f with sampled points and average-g with Sobol points in a vacuum cube
+# (tests/golden/ref_pins_exact.npz).  One material each: the reference orders its bins by Material pointer otherwise.
+EXACT_PI_CASES = (("PUa-cube_carter_exact_min.yaml", 2000, 8, 3), ("PUa-cube_carter_exact_avgf.yaml", 2000, 8, 3),
+                  ("PUa-cube_carter_exact_avgg.yaml", 2000, 8, 3))
+ALL_PI_CASES = POWER_ITERATION_CASES + IMPLICIT_POWER_ITERATION_CASES + BRANCHLESS_PI_CASES + EXACT_PI_CASES
 IMPLICIT_PI_RANGE = range(len(POWER_ITERATION_CASES), len(POWER_ITERATION_CASES) + len(IMPLICIT_POWER_ITERATION_CASES))
-BRANCHLESS_PI_RANGE = range(IMPLICIT_PI_RANGE.stop, len(ALL_PI_CASES))
+BRANCHLESS_PI_RANGE = range(IMPLICIT_PI_RANGE.stop, IMPLICIT_PI_RANGE.stop + len(BRANCHLESS_PI_CASES))
+EXACT_PI_RANGE = range(BRANCHLESS_PI_RANGE.stop, len(ALL_PI_CASES))
 
 
 def pi_golden_file(ci: int) -> str:
     """The file under tests/golden/ that holds the reference's output for ALL_PI_CASES[ci]."""
+    if ci in EXACT_PI_RANGE:
+        return "ref_pins_exact.npz"
     return "ref_pins_branchless.npz" if ci in BRANCHLESS_PI_RANGE else ("ref_pins_implicit.npz" if ci in IMPLICIT_PI_RANGE else "ref_pins.npz")
 
 
@@ -759,4 +767,13 @@ def power_iteration_through_gpu_transporter(only: int, host_library: str, yaml_d
             L.ref_gpu_tally_get(C.c_int(t), C.c_int(which), _d(v), C.c_uint64(size))
             out[f"pi_{name}_tally{t}_{wname}"] = v
     L.ref_gpu_release()
+    return out
+
+
+def sobol_points(impl: str, n: int = 5000) -> np.ndarray:
+    """The first n points of the 3-d Sobol sequence BasicExactMGCancelator samples its bins with: the reference's vendored table
+    (vendor/sobol) or the oracle's matrices generated from the Joe-Kuo recurrence."""
+    out = np.zeros((n, 3))
+    L = ref_lib() if impl == "reference" else api.lib()
+    getattr(L, "ref_sobol_points" if impl == "reference" else "orc_sobol_points")(C.c_int(n), _d(out))
     return out

@@ -49,6 +49,8 @@
 #include <simulation/implicit_leakage_delta_tracker.hpp>
 #include <simulation/flat_vibration_noise_source.hpp>
 #include <simulation/approximate_mesh_cancelator.hpp>
+#include <simulation/basic_exact_mg_cancelator.hpp>
+#include <sobol/sobol.hpp>
 #include <simulation/box.hpp>
 #include <simulation/entropy.hpp>
 #include <simulation/isotropic.hpp>
@@ -1028,7 +1030,16 @@ DriverParts driver_parts(const char* text) {
     } else if (key == "cancelator") {
       int on;
       ls >> on;
-      if (on) {
+      if (on == 2) {  // type: basic-exact (src/basic_exact_mg_cancelator.cpp:610-705): beta 0 zero, 1 minimum, 2 average-f, 3 average-g
+        uint32_t nx, ny, nz, nsmp;
+        double lo[3], hi[3];
+        int beta, sobol;
+        ls >> nx >> ny >> nz >> lo[0] >> lo[1] >> lo[2] >> hi[0] >> hi[1] >> hi[2] >> beta >> sobol >> nsmp;
+        const BasicExactMGCancelator::BetaMode modes[4] = {BasicExactMGCancelator::BetaMode::Zero, BasicExactMGCancelator::BetaMode::Minimum,
+                                                           BasicExactMGCancelator::BetaMode::OptAverageF, BasicExactMGCancelator::BetaMode::OptAverageGain};
+        d.cancelator = std::make_shared<BasicExactMGCancelator>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), nx, ny, nz,
+                                                                modes[beta], sobol != 0, nsmp);
+      } else if (on) {
         uint32_t nx, ny, nz;
         double lo[3], hi[3];
         size_t ne;
@@ -1086,6 +1097,11 @@ void run_iterator(DriverParts& d, int ngen, double* kcol, double* ktrk, double* 
 }  // namespace
 
 extern "C" {
+// the reference's vendored Sobol sequence (vendor/sobol), the points BasicExactMGCancelator::sample_position_sobol uses
+void ref_sobol_points(int n, double* out3n) {
+  for (int i = 0; i < n; i++)
+    for (unsigned d = 0; d < 3; d++) out3n[3 * i + d] = sobol::sample(static_cast<unsigned long long>(i), d);
+}
 // size of the source bank the last ref_power_iteration ended with (after combing, for a branchless deck)
 uint64_t ref_last_bank_size() { return g_last_bank_size; }
 
