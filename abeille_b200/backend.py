@@ -525,6 +525,21 @@ class Backend:
         s = _device_struct(bank, n)
         self._check(self.L.abl_cancel_device(self.h, C.byref(s), self._stream()))
 
+    def parent_info(self, n: int) -> np.ndarray:
+        """[n, 4]: the parents' previous position and sampling cross section of the rows of the last fission bank (problems
+        with an exact cancelator; BankedParticle::parents_previous_position / Esmp_parent)."""
+        cols = [np.zeros(n) for _ in range(4)]
+        self._check(self.L.abl_parent_info_download(self.h, C.c_uint64(n), *[c.ctypes.data_as(_PD) for c in cols]))
+        return np.stack(cols, axis=1)
+
+    def cancel_exact_device(self, bank: dict, n: int, rng2):
+        """abl_cancel_exact_device: BasicExactMGCancelator on the fission bank of the last transport call (torch tensors of
+        capacity len(bank['x'])).  Returns (rows afterwards, (state, increment) of the global engine afterwards)."""
+        s = _device_struct(bank, n)
+        r = (C.c_uint64 * 2)(int(rng2[0]), int(rng2[1]))
+        self._check(self.L.abl_cancel_exact_device(self.h, C.byref(s), C.c_uint64(len(bank["x"])), r, self._stream()))
+        return int(s.n), (int(r[0]), int(r[1]))
+
     def cancel_accumulate_device(self, bank: dict, n: int):
         s = _device_struct(bank, n)
         self._check(self.L.abl_cancel_accumulate_device(self.h, C.byref(s), self._stream()))

@@ -15,6 +15,7 @@
 #include <limits>
 #include <string>
 #include <type_traits>
+#include <unordered_map>
 #include <functional>
 #include <vector>
 
@@ -69,6 +70,19 @@ struct abl_context {
   uint64_t pending_rows = 0;  // abl_transport_begin .. abl_transport_finish: rows of the fission bank waiting in stage_out
   uint32_t* site_inv = nullptr;  // bank row -> scratch site (place_sites_kernel)
   uint64_t inv_cap = 0;
+  // exact cancelators: {parent's previous position, sampling xs} of the scratch sites, and of the rows of the last fission bank
+  double* site_parent = nullptr;
+  uint64_t site_parent_cap = 0;
+  double* parent_info = nullptr;  // [4][parent_cap]: x, y, z, Esmp in bank order
+  uint64_t parent_cap = 0, parent_n = 0;
+  // BasicExactMGCancelator::bins.  Kept across calls and clear()ed like the reference's: the bucket array survives, and with it
+  // the order the map is walked in (which orders the uniform particles).  Outer key k + Nz (j + Ny i) -- the value the reference's
+  // KeyHash feeds std::hash<int> --, inner key the material index.
+  struct ExactBin {
+    double uniform_wgt = 0., uniform_wgt2 = 0., W = 0., W2 = 0.;
+    std::vector<uint64_t> particles;
+  };
+  std::unordered_map<int, std::unordered_map<int, ExactBin>> exact_bins;
   int nm_blocks_per_sm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   int implicit_blocks_per_sm[3] = {0, 0, 0};  // implicit-leakage delta tracking: per-lane kernel in modes 0 | 1 | 2
   // host-buffer entry point: the bank is copied in row chunks on its own stream while the history kernel runs
@@ -176,6 +190,11 @@ int validate(abl_handle h, const abl_problem* p) {
   if (p->mode == ABL_MODE_NOISE) {
     if (p->n_noise_sources < 1 || !p->noise_sources) return fail(h, ABL_ERR_INVALID, "noise mode without a noise source");
     if (!(p->w_noise > 0.)) return fail(h, ABL_ERR_INVALID, "noise mode needs a positive noise-angular-frequency");
+  }
+  if (p->cancelator.present && p->cancelator.kind == ABL_CANCEL_BASIC_EXACT) {
+    if (p->tracking != ABL_TRACK_DELTA && p->tracking != ABL_TRACK_CARTER)
+      return fail(h, ABL_ERR_UNSUPPORTED, "basic-exact cancelators need delta or carter tracking (src/cancelator.cpp:43-47)");
+    if (p->cancelator.beta < ABL_BETA_ZERO || p->cancelator.beta > ABL_BETA_AVERAGE_G) return fail(h, ABL_ERR_INVALID, "cancelator beta");
   }
   if (p->ntallies > ABL_MAX_TALLIES) return fail(h, ABL_ERR_UNSUPPORTED, "more than ABL_MAX_TALLIES mesh tallies");
   if (p->root_universe < 0 || p->root_universe >= p->nuniverses) return fail(h, ABL_ERR_INVALID, "root universe");
@@ -419,6 +438,28 @@ int ensure_sites(abl_handle h, uint64_t cap) {
     ABL_CUDA(h, cudaMalloc(&h->sites, cap * sizeof(Site)));
     h->site_cap = cap;
   }
+  if (h->P.exact_cancel && cap > h->site_parent_cap) {
+    if (h->site_parent) cudaFree(h->site_parent);
+    h->site_parent = nullptr;
+    h->site_parent_cap = 0;
+    ABL_CUDA(h, cudaMalloc(&h->site_parent, cap * 4 * sizeof(double)));
+    h->site_parent_cap = cap;
+  }
+  return ABL_OK;
+}
+
+// rows of the exact cancelators' side table (x, y, z, Esmp columns of `cap` entries each); contents of the first `keep` rows survive
+int ensure_parent_info(abl_handle h, uint64_t cap, uint64_t keep) {
+  if (cap <= h->parent_cap) return ABL_OK;
+  double* n = nullptr;
+  ABL_CUDA(h, cudaMalloc(&n, cap * 4 * sizeof(double)));
+  ABL_CUDA(h, cudaMemset(n, 0, cap * 4 * sizeof(double)));
+  if (h->parent_info && keep)
+    for (int q = 0; q < 4; q++)
+      ABL_CUDA(h, cudaMemcpy(n + q * cap, h->parent_info + q * h->parent_cap, keep * sizeof(double), cudaMemcpyDeviceToDevice));
+  if (h->parent_info) cudaFree(h->parent_info);
+  h->parent_info = n;
+  h->parent_cap = cap;
   return ABL_OK;
 }
 
@@ -683,7 +724,8 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
   // it goes through the staged kernel; noise particles and sampling generations use the per-lane kernel (noise.cuh)
   // fixed-source problems (fission neutrons as secondaries of their history) run the per-lane kernel in its k-eigenvalue mode
   // and so do branchless collisions (their splitting needs the secondaries LIFO as well)
-  const bool fixed_source = h->P.mode == ABL_MODE_FIXED_SOURCE || h->P.mode == ABL_MODE_BRANCHLESS;
+  // and problems with an exact cancelator (the per-lane kernel carries the parent's previous position and sampling xs)
+  const bool fixed_source = h->P.mode == ABL_MODE_FIXED_SOURCE || h->P.mode == ABL_MODE_BRANCHLESS || (h->P.exact_cancel && !noise_mode);
   const bool lane_kernel_call = (noise_mode && (params->noise != 0 || sample_noise)) || fixed_source;
   if ((params->noise || sample_noise) && !noise_mode)
     return fail(h, ABL_ERR_INVALID, "noise transport / noise-source sampling needs a problem with simulation: noise");
@@ -738,6 +780,7 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
   A.counters = h->small_dev->counters;
   A.error = h->small_dev->error;
   A.secondaries = nullptr;
+  A.site_parent = h->P.exact_cancel ? h->site_parent : nullptr;
   A.k_col = params->k_col;
   A.keff = params->keff;
   A.converged = params->converged;
@@ -792,6 +835,7 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
   if (counters)
     for (int i = 0; i < 8; i++) counters[i] = sm.counters[i];
   *n_fission = sm.n_sites;
+  h->parent_n = A.site_parent ? sm.n_sites : 0;
   rc = status_from_device_error(h, sm);
   if (rc) return rc;
   if (sm.n_sites > out.n) {
@@ -805,6 +849,11 @@ int transport_impl(abl_handle h, const BankView& in, const abl_gen_params* param
     place_sites_kernel<<<grid_for(h, sm.n_sites, 256), 256, 0, s>>>(h->sites, sm.n_sites, h->site_inv, in, out,
                                                                      lane_kernel_call ? h->site_did : nullptr);
     h->launches += 2;
+    if (A.site_parent) {
+      if ((rc = ensure_parent_info(h, out.n, 0)) != 0) return rc;
+      place_parent_info_kernel<<<grid_for(h, sm.n_sites, 256), 256, 0, s>>>(h->site_parent, sm.n_sites, h->site_inv, h->parent_info, h->parent_cap);
+      h->launches += 1;
+    }
     ABL_CUDA(h, cudaGetLastError());
   }
   if (sample_noise) {
@@ -844,7 +893,8 @@ void abl_destroy(abl_handle h) {
                   (void*)h->tr_virtual, (void*)h->tr_hash, (void*)h->tr_rng, (void*)h->small_dev, (void*)h->secondaries,
                   (void*)h->cancel.sum_pos, (void*)h->cancel.sum_neg, (void*)h->cancel.sum_pos2, (void*)h->cancel.sum_neg2,
                   (void*)h->cancel.count, (void*)h->probe_buf, (void*)h->rng_scratch,
-                  (void*)h->nsites, (void*)h->nnoise, (void*)h->noffsets, (void*)h->ntile_sums, (void*)h->site_did, (void*)h->nsite_did, (void*)h->site_inv})
+                  (void*)h->nsites, (void*)h->nnoise, (void*)h->noffsets, (void*)h->ntile_sums, (void*)h->site_did, (void*)h->nsite_did, (void*)h->site_inv,
+                  (void*)h->site_parent, (void*)h->parent_info})
     if (p) cudaFree(p);
   free_bank(h->stage_in);
   free_bank(h->stage_out);
@@ -1111,6 +1161,9 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
   }
   P.entropy = make_mesh3(p->entropy, teb);
   P.cancel = make_mesh3(p->cancelator, teb);
+  P.cancel.kind = p->cancelator.present ? (p->cancelator.kind == ABL_CANCEL_BASIC_EXACT ? ABL_CANCEL_BASIC_EXACT : ABL_CANCEL_APPROXIMATE) : 0;
+  P.cancel.beta = p->cancelator.beta;
+  P.exact_cancel = P.cancel.kind == ABL_CANCEL_BASIC_EXACT ? 1 : 0;
 #undef UP
   if (CU(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return bail(ABL_ERR_CUDA);
   *out = h;
@@ -1217,7 +1270,7 @@ int transport_upload_and_run(abl_handle h, const abl_bank* bank, const abl_gen_p
   // kernel polls before it loads a row -- the PCIe copy (17 ms for 1e7 particles) hides behind the kernel.
   constexpr int NCHUNK = 16;
   // (only the staged kernel polls the arrival counter of a streamed bank)
-  const bool streamed = h->P.mode != ABL_MODE_NOISE && !params->noise && N >= (1u << 18) && h->P.tracking != ABL_TRACK_IMPLICIT_LEAKAGE;
+  const bool streamed = h->P.mode == ABL_MODE_K_EIGENVALUE && !h->P.exact_cancel && !params->noise && N >= (1u << 18) && h->P.tracking != ABL_TRACK_IMPLICIT_LEAKAGE;
   if (streamed) {
     if (!h->copy_stream) {
       ABL_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -1531,7 +1584,7 @@ int abl_score_source_device(abl_handle h, const abl_bank* bank_dev, int noise_so
 namespace {
 int ensure_cancel_bins(abl_handle h, uint64_t* nbins_out) {
   const DevMesh3& m = h->P.cancel;
-  if (!m.present) return fail(h, ABL_ERR_INVALID, "problem has no approximate cancelator");
+  if (!m.present || m.kind == ABL_CANCEL_BASIC_EXACT) return fail(h, ABL_ERR_INVALID, "problem has no approximate cancelator");
   const uint64_t nbins = (uint64_t)m.Nx * m.Ny * m.Nz * m.Ne;
   if (!h->cancel.count) {
     ABL_CUDA(h, cudaMalloc(&h->cancel.count, nbins * sizeof(uint32_t)));
@@ -1591,6 +1644,152 @@ int abl_cancel_device(abl_handle h, abl_bank* bank_dev, void* stream) {
   int rc = abl_cancel_accumulate_device(h, bank_dev, stream);
   if (rc) return rc;
   return abl_cancel_apply_device(h, bank_dev, stream);
+}
+
+// ---- BasicExactMGCancelator ------------------------------------------------------------------------------------------------------
+int abl_parent_info_download(abl_handle h, uint64_t n, double* x, double* y, double* z, double* esmp) {
+  if (!h) return ABL_ERR_INVALID;
+  if (!h->P.exact_cancel) return fail(h, ABL_ERR_INVALID, "problem has no exact cancelator");
+  if (n > h->parent_n) return fail(h, ABL_ERR_INVALID, "more rows than the last fission bank holds");
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  double* dst[4] = {x, y, z, esmp};
+  for (int q = 0; q < 4; q++)
+    if (dst[q] && n) ABL_CUDA(h, cudaMemcpy(dst[q], h->parent_info + q * h->parent_cap, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return ABL_OK;
+}
+
+int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity, uint64_t rng2[2], void* stream) {
+  if (!h || !bank_dev || !rng2) return ABL_ERR_INVALID;
+  const DevMesh3& m = h->P.cancel;
+  if (!m.present || m.kind != ABL_CANCEL_BASIC_EXACT) return fail(h, ABL_ERR_INVALID, "problem has no basic-exact cancelator");
+  const uint64_t n = bank_dev->n;
+  if (n != h->parent_n) return fail(h, ABL_ERR_INVALID, "abl_cancel_exact_device takes the fission bank of the last transport call");
+  if (rng2[1] != 5ULL) return fail(h, ABL_ERR_UNSUPPORTED, "the global engine must be on stream 2 (settings::initialize_global_rng)");
+  if (m.beta == ABL_BETA_ZERO || n == 0) return ABL_OK;  // perform_cancellation / get_new_particles return at once (:458, :559)
+  if (m.beta != ABL_BETA_MINIMUM)
+    return fail(h, ABL_ERR_UNSUPPORTED, "basic-exact cancelator on the device: beta zero and minimum (average-f / average-g sample points in "
+                                        "every bin; the reference's own cancelator runs them over abl_parent_info_download)");
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  const BankView b = view_of(bank_dev);
+  // (1) per-particle columns on the device
+  int32_t *key_d = nullptr, *mat_d = nullptr;
+  double *f_d = nullptr, *fmin_d = nullptr;
+  auto release = [&]() {
+    for (void* p : {(void*)key_d, (void*)mat_d, (void*)f_d, (void*)fmin_d})
+      if (p) cudaFree(p);
+  };
+  auto CU = [&](cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return false;
+    h->error = std::string(what) + ": " + cudaGetErrorString(e);
+    return true;
+  };
+  if (CU(cudaMalloc(&key_d, n * 4), "cudaMalloc") || CU(cudaMalloc(&mat_d, n * 4), "cudaMalloc") || CU(cudaMalloc(&f_d, n * 8), "cudaMalloc") ||
+      CU(cudaMalloc(&fmin_d, n * 8), "cudaMalloc")) {
+    release();
+    return ABL_ERR_CUDA;
+  }
+  exact_prepare_kernel<<<grid_for(h, n, 128), 128, 0, s>>>(h->P, m, b, h->parent_info, h->parent_cap, n, key_d, mat_d, f_d, fmin_d);
+  h->launches++;
+  std::vector<int32_t> key(n), mat(n);
+  std::vector<double> f(n), fmin(n), w(n), w2(n, 0.);
+  bool bad = CU(cudaMemcpyAsync(key.data(), key_d, n * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
+             CU(cudaMemcpyAsync(mat.data(), mat_d, n * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
+             CU(cudaMemcpyAsync(f.data(), f_d, n * 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
+             CU(cudaMemcpyAsync(fmin.data(), fmin_d, n * 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
+             CU(cudaMemcpyAsync(w.data(), b.wgt, n * 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
+             (b.wgt2 && CU(cudaMemcpyAsync(w2.data(), b.wgt2, n * 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync")) ||
+             CU(cudaStreamSynchronize(s), "exact_prepare_kernel");
+  release();
+  if (bad) return ABL_ERR_CUDA;
+  // (2) the bins, replayed in the reference's order (add_particle :68-108, perform_cancellation :457-555, cancel_bin :408-455)
+  auto& bins = h->exact_bins;
+  for (uint64_t i = 0; i < n; i++) {
+    if (key[i] < 0) continue;
+    if (bins.find(key[i]) == bins.end()) bins[key[i]] = std::unordered_map<int, abl_context::ExactBin>();
+    if (bins[key[i]].find(mat[i]) == bins[key[i]].end()) bins[key[i]][mat[i]] = abl_context::ExactBin();
+    abl_context::ExactBin& bin = bins[key[i]][mat[i]];
+    bin.particles.push_back(i);
+    bin.W += w[i];
+    bin.W2 += w2[i];
+  }
+  bool touched = false, touched2 = false;
+  auto cancel_bin = [&](abl_context::ExactBin& bin, bool first) {
+    std::vector<double>& wv = first ? w : w2;
+    for (uint64_t i : bin.particles) {
+      const double wgt = wv[i];
+      if (wgt == 0.) return;
+      const double B = fmin[i], fi = f[i];
+      const double P_p = (fi - B) / fi, P_u = B / fi;
+      if (std::isinf(P_u) || std::isinf(P_p) || std::isnan(P_u) || std::isnan(P_p)) return;
+      (first ? bin.uniform_wgt : bin.uniform_wgt2) += wv[i] * P_u;
+      wv[i] *= P_p;
+      (first ? touched : touched2) = true;
+    }
+  };
+  for (auto& kb : bins)
+    for (auto& mb : kb.second) {
+      abl_context::ExactBin& bin = mb.second;
+      if (bin.particles.size() > 1) {
+        bool p1 = false, n1 = false, p2 = false, n2 = false;
+        for (uint64_t i : bin.particles) {
+          if (w[i] > 0.) p1 = true; else if (w[i] < 0.) n1 = true;
+          if (w2[i] > 0.) p2 = true; else if (w2[i] < 0.) n2 = true;
+          if (p1 && n1 && p2 && n2) break;
+        }
+        if (p1 && n1) cancel_bin(bin, true);
+        if (p2 && n2) cancel_bin(bin, false);
+        bin.particles.clear();
+      }
+    }
+  // (3) get_new_particles (:557-617): which bins emit how many uniform particles, in the map's order
+  std::vector<double> list;
+  uint64_t n_new = 0;
+  for (auto& kb : bins)
+    for (auto& mb : kb.second) {
+      abl_context::ExactBin& bin = mb.second;
+      const uint32_t N = static_cast<uint32_t>(std::ceil(std::max(std::abs(bin.uniform_wgt), std::abs(bin.uniform_wgt2))));
+      if (N > 0) {
+        list.insert(list.end(), {(double)kb.first, (double)mb.first, (double)N, bin.uniform_wgt / N, bin.uniform_wgt2 / N});
+        n_new += N;
+      }
+      bin.uniform_wgt = 0.;
+      bin.uniform_wgt2 = 0.;
+    }
+  bins.clear();
+  if (n + n_new > capacity) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "exact cancelator: %llu particles + %llu uniform particles exceed the bank capacity %llu",
+             (unsigned long long)n, (unsigned long long)n_new, (unsigned long long)capacity);
+    return fail(h, ABL_ERR_BANK_OVERFLOW, buf);
+  }
+  if (touched) ABL_CUDA(h, cudaMemcpyAsync(b.wgt, w.data(), n * 8, cudaMemcpyHostToDevice, s));
+  if (touched2 && b.wgt2) ABL_CUDA(h, cudaMemcpyAsync(b.wgt2, w2.data(), n * 8, cudaMemcpyHostToDevice, s));
+  if (n_new) {
+    int rc = ensure_parent_info(h, n + n_new, n);
+    if (rc) return rc;
+    double* list_d = nullptr;
+    uint64_t* st_d = nullptr;
+    ABL_CUDA(h, cudaMalloc(&list_d, list.size() * 8));
+    ABL_CUDA(h, cudaMalloc(&st_d, 3 * 8));
+    unsigned long long st[3] = {rng2[0], 0, 0};
+    ABL_CUDA(h, cudaMemcpyAsync(list_d, list.data(), list.size() * 8, cudaMemcpyHostToDevice, s));
+    ABL_CUDA(h, cudaMemcpyAsync(st_d, st, 3 * 8, cudaMemcpyHostToDevice, s));
+    exact_uniform_kernel<<<1, 1, 0, s>>>(h->P, m, list_d, list.size() / 5, st_d, b, n, capacity, h->parent_info, h->parent_cap,
+                                          reinterpret_cast<unsigned long long*>(st_d + 1));
+    h->launches++;
+    ABL_CUDA(h, cudaMemcpyAsync(st, st_d, 3 * 8, cudaMemcpyDeviceToHost, s));
+    ABL_CUDA(h, cudaStreamSynchronize(s));
+    cudaFree(list_d);
+    cudaFree(st_d);
+    if (st[2]) return fail(h, ABL_ERR_LOST, "Couldn't sample position for uniform particle.");
+    rng2[0] = st[0];
+    bank_dev->n = st[1];
+    h->parent_n = st[1];
+  } else {
+    ABL_CUDA(h, cudaStreamSynchronize(s));
+  }
+  return ABL_OK;
 }
 
 // ---- device memory helpers ---------------------------------------------------------------------------------------------------

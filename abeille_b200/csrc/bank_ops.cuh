@@ -131,6 +131,16 @@ __global__ void __launch_bounds__(256) place_sites_kernel(const Site* __restrict
   }
 }
 
+// the exact cancelators' side table follows the sites to their rows (columns x, y, z, Esmp of `cap` entries)
+__global__ void __launch_bounds__(256) place_parent_info_kernel(const double* __restrict__ site_parent, uint64_t n_sites,
+                                                                const uint32_t* __restrict__ inv, double* __restrict__ out, uint64_t cap) {
+  for (uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < n_sites; pos += (uint64_t)gridDim.x * blockDim.x) {
+    const double2* src = reinterpret_cast<const double2*>(site_parent + 4 * (uint64_t)inv[pos]);
+    const double2 a = __ldcs(src), b = __ldcs(src + 1);
+    out[pos] = a.x; out[cap + pos] = a.y; out[2 * cap + pos] = b.x; out[3 * cap + pos] = b.y;
+  }
+}
+
 // ---- weights ------------------------------------------------------------------------------------------------------
 // out[0..3] += Npos, Nneg, Wpos, Wneg   (Wneg accumulated as a positive number, as the reference does)
 __global__ void __launch_bounds__(256) weight_stats_kernel(const double* __restrict__ w, uint64_t n, double* out) {
@@ -432,6 +442,121 @@ __global__ void __launch_bounds__(256) seed_streams_kernel(const DevProblem P, c
                                                            uint64_t* __restrict__ state) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
     state[i] = pcg_advance(P.seed_state, P.stride * history_id[i], P.jump);
+}
+
+// ---- BasicExactMGCancelator (src/basic_exact_mg_cancelator.cpp) ---------------------------------------------------------------
+// The per-particle part, in parallel: the bin and the material a fission site falls in (add_particle :68-108, get_material
+// :178-196), its point density f(r | r_parent, Esmp) = exp(-Esmp d) / d^2 (get_f :198-224) and the smallest f over the eight
+// corners of its bin (get_min_f :226-262, the beta of mode `minimum`).  The bins themselves -- an unordered_map walked in
+// insertion-dependent order, sums taken particle by particle -- are replayed on the host from these columns (api.cu).
+__device__ __forceinline__ double exact_f(double x, double y, double z, double px, double py, double pz, double Esmp) {
+  const double d = sqrt((x - px) * (x - px) + (y - py) * (y - py) + (z - pz) * (z - pz));
+  return (1. / (d * d)) * det_exp(-Esmp * d);
+}
+__device__ __forceinline__ double min_ref(double a, double b) { return (b < a) ? b : a; }  // std::min
+__global__ void __launch_bounds__(128) exact_prepare_kernel(const DevProblem P, const DevMesh3 m, BankView b, const double* __restrict__ parent,
+                                                            uint64_t pcap, uint64_t n, int32_t* __restrict__ key, int32_t* __restrict__ mat,
+                                                            double* __restrict__ f, double* __restrict__ fmin) {
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
+    const double x = b.x[q], y = b.y[q], z = b.z[q];
+    const int i = (int)floor((x - m.lowx) / m.dx), j = (int)floor((y - m.lowy) / m.dy), k = (int)floor((z - m.lowz) / m.dz);
+    if (i < 0 || j < 0 || k < 0 || i >= m.Nx || j >= m.Ny || k >= m.Nz) {
+      key[q] = -1;
+      continue;
+    }
+    key[q] = k + m.Nz * (j + m.Ny * i);
+    Cursor c;
+    c.err = 0;
+    c.token = 0;
+    cursor_restart(P, c, V3{x, y, z}, V3{1., 0., 0.});
+    mat[q] = c.cell < 0 ? -1 : c.mat;
+    const double px = parent[q], py = parent[pcap + q], pz = parent[2 * pcap + q], Esmp = parent[3 * pcap + q];
+    f[q] = exact_f(x, y, z, px, py, pz, Esmp);
+    const double Xl = m.lowx + i * m.dx, Xh = Xl + m.dx, Yl = m.lowy + j * m.dy, Yh = Yl + m.dy, Zl = m.lowz + k * m.dz, Zh = Zl + m.dz;
+    const double f1 = exact_f(Xh, Yh, Zh, px, py, pz, Esmp), f2 = exact_f(Xh, Yh, Zl, px, py, pz, Esmp), f3 = exact_f(Xh, Yl, Zh, px, py, pz, Esmp),
+                 f4 = exact_f(Xh, Yl, Zl, px, py, pz, Esmp), f5 = exact_f(Xl, Yh, Zh, px, py, pz, Esmp), f6 = exact_f(Xl, Yh, Zl, px, py, pz, Esmp),
+                 f7 = exact_f(Xl, Yl, Zh, px, py, pz, Esmp), f8 = exact_f(Xl, Yl, Zl, px, py, pz, Esmp);
+    fmin[q] = min_ref(min_ref(min_ref(f1, f2), min_ref(f3, f4)), min_ref(min_ref(f5, f6), min_ref(f7, f8)));
+  }
+}
+
+// settings::rng on the device: pcg32 on stream 2 (increment 5; settings.cpp:116-119)
+struct GlobalStreamMath {
+  static __device__ __forceinline__ uint32_t next(uint64_t& state) {
+    const uint64_t old = state;
+    state = old * ABL_PCG_MULT + 5ULL;
+    const uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+    const uint32_t rot = (uint32_t)(old >> 59u);
+    return __funnelshift_r(xorshifted, xorshifted, rot);
+  }
+  static __device__ __forceinline__ double rand(uint64_t& s) {
+    const uint32_t lo = next(s);
+    const uint32_t hi = next(s);
+    double sum = (double)lo;
+    sum += (double)hi * 4294967296.0;
+    double ret = sum / 18446744073709551616.0;
+    if (ret >= 1.0) ret = 0.99999999999999988897769753748;
+    return ret;
+  }
+  static __device__ __forceinline__ double div(double a, double b) { return a / b; }
+  static __device__ __forceinline__ double sqrt_(double a) { return sqrt(a); }
+};
+
+// get_new_particles (:557-617): the uniform particles of every bin that gathered cancelled weight, drawn one after the other from
+// the global engine -- position by rejection on the bin's material (up to 100 tries), then MGNuclide::sample_fission(0, +z, group
+// 0, P_delayed 0).  One thread: every draw depends on how many the particle before it took.  list rows: key, material, N, w, w2.
+__global__ void exact_uniform_kernel(const DevProblem P, const DevMesh3 m, const double* __restrict__ list, uint64_t nlist, uint64_t* rng_state,
+                                     BankView b, uint64_t first, uint64_t capacity, double* parent, uint64_t pcap, unsigned long long* out2) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint64_t rng = *rng_state;
+  uint64_t row = first;
+  unsigned long long failed = 0;
+  for (uint64_t e = 0; e < nlist && !failed; e++) {
+    const int key = (int)list[5 * e], mat = (int)list[5 * e + 1];
+    const uint64_t N = (uint64_t)list[5 * e + 2];
+    const double w = list[5 * e + 3], w2 = list[5 * e + 4];
+    const int k = key % m.Nz, j = (key / m.Nz) % m.Ny, i = key / (m.Nz * m.Ny);
+    const double Xl = m.lowx + i * m.dx, Yl = m.lowy + j * m.dy, Zl = m.lowz + k * m.dz;
+    for (uint64_t q = 0; q < N; q++) {
+      V3 r{0., 0., 0.};
+      bool ok = false;
+      for (int t = 0; t < 100 && !ok; t++) {
+        const double x = Xl + GlobalStreamMath::rand(rng) * m.dx;
+        const double y = Yl + GlobalStreamMath::rand(rng) * m.dy;
+        const double z = Zl + GlobalStreamMath::rand(rng) * m.dz;
+        r = V3{x, y, z};
+        Cursor c;
+        c.err = 0;
+        c.token = 0;
+        cursor_restart(P, c, r, V3{1., 0., 0.});
+        ok = (c.cell < 0 ? -1 : c.mat) == mat;
+      }
+      if (!ok) {  // "Couldn't sample position for uniform particle."
+        failed = 1;
+        break;
+      }
+      const int mg = mat * P.G;
+      int ei = 0;
+      if (P.G >= 2) ei = rng_discrete<GlobalStreamMath>(rng, P.chi_cp + (size_t)mg * P.G, P.G);
+      const double mu = 2. * GlobalStreamMath::rand(rng) - 1.;
+      const double phi = 2. * ABL_PI * GlobalStreamMath::rand(rng);
+      const V3 dir = rotate_dir<GlobalStreamMath>(V3{0., 0., 1.}, mu, phi);
+      (void)GlobalStreamMath::rand(rng);  // the delayed-neutron draw against P_delayed = 0
+      if (row < capacity) {
+        b.x[row] = r.x; b.y[row] = r.y; b.z[row] = r.z;
+        b.ux[row] = dir.x; b.uy[row] = dir.y; b.uz[row] = dir.z;
+        b.E[row] = ldt(&P.gmid[ei]);
+        b.wgt[row] = w;
+        if (b.wgt2) b.wgt2[row] = w2;
+        b.id_a[row] = 0; b.id_b[row] = 0; b.id_c[row] = 0;
+        if (row < pcap) { parent[row] = 0.; parent[pcap + row] = 0.; parent[2 * pcap + row] = 0.; parent[3 * pcap + row] = 0.; }
+      }
+      row++;
+    }
+  }
+  *rng_state = rng;
+  out2[0] = row;
+  out2[1] = failed;
 }
 
 }  // namespace abl

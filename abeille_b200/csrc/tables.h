@@ -55,6 +55,7 @@ struct DevNoiseSrc {  // a noise source region (box) with the run's frequency al
 
 struct DevMesh3 {
   int32_t present, Nx, Ny, Nz, Ne;
+  int32_t kind, beta;  // cancelator only: ABL_CANCEL_*, ABL_BETA_*
   const double* eedges;  // Ne+1 or null
   double lowx, lowy, lowz, hix, hiy, hiz, dx, dy, dz;
 };
@@ -80,6 +81,7 @@ struct DevProblem {
   // (api.cu: boundary_planes): |p0 - r[axis]| of the nearest one is a lower bound of the distance to any boundary condition
   // in any direction, which lets the surface tracker skip the boundary-condition search of a flight that ends far inside
   // (geom.cuh: cursor_nearest_boundary_lazy).  n_bc_planes = 0: no such bound.
+  int32_t exact_cancel;  // the problem has an exact cancelator: the per-lane kernel records what it reads (transport.cuh Hist::rprev / esmp)
   int32_t branchless;  // ABL_BRANCHLESS_* bits (mode == ABL_MODE_BRANCHLESS)
   int32_t has_hex;  // the geometry holds a hexagonal lattice (the fixed-shape kernel builds leave those branches out)
   int32_t n_bc_planes;

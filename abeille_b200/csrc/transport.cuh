@@ -62,7 +62,9 @@ struct RunArgs {
   double* scores;                  // [6] k_col, k_abs, k_trk, k_tot, leak, mig
   unsigned long long* counters;    // [8]
   int* error;                      // [0] code (min = most severe first seen), [1..2] history id lo/hi
-  double* secondaries;             // [ABL_SEC_CAP][9][nthreads] or null
+  double* secondaries;             // [ABL_SEC_CAP][ABL_SEC_FIELDS][nthreads] or null
+  double* site_parent;             // [site_capacity][4] or null: the parent's previous position and sampling cross section of every
+                                   // scratch site (BankedParticle::parents_previous_position / Esmp_parent, for the exact cancelators)
   double k_col, keff;
   int converged;
   // rows of the bank that have arrived in HBM (host-buffer entry point: the copy overlaps the kernel), or null
@@ -96,6 +98,10 @@ struct Hist {
   int nsec;
   bool alive;
   bool emid;  // E is exactly the mid-point of group g (true after any scatter / for fission sites): tally bins by table
+  // Particle::previous_position / reflected / Esmp_ (particle.hpp:104-133,229-237), kept when the problem has an exact cancelator
+  bool refl;
+  V3 rprev;
+  double esmp;
 };
 
 struct Acc {  // per-thread accumulators, reduced once at kernel exit
@@ -184,7 +190,8 @@ struct FissionTables {
 template <class M>
 static __device__ __noinline__ void bank_fission_sites(const FissionTables T, Site* sites, unsigned long long* n_sites, uint64_t capacity,
                                                 uint64_t& rng, const V3 r, const V3 u, double w, uint32_t parent, uint32_t daughter0,
-                                                int n_new, int mat, int mg, double P_delayed) {
+                                                int n_new, int mat, int mg, double P_delayed, double* site_parent = nullptr,
+                                                const V3 rprev = V3{0., 0., 0.}, double esmp = 0.) {
   const int dg0 = ldt(&T.dg_off[mat]), ndg = ldt(&T.dg_off[mat + 1]) - dg0;
   for (int i = 0; i < n_new; i++) {
     int ei = 0;
@@ -214,6 +221,11 @@ static __device__ __noinline__ void bank_fission_sites(const FissionTables T, Si
       double2* dst = reinterpret_cast<double2*>(sites + slot);
 #pragma unroll
       for (int q = 0; q < 5; q++) dst[q] = src[q];
+      if (site_parent) {
+        double2* pp = reinterpret_cast<double2*>(site_parent + 4 * slot);
+        pp[0] = make_double2(rprev.x, rprev.y);
+        pp[1] = make_double2(rprev.z, esmp);
+      }
     }
   }
 }
@@ -342,6 +354,11 @@ static __device__ __noinline__ void branchless_collision(const DevProblem& P, co
       double2* dst = reinterpret_cast<double2*>(A.sites + slot);
 #pragma unroll
       for (int q = 0; q < 5; q++) dst[q] = src[q];
+      if (A.site_parent) {
+        double2* pp = reinterpret_cast<double2*>(A.site_parent + 4 * slot);
+        pp[0] = make_double2(h.rprev.x, h.rprev.y);
+        pp[1] = make_double2(h.rprev.z, h.esmp);
+      }
     }
     h.daughter += 1u;
     h.n_fis += 1u;
@@ -393,7 +410,7 @@ __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A,
       acc.sites += (uint32_t)n_new;
     } else {
       bank_fission_sites<M>(ft, A.sites, A.n_sites, A.site_capacity, h.rng, h.r, h.u, h.w, h.idx, h.daughter, n_new, h.mat, mg,
-                            ldt(&P.nud[mg]) / nu);
+                            ldt(&P.nud[mg]) / nu, A.site_parent, h.rprev, h.esmp);
       h.daughter += (uint32_t)n_new;
       h.n_fis += (uint32_t)n_new;
       acc.sites += (uint32_t)n_new;
@@ -642,6 +659,7 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
   } else {
     // DeltaTracker / CarterTracker loop body (delta_tracker.cpp:100-195, carter_tracker.cpp:120-230)
     const double Esample = MODE == 2 ? ldt(&P.smp[h.g]) + noise_xs<MODE>(P, h.mat, h.g) : ldt(&P.smp[h.g]);
+    h.esmp = Esample;  // "Sampling XS saved for cancellation" (delta_tracker.cpp:111, carter_tracker.cpp:130)
     const double d_coll = rng_exponential(h.rng, Esample);
     Boundary bound{ABL_INF, -1, ABL_BC_NORMAL, 0};
     bool crossed = false;
@@ -662,10 +680,19 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
         note(h, 0x3000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
         leak(h, acc, bound);
       } else if (bound.btype == ABL_BC_REFLECTIVE) {
+        // Tracker::do_reflection keeps the un-folded flight for the cancelators (tracker.hpp:330-352): the previous position
+        // becomes the mirror image, a distance (this leg + what was flown since the last collision) behind the surface
+        const V3 r_pre_refs = h.refl ? h.rprev : h.r;
+        const V3 back{h.r.x - r_pre_refs.x, h.r.y - r_pre_refs.y, h.r.z - r_pre_refs.z};
         if (!do_reflection(P, c, h, bound) || c.cell < 0) {
           raise_error(A, ABL_ERR_LOST, hid);
           h.alive = false;
           return;
+        }
+        if (P.exact_cancel) {
+          const double d = bound.distance + norm3<InlineMath>(back);
+          h.rprev = V3{h.r.x - d * h.u.x, h.r.y - d * h.u.y, h.r.z - d * h.u.z};
+          h.refl = true;
         }
         note(h, 0x4000000000000000ULL | (uint64_t)(uint32_t)(c.cell + 1));
       } else {
@@ -674,6 +701,8 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
         return;
       }
     } else {
+      if (!h.refl) h.rprev = h.r;  // Particle::move (particle.hpp:125-133)
+      h.refl = false;
       h.r.x = h.r.x + d_coll * h.u.x;
       h.r.y = h.r.y + d_coll * h.u.y;
       h.r.z = h.r.z + d_coll * h.u.z;
@@ -777,6 +806,9 @@ __global__ void __launch_bounds__(TK_THREADS, 1) transport_kernel(const DevProbl
       h.n_flights = h.n_real = h.n_virtual = h.n_fis = h.n_noise = 0;
       h.nsec = 0;
       h.alive = true;
+      h.refl = false;
+      h.rprev = V3{0., 0., 0.};
+      h.esmp = 0.;
       c.token = 0;
       cursor_restart_nl(geo_tables(P), c, h.r, h.u);
       h.mat = c.mat;

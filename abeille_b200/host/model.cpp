@@ -672,11 +672,29 @@ Problem Problem::from_yaml(const Node& input) {
     const Node& c = input["cancelator"];
     if (!c || !c.IsMap()) fatal_error("Regional cancelation is activated, but no cancelator entry is provided.");
     const std::string type = c["type"] ? c["type"].as_string() : std::string("");
-    if (type != "approximate") fatal_error("Cancelator type \"" + type + "\" is not provided by the B200 backend (approximate only).");
+    if (type == "basic-exact") {  // src/cancelator.cpp:42-57, src/basic_exact_mg_cancelator.cpp:610-705
+      if (P.settings.tracking == ABL_TRACK_SURFACE) fatal_error("basic-exect cancelators may not be used with surface-tracking.");
+      if (P.settings.tracking == ABL_TRACK_IMPLICIT_LEAKAGE)
+        fatal_error("basic-exact cancelators need the sampling cross section of a flight: delta-tracking or carter-tracking.");
+      P.cancelator = make_mesh_spec(c, "basic exact MG cancelator");
+      P.cancelator.kind = ABL_CANCEL_BASIC_EXACT;
+      if (!c["beta"] || !c["beta"].IsScalar()) fatal_error("No valid beta entry for basic exact MG cancelator.");
+      const std::string beta = c["beta"].as_string();
+      if (beta == "zero") P.cancelator.beta = ABL_BETA_ZERO;
+      else if (beta == "minimum") P.cancelator.beta = ABL_BETA_MINIMUM;
+      // (average-f / average-g: the kernels record what the cancelator reads, so the reference's own cancelator runs over the
+      // GPU transporter; abl_cancel_exact_device itself provides zero and minimum and says so)
+      else if (beta == "average-f") P.cancelator.beta = ABL_BETA_AVERAGE_F;
+      else if (beta == "average-g") P.cancelator.beta = ABL_BETA_AVERAGE_G;
+      else fatal_error("Unkown beta entry \"" + beta + "\" for basic exact MG cancelator.");
+    } else {
+    if (type != "approximate") fatal_error("Cancelator type \"" + type + "\" is not provided by the B200 backend (approximate, basic-exact).");
     P.cancelator = make_mesh_spec(c, "approximate mesh cancelator");
+    P.cancelator.kind = ABL_CANCEL_APPROXIMATE;
     if (c["energy-bounds"]) {
       if (!c["energy-bounds"].IsSequence()) fatal_error("No valid energy-bounds entry for approximate mesh cancelator.");
       P.cancelator.energy_edges = c["energy-bounds"].as_doubles();
+    }
     }
   }
   // sources
@@ -967,6 +985,8 @@ void Problem::flatten(FlatProblem& F) const {
   };
   p.entropy = mesh3(entropy);
   p.cancelator = mesh3(cancelator);
+  p.cancelator.kind = cancelator.kind;
+  p.cancelator.beta = cancelator.beta;
   if (F.tally_eb.empty()) F.tally_eb.push_back(0.);
   p.ntallies = static_cast<int32_t>(F.tallies.size());
   p.n_tally_energy_bounds = static_cast<int32_t>(F.tally_eb.size());

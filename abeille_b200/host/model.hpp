@@ -97,6 +97,7 @@ struct MeshSpec {
   std::array<int, 3> N{1, 1, 1};
   std::array<double, 3> low{0, 0, 0}, hi{0, 0, 0};
   std::vector<double> energy_edges;
+  int kind = 0, beta = 0;  // cancelator: ABL_CANCEL_*, ABL_BETA_* (src/cancelator.cpp:40-57, basic_exact_mg_cancelator.cpp:650-668)
 };
 
 // Owns the vectors an abl_problem points into

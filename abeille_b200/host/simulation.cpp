@@ -367,6 +367,7 @@ void PowerIterator::run_host(int ngenerations, int nignored) {
   for (const auto& t : problem.tallies)
     if (t.flat.estimator == ABL_EST_SOURCE && !t.flat.noise_source) have_source_tally = true;
   const bool cancel = st.regional_cancellation && problem.cancelator.present;
+  const bool exact = cancel && problem.cancelator.kind == ABL_CANCEL_BASIC_EXACT;
   // branchless-k-eigenvalue: the normalised bank is combed before the source tally sees it (branchless_power_iterator.cpp:358-384)
   const bool comb = st.mode == ABL_MODE_BRANCHLESS && st.branchless_combing;
   const auto t0 = std::chrono::steady_clock::now();
@@ -394,7 +395,7 @@ void PowerIterator::run_host(int ngenerations, int nignored) {
     const bool device_block = cancel || (have_source_tally && transporter->converged && !comb);
     if (device_block) {
       // cancellation and the source mesh tally run on the device (bank_ops.cuh) on an uploaded copy
-      const uint64_t M = next_gen.size();
+      uint64_t M = next_gen.size();
       std::vector<double> f[9];
       std::vector<uint64_t> ia(M), ib(M), ic(M);
       for (auto& v : f) v.resize(M);
@@ -410,9 +411,28 @@ void PowerIterator::run_host(int ngenerations, int nignored) {
       host.uz = f[5].data(); host.E = f[6].data(); host.wgt = f[7].data(); host.wgt2 = f[8].data();
       host.id_a = ia.data(); host.id_b = ib.data(); host.id_c = ic.data();
       DeviceBank d;
-      alloc_device_bank(d, M);
+      alloc_device_bank(d, exact ? 2 * M + 4096 : M);
       check(h, abl_bank_upload(h, &host, &d.b), "abl_bank_upload");
-      if (cancel) check(h, abl_cancel_device(h, &d.b, nullptr), "abl_cancel_device");
+      if (cancel && exact) {
+        // BasicExactMGCancelator on the device copy (its rows are the rows of the transport call's bank, whose parents' data the
+        // handle holds); the uniform particles it appends come back with the weights
+        uint64_t rng2[2] = {global_rng_.state, global_rng_.inc};
+        check(h, abl_cancel_exact_device(h, &d.b, d.cap, rng2, nullptr), "abl_cancel_exact_device");
+        global_rng_.state = rng2[0];
+        if (d.b.n > M) {
+          HostColumns cols;
+          cols.resize(d.b.n);
+          abl_bank all = cols.view();
+          check(h, abl_bank_download(h, &d.b, d.b.n, &all), "abl_bank_download");
+          std::vector<BankedParticle> grown;
+          cols.to(grown);
+          for (uint64_t i = M; i < d.b.n; i++) next_gen.push_back(grown[i]);
+          M = d.b.n;
+          for (auto& v : f) v.resize(M);
+        }
+      } else if (cancel) {
+        check(h, abl_cancel_device(h, &d.b, nullptr), "abl_cancel_device");
+      }
       if (!comb) {
         double ws[4];
         check(h, abl_bank_weight_stats_device(h, &d.b, ws, nullptr), "abl_bank_weight_stats_device");
@@ -476,6 +496,8 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
   const uint64_t N0 = bank_.size();
   // (the first generation runs with k_col = 1, so it banks about k_inf sites per particle: tallies.cpp:48)
   uint64_t cap = abl_fission_capacity_hint(h, std::max<uint64_t>(N0, static_cast<uint64_t>(st.nparticles)), 0., std::min(1., tallies->kcol()));
+  const bool exact_cancel = st.regional_cancellation && problem.cancelator.present && problem.cancelator.kind == ABL_CANCEL_BASIC_EXACT;
+  if (exact_cancel) cap = 2 * cap + 4096;  // room for the uniform particles the cancelator appends
   // cur / nxt are views (n and id_c change per generation); *_alloc keep the full allocations
   DeviceBank cur, nxt;
   alloc_device_bank(cur, cap);
@@ -509,6 +531,7 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
   std::vector<double> ebins(nebins + 1, 0.);
   if (have_entropy) check(h, abl_device_alloc(h, (nebins + 1) * sizeof(double), reinterpret_cast<void**>(&ebins_dev)), "abl_device_alloc");
   const bool cancel = st.regional_cancellation && problem.cancelator.present;
+  const bool exact = cancel && problem.cancelator.kind == ABL_CANCEL_BASIC_EXACT;
   const bool comb = st.mode == ABL_MODE_BRANCHLESS && st.branchless_combing;
   const auto t0 = std::chrono::steady_clock::now();
   for (int g = 1; g <= ngenerations; g++) {
@@ -556,7 +579,15 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
       entropy = entropy_from_bins(std::vector<double>(ebins.begin(), ebins.begin() + static_cast<long>(nebins)), total);
     }
     tallies->calc_gen_values();
-    if (cancel) check(h, abl_cancel_device(h, &out, nullptr), "abl_cancel_device");
+    if (cancel && exact) {
+      // (the uniform particles are appended to the bank: the banks of such a problem are allocated with room for as many again)
+      uint64_t rng2[2] = {global_rng_.state, global_rng_.inc};
+      check(h, abl_cancel_exact_device(h, &out, nxt.cap, rng2, nullptr), "abl_cancel_exact_device");
+      global_rng_.state = rng2[0];
+      n_fis = out.n;
+    } else if (cancel) {
+      check(h, abl_cancel_device(h, &out, nullptr), "abl_cancel_device");
+    }
     if (!comb) {
       double ws[4];
       check(h, abl_bank_weight_stats_device(h, &out, ws, nullptr), "abl_bank_weight_stats_device");
@@ -610,7 +641,7 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
     cur.b.id_c = nullptr;
     nxt.b = nxt_alloc.b;
     nxt.cap = nxt_alloc.cap;
-    const uint64_t want = abl_fission_capacity_hint(h, n_fis, static_cast<double>(st.nparticles), tallies->kcol());
+    const uint64_t want = (exact_cancel ? 2 : 1) * abl_fission_capacity_hint(h, n_fis, static_cast<double>(st.nparticles), tallies->kcol());
     if (want > nxt.cap) {  // the population drifted upwards: regrow the output bank
       free_device_bank(nxt_alloc);
       alloc_device_bank(nxt_alloc, want + want / 8);

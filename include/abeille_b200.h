@@ -131,7 +131,11 @@ typedef struct abl_mesh3 {       /* entropy mesh (entropy.cpp) / approximate can
   double low[3], hi[3];
   int32_t n_energy_edges;        /* cancelator only; 0 = no energy binning                             */
   int32_t eedges_offset;         /* slice of abl_problem.tally_energy_bounds                           */
+  int32_t kind;                  /* cancelator only: ABL_CANCEL_* (0 reads as approximate)             */
+  int32_t beta;                  /* basic-exact cancelator: ABL_BETA_*                                 */
 } abl_mesh3;
+enum { ABL_CANCEL_APPROXIMATE = 1, ABL_CANCEL_BASIC_EXACT = 2 };  /* src/cancelator.cpp:40-57 */
+enum { ABL_BETA_ZERO = 0, ABL_BETA_MINIMUM = 1, ABL_BETA_AVERAGE_F = 2, ABL_BETA_AVERAGE_G = 3 };  /* BasicExactMGCancelator::BetaMode */
 
 enum { ABL_NOISE_SQUARE_OSCILLATION = 0, ABL_NOISE_FLAT_VIBRATION = 1 };
 typedef struct abl_noise_source { /* square_oscillation_noise_source.cpp:38-83, flat_vibration_noise_source.cpp:34-118 */
@@ -286,6 +290,16 @@ int abl_cancel_device(abl_handle h, abl_bank* bank_dev, void* stream);
 int abl_cancel_accumulate_device(abl_handle h, const abl_bank* bank_dev, void* stream);
 int abl_cancel_apply_device(abl_handle h, abl_bank* bank_dev, void* stream);
 int abl_cancel_bins_device(abl_handle h, double* sums_dev[4], uint32_t** count_dev, uint64_t* nbins);
+
+/* BasicExactMGCancelator (src/basic_exact_mg_cancelator.cpp; PowerIterator::perform_regional_cancellation, src/power_iterator.cpp:
+ * 751-777) on the fission bank the LAST transport call of this handle produced: with an exact cancelator in the problem the
+ * transport kernels keep, per fission site, the parent's previous position and the sampling cross section of its flight
+ * (BankedParticle::parents_previous_position / Esmp_parent, particle.hpp:52-57) in a side table of the handle, in bank order.
+ * Weights are reduced in place, the uniform particles the cancelled weight turns into are appended (bank_dev->n grows, at most
+ * `capacity` rows), rng2 = {state, increment} of settings::rng is advanced by what they drew.  beta: minimum and zero.
+ * abl_parent_info_download hands the side table to a caller that runs the reference's own cancelator on the host.           */
+int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity, uint64_t rng2[2], void* stream);
+int abl_parent_info_download(abl_handle h, uint64_t n, double* x, double* y, double* z, double* esmp);
 
 /* ---- device memory helpers for callers that do not link a CUDA runtime themselves ------------------------ */
 int abl_bank_alloc_device(abl_handle h, uint64_t capacity, abl_bank* out_dev); /* all 12 arrays, out_dev->n = capacity */

@@ -44,6 +44,7 @@ class GPUTransporter : public Transporter {
     fetch_ = reinterpret_cast<fetch_fn>(dlsym(lib_, "abl_tally_fetch"));
     shape_ = reinterpret_cast<shape_fn>(dlsym(lib_, "abl_tally_shape"));
     count_ = reinterpret_cast<count_fn>(dlsym(lib_, "abl_tally_count"));
+    parent_ = reinterpret_cast<parent_fn>(dlsym(lib_, "abl_parent_info_download"));
     if (!open_ || !close_ || !backend_ || !transport_ || !last_error_ || !record_ || !clear_ || !fetch_ || !shape_ || !count_)
       fatal_error("GPUTransporter: C ABI symbols missing");
     char err[512] = {0};
@@ -115,6 +116,16 @@ class GPUTransporter : public Transporter {
       f.E = oE_[i]; f.wgt = ow_[i]; f.wgt2 = 0.;
       f.parent_history_id = oa_[i]; f.parent_daughter_id = ob_[i]; f.family_id = oc_[i];
     }
+    // what the reference's exact cancelators read from the bank (particle.hpp:52-57): kept by the kernels when the deck has one
+    if (settings::regional_cancellation && parent_ && m > 0) {
+      for (auto* v : {&px_, &py_, &pz_, &pe_}) v->resize(m);
+      if (parent_(h_, m, px_.data(), py_.data(), pz_.data(), pe_.data()) == 0) {
+        for (std::size_t i = 0; i < m; i++) {
+          fis[i].parents_previous_position = Position(px_[i], py_[i], pz_[i]);
+          fis[i].Esmp_parent = pe_[i];
+        }
+      }
+    }
     return fis;
   }
 
@@ -129,6 +140,9 @@ class GPUTransporter : public Transporter {
   using fetch_fn = int (*)(abl_handle, int, int, double*);
   using shape_fn = int (*)(abl_handle, int, uint64_t*);
   using count_fn = int (*)(abl_handle);
+  using parent_fn = int (*)(abl_handle, uint64_t, double*, double*, double*, double*);
+  parent_fn parent_ = nullptr;
+  std::vector<double> px_, py_, pz_, pe_;
   record_fn record_ = nullptr; clear_fn clear_ = nullptr; fetch_fn fetch_ = nullptr; shape_fn shape_ = nullptr; count_fn count_ = nullptr;
   bool scored_ = false;
   void* lib_ = nullptr;

@@ -264,6 +264,28 @@ class Oracle:
         s = _as_struct(bank)
         lib().orc_cancel(self.h, C.byref(s))
 
+    def last_parent_info(self, n: int) -> np.ndarray:
+        """[n, 4]: BankedParticle::parents_previous_position and Esmp_parent of the fission bank the last transport() returned."""
+        out = np.zeros((n, 4))
+        lib().orc_last_parent_info.restype = C.c_uint64
+        m = lib().orc_last_parent_info(self.h, out.ctypes.data_as(_PD), C.c_uint64(n))
+        assert m == n, (m, n)
+        return out
+
+    def cancel_exact(self, bank: dict, parent_info: np.ndarray, rng2):
+        """PowerIterator::perform_regional_cancellation with the deck's BasicExactMGCancelator: weights reduced in place, uniform
+        particles appended.  Returns (bank, (state, increment) of the global engine afterwards)."""
+        n = len(bank["x"])
+        out = new_bank(3 * n + 4096)
+        r = np.array(rng2, dtype=np.uint64)
+        nout = C.c_uint64(0)
+        pi = np.ascontiguousarray(parent_info, dtype=np.float64)
+        if lib().orc_cancel_exact(self.h, C.byref(_as_struct(bank)), pi.ctypes.data_as(_PD), C.byref(_as_struct(out)), C.byref(nout),
+                                  r.ctypes.data_as(_PU64)) != 0:
+            raise RuntimeError("oracle: " + self._err())
+        m = int(nout.value)
+        return {k: v[:m].copy() for k, v in out.items()}, (int(r[0]), int(r[1]))
+
     def comb(self, bank: dict, rng2):
         """BranchlessPowerIterator::comb_particles on a (normalised) fission bank; rng2 = (state, increment) of the global
         engine.  Returns (combed bank, (state, increment) afterwards)."""

@@ -148,6 +148,7 @@ struct Problem {
   bool converged = false;
   uint64_t histories_counter = 0, global_histories_counter = 0;
   Pcg32Stream global_rng;  // settings::rng
+  std::vector<double> last_parent_info;  // x, y, z, Esmp per row of the fission bank of the last orc_transport call
   ExactBins exact_bins;    // BasicExactMGCancelator::bins (kept across generations: clear() keeps the bucket array)
   Counters counters;
   std::string error;
@@ -2072,6 +2073,41 @@ int orc_transport(void* h, const orc_bank* in, int noise, orc_bank* out, uint64_
     scores6[3] = T.k_tot_score - b[3]; scores6[4] = T.leak_score - b[4]; scores6[5] = T.mig_area_score - b[5];
     *n_out = fis.size();
     bank_to(fis, out);
+    P.last_parent_info.resize(4 * fis.size());
+    for (size_t i = 0; i < fis.size(); i++) {
+      P.last_parent_info[4 * i] = fis[i].parents_previous_position.x; P.last_parent_info[4 * i + 1] = fis[i].parents_previous_position.y;
+      P.last_parent_info[4 * i + 2] = fis[i].parents_previous_position.z; P.last_parent_info[4 * i + 3] = fis[i].Esmp_parent;
+    }
+    return 0;
+  } catch (const std::exception& e) { P.error = e.what(); return 1; }
+}
+
+// BankedParticle::parents_previous_position / Esmp_parent of the fission bank the last orc_transport returned ([n][4])
+uint64_t orc_last_parent_info(void* h, double* out4n, uint64_t n) {
+  Problem& P = *static_cast<Problem*>(h);
+  const uint64_t m = std::min<uint64_t>(n, P.last_parent_info.size() / 4);
+  for (uint64_t i = 0; i < 4 * m; i++) out4n[i] = P.last_parent_info[i];
+  return m;
+}
+
+// PowerIterator::perform_regional_cancellation with the exact cancelator on a bank + its parent info ([n][4]); rng2 = {state,
+// increment} of settings::rng.  out->n = capacity on entry; the uniform particles follow the n input rows.
+int orc_cancel_exact(void* h, const orc_bank* in, const double* parent4n, orc_bank* out, uint64_t* n_out, uint64_t* rng2) {
+  Problem& P = *static_cast<Problem*>(h);
+  try {
+    std::vector<BankedParticle> v(in->n);
+    for (size_t i = 0; i < v.size(); i++) {
+      v[i].r = {in->x[i], in->y[i], in->z[i]}; v[i].u = {in->ux[i], in->uy[i], in->uz[i]};
+      v[i].E = in->E[i]; v[i].wgt = in->wgt[i]; v[i].wgt2 = in->wgt2[i];
+      v[i].parent_history_id = in->id_a[i]; v[i].parent_daughter_id = in->id_b[i]; v[i].family_id = in->id_c[i];
+      v[i].parents_previous_position = {parent4n[4 * i], parent4n[4 * i + 1], parent4n[4 * i + 2]};
+      v[i].Esmp_parent = parent4n[4 * i + 3];
+    }
+    P.global_rng.state = rng2[0]; P.global_rng.inc = rng2[1];
+    perform_exact_cancellation(P, v);
+    rng2[0] = P.global_rng.state; rng2[1] = P.global_rng.inc;
+    *n_out = v.size();
+    bank_to(v, out);
     return 0;
   } catch (const std::exception& e) { P.error = e.what(); return 1; }
 }

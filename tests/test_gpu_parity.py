@@ -785,3 +785,46 @@ def test_branchless_power_iteration_matches_oracle(ab, oracle_api, tmp_path, dec
             assert np.allclose(gpu.tally(t, "avg"), orc.tally(t, "avg"), rtol=1e-9, atol=1e-300)
         if "comb" in deck or deck.startswith("c5g7"):  # a combed bank holds nparticles (or one more) particles of equal weight
             assert all(abs(int(v) - n) <= 1 for v in g["nbank"][1:])
+
+
+def test_exact_cancellation_matches_oracle(ab, oracle_api, tmp_path):
+    """cancelator: {type: basic-exact, beta: minimum} (src/basic_exact_mg_cancelator.cpp) under carter tracking with negative
+    weights: the per-site parent data the kernels keep for it (BankedParticle::parents_previous_position through reflections,
+    Esmp_parent), the cancelled weights and the appended uniform particles, all bit for bit against the oracle (whose driver is
+    pinned on the reference's, tests/test_reference_pins.py); then whole simulations on both host paths."""
+    import torch
+    n = 6000
+    orc, gpu = _pair(ab, oracle_api, tmp_path, "PUa-cube_carter_exact_min.yaml", {"settings": {"nparticles": n}})
+    bank = orc.sample_source(n)
+    fis, _, _ = orc.transport({k: v.copy() for k, v in bank.items()})
+    nxt = _next_bank(fis, n)                     # a second generation: both signs, reflections behind the parents
+    m_in = len(nxt["x"])
+    ofis, _, om = orc.transport({k: (v.copy() if v is not None else None) for k, v in nxt.items()})
+    opar = orc.last_parent_info(om)
+    assert (ofis["wgt"] < 0).any() and (ofis["wgt"] > 0).any()
+    dev_in, dev_out = gpu.new_device_bank(m_in), gpu.new_device_bank(3 * om + 4096)
+    for k, v in nxt.items():
+        if v is not None:
+            dev_in[k].copy_(torch.from_numpy(v.view(np.int64) if v.dtype == np.uint64 else v))
+    gm, _, _ = gpu.transport_device(dev_in, m_in, dev_out)
+    assert gm == om
+    gpar = gpu.parent_info(gm)
+    assert np.array_equal(gpar, opar)
+    assert np.abs(opar[:, :3]).max() > 5.0       # mirror images behind the reflective faces of the +-5 cm cube
+    state = ab.global_rng_state()
+    ocb, ostate = orc.cancel_exact({k: v.copy() for k, v in ofis.items()}, opar, state)
+    gn, gstate = gpu.cancel_exact_device(dev_out, gm, state)
+    assert gn == len(ocb["x"]) and gn > om and gstate == ostate
+    for k in ("x", "y", "z", "ux", "uy", "uz", "E", "wgt"):
+        assert np.array_equal(dev_out[k][:gn].cpu().numpy(), ocb[k]), k
+    assert np.abs(ocb["wgt"][:om]).sum() < np.abs(ofis["wgt"]).sum()   # weight was cancelled
+    n, ngen, nign = 4000, 7, 2
+    ov = {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}}
+    for resident in (False, True):
+        orc, gpu = _pair(ab, oracle_api, tmp_path, "PUa-cube_carter_exact_min.yaml", ov, name=f"ex{int(resident)}.yaml")
+        o = orc.run_power_iteration(ngen, nign)
+        g = gpu.run_power_iteration(ngen, nign, resident=resident)
+        assert np.array_equal(g["nbank"], o["nbank"]), (resident, g["nbank"], o["nbank"])
+        assert np.allclose(g["kcol"], o["kcol"], rtol=1e-10)
+        assert np.allclose(g["mig"], o["mig"], rtol=1e-10)
+        assert np.allclose(g["entropy"], o["entropy"], rtol=1e-10)
