@@ -195,6 +195,8 @@ int validate(abl_handle h, const abl_problem* p) {
     if (p->tracking != ABL_TRACK_DELTA && p->tracking != ABL_TRACK_CARTER)
       return fail(h, ABL_ERR_UNSUPPORTED, "basic-exact cancelators need delta or carter tracking (src/cancelator.cpp:43-47)");
     if (p->cancelator.beta < ABL_BETA_ZERO || p->cancelator.beta > ABL_BETA_AVERAGE_G) return fail(h, ABL_ERR_INVALID, "cancelator beta");
+    if (p->cancelator.beta >= ABL_BETA_AVERAGE_F && (p->cancelator.n_samples < 1 || p->cancelator.n_samples > ABL_EXACT_MAX_SAMPLES))
+      return fail(h, ABL_ERR_UNSUPPORTED, "basic-exact cancelator: n-samples between 1 and 64");
   }
   if (p->ntallies > ABL_MAX_TALLIES) return fail(h, ABL_ERR_UNSUPPORTED, "more than ABL_MAX_TALLIES mesh tallies");
   if (p->root_universe < 0 || p->root_universe >= p->nuniverses) return fail(h, ABL_ERR_INVALID, "root universe");
@@ -1163,6 +1165,8 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
   P.cancel = make_mesh3(p->cancelator, teb);
   P.cancel.kind = p->cancelator.present ? (p->cancelator.kind == ABL_CANCEL_BASIC_EXACT ? ABL_CANCEL_BASIC_EXACT : ABL_CANCEL_APPROXIMATE) : 0;
   P.cancel.beta = p->cancelator.beta;
+  P.cancel.sobol = p->cancelator.sobol;
+  P.cancel.nsamples = p->cancelator.n_samples;
   P.exact_cancel = P.cancel.kind == ABL_CANCEL_BASIC_EXACT ? 1 : 0;
 #undef UP
   if (CU(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return bail(ABL_ERR_CUDA);
@@ -1666,9 +1670,6 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
   if (n != h->parent_n) return fail(h, ABL_ERR_INVALID, "abl_cancel_exact_device takes the fission bank of the last transport call");
   if (rng2[1] != 5ULL) return fail(h, ABL_ERR_UNSUPPORTED, "the global engine must be on stream 2 (settings::initialize_global_rng)");
   if (m.beta == ABL_BETA_ZERO || n == 0) return ABL_OK;  // perform_cancellation / get_new_particles return at once (:458, :559)
-  if (m.beta != ABL_BETA_MINIMUM)
-    return fail(h, ABL_ERR_UNSUPPORTED, "basic-exact cancelator on the device: beta zero and minimum (average-f / average-g sample points in "
-                                        "every bin; the reference's own cancelator runs them over abl_parent_info_download)");
   ABL_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = use_stream(h, (cudaStream_t)stream);
   const BankView b = view_of(bank_dev);
@@ -1713,23 +1714,18 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
     bin.W += w[i];
     bin.W2 += w2[i];
   }
-  bool touched = false, touched2 = false;
-  auto cancel_bin = [&](abl_context::ExactBin& bin, bool first) {
-    std::vector<double>& wv = first ? w : w2;
-    for (uint64_t i : bin.particles) {
-      const double wgt = wv[i];
-      if (wgt == 0.) return;
-      const double B = fmin[i], fi = f[i];
-      const double P_p = (fi - B) / fi, P_u = B / fi;
-      if (std::isinf(P_u) || std::isinf(P_p) || std::isnan(P_u) || std::isnan(P_p)) return;
-      (first ? bin.uniform_wgt : bin.uniform_wgt2) += wv[i] * P_u;
-      wv[i] *= P_p;
-      (first ? touched : touched2) = true;
-    }
-  };
+  // bins with two or more particles of both signs are the ones cancel_bin works on
+  struct Work { abl_context::ExactBin* bin; int key, mat; bool w1, w2; uint64_t first, advance; int can_cancel; };
+  std::vector<Work> work;
+  const bool averages = m.beta == ABL_BETA_AVERAGE_F || m.beta == ABL_BETA_AVERAGE_G;
+  uint64_t seed_advance = 0;  // per-bin offsets into the global engine's sequence (:476-490)
+  const uint64_t max_rn_per_part = (uint64_t)m.nsamples * 100ULL * (m.beta == ABL_BETA_AVERAGE_G ? 2 : 1);
+  std::vector<unsigned long long> rows;
   for (auto& kb : bins)
     for (auto& mb : kb.second) {
       abl_context::ExactBin& bin = mb.second;
+      const uint64_t my_advance = seed_advance;
+      seed_advance += bin.particles.size() * max_rn_per_part;
       if (bin.particles.size() > 1) {
         bool p1 = false, n1 = false, p2 = false, n2 = false;
         for (uint64_t i : bin.particles) {
@@ -1737,11 +1733,122 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
           if (w2[i] > 0.) p2 = true; else if (w2[i] < 0.) n2 = true;
           if (p1 && n1 && p2 && n2) break;
         }
-        if (p1 && n1) cancel_bin(bin, true);
-        if (p2 && n2) cancel_bin(bin, false);
-        bin.particles.clear();
+        if ((p1 && n1) || (p2 && n2)) {
+          work.push_back({&bin, kb.first, mb.first, p1 && n1, p2 && n2, rows.size(), my_advance, 1});
+          rows.insert(rows.end(), bin.particles.begin(), bin.particles.end());
+        }
       }
     }
+  // get_averages / get_averages_sobol (:264-364) of those bins on the device
+  std::vector<double> avg_f, avg_finv;
+  if (averages && !work.empty()) {
+    std::vector<unsigned long long> desc(5 * work.size());
+    for (size_t q = 0; q < work.size(); q++) {
+      desc[5 * q] = (unsigned long long)work[q].key; desc[5 * q + 1] = (unsigned long long)(long long)work[q].mat;
+      desc[5 * q + 2] = work[q].first; desc[5 * q + 3] = work[q].bin->particles.size(); desc[5 * q + 4] = work[q].advance;
+    }
+    SobolMatrices3 SM;  // the first three dimensions of the Joe-Kuo sequence (vendor/sobol), from the recurrence (oracle/orc_main.cpp)
+    {
+      unsigned long long d1[53], d2[53];
+      d1[1] = 1;
+      for (int i = 2; i <= 52; i++) d1[i] = (2 * d1[i - 1]) ^ d1[i - 1];
+      d2[1] = 1; d2[2] = 3;
+      for (int i = 3; i <= 52; i++) d2[i] = (2 * d2[i - 1]) ^ (4 * d2[i - 2]) ^ d2[i - 2];
+      for (int i = 1; i <= 52; i++) {
+        SM.m[0][i - 1] = 1ULL << (52 - i);
+        SM.m[1][i - 1] = d1[i] << (52 - i);
+        SM.m[2][i - 1] = d2[i] << (52 - i);
+      }
+    }
+    unsigned long long *desc_d = nullptr, *rows_d = nullptr;
+    double *af_d = nullptr, *afi_d = nullptr;
+    int32_t* cc_d = nullptr;
+    auto release2 = [&]() {
+      for (void* p : {(void*)desc_d, (void*)rows_d, (void*)af_d, (void*)afi_d, (void*)cc_d})
+        if (p) cudaFree(p);
+    };
+    avg_f.resize(rows.size());
+    avg_finv.resize(rows.size());
+    std::vector<int32_t> cc(work.size());
+    bool bad2 = CU(cudaMalloc(&desc_d, desc.size() * 8), "cudaMalloc") || CU(cudaMalloc(&rows_d, rows.size() * 8), "cudaMalloc") ||
+                CU(cudaMalloc(&af_d, rows.size() * 8), "cudaMalloc") || CU(cudaMalloc(&afi_d, rows.size() * 8), "cudaMalloc") ||
+                CU(cudaMalloc(&cc_d, work.size() * 4), "cudaMalloc") ||
+                CU(cudaMemcpyAsync(desc_d, desc.data(), desc.size() * 8, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync") ||
+                CU(cudaMemcpyAsync(rows_d, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync") ||
+                CU(cudaMemsetAsync(af_d, 0, rows.size() * 8, s), "cudaMemsetAsync") || CU(cudaMemsetAsync(afi_d, 0, rows.size() * 8, s), "cudaMemsetAsync");
+    if (!bad2) {
+      exact_average_kernel<<<grid_for(h, work.size(), 64), 64, 0, s>>>(h->P, m, SM, work.size(), desc_d, rows_d, b, h->parent_info, h->parent_cap,
+                                                                       m.nsamples, m.sobol, rng2[0], af_d, afi_d, cc_d);
+      h->launches++;
+      bad2 = CU(cudaMemcpyAsync(avg_f.data(), af_d, rows.size() * 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
+             CU(cudaMemcpyAsync(avg_finv.data(), afi_d, rows.size() * 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
+             CU(cudaMemcpyAsync(cc.data(), cc_d, work.size() * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
+             CU(cudaStreamSynchronize(s), "exact_average_kernel");
+    }
+    release2();
+    if (bad2) return ABL_ERR_CUDA;
+    for (size_t q = 0; q < work.size(); q++) work[q].can_cancel = cc[q];
+  }
+  // cancel_bin (:408-455) with get_beta (:366-406), particle by particle in bank order
+  bool touched = false, touched2 = false;
+  for (Work& wk : work) {
+    abl_context::ExactBin& bin = *wk.bin;
+    const size_t np = bin.particles.size();
+    double sum_c = 0., sum_c_wgt = 0., sum_c_wgt2 = 0.;
+    if (m.beta == ABL_BETA_AVERAGE_G && wk.can_cancel) {
+      auto C = [](double fa, double fi) { return 1. / (2. * fa * fi - 1.); };
+      for (size_t e = 0; e < np; e++) sum_c += C(avg_f[wk.first + e], avg_finv[wk.first + e]);
+      for (size_t e = 0; e < np; e++) {
+        sum_c_wgt += C(avg_f[wk.first + e], avg_finv[wk.first + e]) * w[bin.particles[e]];
+        sum_c_wgt2 += C(avg_f[wk.first + e], avg_finv[wk.first + e]) * w2[bin.particles[e]];
+      }
+    }
+    for (int pass = 0; pass < 2; pass++) {
+      const bool first = pass == 0;
+      if (!(first ? wk.w1 : wk.w2)) continue;
+      std::vector<double>& wv = first ? w : w2;
+      for (size_t e = 0; e < np; e++) {
+        const uint64_t i = bin.particles[e];
+        const double wgt = wv[i];
+        if (wgt == 0.) break;
+        double B = 0.;
+        if (wk.can_cancel) {
+          if (m.beta == ABL_BETA_MINIMUM) {
+            B = fmin[i];
+          } else if (m.beta == ABL_BETA_AVERAGE_F) {
+            const double fa = avg_f[wk.first + e];
+            const double N = static_cast<double>(np);
+            const double W = first ? bin.W : bin.W2;
+            B = fa * (1. - ((W) / ((N + 1.) * wgt)));
+          } else {
+            const double scw = first ? sum_c_wgt : sum_c_wgt2;
+            const double S = scw / (1. + sum_c);
+            const double fa = avg_f[wk.first + e], fi = avg_finv[wk.first + e];
+            B = fa * (1. / (2. * fa * fi - 1.)) * (1. - (S / wgt));
+          }
+        }
+        const double fi = f[i];
+        const double P_p = (fi - B) / fi, P_u = B / fi;
+        if (std::isinf(P_u) || std::isinf(P_p) || std::isnan(P_u) || std::isnan(P_p)) break;
+        (first ? bin.uniform_wgt : bin.uniform_wgt2) += wv[i] * P_u;
+        wv[i] *= P_p;
+        (first ? touched : touched2) = true;
+      }
+    }
+  }
+  if (m.beta != ABL_BETA_MINIMUM) {  // rng.advance(seed_advance) (:552-554)
+    uint64_t acc_mult = 1, acc_plus = 0, cur_mult = 6364136223846793005ULL, cur_plus = rng2[1], delta = seed_advance;
+    while (delta > 0) {
+      if (delta & 1) {
+        acc_mult *= cur_mult;
+        acc_plus = acc_plus * cur_mult + cur_plus;
+      }
+      cur_plus = (cur_mult + 1) * cur_plus;
+      cur_mult *= cur_mult;
+      delta >>= 1;
+    }
+    rng2[0] = acc_mult * rng2[0] + acc_plus;
+  }
   // (3) get_new_particles (:557-617): which bins emit how many uniform particles, in the map's order
   std::vector<double> list;
   uint64_t n_new = 0;

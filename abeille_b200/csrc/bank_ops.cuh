@@ -559,4 +559,85 @@ __global__ void exact_uniform_kernel(const DevProblem P, const DevMesh3 m, const
   out2[1] = failed;
 }
 
+// get_averages / get_averages_sobol (:264-364) for the bins that need them, one thread per bin: n_samples points of the bin that
+// lie in the bin's material -- from the Sobol sequence (restarted in every bin) or from the global engine advanced to the bin's
+// offset --, then for every particle of the bin the mean of f and of 1/f over those points.  desc rows: key, material, first row
+// in `rows`, count, engine offset.  A bin that cannot place a point within 100 tries per sample is marked (can_cancel = false).
+#define ABL_EXACT_MAX_SAMPLES 64
+struct SobolMatrices3 {
+  unsigned long long m[3][52];
+};
+__device__ __forceinline__ double sobol_sample(const SobolMatrices3& M, unsigned long long index, int dim) {
+  unsigned long long result = 0;
+  for (int i = 0; index; index >>= 1, ++i)
+    if (index & 1) result ^= M.m[dim][i];
+  return (double)result * (1.0 / 4503599627370496.0);  // 2^-52
+}
+__device__ __forceinline__ uint64_t stream_advance(uint64_t state, uint64_t delta) {  // pcg advance with increment 5
+  uint64_t acc_mult = 1, acc_plus = 0, cur_mult = ABL_PCG_MULT, cur_plus = 5ULL;
+  while (delta > 0) {
+    if (delta & 1) {
+      acc_mult *= cur_mult;
+      acc_plus = acc_plus * cur_mult + cur_plus;
+    }
+    cur_plus = (cur_mult + 1) * cur_plus;
+    cur_mult *= cur_mult;
+    delta >>= 1;
+  }
+  return acc_mult * state + acc_plus;
+}
+__global__ void __launch_bounds__(64) exact_average_kernel(const DevProblem P, const DevMesh3 m, const SobolMatrices3 SM, uint64_t nbins,
+                                                           const unsigned long long* __restrict__ desc, const unsigned long long* __restrict__ rows,
+                                                           BankView b, const double* __restrict__ parent, uint64_t pcap, int nsamples, int use_sobol,
+                                                           uint64_t rng0, double* __restrict__ avg_f, double* __restrict__ avg_finv,
+                                                           int32_t* __restrict__ can_cancel) {
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nbins; q += (uint64_t)gridDim.x * blockDim.x) {
+    const int key = (int)desc[5 * q], mat = (int)(long long)desc[5 * q + 1];
+    const uint64_t first = desc[5 * q + 2], count = desc[5 * q + 3];
+    uint64_t rng = stream_advance(rng0, desc[5 * q + 4]);
+    const int k = key % m.Nz, j = (key / m.Nz) % m.Ny, i = key / (m.Nz * m.Ny);
+    const double Xl = m.lowx + i * m.dx, Yl = m.lowy + j * m.dy, Zl = m.lowz + k * m.dz;
+    double rs[ABL_EXACT_MAX_SAMPLES][3];
+    unsigned long long sobol_index = 0;
+    bool ok_all = true;
+    for (int sidx = 0; sidx < nsamples && ok_all; sidx++) {
+      bool ok = false;
+      for (int t = 0; t < 100 && !ok; t++) {
+        double x, y, z;
+        if (use_sobol) {
+          x = Xl + sobol_sample(SM, sobol_index, 0) * m.dx;
+          y = Yl + sobol_sample(SM, sobol_index, 1) * m.dy;
+          z = Zl + sobol_sample(SM, sobol_index, 2) * m.dz;
+          sobol_index++;
+        } else {
+          x = Xl + GlobalStreamMath::rand(rng) * m.dx;
+          y = Yl + GlobalStreamMath::rand(rng) * m.dy;
+          z = Zl + GlobalStreamMath::rand(rng) * m.dz;
+        }
+        Cursor c;
+        c.err = 0;
+        c.token = 0;
+        cursor_restart(P, c, V3{x, y, z}, V3{1., 0., 0.});
+        ok = (c.cell < 0 ? -1 : c.mat) == mat;
+        rs[sidx][0] = x; rs[sidx][1] = y; rs[sidx][2] = z;
+      }
+      ok_all = ok;
+    }
+    can_cancel[q] = ok_all ? 1 : 0;
+    if (!ok_all) continue;
+    for (uint64_t e = 0; e < count; e++) {
+      const uint64_t row = rows[first + e];
+      const double px = parent[row], py = parent[pcap + row], pz = parent[2 * pcap + row], Esmp = parent[3 * pcap + row];
+      double sum_f = 0., sum_f_inv = 0.;
+      for (int sidx = 0; sidx < nsamples; sidx++) {
+        const double f = exact_f(rs[sidx][0], rs[sidx][1], rs[sidx][2], px, py, pz, Esmp);
+        sum_f += f;
+        sum_f_inv += 1. / f;
+      }
+      avg_f[first + e] = sum_f / (double)nsamples;
+      avg_finv[first + e] = sum_f_inv / (double)nsamples;
+    }
+  }
+}
+
 }  // namespace abl

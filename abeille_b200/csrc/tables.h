@@ -55,7 +55,7 @@ struct DevNoiseSrc {  // a noise source region (box) with the run's frequency al
 
 struct DevMesh3 {
   int32_t present, Nx, Ny, Nz, Ne;
-  int32_t kind, beta;  // cancelator only: ABL_CANCEL_*, ABL_BETA_*
+  int32_t kind, beta, sobol, nsamples;  // cancelator only: ABL_CANCEL_*, ABL_BETA_*, Sobol points or engine draws, points per bin
   const double* eedges;  // Ne+1 or null
   double lowx, lowy, lowz, hix, hiy, hiz, dx, dy, dz;
 };

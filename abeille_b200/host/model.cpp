@@ -682,11 +682,12 @@ Problem Problem::from_yaml(const Node& input) {
       const std::string beta = c["beta"].as_string();
       if (beta == "zero") P.cancelator.beta = ABL_BETA_ZERO;
       else if (beta == "minimum") P.cancelator.beta = ABL_BETA_MINIMUM;
-      // (average-f / average-g: the kernels record what the cancelator reads, so the reference's own cancelator runs over the
-      // GPU transporter; abl_cancel_exact_device itself provides zero and minimum and says so)
       else if (beta == "average-f") P.cancelator.beta = ABL_BETA_AVERAGE_F;
       else if (beta == "average-g") P.cancelator.beta = ABL_BETA_AVERAGE_G;
       else fatal_error("Unkown beta entry \"" + beta + "\" for basic exact MG cancelator.");
+      if (c["sobol"]) P.cancelator.sobol = c["sobol"].as_bool() ? 1 : 0;
+      if (c["n-samples"]) P.cancelator.n_samples = static_cast<int>(c["n-samples"].as_int());
+      if (P.cancelator.n_samples <= 0) fatal_error("n-samples must be greater than zero.");
     } else {
     if (type != "approximate") fatal_error("Cancelator type \"" + type + "\" is not provided by the B200 backend (approximate, basic-exact).");
     P.cancelator = make_mesh_spec(c, "approximate mesh cancelator");
@@ -987,6 +988,8 @@ void Problem::flatten(FlatProblem& F) const {
   p.cancelator = mesh3(cancelator);
   p.cancelator.kind = cancelator.kind;
   p.cancelator.beta = cancelator.beta;
+  p.cancelator.sobol = cancelator.sobol;
+  p.cancelator.n_samples = cancelator.n_samples;
   if (F.tally_eb.empty()) F.tally_eb.push_back(0.);
   p.ntallies = static_cast<int32_t>(F.tallies.size());
   p.n_tally_energy_bounds = static_cast<int32_t>(F.tally_eb.size());

@@ -97,6 +97,7 @@ struct MeshSpec {
   std::array<int, 3> N{1, 1, 1};
   std::array<double, 3> low{0, 0, 0}, hi{0, 0, 0};
   std::vector<double> energy_edges;
+  int sobol = 1, n_samples = 10;  // basic-exact defaults (basic_exact_mg_cancelator.cpp:670-686)
   int kind = 0, beta = 0;  // cancelator: ABL_CANCEL_*, ABL_BETA_* (src/cancelator.cpp:40-57, basic_exact_mg_cancelator.cpp:650-668)
 };
 

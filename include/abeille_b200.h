@@ -133,6 +133,7 @@ typedef struct abl_mesh3 {       /* entropy mesh (entropy.cpp) / approximate can
   int32_t eedges_offset;         /* slice of abl_problem.tally_energy_bounds                           */
   int32_t kind;                  /* cancelator only: ABL_CANCEL_* (0 reads as approximate)             */
   int32_t beta;                  /* basic-exact cancelator: ABL_BETA_*                                 */
+  int32_t sobol, n_samples;      /* ... average-f / average-g: Sobol points (else engine draws), points per bin (<= 64) */
 } abl_mesh3;
 enum { ABL_CANCEL_APPROXIMATE = 1, ABL_CANCEL_BASIC_EXACT = 2 };  /* src/cancelator.cpp:40-57 */
 enum { ABL_BETA_ZERO = 0, ABL_BETA_MINIMUM = 1, ABL_BETA_AVERAGE_F = 2, ABL_BETA_AVERAGE_G = 3 };  /* BasicExactMGCancelator::BetaMode */
@@ -296,7 +297,7 @@ int abl_cancel_bins_device(abl_handle h, double* sums_dev[4], uint32_t** count_d
  * transport kernels keep, per fission site, the parent's previous position and the sampling cross section of its flight
  * (BankedParticle::parents_previous_position / Esmp_parent, particle.hpp:52-57) in a side table of the handle, in bank order.
  * Weights are reduced in place, the uniform particles the cancelled weight turns into are appended (bank_dev->n grows, at most
- * `capacity` rows), rng2 = {state, increment} of settings::rng is advanced by what they drew.  beta: minimum and zero.
+ * `capacity` rows), rng2 = {state, increment} of settings::rng is advanced as the reference advances it.  All four beta modes.
  * abl_parent_info_download hands the side table to a caller that runs the reference's own cancelator on the host.           */
 int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity, uint64_t rng2[2], void* stream);
 int abl_parent_info_download(abl_handle h, uint64_t n, double* x, double* y, double* z, double* esmp);

@@ -787,14 +787,16 @@ def test_branchless_power_iteration_matches_oracle(ab, oracle_api, tmp_path, dec
             assert all(abs(int(v) - n) <= 1 for v in g["nbank"][1:])
 
 
-def test_exact_cancellation_matches_oracle(ab, oracle_api, tmp_path):
-    """cancelator: {type: basic-exact, beta: minimum} (src/basic_exact_mg_cancelator.cpp) under carter tracking with negative
-    weights: the per-site parent data the kernels keep for it (BankedParticle::parents_previous_position through reflections,
-    Esmp_parent), the cancelled weights and the appended uniform particles, all bit for bit against the oracle (whose driver is
-    pinned on the reference's, tests/test_reference_pins.py); then whole simulations on both host paths."""
+@pytest.mark.parametrize("deck", ["PUa-cube_carter_exact_min.yaml", "PUa-cube_carter_exact_avgf.yaml", "PUa-cube_carter_exact_avgg.yaml"])
+def test_exact_cancellation_matches_oracle(ab, oracle_api, tmp_path, deck):
+    """cancelator: {type: basic-exact} (src/basic_exact_mg_cancelator.cpp; beta minimum, average-f with points drawn from the global
+    engine, average-g with Sobol points) under carter tracking with negative weights: the per-site parent data the kernels keep for
+    it (BankedParticle::parents_previous_position through reflections, Esmp_parent), the cancelled weights, the appended uniform
+    particles and the engine state afterwards, all bit for bit against the oracle (whose driver is pinned on the reference's,
+    tests/test_reference_pins.py); then whole simulations on both host paths."""
     import torch
     n = 6000
-    orc, gpu = _pair(ab, oracle_api, tmp_path, "PUa-cube_carter_exact_min.yaml", {"settings": {"nparticles": n}})
+    orc, gpu = _pair(ab, oracle_api, tmp_path, deck, {"settings": {"nparticles": n}})
     bank = orc.sample_source(n)
     fis, _, _ = orc.transport({k: v.copy() for k, v in bank.items()})
     nxt = _next_bank(fis, n)                     # a second generation: both signs, reflections behind the parents
@@ -810,7 +812,8 @@ def test_exact_cancellation_matches_oracle(ab, oracle_api, tmp_path):
     assert gm == om
     gpar = gpu.parent_info(gm)
     assert np.array_equal(gpar, opar)
-    assert np.abs(opar[:, :3]).max() > 5.0       # mirror images behind the reflective faces of the +-5 cm cube
+    if "min" in deck:
+        assert np.abs(opar[:, :3]).max() > 5.0   # mirror images behind the reflective faces of the +-5 cm cube
     state = ab.global_rng_state()
     ocb, ostate = orc.cancel_exact({k: v.copy() for k, v in ofis.items()}, opar, state)
     gn, gstate = gpu.cancel_exact_device(dev_out, gm, state)
@@ -821,7 +824,7 @@ def test_exact_cancellation_matches_oracle(ab, oracle_api, tmp_path):
     n, ngen, nign = 4000, 7, 2
     ov = {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}}
     for resident in (False, True):
-        orc, gpu = _pair(ab, oracle_api, tmp_path, "PUa-cube_carter_exact_min.yaml", ov, name=f"ex{int(resident)}.yaml")
+        orc, gpu = _pair(ab, oracle_api, tmp_path, deck, ov, name=f"ex{int(resident)}.yaml")
         o = orc.run_power_iteration(ngen, nign)
         g = gpu.run_power_iteration(ngen, nign, resident=resident)
         assert np.array_equal(g["nbank"], o["nbank"]), (resident, g["nbank"], o["nbank"])
