@@ -831,3 +831,18 @@ def test_exact_cancellation_matches_oracle(ab, oracle_api, tmp_path, deck):
         assert np.allclose(g["kcol"], o["kcol"], rtol=1e-10)
         assert np.allclose(g["mig"], o["mig"], rtol=1e-10)
         assert np.allclose(g["entropy"], o["entropy"], rtol=1e-10)
+
+
+def test_exact_cancellation_in_bins_that_hold_several_materials(ab, oracle_api, tmp_path):
+    """The shipped c5g7.yaml's cancelator kind (basic-exact, average-g, Sobol points) on the carter-tracking c5g7 deck, on a mesh
+    whose bins span fuel, cladding-free moderator and guide tubes: the rejection sampling of bin points on the bin's material, bins
+    keyed by (mesh cell, material), whole simulations against the oracle (bank sizes -- uniform particles included -- exactly)."""
+    n, ngen, nign = 8000, 5, 2
+    ov = {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}}
+    for resident in (True, False):
+        orc, gpu = _pair(ab, oracle_api, tmp_path, "c5g7_carter_exact_avgg.yaml", ov, name=f"c5e{int(resident)}.yaml")
+        o = orc.run_power_iteration(ngen, nign)
+        g = gpu.run_power_iteration(ngen, nign, resident=resident)
+        assert np.array_equal(g["nbank"], o["nbank"]), (resident, g["nbank"], o["nbank"])
+        assert np.allclose(g["kcol"], o["kcol"], rtol=1e-10)
+        assert np.allclose(g["entropy"], o["entropy"], rtol=1e-10)
