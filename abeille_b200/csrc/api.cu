@@ -195,6 +195,8 @@ int validate(abl_handle h, const abl_problem* p) {
     if (p->tracking != ABL_TRACK_DELTA && p->tracking != ABL_TRACK_CARTER)
       return fail(h, ABL_ERR_UNSUPPORTED, "basic-exact cancelators need delta or carter tracking (src/cancelator.cpp:43-47)");
     if (p->cancelator.beta < ABL_BETA_ZERO || p->cancelator.beta > ABL_BETA_AVERAGE_G) return fail(h, ABL_ERR_INVALID, "cancelator beta");
+    if (p->mode == ABL_MODE_NOISE)
+      return fail(h, ABL_ERR_UNSUPPORTED, "basic-exact cancelators in noise mode (the noise kernels do not carry the parents' data)");
     if (p->cancelator.beta >= ABL_BETA_AVERAGE_F && (p->cancelator.n_samples < 1 || p->cancelator.n_samples > ABL_EXACT_MAX_SAMPLES))
       return fail(h, ABL_ERR_UNSUPPORTED, "basic-exact cancelator: n-samples between 1 and 64");
   }

@@ -273,10 +273,36 @@ __device__ __forceinline__ void russian_roulette(const DevProblem& P, Hist& h) {
 // multiplicity m = (nu Sigma_f + Sigma_s) / Sigma_t in its weight, OR a fission that banks one site of weight w*m and ends the
 // particle.  One nuclide per material (atoms_bcm = 1), so sample_nuclide / sample_branchless_nuclide reduce to their single draw.
 // A function call: only branchless-k-eigenvalue problems come here.
+// (the tables it reads travel by value: a reference to the kernel's DevProblem parameter would make every thread copy the
+// whole 2.5 KB structure to its stack)
+struct BranchlessTables {
+  const double *Et, *Ea, *Ef, *nu, *nud, *ps_cp, *chi_cp, *dg_cp, *gmid, *acdf, *amu, *apdf;
+  const abl_angle_table* angle;
+  const int32_t* dg_off;
+  int G, branchless;
+  double wgt_cutoff, wgt_survival, wgt_split, min_energy;
+};
+__device__ __forceinline__ BranchlessTables branchless_tables(const DevProblem& P) {
+  return BranchlessTables{P.Et, P.Ea, P.Ef, P.nu, P.nud, P.ps_cp, P.chi_cp, P.dg_cp, P.gmid, P.acdf, P.amu, P.apdf, P.angle, P.dg_off,
+                          P.G, P.branchless, P.wgt_cutoff, P.wgt_survival, P.wgt_split, P.min_energy};
+}
 template <class M>
-static __device__ __noinline__ void branchless_collision(const DevProblem& P, const RunArgs& A, Hist& h, Acc& acc, uint32_t tid,
+static __device__ __noinline__ void branchless_collision(const BranchlessTables P, const RunArgs& A, Hist& h, Acc& acc, uint32_t tid,
                                                          uint32_t nthreads) {
   const int mg = h.mat * P.G + h.g;
+  auto roulette = [&](Hist& q) {  // russian_roulette (transporter.cpp:35-58)
+    if (fabs(q.w) < P.wgt_cutoff) {
+      const double P_kill = 1.0 - M::div(fabs(q.w), P.wgt_survival);
+      if (M::rand(q.rng) < P_kill) q.w = 0.;
+      else q.w = copysign(P.wgt_survival, q.w);
+    }
+    if (fabs(q.w2) < P.wgt_cutoff) {
+      const double P_kill = 1.0 - ddiv_pos<M>(fabs(q.w2), P.wgt_survival);
+      if (M::rand(q.rng) < P_kill) q.w2 = 0.;
+      else q.w2 = copysign(P.wgt_survival, q.w2);
+    }
+    if (q.w == 0. && q.w2 == 0.) q.alive = false;
+  };
   const double Et = ldt(&P.Et[mg]), Ea = ldt(&P.Ea[mg]), Ef = ldt(&P.Ef[mg]), nu = ldt(&P.nu[mg]);
   const double vEf_i = nu * Ef, Es_i = Et - Ea;
   bool scatter = false;
@@ -291,22 +317,28 @@ static __device__ __noinline__ void branchless_collision(const DevProblem& P, co
     (void)M::rand(h.rng);  // sample_branchless_nuclide: xi = rand * sum (material_helper.hpp:249)
     const double m_i = ddiv_pos<M>(vEf_i + Es_i, Et);
     acc.k_abs += (m / m_i) * h.w * nu * Ef / Et;
-    russian_roulette<false, M>(P, h);
+    roulette(h);
     if (!h.alive) return;
   } else {
     (void)M::rand(h.rng);  // sample_nuclide (material_helper.hpp:189)
     acc.k_abs += h.w * nu * Ef / Et;
     const double Pscatter = Es_i / (vEf_i + Es_i);
     m = (vEf_i + Es_i) / Et;
-    russian_roulette<false, M>(P, h);
+    roulette(h);
     if (!h.alive) return;
     if (M::rand(h.rng) < Pscatter) scatter = true;
   }
   if (scatter) {
     int ei = 0;
     if (P.G >= 2) ei = rng_discrete<M>(h.rng, P.ps_cp + (size_t)mg * P.G, P.G);
-    const double E_out = group_mid(P, ei);
-    const double mu = sample_mu<M>(P, P.angle + (size_t)mg * P.G + ei, h.rng);
+    const double E_out = ldt(&P.gmid[ei]);
+    double mu;
+    {  // MGAngleDistribution::sample_mu (as sample_mu<M> above)
+      const abl_angle_table* at = P.angle + (size_t)mg * P.G + ei;
+      const double xi = M::rand(h.rng);
+      const int off = ldt(&at->offset), n = ldt(&at->n);
+      mu = n < 0 ? -1. + ((xi - 0.) / 0.5) : sample_mu_table(P.acdf, P.amu, P.apdf, off, n, xi);
+    }
     const double phi = 2. * ABL_PI * M::rand(h.rng);
     h.u = rotate_dir<M>(h.u, mu, phi);
     h.E = E_out;
@@ -391,7 +423,7 @@ __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A,
     acc.mig += mig_area_scr;
   }
   if (!NOISE && P.mode == ABL_MODE_BRANCHLESS) {  // transporter.cpp:80-88
-    branchless_collision<M>(P, A, h, acc, tid, nthreads);
+    branchless_collision<M>(branchless_tables(P), A, h, acc, tid, nthreads);
     note(h, 0x6000000000000000ULL | (h.alive ? (uint64_t)(h.g + 1) : 0ULL));
     return;
   }
