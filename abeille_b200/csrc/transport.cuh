@@ -187,7 +187,7 @@ struct FissionTables {
   const double* gmid;
   int G;
 };
-template <class M>
+template <class M, bool PARENT = false>  // PARENT: also write the exact cancelators' side record (the per-lane kernel's calls)
 static __device__ __noinline__ void bank_fission_sites(const FissionTables T, Site* sites, unsigned long long* n_sites, uint64_t capacity,
                                                 uint64_t& rng, const V3 r, const V3 u, double w, uint32_t parent, uint32_t daughter0,
                                                 int n_new, int mat, int mg, double P_delayed, double* site_parent = nullptr,
@@ -221,7 +221,7 @@ static __device__ __noinline__ void bank_fission_sites(const FissionTables T, Si
       double2* dst = reinterpret_cast<double2*>(sites + slot);
 #pragma unroll
       for (int q = 0; q < 5; q++) dst[q] = src[q];
-      if (site_parent) {
+      if (PARENT && site_parent) {
         double2* pp = reinterpret_cast<double2*>(site_parent + 4 * slot);
         pp[0] = make_double2(rprev.x, rprev.y);
         pp[1] = make_double2(rprev.z, esmp);
@@ -441,8 +441,8 @@ __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A,
       h.daughter += (uint32_t)n_new;  // (Particle::make_secondary does not number daughters; kept for the trace only)
       acc.sites += (uint32_t)n_new;
     } else {
-      bank_fission_sites<M>(ft, A.sites, A.n_sites, A.site_capacity, h.rng, h.r, h.u, h.w, h.idx, h.daughter, n_new, h.mat, mg,
-                            ldt(&P.nud[mg]) / nu, A.site_parent, h.rprev, h.esmp);
+      bank_fission_sites<M, true>(ft, A.sites, A.n_sites, A.site_capacity, h.rng, h.r, h.u, h.w, h.idx, h.daughter, n_new, h.mat, mg,
+                                  ldt(&P.nud[mg]) / nu, A.site_parent, h.rprev, h.esmp);
       h.daughter += (uint32_t)n_new;
       h.n_fis += (uint32_t)n_new;
       acc.sites += (uint32_t)n_new;

@@ -45,6 +45,7 @@ class GPUTransporter : public Transporter {
     shape_ = reinterpret_cast<shape_fn>(dlsym(lib_, "abl_tally_shape"));
     count_ = reinterpret_cast<count_fn>(dlsym(lib_, "abl_tally_count"));
     parent_ = reinterpret_cast<parent_fn>(dlsym(lib_, "abl_parent_info_download"));
+    transport_noise_ = reinterpret_cast<transport_noise_fn>(dlsym(lib_, "abl_transport_noise"));
     if (!open_ || !close_ || !backend_ || !transport_ || !last_error_ || !record_ || !clear_ || !fetch_ || !shape_ || !count_)
       fatal_error("GPUTransporter: C ABI symbols missing");
     char err[512] = {0};
@@ -80,31 +81,48 @@ class GPUTransporter : public Transporter {
   std::vector<BankedParticle> transport(std::vector<Particle>& bank, bool noise = false,
                                         std::vector<BankedParticle>* noise_bank = nullptr,
                                         const NoiseMaker* noise_maker = nullptr) override {
-    if (noise || noise_bank || noise_maker) fatal_error("GPUTransporter (integration demo): k-eigenvalue mode only");
-    close_generation();
-    scored_ = settings::converged;
+    // transport(bank, false, &noise_bank, &noise_maker) also samples the noise source (src/noise.cpp:312-314); transport(nbank,
+    // true, ...) moves noise particles with their complex weights (:492).  The noise sources themselves are in the problem tables.
+    const bool sample_noise = noise_bank != nullptr && noise_maker != nullptr;
+    const bool noise_run = settings::mode == settings::SimulationMode::NOISE;
+    // (the Noise driver records its tallies per batch with a multiplier, src/noise.cpp: the per-generation bookkeeping below is
+    // the k-eigenvalue one, so in a noise run the device's mesh tallies are left to the INTEGRATION.md forwarding edit)
+    if (!noise_run) {
+      close_generation();
+      scored_ = settings::converged;
+    }
     const std::size_t N = bank.size();
-    for (auto* v : {&x_, &y_, &z_, &ux_, &uy_, &uz_, &E_, &w_}) v->resize(N);
+    for (auto* v : {&x_, &y_, &z_, &ux_, &uy_, &uz_, &E_, &w_, &w2_}) v->resize(N);
     id_.resize(N); fam_.resize(N); rng_.resize(N);
     for (std::size_t i = 0; i < N; i++) {  // AoS -> SoA (particle.hpp:68-243)
       const Particle& p = bank[i];
       x_[i] = p.r().x(); y_[i] = p.r().y(); z_[i] = p.r().z();
       ux_[i] = p.u().x(); uy_[i] = p.u().y(); uz_[i] = p.u().z();
-      E_[i] = p.E(); w_[i] = p.wgt();
+      E_[i] = p.E(); w_[i] = p.wgt(); w2_[i] = p.wgt2();
       id_[i] = p.history_id(); fam_[i] = p.family_id();
       rng_[i] = p.rng.state_;  // source particles continue the stream they were sampled with (src/simulation.cpp:70-73)
     }
-    const std::size_t cap = 3 * N + 4096;
-    for (auto* v : {&ox_, &oy_, &oz_, &oux_, &ouy_, &ouz_, &oE_, &ow_}) v->resize(cap);
+    const bool complex_out = noise || sample_noise;
+    const std::size_t cap = 3 * N + 4096, ncap = sample_noise ? 6 * N + 4096 : 0;
+    for (auto* v : {&ox_, &oy_, &oz_, &oux_, &ouy_, &ouz_, &oE_, &ow_, &ow2_}) v->resize(cap);
     oa_.resize(cap); ob_.resize(cap); oc_.resize(cap);
-    abl_bank in{N, x_.data(), y_.data(), z_.data(), ux_.data(), uy_.data(), uz_.data(), E_.data(), w_.data(), nullptr,
+    abl_bank in{N, x_.data(), y_.data(), z_.data(), ux_.data(), uy_.data(), uz_.data(), E_.data(), w_.data(), noise ? w2_.data() : nullptr,
                 id_.data(), fam_.data(), rng_.data()};
-    abl_bank out{cap, ox_.data(), oy_.data(), oz_.data(), oux_.data(), ouy_.data(), ouz_.data(), oE_.data(), ow_.data(), nullptr,
-                 oa_.data(), ob_.data(), oc_.data()};
-    abl_gen_params gp{tallies->kcol(), tallies->keff(), settings::converged ? 1 : 0, 0, 0, 0};
-    uint64_t m = 0, counters[8];
+    abl_bank out{cap, ox_.data(), oy_.data(), oz_.data(), oux_.data(), ouy_.data(), ouz_.data(), oE_.data(), ow_.data(),
+                 complex_out ? ow2_.data() : nullptr, oa_.data(), ob_.data(), oc_.data()};
+    abl_gen_params gp{tallies->kcol(), tallies->keff(), settings::converged ? 1 : 0, noise ? 1 : 0, 0, sample_noise ? 1 : 0};
+    uint64_t m = 0, mn = 0, counters[8];
     double s[6];
-    if (transport_(h_, &in, &gp, &out, &m, s, counters) != 0) fatal_error(std::string("GPUTransporter: ") + last_error_(h_));
+    if (sample_noise) {
+      if (!transport_noise_) fatal_error("GPUTransporter: abl_transport_noise missing");
+      for (auto* v : {&nx_, &ny_, &nz_, &nux_, &nuy_, &nuz_, &nE_, &nw_, &nw2_}) v->resize(ncap);
+      na_.resize(ncap); nb_.resize(ncap); nc_.resize(ncap);
+      abl_bank nout{ncap, nx_.data(), ny_.data(), nz_.data(), nux_.data(), nuy_.data(), nuz_.data(), nE_.data(), nw_.data(), nw2_.data(),
+                    na_.data(), nb_.data(), nc_.data()};
+      if (transport_noise_(h_, &in, &gp, &out, &m, &nout, &mn, s, counters) != 0) fatal_error(std::string("GPUTransporter: ") + last_error_(h_));
+    } else if (transport_(h_, &in, &gp, &out, &m, s, counters) != 0) {
+      fatal_error(std::string("GPUTransporter: ") + last_error_(h_));
+    }
     tallies->score_k_col(s[0]); tallies->score_k_abs(s[1]); tallies->score_k_trk(s[2]); tallies->score_k_tot(s[3]);
     tallies->score_leak(s[4]); tallies->score_mig_area(s[5]);  // tallies.hpp:97-102
     std::vector<BankedParticle> fis(m);  // already in the reference's order (bank order, then creation order)
@@ -113,9 +131,19 @@ class GPUTransporter : public Transporter {
       f.r = Position(ox_[i], oy_[i], oz_[i]);
       const double u3[3] = {oux_[i], ouy_[i], ouz_[i]};
       std::memcpy(static_cast<void*>(&f.u), u3, sizeof(Direction));  // bit for bit: Direction(x, y, z) would renormalise
-      f.E = oE_[i]; f.wgt = ow_[i]; f.wgt2 = 0.;
+      f.E = oE_[i]; f.wgt = ow_[i]; f.wgt2 = noise ? ow2_[i] : 0.;
       f.parent_history_id = oa_[i]; f.parent_daughter_id = ob_[i]; f.family_id = oc_[i];
     }
+    for (std::size_t i = 0; i < mn; i++) {  // Particle::empty_noise_bank order: bank order, then creation order
+      BankedParticle f;
+      f.r = Position(nx_[i], ny_[i], nz_[i]);
+      const double u3[3] = {nux_[i], nuy_[i], nuz_[i]};
+      std::memcpy(static_cast<void*>(&f.u), u3, sizeof(Direction));
+      f.E = nE_[i]; f.wgt = nw_[i]; f.wgt2 = nw2_[i];
+      f.parent_history_id = na_[i]; f.parent_daughter_id = nb_[i]; f.family_id = nc_[i];
+      noise_bank->push_back(f);
+    }
+    bank.clear();  // as the reference's trackers leave it (src/delta_tracker.cpp:262)
     // what the reference's exact cancelators read from the bank (particle.hpp:52-57): kept by the kernels when the deck has one
     if (settings::regional_cancellation && parent_ && m > 0) {
       for (auto* v : {&px_, &py_, &pz_, &pe_}) v->resize(m);
@@ -141,6 +169,10 @@ class GPUTransporter : public Transporter {
   using shape_fn = int (*)(abl_handle, int, uint64_t*);
   using count_fn = int (*)(abl_handle);
   using parent_fn = int (*)(abl_handle, uint64_t, double*, double*, double*, double*);
+  using transport_noise_fn = int (*)(abl_handle, const abl_bank*, const abl_gen_params*, abl_bank*, uint64_t*, abl_bank*, uint64_t*, double*, uint64_t*);
+  transport_noise_fn transport_noise_ = nullptr;
+  std::vector<double> w2_, ow2_, nx_, ny_, nz_, nux_, nuy_, nuz_, nE_, nw_, nw2_;
+  std::vector<uint64_t> na_, nb_, nc_;
   parent_fn parent_ = nullptr;
   std::vector<double> px_, py_, pz_, pe_;
   record_fn record_ = nullptr; clear_fn clear_ = nullptr; fetch_fn fetch_ = nullptr; shape_fn shape_ = nullptr; count_fn count_ = nullptr;

@@ -770,6 +770,25 @@ def power_iteration_through_gpu_transporter(only: int, host_library: str, yaml_d
     return out
 
 
+def noise_through_gpu_transporter(only: int, host_library: str, yaml_deck: str, device: int = 0) -> dict:
+    """The reference's own Noise::run() with its transporter replaced by GPUTransporter (integration/gpu_transporter.hpp):
+    transport(bank), transport(bank, false, &noise_bank, &noise_maker) and transport(nbank, true) all through the C ABI.
+    Needs a GPU; one case per process."""
+    from . import deck as _deck
+    fname, n, nb, nign, nskip = NOISE_DRIVER_CASES[only]
+    deck = _deck.load_yaml(yaml_deck)
+    L = ref_lib()
+    kc, nk, fb3 = np.zeros(4096), C.c_int(0), np.zeros(3, dtype=np.uint64)
+    L.ref_set_threads(C.c_int(1))
+    rc = L.ref_noise_run_gpu(_deck.deck_to_text(deck).encode(), host_library.encode(), yaml_deck.encode(), C.c_int(device), C.c_int(nb),
+                             C.c_int(nign), C.c_int(nskip), _d(kc), C.byref(nk), fb3.ctypes.data_as(C.POINTER(C.c_uint64)))
+    assert rc == 0
+    kcol = kc[:nk.value]
+    name = fname.split(".")[0]
+    L.ref_gpu_release()
+    return {f"nd_{name}_kcol": np.ascontiguousarray(kcol[kcol != 0.0]), f"nd_{name}_final_bank": fb3}
+
+
 def sobol_points(impl: str, n: int = 5000) -> np.ndarray:
     """The first n points of the 3-d Sobol sequence BasicExactMGCancelator samples its bins with: the reference's vendored table
     (vendor/sobol) or the oracle's matrices generated from the Joe-Kuo recurrence."""

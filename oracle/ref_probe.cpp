@@ -1206,9 +1206,27 @@ int ref_fixed_source(const char* text, int nbatches, double* kcol, double* leak,
   }
 }
 
+int ref_noise_run_gpu(const char* text, const char* host_library, const char* yaml_deck, int device, int nbatches, int nignored, int nskip,
+                      double* kcol, int* n_kcol, uint64_t* final_bank3);
 int ref_noise_run(const char* text, int nbatches, int nignored, int nskip, double* kcol, int* n_kcol, uint64_t* final_bank3) {
+  return ref_noise_run_gpu(text, nullptr, nullptr, 0, nbatches, nignored, nskip, kcol, n_kcol, final_bank3);
+}
+// ... with host_library != nullptr: the reference's own Noise::run() over GPUTransporter (integration/gpu_transporter.hpp) -- the
+// power-iteration generations, the generations that sample the noise source and the noise particles' inner generations all go
+// through abl_transport / abl_transport_noise; source normalisation, cancellation of the noise banks and bank hand-over stay the
+// reference's
+int ref_noise_run_gpu(const char* text, const char* host_library, const char* yaml_deck, int device, int nbatches, int nignored, int nskip,
+                      double* kcol, int* n_kcol, uint64_t* final_bank3) {
   try {
     if (ref_problem_load(text) != 0) return 1;
+    if (host_library) {
+      g_tallies = std::make_shared<Tallies>(static_cast<double>(settings::nparticles));
+      g_tallies->set_keff(settings::keff);
+      g_tally_gen.clear();
+      g_mesh_tallies.clear();
+      g_gpu_transporter = std::make_shared<GPUTransporter>(g_tallies, host_library, yaml_deck, device);
+      g_transporter = g_gpu_transporter;
+    }
     omp_set_num_threads(g_threads);
     settings::ngenerations = nbatches;
     settings::nignored = nignored;

@@ -224,3 +224,43 @@ def test_references_power_iterator_drives_the_gpu_transporter(ab, golden, tmp_pa
         scale = np.abs(golden[key]).max()
         assert got[key].shape == golden[key].shape
         assert np.abs(got[key] - golden[key]).max() <= 1e-9 * scale, (key, np.abs(got[key] - golden[key]).max(), scale)
+
+
+@pytest.mark.parametrize("ci", range(len(ref_pins.NOISE_DRIVER_CASES)), ids=[c[0].split(".")[0] for c in ref_pins.NOISE_DRIVER_CASES])
+def test_references_noise_driver_drives_the_gpu_transporter(ab, oracle_api, golden, tmp_path, ci):
+    """The drop-in in noise mode: the reference's OWN Noise::initialize() + run() (compiled into oracle/_ref) over
+    integration/gpu_transporter.hpp -- plain generations through abl_transport, the generations that sample the noise source
+    through abl_transport_noise (transport(bank, false, &noise_bank, &noise_maker)), the noise particles' inner generations
+    through abl_transport with their complex weights (transport(nbank, true)).  Source normalisation, regional cancellation of
+    the noise banks and the bank hand-over are the reference's, unchanged.  k_col of every power-iteration generation against
+    what the reference obtained with its own CPU trackers (1e-9); the final bank, its first history id and the history counter
+    -- which counts every noise particle of every inner generation -- EXACTLY against the oracle's Noise driver in the device's
+    math mode (the inner-generation chain follows fdlibm on the device and glibc in the reference: the golden counter of the
+    first case differs for that reason alone, the other two agree with the golden file as well)."""
+    import subprocess
+    import sys
+    from oracle import deck as _deck
+    if not os.path.exists(ref_pins.REF_LIB):
+        pytest.skip("oracle/_ref/libabeille_ref.so was not built (needs /root/reference at build time)")
+    from abeille_b200 import backend
+    _, host_lib = backend.lib_paths()
+    fname, n, nb, nign, nskip = ref_pins.NOISE_DRIVER_CASES[ci]
+    name = fname.split(".")[0]
+    ov = {"settings": {"nparticles": n, "ngenerations": nb, "nignored": nign, "nskip": nskip}}
+    path = write_deck(load_deck(fname), tmp_path / fname, ov)
+    out = str(tmp_path / "nd_gpu.npz")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (f"import sys; sys.path.insert(0, {root!r}); import numpy as np; from oracle import ref_pins; "
+            f"np.savez({out!r}, **ref_pins.noise_through_gpu_transporter({ci}, {host_lib!r}, {str(path)!r}))")
+    subprocess.run([sys.executable, "-c", code], check=True, stdout=subprocess.DEVNULL)  # one simulation per process
+    got = dict(np.load(out))
+    ref_k, ref_fb = golden[f"nd_{name}_kcol"], golden[f"nd_{name}_final_bank"]
+    assert np.allclose(got[f"nd_{name}_kcol"], ref_k, rtol=1e-9), (got[f"nd_{name}_kcol"], ref_k)
+    fb = [int(v) for v in got[f"nd_{name}_final_bank"]]
+    orc = oracle_api.Oracle(str(path))
+    o = orc.run_noise(_deck.load_yaml(str(path))["settings"])
+    assert fb == [int(v) for v in o["final_bank"]], (fb, o["final_bank"])
+    assert fb[:2] == [int(v) for v in ref_fb[:2]]                        # the last power-iteration bank, as the reference's
+    assert fb[2] > 1.5 * n * (nign + nb * nskip)                         # (most histories of the run are noise particles)
+    if ci > 0:
+        assert fb[2] == int(ref_fb[2])
