@@ -167,7 +167,7 @@ def dump_tables(yaml_path: str) -> dict:
     tables = {}
     for line in out.value.decode().splitlines():
         name, *vals = line.split()
-        if name in ("rpn", "universe_cells", "lattice_tiles", "angle"):
+        if name in ("rpn", "universe_cells", "lattice_tiles", "angle", "cells", "root"):
             tables[name] = np.array([int(v) for v in vals], dtype=np.int64)
         else:
             tables[name] = np.array([float(v) for v in vals], dtype=np.float64)

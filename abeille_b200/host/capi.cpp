@@ -98,6 +98,21 @@ int ablh_dump_tables(const char* yaml_path, char* out, int64_t out_cap, char* er
     std::vector<int32_t> ang;
     for (const auto& a : F.angle) { ang.push_back(a.offset); ang.push_back(a.n); }
     dumpi("angle", ang);
+    // geometry records (compared with integration/flatten_problem.hpp, which builds them from the reference's live objects)
+    std::vector<double> geo;
+    for (const auto& sf : F.surfaces) { geo.push_back(sf.type); geo.push_back(sf.bc); for (double v : sf.p) geo.push_back(v); }
+    dump("surfaces", geo);
+    std::vector<int32_t> cl;
+    for (const auto& c : F.cells) { cl.push_back(c.rpn_offset); cl.push_back(c.rpn_len); cl.push_back(c.simple); cl.push_back(c.vac_or_refl); cl.push_back(c.fill_universe); cl.push_back(c.material); }
+    dumpi("cells", cl);
+    std::vector<double> un;
+    for (const auto& u : F.universes) {
+      for (double v : {(double)u.type, (double)u.has_bc, (double)u.cell_offset, (double)u.ncells, (double)u.N[0], (double)u.N[1], (double)u.N[2],
+                       (double)u.tile_offset, (double)u.outer, u.P[0], u.P[1], u.P[2], u.Pinv[0], u.Pinv[1], u.Pinv[2], u.Xl[0], u.Xl[1], u.Xl[2]})
+        un.push_back(v);
+    }
+    dump("universes", un);
+    dumpi("root", {F.p.root_universe});
     if (static_cast<int64_t>(s.size()) + 1 > out_cap) throw std::runtime_error("dump buffer too small");
     std::memcpy(out, s.c_str(), s.size() + 1);
     return 0;

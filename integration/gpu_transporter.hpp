@@ -53,8 +53,30 @@ class GPUTransporter : public Transporter {
     if (!ctx_) fatal_error(std::string("GPUTransporter: ") + err);
     h_ = backend_(ctx_);
   }
+  // From the reference's live objects: `problem` comes from flatten_problem() (integration/flatten_problem.hpp), the library is
+  // libabeille_b200.so itself -- this repo's C++ host library and its YAML parser are not involved.
+  GPUTransporter(std::shared_ptr<Tallies> tallies, const std::string& cuda_library, const abl_problem& problem, int device)
+      : Transporter(tallies) {
+    lib_ = dlopen(cuda_library.c_str(), RTLD_NOW | RTLD_GLOBAL);
+    if (!lib_) fatal_error(std::string("GPUTransporter: ") + dlerror());
+    create_ = reinterpret_cast<create_fn>(dlsym(lib_, "abl_create"));
+    destroy_ = reinterpret_cast<destroy_fn>(dlsym(lib_, "abl_destroy"));
+    transport_ = reinterpret_cast<transport_fn>(dlsym(lib_, "abl_transport"));
+    last_error_ = reinterpret_cast<error_fn>(dlsym(lib_, "abl_last_error"));
+    record_ = reinterpret_cast<record_fn>(dlsym(lib_, "abl_tallies_record"));
+    clear_ = reinterpret_cast<clear_fn>(dlsym(lib_, "abl_tallies_clear"));
+    fetch_ = reinterpret_cast<fetch_fn>(dlsym(lib_, "abl_tally_fetch"));
+    shape_ = reinterpret_cast<shape_fn>(dlsym(lib_, "abl_tally_shape"));
+    count_ = reinterpret_cast<count_fn>(dlsym(lib_, "abl_tally_count"));
+    parent_ = reinterpret_cast<parent_fn>(dlsym(lib_, "abl_parent_info_download"));
+    transport_noise_ = reinterpret_cast<transport_noise_fn>(dlsym(lib_, "abl_transport_noise"));
+    if (!create_ || !destroy_ || !transport_ || !last_error_ || !record_ || !clear_ || !fetch_ || !shape_ || !count_)
+      fatal_error("GPUTransporter: C ABI symbols missing");
+    if (create_(&problem, device, &h_) != 0) fatal_error(std::string("GPUTransporter: ") + last_error_(nullptr));
+  }
   ~GPUTransporter() {
     if (ctx_) close_(ctx_);
+    else if (h_ && destroy_) destroy_(h_);
   }
 
   // Mesh tallies live in HBM and are scored inside the kernels.  Between two transport() calls the reference does
@@ -168,6 +190,10 @@ class GPUTransporter : public Transporter {
   using fetch_fn = int (*)(abl_handle, int, int, double*);
   using shape_fn = int (*)(abl_handle, int, uint64_t*);
   using count_fn = int (*)(abl_handle);
+  using create_fn = int (*)(const abl_problem*, int, abl_handle*);
+  using destroy_fn = void (*)(abl_handle);
+  create_fn create_ = nullptr;
+  destroy_fn destroy_ = nullptr;
   using parent_fn = int (*)(abl_handle, uint64_t, double*, double*, double*, double*);
   using transport_noise_fn = int (*)(abl_handle, const abl_bank*, const abl_gen_params*, abl_bank*, uint64_t*, abl_bank*, uint64_t*, double*, uint64_t*);
   transport_noise_fn transport_noise_ = nullptr;

@@ -742,12 +742,31 @@ def evaluate_noise_driver(impl: str, only: int | None = None) -> dict:
     return out
 
 
-def power_iteration_through_gpu_transporter(only: int, host_library: str, yaml_deck: str, device: int = 0) -> dict:
+def flatten_dump(yaml_deck: str) -> dict:
+    """integration/flatten_problem.hpp on the reference's live objects for this deck (oracle/_ref): the tables of abl_problem, in
+    the layout of abeille_b200.dump_tables (which flattens the same deck through this repo's host library)."""
+    from . import deck as _deck
+    L = ref_lib()
+    out = C.create_string_buffer(1 << 24)
+    rc = L.ref_flatten_dump(_deck.deck_to_text(_deck.load_yaml(yaml_deck)).encode(), out, C.c_longlong(1 << 24))
+    assert rc == 0, rc
+    tables = {}
+    for line in out.value.decode().splitlines():
+        name, *vals = line.split()
+        tables[name] = np.array([float(v) for v in vals])
+    return tables
+
+
+def power_iteration_through_gpu_transporter(only: int, host_library: str, yaml_deck: str, device: int = 0, from_objects: bool = False) -> dict:
     """The reference's own PowerIterator::run() with its transporter replaced by GPUTransporter
-    (integration/gpu_transporter.hpp): the drop-in of INTEGRATION.md, live.  Needs a GPU; one case per process."""
+    (integration/gpu_transporter.hpp): the drop-in of INTEGRATION.md, live.  Needs a GPU; one case per process.
+    from_objects: `host_library` is libabeille_b200.so and the problem tables come from flatten_problem() on the reference's live
+    objects instead of this repo's host library parsing the YAML deck."""
     from . import deck as _deck
     fname, n, ngen, nign = ALL_PI_CASES[only]
     deck = _deck.load_yaml(yaml_deck)
+    if from_objects:
+        yaml_deck = ""
     L = ref_lib()
     keys = ("kcol", "ktrk", "leak", "mig", "entropy")
     a = {k: np.zeros(ngen) for k in keys}

@@ -75,6 +75,7 @@
 #include <omp.h>
 
 #include "../integration/gpu_transporter.hpp"
+#include "../integration/flatten_problem.hpp"
 
 #include <cstdio>
 #include <cstring>
@@ -1097,6 +1098,61 @@ void run_iterator(DriverParts& d, int ngen, double* kcol, double* ktrk, double* 
 }  // namespace
 
 extern "C" {
+// flatten_problem() on the deck's live objects, dumped in the format of ablh_dump_tables (abeille_b200/host/capi.cpp) so that the
+// two flatteners -- this one from the reference's objects, that one from the YAML deck -- can be compared value for value
+int ref_flatten_dump(const char* text, char* out, long long out_cap) {
+  try {
+    if (ref_problem_load(text) != 0) return 1;
+    DriverParts d = driver_parts(text);
+    abl_integration::FlatProblem F;
+    abl_integration::flatten_problem(F, *g_tallies, d.cancelator.get());
+    std::string s;
+    char buf[64];
+    auto dump = [&](const char* name, const std::vector<double>& v) {
+      s += name;
+      for (double x : v) {
+        std::snprintf(buf, sizeof buf, " %.17g", x);
+        s += buf;
+      }
+      s += "\n";
+    };
+    auto dumpi = [&](const char* name, const std::vector<int32_t>& v) {
+      s += name;
+      for (int32_t x : v) s += " " + std::to_string(x);
+      s += "\n";
+    };
+    dump("Et", F.Et); dump("Ea", F.Ea); dump("Ef", F.Ef); dump("Es", F.Es); dump("nu", F.nu); dump("nud", F.nud);
+    dump("chi_cdf", F.chi_cdf); dump("scatter_cdf", F.scatter_cdf); dump("amu", F.amu); dump("apdf", F.apdf); dump("acdf", F.acdf);
+    dump("smp", F.smp);
+    dumpi("rpn", std::vector<int32_t>(F.rpn.begin(), F.rpn.begin() + F.p.nrpn)); dumpi("universe_cells", F.universe_cells);
+    dumpi("lattice_tiles", std::vector<int32_t>(F.lattice_tiles.begin(), F.lattice_tiles.begin() + F.p.n_lattice_tiles));
+    std::vector<int32_t> ang;
+    for (const auto& a : F.angle) { ang.push_back(a.offset); ang.push_back(a.n); }
+    dumpi("angle", ang);
+    // geometry records and tallies, which ablh_dump_tables does not print: surfaces (type, bc, parameters), cells, universes
+    std::vector<double> geo;
+    for (const auto& sf : F.surfaces) { geo.push_back(sf.type); geo.push_back(sf.bc); for (double v : sf.p) geo.push_back(v); }
+    dump("surfaces", geo);
+    std::vector<int32_t> cl;
+    for (const auto& c : F.cells) { cl.push_back(c.rpn_offset); cl.push_back(c.rpn_len); cl.push_back(c.simple); cl.push_back(c.vac_or_refl); cl.push_back(c.fill_universe); cl.push_back(c.material); }
+    dumpi("cells", cl);
+    std::vector<double> un;
+    for (const auto& u : F.universes) {
+      for (double v : {(double)u.type, (double)u.has_bc, (double)u.cell_offset, (double)u.ncells, (double)u.N[0], (double)u.N[1], (double)u.N[2],
+                       (double)u.tile_offset, (double)u.outer, u.P[0], u.P[1], u.P[2], u.Pinv[0], u.Pinv[1], u.Pinv[2], u.Xl[0], u.Xl[1], u.Xl[2]})
+        un.push_back(v);
+    }
+    dump("universes", un);
+    dumpi("root", {F.p.root_universe});
+    if (static_cast<long long>(s.size()) + 1 > out_cap) return 2;
+    std::memcpy(out, s.c_str(), s.size() + 1);
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "ref_flatten_dump: %s\n", e.what());
+    return 1;
+  }
+}
+
 // the reference's vendored Sobol sequence (vendor/sobol), the points BasicExactMGCancelator::sample_position_sobol uses
 void ref_sobol_points(int n, double* out3n) {
   for (int i = 0; i < n; i++)
@@ -1125,18 +1181,24 @@ int ref_power_iteration_gpu(const char* text, const char* host_library, const ch
                             double* kcol, double* ktrk, double* leak, double* mig, double* entropy, double* summary) {
   try {
     if (ref_problem_load(text) != 0) return 1;
+    DriverParts d = driver_parts(text);
     if (host_library) {
+      // yaml_deck empty: `host_library` is libabeille_b200.so itself and the problem tables come from the reference's live objects
+      // (integration/flatten_problem.hpp) -- settings, geometry::, materials, the mesh tallies ref_problem_load gave the Tallies object
+      abl_integration::FlatProblem flat;
+      const bool from_objects = yaml_deck == nullptr || yaml_deck[0] == 0;
+      if (from_objects) abl_integration::flatten_problem(flat, *g_tallies, d.cancelator.get());
       g_tallies = std::make_shared<Tallies>(static_cast<double>(settings::nparticles));
       g_tallies->set_keff(settings::keff);
       g_tally_gen.clear();
       g_mesh_tallies.clear();
-      g_gpu_transporter = std::make_shared<GPUTransporter>(g_tallies, host_library, yaml_deck, device);
+      g_gpu_transporter = from_objects ? std::make_shared<GPUTransporter>(g_tallies, host_library, flat.p, device)
+                                       : std::make_shared<GPUTransporter>(g_tallies, host_library, yaml_deck, device);
       g_transporter = g_gpu_transporter;
     }
     omp_set_num_threads(g_threads);
     settings::ngenerations = ngen;
     settings::nignored = nignored;
-    DriverParts d = driver_parts(text);
     // branchless-k-eigenvalue decks run the reference's BranchlessPowerIterator (src/branchless_power_iterator.cpp: the same loop
     // plus comb_particles), which draws from settings::rng as ref_problem_load left it (seeded, stream 2, no colour draws)
     if (settings::mode == settings::SimulationMode::BRANCHLESS_K_EIGENVALUE)

@@ -264,3 +264,36 @@ def test_references_noise_driver_drives_the_gpu_transporter(ab, oracle_api, gold
     assert fb[2] > 1.5 * n * (nign + nb * nskip)                         # (most histories of the run are noise particles)
     if ci > 0:
         assert fb[2] == int(ref_fb[2])
+
+
+@pytest.mark.parametrize("fname", ["c5g7_delta_collision.yaml", "ref_sqr_c5g7_surface_tl.yaml", "c5g7_carter_cancel.yaml", "PUa-1-0-IN.yaml",
+                                   "PUa-cube_carter_exact_avgg.yaml", "UD2O-2-1-SL_branchless_split_comb.yaml"])
+def test_references_power_iterator_drives_a_transporter_built_from_its_own_objects(ab, golden, tmp_path, fname):
+    """The drop-in without this repo's host library: abl_problem comes from integration/flatten_problem.hpp -- the reference's
+    settings, geometry::, materials and mesh tallies, read where they live -- and goes straight to abl_create of
+    libabeille_b200.so; the reference's own PowerIterator (or BranchlessPowerIterator, or its exact cancelator) runs over that
+    transporter and reproduces its CPU results to 1e-9, mesh tallies included."""
+    import subprocess
+    import sys
+    if not os.path.exists(ref_pins.REF_LIB):
+        pytest.skip("oracle/_ref/libabeille_ref.so was not built (needs /root/reference at build time)")
+    from abeille_b200 import backend
+    cuda_lib, _ = backend.lib_paths()
+    ci = [c[0] for c in ref_pins.ALL_PI_CASES].index(fname)
+    _, n, ngen, nign = ref_pins.ALL_PI_CASES[ci]
+    if ci >= len(ref_pins.POWER_ITERATION_CASES):
+        golden = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", ref_pins.pi_golden_file(ci))))
+    name = fname.split(".")[0]
+    path = write_deck(load_deck(fname), tmp_path / fname, {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}})
+    out = str(tmp_path / "pi_flat.npz")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (f"import sys; sys.path.insert(0, {root!r}); import numpy as np; from oracle import ref_pins; "
+            f"np.savez({out!r}, **ref_pins.power_iteration_through_gpu_transporter({ci}, {cuda_lib!r}, {str(path)!r}, from_objects=True))")
+    subprocess.run([sys.executable, "-c", code], check=True, stdout=subprocess.DEVNULL)
+    got = dict(np.load(out))
+    for k in ("kcol", "ktrk", "leak", "mig", "entropy"):
+        assert np.allclose(got[f"pi_{name}_{k}"], golden[f"pi_{name}_{k}"], rtol=1e-9, atol=1e-12), (k, got[f"pi_{name}_{k}"])
+    assert np.allclose(got[f"pi_{name}_summary"], golden[f"pi_{name}_summary"], rtol=1e-7, atol=1e-12)
+    for key in [k for k in got if "_tally" in k and k in golden]:
+        scale = np.abs(golden[key]).max()
+        assert np.abs(got[key] - golden[key]).max() <= 1e-9 * scale, key
