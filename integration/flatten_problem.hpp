@@ -179,8 +179,18 @@ inline void flatten_problem(FlatProblem& F, const Tallies& tallies, const Cancel
       fu.tile_offset = static_cast<int32_t>(F.lattice_tiles.size());
       for (int32_t t : rl->lattice_universes) F.lattice_tiles.push_back(t);
       fu.outer = rl->outer_universe_index;
+    } else if (auto* hl = dynamic_cast<const HexLattice*>(up.get())) {  // layout: include/abeille_b200.h, abl_universe
+      fu.type = ABL_UNI_HEX;
+      fu.N[0] = static_cast<int32_t>(hl->width); fu.N[1] = static_cast<int32_t>(hl->width); fu.N[2] = static_cast<int32_t>(hl->Nz);
+      fu.pad_ = static_cast<int32_t>(hl->Nrings) | ((hl->top_ == HexLattice::Top::Flat ? 1 : 0) << 16);
+      fu.P[0] = hl->pitch_; fu.P[1] = hl->sin_pi_3; fu.P[2] = hl->pitch_z_;
+      fu.Pinv[0] = hl->cos_pi_6; fu.Pinv[1] = hl->sin_pi_6; fu.Pinv[2] = hl->cos_pi_3;
+      fu.Xl[0] = hl->X_o; fu.Xl[1] = hl->Y_o; fu.Xl[2] = hl->Z_o;
+      fu.tile_offset = static_cast<int32_t>(F.lattice_tiles.size());
+      for (int32_t t : hl->lattice_universes) F.lattice_tiles.push_back(t);
+      fu.outer = hl->outer_universe_index;
     } else {
-      fatal_error("flatten_problem: hexagonal lattices go through the YAML constructor of GPUTransporter");
+      fatal_error("flatten_problem: unknown Universe subclass");
     }
     F.universes.push_back(fu);
   }
