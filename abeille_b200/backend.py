@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "abl_tally_fetch", "abl_tally_device_ptr", "abl_sample_source_device", "abl_bank_weight_stats_device",
     "abl_bank_scale_weights_device", "abl_bank_to_particles_device", "abl_entropy_bin_device",
     "abl_score_source_device", "abl_cancel_device", "abl_cancel_accumulate_device", "abl_cancel_apply_device",
-    "abl_cancel_bins_device", "abl_cancel_exact_device", "abl_parent_info_download", "abl_bank_alloc_device", "abl_bank_free_device",
+    "abl_cancel_bins_device", "abl_cancel_exact_device", "abl_parent_info_download", "abl_parent_state_download", "abl_bank_alloc_device", "abl_bank_free_device",
     "abl_bank_upload", "abl_bank_download", "abl_device_alloc", "abl_device_free", "abl_device_zero",
     "abl_device_read", "abl_find_cells", "abl_rng_probe", "abl_math_probe", "abl_surface_probe", "abl_set_sampling_xs", "abl_fission_capacity_hint")
 
@@ -530,6 +530,13 @@ class Backend:
         with an exact cancelator; BankedParticle::parents_previous_position / Esmp_parent)."""
         cols = [np.zeros(n) for _ in range(4)]
         self._check(self.L.abl_parent_info_download(self.h, C.c_uint64(n), *[c.ctypes.data_as(_PD) for c in cols]))
+        return np.stack(cols, axis=1)
+
+    def parent_state(self, n: int) -> np.ndarray:
+        """[n, 6]: parents_previous_direction, the parent's energy before its last scatter, its energy at the fission, and whether
+        its collision before was virtual (what the reference's `type: exact` cancelator reads on top of parent_info)."""
+        cols = [np.zeros(n) for _ in range(6)]
+        self._check(self.L.abl_parent_state_download(self.h, C.c_uint64(n), *[c.ctypes.data_as(_PD) for c in cols]))
         return np.stack(cols, axis=1)
 
     def cancel_exact_device(self, bank: dict, n: int, rng2):

@@ -73,7 +73,7 @@ struct abl_context {
   // exact cancelators: {parent's previous position, sampling xs} of the scratch sites, and of the rows of the last fission bank
   double* site_parent = nullptr;
   uint64_t site_parent_cap = 0;
-  double* parent_info = nullptr;  // [4][parent_cap]: x, y, z, Esmp in bank order
+  double* parent_info = nullptr;  // [ABL_PARENT_FIELDS][parent_cap] in bank order: x, y, z, Esmp, ux, uy, uz, E before the last scatter, E, was_virtual
   uint64_t parent_cap = 0, parent_n = 0;
   // BasicExactMGCancelator::bins.  Kept across calls and clear()ed like the reference's: the bucket array survives, and with it
   // the order the map is walked in (which orders the uniform particles).  Outer key k + Nz (j + Ny i) -- the value the reference's
@@ -190,6 +190,11 @@ int validate(abl_handle h, const abl_problem* p) {
   if (p->mode == ABL_MODE_NOISE) {
     if (p->n_noise_sources < 1 || !p->noise_sources) return fail(h, ABL_ERR_INVALID, "noise mode without a noise source");
     if (!(p->w_noise > 0.)) return fail(h, ABL_ERR_INVALID, "noise mode needs a positive noise-angular-frequency");
+  }
+  if (p->cancelator.present && p->cancelator.kind == ABL_CANCEL_EXACT) {
+    if (p->tracking != ABL_TRACK_DELTA && p->tracking != ABL_TRACK_CARTER)
+      return fail(h, ABL_ERR_UNSUPPORTED, "exact cancelators need delta or carter tracking (src/cancelator.cpp:59-63)");
+    if (p->mode == ABL_MODE_NOISE) return fail(h, ABL_ERR_UNSUPPORTED, "exact cancelators in noise mode (the noise kernels do not carry the parents' data)");
   }
   if (p->cancelator.present && p->cancelator.kind == ABL_CANCEL_BASIC_EXACT) {
     if (p->tracking != ABL_TRACK_DELTA && p->tracking != ABL_TRACK_CARTER)
@@ -446,7 +451,7 @@ int ensure_sites(abl_handle h, uint64_t cap) {
     if (h->site_parent) cudaFree(h->site_parent);
     h->site_parent = nullptr;
     h->site_parent_cap = 0;
-    ABL_CUDA(h, cudaMalloc(&h->site_parent, cap * 4 * sizeof(double)));
+    ABL_CUDA(h, cudaMalloc(&h->site_parent, cap * ABL_PARENT_FIELDS * sizeof(double)));
     h->site_parent_cap = cap;
   }
   return ABL_OK;
@@ -456,10 +461,10 @@ int ensure_sites(abl_handle h, uint64_t cap) {
 int ensure_parent_info(abl_handle h, uint64_t cap, uint64_t keep) {
   if (cap <= h->parent_cap) return ABL_OK;
   double* n = nullptr;
-  ABL_CUDA(h, cudaMalloc(&n, cap * 4 * sizeof(double)));
-  ABL_CUDA(h, cudaMemset(n, 0, cap * 4 * sizeof(double)));
+  ABL_CUDA(h, cudaMalloc(&n, cap * ABL_PARENT_FIELDS * sizeof(double)));
+  ABL_CUDA(h, cudaMemset(n, 0, cap * ABL_PARENT_FIELDS * sizeof(double)));
   if (h->parent_info && keep)
-    for (int q = 0; q < 4; q++)
+    for (int q = 0; q < ABL_PARENT_FIELDS; q++)
       ABL_CUDA(h, cudaMemcpy(n + q * cap, h->parent_info + q * h->parent_cap, keep * sizeof(double), cudaMemcpyDeviceToDevice));
   if (h->parent_info) cudaFree(h->parent_info);
   h->parent_info = n;
@@ -1165,11 +1170,11 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
   }
   P.entropy = make_mesh3(p->entropy, teb);
   P.cancel = make_mesh3(p->cancelator, teb);
-  P.cancel.kind = p->cancelator.present ? (p->cancelator.kind == ABL_CANCEL_BASIC_EXACT ? ABL_CANCEL_BASIC_EXACT : ABL_CANCEL_APPROXIMATE) : 0;
+  P.cancel.kind = p->cancelator.present ? (p->cancelator.kind == ABL_CANCEL_BASIC_EXACT || p->cancelator.kind == ABL_CANCEL_EXACT ? p->cancelator.kind : ABL_CANCEL_APPROXIMATE) : 0;
   P.cancel.beta = p->cancelator.beta;
   P.cancel.sobol = p->cancelator.sobol;
   P.cancel.nsamples = p->cancelator.n_samples;
-  P.exact_cancel = P.cancel.kind == ABL_CANCEL_BASIC_EXACT ? 1 : 0;
+  P.exact_cancel = (P.cancel.kind == ABL_CANCEL_BASIC_EXACT || P.cancel.kind == ABL_CANCEL_EXACT) ? 1 : 0;
 #undef UP
   if (CU(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return bail(ABL_ERR_CUDA);
   *out = h;
@@ -1590,7 +1595,7 @@ int abl_score_source_device(abl_handle h, const abl_bank* bank_dev, int noise_so
 namespace {
 int ensure_cancel_bins(abl_handle h, uint64_t* nbins_out) {
   const DevMesh3& m = h->P.cancel;
-  if (!m.present || m.kind == ABL_CANCEL_BASIC_EXACT) return fail(h, ABL_ERR_INVALID, "problem has no approximate cancelator");
+  if (!m.present || m.kind == ABL_CANCEL_BASIC_EXACT || m.kind == ABL_CANCEL_EXACT) return fail(h, ABL_ERR_INVALID, "problem has no approximate cancelator");
   const uint64_t nbins = (uint64_t)m.Nx * m.Ny * m.Nz * m.Ne;
   if (!h->cancel.count) {
     ABL_CUDA(h, cudaMalloc(&h->cancel.count, nbins * sizeof(uint32_t)));
@@ -1664,9 +1669,24 @@ int abl_parent_info_download(abl_handle h, uint64_t n, double* x, double* y, dou
   return ABL_OK;
 }
 
+int abl_parent_state_download(abl_handle h, uint64_t n, double* ux, double* uy, double* uz, double* e_before_last_scatter, double* e_parent,
+                              double* was_virtual) {
+  if (!h) return ABL_ERR_INVALID;
+  if (!h->P.exact_cancel) return fail(h, ABL_ERR_INVALID, "problem has no exact cancelator");
+  if (n > h->parent_n) return fail(h, ABL_ERR_INVALID, "more rows than the last fission bank holds");
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  double* dst[6] = {ux, uy, uz, e_before_last_scatter, e_parent, was_virtual};
+  for (int q = 0; q < 6; q++)
+    if (dst[q] && n) ABL_CUDA(h, cudaMemcpy(dst[q], h->parent_info + (4 + q) * h->parent_cap, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return ABL_OK;
+}
+
 int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity, uint64_t rng2[2], void* stream) {
   if (!h || !bank_dev || !rng2) return ABL_ERR_INVALID;
   const DevMesh3& m = h->P.cancel;
+  if (m.present && m.kind == ABL_CANCEL_EXACT)
+    return fail(h, ABL_ERR_UNSUPPORTED, "cancelator type exact: not provided on the device (the reference's own ExactMGCancelator runs over "
+                                        "abl_parent_info_download / abl_parent_state_download)");
   if (!m.present || m.kind != ABL_CANCEL_BASIC_EXACT) return fail(h, ABL_ERR_INVALID, "problem has no basic-exact cancelator");
   const uint64_t n = bank_dev->n;
   if (n != h->parent_n) return fail(h, ABL_ERR_INVALID, "abl_cancel_exact_device takes the fission bank of the last transport call");

@@ -131,13 +131,18 @@ __global__ void __launch_bounds__(256) place_sites_kernel(const Site* __restrict
   }
 }
 
-// the exact cancelators' side table follows the sites to their rows (columns x, y, z, Esmp of `cap` entries)
+// the exact cancelators' side table follows the sites to their rows (ABL_PARENT_FIELDS columns of `cap` entries: x, y, z, Esmp,
+// ux, uy, uz, previous previous energy, previous energy, was_virtual)
 __global__ void __launch_bounds__(256) place_parent_info_kernel(const double* __restrict__ site_parent, uint64_t n_sites,
                                                                 const uint32_t* __restrict__ inv, double* __restrict__ out, uint64_t cap) {
   for (uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < n_sites; pos += (uint64_t)gridDim.x * blockDim.x) {
-    const double2* src = reinterpret_cast<const double2*>(site_parent + 4 * (uint64_t)inv[pos]);
-    const double2 a = __ldcs(src), b = __ldcs(src + 1);
-    out[pos] = a.x; out[cap + pos] = a.y; out[2 * cap + pos] = b.x; out[3 * cap + pos] = b.y;
+    const double2* src = reinterpret_cast<const double2*>(site_parent + (size_t)ABL_PARENT_FIELDS * inv[pos]);
+#pragma unroll
+    for (int q = 0; q < ABL_PARENT_FIELDS / 2; q++) {
+      const double2 a = __ldcs(src + q);
+      out[(2 * q) * cap + pos] = a.x;
+      out[(2 * q + 1) * cap + pos] = a.y;
+    }
   }
 }
 
@@ -549,7 +554,9 @@ __global__ void exact_uniform_kernel(const DevProblem P, const DevMesh3 m, const
         b.wgt[row] = w;
         if (b.wgt2) b.wgt2[row] = w2;
         b.id_a[row] = 0; b.id_b[row] = 0; b.id_c[row] = 0;
-        if (row < pcap) { parent[row] = 0.; parent[pcap + row] = 0.; parent[2 * pcap + row] = 0.; parent[3 * pcap + row] = 0.; }
+        if (row < pcap) {  // a default-constructed BankedParticle's fields (particle.hpp:52-57)
+          for (int q = 0; q < ABL_PARENT_FIELDS; q++) parent[q * pcap + row] = q == 4 ? 1. : 0.;
+        }
       }
       row++;
     }

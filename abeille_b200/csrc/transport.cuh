@@ -48,6 +48,7 @@ struct BankView {  // SoA device arrays (abl_bank with device pointers)
 
 #define ABL_SEC_CAP 24     // LIFO entries a single history may hold at once (an entry is one secondary or `count` identical copies)
 #define ABL_SEC_FIELDS 10  // r, u, E, wgt, wgt2, count
+#define ABL_PARENT_FIELDS 10  // exact cancelators' side record per fission site (RunArgs::site_parent)
 
 struct RunArgs {
   BankView bank;
@@ -63,8 +64,9 @@ struct RunArgs {
   unsigned long long* counters;    // [8]
   int* error;                      // [0] code (min = most severe first seen), [1..2] history id lo/hi
   double* secondaries;             // [ABL_SEC_CAP][ABL_SEC_FIELDS][nthreads] or null
-  double* site_parent;             // [site_capacity][4] or null: the parent's previous position and sampling cross section of every
-                                   // scratch site (BankedParticle::parents_previous_position / Esmp_parent, for the exact cancelators)
+  double* site_parent;             // [site_capacity][ABL_PARENT_FIELDS] or null: what the exact cancelators read of every scratch site
+                                   // (BankedParticle::parents_previous_position, Esmp_parent, parents_previous_direction,
+                                   // parents_previous_previous_energy, parents_previous_energy, parents_previous_was_virtual)
   double k_col, keff;
   int converged;
   // rows of the bank that have arrived in HBM (host-buffer entry point: the copy overlaps the kernel), or null
@@ -99,10 +101,20 @@ struct Hist {
   bool alive;
   bool emid;  // E is exactly the mid-point of group g (true after any scatter / for fission sites): tally bins by table
   // Particle::previous_position / reflected / Esmp_ (particle.hpp:104-133,229-237), kept when the problem has an exact cancelator
-  bool refl;
-  V3 rprev;
-  double esmp;
+  bool refl, virt;   // virt: Particle::previous_collision_virtual (delta_tracker.cpp:188-195)
+  V3 rprev, uprev;   // uprev / Eprev: Particle::previous_direction / previous_energy (set_direction / set_energy keep what they replace)
+  double esmp, Eprev;
 };
+
+// the side record of a fission site (the order of abl_parent_info_download / abl_parent_state_download)
+__device__ __forceinline__ void write_parent_record(double* site_parent, unsigned long long slot, const Hist& h) {
+  double2* pp = reinterpret_cast<double2*>(site_parent + (size_t)ABL_PARENT_FIELDS * slot);
+  pp[0] = make_double2(h.rprev.x, h.rprev.y);
+  pp[1] = make_double2(h.rprev.z, h.esmp);
+  pp[2] = make_double2(h.uprev.x, h.uprev.y);
+  pp[3] = make_double2(h.uprev.z, h.Eprev);
+  pp[4] = make_double2(h.E, h.virt ? 1. : 0.);
+}
 
 struct Acc {  // per-thread accumulators, reduced once at kernel exit
   double k_col, k_abs, k_trk, leak, mig;
@@ -191,7 +203,7 @@ template <class M, bool PARENT = false>  // PARENT: also write the exact cancela
 static __device__ __noinline__ void bank_fission_sites(const FissionTables T, Site* sites, unsigned long long* n_sites, uint64_t capacity,
                                                 uint64_t& rng, const V3 r, const V3 u, double w, uint32_t parent, uint32_t daughter0,
                                                 int n_new, int mat, int mg, double P_delayed, double* site_parent = nullptr,
-                                                const V3 rprev = V3{0., 0., 0.}, double esmp = 0.) {
+                                                const Hist* parent_state = nullptr) {
   const int dg0 = ldt(&T.dg_off[mat]), ndg = ldt(&T.dg_off[mat + 1]) - dg0;
   for (int i = 0; i < n_new; i++) {
     int ei = 0;
@@ -221,11 +233,7 @@ static __device__ __noinline__ void bank_fission_sites(const FissionTables T, Si
       double2* dst = reinterpret_cast<double2*>(sites + slot);
 #pragma unroll
       for (int q = 0; q < 5; q++) dst[q] = src[q];
-      if (PARENT && site_parent) {
-        double2* pp = reinterpret_cast<double2*>(site_parent + 4 * slot);
-        pp[0] = make_double2(rprev.x, rprev.y);
-        pp[1] = make_double2(rprev.z, esmp);
-      }
+      if (PARENT && site_parent) write_parent_record(site_parent, slot, *parent_state);
     }
   }
 }
@@ -340,6 +348,8 @@ static __device__ __noinline__ void branchless_collision(const BranchlessTables 
       mu = n < 0 ? -1. + ((xi - 0.) / 0.5) : sample_mu_table(P.acdf, P.amu, P.apdf, off, n, xi);
     }
     const double phi = 2. * ABL_PI * M::rand(h.rng);
+    h.uprev = h.u;
+    h.Eprev = h.E;
     h.u = rotate_dir<M>(h.u, mu, phi);
     h.E = E_out;
     h.g = ei;
@@ -386,11 +396,7 @@ static __device__ __noinline__ void branchless_collision(const BranchlessTables 
       double2* dst = reinterpret_cast<double2*>(A.sites + slot);
 #pragma unroll
       for (int q = 0; q < 5; q++) dst[q] = src[q];
-      if (A.site_parent) {
-        double2* pp = reinterpret_cast<double2*>(A.site_parent + 4 * slot);
-        pp[0] = make_double2(h.rprev.x, h.rprev.y);
-        pp[1] = make_double2(h.rprev.z, h.esmp);
-      }
+      if (A.site_parent) write_parent_record(A.site_parent, slot, h);
     }
     h.daughter += 1u;
     h.n_fis += 1u;
@@ -442,7 +448,7 @@ __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A,
       acc.sites += (uint32_t)n_new;
     } else {
       bank_fission_sites<M, true>(ft, A.sites, A.n_sites, A.site_capacity, h.rng, h.r, h.u, h.w, h.idx, h.daughter, n_new, h.mat, mg,
-                                  ldt(&P.nud[mg]) / nu, A.site_parent, h.rprev, h.esmp);
+                                  ldt(&P.nud[mg]) / nu, A.site_parent, &h);
       h.daughter += (uint32_t)n_new;
       h.n_fis += (uint32_t)n_new;
       acc.sites += (uint32_t)n_new;
@@ -461,6 +467,8 @@ __device__ __forceinline__ void collision(const DevProblem& P, const RunArgs& A,
     const double E_out = group_mid(P, ei);
     const double mu = sample_mu<M>(P, P.angle + (size_t)mg * P.G + ei, h.rng);
     const double phi = 2. * ABL_PI * M::rand(h.rng);
+    h.uprev = h.u;  // Particle::set_direction / set_energy (particle.hpp:108-117)
+    h.Eprev = h.E;
     h.u = rotate_dir<M>(h.u, mu, phi);
     h.E = E_out;
     h.g = ei;
@@ -716,6 +724,7 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
         // becomes the mirror image, a distance (this leg + what was flown since the last collision) behind the surface
         const V3 r_pre_refs = h.refl ? h.rprev : h.r;
         const V3 back{h.r.x - r_pre_refs.x, h.r.y - r_pre_refs.y, h.r.z - r_pre_refs.z};
+        h.uprev = h.u;  // (p.set_direction(u_new), tracker.hpp:353)
         if (!do_reflection(P, c, h, bound) || c.cell < 0) {
           raise_error(A, ABL_ERR_LOST, hid);
           h.alive = false;
@@ -765,7 +774,9 @@ __device__ __forceinline__ void flight(const DevProblem& P, const RunArgs& A, Hi
     }
     if (h.alive && had_collision) {
       collide<MODE>(P, A, h, acc, tid, nthreads);
+      h.virt = false;  // set_previous_collision_real, whatever became of the particle (delta_tracker.cpp:188-192)
     } else if (h.alive) {
+      h.virt = true;   // also after a boundary crossing (:193-195)
       if (!crossed) {
         acc.virt++;
         h.n_virtual++;
@@ -839,8 +850,11 @@ __global__ void __launch_bounds__(TK_THREADS, 1) transport_kernel(const DevProbl
       h.nsec = 0;
       h.alive = true;
       h.refl = false;
+      h.virt = false;
       h.rprev = V3{0., 0., 0.};
+      h.uprev = V3{1., 0., 0.};  // Direction() (direction.hpp:36)
       h.esmp = 0.;
+      h.Eprev = 0.;
       c.token = 0;
       cursor_restart_nl(geo_tables(P), c, h.r, h.u);
       h.mat = c.mat;

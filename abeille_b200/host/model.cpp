@@ -688,8 +688,15 @@ Problem Problem::from_yaml(const Node& input) {
       if (c["sobol"]) P.cancelator.sobol = c["sobol"].as_bool() ? 1 : 0;
       if (c["n-samples"]) P.cancelator.n_samples = static_cast<int>(c["n-samples"].as_int());
       if (P.cancelator.n_samples <= 0) fatal_error("n-samples must be greater than zero.");
+    } else if (type == "exact") {  // src/cancelator.cpp:58-72, src/exact_mg_cancelator.cpp:594-686
+      // the kernels keep what this cancelator reads from the bank, so the reference's own ExactMGCancelator runs over the GPU
+      // transporter; this repo's drivers do not run it themselves (PowerIterator says so when it gets there)
+      if (P.settings.tracking != ABL_TRACK_DELTA && P.settings.tracking != ABL_TRACK_CARTER)
+        fatal_error("exact cancelators may not be used with surface-tracking.");
+      P.cancelator = make_mesh_spec(c, "exact MG cancelator");
+      P.cancelator.kind = ABL_CANCEL_EXACT;
     } else {
-    if (type != "approximate") fatal_error("Cancelator type \"" + type + "\" is not provided by the B200 backend (approximate, basic-exact).");
+    if (type != "approximate") fatal_error("Cancelator type \"" + type + "\" is not provided by the B200 backend (approximate, basic-exact, exact).");
     P.cancelator = make_mesh_spec(c, "approximate mesh cancelator");
     P.cancelator.kind = ABL_CANCEL_APPROXIMATE;
     if (c["energy-bounds"]) {

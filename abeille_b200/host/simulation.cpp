@@ -368,6 +368,8 @@ void PowerIterator::run_host(int ngenerations, int nignored) {
     if (t.flat.estimator == ABL_EST_SOURCE && !t.flat.noise_source) have_source_tally = true;
   const bool cancel = st.regional_cancellation && problem.cancelator.present;
   const bool exact = cancel && problem.cancelator.kind == ABL_CANCEL_BASIC_EXACT;
+  if (cancel && problem.cancelator.kind == ABL_CANCEL_EXACT)
+    fatal_error("cancelator type exact is not run by this driver (the reference's own ExactMGCancelator runs over the GPU transporter).");
   // branchless-k-eigenvalue: the normalised bank is combed before the source tally sees it (branchless_power_iterator.cpp:358-384)
   const bool comb = st.mode == ABL_MODE_BRANCHLESS && st.branchless_combing;
   const auto t0 = std::chrono::steady_clock::now();
@@ -532,6 +534,8 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
   if (have_entropy) check(h, abl_device_alloc(h, (nebins + 1) * sizeof(double), reinterpret_cast<void**>(&ebins_dev)), "abl_device_alloc");
   const bool cancel = st.regional_cancellation && problem.cancelator.present;
   const bool exact = cancel && problem.cancelator.kind == ABL_CANCEL_BASIC_EXACT;
+  if (cancel && problem.cancelator.kind == ABL_CANCEL_EXACT)
+    fatal_error("cancelator type exact is not run by this driver (the reference's own ExactMGCancelator runs over the GPU transporter).");
   const bool comb = st.mode == ABL_MODE_BRANCHLESS && st.branchless_combing;
   const auto t0 = std::chrono::steady_clock::now();
   for (int g = 1; g <= ngenerations; g++) {

@@ -135,7 +135,10 @@ typedef struct abl_mesh3 {       /* entropy mesh (entropy.cpp) / approximate can
   int32_t beta;                  /* basic-exact cancelator: ABL_BETA_*                                 */
   int32_t sobol, n_samples;      /* ... average-f / average-g: Sobol points (else engine draws), points per bin (<= 64) */
 } abl_mesh3;
-enum { ABL_CANCEL_APPROXIMATE = 1, ABL_CANCEL_BASIC_EXACT = 2 };  /* src/cancelator.cpp:40-57 */
+enum { ABL_CANCEL_APPROXIMATE = 1, ABL_CANCEL_BASIC_EXACT = 2,
+       ABL_CANCEL_EXACT = 3 };  /* src/cancelator.cpp:40-72.  EXACT (src/exact_mg_cancelator.cpp): the kernels keep what it reads
+                                   (abl_parent_info_download, abl_parent_state_download) for the reference's own cancelator;
+                                   abl_cancel_exact_device itself provides BASIC_EXACT */
 enum { ABL_BETA_ZERO = 0, ABL_BETA_MINIMUM = 1, ABL_BETA_AVERAGE_F = 2, ABL_BETA_AVERAGE_G = 3 };  /* BasicExactMGCancelator::BetaMode */
 
 enum { ABL_NOISE_SQUARE_OSCILLATION = 0, ABL_NOISE_FLAT_VIBRATION = 1 };
@@ -301,6 +304,11 @@ int abl_cancel_bins_device(abl_handle h, double* sums_dev[4], uint32_t** count_d
  * abl_parent_info_download hands the side table to a caller that runs the reference's own cancelator on the host.           */
 int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity, uint64_t rng2[2], void* stream);
 int abl_parent_info_download(abl_handle h, uint64_t n, double* x, double* y, double* z, double* esmp);
+/* ... and what `type: exact` reads on top (src/exact_mg_cancelator.cpp:319-327): parents_previous_direction, parents_previous_
+ * previous_energy (the parent's energy before its last scatter), parents_previous_energy (its energy at the fission) and
+ * parents_previous_was_virtual (0 / 1), so that the reference's ExactMGCancelator too runs unchanged over the adapter.     */
+int abl_parent_state_download(abl_handle h, uint64_t n, double* ux, double* uy, double* uz, double* e_before_last_scatter, double* e_parent,
+                              double* was_virtual);
 
 /* ---- device memory helpers for callers that do not link a CUDA runtime themselves ------------------------ */
 int abl_bank_alloc_device(abl_handle h, uint64_t capacity, abl_bank* out_dev); /* all 12 arrays, out_dev->n = capacity */

@@ -28,6 +28,7 @@
 #include <materials/mg_nuclide.hpp>
 #include <simulation/basic_exact_mg_cancelator.hpp>
 #include <simulation/cancelator.hpp>
+#include <simulation/exact_mg_cancelator.hpp>
 #include <simulation/collision_mesh_tally.hpp>
 #include <simulation/tallies.hpp>
 #include <simulation/track_length_mesh_tally.hpp>
@@ -315,6 +316,11 @@ inline void flatten_problem(FlatProblem& F, const Tallies& tallies, const Cancel
     p.cancelator.beta = static_cast<int32_t>(be->beta_mode);
     p.cancelator.sobol = be->use_sobol ? 1 : 0;
     p.cancelator.n_samples = static_cast<int32_t>(std::min<uint32_t>(be->N_SAMPLES, 64));
+  } else if (dynamic_cast<const ExactMGCancelator*>(cancelator)) {
+    p.cancelator.present = 1;
+    p.cancelator.kind = ABL_CANCEL_EXACT;  // (its mesh stays with the reference's object: only the kind matters to the kernels)
+    p.cancelator.N[0] = p.cancelator.N[1] = p.cancelator.N[2] = 1;
+    p.cancelator.hi[0] = p.cancelator.hi[1] = p.cancelator.hi[2] = 1.;
   }
 }
 

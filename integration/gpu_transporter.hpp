@@ -45,6 +45,7 @@ class GPUTransporter : public Transporter {
     shape_ = reinterpret_cast<shape_fn>(dlsym(lib_, "abl_tally_shape"));
     count_ = reinterpret_cast<count_fn>(dlsym(lib_, "abl_tally_count"));
     parent_ = reinterpret_cast<parent_fn>(dlsym(lib_, "abl_parent_info_download"));
+    parent_state_ = reinterpret_cast<parent_state_fn>(dlsym(lib_, "abl_parent_state_download"));
     transport_noise_ = reinterpret_cast<transport_noise_fn>(dlsym(lib_, "abl_transport_noise"));
     if (!open_ || !close_ || !backend_ || !transport_ || !last_error_ || !record_ || !clear_ || !fetch_ || !shape_ || !count_)
       fatal_error("GPUTransporter: C ABI symbols missing");
@@ -69,6 +70,7 @@ class GPUTransporter : public Transporter {
     shape_ = reinterpret_cast<shape_fn>(dlsym(lib_, "abl_tally_shape"));
     count_ = reinterpret_cast<count_fn>(dlsym(lib_, "abl_tally_count"));
     parent_ = reinterpret_cast<parent_fn>(dlsym(lib_, "abl_parent_info_download"));
+    parent_state_ = reinterpret_cast<parent_state_fn>(dlsym(lib_, "abl_parent_state_download"));
     transport_noise_ = reinterpret_cast<transport_noise_fn>(dlsym(lib_, "abl_transport_noise"));
     if (!create_ || !destroy_ || !transport_ || !last_error_ || !record_ || !clear_ || !fetch_ || !shape_ || !count_)
       fatal_error("GPUTransporter: C ABI symbols missing");
@@ -174,6 +176,16 @@ class GPUTransporter : public Transporter {
           fis[i].parents_previous_position = Position(px_[i], py_[i], pz_[i]);
           fis[i].Esmp_parent = pe_[i];
         }
+        for (auto* v : {&qx_, &qy_, &qz_, &qe1_, &qe3_, &qv_}) v->resize(m);
+        if (parent_state_ && parent_state_(h_, m, qx_.data(), qy_.data(), qz_.data(), qe1_.data(), qe3_.data(), qv_.data()) == 0) {
+          for (std::size_t i = 0; i < m; i++) {  // (`type: exact`, src/exact_mg_cancelator.cpp:319-327)
+            const double u3[3] = {qx_[i], qy_[i], qz_[i]};
+            std::memcpy(static_cast<void*>(&fis[i].parents_previous_direction), u3, sizeof(Direction));
+            fis[i].parents_previous_previous_energy = qe1_[i];
+            fis[i].parents_previous_energy = qe3_[i];
+            fis[i].parents_previous_was_virtual = qv_[i] != 0.;
+          }
+        }
       }
     }
     return fis;
@@ -200,7 +212,9 @@ class GPUTransporter : public Transporter {
   std::vector<double> w2_, ow2_, nx_, ny_, nz_, nux_, nuy_, nuz_, nE_, nw_, nw2_;
   std::vector<uint64_t> na_, nb_, nc_;
   parent_fn parent_ = nullptr;
-  std::vector<double> px_, py_, pz_, pe_;
+  using parent_state_fn = int (*)(abl_handle, uint64_t, double*, double*, double*, double*, double*, double*);
+  parent_state_fn parent_state_ = nullptr;
+  std::vector<double> px_, py_, pz_, pe_, qx_, qy_, qz_, qe1_, qe3_, qv_;
   record_fn record_ = nullptr; clear_fn clear_ = nullptr; fetch_fn fetch_ = nullptr; shape_fn shape_ = nullptr; count_fn count_ = nullptr;
   bool scored_ = false;
   void* lib_ = nullptr;

@@ -272,6 +272,15 @@ class Oracle:
         assert m == n, (m, n)
         return out
 
+    def last_parent_state(self, n: int) -> np.ndarray:
+        """[n, 6]: parents_previous_direction, parents_previous_previous_energy, parents_previous_energy, parents_previous_was_virtual
+        (what `type: exact` reads, exact_mg_cancelator.cpp:319-327) of the fission bank the last transport() returned."""
+        out = np.zeros((n, 6))
+        lib().orc_last_parent_state.restype = C.c_uint64
+        m = lib().orc_last_parent_state(self.h, out.ctypes.data_as(_PD), C.c_uint64(n))
+        assert m == n, (m, n)
+        return out
+
     def cancel_exact(self, bank: dict, parent_info: np.ndarray, rng2):
         """PowerIterator::perform_regional_cancellation with the deck's BasicExactMGCancelator: weights reduced in place, uniform
         particles appended.  Returns (bank, (state, increment) of the global engine afterwards)."""

@@ -203,6 +203,11 @@ def deck_to_text(deck: dict) -> str:
         beta = {"zero": 0, "minimum": 1, "average-f": 2, "average-g": 3}[c["beta"]]
         out.append(f"cancelator 2 {int(sh[0])} {int(sh[1])} {int(sh[2])} {_fl(c['low'])} {_fl(c['hi'])} {beta} "
                    f"{int(bool(c.get('sobol', True)))} {int(c.get('n-samples', 10))}")
+    elif c and c.get("type") == "exact":  # src/exact_mg_cancelator.cpp:594-686 (read by the compiled reference only: oracle/ref_probe.cpp)
+        sh = c["shape"]
+        gb = c.get("group-bins", [])
+        bins = " ".join(f"{len(b)} " + " ".join(str(int(g)) for g in b) for b in gb)
+        out.append(f"cancelator 3 {int(sh[0])} {int(sh[1])} {int(sh[2])} {_fl(c['low'])} {_fl(c['hi'])} {int(c.get('n-samples', 10))} {len(gb)} {bins}".rstrip())
     else:
         out.append("cancelator 0")
     e = deck.get("entropy")

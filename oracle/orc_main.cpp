@@ -149,6 +149,7 @@ struct Problem {
   uint64_t histories_counter = 0, global_histories_counter = 0;
   Pcg32Stream global_rng;  // settings::rng
   std::vector<double> last_parent_info;  // x, y, z, Esmp per row of the fission bank of the last orc_transport call
+  std::vector<double> last_parent_state;  // ... previous direction, previous previous energy, previous energy, was_virtual
   ExactBins exact_bins;    // BasicExactMGCancelator::bins (kept across generations: clear() keeps the bucket array)
   Counters counters;
   std::string error;
@@ -655,6 +656,10 @@ static void make_fission_neutrons(Ctx& cx, Particle& p, const MicroXS& microxs, 
     BankedParticle fp{p.r(), finfo.direction, finfo.energy, wgt, wgt2, p.history_id, p.daughter_counter(), p.family_id};
     fp.parents_previous_position = p.previous_position;
     fp.Esmp_parent = p.Esmp_;
+    fp.parents_previous_direction = p.previous_direction;
+    fp.parents_previous_previous_energy = p.previous_energy;
+    fp.parents_previous_energy = p.E();
+    fp.parents_previous_was_virtual = p.previous_collision_virtual;
     if (st.mode == Settings::FIXED_SOURCE) {  // transporter.cpp:460-463: the fission neutron continues the history
       p.make_secondary(fp.u, fp.E, fp.wgt, fp.wgt2);
     } else if (st.mode == Settings::K_EIGENVALUE || !noise || st.inner_generations) {
@@ -701,8 +706,8 @@ static void branchless_collision(Ctx& cx, Particle& p, const Mat& mat) {
   }
   if (scatter) {
     ScatterInfo s = sample_scatter(*cx.P, nuc, p.u(), microxs.energy_index, p.rng);  // (yield == 1 in multi-group)
-    p.state.energy = s.energy;
-    p.state.direction = s.direction;
+    p.set_energy(s.energy);
+    p.set_direction(s.direction);
     p.state.weight = p.wgt() * m * 1.;
     p.state.weight2 = p.wgt2() * m * 1.;
     if (p.E() < st.min_energy) p.kill();
@@ -717,6 +722,10 @@ static void branchless_collision(Ctx& cx, Particle& p, const Mat& mat) {
     BankedParticle fp{p.r(), finfo.direction, finfo.energy, p.wgt() * m, p.wgt2() * m, p.history_id, p.daughter_counter(), p.family_id};
     fp.parents_previous_position = p.previous_position;
     fp.Esmp_parent = p.Esmp_;
+    fp.parents_previous_direction = p.previous_direction;
+    fp.parents_previous_previous_energy = p.previous_energy;
+    fp.parents_previous_energy = p.E();
+    fp.parents_previous_was_virtual = p.previous_collision_virtual;
     p.history_fission_bank.push_back(fp);
     p.n_fission++;
     cx.cn.fission_sites++;
@@ -773,8 +782,8 @@ static void collision(Ctx& cx, Particle& p, const Mat& mat, bool noise) {  // :6
   russian_roulette(st, p);
   if (p.alive) {
     ScatterInfo s = sample_scatter(P, nuc, p.u(), microxs.energy_index, p.rng);  // do_scatter :314-347 (yield == 1)
-    p.state.direction = s.direction;
-    p.state.energy = s.energy;
+    p.set_direction(s.direction);
+    p.set_energy(s.energy);
     p.state.weight = p.wgt() * 1.;
     p.state.weight2 = p.wgt2() * 1.;
     if (p.E() < st.min_energy) p.kill();
@@ -801,7 +810,7 @@ static void do_reflection(Tracker& trkr, Particle& p, const Boundary& boundary) 
   Vec r_prev = r_on_surf - d * u_new;
   p.set_position(r_on_surf);
   p.previous_position = r_prev;
-  p.state.direction = u_new;
+  p.set_direction(u_new);
   p.reflected = true;
   trkr.set_r(p.r());  // NB: wipes the token again
   trkr.set_u(p.u());
@@ -2074,9 +2083,13 @@ int orc_transport(void* h, const orc_bank* in, int noise, orc_bank* out, uint64_
     *n_out = fis.size();
     bank_to(fis, out);
     P.last_parent_info.resize(4 * fis.size());
+    P.last_parent_state.resize(6 * fis.size());
     for (size_t i = 0; i < fis.size(); i++) {
       P.last_parent_info[4 * i] = fis[i].parents_previous_position.x; P.last_parent_info[4 * i + 1] = fis[i].parents_previous_position.y;
       P.last_parent_info[4 * i + 2] = fis[i].parents_previous_position.z; P.last_parent_info[4 * i + 3] = fis[i].Esmp_parent;
+      P.last_parent_state[6 * i] = fis[i].parents_previous_direction.x; P.last_parent_state[6 * i + 1] = fis[i].parents_previous_direction.y;
+      P.last_parent_state[6 * i + 2] = fis[i].parents_previous_direction.z; P.last_parent_state[6 * i + 3] = fis[i].parents_previous_previous_energy;
+      P.last_parent_state[6 * i + 4] = fis[i].parents_previous_energy; P.last_parent_state[6 * i + 5] = fis[i].parents_previous_was_virtual ? 1. : 0.;
     }
     return 0;
   } catch (const std::exception& e) { P.error = e.what(); return 1; }
@@ -2087,6 +2100,14 @@ uint64_t orc_last_parent_info(void* h, double* out4n, uint64_t n) {
   Problem& P = *static_cast<Problem*>(h);
   const uint64_t m = std::min<uint64_t>(n, P.last_parent_info.size() / 4);
   for (uint64_t i = 0; i < 4 * m; i++) out4n[i] = P.last_parent_info[i];
+  return m;
+}
+
+// ... parents_previous_direction, parents_previous_previous_energy, parents_previous_energy, parents_previous_was_virtual ([n][6])
+uint64_t orc_last_parent_state(void* h, double* out6n, uint64_t n) {
+  Problem& P = *static_cast<Problem*>(h);
+  const uint64_t m = std::min<uint64_t>(n, P.last_parent_state.size() / 6);
+  for (uint64_t i = 0; i < 6 * m; i++) out6n[i] = P.last_parent_state[i];
   return m;
 }
 

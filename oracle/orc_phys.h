@@ -191,6 +191,11 @@ struct BankedParticle {
   // and the sampling cross section of that flight
   Vec parents_previous_position{0, 0, 0};
   double Esmp_parent = 0.;
+  // ... and what `type: exact` reads on top (exact_mg_cancelator.cpp:319-327): the parent's direction and energy before its last
+  // scatter, its energy at the fission, and whether the collision before was a virtual one
+  Vec parents_previous_direction{1, 0, 0};
+  double parents_previous_previous_energy = 0., parents_previous_energy = 0.;
+  bool parents_previous_was_virtual = false;
 };
 
 struct ParticleState { Vec position, direction; double energy, weight, weight2; };
@@ -203,6 +208,10 @@ struct Particle {  // particle.hpp:68-243
   bool alive = true, reflected = false, previous_collision_virtual = false;
   Vec previous_position{0, 0, 0}, r_birth{0, 0, 0};
   double Esmp_ = 0.;  // sampling cross section of the current flight (delta_tracker.cpp:111, carter_tracker.cpp:130)
+  Vec previous_direction{1, 0, 0};  // Direction() (direction.hpp:36); set_direction / set_energy keep the value they replace
+  double previous_energy = 0.;
+  void set_direction(Vec u) { previous_direction = state.direction; state.direction = u; }
+  void set_energy(double E) { previous_energy = state.energy; state.energy = E; }
   Pcg32 rng;
   // instrumentation (not in the reference): per-history integer outcomes
   uint32_t n_flights = 0, n_real = 0, n_virtual = 0, n_fission = 0, n_boundary = 0;

@@ -405,7 +405,11 @@ IMPLICIT_CASES = (
 )
 
 
-def evaluate_transport(impl: str, cases=None, seed0: int = 500) -> dict:
+# transport calls whose fission banks are compared down to the fields the exact cancelators read (tests/golden/ref_pins_exact.npz)
+EXACT_TRANSPORT_CASES = (("c5g7_carter_cancel.yaml", 3000, 1.1), ("PUa-cube_carter_exact_min.yaml", 3000, 2.5))
+
+
+def evaluate_transport(impl: str, cases=None, seed0: int = 500, parents: bool = False) -> dict:
     """One Transporter::transport(bank) per case through the reference's own SurfaceTracker / DeltaTracker / CarterTracker
     (oracle/_ref, one OpenMP thread) or the oracle (glibc math, one thread): the fission bank in the order it is returned
     (9 doubles and parent history id, daughter id, family id per site), the six generation values of
@@ -432,6 +436,10 @@ def evaluate_transport(impl: str, cases=None, seed0: int = 500) -> dict:
                                      C.c_double(k_col), C.c_int(1), C.c_uint64(cap), _d(f9), ids.ctypes.data_as(PU), C.byref(nout), _d(k6))
                 assert rc == 0 and nout.value <= cap
                 f9, ids = f9[:nout.value].copy(), ids[:nout.value].copy()
+                if parents:
+                    par = np.zeros((nout.value, 10))
+                    L.ref_last_parents.restype = C.c_uint64
+                    assert L.ref_last_parents(_d(par), C.c_uint64(nout.value)) == nout.value
                 L.ref_tally_size.restype = C.c_uint64
                 tallies = []
                 for t in range(L.ref_ntallies()):
@@ -452,8 +460,12 @@ def evaluate_transport(impl: str, cases=None, seed0: int = 500) -> dict:
                 f9 = np.ascontiguousarray(np.stack([fb[k] for k in api.BANK_F64], 1))
                 ids = np.ascontiguousarray(np.stack([fb["id_a"], fb["id_b"], fb["id_c"]], 1))
                 k6 = scores / float(n)
+                if parents:
+                    par = np.concatenate([o.last_parent_info(m), o.last_parent_state(m)], axis=1)
                 o.close()
             out[f"transport_{name}_sites"], out[f"transport_{name}_ids"], out[f"transport_{name}_k"] = f9, ids, k6
+            if parents:  # parents_previous_position, Esmp_parent, parents_previous_direction, previous previous energy, previous energy, was_virtual
+                out[f"transport_{name}_parents"] = par
             for t, a in enumerate(tallies):
                 out[f"transport_{name}_tally{t}"] = a
     return out
@@ -544,15 +556,20 @@ BRANCHLESS_PI_CASES = (("c5g7_delta_branchless.yaml", 3000, 8, 3), ("PUa-1-0-SL_
 # (tests/golden/ref_pins_exact.npz).  One material each: the reference orders its bins by Material pointer otherwise.
 EXACT_PI_CASES = (("PUa-cube_carter_exact_min.yaml", 2000, 8, 3), ("PUa-cube_carter_exact_avgf.yaml", 2000, 8, 3),
                   ("PUa-cube_carter_exact_avgg.yaml", 2000, 8, 3))
-ALL_PI_CASES = POWER_ITERATION_CASES + IMPLICIT_POWER_ITERATION_CASES + BRANCHLESS_PI_CASES + EXACT_PI_CASES
+# ... and with the reference's second exact cancelator (`type: exact`, src/exact_mg_cancelator.cpp).  Reference-only cases: the
+# oracle does not restate that cancelator; on the device path it runs as the reference's own code over the GPU transporter, fed by
+# abl_parent_info_download / abl_parent_state_download, and these are the numbers that run must reproduce.
+EXACT_FULL_PI_CASES = (("PUa-cube_carter_exact_full.yaml", 2000, 8, 3), ("c5g7_carter_exact_full.yaml", 3000, 6, 2))
+ALL_PI_CASES = POWER_ITERATION_CASES + IMPLICIT_POWER_ITERATION_CASES + BRANCHLESS_PI_CASES + EXACT_PI_CASES + EXACT_FULL_PI_CASES
 IMPLICIT_PI_RANGE = range(len(POWER_ITERATION_CASES), len(POWER_ITERATION_CASES) + len(IMPLICIT_POWER_ITERATION_CASES))
 BRANCHLESS_PI_RANGE = range(IMPLICIT_PI_RANGE.stop, IMPLICIT_PI_RANGE.stop + len(BRANCHLESS_PI_CASES))
-EXACT_PI_RANGE = range(BRANCHLESS_PI_RANGE.stop, len(ALL_PI_CASES))
+EXACT_PI_RANGE = range(BRANCHLESS_PI_RANGE.stop, BRANCHLESS_PI_RANGE.stop + len(EXACT_PI_CASES))
+EXACT_FULL_PI_RANGE = range(EXACT_PI_RANGE.stop, len(ALL_PI_CASES))
 
 
 def pi_golden_file(ci: int) -> str:
     """The file under tests/golden/ that holds the reference's output for ALL_PI_CASES[ci]."""
-    if ci in EXACT_PI_RANGE:
+    if ci in EXACT_PI_RANGE or ci in EXACT_FULL_PI_RANGE:
         return "ref_pins_exact.npz"
     return "ref_pins_branchless.npz" if ci in BRANCHLESS_PI_RANGE else ("ref_pins_implicit.npz" if ci in IMPLICIT_PI_RANGE else "ref_pins.npz")
 

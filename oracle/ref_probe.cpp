@@ -50,6 +50,7 @@
 #include <simulation/flat_vibration_noise_source.hpp>
 #include <simulation/approximate_mesh_cancelator.hpp>
 #include <simulation/basic_exact_mg_cancelator.hpp>
+#include <simulation/exact_mg_cancelator.hpp>
 #include <sobol/sobol.hpp>
 #include <simulation/box.hpp>
 #include <simulation/entropy.hpp>
@@ -122,6 +123,13 @@ bool regional_cancellation_noise = false;
 bool inner_generations = true;
 bool normalize_noise_source = true;
 bool rng_stride_warnings = false;
+// settings::group (src/settings.cpp:95-104, not among the compiled sources: the globals of that file are defined here): index of
+// the first group whose closed interval holds E, 0 when there is none
+std::size_t group(double E) {
+  for (std::size_t g = 0; g + 1 < energy_bounds.size(); g++)
+    if (!(E < energy_bounds[g]) && !(E > energy_bounds[g + 1])) return g;
+  return 0;
+}
 bool branchless_splitting = false;
 bool branchless_combing = false;
 bool branchless_material = true;
@@ -879,6 +887,22 @@ int ref_problem_load(const char* text) {
 // generation in the tallies.  Out: the fission bank in the order transport() returns it (9 doubles + parent history id,
 // parent daughter id, family id per site) and the generation values Tallies::calc_gen_values makes of the scores (k_col,
 // k_abs, k_trk, k_tot, leakage, migration area).  ref_set_threads(1) (the default) accumulates the score sums in bank order.
+// what the exact cancelators read from the fission bank of the last ref_transport (particle.hpp:52-57), [n][10]:
+// parents_previous_position, Esmp_parent, parents_previous_direction, parents_previous_previous_energy, parents_previous_energy,
+// parents_previous_was_virtual
+static std::vector<BankedParticle> g_last_fission;
+uint64_t ref_last_parents(double* out10n, uint64_t n) {
+  const uint64_t m = std::min<uint64_t>(n, g_last_fission.size());
+  for (uint64_t i = 0; i < m; i++) {
+    const BankedParticle& f = g_last_fission[i];
+    double* o = out10n + 10 * i;
+    o[0] = f.parents_previous_position.x(); o[1] = f.parents_previous_position.y(); o[2] = f.parents_previous_position.z();
+    o[3] = f.Esmp_parent;
+    o[4] = f.parents_previous_direction.x(); o[5] = f.parents_previous_direction.y(); o[6] = f.parents_previous_direction.z();
+    o[7] = f.parents_previous_previous_energy; o[8] = f.parents_previous_energy; o[9] = f.parents_previous_was_virtual ? 1. : 0.;
+  }
+  return m;
+}
 int ref_transport(uint64_t n, const double* r3, const double* u3, const double* E, const double* wgt, const uint64_t* hid,
                   const uint64_t* family, double k_col, int converged, uint64_t cap, double* out9, uint64_t* out_ids3, uint64_t* n_out, double* scores6) {
   try {
@@ -900,6 +924,7 @@ int ref_transport(uint64_t n, const double* r3, const double* u3, const double* 
     scores6[0] = g_tallies->kcol(); scores6[1] = g_tallies->kabs(); scores6[2] = g_tallies->ktrk();
     scores6[3] = g_tallies->ktot(); scores6[4] = g_tallies->leakage(); scores6[5] = g_tallies->mig_area();
     *n_out = fis.size();
+    g_last_fission = fis;
     for (uint64_t i = 0; i < fis.size() && i < cap; i++) {
       double* o = out9 + 9 * i;
       o[0] = fis[i].r.x(); o[1] = fis[i].r.y(); o[2] = fis[i].r.z();
@@ -1040,6 +1065,21 @@ DriverParts driver_parts(const char* text) {
                                                            BasicExactMGCancelator::BetaMode::OptAverageF, BasicExactMGCancelator::BetaMode::OptAverageGain};
         d.cancelator = std::make_shared<BasicExactMGCancelator>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]), nx, ny, nz,
                                                                 modes[beta], sobol != 0, nsmp);
+      } else if (on == 3) {  // type: exact (src/exact_mg_cancelator.cpp:594-686): n-samples, group bins (count, then groups per bin)
+        size_t nx, ny, nz, nbins;
+        double lo[3], hi[3];
+        uint32_t nsmp;
+        ls >> nx >> ny >> nz >> lo[0] >> lo[1] >> lo[2] >> hi[0] >> hi[1] >> hi[2] >> nsmp >> nbins;
+        std::vector<std::vector<std::size_t>> group_bins(nbins);
+        for (auto& b : group_bins) {
+          size_t cnt;
+          ls >> cnt;
+          b.resize(cnt);
+          for (auto& g : b) ls >> g;
+        }
+        d.cancelator = std::make_shared<ExactMGCancelator>(Position(lo[0], lo[1], lo[2]), Position(hi[0], hi[1], hi[2]),
+                                                           std::array<std::size_t, 4>{nx, ny, nz, nbins}, group_bins, settings::chi_matrix,
+                                                           settings::use_virtual_collisions, nsmp);
       } else if (on) {
         uint32_t nx, ny, nz;
         double lo[3], hi[3];

@@ -1,2 +1,2 @@
 export ABEILLE_B200_KERNEL_TIMEOUT_S=60
-timeout 900 python -m pytest tests -m gpu -x -q -k "built_from_its_own_objects" 2>&1 | tail -25
+timeout 900 python -m pytest tests -m gpu -x -q -k "exact" 2>&1 | tail -25

@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 from oracle import ref_pins  # noqa: E402
 
 out = {}
-for i in ref_pins.EXACT_PI_RANGE:  # one simulation per process (the reference keeps its state in process globals)
+for i in list(ref_pins.EXACT_PI_RANGE) + list(ref_pins.EXACT_FULL_PI_RANGE):  # one simulation per process (the reference keeps its state in process globals)
     with tempfile.TemporaryDirectory() as td:
         tmp = os.path.join(td, "pi.npz")
         code = (f"import sys; sys.path.insert(0, {ROOT!r}); import numpy as np; from oracle import ref_pins; "
@@ -28,6 +28,9 @@ for i in ref_pins.EXACT_PI_RANGE:  # one simulation per process (the reference k
         subprocess.run([sys.executable, "-c", code], check=True, stdout=subprocess.DEVNULL)
         out.update(dict(np.load(tmp)))
 out["sobol_points"] = ref_pins.sobol_points("reference")
+# the bank fields the exact cancelators read, from the reference's own trackers: one transport call per case
+ex = ref_pins.evaluate_transport("reference", ref_pins.EXACT_TRANSPORT_CASES, seed0=1300, parents=True)
+out.update({k.replace("transport_", "extransport_"): v for k, v in ex.items()})
 path = os.path.join(ROOT, "tests", "golden", "ref_pins_exact.npz")
 np.savez_compressed(path, **out)
 print(f"{path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")

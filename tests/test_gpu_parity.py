@@ -812,6 +812,9 @@ def test_exact_cancellation_matches_oracle(ab, oracle_api, tmp_path, deck):
     assert gm == om
     gpar = gpu.parent_info(gm)
     assert np.array_equal(gpar, opar)
+    ostate = orc.last_parent_state(om)           # previous direction, energy before the last scatter, energy, was_virtual
+    assert np.array_equal(gpu.parent_state(gm), ostate)
+    assert 0.02 < ostate[:, 5].mean() < 0.98 and (ostate[:, 0] != 1.0).any()
     if "min" in deck:
         assert np.abs(opar[:, :3]).max() > 5.0   # mirror images behind the reflective faces of the +-5 cm cube
     state = ab.global_rng_state()
