@@ -66,6 +66,7 @@ struct Cancelator {  // kind 1: ApproximateMeshCancelator, kind 2: BasicExactMGC
   int kind = 1, beta = 0;
   bool sobol = true;
   uint32_t nsamples = 10;
+  std::vector<std::vector<size_t>> group_bins;  // kind 3 (ExactMGCancelator): groups of every energy bin
   Vec low{0, 0, 0}, hi{0, 0, 0};
   uint32_t shape[4] = {1, 1, 1, 1};
   std::vector<double> energy_edges;
@@ -150,6 +151,7 @@ struct Problem {
   Pcg32Stream global_rng;  // settings::rng
   std::vector<double> last_parent_info;  // x, y, z, Esmp per row of the fission bank of the last orc_transport call
   std::vector<double> last_parent_state;  // ... previous direction, previous previous energy, previous energy, was_virtual
+  bool chi_matrix = false;  // settings::chi_matrix
   ExactBins exact_bins;    // BasicExactMGCancelator::bins (kept across generations: clear() keeps the bucket array)
   Counters counters;
   std::string error;
@@ -272,6 +274,11 @@ static Problem* load_problem(const char* path) {
     tk.expect("chi");
     size_t nrows = (size_t)tk.ll();
     mat.chi.assign(G, std::vector<double>(G, 0.));
+    {
+      bool fissile_xs = false;
+      for (double v : mat.Ef) if (v > 0.) fissile_xs = true;
+      if (fissile_xs && nrows == G) P->chi_matrix = true;  // settings::chi_matrix (mg_nuclide.cpp:836-850; one group counts as a matrix)
+    }
     if (nrows == 1) {
       auto row = tk.dv(G);
       for (size_t i = 0; i < G; i++) mat.chi[i] = row;  // mg_nuclide.cpp:836-850
@@ -478,6 +485,14 @@ static Problem* load_problem(const char* path) {
     c.hi = {tk.d(), tk.d(), tk.d()};
     if (c.kind == 2) {
       c.beta = (int)tk.ll(); c.sobol = tk.ll() != 0; c.nsamples = (uint32_t)tk.ll();
+    } else if (c.kind == 3) {
+      c.nsamples = (uint32_t)tk.ll();
+      c.group_bins.resize((size_t)tk.ll());
+      for (auto& b : c.group_bins) {
+        b.resize((size_t)tk.ll());
+        for (auto& g : b) g = (size_t)tk.ll();
+      }
+      c.shape[3] = c.group_bins.empty() ? 1 : (uint32_t)c.group_bins.size();
     } else {
       size_t ne = (size_t)tk.ll();
       c.energy_edges = tk.dv(ne);
@@ -1332,7 +1347,7 @@ static void sample_noise_source(Ctx& cx, Particle& p, const Mat& mat, double kef
 static void perform_exact_cancellation(Problem& P, std::vector<BankedParticle>& next_gen);
 static void perform_regional_cancellation(Problem& P, std::vector<BankedParticle>& next_gen) {  // power_iterator.cpp:751-777
   const Cancelator& c = P.cancel;
-  if (c.kind == 2) return perform_exact_cancellation(P, next_gen);
+  if (c.kind == 2 || c.kind == 3) return perform_exact_cancellation(P, next_gen);
   std::unordered_map<int, std::vector<BankedParticle*>> bins;
   for (auto& p : next_gen) {  // approximate_mesh_cancelator.cpp:97-145
     int i = static_cast<int>(std::floor((p.r.x - c.low.x) / c.dx));
@@ -1376,18 +1391,21 @@ static void perform_regional_cancellation(Problem& P, std::vector<BankedParticle
 // dimensions, generated from the published recurrence instead of the table: dimension 0 is the van der Corput sequence (m_i = 1),
 // dimension 1 has the polynomial x + 1 with m_1 = 1, dimension 2 has x^2 + x + 1 with m = {1, 3}.  Checked against the
 // reference's vendored table by tests/test_reference_pins.py.
-struct SobolMatrices {
-  unsigned long long m[3][52];
+struct SobolMatrices {  // (dimension 3: x^3 + x + 1 with m = {1, 3, 1}; ExactMGCancelator::sample_point draws the energy group from it)
+  unsigned long long m[4][52];
   SobolMatrices() {
-    unsigned long long d1[53], d2[53];
+    unsigned long long d1[53], d2[53], d3[53];
     d1[1] = 1;
     for (int i = 2; i <= 52; i++) d1[i] = (2 * d1[i - 1]) ^ d1[i - 1];                       // s = 1, a = 0
     d2[1] = 1; d2[2] = 3;
     for (int i = 3; i <= 52; i++) d2[i] = (2 * d2[i - 1]) ^ (4 * d2[i - 2]) ^ d2[i - 2];     // s = 2, a_1 = 1
+    d3[1] = 1; d3[2] = 3; d3[3] = 1;
+    for (int i = 4; i <= 52; i++) d3[i] = (4 * d3[i - 2]) ^ (8 * d3[i - 3]) ^ d3[i - 3];     // s = 3, a_1 = 0, a_2 = 1
     for (int i = 1; i <= 52; i++) {
       m[0][i - 1] = 1ULL << (52 - i);
       m[1][i - 1] = d1[i] << (52 - i);
       m[2][i - 1] = d2[i] << (52 - i);
+      m[3][i - 1] = d3[i] << (52 - i);
     }
   }
 };
@@ -1620,9 +1638,243 @@ struct ExactCancel {
   }
 };
 
+// ---- ExactMGCancelator (src/exact_mg_cancelator.cpp; cancelator: {type: exact}) -----------------------------------------------
+// As BasicExactMGCancelator with beta = average-g and Sobol points, for general multi-group physics: the density of a fission
+// site also carries the parent's scattering-angle pdf towards the site and, with a chi matrix, the chi element; bins are keyed by
+// mesh cell and energy bin.
+struct ExactFullBin {
+  struct Averages { double f = 0., f_inv = 0.; };
+  double uniform_wgt = 0., uniform_wgt2 = 0., W = 0., W2 = 0., sum_c = 0., sum_c_wgt = 0., sum_c_wgt2 = 0.;
+  bool can_cancel = true;
+  std::vector<BankedParticle*> particles;
+  std::vector<Averages> averages;
+};
+struct ExactFullKey { size_t i, j, k, e; };
+struct ExactFullCancel {
+  Problem& P;
+  const Cancelator& c;
+  // outer key: Key::hash_key() (exact_mg_cancelator.hpp:78-80), which std::hash<size_t> passes through; the key itself beside it
+  std::unordered_map<size_t, std::unordered_map<int, ExactFullBin>>& bins;
+  std::unordered_map<size_t, ExactFullKey>& keys;
+  static constexpr uint32_t N_MAX_POS = 100;
+  ExactFullCancel(Problem& p, std::unordered_map<size_t, std::unordered_map<int, ExactFullBin>>& b, std::unordered_map<size_t, ExactFullKey>& k)
+      : P(p), c(p.cancel), bins(b), keys(k) {}
+  static size_t group(const Settings& st, double E) {  // settings::group (src/settings.cpp:95-104): closed intervals, first hit
+    if (st.energy_bounds.size() <= 1) return 0;
+    for (size_t g = 0; g < st.energy_bounds.size() - 1; g++)
+      if (st.energy_bounds[g] <= E && E <= st.energy_bounds[g + 1]) return g;
+    return 0;
+  }
+  int get_material(const Vec& r) const {
+    Tracker t(&P.geo, r, Vec{1., 0., 0.});
+    return t.is_lost() ? -1 : t.current_mat;
+  }
+  size_t hash_key(const ExactFullKey& k) const { return k.e + c.shape[3] * (k.k + c.shape[2] * (k.j + c.shape[1] * k.i)); }
+  bool get_key(const Vec& r, size_t g, ExactFullKey& key) const {  // :115-152
+    if (r.x < c.low.x || r.x > c.hi.x || r.y < c.low.y || r.y > c.hi.y || r.z < c.low.z || r.z > c.hi.z) return false;
+    key.i = static_cast<size_t>(std::floor((r.x - c.low.x) / c.dx));
+    key.j = static_cast<size_t>(std::floor((r.y - c.low.y) / c.dy));
+    key.k = static_cast<size_t>(std::floor((r.z - c.low.z) / c.dz));
+    bool e_determined = false;
+    size_t e = 0;
+    for (e = 0; e < c.group_bins.size(); e++) {
+      for (size_t q = 0; q < c.group_bins[e].size(); q++)
+        if (g == c.group_bins[e][q]) { e_determined = true; break; }
+      if (e_determined) break;
+    }
+    if (!e_determined && P.chi_matrix) return false;
+    key.e = e;
+    return true;
+  }
+  bool add_particle(BankedParticle& p) {  // :173-213 (USE_VIRTUAL_COLLISIONS is true: settings::use_virtual_collisions)
+    ExactFullKey key{};
+    if (!get_key(p.r, group(P.st, p.E), key)) return false;
+    const size_t hk = hash_key(key);
+    if (bins.find(hk) == bins.end()) { bins[hk] = std::unordered_map<int, ExactFullBin>(); keys[hk] = key; }
+    const int mat = get_material(p.r);
+    if (bins[hk].find(mat) == bins[hk].end()) bins[hk][mat] = ExactFullBin();
+    ExactFullBin& b = bins[hk][mat];
+    b.particles.push_back(&p);
+    b.W += p.wgt;
+    b.W2 += p.wgt2;
+    return true;
+  }
+  double get_f(const Vec& r1, const Vec& u1, size_t g1, size_t g3, const Vec& r4, size_t g4, double Esmp, const Material& nuc) const {  // :215-235
+    const double d = (r4 - r1).norm();
+    const Vec u = make_direction(r4.x - r1.x, r4.y - r1.y, r4.z - r1.z);
+    const double mu = u.dot(u1);
+    const double pdf_mu = nuc.angle[g1][g3].pdf_at(mu);
+    const double pdf_chi = P.chi_matrix ? nuc.chi[g3][g4] : 1.;
+    return (pdf_mu * pdf_chi / (d * d)) * g_math.exp(-Esmp * d);
+  }
+  bool sample_point(const ExactFullKey& key, int mat, unsigned long long& idx, Vec& r, size_t& g) const {  // :249-294
+    double Xl = c.low.x + static_cast<double>(key.i) * c.dx, Yl = c.low.y + static_cast<double>(key.j) * c.dy,
+           Zl = c.low.z + static_cast<double>(key.k) * c.dz;
+    uint32_t N_TRIES = 0;
+    bool position_sampled = false;
+    while (N_TRIES < N_MAX_POS && !position_sampled) {
+      double x = Xl + sobol_sample(idx, 0) * c.dx;
+      double y = Yl + sobol_sample(idx, 1) * c.dy;
+      double z = Zl + sobol_sample(idx, 2) * c.dz;
+      r = Vec{x, y, z};
+      if (get_material(r) == mat) position_sampled = true;
+      N_TRIES++;
+      idx++;
+    }
+    if (!position_sampled) return false;
+    g = 0;
+    if (P.chi_matrix) {
+      const double xi = sobol_sample(idx - 1, 3);
+      const size_t g_index = static_cast<size_t>(std::floor(xi * static_cast<double>(c.group_bins[key.e].size())));
+      g = c.group_bins[key.e][g_index];
+    }
+    return true;
+  }
+  void compute_averages(const ExactFullKey& key, int mat, ExactFullBin& bin) const {  // :296-364
+    const Material& nuc = P.materials[(size_t)mat];
+    bin.averages.resize(bin.particles.size());
+    std::vector<std::pair<Vec, size_t>> smps;
+    unsigned long long sobol_index = 0;
+    for (size_t j = 0; j < c.nsamples; j++) {
+      Vec r;
+      size_t g;
+      if (!sample_point(key, mat, sobol_index, r, g)) { bin.can_cancel = false; return; }
+      smps.push_back({r, g});
+    }
+    for (size_t i = 0; i < bin.particles.size(); i++) {
+      const BankedParticle& p = *bin.particles[i];
+      const size_t g1 = group(P.st, p.parents_previous_previous_energy), g3 = group(P.st, p.parents_previous_energy);
+      double sum_f = 0., sum_f_inv = 0.;
+      for (const auto& sm : smps) {
+        double f = get_f(p.parents_previous_position, p.parents_previous_direction, g1, g3, sm.first, sm.second, p.Esmp_parent, nuc);
+        if (f == 0.) { bin.can_cancel = false; return; }
+        sum_f += f;
+        sum_f_inv += 1. / f;
+      }
+      bin.averages[i].f = sum_f / static_cast<double>(c.nsamples);
+      bin.averages[i].f_inv = sum_f_inv / static_cast<double>(c.nsamples);
+    }
+    auto C = [](double f, double f_inv) { return 1. / (2. * f * f_inv - 1.); };
+    double sum_c = 0.;
+    for (size_t i = 0; i < bin.particles.size(); i++) sum_c += C(bin.averages[i].f, bin.averages[i].f_inv);
+    double sum_c_wgt = 0., sum_c_wgt2 = 0.;
+    for (size_t i = 0; i < bin.particles.size(); i++) {
+      sum_c_wgt += C(bin.averages[i].f, bin.averages[i].f_inv) * bin.particles[i]->wgt;
+      sum_c_wgt2 += C(bin.averages[i].f, bin.averages[i].f_inv) * bin.particles[i]->wgt2;
+    }
+    bin.sum_c = sum_c; bin.sum_c_wgt = sum_c_wgt; bin.sum_c_wgt2 = sum_c_wgt2;
+  }
+  double get_beta(const ExactFullBin& bin, size_t i, bool wgt_1) const {  // :237-247
+    if (!bin.can_cancel) return 0.;
+    const double wgt = wgt_1 ? bin.particles[i]->wgt : bin.particles[i]->wgt2;
+    const double sum_c_wgt = wgt_1 ? bin.sum_c_wgt : bin.sum_c_wgt2;
+    const double S = sum_c_wgt / (1. + bin.sum_c);
+    const double f = bin.averages[i].f, f_inv = bin.averages[i].f_inv;
+    return f * (1. / (2. * f * f_inv - 1.)) * (1. - (S / wgt));
+  }
+  void cancel_bin(ExactFullBin& bin, int mat, bool first_wgt) const {  // :366-401
+    const Material& nuc = P.materials[(size_t)mat];
+    for (size_t i = 0; i < bin.particles.size(); i++) {
+      BankedParticle& p = *bin.particles[i];
+      const size_t g1 = group(P.st, p.parents_previous_previous_energy), g3 = group(P.st, p.parents_previous_energy), g4 = group(P.st, p.E);
+      const double B = get_beta(bin, i, first_wgt);
+      const double f = get_f(p.parents_previous_position, p.parents_previous_direction, g1, g3, p.r, g4, p.Esmp_parent, nuc);
+      const double P_p = (f - B) / f, P_u = B / f;
+      if (std::isinf(P_u) || std::isinf(P_p) || std::isnan(P_u) || std::isnan(P_p)) return;
+      if (first_wgt) { bin.uniform_wgt += p.wgt * P_u; p.wgt *= P_p; }
+      else { bin.uniform_wgt2 += p.wgt2 * P_u; p.wgt2 *= P_p; }
+    }
+  }
+  void perform_cancellation() {  // :403-476
+    if (bins.size() == 0) return;
+    for (auto& kb : bins)
+      for (auto& mb : kb.second) {
+        ExactFullBin& bin = mb.second;
+        if (bin.particles.size() > 1) {
+          bool p1 = false, n1 = false, p2 = false, n2 = false;
+          for (const auto& p : bin.particles) {
+            if (p->wgt > 0.) p1 = true; else if (p->wgt < 0.) n1 = true;
+            if (p->wgt2 > 0.) p2 = true; else if (p->wgt2 < 0.) n2 = true;
+            if (p1 && n1 && p2 && n2) break;
+          }
+          if ((p1 && n1) || (p2 && n2)) compute_averages(keys[kb.first], mb.first, bin);
+          if (p1 && n1) cancel_bin(bin, mb.first, true);
+          if (p2 && n2) cancel_bin(bin, mb.first, false);
+          bin.particles.clear();
+          bin.averages.clear();
+          bin.sum_c = 0.; bin.sum_c_wgt = 0.; bin.sum_c_wgt2 = 0.;
+        }
+      }
+  }
+  std::vector<BankedParticle> get_new_particles(Pcg32Stream& rng) {  // :511-590
+    std::vector<BankedParticle> uniform_particles;
+    for (auto& kb : bins) {
+      const ExactFullKey key = keys[kb.first];
+      for (auto& mb : kb.second) {
+        const int mat = mb.first;
+        ExactFullBin& bin = mb.second;
+        uint32_t N = static_cast<uint32_t>(std::ceil(std::max(std::abs(bin.uniform_wgt), std::abs(bin.uniform_wgt2))));
+        if (N > 0) {
+          double w = bin.uniform_wgt / N, w2 = bin.uniform_wgt2 / N;
+          const Material& nuc = P.materials[(size_t)mat];
+          double Xl = c.low.x + static_cast<double>(key.i) * c.dx, Yl = c.low.y + static_cast<double>(key.j) * c.dy,
+                 Zl = c.low.z + static_cast<double>(key.k) * c.dz;
+          for (size_t i = 0; i < N; i++) {
+            Vec r{0, 0, 0};
+            uint32_t N_TRIES = 0;
+            bool position_sampled = false;
+            while (N_TRIES < N_MAX_POS && !position_sampled) {  // sample_position :478-509
+              double x = Xl + rng_rand(rng) * c.dx;
+              double y = Yl + rng_rand(rng) * c.dy;
+              double z = Zl + rng_rand(rng) * c.dz;
+              r = Vec{x, y, z};
+              if (get_material(r) == mat) position_sampled = true;
+              N_TRIES++;
+            }
+            if (!position_sampled) throw std::runtime_error("Couldn't sample position for uniform particle.");
+            size_t e_index = 0;
+            if (P.chi_matrix) {
+              const double xi_E = rng_rand(rng);
+              size_t g_index = static_cast<size_t>(std::floor(xi_E * static_cast<double>(c.group_bins[key.e].size())));
+              e_index = c.group_bins[key.e][g_index];
+            } else {
+              e_index = static_cast<size_t>(rng_discrete(rng, nuc.chi_cp[0]));
+            }
+            double E_smp = 0.5 * (P.st.energy_bounds[e_index] + P.st.energy_bounds[e_index + 1]);
+            // Direction u_smp(2. * RNG::rand(rng) - 1., 2. * PI * RNG::rand(rng)) (:573): two draws inside one argument list, whose
+            // order the language leaves open -- g++ evaluates the arguments from the right, so phi takes the first draw
+            double phi = 2. * PI * rng_rand(rng);
+            double mu = 2. * rng_rand(rng) - 1.;
+            if (mu < -1.) mu = -1.; else if (mu > 1.) mu = 1.;
+            if (phi < 0.) phi = 0.; else if (phi > 2 * PI) phi = 2 * PI;
+            const Vec u_smp = make_direction(std::sqrt(1. - mu * mu) * g_math.cos(phi), std::sqrt(1. - mu * mu) * g_math.sin(phi), mu);
+            BankedParticle up{r, u_smp, E_smp, w, w2, 0, 0, 0};  // (the reference leaves the three ids uninitialised)
+            uniform_particles.push_back(up);
+          }
+        }
+        bin.uniform_wgt = 0.;
+        bin.uniform_wgt2 = 0.;
+      }
+    }
+    return uniform_particles;
+  }
+};
+static std::unordered_map<Problem*, std::pair<std::unordered_map<size_t, std::unordered_map<int, ExactFullBin>>, std::unordered_map<size_t, ExactFullKey>>> g_exact_full;
+
 // PowerIterator::perform_regional_cancellation with an exact cancelator (power_iterator.cpp:751-777): the uniform particles are
 // appended to the bank
 static void perform_exact_cancellation(Problem& P, std::vector<BankedParticle>& next_gen) {
+  if (P.cancel.kind == 3) {
+    auto& st = g_exact_full[&P];
+    ExactFullCancel ec(P, st.first, st.second);
+    for (auto& p : next_gen) (void)ec.add_particle(p);
+    ec.perform_cancellation();
+    auto tmp = ec.get_new_particles(P.global_rng);
+    next_gen.insert(next_gen.end(), tmp.begin(), tmp.end());
+    st.first.clear();   // cancelator->clear(): the bucket array survives
+    st.second.clear();
+    return;
+  }
   ExactCancel ec(P);
   for (auto& p : next_gen) (void)ec.add_particle(p);
   ec.perform_cancellation(P.global_rng);
@@ -2214,9 +2466,9 @@ int orc_cancel_and_normalize(void* h, orc_bank* b, int do_cancel, double* stats6
   return 0;
 }
 
-void orc_sobol_points(int n, double* out3n) {
+void orc_sobol_points(int n, double* out4n) {
   for (int i = 0; i < n; i++)
-    for (unsigned d = 0; d < 3; d++) out3n[3 * i + d] = sobol_sample(static_cast<unsigned long long>(i), d);
+    for (unsigned d = 0; d < 4; d++) out4n[4 * i + d] = sobol_sample(static_cast<unsigned long long>(i), d);
 }
 
 // BranchlessPowerIterator::comb_particles alone.  rng2 = {state, increment} of settings::rng, updated; out->n = capacity on entry.

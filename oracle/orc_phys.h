@@ -34,6 +34,15 @@ struct AngleDist {
     double m = (pdf[l + 1] - pdf[l]) / (mu[l + 1] - mu[l]);                // linear_interp :96-101
     return mu[l] + (1. / m) * (std::sqrt(pdf[l] * pdf[l] + 2. * m * (xi - cdf[l])) - pdf[l]);
   }
+  double pdf_at(double x) const {  // MGAngleDistribution::pdf (mg_angle_distribution.hpp:62-75)
+    if (x < mu.front()) return pdf.front();
+    if (x > mu.back()) return pdf.back();
+    size_t l = static_cast<size_t>(std::lower_bound(mu.begin(), mu.end(), x) - mu.begin());
+    if (x == mu[l]) return pdf[l];
+    l--;
+    const double m = (pdf[l + 1] - pdf[l]) / (mu[l + 1] - mu[l]);
+    return m * (x - mu[l]) + pdf[l];
+  }
 };
 
 // include/materials/legendre_distribution.hpp:155-200 + src/legendre_distribution.cpp:105-155

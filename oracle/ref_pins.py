@@ -556,9 +556,8 @@ BRANCHLESS_PI_CASES = (("c5g7_delta_branchless.yaml", 3000, 8, 3), ("PUa-1-0-SL_
 # (tests/golden/ref_pins_exact.npz).  One material each: the reference orders its bins by Material pointer otherwise.
 EXACT_PI_CASES = (("PUa-cube_carter_exact_min.yaml", 2000, 8, 3), ("PUa-cube_carter_exact_avgf.yaml", 2000, 8, 3),
                   ("PUa-cube_carter_exact_avgg.yaml", 2000, 8, 3))
-# ... and with the reference's second exact cancelator (`type: exact`, src/exact_mg_cancelator.cpp).  Reference-only cases: the
-# oracle does not restate that cancelator; on the device path it runs as the reference's own code over the GPU transporter, fed by
-# abl_parent_info_download / abl_parent_state_download, and these are the numbers that run must reproduce.
+# ... and with the reference's second exact cancelator (`type: exact`, src/exact_mg_cancelator.cpp): one-group cube (which counts as a
+# chi matrix: energy bins, the fourth Sobol dimension) and c5g7 (chi vector, several materials per mesh cell)
 EXACT_FULL_PI_CASES = (("PUa-cube_carter_exact_full.yaml", 2000, 8, 3), ("c5g7_carter_exact_full.yaml", 3000, 6, 2))
 ALL_PI_CASES = POWER_ITERATION_CASES + IMPLICIT_POWER_ITERATION_CASES + BRANCHLESS_PI_CASES + EXACT_PI_CASES + EXACT_FULL_PI_CASES
 IMPLICIT_PI_RANGE = range(len(POWER_ITERATION_CASES), len(POWER_ITERATION_CASES) + len(IMPLICIT_POWER_ITERATION_CASES))
@@ -826,9 +825,10 @@ def noise_through_gpu_transporter(only: int, host_library: str, yaml_deck: str, 
 
 
 def sobol_points(impl: str, n: int = 5000) -> np.ndarray:
-    """The first n points of the 3-d Sobol sequence BasicExactMGCancelator samples its bins with: the reference's vendored table
-    (vendor/sobol) or the oracle's matrices generated from the Joe-Kuo recurrence."""
-    out = np.zeros((n, 3))
+    """The first n points of the 4-d Sobol sequence the exact cancelators sample their bins with (three coordinates; ExactMGCancelator
+    takes the energy group from the fourth): the reference's vendored table (vendor/sobol) or the oracle's matrices generated from
+    the Joe-Kuo recurrence."""
+    out = np.zeros((n, 4))
     L = ref_lib() if impl == "reference" else api.lib()
     getattr(L, "ref_sobol_points" if impl == "reference" else "orc_sobol_points")(C.c_int(n), _d(out))
     return out

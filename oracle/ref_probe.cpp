@@ -1194,9 +1194,9 @@ int ref_flatten_dump(const char* text, char* out, long long out_cap) {
 }
 
 // the reference's vendored Sobol sequence (vendor/sobol), the points BasicExactMGCancelator::sample_position_sobol uses
-void ref_sobol_points(int n, double* out3n) {
+void ref_sobol_points(int n, double* out4n) {
   for (int i = 0; i < n; i++)
-    for (unsigned d = 0; d < 3; d++) out3n[3 * i + d] = sobol::sample(static_cast<unsigned long long>(i), d);
+    for (unsigned d = 0; d < 4; d++) out4n[4 * i + d] = sobol::sample(static_cast<unsigned long long>(i), d);
 }
 // size of the source bank the last ref_power_iteration ended with (after combing, for a branchless deck)
 uint64_t ref_last_bank_size() { return g_last_bank_size; }
