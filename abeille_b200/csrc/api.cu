@@ -83,6 +83,7 @@ struct abl_context {
     std::vector<uint64_t> particles;
   };
   std::unordered_map<int, std::unordered_map<int, ExactBin>> exact_bins;
+  bool exact_full_ready = false;  // kind ABL_CANCEL_EXACT with its tables (chi rows, energy bins) on the device
   int nm_blocks_per_sm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   int implicit_blocks_per_sm[3] = {0, 0, 0};  // implicit-leakage delta tracking: per-lane kernel in modes 0 | 1 | 2
   // host-buffer entry point: the bank is copied in row chunks on its own stream while the history kernel runs
@@ -1175,6 +1176,20 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
   P.cancel.sobol = p->cancelator.sobol;
   P.cancel.nsamples = p->cancelator.n_samples;
   P.exact_cancel = (P.cancel.kind == ABL_CANCEL_BASIC_EXACT || P.cancel.kind == ABL_CANCEL_EXACT) ? 1 : 0;
+  P.chi_matrix = p->chi_matrix;
+  if (P.cancel.kind == ABL_CANCEL_EXACT && p->chi_pdf && p->exact_group_bins && p->n_exact_group_bins >= 1) {
+    // ExactMGCancelator's tables: the chi rows themselves and the energy bins (Key::shape[3] is at least 1, exact_mg_cancelator.cpp:105-111)
+    double* chi_d = nullptr;
+    int32_t* egb_d = nullptr;
+    if (CU(cudaMalloc(&chi_d, MGG * sizeof(double)), "cudaMalloc") || CU(cudaMalloc(&egb_d, (size_t)p->n_exact_group_bins * sizeof(int32_t)), "cudaMalloc") ||
+        CU(cudaMemcpy(chi_d, p->chi_pdf, MGG * sizeof(double), cudaMemcpyHostToDevice), "cudaMemcpy") ||
+        CU(cudaMemcpy(egb_d, p->exact_group_bins, (size_t)p->n_exact_group_bins * sizeof(int32_t), cudaMemcpyHostToDevice), "cudaMemcpy"))
+      return bail(ABL_ERR_CUDA);
+    P.chi_pdf = chi_d;
+    P.egb = egb_d;
+    P.cancel.Ne = p->exact_group_bins[0] > 0 ? p->exact_group_bins[0] : 1;
+    h->exact_full_ready = true;
+  }
 #undef UP
   if (CU(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return bail(ABL_ERR_CUDA);
   *out = h;
@@ -1684,14 +1699,16 @@ int abl_parent_state_download(abl_handle h, uint64_t n, double* ux, double* uy, 
 int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity, uint64_t rng2[2], void* stream) {
   if (!h || !bank_dev || !rng2) return ABL_ERR_INVALID;
   const DevMesh3& m = h->P.cancel;
-  if (m.present && m.kind == ABL_CANCEL_EXACT)
-    return fail(h, ABL_ERR_UNSUPPORTED, "cancelator type exact: not provided on the device (the reference's own ExactMGCancelator runs over "
-                                        "abl_parent_info_download / abl_parent_state_download)");
-  if (!m.present || m.kind != ABL_CANCEL_BASIC_EXACT) return fail(h, ABL_ERR_INVALID, "problem has no basic-exact cancelator");
+  const bool full = m.present && m.kind == ABL_CANCEL_EXACT;  // ExactMGCancelator: averages always, Sobol points, no engine offsets
+  if (full && !h->exact_full_ready)
+    return fail(h, ABL_ERR_INVALID, "cancelator type exact needs abl_problem::chi_pdf and exact_group_bins");
+  if (full && (double)m.Nx * m.Ny * m.Nz * m.Ne >= 2147483647.)
+    return fail(h, ABL_ERR_UNSUPPORTED, "cancelator type exact: more than 2^31 bins");
+  if (!m.present || (m.kind != ABL_CANCEL_BASIC_EXACT && !full)) return fail(h, ABL_ERR_INVALID, "problem has no exact cancelator");
   const uint64_t n = bank_dev->n;
   if (n != h->parent_n) return fail(h, ABL_ERR_INVALID, "abl_cancel_exact_device takes the fission bank of the last transport call");
   if (rng2[1] != 5ULL) return fail(h, ABL_ERR_UNSUPPORTED, "the global engine must be on stream 2 (settings::initialize_global_rng)");
-  if (m.beta == ABL_BETA_ZERO || n == 0) return ABL_OK;  // perform_cancellation / get_new_particles return at once (:458, :559)
+  if ((!full && m.beta == ABL_BETA_ZERO) || n == 0) return ABL_OK;  // perform_cancellation / get_new_particles return at once (:458, :559)
   ABL_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = use_stream(h, (cudaStream_t)stream);
   const BankView b = view_of(bank_dev);
@@ -1712,14 +1729,15 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
     release();
     return ABL_ERR_CUDA;
   }
-  exact_prepare_kernel<<<grid_for(h, n, 128), 128, 0, s>>>(h->P, m, b, h->parent_info, h->parent_cap, n, key_d, mat_d, f_d, fmin_d);
+  if (full) exact_full_prepare_kernel<<<grid_for(h, n, 128), 128, 0, s>>>(h->P, m, b, h->parent_info, h->parent_cap, n, key_d, mat_d, f_d);
+  else exact_prepare_kernel<<<grid_for(h, n, 128), 128, 0, s>>>(h->P, m, b, h->parent_info, h->parent_cap, n, key_d, mat_d, f_d, fmin_d);
   h->launches++;
   std::vector<int32_t> key(n), mat(n);
   std::vector<double> f(n), fmin(n), w(n), w2(n, 0.);
   bool bad = CU(cudaMemcpyAsync(key.data(), key_d, n * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
              CU(cudaMemcpyAsync(mat.data(), mat_d, n * 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
              CU(cudaMemcpyAsync(f.data(), f_d, n * 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
-             CU(cudaMemcpyAsync(fmin.data(), fmin_d, n * 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
+             (!full && CU(cudaMemcpyAsync(fmin.data(), fmin_d, n * 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync")) ||
              CU(cudaMemcpyAsync(w.data(), b.wgt, n * 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
              (b.wgt2 && CU(cudaMemcpyAsync(w2.data(), b.wgt2, n * 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync")) ||
              CU(cudaStreamSynchronize(s), "exact_prepare_kernel");
@@ -1739,9 +1757,10 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
   // bins with two or more particles of both signs are the ones cancel_bin works on
   struct Work { abl_context::ExactBin* bin; int key, mat; bool w1, w2; uint64_t first, advance; int can_cancel; };
   std::vector<Work> work;
-  const bool averages = m.beta == ABL_BETA_AVERAGE_F || m.beta == ABL_BETA_AVERAGE_G;
+  const bool averages = full || m.beta == ABL_BETA_AVERAGE_F || m.beta == ABL_BETA_AVERAGE_G;
+  const int beta = full ? ABL_BETA_AVERAGE_G : m.beta;  // ExactMGCancelator::get_beta is the average-g rule (:237-247)
   uint64_t seed_advance = 0;  // per-bin offsets into the global engine's sequence (:476-490)
-  const uint64_t max_rn_per_part = (uint64_t)m.nsamples * 100ULL * (m.beta == ABL_BETA_AVERAGE_G ? 2 : 1);
+  const uint64_t max_rn_per_part = (uint64_t)m.nsamples * 100ULL * (beta == ABL_BETA_AVERAGE_G ? 2 : 1);
   std::vector<unsigned long long> rows;
   for (auto& kb : bins)
     for (auto& mb : kb.second) {
@@ -1776,10 +1795,14 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
       for (int i = 2; i <= 52; i++) d1[i] = (2 * d1[i - 1]) ^ d1[i - 1];
       d2[1] = 1; d2[2] = 3;
       for (int i = 3; i <= 52; i++) d2[i] = (2 * d2[i - 1]) ^ (4 * d2[i - 2]) ^ d2[i - 2];
+      unsigned long long d3[53];
+      d3[1] = 1; d3[2] = 3; d3[3] = 1;
+      for (int i = 4; i <= 52; i++) d3[i] = (4 * d3[i - 2]) ^ (8 * d3[i - 3]) ^ d3[i - 3];
       for (int i = 1; i <= 52; i++) {
         SM.m[0][i - 1] = 1ULL << (52 - i);
         SM.m[1][i - 1] = d1[i] << (52 - i);
         SM.m[2][i - 1] = d2[i] << (52 - i);
+        SM.m[3][i - 1] = d3[i] << (52 - i);
       }
     }
     unsigned long long *desc_d = nullptr, *rows_d = nullptr;
@@ -1799,8 +1822,12 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
                 CU(cudaMemcpyAsync(rows_d, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync") ||
                 CU(cudaMemsetAsync(af_d, 0, rows.size() * 8, s), "cudaMemsetAsync") || CU(cudaMemsetAsync(afi_d, 0, rows.size() * 8, s), "cudaMemsetAsync");
     if (!bad2) {
-      exact_average_kernel<<<grid_for(h, work.size(), 64), 64, 0, s>>>(h->P, m, SM, work.size(), desc_d, rows_d, b, h->parent_info, h->parent_cap,
-                                                                       m.nsamples, m.sobol, rng2[0], af_d, afi_d, cc_d);
+      if (full)
+        exact_full_average_kernel<<<grid_for(h, work.size(), 64), 64, 0, s>>>(h->P, m, SM, work.size(), desc_d, rows_d, h->parent_info, h->parent_cap,
+                                                                              m.nsamples, af_d, afi_d, cc_d);
+      else
+        exact_average_kernel<<<grid_for(h, work.size(), 64), 64, 0, s>>>(h->P, m, SM, work.size(), desc_d, rows_d, b, h->parent_info, h->parent_cap,
+                                                                         m.nsamples, m.sobol, rng2[0], af_d, afi_d, cc_d);
       h->launches++;
       bad2 = CU(cudaMemcpyAsync(avg_f.data(), af_d, rows.size() * 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
              CU(cudaMemcpyAsync(avg_finv.data(), afi_d, rows.size() * 8, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync") ||
@@ -1817,7 +1844,7 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
     abl_context::ExactBin& bin = *wk.bin;
     const size_t np = bin.particles.size();
     double sum_c = 0., sum_c_wgt = 0., sum_c_wgt2 = 0.;
-    if (m.beta == ABL_BETA_AVERAGE_G && wk.can_cancel) {
+    if (beta == ABL_BETA_AVERAGE_G && wk.can_cancel) {
       auto C = [](double fa, double fi) { return 1. / (2. * fa * fi - 1.); };
       for (size_t e = 0; e < np; e++) sum_c += C(avg_f[wk.first + e], avg_finv[wk.first + e]);
       for (size_t e = 0; e < np; e++) {
@@ -1832,12 +1859,12 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
       for (size_t e = 0; e < np; e++) {
         const uint64_t i = bin.particles[e];
         const double wgt = wv[i];
-        if (wgt == 0.) break;
+        if (wgt == 0. && !full) break;  // (BasicExactMGCancelator::cancel_bin only, :432-434)
         double B = 0.;
         if (wk.can_cancel) {
-          if (m.beta == ABL_BETA_MINIMUM) {
+          if (beta == ABL_BETA_MINIMUM) {
             B = fmin[i];
-          } else if (m.beta == ABL_BETA_AVERAGE_F) {
+          } else if (beta == ABL_BETA_AVERAGE_F) {
             const double fa = avg_f[wk.first + e];
             const double N = static_cast<double>(np);
             const double W = first ? bin.W : bin.W2;
@@ -1858,7 +1885,7 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
       }
     }
   }
-  if (m.beta != ABL_BETA_MINIMUM) {  // rng.advance(seed_advance) (:552-554)
+  if (!full && m.beta != ABL_BETA_MINIMUM) {  // rng.advance(seed_advance) (:552-554; ExactMGCancelator does not touch the engine here)
     uint64_t acc_mult = 1, acc_plus = 0, cur_mult = 6364136223846793005ULL, cur_plus = rng2[1], delta = seed_advance;
     while (delta > 0) {
       if (delta & 1) {
@@ -1904,8 +1931,12 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
     unsigned long long st[3] = {rng2[0], 0, 0};
     ABL_CUDA(h, cudaMemcpyAsync(list_d, list.data(), list.size() * 8, cudaMemcpyHostToDevice, s));
     ABL_CUDA(h, cudaMemcpyAsync(st_d, st, 3 * 8, cudaMemcpyHostToDevice, s));
-    exact_uniform_kernel<<<1, 1, 0, s>>>(h->P, m, list_d, list.size() / 5, st_d, b, n, capacity, h->parent_info, h->parent_cap,
-                                          reinterpret_cast<unsigned long long*>(st_d + 1));
+    if (full)
+      exact_full_uniform_kernel<<<1, 1, 0, s>>>(h->P, m, list_d, list.size() / 5, st_d, b, n, capacity, h->parent_info, h->parent_cap,
+                                                 reinterpret_cast<unsigned long long*>(st_d + 1));
+    else
+      exact_uniform_kernel<<<1, 1, 0, s>>>(h->P, m, list_d, list.size() / 5, st_d, b, n, capacity, h->parent_info, h->parent_cap,
+                                            reinterpret_cast<unsigned long long*>(st_d + 1));
     h->launches++;
     ABL_CUDA(h, cudaMemcpyAsync(st, st_d, 3 * 8, cudaMemcpyDeviceToHost, s));
     ABL_CUDA(h, cudaStreamSynchronize(s));

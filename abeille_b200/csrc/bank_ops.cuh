@@ -571,8 +571,8 @@ __global__ void exact_uniform_kernel(const DevProblem P, const DevMesh3 m, const
 // offset --, then for every particle of the bin the mean of f and of 1/f over those points.  desc rows: key, material, first row
 // in `rows`, count, engine offset.  A bin that cannot place a point within 100 tries per sample is marked (can_cancel = false).
 #define ABL_EXACT_MAX_SAMPLES 64
-struct SobolMatrices3 {
-  unsigned long long m[3][52];
+struct SobolMatrices3 {  // (four dimensions: the `type: exact` cancelator takes the energy group of a point from the fourth)
+  unsigned long long m[4][52];
 };
 __device__ __forceinline__ double sobol_sample(const SobolMatrices3& M, unsigned long long index, int dim) {
   unsigned long long result = 0;
@@ -645,6 +645,221 @@ __global__ void __launch_bounds__(64) exact_average_kernel(const DevProblem P, c
       avg_finv[first + e] = sum_f_inv / (double)nsamples;
     }
   }
+}
+
+// ---- ExactMGCancelator (src/exact_mg_cancelator.cpp; cancelator: {type: exact}) ------------------------------------------------
+// The same division of labour as for basic-exact: per-particle densities and per-bin averages here, the unordered_map of bins
+// replayed on the host.  The density of a site also carries the parent's scattering-angle pdf towards the site and, with a chi
+// matrix, the chi element (get_f :215-235); bins are keyed by mesh cell and energy bin (get_key :115-152).
+__device__ __forceinline__ int group_closed(const DevProblem& P, double E) {  // settings::group (src/settings.cpp:95-104)
+  for (int g = 0; g < P.G; g++)
+    if (P.ebounds[g] <= E && E <= P.ebounds[g + 1]) return g;
+  return 0;
+}
+__device__ inline double angle_pdf_at(const DevProblem& P, int mat, int g1, int g3, double x) {  // MGAngleDistribution::pdf (:62-75)
+  const abl_angle_table at = P.angle[((size_t)mat * P.G + g1) * P.G + g3];
+  if (at.n < 0) {  // the default isotropic table {-1, 1} / {0.5, 0.5}
+    if (x < -1. || x > 1. || x == -1. || x == 1.) return 0.5;
+    return 0. * (x - -1.) + 0.5;
+  }
+  const double* mu = P.amu + at.offset;
+  const double* pdf = P.apdf + at.offset;
+  if (x < mu[0]) return pdf[0];
+  if (x > mu[at.n - 1]) return pdf[at.n - 1];
+  int lo = 0, len = at.n;
+  while (len > 0) {  // std::lower_bound
+    const int half = len >> 1;
+    if (mu[lo + half] < x) {
+      lo = lo + half + 1;
+      len = len - half - 1;
+    } else {
+      len = half;
+    }
+  }
+  if (x == mu[lo]) return pdf[lo];
+  lo--;
+  const double m = (pdf[lo + 1] - pdf[lo]) / (mu[lo + 1] - mu[lo]);
+  return m * (x - mu[lo]) + pdf[lo];
+}
+__device__ inline double exact_full_f(const DevProblem& P, int mat, double r1x, double r1y, double r1z, double u1x, double u1y, double u1z,
+                                      int g1, int g3, double r4x, double r4y, double r4z, int g4, double Esmp) {
+  const double dx = r4x - r1x, dy = r4y - r1y, dz = r4z - r1z;
+  const double d = sqrt(dx * dx + dy * dy + dz * dz);
+  const V3 u = make_direction(dx, dy, dz);
+  const double mu = u.x * u1x + u.y * u1y + u.z * u1z;
+  const double pdf_mu = angle_pdf_at(P, mat, g1, g3, mu);
+  const double pdf_chi = P.chi_matrix ? P.chi_pdf[((size_t)mat * P.G + g3) * P.G + g4] : 1.;
+  return (pdf_mu * pdf_chi / (d * d)) * det_exp(-Esmp * d);
+}
+// energy bin of group g: the first bin that lists it; the number of bins when none does (get_key :133-147)
+__device__ inline int exact_energy_bin(const int32_t* egb, int g, bool& found) {
+  const int nbins = egb ? egb[0] : 0;
+  int pos = 1;
+  found = false;
+  for (int e = 0; e < nbins; e++) {
+    const int cnt = egb[pos];
+    for (int q = 0; q < cnt; q++)
+      if (egb[pos + 1 + q] == g) { found = true; return e; }
+    pos += 1 + cnt;
+  }
+  return nbins;
+}
+__device__ inline const int32_t* exact_bin_groups(const int32_t* egb, int e, int& cnt) {
+  int pos = 1;
+  for (int q = 0; q < e; q++) pos += 1 + egb[pos];
+  cnt = egb[pos];
+  return egb + pos + 1;
+}
+__global__ void __launch_bounds__(128) exact_full_prepare_kernel(const DevProblem P, const DevMesh3 m, BankView b, const double* __restrict__ parent,
+                                                                 uint64_t pcap, uint64_t n, int32_t* __restrict__ key, int32_t* __restrict__ mat,
+                                                                 double* __restrict__ f) {
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) {
+    const double x = b.x[q], y = b.y[q], z = b.z[q];
+    const int g4 = group_closed(P, b.E[q]);
+    key[q] = -1;
+    if (x < m.lowx || x > m.hix || y < m.lowy || y > m.hiy || z < m.lowz || z > m.hiz) continue;
+    const long long i = (long long)floor((x - m.lowx) / m.dx), j = (long long)floor((y - m.lowy) / m.dy), k = (long long)floor((z - m.lowz) / m.dz);
+    bool found;
+    const int e = exact_energy_bin(P.egb, g4, found);
+    if (!found && P.chi_matrix) continue;
+    key[q] = (int32_t)(e + (long long)m.Ne * (k + (long long)m.Nz * (j + (long long)m.Ny * i)));
+    Cursor c;
+    c.err = 0;
+    c.token = 0;
+    cursor_restart(P, c, V3{x, y, z}, V3{1., 0., 0.});
+    const int mt = c.cell < 0 ? -1 : c.mat;
+    mat[q] = mt;
+    if (mt < 0) { f[q] = 0.; continue; }
+    const int g1 = group_closed(P, parent[7 * pcap + q]), g3 = group_closed(P, parent[8 * pcap + q]);
+    f[q] = exact_full_f(P, mt, parent[q], parent[pcap + q], parent[2 * pcap + q], parent[4 * pcap + q], parent[5 * pcap + q], parent[6 * pcap + q],
+                        g1, g3, x, y, z, g4, parent[3 * pcap + q]);
+  }
+}
+// compute_averages (:296-364): one thread per bin that holds both signs.  desc rows: key, material, first row in `rows`, count, unused.
+__global__ void __launch_bounds__(64) exact_full_average_kernel(const DevProblem P, const DevMesh3 m, const SobolMatrices3 SM, uint64_t nbins,
+                                                                const unsigned long long* __restrict__ desc, const unsigned long long* __restrict__ rows,
+                                                                const double* __restrict__ parent, uint64_t pcap, int nsamples,
+                                                                double* __restrict__ avg_f, double* __restrict__ avg_finv, int32_t* __restrict__ can_cancel) {
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nbins; q += (uint64_t)gridDim.x * blockDim.x) {
+    const long long hk = (long long)desc[5 * q];
+    const int mat = (int)(long long)desc[5 * q + 1];
+    const uint64_t first = desc[5 * q + 2], count = desc[5 * q + 3];
+    const int e = (int)(hk % m.Ne);
+    const long long k = (hk / m.Ne) % m.Nz, j = (hk / ((long long)m.Ne * m.Nz)) % m.Ny, i = hk / ((long long)m.Ne * m.Nz * m.Ny);
+    const double Xl = m.lowx + (double)i * m.dx, Yl = m.lowy + (double)j * m.dy, Zl = m.lowz + (double)k * m.dz;
+    double rs[ABL_EXACT_MAX_SAMPLES][3];
+    int gs[ABL_EXACT_MAX_SAMPLES];
+    unsigned long long sobol_index = 0;
+    bool ok_all = mat >= 0;
+    for (int sidx = 0; sidx < nsamples && ok_all; sidx++) {  // sample_point :249-294
+      bool ok = false;
+      for (int t = 0; t < 100 && !ok; t++) {
+        const double x = Xl + sobol_sample(SM, sobol_index, 0) * m.dx;
+        const double y = Yl + sobol_sample(SM, sobol_index, 1) * m.dy;
+        const double z = Zl + sobol_sample(SM, sobol_index, 2) * m.dz;
+        sobol_index++;
+        Cursor c;
+        c.err = 0;
+        c.token = 0;
+        cursor_restart(P, c, V3{x, y, z}, V3{1., 0., 0.});
+        ok = (c.cell < 0 ? -1 : c.mat) == mat;
+        rs[sidx][0] = x; rs[sidx][1] = y; rs[sidx][2] = z;
+      }
+      gs[sidx] = 0;
+      if (ok && P.chi_matrix) {
+        const double xi = sobol_sample(SM, sobol_index - 1, 3);
+        int cnt;
+        const int32_t* groups = exact_bin_groups(P.egb, e, cnt);
+        gs[sidx] = groups[(int)floor(xi * (double)cnt)];
+      }
+      ok_all = ok;
+    }
+    for (uint64_t pe = 0; pe < count && ok_all; pe++) {
+      const uint64_t row = rows[first + pe];
+      const int g1 = group_closed(P, parent[7 * pcap + row]), g3 = group_closed(P, parent[8 * pcap + row]);
+      double sum_f = 0., sum_f_inv = 0.;
+      for (int sidx = 0; sidx < nsamples; sidx++) {
+        const double f = exact_full_f(P, mat, parent[row], parent[pcap + row], parent[2 * pcap + row], parent[4 * pcap + row], parent[5 * pcap + row],
+                                      parent[6 * pcap + row], g1, g3, rs[sidx][0], rs[sidx][1], rs[sidx][2], gs[sidx], parent[3 * pcap + row]);
+        if (f == 0.) {  // "bin.can_cancel = false; return;"
+          ok_all = false;
+          break;
+        }
+        sum_f += f;
+        sum_f_inv += 1. / f;
+      }
+      avg_f[first + pe] = sum_f / (double)nsamples;
+      avg_finv[first + pe] = sum_f_inv / (double)nsamples;
+    }
+    can_cancel[q] = ok_all ? 1 : 0;
+  }
+}
+// get_new_particles (:511-590), one thread.  list rows: key, material, N, w, w2.
+__global__ void exact_full_uniform_kernel(const DevProblem P, const DevMesh3 m, const double* __restrict__ list, uint64_t nlist, uint64_t* rng_state,
+                                          BankView b, uint64_t first, uint64_t capacity, double* parent, uint64_t pcap, unsigned long long* out2) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint64_t rng = *rng_state;
+  uint64_t row = first;
+  unsigned long long failed = 0;
+  for (uint64_t en = 0; en < nlist && !failed; en++) {
+    const long long hk = (long long)list[5 * en];
+    const int mat = (int)list[5 * en + 1];
+    const uint64_t N = (uint64_t)list[5 * en + 2];
+    const double w = list[5 * en + 3], w2 = list[5 * en + 4];
+    const int e = (int)(hk % m.Ne);
+    const long long k = (hk / m.Ne) % m.Nz, j = (hk / ((long long)m.Ne * m.Nz)) % m.Ny, i = hk / ((long long)m.Ne * m.Nz * m.Ny);
+    const double Xl = m.lowx + (double)i * m.dx, Yl = m.lowy + (double)j * m.dy, Zl = m.lowz + (double)k * m.dz;
+    for (uint64_t q = 0; q < N; q++) {
+      V3 r{0., 0., 0.};
+      bool ok = false;
+      for (int t = 0; t < 100 && !ok; t++) {
+        const double x = Xl + GlobalStreamMath::rand(rng) * m.dx;
+        const double y = Yl + GlobalStreamMath::rand(rng) * m.dy;
+        const double z = Zl + GlobalStreamMath::rand(rng) * m.dz;
+        r = V3{x, y, z};
+        Cursor c;
+        c.err = 0;
+        c.token = 0;
+        cursor_restart(P, c, r, V3{1., 0., 0.});
+        ok = (c.cell < 0 ? -1 : c.mat) == mat;
+      }
+      if (!ok) {
+        failed = 1;
+        break;
+      }
+      int e_index = 0;
+      if (P.chi_matrix) {
+        const double xi_E = GlobalStreamMath::rand(rng);
+        int cnt;
+        const int32_t* groups = exact_bin_groups(P.egb, e, cnt);
+        e_index = groups[(int)floor(xi_E * (double)cnt)];
+      } else if (P.G >= 2) {
+        e_index = rng_discrete<GlobalStreamMath>(rng, P.chi_cp + (size_t)mat * P.G * P.G, P.G);  // RNG::discrete(rng, nuclide->chi()[0])
+      }
+      // Direction u_smp(2 rand - 1, 2 pi rand): g++ evaluates the two arguments from the right, so phi takes the first draw
+      double phi = 2. * ABL_PI * GlobalStreamMath::rand(rng);
+      double mu = 2. * GlobalStreamMath::rand(rng) - 1.;
+      if (mu < -1.) mu = -1.; else if (mu > 1.) mu = 1.;
+      if (phi < 0.) phi = 0.; else if (phi > 2 * ABL_PI) phi = 2 * ABL_PI;
+      double sn, cs;
+      det_sincos(phi, &sn, &cs);
+      const V3 dir = make_direction(sqrt(1. - mu * mu) * cs, sqrt(1. - mu * mu) * sn, mu);
+      if (row < capacity) {
+        b.x[row] = r.x; b.y[row] = r.y; b.z[row] = r.z;
+        b.ux[row] = dir.x; b.uy[row] = dir.y; b.uz[row] = dir.z;
+        b.E[row] = ldt(&P.gmid[e_index]);
+        b.wgt[row] = w;
+        if (b.wgt2) b.wgt2[row] = w2;
+        b.id_a[row] = 0; b.id_b[row] = 0; b.id_c[row] = 0;
+        if (row < pcap)
+          for (int f = 0; f < ABL_PARENT_FIELDS; f++) parent[f * pcap + row] = f == 4 ? 1. : 0.;
+      }
+      row++;
+    }
+  }
+  *rng_state = rng;
+  out2[0] = row;
+  out2[1] = failed;
 }
 
 }  // namespace abl

@@ -91,6 +91,9 @@ struct DevProblem {
   int32_t M;
   const double *Et, *Ea, *Ef, *Es, *nu, *nud, *speed;
   const double *chi_cp, *ps_cp;  // [M*G*G]
+  const double* chi_pdf;         // [M*G*G] normalised chi rows (type: exact cancelator) or null
+  const int32_t* egb;            // its energy bins: {number of bins, per bin: size, groups} or null
+  int32_t chi_matrix;            // settings::chi_matrix
   const abl_angle_table* angle;  // [M*G*G]
   const double *amu, *apdf, *acdf;
   const int32_t* dg_off;  // [M+1]

@@ -222,6 +222,7 @@ MGNuclide make_mg_nuclide(const Node& mat, uint32_t id, const Settings& st) {
   if (fissile) {
     const Node& c = mat["chi"];
     if (!c || !c.IsSequence() || (c.size() != 1 && c.size() != G)) fatal_error("Invalid chi matrix entry in material " + sid + ".");
+    n.chi_is_matrix = c.size() == G;
     for (size_t ei = 0; ei < G; ei++) {
       n.chi[ei] = doubles(c[c.size() == G ? ei : 0], G, "chi row (material " + sid + ")");
       for (double v : n.chi[ei])
@@ -615,6 +616,7 @@ Problem Problem::from_yaml(const Node& input) {
     if (P.material_id_to_indx.count(id)) fatal_error("Material id " + std::to_string(id) + " appears more than once.");
     P.material_id_to_indx[id] = static_cast<int>(P.materials.size());
     P.materials.push_back(make_mg_nuclide(mat, id, P.settings));
+    if (P.materials.back().chi_is_matrix) P.settings.chi_matrix = true;
   }
   P.settings.min_energy = P.settings.energy_bounds.front();  // parser.cpp:158-168, mg_nuclide.cpp:425-427
   P.settings.max_energy = P.settings.energy_bounds.back();
@@ -695,6 +697,21 @@ Problem Problem::from_yaml(const Node& input) {
         fatal_error("exact cancelators may not be used with surface-tracking.");
       P.cancelator = make_mesh_spec(c, "exact MG cancelator");
       P.cancelator.kind = ABL_CANCEL_EXACT;
+      if (c["group-bins"] && c["group-bins"].IsSequence()) {
+        for (size_t b = 0; b < c["group-bins"].size(); b++) {
+          std::vector<int> bin;
+          for (size_t q = 0; q < c["group-bins"][b].size(); q++) {
+            const long long g = c["group-bins"][b][q].as_int();
+            if (g < 0 || g >= P.settings.ngroups) fatal_error("Invalid group index in group-bins of the exact MG cancelator.");
+            bin.push_back(static_cast<int>(g));
+          }
+          P.cancelator.group_bins.push_back(bin);
+        }
+      } else if (P.settings.chi_matrix) {
+        fatal_error("Chi matrix is used, but no group_bins provided.\nImpossible to have exact cancellation.");
+      }
+      if (c["n-samples"]) P.cancelator.n_samples = static_cast<int>(c["n-samples"].as_int());
+      if (P.cancelator.n_samples <= 0) fatal_error("n-samples must be greater than zero.");
     } else {
     if (type != "approximate") fatal_error("Cancelator type \"" + type + "\" is not provided by the B200 backend (approximate, basic-exact, exact).");
     P.cancelator = make_mesh_spec(c, "approximate mesh cancelator");
@@ -997,6 +1014,18 @@ void Problem::flatten(FlatProblem& F) const {
   p.cancelator.beta = cancelator.beta;
   p.cancelator.sobol = cancelator.sobol;
   p.cancelator.n_samples = cancelator.n_samples;
+  F.chi_pdf.clear();
+  for (const auto& n : materials)
+    for (size_t g = 0; g < G; g++) F.chi_pdf.insert(F.chi_pdf.end(), n.chi[g].begin(), n.chi[g].end());
+  F.exact_group_bins.assign(1, static_cast<int32_t>(cancelator.group_bins.size()));
+  for (const auto& b : cancelator.group_bins) {
+    F.exact_group_bins.push_back(static_cast<int32_t>(b.size()));
+    F.exact_group_bins.insert(F.exact_group_bins.end(), b.begin(), b.end());
+  }
+  p.chi_pdf = F.chi_pdf.data();
+  p.exact_group_bins = F.exact_group_bins.data();
+  p.n_exact_group_bins = static_cast<int32_t>(F.exact_group_bins.size());
+  p.chi_matrix = st.chi_matrix ? 1 : 0;
   if (F.tally_eb.empty()) F.tally_eb.push_back(0.);
   p.ntallies = static_cast<int32_t>(F.tallies.size());
   p.n_tally_energy_bounds = static_cast<int32_t>(F.tally_eb.size());

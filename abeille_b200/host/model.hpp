@@ -21,6 +21,7 @@ struct Settings {  // include/utils/settings.hpp:54-128, defaults src/settings.c
   int mode = ABL_MODE_K_EIGENVALUE;
   bool fixed_source = false;  // simulation: modified-fixed-source (transport is the k-eigenvalue one; no ignored generations)
   bool branchless_splitting = false, branchless_combing = true, branchless_material = true;  // settings.cpp:87-89
+  bool chi_matrix = false;  // a fissile material gave one chi row per group (mg_nuclide.cpp:836-850)
   int tracking = ABL_TRACK_SURFACE;
   int ngroups = 0;
   std::vector<double> energy_bounds;
@@ -77,6 +78,7 @@ struct MGNuclide {  // src/mg_nuclide.cpp:30-118,579-922 ; one per material in M
   std::vector<std::vector<AngleTable>> angles;
   std::vector<double> P_delayed_group, decay_constants;
   bool fissile = false;
+  bool chi_is_matrix = false;  // one chi row per group was given (sets settings::chi_matrix, mg_nuclide.cpp:808-810)
 };
 
 struct Source {
@@ -97,6 +99,7 @@ struct MeshSpec {
   std::array<int, 3> N{1, 1, 1};
   std::array<double, 3> low{0, 0, 0}, hi{0, 0, 0};
   std::vector<double> energy_edges;
+  std::vector<std::vector<int>> group_bins;  // type: exact (exact_mg_cancelator.cpp:634-662)
   int sobol = 1, n_samples = 10;  // basic-exact defaults (basic_exact_mg_cancelator.cpp:670-686)
   int kind = 0, beta = 0;  // cancelator: ABL_CANCEL_*, ABL_BETA_* (src/cancelator.cpp:40-57, basic_exact_mg_cancelator.cpp:650-668)
 };
@@ -106,7 +109,8 @@ struct FlatProblem {
   abl_problem p{};
   std::vector<abl_surface> surfaces;
   std::vector<abl_cell> cells;
-  std::vector<int32_t> rpn, universe_cells, lattice_tiles, delayed_offset, fissile;
+  std::vector<int32_t> rpn, universe_cells, lattice_tiles, delayed_offset, fissile, exact_group_bins;
+  std::vector<double> chi_pdf;
   std::vector<abl_universe> universes;
   std::vector<double> Et, Ea, Ef, Es, nu, nud, speeds, chi_cdf, scatter_cdf, amu, apdf, acdf, dcdf, dlambda, smp, tally_eb;
   std::vector<abl_angle_table> angle;

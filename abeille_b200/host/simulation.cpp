@@ -367,9 +367,7 @@ void PowerIterator::run_host(int ngenerations, int nignored) {
   for (const auto& t : problem.tallies)
     if (t.flat.estimator == ABL_EST_SOURCE && !t.flat.noise_source) have_source_tally = true;
   const bool cancel = st.regional_cancellation && problem.cancelator.present;
-  const bool exact = cancel && problem.cancelator.kind == ABL_CANCEL_BASIC_EXACT;
-  if (cancel && problem.cancelator.kind == ABL_CANCEL_EXACT)
-    fatal_error("cancelator type exact is not run by this driver (the reference's own ExactMGCancelator runs over the GPU transporter).");
+  const bool exact = cancel && (problem.cancelator.kind == ABL_CANCEL_BASIC_EXACT || problem.cancelator.kind == ABL_CANCEL_EXACT);
   // branchless-k-eigenvalue: the normalised bank is combed before the source tally sees it (branchless_power_iterator.cpp:358-384)
   const bool comb = st.mode == ABL_MODE_BRANCHLESS && st.branchless_combing;
   const auto t0 = std::chrono::steady_clock::now();
@@ -498,7 +496,8 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
   const uint64_t N0 = bank_.size();
   // (the first generation runs with k_col = 1, so it banks about k_inf sites per particle: tallies.cpp:48)
   uint64_t cap = abl_fission_capacity_hint(h, std::max<uint64_t>(N0, static_cast<uint64_t>(st.nparticles)), 0., std::min(1., tallies->kcol()));
-  const bool exact_cancel = st.regional_cancellation && problem.cancelator.present && problem.cancelator.kind == ABL_CANCEL_BASIC_EXACT;
+  const bool exact_cancel = st.regional_cancellation && problem.cancelator.present &&
+                            (problem.cancelator.kind == ABL_CANCEL_BASIC_EXACT || problem.cancelator.kind == ABL_CANCEL_EXACT);
   if (exact_cancel) cap = 2 * cap + 4096;  // room for the uniform particles the cancelator appends
   // cur / nxt are views (n and id_c change per generation); *_alloc keep the full allocations
   DeviceBank cur, nxt;
@@ -533,9 +532,7 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
   std::vector<double> ebins(nebins + 1, 0.);
   if (have_entropy) check(h, abl_device_alloc(h, (nebins + 1) * sizeof(double), reinterpret_cast<void**>(&ebins_dev)), "abl_device_alloc");
   const bool cancel = st.regional_cancellation && problem.cancelator.present;
-  const bool exact = cancel && problem.cancelator.kind == ABL_CANCEL_BASIC_EXACT;
-  if (cancel && problem.cancelator.kind == ABL_CANCEL_EXACT)
-    fatal_error("cancelator type exact is not run by this driver (the reference's own ExactMGCancelator runs over the GPU transporter).");
+  const bool exact = cancel && (problem.cancelator.kind == ABL_CANCEL_BASIC_EXACT || problem.cancelator.kind == ABL_CANCEL_EXACT);
   const bool comb = st.mode == ABL_MODE_BRANCHLESS && st.branchless_combing;
   const auto t0 = std::chrono::steady_clock::now();
   for (int g = 1; g <= ngenerations; g++) {

@@ -136,9 +136,7 @@ typedef struct abl_mesh3 {       /* entropy mesh (entropy.cpp) / approximate can
   int32_t sobol, n_samples;      /* ... average-f / average-g: Sobol points (else engine draws), points per bin (<= 64) */
 } abl_mesh3;
 enum { ABL_CANCEL_APPROXIMATE = 1, ABL_CANCEL_BASIC_EXACT = 2,
-       ABL_CANCEL_EXACT = 3 };  /* src/cancelator.cpp:40-72.  EXACT (src/exact_mg_cancelator.cpp): the kernels keep what it reads
-                                   (abl_parent_info_download, abl_parent_state_download) for the reference's own cancelator;
-                                   abl_cancel_exact_device itself provides BASIC_EXACT */
+       ABL_CANCEL_EXACT = 3 };  /* src/cancelator.cpp:40-72.  EXACT: src/exact_mg_cancelator.cpp */
 enum { ABL_BETA_ZERO = 0, ABL_BETA_MINIMUM = 1, ABL_BETA_AVERAGE_F = 2, ABL_BETA_AVERAGE_G = 3 };  /* BasicExactMGCancelator::BetaMode */
 
 enum { ABL_NOISE_SQUARE_OSCILLATION = 0, ABL_NOISE_FLAT_VIBRATION = 1 };
@@ -189,6 +187,13 @@ typedef struct abl_problem {
   /* noise sources (noise mode; noise_maker.cpp:39-58) */
   int32_t n_noise_sources, pad2_;
   const abl_noise_source* noise_sources;
+  /* `type: exact` cancelator (src/exact_mg_cancelator.cpp): the normalised chi rows themselves ([M*G*G], MGNuclide::chi()), whether
+   * any fissile material gave a chi matrix (settings::chi_matrix; one group counts), and the energy bins as a flat list
+   * {number of bins, then per bin: its size, its groups}; NULL / 0 when the problem has no such cancelator.
+   * Its mesh is `cancelator` (kind ABL_CANCEL_EXACT, n_samples). */
+  const double* chi_pdf;
+  const int32_t* exact_group_bins;
+  int32_t n_exact_group_bins, chi_matrix;
 } abl_problem;
 
 /* ---- banks --------------------------------------------------------------------------------------

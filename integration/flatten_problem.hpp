@@ -52,7 +52,8 @@ struct FlatProblem {  // owns what the abl_problem points into
   std::vector<abl_surface> surfaces;
   std::vector<abl_cell> cells;
   std::vector<abl_universe> universes;
-  std::vector<int32_t> rpn, universe_cells, lattice_tiles, delayed_offset, fissile;
+  std::vector<int32_t> rpn, universe_cells, lattice_tiles, delayed_offset, fissile, exact_group_bins;
+  std::vector<double> chi_pdf;
   std::vector<double> energy_bounds, Et, Ea, Ef, Es, nu, nud, speeds, chi_cdf, scatter_cdf, amu, apdf, acdf, dcdf, dlambda, smp, tally_eb;
   std::vector<abl_angle_table> angle;
   std::vector<abl_mesh_tally> tallies;
@@ -316,11 +317,27 @@ inline void flatten_problem(FlatProblem& F, const Tallies& tallies, const Cancel
     p.cancelator.beta = static_cast<int32_t>(be->beta_mode);
     p.cancelator.sobol = be->use_sobol ? 1 : 0;
     p.cancelator.n_samples = static_cast<int32_t>(std::min<uint32_t>(be->N_SAMPLES, 64));
-  } else if (dynamic_cast<const ExactMGCancelator*>(cancelator)) {
+  } else if (const auto* ex = dynamic_cast<const ExactMGCancelator*>(cancelator)) {
+    using Key = ExactMGCancelator::Key;  // (its mesh lives in static members)
     p.cancelator.present = 1;
-    p.cancelator.kind = ABL_CANCEL_EXACT;  // (its mesh stays with the reference's object: only the kind matters to the kernels)
-    p.cancelator.N[0] = p.cancelator.N[1] = p.cancelator.N[2] = 1;
-    p.cancelator.hi[0] = p.cancelator.hi[1] = p.cancelator.hi[2] = 1.;
+    p.cancelator.kind = ABL_CANCEL_EXACT;
+    for (int k = 0; k < 3; k++) p.cancelator.N[k] = static_cast<int32_t>(Key::shape[static_cast<size_t>(k)]);
+    p.cancelator.low[0] = Key::r_low.x(); p.cancelator.low[1] = Key::r_low.y(); p.cancelator.low[2] = Key::r_low.z();
+    p.cancelator.hi[0] = Key::r_hi.x(); p.cancelator.hi[1] = Key::r_hi.y(); p.cancelator.hi[2] = Key::r_hi.z();
+    p.cancelator.n_samples = static_cast<int32_t>(std::min<uint32_t>(ex->N_SAMPLES, 64));
+    F.exact_group_bins.assign(1, static_cast<int32_t>(Key::group_bins.size()));
+    for (const auto& b : Key::group_bins) {
+      F.exact_group_bins.push_back(static_cast<int32_t>(b.size()));
+      for (std::size_t g : b) F.exact_group_bins.push_back(static_cast<int32_t>(g));
+    }
+    for (Material* m : mats) {
+      const auto* n = static_cast<const MGNuclide*>(m->components()[0].nuclide.get());
+      for (size_t g = 0; g < G; g++) F.chi_pdf.insert(F.chi_pdf.end(), n->chi_[g].begin(), n->chi_[g].end());
+    }
+    p.chi_pdf = F.chi_pdf.data();
+    p.exact_group_bins = F.exact_group_bins.data();
+    p.n_exact_group_bins = static_cast<int32_t>(F.exact_group_bins.size());
+    p.chi_matrix = settings::chi_matrix ? 1 : 0;
   }
 }
 

@@ -281,7 +281,7 @@ class Oracle:
         assert m == n, (m, n)
         return out
 
-    def cancel_exact(self, bank: dict, parent_info: np.ndarray, rng2):
+    def cancel_exact(self, bank: dict, parent_info: np.ndarray, rng2, parent_state: np.ndarray | None = None):
         """PowerIterator::perform_regional_cancellation with the deck's BasicExactMGCancelator: weights reduced in place, uniform
         particles appended.  Returns (bank, (state, increment) of the global engine afterwards)."""
         n = len(bank["x"])
@@ -289,8 +289,9 @@ class Oracle:
         r = np.array(rng2, dtype=np.uint64)
         nout = C.c_uint64(0)
         pi = np.ascontiguousarray(parent_info, dtype=np.float64)
-        if lib().orc_cancel_exact(self.h, C.byref(_as_struct(bank)), pi.ctypes.data_as(_PD), C.byref(_as_struct(out)), C.byref(nout),
-                                  r.ctypes.data_as(_PU64)) != 0:
+        ps = np.ascontiguousarray(parent_state, dtype=np.float64) if parent_state is not None else None
+        if lib().orc_cancel_exact_state(self.h, C.byref(_as_struct(bank)), pi.ctypes.data_as(_PD), ps.ctypes.data_as(_PD) if ps is not None else None,
+                                        C.byref(_as_struct(out)), C.byref(nout), r.ctypes.data_as(_PU64)) != 0:
             raise RuntimeError("oracle: " + self._err())
         m = int(nout.value)
         return {k: v[:m].copy() for k, v in out.items()}, (int(r[0]), int(r[1]))

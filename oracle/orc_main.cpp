@@ -2365,7 +2365,12 @@ uint64_t orc_last_parent_state(void* h, double* out6n, uint64_t n) {
 
 // PowerIterator::perform_regional_cancellation with the exact cancelator on a bank + its parent info ([n][4]); rng2 = {state,
 // increment} of settings::rng.  out->n = capacity on entry; the uniform particles follow the n input rows.
+int orc_cancel_exact_state(void* h, const orc_bank* in, const double* parent4n, const double* state6n, orc_bank* out, uint64_t* n_out, uint64_t* rng2);
 int orc_cancel_exact(void* h, const orc_bank* in, const double* parent4n, orc_bank* out, uint64_t* n_out, uint64_t* rng2) {
+  return orc_cancel_exact_state(h, in, parent4n, nullptr, out, n_out, rng2);
+}
+// ... state6n ([n][6], may be NULL): parents_previous_direction, _previous_energy, _energy, _was_virtual, which `type: exact` reads
+int orc_cancel_exact_state(void* h, const orc_bank* in, const double* parent4n, const double* state6n, orc_bank* out, uint64_t* n_out, uint64_t* rng2) {
   Problem& P = *static_cast<Problem*>(h);
   try {
     std::vector<BankedParticle> v(in->n);
@@ -2375,6 +2380,12 @@ int orc_cancel_exact(void* h, const orc_bank* in, const double* parent4n, orc_ba
       v[i].parent_history_id = in->id_a[i]; v[i].parent_daughter_id = in->id_b[i]; v[i].family_id = in->id_c[i];
       v[i].parents_previous_position = {parent4n[4 * i], parent4n[4 * i + 1], parent4n[4 * i + 2]};
       v[i].Esmp_parent = parent4n[4 * i + 3];
+      if (state6n) {
+        v[i].parents_previous_direction = {state6n[6 * i], state6n[6 * i + 1], state6n[6 * i + 2]};
+        v[i].parents_previous_previous_energy = state6n[6 * i + 3];
+        v[i].parents_previous_energy = state6n[6 * i + 4];
+        v[i].parents_previous_was_virtual = state6n[6 * i + 5] != 0.;
+      }
     }
     P.global_rng.state = rng2[0]; P.global_rng.inc = rng2[1];
     perform_exact_cancellation(P, v);

@@ -787,10 +787,11 @@ def test_branchless_power_iteration_matches_oracle(ab, oracle_api, tmp_path, dec
             assert all(abs(int(v) - n) <= 1 for v in g["nbank"][1:])
 
 
-@pytest.mark.parametrize("deck", ["PUa-cube_carter_exact_min.yaml", "PUa-cube_carter_exact_avgf.yaml", "PUa-cube_carter_exact_avgg.yaml"])
+@pytest.mark.parametrize("deck", ["PUa-cube_carter_exact_min.yaml", "PUa-cube_carter_exact_avgf.yaml", "PUa-cube_carter_exact_avgg.yaml",
+                                  "PUa-cube_carter_exact_full.yaml"])
 def test_exact_cancellation_matches_oracle(ab, oracle_api, tmp_path, deck):
     """cancelator: {type: basic-exact} (src/basic_exact_mg_cancelator.cpp; beta minimum, average-f with points drawn from the global
-    engine, average-g with Sobol points) under carter tracking with negative weights: the per-site parent data the kernels keep for
+    engine, average-g with Sobol points) and {type: exact} (src/exact_mg_cancelator.cpp) under carter tracking with negative weights: the per-site parent data the kernels keep for
     it (BankedParticle::parents_previous_position through reflections, Esmp_parent), the cancelled weights, the appended uniform
     particles and the engine state afterwards, all bit for bit against the oracle (whose driver is pinned on the reference's,
     tests/test_reference_pins.py); then whole simulations on both host paths."""
@@ -812,13 +813,13 @@ def test_exact_cancellation_matches_oracle(ab, oracle_api, tmp_path, deck):
     assert gm == om
     gpar = gpu.parent_info(gm)
     assert np.array_equal(gpar, opar)
-    ostate = orc.last_parent_state(om)           # previous direction, energy before the last scatter, energy, was_virtual
-    assert np.array_equal(gpu.parent_state(gm), ostate)
-    assert 0.02 < ostate[:, 5].mean() < 0.98 and (ostate[:, 0] != 1.0).any()
+    opst = orc.last_parent_state(om)             # previous direction, energy before the last scatter, energy, was_virtual
+    assert np.array_equal(gpu.parent_state(gm), opst)
+    assert 0.02 < opst[:, 5].mean() < 0.98 and (opst[:, 0] != 1.0).any()
     if "min" in deck:
         assert np.abs(opar[:, :3]).max() > 5.0   # mirror images behind the reflective faces of the +-5 cm cube
     state = ab.global_rng_state()
-    ocb, ostate = orc.cancel_exact({k: v.copy() for k, v in ofis.items()}, opar, state)
+    ocb, ostate = orc.cancel_exact({k: v.copy() for k, v in ofis.items()}, opar, state, orc.last_parent_state(om))
     gn, gstate = gpu.cancel_exact_device(dev_out, gm, state)
     assert gn == len(ocb["x"]) and gn > om and gstate == ostate
     for k in ("x", "y", "z", "ux", "uy", "uz", "E", "wgt"):
@@ -842,10 +843,11 @@ def test_exact_cancellation_in_bins_that_hold_several_materials(ab, oracle_api, 
     keyed by (mesh cell, material), whole simulations against the oracle (bank sizes -- uniform particles included -- exactly)."""
     n, ngen, nign = 8000, 5, 2
     ov = {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}}
-    for resident in (True, False):
-        orc, gpu = _pair(ab, oracle_api, tmp_path, "c5g7_carter_exact_avgg.yaml", ov, name=f"c5e{int(resident)}.yaml")
-        o = orc.run_power_iteration(ngen, nign)
-        g = gpu.run_power_iteration(ngen, nign, resident=resident)
-        assert np.array_equal(g["nbank"], o["nbank"]), (resident, g["nbank"], o["nbank"])
-        assert np.allclose(g["kcol"], o["kcol"], rtol=1e-10)
-        assert np.allclose(g["entropy"], o["entropy"], rtol=1e-10)
+    for deck in ("c5g7_carter_exact_avgg.yaml", "c5g7_carter_exact_full.yaml"):   # ... and the same mesh under `type: exact`
+        for resident in (True, False):
+            orc, gpu = _pair(ab, oracle_api, tmp_path, deck, ov, name=f"c5e{int(resident)}.yaml")
+            o = orc.run_power_iteration(ngen, nign)
+            g = gpu.run_power_iteration(ngen, nign, resident=resident)
+            assert np.array_equal(g["nbank"], o["nbank"]), (deck, resident, g["nbank"], o["nbank"])
+            assert np.allclose(g["kcol"], o["kcol"], rtol=1e-10)
+            assert np.allclose(g["entropy"], o["entropy"], rtol=1e-10)

@@ -139,9 +139,6 @@ def test_power_iteration_reproduces_the_references_power_iterator(ab, golden, tm
     migration area and entropy, and the final averages and errors, to 1e-9 relative (floating-point sums are taken in a
     different order on the device; the histories themselves are the same)."""
     fname, n, ngen, nign = ref_pins.ALL_PI_CASES[ci]
-    if ci in ref_pins.EXACT_FULL_PI_RANGE:
-        pytest.skip("cancelator type exact runs as the reference's own code over the GPU transporter "
-                    "(test_references_power_iterator_drives_the_gpu_transporter); this repo's driver provides basic-exact")
     if ci >= len(ref_pins.POWER_ITERATION_CASES):  # the implicit-leakage tracker's and the branchless iterator's simulations
         golden = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", ref_pins.pi_golden_file(ci))))
     name = fname.split(".")[0]
