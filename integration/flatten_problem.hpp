@@ -8,9 +8,9 @@
  *   materials (one MGNuclide each, atoms_bcm = 1) (include/materials/material.hpp, mg_nuclide.hpp, mg_angle_distribution.hpp)
  *   the Tallies object's collision / track-length mesh tallies (include/simulation/tallies.hpp, mesh_tally.hpp)
  *   the cancelator, when it is one the kernels must keep the parents' data for (BasicExactMGCancelator)
+ *   the NoiseMaker's square-oscillation and flat-vibration sources, in a noise run
  * Sources, the entropy mesh and the approximate cancelator mesh are not flattened: Transporter::transport does not use them (the
- * reference's drivers sample, bin and cancel on their side of the boundary).  Noise sources are not flattened either (a noise deck
- * goes through the YAML constructor of GPUTransporter).
+ * reference's drivers sample, bin and cancel on their side of the boundary).
  *
  * The reference keeps most of this in private members without accessors; this header reads them directly and is compiled with
  * -fno-access-control in oracle/_ref (a maintainer would add the accessors or a friend declaration).  Tested in two ways: the
@@ -29,6 +29,9 @@
 #include <simulation/basic_exact_mg_cancelator.hpp>
 #include <simulation/cancelator.hpp>
 #include <simulation/exact_mg_cancelator.hpp>
+#include <simulation/flat_vibration_noise_source.hpp>
+#include <simulation/noise_maker.hpp>
+#include <simulation/square_oscillation_noise_source.hpp>
 #include <simulation/collision_mesh_tally.hpp>
 #include <simulation/tallies.hpp>
 #include <simulation/track_length_mesh_tally.hpp>
@@ -57,6 +60,7 @@ struct FlatProblem {  // owns what the abl_problem points into
   std::vector<double> energy_bounds, Et, Ea, Ef, Es, nu, nud, speeds, chi_cdf, scatter_cdf, amu, apdf, acdf, dcdf, dlambda, smp, tally_eb;
   std::vector<abl_angle_table> angle;
   std::vector<abl_mesh_tally> tallies;
+  std::vector<abl_noise_source> noise_sources;
 };
 
 // std::discrete_distribution's table as RNG::discrete uses it (include/utils/rng.hpp:88-96; libstdc++ random.tcc:2655-2713):
@@ -100,7 +104,8 @@ inline abl_surface flatten_surface(const Surface& s) {
 }
 
 // cancelator: only its kind matters to the transporter (an exact cancelator makes the kernels keep the parents' data)
-inline void flatten_problem(FlatProblem& F, const Tallies& tallies, const Cancelator* cancelator) {
+// noise_maker: the NoiseMaker of a noise run (its square-oscillation and flat-vibration sources), else null
+inline void flatten_problem(FlatProblem& F, const Tallies& tallies, const Cancelator* cancelator, const NoiseMaker* noise_maker = nullptr) {
   abl_problem& p = F.p;
   p = abl_problem{};
   const size_t G = settings::ngroups;
@@ -109,7 +114,9 @@ inline void flatten_problem(FlatProblem& F, const Tallies& tallies, const Cancel
     case settings::SimulationMode::MODIFIED_FIXED_SOURCE: p.mode = ABL_MODE_K_EIGENVALUE; break;
     case settings::SimulationMode::FIXED_SOURCE: p.mode = ABL_MODE_FIXED_SOURCE; break;
     case settings::SimulationMode::BRANCHLESS_K_EIGENVALUE: p.mode = ABL_MODE_BRANCHLESS; break;
-    default: fatal_error("flatten_problem: noise decks go through the YAML constructor of GPUTransporter");
+    default:
+      p.mode = ABL_MODE_NOISE;
+      if (!noise_maker) fatal_error("flatten_problem: a noise run needs its NoiseMaker");
   }
   p.branchless_flags = (settings::branchless_material ? ABL_BRANCHLESS_MATERIAL : 0) | (settings::branchless_splitting ? ABL_BRANCHLESS_SPLITTING : 0);
   switch (settings::tracking) {
@@ -304,6 +311,36 @@ inline void flatten_problem(FlatProblem& F, const Tallies& tallies, const Cancel
   p.n_tally_energy_bounds = static_cast<int32_t>(F.tally_eb.size());
   p.tallies = F.tallies.data();
   p.tally_energy_bounds = F.tally_eb.data();
+
+  // noise sources (src/noise_maker.cpp:39-58): vibrations, then oscillations, as the NoiseMaker holds them
+  if (noise_maker) {
+    for (const auto& vs : noise_maker->vibration_noise_sources_) {
+      const auto* fv = dynamic_cast<const FlatVibrationNoiseSource*>(vs.get());
+      if (!fv) fatal_error("flatten_problem: unknown VibrationNoiseSource subclass");
+      abl_noise_source ns{};
+      ns.type = ABL_NOISE_FLAT_VIBRATION;
+      ns.low[0] = fv->low_.x(); ns.low[1] = fv->low_.y(); ns.low[2] = fv->low_.z();
+      ns.hi[0] = fv->hi_.x(); ns.hi[1] = fv->hi_.y(); ns.hi[2] = fv->hi_.z();
+      ns.angular_frequency = fv->w0_;
+      ns.basis = static_cast<int32_t>(fv->basis_);
+      ns.material_pos = material_index(fv->material_pos_.get());
+      ns.material_neg = material_index(fv->material_neg_.get());
+      F.noise_sources.push_back(ns);
+    }
+    for (const auto& os : noise_maker->oscillation_noise_sources_) {
+      const auto* so = dynamic_cast<const SquareOscillationNoiseSource*>(os.get());
+      if (!so) fatal_error("flatten_problem: unknown OscillationNoiseSource subclass");
+      abl_noise_source ns{};
+      ns.type = ABL_NOISE_SQUARE_OSCILLATION;
+      ns.low[0] = so->low_.x(); ns.low[1] = so->low_.y(); ns.low[2] = so->low_.z();
+      ns.hi[0] = so->hi_.x(); ns.hi[1] = so->hi_.y(); ns.hi[2] = so->hi_.z();
+      ns.angular_frequency = so->w0_;
+      ns.eps_total = so->eps_t_; ns.eps_fission = so->eps_f_; ns.eps_scatter = so->eps_s_;
+      F.noise_sources.push_back(ns);
+    }
+    p.n_noise_sources = static_cast<int32_t>(F.noise_sources.size());
+    p.noise_sources = F.noise_sources.data();
+  }
 
   // the cancelator's kind (the mesh itself stays on the reference's side of the boundary)
   if (const auto* be = dynamic_cast<const BasicExactMGCancelator*>(cancelator)) {

@@ -805,13 +805,15 @@ def power_iteration_through_gpu_transporter(only: int, host_library: str, yaml_d
     return out
 
 
-def noise_through_gpu_transporter(only: int, host_library: str, yaml_deck: str, device: int = 0) -> dict:
+def noise_through_gpu_transporter(only: int, host_library: str, yaml_deck: str, device: int = 0, from_objects: bool = False) -> dict:
     """The reference's own Noise::run() with its transporter replaced by GPUTransporter (integration/gpu_transporter.hpp):
     transport(bank), transport(bank, false, &noise_bank, &noise_maker) and transport(nbank, true) all through the C ABI.
     Needs a GPU; one case per process."""
     from . import deck as _deck
     fname, n, nb, nign, nskip = NOISE_DRIVER_CASES[only]
     deck = _deck.load_yaml(yaml_deck)
+    if from_objects:  # host_library is libabeille_b200.so; flatten_problem() on the reference's live objects
+        yaml_deck = ""
     L = ref_lib()
     kc, nk, fb3 = np.zeros(4096), C.c_int(0), np.zeros(3, dtype=np.uint64)
     L.ref_set_threads(C.c_int(1))

@@ -1322,11 +1322,18 @@ int ref_noise_run_gpu(const char* text, const char* host_library, const char* ya
   try {
     if (ref_problem_load(text) != 0) return 1;
     if (host_library) {
+      abl_integration::FlatProblem flat;  // yaml_deck empty: the tables come from the reference's live objects, noise sources included
+      const bool from_objects = yaml_deck == nullptr || yaml_deck[0] == 0;
+      if (from_objects) {
+        DriverParts dp = driver_parts(text);
+        abl_integration::flatten_problem(flat, *g_tallies, dp.cancelator.get(), g_noise_maker.get());
+      }
       g_tallies = std::make_shared<Tallies>(static_cast<double>(settings::nparticles));
       g_tallies->set_keff(settings::keff);
       g_tally_gen.clear();
       g_mesh_tallies.clear();
-      g_gpu_transporter = std::make_shared<GPUTransporter>(g_tallies, host_library, yaml_deck, device);
+      g_gpu_transporter = from_objects ? std::make_shared<GPUTransporter>(g_tallies, host_library, flat.p, device)
+                                       : std::make_shared<GPUTransporter>(g_tallies, host_library, yaml_deck, device);
       g_transporter = g_gpu_transporter;
     }
     omp_set_num_threads(g_threads);

@@ -257,6 +257,15 @@ def test_references_noise_driver_drives_the_gpu_transporter(ab, oracle_api, gold
     ref_k, ref_fb = golden[f"nd_{name}_kcol"], golden[f"nd_{name}_final_bank"]
     assert np.allclose(got[f"nd_{name}_kcol"], ref_k, rtol=1e-9), (got[f"nd_{name}_kcol"], ref_k)
     fb = [int(v) for v in got[f"nd_{name}_final_bank"]]
+    # ... and the same run over a transporter built from the reference's live objects (flatten_problem(): noise sources from the
+    # NoiseMaker, no YAML, no host library)
+    cuda_lib, _ = backend.lib_paths()
+    code = (f"import sys; sys.path.insert(0, {root!r}); import numpy as np; from oracle import ref_pins; "
+            f"np.savez({out!r}, **ref_pins.noise_through_gpu_transporter({ci}, {cuda_lib!r}, {str(path)!r}, from_objects=True))")
+    subprocess.run([sys.executable, "-c", code], check=True, stdout=subprocess.DEVNULL)
+    flat = dict(np.load(out))
+    # (k is a sum of atomically added block sums: equal to rounding between two runs; the counters are integers)
+    assert np.allclose(flat[f"nd_{name}_kcol"], got[f"nd_{name}_kcol"], rtol=1e-12) and [int(v) for v in flat[f"nd_{name}_final_bank"]] == fb
     orc = oracle_api.Oracle(str(path))
     o = orc.run_noise(_deck.load_yaml(str(path))["settings"])
     assert fb == [int(v) for v in o["final_bank"]], (fb, o["final_bank"])
