@@ -1160,8 +1160,8 @@ int abl_create(const abl_problem* p, int device, abl_handle* out) {
         ns[i].eps = (f.hi[f.basis] - f.low[f.basis]) / 2.;
         const double verr = ((n * w0) - w) / w;
         ns[i].harmonic = std::abs(verr) > 0.01 ? 0 : n;
-        if (ns[i].harmonic < 0 || ns[i].harmonic > 2) {  // C_R / C_L for n = 0 need asin, for n >= 3 sin / acos / exp
-          h->error = "flat-vibration noise source: only the first and second harmonic of the source frequency are implemented";
+        if (ns[i].harmonic < 0) {  // (a negative noise frequency; n = 0 cannot pass the gate above: its relative error is 1)
+          h->error = "flat-vibration noise source: negative noise frequency";
           return bail(ABL_ERR_UNSUPPORTED);
         }
       }

@@ -227,6 +227,48 @@ static __device__ ABL_HOT_CALL void det_sincos(double x, double* sn, double* cs)
 }
 
 // fdlibm e_exp.c with IEEE operations only (implicit-leakage delta tracking: P_leak = exp(-Emaj d))
+// acos, for the higher harmonics of the flat-vibration noise source (same operation sequence as orc_acos in oracle/orc_detmath.h)
+static __device__ __noinline__ double det_acos(double x) {
+  // fdlibm e_acos.c: a rational approximation of (asin(x) - x) / x^3 on [0, 0.5], the half-angle identity outside
+  const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17, pi = 3.14159265358979311600e+00,
+               pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01, pS2 = 2.01212532134862925881e-01,
+               pS3 = -4.00555345006794114027e-02, pS4 = 7.91534994289814532176e-04, pS5 = 3.47933107596021167570e-05,
+               qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00, qS3 = -6.88283971605453293030e-01,
+               qS4 = 7.70381505559019352791e-02;
+  const int32_t hx = dm_hi(x);
+  const int32_t ix = hx & 0x7fffffff;
+  if (ix >= 0x3ff00000) {  // |x| >= 1
+    if (((uint32_t)(ix - 0x3ff00000) | dm_lo(x)) == 0) return hx > 0 ? 0.0 : pi + 2.0 * pio2_lo;
+    return (x - x) / (x - x);
+  }
+  if (ix < 0x3fe00000) {  // |x| < 0.5
+    if (ix <= 0x3c600000) return pio2_hi + pio2_lo;
+    const double z = x * x;
+    const double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const double r = p / q;
+    return pio2_hi - (x - (pio2_lo - x * r));
+  } else if (hx < 0) {  // x < -0.5
+    const double z = (1.0 + x) * 0.5;
+    const double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const double s = sqrt(z);
+    const double r = p / q;
+    const double w = r * s - pio2_lo;
+    return pi - 2.0 * (s + w);
+  } else {  // x > 0.5
+    const double z = (1.0 - x) * 0.5;
+    const double s = sqrt(z);
+    const double df = __hiloint2double(__double2hiint(s), 0);
+    const double c = (z - df * df) / (s + df);
+    const double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const double r = p / q;
+    const double w = r * s + c;
+    return 2.0 * (df + w);
+  }
+}
+
 static __device__ __noinline__ double det_exp(double x) {
   const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10,
                invln2 = 1.44269504088896338700e+00, P1 = 1.66666666666666019037e-01,

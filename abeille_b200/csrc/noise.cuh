@@ -87,12 +87,21 @@ __device__ __forceinline__ Cplx delayed_factor(double wr, double wi, double lamb
   return cmul(wr, wi, lambda * lambda / denom, -lambda * w_noise / denom);
 }
 
-// FlatVibrationNoiseSource::C_R / C_L (flat_vibration_noise_source.cpp:155-192) for the harmonics 1 and 2 (abl_create
-// rejects the others); C_L == C_R for n != 0
+// FlatVibrationNoiseSource::C_R / C_L (flat_vibration_noise_source.cpp:155-192); C_L == C_R for n != 0, and n = 0 never passes
+// the frequency gate of dEt / dN.  n >= 3: (2 / n) sin(n acos(rel_diff)) exp(-i n pi / 2) -- a function call, off the usual path.
+static __device__ __noinline__ Cplx vib_C_high(int n, double rel_diff) {
+  const double dn = (double)n;
+  double sn, cs;
+  det_sincos(dn * det_acos(rel_diff), &sn, &cs);
+  const double a = (2. / dn) * sn;
+  det_sincos(-dn * ABL_PI * 0.5, &sn, &cs);  // std::exp of (-0, -n pi / 2): polar(1, -n pi / 2)
+  return Cplx{a * cs, a * sn};
+}
 __device__ __forceinline__ Cplx vib_C(const DevNoiseSrc& ns, double x) {
   double rel_diff = (x - ns.x0) / ns.eps;
   if (rel_diff > 1.) rel_diff = 1.;
   else if (rel_diff < -1.) rel_diff = -1.;
+  if (ns.harmonic >= 3) return vib_C_high(ns.harmonic, rel_diff);
   const double root = sqrt(1. - (rel_diff * rel_diff));
   if (ns.harmonic == 1) return Cplx{0., -2. * root};
   return Cplx{-2. * rel_diff * root, 0.};

@@ -505,6 +505,14 @@ def rng_discrete(seed, stride, hid, weights, ndraws):
     return out, int(nd)
 
 
+def acos_probe(x):
+    """acos of the current math mode (libm, or the deterministic sequence the kernels share)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros(len(x))
+    lib().orc_acos_eval(C.c_int(len(x)), x.ctypes.data_as(_PD), out.ctypes.data_as(_PD))
+    return out
+
+
 def math_eval(x):
     x = np.ascontiguousarray(x, dtype=np.float64)
     lg, sn, cs = np.zeros_like(x), np.zeros_like(x), np.zeros_like(x)

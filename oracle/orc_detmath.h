@@ -19,6 +19,7 @@
 #ifndef ORC_DETMATH_H
 #define ORC_DETMATH_H
 #include <stdint.h>
+#include <math.h>
 #include <string.h>
 
 static inline uint64_t orc_d2u(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
@@ -229,6 +230,48 @@ static inline void orc_sincos(double x, double* sn, double* cs) {
     default: *sn = -c; *cs = s; break;
   }
 }
+// acos, for the higher harmonics of the flat-vibration noise source (same operation sequence as det_acos in detmath.cuh)
+static inline double orc_acos(double x) {
+  // fdlibm e_acos.c: a rational approximation of (asin(x) - x) / x^3 on [0, 0.5], the half-angle identity outside
+  const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17, pi = 3.14159265358979311600e+00,
+               pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01, pS2 = 2.01212532134862925881e-01,
+               pS3 = -4.00555345006794114027e-02, pS4 = 7.91534994289814532176e-04, pS5 = 3.47933107596021167570e-05,
+               qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00, qS3 = -6.88283971605453293030e-01,
+               qS4 = 7.70381505559019352791e-02;
+  const int32_t hx = orc_hi(x);
+  const int32_t ix = hx & 0x7fffffff;
+  if (ix >= 0x3ff00000) {  // |x| >= 1
+    if (((uint32_t)(ix - 0x3ff00000) | orc_lo(x)) == 0) return hx > 0 ? 0.0 : pi + 2.0 * pio2_lo;
+    return (x - x) / (x - x);
+  }
+  if (ix < 0x3fe00000) {  // |x| < 0.5
+    if (ix <= 0x3c600000) return pio2_hi + pio2_lo;
+    const double z = x * x;
+    const double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const double r = p / q;
+    return pio2_hi - (x - (pio2_lo - x * r));
+  } else if (hx < 0) {  // x < -0.5
+    const double z = (1.0 + x) * 0.5;
+    const double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const double s = sqrt(z);
+    const double r = p / q;
+    const double w = r * s - pio2_lo;
+    return pi - 2.0 * (s + w);
+  } else {  // x > 0.5
+    const double z = (1.0 - x) * 0.5;
+    const double s = sqrt(z);
+    const double df = orc_u2d(orc_d2u(s) & 0xffffffff00000000ULL);
+    const double c = (z - df * df) / (s + df);
+    const double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    const double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    const double r = p / q;
+    const double w = r * s + c;
+    return 2.0 * (df + w);
+  }
+}
+
 static inline double orc_sin(double x) { double s, c; orc_sincos(x, &s, &c); return s; }
 static inline double orc_cos(double x) { double s, c; orc_sincos(x, &s, &c); return c; }
 #endif

@@ -50,7 +50,8 @@ static double libm_log(double x) { return std::log(x); }
 static double libm_sin(double x) { return std::sin(x); }
 static double libm_cos(double x) { return std::cos(x); }
 static double libm_exp(double x) { return std::exp(x); }
-MathFns g_math = {libm_log, libm_sin, libm_cos, libm_exp};
+static double libm_acos(double x) { return std::acos(x); }
+MathFns g_math = {libm_log, libm_sin, libm_cos, libm_exp, libm_acos};
 
 // ------------------------------------------------------------------------------------
 struct Source {  // src/source.cpp, box.cpp, point.cpp, isotropic.cpp, mono_energetic.cpp
@@ -1147,15 +1148,20 @@ static bool sqosc_on(const NoiseSource& ns, double w) {
 }
 
 // FlatVibrationNoiseSource::C_R / C_L (src/flat_vibration_noise_source.cpp:155-192) for the harmonics this restatement
-// covers (n = 1, 2; n = 0 needs asin, n >= 3 sin/acos/exp -- the shipped deck runs at the fundamental).  C_L differs from
-// C_R for n = 0 only.
+// (n = 0 cannot pass the frequency gate: its relative error is 1).  C_L differs from C_R for n = 0 only.
 static std::complex<double> vib_C(const NoiseSource& ns, uint32_t n, double x) {
   double rel_diff = (x - ns.x0) / ns.eps;
   if (rel_diff > 1.) rel_diff = 1.;
   else if (rel_diff < -1.) rel_diff = -1.;
   if (n == 1) return {0., -2. * std::sqrt(1. - (rel_diff * rel_diff))};
   if (n == 2) return {-2. * rel_diff * std::sqrt(1. - (rel_diff * rel_diff)), 0.};
-  throw std::runtime_error("oracle: flat-vibration harmonics other than 1 and 2 are not restated");
+  if (n == 0) throw std::runtime_error("oracle: the zeroth harmonic never passes the frequency gate of dEt / dN");
+  // n >= 3 (:176-179): (2 / n) sin(n acos(rel_diff)) exp(-i n pi / 2); std::exp of the complex argument (-0, -n pi / 2) is
+  // polar(exp(-0), -n pi / 2) = (cos, sin) of the imaginary part
+  const double dn = static_cast<double>(n);
+  const double a = (2. / dn) * g_math.sin(dn * g_math.acos(rel_diff));
+  const double th = -dn * PI * 0.5;
+  return a * std::complex<double>{g_math.cos(th), g_math.sin(th)};
 }
 // the frequency gate and harmonic of dEt / dN (:222-244,277-312): 0 = no component at this frequency
 static int vib_harmonic(const NoiseSource& ns, double w) {
@@ -2022,8 +2028,8 @@ static int g_math_mode = 0;
 int orc_get_math() { return g_math_mode; }
 void orc_set_math(int mode) {
   g_math_mode = mode == 0 ? 0 : 1;
-  if (mode == 0) g_math = {libm_log, libm_sin, libm_cos, libm_exp};
-  else g_math = {orc_log, orc_sin, orc_cos, orc_exp};
+  if (mode == 0) g_math = {libm_log, libm_sin, libm_cos, libm_exp, libm_acos};
+  else g_math = {orc_log, orc_sin, orc_cos, orc_exp, orc_acos};
 }
 void orc_set_threads(int n) { omp_set_num_threads(n); }
 int orc_max_threads() { return omp_get_max_threads(); }
@@ -2190,6 +2196,9 @@ double orc_rng_discrete_probe(uint64_t seed, uint64_t stride, uint64_t history_i
   auto cp = discrete_table(w, (size_t)nw);
   for (int i = 0; i < ndraws; i++) out[i] = rng_discrete(g, cp);
   return rng_rand(g);
+}
+void orc_acos_eval(int n, const double* x, double* out) {
+  for (int i = 0; i < n; i++) out[i] = g_math.acos(x[i]);
 }
 void orc_math_eval(int n, const double* x, double* lg, double* sn, double* cs) {
   for (int i = 0; i < n; i++) { lg[i] = g_math.log(x[i]); sn[i] = g_math.sin(x[i]); cs[i] = g_math.cos(x[i]); }

@@ -34,6 +34,7 @@ struct MathFns {
   double (*sin)(double);
   double (*cos)(double);
   double (*exp)(double);
+  double (*acos)(double);
 };
 extern MathFns g_math;  // selected by orc_set_math()
 

@@ -476,6 +476,8 @@ NOISE_CASES = (("noise_oscillation.yaml", 4000), ("noise_oscillation_delta.yaml"
 
 
 IMPLICIT_NOISE_CASES = (("noise_oscillation_implicit.yaml", 4000),)
+# the flat-vibration source at its third harmonic (tests/golden/ref_pins_vibration.npz, scripts/make_ref_pins_vibration.py)
+HARMONIC_NOISE_CASES = (("noise_vibration_h3.yaml", 4000),)
 
 
 def evaluate_noise(impl: str, cases=None, seed0: int = 900) -> dict:

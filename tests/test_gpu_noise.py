@@ -59,7 +59,7 @@ def _particles(fis, first):
 
 
 @pytest.mark.parametrize("deck", ["noise_oscillation.yaml", "noise_oscillation_delta.yaml", "noise_vibration.yaml",
-                                  "noise_oscillation_implicit.yaml"])
+                                  "noise_oscillation_implicit.yaml", "noise_vibration_h3.yaml"])
 def test_noise_source_and_noise_transport_bit_exact(ab, oracle_api, tmp_path, deck):
     path = write_deck(load_deck(deck), tmp_path / deck, {"settings": {"nparticles": 6000}})
     keff = float(load_deck(deck)["settings"]["keff"])

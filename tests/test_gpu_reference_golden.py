@@ -102,13 +102,26 @@ def test_kernels_reproduce_the_references_noise_mode(ab, golden, tmp_path, ci):
     generation that samples the noise source, (B) a noise generation with complex weights -- through the C++ adapter
     GPUTransporter::transport(bank, noise, &noise_bank, &noise_maker)."""
     fname, n = ref_pins.NOISE_CASES[ci]
+    _noise_case(ab, golden, tmp_path, fname, n, 900 + ci, 950 + ci)
+
+
+def test_kernels_reproduce_the_references_vibration_at_its_third_harmonic(ab, tmp_path):
+    """The flat-vibration source observed at three times its frequency (FlatVibrationNoiseSource::C_R for n >= 3: acos, sin and the
+    complex exponential, src/flat_vibration_noise_source.cpp:176-179; scripts/make_ref_pins_vibration.py)."""
+    gold = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pins_vibration.npz")))
+    fname, n = ref_pins.HARMONIC_NOISE_CASES[0]
+    _noise_case(ab, gold, tmp_path, fname, n, 1500, 1550)
+    assert len(gold["noise_noise_vibration_h3_A_source"]) > 20
+
+
+def _noise_case(ab, golden, tmp_path, fname, n, seed_bank, seed_w2):
     name = fname.split(".")[0]
     deck = load_deck(fname)
     path = write_deck(deck, tmp_path / fname, {"settings": {"nparticles": n}})
     deck["settings"]["nparticles"] = n
     keff = float(deck["settings"].get("keff", 1.0))
-    r, u, E, w, hid = ref_pins.transport_bank(deck, n, 900 + ci, False)
-    w2 = np.random.default_rng(950 + ci).uniform(-0.8, 0.8, n)
+    r, u, E, w, hid = ref_pins.transport_bank(deck, n, seed_bank, False)
+    w2 = np.random.default_rng(seed_w2).uniform(-0.8, 0.8, n)
     gpu = ab.Backend(path, 0)
     for phase, noise, sample, wb in (("A", False, True, np.zeros(n)), ("B", True, False, w2)):
         bank = {k: np.ascontiguousarray(v) for k, v in zip(("x", "y", "z"), r.T)}
