@@ -29,7 +29,7 @@ ABI_SYMBOLS = (
     "abl_bank_scale_weights_device", "abl_bank_to_particles_device", "abl_entropy_bin_device",
     "abl_score_source_device", "abl_cancel_device", "abl_cancel_accumulate_device", "abl_cancel_apply_device",
     "abl_cancel_bins_device", "abl_cancel_exact_device", "abl_parent_info_download", "abl_parent_state_download", "abl_bank_alloc_device", "abl_bank_free_device",
-    "abl_bank_upload", "abl_bank_download", "abl_device_alloc", "abl_device_free", "abl_device_zero",
+    "abl_bank_upload", "abl_bank_download", "abl_bank_gather_device", "abl_device_alloc", "abl_device_free", "abl_device_zero",
     "abl_device_read", "abl_find_cells", "abl_rng_probe", "abl_math_probe", "abl_surface_probe", "abl_set_sampling_xs", "abl_fission_capacity_hint")
 
 

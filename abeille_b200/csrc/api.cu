@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
@@ -83,6 +84,7 @@ struct abl_context {
     std::vector<uint64_t> particles;
   };
   std::unordered_map<int, std::unordered_map<int, ExactBin>> exact_bins;
+  std::vector<int32_t> exact_slot_of_key;  // dense key -> slot table of abl_cancel_exact_device (all -1 between calls)
   bool exact_full_ready = false;  // kind ABL_CANCEL_EXACT with its tables (chi rows, energy bins) on the device
   int nm_blocks_per_sm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   int implicit_blocks_per_sm[3] = {0, 0, 0};  // implicit-leakage delta tracking: per-lane kernel in modes 0 | 1 | 2
@@ -1672,6 +1674,28 @@ int abl_cancel_device(abl_handle h, abl_bank* bank_dev, void* stream) {
   return abl_cancel_apply_device(h, bank_dev, stream);
 }
 
+int abl_bank_gather_device(abl_handle h, const abl_bank* src_dev, const uint32_t* rows_host, const double* wgts_host, uint64_t n,
+                           abl_bank* dst_dev, void* stream) {
+  if (!h || !src_dev || !dst_dev || (n && !rows_host)) return ABL_ERR_INVALID;
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  dst_dev->n = n;
+  if (n == 0) return ABL_OK;
+  uint32_t* rows_d = nullptr;
+  double* wgts_d = nullptr;
+  ABL_CUDA(h, cudaMalloc(&rows_d, n * sizeof(uint32_t)));
+  if (wgts_host) ABL_CUDA(h, cudaMalloc(&wgts_d, n * sizeof(double)));
+  ABL_CUDA(h, cudaMemcpyAsync(rows_d, rows_host, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  if (wgts_host) ABL_CUDA(h, cudaMemcpyAsync(wgts_d, wgts_host, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  bank_gather_kernel<<<grid_for(h, n, 256), 256, 0, s>>>(view_of(src_dev), rows_d, wgts_d, n, view_of(dst_dev));
+  h->launches++;
+  ABL_CUDA(h, cudaGetLastError());
+  ABL_CUDA(h, cudaStreamSynchronize(s));
+  cudaFree(rows_d);
+  if (wgts_d) cudaFree(wgts_d);
+  return ABL_OK;
+}
+
 // ---- BasicExactMGCancelator ------------------------------------------------------------------------------------------------------
 int abl_parent_info_download(abl_handle h, uint64_t n, double* x, double* y, double* z, double* esmp) {
   if (!h) return ABL_ERR_INVALID;
@@ -1700,6 +1724,11 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
   if (!h || !bank_dev || !rng2) return ABL_ERR_INVALID;
   const DevMesh3& m = h->P.cancel;
   const bool full = m.present && m.kind == ABL_CANCEL_EXACT;  // ExactMGCancelator: averages always, Sobol points, no engine offsets
+  const bool timing = getenv("ABEILLE_B200_EXACT_TIMING") != nullptr;  // (development aid: where a call spends its time)
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+  const auto t_start = now();
+  double t_cols = 0., t_bins = 0., t_avg = 0., t_cancel = 0.;
   if (full && !h->exact_full_ready)
     return fail(h, ABL_ERR_INVALID, "cancelator type exact needs abl_problem::chi_pdf and exact_group_bins");
   if (full && (double)m.Nx * m.Ny * m.Nz * m.Ne >= 2147483647.)
@@ -1743,17 +1772,55 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
              CU(cudaStreamSynchronize(s), "exact_prepare_kernel");
   release();
   if (bad) return ABL_ERR_CUDA;
+  t_cols = ms_since(t_start);
   // (2) the bins, replayed in the reference's order (add_particle :68-108, perform_cancellation :457-555, cancel_bin :408-455)
+  // The maps see exactly the insertions the reference's add_particle makes (a key when it first appears, a material when it first
+  // appears under its key) in the same order, so they are walked in the same order afterwards; the per-particle lookups go through
+  // a dense table key -> slot instead of the hash tables (node addresses of an unordered_map survive its rehashes).
   auto& bins = h->exact_bins;
+  struct KeySlot {
+    std::unordered_map<int, abl_context::ExactBin>* inner;
+    std::vector<std::pair<int, abl_context::ExactBin*>> mats;
+  };
+  std::vector<KeySlot> slots;
+  const uint64_t total_keys = (uint64_t)m.Nx * m.Ny * m.Nz * (full ? (uint64_t)m.Ne : 1ULL);
+  std::vector<int32_t>& slot_of_key = h->exact_slot_of_key;
+  if (slot_of_key.size() < total_keys) slot_of_key.assign(total_keys, -1);
+  std::vector<int32_t> touched_keys;
   for (uint64_t i = 0; i < n; i++) {
-    if (key[i] < 0) continue;
-    if (bins.find(key[i]) == bins.end()) bins[key[i]] = std::unordered_map<int, abl_context::ExactBin>();
-    if (bins[key[i]].find(mat[i]) == bins[key[i]].end()) bins[key[i]][mat[i]] = abl_context::ExactBin();
-    abl_context::ExactBin& bin = bins[key[i]][mat[i]];
-    bin.particles.push_back(i);
-    bin.W += w[i];
-    bin.W2 += w2[i];
+    const int32_t k = key[i];
+    if (k < 0) continue;
+    abl_context::ExactBin* bin = nullptr;
+    if ((uint64_t)k < total_keys) {
+      int32_t sl = slot_of_key[(size_t)k];
+      if (sl < 0) {
+        sl = (int32_t)slots.size();
+        slot_of_key[(size_t)k] = sl;
+        touched_keys.push_back(k);
+        auto it = bins.find(k);  // (cannot be there: clear()ed at the end of every call; kept for the shape of add_particle)
+        if (it == bins.end()) it = bins.emplace(k, std::unordered_map<int, abl_context::ExactBin>()).first;
+        slots.push_back(KeySlot{&it->second, {}});
+      }
+      KeySlot& ks = slots[(size_t)sl];
+      for (auto& mp : ks.mats)
+        if (mp.first == mat[i]) { bin = mp.second; break; }
+      if (!bin) {
+        bin = &ks.inner->emplace(mat[i], abl_context::ExactBin()).first->second;
+        ks.mats.emplace_back(mat[i], bin);
+      }
+    } else {  // (a site exactly on the upper face of the `type: exact` mesh: an index one past the end, as in the reference)
+      auto it = bins.find(k);
+      if (it == bins.end()) it = bins.emplace(k, std::unordered_map<int, abl_context::ExactBin>()).first;
+      auto jt = it->second.find(mat[i]);
+      if (jt == it->second.end()) jt = it->second.emplace(mat[i], abl_context::ExactBin()).first;
+      bin = &jt->second;
+    }
+    bin->particles.push_back(i);
+    bin->W += w[i];
+    bin->W2 += w2[i];
   }
+  for (int32_t k : touched_keys) slot_of_key[(size_t)k] = -1;
+  t_bins = ms_since(t_start);
   // bins with two or more particles of both signs are the ones cancel_bin works on
   struct Work { abl_context::ExactBin* bin; int key, mat; bool w1, w2; uint64_t first, advance; int can_cancel; };
   std::vector<Work> work;
@@ -1838,6 +1905,7 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
     if (bad2) return ABL_ERR_CUDA;
     for (size_t q = 0; q < work.size(); q++) work[q].can_cancel = cc[q];
   }
+  t_avg = ms_since(t_start);
   // cancel_bin (:408-455) with get_beta (:366-406), particle by particle in bank order
   bool touched = false, touched2 = false;
   for (Work& wk : work) {
@@ -1898,6 +1966,7 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
     }
     rng2[0] = acc_mult * rng2[0] + acc_plus;
   }
+  t_cancel = ms_since(t_start);
   // (3) get_new_particles (:557-617): which bins emit how many uniform particles, in the map's order
   std::vector<double> list;
   uint64_t n_new = 0;
@@ -1931,17 +2000,24 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
     unsigned long long st[3] = {rng2[0], 0, 0};
     ABL_CUDA(h, cudaMemcpyAsync(list_d, list.data(), list.size() * 8, cudaMemcpyHostToDevice, s));
     ABL_CUDA(h, cudaMemcpyAsync(st_d, st, 3 * 8, cudaMemcpyHostToDevice, s));
+    // (one warp: every lane draws the particle it would own if all before it took one position try -- bank_ops.cuh)
+    std::vector<unsigned long long> cum(list.size() / 5 + 1, 0);
+    for (size_t e = 0; e < list.size() / 5; e++) cum[e + 1] = cum[e] + (unsigned long long)list[5 * e + 2];
+    unsigned long long* cum_d = nullptr;
+    ABL_CUDA(h, cudaMalloc(&cum_d, cum.size() * 8));
+    ABL_CUDA(h, cudaMemcpyAsync(cum_d, cum.data(), cum.size() * 8, cudaMemcpyHostToDevice, s));
     if (full)
-      exact_full_uniform_kernel<<<1, 1, 0, s>>>(h->P, m, list_d, list.size() / 5, st_d, b, n, capacity, h->parent_info, h->parent_cap,
-                                                 reinterpret_cast<unsigned long long*>(st_d + 1));
+      exact_uniform_warp_kernel<true><<<1, 32, 0, s>>>(h->P, m, list_d, cum_d, list.size() / 5, n_new, st_d, b, n, capacity, h->parent_info,
+                                                       h->parent_cap, reinterpret_cast<unsigned long long*>(st_d + 1));
     else
-      exact_uniform_kernel<<<1, 1, 0, s>>>(h->P, m, list_d, list.size() / 5, st_d, b, n, capacity, h->parent_info, h->parent_cap,
-                                            reinterpret_cast<unsigned long long*>(st_d + 1));
+      exact_uniform_warp_kernel<false><<<1, 32, 0, s>>>(h->P, m, list_d, cum_d, list.size() / 5, n_new, st_d, b, n, capacity, h->parent_info,
+                                                        h->parent_cap, reinterpret_cast<unsigned long long*>(st_d + 1));
     h->launches++;
     ABL_CUDA(h, cudaMemcpyAsync(st, st_d, 3 * 8, cudaMemcpyDeviceToHost, s));
     ABL_CUDA(h, cudaStreamSynchronize(s));
     cudaFree(list_d);
     cudaFree(st_d);
+    cudaFree(cum_d);
     if (st[2]) return fail(h, ABL_ERR_LOST, "Couldn't sample position for uniform particle.");
     rng2[0] = st[0];
     bank_dev->n = st[1];
@@ -1949,6 +2025,9 @@ int abl_cancel_exact_device(abl_handle h, abl_bank* bank_dev, uint64_t capacity,
   } else {
     ABL_CUDA(h, cudaStreamSynchronize(s));
   }
+  if (timing)
+    fprintf(stderr, "abl_cancel_exact_device: n %llu, +%llu uniform; columns %.1f ms, bins %.1f, averages %.1f, cancel %.1f, total %.1f ms\n",
+            (unsigned long long)n, (unsigned long long)n_new, t_cols, t_bins - t_cols, t_avg - t_bins, t_cancel - t_avg, ms_since(t_start));
   return ABL_OK;
 }
 

@@ -146,6 +146,20 @@ __global__ void __launch_bounds__(256) place_parent_info_kernel(const double* __
   }
 }
 
+// dst row k = src row rows[k]; wgt from wgts when given (abl_bank_gather_device)
+__global__ void __launch_bounds__(256) bank_gather_kernel(BankView src, const uint32_t* __restrict__ rows, const double* __restrict__ wgts,
+                                                          uint64_t n, BankView dst) {
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = rows[k];
+    dst.x[k] = src.x[r]; dst.y[k] = src.y[r]; dst.z[k] = src.z[r];
+    dst.ux[k] = src.ux[r]; dst.uy[k] = src.uy[r]; dst.uz[k] = src.uz[r];
+    dst.E[k] = src.E[r];
+    dst.wgt[k] = wgts ? wgts[k] : src.wgt[r];
+    if (dst.wgt2) dst.wgt2[k] = src.wgt2 ? src.wgt2[r] : 0.;
+    dst.id_a[k] = src.id_a[r]; dst.id_b[k] = src.id_b[r]; dst.id_c[k] = src.id_c[r];
+  }
+}
+
 // ---- weights ------------------------------------------------------------------------------------------------------
 // out[0..3] += Npos, Nneg, Wpos, Wneg   (Wneg accumulated as a positive number, as the reference does)
 __global__ void __launch_bounds__(256) weight_stats_kernel(const double* __restrict__ w, uint64_t n, double* out) {
@@ -507,65 +521,6 @@ struct GlobalStreamMath {
   static __device__ __forceinline__ double sqrt_(double a) { return sqrt(a); }
 };
 
-// get_new_particles (:557-617): the uniform particles of every bin that gathered cancelled weight, drawn one after the other from
-// the global engine -- position by rejection on the bin's material (up to 100 tries), then MGNuclide::sample_fission(0, +z, group
-// 0, P_delayed 0).  One thread: every draw depends on how many the particle before it took.  list rows: key, material, N, w, w2.
-__global__ void exact_uniform_kernel(const DevProblem P, const DevMesh3 m, const double* __restrict__ list, uint64_t nlist, uint64_t* rng_state,
-                                     BankView b, uint64_t first, uint64_t capacity, double* parent, uint64_t pcap, unsigned long long* out2) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  uint64_t rng = *rng_state;
-  uint64_t row = first;
-  unsigned long long failed = 0;
-  for (uint64_t e = 0; e < nlist && !failed; e++) {
-    const int key = (int)list[5 * e], mat = (int)list[5 * e + 1];
-    const uint64_t N = (uint64_t)list[5 * e + 2];
-    const double w = list[5 * e + 3], w2 = list[5 * e + 4];
-    const int k = key % m.Nz, j = (key / m.Nz) % m.Ny, i = key / (m.Nz * m.Ny);
-    const double Xl = m.lowx + i * m.dx, Yl = m.lowy + j * m.dy, Zl = m.lowz + k * m.dz;
-    for (uint64_t q = 0; q < N; q++) {
-      V3 r{0., 0., 0.};
-      bool ok = false;
-      for (int t = 0; t < 100 && !ok; t++) {
-        const double x = Xl + GlobalStreamMath::rand(rng) * m.dx;
-        const double y = Yl + GlobalStreamMath::rand(rng) * m.dy;
-        const double z = Zl + GlobalStreamMath::rand(rng) * m.dz;
-        r = V3{x, y, z};
-        Cursor c;
-        c.err = 0;
-        c.token = 0;
-        cursor_restart(P, c, r, V3{1., 0., 0.});
-        ok = (c.cell < 0 ? -1 : c.mat) == mat;
-      }
-      if (!ok) {  // "Couldn't sample position for uniform particle."
-        failed = 1;
-        break;
-      }
-      const int mg = mat * P.G;
-      int ei = 0;
-      if (P.G >= 2) ei = rng_discrete<GlobalStreamMath>(rng, P.chi_cp + (size_t)mg * P.G, P.G);
-      const double mu = 2. * GlobalStreamMath::rand(rng) - 1.;
-      const double phi = 2. * ABL_PI * GlobalStreamMath::rand(rng);
-      const V3 dir = rotate_dir<GlobalStreamMath>(V3{0., 0., 1.}, mu, phi);
-      (void)GlobalStreamMath::rand(rng);  // the delayed-neutron draw against P_delayed = 0
-      if (row < capacity) {
-        b.x[row] = r.x; b.y[row] = r.y; b.z[row] = r.z;
-        b.ux[row] = dir.x; b.uy[row] = dir.y; b.uz[row] = dir.z;
-        b.E[row] = ldt(&P.gmid[ei]);
-        b.wgt[row] = w;
-        if (b.wgt2) b.wgt2[row] = w2;
-        b.id_a[row] = 0; b.id_b[row] = 0; b.id_c[row] = 0;
-        if (row < pcap) {  // a default-constructed BankedParticle's fields (particle.hpp:52-57)
-          for (int q = 0; q < ABL_PARENT_FIELDS; q++) parent[q * pcap + row] = q == 4 ? 1. : 0.;
-        }
-      }
-      row++;
-    }
-  }
-  *rng_state = rng;
-  out2[0] = row;
-  out2[1] = failed;
-}
-
 // get_averages / get_averages_sobol (:264-364) for the bins that need them, one thread per bin: n_samples points of the bin that
 // lie in the bin's material -- from the Sobol sequence (restarted in every bin) or from the global engine advanced to the bin's
 // offset --, then for every particle of the bin the mean of f and of 1/f over those points.  desc rows: key, material, first row
@@ -794,25 +749,82 @@ __global__ void __launch_bounds__(64) exact_full_average_kernel(const DevProblem
     can_cancel[q] = ok_all ? 1 : 0;
   }
 }
-// get_new_particles (:511-590), one thread.  list rows: key, material, N, w, w2.
-__global__ void exact_full_uniform_kernel(const DevProblem P, const DevMesh3 m, const double* __restrict__ list, uint64_t nlist, uint64_t* rng_state,
-                                          BankView b, uint64_t first, uint64_t capacity, double* parent, uint64_t pcap, unsigned long long* out2) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  uint64_t rng = *rng_state;
-  uint64_t row = first;
+// get_new_particles of both exact cancelators on one warp.  The uniform particles are drawn one after the other from the one global
+// engine, and how many draws a particle takes depends on how many position tries it needs -- but almost every particle needs one
+// (its bin holds its material almost everywhere).  So lane l assumes that the l particles before it took one try each, jumps the
+// engine to its own offset and draws its particle; the lanes up to the first one whose first try missed are right and are
+// committed, that lane finishes its particle serially, and the next round starts behind it.  The bank is the reference's,
+// particle for particle.  cum: exclusive prefix sums of the list's N column (uniform particles before every entry).
+template <bool FULL>
+__global__ void __launch_bounds__(32) exact_uniform_warp_kernel(const DevProblem P, const DevMesh3 m, const double* __restrict__ list,
+                                                                const unsigned long long* __restrict__ cum, uint64_t nlist, uint64_t total,
+                                                                uint64_t* rng_state, BankView b, uint64_t first, uint64_t capacity,
+                                                                double* parent, uint64_t pcap, unsigned long long* out2) {
+  const int lane = threadIdx.x;
+  // engine outputs one particle consumes when its first position try hits: 3 position draws, the energy draw (if any), the two
+  // direction draws and, for basic-exact (MGNuclide::sample_fission), the delayed-neutron draw; two outputs per draw
+  const int energy_draw = FULL ? ((P.chi_matrix || P.G >= 2) ? 1 : 0) : (P.G >= 2 ? 1 : 0);
+  const uint64_t D2 = 2ULL * (uint64_t)(3 + energy_draw + 2 + (FULL ? 0 : 1));
+  uint64_t rng_base = *rng_state;
+  uint64_t base_q = 0;
   unsigned long long failed = 0;
-  for (uint64_t en = 0; en < nlist && !failed; en++) {
-    const long long hk = (long long)list[5 * en];
-    const int mat = (int)list[5 * en + 1];
-    const uint64_t N = (uint64_t)list[5 * en + 2];
-    const double w = list[5 * en + 3], w2 = list[5 * en + 4];
-    const int e = (int)(hk % m.Ne);
-    const long long k = (hk / m.Ne) % m.Nz, j = (hk / ((long long)m.Ne * m.Nz)) % m.Ny, i = hk / ((long long)m.Ne * m.Nz * m.Ny);
-    const double Xl = m.lowx + (double)i * m.dx, Yl = m.lowy + (double)j * m.dy, Zl = m.lowz + (double)k * m.dz;
-    for (uint64_t q = 0; q < N; q++) {
-      V3 r{0., 0., 0.};
-      bool ok = false;
-      for (int t = 0; t < 100 && !ok; t++) {
+  // the engine's jump over lane * D2 outputs (state' = jm * state + jp), once: the O(log) advance costs more than a round otherwise
+  uint64_t jm = 1, jp = 0;
+  {
+    uint64_t cur_mult = ABL_PCG_MULT, cur_plus = 5ULL, delta = (uint64_t)lane * D2;
+    while (delta > 0) {
+      if (delta & 1) {
+        jm *= cur_mult;
+        jp = jp * cur_mult + cur_plus;
+      }
+      cur_plus = (cur_mult + 1) * cur_plus;
+      cur_mult *= cur_mult;
+      delta >>= 1;
+    }
+  }
+  while (base_q < total && !failed) {
+    const uint64_t q = base_q + (uint64_t)lane;
+    const bool active = q < total;
+    uint64_t rng = jm * rng_base + jp;
+    bool ok = false;
+    V3 r{0., 0., 0.};
+    int mat = -1, e = 0;
+    double w = 0., w2 = 0., Xl = 0., Yl = 0., Zl = 0.;
+    if (active) {
+      uint64_t lo = 0, hi = nlist;  // the entry with cum[entry] <= q < cum[entry + 1]
+      while (hi - lo > 1) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (cum[mid] <= q) lo = mid; else hi = mid;
+      }
+      const long long hk = (long long)list[5 * lo];
+      mat = (int)list[5 * lo + 1];
+      w = list[5 * lo + 3];
+      w2 = list[5 * lo + 4];
+      long long i, j, k;
+      if (FULL) {
+        e = (int)(hk % m.Ne);
+        k = (hk / m.Ne) % m.Nz; j = (hk / ((long long)m.Ne * m.Nz)) % m.Ny; i = hk / ((long long)m.Ne * m.Nz * m.Ny);
+      } else {
+        k = hk % m.Nz; j = (hk / m.Nz) % m.Ny; i = hk / ((long long)m.Nz * m.Ny);
+      }
+      Xl = m.lowx + (double)i * m.dx; Yl = m.lowy + (double)j * m.dy; Zl = m.lowz + (double)k * m.dz;
+      const double x = Xl + GlobalStreamMath::rand(rng) * m.dx;
+      const double y = Yl + GlobalStreamMath::rand(rng) * m.dy;
+      const double z = Zl + GlobalStreamMath::rand(rng) * m.dz;
+      r = V3{x, y, z};
+      Cursor c;
+      c.err = 0;
+      c.token = 0;
+      cursor_restart(P, c, r, V3{1., 0., 0.});
+      ok = (c.cell < 0 ? -1 : c.mat) == mat;
+    }
+    const unsigned miss = __ballot_sync(0xffffffffu, active && !ok);
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    const int first_miss = miss ? __ffs(miss) - 1 : 32;
+    const int nact = __popc(act);
+    const bool mine = active && lane <= first_miss;  // lanes before the first miss are right; that lane goes on alone
+    if (mine && lane == first_miss) {
+      for (int t = 1; t < 100 && !ok; t++) {
         const double x = Xl + GlobalStreamMath::rand(rng) * m.dx;
         const double y = Yl + GlobalStreamMath::rand(rng) * m.dy;
         const double z = Zl + GlobalStreamMath::rand(rng) * m.dz;
@@ -823,27 +835,36 @@ __global__ void exact_full_uniform_kernel(const DevProblem P, const DevMesh3 m, 
         cursor_restart(P, c, r, V3{1., 0., 0.});
         ok = (c.cell < 0 ? -1 : c.mat) == mat;
       }
-      if (!ok) {
-        failed = 1;
-        break;
-      }
+      if (!ok) failed = 1;  // "Couldn't sample position for uniform particle."
+    }
+    if (mine && ok) {
       int e_index = 0;
-      if (P.chi_matrix) {
-        const double xi_E = GlobalStreamMath::rand(rng);
-        int cnt;
-        const int32_t* groups = exact_bin_groups(P.egb, e, cnt);
-        e_index = groups[(int)floor(xi_E * (double)cnt)];
-      } else if (P.G >= 2) {
-        e_index = rng_discrete<GlobalStreamMath>(rng, P.chi_cp + (size_t)mat * P.G * P.G, P.G);  // RNG::discrete(rng, nuclide->chi()[0])
+      V3 dir;
+      if (FULL) {  // ExactMGCancelator::get_new_particles (:511-590)
+        if (P.chi_matrix) {
+          const double xi_E = GlobalStreamMath::rand(rng);
+          int cnt;
+          const int32_t* groups = exact_bin_groups(P.egb, e, cnt);
+          e_index = groups[(int)floor(xi_E * (double)cnt)];
+        } else if (P.G >= 2) {
+          e_index = rng_discrete<GlobalStreamMath>(rng, P.chi_cp + (size_t)mat * P.G * P.G, P.G);
+        }
+        // Direction u_smp(2 rand - 1, 2 pi rand): g++ evaluates the two arguments from the right, so phi takes the first draw
+        double phi = 2. * ABL_PI * GlobalStreamMath::rand(rng);
+        double mu = 2. * GlobalStreamMath::rand(rng) - 1.;
+        if (mu < -1.) mu = -1.; else if (mu > 1.) mu = 1.;
+        if (phi < 0.) phi = 0.; else if (phi > 2 * ABL_PI) phi = 2 * ABL_PI;
+        double sn, cs;
+        det_sincos(phi, &sn, &cs);
+        dir = make_direction(sqrt(1. - mu * mu) * cs, sqrt(1. - mu * mu) * sn, mu);
+      } else {  // BasicExactMGCancelator::get_new_particles (:557-617): MGNuclide::sample_fission(0, +z, group 0, P_delayed 0)
+        if (P.G >= 2) e_index = rng_discrete<GlobalStreamMath>(rng, P.chi_cp + (size_t)mat * P.G * P.G, P.G);
+        const double mu = 2. * GlobalStreamMath::rand(rng) - 1.;
+        const double phi = 2. * ABL_PI * GlobalStreamMath::rand(rng);
+        dir = rotate_dir<GlobalStreamMath>(V3{0., 0., 1.}, mu, phi);
+        (void)GlobalStreamMath::rand(rng);  // the delayed-neutron draw against P_delayed = 0
       }
-      // Direction u_smp(2 rand - 1, 2 pi rand): g++ evaluates the two arguments from the right, so phi takes the first draw
-      double phi = 2. * ABL_PI * GlobalStreamMath::rand(rng);
-      double mu = 2. * GlobalStreamMath::rand(rng) - 1.;
-      if (mu < -1.) mu = -1.; else if (mu > 1.) mu = 1.;
-      if (phi < 0.) phi = 0.; else if (phi > 2 * ABL_PI) phi = 2 * ABL_PI;
-      double sn, cs;
-      det_sincos(phi, &sn, &cs);
-      const V3 dir = make_direction(sqrt(1. - mu * mu) * cs, sqrt(1. - mu * mu) * sn, mu);
+      const uint64_t row = first + q;
       if (row < capacity) {
         b.x[row] = r.x; b.y[row] = r.y; b.z[row] = r.z;
         b.ux[row] = dir.x; b.uy[row] = dir.y; b.uz[row] = dir.z;
@@ -854,12 +875,21 @@ __global__ void exact_full_uniform_kernel(const DevProblem P, const DevMesh3 m, 
         if (row < pcap)
           for (int f = 0; f < ABL_PARENT_FIELDS; f++) parent[f * pcap + row] = f == 4 ? 1. : 0.;
       }
-      row++;
+    }
+    failed = __any_sync(0xffffffffu, failed != 0) ? 1 : 0;
+    if (first_miss < 32) {  // the engine continues where the lane that went on alone left it
+      rng_base = __shfl_sync(0xffffffffu, rng, first_miss);
+      base_q += (uint64_t)first_miss + 1;
+    } else {
+      rng_base = stream_advance(rng_base, (uint64_t)nact * D2);
+      base_q += (uint64_t)nact;
     }
   }
-  *rng_state = rng;
-  out2[0] = row;
-  out2[1] = failed;
+  if (lane == 0) {
+    *rng_state = rng_base;
+    out2[0] = first + total;
+    out2[1] = failed;
+  }
 }
 
 }  // namespace abl

@@ -240,48 +240,75 @@ double GlobalRng::rand() {
   return ret;
 }
 
-void comb_particles(std::vector<BankedParticle>& next_gen, GlobalRng& rng) {
-  std::vector<BankedParticle> positive_particles, negative_particles;
-  positive_particles.reserve(next_gen.size());
-  negative_particles.reserve(next_gen.size() / 3);
+void comb_rows(const std::vector<double>& wgt, GlobalRng& rng, std::vector<uint32_t>& rows, std::vector<double>& wgts) {
+  // The three std::shuffle calls of the reference permute vectors of 112-byte particles; which elements a shuffle swaps depends on
+  // the length of the range and on the engine only, so the same calls on index vectors of the same lengths give the same
+  // permutations -- and the comb needs nothing of a particle but its weight.  pos / neg: rows of the positive / other particles.
+  std::vector<uint32_t> pos, neg;
+  pos.reserve(wgt.size());
   double Wpos = 0., Wneg = 0.;
-  for (const auto& p : next_gen) {
-    if (p.wgt > 0.) { Wpos += p.wgt; positive_particles.push_back(p); }
-    else { Wneg += p.wgt; negative_particles.push_back(p); }
+  for (size_t i = 0; i < wgt.size(); i++) {
+    if (wgt[i] > 0.) { Wpos += wgt[i]; pos.push_back(static_cast<uint32_t>(i)); }
+    else { Wneg += wgt[i]; neg.push_back(static_cast<uint32_t>(i)); }
   }
-  next_gen.clear();
   const size_t Npos = static_cast<size_t>(std::ceil(Wpos));
   const size_t Nneg = static_cast<size_t>(std::ceil(std::abs(Wneg)));
-  next_gen.reserve(Npos + Nneg);
+  std::vector<uint32_t> picked;  // combed bank before its shuffle: row of every tooth's particle
+  std::vector<double> picked_wgt;
+  picked.reserve(Npos + Nneg);
+  picked_wgt.reserve(Npos + Nneg);
   // teeth every avg_pos_wgt along the shuffled positive weight, the first one at a random offset
-  std::shuffle(positive_particles.begin(), positive_particles.end(), rng);
+  std::shuffle(pos.begin(), pos.end(), rng);
   const double avg_pos_wgt = Wpos / static_cast<double>(Npos);
   double comb_pos = rng.rand() * avg_pos_wgt;
   double current_particle = 0.;
-  for (size_t i = 0; i < positive_particles.size(); i++) {
-    current_particle += positive_particles[i].wgt;
+  for (size_t i = 0; i < pos.size(); i++) {
+    current_particle += wgt[pos[i]];
     while (comb_pos < current_particle) {
-      next_gen.push_back(positive_particles[i]);
-      next_gen.back().wgt = avg_pos_wgt;
+      picked.push_back(pos[i]);
+      picked_wgt.push_back(avg_pos_wgt);
       comb_pos += avg_pos_wgt;
     }
   }
   // the negative comb as the reference has it: its tooth spacing divides by Npos and it copies the i-th POSITIVE particle
   // (branchless_power_iterator.cpp:637-646); with no negative weights only its one draw is taken
-  std::shuffle(negative_particles.begin(), negative_particles.end(), rng);
+  std::shuffle(neg.begin(), neg.end(), rng);
   const double avg_neg_wgt = std::abs(Wneg) / static_cast<double>(Npos);
   comb_pos = rng.rand() * avg_neg_wgt;
   current_particle = 0.;
-  for (size_t i = 0; i < negative_particles.size(); i++) {
-    current_particle -= negative_particles[i].wgt;
+  for (size_t i = 0; i < neg.size(); i++) {
+    current_particle -= wgt[neg[i]];
     while (comb_pos < current_particle) {
-      if (i >= positive_particles.size()) fatal_error("comb_particles: more negative than positive particles (the reference reads past its buffer here).");
-      next_gen.push_back(positive_particles[i]);
-      next_gen.back().wgt = -avg_neg_wgt;
+      if (i >= pos.size()) fatal_error("comb_particles: more negative than positive particles (the reference reads past its buffer here).");
+      picked.push_back(pos[i]);
+      picked_wgt.push_back(-avg_neg_wgt);
       comb_pos += avg_neg_wgt;
     }
   }
-  std::shuffle(next_gen.begin(), next_gen.end(), rng);
+  // the last shuffle, of the combed bank
+  std::vector<uint32_t> order(picked.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = static_cast<uint32_t>(i);
+  std::shuffle(order.begin(), order.end(), rng);
+  rows.resize(order.size());
+  wgts.resize(order.size());
+  for (size_t i = 0; i < order.size(); i++) {
+    rows[i] = picked[order[i]];
+    wgts[i] = picked_wgt[order[i]];
+  }
+}
+
+void comb_particles(std::vector<BankedParticle>& next_gen, GlobalRng& rng) {
+  std::vector<double> wgt(next_gen.size());
+  for (size_t i = 0; i < next_gen.size(); i++) wgt[i] = next_gen[i].wgt;
+  std::vector<uint32_t> rows;
+  std::vector<double> wgts;
+  comb_rows(wgt, rng, rows, wgts);
+  std::vector<BankedParticle> combed(rows.size());
+  for (size_t i = 0; i < rows.size(); i++) {
+    combed[i] = next_gen[rows[i]];
+    combed[i].wgt = wgts[i];
+  }
+  next_gen.swap(combed);
 }
 
 PowerIterator::PowerIterator(const Problem& p, int device) : problem(p), device_(device) {
@@ -595,34 +622,37 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
       const double w_per_part = static_cast<double>(st.nparticles) / (ws[2] - ws[3]);
       check(h, abl_bank_scale_weights_device(h, &out, w_per_part, nullptr), "abl_bank_scale_weights_device");
     } else {
-      // the comb is the reference's serial host step on the gathered bank (std::shuffle on the one global engine): the bank makes
-      // one round trip through host memory per generation.  The weights are normalised there too, in the reference's serial
-      // order -- ceil(sum of weights) decides the combed population and that sum sits within rounding of an integer.
-      HostColumns cols;
-      cols.resize(n_fis);
-      abl_bank host = cols.view();
-      check(h, abl_bank_download(h, &out, n_fis, &host), "abl_bank_download");
-      std::vector<BankedParticle> next_gen;
-      cols.to(next_gen);
+      // the comb is the reference's serial host step on the gathered bank (std::shuffle on the one global engine).  It is a function
+      // of the weights alone, so only the weights come to the host; they are normalised there too, in the reference's serial order
+      // (ceil(sum of weights) decides the combed population and that sum sits within rounding of an integer), and the combed bank
+      // is a gather of the device bank's rows.
+      std::vector<double> wgt(n_fis);
+      abl_bank wonly{};
+      wonly.n = n_fis;
+      wonly.wgt = wgt.data();
+      check(h, abl_bank_download(h, &out, n_fis, &wonly), "abl_bank_download");
       double W_neg = 0., W_pos = 0.;
-      for (const auto& p : next_gen) {
-        if (p.wgt > 0.) W_pos += p.wgt;
-        else W_neg -= p.wgt;
+      for (double v : wgt) {
+        if (v > 0.) W_pos += v;
+        else W_neg -= v;
       }
       const double w_per_part = static_cast<double>(st.nparticles) / (W_pos - W_neg);
-      for (auto& p : next_gen) p.wgt *= w_per_part;
-      comb_particles(next_gen, global_rng_);
-      cols.from(next_gen);
-      host = cols.view();
-      if (host.n > nxt.cap) {
-        free_device_bank(nxt_alloc);
-        alloc_device_bank(nxt_alloc, host.n + host.n / 8 + 4096);
-        nxt.b = nxt_alloc.b;
-        nxt.cap = nxt_alloc.cap;
+      for (double& v : wgt) v *= w_per_part;
+      std::vector<uint32_t> rows;
+      std::vector<double> wgts;
+      comb_rows(wgt, global_rng_, rows, wgts);
+      // gather into the bank the generation came from (its particles are spent); it then already is the next `cur`
+      if (rows.size() > cur_alloc.cap) {
+        free_device_bank(cur_alloc);
+        alloc_device_bank(cur_alloc, rows.size() + rows.size() / 8 + 4096);
       }
+      abl_bank dst = cur_alloc.b;
+      check(h, abl_bank_gather_device(h, &out, rows.data(), wgts.data(), rows.size(), &dst, nullptr), "abl_bank_gather_device");
+      std::swap(cur_alloc, nxt_alloc);  // (undone by the swap at the end of the generation: the combed bank becomes `cur`)
+      nxt.b = nxt_alloc.b;
+      nxt.cap = nxt_alloc.cap;
       out = nxt.b;
-      check(h, abl_bank_upload(h, &host, &out), "abl_bank_upload");
-      n_fis = host.n;
+      n_fis = rows.size();
       out.n = n_fis;
     }
     if (transporter->converged) {

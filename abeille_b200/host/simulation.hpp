@@ -163,6 +163,8 @@ struct GlobalRng {
 // BranchlessPowerIterator::comb_particles (src/branchless_power_iterator.cpp:592-651): a serial host step on the gathered bank in
 // the reference too; std::shuffle of this libstdc++ on the global engine, so the combed bank is the reference's particle for particle.
 void comb_particles(std::vector<BankedParticle>& next_gen, GlobalRng& rng);
+// ... the same from the weights alone: the combed bank is row rows[k] of the bank with weight wgts[k], k = 0 .. rows.size() - 1
+void comb_rows(const std::vector<double>& wgt, GlobalRng& rng, std::vector<uint32_t>& rows, std::vector<double>& wgts);
 
 class PowerIterator {  // src/power_iterator.cpp (and src/branchless_power_iterator.cpp: the same loop plus the comb)
  public:

@@ -320,6 +320,11 @@ int abl_bank_alloc_device(abl_handle h, uint64_t capacity, abl_bank* out_dev); /
 int abl_bank_free_device(abl_handle h, abl_bank* bank_dev);
 int abl_bank_upload(abl_handle h, const abl_bank* host, abl_bank* bank_dev);   /* copies host->n entries, sets bank_dev->n */
 int abl_bank_download(abl_handle h, const abl_bank* bank_dev, uint64_t n, abl_bank* host);
+/* dst row k = src row rows_host[k] (every column), with wgt = wgts_host[k] when wgts_host is given: what a comb or any other
+ * selection of the bank made on the host from the weights alone amounts to (BranchlessPowerIterator::comb_particles,
+ * src/branchless_power_iterator.cpp:592-651); the bank itself stays in HBM.  src and dst must not overlap; sets dst_dev->n. */
+int abl_bank_gather_device(abl_handle h, const abl_bank* src_dev, const uint32_t* rows_host, const double* wgts_host, uint64_t n,
+                           abl_bank* dst_dev, void* stream);
 int abl_device_alloc(abl_handle h, uint64_t bytes, void** out_dev);            /* zero-initialised */
 int abl_device_free(abl_handle h, void* dev);
 int abl_device_zero(abl_handle h, void* dev, uint64_t bytes, void* stream);
