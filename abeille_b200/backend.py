@@ -197,6 +197,23 @@ def comb_particles(bank: dict, rng2):
     return {k: v[:m].copy() for k, v in out.items()}, (int(r[0]), int(r[1]))
 
 
+def comb_rows(wgt: np.ndarray, rng2):
+    """The comb from the weights alone (abeille::comb_rows): returns (rows uint32, weights, (state, increment) afterwards) -- the
+    combed bank is row rows[k] of the bank with weight weights[k]."""
+    L = load_host_lib()
+    wgt = np.ascontiguousarray(wgt, dtype=np.float64)
+    cap = int(np.ceil(np.abs(wgt).sum())) + len(wgt) + 16
+    rows, wgts = np.zeros(cap, dtype=np.uint32), np.zeros(cap)
+    r = (C.c_uint64 * 2)(int(rng2[0]), int(rng2[1]))
+    nout = C.c_uint64(0)
+    rc = L.ablh_comb_rows(wgt.ctypes.data_as(_PD), C.c_uint64(len(wgt)), r, rows.ctypes.data_as(C.POINTER(C.c_uint32)), wgts.ctypes.data_as(_PD),
+                          C.c_uint64(cap), C.byref(nout))
+    if rc != 0:
+        raise BackendError(rc, L.ablh_last_error(None).decode())
+    m = int(nout.value)
+    return rows[:m].copy(), wgts[:m].copy(), (int(r[0]), int(r[1]))
+
+
 def yaml_roundtrip(text: str) -> str:
     L = load_host_lib()
     cap = 1 << 22
@@ -546,6 +563,15 @@ class Backend:
         r = (C.c_uint64 * 2)(int(rng2[0]), int(rng2[1]))
         self._check(self.L.abl_cancel_exact_device(self.h, C.byref(s), C.c_uint64(len(bank["x"])), r, self._stream()))
         return int(s.n), (int(r[0]), int(r[1]))
+
+    def bank_gather_device(self, src: dict, rows: np.ndarray, wgts, dst: dict) -> int:
+        """abl_bank_gather_device: dst row k = src row rows[k] (weight wgts[k] when given); torch banks; returns the row count."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        ssrc, sdst = _device_struct(src, len(src["x"])), _device_struct(dst, len(dst["x"]))
+        wp = np.ascontiguousarray(wgts, dtype=np.float64).ctypes.data_as(_PD) if wgts is not None else None
+        self._check(self.L.abl_bank_gather_device(self.h, C.byref(ssrc), rows.ctypes.data_as(C.POINTER(C.c_uint32)), wp, C.c_uint64(len(rows)),
+                                                  C.byref(sdst), self._stream()))
+        return len(rows)
 
     def cancel_accumulate_device(self, bank: dict, n: int):
         s = _device_struct(bank, n)

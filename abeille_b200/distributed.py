@@ -35,21 +35,25 @@ def even_split(total: int, world: int):
     return counts, bounds
 
 
-def rebalance_plan(counts, rank: int):
-    """Order-preserving re-partition: rank r holds global range [B_r, B_r+1) and must end with [B'_r, B'_r+1).
+def rebalance_plan(counts, rank: int, target=None):
+    """Order-preserving re-partition: rank r holds global range [B_r, B_r+1) and must end with [B'_r, B'_r+1) -- an even split, or
+    the counts `target` (e.g. everything on rank 0: the reference's particles_to_master).
     Returns (send_splits, recv_splits) for all_to_all_single; pieces arrive in source-rank order == global order."""
     world = len(counts)
     old = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-    _, new = even_split(int(old[-1]), world)
+    if target is None:
+        _, new = even_split(int(old[-1]), world)
+    else:
+        new = np.concatenate([[0], np.cumsum(target)]).astype(np.int64)
     send = [int(max(0, min(old[rank + 1], new[q + 1]) - max(old[rank], new[q]))) for q in range(world)]
     recv = [int(max(0, min(old[q + 1], new[rank + 1]) - max(old[q], new[rank]))) for q in range(world)]
     return send, recv
 
 
-def rebalance_bank(src: dict, dst: dict, keys, counts, rank: int, group=None) -> int:
+def rebalance_bank(src: dict, dst: dict, keys, counts, rank: int, group=None, target=None) -> int:
     """Order-preserving all_to_all of every bank array: src[k][:counts[rank]] -> dst[k][:new count].  Works on any
     backend (NCCL on the GPUs, gloo in the CPU tests); returns this rank's new count."""
-    send, recv = rebalance_plan(counts, rank)
+    send, recv = rebalance_plan(counts, rank, target)
     m_new = int(sum(recv))
     via_host = dist.get_backend(group) == "gloo"  # (gloo exchanges host tensors only: two test ranks sharing one GPU)
     for k in keys:
@@ -100,14 +104,16 @@ class DistributedPowerIterator:
         self.n_total = self.n_local * self.world  # tallies->total_weight; the deck's nparticles must equal this
         if self.gpu.info["nparticles"] != self.n_total:
             raise ValueError(f"deck nparticles {self.gpu.info['nparticles']} != world*n_local {self.n_total}")
+        self.comb = False
         if self.gpu.info["mode"] == 3:  # ABL_MODE_BRANCHLESS
             import yaml
+            from .backend import global_rng_state
             with open(deck_path) as f:
-                if yaml.safe_load(f)["settings"].get("branchless-combing", True):
-                    # comb_particles shuffles the gathered bank with the one global engine on rank 0 (branchless_power_iterator.cpp:
-                    # 592-651): a serial host step, provided by the one-GPU driver (Backend.run_power_iteration)
-                    raise NotImplementedError("branchless-combing is a serial step on the gathered bank: run it through "
-                                              "Backend.run_power_iteration, or set branchless-combing: false for the sharded driver")
+                st = yaml.safe_load(f)["settings"]
+            # comb_particles works on the gathered bank with the one global engine on rank 0 (branchless_power_iterator.cpp:353-363,
+            # 592-651): the slices go to rank 0 in bank order, are combed there and come back as an even split
+            self.comb = bool(st.get("branchless-combing", True))
+            self.global_rng = global_rng_state(int(st.get("seed", 19073486328125)))
         # output bank sized from the problem (the first generation runs with k_col = 1 and banks ~ k_inf sites per particle)
         self.cap = self.gpu.fission_capacity(self.n_local, k_col=1.0)
         self.cur = self.gpu.new_device_bank(self.cap)
@@ -253,10 +259,39 @@ class DistributedPowerIterator:
             out[:, k] = self.cur[key][:m].cpu().numpy()
         return out
 
-    def _rebalance(self, counts):
-        """Moves partition boundaries back to an even split, preserving global order."""
+    def _comb(self, counts):
+        """normalize_weights + comb_particles on rank 0 (branchless_power_iterator.cpp:353-363): returns the new counts (even split
+        of the combed bank) and this rank's count.  Only the weights come to the host; the combed bank is a gather of rows."""
+        from .backend import comb_rows
+        m_total = int(sum(counts))
+        if self.world > 1:  # particles_to_master, in bank order
+            target = [m_total] + [0] * (self.world - 1)
+            self._grow(m_total if self.rank == 0 else 1)
+            self._rebalance(counts, target)
+        n_comb = np.zeros(1)
+        if self.rank == 0:
+            w = self.nxt["wgt"][:m_total].cpu().numpy()
+            # serial sums, as normalize_weights takes them (a cumulative sum adds in order; ceil(sum) decides the combed population)
+            w_pos = float(np.cumsum(np.where(w > 0., w, 0.))[-1])
+            w_neg = float(np.cumsum(np.where(w > 0., 0., -w))[-1])
+            w = w * (self.n_total / (w_pos - w_neg))
+            rows, wgts, self.global_rng = comb_rows(w, self.global_rng)
+            self._grow(len(rows))
+            self.gpu.bank_gather_device(self.nxt, rows, wgts, self.cur)
+            self.cur, self.nxt = self.nxt, self.cur  # the combed bank is the fission bank now
+            n_comb[0] = len(rows)
+        n_comb = int(self._gather(n_comb).sum())
+        new_counts, _ = even_split(n_comb, self.world)
+        m = n_comb
+        if self.world > 1:  # distribute_particles: an even split, in bank order
+            self._grow(max(new_counts))
+            m = self._rebalance([n_comb] + [0] * (self.world - 1), new_counts)
+        return new_counts, m
+
+    def _rebalance(self, counts, target=None):
+        """Moves partition boundaries back to an even split (or to `target`), preserving global order."""
         keys = [k for k in BANK_F64 if k != "wgt2"] + ["id_a", "id_b", "id_c"]
-        m_new = rebalance_bank(self.nxt, self.cur, keys, counts, self.rank, self.group)  # the consumed bank receives
+        m_new = rebalance_bank(self.nxt, self.cur, keys, counts, self.rank, self.group, target)  # the consumed bank receives
         self.cur, self.nxt = self.nxt, self.cur  # keep the invariant: the fission bank lives in self.nxt
         return m_new
 
@@ -299,10 +334,15 @@ class DistributedPowerIterator:
         self.entropy_series.append(self._entropy(m))  # Entropy::add_point over the un-normalised fission bank (power_iterator.cpp:341-353)
         if self.cancellation:
             self._cancel(m)
-        # weight normalisation over the global bank (src/power_iterator.cpp:538-586)
-        ws = gpu.weight_stats_device(self.nxt, m)
-        wall = self._gather(ws).sum(axis=0)
-        gpu.scale_weights_device(self.nxt, m, self.n_total / (wall[2] - wall[3]))
+        if self.comb:
+            # branchless-k-eigenvalue: normalisation and comb on the gathered bank, then an even split again
+            counts, m = self._comb(counts)
+            m_total = int(sum(counts))
+        else:
+            # weight normalisation over the global bank (src/power_iterator.cpp:538-586)
+            ws = gpu.weight_stats_device(self.nxt, m)
+            wall = self._gather(ws).sum(axis=0)
+            gpu.scale_weights_device(self.nxt, m, self.n_total / (wall[2] - wall[3]))
         if self.converged:
             gpu.score_source_device(self.nxt, m)  # SourceMeshTally::score_source on the normalised bank (power_iterator.cpp:366-372)
             if self.world > 1:

@@ -306,6 +306,27 @@ int ablh_comb_particles(const abl_bank* in, abl_bank* out, uint64_t* n_out, uint
   }
 }
 
+/* ... from the weights alone (abeille::comb_rows): the combed bank is row rows[k] of the bank with weight wgts[k]; at most cap
+ * entries are written, *n_out = the combed population */
+int ablh_comb_rows(const double* wgt, uint64_t n, uint64_t rng2[2], uint32_t* rows, double* wgts, uint64_t cap, uint64_t* n_out) {
+  try {
+    abeille::GlobalRng rng;
+    rng.state = rng2[0];
+    rng.inc = rng2[1];
+    std::vector<uint32_t> r;
+    std::vector<double> w;
+    abeille::comb_rows(std::vector<double>(wgt, wgt + n), rng, r, w);
+    rng2[0] = rng.state;
+    rng2[1] = rng.inc;
+    *n_out = r.size();
+    for (uint64_t i = 0; i < r.size() && i < cap; i++) { rows[i] = r[i]; wgts[i] = w[i]; }
+    return r.size() > cap ? 2 : 0;
+  } catch (const std::exception& e) {
+    g_open_error = e.what();
+    return 1;
+  }
+}
+
 /* yaml_lite self-test hook: parses text, returns a canonical one-line rendering */
 int ablh_yaml_roundtrip(const char* text, char* out, int64_t out_cap) {
   try {

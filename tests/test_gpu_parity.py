@@ -588,7 +588,7 @@ def _sharded_pi_worker(rank, world, port, path, n_local, gens, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("deck", ["c5g7_delta_collision.yaml", "c5g7_carter_cancel.yaml"])
+@pytest.mark.parametrize("deck", ["c5g7_delta_collision.yaml", "c5g7_carter_cancel.yaml", "c5g7_delta_branchless.yaml"])
 def test_power_iteration_sharded_over_two_ranks_matches_one_rank(ab, tmp_path, deck):
     import socket
     import torch.multiprocessing as mp
@@ -602,6 +602,11 @@ def test_power_iteration_sharded_over_two_ranks_matches_one_rank(ab, tmp_path, d
     ref = {"nbank": [int(v) for v in one.nbank_series], "k_col": [float(v) for v in one.kcol_series],
            "collisions": float(one.counters[1]), "tallies": [one.gpu.tally(t, "avg") for t in range(one.gpu.ntallies())]}
     del one
+    if "branchless" in deck:
+        # the comb in the sharded driver (slices to rank 0 in bank order, normalised and combed there from the weights, an even
+        # split back) against the one-GPU C++ loop, which is pinned on the oracle and the reference
+        host = ab.Backend(path, 0).run_power_iteration(gens, 1, resident=True)
+        assert ref["nbank"] == [int(v) for v in host["nbank"]] and np.allclose(ref["k_col"], host["kcol"], rtol=1e-10)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
