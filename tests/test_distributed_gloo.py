@@ -27,6 +27,30 @@ def test_even_split_and_plan_cover_everything():
                     assert sends[r][q] == recvs[q][r]
 
 
+def test_plan_to_the_master_and_back():
+    """particles_to_master / distribute_particles of the sharded comb: any target partition, order-preserving."""
+    for world in (1, 2, 3, 8):
+        for counts in ([5] * world, list(range(1, world + 1)), [17, 0, 3, 99, 1, 0, 0, 5][:world]):
+            total = sum(counts)
+            for target in ([total] + [0] * (world - 1), even_split(total, world)[0], counts[::-1]):
+                sends = [rebalance_plan(counts, r, target)[0] for r in range(world)]
+                recvs = [rebalance_plan(counts, r, target)[1] for r in range(world)]
+                for r in range(world):
+                    assert sum(sends[r]) == counts[r] and sum(recvs[r]) == target[r]
+                    for q in range(world):
+                        assert sends[r][q] == recvs[q][r]
+                # global order: what rank r receives from rank q precedes what it receives from rank q + 1, and the pieces a rank
+                # sends go to ranks in increasing order of their target ranges
+                old = np.concatenate([[0], np.cumsum(counts)])
+                new = np.concatenate([[0], np.cumsum(target)])
+                for r in range(world):
+                    pos = old[r]
+                    for q in range(world):
+                        if sends[r][q]:
+                            assert new[q] <= pos and pos + sends[r][q] <= new[q + 1]
+                            pos += sends[r][q]
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
