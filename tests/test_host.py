@@ -175,3 +175,17 @@ def test_unknown_surface_in_region_is_rejected(native_libs, tmp_path):
     with pytest.raises(BackendError) as e:
         native_libs.parse_only(path)
     assert "surface" in str(e.value)
+
+
+def test_cpp_multi_gpu_driver_is_built_and_links():
+    """abeille_b200/lib/abl_pi_nccl (host/distributed_main.cpp: the sharded generation loop in C++, NCCL called directly) resolves its
+    libraries and explains itself when started without arguments; it is exercised on 2 and 8 GPUs by scripts/nccl_pi_check.py
+    (profiles/t9b_*, t9c_*, t9d_*)."""
+    import subprocess
+    from abeille_b200 import backend
+    cuda_lib, _ = backend.lib_paths()
+    binary = os.path.join(os.path.dirname(cuda_lib), "abl_pi_nccl")
+    if not os.path.exists(binary):
+        pytest.skip("abl_pi_nccl was not built (nccl.h / libnccl missing at build time)")
+    p = subprocess.run([binary], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 1 and "usage: abl_pi_nccl" in p.stderr
