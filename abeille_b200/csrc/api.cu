@@ -242,6 +242,10 @@ int validate(abl_handle h, const abl_problem* p) {
     }
   }
   if (p->tracking != ABL_TRACK_SURFACE && !p->sampling_xs) return fail(h, ABL_ERR_INVALID, "sampling_xs missing");
+  // Source::generate_particle's energy rejection (src/source.cpp:48-58): a mono-energetic source outside (min, max) never passes
+  for (int s = 0; s < p->nsources; s++)
+    if (p->sources[s].energy <= p->min_energy || p->energy_bounds[p->ngroups] <= p->sources[s].energy)
+      return fail(h, ABL_ERR_INVALID, "source energy outside (min_energy, max_energy): Exceded 200 samplings of energy.");
   return ABL_OK;
 }
 

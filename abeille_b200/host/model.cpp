@@ -727,6 +727,10 @@ Problem Problem::from_yaml(const Node& input) {
     for (size_t s = 0; s < input["sources"].size(); s++) P.sources.push_back(make_source(input["sources"][s]));
   else
     fatal_error("No source specified for problem.");
+  // Source::generate_particle redraws the energy until it lies inside (min_energy, max_energy) and gives up after 200 draws
+  // (src/source.cpp:48-58); a mono-energetic source outside the range can only ever end there
+  for (const Source& src : P.sources)
+    if (src.flat.energy <= P.settings.min_energy || P.settings.max_energy <= src.flat.energy) fatal_error("Exceded 200 samplings of energy.");
   if (input["entropy"] && input["entropy"].IsMap()) P.entropy = make_mesh_spec(input["entropy"], "entropy mesh");
   // noise sources (src/noise_maker.cpp:39-58, src/square_oscillation_noise_source.cpp:38-83,177-250)
   if (input["noise-sources"] && input["noise-sources"].IsSequence())

@@ -167,6 +167,19 @@ def test_parser_errors(native_libs, tmp_path, bad, msg):
     assert msg in str(e.value)
 
 
+@pytest.mark.parametrize("energy", [7.0, 9.5, 0.0])
+def test_source_energy_outside_the_group_structure_is_fatal(native_libs, tmp_path, energy):
+    """Source::generate_particle redraws the energy while E <= min_energy or max_energy <= E and stops the run after 200 draws
+    (src/source.cpp:48-58); a mono-energetic source can only end there, and the parser says so with the reference's words."""
+    from abeille_b200 import BackendError
+    deck = load_deck("c5g7_delta_collision.yaml")   # energy-bounds [0, ..., 7]
+    deck["sources"][0]["energy"]["energy"] = energy
+    path = write_deck(deck, tmp_path / "bad.yaml")
+    with pytest.raises(BackendError) as e:
+        native_libs.parse_only(path)
+    assert "200 samplings of energy" in str(e.value)
+
+
 def test_unknown_surface_in_region_is_rejected(native_libs, tmp_path):
     from abeille_b200 import BackendError
     deck = load_deck("PUa-1-0-IN.yaml")
