@@ -180,6 +180,9 @@ def deck_to_text(deck: dict) -> str:
             pos = "point " + _fl(sp["position"])
         else:
             raise ValueError("oracle: box/point sources only")
+        e_src = float(s["energy"]["energy"])
+        if e_src <= float(eb[0]) or float(eb[-1]) <= e_src:  # Source::generate_particle's rejection loop (src/source.cpp:48-58)
+            raise ValueError("Exceded 200 samplings of energy.")
         out.append(f"src {_f(s['weight'])} {fo} {pos} energy {_f(s['energy']['energy'])}")
 
     tallies = deck.get("tallies", []) or []
