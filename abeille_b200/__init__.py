@@ -10,7 +10,7 @@ torch.distributed in :mod:`abeille_b200.distributed`).  There is no CPU fallback
 in the CUDA library and raises if it is missing or no device is present.
 """
 from .backend import (Backend, BackendError, lib_paths, load_backend_lib, load_host_lib, new_bank, parse_only,
-                      dump_tables, yaml_roundtrip, comb_particles, comb_rows, global_rng_state, BANK_F64, BANK_U64, COUNTER_KEYS)
+                      dump_tables, source_records, yaml_roundtrip, comb_particles, comb_rows, global_rng_state, BANK_F64, BANK_U64, COUNTER_KEYS)
 
 __all__ = ["Backend", "BackendError", "lib_paths", "load_backend_lib", "load_host_lib", "new_bank", "parse_only",
-           "dump_tables", "yaml_roundtrip", "comb_particles", "comb_rows", "global_rng_state", "BANK_F64", "BANK_U64", "COUNTER_KEYS"]
+           "dump_tables", "source_records", "yaml_roundtrip", "comb_particles", "comb_rows", "global_rng_state", "BANK_F64", "BANK_U64", "COUNTER_KEYS"]

@@ -156,6 +156,18 @@ def parse_only(yaml_path: str):
     return d, np.array(maj[: d["ngroups"]])
 
 
+def source_records(yaml_path: str) -> np.ndarray:
+    """Host-only: the flattened abl_source records of a deck, [nsources, 15]: weight, fissile_only, is_box, low[3], hi[3], energy,
+    direction_kind (ABL_DIR_*), dir[3] (normalised), cos_aperture."""
+    L = load_host_lib()
+    out = np.zeros(16 * 64)
+    err = C.create_string_buffer(1024)
+    n = L.ablh_sources(yaml_path.encode(), out.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(len(out)), err, 1024)
+    if n < 0:
+        raise BackendError(1, err.value.decode())
+    return out[: 16 * n].reshape(n, 16)[:, :15].copy()
+
+
 def dump_tables(yaml_path: str) -> dict:
     L = load_host_lib()
     cap = 1 << 24

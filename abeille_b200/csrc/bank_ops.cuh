@@ -346,9 +346,21 @@ __global__ void __launch_bounds__(128) sample_source_kernel(const DevProblem P, 
     int si = 0;
     if (P.nsources >= 2) si = rng_discrete(rng, P.source_cp, P.nsources);
     const abl_source* S = P.sources + si;
-    const double mu = 2. * rng_rand(rng) - 1.;  // isotropic.cpp:28-36
-    const double phi = 2. * ABL_PI * rng_rand(rng);
-    const V3 u = make_direction_mu_phi(mu, phi);
+    const int dkind = ldt(&S->direction_kind);
+    V3 u;
+    if (dkind == ABL_DIR_ISOTROPIC) {  // isotropic.cpp:28-36
+      const double mu = 2. * rng_rand(rng) - 1.;
+      const double phi = 2. * ABL_PI * rng_rand(rng);
+      u = make_direction_mu_phi(mu, phi);
+    } else {
+      u = {ldt(&S->dir[0]), ldt(&S->dir[1]), ldt(&S->dir[2])};  // mono_directional.hpp:38: the stored direction, no draw
+      if (dkind == ABL_DIR_CONE) {  // cone.cpp:34-42: mu in [cos(aperture), 1], phi in [0, 2 pi], about the axis
+        const double ca = ldt(&S->cos_aperture);
+        const double mu = (1. - ca) * rng_rand(rng) + ca;
+        const double phi = 2. * ABL_PI * rng_rand(rng);
+        u = rotate_direction(u, mu, phi);
+      }
+    }
     const double E = ldt(&S->energy);
     const bool is_box = ldt(&S->is_box) != 0;
     const double lx = ldt(&S->low[0]), ly = ldt(&S->low[1]), lz = ldt(&S->low[2]);

@@ -557,8 +557,28 @@ Source make_source(const Node& s) {  // src/source.cpp:92-140
   } else {
     fatal_error("Spatial distribution \"" + stype + "\" is not provided by the B200 backend (box, point).");
   }
-  if (!s["direction"] || !s["direction"]["type"] || s["direction"]["type"].as_string() != "isotropic")
-    fatal_error("Only isotropic source directions are provided by the B200 backend.");
+  // src/direction_distribution.cpp:36-56
+  if (!s["direction"] || !s["direction"].IsMap()) fatal_error("No valid direction distribution entry provided for source.");
+  if (!s["direction"]["type"] || !s["direction"]["type"].IsScalar()) fatal_error("No valid type provided to direction distribution entry.");
+  const std::string dtype = s["direction"]["type"].as_string();
+  if (dtype == "isotropic") {
+    f.direction_kind = ABL_DIR_ISOTROPIC;
+  } else if (dtype == "mono-directional" || dtype == "cone") {  // src/mono_directional.cpp:28-42, src/cone.cpp:46-65
+    const std::string what = dtype == "cone" ? "cone" : "mono-directional";
+    const Node& dn = s["direction"]["direction"];
+    if (!dn || !dn.IsSequence() || dn.size() != 3) fatal_error("No valid direction entry for " + what + " distribution.");
+    const double x = dn[0].as_double(), y = dn[1].as_double(), z = dn[2].as_double();
+    const double m = std::sqrt(x * x + y * y + z * z);  // Direction(x, y, z) renormalises (direction.hpp:37-42)
+    f.dir[0] = x / m; f.dir[1] = y / m; f.dir[2] = z / m;
+    f.direction_kind = ABL_DIR_MONO;
+    if (dtype == "cone") {
+      if (!s["direction"]["aperture"] || !s["direction"]["aperture"].IsScalar()) fatal_error("No valid aperture entry for cone distribution.");
+      f.cos_aperture = std::cos(s["direction"]["aperture"].as_double());  // Cone::Cone keeps the cosine (cone.cpp:31-32)
+      f.direction_kind = ABL_DIR_CONE;
+    }
+  } else {
+    fatal_error("Invalid direction distribution type " + dtype + ".");
+  }
   if (!s["energy"] || !s["energy"]["type"] || s["energy"]["type"].as_string() != "mono-energetic")
     fatal_error("Only mono-energetic source energies are provided by the B200 backend.");
   f.energy = s["energy"]["energy"].as_double();

@@ -118,11 +118,19 @@ typedef struct abl_mesh_tally {
   double net_weight;             /* tallies->total_weight (parser.cpp:870-871)                         */
 } abl_mesh_tally;
 
-typedef struct abl_source {      /* box | point, isotropic, mono-energetic (source.cpp:44-90)          */
+/* direction distribution of a source (src/direction_distribution.cpp:36-56) */
+#define ABL_DIR_ISOTROPIC 0      /* src/isotropic.cpp:28-36: two draws                                 */
+#define ABL_DIR_MONO 1           /* src/mono_directional.cpp, include/simulation/mono_directional.hpp:38: no draw */
+#define ABL_DIR_CONE 2           /* src/cone.cpp:31-42: mu uniform in [cos(aperture), 1], phi, rotate_direction */
+
+typedef struct abl_source {      /* box | point; isotropic | mono-directional | cone; mono-energetic (source.cpp:44-90) */
   double weight;
   int32_t fissile_only, is_box;
   double low[3], hi[3];          /* point: low == position                                             */
   double energy;
+  int32_t direction_kind, pad_;  /* ABL_DIR_*                                                          */
+  double dir[3];                 /* mono-directional / cone axis, NORMALISED as Direction(x, y, z) does (direction.hpp:37-42) */
+  double cos_aperture;           /* cone: std::cos(aperture), taken once on the host (cone.cpp:31-32)  */
 } abl_source;
 
 typedef struct abl_mesh3 {       /* entropy mesh (entropy.cpp) / approximate cancelator mesh           */

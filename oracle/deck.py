@@ -171,8 +171,17 @@ def deck_to_text(deck: dict) -> str:
     out.append(f"nsrc {len(srcs)}")
     for s in srcs:
         sp = s["spatial"]
-        if s["direction"]["type"] != "isotropic" or s["energy"]["type"] != "mono-energetic":
-            raise ValueError("oracle: isotropic mono-energetic sources only")
+        if s["energy"]["type"] != "mono-energetic":
+            raise ValueError("oracle: mono-energetic sources only")
+        dd = s["direction"]
+        if dd["type"] == "isotropic":
+            dirn = "dir iso"
+        elif dd["type"] == "mono-directional":  # src/mono_directional.cpp:28-42
+            dirn = "dir mono " + _fl(dd["direction"])
+        elif dd["type"] == "cone":  # src/cone.cpp:46-65 (aperture in radians)
+            dirn = "dir cone " + _fl(dd["direction"]) + " " + _f(dd["aperture"])
+        else:
+            raise ValueError("Invalid direction distribution type " + str(dd["type"]) + ".")
         fo = int(bool(s.get("fissile-only", False)))  # read at SOURCE level only (src/source.cpp:104-110)
         if sp["type"] == "box":
             pos = "box " + _fl(sp["low"]) + " " + _fl(sp["hi"])
@@ -183,7 +192,7 @@ def deck_to_text(deck: dict) -> str:
         e_src = float(s["energy"]["energy"])
         if e_src <= float(eb[0]) or float(eb[-1]) <= e_src:  # Source::generate_particle's rejection loop (src/source.cpp:48-58)
             raise ValueError("Exceded 200 samplings of energy.")
-        out.append(f"src {_f(s['weight'])} {fo} {pos} energy {_f(s['energy']['energy'])}")
+        out.append(f"src {_f(s['weight'])} {fo} {pos} energy {_f(s['energy']['energy'])} {dirn}")
 
     tallies = deck.get("tallies", []) or []
     out.append(f"ntally {len(tallies)}")

@@ -60,6 +60,9 @@ struct Source {  // src/source.cpp, box.cpp, point.cpp, isotropic.cpp, mono_ener
   bool is_box = true;
   Vec low{0, 0, 0}, hi{0, 0, 0};  // point: low == position
   double energy = 1.;
+  int dir_kind = 0;               // 0 isotropic, 1 mono-directional (mono_directional.hpp:38), 2 cone (cone.cpp:31-42)
+  Vec dir{0, 0, 1};               // normalised, as Direction(x, y, z) leaves it
+  double cos_aperture = 1.;       // Cone::Cone stores std::cos(aperture)
 };
 
 struct Cancelator {  // kind 1: ApproximateMeshCancelator, kind 2: BasicExactMGCancelator (beta 0 zero, 1 minimum, 2 average-f, 3 average-g)
@@ -454,6 +457,19 @@ static Problem* load_problem(const char* path) {
     }
     tk.expect("energy");
     src.energy = tk.d();
+    tk.expect("dir");
+    const std::string dk = tk.next();
+    if (dk == "mono" || dk == "cone") {
+      const double dx = tk.d(), dy = tk.d(), dz = tk.d();
+      src.dir = make_direction(dx, dy, dz);
+      src.dir_kind = 1;
+      if (dk == "cone") {
+        src.cos_aperture = std::cos(tk.d());  // the host's libm, once, like the reference's constructor
+        src.dir_kind = 2;
+      }
+    } else if (dk != "iso") {
+      throw std::runtime_error("unknown source direction kind " + dk);
+    }
     P->sources.push_back(src);
   }
   tk.expect("ntally");
@@ -1966,10 +1982,16 @@ static std::vector<Particle> sample_sources(Problem& P, size_t N) {
     rng.advance(P.st.rng_stride * history_id);
     size_t indx = (size_t)rng_discrete(rng, src_cp);
     const Source& S = P.sources[indx];
-    // src/isotropic.cpp:28-36
-    double mu = 2. * rng_rand(rng) - 1.;
-    double phi = 2. * PI * rng_rand(rng);
-    Vec u = make_direction_mu_phi(mu, phi);
+    Vec u = S.dir;  // mono-directional: the stored direction, no draw
+    if (S.dir_kind == 0) {  // src/isotropic.cpp:28-36
+      double mu = 2. * rng_rand(rng) - 1.;
+      double phi = 2. * PI * rng_rand(rng);
+      u = make_direction_mu_phi(mu, phi);
+    } else if (S.dir_kind == 2) {  // src/cone.cpp:34-42
+      double mu = (1. - S.cos_aperture) * rng_rand(rng) + S.cos_aperture;
+      double phi = 2. * PI * rng_rand(rng);
+      u = rotate_direction(S.dir, mu, phi);
+    }
     double E = S.energy;  // mono-energetic: sampled twice, no draws (source.cpp:49-58)
     auto sample_pos = [&]() -> Vec {
       if (!S.is_box) return S.low;

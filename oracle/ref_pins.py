@@ -649,12 +649,20 @@ NOISE_DRIVER_CASES = (("noise_oscillation.yaml", 600, 2, 1, 2), ("noise_oscillat
 MFS_CASES = (("PUa-1-0-SL_subcritical_mfs.yaml", 3000, 6),)
 # fixed-source (fission neutrons as secondaries): deck, particles per batch, batches
 FS_CASES = (("PUa-1-0-SL_subcritical_fs.yaml", 3000, 6),)
+# the same driver with beam sources (mono-directional, cone from a box, cone about the pole, isotropic; four sources picked by weight)
+BEAM_CASES = (("PUa-1-0-SL_subcritical_fs_beam.yaml", 3000, 6),)
 
 
 def evaluate_fixed_source(impl: str) -> dict:
     """The reference's own FixedSource::run() (oracle/_ref) against the oracle's driver: k_col, leakage and migration area of
     every batch and the mesh tallies' average and error of the mean."""
     return evaluate_modified_fixed_source(impl, FS_CASES, "fs")
+
+
+def evaluate_beam_sources(impl: str) -> dict:
+    """FixedSource::run() over sources with MonoDirectional and Cone direction distributions (src/mono_directional.cpp,
+    src/cone.cpp, include/simulation/mono_directional.hpp:38), the reference's own against the oracle's."""
+    return evaluate_modified_fixed_source(impl, BEAM_CASES, "fs")
 
 
 def evaluate_modified_fixed_source(impl: str, cases=None, kind: str = "mfs") -> dict:

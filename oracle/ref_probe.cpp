@@ -54,7 +54,9 @@
 #include <sobol/sobol.hpp>
 #include <simulation/box.hpp>
 #include <simulation/entropy.hpp>
+#include <simulation/cone.hpp>
 #include <simulation/isotropic.hpp>
+#include <simulation/mono_directional.hpp>
 #include <simulation/mono_energetic.hpp>
 #include <simulation/noise.hpp>
 #include <simulation/noise_maker.hpp>
@@ -1045,8 +1047,20 @@ DriverParts driver_parts(const char* text) {
         sp = std::make_shared<Point>(Position(lo[0], lo[1], lo[2]));
       }
       ls >> ekey >> E;
-      d.sources.push_back(std::make_shared<Source>(sp, std::make_shared<Isotropic>(), std::make_shared<MonoEnergetic>(E),
-                                                   fissile_only != 0, w));
+      std::string dkey, dkind;
+      ls >> dkey >> dkind;
+      std::shared_ptr<DirectionDistribution> dd = std::make_shared<Isotropic>();
+      if (dkind == "mono" || dkind == "cone") {
+        double x, y, z, aperture = 0.;
+        ls >> x >> y >> z;
+        if (dkind == "cone") {
+          ls >> aperture;
+          dd = std::make_shared<Cone>(Direction(x, y, z), aperture);
+        } else {
+          dd = std::make_shared<MonoDirectional>(Direction(x, y, z));
+        }
+      }
+      d.sources.push_back(std::make_shared<Source>(sp, dd, std::make_shared<MonoEnergetic>(E), fissile_only != 0, w));
     } else if (key == "cancel") {
       int a, b, c;
       ls >> a >> b >> c;

@@ -120,7 +120,8 @@ def test_find_cells_matches_oracle(ab, oracle_api, deck, box):
 
 def test_source_sampling_bit_exact(ab, oracle_api, tmp_path):
     import torch
-    for deck in ("c5g7_delta_collision.yaml", "PUa-1-0-IN.yaml"):
+    # (the beam deck: mono-directional, cone from a box, cone about the pole, isotropic -- four sources picked by weight)
+    for deck in ("c5g7_delta_collision.yaml", "PUa-1-0-IN.yaml", "PUa-1-0-SL_subcritical_fs_beam.yaml"):
         orc, gpu = _pair(ab, oracle_api, tmp_path, deck, {"settings": {"nparticles": 20000}})
         ob = orc.sample_source(20000)
         db = gpu.new_device_bank(20000)
@@ -706,13 +707,15 @@ def test_two_phase_host_transport_matches_the_resident_loop(ab, tmp_path):
     assert loop.h2d_bytes > 0 and loop.d2h_bytes > 0
 
 
-def test_fixed_source_driver_matches_oracle_and_reference(ab, oracle_api, tmp_path):
+@pytest.mark.parametrize("cases,golden_file", [("FS_CASES", "ref_pins_mfs.npz"), ("BEAM_CASES", "ref_pins_beam.npz")])
+def test_fixed_source_driver_matches_oracle_and_reference(ab, oracle_api, tmp_path, cases, golden_file):
     """abeille_b200.fixed_source.FixedSource (the reference's FixedSource::run: fission neutrons continue their history as
     secondaries, transport returns an empty bank) on a subcritical slab against the oracle's driver and the reference's own
-    run (tests/golden/ref_pins_mfs.npz)."""
+    run (tests/golden/ref_pins_mfs.npz); and the same slab lit by mono-directional and cone sources (src/mono_directional.cpp,
+    src/cone.cpp; tests/golden/ref_pins_beam.npz)."""
     from abeille_b200.fixed_source import FixedSource
     from oracle import ref_pins
-    fname, n, nb = ref_pins.FS_CASES[0]
+    fname, n, nb = getattr(ref_pins, cases)[0]
     path = write_deck(load_deck(fname), tmp_path / fname, {"settings": {"nparticles": n, "ngenerations": nb}})
     orc = oracle_api.Oracle(path)
     ref = orc.run_fixed_source(nb)
@@ -724,7 +727,7 @@ def test_fixed_source_driver_matches_oracle_and_reference(ab, oracle_api, tmp_pa
         for which in ("avg", "std"):
             a, b = sim.tally(t, which), orc.tally(t, which)
             assert np.allclose(a, b, rtol=1e-8, atol=1e-12 * np.abs(b).max()), (t, which)
-    gold = dict(np.load(os.path.join(GOLDEN, "ref_pins_mfs.npz")))
+    gold = dict(np.load(os.path.join(GOLDEN, golden_file)))
     name = fname.split(".")[0]
     for k in ("kcol", "leak", "mig"):
         assert np.allclose(got[k], gold[f"fs_{name}_{k}"], rtol=1e-9), k

@@ -1,5 +1,6 @@
 """CPU: host-side logic of the product (YAML reader, object model, flattening) and the C-ABI export check.
 No compute call is made here (there is no GPU in the build container)."""
+import copy
 import ctypes
 import re
 import os
@@ -178,6 +179,28 @@ def test_source_energy_outside_the_group_structure_is_fatal(native_libs, tmp_pat
     with pytest.raises(BackendError) as e:
         native_libs.parse_only(path)
     assert "200 samplings of energy" in str(e.value)
+
+
+def test_source_direction_distributions(native_libs, tmp_path):
+    """direction: isotropic | mono-directional | cone (src/direction_distribution.cpp:36-56): the axis is normalised as
+    Direction(x, y, z) does, the cone keeps cos(aperture) (src/cone.cpp:31-32); the reference's messages for what is missing."""
+    from abeille_b200 import BackendError
+    r = native_libs.source_records(deck_path("PUa-1-0-SL_subcritical_fs_beam.yaml"))
+    assert r.shape == (4, 15)
+    assert list(r[:, 10]) == [1, 2, 2, 0] and list(r[:, 0]) == [2.0, 1.5, 0.5, 1.0] and list(r[:, 2]) == [0, 1, 0, 1]
+    ax = np.array([3.0, 1.0, -0.5])
+    assert np.array_equal(r[0, 11:14], ax / np.sqrt((ax * ax).sum()))
+    assert r[1, 14] == np.cos(0.4) and r[2, 14] == np.cos(0.05) and np.array_equal(r[2, 11:14], [0.0, 0.0, -1.0])
+    deck = load_deck("PUa-1-0-SL_subcritical_fs_beam.yaml")
+    for edit, msg in ((lambda d: d["sources"][0]["direction"].pop("direction"), "No valid direction entry for mono-directional distribution."),
+                      (lambda d: d["sources"][1]["direction"].pop("aperture"), "No valid aperture entry for cone distribution."),
+                      (lambda d: d["sources"][1]["direction"].update(direction=[1.0, 0.0]), "No valid direction entry for cone distribution."),
+                      (lambda d: d["sources"][3]["direction"].update(type="lambertian"), "Invalid direction distribution type lambertian.")):
+        bad = copy.deepcopy(deck)
+        edit(bad)
+        with pytest.raises(BackendError) as e:
+            native_libs.source_records(write_deck(bad, tmp_path / "bad.yaml"))
+        assert msg in str(e.value)
 
 
 def test_unknown_surface_in_region_is_rejected(native_libs, tmp_path):
