@@ -157,15 +157,15 @@ def parse_only(yaml_path: str):
 
 
 def source_records(yaml_path: str) -> np.ndarray:
-    """Host-only: the flattened abl_source records of a deck, [nsources, 15]: weight, fissile_only, is_box, low[3], hi[3], energy,
-    direction_kind (ABL_DIR_*), dir[3] (normalised), cos_aperture."""
+    """Host-only: the flattened abl_source records of a deck, [nsources, 18]: weight, fissile_only, is_box, low[3], hi[3], energy,
+    direction_kind (ABL_DIR_*), dir[3] (normalised), cos_aperture, energy_kind (ABL_EN_*), en_a, en_b."""
     L = load_host_lib()
-    out = np.zeros(16 * 64)
+    out = np.zeros(20 * 64)
     err = C.create_string_buffer(1024)
     n = L.ablh_sources(yaml_path.encode(), out.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(len(out)), err, 1024)
     if n < 0:
         raise BackendError(1, err.value.decode())
-    return out[: 16 * n].reshape(n, 16)[:, :15].copy()
+    return out[: 20 * n].reshape(n, 20)[:, :18].copy()
 
 
 def dump_tables(yaml_path: str) -> dict:

@@ -244,8 +244,15 @@ int validate(abl_handle h, const abl_problem* p) {
   if (p->tracking != ABL_TRACK_SURFACE && !p->sampling_xs) return fail(h, ABL_ERR_INVALID, "sampling_xs missing");
   // Source::generate_particle's energy rejection (src/source.cpp:48-58): a mono-energetic source outside (min, max) never passes
   for (int s = 0; s < p->nsources; s++)
-    if (p->sources[s].energy <= p->min_energy || p->energy_bounds[p->ngroups] <= p->sources[s].energy)
+    if (p->sources[s].energy_kind == ABL_EN_MONO && (p->sources[s].energy <= p->min_energy || p->energy_bounds[p->ngroups] <= p->sources[s].energy))
       return fail(h, ABL_ERR_INVALID, "source energy outside (min_energy, max_energy): Exceded 200 samplings of energy.");
+  for (int s = 0; s < p->nsources; s++) {
+    const abl_source& f = p->sources[s];
+    if (f.direction_kind < ABL_DIR_ISOTROPIC || f.direction_kind > ABL_DIR_CONE) return fail(h, ABL_ERR_INVALID, "source direction kind");
+    if (f.energy_kind < ABL_EN_MONO || f.energy_kind > ABL_EN_WATT) return fail(h, ABL_ERR_INVALID, "source energy kind");
+    if (f.energy_kind != ABL_EN_MONO && !(f.en_a > 0.)) return fail(h, ABL_ERR_INVALID, "source energy parameter a must be > 0");
+    if (f.energy_kind == ABL_EN_WATT && !(f.en_b > 0.)) return fail(h, ABL_ERR_INVALID, "source energy parameter b must be > 0");
+  }
   return ABL_OK;
 }
 

@@ -361,14 +361,36 @@ __global__ void __launch_bounds__(128) sample_source_kernel(const DevProblem P, 
         u = rotate_direction(u, mu, phi);
       }
     }
-    const double E = ldt(&S->energy);
+    // Source::generate_particle draws the energy once, then again until it lies inside (min_energy, max_energy), at most 201
+    // more times (source.cpp:48-58); a mono-energetic source draws nothing
+    double E = ldt(&S->energy);
+    bool bad = false;
+    const int ekind = ldt(&S->energy_kind);
+    if (ekind != ABL_EN_MONO) {
+      const double ea = ldt(&S->en_a), eb = ldt(&S->en_b);
+      const double emin = P.min_energy, emax = ldt(&P.ebounds[P.G]);
+      auto sample_energy = [&]() {
+        const double xi1 = rng_rand(rng), xi2 = rng_rand(rng), xi3 = rng_rand(rng);  // maxwellian.cpp:34-42
+        double sn, c;
+        det_sincos(ABL_PI * xi3 / 2., &sn, &c);
+        const double w = -ea * (det_log(xi1) + det_log(xi2) * c * c);
+        if (ekind == ABL_EN_MAXWELLIAN) return w;
+        return w + 0.25 * ea * ea * eb + (2. * rng_rand(rng) - 1.) * sqrt(ea * ea * eb * w);  // watt.cpp:42-47
+      };
+      E = sample_energy();
+      int e_count = 0;
+      do {
+        if (e_count > 200) { bad = true; break; }
+        E = sample_energy();
+        e_count++;
+      } while (E <= emin || emax <= E);
+    }
     const bool is_box = ldt(&S->is_box) != 0;
     const double lx = ldt(&S->low[0]), ly = ldt(&S->low[1]), lz = ldt(&S->low[2]);
     const double hx = ldt(&S->hi[0]), hy = ldt(&S->hi[1]), hz = ldt(&S->hi[2]);
     V3 r;
     Cursor c;
     c.err = 0;
-    bool bad = false;
     auto sample_pos = [&]() {
       if (is_box) {  // box.cpp:37-42
         r.x = (hx - lx) * rng_rand(rng) + lx;

@@ -125,17 +125,18 @@ int ablh_dump_tables(const char* yaml_path, char* out, int64_t out_cap, char* er
   }
 }
 
-/* The flattened source records of a deck (host only): 16 doubles per source -- weight, fissile_only, is_box, low[3], hi[3], energy,
- * direction_kind, dir[3], cos_aperture.  Returns the number of sources, or -1 with the parser's message. */
+/* The flattened source records of a deck (host only): 20 doubles per source -- weight, fissile_only, is_box, low[3], hi[3], energy,
+ * direction_kind, dir[3], cos_aperture, energy_kind, en_a, en_b.  Returns the number of sources, or -1 with the parser's message. */
 int ablh_sources(const char* yaml_path, double* out, int64_t cap, char* errbuf, int errlen) {
   try {
     Problem P = Problem::from_yaml(yaml_lite::LoadFile(yaml_path));
     int64_t k = 0;
     for (const Source& src : P.sources) {
       const abl_source& f = src.flat;
-      const double row[16] = {f.weight, (double)f.fissile_only, (double)f.is_box, f.low[0], f.low[1], f.low[2], f.hi[0], f.hi[1], f.hi[2],
-                              f.energy, (double)f.direction_kind, f.dir[0], f.dir[1], f.dir[2], f.cos_aperture, 0.};
-      if (k + 16 > cap) throw std::runtime_error("source buffer too small");
+      const double row[20] = {f.weight, (double)f.fissile_only, (double)f.is_box, f.low[0], f.low[1], f.low[2], f.hi[0], f.hi[1], f.hi[2],
+                              f.energy, (double)f.direction_kind, f.dir[0], f.dir[1], f.dir[2], f.cos_aperture, (double)f.energy_kind,
+                              f.en_a, f.en_b, 0., 0.};
+      if (k + 20 > cap) throw std::runtime_error("source buffer too small");
       for (double v : row) out[k++] = v;
     }
     return static_cast<int>(P.sources.size());

@@ -579,9 +579,33 @@ Source make_source(const Node& s) {  // src/source.cpp:92-140
   } else {
     fatal_error("Invalid direction distribution type " + dtype + ".");
   }
-  if (!s["energy"] || !s["energy"]["type"] || s["energy"]["type"].as_string() != "mono-energetic")
-    fatal_error("Only mono-energetic source energies are provided by the B200 backend.");
-  f.energy = s["energy"]["energy"].as_double();
+  // src/energy_distribution.cpp:36-58
+  if (!s["energy"] || !s["energy"].IsMap()) fatal_error("No valid energy distribution entry provided for source.");
+  if (!s["energy"]["type"] || !s["energy"]["type"].IsScalar()) fatal_error("No valid type provided to energy distribution entry.");
+  const std::string etype = s["energy"]["type"].as_string();
+  const Node& en = s["energy"];
+  if (etype == "mono-energetic") {  // src/mono_energetic.cpp
+    if (!en["energy"] || !en["energy"].IsScalar()) fatal_error("No valid energy entry for mono-energetic distribution.");
+    f.energy_kind = ABL_EN_MONO;
+    f.energy = en["energy"].as_double();
+  } else if (etype == "maxwellian") {  // src/maxwellian.cpp:44-55
+    if (!en["a"] || !en["a"].IsScalar()) fatal_error("No valid \"a\" entry in maxwellian distribution.");
+    f.energy_kind = ABL_EN_MAXWELLIAN;
+    f.en_a = en["a"].as_double();
+    if (f.en_a <= 0.) fatal_error("Maxwellian parameter a must be >= 0.");
+  } else if (etype == "watt") {  // src/watt.cpp:49-66
+    if (!en["a"] || !en["a"].IsScalar()) fatal_error("No valid \"a\" entry in watt distribution.");
+    f.en_a = en["a"].as_double();
+    if (f.en_a <= 0.) fatal_error("Watt parameter a must be >= 0.");
+    if (!en["b"] || !en["b"].IsScalar()) fatal_error("No valid \"b\" entry in watt distribution.");
+    f.en_b = en["b"].as_double();
+    if (f.en_b <= 0.) fatal_error("Watt parameter b must be >= 0.");
+    f.energy_kind = ABL_EN_WATT;
+  } else if (etype == "tabulated") {
+    fatal_error("Energy distribution \"tabulated\" (PapillonNDL's PCTable) is not provided by the B200 backend.");
+  } else {
+    fatal_error("Invalid energy distribution type " + etype + ".");
+  }
   f.fissile_only = (s["fissile-only"] && s["fissile-only"].as_bool()) ? 1 : 0;  // SOURCE level only (source.cpp:104-110)
   if (!s["weight"] || !s["weight"].IsScalar()) fatal_error("No weight given to source.");
   f.weight = s["weight"].as_double();
@@ -750,7 +774,7 @@ Problem Problem::from_yaml(const Node& input) {
   // Source::generate_particle redraws the energy until it lies inside (min_energy, max_energy) and gives up after 200 draws
   // (src/source.cpp:48-58); a mono-energetic source outside the range can only ever end there
   for (const Source& src : P.sources)
-    if (src.flat.energy <= P.settings.min_energy || P.settings.max_energy <= src.flat.energy) fatal_error("Exceded 200 samplings of energy.");
+    if (src.flat.energy_kind == ABL_EN_MONO && (src.flat.energy <= P.settings.min_energy || P.settings.max_energy <= src.flat.energy)) fatal_error("Exceded 200 samplings of energy.");
   if (input["entropy"] && input["entropy"].IsMap()) P.entropy = make_mesh_spec(input["entropy"], "entropy mesh");
   // noise sources (src/noise_maker.cpp:39-58, src/square_oscillation_noise_source.cpp:38-83,177-250)
   if (input["noise-sources"] && input["noise-sources"].IsSequence())

@@ -123,7 +123,12 @@ typedef struct abl_mesh_tally {
 #define ABL_DIR_MONO 1           /* src/mono_directional.cpp, include/simulation/mono_directional.hpp:38: no draw */
 #define ABL_DIR_CONE 2           /* src/cone.cpp:31-42: mu uniform in [cos(aperture), 1], phi, rotate_direction */
 
-typedef struct abl_source {      /* box | point; isotropic | mono-directional | cone; mono-energetic (source.cpp:44-90) */
+/* energy distribution of a source (src/energy_distribution.cpp:36-58); `tabulated` needs PapillonNDL's PCTable and is not provided */
+#define ABL_EN_MONO 0            /* src/mono_energetic.cpp: no draw                                    */
+#define ABL_EN_MAXWELLIAN 1      /* src/maxwellian.cpp:34-42: three draws, -a (log xi1 + log xi2 cos^2(pi xi3 / 2)) */
+#define ABL_EN_WATT 2            /* src/watt.cpp:42-47: a Maxwellian(a) sample w and one more draw     */
+
+typedef struct abl_source {      /* box | point; isotropic | mono-directional | cone; mono-energetic | maxwellian | watt (source.cpp:44-90) */
   double weight;
   int32_t fissile_only, is_box;
   double low[3], hi[3];          /* point: low == position                                             */
@@ -131,6 +136,8 @@ typedef struct abl_source {      /* box | point; isotropic | mono-directional | 
   int32_t direction_kind, pad_;  /* ABL_DIR_*                                                          */
   double dir[3];                 /* mono-directional / cone axis, NORMALISED as Direction(x, y, z) does (direction.hpp:37-42) */
   double cos_aperture;           /* cone: std::cos(aperture), taken once on the host (cone.cpp:31-32)  */
+  int32_t energy_kind, pad2_;    /* ABL_EN_*; `energy` is the mono-energetic value                     */
+  double en_a, en_b;             /* maxwellian: a; watt: a, b                                          */
 } abl_source;
 
 typedef struct abl_mesh3 {       /* entropy mesh (entropy.cpp) / approximate cancelator mesh           */

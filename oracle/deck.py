@@ -171,8 +171,18 @@ def deck_to_text(deck: dict) -> str:
     out.append(f"nsrc {len(srcs)}")
     for s in srcs:
         sp = s["spatial"]
-        if s["energy"]["type"] != "mono-energetic":
-            raise ValueError("oracle: mono-energetic sources only")
+        ee = s["energy"]
+        if ee["type"] == "mono-energetic":
+            e_src = float(ee["energy"])
+            if e_src <= float(eb[0]) or float(eb[-1]) <= e_src:  # Source::generate_particle's rejection loop (src/source.cpp:48-58)
+                raise ValueError("Exceded 200 samplings of energy.")
+            en = f"energy {_f(ee['energy'])}"
+        elif ee["type"] == "maxwellian":  # src/maxwellian.cpp
+            en = f"energy 0 maxwellian {_f(ee['a'])}"
+        elif ee["type"] == "watt":  # src/watt.cpp
+            en = f"energy 0 watt {_f(ee['a'])} {_f(ee['b'])}"
+        else:
+            raise ValueError("oracle: mono-energetic, maxwellian and watt sources only")
         dd = s["direction"]
         if dd["type"] == "isotropic":
             dirn = "dir iso"
@@ -189,10 +199,7 @@ def deck_to_text(deck: dict) -> str:
             pos = "point " + _fl(sp["position"])
         else:
             raise ValueError("oracle: box/point sources only")
-        e_src = float(s["energy"]["energy"])
-        if e_src <= float(eb[0]) or float(eb[-1]) <= e_src:  # Source::generate_particle's rejection loop (src/source.cpp:48-58)
-            raise ValueError("Exceded 200 samplings of energy.")
-        out.append(f"src {_f(s['weight'])} {fo} {pos} energy {_f(s['energy']['energy'])} {dirn}")
+        out.append(f"src {_f(s['weight'])} {fo} {pos} {en} {dirn}")
 
     tallies = deck.get("tallies", []) or []
     out.append(f"ntally {len(tallies)}")

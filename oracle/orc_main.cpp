@@ -63,6 +63,8 @@ struct Source {  // src/source.cpp, box.cpp, point.cpp, isotropic.cpp, mono_ener
   int dir_kind = 0;               // 0 isotropic, 1 mono-directional (mono_directional.hpp:38), 2 cone (cone.cpp:31-42)
   Vec dir{0, 0, 1};               // normalised, as Direction(x, y, z) leaves it
   double cos_aperture = 1.;       // Cone::Cone stores std::cos(aperture)
+  int en_kind = 0;                // 0 mono-energetic, 1 maxwellian (maxwellian.cpp:34-42), 2 watt (watt.cpp:42-47)
+  double en_a = 0., en_b = 0.;
 };
 
 struct Cancelator {  // kind 1: ApproximateMeshCancelator, kind 2: BasicExactMGCancelator (beta 0 zero, 1 minimum, 2 average-f, 3 average-g)
@@ -247,6 +249,9 @@ static Problem* load_problem(const char* path) {
   const size_t G = st.ngroups;
   tk.expect("ebounds");
   st.energy_bounds = tk.dv(G + 1);
+  // parser.cpp:158-168 with mg_nuclide.cpp:425-427: the materials' common energy range narrows the defaults
+  if (st.energy_bounds.front() > st.min_energy) st.min_energy = st.energy_bounds.front();
+  if (st.energy_bounds.back() < st.max_energy) st.max_energy = st.energy_bounds.back();
   tk.expect("nparticles"); st.nparticles = (int)tk.ll();
   tk.expect("ngenerations"); st.ngenerations = (int)tk.ll();
   tk.expect("nignored"); st.nignored = (int)tk.ll();
@@ -457,8 +462,15 @@ static Problem* load_problem(const char* path) {
     }
     tk.expect("energy");
     src.energy = tk.d();
-    tk.expect("dir");
-    const std::string dk = tk.next();
+    std::string dk = tk.next();
+    if (dk == "maxwellian" || dk == "watt") {
+      src.en_kind = dk == "watt" ? 2 : 1;
+      src.en_a = tk.d();
+      if (src.en_kind == 2) src.en_b = tk.d();
+      dk = tk.next();
+    }
+    if (dk != "dir") throw std::runtime_error("expected dir, got " + dk);
+    dk = tk.next();
     if (dk == "mono" || dk == "cone") {
       const double dx = tk.d(), dy = tk.d(), dz = tk.d();
       src.dir = make_direction(dx, dy, dz);
@@ -1993,6 +2005,22 @@ static std::vector<Particle> sample_sources(Problem& P, size_t N) {
       u = rotate_direction(S.dir, mu, phi);
     }
     double E = S.energy;  // mono-energetic: sampled twice, no draws (source.cpp:49-58)
+    if (S.en_kind != 0) {
+      auto sample_energy = [&]() {
+        const double xi1 = rng_rand(rng), xi2 = rng_rand(rng), xi3 = rng_rand(rng);  // maxwellian.cpp:34-42
+        const double c = g_math.cos(PI * xi3 / 2.);
+        const double w = -S.en_a * (g_math.log(xi1) + g_math.log(xi2) * c * c);
+        if (S.en_kind == 1) return w;
+        return w + 0.25 * S.en_a * S.en_a * S.en_b + (2. * rng_rand(rng) - 1.) * std::sqrt(S.en_a * S.en_a * S.en_b * w);  // watt.cpp:42-47
+      };
+      E = sample_energy();
+      int E_count = 0;
+      do {  // source.cpp:50-58
+        if (E_count > 200) throw std::runtime_error("Exceded 200 samplings of energy.");
+        E = sample_energy();
+        E_count++;
+      } while (E <= P.st.min_energy || P.st.max_energy <= E);
+    }
     auto sample_pos = [&]() -> Vec {
       if (!S.is_box) return S.low;
       double x = (S.hi.x - S.low.x) * rng_rand(rng) + S.low.x;  // box.cpp:37-42

@@ -650,7 +650,9 @@ MFS_CASES = (("PUa-1-0-SL_subcritical_mfs.yaml", 3000, 6),)
 # fixed-source (fission neutrons as secondaries): deck, particles per batch, batches
 FS_CASES = (("PUa-1-0-SL_subcritical_fs.yaml", 3000, 6),)
 # the same driver with beam sources (mono-directional, cone from a box, cone about the pole, isotropic; four sources picked by weight)
-BEAM_CASES = (("PUa-1-0-SL_subcritical_fs_beam.yaml", 3000, 6),)
+BEAM_CASES = (("PUa-1-0-SL_subcritical_fs_beam.yaml", 3000, 6),
+              # ... and with energy distributions: Maxwellian, Watt with a rejected tail, mono-energetic, on a two-group slab
+              ("UD2O-2-1-SL_subcritical_fs_spectra.yaml", 3000, 6))
 
 
 def evaluate_fixed_source(impl: str) -> dict:
@@ -659,10 +661,12 @@ def evaluate_fixed_source(impl: str) -> dict:
     return evaluate_modified_fixed_source(impl, FS_CASES, "fs")
 
 
-def evaluate_beam_sources(impl: str) -> dict:
+def evaluate_beam_sources(impl: str, only: int | None = None) -> dict:
     """FixedSource::run() over sources with MonoDirectional and Cone direction distributions (src/mono_directional.cpp,
-    src/cone.cpp, include/simulation/mono_directional.hpp:38), the reference's own against the oracle's."""
-    return evaluate_modified_fixed_source(impl, BEAM_CASES, "fs")
+    src/cone.cpp, include/simulation/mono_directional.hpp:38) and Maxwellian and Watt energy distributions (src/maxwellian.cpp,
+    src/watt.cpp), the reference's own against the oracle's.  `only`: one case (the reference keeps its state in process
+    globals: one case per process)."""
+    return evaluate_modified_fixed_source(impl, BEAM_CASES if only is None else BEAM_CASES[only:only + 1], "fs")
 
 
 def evaluate_modified_fixed_source(impl: str, cases=None, kind: str = "mfs") -> dict:

@@ -56,8 +56,10 @@
 #include <simulation/entropy.hpp>
 #include <simulation/cone.hpp>
 #include <simulation/isotropic.hpp>
+#include <simulation/maxwellian.hpp>
 #include <simulation/mono_directional.hpp>
 #include <simulation/mono_energetic.hpp>
+#include <simulation/watt.hpp>
 #include <simulation/noise.hpp>
 #include <simulation/noise_maker.hpp>
 #include <simulation/point.hpp>
@@ -1047,8 +1049,22 @@ DriverParts driver_parts(const char* text) {
         sp = std::make_shared<Point>(Position(lo[0], lo[1], lo[2]));
       }
       ls >> ekey >> E;
+      std::shared_ptr<EnergyDistribution> ed;
       std::string dkey, dkind;
-      ls >> dkey >> dkind;
+      ls >> dkey;
+      if (dkey == "maxwellian" || dkey == "watt") {
+        double a, b;
+        ls >> a;
+        if (dkey == "watt") {
+          ls >> b;
+          ed = std::make_shared<Watt>(a, b);
+        } else {
+          ed = std::make_shared<Maxwellian>(a);
+        }
+        ls >> dkey;
+      }
+      if (!ed) ed = std::make_shared<MonoEnergetic>(E);
+      ls >> dkind;
       std::shared_ptr<DirectionDistribution> dd = std::make_shared<Isotropic>();
       if (dkind == "mono" || dkind == "cone") {
         double x, y, z, aperture = 0.;
@@ -1060,7 +1076,7 @@ DriverParts driver_parts(const char* text) {
           dd = std::make_shared<MonoDirectional>(Direction(x, y, z));
         }
       }
-      d.sources.push_back(std::make_shared<Source>(sp, dd, std::make_shared<MonoEnergetic>(E), fissile_only != 0, w));
+      d.sources.push_back(std::make_shared<Source>(sp, dd, ed, fissile_only != 0, w));
     } else if (key == "cancel") {
       int a, b, c;
       ls >> a >> b >> c;

@@ -121,7 +121,9 @@ def test_find_cells_matches_oracle(ab, oracle_api, deck, box):
 def test_source_sampling_bit_exact(ab, oracle_api, tmp_path):
     import torch
     # (the beam deck: mono-directional, cone from a box, cone about the pole, isotropic -- four sources picked by weight)
-    for deck in ("c5g7_delta_collision.yaml", "PUa-1-0-IN.yaml", "PUa-1-0-SL_subcritical_fs_beam.yaml"):
+    # (the spectra deck: Maxwellian and Watt energies with the rejection loop of Source::generate_particle, a cone, a point)
+    for deck in ("c5g7_delta_collision.yaml", "PUa-1-0-IN.yaml", "PUa-1-0-SL_subcritical_fs_beam.yaml",
+                 "UD2O-2-1-SL_subcritical_fs_spectra.yaml"):
         orc, gpu = _pair(ab, oracle_api, tmp_path, deck, {"settings": {"nparticles": 20000}})
         ob = orc.sample_source(20000)
         db = gpu.new_device_bank(20000)
@@ -707,15 +709,17 @@ def test_two_phase_host_transport_matches_the_resident_loop(ab, tmp_path):
     assert loop.h2d_bytes > 0 and loop.d2h_bytes > 0
 
 
-@pytest.mark.parametrize("cases,golden_file", [("FS_CASES", "ref_pins_mfs.npz"), ("BEAM_CASES", "ref_pins_beam.npz")])
-def test_fixed_source_driver_matches_oracle_and_reference(ab, oracle_api, tmp_path, cases, golden_file):
+@pytest.mark.parametrize("cases,ci,golden_file", [("FS_CASES", 0, "ref_pins_mfs.npz"), ("BEAM_CASES", 0, "ref_pins_beam.npz"),
+                                                  ("BEAM_CASES", 1, "ref_pins_beam.npz")])
+def test_fixed_source_driver_matches_oracle_and_reference(ab, oracle_api, tmp_path, cases, ci, golden_file):
     """abeille_b200.fixed_source.FixedSource (the reference's FixedSource::run: fission neutrons continue their history as
     secondaries, transport returns an empty bank) on a subcritical slab against the oracle's driver and the reference's own
     run (tests/golden/ref_pins_mfs.npz); and the same slab lit by mono-directional and cone sources (src/mono_directional.cpp,
-    src/cone.cpp; tests/golden/ref_pins_beam.npz)."""
+    src/cone.cpp; tests/golden/ref_pins_beam.npz), and a two-group slab lit by Maxwellian and Watt spectra (src/maxwellian.cpp,
+    src/watt.cpp)."""
     from abeille_b200.fixed_source import FixedSource
     from oracle import ref_pins
-    fname, n, nb = getattr(ref_pins, cases)[0]
+    fname, n, nb = getattr(ref_pins, cases)[ci]
     path = write_deck(load_deck(fname), tmp_path / fname, {"settings": {"nparticles": n, "ngenerations": nb}})
     orc = oracle_api.Oracle(path)
     ref = orc.run_fixed_source(nb)

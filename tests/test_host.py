@@ -186,7 +186,7 @@ def test_source_direction_distributions(native_libs, tmp_path):
     Direction(x, y, z) does, the cone keeps cos(aperture) (src/cone.cpp:31-32); the reference's messages for what is missing."""
     from abeille_b200 import BackendError
     r = native_libs.source_records(deck_path("PUa-1-0-SL_subcritical_fs_beam.yaml"))
-    assert r.shape == (4, 15)
+    assert r.shape == (4, 18) and not r[:, 15:].any()   # all mono-energetic
     assert list(r[:, 10]) == [1, 2, 2, 0] and list(r[:, 0]) == [2.0, 1.5, 0.5, 1.0] and list(r[:, 2]) == [0, 1, 0, 1]
     ax = np.array([3.0, 1.0, -0.5])
     assert np.array_equal(r[0, 11:14], ax / np.sqrt((ax * ax).sum()))
@@ -196,6 +196,28 @@ def test_source_direction_distributions(native_libs, tmp_path):
                       (lambda d: d["sources"][1]["direction"].pop("aperture"), "No valid aperture entry for cone distribution."),
                       (lambda d: d["sources"][1]["direction"].update(direction=[1.0, 0.0]), "No valid direction entry for cone distribution."),
                       (lambda d: d["sources"][3]["direction"].update(type="lambertian"), "Invalid direction distribution type lambertian.")):
+        bad = copy.deepcopy(deck)
+        edit(bad)
+        with pytest.raises(BackendError) as e:
+            native_libs.source_records(write_deck(bad, tmp_path / "bad.yaml"))
+        assert msg in str(e.value)
+
+
+def test_source_energy_distributions(native_libs, tmp_path):
+    """energy: mono-energetic | maxwellian | watt (src/energy_distribution.cpp:36-58, src/maxwellian.cpp:44-55, src/watt.cpp:49-66);
+    `tabulated` needs PapillonNDL's PCTable and is refused by name."""
+    from abeille_b200 import BackendError
+    r = native_libs.source_records(deck_path("UD2O-2-1-SL_subcritical_fs_spectra.yaml"))
+    assert r.shape == (3, 18)
+    assert list(r[:, 15]) == [1, 2, 0] and list(r[:, 16]) == [0.45, 0.35, 0.0] and list(r[:, 17]) == [0.0, 2.0, 0.0] and r[2, 9] == 1.5
+    assert list(r[:, 10]) == [0, 2, 0] and r[1, 14] == np.cos(0.6)
+    deck = load_deck("UD2O-2-1-SL_subcritical_fs_spectra.yaml")
+    for edit, msg in ((lambda d: d["sources"][0]["energy"].pop("a"), 'No valid "a" entry in maxwellian distribution.'),
+                      (lambda d: d["sources"][0]["energy"].update(a=-1.0), "Maxwellian parameter a must be >= 0."),
+                      (lambda d: d["sources"][1]["energy"].pop("b"), 'No valid "b" entry in watt distribution.'),
+                      (lambda d: d["sources"][1]["energy"].update(b=0.0), "Watt parameter b must be >= 0."),
+                      (lambda d: d["sources"][2]["energy"].update(type="tabulated"), "tabulated"),
+                      (lambda d: d["sources"][2]["energy"].update(type="thermal"), "Invalid energy distribution type thermal.")):
         bad = copy.deepcopy(deck)
         edit(bad)
         with pytest.raises(BackendError) as e:
