@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "abl_transport_noise", "abl_transport_begin", "abl_transport_finish", "abl_get_trace",
     "abl_transport_device", "abl_transport_noise_device", "abl_bank_weight_magnitude_device", "abl_bank_divide_weights_device",
     "abl_tally_count", "abl_tally_shape", "abl_tallies_record", "abl_tallies_clear",
-    "abl_tally_fetch", "abl_tally_device_ptr", "abl_sample_source_device", "abl_bank_weight_stats_device",
+    "abl_tally_fetch", "abl_tally_device_ptr", "abl_sample_source_device", "abl_bank_weight_stats_device", "abl_bank_moments_device",
     "abl_bank_scale_weights_device", "abl_bank_to_particles_device", "abl_entropy_bin_device",
     "abl_score_source_device", "abl_cancel_device", "abl_cancel_accumulate_device", "abl_cancel_apply_device",
     "abl_cancel_bins_device", "abl_cancel_exact_device", "abl_parent_info_download", "abl_parent_state_download", "abl_bank_alloc_device", "abl_bank_free_device",
@@ -532,6 +532,14 @@ class Backend:
         st = np.zeros(4)
         self._check(self.L.abl_bank_weight_stats_device(self.h, C.byref(s), st.ctypes.data_as(_PD), self._stream()))
         return st
+
+    def moments_device(self, bank: dict, n: int, origin=(0., 0., 0.)) -> np.ndarray:
+        """abl_bank_moments_device: [sum w, sum w (r - o) (3), sum w |r - o|^2] of the first n rows."""
+        s = _device_struct(bank, n)
+        o = np.asarray(origin, dtype=np.float64)
+        out = np.zeros(5)
+        self._check(self.L.abl_bank_moments_device(self.h, C.byref(s), o.ctypes.data_as(_PD), out.ctypes.data_as(_PD), self._stream()))
+        return out
 
     def scale_weights_device(self, bank: dict, n: int, factor: float):
         s = _device_struct(bank, n)

@@ -38,6 +38,7 @@ struct DevSmall {  // small per-call block, zeroed before every transport launch
   unsigned long long n_nsites;
   unsigned long long eq_stats[16];  // event kernel: tasks and lanes per event (ABEILLE_B200_EQ_STATS=1)
   unsigned long long avail;  // rows of a streamed input bank that have arrived (abl_transport)
+  double moments[8];         // abl_bank_moments_device
 };
 
 thread_local std::string g_create_error;
@@ -1563,6 +1564,23 @@ int abl_bank_weight_stats_device(abl_handle h, const abl_bank* bank_dev, double 
   ABL_CUDA(h, cudaMemcpyAsync(h->small_host->stats, h->small_dev->stats, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
   ABL_CUDA(h, cudaStreamSynchronize(s));
   for (int i = 0; i < 4; i++) stats[i] = h->small_host->stats[i];
+  return ABL_OK;
+}
+
+int abl_bank_moments_device(abl_handle h, const abl_bank* bank_dev, const double origin[3], double moments[5], void* stream) {
+  if (!h || !bank_dev || !origin || !moments) return ABL_ERR_INVALID;
+  if (bank_dev->n && (!bank_dev->x || !bank_dev->y || !bank_dev->z || !bank_dev->wgt)) return fail(h, ABL_ERR_INVALID, "null bank array");
+  ABL_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = use_stream(h, (cudaStream_t)stream);
+  ABL_CUDA(h, cudaMemsetAsync(h->small_dev->moments, 0, sizeof(double) * 8, s));
+  if (bank_dev->n) {
+    bank_moments_kernel<<<grid_for(h, bank_dev->n, 256), 256, 0, s>>>(bank_dev->x, bank_dev->y, bank_dev->z, bank_dev->wgt, bank_dev->n, origin[0],
+                                                                     origin[1], origin[2], h->small_dev->moments);
+    h->launches++;
+  }
+  ABL_CUDA(h, cudaMemcpyAsync(h->small_host->moments, h->small_dev->moments, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
+  ABL_CUDA(h, cudaStreamSynchronize(s));
+  for (int i = 0; i < 5; i++) moments[i] = h->small_host->moments[i];
   return ABL_OK;
 }
 

@@ -185,6 +185,38 @@ __global__ void __launch_bounds__(256) weight_stats_kernel(const double* __restr
   }
 }
 
+// Weighted moments of the bank about a point o: out[0..4] += sum w, sum w (x - ox), sum w (y - oy), sum w (z - oz), sum w |r - o|^2.
+// PowerIterator::compute_pair_dist_sqrd (src/power_iterator.cpp:637-663) is the double sum over all pairs
+// sum_ij w_i w_j |r_i - r_j|^2 / (2 W^2), 1e14 terms at the bench size; it equals sum_i w_i |r_i - c|^2 / W about the weighted
+// centroid c = sum w r / W, which is two passes of this kernel.
+__global__ void __launch_bounds__(256) bank_moments_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                           const double* __restrict__ z, const double* __restrict__ w, uint64_t n,
+                                                           double ox, double oy, double oz, double* out) {
+  double vals[5] = {0., 0., 0., 0., 0.};
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double wi = w[i], dx = x[i] - ox, dy = y[i] - oy, dz = z[i] - oz;
+    vals[0] += wi;
+    vals[1] += wi * dx;
+    vals[2] += wi * dy;
+    vals[3] += wi * dz;
+    vals[4] += wi * (dx * dx + dy * dy + dz * dz);
+  }
+  __shared__ double sm[8][5];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 5; q++) {
+    double v = vals[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[wid][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double v = 0.;
+    for (int k = 0; k < 8; k++) v += sm[k][threadIdx.x];
+    atomicAdd(&out[threadIdx.x], v);
+  }
+}
+
 // noise.cpp:438-456: sum of |w| over complex weights; w /= d
 __global__ void __launch_bounds__(256) weight_magnitude_kernel(const double* __restrict__ w, const double* __restrict__ w2, uint64_t n, double* out) {
   double v = 0.;

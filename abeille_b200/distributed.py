@@ -134,6 +134,13 @@ class DistributedPowerIterator:
         with open(deck_path) as f:
             deck = yaml.safe_load(f)
         self.cancellation = bool(deck.get("settings", {}).get("cancellation", False)) and "cancelator" in deck
+        # optional per-generation diagnostics of PowerIterator (settings: pair-distance-sqrd, families, empty-entropy-bins;
+        # src/parser.cpp:833-858, src/power_iterator.cpp:283-297,326-331,362-365,613-615)
+        st = deck.get("settings", {})
+        self.pair_distance = bool(st.get("pair-distance-sqrd", False))
+        self.families = bool(st.get("families", False))
+        self.empty_entropy_bins = bool(st.get("empty-entropy-bins", False)) and "entropy" in deck
+        self.r_sqrd_series, self.families_series, self.empty_entropy_frac_series = [], [], []
         # Shannon entropy of the fission source (src/entropy.cpp:32-93): bins + total weight, summed over the ranks
         self.entropy_series = []
         self._ebins = None
@@ -196,10 +203,22 @@ class DistributedPowerIterator:
             torch.cuda.current_stream().synchronize()
             dist.all_reduce(self._ebins, group=self.group)
         b = self._ebins.cpu().numpy()
+        if self.empty_entropy_bins:  # Entropy::calculate_empty_fraction (src/entropy.cpp:95-105)
+            self.empty_entropy_frac_series.append(float((b[:-1] == 0.).sum()) / (len(b) - 1))
         total = b[-1]
         p = np.abs(b[:-1]) / total
         p = p[(p != 0.) & (p <= 1.0)]
         return float(-(p * np.log2(p)).sum())
+
+    def _pair_distance_sqrd(self, m: int) -> float:
+        """PowerIterator::compute_pair_dist_sqrd (src/power_iterator.cpp:637-663) over the global normalised fission bank: the
+        reference's double sum over all pairs, sum_ij w_i w_j |r_i - r_j|^2 / (2 W^2), is sum_i w_i |r_i - c|^2 / W about the
+        weighted centroid c -- two passes of abl_bank_moments_device and two small gathers instead of N^2 terms."""
+        m1 = self._gather(self.gpu.moments_device(self.nxt, m)).sum(axis=0)
+        c = m1[1:4] / m1[0]
+        m2 = self._gather(self.gpu.moments_device(self.nxt, m, c)).sum(axis=0)
+        # (the centroid of the second pass is exact only to rounding: remove what is left of it)
+        return float((m2[4] - (m2[1:4] ** 2).sum() / m2[0]) / m2[0])
 
     # ---- Simulation::sample_sources: rank r samples the ids [r*n, (r+1)*n) ----
     def initialize(self):
@@ -302,6 +321,11 @@ class DistributedPowerIterator:
         gpu = self.gpu
         n_in = self.n_cur
         from .backend import BackendError
+        if self.families:
+            # the families that enter the generation: every rank counts its own set and the counts are summed, as
+            # mpi::Reduce_sum(families.size()) does (src/power_iterator.cpp:326-331,288-292)
+            nfam = torch.unique(self.cur["id_b"][:n_in]).numel() if n_in else 0
+            self.families_series.append(int(self._gather(np.array([float(nfam)])).sum()))
         for attempt in range(3):
             try:
                 m, scores, cn = gpu.transport_device(self.cur, n_in, self.nxt, k_col=self.k_col, converged=self.converged,
@@ -343,6 +367,8 @@ class DistributedPowerIterator:
             ws = gpu.weight_stats_device(self.nxt, m)
             wall = self._gather(ws).sum(axis=0)
             gpu.scale_weights_device(self.nxt, m, self.n_total / (wall[2] - wall[3]))
+        if self.pair_distance:
+            self.r_sqrd_series.append(self._pair_distance_sqrd(m))  # after normalize_weights (src/power_iterator.cpp:358-366)
         if self.converged:
             gpu.score_source_device(self.nxt, m)  # SourceMeshTally::score_source on the normalised bank (power_iterator.cpp:366-372)
             if self.world > 1:

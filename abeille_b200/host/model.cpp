@@ -101,6 +101,11 @@ void make_settings(const Node& input, Settings& st) {
   if (s["keff"]) st.keff = s["keff"].as_double();
   if (s["inner-generations"]) st.inner_generations = s["inner-generations"].as_bool();
   if (s["normalize-noise-source"]) st.normalize_noise_source = s["normalize-noise-source"].as_bool();
+  // optional diagnostics of the power iteration (src/parser.cpp:833-858)
+  if (s["pair-distance-sqrd"] && s["pair-distance-sqrd"].IsScalar()) st.pair_distance_sqrd = s["pair-distance-sqrd"].as_bool();
+  if (s["families"] && s["families"].IsScalar()) st.families = s["families"].as_bool();
+  else if (s["families"]) fatal_error("The settings option \"families\" must be a single boolean value.");
+  if (s["empty-entropy-bins"] && s["empty-entropy-bins"].IsScalar()) st.empty_entropy_bins = s["empty-entropy-bins"].as_bool();
 }
 
 // ---- materials (src/mg_nuclide.cpp:546-922, src/legendre_distribution.cpp) ----------------------------

@@ -33,6 +33,7 @@ struct Settings {  // include/utils/settings.hpp:54-128, defaults src/settings.c
   bool regional_cancellation = false, regional_cancellation_noise = false;
   int n_cancel_noise_gens = INT32_MAX;
   bool inner_generations = true, normalize_noise_source = true;
+  bool pair_distance_sqrd = false, families = false, empty_entropy_bins = false;  // settings.cpp:74-76, parser.cpp:833-858
   double w_noise = -1., eta = 1., keff = 1.;
 };
 

@@ -570,6 +570,15 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
     gp.k_col = tallies->kcol();
     gp.keff = tallies->keff();
     gp.converged = transporter->converged ? 1 : 0;
+    if (st.families) {  // the families that enter the generation (src/power_iterator.cpp:326-331): distinct family ids of the bank
+      std::vector<uint64_t> fam(N);
+      abl_bank ids{};
+      ids.n = N;
+      ids.id_b = fam.data();
+      check(h, abl_bank_download(h, &cur.b, N, &ids), "abl_bank_download");
+      std::sort(fam.begin(), fam.end());
+      families_vec.push_back(static_cast<double>(std::unique(fam.begin(), fam.end()) - fam.begin()));
+    }
     abl_bank out = nxt.b;
     out.n = nxt.cap;
     uint64_t n_fis = 0, cn[8];
@@ -605,6 +614,9 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
       check(h, abl_device_read(h, ebins.data(), ebins_dev, (nebins + 1) * sizeof(double), nullptr), "abl_device_read");
       const double total = ebins[nebins];
       entropy = entropy_from_bins(std::vector<double>(ebins.begin(), ebins.begin() + static_cast<long>(nebins)), total);
+      if (st.empty_entropy_bins)  // Entropy::calculate_empty_fraction (src/entropy.cpp:95-105)
+        empty_entropy_frac_vec.push_back(static_cast<double>(std::count(ebins.begin(), ebins.begin() + static_cast<long>(nebins), 0.)) /
+                                         static_cast<double>(nebins));
     }
     tallies->calc_gen_values();
     if (cancel && exact) {
@@ -654,6 +666,16 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
       out = nxt.b;
       n_fis = rows.size();
       out.n = n_fis;
+    }
+    if (st.pair_distance_sqrd) {
+      // PowerIterator::compute_pair_dist_sqrd over the normalised bank (src/power_iterator.cpp:362-365,637-663): the double sum over
+      // all pairs equals the weighted second moment about the weighted centroid -- two passes of abl_bank_moments_device
+      const double zero[3] = {0., 0., 0.};
+      double m1[5], m2[5];
+      check(h, abl_bank_moments_device(h, &out, zero, m1, nullptr), "abl_bank_moments_device");
+      const double c[3] = {m1[1] / m1[0], m1[2] / m1[0], m1[3] / m1[0]};
+      check(h, abl_bank_moments_device(h, &out, c, m2, nullptr), "abl_bank_moments_device");
+      r_sqrd_vec.push_back((m2[4] - (m2[1] * m2[1] + m2[2] * m2[2] + m2[3] * m2[3]) / m2[0]) / m2[0]);
     }
     if (transporter->converged) {
       check(h, abl_score_source_device(h, &out, 0, nullptr), "abl_score_source_device");
@@ -735,6 +757,10 @@ void PowerIterator::write_results(const std::string& dir) const {
   write_npy(dir + "/leakage.npy", tallies->leak_vec, {tallies->leak_vec.size()});
   write_npy(dir + "/mig-area.npy", tallies->mig_vec, {tallies->mig_vec.size()});
   write_npy(dir + "/entropy.npy", entropy_vec, {entropy_vec.size()});
+  // results/families, results/pair-dist-sqrd, results/empty-entropy-frac (src/power_iterator.cpp:475-503)
+  if (!families_vec.empty()) write_npy(dir + "/families.npy", families_vec, {families_vec.size()});
+  if (!r_sqrd_vec.empty()) write_npy(dir + "/pair-dist-sqrd.npy", r_sqrd_vec, {r_sqrd_vec.size()});
+  if (!empty_entropy_frac_vec.empty()) write_npy(dir + "/empty-entropy-frac.npy", empty_entropy_frac_vec, {empty_entropy_frac_vec.size()});
   for (int t = 0; t < abl_tally_count(h); t++) {
     uint64_t sh[4];
     check(h, abl_tally_shape(h, t, sh), "abl_tally_shape");

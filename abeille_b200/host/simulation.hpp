@@ -180,6 +180,8 @@ class PowerIterator {  // src/power_iterator.cpp (and src/branchless_power_itera
   std::shared_ptr<Tallies> tallies;
   std::shared_ptr<GPUTransporter> transporter;
   std::vector<double> entropy_vec;
+  // settings: pair-distance-sqrd, families, empty-entropy-bins (src/power_iterator.cpp:283-297; the device-resident loop fills them)
+  std::vector<double> r_sqrd_vec, families_vec, empty_entropy_frac_vec;
   std::vector<uint64_t> nbank_vec;
   double seconds = 0., active_particles = 0.;
   const Problem& problem;

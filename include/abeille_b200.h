@@ -299,6 +299,11 @@ int abl_tally_device_ptr(abl_handle h, int tally, int which, double** out_dev, u
 int abl_sample_source_device(abl_handle h, uint64_t n, uint64_t first_history_id, abl_bank* bank_dev, void* stream);
 /* stats[6] = Npos, Nneg, Wpos, Wneg (unnormalised), and after scaling Wpos', Wneg'                      */
 int abl_bank_weight_stats_device(abl_handle h, const abl_bank* bank_dev, double stats[4], void* stream);
+/* Weighted moments of a device bank about `origin`: moments = { sum w, sum w (x - ox), sum w (y - oy), sum w (z - oz), sum w |r - o|^2 }.
+ * Replaces PowerIterator::compute_pair_dist_sqrd (src/power_iterator.cpp:637-663, settings: pair-distance-sqrd), a double sum over all
+ * pairs of the normalised fission bank: sum_ij w_i w_j |r_i - r_j|^2 / (2 W^2) = sum_i w_i |r_i - c|^2 / W about the weighted centroid
+ * c, i.e. one call about any origin for c and one about c.  The sums of several ranks add. */
+int abl_bank_moments_device(abl_handle h, const abl_bank* bank_dev, const double origin[3], double moments[5], void* stream);
 int abl_bank_scale_weights_device(abl_handle h, abl_bank* bank_dev, double factor, void* stream);
 /* fission bank -> next particle bank: history ids first_id + i, family kept, rng from seed/stride       */
 int abl_bank_to_particles_device(abl_handle h, abl_bank* bank_dev, uint64_t first_history_id, void* stream);

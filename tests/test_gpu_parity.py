@@ -739,6 +739,53 @@ def test_fixed_source_driver_matches_oracle_and_reference(ab, oracle_api, tmp_pa
     sim.close()
 
 
+def test_power_iterator_diagnostics_match_the_references_definitions(ab, tmp_path):
+    """settings: pair-distance-sqrd, families, empty-entropy-bins (src/parser.cpp:833-858).  The pair distance is the reference's
+    double sum over all pairs of the normalised fission bank (PowerIterator::compute_pair_dist_sqrd, src/power_iterator.cpp:637-663),
+    evaluated here term by term in numpy; the device gets it from two passes of abl_bank_moments_device.  Families: the distinct
+    family ids entering a generation (src/power_iterator.cpp:326-331).  Empty entropy bins: Entropy::calculate_empty_fraction
+    (src/entropy.cpp:95-105) against a histogram of the bank's positions."""
+    from abeille_b200.distributed import DistributedPowerIterator
+    n = 2500
+    deck = load_deck("c5g7_delta_collision.yaml")
+    path = write_deck(deck, tmp_path / "d.yaml", {"settings": {"nparticles": n, "ngenerations": 5, "nignored": 2, "pair-distance-sqrd": True,
+                                                               "families": True, "empty-entropy-bins": True}})
+    sim = DistributedPowerIterator(path, 0, n)
+    sim.initialize()
+    ent = deck["entropy"]
+    edges = [np.linspace(ent["low"][k], ent["hi"][k], int(ent["shape"][k]) + 1) for k in range(3)]
+    for g in range(4):
+        fam_in = len(np.unique(sim.cur["id_b"][:sim.n_cur].cpu().numpy()))
+        sim.generation(converged=g >= 2)
+        assert sim.families_series[-1] == fam_in
+        m = sim.n_cur
+        r = np.stack([sim.cur[k][:m].cpu().numpy() for k in ("x", "y", "z")], 1)
+        w = sim.cur["wgt"][:m].cpu().numpy()
+        d2 = ((r[:, None, :] - r[None, :, :]) ** 2).sum(axis=2)               # r.dot(r) of every pair
+        ref = float((d2 * w[:, None] * w[None, :]).sum() / (2.0 * w.sum() ** 2))
+        assert abs(sim.r_sqrd_series[-1] - ref) < 1e-10 * ref, (g, sim.r_sqrd_series[-1], ref)
+        hist, _ = np.histogramdd(r, bins=edges)
+        assert abs(sim.empty_entropy_frac_series[-1] - float((hist == 0).sum()) / hist.size) < 2.0 / hist.size
+    assert sim.families_series[0] == n and sim.families_series[-1] < sim.families_series[1] <= n   # families die out
+    assert 0.0 < sim.empty_entropy_frac_series[-1] < 1.0 and sim.r_sqrd_series[-1] > 100.0
+    # moments about a far origin and about the centroid give the same second central moment
+    mo = sim.gpu.moments_device(sim.cur, sim.n_cur, (1.0e3, -2.0e3, 5.0e2))
+    c = np.array([1.0e3, -2.0e3, 5.0e2]) + mo[1:4] / mo[0]
+    mc = sim.gpu.moments_device(sim.cur, sim.n_cur, c)
+    assert abs(mc[4] / mc[0] - sim.r_sqrd_series[-1]) < 1e-9 * sim.r_sqrd_series[-1] and np.abs(mc[1:4]).max() < 1e-6 * mo[0]
+    empty = sim.gpu.moments_device(sim.cur, 0)
+    assert not empty.any()
+    # the C++ host's device-resident PowerIterator keeps the same three series and writes them under the reference's dataset
+    # names (results/families, results/pair-dist-sqrd, results/empty-entropy-frac: src/power_iterator.cpp:475-503)
+    gpu = ab.Backend(path, 0)
+    gpu.run_power_iteration(4, 2, resident=True)
+    out = tmp_path / "results"
+    gpu.write_results(str(out))
+    assert np.array_equal(np.load(out / "families.npy"), np.array(sim.families_series, dtype=float))
+    assert np.allclose(np.load(out / "pair-dist-sqrd.npy"), sim.r_sqrd_series, rtol=1e-10, atol=0.0)
+    assert np.allclose(np.load(out / "empty-entropy-frac.npy"), sim.empty_entropy_frac_series, rtol=0.0, atol=1e-15)
+
+
 def test_restart_from_a_saved_source_matches_oracle(ab, oracle_api, tmp_path):
     """settings: insource (PowerIterator::load_source_from_file, power_iterator.cpp:60-133): the saved [N, 9] source
     becomes the bank, history ids are the row numbers, the streams are seeded from them and nparticles is the rounded
