@@ -378,6 +378,10 @@ class Backend:
                                              *[arr[k].ctypes.data_as(_PD) for k in ("kcol", "ktrk", "leak", "mig", "entropy")],
                                              nbank.ctypes.data_as(_PU64), summ.ctypes.data_as(_PD))
         self._hcheck(rc)
+        ran = int(np.count_nonzero(nbank))  # fewer than ngen when settings: max-run-time ended the run (PowerIterator::check_time)
+        if ran < ngen:
+            arr = {k: v[:ran] for k, v in arr.items()}
+            nbank = nbank[:ran]
         arr["nbank"] = nbank
         arr.update(kcol_avg=summ[0], kcol_err=summ[1], ktrk_avg=summ[2], ktrk_err=summ[3], leak_avg=summ[4],
                    leak_err=summ[5], seconds=summ[6], active_particles=summ[7], real_collisions=summ[8], flights=summ[9])

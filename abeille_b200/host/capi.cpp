@@ -4,6 +4,7 @@
  * ablh_last_error() gives the text (the reference's fatal_error() exits the process instead,
  * src/error.cpp:36-45).
  */
+#include <algorithm>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -271,7 +272,9 @@ int ablh_run_power_iteration(void* c, int ngen, int nignored, int resident, doub
     const size_t g0 = S.tallies->k_col_vec.size();
     S.run(ngen, nignored, resident != 0);
     const Tallies& T = *S.tallies;
-    for (int g = 0; g < ngen; g++) {
+    // (settings: max-run-time may have ended the loop early: the generations that did not run keep the caller's zeros)
+    const int ran = static_cast<int>(std::min<size_t>(static_cast<size_t>(ngen), T.k_col_vec.size() - g0));
+    for (int g = 0; g < ran; g++) {
       const size_t k = g0 + static_cast<size_t>(g);
       kcol[g] = T.k_col_vec[k]; ktrk[g] = T.k_trk_vec[k]; leak[g] = T.leak_vec[k]; mig[g] = T.mig_vec[k];
       entropy[g] = S.entropy_vec[k]; nbank[g] = S.nbank_vec[k];

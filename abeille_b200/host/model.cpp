@@ -101,6 +101,7 @@ void make_settings(const Node& input, Settings& st) {
   if (s["keff"]) st.keff = s["keff"].as_double();
   if (s["inner-generations"]) st.inner_generations = s["inner-generations"].as_bool();
   if (s["normalize-noise-source"]) st.normalize_noise_source = s["normalize-noise-source"].as_bool();
+  if (s["max-run-time"] && s["max-run-time"].IsScalar()) st.max_time = s["max-run-time"].as_double() * 60.;  // minutes (parser.cpp:703-711)
   // optional diagnostics of the power iteration (src/parser.cpp:833-858)
   if (s["pair-distance-sqrd"] && s["pair-distance-sqrd"].IsScalar()) st.pair_distance_sqrd = s["pair-distance-sqrd"].as_bool();
   if (s["families"] && s["families"].IsScalar()) st.families = s["families"].as_bool();

@@ -34,6 +34,7 @@ struct Settings {  // include/utils/settings.hpp:54-128, defaults src/settings.c
   int n_cancel_noise_gens = INT32_MAX;
   bool inner_generations = true, normalize_noise_source = true;
   bool pair_distance_sqrd = false, families = false, empty_entropy_bins = false;  // settings.cpp:74-76, parser.cpp:833-858
+  double max_time = 1.e300;  // [s] settings: max-run-time, given in minutes (settings.cpp:46, parser.cpp:703-711)
   double w_noise = -1., eta = 1., keff = 1.;
 };
 

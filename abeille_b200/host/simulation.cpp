@@ -510,6 +510,7 @@ void PowerIterator::run_host(int ngenerations, int nignored) {
       bank_.push_back(np);
     }
     global_histories_counter_ += next_gen.size();
+    if (out_of_time(g, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count())) break;  // check_time(g)
     if (g == nignored) transporter->converged = true;
   }
   seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -701,6 +702,7 @@ void PowerIterator::run_resident(int ngenerations, int nignored) {
       nxt.b = nxt_alloc.b;
       nxt.cap = nxt_alloc.cap;
     }
+    if (out_of_time(g, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count())) break;  // check_time(g)
     if (g == nignored) transporter->converged = true;
   }
   seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -747,6 +749,12 @@ void write_npy(const std::string& path, const std::vector<double>& data, const s
   f.write(reinterpret_cast<const char*>(&hlen), 2);
   f.write(dict.data(), static_cast<std::streamsize>(dict.size()));
   f.write(reinterpret_cast<const char*>(data.data()), static_cast<std::streamsize>(data.size() * sizeof(double)));
+}
+
+bool PowerIterator::out_of_time(int gen, double loop_seconds) const {
+  const double T_avg = loop_seconds / static_cast<double>(gen);
+  const double T_used = seconds + loop_seconds;  // (the reference's alpha_omega_timer also holds the parse; here: every loop so far)
+  return problem.settings.max_time - T_used < 2. * T_avg;
 }
 
 void PowerIterator::write_results(const std::string& dir) const {

@@ -182,6 +182,9 @@ class PowerIterator {  // src/power_iterator.cpp (and src/branchless_power_itera
   std::vector<double> entropy_vec;
   // settings: pair-distance-sqrd, families, empty-entropy-bins (src/power_iterator.cpp:283-297; the device-resident loop fills them)
   std::vector<double> r_sqrd_vec, families_vec, empty_entropy_frac_vec;
+  // PowerIterator::out_of_time / check_time (src/power_iterator.cpp:715-749): true when less than two average generations of
+  // settings: max-run-time are left; the loop then ends as if `gen` had been the last generation
+  bool out_of_time(int gen, double loop_seconds) const;
   std::vector<uint64_t> nbank_vec;
   double seconds = 0., active_particles = 0.;
   const Problem& problem;

@@ -452,6 +452,30 @@ def test_results_written_as_npy(ab, tmp_path):
     assert abs(src[:, 7].sum() - 2000.0) < 1e-6  # the bank leaves the last generation normalised to nparticles
 
 
+def test_max_run_time_ends_the_run_after_a_whole_generation(ab, tmp_path):
+    """settings: max-run-time (minutes; src/parser.cpp:703-711).  PowerIterator::check_time (src/power_iterator.cpp:715-749) ends
+    the loop after a generation -- recorded, normalised, written -- once less than two average generations of the budget are
+    left; with no budget at all that is the first generation, on the host-buffer path and on the device-resident one."""
+    for resident in (True, False):
+        path = write_deck(load_deck("c5g7_delta_collision.yaml"), tmp_path / f"t{int(resident)}.yaml",
+                          {"settings": {"nparticles": 2000, "ngenerations": 6, "nignored": 2, "max-run-time": 1.0e-9}})
+        gpu = ab.Backend(path, 0)
+        r = gpu.run_power_iteration(6, 2, resident=resident)
+        assert r["kcol"].shape == (1,) and r["nbank"][0] == 2000 and 0.5 < r["kcol"][0] < 2.0
+        out = tmp_path / f"results{int(resident)}"
+        gpu.write_results(str(out))
+        assert np.load(out / "kcol.npy").shape == (1,)
+        src = np.load(out / "source.npy")
+        assert abs(src[:, 7].sum() - 2000.0) < 1e-6  # the bank of the generation that ran, normalised
+        gpu.close()
+    # a generous budget changes nothing
+    path = write_deck(load_deck("c5g7_delta_collision.yaml"), tmp_path / "t2.yaml",
+                      {"settings": {"nparticles": 2000, "ngenerations": 4, "nignored": 2, "max-run-time": 600.0}})
+    gpu = ab.Backend(path, 0)
+    assert gpu.run_power_iteration(4, 2, resident=True)["kcol"].shape == (4,)
+    gpu.close()
+
+
 def test_full_size_generation_properties(ab, tmp_path):
     """BASELINE size (10^7 histories, the deck's own 1224x1224x10x7 mesh): properties that do not need the oracle.
     Every flight ends in exactly one of a real collision, a virtual collision or a boundary event; the collision
