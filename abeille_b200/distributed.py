@@ -78,6 +78,17 @@ def gather_vector(vec: np.ndarray, world: int, device, group=None) -> np.ndarray
     return out.cpu().numpy().reshape(world, len(vec))
 
 
+def pair_distance_sqrd(moments, gather) -> float:
+    """sum_ij w_i w_j |r_i - r_j|^2 / (2 W^2) over the bank all ranks hold together (PowerIterator::compute_pair_dist_sqrd,
+    src/power_iterator.cpp:637-663) from two passes of this rank's `moments(origin)` = [sum w, sum w (r - o) (3), sum w |r - o|^2]
+    (abl_bank_moments_device) and two gathers: about the origin for the weighted centroid c, then about c."""
+    m1 = gather(np.asarray(moments((0., 0., 0.)), dtype=np.float64)).sum(axis=0)
+    c = m1[1:4] / m1[0]
+    m2 = gather(np.asarray(moments(c), dtype=np.float64)).sum(axis=0)
+    # (the centroid of the second pass is exact only to rounding: remove what is left of it)
+    return float((m2[4] - (m2[1:4] ** 2).sum() / m2[0]) / m2[0])
+
+
 def global_first_ids(counts, rank: int, global_counter: int) -> int:
     """First history id of this rank's slice: exclusive scan of the gathered counts (power_iterator.cpp:389-394)."""
     return int(global_counter) + int(sum(counts[:rank]))
@@ -214,11 +225,7 @@ class DistributedPowerIterator:
         """PowerIterator::compute_pair_dist_sqrd (src/power_iterator.cpp:637-663) over the global normalised fission bank: the
         reference's double sum over all pairs, sum_ij w_i w_j |r_i - r_j|^2 / (2 W^2), is sum_i w_i |r_i - c|^2 / W about the
         weighted centroid c -- two passes of abl_bank_moments_device and two small gathers instead of N^2 terms."""
-        m1 = self._gather(self.gpu.moments_device(self.nxt, m)).sum(axis=0)
-        c = m1[1:4] / m1[0]
-        m2 = self._gather(self.gpu.moments_device(self.nxt, m, c)).sum(axis=0)
-        # (the centroid of the second pass is exact only to rounding: remove what is left of it)
-        return float((m2[4] - (m2[1:4] ** 2).sum() / m2[0]) / m2[0])
+        return pair_distance_sqrd(lambda origin: self.gpu.moments_device(self.nxt, m, origin), self._gather)
 
     # ---- Simulation::sample_sources: rank r samples the ids [r*n, (r+1)*n) ----
     def initialize(self):

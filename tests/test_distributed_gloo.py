@@ -10,7 +10,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from abeille_b200.distributed import even_split, gather_vector, global_first_ids, rebalance_bank, rebalance_plan
+from abeille_b200.distributed import (even_split, gather_vector, global_first_ids, pair_distance_sqrd, rebalance_bank,
+                                      rebalance_plan)
 
 
 def test_even_split_and_plan_cover_everything():
@@ -100,3 +101,51 @@ def test_rebalance_preserves_global_order_on_two_ranks(counts):
     for r in res:
         assert np.array_equal(r[4][:, 1], [0.0, 1.0]) and np.all(r[4][:, 2] == 2.5)
         assert r[5] == 1000 + int(bounds[r[0]])                             # contiguous global history ids
+
+
+def _cloud(n=900, seed=3):
+    rng = np.random.default_rng(seed)
+    r = rng.normal(size=(n, 3)) * np.array([20.0, 20.0, 60.0]) + np.array([5.0, -3.0, 40.0])
+    w = rng.uniform(0.2, 1.8, n)
+    w[rng.random(n) < 0.05] *= -1.0   # a few negative weights, as carter tracking leaves them
+    return r, w
+
+
+def _moments(r, w, origin):  # what abl_bank_moments_device returns for a slice
+    d = r - np.asarray(origin, dtype=np.float64)
+    return np.array([w.sum(), *(w[:, None] * d).sum(axis=0), (w * (d * d).sum(axis=1)).sum()])
+
+
+def _pair_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        r, w = _cloud()
+        lo, hi = (0, 350) if rank == 0 else (350, len(w))    # uneven slices
+        got = pair_distance_sqrd(lambda o: _moments(r[lo:hi], w[lo:hi], o), lambda v: gather_vector(v, world, torch.device("cpu")))
+        q.put((rank, got))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pair_distance_of_a_sharded_bank_is_the_references_double_sum():
+    """settings: pair-distance-sqrd on two ranks: the sums of the slices' moments give the reference's double sum over all pairs of
+    the WHOLE bank (PowerIterator::compute_pair_dist_sqrd, src/power_iterator.cpp:637-663, evaluated here term by term), and the
+    one-rank value."""
+    r, w = _cloud()
+    d2 = ((r[:, None, :] - r[None, :, :]) ** 2).sum(axis=2)
+    ref = float((d2 * w[:, None] * w[None, :]).sum() / (2.0 * w.sum() ** 2))
+    one = pair_distance_sqrd(lambda o: _moments(r, w, o), lambda v: v[None, :])
+    assert abs(one - ref) < 1e-12 * abs(ref)
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pair_worker, args=(k, world, port, q)) for k in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1] and abs(res[0][1] - ref) < 1e-12 * abs(ref)
