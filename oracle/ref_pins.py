@@ -640,6 +640,39 @@ def evaluate_power_iteration(impl: str, only: int | None = None) -> dict:
     return out
 
 
+# the power iteration's optional diagnostics: deck, particles, generations, ignored generations (carter: negative weights)
+DIAG_CASES = (("c5g7_delta_collision.yaml", 1500, 5, 2), ("c5g7_carter_cancel.yaml", 1500, 4, 1))
+
+
+def evaluate_pi_diagnostics(only: int) -> dict:
+    """The reference's own PowerIterator::run() with settings pair-distance-sqrd, families and empty-entropy-bins on
+    (src/power_iterator.cpp:283-297,326-331,362-365,613-615,637-663): the three per-generation series, k_col, and the final
+    bank [n, 4] = x y z wgt the last pair distance was taken over.  One case per process (oracle/_ref only)."""
+    from . import deck as _deck
+    L = ref_lib()
+    fname, n, ngen, nign = DIAG_CASES[only]
+    decks = os.path.join(os.path.dirname(_HERE), "tests", "decks")
+    deck = _deck.apply_overrides(_deck.load_yaml(os.path.join(decks, fname)), {"settings": {"nparticles": n, "ngenerations": ngen, "nignored": nign}})
+    keys = ("kcol", "ktrk", "leak", "mig", "entropy")
+    a = {k: np.zeros(ngen) for k in keys}
+    summ = np.zeros(6)
+    L.ref_set_threads(C.c_int(1))
+    L.ref_set_diagnostics(C.c_int(1), C.c_int(1), C.c_int(1))
+    rc = L.ref_power_iteration(_deck.deck_to_text(deck).encode(), C.c_int(ngen), C.c_int(nign), *[_d(a[k]) for k in keys], _d(summ))
+    assert rc == 0
+    ser = [np.zeros(ngen) for _ in range(3)]
+    n3 = (C.c_uint64 * 3)()
+    L.ref_pi_diagnostics(_d(ser[0]), _d(ser[1]), _d(ser[2]), C.c_uint64(ngen), n3)
+    assert list(n3) == [ngen, ngen, ngen]
+    L.ref_last_bank_get.restype = C.c_uint64
+    bank = np.zeros((4 * n, 4))
+    nb = int(L.ref_last_bank_get(_d(bank), C.c_uint64(len(bank))))
+    assert 0 < nb <= len(bank)
+    name = fname.split(".")[0]
+    return {f"diag_{name}_r_sqrd": ser[0], f"diag_{name}_families": ser[1], f"diag_{name}_empty": ser[2], f"diag_{name}_kcol": a["kcol"],
+            f"diag_{name}_entropy": a["entropy"], f"diag_{name}_bank": np.ascontiguousarray(bank[:nb])}
+
+
 # whole noise simulations: deck, particles, noise batches, ignored generations, nskip
 NOISE_DRIVER_CASES = (("noise_oscillation.yaml", 600, 2, 1, 2), ("noise_oscillation_delta.yaml", 500, 2, 2, 1),
                       ("noise_vibration.yaml", 500, 2, 1, 2))

@@ -1129,6 +1129,8 @@ DriverParts driver_parts(const char* text) {
   return d;
 }
 uint64_t g_last_bank_size = 0;
+// settings: pair-distance-sqrd / families / empty-entropy-bins of the last run (src/power_iterator.cpp:283-297) and its final bank
+std::vector<double> g_diag_r_sqrd, g_diag_families, g_diag_empty, g_last_bank_xyzw;
 void set_entropy(Simulation& sim, const std::vector<std::string>& lines) {
   for (const auto& el : lines) {
     std::istringstream ls(el);
@@ -1159,6 +1161,12 @@ void run_iterator(DriverParts& d, int ngen, double* kcol, double* ktrk, double* 
   pi->run();
   g_last_simulation_seconds = pi->simulation_timer.elapsed_time();  // the generation loop (src/power_iterator.cpp:316-318,432)
   g_last_bank_size = pi->bank.size();
+  g_diag_r_sqrd = pi->r_sqrd_vec;
+  g_diag_families.assign(pi->families_vec.begin(), pi->families_vec.end());
+  g_diag_empty = pi->empty_entropy_frac_vec;
+  g_last_bank_xyzw.clear();
+  for (const Particle& p : pi->bank)
+    for (double v : {p.r().x(), p.r().y(), p.r().z(), p.wgt()}) g_last_bank_xyzw.push_back(v);
   const Tallies& T = *g_tallies;
   for (int g = 0; g < ngen; g++) {
     kcol[g] = T.k_col_vec[(size_t)g]; ktrk[g] = T.k_trk_vec[(size_t)g]; leak[g] = T.leak_vec[(size_t)g]; mig[g] = T.mig_vec[(size_t)g];
@@ -1230,6 +1238,27 @@ void ref_sobol_points(int n, double* out4n) {
 }
 // size of the source bank the last ref_power_iteration ended with (after combing, for a branchless deck)
 uint64_t ref_last_bank_size() { return g_last_bank_size; }
+// the optional diagnostics of the next ref_power_iteration (settings::pair_distance_sqrd, families, empty_entropy_bins) ...
+void ref_set_diagnostics(int pair_distance, int families, int empty_entropy) {
+  settings::pair_distance_sqrd = pair_distance != 0;
+  settings::families = families != 0;
+  settings::empty_entropy_bins = empty_entropy != 0;
+}
+// ... their per-generation series after it (each array holds ngen values when its option was on, else nothing is written;
+// the three lengths are returned in n3) and the final bank, [n][4] = x y z wgt, normalised, in bank order
+void ref_pi_diagnostics(double* r_sqrd, double* families, double* empty, uint64_t cap, uint64_t n3[3]) {
+  const std::vector<double>* v[3] = {&g_diag_r_sqrd, &g_diag_families, &g_diag_empty};
+  double* out[3] = {r_sqrd, families, empty};
+  for (int k = 0; k < 3; k++) {
+    n3[k] = v[k]->size();
+    for (uint64_t i = 0; i < v[k]->size() && i < cap; i++) out[k][i] = (*v[k])[i];
+  }
+}
+uint64_t ref_last_bank_get(double* xyzw, uint64_t cap_rows) {
+  const uint64_t n = g_last_bank_xyzw.size() / 4;
+  for (uint64_t i = 0; i < 4 * std::min(n, cap_rows); i++) xyzw[i] = g_last_bank_xyzw[i];
+  return n;
+}
 
 // The reference's own PowerIterator::initialize() + run() (src/power_iterator.cpp:170-473) on the deck text: sources,
 // entropy mesh and cancelator are built through their plain constructors from the "src", "entropy" and "cancelator" lines
