@@ -467,6 +467,16 @@ class Oracle:
         return arr
 
 
+    def set_pi_diagnostics(self, on: bool = True):
+        """settings: pair-distance-sqrd, families, empty-entropy-bins for the generation loops below (the pair distance is the
+        reference's sum over all pairs: keep nparticles small)."""
+        lib().orc_pi_set_diagnostics(self.h, C.c_int(int(bool(on))))
+
+    def pi_diagnostics(self, ngen: int) -> dict:
+        a = [np.zeros(ngen) for _ in range(3)]
+        n = lib().orc_pi_diagnostics(self.h, *[v.ctypes.data_as(_PD) for v in a], C.c_int(ngen))
+        return {"r_sqrd": a[0][:n], "families": a[1][:n], "empty": a[2][:n]}
+
     # stateful generation loop (bench.py CPU legs)
     def pi_init(self, nignored: int):
         if lib().orc_pi_init(self.h, C.c_int(int(nignored))) != 0:

@@ -35,6 +35,7 @@
 #include <cstring>
 #include <fstream>
 #include <memory>
+#include <set>
 #include <sstream>
 #include <unordered_map>
 
@@ -2582,6 +2583,9 @@ struct PIState {
   std::vector<Particle> bank;
   int gen = 0, nignored = 0;
   double active_particles = 0;
+  // settings: pair-distance-sqrd, families, empty-entropy-bins (power_iterator.cpp:283-297), per generation when `diagnostics` is on
+  bool diagnostics = false;
+  std::vector<double> r_sqrd, families, empty_frac;
 };
 static std::map<Problem*, PIState> g_pi;
 
@@ -2598,6 +2602,21 @@ static void pi_init(Problem& P, int nignored) {
   S.gen = 0;
   S.nignored = nignored;
   S.active_particles = 0;
+  S.r_sqrd.clear(); S.families.clear(); S.empty_frac.clear();
+}
+
+// PowerIterator::compute_pair_dist_sqrd (power_iterator.cpp:637-663), one thread: the sum over all pairs in the reference's order
+static double compute_pair_dist_sqrd(const std::vector<BankedParticle>& next_gen) {
+  double Ntot = 0., r_sqr = 0.;
+  for (size_t i = 0; i < next_gen.size(); i++) {
+    Ntot += next_gen[i].wgt;
+    for (size_t j = 0; j < next_gen.size(); j++) {
+      const Vec r = next_gen[i].r - next_gen[j].r;
+      r_sqr += r.dot(r) * next_gen[i].wgt * next_gen[j].wgt;
+    }
+  }
+  r_sqr /= 2. * Ntot * Ntot;
+  return r_sqr;
 }
 
 // one generation; out5 = k_col, k_trk, leak, mig, entropy
@@ -2608,12 +2627,23 @@ static void pi_generation(Problem& P, double* out5, uint64_t* nbank_in) {
   const int g = ++S.gen;
   if (P.converged) S.active_particles += (double)bank.size();
   *nbank_in = bank.size();
+  if (S.diagnostics) {  // the families that enter the generation (power_iterator.cpp:326-331)
+    std::set<uint64_t> fam;
+    for (const auto& p : bank) fam.insert(p.family_id);
+    S.families.push_back((double)fam.size());
+  }
   auto next_gen = transport(P, bank, false, nullptr, false);
   if (next_gen.empty()) throw std::runtime_error("No fission neutrons were produced.");
   if (P.entropy.present) for (auto& p : next_gen) P.entropy.add_point(p.r, p.wgt);
+  if (S.diagnostics && P.entropy.present) {  // Entropy::calculate_empty_fraction (entropy.cpp:95-105) at power_iterator.cpp:613-615
+    double num_empty_bins = 0.;
+    for (double b : P.entropy.bins) if (b == 0.) num_empty_bins += 1.;
+    S.empty_frac.push_back(num_empty_bins / static_cast<double>(P.entropy.bins.size()));
+  }
   T.calc_gen_values();
   if (P.st.regional_cancellation && P.cancel.present) perform_regional_cancellation(P, next_gen);
   normalize_weights(P, next_gen);
+  if (S.diagnostics) S.r_sqrd.push_back(compute_pair_dist_sqrd(next_gen));  // power_iterator.cpp:361-365
   if (P.st.mode == Settings::BRANCHLESS && P.st.branchless_combing) comb_particles(P, next_gen);  // branchless_power_iterator.cpp:361-363
   if (P.converged) {
     for (const auto& p : next_gen)
@@ -2640,6 +2670,19 @@ static void pi_generation(Problem& P, double* out5, uint64_t* nbank_in) {
 void orc_free(void* h) {
   g_pi.erase(static_cast<Problem*>(h));
   delete static_cast<Problem*>(h);
+}
+
+// the optional diagnostics of the generation loop: on / off, and the series since pi_init (three arrays of up to cap values;
+// returns the number of generations)
+void orc_pi_set_diagnostics(void* h, int on) { g_pi[static_cast<Problem*>(h)].diagnostics = on != 0; }
+int orc_pi_diagnostics(void* h, double* r_sqrd, double* families, double* empty_frac, int cap) {
+  const PIState& S = g_pi[static_cast<Problem*>(h)];
+  for (int g = 0; g < cap; g++) {
+    if ((size_t)g < S.r_sqrd.size()) r_sqrd[g] = S.r_sqrd[(size_t)g];
+    if ((size_t)g < S.families.size()) families[g] = S.families[(size_t)g];
+    if ((size_t)g < S.empty_frac.size()) empty_frac[g] = S.empty_frac[(size_t)g];
+  }
+  return (int)S.families.size();
 }
 
 int orc_pi_init(void* h, int nignored) {
