@@ -492,7 +492,7 @@ Universe make_universe(const Node& u, const Problem& P) {
     if (!ids || !ids.IsSequence() || ids.size() != nt) fatal_error("Lattice " + std::to_string(uni.id) + " has an invalid number of universes.");
     for (size_t i = 0; i < nt; i++) uni.tile_ids.push_back(ids[i].as_int());
   } else {
-    fatal_error("Universe " + std::to_string(uni.id) + " is neither a cell universe nor a lattice.");
+    fatal_error("Invalid universe definition.");  // src/parser.cpp:302-308 (neither `cells` nor `pitch`: e.g. the old `lattice: n` form)
   }
   return uni;
 }

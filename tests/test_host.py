@@ -159,6 +159,8 @@ def test_legendre_tables_for_anisotropic_deck(native_libs):
     ({"settings": {"energy-mode": "continuous-energy"}}, "multi-group"),
     ({"root-universe": 12345}, "Could not find universe"),
     ({"settings": {"nignored": 5000}}, "ignored"),
+    # the old `lattice: n` universe form of the shipped ref_sqr_c5g7.yaml, which the reference's own parser refuses (src/parser.cpp:302-308)
+    ({"universes": [{"lattice": 1, "id": 10, "name": "old form"}], "root-universe": 10}, "Invalid universe definition."),
 ])
 def test_parser_errors(native_libs, tmp_path, bad, msg):
     from abeille_b200 import BackendError
