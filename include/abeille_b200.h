@@ -295,7 +295,10 @@ int abl_tally_fetch(abl_handle h, int tally, int which, double* out_host);
 int abl_tally_device_ptr(abl_handle h, int tally, int which, double** out_dev, uint64_t* n);
 
 /* ---- inter-generation bank pipeline on the device (power_iterator.cpp:341-404,538-586) ---------------- */
-/* Source sampling (simulation.cpp:55-77): n particles with history ids first_id.., written to bank_dev */
+/* Source sampling (simulation.cpp:55-77, Source::generate_particle source.cpp:44-90): n particles with history ids first_id.., written
+ * to bank_dev.  Per particle, on its own stream: the source by weight, the direction (abl_source.direction_kind), the energy once and
+ * then again until it lies inside (min_energy, max_energy) -- ABL_ERR_INVALID after 201 redraws --, the position until it is inside the
+ * geometry (and, fissile-only, inside a fissile material: ABL_ERR_INVALID after 201 attempts). */
 int abl_sample_source_device(abl_handle h, uint64_t n, uint64_t first_history_id, abl_bank* bank_dev, void* stream);
 /* stats[6] = Npos, Nneg, Wpos, Wneg (unnormalised), and after scaling Wpos', Wneg'                      */
 int abl_bank_weight_stats_device(abl_handle h, const abl_bank* bank_dev, double stats[4], void* stream);
