@@ -719,7 +719,7 @@ int status_from_device_error(abl_handle h, const DevSmall& sm) {
     case ABL_ERR_GEOMETRY: what = "geometry nesting deeper than ABL_MAX_PADS / ABL_MAX_FRAMES"; break;
     case ABL_ERR_BANK_OVERFLOW: what = "secondary stack overflow (ABL_SEC_CAP)"; break;
     case ABL_ERR_TIMEOUT: what = "history kernel ran past its deadline and was wound down (ABEILLE_B200_KERNEL_TIMEOUT_S)"; break;
-    case ABL_ERR_INVALID: what = "source sampling failed (point source outside the geometry or fissile-only rejection limit)"; break;
+    case ABL_ERR_INVALID: what = "source sampling failed (point source outside the geometry, fissile-only rejection limit, or 200 samplings of energy exceeded)"; break;
   }
   snprintf(buf, sizeof buf, "%s (history %llu)", what, (unsigned long long)hid);
   h->error = buf;
